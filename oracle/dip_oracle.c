@@ -1,0 +1,334 @@
+/*
+ * dip_oracle.c -- CPU restatement of DIP's pricing round (see dip_oracle.h).
+ *
+ * TEST INFRASTRUCTURE ONLY: the checker for the CUDA path and the "port" CPU
+ * baseline of bench.py.  Never linked into libdipgpu.
+ *
+ * Every function cites the reference lines (relative to /root/reference) whose
+ * arithmetic it restates.  Written from the behaviour of those lines; no
+ * reference source is copied.
+ */
+#include "dip_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ---------------------------------------------------------------- duals -- */
+
+void dip_oracle_adjust_duals(const double *uOld, int nMasterRows, int nBaseCoreRows,
+                             int numConvex, double *uNew)
+{
+    /* DecompAlgo.cpp:4566 -- core (original + branch) rows keep their slot */
+    memcpy(uNew, uOld, sizeof(double) * (size_t)nBaseCoreRows);
+    /* DecompAlgo.cpp:4595-4597 -- cut rows slide down over the convexity rows */
+    int nCuts = nMasterRows - nBaseCoreRows - numConvex;
+    if (nCuts > 0)
+        memcpy(uNew + nBaseCoreRows, uOld + nBaseCoreRows + numConvex,
+               sizeof(double) * (size_t)nCuts);
+}
+
+/* ------------------------------------------------------------ red. cost -- */
+
+void dip_oracle_calc_redcost(int R, int N, const int64_t *rowStart, const int32_t *colInd,
+                             const double *val, const double *uAdj, const double *c,
+                             int phase1, double *redCostX)
+{
+    /* DecompAlgo.cpp:4532: modelCore->M->transposeTimes(u, redCostX) on a
+     * row-ordered matrix (DecompConstraintSet.cpp:41-43) = scatter of u[i]*row i.
+     * CoinUtils walks the major vectors from the last to the first and skips
+     * exact-zero multipliers (un-vendored; order is "parity unpinned"). */
+    for (int j = 0; j < N; ++j) redCostX[j] = 0.0;
+    for (int i = R - 1; i >= 0; --i) {
+        const double ui = uAdj[i];
+        if (ui == 0.0) continue;
+        for (int64_t k = rowStart[i]; k < rowStart[i + 1]; ++k)
+            redCostX[colInd[k]] += ui * val[k];
+    }
+    if (phase1) { /* DecompAlgo.cpp:4538-4541 */
+        for (int j = 0; j < N; ++j) redCostX[j] = -redCostX[j];
+    } else { /* DecompAlgo.cpp:4543-4545 */
+        for (int j = 0; j < N; ++j) redCostX[j] = c[j] - redCostX[j];
+    }
+}
+
+/* ------------------------------------------------------------- knapsack -- */
+
+double dip_oracle_knapsack01(int n, const double *obj, const int32_t *weights, int capacity,
+                             int32_t *solution, int *nSol, uint8_t *added)
+{
+    /* gap_func.py:139-141 */
+    if (nSol) *nSol = 0;
+    if (n <= 0) return 0.0;
+
+    const size_t W = (size_t)capacity + 1;
+    uint8_t *tab = added ? added : (uint8_t *)calloc((size_t)n * W, 1);
+    if (added) memset(tab, 0, (size_t)n * W);
+    double *row = (double *)calloc(W, sizeof(double)); /* c[i-1][.], row -1 == 0 */
+
+    /* gap_func.py:160-170.  The two-row table is evaluated in place with the
+     * capacity index descending, which reads exactly c[i-1][j - w]; cells with
+     * w > j keep c[i-1][j].  The take test is the strict '>' of :166. */
+    for (int i = 0; i < n; ++i) {
+        const int w = weights[i];
+        const double p = obj[i];
+        uint8_t *t = tab + (size_t)i * W;
+        if (w > capacity) continue;
+        for (int j = capacity; j >= w; --j) {
+            const double cand = p + row[j - w];
+            if (cand > row[j]) {
+                row[j] = cand;
+                t[j] = 1;
+            }
+        }
+    }
+    const double z = row[capacity];
+
+    /* gap_func.py:173-181: walk items from the last one down */
+    int cnt = 0;
+    int j = capacity;
+    for (int i = n - 1; i >= 0 && j >= 0; --i) {
+        if (tab[(size_t)i * W + (size_t)j]) {
+            if (solution) solution[cnt] = i;
+            ++cnt;
+            j -= weights[i];
+        }
+    }
+    if (nSol) *nSol = cnt;
+    free(row);
+    if (!added) free(tab);
+    return z;
+}
+
+/* Dip/src/UtilMacros.h:521-531 */
+static double util_frac_part(double x)
+{
+    const double fl = floor(x);
+    const double flp = floor(x + 0.5);
+    if (fabs(flp - x) < 1.0e-6 * (fabs(flp) + 1.0)) return 0.0;
+    return x - fl;
+}
+
+/* Dip/src/UtilMacros.h:548-552 */
+static int util_is_zero(double x) { return fabs(x) < 1.0e-8; }
+
+int dip_oracle_calc_scale_factor(int n, const double *redCost, double *work)
+{
+    /* GAP_KnapPisinger.h:89-143, epsTol = 1e-4 */
+    const double epsTol = 1.0e-4;
+    const double oneOverEps = 1.0 / epsTol;
+    int scale = 1, nFrac = 0;
+    for (int i = 0; i < n; ++i) {
+        if (redCost[i] >= 0) continue;
+        double frac = util_frac_part(-redCost[i]);
+        if (!util_is_zero(frac)) {
+            frac *= oneOverEps;
+            work[nFrac++] = (int)frac * (double)epsTol; /* truncate to 1e-4 */
+        }
+    }
+    for (int i = 0; i < nFrac; ++i) {
+        int tooBig = 0;
+        work[i] *= scale;
+        while (!util_is_zero(util_frac_part(work[i]))) {
+            scale *= 10;
+            if (scale >= oneOverEps) {
+                tooBig = 1;
+                break;
+            }
+            work[i] *= 10;
+        }
+        if (tooBig) break;
+    }
+    return scale;
+}
+
+int dip_oracle_solve_block(int n, const double *redCost, const double *origCost,
+                           const int32_t *weight, int capacity, int colOffset, int profitMode,
+                           int32_t *ind, double *varRedCost, double *varOrigCost, double *zOut,
+                           int64_t *cellsOut)
+{
+    int32_t *toOrig = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    int32_t *w = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    double *p = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    uint8_t *x = (uint8_t *)calloc((size_t)(n > 0 ? n : 1), 1);
+    int nItems = 0;
+    long weightSum = 0;
+    double z = 0.0;
+
+    if (profitMode == 0) {
+        /* gap_func.py:102-105: tasks with negative reduced cost, obj = -rc */
+        for (int j = 0; j < n; ++j) {
+            if (redCost[j] < 0) {
+                toOrig[nItems] = j;
+                w[nItems] = weight[j];
+                p[nItems] = -redCost[j];
+                ++nItems;
+            }
+        }
+    } else {
+        /* GAP_KnapPisinger.h:167-186 */
+        double *work = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+        const int scale = dip_oracle_calc_scale_factor(n, redCost, work);
+        free(work);
+        for (int j = 0; j < n; ++j) {
+            if (redCost[j] < 0.0) {
+                const double scaled = (-redCost[j]) * scale;
+                toOrig[nItems] = j;
+                w[nItems] = weight[j];
+                p[nItems] = (double)(long)floor(scaled + 0.5);
+                weightSum += weight[j];
+                ++nItems;
+            }
+        }
+    }
+
+    int64_t cells = 0;
+    int solved = 0;
+    if (profitMode == 1) {
+        /* GAP_KnapPisinger.h:203-238: trivial cases before combo */
+        if (nItems == 1) {
+            x[0] = 1;
+            z = p[0];
+            solved = 1;
+        } else if (nItems >= 1 && weightSum <= capacity) {
+            for (int i = 0; i < nItems; ++i) {
+                x[i] = 1;
+                z += p[i];
+            }
+            solved = 1;
+        } else if (nItems == 2) {
+            double best = 0;
+            if (w[1] <= capacity && p[1] > best) { best = p[1]; x[0] = 0; x[1] = 1; }
+            if (w[0] <= capacity && p[0] > best) { best = p[0]; x[0] = 1; x[1] = 0; }
+            if (w[0] + w[1] <= capacity && p[0] + p[1] > best) { best = p[0] + p[1]; x[0] = 1; x[1] = 1; }
+            z = best;
+            solved = 1;
+        }
+    }
+    if (!solved && nItems > 0) {
+        /* gap_func.py:107 / GAP_KnapPisinger.h:243-249 (combo stand-in) */
+        int32_t *sol = (int32_t *)malloc(sizeof(int32_t) * (size_t)nItems);
+        int nSol = 0;
+        z = dip_oracle_knapsack01(nItems, p, w, capacity, sol, &nSol, NULL);
+        for (int k = 0; k < nSol; ++k) x[sol[k]] = 1;
+        free(sol);
+        for (int i = 0; i < nItems; ++i)
+            if (w[i] <= capacity) cells += (int64_t)capacity + 1;
+    }
+
+    /* GAP_KnapPisinger.h:263-272 + GAP_DecompApp.cpp:252-253: x-space indices,
+     * element 1.0, sums of the TRUE reduced / original costs.  Emission order
+     * here is ascending index (Appendix A.8 (iv) of SURVEY.md). */
+    int nnz = 0;
+    double rc = 0.0, oc = 0.0;
+    for (int i = 0; i < nItems; ++i) {
+        if (x[i]) {
+            const int j = toOrig[i];
+            rc += redCost[j];
+            oc += origCost[j];
+            if (ind) ind[nnz] = colOffset + j;
+            ++nnz;
+        }
+    }
+    *varRedCost = rc;
+    *varOrigCost = oc;
+    if (zOut) *zOut = z;
+    if (cellsOut) *cellsOut = cells;
+    free(toOrig);
+    free(w);
+    free(p);
+    free(x);
+    return nnz;
+}
+
+int dip_oracle_solve_blocks(int m, const int32_t *blockColStart, const int32_t *weight,
+                            const int32_t *capacity, int profitMode, const double *redCostX,
+                            const double *origCost, const double *alpha, double redCostEps,
+                            int nThreads, int maxBlockCols, int32_t *colNnz,
+                            double *colRedCost, double *colOrigCost, int32_t *colKeep,
+                            double *mostNegRC, double *z, int32_t *colIndOut,
+                            double *mostNegReducedCost, int64_t *cellsOut)
+{
+    int64_t cellsTotal = 0;
+    (void)nThreads;
+    /* DecompAlgo.cpp:4815-4848: one task per block, dynamic schedule */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nThreads > 0 ? nThreads : 1) reduction(+ : cellsTotal)
+#endif
+    for (int b = 0; b < m; ++b) {
+        const int s = blockColStart[b];
+        const int n = blockColStart[b + 1] - s;
+        double rc = 0, oc = 0, zb = 0;
+        int64_t cells = 0;
+        int32_t *ind = colIndOut ? colIndOut + (size_t)b * (size_t)maxBlockCols : NULL;
+        /* GAP_DecompApp.cpp:247-281 */
+        const int nnz = dip_oracle_solve_block(n, redCostX + s, origCost + s, weight + s,
+                                               capacity[b], s, profitMode, ind, &rc, &oc, &zb,
+                                               &cells);
+        colNnz[b] = nnz;
+        /* DecompAlgo.cpp:6350-6356: the driver subtracts alpha for Point vars */
+        colRedCost[b] = rc - alpha[b];
+        colOrigCost[b] = oc;
+        if (z) z[b] = zb;
+        cellsTotal += cells;
+    }
+    /* DecompAlgo.cpp:4761, 5151-5232 */
+    int kept = 0;
+    double sum = 0.0;
+    for (int b = 0; b < m; ++b) {
+        double mn = 0.0;
+        if (colRedCost[b] < mn) mn = colRedCost[b];
+        mostNegRC[b] = mn;
+        colKeep[b] = colRedCost[b] < -redCostEps ? 1 : 0;
+        kept += colKeep[b];
+    }
+    for (int b = 0; b < m; ++b) sum += mostNegRC[b];
+    if (mostNegReducedCost) *mostNegReducedCost = sum;
+    if (cellsOut) *cellsOut = cellsTotal;
+    return kept;
+}
+
+int dip_oracle_price_round(int R, int N, const int64_t *rowStart, const int32_t *colInd,
+                           const double *val, const double *c, const double *u, int nBase,
+                           int phase1, int m, const int32_t *blockColStart,
+                           const int32_t *weight, const int32_t *capacity, int profitMode,
+                           double redCostEps, int nThreads, int maxBlockCols,
+                           double *redCostX, int32_t *colNnz, double *colRedCost,
+                           double *colOrigCost, int32_t *colKeep, double *mostNegRC,
+                           double *z, int32_t *colIndOut, double *mostNegReducedCost,
+                           int64_t *cellsOut)
+{
+    /* DecompAlgo.cpp:4692-4726 */
+    double *uAdj = (double *)malloc(sizeof(double) * (size_t)(R > 0 ? R : 1));
+    dip_oracle_adjust_duals(u, R + m, nBase, m, uAdj);
+    dip_oracle_calc_redcost(R, N, rowStart, colInd, val, uAdj, c, phase1, redCostX);
+    free(uAdj);
+    /* DecompAlgo.cpp:4820: alpha_b = u[nBaseCoreRows + b] */
+    const int kept = dip_oracle_solve_blocks(m, blockColStart, weight, capacity, profitMode,
+                                             redCostX, c, u + nBase, redCostEps, nThreads,
+                                             maxBlockCols, colNnz, colRedCost, colOrigCost,
+                                             colKeep, mostNegRC, z, colIndOut,
+                                             mostNegReducedCost, cellsOut);
+    return kept;
+}
+
+int dip_oracle_string_hash(int len, const int32_t *ind, const double *els, char *buf,
+                           int bufLen)
+{
+    /* UtilHash.cpp:52-68: "ind_el_" per non-zero element, default precision 6 */
+    int pos = 0;
+    if (bufLen < 1) return -1;
+    buf[0] = '\0';
+    for (int i = 0; i < len; ++i) {
+        if (fabs(els[i]) < 1.0e-8) continue;
+        int k = snprintf(buf + pos, (size_t)(bufLen - pos), "%d_%.6g_", ind[i], els[i]);
+        if (k < 0 || k >= bufLen - pos) return -1;
+        pos += k;
+    }
+    return pos;
+}

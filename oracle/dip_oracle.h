@@ -1,0 +1,116 @@
+/*
+ * dip_oracle.h -- CPU restatement of DIP's column-generation pricing round.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (dip_b200/, include/)
+ * may include, link or call this.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py use it, as the checker.
+ *
+ * Parity pinning status (see DESIGN.md "Oracle"):
+ *   - knapsack01 DP: PINNED against the reference's own Python function
+ *     (Dip/src/dippy/examples/gap/gap_func.py:132-183), executed unchanged via
+ *     AST extraction by oracle/gen_golden.py -> tests/golden/knapsack01_*.json,
+ *     and cross-checked on integer-profit cases against the reference's
+ *     Horowitz-Sahni B&B compiled from Dip/src/UtilKnapsack.cpp (oracle/_ref).
+ *   - reduced costs: restates DecompAlgo.cpp:4506-4619; the inner product is
+ *     CoinUtils' CoinPackedMatrix::transposeTimes (CoinUtils 2.11, NOT vendored
+ *     in /root/reference) -> summation ORDER is "parity unpinned"; values are
+ *     checked to 1e-12 relative, which any order satisfies.
+ *   - Pisinger-mode argmax: combo.c is not vendored -> "parity unpinned" for
+ *     the argmax on ties; optimal VALUES are unique (integer profits).
+ *
+ * All paths below are relative to /root/reference.
+ */
+#ifndef DIP_ORACLE_H
+#define DIP_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* DecompAlgo::generateVarsAdjustDuals, Dip/src/DecompAlgo.cpp:4550-4619.
+ * uOld has nMasterRows entries laid out [core rows 0..nBase) | numConvex
+ * convexity rows | cut rows]; uNew gets nMasterRows - numConvex entries. */
+void dip_oracle_adjust_duals(const double *uOld, int nMasterRows, int nBaseCoreRows,
+                             int numConvex, double *uNew);
+
+/* DecompAlgo::generateVarsCalcRedCost, Dip/src/DecompAlgo.cpp:4506-4547, with
+ * CoinPackedMatrix::transposeTimes restated as the row-major scatter
+ * (rows descending, zero duals skipped).  phase1 != 0 -> c is taken as 0. */
+void dip_oracle_calc_redcost(int R, int N, const int64_t *rowStart, const int32_t *colInd,
+                             const double *val, const double *uAdj, const double *c,
+                             int phase1, double *redCostX);
+
+/* knapsack01, Dip/src/dippy/examples/gap/gap_func.py:132-183.
+ * max sum obj*x, sum w*x <= capacity; strict '>' take rule, backtrack from
+ * (n-1, capacity).  solution[] receives the chosen item indices in the
+ * reference's (descending) order, *nSol their count.  added (optional,
+ * n*(capacity+1) bytes) receives the decision table.  Returns z = c[n-1][cap].
+ * Documented divergence: n==1 is evaluated as a standard 0-1 DP (the Python
+ * aliases row -1 onto row 0 for n==1). */
+double dip_oracle_knapsack01(int n, const double *obj, const int32_t *weights, int capacity,
+                             int32_t *solution, int *nSol, uint8_t *added);
+
+/* GAP_KnapPisinger::calcScaleFactor, Dip/examples/GAP/GAP_KnapPisinger.h:89-143
+ * (UtilFracPart/UtilIsZero from Dip/src/UtilMacros.h:521-552). */
+int dip_oracle_calc_scale_factor(int n, const double *redCost, double *work);
+
+/* One block of pricing = GAP_DecompApp::solveRelaxed
+ * (Dip/examples/GAP/GAP_DecompApp.cpp:235-285) around a knapsack solve.
+ *   profitMode 0: items = {j : redCost[j] < 0} ascending, obj = -redCost (fp64),
+ *                 solved by knapsack01 (gap_func.py:96-130 solve_subproblem).
+ *   profitMode 1: GAP_KnapPisinger::solve (GAP_KnapPisinger.h:146-273): scaled
+ *                 integer profits, n==1 / all-fit / n==2 shortcuts, else exact
+ *                 solve (combo.c is not vendored: the DP stands in; same z*).
+ * redCost/origCost/weight point at the block's slice (length n).  colOffset is
+ * added to the local index to form the x-space index.  ind[] (capacity n) gets
+ * the chosen indices ASCENDING; varRedCost / varOrigCost are summed in that
+ * order and exclude alpha.  *zOut = knapsack optimum (in DP profit units).
+ * Returns the column's nnz. */
+int dip_oracle_solve_block(int n, const double *redCost, const double *origCost,
+                           const int32_t *weight, int capacity, int colOffset, int profitMode,
+                           int32_t *ind, double *varRedCost, double *varOrigCost, double *zOut,
+                           int64_t *cellsOut);
+
+/* A full pricing round = DecompAlgo::generateVars, Dip/src/DecompAlgo.cpp:4622-5260
+ * for an application whose blocks are knapsacks over contiguous column ranges.
+ *   u: master duals, [0,nBase) core rows | m convexity | cuts  (length R + m)
+ *   outputs (caller-allocated):
+ *     redCostX[N]; per block: colNnz[m], colRedCost[m] (= sum - alpha,
+ *     DecompAlgo.cpp:6350-6356), colOrigCost[m], colKeep[m] (rc < -eps, :5216),
+ *     mostNegRC[m] (= min(0, rc), :4761 + :5212-5214), z[m];
+ *     colInd: m * maxBlockCols entries, block b's indices start at
+ *     b*maxBlockCols.  *mostNegReducedCost = sum_b mostNegRC[b] in block order
+ *     (:5229-5232).  nThreads > 1 runs blocks under an OpenMP dynamic,1
+ *     schedule like DecompAlgo.cpp:4815.  Returns number of kept columns. */
+int dip_oracle_price_round(int R, int N, const int64_t *rowStart, const int32_t *colInd,
+                           const double *val, const double *c, const double *u, int nBase,
+                           int phase1, int m, const int32_t *blockColStart,
+                           const int32_t *weight, const int32_t *capacity, int profitMode,
+                           double redCostEps, int nThreads, int maxBlockCols,
+                           double *redCostX, int32_t *colNnz, double *colRedCost,
+                           double *colOrigCost, int32_t *colKeep, double *mostNegRC,
+                           double *z, int32_t *colIndOut, double *mostNegReducedCost,
+                           int64_t *cellsOut);
+
+/* Stage (b)+(c) only, given redCostX and alpha (the loop of
+ * DecompAlgo::solveRelaxed calls + filter).  Same outputs as above. */
+int dip_oracle_solve_blocks(int m, const int32_t *blockColStart, const int32_t *weight,
+                            const int32_t *capacity, int profitMode, const double *redCostX,
+                            const double *origCost, const double *alpha, double redCostEps,
+                            int nThreads, int maxBlockCols, int32_t *colNnz,
+                            double *colRedCost, double *colOrigCost, int32_t *colKeep,
+                            double *mostNegRC, double *z, int32_t *colIndOut,
+                            double *mostNegReducedCost, int64_t *cellsOut);
+
+/* UtilCreateStringHash, Dip/src/UtilHash.cpp:52-68 (ind_el_ at 6 significant
+ * digits) for a 0/1 column: writes a NUL-terminated string, returns its length
+ * (excluding NUL), or -1 if bufLen is too small. */
+int dip_oracle_string_hash(int len, const int32_t *ind, const double *els, char *buf,
+                           int bufLen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
