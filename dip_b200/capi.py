@@ -1,0 +1,129 @@
+"""ctypes binding of libdipgpu.so (include/dipgpu.h) -- the only way Python reaches the GPU path.
+
+There is no CPU fallback: importing this module without the built library raises,
+and every compute entry point raises ``DipGpuError`` when no sm_100 device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdipgpu.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED, ERR_OVERFLOW = range(7)
+PROFIT_FP64, PROFIT_PISINGER_INT = 0, 1
+PHASE_PRICE1, PHASE_PRICE2 = 1, 2
+
+_ERR_NAMES = {
+    ERR_INVALID: "DIPGPU_ERR_INVALID", ERR_CUDA: "DIPGPU_ERR_CUDA", ERR_NOMEM: "DIPGPU_ERR_NOMEM",
+    ERR_STATE: "DIPGPU_ERR_STATE", ERR_UNSUPPORTED: "DIPGPU_ERR_UNSUPPORTED",
+    ERR_OVERFLOW: "DIPGPU_ERR_OVERFLOW",
+}
+
+# every symbol include/dipgpu.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "dipgpu_abi_version", "dipgpu_create", "dipgpu_destroy", "dipgpu_last_error",
+    "dipgpu_host_alloc", "dipgpu_host_free", "dipgpu_set_core_csr", "dipgpu_append_core_rows",
+    "dipgpu_set_objective", "dipgpu_set_knapsack_blocks", "dipgpu_calc_redcost",
+    "dipgpu_solve_blocks", "dipgpu_price_round", "dipgpu_set_block_range",
+    "dipgpu_price_round_dev", "dipgpu_solve_blocks_dev", "dipgpu_result_dev",
+    "dipgpu_result_max_bytes", "dipgpu_unpack_result", "dipgpu_redcost_dev",
+    "dipgpu_get_counters", "dipgpu_last_stage_ms", "dipgpu_set_option",
+]
+
+
+class DipGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{_ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Cols(C.Structure):
+    """struct dipgpu_cols (include/dipgpu.h)."""
+    _fields_ = [
+        ("capBlocks", C.c_int32), ("capCols", C.c_int32), ("capInd", C.c_int64),
+        ("blockRedCost", C.c_void_p), ("blockMostNegRC", C.c_void_p), ("blockOrigCost", C.c_void_p),
+        ("blockObj", C.c_void_p), ("blockNnz", C.c_void_p),
+        ("nCols", C.c_int32), ("colBlock", C.c_void_p), ("colRedCost", C.c_void_p),
+        ("colOrigCost", C.c_void_p), ("colStart", C.c_void_p), ("colInd", C.c_void_p),
+        ("nInd", C.c_int64), ("mostNegReducedCost", C.c_double), ("cells", C.c_int64),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m dip_b200._build` "
+            "(the pricing path is CUDA-only; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    sig = {
+        "dipgpu_abi_version": ([], C.c_int),
+        "dipgpu_create": ([C.POINTER(vp), C.c_int], C.c_int),
+        "dipgpu_destroy": ([vp], C.c_int),
+        "dipgpu_last_error": ([vp, C.c_char_p, C.c_size_t], C.c_int),
+        "dipgpu_host_alloc": ([C.POINTER(vp), C.c_size_t], C.c_int),
+        "dipgpu_host_free": ([vp], C.c_int),
+        "dipgpu_set_core_csr": ([vp, i32, i32, vp, vp, vp, i32, i32], C.c_int),
+        "dipgpu_append_core_rows": ([vp, i32, vp, vp, vp], C.c_int),
+        "dipgpu_set_objective": ([vp, vp, i32], C.c_int),
+        "dipgpu_set_knapsack_blocks": ([vp, i32, vp, vp, vp, i32], C.c_int),
+        "dipgpu_calc_redcost": ([vp, vp, i32, i32, vp], C.c_int),
+        "dipgpu_solve_blocks": ([vp, vp, vp, dbl, C.POINTER(Cols)], C.c_int),
+        "dipgpu_price_round": ([vp, vp, i32, i32, dbl, C.POINTER(Cols), vp], C.c_int),
+        "dipgpu_set_block_range": ([vp, i32, i32], C.c_int),
+        "dipgpu_price_round_dev": ([vp, vp, i32, i32, dbl, vp], C.c_int),
+        "dipgpu_solve_blocks_dev": ([vp, vp, vp, dbl, vp], C.c_int),
+        "dipgpu_result_dev": ([vp, C.POINTER(vp), C.POINTER(C.c_size_t)], C.c_int),
+        "dipgpu_result_max_bytes": ([vp, C.POINTER(C.c_size_t)], C.c_int),
+        "dipgpu_unpack_result": ([vp, C.c_size_t, C.POINTER(Cols)], C.c_int),
+        "dipgpu_redcost_dev": ([vp, C.POINTER(vp)], C.c_int),
+        "dipgpu_get_counters": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], C.c_int),
+        "dipgpu_last_stage_ms": ([vp, C.POINTER(C.c_float)], C.c_int),
+        "dipgpu_set_option": ([vp, C.c_char_p, i64], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = L
+    return L
+
+
+def ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data
+
+
+class PinnedArray:
+    """A numpy view over page-locked host memory from dipgpu_host_alloc."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        self._ptr = C.c_void_p()
+        rc = lib().dipgpu_host_alloc(C.byref(self._ptr), max(n * self.dtype.itemsize, 1))
+        if rc != OK:
+            raise DipGpuError(rc, "dipgpu_host_alloc failed")
+        buf = (C.c_char * max(n * self.dtype.itemsize, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=n).reshape(shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            lib().dipgpu_host_free(self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,170 @@
+// common.cuh -- shared declarations of libdipgpu (sm_100a only).
+//
+// The library implements DIP's pricing round (DecompAlgo::generateVars,
+// Dip/src/DecompAlgo.cpp:4622-5260) as CUDA stages; this header holds the
+// context, the packed result layout and the launcher prototypes.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/dipgpu.h"
+
+namespace dipgpu {
+
+// ---------------------------------------------------------------- packed result
+//
+// One contiguous buffer, identical on device and host, so that a shard's result
+// can travel as raw bytes (D2H copy, NCCL gather) and be decoded anywhere.
+//
+//   ResultHeader                       64 B
+//   double  blockRedCost[m]            sum rc - alpha          (all blocks)
+//   double  blockMostNeg[m]            min(0, .)
+//   double  blockOrigCost[m]
+//   double  blockObj[m]                knapsack optimum
+//   int64   keptStart[m + 1]           offsets into keptInd of the kept columns
+//   int32   blockNnz[m]
+//   int32   keptBlock[m]               LOCAL block ids of the kept columns
+//   (pad to 16 B)
+//   int32   keptInd[indCap]            x-space indices, ascending per column
+struct ResultHeader {
+    uint32_t magic;      // 'DIPR'
+    int32_t m;           // blocks in this shard
+    int32_t firstBlock;  // global id of local block 0
+    int32_t nKept;
+    int64_t nInd;
+    int64_t cells;
+    int64_t indCap;
+    int64_t reserved[3];
+};
+static_assert(sizeof(ResultHeader) == 64, "header is 64 bytes");
+constexpr uint32_t kResultMagic = 0x52504944u;
+
+struct ResultLayout {
+    size_t offRedCost, offMostNeg, offOrigCost, offObj, offKeptStart, offNnz, offKeptBlock, offInd;
+    size_t bytes;  // total with indCap indices
+    __host__ __device__ static inline size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
+    __host__ __device__ static inline ResultLayout make(int m, int64_t indCap)
+    {
+        ResultLayout L;
+        size_t o = sizeof(ResultHeader);
+        L.offRedCost = o;  o += sizeof(double) * (size_t)m;
+        L.offMostNeg = o;  o += sizeof(double) * (size_t)m;
+        L.offOrigCost = o; o += sizeof(double) * (size_t)m;
+        L.offObj = o;      o += sizeof(double) * (size_t)m;
+        L.offKeptStart = o; o += sizeof(int64_t) * ((size_t)m + 1);
+        L.offNnz = o;      o += sizeof(int32_t) * (size_t)m;
+        L.offKeptBlock = o; o += sizeof(int32_t) * (size_t)m;
+        o = alignUp(o, 16);
+        L.offInd = o;      o += sizeof(int32_t) * (size_t)indCap;
+        L.bytes = alignUp(o, 16);
+        return L;
+    }
+};
+
+// ------------------------------------------------------------------ DP geometry
+//
+// A knapsack's DP row of (capacity+1) cells is owned by T threads, S cells each,
+// interleaved: thread t holds cells t, t+T, ..., t+(S-1)T in registers.
+struct DpGeom {
+    int T;         // threads per knapsack (CTA size)
+    int S;         // cells per thread
+    int rowCells;  // T*S >= maxCapacity+1
+    int chunkCols; // columns staged per TMA chunk
+    size_t smemBytes;
+};
+
+// ---------------------------------------------------------------------- context
+struct Ctx {
+    int device = -1;
+    int smCount = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // core matrix (host copy in CSR for appends; device copy transposed)
+    int R = 0, N = 0, nBaseRows = 0, numConvex = 0;
+    std::vector<int64_t> hRowStart;
+    std::vector<int32_t> hColInd;
+    std::vector<double> hVal;
+    bool haveCore = false;
+    int64_t nnz = 0;
+    int64_t *dColStart = nullptr;   // N+1, CSC of A''
+    int32_t *dRowMaster = nullptr;  // nnz, MASTER dual index of each entry's row
+    double *dVal = nullptr;         // nnz
+    int spmvLanes = 0;              // 0 = auto
+
+    double *dObj = nullptr;  // c[N]
+    bool haveObj = false;
+
+    // blocks
+    int m = 0;              // all blocks
+    int nBlockCols = 0;     // blockColStart[m]
+    bool haveBlocks = false;
+    int profitMode = 0;
+    std::vector<int32_t> hBlockColStart, hCapacity;
+    int32_t *dBlockColStart = nullptr;  // m+1
+    int32_t *dWeight = nullptr;         // nBlockCols (+pad)
+    int32_t *dCapacity = nullptr;       // m
+    int64_t *dBitsOff = nullptr;        // m+1 word offsets into dBits (shard-local)
+    uint32_t *dBits = nullptr;          // decision bits [word][cell]
+    size_t bitsWords = 0;
+    int32_t *dItemW = nullptr;          // per column slot: weight of compacted item k of block b
+    int32_t *dItemCol = nullptr;        // per column slot: local column of compacted item
+    int32_t *dNItems = nullptr;         // m
+    int32_t *dCandInd = nullptr;        // per column slot: candidate column indices (ascending)
+    int32_t *dScratch = nullptr;        // per column slot: descending taken list
+    int maxCapacity = 0;
+    int optThreads = 0, optCellsPerThread = 0;
+    DpGeom geom{};
+
+    // shard
+    int firstBlock = 0, nLocal = 0;
+
+    // duals / reduced costs
+    double *dU = nullptr;        // uLen capacity
+    size_t uCap = 0;
+    double *dRedCost = nullptr;  // N (+pad)
+    double *dAlpha = nullptr;    // m
+
+    // results
+    void *dResult = nullptr;
+    void *hResult = nullptr;  // pinned mirror
+    size_t resultBytes = 0;
+    int64_t indCap = 0;
+    ResultLayout layout{};
+
+    // pinned staging for pageable inputs
+    double *hStage = nullptr;
+    size_t hStageBytes = 0;
+
+    // counters / timing
+    int64_t launches = 0, h2d = 0, d2h = 0;
+    bool stageTiming = false;
+    cudaEvent_t ev[8] = {};
+    float stageMs[6] = {0, 0, 0, 0, 0, 0};
+};
+
+int fail(Ctx *c, int code, const char *fmt, ...);
+int cudaFail(Ctx *c, cudaError_t e, const char *what);
+
+#define DIPGPU_CUDA(c, call)                                            \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return ::dipgpu::cudaFail((c), e__, #call); \
+    } while (0)
+
+// ------------------------------------------------------------------- launchers
+// redcost.cu -- stage (a)
+int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st);
+// knapsack.cu -- stage (b)
+int chooseDpGeom(Ctx *c, DpGeom *g);
+int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st);
+int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_t st);
+// filter.cu -- stage (c)
+int launchFilter(Ctx *c, double redCostEps, cudaStream_t st);
+
+}  // namespace dipgpu

@@ -1,0 +1,607 @@
+// dipgpu_api.cu -- the C ABI of libdipgpu (include/dipgpu.h): context lifetime,
+// model upload, and the orchestration of one pricing round
+// (DecompAlgo::generateVars, Dip/src/DecompAlgo.cpp:4622-5260) as
+//   H2D(u) -> reduced costs -> knapsack DP -> backtrack+emit -> filter -> D2H.
+// No CPU fallback: every compute entry point needs a live sm_100 device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace dipgpu {
+
+int fail(Ctx *c, int code, const char *fmt, ...)
+{
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+int cudaFail(Ctx *c, cudaError_t e, const char *what)
+{
+    return fail(c, e == cudaErrorMemoryAllocation ? DIPGPU_ERR_NOMEM : DIPGPU_ERR_CUDA, "CUDA error %d (%s) at %s",
+                (int)e, cudaGetErrorString(e), what);
+}
+
+template <typename T>
+static int devAlloc(Ctx *c, T **p, size_t count)
+{
+    if (*p) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (count == 0) count = 1;
+    DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T)));
+    return DIPGPU_OK;
+}
+
+template <typename T>
+static void devFree(T **p)
+{
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+}
+
+static int bind(Ctx *c)
+{
+    DIPGPU_CUDA(c, cudaSetDevice(c->device));
+    return DIPGPU_OK;
+}
+
+// Transpose the host CSR of A'' into the device CSC, folding the master-dual row
+// mapping (rows >= nBaseRows sit numConvex further down, DecompAlgo.cpp:4595-4597).
+static int uploadCore(Ctx *c)
+{
+    const int R = c->R, N = c->N;
+    const int64_t nnz = c->hRowStart[R];
+    std::vector<int64_t> colStart((size_t)N + 1, 0);
+    for (int64_t k = 0; k < nnz; ++k) colStart[(size_t)c->hColInd[k] + 1]++;
+    for (int j = 0; j < N; ++j) colStart[j + 1] += colStart[j];
+    std::vector<int64_t> fill(colStart.begin(), colStart.end() - 1);
+    std::vector<int32_t> rowMaster((size_t)std::max<int64_t>(nnz, 1));
+    std::vector<double> val((size_t)std::max<int64_t>(nnz, 1));
+    for (int i = 0; i < R; ++i) {
+        const int32_t rm = i < c->nBaseRows ? i : i + c->numConvex;
+        for (int64_t k = c->hRowStart[i]; k < c->hRowStart[i + 1]; ++k) {
+            const int64_t dst = fill[c->hColInd[k]]++;
+            rowMaster[dst] = rm;
+            val[dst] = c->hVal[k];
+        }
+    }
+    c->nnz = nnz;
+    int rc;
+    if ((rc = devAlloc(c, &c->dColStart, (size_t)N + 1))) return rc;
+    if ((rc = devAlloc(c, &c->dRowMaster, (size_t)nnz + 4))) return rc;
+    if ((rc = devAlloc(c, &c->dVal, (size_t)nnz + 4))) return rc;
+    DIPGPU_CUDA(c, cudaMemcpy(c->dColStart, colStart.data(), sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyHostToDevice));
+    if (nnz > 0) {
+        DIPGPU_CUDA(c, cudaMemcpy(c->dRowMaster, rowMaster.data(), sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+        DIPGPU_CUDA(c, cudaMemcpy(c->dVal, val.data(), sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+    }
+    return DIPGPU_OK;
+}
+
+static int ensureObjective(Ctx *c, int n)
+{
+    if (c->dObj) return DIPGPU_OK;
+    int rc;
+    if ((rc = devAlloc(c, &c->dObj, (size_t)n + 16))) return rc;
+    DIPGPU_CUDA(c, cudaMemset(c->dObj, 0, sizeof(double) * ((size_t)n + 16)));
+    return DIPGPU_OK;
+}
+
+static int setBlockRange(Ctx *c, int first, int count)
+{
+    if (!c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "set_knapsack_blocks has not been called");
+    if (first < 0 || count < 0 || first + count > c->m)
+        return fail(c, DIPGPU_ERR_INVALID, "block range [%d,%d) outside [0,%d)", first, first + count, c->m);
+    c->firstBlock = first;
+    c->nLocal = count;
+    int maxCap = 0;
+    for (int b = first; b < first + count; ++b) maxCap = std::max(maxCap, c->hCapacity[b]);
+    c->maxCapacity = maxCap;
+    int rc;
+    if ((rc = chooseDpGeom(c, &c->geom))) return rc;
+    // decision bits: ceil(n_b/32) words per cell, rowCells cells per block
+    std::vector<int64_t> off((size_t)count + 1, 0);
+    for (int lb = 0; lb < count; ++lb) {
+        const int n = c->hBlockColStart[first + lb + 1] - c->hBlockColStart[first + lb];
+        off[lb + 1] = off[lb] + (int64_t)((n + 31) / 32) * c->geom.rowCells;
+    }
+    c->bitsWords = (size_t)off[count];
+    if ((rc = devAlloc(c, &c->dBitsOff, (size_t)count + 1))) return rc;
+    DIPGPU_CUDA(c, cudaMemcpy(c->dBitsOff, off.data(), sizeof(int64_t) * ((size_t)count + 1), cudaMemcpyHostToDevice));
+    if ((rc = devAlloc(c, &c->dBits, c->bitsWords))) return rc;
+    if ((rc = devAlloc(c, &c->dNItems, (size_t)count))) return rc;
+    // packed result
+    c->indCap = count > 0 ? (int64_t)(c->hBlockColStart[first + count] - c->hBlockColStart[first]) : 0;
+    c->layout = ResultLayout::make(count, c->indCap);
+    c->resultBytes = c->layout.bytes;
+    if (c->dResult) cudaFree(c->dResult);
+    c->dResult = nullptr;
+    DIPGPU_CUDA(c, cudaMalloc(&c->dResult, c->resultBytes));
+    DIPGPU_CUDA(c, cudaMemset(c->dResult, 0, c->resultBytes));
+    if (c->hResult) cudaFreeHost(c->hResult);
+    c->hResult = nullptr;
+    DIPGPU_CUDA(c, cudaMallocHost(&c->hResult, c->resultBytes));
+    return DIPGPU_OK;
+}
+
+// Enqueue stages (b) and (c) on `st`; dRedCost/dAlpha are device pointers
+// (alpha indexed by global block id).
+static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, double eps, cudaStream_t st,
+                        bool timed)
+{
+    int rc;
+    if ((rc = launchKnapsackDp(c, dRedCost, st))) return rc;
+    if (timed) cudaEventRecord(c->ev[3], st);
+    if ((rc = launchBacktrackEmit(c, dRedCost, dAlpha, st))) return rc;
+    if (timed) cudaEventRecord(c->ev[4], st);
+    if ((rc = launchFilter(c, eps, st))) return rc;
+    if (timed) cudaEventRecord(c->ev[5], st);
+    return DIPGPU_OK;
+}
+
+static int unpack(Ctx *c, const void *packed, size_t bytes, dipgpu_cols *out)
+{
+    if (!packed || !out || bytes < sizeof(ResultHeader)) return fail(c, DIPGPU_ERR_INVALID, "bad packed result");
+    const char *p = static_cast<const char *>(packed);
+    const ResultHeader *h = reinterpret_cast<const ResultHeader *>(p);
+    if (h->magic != kResultMagic) return fail(c, DIPGPU_ERR_INVALID, "packed result: bad magic");
+    const int m = h->m;
+    const ResultLayout L = ResultLayout::make(m, h->indCap);
+    if (bytes < L.offInd + sizeof(int32_t) * (size_t)h->nInd)
+        return fail(c, DIPGPU_ERR_INVALID, "packed result truncated");
+    const double *rc = reinterpret_cast<const double *>(p + L.offRedCost);
+    const double *mn = reinterpret_cast<const double *>(p + L.offMostNeg);
+    const double *oc = reinterpret_cast<const double *>(p + L.offOrigCost);
+    const double *ob = reinterpret_cast<const double *>(p + L.offObj);
+    const int64_t *ks = reinterpret_cast<const int64_t *>(p + L.offKeptStart);
+    const int32_t *nz = reinterpret_cast<const int32_t *>(p + L.offNnz);
+    const int32_t *kb = reinterpret_cast<const int32_t *>(p + L.offKeptBlock);
+    const int32_t *ki = reinterpret_cast<const int32_t *>(p + L.offInd);
+    out->nCols = h->nKept;
+    out->nInd = h->nInd;
+    out->cells = h->cells;
+    const bool wantBlocks = out->blockRedCost || out->blockMostNegRC || out->blockOrigCost || out->blockObj || out->blockNnz;
+    if (wantBlocks && out->capBlocks < h->firstBlock + m)
+        return fail(c, DIPGPU_ERR_OVERFLOW, "capBlocks %d < %d", out->capBlocks, h->firstBlock + m);
+    double sum = 0.0;
+    for (int lb = 0; lb < m; ++lb) {
+        const int b = h->firstBlock + lb;
+        if (out->blockRedCost) out->blockRedCost[b] = rc[lb];
+        if (out->blockMostNegRC) out->blockMostNegRC[b] = mn[lb];
+        if (out->blockOrigCost) out->blockOrigCost[b] = oc[lb];
+        if (out->blockObj) out->blockObj[b] = ob[lb];
+        if (out->blockNnz) out->blockNnz[b] = nz[lb];
+        sum += mn[lb];  // block order, DecompAlgo.cpp:5229-5232
+    }
+    out->mostNegReducedCost = sum;
+    if (h->nKept > out->capCols || h->nInd > out->capInd)
+        return fail(c, DIPGPU_ERR_OVERFLOW, "kept columns need capCols >= %d, capInd >= %lld", h->nKept,
+                    (long long)h->nInd);
+    for (int k = 0; k < h->nKept; ++k) {
+        const int lb = kb[k];
+        if (out->colBlock) out->colBlock[k] = h->firstBlock + lb;
+        if (out->colRedCost) out->colRedCost[k] = rc[lb];
+        if (out->colOrigCost) out->colOrigCost[k] = oc[lb];
+        if (out->colStart) out->colStart[k] = ks[k];
+    }
+    if (out->colStart) out->colStart[h->nKept] = h->nInd;
+    if (out->colInd && h->nInd > 0) memcpy(out->colInd, ki, sizeof(int32_t) * (size_t)h->nInd);
+    return DIPGPU_OK;
+}
+
+// D2H of the packed result: one speculative copy (header + per-block arrays +
+// the first 64 KiB of indices), a second one only if more indices were kept.
+static int fetchResult(Ctx *c, cudaStream_t st)
+{
+    const size_t spec = std::min(c->resultBytes, c->layout.offInd + (size_t)65536);
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->hResult, c->dResult, spec, cudaMemcpyDeviceToHost, st));
+    if (c->stageTiming) cudaEventRecord(c->ev[6], st);
+    DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+    c->d2h += (int64_t)spec;
+    const ResultHeader *h = static_cast<const ResultHeader *>(c->hResult);
+    const size_t need = c->layout.offInd + sizeof(int32_t) * (size_t)h->nInd;
+    if (need > spec) {
+        DIPGPU_CUDA(c, cudaMemcpyAsync(static_cast<char *>(c->hResult) + spec, static_cast<char *>(c->dResult) + spec,
+                                       need - spec, cudaMemcpyDeviceToHost, st));
+        DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+        c->d2h += (int64_t)(need - spec);
+    }
+    return DIPGPU_OK;
+}
+
+static void collectStageMs(Ctx *c)
+{
+    if (!c->stageTiming) return;
+    for (int i = 0; i < 6; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]) != cudaSuccess) ms = 0.f;
+        c->stageMs[i] = ms;
+    }
+    (void)cudaGetLastError();
+}
+
+}  // namespace dipgpu
+
+using namespace dipgpu;
+
+#define CTX_OR_FAIL(ctx)                        \
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);      \
+    if (!c) return DIPGPU_ERR_INVALID;          \
+    {                                           \
+        int rc__ = bind(c);                     \
+        if (rc__) return rc__;                  \
+    }
+
+extern "C" {
+
+int dipgpu_abi_version(void) { return DIPGPU_ABI_VERSION; }
+
+int dipgpu_create(dipgpu_ctx **ctx, int device)
+{
+    if (!ctx) return DIPGPU_ERR_INVALID;
+    *ctx = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        (void)cudaGetLastError();
+        return DIPGPU_ERR_CUDA;  // no CPU fallback by design
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DIPGPU_ERR_CUDA;
+    if (prop.major != 10) return DIPGPU_ERR_CUDA;  // kernels are built for sm_100a only
+    Ctx *c = new (std::nothrow) Ctx();
+    if (!c) return DIPGPU_ERR_NOMEM;
+    c->device = device;
+    c->smCount = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return DIPGPU_ERR_CUDA;
+    }
+    for (auto &e : c->ev) cudaEventCreate(&e);
+    *ctx = reinterpret_cast<dipgpu_ctx *>(c);
+    return DIPGPU_OK;
+}
+
+int dipgpu_destroy(dipgpu_ctx *ctx)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c) return DIPGPU_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    devFree(&c->dColStart); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
+    devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
+    devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems);
+    devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
+    if (c->dResult) cudaFree(c->dResult);
+    if (c->hResult) cudaFreeHost(c->hResult);
+    if (c->hStage) cudaFreeHost(c->hStage);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return DIPGPU_OK;
+}
+
+int dipgpu_last_error(const dipgpu_ctx *ctx, char *buf, size_t bufLen)
+{
+    const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
+    if (!buf || bufLen == 0) return DIPGPU_ERR_INVALID;
+    const char *s = c ? c->err.c_str() : "null context";
+    snprintf(buf, bufLen, "%s", s);
+    return DIPGPU_OK;
+}
+
+int dipgpu_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return DIPGPU_ERR_INVALID;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? DIPGPU_ERR_NOMEM : DIPGPU_ERR_CUDA;
+    }
+    return DIPGPU_OK;
+}
+
+int dipgpu_host_free(void *ptr)
+{
+    if (!ptr) return DIPGPU_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? DIPGPU_OK : DIPGPU_ERR_CUDA;
+}
+
+int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *rowStart, const int32_t *colInd,
+                        const double *val, int32_t nBaseRows, int32_t numConvex)
+{
+    CTX_OR_FAIL(ctx);
+    if (R < 0 || N < 0 || !rowStart || nBaseRows < 0 || nBaseRows > R || numConvex < 0)
+        return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: bad dimensions R=%d N=%d nBaseRows=%d numConvex=%d", R, N, nBaseRows, numConvex);
+    if (rowStart[0] != 0) return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: rowStart[0] != 0");
+    for (int i = 0; i < R; ++i)
+        if (rowStart[i + 1] < rowStart[i]) return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: rowStart not monotone at row %d", i);
+    const int64_t nnz = rowStart[R];
+    if (nnz > 0 && (!colInd || !val)) return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: NULL colInd/val");
+    for (int64_t k = 0; k < nnz; ++k)
+        if (colInd[k] < 0 || colInd[k] >= N) return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: column index %d out of range at %lld", colInd[k], (long long)k);
+    if (c->haveBlocks && c->nBlockCols > N) return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: N=%d < block columns %d", N, c->nBlockCols);
+    if (c->haveObj && c->N != N) { devFree(&c->dObj); c->haveObj = false; }
+    if (c->N != N) devFree(&c->dRedCost);
+    c->R = R; c->N = N; c->nBaseRows = nBaseRows; c->numConvex = numConvex;
+    c->hRowStart.assign(rowStart, rowStart + R + 1);
+    c->hColInd.assign(colInd, colInd + nnz);
+    c->hVal.assign(val, val + nnz);
+    int rc;
+    if ((rc = uploadCore(c))) return rc;
+    if (!c->dRedCost) {
+        if ((rc = devAlloc(c, &c->dRedCost, (size_t)N + 16))) return rc;
+        DIPGPU_CUDA(c, cudaMemset(c->dRedCost, 0, sizeof(double) * ((size_t)N + 16)));
+    }
+    c->haveCore = true;
+    return DIPGPU_OK;
+}
+
+int dipgpu_append_core_rows(dipgpu_ctx *ctx, int32_t nNew, const int64_t *rowStart, const int32_t *colInd, const double *val)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->haveCore) return fail(c, DIPGPU_ERR_STATE, "append_core_rows before set_core_csr");
+    if (nNew < 0 || !rowStart || rowStart[0] != 0) return fail(c, DIPGPU_ERR_INVALID, "append_core_rows: bad arguments");
+    for (int i = 0; i < nNew; ++i)
+        if (rowStart[i + 1] < rowStart[i]) return fail(c, DIPGPU_ERR_INVALID, "append_core_rows: rowStart not monotone");
+    const int64_t add = rowStart[nNew];
+    for (int64_t k = 0; k < add; ++k)
+        if (colInd[k] < 0 || colInd[k] >= c->N) return fail(c, DIPGPU_ERR_INVALID, "append_core_rows: column index out of range");
+    const int64_t base = c->hRowStart[c->R];
+    for (int i = 1; i <= nNew; ++i) c->hRowStart.push_back(base + rowStart[i]);
+    c->hColInd.insert(c->hColInd.end(), colInd, colInd + add);
+    c->hVal.insert(c->hVal.end(), val, val + add);
+    c->R += nNew;
+    return uploadCore(c);
+}
+
+int dipgpu_set_objective(dipgpu_ctx *ctx, const double *obj, int32_t N)
+{
+    CTX_OR_FAIL(ctx);
+    if (!obj || N < 0) return fail(c, DIPGPU_ERR_INVALID, "set_objective: bad arguments");
+    if (c->haveCore && N != c->N) return fail(c, DIPGPU_ERR_INVALID, "set_objective: N=%d but core has %d columns", N, c->N);
+    if (!c->haveCore && c->haveBlocks && N < c->nBlockCols) return fail(c, DIPGPU_ERR_INVALID, "set_objective: N=%d < block columns %d", N, c->nBlockCols);
+    int rc;
+    devFree(&c->dObj);
+    if ((rc = devAlloc(c, &c->dObj, (size_t)N + 16))) return rc;
+    DIPGPU_CUDA(c, cudaMemset(c->dObj, 0, sizeof(double) * ((size_t)N + 16)));
+    DIPGPU_CUDA(c, cudaMemcpy(c->dObj, obj, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice));
+    if (!c->haveCore) c->N = std::max(c->N, (int)N);
+    c->haveObj = true;
+    return DIPGPU_OK;
+}
+
+int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockColStart, const int32_t *weight,
+                               const int32_t *capacity, int32_t profitMode)
+{
+    CTX_OR_FAIL(ctx);
+    if (m < 0 || !blockColStart || (m > 0 && !capacity)) return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: bad arguments");
+    if (profitMode != DIPGPU_PROFIT_FP64 && profitMode != DIPGPU_PROFIT_PISINGER_INT)
+        return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: unknown profitMode %d", profitMode);
+    if (profitMode == DIPGPU_PROFIT_PISINGER_INT)
+        return fail(c, DIPGPU_ERR_UNSUPPORTED, "set_knapsack_blocks: DIPGPU_PROFIT_PISINGER_INT is not built yet");
+    if (blockColStart[0] < 0) return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: negative column start");
+    for (int b = 0; b < m; ++b) {
+        if (blockColStart[b + 1] < blockColStart[b]) return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: blockColStart not monotone at block %d", b);
+        if (capacity[b] < 0) return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: negative capacity at block %d", b);
+    }
+    const int nCols = blockColStart[m];
+    if (nCols > 0 && !weight) return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: NULL weight");
+    for (int j = blockColStart[0]; j < nCols; ++j)
+        if (weight[j] < 0) return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: negative weight at column %d", j);
+    if (c->haveCore && nCols > c->N) return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: %d block columns > N=%d", nCols, c->N);
+    c->m = m;
+    c->nBlockCols = nCols;
+    c->profitMode = profitMode;
+    c->hBlockColStart.assign(blockColStart, blockColStart + m + 1);
+    c->hCapacity.assign(capacity, capacity + m);
+    int rc;
+    if ((rc = devAlloc(c, &c->dBlockColStart, (size_t)m + 1))) return rc;
+    if ((rc = devAlloc(c, &c->dCapacity, (size_t)m))) return rc;
+    if ((rc = devAlloc(c, &c->dWeight, (size_t)nCols + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dItemW, (size_t)nCols + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dItemCol, (size_t)nCols + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dCandInd, (size_t)nCols + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dScratch, (size_t)nCols + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dAlpha, (size_t)m))) return rc;
+    DIPGPU_CUDA(c, cudaMemcpy(c->dBlockColStart, blockColStart, sizeof(int32_t) * ((size_t)m + 1), cudaMemcpyHostToDevice));
+    if (m > 0) DIPGPU_CUDA(c, cudaMemcpy(c->dCapacity, capacity, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice));
+    DIPGPU_CUDA(c, cudaMemset(c->dWeight, 0, sizeof(int32_t) * ((size_t)nCols + 16)));
+    if (nCols > 0) DIPGPU_CUDA(c, cudaMemcpy(c->dWeight, weight, sizeof(int32_t) * (size_t)nCols, cudaMemcpyHostToDevice));
+    if (!c->haveCore) {
+        c->N = std::max(c->N, nCols);
+        if ((rc = devAlloc(c, &c->dRedCost, (size_t)c->N + 16))) return rc;
+        DIPGPU_CUDA(c, cudaMemset(c->dRedCost, 0, sizeof(double) * ((size_t)c->N + 16)));
+    }
+    c->haveBlocks = true;
+    return setBlockRange(c, 0, m);
+}
+
+int dipgpu_set_block_range(dipgpu_ctx *ctx, int32_t first, int32_t count)
+{
+    CTX_OR_FAIL(ctx);
+    return setBlockRange(c, first, count);
+}
+
+int dipgpu_calc_redcost(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase, double *redCostX)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->haveCore) return fail(c, DIPGPU_ERR_STATE, "calc_redcost before set_core_csr");
+    if (phase != DIPGPU_PHASE_PRICE1 && !c->haveObj) return fail(c, DIPGPU_ERR_STATE, "calc_redcost (phase 2) before set_objective");
+    if (!u || !redCostX || uLen != c->R + c->numConvex)
+        return fail(c, DIPGPU_ERR_INVALID, "calc_redcost: uLen=%d, expected R+numConvex=%d", uLen, c->R + c->numConvex);
+    int rc;
+    if ((rc = ensureObjective(c, c->N))) return rc;
+    if ((size_t)uLen > c->uCap) {
+        if ((rc = devAlloc(c, &c->dU, (size_t)uLen + 16))) return rc;
+        c->uCap = (size_t)uLen;
+    }
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, u, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, c->stream));
+    c->h2d += (int64_t)sizeof(double) * uLen;
+    if ((rc = launchRedCost(c, c->dU, phase, c->stream))) return rc;
+    DIPGPU_CUDA(c, cudaMemcpyAsync(redCostX, c->dRedCost, sizeof(double) * (size_t)c->N, cudaMemcpyDeviceToHost, c->stream));
+    c->d2h += (int64_t)sizeof(double) * c->N;
+    DIPGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    return DIPGPU_OK;
+}
+
+int dipgpu_solve_blocks(dipgpu_ctx *ctx, const double *redCostX, const double *alpha, double redCostEps, dipgpu_cols *out)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "solve_blocks before set_knapsack_blocks");
+    if (!redCostX || !alpha || !out) return fail(c, DIPGPU_ERR_INVALID, "solve_blocks: NULL argument");
+    int rc;
+    if ((rc = ensureObjective(c, c->N))) return rc;
+    const bool timed = c->stageTiming;
+    cudaStream_t st = c->stream;
+    if (timed) cudaEventRecord(c->ev[0], st);
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dRedCost, redCostX, sizeof(double) * (size_t)c->nBlockCols, cudaMemcpyHostToDevice, st));
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dAlpha, alpha, sizeof(double) * (size_t)c->m, cudaMemcpyHostToDevice, st));
+    c->h2d += (int64_t)sizeof(double) * ((int64_t)c->nBlockCols + c->m);
+    if (timed) { cudaEventRecord(c->ev[1], st); cudaEventRecord(c->ev[2], st); }
+    if ((rc = enqueueSolve(c, c->dRedCost, c->dAlpha, redCostEps, st, timed))) return rc;
+    if ((rc = fetchResult(c, st))) return rc;
+    collectStageMs(c);
+    return unpack(c, c->hResult, c->resultBytes, out);
+}
+
+int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase, double redCostEps,
+                       dipgpu_cols *out, double *redCostXOpt)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "price_round needs set_core_csr and set_knapsack_blocks");
+    if (phase != DIPGPU_PHASE_PRICE1 && !c->haveObj) return fail(c, DIPGPU_ERR_STATE, "price_round (phase 2) before set_objective");
+    if (!u || !out || uLen != c->R + c->numConvex)
+        return fail(c, DIPGPU_ERR_INVALID, "price_round: uLen=%d, expected R+numConvex=%d", uLen, c->R + c->numConvex);
+    if (c->numConvex != c->m) return fail(c, DIPGPU_ERR_INVALID, "price_round: numConvex=%d but %d blocks", c->numConvex, c->m);
+    int rc;
+    if ((rc = ensureObjective(c, c->N))) return rc;
+    if ((size_t)uLen > c->uCap) {
+        if ((rc = devAlloc(c, &c->dU, (size_t)uLen + 16))) return rc;
+        c->uCap = (size_t)uLen;
+    }
+    const bool timed = c->stageTiming;
+    cudaStream_t st = c->stream;
+    if (timed) cudaEventRecord(c->ev[0], st);
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, u, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, st));
+    c->h2d += (int64_t)sizeof(double) * uLen;
+    if (timed) cudaEventRecord(c->ev[1], st);
+    if ((rc = launchRedCost(c, c->dU, phase, st))) return rc;
+    if (timed) cudaEventRecord(c->ev[2], st);
+    // alpha_b = u[nBaseRows + b]  (DecompAlgo.cpp:4820)
+    if ((rc = enqueueSolve(c, c->dRedCost, c->dU + c->nBaseRows, redCostEps, st, timed))) return rc;
+    if (redCostXOpt) {
+        DIPGPU_CUDA(c, cudaMemcpyAsync(redCostXOpt, c->dRedCost, sizeof(double) * (size_t)c->N, cudaMemcpyDeviceToHost, st));
+        c->d2h += (int64_t)sizeof(double) * c->N;
+    }
+    if ((rc = fetchResult(c, st))) return rc;
+    collectStageMs(c);
+    return unpack(c, c->hResult, c->resultBytes, out);
+}
+
+int dipgpu_price_round_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, int32_t phase, double redCostEps, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "price_round_dev needs set_core_csr and set_knapsack_blocks");
+    if (!uDev || uLen != c->R + c->numConvex) return fail(c, DIPGPU_ERR_INVALID, "price_round_dev: bad dual vector");
+    if (c->numConvex != c->m) return fail(c, DIPGPU_ERR_INVALID, "price_round_dev: numConvex=%d but %d blocks", c->numConvex, c->m);
+    int rc;
+    if ((rc = ensureObjective(c, c->N))) return rc;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    if ((rc = launchRedCost(c, uDev, phase, st))) return rc;
+    return enqueueSolve(c, c->dRedCost, uDev + c->nBaseRows, redCostEps, st, false);
+}
+
+int dipgpu_solve_blocks_dev(dipgpu_ctx *ctx, const double *redCostXDev, const double *alphaDev, double redCostEps, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "solve_blocks_dev before set_knapsack_blocks");
+    if (!redCostXDev || !alphaDev) return fail(c, DIPGPU_ERR_INVALID, "solve_blocks_dev: NULL argument");
+    if ((reinterpret_cast<uintptr_t>(redCostXDev) & 15u) != 0) return fail(c, DIPGPU_ERR_INVALID, "solve_blocks_dev: redCostXDev must be 16-byte aligned");
+    int rc;
+    if ((rc = ensureObjective(c, c->N))) return rc;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    return enqueueSolve(c, redCostXDev, alphaDev, redCostEps, st, false);
+}
+
+int dipgpu_result_dev(dipgpu_ctx *ctx, void **devPtr, size_t *bytes)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !devPtr || !bytes) return DIPGPU_ERR_INVALID;
+    if (!c->dResult) return fail(c, DIPGPU_ERR_STATE, "no result buffer yet");
+    *devPtr = c->dResult;
+    *bytes = c->resultBytes;
+    return DIPGPU_OK;
+}
+
+int dipgpu_result_max_bytes(const dipgpu_ctx *ctx, size_t *bytes)
+{
+    const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
+    if (!c || !bytes) return DIPGPU_ERR_INVALID;
+    *bytes = c->resultBytes;
+    return DIPGPU_OK;
+}
+
+int dipgpu_unpack_result(const void *packedHost, size_t bytes, dipgpu_cols *out)
+{
+    return unpack(nullptr, packedHost, bytes, out);
+}
+
+int dipgpu_redcost_dev(dipgpu_ctx *ctx, double **devPtr)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !devPtr) return DIPGPU_ERR_INVALID;
+    if (!c->dRedCost) return fail(c, DIPGPU_ERR_STATE, "no reduced-cost buffer yet");
+    *devPtr = c->dRedCost;
+    return DIPGPU_OK;
+}
+
+int dipgpu_get_counters(const dipgpu_ctx *ctx, int64_t *kernelLaunches, int64_t *h2dBytes, int64_t *d2hBytes)
+{
+    const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
+    if (!c) return DIPGPU_ERR_INVALID;
+    if (kernelLaunches) *kernelLaunches = c->launches;
+    if (h2dBytes) *h2dBytes = c->h2d;
+    if (d2hBytes) *d2hBytes = c->d2h;
+    return DIPGPU_OK;
+}
+
+int dipgpu_last_stage_ms(const dipgpu_ctx *ctx, float *ms6)
+{
+    const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
+    if (!c || !ms6) return DIPGPU_ERR_INVALID;
+    for (int i = 0; i < 6; ++i) ms6[i] = c->stageMs[i];
+    return DIPGPU_OK;
+}
+
+int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !name) return DIPGPU_ERR_INVALID;
+    if (!strcmp(name, "stage_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "spmv_lanes")) { c->spmvLanes = (int)value; return DIPGPU_OK; }
+    if (!strcmp(name, "dp_threads") || !strcmp(name, "dp_cells_per_thread")) {
+        if (!strcmp(name, "dp_threads")) c->optThreads = (int)value; else c->optCellsPerThread = (int)value;
+        if (c->haveBlocks) {
+            int rc = bind(c);
+            if (rc) return rc;
+            return setBlockRange(c, c->firstBlock, c->nLocal);
+        }
+        return DIPGPU_OK;
+    }
+    return fail(c, DIPGPU_ERR_INVALID, "unknown option '%s'", name);
+}
+
+}  // extern "C"

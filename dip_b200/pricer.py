@@ -1,0 +1,285 @@
+"""Host-side mirror of DIP's pricing plugin surface over libdipgpu (Python front end used by
+the tests and bench.py; the C++ adapter with the same shape is include/dipgpu_decomp.hpp).
+
+Names follow the reference:
+  * ``GpuPricer.generateVars(u, phase)``      <-> DecompAlgo::generateVars
+    (Dip/src/DecompAlgo.h:430, DecompAlgo.cpp:4622-5260)
+  * ``GpuPricer.solveRelaxed(whichBlock, redCostX, target)`` <-> DecompApp::solveRelaxed
+    (Dip/src/DecompApp.h:344-349; GAP_DecompApp.cpp:235-285)
+  * ``DecompVar`` <-> Dip/src/DecompVar.h:217-239 (sparse 0/1 column, origCost, redCost, blockId)
+
+The compute is entirely in the CUDA library; this module only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .capi import DipGpuError, PHASE_PRICE1, PHASE_PRICE2, PROFIT_FP64, PROFIT_PISINGER_INT  # noqa: F401
+
+DecompSolStatOptimal = 2   # Dip/src/Decomp.h:213-219 (DecompSolverStatus)
+DecompSolStatNoSolution = 4
+
+
+@dataclass
+class DecompVar:
+    """Dip/src/DecompVar.h:217-239: column in x-space; all elements are 1.0 for knapsack blocks."""
+    ind: np.ndarray          # m_s indices (ascending, DecompVar.h:237)
+    origCost: float          # m_origCost
+    redCost: float           # m_redCost
+    blockId: int             # m_blockId
+
+    @property
+    def els(self) -> np.ndarray:
+        return np.ones(len(self.ind), np.float64)
+
+
+class RoundResult:
+    """Flat view of one pricing round (struct dipgpu_cols)."""
+
+    def __init__(self, m: int, cap_cols: int, cap_ind: int):
+        self.m = m
+        self.blockRedCost = np.zeros(m, np.float64)
+        self.blockMostNegRC = np.zeros(m, np.float64)
+        self.blockOrigCost = np.zeros(m, np.float64)
+        self.blockObj = np.zeros(m, np.float64)
+        self.blockNnz = np.zeros(m, np.int32)
+        self.colBlock = np.zeros(max(cap_cols, 1), np.int32)
+        self.colRedCost = np.zeros(max(cap_cols, 1), np.float64)
+        self.colOrigCost = np.zeros(max(cap_cols, 1), np.float64)
+        self.colStart = np.zeros(max(cap_cols, 1) + 1, np.int64)
+        self.colInd = np.zeros(max(cap_ind, 1), np.int32)
+        s = capi.Cols()
+        s.capBlocks, s.capCols, s.capInd = m, cap_cols, cap_ind
+        s.blockRedCost, s.blockMostNegRC = capi.ptr(self.blockRedCost), capi.ptr(self.blockMostNegRC)
+        s.blockOrigCost, s.blockObj, s.blockNnz = (capi.ptr(self.blockOrigCost), capi.ptr(self.blockObj),
+                                                   capi.ptr(self.blockNnz))
+        s.colBlock, s.colRedCost, s.colOrigCost = (capi.ptr(self.colBlock), capi.ptr(self.colRedCost),
+                                                   capi.ptr(self.colOrigCost))
+        s.colStart, s.colInd = capi.ptr(self.colStart), capi.ptr(self.colInd)
+        self.c = s
+
+    @property
+    def nCols(self) -> int:
+        return self.c.nCols
+
+    @property
+    def mostNegReducedCost(self) -> float:
+        return self.c.mostNegReducedCost
+
+    @property
+    def cells(self) -> int:
+        return self.c.cells
+
+    def column(self, k: int) -> np.ndarray:
+        return self.colInd[self.colStart[k]:self.colStart[k + 1]]
+
+    def vars(self) -> list[DecompVar]:
+        return [DecompVar(self.column(k).copy(), float(self.colOrigCost[k]), float(self.colRedCost[k]),
+                          int(self.colBlock[k])) for k in range(self.nCols)]
+
+
+class GpuPricer:
+    """One libdipgpu context = one GPU driven from one host thread."""
+
+    def __init__(self, device: int = 0):
+        self._lib = capi.lib()
+        self._ctx = C.c_void_p()
+        rc = self._lib.dipgpu_create(C.byref(self._ctx), device)
+        if rc != capi.OK:
+            raise DipGpuError(rc, f"dipgpu_create(device={device}) failed: no usable sm_100 GPU "
+                                  "(libdipgpu has no CPU fallback)")
+        self.m = 0
+        self.N = 0
+        self.R = 0
+        self.numConvex = 0
+        self.nBaseRows = 0
+        self.nBlockCols = 0
+        self._keep = []           # arrays that must outlive the C calls
+        self._result = None
+        self._relax_cache = None  # (fingerprint, RoundResult) for solveRelaxed
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int):
+        if rc != capi.OK:
+            buf = C.create_string_buffer(512)
+            self._lib.dipgpu_last_error(self._ctx, buf, len(buf))
+            raise DipGpuError(rc, buf.value.decode(errors="replace"))
+
+    def close(self):
+        if self._ctx:
+            self._lib.dipgpu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.dipgpu_set_option(self._ctx, name.encode(), int(value)))
+
+    def counters(self) -> dict:
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self._lib.dipgpu_get_counters(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(kernel_launches=a.value, h2d_bytes=b.value, d2h_bytes=c.value)
+
+    def last_stage_ms(self) -> dict:
+        ms = (C.c_float * 6)()
+        self._check(self._lib.dipgpu_last_stage_ms(self._ctx, ms))
+        return dict(zip(["h2d", "redcost", "knapsack_dp", "backtrack_emit", "filter", "d2h"], list(ms)))
+
+    # --------------------------------------------------------------------- model
+    def setModelCore(self, R, N, row_start, col_ind, val, n_base_rows, num_convex):
+        """DecompConstraintSet::M, row-ordered (Dip/src/DecompConstraintSet.h:32, .cpp:41-43)."""
+        rs = np.ascontiguousarray(row_start, np.int64)
+        ci = np.ascontiguousarray(col_ind, np.int32)
+        v = np.ascontiguousarray(val, np.float64)
+        self._check(self._lib.dipgpu_set_core_csr(self._ctx, R, N, capi.ptr(rs), capi.ptr(ci), capi.ptr(v),
+                                                  n_base_rows, num_convex))
+        self.R, self.N, self.nBaseRows, self.numConvex = R, N, n_base_rows, num_convex
+
+    def appendCoreRows(self, row_start, col_ind, val):
+        """DecompConstraintSet::appendRow (Dip/src/DecompConstraintSet.h:143-163) for cut rows."""
+        rs = np.ascontiguousarray(row_start, np.int64)
+        ci = np.ascontiguousarray(col_ind, np.int32)
+        v = np.ascontiguousarray(val, np.float64)
+        self._check(self._lib.dipgpu_append_core_rows(self._ctx, len(rs) - 1, capi.ptr(rs), capi.ptr(ci),
+                                                      capi.ptr(v)))
+        self.R += len(rs) - 1
+
+    def setObjective(self, c):
+        c = np.ascontiguousarray(c, np.float64)
+        self._check(self._lib.dipgpu_set_objective(self._ctx, capi.ptr(c), len(c)))
+        self.N = max(self.N, len(c))
+
+    def setKnapsackBlocks(self, block_col_start, weight, capacity, profit_mode=PROFIT_FP64):
+        """One knapsack per block (GAP_DecompApp.cpp:52-58, GAP_KnapPisinger.h:276-294)."""
+        bcs = np.ascontiguousarray(block_col_start, np.int32)
+        w = np.ascontiguousarray(weight, np.int32)
+        cap = np.ascontiguousarray(capacity, np.int32)
+        m = len(bcs) - 1
+        self._check(self._lib.dipgpu_set_knapsack_blocks(self._ctx, m, capi.ptr(bcs), capi.ptr(w),
+                                                         capi.ptr(cap), profit_mode))
+        self.m = m
+        self.nBlockCols = int(bcs[-1])
+        self.N = max(self.N, self.nBlockCols)
+        self._result = None
+        self._relax_cache = None
+
+    def setModel(self, model, profit_mode=PROFIT_FP64):
+        """Upload a dip_b200.instances.PricingModel."""
+        self.setModelCore(model.R, model.N, model.row_start, model.col_ind, model.val, model.n_base_rows,
+                          model.m)
+        self.setObjective(model.objective)
+        self.setKnapsackBlocks(model.block_col_start, model.weight, model.capacity, profit_mode)
+
+    def setBlockRange(self, first: int, count: int):
+        self._check(self._lib.dipgpu_set_block_range(self._ctx, first, count))
+
+    def _res(self) -> RoundResult:
+        if self._result is None:
+            self._result = RoundResult(self.m, self.m, max(self.nBlockCols, 1))
+        return self._result
+
+    # ------------------------------------------------------------------- pricing
+    def calcRedCost(self, u, phase=PHASE_PRICE2) -> np.ndarray:
+        """generateVarsAdjustDuals + generateVarsCalcRedCost (DecompAlgo.cpp:4506-4619)."""
+        u = np.ascontiguousarray(u, np.float64)
+        out = np.empty(self.N, np.float64)
+        self._check(self._lib.dipgpu_calc_redcost(self._ctx, capi.ptr(u), len(u), phase, capi.ptr(out)))
+        return out
+
+    def solveBlocks(self, redCostX, alpha, redCostEps=1e-4, result: RoundResult | None = None) -> RoundResult:
+        """The loop of DecompApp::solveRelaxed over all blocks + the filter of
+        DecompAlgo.cpp:5151-5232, for a caller-supplied reduced-cost vector."""
+        rc = np.ascontiguousarray(redCostX, np.float64)
+        al = np.ascontiguousarray(alpha, np.float64)
+        if len(rc) < self.nBlockCols or len(al) < self.m:
+            raise ValueError("redCostX / alpha shorter than the block structure")
+        res = result or self._res()
+        self._check(self._lib.dipgpu_solve_blocks(self._ctx, capi.ptr(rc), capi.ptr(al), float(redCostEps),
+                                                  C.byref(res.c)))
+        return res
+
+    def priceRound(self, u, phase=PHASE_PRICE2, redCostEps=1e-4, want_redcost=False,
+                   result: RoundResult | None = None):
+        """One whole pricing round in one submission; returns RoundResult (and redCostX)."""
+        u = np.ascontiguousarray(u, np.float64)
+        res = result or self._res()
+        rcx = np.empty(self.N, np.float64) if want_redcost else None
+        self._check(self._lib.dipgpu_price_round(self._ctx, capi.ptr(u), len(u), phase, float(redCostEps),
+                                                 C.byref(res.c), capi.ptr(rcx)))
+        return (res, rcx) if want_redcost else res
+
+    def priceRoundRaw(self, u_ptr: int, u_len: int, phase: int, eps: float, res: RoundResult):
+        """Same call with a raw host pointer (pinned buffers in bench.py): no numpy marshalling."""
+        rc = self._lib.dipgpu_price_round(self._ctx, u_ptr, u_len, phase, eps, C.byref(res.c), None)
+        if rc != capi.OK:
+            self._check(rc)
+
+    # ---- the reference's two plugin surfaces ---------------------------------
+    def generateVars(self, u, phase=PHASE_PRICE2, redCostEps=1e-4):
+        """DecompAlgo::generateVars(newVars, mostNegReducedCost): returns (newVars, mostNegRC)."""
+        res = self.priceRound(u, phase, redCostEps)
+        return res.vars(), res.mostNegReducedCost
+
+    def solveRelaxed(self, whichBlock: int, redCostX, target: float):
+        """DecompApp::solveRelaxed(whichBlock, redCostX, target, varList): returns
+        (DecompSolStatOptimal, [DecompVar]).  As in GAP_DecompApp.cpp:278-284 exactly one
+        (possibly empty) column comes back per block, its redCost EXCLUDING the convexity dual
+        (the caller subtracts it, DecompAlgo.cpp:6350-6356).  All blocks of a round are solved in
+        one GPU submission the first time a new redCostX is seen; later calls are served from it."""
+        rc = np.ascontiguousarray(redCostX, np.float64)
+        fp = (rc.ctypes.data, hash(rc.tobytes()))
+        if self._relax_cache is None or self._relax_cache[0] != fp:
+            res = RoundResult(self.m, self.m, max(self.nBlockCols, 1))
+            self.solveBlocks(rc, np.zeros(self.m), redCostEps=-np.inf, result=res)
+            self._relax_cache = (fp, res)
+        res = self._relax_cache[1]
+        # every block is "kept" with eps = -inf, in block order
+        k = int(whichBlock)
+        assert res.colBlock[k] == k
+        var = DecompVar(res.column(k).copy(), float(res.colOrigCost[k]), float(res.colRedCost[k]), k)
+        return DecompSolStatOptimal, [var]
+
+    # ---- device-resident variants (multi-GPU driver) ---------------------------
+    def priceRoundDev(self, u_dev_ptr: int, u_len: int, phase=PHASE_PRICE2, redCostEps=1e-4, stream: int = 0):
+        self._check(self._lib.dipgpu_price_round_dev(self._ctx, u_dev_ptr, u_len, phase, float(redCostEps),
+                                                     stream or None))
+
+    def solveBlocksDev(self, rc_dev_ptr: int, alpha_dev_ptr: int, redCostEps=1e-4, stream: int = 0):
+        self._check(self._lib.dipgpu_solve_blocks_dev(self._ctx, rc_dev_ptr, alpha_dev_ptr, float(redCostEps),
+                                                      stream or None))
+
+    def resultDev(self) -> tuple[int, int]:
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.dipgpu_result_dev(self._ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def redCostDev(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.dipgpu_redcost_dev(self._ctx, C.byref(p)))
+        return p.value
+
+
+def unpack_result(packed: np.ndarray, m_total: int, cap_ind: int, result: RoundResult | None = None) -> RoundResult:
+    """dipgpu_unpack_result on a host copy of a shard's packed result (block ids are global).
+    Block arrays of `result` are filled at the shard's global positions; kept columns are
+    those of this shard only."""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    res = result or RoundResult(m_total, m_total, cap_ind)
+    rc = capi.lib().dipgpu_unpack_result(capi.ptr(packed), packed.nbytes, C.byref(res.c))
+    if rc != capi.OK:
+        raise DipGpuError(rc, "dipgpu_unpack_result failed")
+    return res

@@ -1,0 +1,229 @@
+/*
+ * dipgpu.h -- C ABI of libdipgpu: the B200 (sm_100a) pricing round behind DIP's
+ * DecompApp::solveRelaxed / DecompAlgo::generateVars plugin surface.
+ *
+ * Plain C: opaque context, caller-owned host buffers, plain pointers and sizes,
+ * integer status codes (never throws).  One context drives one GPU from one
+ * host thread.  There is NO CPU fallback: every entry point that computes
+ * returns DIPGPU_ERR_CUDA when no sm_100 device / driver is usable.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to
+ * the coin-or/Dip tree).  INTEGRATION.md shows the reference-side binding.
+ */
+#ifndef DIPGPU_H
+#define DIPGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* the library is built with -fvisibility=hidden; only this header is exported */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define DIPGPU_ABI_VERSION 1
+
+typedef struct dipgpu_ctx dipgpu_ctx;
+
+enum {
+    DIPGPU_OK = 0,
+    DIPGPU_ERR_INVALID = 1,     /* bad argument (NULL, negative size, unsorted starts, w < 0 ...) */
+    DIPGPU_ERR_CUDA = 2,        /* CUDA runtime / driver error, or no usable sm_100 device */
+    DIPGPU_ERR_NOMEM = 3,       /* device or pinned-host allocation failed */
+    DIPGPU_ERR_STATE = 4,       /* call order: model / blocks / objective not set yet */
+    DIPGPU_ERR_UNSUPPORTED = 5, /* e.g. capacity beyond what one thread-block cluster can stage */
+    DIPGPU_ERR_OVERFLOW = 6     /* caller's output buffers too small; required sizes are reported */
+};
+
+/* Profit arithmetic of the block knapsacks. */
+enum {
+    /* fp64 profits = -redCost, the reference's own DP: knapsack01(),
+     * Dip/src/dippy/examples/gap/gap_func.py:132-183 (+ :96-130). */
+    DIPGPU_PROFIT_FP64 = 0,
+    /* scaled-integer profits + n==1 / all-fit / n==2 shortcuts of
+     * GAP_KnapPisinger::solve, Dip/examples/GAP/GAP_KnapPisinger.h:89-273. */
+    DIPGPU_PROFIT_PISINGER_INT = 1
+};
+
+/* DecompPhase as far as pricing cares (Dip/src/Decomp.h:170-176):
+ * phase 1 prices with c = 0 (Dip/src/DecompAlgo.cpp:4538-4541). */
+enum { DIPGPU_PHASE_PRICE1 = 1, DIPGPU_PHASE_PRICE2 = 2 };
+
+/*
+ * Result of one pricing round: what DecompAlgo::generateVars hands back
+ * (Dip/src/DecompAlgo.cpp:4622-5260) in flat arrays.  All pointers are
+ * caller-owned host memory; capacities are inputs, counts are outputs.
+ *
+ * Per block b (arrays of length >= m, may be NULL to skip):
+ *   blockRedCost[b]  = sum_j redCost[j] x_j - alpha_b   (DecompAlgo.cpp:6350-6356)
+ *   blockMostNegRC[b]= min(0, blockRedCost[b])          (:4761, :5212-5214)
+ *   blockOrigCost[b] = sum_j c[j] x_j                   (GAP_KnapPisinger.h:268)
+ *   blockObj[b]      = knapsack optimum in DP profit units
+ *   blockNnz[b]      = |column b|
+ * Kept columns (rc < -redCostEps, :5216), in block order:
+ *   colBlock[k] (DecompVar::setBlockId), colRedCost[k], colOrigCost[k],
+ *   colStart[k]..colStart[k+1] into colInd: x-space indices ascending, every
+ *   element is 1.0 (GAP_KnapPisinger.h:265-270).
+ * mostNegReducedCost = sum_b blockMostNegRC[b], added in block order (:5229-5232).
+ */
+typedef struct dipgpu_cols {
+    /* in: capacities of the arrays below */
+    int32_t capBlocks; /* length of the block* arrays (>= m) */
+    int32_t capCols;   /* length of colBlock/colRedCost/colOrigCost; colStart has capCols+1 */
+    int64_t capInd;    /* length of colInd */
+    /* out: per block */
+    double *blockRedCost;
+    double *blockMostNegRC;
+    double *blockOrigCost;
+    double *blockObj;
+    int32_t *blockNnz;
+    /* out: kept columns */
+    int32_t nCols;
+    int32_t *colBlock;
+    double *colRedCost;
+    double *colOrigCost;
+    int64_t *colStart;
+    int32_t *colInd;
+    int64_t nInd; /* total indices of the kept columns (required capInd on overflow) */
+    double mostNegReducedCost;
+    int64_t cells; /* DP cell updates performed: sum over active items of (capacity+1) */
+} dipgpu_cols;
+
+/* ---------------------------------------------------------------- lifetime */
+
+int dipgpu_abi_version(void);
+
+/* Opens CUDA device `device`, requires compute capability 10.x. */
+int dipgpu_create(dipgpu_ctx **ctx, int device);
+int dipgpu_destroy(dipgpu_ctx *ctx);
+
+/* Copies the last error text of this context (NUL-terminated) into buf. */
+int dipgpu_last_error(const dipgpu_ctx *ctx, char *buf, size_t bufLen);
+
+/* Pinned host memory for the dual vector / outputs (optional: any host pointer
+ * is accepted, pinned ones are copied without a staging pass). */
+int dipgpu_host_alloc(void **ptr, size_t bytes);
+int dipgpu_host_free(void *ptr);
+
+/* ------------------------------------------------------------------- model */
+
+/*
+ * Core constraint matrix A'' in the layout DIP holds it: row-ordered
+ * CoinPackedMatrix (DecompConstraintSet::M, Dip/src/DecompConstraintSet.h:32,
+ * forced row-major at DecompConstraintSet.cpp:41-43).  R rows incl. the
+ * 2*nInt branch rows appended by coreMatrixAppendColBounds
+ * (Dip/src/DecompAlgo.cpp:1399-1502); nBaseRows = modelCore->nBaseRows
+ * (rows >= nBaseRows are cuts).  numConvex = m_numConvexCon: the master dual
+ * vector is laid out [0,nBaseRows) | numConvex convexity rows | cut rows
+ * (Dip/src/DecompAlgo.cpp:4550-4619), and that is how `u` is read below.
+ */
+int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *rowStart,
+                        const int32_t *colInd, const double *val, int32_t nBaseRows,
+                        int32_t numConvex);
+
+/* Cut rows appended to A'' during the run (DecompConstraintSet::appendRow,
+ * Dip/src/DecompConstraintSet.h:143-163; DecompAlgo.cpp:6074).  rowStart has
+ * nNew+1 entries starting at 0. */
+int dipgpu_append_core_rows(dipgpu_ctx *ctx, int32_t nNew, const int64_t *rowStart,
+                            const int32_t *colInd, const double *val);
+
+/* Original objective c (DecompApp::m_objective, Dip/src/DecompApp.h:85). */
+int dipgpu_set_objective(dipgpu_ctx *ctx, const double *c, int32_t N);
+
+/*
+ * The relaxation: m independent 0-1 knapsacks, block b owning the contiguous
+ * x-space columns [blockColStart[b], blockColStart[b+1]) with integer weights
+ * and capacity -- what GAP_DecompApp builds one GAP_KnapPisinger per block from
+ * (Dip/examples/GAP/GAP_DecompApp.cpp:52-58, GAP_KnapPisinger.h:276-294).
+ * weight is indexed by x-space column (length blockColStart[m]).
+ */
+int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockColStart,
+                               const int32_t *weight, const int32_t *capacity,
+                               int32_t profitMode);
+
+/* ----------------------------------------------------------------- pricing */
+
+/*
+ * Stage (a): generateVarsAdjustDuals + generateVarsCalcRedCost
+ * (Dip/src/DecompAlgo.cpp:4550-4619, 4506-4547).  u = master duals of length
+ * R + numConvex; redCostX (length N) receives c - A''^T u (phase 2) or
+ * -A''^T u (phase 1).
+ */
+int dipgpu_calc_redcost(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase,
+                        double *redCostX);
+
+/*
+ * Stages (b)+(c) for a caller-supplied reduced-cost vector: the loop of
+ * DecompApp::solveRelaxed(whichBlock, redCostX, alpha_b, varList) calls
+ * (Dip/src/DecompApp.h:344-349; GAP_DecompApp.cpp:235-285) over all blocks,
+ * followed by the filter of DecompAlgo.cpp:5151-5232.  alpha has m entries.
+ * redCostEps = DecompParam::RedCostEpsilon (1e-4); pass -INFINITY to keep every
+ * candidate (per-block plugin surface).
+ */
+int dipgpu_solve_blocks(dipgpu_ctx *ctx, const double *redCostX, const double *alpha,
+                        double redCostEps, dipgpu_cols *out);
+
+/*
+ * The whole pricing round = DecompAlgo::generateVars
+ * (Dip/src/DecompAlgo.h:430, DecompAlgo.cpp:4622-5260): (a) then (b) then (c)
+ * in one submission.  alpha_b = u[nBaseRows + b] (:4820).  redCostXOpt (length
+ * N) may be NULL.
+ */
+int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase,
+                       double redCostEps, dipgpu_cols *out, double *redCostXOpt);
+
+/* ---------------------------------------- device-resident variants (multi-GPU)
+ *
+ * For the block-sharded multi-GPU driver: the dual vector is already in device
+ * memory (NCCL broadcast) and the packed result stays in device memory for the
+ * gather.  `stream` is a cudaStream_t (NULL = the context's own stream); the
+ * call only enqueues work.
+ */
+
+/* Restrict pricing to blocks [first, first+count) (a rank's shard). */
+int dipgpu_set_block_range(dipgpu_ctx *ctx, int32_t first, int32_t count);
+
+int dipgpu_price_round_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, int32_t phase,
+                           double redCostEps, void *stream);
+int dipgpu_solve_blocks_dev(dipgpu_ctx *ctx, const double *redCostXDev, const double *alphaDev,
+                            double redCostEps, void *stream);
+
+/* Device pointer + byte size of the packed result of the last *_dev call. */
+int dipgpu_result_dev(dipgpu_ctx *ctx, void **devPtr, size_t *bytes);
+/* Fixed upper bound of the packed result size for this context's shard. */
+int dipgpu_result_max_bytes(const dipgpu_ctx *ctx, size_t *bytes);
+/* Decode a packed result (host copy) into `out`; block ids are global. */
+int dipgpu_unpack_result(const void *packedHost, size_t bytes, dipgpu_cols *out);
+
+/* Device pointer of the last reduced-cost vector (length N). */
+int dipgpu_redcost_dev(dipgpu_ctx *ctx, double **devPtr);
+
+/* ------------------------------------------------------------ introspection */
+
+/* Counters since creation: kernel launches issued by this library, H2D / D2H
+ * bytes moved by it. */
+int dipgpu_get_counters(const dipgpu_ctx *ctx, int64_t *kernelLaunches, int64_t *h2dBytes,
+                        int64_t *d2hBytes);
+
+/* Device time (ms, CUDA events on the context's stream) of the stages of the
+ * last host-buffer call: [0] H2D, [1] reduced costs, [2] knapsack DP,
+ * [3] backtrack+emit, [4] filter, [5] D2H.  Valid only when timing was switched
+ * on with dipgpu_set_option("stage_timing", 1). */
+int dipgpu_last_stage_ms(const dipgpu_ctx *ctx, float *ms6);
+
+/* Tuning / diagnostics knobs: "stage_timing", "dp_threads", "dp_cells_per_thread",
+ * "spmv_lanes".  Unknown names return DIPGPU_ERR_INVALID. */
+int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIPGPU_H */

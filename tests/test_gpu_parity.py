@@ -1,0 +1,266 @@
+"""Parity of the CUDA pricing path (through the C ABI) against the CPU oracle and the committed
+golden vectors.  Bar (BASELINE.json north_star): knapsack optima BIT-EXACT, column sets identical,
+reduced costs within 1e-12 relative."""
+import numpy as np
+import pytest
+
+from dip_b200 import instances as I
+
+pytestmark = pytest.mark.gpu
+RC_RTOL = 1e-12  # north_star: "Reduced costs must agree within 1e-12 relative"
+
+
+def _batch_from_cases(cases):
+    n = np.array([len(c["w"]) for c in cases])
+    bcs = np.zeros(len(cases) + 1, np.int32)
+    np.cumsum(n, out=bcs[1:])
+    w = np.concatenate([c["w"] for c in cases]).astype(np.int32)
+    rc = -np.concatenate([c["obj"] for c in cases])
+    cap = np.array([c["cap"] for c in cases], np.int32)
+    return bcs, w, cap, rc
+
+
+def _check_against_oracle(oracle, pricer, bcs, w, cap, rc, oc, alpha, eps=1e-4):
+    m = len(cap)
+    pricer.setObjective(oc)
+    pricer.setKnapsackBlocks(bcs, w, cap)
+    res = pricer.solveBlocks(rc, alpha, eps)
+    ref = oracle.solve_blocks(bcs, w, cap, rc, oc, alpha, red_cost_eps=eps)
+    np.testing.assert_array_equal(res.blockObj, ref.z)                 # bit-exact optimum
+    np.testing.assert_array_equal(res.blockNnz, ref.col_nnz)
+    np.testing.assert_allclose(res.blockRedCost, ref.col_red_cost, rtol=RC_RTOL, atol=1e-12)
+    np.testing.assert_allclose(res.blockOrigCost, ref.col_orig_cost, rtol=RC_RTOL, atol=1e-12)
+    np.testing.assert_array_equal(res.blockMostNegRC, np.minimum(0.0, res.blockRedCost))
+    kept = [b for b in range(m) if ref.col_keep[b]]
+    # a block whose rc sits within rounding of -eps may legitimately flip; none in these inputs
+    assert res.nCols == len(kept)
+    assert list(res.colBlock[:res.nCols]) == kept
+    for k, b in enumerate(kept):
+        assert list(res.column(k)) == list(ref.col_ind[b]), f"block {b}"
+        assert res.colRedCost[k] == res.blockRedCost[b]
+        assert res.colOrigCost[k] == res.blockOrigCost[b]
+    assert res.cells == ref.cells
+    assert abs(res.mostNegReducedCost - ref.most_neg_reduced_cost) <= RC_RTOL * max(1.0, abs(ref.most_neg_reduced_cost))
+    return res, ref
+
+
+def test_golden_knapsack01_cases(pricer, golden_knapsack):
+    """Every golden case (outputs of the reference's own knapsack01) as one block of one batch."""
+    cases = [c for c in golden_knapsack if len(c["w"]) >= 2]  # n==1: documented divergence of the Python
+    bcs, w, cap, rc = _batch_from_cases(cases)
+    pricer.setObjective(np.zeros(len(w)))
+    pricer.setKnapsackBlocks(bcs, w, cap)
+    res = pricer.solveBlocks(rc, np.zeros(len(cases)), redCostEps=-np.inf)
+    assert res.nCols == len(cases)
+    for k, c in enumerate(cases):
+        assert res.blockObj[k] == c["z"], c["tag"]
+        got = [int(j - bcs[k]) for j in res.column(k)]
+        assert got == sorted(c["solution"]), c["tag"]
+
+
+def test_golden_gap0515_rounds(pricer, golden_gap0515):
+    g = golden_gap0515
+    inst = I.GapInstance(g["m"], g["n"], np.array(g["cost"]).reshape(g["m"], g["n"]),
+                         np.array(g["weight"], np.int32).reshape(g["m"], g["n"]),
+                         np.array(g["capacity"], np.int32))
+    model = I.gap_pricing_model(inst)
+    pricer.setModel(model)
+    for r in g["rounds"]:
+        res, rcx = pricer.priceRound(r["u"], redCostEps=-np.inf, want_redcost=True)
+        np.testing.assert_allclose(rcx, r["red_cost"], rtol=RC_RTOL, atol=0)
+        # the DP consumed the GPU's own reduced costs: identical inputs only if they are bit-equal
+        if np.array_equal(rcx, r["red_cost"]):
+            for b, gb in enumerate(r["blocks"]):
+                assert res.blockObj[b] == gb["z"]
+                assert list(res.column(b)) == gb["ind"]
+        # stage (b) alone on the golden reduced costs is always bit-exact
+        alpha = r["u"][model.n_base_rows:model.n_base_rows + model.m]
+        res2 = pricer.solveBlocks(r["red_cost"], alpha, redCostEps=-np.inf)
+        for b, gb in enumerate(r["blocks"]):
+            assert res2.blockObj[b] == gb["z"]
+            assert list(res2.column(b)) == gb["ind"]
+
+
+@pytest.mark.parametrize("seed,m,nhi,caphi", [(1, 64, 40, 90), (2, 300, 130, 700), (3, 33, 700, 2500),
+                                              (4, 7, 2300, 9000), (5, 1, 50, 12000)])
+def test_random_ragged_batches(oracle, pricer, seed, m, nhi, caphi):
+    b = I.random_batch(m, 0, nhi, 0, caphi, seed)
+    _check_against_oracle(oracle, pricer, b.block_col_start, b.weight, b.capacity, b.red_cost, b.orig_cost, b.alpha)
+
+
+def test_tie_heavy_integer_profits(oracle, pricer):
+    b = I.random_batch(200, 1, 60, 1, 60, seed=11, int_profits=True)
+    _check_against_oracle(oracle, pricer, b.block_col_start, b.weight, b.capacity, b.red_cost, b.orig_cost, b.alpha)
+
+
+def test_edge_blocks(oracle, pricer):
+    """Empty block, all-inactive block, capacity 0, zero-weight items, item heavier than capacity."""
+    bcs = np.array([0, 0, 3, 6, 9, 12], np.int32)
+    w = np.array([1, 2, 3, 1, 1, 1, 0, 0, 5, 9, 9, 2], np.int32)
+    cap = np.array([5, 4, 0, 3, 4], np.int32)
+    rc = np.array([1.0, 0.0, 2.0, -1.0, -2.0, -3.0, -1.5, -2.5, -9.0, -7.0, -8.0, -1.0])
+    oc = np.arange(12, dtype=np.float64)
+    alpha = np.array([0.0, -1.0, 0.0, 0.5, -0.25])
+    res, ref = _check_against_oracle(oracle, pricer, bcs, w, cap, rc, oc, alpha)
+    assert res.blockNnz[0] == 0 and res.blockNnz[1] == 0
+    assert res.blockRedCost[1] == 1.0  # empty column: 0 - alpha
+
+
+@pytest.mark.parametrize("T,S", [(32, 8), (64, 8), (256, 4), (1024, 4)])
+def test_forced_dp_geometries(oracle, pricer, T, S):
+    """Same results whatever the (threads, cells/thread) shape of the DP row."""
+    pricer.set_option("dp_threads", T)
+    pricer.set_option("dp_cells_per_thread", S)
+    b = I.random_batch(40, 0, 200, 0, T * S - 1, seed=100 + T + S)
+    _check_against_oracle(oracle, pricer, b.block_col_start, b.weight, b.capacity, b.red_cost, b.orig_cost, b.alpha)
+
+
+def _check_round(oracle, pricer, model, u, phase1=False):
+    from dip_b200.pricer import PHASE_PRICE1, PHASE_PRICE2
+    res, rcx = pricer.priceRound(u, PHASE_PRICE1 if phase1 else PHASE_PRICE2, want_redcost=True)
+    ref = oracle.price_round(model.R, model.N, model.row_start, model.col_ind, model.val, model.objective, u,
+                             model.n_base_rows, model.m, model.block_col_start, model.weight, model.capacity,
+                             phase1=phase1)
+    scale = np.maximum(np.abs(ref.red_cost_x), 1e-300)
+    assert np.max(np.abs(rcx - ref.red_cost_x) / scale) <= RC_RTOL
+    # stages (b)+(c) on identical inputs (the GPU's reduced costs) must be bit-exact
+    alpha = u[model.n_base_rows:model.n_base_rows + model.m]
+    ref2 = oracle.solve_blocks(model.block_col_start, model.weight, model.capacity, rcx,
+                               np.zeros(model.N) if False else model.objective, alpha)
+    np.testing.assert_array_equal(res.blockObj, ref2.z)
+    np.testing.assert_array_equal(res.blockNnz, ref2.col_nnz)
+    kept = [b for b in range(model.m) if ref2.col_keep[b]]
+    assert list(res.colBlock[:res.nCols]) == kept
+    for k, b in enumerate(kept):
+        assert list(res.column(k)) == list(ref2.col_ind[b])
+    np.testing.assert_allclose(res.blockRedCost, ref2.col_red_cost, rtol=RC_RTOL, atol=1e-12)
+    return res, ref
+
+
+def test_gap_d_round(oracle, pricer):
+    model = I.gap_pricing_model(I.gap_class_d())
+    pricer.setModel(model)
+    rng = np.random.default_rng(5)
+    for r in range(3):
+        _check_round(oracle, pricer, model, I.gap_duals(model, rng))
+    _check_round(oracle, pricer, model, I.gap_duals(model, rng), phase1=True)
+
+
+def test_gap_e_round(oracle, pricer):
+    model = I.gap_pricing_model(I.gap_class_e())
+    pricer.setModel(model)
+    rng = np.random.default_rng(6)
+    for r in range(2):
+        res, _ = _check_round(oracle, pricer, model, I.gap_duals(model, rng))
+        assert res.nCols > 0
+
+
+def test_gap12_class_c_round(oracle, pricer):
+    model = I.gap_pricing_model(I.gap_class_c())
+    pricer.setModel(model)
+    _check_round(oracle, pricer, model, I.gap_duals(model, np.random.default_rng(12)))
+
+
+def test_spmv_random_csr_with_cuts(oracle, pricer):
+    """General sparse A'' (not GAP-shaped), zero duals skipped, then cut rows appended."""
+    rng = np.random.default_rng(9)
+    R, N, m, nBase = 300, 5000, 10, 260
+    nnz = 40_000
+    r = np.sort(rng.integers(0, R, size=nnz))
+    rs = np.zeros(R + 1, np.int64)
+    np.cumsum(np.bincount(r, minlength=R), out=rs[1:])
+    ci = rng.integers(0, N, size=nnz).astype(np.int32)
+    v = rng.uniform(-10, 10, size=nnz)
+    c = rng.uniform(0, 100, size=N)
+    pricer.setModelCore(R, N, rs, ci, v, nBase, m)
+    pricer.setObjective(c)
+    u = rng.standard_normal(R + m)
+    u[rng.random(R + m) < 0.3] = 0.0
+    for phase1 in (False, True):
+        got = pricer.calcRedCost(u, 1 if phase1 else 2)
+        ref = oracle.calc_redcost(R, N, rs, ci, v, oracle.adjust_duals(u, nBase, m), c, phase1)
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-9)) <= 1e-11  # cancellation near 0
+        assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref)) * 50
+    # append 25 cut rows
+    k = 25
+    nn = 900
+    r2 = np.sort(rng.integers(0, k, size=nn))
+    rs2 = np.zeros(k + 1, np.int64)
+    np.cumsum(np.bincount(r2, minlength=k), out=rs2[1:])
+    ci2 = rng.integers(0, N, size=nn).astype(np.int32)
+    v2 = rng.uniform(-5, 5, size=nn)
+    pricer.appendCoreRows(rs2, ci2, v2)
+    u2 = rng.standard_normal(R + k + m)
+    got = pricer.calcRedCost(u2)
+    rsA = np.concatenate([rs, rs[-1] + rs2[1:]])
+    ref = oracle.calc_redcost(R + k, N, rsA, np.concatenate([ci, ci2]), np.concatenate([v, v2]),
+                              oracle.adjust_duals(u2, nBase, m), c)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref)) * 50
+
+
+def test_solve_relaxed_plugin_surface(oracle, pricer):
+    """DecompApp::solveRelaxed semantics: one (possibly empty) column per block, redCost without alpha."""
+    from dip_b200.pricer import DecompSolStatOptimal
+    b = I.random_batch(12, 0, 50, 5, 90, seed=21)
+    pricer.setObjective(b.orig_cost)
+    pricer.setKnapsackBlocks(b.block_col_start, b.weight, b.capacity)
+    ref = oracle.solve_blocks(b.block_col_start, b.weight, b.capacity, b.red_cost, b.orig_cost, np.zeros(12))
+    for blk in range(12):
+        st, vs = pricer.solveRelaxed(blk, b.red_cost, target=b.alpha[blk])
+        assert st == DecompSolStatOptimal and len(vs) == 1
+        v = vs[0]
+        assert v.blockId == blk and list(v.ind) == list(ref.col_ind[blk])
+        assert abs(v.redCost - ref.col_red_cost[blk]) <= 1e-12 * max(1, abs(ref.col_red_cost[blk]))
+        assert abs(v.origCost - ref.col_orig_cost[blk]) <= 1e-12 * max(1, abs(ref.col_orig_cost[blk]))
+    assert pricer.counters()["kernel_launches"] <= 4  # one submission served all 12 calls
+
+
+def test_generate_vars_surface(oracle, pricer):
+    model = I.gap_pricing_model(I.gap_class_d(6, 40, seed=3))
+    pricer.setModel(model)
+    u = I.gap_duals(model, np.random.default_rng(1))
+    new_vars, most_neg = pricer.generateVars(u)
+    ref = oracle.price_round(model.R, model.N, model.row_start, model.col_ind, model.val, model.objective, u,
+                             model.n_base_rows, model.m, model.block_col_start, model.weight, model.capacity)
+    assert len(new_vars) == ref.n_kept
+    assert abs(most_neg - ref.most_neg_reduced_cost) <= 1e-12 * max(1, abs(ref.most_neg_reduced_cost))
+    for v in new_vars:
+        assert v.redCost < -1e-4
+        assert list(v.ind) == list(ref.col_ind[v.blockId])
+
+
+def test_error_codes(pricer):
+    from dip_b200.capi import DipGpuError, ERR_STATE, ERR_INVALID, ERR_UNSUPPORTED
+    with pytest.raises(DipGpuError) as e:
+        pricer.priceRound(np.zeros(4))
+    assert e.value.code == ERR_STATE
+    with pytest.raises(DipGpuError) as e:
+        pricer.setKnapsackBlocks([0, 2], [1, -1], [3])
+    assert e.value.code == ERR_INVALID
+    with pytest.raises(DipGpuError) as e:
+        pricer.setKnapsackBlocks([0, 2], [1, 1], [10_000_000])
+    assert e.value.code == ERR_UNSUPPORTED
+
+
+def test_csp_full_size_properties(oracle, pricer):
+    """BASELINE config 4 at full size (10^4 x 500 x 10^4): size-independent properties on every
+    block + bit-exact oracle parity on a sample of blocks."""
+    b = I.csp_batch()
+    pricer.setObjective(b.orig_cost)
+    pricer.setKnapsackBlocks(b.block_col_start, b.weight, b.capacity)
+    res = pricer.solveBlocks(b.red_cost, b.alpha, redCostEps=-np.inf)
+    assert res.nCols == b.m and res.cells == b.cells
+    w64 = b.weight.astype(np.int64)
+    for k in range(b.m):
+        ind = res.column(k)
+        assert ind.size == 0 or (np.all(np.diff(ind) > 0) and ind[0] >= b.block_col_start[k]
+                                 and ind[-1] < b.block_col_start[k + 1])
+        assert w64[ind].sum() <= b.capacity[k]                      # feasible
+        z = -b.red_cost[ind].sum()
+        assert abs(z - res.blockObj[k]) <= 1e-9 * max(1.0, z)        # column value == DP optimum
+    rng = np.random.default_rng(0)
+    for k in rng.choice(b.m, size=24, replace=False):
+        s, e = b.block_col_start[k], b.block_col_start[k + 1]
+        z, sol = oracle.knapsack01(-b.red_cost[s:e], b.weight[s:e], int(b.capacity[k]))
+        assert z == res.blockObj[k]
+        assert sorted(int(s + i) for i in sol) == list(res.column(k))

@@ -1,0 +1,102 @@
+"""The CPU oracle against the reference's own outputs (tests/golden, made by oracle/gen_golden.py
+from gap_func.knapsack01 executed unchanged, KnapsackOptimizeHS compiled from the reference, and
+the in-tree instance gap0515-2.dat)."""
+import numpy as np
+
+from dip_b200.instances import GapInstance, gap_pricing_model
+
+
+def test_knapsack01_matches_reference_function(oracle, golden_knapsack):
+    assert len(golden_knapsack) >= 150
+    for c in golden_knapsack:
+        z, sol = oracle.knapsack01(c["obj"], c["w"], c["cap"])
+        assert z == c["z"], c["tag"]                      # bit-exact optimum
+        assert list(sol) == c["solution"], c["tag"]       # same argmax, same (descending) order
+
+
+def test_knapsack01_decision_table_backtrack(oracle, golden_knapsack):
+    for c in golden_knapsack[:40]:
+        z, sol, added = oracle.knapsack01(c["obj"], c["w"], c["cap"], want_table=True)
+        j, i, walk = c["cap"], len(c["w"]) - 1, []
+        while i >= 0 and j >= 0:
+            if added[i, j]:
+                walk.append(i)
+                j -= int(c["w"][i])
+            i -= 1
+        assert walk == list(sol)
+
+
+def test_integer_cases_match_reference_hs(oracle, golden_knapsack):
+    """Integer profits: z* is unique, so the reference's B&B must equal the DP value."""
+    n = 0
+    for c in golden_knapsack:
+        if c["hs_z"] is None or c["hs_status"] != 0:
+            continue
+        z, _ = oracle.knapsack01(c["obj"], c["w"], c["cap"])
+        assert z == c["hs_z"], c["tag"]
+        n += 1
+    assert n >= 20
+
+
+def test_live_reference_hs_if_built(oracle):
+    if not oracle.have_ref():
+        import pytest
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(7)
+    for _ in range(50):
+        n = int(rng.integers(3, 30))
+        w = rng.integers(1, 30, size=n)
+        p = rng.integers(1, 60, size=n).astype(np.float64)
+        cap = int(rng.integers(10, 120))
+        st, zhs, x = oracle.ref_knapsack_hs(p, w, cap)
+        z, sol = oracle.knapsack01(p, w.astype(np.int32), cap)
+        if st == 0:
+            assert z == zhs
+            assert (w * x).sum() <= cap
+
+
+def _gap0515(g):
+    inst = GapInstance(g["m"], g["n"], np.array(g["cost"]).reshape(g["m"], g["n"]),
+                       np.array(g["weight"], np.int32).reshape(g["m"], g["n"]),
+                       np.array(g["capacity"], np.int32), "gap0515-2")
+    return gap_pricing_model(inst)
+
+
+def test_gap0515_rounds(oracle, golden_gap0515):
+    g = golden_gap0515
+    model = _gap0515(g)
+    assert model.R == g["n"] + 2 * g["m"] * g["n"]
+    for r in g["rounds"]:
+        res = oracle.price_round(model.R, model.N, model.row_start, model.col_ind, model.val, model.objective,
+                                 r["u"], model.n_base_rows, model.m, model.block_col_start, model.weight,
+                                 model.capacity)
+        np.testing.assert_array_equal(res.red_cost_x, r["red_cost"])   # same order -> bit-exact
+        alpha = r["u"][model.n_base_rows:model.n_base_rows + model.m]
+        for b, gb in enumerate(r["blocks"]):
+            assert res.z[b] == gb["z"]
+            assert list(res.col_ind[b]) == gb["ind"]
+            rc = sum(r["red_cost"][j] for j in gb["ind"]) - alpha[b]
+            assert abs(res.col_red_cost[b] - rc) <= 1e-12 * max(1.0, abs(rc))
+            assert res.most_neg_rc[b] == min(0.0, res.col_red_cost[b])
+            assert bool(res.col_keep[b]) == (res.col_red_cost[b] < -1e-4)
+        assert res.most_neg_reduced_cost == float(np.add.reduce(res.most_neg_rc)) or \
+            abs(res.most_neg_reduced_cost - res.most_neg_rc.sum()) < 1e-12
+
+
+def test_adjust_duals_and_phase1(oracle):
+    u = np.arange(10, dtype=np.float64)
+    out = oracle.adjust_duals(u, n_base=4, m=3)
+    np.testing.assert_array_equal(out, [0, 1, 2, 3, 7, 8, 9])
+    # 2 rows, 3 cols
+    rs = np.array([0, 2, 3], np.int64)
+    ci = np.array([0, 2, 1], np.int32)
+    v = np.array([1.0, 2.0, 3.0])
+    c = np.array([10.0, 20.0, 30.0])
+    ua = np.array([0.5, -1.0])
+    np.testing.assert_array_equal(oracle.calc_redcost(2, 3, rs, ci, v, ua, c), [9.5, 23.0, 29.0])
+    np.testing.assert_array_equal(oracle.calc_redcost(2, 3, rs, ci, v, ua, c, phase1=True), [-0.5, 3.0, -1.0])
+
+
+def test_string_hash(oracle):
+    assert oracle.string_hash([3, 17, 42], [1.0, 1.0, 1.0]) == "3_1_17_1_42_1_"
+    assert oracle.string_hash([5], [0.123456789]) == "5_0.123457_"
