@@ -1,0 +1,514 @@
+#!/usr/bin/env python3
+"""bench.py -- pricing rounds/s on GAP-E 80x1600 (BASELINE.json `metric`), with the knapsack-DP
+GCUPS (CSP batch) and the reduced-cost SpMV GB/s (MILPBlock shape) reported beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One STEP = one pricing round of DIP's price-and-cut loop (DecompAlgo::generateVars,
+Dip/src/DecompAlgo.cpp:4622-5260) for ONE master dual vector over all 80 blocks:
+reduced costs c - A''^T u  ->  80 knapsack DPs  ->  backtrack  ->  negative-reduced-cost filter.
+
+  value : rounds/s with the dual vector already in HBM (device-resident entry point), device time
+          by CUDA events per step on the launching stream, L2 flushed between steps.
+  e2e   : the same metric through the reference-facing C-ABI call dipgpu_price_round with HOST
+          buffers (pinned u in, packed columns out), H2D + D2H inside the timed region.
+  N > 1 : one process per GPU (torchrun).  `value` is weak scaling -- every rank prices its own
+          GAP-E rounds (independent subproblem batches, no data-path collective); the `sharded`
+          object reports ONE round's 80 blocks partitioned across the N GPUs with the dual
+          broadcast and the column gather over NCCL (north_star's exchange step).
+
+--impl reference runs the CPU pricing round (the oracle's restatement of the reference path,
+OpenMP over blocks like DecompAlgo.cpp:4815) on the host cores for the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from dip_b200 import instances as I  # noqa: E402
+
+METRIC = "pricing_rounds_per_s_gap_e_80x1600"
+UNIT = "rounds/s"
+N_DUALS = 16          # distinct master dual vectors cycled through the steps
+RC_EPS = 1e-4         # DecompParam::RedCostEpsilon (Dip/src/DecompParam.h:691)
+
+
+def load_peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload():
+    model = I.gap_pricing_model(I.gap_class_e())
+    rng = np.random.default_rng(801600)
+    duals = [I.gap_duals(model, rng) for _ in range(N_DUALS)]
+    return model, duals
+
+
+# ------------------------------------------------------------------------ clocks sampler
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {}
+        for k in dir(nv):
+            if k.startswith("nvmlClocksThrottleReason") or k.startswith("nvmlClocksEventReason"):
+                v = getattr(nv, k)
+                if isinstance(v, int) and v:
+                    names.setdefault(v, k.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", ""))
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if bit & (bit - 1) == 0 and r & bit and nm not in ("GpuIdle", "None", "All"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------- CPU baseline
+
+
+def cpu_round_fn(model, threads):
+    from oracle import dip_oracle as orc
+    orc.build()
+
+    def run(u):
+        return orc.price_round(model.R, model.N, model.row_start, model.col_ind, model.val, model.objective, u,
+                               model.n_base_rows, model.m, model.block_col_start, model.weight, model.capacity,
+                               red_cost_eps=RC_EPS, n_threads=threads, want_ind=True)
+    return run
+
+
+def cpu_baseline(model, duals, budget_s=10.0):
+    """The oracle ("port") timed on the host cores: whole pricing rounds, OpenMP over blocks."""
+    cores = os.cpu_count() or 1
+    run = cpu_round_fn(model, cores)
+    run(duals[0])
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        run(duals[n % len(duals)])
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 2000:
+            break
+    return {"value": n / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} whole GAP-E 80x1600 pricing rounds in {el:.2f} s (oracle/dip_oracle.c, "
+                      f"SpMV single-thread as DIP, knapsacks OpenMP dynamic,1 over blocks on {cores} threads)"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    model, duals = workload()
+    cores = os.cpu_count() or 1
+    run = cpu_round_fn(model, cores)
+    for k in range(max(args.warmup, 1)):
+        run(duals[k % N_DUALS])
+    # a CPU round takes milliseconds: bound the run to a few minutes
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        run(duals[k % N_DUALS])
+    el = time.perf_counter() - t0
+    val = args.steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "GAP-E 80x1600 pricing round (SpMV + 80 knapsack DPs + filter), one dual vector per step",
+                   "blocks": model.m, "cols": model.N, "rows": model.R, "nnz": model.nnz},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} whole rounds; the reference's GAP pricing needs Pisinger's combo.c "
+                                   "(not vendored) so the oracle's restatement of knapsack01 + generateVars is timed"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-extras", action="store_true", help="skip the CSP GCUPS / SpMV / CPU legs")
+    ap.add_argument("--csp-blocks", type=int, default=10_000)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from dip_b200.pricer import GpuPricer, RoundResult, unpack_result
+    from dip_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the pricing path is CUDA-only (no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    hbm_peak, peak_src = load_peaks()
+    model, duals = workload()
+    K, W = args.steps, args.warmup
+    pr = GpuPricer(local_rank)
+    pr.setModel(model)
+    # a non-default stream: the library treats a NULL stream as "use the context's own"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+    assert sptr != 0
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    u_dev = [torch.from_numpy(u).to(dev) for u in duals]
+    u_pin = capi.PinnedArray((N_DUALS, model.u_len), np.float64)
+    for k, u in enumerate(duals):
+        u_pin.array[k] = u
+    res = RoundResult(model.m, model.m, model.N)
+
+    # ---- parity spot check of what is about to be timed (device-resident vs host-buffer entry points)
+    pr.priceRoundDev(u_dev[0].data_ptr(), model.u_len, redCostEps=RC_EPS, stream=sptr)
+    torch.cuda.synchronize()
+    r0 = pr.priceRound(duals[0], redCostEps=RC_EPS, result=res)
+    cells_per_round = [pr.priceRound(duals[k], redCostEps=RC_EPS, result=res).cells for k in range(N_DUALS)]
+    kept0 = r0.nCols
+
+    # ---- device-resident rounds (value)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(W):
+        flush_l2()
+        pr.priceRoundDev(u_dev[k % N_DUALS].data_ptr(), model.u_len, redCostEps=RC_EPS, stream=sptr)
+    barrier()
+    c0 = pr.counters()
+    wall0 = time.perf_counter()
+    with ClockSampler(local_rank) as clk:
+        for k in range(K):
+            flush_l2()
+            ev[k][0].record(stream)
+            pr.priceRoundDev(u_dev[k % N_DUALS].data_ptr(), model.u_len, redCostEps=RC_EPS, stream=sptr)
+            ev[k][1].record(stream)
+        barrier()
+    wall_dev = time.perf_counter() - wall0
+    c1 = pr.counters()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    dev_ms = max_over_ranks(dev_ms)
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+    value = world * K / (dev_ms * 1e-3)
+
+    # ---- end-to-end rounds through the host-buffer C-ABI call (e2e)
+    for k in range(W):
+        pr.priceRoundRaw(u_pin.array[k % N_DUALS].ctypes.data, model.u_len, capi.PHASE_PRICE2, RC_EPS, res)
+    ptrs = [u_pin.array[k].ctypes.data for k in range(N_DUALS)]
+    barrier()
+    c0 = pr.counters()
+    e2e_s = 0.0
+    for k in range(K):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pr.priceRoundRaw(ptrs[k % N_DUALS], model.u_len, capi.PHASE_PRICE2, RC_EPS, res)
+        e2e_s += time.perf_counter() - t0
+    c1 = pr.counters()
+    e2e_s = max_over_ranks(e2e_s)
+    e2e = {"value": world * K / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) // K,
+           "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) // K,
+           "ms_per_step": 1e3 * e2e_s / K,
+           "timing": "host wall clock around the synchronous dipgpu_price_round call (pinned u in, columns out)"}
+
+    # ---- per-stage device times of the timed workload (CUDA events on the library's stream)
+    pr.set_option("stage_timing", 1)
+    stage = {}
+    for k in range(min(K, 100)):
+        flush_l2()
+        torch.cuda.synchronize()
+        pr.priceRoundRaw(ptrs[k % N_DUALS], model.u_len, capi.PHASE_PRICE2, RC_EPS, res)
+        for nm, ms in pr.last_stage_ms().items():
+            stage.setdefault(nm, []).append(ms)
+    pr.set_option("stage_timing", 0)
+    stage_ms = {nm: float(np.mean(v)) for nm, v in stage.items()}
+
+    extras = {}
+    smem_peak = None
+    if not args.skip_extras:
+        smem_peak = pr.measureSmemGBs()
+    cells_mean = float(np.mean(cells_per_round))
+    dp_ms = stage_ms["knapsack_dp"]
+    # dominant kernel of the step = knap_dp_kernel; algorithmic shared-memory bytes = 24 B / cell
+    roofline = {
+        "kernel": "knap_dp_kernel", "bound": "smem",
+        "achieved": cells_mean * 24.0 / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None,
+        "peak": smem_peak, "unit": "GB/s",
+        "frac": (cells_mean * 24.0 / (dp_ms * 1e-3) / 1e9 / smem_peak) if (smem_peak and dp_ms > 0) else None,
+        "traffic": None,
+        "peak_source": "in-library shared-memory copy microbenchmark (dipgpu_measure_smem_gbs), this run",
+        "note": "80 one-warp..few-warp CTAs on 148 SMs: the GAP-E round is latency-bound, see roofline_dp_csp "
+                "for the bandwidth-bound shape of the same kernel",
+        "avg_launch_ms": dp_ms, "cells_per_launch": cells_mean,
+        "gcups": cells_mean / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None,
+    }
+
+    # ---- N > 1: one round's blocks sharded across the ranks, NCCL broadcast + gather
+    sharded = None
+    if world > 1:
+        sharded = sharded_rounds(dist, torch, dev, pr, model, u_dev, K, W, world, rank, flush_l2, barrier,
+                                 max_over_ranks, unpack_result, RoundResult, kept0)
+        pr.setBlockRange(0, model.m)
+
+    if not args.skip_extras:
+        extras["dp_csp"] = bench_csp(torch, dev, pr, args, world, rank, barrier, max_over_ranks, smem_peak, flush_l2)
+        extras["spmv_milpblock"] = bench_spmv(torch, dev, local_rank, hbm_peak, peak_src, flush_l2, world, rank,
+                                              max_over_ranks, barrier)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_extras:
+        cpu = cpu_baseline(model, duals)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "GAP-E 80x1600 pricing round (SpMV c-A''^T u + 80 knapsack DPs + backtrack + filter), "
+                            "one master dual vector per step, 16 dual vectors cycled",
+                "blocks": model.m, "cols": model.N, "rows": model.R, "nnz": model.nnz,
+                "cells_per_round": cells_mean, "kept_columns_round0": kept0, "red_cost_eps": RC_EPS,
+                "l2": "flushed between steps (256 MiB fill, outside the per-step CUDA-event pairs)",
+                "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, independent rounds per rank (weak); "
+                                                          "see `sharded` for one round partitioned over NCCL",
+            },
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+            "wall_s_device_loop": wall_dev, "stage_ms": stage_ms, "roofline": roofline,
+        }
+        if "dp_csp" in extras:
+            line["roofline_dp_csp"] = extras["dp_csp"]
+        if "spmv_milpblock" in extras:
+            line["roofline_spmv"] = extras["spmv_milpblock"]
+        if sharded is not None:
+            line["sharded"] = sharded
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    pr.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def sharded_rounds(dist, torch, dev, pr, model, u_dev, K, W, world, rank, flush_l2, barrier, max_over_ranks,
+                   unpack_result, RoundResult, kept_expected):
+    """One GAP-E round partitioned over the ranks: rank 0 owns the dual vector, ncclBroadcast(u),
+    every rank prices its contiguous block range, all_gather of the packed per-shard results
+    (fixed-size buffers), rank 0 decodes.  Strong scaling of a single round (latency-bound)."""
+    m = model.m
+    per = (m + world - 1) // world
+    first = min(rank * per, m)
+    count = max(0, min(per, m - first))
+    pr.setBlockRange(first, count)
+    dptr, nbytes = pr.resultDev()
+    sizes = torch.tensor([nbytes], dtype=torch.int64, device=dev)
+    dist.all_reduce(sizes, op=dist.ReduceOp.MAX)
+    maxb = int(sizes.item())
+    maxb = (maxb + 15) // 16 * 16
+    send = torch.zeros(maxb, dtype=torch.uint8, device=dev)
+    recv = torch.zeros(maxb * world, dtype=torch.uint8, device=dev)
+    ubuf = torch.empty(model.u_len, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    class _DevBytes:  # torch view of the library's packed-result buffer (no copy)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    packed = torch.as_tensor(_DevBytes(dptr, nbytes), device=dev)
+
+    def one_round(k):
+        if rank == 0:
+            ubuf.copy_(u_dev[k % len(u_dev)])
+        dist.broadcast(ubuf, src=0)
+        pr.priceRoundDev(ubuf.data_ptr(), model.u_len, redCostEps=RC_EPS, stream=sptr)
+        # packed shard result -> fixed-size send buffer (device-to-device on the same stream)
+        send[:nbytes].copy_(packed, non_blocking=True)
+        dist.all_gather_into_tensor(recv, send)
+
+    for k in range(W):
+        one_round(k)
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(K):
+        flush_l2()
+        evs[k][0].record(stream)
+        one_round(k)
+        evs[k][1].record(stream)
+    barrier()
+    ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+    # decode on rank 0 and check against the unsharded result
+    ok = None
+    if rank == 0:
+        host = recv.cpu().numpy()
+        total = RoundResult(m, m, model.N)
+        kept = 0
+        for r in range(world):
+            part = unpack_result(host[r * maxb:(r + 1) * maxb], m, model.N,
+                                 RoundResult(m, m, model.N))
+            kept += part.nCols
+        k_last = (K - 1) % len(u_dev)
+        pr.setBlockRange(0, m)
+        full = pr.priceRound(u_dev[k_last].cpu().numpy(), redCostEps=RC_EPS, result=total)
+        ok = bool(kept == full.nCols)
+    return {"rounds_per_s": K / (ms * 1e-3), "ms_per_round": ms / K, "scaling": "strong",
+            "blocks_per_gpu": per, "collectives": "ncclBroadcast(u, %d B) + ncclAllGather(%d B per rank)" % (
+                model.u_len * 8, maxb), "kept_columns_match_unsharded": ok}
+
+
+def bench_csp(torch, dev, pr_unused, args, world, rank, barrier, max_over_ranks, smem_peak, flush_l2):
+    """Knapsack DP GCUPS on the cutting-stock batch (BASELINE.json configs[3]): 10^4 knapsacks,
+    n = 500, capacity 10^4, split evenly over the ranks (strong scaling, no collective)."""
+    from dip_b200.pricer import GpuPricer
+    m_total = args.csp_blocks
+    per = (m_total + world - 1) // world
+    first = min(rank * per, m_total)
+    count = max(0, min(per, m_total - first))
+    b = I.csp_batch(m=m_total)
+    n = 500
+    lo, hi = first * n, (first + count) * n
+    pr = GpuPricer(torch.cuda.current_device())
+    pr.setObjective(b.orig_cost[lo:hi])
+    pr.setKnapsackBlocks((np.arange(count + 1) * n).astype(np.int32), b.weight[lo:hi], b.capacity[first:first + count])
+    pr.set_option("stage_timing", 1)
+    rc = b.red_cost[lo:hi].copy()
+    alpha = np.zeros(count)
+    res = pr.solveBlocks(rc, alpha, redCostEps=-np.inf)
+    cells_local = res.cells
+    times = []
+    for rep in range(4):
+        flush_l2()
+        torch.cuda.synchronize()
+        barrier()
+        pr.solveBlocks(rc, alpha, redCostEps=-np.inf, result=res)
+        times.append(pr.last_stage_ms())
+    best = min(times[1:], key=lambda d: d["knapsack_dp"])
+    dp_ms = max_over_ranks(best["knapsack_dp"])
+    bt_ms = max_over_ranks(best["backtrack_emit"])
+    cells = m_total * n * (10_000 + 1)
+    pr.close()
+    ach = cells * 24.0 / (dp_ms * 1e-3) / 1e9
+    return {"kernel": "knap_dp_kernel", "workload": f"CSP batch {m_total} x n=500 x cap=10^4, {world} GPU(s)",
+            "bound": "smem", "gcups": cells / (dp_ms * 1e-3) / 1e9, "dp_ms": dp_ms, "backtrack_ms": bt_ms,
+            "achieved": ach, "peak": (smem_peak * world) if smem_peak else None, "unit": "GB/s",
+            "frac": ach / (smem_peak * world) if smem_peak else None,
+            "algorithmic_bytes_per_cell": 24, "cells": cells, "cells_this_rank": cells_local, "traffic": None,
+            "peak_source": "in-library shared-memory copy microbenchmark x n_gpus"}
+
+
+def bench_spmv(torch, dev, local_rank, hbm_peak, peak_src, flush_l2, world, rank, max_over_ranks, barrier):
+    """Reduced-cost SpMV sweep on the MILPBlock shape (BASELINE.json configs[4]): 256 blocks,
+    10^7-nnz linking rows; every rank sweeps the whole matrix (replicas), rank 0 reports."""
+    from dip_b200.pricer import GpuPricer
+    model, u = I.milpblock_model()
+    pr = GpuPricer(local_rank)
+    pr.setModelCore(model.R, model.N, model.row_start, model.col_ind, model.val, model.n_base_rows, model.m)
+    pr.setObjective(model.objective)
+    ud = torch.from_numpy(u).to(dev)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    for _ in range(3):
+        pr.calcRedCostDev(ud.data_ptr(), model.u_len, stream=sptr)
+    times = []
+    for _ in range(20):
+        flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        pr.calcRedCostDev(ud.data_ptr(), model.u_len, stream=sptr)
+        b.record(stream)
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = float(np.mean(times))
+    pr.close()
+    by = model.spmv_bytes()
+    ach = by / (ms * 1e-3) / 1e9
+    return {"kernel": "redcost_csc_kernel", "workload": model.name, "bound": "hbm", "achieved": ach,
+            "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "avg_launch_ms": ms,
+            "min_launch_ms": float(np.min(times)), "algorithmic_bytes": by, "peak_source": peak_src,
+            "l2": "flushed before every sweep (inputs 141 MB vs 126 MB L2)"}
+
+
+if __name__ == "__main__":
+    main()

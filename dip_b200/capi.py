@@ -32,6 +32,7 @@ SYMBOLS = [
     "dipgpu_price_round_dev", "dipgpu_solve_blocks_dev", "dipgpu_result_dev",
     "dipgpu_result_max_bytes", "dipgpu_unpack_result", "dipgpu_redcost_dev",
     "dipgpu_get_counters", "dipgpu_last_stage_ms", "dipgpu_set_option",
+    "dipgpu_calc_redcost_dev", "dipgpu_measure_smem_gbs",
 ]
 
 
@@ -82,6 +83,8 @@ def lib() -> C.CDLL:
         "dipgpu_price_round": ([vp, vp, i32, i32, dbl, C.POINTER(Cols), vp], C.c_int),
         "dipgpu_set_block_range": ([vp, i32, i32], C.c_int),
         "dipgpu_price_round_dev": ([vp, vp, i32, i32, dbl, vp], C.c_int),
+        "dipgpu_calc_redcost_dev": ([vp, vp, i32, i32, vp], C.c_int),
+        "dipgpu_measure_smem_gbs": ([vp, C.POINTER(dbl)], C.c_int),
         "dipgpu_solve_blocks_dev": ([vp, vp, vp, dbl, vp], C.c_int),
         "dipgpu_result_dev": ([vp, C.POINTER(vp), C.POINTER(C.c_size_t)], C.c_int),
         "dipgpu_result_max_bytes": ([vp, C.POINTER(C.c_size_t)], C.c_int),

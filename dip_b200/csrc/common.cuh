@@ -68,13 +68,15 @@ struct ResultLayout {
 
 // ------------------------------------------------------------------ DP geometry
 //
-// A knapsack's DP row of (capacity+1) cells is owned by T threads, S cells each,
-// interleaved: thread t holds cells t, t+T, ..., t+(S-1)T in registers.
+// A knapsack's DP row of (capacity+1) cells is owned by T threads, S consecutive
+// cells each: thread t holds cells [t*S, t*S+S) in registers.
 struct DpGeom {
-    int T;         // threads per knapsack (CTA size)
-    int S;         // cells per thread
+    int T;         // threads per knapsack (CTA size, multiple of 32)
+    int S;         // cells per thread (odd)
+    int items;     // items advanced per barrier (1 or 2)
     int rowCells;  // T*S >= maxCapacity+1
     int chunkCols; // columns staged per TMA chunk
+    int guard;     // -inf cells in front of each row buffer (0 = predicated reads)
     size_t smemBytes;
 };
 
@@ -117,8 +119,13 @@ struct Ctx {
     int32_t *dNItems = nullptr;         // m
     int32_t *dCandInd = nullptr;        // per column slot: candidate column indices (ascending)
     int32_t *dScratch = nullptr;        // per column slot: descending taken list
-    int maxCapacity = 0;
-    int optThreads = 0, optCellsPerThread = 0;
+    int maxCapacity = 0;       // of the shard
+    int maxBlockCols = 0;      // of the shard
+    int maxUsableWeight = 0;   // of the shard: max weight <= its block's capacity
+    std::vector<int32_t> hMaxUsableW;  // per block
+    int optThreads = 0, optCellsPerThread = 0, optItemsPerStep = 0, optNoGuard = 0;
+    void *dpFnConfigured = nullptr;
+    size_t dpFnSmem = 0;
     DpGeom geom{};
 
     // shard
@@ -166,5 +173,7 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st);
 int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_t st);
 // filter.cu -- stage (c)
 int launchFilter(Ctx *c, double redCostEps, cudaStream_t st);
+// microbench.cu -- roofline denominators measured on the device
+int measureSmemGbs(Ctx *c, double *gbs);
 
 }  // namespace dipgpu

@@ -107,9 +107,15 @@ static int setBlockRange(Ctx *c, int first, int count)
         return fail(c, DIPGPU_ERR_INVALID, "block range [%d,%d) outside [0,%d)", first, first + count, c->m);
     c->firstBlock = first;
     c->nLocal = count;
-    int maxCap = 0;
-    for (int b = first; b < first + count; ++b) maxCap = std::max(maxCap, c->hCapacity[b]);
+    int maxCap = 0, maxCols = 0, maxW = 0;
+    for (int b = first; b < first + count; ++b) {
+        maxCap = std::max(maxCap, c->hCapacity[b]);
+        maxCols = std::max(maxCols, c->hBlockColStart[b + 1] - c->hBlockColStart[b]);
+        maxW = std::max(maxW, c->hMaxUsableW[b]);
+    }
     c->maxCapacity = maxCap;
+    c->maxBlockCols = maxCols;
+    c->maxUsableWeight = maxW;
     int rc;
     if ((rc = chooseDpGeom(c, &c->geom))) return rc;
     // decision bits: ceil(n_b/32) words per cell, rowCells cells per block
@@ -407,6 +413,13 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
     c->profitMode = profitMode;
     c->hBlockColStart.assign(blockColStart, blockColStart + m + 1);
     c->hCapacity.assign(capacity, capacity + m);
+    c->hMaxUsableW.assign((size_t)m, 0);
+    for (int b = 0; b < m; ++b) {
+        int mw = 0;
+        for (int j = blockColStart[b]; j < blockColStart[b + 1]; ++j)
+            if (weight[j] <= capacity[b]) mw = std::max(mw, weight[j]);
+        c->hMaxUsableW[b] = mw;
+    }
     int rc;
     if ((rc = devAlloc(c, &c->dBlockColStart, (size_t)m + 1))) return rc;
     if ((rc = devAlloc(c, &c->dCapacity, (size_t)m))) return rc;
@@ -524,6 +537,25 @@ int dipgpu_price_round_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, in
     return enqueueSolve(c, c->dRedCost, uDev + c->nBaseRows, redCostEps, st, false);
 }
 
+int dipgpu_calc_redcost_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, int32_t phase, void *stream)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->haveCore) return fail(c, DIPGPU_ERR_STATE, "calc_redcost_dev before set_core_csr");
+    if (phase != DIPGPU_PHASE_PRICE1 && !c->haveObj) return fail(c, DIPGPU_ERR_STATE, "calc_redcost_dev (phase 2) before set_objective");
+    if (!uDev || uLen != c->R + c->numConvex) return fail(c, DIPGPU_ERR_INVALID, "calc_redcost_dev: bad dual vector");
+    int rc;
+    if ((rc = ensureObjective(c, c->N))) return rc;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    return launchRedCost(c, uDev, phase, st);
+}
+
+int dipgpu_measure_smem_gbs(dipgpu_ctx *ctx, double *gbs)
+{
+    CTX_OR_FAIL(ctx);
+    if (!gbs) return fail(c, DIPGPU_ERR_INVALID, "measure_smem_gbs: NULL output");
+    return measureSmemGbs(c, gbs);
+}
+
 int dipgpu_solve_blocks_dev(dipgpu_ctx *ctx, const double *redCostXDev, const double *alphaDev, double redCostEps, void *stream)
 {
     CTX_OR_FAIL(ctx);
@@ -592,8 +624,12 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!c || !name) return DIPGPU_ERR_INVALID;
     if (!strcmp(name, "stage_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "spmv_lanes")) { c->spmvLanes = (int)value; return DIPGPU_OK; }
-    if (!strcmp(name, "dp_threads") || !strcmp(name, "dp_cells_per_thread")) {
-        if (!strcmp(name, "dp_threads")) c->optThreads = (int)value; else c->optCellsPerThread = (int)value;
+    if (!strcmp(name, "dp_threads") || !strcmp(name, "dp_cells_per_thread") || !strcmp(name, "dp_items_per_step") ||
+        !strcmp(name, "dp_no_guard")) {
+        if (!strcmp(name, "dp_threads")) c->optThreads = (int)value;
+        else if (!strcmp(name, "dp_cells_per_thread")) c->optCellsPerThread = (int)value;
+        else if (!strcmp(name, "dp_items_per_step")) c->optItemsPerStep = (int)value;
+        else c->optNoGuard = (int)value;
         if (c->haveBlocks) {
             int rc = bind(c);
             if (rc) return rc;

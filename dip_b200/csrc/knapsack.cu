@@ -14,14 +14,16 @@
 // optimum and the decision table are bit-identical whatever the parallel shape.
 //
 // Shape: one CTA per knapsack, items sequential, capacity parallel.  Thread t of
-// T owns cells t, t+T, ... (S of them) IN REGISTERS; shared memory only carries
-// the shifted row c[i-1][j-w] between threads (double-buffered, one barrier per
-// item): 16 B of shared-memory traffic per cell instead of the 24 B of a
-// row-in-smem formulation.  The block's reduced costs and weights are staged by
+// T owns the S consecutive cells [t*S, t*S+S) IN REGISTERS; shared memory only
+// carries the shifted row c[i-1][j-w] between threads (double-buffered, one
+// barrier per item or per two items): 16 B of shared-memory traffic per cell
+// instead of the 24 B of a row-in-smem formulation.  The block's reduced costs and weights are staged by
 // TMA bulk copies (cp.async.bulk + mbarrier) and compacted in shared memory.
 // Decisions are bit-packed per CELL over 32 consecutive items (one register per
 // owned cell) and streamed to HBM as coalesced 32-bit words, laid out
 // [itemWord][cell] so that the backtrack can skip 1024 items per warp load.
+#include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 
@@ -73,8 +75,6 @@ __device__ __forceinline__ void tmaLoad1d(void *dstSmem, const void *srcGlobal, 
 
 // ------------------------------------------------------------------- DP kernel
 
-// Shifted reads below cell 0 see -inf, so "p + c[i-1][j-w] > c[i-1][j]" is false
-// there, which is the reference's "w > j: keep c[i-1][j]" branch.
 #define kNegInf (__longlong_as_double((long long)0xfff0000000000000ULL))
 
 struct KnapArgs {
@@ -89,32 +89,45 @@ struct KnapArgs {
     int32_t *nItems;               // local block -> number of active items
     double *blockObj;              // local block -> knapsack optimum
     int firstBlock;
-    int chunkCols;
+    int chunkCols;                 // columns staged per TMA chunk (multiple of 4)
+    int guard;                     // -inf cells in front of each row buffer (even; 0 = predicated reads)
 };
 
-__host__ __device__ inline size_t dpSmemBytes(int rowCells, int chunkCols)
+__host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunkCols)
 {
     size_t b = 0;
-    b += sizeof(double) * 2 * (size_t)rowCells;        // double-buffered row
+    b += sizeof(double) * 2 * ((size_t)rowCells + (size_t)guard);  // two row buffers, each behind its guard
     b += sizeof(double) * ((size_t)chunkCols + 2);      // raw reduced costs (TMA dst)
-    b += sizeof(double) * ((size_t)chunkCols + 2);      // compacted profits (+1 prefetch pad)
+    b += sizeof(double) * ((size_t)chunkCols + 4);      // compacted profits (+ prefetch pad)
     b += sizeof(int32_t) * ((size_t)chunkCols + 4);     // raw weights (TMA dst)
-    b += sizeof(int32_t) * ((size_t)chunkCols + 4);     // compacted weights (+1 prefetch pad)
+    b += sizeof(int32_t) * ((size_t)chunkCols + 4);     // compacted weights (+ prefetch pad)
     b += sizeof(int32_t) * 32;                          // per-warp counts
     b += 16;                                            // mbarrier
     return b;
 }
 
-template <int T, int S>
-__global__ void __launch_bounds__(T) knap_dp_kernel(const KnapArgs a)
+// One CTA per knapsack; T = blockDim.x threads (a multiple of 32), thread t owns
+// the S consecutive cells [t*S, t*S+S) of the DP row in registers.  S is odd, so
+// the 64-bit shared-memory accesses of a half-warp (stride S doubles) hit 16
+// distinct bank pairs.  GUARD: each row buffer is preceded by `guard` cells of
+// -inf so that the shifted read c[i-1][j-w] needs no j >= w predicate.
+// ITEMS == 2 advances two items per barrier (latency-bound shapes): the
+// intermediate row c[i][.] is rebuilt in registers at j and j-w' from three
+// shifted reads of c[i-1][.], with exactly the additions and strict compares
+// the one-item step performs, so values and decisions are unchanged.
+template <int S, bool GUARD, int ITEMS, int MAXT>
+__global__ void __launch_bounds__(MAXT) knap_dp_kernel(const KnapArgs a)
 {
-    constexpr int RC = T * S;
     extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int T = blockDim.x;
+    const int RC = T * S;
+    const int G = a.guard;
     const int CH = a.chunkCols;
-    double *row = reinterpret_cast<double *>(smemRaw);
-    double *rawRc = row + 2 * RC;
+    double *rowBase = reinterpret_cast<double *>(smemRaw);
+    const int bufStride = RC + G;
+    double *rawRc = rowBase + 2 * bufStride;
     double *itP = rawRc + (CH + 2);
-    int32_t *rawW = reinterpret_cast<int32_t *>(itP + (CH + 2));
+    int32_t *rawW = reinterpret_cast<int32_t *>(itP + (CH + 4));
     int32_t *itW = rawW + (CH + 4);
     int32_t *warpCnt = itW + (CH + 4);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(warpCnt + 32);
@@ -122,15 +135,21 @@ __global__ void __launch_bounds__(T) knap_dp_kernel(const KnapArgs a)
     const int t = threadIdx.x;
     const int lane = t & 31;
     const int warp = t >> 5;
+    const int nWarps = T >> 5;
     const int lb = blockIdx.x;
     const int b = a.firstBlock + lb;
     const int colStart = a.blockColStart[b];
     const int nCols = a.blockColStart[b + 1] - colStart;
     const int cap = a.capacity[b];
     uint32_t *bitsBase = a.bits + a.bitsOff[lb];
+    const int j0 = t * S;  // first owned cell
 
     if (t == 0) mbarInit(mbar, 1);
-    for (int j = t; j < RC; j += T) row[j] = 0.0;  // c[-1][.] = 0  (gap_func.py:156)
+    // c[-1][.] = 0 (gap_func.py:156); guards = -inf
+    for (int j = t; j < 2 * bufStride; j += T) {
+        const int r = j >= bufStride ? j - bufStride : j;
+        rowBase[j] = r < G ? kNegInf : 0.0;
+    }
     __syncthreads();
 
     double mine[S];
@@ -175,12 +194,11 @@ __global__ void __launch_bounds__(T) knap_dp_kernel(const KnapArgs a)
             const unsigned bal = __ballot_sync(0xffffffffu, flag);
             const int wpre = __popc(bal & ((1u << lane) - 1u));
             int off = 0, tot = __popc(bal);
-            if (T > 32) {
+            if (nWarps > 1) {
                 if (lane == 0) warpCnt[warp] = tot;
                 __syncthreads();
                 tot = 0;
-#pragma unroll
-                for (int v = 0; v < T / 32; ++v) {
+                for (int v = 0; v < nWarps; ++v) {
                     const int cv = warpCnt[v];
                     off += v < warp ? cv : 0;
                     tot += cv;
@@ -199,35 +217,81 @@ __global__ void __launch_bounds__(T) knap_dp_kernel(const KnapArgs a)
         }
         __syncthreads();
 
-        // ---- the DP proper: items sequential, cells parallel
-        int wNext = nIt > 0 ? itW[0] : 0;
-        double pNext = nIt > 0 ? itP[0] : 0.0;
-        for (int i = 0; i < nIt; ++i) {
-            const int w = wNext;
-            const double p = pNext;
-            const double *rd = row + cur * RC + (t - w);
-            double *wr = row + (cur ^ 1) * RC + t;
+        // ---- the DP proper: items sequential, cells parallel.  (w0,p0),(w1,p1) hold
+        // items i and i+1, fetched one step ahead (itP/itW are padded by four entries).
+        int w0 = itW[0], w1 = itW[1];
+        double p0 = itP[0], p1 = itP[1];
+        int i = 0;
+        while (i < nIt) {
             const int bitpos = (kGlobal + i) & 31;
-            const uint32_t bm = 1u << bitpos;
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                const int src = t + s * T - w;
-                // c[i-1][j-w]; j < w keeps c[i-1][j]  (gap_func.py:161-162)
-                const double sh = src >= 0 ? rd[s * T] : kNegInf;
-                const double cand = p + sh;           // :164
-                const bool take = cand > mine[s];     // :166 strict
-                mine[s] = take ? cand : mine[s];
-                acc[s] |= take ? bm : 0u;             // added[i][j]  (:168)
-                wr[s * T] = mine[s];
-            }
-            // prefetch the next item before the barrier (itP/itW are padded by one)
-            wNext = itW[i + 1];
-            pNext = itP[i + 1];
-            if (bitpos == 31) {
-                uint32_t *dst = bitsBase + (size_t)((kGlobal + i) >> 5) * RC + t;
+            const double *base = rowBase + cur * bufStride + G + j0;
+            double *wr = rowBase + (cur ^ 1) * bufStride + G + j0;
+            if (ITEMS == 2 && i + 1 < nIt && (bitpos & 1) == 0) {
+                const int wA = w0, wB = w1;
+                const double pA = p0, pB = p1;
+                const double *rdA = base - wA;
+                const double *rdB = base - wB;
+                const double *rdAB = rdA - wB;
+                const uint32_t bmA = 1u << bitpos, bmB = 2u << bitpos;
+                double shA[S], shB[S], shAB[S];
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    dst[s * T] = acc[s];
+                    const int j = j0 + s;
+                    shA[s] = (GUARD || j >= wA) ? rdA[s] : kNegInf;
+                    shB[s] = (GUARD || j >= wB) ? rdB[s] : kNegInf;
+                    shAB[s] = (GUARD || j >= wA + wB) ? rdAB[s] : kNegInf;
+                }
+                w0 = itW[i + 2];
+                p0 = itP[i + 2];
+                w1 = itW[i + 3];
+                p1 = itP[i + 3];
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    // item A at cell j  (gap_func.py:164-168)
+                    const double candA = pA + shA[s];
+                    const bool takeA = candA > mine[s];
+                    const double r1 = takeA ? candA : mine[s];
+                    // item A at cell j - wB, i.e. c[i][j-wB], which item B reads
+                    const double candAB = pA + shAB[s];
+                    const double r1B = candAB > shB[s] ? candAB : shB[s];
+                    // item B at cell j
+                    const double candB = pB + r1B;
+                    const bool takeB = candB > r1;
+                    mine[s] = takeB ? candB : r1;
+                    acc[s] |= (takeA ? bmA : 0u) | (takeB ? bmB : 0u);
+                    wr[s] = mine[s];
+                }
+                i += 2;
+            } else {
+                const int w = w0;
+                const double p = p0;
+                const double *rd = base - w;
+                const uint32_t bm = 1u << bitpos;
+                double sh[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    // c[i-1][j-w]; j < w keeps c[i-1][j]  (gap_func.py:161-162)
+                    sh[s] = (GUARD || j0 + s >= w) ? rd[s] : kNegInf;
+                }
+                w0 = w1;
+                p0 = p1;
+                w1 = itW[i + 2];
+                p1 = itP[i + 2];
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    const double cand = p + sh[s];        // :164
+                    const bool take = cand > mine[s];     // :166 strict
+                    mine[s] = take ? cand : mine[s];
+                    acc[s] |= take ? bm : 0u;             // added[i][j]  (:168)
+                    wr[s] = mine[s];
+                }
+                i += 1;
+            }
+            if (((kGlobal + i) & 31) == 0) {  // a 32-item word is complete
+                uint32_t *dst = bitsBase + (size_t)((kGlobal + i - 1) >> 5) * RC + j0;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    dst[s] = acc[s];
                     acc[s] = 0u;
                 }
             }
@@ -238,73 +302,135 @@ __global__ void __launch_bounds__(T) knap_dp_kernel(const KnapArgs a)
     }
 
     if ((kGlobal & 31) != 0) {
-        uint32_t *dst = bitsBase + (size_t)(kGlobal >> 5) * RC + t;
+        uint32_t *dst = bitsBase + (size_t)(kGlobal >> 5) * RC + j0;
 #pragma unroll
-        for (int s = 0; s < S; ++s) dst[s * T] = acc[s];
+        for (int s = 0; s < S; ++s) dst[s] = acc[s];
     }
     // z = c[n-1][capacity]  (gap_func.py:183)
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        if (t + s * T == cap) a.blockObj[lb] = mine[s];
+        if (j0 + s == cap) a.blockObj[lb] = mine[s];
     }
     if (t == 0) a.nItems[lb] = kGlobal;
 }
 
 // --------------------------------------------------------------- geometry table
 
+typedef void (*KnapFn)(const KnapArgs);
 struct GeomEntry {
-    int T, S;
-    void (*fn)(const KnapArgs);
+    int S, maxT;
+    KnapFn fn[2][2];  // [guard][items-1]
 };
 
-#define GE(T, S) {T, S, knap_dp_kernel<T, S>}
+#define GE(S, MT)                                                                              \
+    {                                                                                          \
+        S, MT,                                                                                 \
+        {                                                                                      \
+            {knap_dp_kernel<S, false, 1, MT>, knap_dp_kernel<S, false, 2, MT>},                \
+            {knap_dp_kernel<S, true, 1, MT>, knap_dp_kernel<S, true, 2, MT>}                   \
+        }                                                                                      \
+    }
 static const GeomEntry kGeoms[] = {
-    GE(32, 1),   GE(32, 2),   GE(32, 3),   GE(32, 4),   GE(32, 5),   GE(32, 6),   GE(32, 7),  GE(32, 8),
-    GE(64, 2),   GE(64, 3),   GE(64, 4),   GE(64, 5),   GE(64, 6),   GE(64, 7),   GE(64, 8),
-    GE(128, 3),  GE(128, 4),  GE(128, 5),  GE(128, 6),  GE(128, 7),  GE(128, 8),
-    GE(256, 4),  GE(256, 5),  GE(256, 6),  GE(256, 7),  GE(256, 8),
-    GE(512, 4),  GE(512, 5),  GE(512, 6),  GE(512, 7),  GE(512, 8),
-    GE(1024, 4), GE(1024, 5), GE(1024, 6), GE(1024, 7), GE(1024, 8), GE(1024, 10), GE(1024, 12),
+    GE(1, 1024), GE(3, 1024), GE(5, 1024), GE(7, 1024), GE(9, 1024), GE(11, 1024),
+    GE(13, 512), GE(15, 512), GE(17, 512), GE(19, 512), GE(21, 512), GE(25, 512),
 };
 #undef GE
 static const int kNumGeoms = (int)(sizeof(kGeoms) / sizeof(kGeoms[0]));
 static const size_t kMaxSmem = 227 * 1024;
 
-static int chunkColsFor(int T) { return T <= 64 ? 512 : T <= 256 ? 1024 : 2048; }
+static const GeomEntry *findGeom(int S)
+{
+    for (int i = 0; i < kNumGeoms; ++i)
+        if (kGeoms[i].S == S) return &kGeoms[i];
+    return nullptr;
+}
+
+// Fills the derived fields of a (T, S) candidate; returns false if it cannot run.
+static bool fitGeom(const Ctx *c, int T, int S, int items, DpGeom *g)
+{
+    const GeomEntry *e = findGeom(S);
+    if (!e || T < 32 || T > e->maxT || (T & 31)) return false;
+    if ((int64_t)T * S < (int64_t)c->maxCapacity + 1) return false;
+    g->T = T;
+    g->S = S;
+    g->items = items;
+    g->rowCells = T * S;
+    int ch = (c->maxBlockCols + 3) & ~3;
+    ch = std::max(4, std::min(ch, 2048));
+    g->chunkCols = ch;
+    // guard: the largest usable weight (x2 when two items advance per barrier)
+    int guard = ((c->maxUsableWeight * items) + 1) & ~1;
+    g->guard = guard;
+    g->smemBytes = dpSmemBytes(g->rowCells, guard, ch);
+    if (g->smemBytes > kMaxSmem || c->optNoGuard) {
+        g->guard = 0;  // predicated shifted reads instead
+        g->smemBytes = dpSmemBytes(g->rowCells, 0, ch);
+    }
+    while (g->smemBytes > kMaxSmem && g->chunkCols > 256) {
+        g->chunkCols = (g->chunkCols / 2 + 3) & ~3;
+        g->smemBytes = dpSmemBytes(g->rowCells, g->guard, g->chunkCols);
+    }
+    return g->smemBytes <= kMaxSmem;
+}
+
+// Cost model (cycles per item step of one CTA, times the number of CTA waves):
+// a step is bounded below by the dependent chain of one warp (shared-memory
+// load -> DADD -> DSETP -> select -> store -> barrier), by the issue slots of
+// the warps resident on a scheduler, and by the shared-memory crossbar
+// (128 B/clk/SM, 16 B per cell).  Constants fitted to B200 measurements
+// (profiles/r01_dp_geometry_sweep.md).
+static double geomCost(const Ctx *c, const DpGeom &g)
+{
+    const int sm = c->smCount > 0 ? c->smCount : 148;
+    const int warps = g.T / 32;
+    int ctasPerSm = std::min(32 / warps, (int)(kMaxSmem / g.smemBytes));  // 1024 threads at <= 64 regs
+    if (g.S > 11) ctasPerSm = std::min(ctasPerSm, 16 / warps);           // 512-thread kernels use <= 128 regs
+    ctasPerSm = std::max(ctasPerSm, 1);
+    const int64_t concurrent = (int64_t)sm * ctasPerSm;
+    const int64_t n = std::max(c->nLocal, 1);
+    const double waves = std::ceil((double)n / (double)concurrent);
+    const double residentCtas = std::min<double>(ctasPerSm, std::ceil((double)n / sm));
+    const double instrWarp = (g.items == 2 ? 16.0 + 21.0 * g.S : 12.0 + 8.5 * g.S) / g.items;
+    const double chain = (g.items == 2 ? 150.0 + 14.0 * g.S : 95.0 + 10.0 * g.S) / g.items + 2.0 * warps / g.items;
+    const double issue = instrWarp * warps * residentCtas / 4.0;
+    const double smem = (double)g.rowCells * 16.0 * residentCtas / 128.0;
+    return waves * std::max(chain, std::max(issue, smem) * 1.25);
+}
 
 int chooseDpGeom(Ctx *c, DpGeom *g)
 {
     const int cells = c->maxCapacity + 1;
-    const GeomEntry *best = nullptr;
-    if (c->optThreads > 0 || c->optCellsPerThread > 0) {
-        for (int i = 0; i < kNumGeoms; ++i) {
-            const GeomEntry &e = kGeoms[i];
-            if (c->optThreads > 0 && e.T != c->optThreads) continue;
-            if (c->optCellsPerThread > 0 && e.S != c->optCellsPerThread) continue;
-            if (e.T * e.S < cells) continue;
-            if (!best || e.T * e.S < best->T * best->S) best = &e;
+    DpGeom best{};
+    double bestCost = 0.0;
+    bool have = false;
+    for (int i = 0; i < kNumGeoms; ++i) {
+        const int S = kGeoms[i].S;
+        if (c->optCellsPerThread > 0 && S != c->optCellsPerThread) continue;
+        int T = ((cells + S - 1) / S + 31) & ~31;
+        if (c->optThreads > 0) {
+            if (c->optThreads < T) continue;
+            T = c->optThreads;
         }
-        if (!best)
+        for (int items = 1; items <= 2; ++items) {
+            if (c->optItemsPerStep > 0 && items != c->optItemsPerStep) continue;
+            DpGeom cand{};
+            if (!fitGeom(c, T, S, items, &cand)) continue;
+            const double cost = geomCost(c, cand);
+            if (!have || cost < bestCost) {
+                best = cand;
+                bestCost = cost;
+                have = true;
+            }
+        }
+    }
+    if (!have) {
+        if (c->optThreads > 0 || c->optCellsPerThread > 0)
             return fail(c, DIPGPU_ERR_INVALID, "no DP geometry with threads=%d cellsPerThread=%d covers %d cells",
                         c->optThreads, c->optCellsPerThread, cells);
-    } else {
-        // smallest thread count whose row fits with S <= 8 (S <= 12 at T = 1024),
-        // then the smallest S that covers the row
-        for (int i = 0; i < kNumGeoms && !best; ++i)
-            if (kGeoms[i].T * kGeoms[i].S >= cells) best = &kGeoms[i];
-        if (!best)
-            return fail(c, DIPGPU_ERR_UNSUPPORTED,
-                        "capacity %d needs %d DP cells; one CTA stages at most %d", c->maxCapacity, cells,
-                        1024 * 12);
+        return fail(c, DIPGPU_ERR_UNSUPPORTED, "capacity %d needs %d DP cells; one CTA stages at most %d",
+                    c->maxCapacity, cells, 512 * 25);
     }
-    g->T = best->T;
-    g->S = best->S;
-    g->rowCells = best->T * best->S;
-    g->chunkCols = chunkColsFor(best->T);
-    g->smemBytes = dpSmemBytes(g->rowCells, g->chunkCols);
-    if (g->smemBytes > kMaxSmem)
-        return fail(c, DIPGPU_ERR_UNSUPPORTED, "DP row of %d cells needs %zu B shared memory (> %zu)",
-                    g->rowCells, g->smemBytes, kMaxSmem);
+    *g = best;
     return DIPGPU_OK;
 }
 
@@ -312,10 +438,9 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st)
 {
     if (c->nLocal == 0) return DIPGPU_OK;
     const DpGeom &g = c->geom;
-    const GeomEntry *e = nullptr;
-    for (int i = 0; i < kNumGeoms; ++i)
-        if (kGeoms[i].T == g.T && kGeoms[i].S == g.S) e = &kGeoms[i];
+    const GeomEntry *e = findGeom(g.S);
     if (!e) return fail(c, DIPGPU_ERR_STATE, "DP geometry not initialised");
+    KnapFn fn = e->fn[g.guard > 0 ? 1 : 0][g.items == 2 ? 1 : 0];
     KnapArgs a;
     a.redCost = dRedCost;
     a.weight = c->dWeight;
@@ -329,9 +454,13 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st)
     a.blockObj = reinterpret_cast<double *>(static_cast<char *>(c->dResult) + c->layout.offObj);
     a.firstBlock = c->firstBlock;
     a.chunkCols = g.chunkCols;
-    DIPGPU_CUDA(c, cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)g.smemBytes));
-    e->fn<<<c->nLocal, g.T, g.smemBytes, st>>>(a);
+    a.guard = g.guard;
+    if (c->dpFnConfigured != (void *)fn || c->dpFnSmem != g.smemBytes) {
+        DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
+        c->dpFnConfigured = (void *)fn;
+        c->dpFnSmem = g.smemBytes;
+    }
+    fn<<<c->nLocal, g.T, g.smemBytes, st>>>(a);
     c->launches++;
     DIPGPU_CUDA(c, cudaGetLastError());
     return DIPGPU_OK;

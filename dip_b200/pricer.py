@@ -258,6 +258,14 @@ class GpuPricer:
         self._check(self._lib.dipgpu_price_round_dev(self._ctx, u_dev_ptr, u_len, phase, float(redCostEps),
                                                      stream or None))
 
+    def calcRedCostDev(self, u_dev_ptr: int, u_len: int, phase=PHASE_PRICE2, stream: int = 0):
+        self._check(self._lib.dipgpu_calc_redcost_dev(self._ctx, u_dev_ptr, u_len, phase, stream or None))
+
+    def measureSmemGBs(self) -> float:
+        g = C.c_double()
+        self._check(self._lib.dipgpu_measure_smem_gbs(self._ctx, C.byref(g)))
+        return g.value
+
     def solveBlocksDev(self, rc_dev_ptr: int, alpha_dev_ptr: int, redCostEps=1e-4, stream: int = 0):
         self._check(self._lib.dipgpu_solve_blocks_dev(self._ctx, rc_dev_ptr, alpha_dev_ptr, float(redCostEps),
                                                       stream or None))

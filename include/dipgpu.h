@@ -192,6 +192,11 @@ int dipgpu_price_round_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, in
 int dipgpu_solve_blocks_dev(dipgpu_ctx *ctx, const double *redCostXDev, const double *alphaDev,
                             double redCostEps, void *stream);
 
+/* Stage (a) alone on a device-resident dual vector; the result stays in the
+ * library's reduced-cost buffer (dipgpu_redcost_dev). */
+int dipgpu_calc_redcost_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, int32_t phase,
+                            void *stream);
+
 /* Device pointer + byte size of the packed result of the last *_dev call. */
 int dipgpu_result_dev(dipgpu_ctx *ctx, void **devPtr, size_t *bytes);
 /* Fixed upper bound of the packed result size for this context's shard. */
@@ -215,8 +220,15 @@ int dipgpu_get_counters(const dipgpu_ctx *ctx, int64_t *kernelLaunches, int64_t 
  * on with dipgpu_set_option("stage_timing", 1). */
 int dipgpu_last_stage_ms(const dipgpu_ctx *ctx, float *ms6);
 
-/* Tuning / diagnostics knobs: "stage_timing", "dp_threads", "dp_cells_per_thread",
- * "spmv_lanes".  Unknown names return DIPGPU_ERR_INVALID. */
+/* Roofline denominator for the shared-memory-bound knapsack DP: runs a
+ * shared-memory copy microbenchmark (every SM, LDS.64 + STS.64 streams) on the
+ * context's device and reports bytes moved / CUDA-event time in GB/s. */
+int dipgpu_measure_smem_gbs(dipgpu_ctx *ctx, double *gbs);
+
+/* Tuning / diagnostics knobs: "stage_timing", "dp_threads" (multiple of 32),
+ * "dp_cells_per_thread" (odd, 1..25), "dp_items_per_step" (1 or 2), "dp_no_guard",
+ * "spmv_lanes"; 0 restores the automatic choice.  Unknown names return
+ * DIPGPU_ERR_INVALID. */
 int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value);
 
 #if defined(__GNUC__)

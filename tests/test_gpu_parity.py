@@ -106,11 +106,15 @@ def test_edge_blocks(oracle, pricer):
     assert res.blockRedCost[1] == 1.0  # empty column: 0 - alpha
 
 
-@pytest.mark.parametrize("T,S", [(32, 8), (64, 8), (256, 4), (1024, 4)])
-def test_forced_dp_geometries(oracle, pricer, T, S):
-    """Same results whatever the (threads, cells/thread) shape of the DP row."""
+@pytest.mark.parametrize("T,S,items,noguard", [(32, 7, 1, 0), (64, 9, 2, 0), (256, 5, 2, 1), (1024, 3, 1, 1),
+                                               (512, 13, 1, 0), (96, 1, 2, 0), (160, 25, 2, 0)])
+def test_forced_dp_geometries(oracle, pricer, T, S, items, noguard):
+    """Same results whatever the shape of the DP row: threads x cells/thread, one or two items per
+    barrier, guard cells or predicated shifted reads."""
     pricer.set_option("dp_threads", T)
     pricer.set_option("dp_cells_per_thread", S)
+    pricer.set_option("dp_items_per_step", items)
+    pricer.set_option("dp_no_guard", noguard)
     b = I.random_batch(40, 0, 200, 0, T * S - 1, seed=100 + T + S)
     _check_against_oracle(oracle, pricer, b.block_col_start, b.weight, b.capacity, b.red_cost, b.orig_cost, b.alpha)
 
