@@ -32,7 +32,8 @@ SYMBOLS = [
     "dipgpu_price_round_dev", "dipgpu_solve_blocks_dev", "dipgpu_result_dev",
     "dipgpu_result_max_bytes", "dipgpu_unpack_result", "dipgpu_redcost_dev",
     "dipgpu_get_counters", "dipgpu_last_stage_ms", "dipgpu_set_option",
-    "dipgpu_calc_redcost_dev", "dipgpu_measure_smem_gbs",
+    "dipgpu_calc_redcost_dev", "dipgpu_measure_smem_gbs", "dipgpu_plan_dp_geometry",
+    "dipgpu_get_dp_geometry",
 ]
 
 
@@ -85,6 +86,8 @@ def lib() -> C.CDLL:
         "dipgpu_price_round_dev": ([vp, vp, i32, i32, dbl, vp], C.c_int),
         "dipgpu_calc_redcost_dev": ([vp, vp, i32, i32, vp], C.c_int),
         "dipgpu_measure_smem_gbs": ([vp, C.POINTER(dbl)], C.c_int),
+        "dipgpu_plan_dp_geometry": ([i32, i32, i32, i32, i32, C.POINTER(i32)], C.c_int),
+        "dipgpu_get_dp_geometry": ([vp, C.POINTER(i32)], C.c_int),
         "dipgpu_solve_blocks_dev": ([vp, vp, vp, dbl, vp], C.c_int),
         "dipgpu_result_dev": ([vp, C.POINTER(vp), C.POINTER(C.c_size_t)], C.c_int),
         "dipgpu_result_max_bytes": ([vp, C.POINTER(C.c_size_t)], C.c_int),
@@ -130,3 +133,12 @@ class PinnedArray:
             self.free()
         except Exception:
             pass
+
+
+def plan_dp_geometry(n_blocks, max_capacity, max_block_cols, max_usable_weight, sm_count=148) -> dict:
+    """Host-only: the DP kernel shape the library picks (dipgpu_plan_dp_geometry)."""
+    out = (C.c_int32 * 6)()
+    rc = lib().dipgpu_plan_dp_geometry(sm_count, n_blocks, max_capacity, max_block_cols, max_usable_weight, out)
+    if rc != OK:
+        raise DipGpuError(rc, "dipgpu_plan_dp_geometry")
+    return dict(zip(["threads", "cells_per_thread", "items_per_step", "guard", "chunk_cols", "smem_bytes"], list(out)))

@@ -169,6 +169,7 @@ int cudaFail(Ctx *c, cudaError_t e, const char *what);
 int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st);
 // knapsack.cu -- stage (b)
 int chooseDpGeom(Ctx *c, DpGeom *g);
+int prepareKnapsackDp(Ctx *c);  // loads the chosen kernel, sets its shared-memory limit
 int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st);
 int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_t st);
 // filter.cu -- stage (c)

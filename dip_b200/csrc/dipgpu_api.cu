@@ -118,6 +118,7 @@ static int setBlockRange(Ctx *c, int first, int count)
     c->maxUsableWeight = maxW;
     int rc;
     if ((rc = chooseDpGeom(c, &c->geom))) return rc;
+    if (count > 0 && (rc = prepareKnapsackDp(c))) return rc;
     // decision bits: ceil(n_b/32) words per cell, rowCells cells per block
     std::vector<int64_t> off((size_t)count + 1, 0);
     for (int lb = 0; lb < count; ++lb) {
@@ -615,6 +616,38 @@ int dipgpu_last_stage_ms(const dipgpu_ctx *ctx, float *ms6)
     const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
     if (!c || !ms6) return DIPGPU_ERR_INVALID;
     for (int i = 0; i < 6; ++i) ms6[i] = c->stageMs[i];
+    return DIPGPU_OK;
+}
+
+static void geomOut(const DpGeom &g, int32_t out[6])
+{
+    out[0] = g.T; out[1] = g.S; out[2] = g.items; out[3] = g.guard; out[4] = g.chunkCols; out[5] = (int32_t)g.smemBytes;
+}
+
+int dipgpu_plan_dp_geometry(int32_t smCount, int32_t nBlocks, int32_t maxCapacity, int32_t maxBlockCols,
+                            int32_t maxUsableWeight, int32_t out[6])
+{
+    if (!out || smCount <= 0 || nBlocks < 0 || maxCapacity < 0 || maxBlockCols < 0 || maxUsableWeight < 0)
+        return DIPGPU_ERR_INVALID;
+    Ctx tmp;
+    tmp.smCount = smCount;
+    tmp.nLocal = nBlocks;
+    tmp.maxCapacity = maxCapacity;
+    tmp.maxBlockCols = maxBlockCols;
+    tmp.maxUsableWeight = maxUsableWeight;
+    DpGeom g{};
+    int rc = chooseDpGeom(&tmp, &g);
+    if (rc) return rc;
+    geomOut(g, out);
+    return DIPGPU_OK;
+}
+
+int dipgpu_get_dp_geometry(const dipgpu_ctx *ctx, int32_t out[6])
+{
+    const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
+    if (!c || !out) return DIPGPU_ERR_INVALID;
+    if (!c->haveBlocks) return DIPGPU_ERR_STATE;
+    geomOut(c->geom, out);
     return DIPGPU_OK;
 }
 

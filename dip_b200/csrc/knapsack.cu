@@ -390,11 +390,17 @@ static double geomCost(const Ctx *c, const DpGeom &g)
     const int64_t n = std::max(c->nLocal, 1);
     const double waves = std::ceil((double)n / (double)concurrent);
     const double residentCtas = std::min<double>(ctasPerSm, std::ceil((double)n / sm));
-    const double instrWarp = (g.items == 2 ? 16.0 + 21.0 * g.S : 12.0 + 8.5 * g.S) / g.items;
-    const double chain = (g.items == 2 ? 150.0 + 14.0 * g.S : 95.0 + 10.0 * g.S) / g.items + 2.0 * warps / g.items;
+    // per item: dependent chain of one warp (GAP-E sweep: ~120 + 22 S cycles; the two-item
+    // step issues 1.5x the instructions and loses in this regime)
+    double chain = 120.0 + 22.0 * g.S + 2.0 * warps;
+    if (g.items == 2) chain *= 1.3;
+    // throughput regime (CSP sweep): shared-memory floor times the measured inefficiency
+    const double ineff = g.S <= 11 ? (g.items == 2 ? 1.52 : 1.61) : g.S <= 21 ? (g.items == 2 ? 1.40 : 1.53)
+                                                                              : (g.items == 2 ? 1.69 : 1.81);
+    const double instrWarp = (g.items == 2 ? 10.0 + 10.5 * g.S : 14.0 + 8.5 * g.S);
     const double issue = instrWarp * warps * residentCtas / 4.0;
-    const double smem = (double)g.rowCells * 16.0 * residentCtas / 128.0;
-    return waves * std::max(chain, std::max(issue, smem) * 1.25);
+    const double smem = (double)g.rowCells * 16.0 * residentCtas / 128.0 * ineff;
+    return waves * std::max(chain, std::max(issue, smem));
 }
 
 int chooseDpGeom(Ctx *c, DpGeom *g)
@@ -434,6 +440,20 @@ int chooseDpGeom(Ctx *c, DpGeom *g)
     return DIPGPU_OK;
 }
 
+int prepareKnapsackDp(Ctx *c)
+{
+    const DpGeom &g = c->geom;
+    const GeomEntry *e = findGeom(g.S);
+    if (!e) return fail(c, DIPGPU_ERR_STATE, "DP geometry not initialised");
+    KnapFn fn = e->fn[g.guard > 0 ? 1 : 0][g.items == 2 ? 1 : 0];
+    if (c->dpFnConfigured != (void *)fn || c->dpFnSmem != g.smemBytes) {
+        DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
+        c->dpFnConfigured = (void *)fn;
+        c->dpFnSmem = g.smemBytes;
+    }
+    return DIPGPU_OK;
+}
+
 int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st)
 {
     if (c->nLocal == 0) return DIPGPU_OK;
@@ -455,10 +475,9 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st)
     a.firstBlock = c->firstBlock;
     a.chunkCols = g.chunkCols;
     a.guard = g.guard;
-    if (c->dpFnConfigured != (void *)fn || c->dpFnSmem != g.smemBytes) {
-        DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
-        c->dpFnConfigured = (void *)fn;
-        c->dpFnSmem = g.smemBytes;
+    {
+        int rc = prepareKnapsackDp(c);
+        if (rc) return rc;
     }
     fn<<<c->nLocal, g.T, g.smemBytes, st>>>(a);
     c->launches++;

@@ -134,6 +134,12 @@ class GpuPricer:
         self._check(self._lib.dipgpu_get_counters(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
         return dict(kernel_launches=a.value, h2d_bytes=b.value, d2h_bytes=c.value)
 
+    def dpGeometry(self) -> dict:
+        out = (C.c_int32 * 6)()
+        self._check(self._lib.dipgpu_get_dp_geometry(self._ctx, out))
+        return dict(zip(["threads", "cells_per_thread", "items_per_step", "guard", "chunk_cols", "smem_bytes"],
+                        list(out)))
+
     def last_stage_ms(self) -> dict:
         ms = (C.c_float * 6)()
         self._check(self._lib.dipgpu_last_stage_ms(self._ctx, ms))

@@ -1,0 +1,28 @@
+#!/usr/bin/env python3
+"""Run the batched knapsack DP a few times on one workload with forced geometry options
+(for ncu):  python scripts/run_dp.py <workload> [S] [items] [noguard] [reps]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dip_b200.pricer import GpuPricer  # noqa: E402
+from scripts.dp_sweep import batch  # noqa: E402
+
+name = sys.argv[1]
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+items = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+noguard = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+b = batch(name)
+with GpuPricer(0) as p:
+    p.setObjective(b.orig_cost)
+    p.set_option("dp_cells_per_thread", S)
+    p.set_option("dp_items_per_step", items)
+    p.set_option("dp_no_guard", noguard)
+    p.setKnapsackBlocks(b.block_col_start, b.weight, b.capacity)
+    p.set_option("stage_timing", 1)
+    for _ in range(reps):
+        res = p.solveBlocks(b.red_cost, b.alpha, redCostEps=-np.inf)
+        print(p.last_stage_ms(), res.cells)

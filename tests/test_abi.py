@@ -65,3 +65,26 @@ def test_unpack_rejects_garbage(gpu_lib):
     buf = (C.c_char * 256)()
     assert gpu_lib.dipgpu_unpack_result(buf, 256, C.byref(cols)) == capi.ERR_INVALID
     assert gpu_lib.dipgpu_unpack_result(None, 0, C.byref(cols)) == capi.ERR_INVALID
+
+
+def test_dp_geometry_planner_host_only():
+    """Host logic of the DP shape choice (no device): covers the row, odd cells/thread, smem limit."""
+    from dip_b200 import capi
+    for nb, cap, cols, mw in [(80, 176, 1600, 60), (10_000, 10_000, 500, 1000), (20, 404, 200, 100),
+                              (1, 0, 1, 0), (5000, 12_000, 300, 12_000), (100_000, 30, 20, 30)]:
+        g = capi.plan_dp_geometry(nb, cap, cols, mw)
+        assert g["threads"] % 32 == 0 and 32 <= g["threads"] <= 1024
+        assert g["cells_per_thread"] % 2 == 1
+        assert g["threads"] * g["cells_per_thread"] >= cap + 1
+        assert g["smem_bytes"] <= 227 * 1024
+        assert g["guard"] == 0 or g["guard"] >= mw * g["items_per_step"]
+    # latency regime (few small knapsacks): one cell per thread, one item per barrier
+    g = capi.plan_dp_geometry(80, 176, 1600, 60)
+    assert (g["cells_per_thread"], g["items_per_step"]) == (1, 1)
+    # throughput regime (many large knapsacks): many cells per thread
+    g = capi.plan_dp_geometry(10_000, 10_000, 500, 1000)
+    assert g["cells_per_thread"] >= 11
+    import pytest
+    with pytest.raises(capi.DipGpuError) as e:
+        capi.plan_dp_geometry(10, 1_000_000, 10, 10)
+    assert e.value.code == capi.ERR_UNSUPPORTED
