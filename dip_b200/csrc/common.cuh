@@ -66,6 +66,13 @@ struct ResultLayout {
     }
 };
 
+constexpr int kFuseFilterMaxBlocks = 256;
+
+// ---------------------------------------------------------------- SpMV tiling
+constexpr int kSpmvThreads = 256;
+constexpr int kSpmvChunk = 3072;    // stored entries per tile (36 KiB of shared memory)
+constexpr int kSpmvMaxCols = 2048;  // columns per tile
+
 // ------------------------------------------------------------------ DP geometry
 //
 // A knapsack's DP row of (capacity+1) cells is owned by T threads, S consecutive
@@ -97,7 +104,10 @@ struct Ctx {
     int64_t *dColStart = nullptr;   // N+1, CSC of A''
     int32_t *dRowMaster = nullptr;  // nnz, MASTER dual index of each entry's row
     double *dVal = nullptr;         // nnz
-    int spmvLanes = 0;              // 0 = auto
+    int spmvLanes = 0;              // 0 = auto (stream kernel when every column fits a tile)
+    int32_t *dColStart32 = nullptr; // N+1 (only when nnz < 2^31)
+    int32_t *dTileCol = nullptr;    // nSpmvTiles+1 column boundaries of the stream kernel's tiles
+    int nSpmvTiles = 0;             // 0 = stream kernel not applicable
 
     double *dObj = nullptr;  // c[N]
     bool haveObj = false;
@@ -130,6 +140,8 @@ struct Ctx {
 
     // shard
     int firstBlock = 0, nLocal = 0;
+    unsigned int *dDoneCounter = nullptr;  // ticket of the fused backtrack+filter kernel
+    int optFuseFilter = -1;                // -1 auto (nLocal <= kFuseFilterMaxBlocks), 0 never, 1 always
 
     // duals / reduced costs
     double *dU = nullptr;        // uLen capacity
@@ -171,7 +183,8 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st);
 int chooseDpGeom(Ctx *c, DpGeom *g);
 int prepareKnapsackDp(Ctx *c);  // loads the chosen kernel, sets its shared-memory limit
 int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st);
-int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_t st);
+int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseFilter,
+                        cudaStream_t st);
 // filter.cu -- stage (c)
 int launchFilter(Ctx *c, double redCostEps, cudaStream_t st);
 // microbench.cu -- roofline denominators measured on the device

@@ -70,7 +70,9 @@ static int uploadCore(Ctx *c)
     std::vector<int64_t> fill(colStart.begin(), colStart.end() - 1);
     std::vector<int32_t> rowMaster((size_t)std::max<int64_t>(nnz, 1));
     std::vector<double> val((size_t)std::max<int64_t>(nnz, 1));
-    for (int i = 0; i < R; ++i) {
+    // rows descending: each column's entries are stored in the order the reference's scatter
+    // adds them (CoinPackedMatrix::transposeTimes on a row-ordered matrix, rows R-1..0)
+    for (int i = R - 1; i >= 0; --i) {
         const int32_t rm = i < c->nBaseRows ? i : i + c->numConvex;
         for (int64_t k = c->hRowStart[i]; k < c->hRowStart[i + 1]; ++k) {
             const int64_t dst = fill[c->hColInd[k]]++;
@@ -80,9 +82,34 @@ static int uploadCore(Ctx *c)
     }
     c->nnz = nnz;
     int rc;
+    // tiles of the stream kernel: consecutive columns, <= kSpmvChunk-4 entries, <= kSpmvMaxCols columns
+    c->nSpmvTiles = 0;
+    if (nnz < (int64_t)1 << 31 && N > 0) {
+        std::vector<int32_t> tileCol;
+        std::vector<int32_t> cs32((size_t)N + 1);
+        for (int j = 0; j <= N; ++j) cs32[j] = (int32_t)colStart[j];
+        bool ok = true;
+        int j = 0;
+        tileCol.push_back(0);
+        while (j < N) {
+            const int64_t a0 = colStart[j] & ~(int64_t)3;
+            int e = j;
+            while (e < N && e - j < kSpmvMaxCols && colStart[e + 1] - a0 <= kSpmvChunk) ++e;
+            if (e == j) { ok = false; break; }  // a single column longer than a tile
+            tileCol.push_back(e);
+            j = e;
+        }
+        if (ok) {
+            if ((rc = devAlloc(c, &c->dColStart32, (size_t)N + 1))) return rc;
+            if ((rc = devAlloc(c, &c->dTileCol, tileCol.size()))) return rc;
+            DIPGPU_CUDA(c, cudaMemcpy(c->dColStart32, cs32.data(), sizeof(int32_t) * cs32.size(), cudaMemcpyHostToDevice));
+            DIPGPU_CUDA(c, cudaMemcpy(c->dTileCol, tileCol.data(), sizeof(int32_t) * tileCol.size(), cudaMemcpyHostToDevice));
+            c->nSpmvTiles = (int)tileCol.size() - 1;
+        }
+    }
     if ((rc = devAlloc(c, &c->dColStart, (size_t)N + 1))) return rc;
-    if ((rc = devAlloc(c, &c->dRowMaster, (size_t)nnz + 4))) return rc;
-    if ((rc = devAlloc(c, &c->dVal, (size_t)nnz + 4))) return rc;
+    if ((rc = devAlloc(c, &c->dRowMaster, (size_t)nnz + 8))) return rc;
+    if ((rc = devAlloc(c, &c->dVal, (size_t)nnz + 8))) return rc;
     DIPGPU_CUDA(c, cudaMemcpy(c->dColStart, colStart.data(), sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyHostToDevice));
     if (nnz > 0) {
         DIPGPU_CUDA(c, cudaMemcpy(c->dRowMaster, rowMaster.data(), sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
@@ -152,9 +179,10 @@ static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, do
     int rc;
     if ((rc = launchKnapsackDp(c, dRedCost, st))) return rc;
     if (timed) cudaEventRecord(c->ev[3], st);
-    if ((rc = launchBacktrackEmit(c, dRedCost, dAlpha, st))) return rc;
+    const bool fuse = c->nLocal > 0 && (c->optFuseFilter < 0 ? c->nLocal <= kFuseFilterMaxBlocks : c->optFuseFilter != 0);
+    if ((rc = launchBacktrackEmit(c, dRedCost, dAlpha, eps, fuse, st))) return rc;
     if (timed) cudaEventRecord(c->ev[4], st);
-    if ((rc = launchFilter(c, eps, st))) return rc;
+    if (!fuse && (rc = launchFilter(c, eps, st))) return rc;
     if (timed) cudaEventRecord(c->ev[5], st);
     return DIPGPU_OK;
 }
@@ -277,6 +305,11 @@ int dipgpu_create(dipgpu_ctx **ctx, int device)
         return DIPGPU_ERR_CUDA;
     }
     for (auto &e : c->ev) cudaEventCreate(&e);
+    if (cudaMalloc(reinterpret_cast<void **>(&c->dDoneCounter), sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(c->dDoneCounter, 0, sizeof(unsigned int)) != cudaSuccess) {
+        delete c;
+        return DIPGPU_ERR_NOMEM;
+    }
     *ctx = reinterpret_cast<dipgpu_ctx *>(c);
     return DIPGPU_OK;
 }
@@ -287,7 +320,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (!c) return DIPGPU_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    devFree(&c->dColStart); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
+    devFree(&c->dDoneCounter); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileCol); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
     devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems);
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
@@ -657,6 +690,7 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!c || !name) return DIPGPU_ERR_INVALID;
     if (!strcmp(name, "stage_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "spmv_lanes")) { c->spmvLanes = (int)value; return DIPGPU_OK; }
+    if (!strcmp(name, "fuse_filter")) { c->optFuseFilter = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "dp_threads") || !strcmp(name, "dp_cells_per_thread") || !strcmp(name, "dp_items_per_step") ||
         !strcmp(name, "dp_no_guard")) {
         if (!strcmp(name, "dp_threads")) c->optThreads = (int)value;

@@ -27,7 +27,7 @@
 #include <cstdarg>
 #include <cstdio>
 
-#include "common.cuh"
+#include "filter.cuh"
 
 namespace dipgpu {
 
@@ -512,13 +512,38 @@ struct BackArgs {
     double *blockOrigCost;
     int32_t *blockNnz;
     int firstBlock, nLocal, rowCells;
+    unsigned int *doneCounter;  // non-NULL: the last CTA to finish runs the filter (stage c)
 };
 
-__global__ void __launch_bounds__(128) knap_backtrack_kernel(const BackArgs a)
+constexpr int kBackThreads = 128;
+
+__device__ __forceinline__ void backtrackOne(const BackArgs &a, int lb, int lane);
+
+// For small shards the filter of stage (c) is fused into this kernel's tail: every CTA
+// publishes its blocks (fence + atomic ticket) and the CTA that draws the last ticket scans
+// all blocks, saving a launch on the latency-bound GAP rounds.
+__global__ void __launch_bounds__(kBackThreads) knap_backtrack_kernel(const BackArgs a, const FilterArgs f)
 {
     const int lane = threadIdx.x & 31;
-    const int lb = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (lb >= a.nLocal) return;
+    const int lb = blockIdx.x * (kBackThreads >> 5) + (threadIdx.x >> 5);
+    if (lb < a.nLocal) backtrackOne(a, lb, lane);
+    if (a.doneCounter == nullptr) return;
+    __shared__ int sLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(a.doneCounter, 1u);
+        sLast = (ticket == gridDim.x - 1) ? 1 : 0;
+        if (sLast) *a.doneCounter = 0u;  // ready for the next round (same stream)
+    }
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+    filterScanBody<kBackThreads>(f);
+}
+
+__device__ __forceinline__ void backtrackOne(const BackArgs &a, int lb, int lane)
+{
     const int b = a.firstBlock + lb;
     const int cs = a.blockColStart[b];
     const int RC = a.rowCells;
@@ -568,7 +593,8 @@ __global__ void __launch_bounds__(128) knap_backtrack_kernel(const BackArgs a)
     }
 }
 
-int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_t st)
+int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseFilter,
+                        cudaStream_t st)
 {
     if (c->nLocal == 0) return DIPGPU_OK;
     char *res = static_cast<char *>(c->dResult);
@@ -591,9 +617,12 @@ int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, cu
     a.firstBlock = c->firstBlock;
     a.nLocal = c->nLocal;
     a.rowCells = c->geom.rowCells;
-    const int warpsPerCta = 4;
+    a.doneCounter = fuseFilter ? c->dDoneCounter : nullptr;
+    FilterArgs f = makeFilterArgs(c, redCostEps);
+    f.fuseCopy = 1;
+    const int warpsPerCta = kBackThreads / 32;
     const int grid = (c->nLocal + warpsPerCta - 1) / warpsPerCta;
-    knap_backtrack_kernel<<<grid, warpsPerCta * 32, 0, st>>>(a);
+    knap_backtrack_kernel<<<grid, kBackThreads, 0, st>>>(a, f);
     c->launches++;
     DIPGPU_CUDA(c, cudaGetLastError());
     return DIPGPU_OK;
