@@ -69,7 +69,6 @@ struct ResultLayout {
 constexpr int kFuseFilterMaxBlocks = 256;
 
 // ---------------------------------------------------------------- SpMV tiling
-constexpr int kSpmvThreads = 256;
 constexpr int kSpmvChunk = 3072;    // stored entries per tile (36 KiB of shared memory)
 constexpr int kSpmvMaxCols = 2048;  // columns per tile
 
@@ -108,6 +107,7 @@ struct Ctx {
     int32_t *dColStart32 = nullptr; // N+1 (only when nnz < 2^31)
     int32_t *dTileCol = nullptr;    // nSpmvTiles+1 column boundaries of the stream kernel's tiles
     int nSpmvTiles = 0;             // 0 = stream kernel not applicable
+    bool spmvAttr = false, spmvAttrU = false;
 
     double *dObj = nullptr;  // c[N]
     bool haveObj = false;
@@ -141,7 +141,9 @@ struct Ctx {
     // shard
     int firstBlock = 0, nLocal = 0;
     unsigned int *dDoneCounter = nullptr;  // ticket of the fused backtrack+filter kernel
-    int optFuseFilter = -1;                // -1 auto (nLocal <= kFuseFilterMaxBlocks), 0 never, 1 always
+    // -1 auto (2 when nLocal <= kFuseFilterMaxBlocks, else 0); 0 three kernels; 1 filter in the
+    // backtrack kernel's tail; 2 backtrack + filter in the DP kernel's tail
+    int optFuseFilter = -1;
 
     // duals / reduced costs
     double *dU = nullptr;        // uLen capacity
@@ -182,7 +184,8 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st);
 // knapsack.cu -- stage (b)
 int chooseDpGeom(Ctx *c, DpGeom *g);
 int prepareKnapsackDp(Ctx *c);  // loads the chosen kernel, sets its shared-memory limit
-int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st);
+int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseTail,
+                     cudaStream_t st);
 int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseFilter,
                         cudaStream_t st);
 // filter.cu -- stage (c)

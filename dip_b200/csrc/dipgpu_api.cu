@@ -177,12 +177,13 @@ static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, do
                         bool timed)
 {
     int rc;
-    if ((rc = launchKnapsackDp(c, dRedCost, st))) return rc;
+    int mode = c->optFuseFilter < 0 ? (c->nLocal <= kFuseFilterMaxBlocks ? 2 : 0) : c->optFuseFilter;
+    if (c->nLocal == 0) mode = 0;
+    if ((rc = launchKnapsackDp(c, dRedCost, dAlpha, eps, mode == 2, st))) return rc;
     if (timed) cudaEventRecord(c->ev[3], st);
-    const bool fuse = c->nLocal > 0 && (c->optFuseFilter < 0 ? c->nLocal <= kFuseFilterMaxBlocks : c->optFuseFilter != 0);
-    if ((rc = launchBacktrackEmit(c, dRedCost, dAlpha, eps, fuse, st))) return rc;
+    if (mode != 2 && (rc = launchBacktrackEmit(c, dRedCost, dAlpha, eps, mode == 1, st))) return rc;
     if (timed) cudaEventRecord(c->ev[4], st);
-    if (!fuse && (rc = launchFilter(c, eps, st))) return rc;
+    if (mode == 0 && (rc = launchFilter(c, eps, st))) return rc;
     if (timed) cudaEventRecord(c->ev[5], st);
     return DIPGPU_OK;
 }

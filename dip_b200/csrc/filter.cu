@@ -16,12 +16,12 @@ namespace dipgpu {
 
 constexpr int kFilterThreads = 1024;
 
-__global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const FilterArgs a)
+__global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(const __grid_constant__ FilterArgs a)
 {
-    filterScanBody<kFilterThreads>(a);
+    filterScanBody(a, kFilterThreads);
 }
 
-__global__ void __launch_bounds__(256) filter_copy_kernel(const FilterArgs a)
+__global__ void __launch_bounds__(256) filter_copy_kernel(const __grid_constant__ FilterArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int nKept = a.hdr->nKept;
@@ -49,7 +49,7 @@ FilterArgs makeFilterArgs(Ctx *c, double redCostEps)
     a.nLocal = c->nLocal;
     a.indCap = c->indCap;
     a.eps = redCostEps;
-    a.fuseCopy = c->nLocal <= 2048 ? 1 : 0;
+    a.fuseCopy = c->nLocal <= kFuseFilterMaxBlocks ? 2 : c->nLocal <= 2048 ? 1 : 0;
     return a;
 }
 

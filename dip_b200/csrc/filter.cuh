@@ -34,15 +34,17 @@ __device__ __forceinline__ void copyColumn(const FilterArgs &a, int k, int lane)
     for (int q = lane; q < n; q += 32) a.keptInd[dst + q] = __ldcg(a.candInd + cs + q);
 }
 
-// The scan over a shard's blocks by ONE CTA of NT threads (see filter.cu for what it restates).
-template <int NT>
-__device__ __forceinline__ void filterScanBody(const FilterArgs &a)
+// The scan over a shard's blocks by ONE CTA of NT threads, NT a multiple of 32 (see filter.cu
+// for what it restates).
+__device__ __forceinline__ void filterScanBody(const FilterArgs &a, const int NT)
 {
     __shared__ int sCnt[32];
     __shared__ long long sNnz[32];
     __shared__ long long sCells[32];
     __shared__ int sCarryCnt;
     __shared__ long long sCarryNnz;
+    __shared__ long long sDst[kFuseFilterMaxBlocks];  // fuseCopy == 2: kept column -> first output index
+    __shared__ int sSrc[kFuseFilterMaxBlocks];        //                 kept column -> first candidate index
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) {
         sCarryCnt = 0;
@@ -94,6 +96,10 @@ __device__ __forceinline__ void filterScanBody(const FilterArgs &a)
             const int pos = cntOff + wpre;
             a.keptBlock[pos] = lb;
             a.keptStart[pos] = nnzOff + (incl - v);
+            if (a.fuseCopy == 2) {
+                sDst[pos] = nnzOff + (incl - v);
+                sSrc[pos] = a.blockColStart[a.firstBlock + lb];
+            }
         }
         __syncthreads();
         if (t == 0) {
@@ -119,7 +125,20 @@ __device__ __forceinline__ void filterScanBody(const FilterArgs &a)
         a.hdr->cells = tot;
         a.hdr->indCap = a.indCap;
     }
-    if (a.fuseCopy) {
+    if (a.fuseCopy == 2) {
+        // small shards (<= kFuseFilterMaxBlocks): flat copy, every index an independent load
+        __syncthreads();
+        const int nKept = sCarryCnt;
+        const long long total = sCarryNnz;
+        for (long long idx = t; idx < total; idx += NT) {
+            int lo = 0, hi = nKept - 1;
+            while (lo < hi) {  // last kept column whose first output index is <= idx
+                const int mid = (lo + hi + 1) >> 1;
+                if (sDst[mid] <= idx) lo = mid; else hi = mid - 1;
+            }
+            a.keptInd[idx] = __ldcg(a.candInd + sSrc[lo] + (int)(idx - sDst[lo]));
+        }
+    } else if (a.fuseCopy) {
         __threadfence_block();
         __syncthreads();
         const int nKept = sCarryCnt;

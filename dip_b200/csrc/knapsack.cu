@@ -73,6 +73,118 @@ __device__ __forceinline__ void tmaLoad1d(void *dstSmem, const void *srcGlobal, 
         : "memory");
 }
 
+// --------------------------------------------------------- backtrack + emit
+//
+// One warp per knapsack walks the decision table from (last item, capacity)
+// (gap_func.py:173-181).  With bits laid out [itemWord][cell], the lanes of a
+// warp fetch the 32 item-words below the current item for the current cell in
+// one gather, so every iteration of the walk lands on the next TAKEN item.
+// The column is emitted with ascending x-space indices; varRedCost/varOrigCost
+// are accumulated in that order (GAP_KnapPisinger.h:263-272), then alpha is
+// subtracted (DecompAlgo.cpp:6350-6356).
+
+struct BackArgs {
+    const double *redCost;
+    const double *obj;
+    const double *alpha;  // indexed by GLOBAL block
+    const int32_t *blockColStart;
+    const int32_t *capacity;
+    const int64_t *bitsOff;
+    const uint32_t *bits;
+    const int32_t *itemW;
+    const int32_t *itemCol;
+    const int32_t *nItems;
+    int32_t *scratch;
+    int32_t *candInd;
+    double *blockRedCost;
+    double *blockOrigCost;
+    int32_t *blockNnz;
+    int firstBlock, nLocal, rowCells;
+    unsigned int *doneCounter;  // non-NULL: the last CTA to finish runs the filter (stage c)
+};
+
+constexpr int kBackThreads = 128;
+
+// nItems = number of active items of the block.  Loads are L2-coherent (ld.global.cg): in the
+// fused path the decision bits were written earlier by this very kernel.
+__device__ __forceinline__ void backtrackOne(const BackArgs &a, int lb, int lane, int nItems)
+{
+    const int b = a.firstBlock + lb;
+    const int cs = a.blockColStart[b];
+    const int RC = a.rowCells;
+    const uint32_t *bitsBase = a.bits + a.bitsOff[lb];
+    int j = a.capacity[b];
+    int i = nItems - 1;
+    int cnt = 0;
+    while (i >= 0) {
+        const int kw = i >> 5;
+        const int wv = kw - lane;
+        uint32_t v = wv >= 0 ? __ldcg(bitsBase + (size_t)wv * RC + j) : 0u;
+        if (lane == 0) v &= 0xffffffffu >> (31 - (i & 31));
+        const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
+        if (nz == 0u) {
+            i = ((kw - 32) << 5) | 31;  // nothing taken in these 1024 items
+            continue;
+        }
+        const int L = __ffs(nz) - 1;
+        const uint32_t vL = __shfl_sync(0xffffffffu, v, L);
+        const int item = ((kw - L) << 5) + (31 - __clz(vL));
+        if (lane == 0) a.scratch[cs + cnt] = __ldcg(a.itemCol + cs + item);
+        ++cnt;
+        j -= __ldcg(a.itemW + cs + item);
+        i = item - 1;
+    }
+    __syncwarp();
+    double rcs = 0.0, ocs = 0.0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int k = base + lane;
+        double r = 0.0, o = 0.0;
+        if (k < cnt) {
+            const int col = cs + __ldcg(a.scratch + cs + cnt - 1 - k);
+            a.candInd[cs + k] = col;
+            r = a.redCost[col];
+            o = a.obj[col];
+        }
+        const int nn = min(32, cnt - base);
+        for (int q = 0; q < nn; ++q) {
+            rcs += __shfl_sync(0xffffffffu, r, q);
+            ocs += __shfl_sync(0xffffffffu, o, q);
+        }
+    }
+    if (lane == 0) {
+        a.blockRedCost[lb] = rcs - a.alpha[b];
+        a.blockOrigCost[lb] = ocs;
+        a.blockNnz[lb] = cnt;
+    }
+}
+
+// Tail shared by the backtrack kernel and the fused DP kernel: every CTA publishes its blocks
+// (fence + atomic ticket); the CTA that draws the last ticket runs the filter of stage (c) over
+// the whole shard, saving a launch on the latency-bound GAP rounds.
+__device__ __forceinline__ void ticketThenFilter(unsigned int *doneCounter, const FilterArgs &f, int nThreads)
+{
+    __shared__ int sLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(doneCounter, 1u);
+        sLast = (ticket == gridDim.x - 1) ? 1 : 0;
+        if (sLast) *doneCounter = 0u;  // ready for the next round (same stream)
+    }
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+    filterScanBody(f, nThreads);
+}
+
+__global__ void __launch_bounds__(kBackThreads) knap_backtrack_kernel(const __grid_constant__ BackArgs a, const __grid_constant__ FilterArgs f)
+{
+    const int lane = threadIdx.x & 31;
+    const int lb = blockIdx.x * (kBackThreads >> 5) + (threadIdx.x >> 5);
+    if (lb < a.nLocal) backtrackOne(a, lb, lane, a.nItems[lb]);
+    if (a.doneCounter != nullptr) ticketThenFilter(a.doneCounter, f, kBackThreads);
+}
+
 // ------------------------------------------------------------------- DP kernel
 
 #define kNegInf (__longlong_as_double((long long)0xfff0000000000000ULL))
@@ -91,6 +203,9 @@ struct KnapArgs {
     int firstBlock;
     int chunkCols;                 // columns staged per TMA chunk (multiple of 4)
     int guard;                     // -inf cells in front of each row buffer (even; 0 = predicated reads)
+    int fuseTail;                  // small shards: backtrack + filter run in this kernel's tail
+    BackArgs back;
+    FilterArgs filt;
 };
 
 __host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunkCols)
@@ -116,7 +231,7 @@ __host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunk
 // shifted reads of c[i-1][.], with exactly the additions and strict compares
 // the one-item step performs, so values and decisions are unchanged.
 template <int S, bool GUARD, int ITEMS, int MAXT>
-__global__ void __launch_bounds__(MAXT) knap_dp_kernel(const KnapArgs a)
+__global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ KnapArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int T = blockDim.x;
@@ -312,6 +427,13 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const KnapArgs a)
         if (j0 + s == cap) a.blockObj[lb] = mine[s];
     }
     if (t == 0) a.nItems[lb] = kGlobal;
+    if (a.fuseTail) {
+        // latency regime: walk this knapsack's decisions right here (they sit in L2, just
+        // written by this CTA), then the last CTA of the grid filters the shard
+        __syncthreads();
+        if (warp == 0) backtrackOne(a.back, lb, lane, kGlobal);
+        ticketThenFilter(a.back.doneCounter, a.filt, T);
+    }
 }
 
 // --------------------------------------------------------------- geometry table
@@ -336,7 +458,7 @@ static const GeomEntry kGeoms[] = {
 };
 #undef GE
 static const int kNumGeoms = (int)(sizeof(kGeoms) / sizeof(kGeoms[0]));
-static const size_t kMaxSmem = 227 * 1024;
+static const size_t kMaxSmem = 227 * 1024 - 6 * 1024;  // the fused tail's static shared memory comes off the 227 KiB
 
 static const GeomEntry *findGeom(int S)
 {
@@ -454,7 +576,32 @@ int prepareKnapsackDp(Ctx *c)
     return DIPGPU_OK;
 }
 
-int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st)
+static void fillBackArgs(Ctx *c, const double *dRedCost, const double *dAlpha, BackArgs *a)
+{
+    char *res = static_cast<char *>(c->dResult);
+    a->redCost = dRedCost;
+    a->obj = c->dObj;
+    a->alpha = dAlpha;
+    a->blockColStart = c->dBlockColStart;
+    a->capacity = c->dCapacity;
+    a->bitsOff = c->dBitsOff;
+    a->bits = c->dBits;
+    a->itemW = c->dItemW;
+    a->itemCol = c->dItemCol;
+    a->nItems = c->dNItems;
+    a->scratch = c->dScratch;
+    a->candInd = c->dCandInd;
+    a->blockRedCost = reinterpret_cast<double *>(res + c->layout.offRedCost);
+    a->blockOrigCost = reinterpret_cast<double *>(res + c->layout.offOrigCost);
+    a->blockNnz = reinterpret_cast<int32_t *>(res + c->layout.offNnz);
+    a->firstBlock = c->firstBlock;
+    a->nLocal = c->nLocal;
+    a->rowCells = c->geom.rowCells;
+    a->doneCounter = c->dDoneCounter;
+}
+
+int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseTail,
+                     cudaStream_t st)
 {
     if (c->nLocal == 0) return DIPGPU_OK;
     const DpGeom &g = c->geom;
@@ -475,6 +622,10 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st)
     a.firstBlock = c->firstBlock;
     a.chunkCols = g.chunkCols;
     a.guard = g.guard;
+    a.fuseTail = fuseTail ? 1 : 0;
+    fillBackArgs(c, dRedCost, dAlpha, &a.back);
+    a.filt = makeFilterArgs(c, redCostEps);
+    a.filt.fuseCopy = c->nLocal <= kFuseFilterMaxBlocks ? 2 : 1;
     {
         int rc = prepareKnapsackDp(c);
         if (rc) return rc;
@@ -485,141 +636,15 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, cudaStream_t st)
     return DIPGPU_OK;
 }
 
-// --------------------------------------------------------- backtrack + emit
-//
-// One warp per knapsack walks the decision table from (last item, capacity)
-// (gap_func.py:173-181).  With bits laid out [itemWord][cell], the lanes of a
-// warp fetch the 32 item-words below the current item for the current cell in
-// one gather, so every iteration of the walk lands on the next TAKEN item.
-// The column is emitted with ascending x-space indices; varRedCost/varOrigCost
-// are accumulated in that order (GAP_KnapPisinger.h:263-272), then alpha is
-// subtracted (DecompAlgo.cpp:6350-6356).
-
-struct BackArgs {
-    const double *redCost;
-    const double *obj;
-    const double *alpha;  // indexed by GLOBAL block
-    const int32_t *blockColStart;
-    const int32_t *capacity;
-    const int64_t *bitsOff;
-    const uint32_t *bits;
-    const int32_t *itemW;
-    const int32_t *itemCol;
-    const int32_t *nItems;
-    int32_t *scratch;
-    int32_t *candInd;
-    double *blockRedCost;
-    double *blockOrigCost;
-    int32_t *blockNnz;
-    int firstBlock, nLocal, rowCells;
-    unsigned int *doneCounter;  // non-NULL: the last CTA to finish runs the filter (stage c)
-};
-
-constexpr int kBackThreads = 128;
-
-__device__ __forceinline__ void backtrackOne(const BackArgs &a, int lb, int lane);
-
-// For small shards the filter of stage (c) is fused into this kernel's tail: every CTA
-// publishes its blocks (fence + atomic ticket) and the CTA that draws the last ticket scans
-// all blocks, saving a launch on the latency-bound GAP rounds.
-__global__ void __launch_bounds__(kBackThreads) knap_backtrack_kernel(const BackArgs a, const FilterArgs f)
-{
-    const int lane = threadIdx.x & 31;
-    const int lb = blockIdx.x * (kBackThreads >> 5) + (threadIdx.x >> 5);
-    if (lb < a.nLocal) backtrackOne(a, lb, lane);
-    if (a.doneCounter == nullptr) return;
-    __shared__ int sLast;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int ticket = atomicAdd(a.doneCounter, 1u);
-        sLast = (ticket == gridDim.x - 1) ? 1 : 0;
-        if (sLast) *a.doneCounter = 0u;  // ready for the next round (same stream)
-    }
-    __syncthreads();
-    if (!sLast) return;
-    __threadfence();
-    filterScanBody<kBackThreads>(f);
-}
-
-__device__ __forceinline__ void backtrackOne(const BackArgs &a, int lb, int lane)
-{
-    const int b = a.firstBlock + lb;
-    const int cs = a.blockColStart[b];
-    const int RC = a.rowCells;
-    const uint32_t *bitsBase = a.bits + a.bitsOff[lb];
-    int j = a.capacity[b];
-    int i = a.nItems[lb] - 1;
-    int cnt = 0;
-    while (i >= 0) {
-        const int kw = i >> 5;
-        const int wv = kw - lane;
-        uint32_t v = wv >= 0 ? __ldg(bitsBase + (size_t)wv * RC + j) : 0u;
-        if (lane == 0) v &= 0xffffffffu >> (31 - (i & 31));
-        const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
-        if (nz == 0u) {
-            i = ((kw - 32) << 5) | 31;  // nothing taken in these 1024 items
-            continue;
-        }
-        const int L = __ffs(nz) - 1;
-        const uint32_t vL = __shfl_sync(0xffffffffu, v, L);
-        const int item = ((kw - L) << 5) + (31 - __clz(vL));
-        if (lane == 0) a.scratch[cs + cnt] = a.itemCol[cs + item];
-        ++cnt;
-        j -= __ldg(a.itemW + cs + item);
-        i = item - 1;
-    }
-    __syncwarp();
-    double rcs = 0.0, ocs = 0.0;
-    for (int base = 0; base < cnt; base += 32) {
-        const int k = base + lane;
-        double r = 0.0, o = 0.0;
-        if (k < cnt) {
-            const int col = cs + a.scratch[cs + cnt - 1 - k];
-            a.candInd[cs + k] = col;
-            r = a.redCost[col];
-            o = a.obj[col];
-        }
-        const int nn = min(32, cnt - base);
-        for (int q = 0; q < nn; ++q) {
-            rcs += __shfl_sync(0xffffffffu, r, q);
-            ocs += __shfl_sync(0xffffffffu, o, q);
-        }
-    }
-    if (lane == 0) {
-        a.blockRedCost[lb] = rcs - a.alpha[b];
-        a.blockOrigCost[lb] = ocs;
-        a.blockNnz[lb] = cnt;
-    }
-}
-
 int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseFilter,
                         cudaStream_t st)
 {
     if (c->nLocal == 0) return DIPGPU_OK;
-    char *res = static_cast<char *>(c->dResult);
     BackArgs a;
-    a.redCost = dRedCost;
-    a.obj = c->dObj;
-    a.alpha = dAlpha;
-    a.blockColStart = c->dBlockColStart;
-    a.capacity = c->dCapacity;
-    a.bitsOff = c->dBitsOff;
-    a.bits = c->dBits;
-    a.itemW = c->dItemW;
-    a.itemCol = c->dItemCol;
-    a.nItems = c->dNItems;
-    a.scratch = c->dScratch;
-    a.candInd = c->dCandInd;
-    a.blockRedCost = reinterpret_cast<double *>(res + c->layout.offRedCost);
-    a.blockOrigCost = reinterpret_cast<double *>(res + c->layout.offOrigCost);
-    a.blockNnz = reinterpret_cast<int32_t *>(res + c->layout.offNnz);
-    a.firstBlock = c->firstBlock;
-    a.nLocal = c->nLocal;
-    a.rowCells = c->geom.rowCells;
+    fillBackArgs(c, dRedCost, dAlpha, &a);
     a.doneCounter = fuseFilter ? c->dDoneCounter : nullptr;
     FilterArgs f = makeFilterArgs(c, redCostEps);
-    f.fuseCopy = 1;
+    f.fuseCopy = c->nLocal <= kFuseFilterMaxBlocks ? 2 : 1;
     const int warpsPerCta = kBackThreads / 32;
     const int grid = (c->nLocal + warpsPerCta - 1) / warpsPerCta;
     knap_backtrack_kernel<<<grid, kBackThreads, 0, st>>>(a, f);

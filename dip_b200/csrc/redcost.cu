@@ -20,69 +20,164 @@
 // (rows R-1..0, y[col] += u[i]*a), so the reduced costs are bit-identical to the
 // CPU restatement, not merely within 1e-12.  Matrices with a column longer than
 // one tile fall back to the lane-cooperative kernel below (tolerance parity).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dipgpu {
 
 __device__ __forceinline__ uint32_t rcSmemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(kSpmvThreads)
-redcost_stream_kernel(const int32_t *__restrict__ tileCol, const int32_t *__restrict__ colStart32,
-                      const int32_t *__restrict__ rowMaster, const double *__restrict__ val,
-                      const double *__restrict__ u, const double *__restrict__ c, int phase1,
-                      double *__restrict__ out)
+__device__ __forceinline__ void rcMbarWait(uint64_t *bar, uint32_t parity)
 {
-    __shared__ __align__(16) double sVal[kSpmvChunk + 4];
-    __shared__ __align__(16) int32_t sRow[kSpmvChunk + 4];
-    __shared__ __align__(8) uint64_t mbar;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(rcSmemAddr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+struct StreamArgs {
+    int nTiles;
+    const int32_t *tileCol;     // nTiles+1 column boundaries
+    const int32_t *colStart32;  // N+1
+    const int32_t *rowMaster;   // per stored entry: MASTER dual index of its row
+    const double *val;
+    const double *u;
+    int uLen;
+    const double *c;
+    int phase1;
+    double *out;
+    int stages;
+};
+
+constexpr int kSpmvStageValBytes = (kSpmvChunk + 4) * 8;
+constexpr int kSpmvStageBytes = kSpmvStageValBytes + (kSpmvChunk + 4) * 4;  // multiple of 16
+constexpr int kSpmvHdrBytes = 64;                                          // mbarriers
+
+// Persistent CTAs (grid <= resident CTAs) walk the tiles with a `stages`-deep TMA
+// pipeline: while tile k is multiplied and reduced out of one stage, the bulk
+// copies of tiles k+1.. are in flight into the others.  U_SMEM keeps the whole
+// dual vector in shared memory (it is gathered 1x per stored entry; from L1 a
+// random 8-byte gather costs a wavefront per lane).
+template <bool U_SMEM, int NT>
+__global__ void __launch_bounds__(NT) redcost_stream_kernel(const StreamArgs a)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(sm);
+    unsigned char *stageBase = sm + kSpmvHdrBytes;
+    const double *sU = reinterpret_cast<const double *>(stageBase + (size_t)a.stages * kSpmvStageBytes);
     const int t = threadIdx.x;
-    const int c0 = tileCol[blockIdx.x], c1 = tileCol[blockIdx.x + 1];
-    const int k0 = colStart32[c0], k1 = colStart32[c1];
-    const int a0 = k0 & ~3;  // 16-byte aligned start for both streams
-    const int len = k1 - a0;
-    if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(&mbar)), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int stages = a.stages;
+
+    auto issue = [&](int tile, int s) {
+        const int c0 = a.tileCol[tile], c1 = a.tileCol[tile + 1];
+        const int k0 = a.colStart32[c0], k1 = a.colStart32[c1];
+        const int a0 = k0 & ~3;  // 16-byte aligned start for both streams
+        const int len = k1 - a0;
+        uint64_t *bar = full + s;
         if (len > 0) {
+            double *dv = reinterpret_cast<double *>(stageBase + (size_t)s * kSpmvStageBytes);
+            int32_t *dr = reinterpret_cast<int32_t *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
             const uint32_t bytesVal = (uint32_t)(((len + 1) & ~1) * 8);
             const uint32_t bytesRow = (uint32_t)(((len + 3) & ~3) * 4);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rcSmemAddr(&mbar)),
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rcSmemAddr(bar)),
                          "r"(bytesVal + bytesRow)
                          : "memory");
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    rcSmemAddr(sVal)),
-                "l"(val + a0), "r"(bytesVal), "r"(rcSmemAddr(&mbar))
+                    rcSmemAddr(dv)),
+                "l"(a.val + a0), "r"(bytesVal), "r"(rcSmemAddr(bar))
                 : "memory");
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    rcSmemAddr(sRow)),
-                "l"(rowMaster + a0), "r"(bytesRow), "r"(rcSmemAddr(&mbar))
+                    rcSmemAddr(dr)),
+                "l"(a.rowMaster + a0), "r"(bytesRow), "r"(rcSmemAddr(bar))
                 : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rcSmemAddr(bar)) : "memory");
+        }
+    };
+
+    if (t == 0) {
+        for (int s = 0; s < stages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full + s)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < stages; ++s) {
+            const int tile = blockIdx.x + s * gridDim.x;
+            if (tile < a.nTiles) issue(tile, s);
         }
     }
-    __syncthreads();
-    if (len > 0) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "WAIT_%=:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-            "@p bra DONE_%=;\n\t"
-            "bra WAIT_%=;\n\t"
-            "DONE_%=:\n\t"
-            "}" ::"r"(rcSmemAddr(&mbar)),
-            "r"(0)
-            : "memory");
-        // products in place: u[i] * a  (unfused, as the reference's  y += u*a)
-        for (int k = (k0 - a0) + t; k < len; k += kSpmvThreads) sVal[k] = __dmul_rn(__ldg(u + sRow[k]), sVal[k]);
+    if (U_SMEM) {
+        double *w = const_cast<double *>(sU);
+        for (int k = t; k < a.uLen; k += NT) w[k] = __ldg(a.u + k);
     }
     __syncthreads();
-    for (int col = c0 + t; col < c1; col += kSpmvThreads) {
-        const int b = colStart32[col] - a0, e = colStart32[col + 1] - a0;
-        double sum = 0.0;
-        for (int k = b; k < e; ++k) sum = __dadd_rn(sum, sVal[k]);
-        out[col] = phase1 ? -sum : c[col] - sum;  // DecompAlgo.cpp:4538-4545
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x, ++it) {
+        const int s = it % stages;
+        const uint32_t parity = (uint32_t)((it / stages) & 1);
+        double *sVal = reinterpret_cast<double *>(stageBase + (size_t)s * kSpmvStageBytes);
+        const int32_t *sRow =
+            reinterpret_cast<const int32_t *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
+        const int c0 = a.tileCol[tile], c1 = a.tileCol[tile + 1];
+        const int k0 = a.colStart32[c0], k1 = a.colStart32[c1];
+        const int a0 = k0 & ~3;
+        const int len = k1 - a0;
+        // this thread's columns of the tile (their extents do not depend on the staged data)
+        const int col = c0 + t;
+        int cb = 0, ce = 0;
+        double cj = 0.0;
+        if (col < c1) {
+            cb = a.colStart32[col] - a0;
+            ce = a.colStart32[col + 1] - a0;
+            cj = a.phase1 ? 0.0 : a.c[col];
+        }
+        rcMbarWait(full + s, parity);
+        // products in place: u[i] * a  (unfused, as the reference's  y += u*a)
+        {
+            int k = (k0 - a0) + t;
+            for (; k + 3 * NT < len; k += 4 * NT) {
+                int r[4];
+                double g[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) r[q] = sRow[k + q * NT];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) g[q] = U_SMEM ? sU[r[q]] : __ldg(a.u + r[q]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sVal[k + q * NT] = __dmul_rn(g[q], sVal[k + q * NT]);
+            }
+            for (; k < len; k += NT) sVal[k] = __dmul_rn(U_SMEM ? sU[sRow[k]] : __ldg(a.u + sRow[k]), sVal[k]);
+        }
+        __syncthreads();
+        if (col < c1) {
+            double sum = 0.0;
+            for (int k = cb; k < ce; ++k) sum = __dadd_rn(sum, sVal[k]);
+            a.out[col] = a.phase1 ? -sum : cj - sum;  // DecompAlgo.cpp:4538-4545
+        }
+        for (int col2 = col + NT; col2 < c1; col2 += NT) {
+            const int b = a.colStart32[col2] - a0, e = a.colStart32[col2 + 1] - a0;
+            double sum = 0.0;
+            for (int k = b; k < e; ++k) sum = __dadd_rn(sum, sVal[k]);
+            a.out[col2] = a.phase1 ? -sum : a.c[col2] - sum;
+        }
+        __syncthreads();
+        if (t == 0) {
+            const int next = tile + stages * gridDim.x;
+            if (next < a.nTiles) {
+                // the stage was written through the generic proxy (products); order those
+                // writes before the async-proxy bulk copies that refill it
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(next, s);
+            }
+        }
     }
 }
 
@@ -132,9 +227,43 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
 {
     if (c->N == 0) return DIPGPU_OK;
     if (c->nSpmvTiles > 0 && c->spmvLanes == 0) {
-        redcost_stream_kernel<<<c->nSpmvTiles, kSpmvThreads, 0, st>>>(
-            c->dTileCol, c->dColStart32, c->dRowMaster, c->dVal, dU, c->dObj,
-            phase == DIPGPU_PHASE_PRICE1 ? 1 : 0, c->dRedCost);
+        StreamArgs a;
+        a.nTiles = c->nSpmvTiles;
+        a.tileCol = c->dTileCol;
+        a.colStart32 = c->dColStart32;
+        a.rowMaster = c->dRowMaster;
+        a.val = c->dVal;
+        a.u = dU;
+        a.uLen = c->R + c->numConvex;
+        a.c = c->dObj;
+        a.phase1 = phase == DIPGPU_PHASE_PRICE1 ? 1 : 0;
+        a.out = c->dRedCost;
+        const int sms = c->smCount > 0 ? c->smCount : 148;
+        const size_t uBytes = (((size_t)a.uLen + 1) & ~(size_t)1) * 8;
+        const size_t withU = kSpmvHdrBytes + 2 * (size_t)kSpmvStageBytes + uBytes;
+        // u in shared memory pays when it is gathered irregularly and re-used: more stored
+        // entries than a few times the dual vector, and the copy fits beside two stages
+        const bool uSmem = withU <= 227 * 1024 && c->nnz >= 8 * (int64_t)a.uLen && c->nSpmvTiles >= 2 * sms;
+        if (uSmem) {
+            a.stages = 2;
+            if (!c->spmvAttrU) {
+                DIPGPU_CUDA(c, cudaFuncSetAttribute(redcost_stream_kernel<true, 1024>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                c->spmvAttrU = true;
+            }
+            const int grid = std::min(c->nSpmvTiles, sms);
+            redcost_stream_kernel<true, 1024><<<grid, 1024, withU, st>>>(a);
+        } else {
+            a.stages = 3;
+            const size_t bytes = kSpmvHdrBytes + 3 * (size_t)kSpmvStageBytes;
+            if (!c->spmvAttr) {
+                DIPGPU_CUDA(c, cudaFuncSetAttribute(redcost_stream_kernel<false, 512>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                c->spmvAttr = true;
+            }
+            const int grid = std::min(c->nSpmvTiles, 2 * sms);
+            redcost_stream_kernel<false, 512><<<grid, 512, bytes, st>>>(a);
+        }
         c->launches++;
         DIPGPU_CUDA(c, cudaGetLastError());
         return DIPGPU_OK;

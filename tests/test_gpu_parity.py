@@ -87,9 +87,10 @@ def test_random_ragged_batches(oracle, pricer, seed, m, nhi, caphi):
     _check_against_oracle(oracle, pricer, b.block_col_start, b.weight, b.capacity, b.red_cost, b.orig_cost, b.alpha)
 
 
-@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("fuse", [0, 1, 2])
 def test_filter_fused_and_standalone(oracle, pricer, fuse):
-    """Stage (c) as the tail of the backtrack kernel (small shards) and as its own kernels."""
+    """Stage (c) as its own kernels (0), as the tail of the backtrack kernel (1), and backtrack +
+    filter as the tail of the DP kernel (2, the automatic choice for small shards)."""
     pricer.set_option("fuse_filter", fuse)
     b = I.random_batch(700, 0, 60, 0, 200, seed=77)
     _check_against_oracle(oracle, pricer, b.block_col_start, b.weight, b.capacity, b.red_cost, b.orig_cost, b.alpha)
