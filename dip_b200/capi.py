@@ -137,8 +137,8 @@ class PinnedArray:
 
 def plan_dp_geometry(n_blocks, max_capacity, max_block_cols, max_usable_weight, sm_count=148) -> dict:
     """Host-only: the DP kernel shape the library picks (dipgpu_plan_dp_geometry)."""
-    out = (C.c_int32 * 6)()
+    out = (C.c_int32 * 7)()
     rc = lib().dipgpu_plan_dp_geometry(sm_count, n_blocks, max_capacity, max_block_cols, max_usable_weight, out)
     if rc != OK:
         raise DipGpuError(rc, "dipgpu_plan_dp_geometry")
-    return dict(zip(["threads", "cells_per_thread", "items_per_step", "guard", "chunk_cols", "smem_bytes"], list(out)))
+    return dict(zip(["threads", "cells_per_thread", "items_per_step", "guard", "chunk_cols", "smem_bytes", "fused_tail"], list(out)))

@@ -83,6 +83,7 @@ struct DpGeom {
     int rowCells;  // T*S >= maxCapacity+1
     int chunkCols; // columns staged per TMA chunk
     int guard;     // -inf cells in front of each row buffer (0 = predicated reads)
+    int fuse;      // 1: backtrack + filter run in the DP kernel's tail, decision bits stay in shared memory
     size_t smemBytes;
 };
 
@@ -182,10 +183,9 @@ int cudaFail(Ctx *c, cudaError_t e, const char *what);
 // redcost.cu -- stage (a)
 int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st);
 // knapsack.cu -- stage (b)
-int chooseDpGeom(Ctx *c, DpGeom *g);
+int chooseDpGeom(Ctx *c, DpGeom *g, bool wantFuse);
 int prepareKnapsackDp(Ctx *c);  // loads the chosen kernel, sets its shared-memory limit
-int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseTail,
-                     cudaStream_t st);
+int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st);
 int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseFilter,
                         cudaStream_t st);
 // filter.cu -- stage (c)

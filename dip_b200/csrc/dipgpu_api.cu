@@ -144,7 +144,8 @@ static int setBlockRange(Ctx *c, int first, int count)
     c->maxBlockCols = maxCols;
     c->maxUsableWeight = maxW;
     int rc;
-    if ((rc = chooseDpGeom(c, &c->geom))) return rc;
+    const bool wantFuse = count > 0 && (c->optFuseFilter < 0 ? count <= kFuseFilterMaxBlocks : c->optFuseFilter == 2);
+    if ((rc = chooseDpGeom(c, &c->geom, wantFuse))) return rc;
     if (count > 0 && (rc = prepareKnapsackDp(c))) return rc;
     // decision bits: ceil(n_b/32) words per cell, rowCells cells per block
     std::vector<int64_t> off((size_t)count + 1, 0);
@@ -177,9 +178,10 @@ static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, do
                         bool timed)
 {
     int rc;
-    int mode = c->optFuseFilter < 0 ? (c->nLocal <= kFuseFilterMaxBlocks ? 2 : 0) : c->optFuseFilter;
+    int mode = c->geom.fuse ? 2 : c->optFuseFilter < 0 ? (c->nLocal <= kFuseFilterMaxBlocks ? 1 : 0)
+                                                       : (c->optFuseFilter == 1 ? 1 : 0);
     if (c->nLocal == 0) mode = 0;
-    if ((rc = launchKnapsackDp(c, dRedCost, dAlpha, eps, mode == 2, st))) return rc;
+    if ((rc = launchKnapsackDp(c, dRedCost, dAlpha, eps, st))) return rc;
     if (timed) cudaEventRecord(c->ev[3], st);
     if (mode != 2 && (rc = launchBacktrackEmit(c, dRedCost, dAlpha, eps, mode == 1, st))) return rc;
     if (timed) cudaEventRecord(c->ev[4], st);
@@ -653,13 +655,14 @@ int dipgpu_last_stage_ms(const dipgpu_ctx *ctx, float *ms6)
     return DIPGPU_OK;
 }
 
-static void geomOut(const DpGeom &g, int32_t out[6])
+static void geomOut(const DpGeom &g, int32_t out[7])
 {
     out[0] = g.T; out[1] = g.S; out[2] = g.items; out[3] = g.guard; out[4] = g.chunkCols; out[5] = (int32_t)g.smemBytes;
+    out[6] = g.fuse;
 }
 
 int dipgpu_plan_dp_geometry(int32_t smCount, int32_t nBlocks, int32_t maxCapacity, int32_t maxBlockCols,
-                            int32_t maxUsableWeight, int32_t out[6])
+                            int32_t maxUsableWeight, int32_t out[7])
 {
     if (!out || smCount <= 0 || nBlocks < 0 || maxCapacity < 0 || maxBlockCols < 0 || maxUsableWeight < 0)
         return DIPGPU_ERR_INVALID;
@@ -670,13 +673,13 @@ int dipgpu_plan_dp_geometry(int32_t smCount, int32_t nBlocks, int32_t maxCapacit
     tmp.maxBlockCols = maxBlockCols;
     tmp.maxUsableWeight = maxUsableWeight;
     DpGeom g{};
-    int rc = chooseDpGeom(&tmp, &g);
+    int rc = chooseDpGeom(&tmp, &g, nBlocks > 0 && nBlocks <= kFuseFilterMaxBlocks);
     if (rc) return rc;
     geomOut(g, out);
     return DIPGPU_OK;
 }
 
-int dipgpu_get_dp_geometry(const dipgpu_ctx *ctx, int32_t out[6])
+int dipgpu_get_dp_geometry(const dipgpu_ctx *ctx, int32_t out[7])
 {
     const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
     if (!c || !out) return DIPGPU_ERR_INVALID;
@@ -691,12 +694,12 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!c || !name) return DIPGPU_ERR_INVALID;
     if (!strcmp(name, "stage_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "spmv_lanes")) { c->spmvLanes = (int)value; return DIPGPU_OK; }
-    if (!strcmp(name, "fuse_filter")) { c->optFuseFilter = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "dp_threads") || !strcmp(name, "dp_cells_per_thread") || !strcmp(name, "dp_items_per_step") ||
-        !strcmp(name, "dp_no_guard")) {
+        !strcmp(name, "dp_no_guard") || !strcmp(name, "fuse_filter")) {
         if (!strcmp(name, "dp_threads")) c->optThreads = (int)value;
         else if (!strcmp(name, "dp_cells_per_thread")) c->optCellsPerThread = (int)value;
         else if (!strcmp(name, "dp_items_per_step")) c->optItemsPerStep = (int)value;
+        else if (!strcmp(name, "fuse_filter")) c->optFuseFilter = (int)value;
         else c->optNoGuard = (int)value;
         if (c->haveBlocks) {
             int rc = bind(c);

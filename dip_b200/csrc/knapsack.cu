@@ -208,7 +208,7 @@ struct KnapArgs {
     FilterArgs filt;
 };
 
-__host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunkCols)
+__host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunkCols, bool fuse)
 {
     size_t b = 0;
     b += sizeof(double) * 2 * ((size_t)rowCells + (size_t)guard);  // two row buffers, each behind its guard
@@ -218,6 +218,10 @@ __host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunk
     b += sizeof(int32_t) * ((size_t)chunkCols + 4);     // compacted weights (+ prefetch pad)
     b += sizeof(int32_t) * 32;                          // per-warp counts
     b += 16;                                            // mbarrier
+    if (fuse) {
+        b += sizeof(int32_t) * 2 * ((size_t)chunkCols + 4);                     // item columns, taken list
+        b += sizeof(uint32_t) * (size_t)((chunkCols + 31) / 32) * (size_t)rowCells;  // decision bits
+    }
     return b;
 }
 
@@ -230,7 +234,10 @@ __host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunk
 // intermediate row c[i][.] is rebuilt in registers at j and j-w' from three
 // shifted reads of c[i-1][.], with exactly the additions and strict compares
 // the one-item step performs, so values and decisions are unchanged.
-template <int S, bool GUARD, int ITEMS, int MAXT>
+// FUSE (small shards, every block a single chunk): the decision bits, the compacted items and
+// the taken list stay in shared memory, warp 0 walks the decisions as soon as the DP is done,
+// and the last CTA of the grid runs the filter -- stages (b) and (c) in one launch.
+template <int S, bool GUARD, int ITEMS, int MAXT, bool FUSE>
 __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ KnapArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -246,6 +253,9 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     int32_t *itW = rawW + (CH + 4);
     int32_t *warpCnt = itW + (CH + 4);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(warpCnt + 32);
+    int32_t *itC = reinterpret_cast<int32_t *>(mbar + 2);             // FUSE only
+    int32_t *sTaken = itC + (CH + 4);                                 // FUSE only
+    uint32_t *sBits = reinterpret_cast<uint32_t *>(sTaken + (CH + 4));  // FUSE only
 
     const int t = threadIdx.x;
     const int lane = t & 31;
@@ -256,7 +266,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const int colStart = a.blockColStart[b];
     const int nCols = a.blockColStart[b + 1] - colStart;
     const int cap = a.capacity[b];
-    uint32_t *bitsBase = a.bits + a.bitsOff[lb];
+    uint32_t *bitsBase = FUSE ? sBits : a.bits + a.bitsOff[lb];
     const int j0 = t * S;  // first owned cell
 
     if (t == 0) mbarInit(mbar, 1);
@@ -324,9 +334,13 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                 const int pos = nIt + off + wpre;
                 itP[pos] = -rc;
                 itW[pos] = w;
-                const int slot = colStart + kGlobal + pos;
-                a.itemW[slot] = w;
-                a.itemCol[slot] = chunkBase + cl;
+                if (FUSE) {
+                    itC[pos] = cl;
+                } else {
+                    const int slot = colStart + kGlobal + pos;
+                    a.itemW[slot] = w;
+                    a.itemCol[slot] = chunkBase + cl;
+                }
             }
             nIt += tot;
         }
@@ -427,11 +441,56 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         if (j0 + s == cap) a.blockObj[lb] = mine[s];
     }
     if (t == 0) a.nItems[lb] = kGlobal;
-    if (a.fuseTail) {
-        // latency regime: walk this knapsack's decisions right here (they sit in L2, just
-        // written by this CTA), then the last CTA of the grid filters the shard
+    if (FUSE) {
         __syncthreads();
-        if (warp == 0) backtrackOne(a.back, lb, lane, kGlobal);
+        if (warp == 0) {
+            // backtrack from (last item, capacity), gap_func.py:173-181, out of shared memory
+            int j = cap;
+            int i = kGlobal - 1;
+            int cnt = 0;
+            while (i >= 0) {
+                const int kw = i >> 5;
+                const int wv = kw - lane;
+                uint32_t v = wv >= 0 ? sBits[(size_t)wv * RC + j] : 0u;
+                if (lane == 0) v &= 0xffffffffu >> (31 - (i & 31));
+                const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
+                if (nz == 0u) {
+                    i = ((kw - 32) << 5) | 31;
+                    continue;
+                }
+                const int L = __ffs(nz) - 1;
+                const uint32_t vL = __shfl_sync(0xffffffffu, v, L);
+                const int item = ((kw - L) << 5) + (31 - __clz(vL));
+                if (lane == 0) sTaken[cnt] = itC[item];
+                ++cnt;
+                j -= itW[item];
+                i = item - 1;
+            }
+            __syncwarp();
+            // emit ascending x-space indices; sums in that order (GAP_KnapPisinger.h:263-272)
+            const int shiftRc = colStart & 1;
+            double rcs = 0.0, ocs = 0.0;
+            for (int base = 0; base < cnt; base += 32) {
+                const int k = base + lane;
+                double r = 0.0, o = 0.0;
+                if (k < cnt) {
+                    const int lc = sTaken[cnt - 1 - k];
+                    a.back.candInd[colStart + k] = colStart + lc;
+                    r = rawRc[shiftRc + lc];
+                    o = a.back.obj[colStart + lc];
+                }
+                const int nn = min(32, cnt - base);
+                for (int q = 0; q < nn; ++q) {
+                    rcs += __shfl_sync(0xffffffffu, r, q);
+                    ocs += __shfl_sync(0xffffffffu, o, q);
+                }
+            }
+            if (lane == 0) {
+                a.back.blockRedCost[lb] = rcs - a.back.alpha[b];  // DecompAlgo.cpp:6350-6356
+                a.back.blockOrigCost[lb] = ocs;
+                a.back.blockNnz[lb] = cnt;
+            }
+        }
         ticketThenFilter(a.back.doneCounter, a.filt, T);
     }
 }
@@ -441,22 +500,26 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
 typedef void (*KnapFn)(const KnapArgs);
 struct GeomEntry {
     int S, maxT;
-    KnapFn fn[2][2];  // [guard][items-1]
+    KnapFn fn[2][2];      // [guard][items-1]
+    KnapFn fnFuse[2][2];  // same, fused tail (NULL where not built)
 };
 
-#define GE(S, MT)                                                                              \
-    {                                                                                          \
-        S, MT,                                                                                 \
-        {                                                                                      \
-            {knap_dp_kernel<S, false, 1, MT>, knap_dp_kernel<S, false, 2, MT>},                \
-            {knap_dp_kernel<S, true, 1, MT>, knap_dp_kernel<S, true, 2, MT>}                   \
-        }                                                                                      \
+#define GE_FNS(S, MT, F)                                                                         \
+    {                                                                                            \
+        {knap_dp_kernel<S, false, 1, MT, F>, knap_dp_kernel<S, false, 2, MT, F>},                \
+        {knap_dp_kernel<S, true, 1, MT, F>, knap_dp_kernel<S, true, 2, MT, F>}                   \
     }
+#define GE_NULL {{nullptr, nullptr}, {nullptr, nullptr}}
+#define GE(S, MT) {S, MT, GE_FNS(S, MT, false), GE_NULL}
+#define GEF(S, MT) {S, MT, GE_FNS(S, MT, false), GE_FNS(S, MT, true)}
 static const GeomEntry kGeoms[] = {
-    GE(1, 1024), GE(3, 1024), GE(5, 1024), GE(7, 1024), GE(9, 1024), GE(11, 1024),
-    GE(13, 512), GE(15, 512), GE(17, 512), GE(19, 512), GE(21, 512), GE(25, 512),
+    GEF(1, 1024), GEF(3, 1024), GEF(5, 1024), GEF(7, 1024), GE(9, 1024), GE(11, 1024),
+    GE(13, 512),  GE(15, 512),  GE(17, 512),  GE(19, 512),  GE(21, 512), GE(25, 512),
 };
 #undef GE
+#undef GEF
+#undef GE_FNS
+#undef GE_NULL
 static const int kNumGeoms = (int)(sizeof(kGeoms) / sizeof(kGeoms[0]));
 static const size_t kMaxSmem = 227 * 1024 - 6 * 1024;  // the fused tail's static shared memory comes off the 227 KiB
 
@@ -468,10 +531,12 @@ static const GeomEntry *findGeom(int S)
 }
 
 // Fills the derived fields of a (T, S) candidate; returns false if it cannot run.
-static bool fitGeom(const Ctx *c, int T, int S, int items, DpGeom *g)
+static bool fitGeom(const Ctx *c, int T, int S, int items, bool fuse, DpGeom *g)
 {
     const GeomEntry *e = findGeom(S);
     if (!e || T < 32 || T > e->maxT || (T & 31)) return false;
+    if (fuse && (e->fnFuse[0][0] == nullptr || c->maxBlockCols > 2048)) return false;
+    g->fuse = fuse ? 1 : 0;
     if ((int64_t)T * S < (int64_t)c->maxCapacity + 1) return false;
     g->T = T;
     g->S = S;
@@ -483,14 +548,14 @@ static bool fitGeom(const Ctx *c, int T, int S, int items, DpGeom *g)
     // guard: the largest usable weight (x2 when two items advance per barrier)
     int guard = ((c->maxUsableWeight * items) + 1) & ~1;
     g->guard = guard;
-    g->smemBytes = dpSmemBytes(g->rowCells, guard, ch);
+    g->smemBytes = dpSmemBytes(g->rowCells, guard, ch, fuse);
     if (g->smemBytes > kMaxSmem || c->optNoGuard) {
         g->guard = 0;  // predicated shifted reads instead
-        g->smemBytes = dpSmemBytes(g->rowCells, 0, ch);
+        g->smemBytes = dpSmemBytes(g->rowCells, 0, ch, fuse);
     }
-    while (g->smemBytes > kMaxSmem && g->chunkCols > 256) {
+    while (!fuse && g->smemBytes > kMaxSmem && g->chunkCols > 256) {
         g->chunkCols = (g->chunkCols / 2 + 3) & ~3;
-        g->smemBytes = dpSmemBytes(g->rowCells, g->guard, g->chunkCols);
+        g->smemBytes = dpSmemBytes(g->rowCells, g->guard, g->chunkCols, false);
     }
     return g->smemBytes <= kMaxSmem;
 }
@@ -525,13 +590,15 @@ static double geomCost(const Ctx *c, const DpGeom &g)
     return waves * std::max(chain, std::max(issue, smem));
 }
 
-int chooseDpGeom(Ctx *c, DpGeom *g)
+int chooseDpGeom(Ctx *c, DpGeom *g, bool wantFuse)
 {
     const int cells = c->maxCapacity + 1;
     DpGeom best{};
     double bestCost = 0.0;
     bool have = false;
+    for (int pass = wantFuse ? 0 : 1; pass < 2 && !have; ++pass)  // fused candidates first, if wanted
     for (int i = 0; i < kNumGeoms; ++i) {
+        const bool fuse = pass == 0;
         const int S = kGeoms[i].S;
         if (c->optCellsPerThread > 0 && S != c->optCellsPerThread) continue;
         int T = ((cells + S - 1) / S + 31) & ~31;
@@ -542,7 +609,7 @@ int chooseDpGeom(Ctx *c, DpGeom *g)
         for (int items = 1; items <= 2; ++items) {
             if (c->optItemsPerStep > 0 && items != c->optItemsPerStep) continue;
             DpGeom cand{};
-            if (!fitGeom(c, T, S, items, &cand)) continue;
+            if (!fitGeom(c, T, S, items, fuse, &cand)) continue;
             const double cost = geomCost(c, cand);
             if (!have || cost < bestCost) {
                 best = cand;
@@ -567,7 +634,7 @@ int prepareKnapsackDp(Ctx *c)
     const DpGeom &g = c->geom;
     const GeomEntry *e = findGeom(g.S);
     if (!e) return fail(c, DIPGPU_ERR_STATE, "DP geometry not initialised");
-    KnapFn fn = e->fn[g.guard > 0 ? 1 : 0][g.items == 2 ? 1 : 0];
+    KnapFn fn = (g.fuse ? e->fnFuse : e->fn)[g.guard > 0 ? 1 : 0][g.items == 2 ? 1 : 0];
     if (c->dpFnConfigured != (void *)fn || c->dpFnSmem != g.smemBytes) {
         DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
         c->dpFnConfigured = (void *)fn;
@@ -600,14 +667,13 @@ static void fillBackArgs(Ctx *c, const double *dRedCost, const double *dAlpha, B
     a->doneCounter = c->dDoneCounter;
 }
 
-int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseTail,
-                     cudaStream_t st)
+int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st)
 {
     if (c->nLocal == 0) return DIPGPU_OK;
     const DpGeom &g = c->geom;
     const GeomEntry *e = findGeom(g.S);
     if (!e) return fail(c, DIPGPU_ERR_STATE, "DP geometry not initialised");
-    KnapFn fn = e->fn[g.guard > 0 ? 1 : 0][g.items == 2 ? 1 : 0];
+    KnapFn fn = (g.fuse ? e->fnFuse : e->fn)[g.guard > 0 ? 1 : 0][g.items == 2 ? 1 : 0];
     KnapArgs a;
     a.redCost = dRedCost;
     a.weight = c->dWeight;
@@ -622,7 +688,7 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, doubl
     a.firstBlock = c->firstBlock;
     a.chunkCols = g.chunkCols;
     a.guard = g.guard;
-    a.fuseTail = fuseTail ? 1 : 0;
+    a.fuseTail = g.fuse;
     fillBackArgs(c, dRedCost, dAlpha, &a.back);
     a.filt = makeFilterArgs(c, redCostEps);
     a.filt.fuseCopy = c->nLocal <= kFuseFilterMaxBlocks ? 2 : 1;

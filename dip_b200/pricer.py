@@ -135,9 +135,9 @@ class GpuPricer:
         return dict(kernel_launches=a.value, h2d_bytes=b.value, d2h_bytes=c.value)
 
     def dpGeometry(self) -> dict:
-        out = (C.c_int32 * 6)()
+        out = (C.c_int32 * 7)()
         self._check(self._lib.dipgpu_get_dp_geometry(self._ctx, out))
-        return dict(zip(["threads", "cells_per_thread", "items_per_step", "guard", "chunk_cols", "smem_bytes"],
+        return dict(zip(["threads", "cells_per_thread", "items_per_step", "guard", "chunk_cols", "smem_bytes", "fused_tail"],
                         list(out)))
 
     def last_stage_ms(self) -> dict:

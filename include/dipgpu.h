@@ -228,11 +228,12 @@ int dipgpu_measure_smem_gbs(dipgpu_ctx *ctx, double *gbs);
 /* Host-only planning (no device needed): the DP kernel shape the library would
  * pick for a shard of nBlocks knapsacks on a GPU with smCount SMs.
  * out = {threads per knapsack, cells per thread, items per barrier, guard cells,
- * TMA chunk columns, shared-memory bytes}.  dipgpu_get_dp_geometry reports the
+ * TMA chunk columns, shared-memory bytes, fused tail (1 = backtrack + filter run
+ * inside the DP kernel)}.  dipgpu_get_dp_geometry reports the
  * shape in use by a context. */
 int dipgpu_plan_dp_geometry(int32_t smCount, int32_t nBlocks, int32_t maxCapacity, int32_t maxBlockCols,
-                            int32_t maxUsableWeight, int32_t out[6]);
-int dipgpu_get_dp_geometry(const dipgpu_ctx *ctx, int32_t out[6]);
+                            int32_t maxUsableWeight, int32_t out[7]);
+int dipgpu_get_dp_geometry(const dipgpu_ctx *ctx, int32_t out[7]);
 
 /* Tuning / diagnostics knobs: "stage_timing", "dp_threads" (multiple of 32),
  * "dp_cells_per_thread" (odd, 1..25), "dp_items_per_step" (1 or 2), "dp_no_guard",
