@@ -69,8 +69,8 @@ struct ResultLayout {
 constexpr int kFuseFilterMaxBlocks = 256;
 
 // ---------------------------------------------------------------- SpMV tiling
-constexpr int kSpmvChunk = 3072;    // stored entries per tile (36 KiB of shared memory)
-constexpr int kSpmvMaxCols = 2048;  // columns per tile
+constexpr int kSpmvChunk = 384;        // stored entries per warp tile (4.5 KiB of shared memory per stage)
+constexpr int kSpmvColsPerLane = 4;    // a warp tile spans at most 32*4 consecutive columns
 
 // ------------------------------------------------------------------ DP geometry
 //
@@ -108,7 +108,7 @@ struct Ctx {
     int32_t *dColStart32 = nullptr; // N+1 (only when nnz < 2^31)
     int32_t *dTileCol = nullptr;    // nSpmvTiles+1 column boundaries of the stream kernel's tiles
     int nSpmvTiles = 0;             // 0 = stream kernel not applicable
-    bool spmvAttr = false, spmvAttrU = false;
+    int spmvAttr = 0, spmvAttrU = 0;  // shared-memory limits already set on the two kernels
 
     double *dObj = nullptr;  // c[N]
     bool haveObj = false;

@@ -82,19 +82,24 @@ static int uploadCore(Ctx *c)
     }
     c->nnz = nnz;
     int rc;
-    // tiles of the stream kernel: consecutive columns, <= kSpmvChunk-4 entries, <= kSpmvMaxCols columns
+    // warp tiles of the stream kernel: consecutive columns, <= kSpmvChunk stored entries (counted
+    // from the 4-aligned start), <= 32*colsPerLane columns with colsPerLane fitted to the density
     c->nSpmvTiles = 0;
     if (nnz < (int64_t)1 << 31 && N > 0) {
         std::vector<int32_t> tileCol;
         std::vector<int32_t> cs32((size_t)N + 1);
         for (int j = 0; j <= N; ++j) cs32[j] = (int32_t)colStart[j];
+        const double avg = (double)nnz / (double)N;
+        int cpl = avg > 0 ? (int)((double)kSpmvChunk / (32.0 * avg)) : kSpmvColsPerLane;
+        cpl = std::max(1, std::min(cpl, kSpmvColsPerLane));
+        const int maxCols = 32 * cpl;
         bool ok = true;
         int j = 0;
         tileCol.push_back(0);
         while (j < N) {
             const int64_t a0 = colStart[j] & ~(int64_t)3;
             int e = j;
-            while (e < N && e - j < kSpmvMaxCols && colStart[e + 1] - a0 <= kSpmvChunk) ++e;
+            while (e < N && e - j < maxCols && colStart[e + 1] - a0 <= kSpmvChunk) ++e;
             if (e == j) { ok = false; break; }  // a single column longer than a tile
             tileCol.push_back(e);
             j = e;

@@ -11,10 +11,10 @@
 // HBM-bound: algorithmic bytes = 12*nnz + 20*N + 8*R.
 //
 // Main kernel (redcost_stream_kernel): the columns are cut on the host into
-// tiles of at most kSpmvChunk stored entries; a CTA pulls its tile's (value,
-// row) stream into shared memory with two TMA bulk copies, multiplies by the
-// gathered duals in place, and then one thread per column adds that column's
-// products SEQUENTIALLY in storage order.  Entries are stored per column in
+// tiles of at most kSpmvChunk stored entries; a warp pulls its tile's (value,
+// row) stream into shared memory with two TMA bulk copies (double-buffered),
+// and one lane per column multiplies by the gathered duals and adds that
+// column's products SEQUENTIALLY in storage order.  Entries are stored per column in
 // DESCENDING row order and the arithmetic is an unfused multiply followed by an
 // add, i.e. exactly the order and rounding of the reference's row-major scatter
 // (rows R-1..0, y[col] += u[i]*a), so the reduced costs are bit-identical to the
@@ -54,27 +54,31 @@ struct StreamArgs {
     const double *c;
     int phase1;
     double *out;
-    int stages;
+    int uSmemBytes;             // 0: gather the duals from global memory
 };
 
 constexpr int kSpmvStageValBytes = (kSpmvChunk + 4) * 8;
 constexpr int kSpmvStageBytes = kSpmvStageValBytes + (kSpmvChunk + 4) * 4;  // multiple of 16
-constexpr int kSpmvHdrBytes = 64;                                          // mbarriers
+constexpr int kSpmvWarpBytes = 16 + 2 * kSpmvStageBytes;                    // 2 mbarriers + 2 stages
 
-// Persistent CTAs (grid <= resident CTAs) walk the tiles with a `stages`-deep TMA
-// pipeline: while tile k is multiplied and reduced out of one stage, the bulk
-// copies of tiles k+1.. are in flight into the others.  U_SMEM keeps the whole
-// dual vector in shared memory (it is gathered 1x per stored entry; from L1 a
-// random 8-byte gather costs a wavefront per lane).
-template <bool U_SMEM, int NT>
-__global__ void __launch_bounds__(NT) redcost_stream_kernel(const StreamArgs a)
+// Every WARP owns a two-stage TMA pipeline over its own tiles (<= 32*kSpmvColsPerLane
+// consecutive columns, <= kSpmvChunk stored entries): lane 0 issues the bulk copies of the
+// (value, row) streams of tile k+2 while the warp reduces tile k out of shared memory, one
+// lane per column, sequentially in storage order.  No CTA-wide barrier in the loop.
+// U_SMEM keeps the whole dual vector in shared memory (it is gathered once per stored
+// entry; from L1 a random 8-byte gather costs a wavefront per lane).
+template <bool U_SMEM>
+__global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_constant__ StreamArgs a)
 {
     extern __shared__ __align__(16) unsigned char sm[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(sm);
-    unsigned char *stageBase = sm + kSpmvHdrBytes;
-    const double *sU = reinterpret_cast<const double *>(stageBase + (size_t)a.stages * kSpmvStageBytes);
-    const int t = threadIdx.x;
-    const int stages = a.stages;
+    const double *sU = reinterpret_cast<const double *>(sm);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    unsigned char *wbase = sm + a.uSmemBytes + (size_t)warp * kSpmvWarpBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
+    unsigned char *stageBase = wbase + 16;
+    const int warpsPerCta = blockDim.x >> 5;
+    const int gw = blockIdx.x * warpsPerCta + warp;
+    const int totalWarps = gridDim.x * warpsPerCta;
 
     auto issue = [&](int tile, int s) {
         const int c0 = a.tileCol[tile], c1 = a.tileCol[tile + 1];
@@ -105,78 +109,76 @@ __global__ void __launch_bounds__(NT) redcost_stream_kernel(const StreamArgs a)
         }
     };
 
-    if (t == 0) {
-        for (int s = 0; s < stages; ++s)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full + s)), "r"(1));
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full)), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full + 1)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int s = 0; s < stages; ++s) {
-            const int tile = blockIdx.x + s * gridDim.x;
-            if (tile < a.nTiles) issue(tile, s);
-        }
+        if (gw < a.nTiles) issue(gw, 0);
+        if (gw + totalWarps < a.nTiles) issue(gw + totalWarps, 1);
     }
     if (U_SMEM) {
         double *w = const_cast<double *>(sU);
-        for (int k = t; k < a.uLen; k += NT) w[k] = __ldg(a.u + k);
+        for (int k = t; k < a.uLen; k += blockDim.x) w[k] = __ldg(a.u + k);
+        __syncthreads();
+    } else {
+        __syncwarp();
     }
-    __syncthreads();
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x, ++it) {
-        const int s = it % stages;
-        const uint32_t parity = (uint32_t)((it / stages) & 1);
-        double *sVal = reinterpret_cast<double *>(stageBase + (size_t)s * kSpmvStageBytes);
+    for (int tile = gw; tile < a.nTiles; tile += totalWarps, ++it) {
+        const int s = it & 1;
+        const uint32_t parity = (uint32_t)((it >> 1) & 1);
+        const double *sVal = reinterpret_cast<const double *>(stageBase + (size_t)s * kSpmvStageBytes);
         const int32_t *sRow =
             reinterpret_cast<const int32_t *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
         const int c0 = a.tileCol[tile], c1 = a.tileCol[tile + 1];
-        const int k0 = a.colStart32[c0], k1 = a.colStart32[c1];
-        const int a0 = k0 & ~3;
-        const int len = k1 - a0;
-        // this thread's columns of the tile (their extents do not depend on the staged data)
-        const int col = c0 + t;
-        int cb = 0, ce = 0;
-        double cj = 0.0;
-        if (col < c1) {
-            cb = a.colStart32[col] - a0;
-            ce = a.colStart32[col + 1] - a0;
-            cj = a.phase1 ? 0.0 : a.c[col];
+        const int a0 = a.colStart32[c0] & ~3;
+        // this lane's columns of the tile: extents and objective do not depend on the staged
+        // data, so these loads overlap the wait for the bulk copies
+        int cb[kSpmvColsPerLane], ce[kSpmvColsPerLane];
+        double cj[kSpmvColsPerLane];
+#pragma unroll
+        for (int q = 0; q < kSpmvColsPerLane; ++q) {
+            const int col = c0 + lane + 32 * q;
+            cb[q] = ce[q] = 0;
+            cj[q] = 0.0;
+            if (col < c1) {
+                cb[q] = a.colStart32[col] - a0;
+                ce[q] = a.colStart32[col + 1] - a0;
+                if (!a.phase1) cj[q] = a.c[col];
+            }
         }
         rcMbarWait(full + s, parity);
-        // products in place: u[i] * a  (unfused, as the reference's  y += u*a)
-        {
-            int k = (k0 - a0) + t;
-            for (; k + 3 * NT < len; k += 4 * NT) {
-                int r[4];
-                double g[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) r[q] = sRow[k + q * NT];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) g[q] = U_SMEM ? sU[r[q]] : __ldg(a.u + r[q]);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) sVal[k + q * NT] = __dmul_rn(g[q], sVal[k + q * NT]);
+        for (int q = 0; q < kSpmvColsPerLane; ++q) {
+            const int col = c0 + lane + 32 * q;
+            if (col < c1) {
+                // y[col] += u[i]*a in storage order, multiply and add unfused (the reference's scatter)
+                int k = cb[q];
+                const int e = ce[q];
+                double sum = 0.0, g = 0.0, v = 0.0;
+                if (k < e) {
+                    const int r = sRow[k];
+                    v = sVal[k];
+                    g = U_SMEM ? sU[r] : __ldg(a.u + r);
+                }
+                while (k < e) {
+                    const double prod = __dmul_rn(g, v);
+                    ++k;
+                    if (k < e) {
+                        const int r = sRow[k];
+                        v = sVal[k];
+                        g = U_SMEM ? sU[r] : __ldg(a.u + r);
+                    }
+                    sum = __dadd_rn(sum, prod);
+                }
+                a.out[col] = a.phase1 ? -sum : cj[q] - sum;  // DecompAlgo.cpp:4538-4545
             }
-            for (; k < len; k += NT) sVal[k] = __dmul_rn(U_SMEM ? sU[sRow[k]] : __ldg(a.u + sRow[k]), sVal[k]);
         }
-        __syncthreads();
-        if (col < c1) {
-            double sum = 0.0;
-            for (int k = cb; k < ce; ++k) sum = __dadd_rn(sum, sVal[k]);
-            a.out[col] = a.phase1 ? -sum : cj - sum;  // DecompAlgo.cpp:4538-4545
-        }
-        for (int col2 = col + NT; col2 < c1; col2 += NT) {
-            const int b = a.colStart32[col2] - a0, e = a.colStart32[col2 + 1] - a0;
-            double sum = 0.0;
-            for (int k = b; k < e; ++k) sum = __dadd_rn(sum, sVal[k]);
-            a.out[col2] = a.phase1 ? -sum : a.c[col2] - sum;
-        }
-        __syncthreads();
-        if (t == 0) {
-            const int next = tile + stages * gridDim.x;
-            if (next < a.nTiles) {
-                // the stage was written through the generic proxy (products); order those
-                // writes before the async-proxy bulk copies that refill it
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(next, s);
-            }
+        __syncwarp();
+        if (lane == 0) {
+            const int next = tile + 2 * totalWarps;
+            if (next < a.nTiles) issue(next, s);
         }
     }
 }
@@ -239,30 +241,34 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
         a.phase1 = phase == DIPGPU_PHASE_PRICE1 ? 1 : 0;
         a.out = c->dRedCost;
         const int sms = c->smCount > 0 ? c->smCount : 148;
+        const size_t maxSmem = 227 * 1024;
         const size_t uBytes = (((size_t)a.uLen + 1) & ~(size_t)1) * 8;
-        const size_t withU = kSpmvHdrBytes + 2 * (size_t)kSpmvStageBytes + uBytes;
-        // u in shared memory pays when it is gathered irregularly and re-used: more stored
-        // entries than a few times the dual vector, and the copy fits beside two stages
-        const bool uSmem = withU <= 227 * 1024 && c->nnz >= 8 * (int64_t)a.uLen && c->nSpmvTiles >= 2 * sms;
+        // u in shared memory pays when it is gathered irregularly and re-used: many more stored
+        // entries than duals, and at least 6 warp pipelines fit beside the copy
+        int warpsU = uBytes < maxSmem ? (int)((maxSmem - uBytes) / kSpmvWarpBytes) : 0;
+        warpsU = std::min(warpsU, 16);
+        const bool uSmem = warpsU >= 6 && c->nnz >= 8 * (int64_t)a.uLen && c->nSpmvTiles >= 4 * sms * warpsU;
         if (uSmem) {
-            a.stages = 2;
-            if (!c->spmvAttrU) {
-                DIPGPU_CUDA(c, cudaFuncSetAttribute(redcost_stream_kernel<true, 1024>,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                c->spmvAttrU = true;
-            }
-            const int grid = std::min(c->nSpmvTiles, sms);
-            redcost_stream_kernel<true, 1024><<<grid, 1024, withU, st>>>(a);
-        } else {
-            a.stages = 3;
-            const size_t bytes = kSpmvHdrBytes + 3 * (size_t)kSpmvStageBytes;
-            if (!c->spmvAttr) {
-                DIPGPU_CUDA(c, cudaFuncSetAttribute(redcost_stream_kernel<false, 512>,
+            a.uSmemBytes = (int)uBytes;
+            const size_t bytes = uBytes + (size_t)warpsU * kSpmvWarpBytes;
+            if (c->spmvAttrU != (int)bytes) {
+                DIPGPU_CUDA(c, cudaFuncSetAttribute(redcost_stream_kernel<true>,
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-                c->spmvAttr = true;
+                c->spmvAttrU = (int)bytes;
             }
-            const int grid = std::min(c->nSpmvTiles, 2 * sms);
-            redcost_stream_kernel<false, 512><<<grid, 512, bytes, st>>>(a);
+            redcost_stream_kernel<true><<<sms, warpsU * 32, bytes, st>>>(a);
+        } else {
+            a.uSmemBytes = 0;
+            const int warps = 8;
+            const size_t bytes = (size_t)warps * kSpmvWarpBytes;
+            if (c->spmvAttr != (int)bytes) {
+                DIPGPU_CUDA(c, cudaFuncSetAttribute(redcost_stream_kernel<false>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                c->spmvAttr = (int)bytes;
+            }
+            const int ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(4, maxSmem / bytes));
+            const int grid = std::max(1, std::min((c->nSpmvTiles + warps - 1) / warps, ctasPerSm * sms));
+            redcost_stream_kernel<false><<<grid, warps * 32, bytes, st>>>(a);
         }
         c->launches++;
         DIPGPU_CUDA(c, cudaGetLastError());

@@ -217,7 +217,7 @@ def test_spmv_random_csr_with_cuts(oracle, pricer):
 
 
 def test_spmv_long_column_fallback(oracle, pricer):
-    """A column with more stored entries than one tile (3072) switches the whole sweep to the
+    """A column with more stored entries than one warp tile (384) switches the whole sweep to the
     lane-cooperative kernel; parity is then the 1e-12 tolerance."""
     rng = np.random.default_rng(10)
     R, N, m = 5000, 64, 2
