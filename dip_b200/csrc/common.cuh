@@ -106,7 +106,7 @@ struct Ctx {
     double *dVal = nullptr;         // nnz
     int spmvLanes = 0;              // 0 = auto (stream kernel when every column fits a tile)
     int32_t *dColStart32 = nullptr; // N+1 (only when nnz < 2^31)
-    int32_t *dTileCol = nullptr;    // nSpmvTiles+1 column boundaries of the stream kernel's tiles
+    int32_t *dTileRec = nullptr;    // nSpmvTiles x {first col, end col, aligned first entry, entries} (int4)
     int nSpmvTiles = 0;             // 0 = stream kernel not applicable
     int spmvAttr = 0, spmvAttrU = 0;  // shared-memory limits already set on the two kernels
 

@@ -106,9 +106,18 @@ static int uploadCore(Ctx *c)
         }
         if (ok) {
             if ((rc = devAlloc(c, &c->dColStart32, (size_t)N + 1))) return rc;
-            if ((rc = devAlloc(c, &c->dTileCol, tileCol.size()))) return rc;
+            const size_t nt = tileCol.size() - 1;
+            std::vector<int32_t> rec(4 * std::max<size_t>(nt, 1));
+            for (size_t k = 0; k < nt; ++k) {
+                const int32_t a0 = cs32[tileCol[k]] & ~3;
+                rec[4 * k + 0] = tileCol[k];
+                rec[4 * k + 1] = tileCol[k + 1];
+                rec[4 * k + 2] = a0;
+                rec[4 * k + 3] = cs32[tileCol[k + 1]] - a0;
+            }
+            if ((rc = devAlloc(c, &c->dTileRec, rec.size()))) return rc;
             DIPGPU_CUDA(c, cudaMemcpy(c->dColStart32, cs32.data(), sizeof(int32_t) * cs32.size(), cudaMemcpyHostToDevice));
-            DIPGPU_CUDA(c, cudaMemcpy(c->dTileCol, tileCol.data(), sizeof(int32_t) * tileCol.size(), cudaMemcpyHostToDevice));
+            DIPGPU_CUDA(c, cudaMemcpy(c->dTileRec, rec.data(), sizeof(int32_t) * rec.size(), cudaMemcpyHostToDevice));
             c->nSpmvTiles = (int)tileCol.size() - 1;
         }
     }
@@ -328,7 +337,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (!c) return DIPGPU_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    devFree(&c->dDoneCounter); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileCol); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
+    devFree(&c->dDoneCounter); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
     devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems);
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);

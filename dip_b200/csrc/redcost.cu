@@ -45,7 +45,7 @@ __device__ __forceinline__ void rcMbarWait(uint64_t *bar, uint32_t parity)
 
 struct StreamArgs {
     int nTiles;
-    const int32_t *tileCol;     // nTiles+1 column boundaries
+    const int4 *tileRec;        // per tile {first column, end column, 4-aligned first entry, entries from there}
     const int32_t *colStart32;  // N+1
     const int32_t *rowMaster;   // per stored entry: MASTER dual index of its row
     const double *val;
@@ -61,12 +61,34 @@ constexpr int kSpmvStageValBytes = (kSpmvChunk + 4) * 8;
 constexpr int kSpmvStageBytes = kSpmvStageValBytes + (kSpmvChunk + 4) * 4;  // multiple of 16
 constexpr int kSpmvWarpBytes = 16 + 2 * kSpmvStageBytes;                    // 2 mbarriers + 2 stages
 
+struct ColMeta {  // one lane's columns of a tile
+    int b[kSpmvColsPerLane], e[kSpmvColsPerLane];
+    double cj[kSpmvColsPerLane];
+};
+
+__device__ __forceinline__ void loadColMeta(const StreamArgs &a, const int4 rec, int lane, ColMeta &m)
+{
+#pragma unroll
+    for (int q = 0; q < kSpmvColsPerLane; ++q) {
+        const int col = rec.x + lane + 32 * q;
+        m.b[q] = m.e[q] = 0;
+        m.cj[q] = 0.0;
+        if (col < rec.y) {
+            m.b[q] = __ldg(a.colStart32 + col) - rec.z;
+            m.e[q] = __ldg(a.colStart32 + col + 1) - rec.z;
+            if (!a.phase1) m.cj[q] = __ldg(a.c + col);
+        }
+    }
+}
+
 // Every WARP owns a two-stage TMA pipeline over its own tiles (<= 32*kSpmvColsPerLane
 // consecutive columns, <= kSpmvChunk stored entries): lane 0 issues the bulk copies of the
 // (value, row) streams of tile k+2 while the warp reduces tile k out of shared memory, one
-// lane per column, sequentially in storage order.  No CTA-wide barrier in the loop.
-// U_SMEM keeps the whole dual vector in shared memory (it is gathered once per stored
-// entry; from L1 a random 8-byte gather costs a wavefront per lane).
+// lane per column, sequentially in storage order.  The per-tile record and the per-column
+// extents / objective entries of tile k+1 are fetched into registers while tile k is being
+// reduced, so no cold global load sits on the warp's critical path; there is no CTA-wide
+// barrier in the loop.  U_SMEM keeps the whole dual vector in shared memory (it is gathered
+// once per stored entry; from L1 a random 8-byte gather costs a wavefront per lane).
 template <bool U_SMEM>
 __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_constant__ StreamArgs a)
 {
@@ -79,13 +101,11 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
     const int warpsPerCta = blockDim.x >> 5;
     const int gw = blockIdx.x * warpsPerCta + warp;
     const int totalWarps = gridDim.x * warpsPerCta;
+    const int4 none = make_int4(0, 0, 0, 0);
 
-    auto issue = [&](int tile, int s) {
-        const int c0 = a.tileCol[tile], c1 = a.tileCol[tile + 1];
-        const int k0 = a.colStart32[c0], k1 = a.colStart32[c1];
-        const int a0 = k0 & ~3;  // 16-byte aligned start for both streams
-        const int len = k1 - a0;
+    auto issue = [&](const int4 rec, int s) {
         uint64_t *bar = full + s;
+        const int len = rec.w;
         if (len > 0) {
             double *dv = reinterpret_cast<double *>(stageBase + (size_t)s * kSpmvStageBytes);
             int32_t *dr = reinterpret_cast<int32_t *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
@@ -97,25 +117,31 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                     rcSmemAddr(dv)),
-                "l"(a.val + a0), "r"(bytesVal), "r"(rcSmemAddr(bar))
+                "l"(a.val + rec.z), "r"(bytesVal), "r"(rcSmemAddr(bar))
                 : "memory");
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                     rcSmemAddr(dr)),
-                "l"(a.rowMaster + a0), "r"(bytesRow), "r"(rcSmemAddr(bar))
+                "l"(a.rowMaster + rec.z), "r"(bytesRow), "r"(rcSmemAddr(bar))
                 : "memory");
         } else {
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rcSmemAddr(bar)) : "memory");
         }
     };
 
+    // tile records: cur = tile being reduced, nxt = the one after (already in flight),
+    // nn = two ahead (issued when cur's stage is free)
+    int4 cur = gw < a.nTiles ? __ldg(a.tileRec + gw) : none;
+    int4 nxt = gw + totalWarps < a.nTiles ? __ldg(a.tileRec + gw + totalWarps) : none;
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full)), "r"(1));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full + 1)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (gw < a.nTiles) issue(gw, 0);
-        if (gw + totalWarps < a.nTiles) issue(gw + totalWarps, 1);
+        if (gw < a.nTiles) issue(cur, 0);
+        if (gw + totalWarps < a.nTiles) issue(nxt, 1);
     }
+    ColMeta mc;
+    loadColMeta(a, cur, lane, mc);
     if (U_SMEM) {
         double *w = const_cast<double *>(sU);
         for (int k = t; k < a.uLen; k += blockDim.x) w[k] = __ldg(a.u + k);
@@ -131,31 +157,19 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
         const double *sVal = reinterpret_cast<const double *>(stageBase + (size_t)s * kSpmvStageBytes);
         const int32_t *sRow =
             reinterpret_cast<const int32_t *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
-        const int c0 = a.tileCol[tile], c1 = a.tileCol[tile + 1];
-        const int a0 = a.colStart32[c0] & ~3;
-        // this lane's columns of the tile: extents and objective do not depend on the staged
-        // data, so these loads overlap the wait for the bulk copies
-        int cb[kSpmvColsPerLane], ce[kSpmvColsPerLane];
-        double cj[kSpmvColsPerLane];
-#pragma unroll
-        for (int q = 0; q < kSpmvColsPerLane; ++q) {
-            const int col = c0 + lane + 32 * q;
-            cb[q] = ce[q] = 0;
-            cj[q] = 0.0;
-            if (col < c1) {
-                cb[q] = a.colStart32[col] - a0;
-                ce[q] = a.colStart32[col + 1] - a0;
-                if (!a.phase1) cj[q] = a.c[col];
-            }
-        }
+        // prefetch (registers) what the next two tiles need; consumed after this tile is done
+        const int tn = tile + totalWarps, tnn = tile + 2 * totalWarps;
+        const int4 nn = tnn < a.nTiles ? __ldg(a.tileRec + tnn) : none;
+        ColMeta mn;
+        loadColMeta(a, nxt, lane, mn);  // nxt is {0,0,0,0} past the end: no loads
         rcMbarWait(full + s, parity);
 #pragma unroll
         for (int q = 0; q < kSpmvColsPerLane; ++q) {
-            const int col = c0 + lane + 32 * q;
-            if (col < c1) {
+            const int col = cur.x + lane + 32 * q;
+            if (col < cur.y) {
                 // y[col] += u[i]*a in storage order, multiply and add unfused (the reference's scatter)
-                int k = cb[q];
-                const int e = ce[q];
+                int k = mc.b[q];
+                const int e = mc.e[q];
                 double sum = 0.0, g = 0.0, v = 0.0;
                 if (k < e) {
                     const int r = sRow[k];
@@ -172,14 +186,15 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
                     }
                     sum = __dadd_rn(sum, prod);
                 }
-                a.out[col] = a.phase1 ? -sum : cj[q] - sum;  // DecompAlgo.cpp:4538-4545
+                a.out[col] = a.phase1 ? -sum : mc.cj[q] - sum;  // DecompAlgo.cpp:4538-4545
             }
         }
         __syncwarp();
-        if (lane == 0) {
-            const int next = tile + 2 * totalWarps;
-            if (next < a.nTiles) issue(next, s);
-        }
+        if (lane == 0 && tnn < a.nTiles) issue(nn, s);
+        (void)tn;
+        cur = nxt;
+        nxt = nn;
+        mc = mn;
     }
 }
 
@@ -231,7 +246,7 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
     if (c->nSpmvTiles > 0 && c->spmvLanes == 0) {
         StreamArgs a;
         a.nTiles = c->nSpmvTiles;
-        a.tileCol = c->dTileCol;
+        a.tileRec = reinterpret_cast<const int4 *>(c->dTileRec);
         a.colStart32 = c->dColStart32;
         a.rowMaster = c->dRowMaster;
         a.val = c->dVal;
