@@ -61,11 +61,13 @@ constexpr int kSpmvStageValBytes = (kSpmvChunk + 4) * 8;
 constexpr int kSpmvStageBytes = kSpmvStageValBytes + (kSpmvChunk + 4) * 4;  // multiple of 16
 constexpr int kSpmvWarpBytes = 16 + 2 * kSpmvStageBytes;                    // 2 mbarriers + 2 stages
 
-struct ColMeta {  // one lane's columns of a tile
-    int b[kSpmvColsPerLane], e[kSpmvColsPerLane];
+struct ColMeta {  // one lane's columns of a tile: RAW loaded values, consumed one tile later
+    int b[kSpmvColsPerLane], e[kSpmvColsPerLane];  // colStart32[col], colStart32[col+1]
     double cj[kSpmvColsPerLane];
 };
 
+// Only issues the loads: nothing here may depend on their results (a warp issues in order,
+// so the first dependent instruction would stall everything behind it).
 __device__ __forceinline__ void loadColMeta(const StreamArgs &a, const int4 rec, int lane, ColMeta &m)
 {
 #pragma unroll
@@ -74,8 +76,8 @@ __device__ __forceinline__ void loadColMeta(const StreamArgs &a, const int4 rec,
         m.b[q] = m.e[q] = 0;
         m.cj[q] = 0.0;
         if (col < rec.y) {
-            m.b[q] = __ldg(a.colStart32 + col) - rec.z;
-            m.e[q] = __ldg(a.colStart32 + col + 1) - rec.z;
+            m.b[q] = __ldg(a.colStart32 + col);
+            m.e[q] = __ldg(a.colStart32 + col + 1);
             if (!a.phase1) m.cj[q] = __ldg(a.c + col);
         }
     }
@@ -143,9 +145,29 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
     ColMeta mc;
     loadColMeta(a, cur, lane, mc);
     if (U_SMEM) {
+        // the dual vector: one bulk copy (16-byte granules) + a plain tail, on its own mbarrier
+        uint64_t *ubar = reinterpret_cast<uint64_t *>(sm + a.uSmemBytes - 16);
         double *w = const_cast<double *>(sU);
-        for (int k = t; k < a.uLen; k += blockDim.x) w[k] = __ldg(a.u + k);
+        const int bulk = (reinterpret_cast<uintptr_t>(a.u) & 15u) == 0 ? (a.uLen & ~1) : 0;
+        if (t == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(ubar)), "r"(1));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if (bulk > 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rcSmemAddr(ubar)),
+                             "r"((uint32_t)bulk * 8u)
+                             : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        rcSmemAddr(w)),
+                    "l"(a.u), "r"((uint32_t)bulk * 8u), "r"(rcSmemAddr(ubar))
+                    : "memory");
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rcSmemAddr(ubar)) : "memory");
+            }
+        }
+        for (int k = bulk + t; k < a.uLen; k += blockDim.x) w[k] = __ldg(a.u + k);
         __syncthreads();
+        rcMbarWait(ubar, 0);
     } else {
         __syncwarp();
     }
@@ -168,8 +190,8 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
             const int col = cur.x + lane + 32 * q;
             if (col < cur.y) {
                 // y[col] += u[i]*a in storage order, multiply and add unfused (the reference's scatter)
-                int k = mc.b[q];
-                const int e = mc.e[q];
+                int k = mc.b[q] - cur.z;
+                const int e = mc.e[q] - cur.z;
                 double sum = 0.0, g = 0.0, v = 0.0;
                 if (k < e) {
                     const int r = sRow[k];
@@ -257,7 +279,7 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
         a.out = c->dRedCost;
         const int sms = c->smCount > 0 ? c->smCount : 148;
         const size_t maxSmem = 227 * 1024;
-        const size_t uBytes = (((size_t)a.uLen + 1) & ~(size_t)1) * 8;
+        const size_t uBytes = (((size_t)a.uLen + 1) & ~(size_t)1) * 8 + 16;  // + the u mbarrier
         // u in shared memory pays when it is gathered irregularly and re-used: many more stored
         // entries than duals, and at least 6 warp pipelines fit beside the copy
         int warpsU = uBytes < maxSmem ? (int)((maxSmem - uBytes) / kSpmvWarpBytes) : 0;
