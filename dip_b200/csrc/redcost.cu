@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
             reinterpret_cast<const int32_t *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
         // prefetch (registers) what the next two tiles need; consumed after this tile is done
         const int tn = tile + totalWarps, tnn = tile + 2 * totalWarps;
-        const int4 nn = tnn < a.nTiles ? __ldg(a.tileRec + tnn) : none;
+        // unconditional (clamped) load: a select on the result would stall the warp right here
+        const int4 nn = __ldg(a.tileRec + min(tnn, a.nTiles - 1));
         ColMeta mn;
         loadColMeta(a, nxt, lane, mn);  // nxt is {0,0,0,0} past the end: no loads
         rcMbarWait(full + s, parity);
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
         if (lane == 0 && tnn < a.nTiles) issue(nn, s);
         (void)tn;
         cur = nxt;
-        nxt = nn;
+        nxt = tnn < a.nTiles ? nn : none;
         mc = mn;
     }
 }
