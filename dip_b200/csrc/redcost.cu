@@ -13,8 +13,8 @@
 // Main kernel (redcost_stream_kernel): the columns are cut on the host into
 // tiles of at most kSpmvChunk stored entries; a warp pulls its tile's (value,
 // row) stream into shared memory with two TMA bulk copies (double-buffered),
-// and one lane per column multiplies by the gathered duals and adds that
-// column's products SEQUENTIALLY in storage order.  Entries are stored per column in
+// all lanes multiply by the gathered duals in place, and then one lane per
+// column adds that column's products SEQUENTIALLY in storage order.  Entries are stored per column in
 // DESCENDING row order and the arithmetic is an unfused multiply followed by an
 // add, i.e. exactly the order and rounding of the reference's row-major scatter
 // (rows R-1..0, y[col] += u[i]*a), so the reduced costs are bit-identical to the
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
     for (int tile = gw; tile < a.nTiles; tile += totalWarps, ++it) {
         const int s = it & 1;
         const uint32_t parity = (uint32_t)((it >> 1) & 1);
-        const double *sVal = reinterpret_cast<const double *>(stageBase + (size_t)s * kSpmvStageBytes);
+        double *sVal = reinterpret_cast<double *>(stageBase + (size_t)s * kSpmvStageBytes);
         const int32_t *sRow =
             reinterpret_cast<const int32_t *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
         // prefetch (registers) what the next two tiles need; consumed after this tile is done
@@ -186,32 +186,51 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
         ColMeta mn;
         loadColMeta(a, nxt, lane, mn);  // nxt is {0,0,0,0} past the end: no loads
         rcMbarWait(full + s, parity);
+        // phase 1, all lanes, coalesced: products u[i]*a in place (unfused multiply, as the
+        // reference's  y += u*a).  Entries in front of the tile's first column (alignment pad)
+        // are real entries of the previous column, so their rows are valid.
+        {
+            const int len = cur.w;
+            int k = lane;
+            for (; k + 96 < len; k += 128) {
+                int r[4];
+                double v[4], g[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r[j] = sRow[k + 32 * j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = sVal[k + 32 * j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g[j] = U_SMEM ? sU[r[j]] : __ldg(a.u + r[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sVal[k + 32 * j] = __dmul_rn(g[j], v[j]);
+            }
+            for (; k < len; k += 32) {
+                const int r = sRow[k];
+                sVal[k] = __dmul_rn(U_SMEM ? sU[r] : __ldg(a.u + r), sVal[k]);
+            }
+        }
+        __syncwarp();
+        // phase 2, one lane per column: add the products sequentially in storage order
 #pragma unroll
         for (int q = 0; q < kSpmvColsPerLane; ++q) {
             const int col = cur.x + lane + 32 * q;
             if (col < cur.y) {
-                // y[col] += u[i]*a in storage order, multiply and add unfused (the reference's scatter)
                 int k = mc.b[q] - cur.z;
                 const int e = mc.e[q] - cur.z;
-                double sum = 0.0, g = 0.0, v = 0.0;
-                if (k < e) {
-                    const int r = sRow[k];
-                    v = sVal[k];
-                    g = U_SMEM ? sU[r] : __ldg(a.u + r);
-                }
+                double sum = 0.0;
+                double p = sVal[k];  // the stage has 4 entries of slack: reading one past is safe
                 while (k < e) {
-                    const double prod = __dmul_rn(g, v);
+                    const double pn = sVal[k + 1];
+                    sum = __dadd_rn(sum, p);
+                    p = pn;
                     ++k;
-                    if (k < e) {
-                        const int r = sRow[k];
-                        v = sVal[k];
-                        g = U_SMEM ? sU[r] : __ldg(a.u + r);
-                    }
-                    sum = __dadd_rn(sum, prod);
                 }
                 a.out[col] = a.phase1 ? -sum : mc.cj[q] - sum;  // DecompAlgo.cpp:4538-4545
             }
         }
+        // the stage was written through the generic proxy; order that before the bulk copy
+        // (async proxy) that refills it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0 && tnn < a.nTiles) issue(nn, s);
         (void)tn;
