@@ -70,7 +70,8 @@ constexpr int kFuseFilterMaxBlocks = 256;
 
 // ---------------------------------------------------------------- SpMV tiling
 constexpr int kSpmvChunk = 384;        // stored entries per warp tile (4.5 KiB of shared memory per stage)
-constexpr int kSpmvColsPerLane = 4;    // a warp tile spans at most 32*4 consecutive columns
+constexpr int kSpmvColsPerLane = 4;    // a warp tile spans at most 32*4 consecutive columns (fewer when the
+                                       // kSpmvChunk entry budget is reached first)
 
 // ------------------------------------------------------------------ DP geometry
 //
@@ -108,7 +109,10 @@ struct Ctx {
     int32_t *dColStart32 = nullptr; // N+1 (only when nnz < 2^31)
     int32_t *dTileRec = nullptr;    // nSpmvTiles x {first col, end col, aligned first entry, entries} (int4)
     int nSpmvTiles = 0;             // 0 = stream kernel not applicable
-    int spmvAttr = 0, spmvAttrU = 0;  // shared-memory limits already set on the two kernels
+    int optSpmvWarps = 0, optSpmvUSmem = -1;  // diagnostics knobs
+    void *spmvFn = nullptr;                   // kernel whose shared-memory limit is already set
+    size_t spmvFnSmem = 0;
+    uint16_t *dRowMaster16 = nullptr;         // rowMaster as uint16 when R + numConvex <= 65536
 
     double *dObj = nullptr;  // c[N]
     bool haveObj = false;

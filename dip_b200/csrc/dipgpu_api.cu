@@ -89,15 +89,14 @@ static int uploadCore(Ctx *c)
         std::vector<int32_t> tileCol;
         std::vector<int32_t> cs32((size_t)N + 1);
         for (int j = 0; j <= N; ++j) cs32[j] = (int32_t)colStart[j];
-        const double avg = (double)nnz / (double)N;
-        int cpl = avg > 0 ? (int)((double)kSpmvChunk / (32.0 * avg)) : kSpmvColsPerLane;
-        cpl = std::max(1, std::min(cpl, kSpmvColsPerLane));
-        const int maxCols = 32 * cpl;
+        const bool row16 = (int64_t)R + c->numConvex <= 65536;
+        const int64_t alignMask = row16 ? 7 : 3;  // 16 bytes of the row stream
+        const int maxCols = 32 * kSpmvColsPerLane;
         bool ok = true;
         int j = 0;
         tileCol.push_back(0);
         while (j < N) {
-            const int64_t a0 = colStart[j] & ~(int64_t)3;
+            const int64_t a0 = colStart[j] & ~alignMask;
             int e = j;
             while (e < N && e - j < maxCols && colStart[e + 1] - a0 <= kSpmvChunk) ++e;
             if (e == j) { ok = false; break; }  // a single column longer than a tile
@@ -109,7 +108,7 @@ static int uploadCore(Ctx *c)
             const size_t nt = tileCol.size() - 1;
             std::vector<int32_t> rec(4 * std::max<size_t>(nt, 1));
             for (size_t k = 0; k < nt; ++k) {
-                const int32_t a0 = cs32[tileCol[k]] & ~3;
+                const int32_t a0 = cs32[tileCol[k]] & ~(int32_t)alignMask;
                 rec[4 * k + 0] = tileCol[k];
                 rec[4 * k + 1] = tileCol[k + 1];
                 rec[4 * k + 2] = a0;
@@ -118,6 +117,13 @@ static int uploadCore(Ctx *c)
             if ((rc = devAlloc(c, &c->dTileRec, rec.size()))) return rc;
             DIPGPU_CUDA(c, cudaMemcpy(c->dColStart32, cs32.data(), sizeof(int32_t) * cs32.size(), cudaMemcpyHostToDevice));
             DIPGPU_CUDA(c, cudaMemcpy(c->dTileRec, rec.data(), sizeof(int32_t) * rec.size(), cudaMemcpyHostToDevice));
+            devFree(&c->dRowMaster16);
+            if (row16) {
+                std::vector<uint16_t> r16((size_t)nnz + 16, 0);
+                for (int64_t k = 0; k < nnz; ++k) r16[k] = (uint16_t)rowMaster[k];
+                if ((rc = devAlloc(c, &c->dRowMaster16, r16.size()))) return rc;
+                DIPGPU_CUDA(c, cudaMemcpy(c->dRowMaster16, r16.data(), sizeof(uint16_t) * r16.size(), cudaMemcpyHostToDevice));
+            }
             c->nSpmvTiles = (int)tileCol.size() - 1;
         }
     }
@@ -337,7 +343,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (!c) return DIPGPU_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    devFree(&c->dDoneCounter); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
+    devFree(&c->dDoneCounter); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
     devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems);
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
@@ -708,6 +714,8 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!c || !name) return DIPGPU_ERR_INVALID;
     if (!strcmp(name, "stage_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "spmv_lanes")) { c->spmvLanes = (int)value; return DIPGPU_OK; }
+    if (!strcmp(name, "spmv_warps")) { c->optSpmvWarps = (int)value; return DIPGPU_OK; }
+    if (!strcmp(name, "spmv_u_smem")) { c->optSpmvUSmem = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "dp_threads") || !strcmp(name, "dp_cells_per_thread") || !strcmp(name, "dp_items_per_step") ||
         !strcmp(name, "dp_no_guard") || !strcmp(name, "fuse_filter")) {
         if (!strcmp(name, "dp_threads")) c->optThreads = (int)value;

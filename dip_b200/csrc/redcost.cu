@@ -21,6 +21,7 @@
 // CPU restatement, not merely within 1e-12.  Matrices with a column longer than
 // one tile fall back to the lane-cooperative kernel below (tolerance parity).
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -47,7 +48,7 @@ struct StreamArgs {
     int nTiles;
     const int4 *tileRec;        // per tile {first column, end column, 4-aligned first entry, entries from there}
     const int32_t *colStart32;  // N+1
-    const int32_t *rowMaster;   // per stored entry: MASTER dual index of its row
+    const void *rowMaster;      // per stored entry: MASTER dual index of its row (int32, or uint16 if ROW16)
     const double *val;
     const double *u;
     int uLen;
@@ -57,9 +58,15 @@ struct StreamArgs {
     int uSmemBytes;             // 0: gather the duals from global memory
 };
 
-constexpr int kSpmvStageValBytes = (kSpmvChunk + 4) * 8;
-constexpr int kSpmvStageBytes = kSpmvStageValBytes + (kSpmvChunk + 4) * 4;  // multiple of 16
-constexpr int kSpmvWarpBytes = 16 + 2 * kSpmvStageBytes;                    // 2 mbarriers + 2 stages
+// A stage holds up to kSpmvChunk entries counted from the aligned start (alignment: 16 bytes
+// of the row stream = 4 int32 or 8 uint16 entries) plus that much slack.
+template <bool ROW16> struct SpmvStage {
+    static constexpr int kAlign = ROW16 ? 8 : 4;
+    static constexpr int kValBytes = (kSpmvChunk + kAlign) * 8;
+    static constexpr int kRowBytes = (kSpmvChunk + kAlign) * (ROW16 ? 2 : 4);
+    static constexpr int kBytes = kValBytes + kRowBytes;  // multiple of 16
+    static constexpr int kWarpBytes = 16 + 2 * kBytes;    // 2 mbarriers + 2 stages
+};
 
 struct ColMeta {  // one lane's columns of a tile: RAW loaded values, consumed one tile later
     int b[kSpmvColsPerLane], e[kSpmvColsPerLane];  // colStart32[col], colStart32[col+1]
@@ -91,9 +98,13 @@ __device__ __forceinline__ void loadColMeta(const StreamArgs &a, const int4 rec,
 // reduced, so no cold global load sits on the warp's critical path; there is no CTA-wide
 // barrier in the loop.  U_SMEM keeps the whole dual vector in shared memory (it is gathered
 // once per stored entry; from L1 a random 8-byte gather costs a wavefront per lane).
-template <bool U_SMEM>
+template <bool U_SMEM, bool ROW16>
 __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_constant__ StreamArgs a)
 {
+    typedef SpmvStage<ROW16> St;
+    typedef typename std::conditional<ROW16, uint16_t, int32_t>::type RowT;
+    constexpr int kSpmvStageBytes = St::kBytes, kSpmvStageValBytes = St::kValBytes, kSpmvWarpBytes = St::kWarpBytes;
+    const RowT *gRow = static_cast<const RowT *>(a.rowMaster);
     extern __shared__ __align__(16) unsigned char sm[];
     const double *sU = reinterpret_cast<const double *>(sm);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -110,9 +121,9 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
         const int len = rec.w;
         if (len > 0) {
             double *dv = reinterpret_cast<double *>(stageBase + (size_t)s * kSpmvStageBytes);
-            int32_t *dr = reinterpret_cast<int32_t *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
+            RowT *dr = reinterpret_cast<RowT *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
             const uint32_t bytesVal = (uint32_t)(((len + 1) & ~1) * 8);
-            const uint32_t bytesRow = (uint32_t)(((len + 3) & ~3) * 4);
+            const uint32_t bytesRow = (uint32_t)(((len + St::kAlign - 1) & ~(St::kAlign - 1)) * sizeof(RowT));
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rcSmemAddr(bar)),
                          "r"(bytesVal + bytesRow)
                          : "memory");
@@ -124,7 +135,7 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                     rcSmemAddr(dr)),
-                "l"(a.rowMaster + rec.z), "r"(bytesRow), "r"(rcSmemAddr(bar))
+                "l"(gRow + rec.z), "r"(bytesRow), "r"(rcSmemAddr(bar))
                 : "memory");
         } else {
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rcSmemAddr(bar)) : "memory");
@@ -177,8 +188,8 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
         const int s = it & 1;
         const uint32_t parity = (uint32_t)((it >> 1) & 1);
         double *sVal = reinterpret_cast<double *>(stageBase + (size_t)s * kSpmvStageBytes);
-        const int32_t *sRow =
-            reinterpret_cast<const int32_t *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
+        const RowT *sRow =
+            reinterpret_cast<const RowT *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
         // prefetch (registers) what the next two tiles need; consumed after this tile is done
         const int tn = tile + totalWarps, tnn = tile + 2 * totalWarps;
         // unconditional (clamped) load: a select on the result would stall the warp right here
@@ -290,7 +301,6 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
         a.nTiles = c->nSpmvTiles;
         a.tileRec = reinterpret_cast<const int4 *>(c->dTileRec);
         a.colStart32 = c->dColStart32;
-        a.rowMaster = c->dRowMaster;
         a.val = c->dVal;
         a.u = dU;
         a.uLen = c->R + c->numConvex;
@@ -299,34 +309,42 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
         a.out = c->dRedCost;
         const int sms = c->smCount > 0 ? c->smCount : 148;
         const size_t maxSmem = 227 * 1024;
+        const bool row16 = c->dRowMaster16 != nullptr;
+        a.rowMaster = row16 ? static_cast<const void *>(c->dRowMaster16) : static_cast<const void *>(c->dRowMaster);
+        const size_t warpBytes = row16 ? SpmvStage<true>::kWarpBytes : SpmvStage<false>::kWarpBytes;
         const size_t uBytes = (((size_t)a.uLen + 1) & ~(size_t)1) * 8 + 16;  // + the u mbarrier
         // u in shared memory pays when it is gathered irregularly and re-used: many more stored
         // entries than duals, and at least 6 warp pipelines fit beside the copy
-        int warpsU = uBytes < maxSmem ? (int)((maxSmem - uBytes) / kSpmvWarpBytes) : 0;
+        int warpsU = uBytes < maxSmem ? (int)((maxSmem - uBytes) / warpBytes) : 0;
         warpsU = std::min(warpsU, 16);
-        const bool uSmem = warpsU >= 6 && c->nnz >= 8 * (int64_t)a.uLen && c->nSpmvTiles >= 4 * sms * warpsU;
+        if (c->optSpmvWarps > 0) warpsU = std::min(warpsU, c->optSpmvWarps);
+        bool uSmem = warpsU >= 6 && c->nnz >= 8 * (int64_t)a.uLen && c->nSpmvTiles >= 4 * sms * warpsU;
+        if (c->optSpmvUSmem >= 0) uSmem = c->optSpmvUSmem != 0 && warpsU >= 1;
+        typedef void (*Fn)(const StreamArgs);
+        Fn fn;
+        size_t bytes;
+        int grid, threads;
         if (uSmem) {
             a.uSmemBytes = (int)uBytes;
-            const size_t bytes = uBytes + (size_t)warpsU * kSpmvWarpBytes;
-            if (c->spmvAttrU != (int)bytes) {
-                DIPGPU_CUDA(c, cudaFuncSetAttribute(redcost_stream_kernel<true>,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-                c->spmvAttrU = (int)bytes;
-            }
-            redcost_stream_kernel<true><<<sms, warpsU * 32, bytes, st>>>(a);
+            bytes = uBytes + (size_t)warpsU * warpBytes;
+            fn = row16 ? redcost_stream_kernel<true, true> : redcost_stream_kernel<true, false>;
+            grid = sms;
+            threads = warpsU * 32;
         } else {
             a.uSmemBytes = 0;
-            const int warps = 8;
-            const size_t bytes = (size_t)warps * kSpmvWarpBytes;
-            if (c->spmvAttr != (int)bytes) {
-                DIPGPU_CUDA(c, cudaFuncSetAttribute(redcost_stream_kernel<false>,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-                c->spmvAttr = (int)bytes;
-            }
+            const int warps = c->optSpmvWarps > 0 ? std::min(c->optSpmvWarps, 16) : 8;
+            bytes = (size_t)warps * warpBytes;
+            fn = row16 ? redcost_stream_kernel<false, true> : redcost_stream_kernel<false, false>;
             const int ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(4, maxSmem / bytes));
-            const int grid = std::max(1, std::min((c->nSpmvTiles + warps - 1) / warps, ctasPerSm * sms));
-            redcost_stream_kernel<false><<<grid, warps * 32, bytes, st>>>(a);
+            grid = std::max(1, std::min((c->nSpmvTiles + warps - 1) / warps, ctasPerSm * sms));
+            threads = warps * 32;
         }
+        if (c->spmvFn != (void *)fn || c->spmvFnSmem != bytes) {
+            DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            c->spmvFn = (void *)fn;
+            c->spmvFnSmem = bytes;
+        }
+        fn<<<grid, threads, bytes, st>>>(a);
         c->launches++;
         DIPGPU_CUDA(c, cudaGetLastError());
         return DIPGPU_OK;
