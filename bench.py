@@ -378,10 +378,11 @@ def sharded_rounds(dist, torch, dev, pr, model, u_dev, K, W, world, rank, flush_
     """One GAP-E round partitioned over the ranks: rank 0 owns the dual vector, ncclBroadcast(u),
     every rank prices its contiguous block range, all_gather of the packed per-shard results
     (fixed-size buffers), rank 0 decodes.  Strong scaling of a single round (latency-bound)."""
+    from dip_b200.sharding import block_range, merge_shards
     m = model.m
-    per = (m + world - 1) // world
-    first = min(rank * per, m)
-    count = max(0, min(per, m - first))
+    work = np.diff(model.block_col_start).astype(np.int64) * (model.capacity.astype(np.int64) + 1)
+    first, count = block_range(m, world, rank, work)
+    per = count
     pr.setBlockRange(first, count)
     dptr, nbytes = pr.resultDev()
     sizes = torch.tensor([nbytes], dtype=torch.int64, device=dev)
@@ -419,23 +420,22 @@ def sharded_rounds(dist, torch, dev, pr, model, u_dev, K, W, world, rank, flush_
         evs[k][1].record(stream)
     barrier()
     ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
-    # decode on rank 0 and check against the unsharded result
+    # decode on rank 0 (dipgpu_unpack_result per shard, merged in block order) and check the last
+    # round against the unsharded result of the same dual vector
     ok = None
     if rank == 0:
         host = recv.cpu().numpy()
-        total = RoundResult(m, m, model.N)
-        kept = 0
-        for r in range(world):
-            part = unpack_result(host[r * maxb:(r + 1) * maxb], m, model.N,
-                                 RoundResult(m, m, model.N))
-            kept += part.nCols
+        merged = merge_shards([host[r * maxb:(r + 1) * maxb] for r in range(world)], m, model.N)
         k_last = (K - 1) % len(u_dev)
         pr.setBlockRange(0, m)
-        full = pr.priceRound(u_dev[k_last].cpu().numpy(), redCostEps=RC_EPS, result=total)
-        ok = bool(kept == full.nCols)
+        full = pr.priceRound(u_dev[k_last].cpu().numpy(), redCostEps=RC_EPS, result=RoundResult(m, m, model.N))
+        ok = bool(merged.nCols == full.nCols and np.array_equal(merged.blockObj, full.blockObj)
+                  and np.array_equal(merged.blockRedCost, full.blockRedCost)
+                  and merged.mostNegReducedCost == full.mostNegReducedCost
+                  and np.array_equal(merged.colInd[:merged.c.nInd], full.colInd[:full.c.nInd]))
     return {"rounds_per_s": K / (ms * 1e-3), "ms_per_round": ms / K, "scaling": "strong",
             "blocks_per_gpu": per, "collectives": "ncclBroadcast(u, %d B) + ncclAllGather(%d B per rank)" % (
-                model.u_len * 8, maxb), "kept_columns_match_unsharded": ok}
+                model.u_len * 8, maxb), "merged_equals_unsharded": ok}
 
 
 def bench_csp(torch, dev, pr_unused, args, world, rank, barrier, max_over_ranks, smem_peak, flush_l2):

@@ -20,7 +20,7 @@ import numpy as np
 from . import capi
 from .capi import DipGpuError, PHASE_PRICE1, PHASE_PRICE2, PROFIT_FP64, PROFIT_PISINGER_INT  # noqa: F401
 
-DecompSolStatOptimal = 2   # Dip/src/Decomp.h:213-219 (DecompSolverStatus)
+DecompSolStatOptimal = 1   # Dip/src/Decomp.h:213-219 (DecompSolverStatus)
 DecompSolStatNoSolution = 4
 
 

@@ -1,0 +1,266 @@
+// dipgpu_decomp.hpp -- header-only C++17 adapter between DIP's pricing plugin surface and the
+// C ABI of libdipgpu (include/dipgpu.h).
+//
+// It mirrors, with the reference's names and semantics, the two surfaces a DIP application or
+// algorithm subclass can put the GPU pricing round behind:
+//
+//   * Pricer::generateVars(newVars, mostNegReducedCost)
+//       <-> virtual int DecompAlgo::generateVars(DecompVarList&, double&)
+//           (Dip/src/DecompAlgo.h:430, Dip/src/DecompAlgo.cpp:4622-5260)
+//   * Pricer::solveRelaxed(whichBlock, redCostX, target, varList)
+//       <-> virtual DecompSolverStatus DecompApp::solveRelaxed(const int, const double*,
+//           const double, DecompVarList&)  (Dip/src/DecompApp.h:344-349;
+//           GAP: Dip/examples/GAP/GAP_DecompApp.cpp:235-285)
+//
+// The variable type is a template parameter: inside DIP pass ::DecompVar / ::DecompVarList
+// (anything constructible from (std::vector<int>, std::vector<double>, redCost, origCost) with
+// setBlockId(int), Dip/src/DecompVar.h:217-239); without COIN-OR the stand-in dipgpu::DecompVar
+// below is used (tests/cpp).  Columns are allocated with `new` in the caller's C++ runtime, because
+// DIP takes ownership and deletes the ones it rejects (DecompAlgo.cpp:5225).
+//
+// Errors: like the reference (UtilException / CoinError) failures throw -- dipgpu::Error carries
+// the library's status code and message.  There is no CPU fallback.
+#ifndef DIPGPU_DECOMP_HPP
+#define DIPGPU_DECOMP_HPP
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <list>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "dipgpu.h"
+
+namespace dipgpu {
+
+// Dip/src/Decomp.h:213-219
+enum DecompSolverStatus {
+    DecompSolStatError,
+    DecompSolStatOptimal,
+    DecompSolStatFeasible,
+    DecompSolStatInfeasible,
+    DecompSolStatNoSolution
+};
+
+// Dip/src/Decomp.h:170-176 (the two pricing phases)
+enum DecompPhase { PHASE_PRICE1 = DIPGPU_PHASE_PRICE1, PHASE_PRICE2 = DIPGPU_PHASE_PRICE2 };
+
+// Stand-in for ::DecompVar when COIN-OR is not available: same constructor shape and accessors
+// (Dip/src/DecompVar.h:217-239, getOriginalCost/getReducedCost/getBlockId).
+struct DecompVar {
+    std::vector<int> ind;      // m_s indices, ascending (DecompVar.h:237 sortVar)
+    std::vector<double> els;   // m_s elements (1.0 for knapsack blocks)
+    double m_origCost;
+    double m_redCost;
+    int m_blockId;
+    DecompVar(const std::vector<int> &i, const std::vector<double> &e, double redCost, double origCost)
+        : ind(i), els(e), m_origCost(origCost), m_redCost(redCost), m_blockId(0) {}
+    void setBlockId(int b) { m_blockId = b; }
+    int getBlockId() const { return m_blockId; }
+    double getOriginalCost() const { return m_origCost; }
+    double getReducedCost() const { return m_redCost; }
+};
+typedef std::list<DecompVar *> DecompVarList;  // Dip/src/Decomp.h (std::list<DecompVar*>)
+
+class Error : public std::runtime_error {
+public:
+    Error(int code, const std::string &what) : std::runtime_error(what), m_code(code) {}
+    int code() const { return m_code; }
+
+private:
+    int m_code;
+};
+
+class Pricer {
+public:
+    explicit Pricer(int device = 0) : m_ctx(nullptr), m_m(0), m_N(0), m_nBlockCols(0), m_roundValid(false)
+    {
+        const int rc = dipgpu_create(&m_ctx, device);
+        if (rc != DIPGPU_OK)
+            throw Error(rc, "dipgpu_create failed: no usable sm_100 GPU (libdipgpu has no CPU fallback)");
+    }
+    ~Pricer() { dipgpu_destroy(m_ctx); }
+    Pricer(const Pricer &) = delete;
+    Pricer &operator=(const Pricer &) = delete;
+
+    dipgpu_ctx *ctx() { return m_ctx; }
+
+    // ---- model (what DecompAlgo holds when generateVars runs) -----------------------------
+    // modelCore->M: row-ordered A'' incl. branch rows (DecompConstraintSet.h:32, .cpp:41-43;
+    // DecompAlgo.cpp:1399-1502).  Start/index types are templates so CoinBigIndex/int arrays of a
+    // CoinPackedMatrix (getVectorStarts/getIndices/getElements) can be passed directly.
+    template <class StartT, class IndexT>
+    void setModelCore(int R, int N, const StartT *rowStart, const IndexT *colInd, const double *val,
+                      int nBaseRows, int numConvex)
+    {
+        std::vector<int64_t> rs(rowStart, rowStart + R + 1);
+        std::vector<int32_t> ci(colInd, colInd + rs[R]);
+        check(dipgpu_set_core_csr(m_ctx, R, N, rs.data(), ci.data(), val, nBaseRows, numConvex));
+        m_N = N;
+        m_roundValid = false;
+    }
+    template <class StartT, class IndexT>
+    void appendCoreRows(int nNew, const StartT *rowStart, const IndexT *colInd, const double *val)
+    {
+        std::vector<int64_t> rs(rowStart, rowStart + nNew + 1);
+        std::vector<int32_t> ci(colInd, colInd + rs[nNew]);
+        check(dipgpu_append_core_rows(m_ctx, nNew, rs.data(), ci.data(), val));
+        m_roundValid = false;
+    }
+    void setObjective(const double *c, int N)
+    {
+        check(dipgpu_set_objective(m_ctx, c, N));
+        if (N > m_N) m_N = N;
+    }
+    // One knapsack per block (GAP_DecompApp.cpp:52-58).
+    void setKnapsackBlocks(int m, const int *blockColStart, const int *weight, const int *capacity,
+                           int profitMode = DIPGPU_PROFIT_FP64)
+    {
+        check(dipgpu_set_knapsack_blocks(m_ctx, m, blockColStart, weight, capacity, profitMode));
+        m_m = m;
+        m_nBlockCols = blockColStart[m];
+        if (m_nBlockCols > m_N) m_N = m_nBlockCols;
+        allocResult();
+        m_roundValid = false;
+    }
+
+    // ---- surface 2: the whole round ------------------------------------------------------------
+    // DecompAlgo::generateVars: u = master duals (length R + numConvex), returns newVars.size().
+    // mostNegReducedCost = sum_b min(0, rc_b) in block order (DecompAlgo.cpp:5229-5232).
+    template <class VarT = DecompVar, class ListT = std::list<VarT *>>
+    int generateVars(const double *u, int uLen, int phase, double redCostEps, ListT &newVars,
+                     double &mostNegReducedCost)
+    {
+        check(dipgpu_price_round(m_ctx, u, uLen, phase, redCostEps, &m_cols, nullptr));
+        mostNegReducedCost = m_cols.mostNegReducedCost;
+        for (int k = 0; k < m_cols.nCols; ++k) newVars.push_back(makeVar<VarT>(k, m_colRedCost[k]));
+        return m_cols.nCols;
+    }
+
+    // ---- surface 1: one block at a time -------------------------------------------------------
+    // DecompApp::solveRelaxed.  Exactly one (possibly empty) column is pushed per call, its reduced
+    // cost EXCLUDING the convexity dual `target` -- DecompAlgo::solveRelaxed subtracts it
+    // (DecompAlgo.cpp:6350-6356) -- and DecompSolStatOptimal is returned
+    // (GAP_DecompApp.cpp:278-284).  All blocks of a round are solved in ONE GPU submission the
+    // first time a new reduced-cost vector is seen; the other calls of the round are served from
+    // that result.  A new round is recognised by (pointer, fingerprint of 64 sampled entries,
+    // block already served); call beginRound() to force it.  Thread-safe across different blocks
+    // only after the round's first call has returned (serialise that one, or use surface 2).
+    template <class VarT = DecompVar, class ListT = std::list<VarT *>>
+    DecompSolverStatus solveRelaxed(int whichBlock, const double *redCostX, double /*target*/,
+                                    ListT &varList)
+    {
+        if (whichBlock < 0 || whichBlock >= m_m) throw Error(DIPGPU_ERR_INVALID, "solveRelaxed: bad block");
+        const uint64_t fp = fingerprint(redCostX);
+        if (!m_roundValid || redCostX != m_roundPtr || fp != m_roundFp || m_served[(size_t)whichBlock]) {
+            std::vector<double> zero((size_t)m_m, 0.0);
+            check(dipgpu_solve_blocks(m_ctx, redCostX, zero.data(),
+                                      -std::numeric_limits<double>::infinity(), &m_cols));
+            m_roundValid = true;
+            m_roundPtr = redCostX;
+            m_roundFp = fp;
+            m_served.assign((size_t)m_m, 0);
+        }
+        m_served[(size_t)whichBlock] = 1;
+        // eps = -inf keeps every block, in block order: kept column k == block k
+        varList.push_back(makeVar<VarT>(whichBlock, m_blockRedCost[(size_t)whichBlock]));
+        return DecompSolStatOptimal;
+    }
+    void beginRound() { m_roundValid = false; }
+
+    // ---- stage (a) alone: generateVarsCalcRedCost (DecompAlgo.cpp:4506-4547) -------------------
+    void calcRedCost(const double *u, int uLen, int phase, double *redCostX)
+    {
+        check(dipgpu_calc_redcost(m_ctx, u, uLen, phase, redCostX));
+    }
+
+    // per-block results of the last round (length m): rc_b - alpha_b, min(0, .), c.s, knapsack optimum
+    const std::vector<double> &blockRedCost() const { return m_blockRedCost; }
+    const std::vector<double> &blockMostNegRC() const { return m_blockMostNeg; }
+    const std::vector<double> &blockOrigCost() const { return m_blockOrigCost; }
+    const std::vector<double> &blockObj() const { return m_blockObj; }
+    int64_t cells() const { return m_cols.cells; }
+
+private:
+    void check(int rc)
+    {
+        if (rc == DIPGPU_OK) return;
+        char buf[512];
+        dipgpu_last_error(m_ctx, buf, sizeof(buf));
+        throw Error(rc, std::string("libdipgpu: ") + buf);
+    }
+    void allocResult()
+    {
+        const size_t m = (size_t)m_m, n = (size_t)(m_nBlockCols > 0 ? m_nBlockCols : 1);
+        m_blockRedCost.assign(m, 0.0);
+        m_blockMostNeg.assign(m, 0.0);
+        m_blockOrigCost.assign(m, 0.0);
+        m_blockObj.assign(m, 0.0);
+        m_blockNnz.assign(m, 0);
+        m_colBlock.assign(m + 1, 0);
+        m_colRedCost.assign(m + 1, 0.0);
+        m_colOrigCost.assign(m + 1, 0.0);
+        m_colStart.assign(m + 2, 0);
+        m_colInd.assign(n, 0);
+        m_served.assign(m, 0);
+        std::memset(&m_cols, 0, sizeof(m_cols));
+        m_cols.capBlocks = m_m;
+        m_cols.capCols = m_m;
+        m_cols.capInd = (int64_t)n;
+        m_cols.blockRedCost = m_blockRedCost.data();
+        m_cols.blockMostNegRC = m_blockMostNeg.data();
+        m_cols.blockOrigCost = m_blockOrigCost.data();
+        m_cols.blockObj = m_blockObj.data();
+        m_cols.blockNnz = m_blockNnz.data();
+        m_cols.colBlock = m_colBlock.data();
+        m_cols.colRedCost = m_colRedCost.data();
+        m_cols.colOrigCost = m_colOrigCost.data();
+        m_cols.colStart = m_colStart.data();
+        m_cols.colInd = m_colInd.data();
+    }
+    template <class VarT>
+    VarT *makeVar(int k, double redCost) const
+    {
+        const int64_t b = m_colStart[(size_t)k], e = m_colStart[(size_t)k + 1];
+        std::vector<int> ind(m_colInd.begin() + b, m_colInd.begin() + e);
+        std::vector<double> els(ind.size(), 1.0);  // GAP_KnapPisinger.h:265-270
+        VarT *v = new VarT(ind, els, redCost, m_colOrigCost[(size_t)k]);
+        v->setBlockId(m_colBlock[(size_t)k]);
+        return v;
+    }
+    uint64_t fingerprint(const double *x) const
+    {
+        uint64_t h = 1469598103934665603ull;
+        const int n = m_nBlockCols;
+        const int step = n > 64 ? n / 64 : 1;
+        for (int i = 0; i < n; i += step) {
+            uint64_t b;
+            std::memcpy(&b, x + i, 8);
+            h = (h ^ b) * 1099511628211ull;
+        }
+        if (n > 0) {
+            uint64_t b;
+            std::memcpy(&b, x + n - 1, 8);
+            h = (h ^ b) * 1099511628211ull;
+        }
+        return h;
+    }
+
+    dipgpu_ctx *m_ctx;
+    int m_m, m_N, m_nBlockCols;
+    dipgpu_cols m_cols;
+    std::vector<double> m_blockRedCost, m_blockMostNeg, m_blockOrigCost, m_blockObj, m_colRedCost, m_colOrigCost;
+    std::vector<int32_t> m_blockNnz, m_colBlock, m_colInd;
+    std::vector<int64_t> m_colStart;
+    bool m_roundValid;
+    const double *m_roundPtr = nullptr;
+    uint64_t m_roundFp = 0;
+    std::vector<char> m_served;
+};
+
+}  // namespace dipgpu
+
+#endif  // DIPGPU_DECOMP_HPP

@@ -1,0 +1,128 @@
+// test_adapter.cpp -- the C++ host mirror (include/dipgpu_decomp.hpp) exercised the way a DIP
+// application would: build a GAP model (Dip/examples/GAP/GAP_DecompApp.cpp:138-232 layout), then
+// call generateVars / solveRelaxed and compare with the CPU oracle (TEST INFRASTRUCTURE:
+// oracle/dip_oracle.h).  Without a GPU the Pricer constructor must throw (no CPU fallback):
+// the program then prints NO_GPU and exits 0.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/dipgpu_decomp.hpp"
+#include "../../oracle/dip_oracle.h"
+
+static uint64_t lcg(uint64_t &s) { s = s * 6364136223846793005ull + 1442695040888963407ull; return s >> 33; }
+static double unif(uint64_t &s) { return (double)(lcg(s) % 1000000) / 1000000.0; }
+
+#define CHECK(c)                                                                     \
+    do {                                                                             \
+        if (!(c)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } \
+    } while (0)
+
+int main()
+{
+    if (dipgpu_abi_version() != DIPGPU_ABI_VERSION) { std::printf("ABI mismatch\n"); return 1; }
+    const int m = 12, n = 90, N = m * n;
+    uint64_t seed = 20200;
+    std::vector<int> weight(N), capacity(m), blockColStart(m + 1);
+    std::vector<double> cost(N);
+    for (int i = 0; i < m; ++i) {
+        long sum = 0;
+        for (int j = 0; j < n; ++j) {
+            weight[i * n + j] = 1 + (int)(lcg(seed) % 100);
+            cost[i * n + j] = 111 - weight[i * n + j] + (int)(lcg(seed) % 21) - 10;
+            sum += weight[i * n + j];
+        }
+        capacity[i] = (int)(0.8 * sum / m);
+        blockColStart[i] = i * n;
+    }
+    blockColStart[m] = N;
+    // A'': n assignment rows, then 2N identity branch rows (DecompAlgo.cpp:1431-1455)
+    const int R = n + 2 * N;
+    std::vector<int64_t> rowStart(R + 1, 0);
+    std::vector<int32_t> colInd;
+    std::vector<double> val;
+    for (int j = 0; j < n; ++j) {
+        for (int i = 0; i < m; ++i) { colInd.push_back(i * n + j); val.push_back(1.0); }
+        rowStart[j + 1] = (int64_t)colInd.size();
+    }
+    for (int r = 0; r < 2 * N; ++r) {
+        colInd.push_back(r % N);
+        val.push_back(1.0);
+        rowStart[n + r + 1] = (int64_t)colInd.size();
+    }
+    // master duals [core rows | m convexity]
+    std::vector<double> u(R + m, 0.0);
+    for (int j = 0; j < n; ++j) u[j] = unif(seed) * 120.0;
+    for (int r = 0; r < 2 * N; ++r)
+        if (lcg(seed) % 50 == 0) u[n + r] = (r < N ? -1.0 : 1.0) * unif(seed) * 3.0;
+    for (int b = 0; b < m; ++b) u[R + b] = -10.0 * unif(seed);
+
+    dipgpu::Pricer *pricer = nullptr;
+    try {
+        pricer = new dipgpu::Pricer(0);
+    } catch (const dipgpu::Error &e) {
+        if (e.code() == DIPGPU_ERR_CUDA) { std::printf("NO_GPU\n"); return 0; }
+        std::printf("unexpected error: %s\n", e.what());
+        return 1;
+    }
+    pricer->setModelCore(R, N, rowStart.data(), colInd.data(), val.data(), R, m);
+    pricer->setObjective(cost.data(), N);
+    pricer->setKnapsackBlocks(m, blockColStart.data(), weight.data(), capacity.data());
+
+    // ---- oracle
+    std::vector<double> redCostX(N), colRedCost(m), colOrigCost(m), mostNeg(m), z(m);
+    std::vector<int32_t> colNnz(m), colKeep(m), ind((size_t)m * n);
+    double mostNegRef = 0;
+    int64_t cells = 0;
+    const int kept = dip_oracle_price_round(R, N, rowStart.data(), colInd.data(), val.data(), cost.data(), u.data(),
+                                            R, 0, m, blockColStart.data(), weight.data(), capacity.data(), 0, 1e-4,
+                                            1, n, redCostX.data(), colNnz.data(), colRedCost.data(),
+                                            colOrigCost.data(), colKeep.data(), mostNeg.data(), z.data(), ind.data(),
+                                            &mostNegRef, &cells);
+
+    // ---- surface 2: DecompAlgo::generateVars
+    dipgpu::DecompVarList newVars;
+    double mostNegRC = 1.0;
+    const int nNew = pricer->generateVars(u.data(), (int)u.size(), dipgpu::PHASE_PRICE2, 1e-4, newVars, mostNegRC);
+    CHECK(nNew == kept && (int)newVars.size() == kept);
+    CHECK(mostNegRC == mostNegRef);
+    CHECK(pricer->cells() == cells);
+    for (int b = 0; b < m; ++b) CHECK(pricer->blockObj()[b] == z[b]);  // bit-exact knapsack optima
+    for (dipgpu::DecompVar *v : newVars) {
+        const int b = v->getBlockId();
+        CHECK(colKeep[b] == 1 && v->getReducedCost() < -1e-4);
+        CHECK((int)v->ind.size() == colNnz[b]);
+        for (int k = 0; k < colNnz[b]; ++k) CHECK(v->ind[k] == ind[(size_t)b * n + k] && v->els[k] == 1.0);
+        CHECK(v->getReducedCost() == colRedCost[b] && v->getOriginalCost() == colOrigCost[b]);
+        delete v;  // the caller owns the columns, as DIP does (DecompAlgo.cpp:5225)
+    }
+
+    // ---- stage (a) alone, then surface 1: DecompApp::solveRelaxed per block on that vector
+    std::vector<double> rcx(N);
+    pricer->calcRedCost(u.data(), (int)u.size(), dipgpu::PHASE_PRICE2, rcx.data());
+    for (int j = 0; j < N; ++j) CHECK(rcx[j] == redCostX[j]);
+    for (int b = 0; b < m; ++b) {
+        dipgpu::DecompVarList vars;
+        const dipgpu::DecompSolverStatus st = pricer->solveRelaxed(b, rcx.data(), u[R + b], vars);
+        CHECK(st == dipgpu::DecompSolStatOptimal && vars.size() == 1);
+        dipgpu::DecompVar *v = vars.front();
+        CHECK(v->getBlockId() == b && (int)v->ind.size() == colNnz[b]);
+        // reduced cost WITHOUT alpha; the driver subtracts it (DecompAlgo.cpp:6350-6356)
+        CHECK(v->getReducedCost() - u[R + b] == colRedCost[b]);
+        delete v;
+    }
+    int64_t launches = 0;
+    dipgpu_get_counters(pricer->ctx(), &launches, nullptr, nullptr);
+    CHECK(launches <= 6);  // 2 (round) + 1 (SpMV) + <=3 (ONE submission served all 12 solveRelaxed calls)
+    // phase 1 prices with c = 0
+    pricer->calcRedCost(u.data(), (int)u.size(), dipgpu::PHASE_PRICE1, rcx.data());
+    std::vector<double> uAdj(R);
+    dip_oracle_adjust_duals(u.data(), R + m, R, m, uAdj.data());
+    dip_oracle_calc_redcost(R, N, rowStart.data(), colInd.data(), val.data(), uAdj.data(), cost.data(), 1,
+                            redCostX.data());
+    for (int j = 0; j < N; ++j) CHECK(rcx[j] == redCostX[j]);
+    delete pricer;
+    std::printf("PARITY_OK kept=%d mostNegRC=%.9f cells=%lld launches=%lld\n", kept, mostNegRC, (long long)cells,
+                (long long)launches);
+    return 0;
+}
