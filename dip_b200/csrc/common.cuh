@@ -132,6 +132,8 @@ struct Ctx {
     int32_t *dItemW = nullptr;          // per column slot: weight of compacted item k of block b
     int32_t *dItemCol = nullptr;        // per column slot: local column of compacted item
     int32_t *dNItems = nullptr;         // m
+    int32_t *dScale = nullptr, *dShortcut = nullptr, *dSel = nullptr;  // Pisinger mode, per local block
+    double *dZShort = nullptr;
     int32_t *dCandInd = nullptr;        // per column slot: candidate column indices (ascending)
     int32_t *dScratch = nullptr;        // per column slot: descending taken list
     int maxCapacity = 0;       // of the shard
@@ -183,9 +185,24 @@ int cudaFail(Ctx *c, cudaError_t e, const char *what);
         if (e__ != cudaSuccess) return ::dipgpu::cudaFail((c), e__, #call); \
     } while (0)
 
+// ------------------------------------------------ Pisinger-mode pre-processing
+struct PrepArgs {
+    const double *redCost;
+    const int32_t *weight;
+    const int32_t *blockColStart;
+    const int32_t *capacity;
+    int firstBlock;
+    int32_t *scale;     // local block -> calcScaleFactor result
+    int32_t *shortcut;  // local block -> 0 solve by DP, 1 take every active item, 2 explicit set (sel)
+    int32_t *sel;       // 2 per local block: chosen local columns ascending, -1 = none
+    double *zShort;     // local block -> optimum of a shortcut block (scaled-integer units)
+};
+
 // ------------------------------------------------------------------- launchers
 // redcost.cu -- stage (a)
 int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st);
+// pisinger.cu -- scale factor + trivial cases of GAP_KnapPisinger::solve (profit mode 1 only)
+int launchKnapsackPrep(Ctx *c, const double *dRedCost, cudaStream_t st);
 // knapsack.cu -- stage (b)
 int chooseDpGeom(Ctx *c, DpGeom *g, bool wantFuse);
 int prepareKnapsackDp(Ctx *c);  // loads the chosen kernel, sets its shared-memory limit

@@ -178,6 +178,11 @@ static int setBlockRange(Ctx *c, int first, int count)
     DIPGPU_CUDA(c, cudaMemcpy(c->dBitsOff, off.data(), sizeof(int64_t) * ((size_t)count + 1), cudaMemcpyHostToDevice));
     if ((rc = devAlloc(c, &c->dBits, c->bitsWords))) return rc;
     if ((rc = devAlloc(c, &c->dNItems, (size_t)count))) return rc;
+    if ((rc = devAlloc(c, &c->dScale, (size_t)count))) return rc;
+    if ((rc = devAlloc(c, &c->dShortcut, (size_t)count))) return rc;
+    if ((rc = devAlloc(c, &c->dSel, 2 * (size_t)count))) return rc;
+    if ((rc = devAlloc(c, &c->dZShort, (size_t)count))) return rc;
+    DIPGPU_CUDA(c, cudaMemset(c->dShortcut, 0, sizeof(int32_t) * std::max<size_t>((size_t)count, 1)));
     // packed result
     c->indCap = count > 0 ? (int64_t)(c->hBlockColStart[first + count] - c->hBlockColStart[first]) : 0;
     c->layout = ResultLayout::make(count, c->indCap);
@@ -201,6 +206,7 @@ static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, do
     int mode = c->geom.fuse ? 2 : c->optFuseFilter < 0 ? (c->nLocal <= kFuseFilterMaxBlocks ? 1 : 0)
                                                        : (c->optFuseFilter == 1 ? 1 : 0);
     if (c->nLocal == 0) mode = 0;
+    if ((rc = launchKnapsackPrep(c, dRedCost, st))) return rc;
     if ((rc = launchKnapsackDp(c, dRedCost, dAlpha, eps, st))) return rc;
     if (timed) cudaEventRecord(c->ev[3], st);
     if (mode != 2 && (rc = launchBacktrackEmit(c, dRedCost, dAlpha, eps, mode == 1, st))) return rc;
@@ -345,7 +351,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (c->stream) cudaStreamSynchronize(c->stream);
     devFree(&c->dDoneCounter); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
-    devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems);
+    devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems); devFree(&c->dScale); devFree(&c->dShortcut); devFree(&c->dSel); devFree(&c->dZShort);
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
     if (c->dResult) cudaFree(c->dResult);
     if (c->hResult) cudaFreeHost(c->hResult);
@@ -453,8 +459,6 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
     if (m < 0 || !blockColStart || (m > 0 && !capacity)) return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: bad arguments");
     if (profitMode != DIPGPU_PROFIT_FP64 && profitMode != DIPGPU_PROFIT_PISINGER_INT)
         return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: unknown profitMode %d", profitMode);
-    if (profitMode == DIPGPU_PROFIT_PISINGER_INT)
-        return fail(c, DIPGPU_ERR_UNSUPPORTED, "set_knapsack_blocks: DIPGPU_PROFIT_PISINGER_INT is not built yet");
     if (blockColStart[0] < 0) return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: negative column start");
     for (int b = 0; b < m; ++b) {
         if (blockColStart[b + 1] < blockColStart[b]) return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: blockColStart not monotone at block %d", b);

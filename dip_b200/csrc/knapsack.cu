@@ -101,14 +101,70 @@ struct BackArgs {
     int32_t *blockNnz;
     int firstBlock, nLocal, rowCells;
     unsigned int *doneCounter;  // non-NULL: the last CTA to finish runs the filter (stage c)
+    const int32_t *shortcut;    // Pisinger mode (else NULL): per local block 0 = DP, 1 = all, 2 = sel
+    const int32_t *sel;         // 2 per local block
 };
 
 constexpr int kBackThreads = 128;
+
+// Pisinger-mode trivial cases (GAP_KnapPisinger.h:203-238), decided by knap_prep_kernel: the
+// column is either every item with negative reduced cost (code 1) or an explicit set of at most
+// two columns (code 2).  Emitted ascending with the sums of GAP_KnapPisinger.h:263-272.
+__device__ __forceinline__ void emitShortcut(const BackArgs &a, int lb, int lane, int code)
+{
+    const int b = a.firstBlock + lb;
+    const int cs = a.blockColStart[b];
+    const int n = a.blockColStart[b + 1] - cs;
+    int cnt = 0;
+    double rcs = 0.0, ocs = 0.0;
+    if (code == 1) {
+        for (int base = 0; base < n; base += 32) {
+            const int j = base + lane;
+            double r = 0.0, o = 0.0;
+            bool act = false;
+            if (j < n) {
+                r = a.redCost[cs + j];
+                act = r < 0.0;
+                if (act) o = a.obj[cs + j];
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, act);
+            if (act) a.candInd[cs + cnt + __popc(bal & ((1u << lane) - 1u))] = cs + j;
+            cnt += __popc(bal);
+            for (unsigned rest = bal; rest; rest &= rest - 1) {  // ascending column order
+                const int q = __ffs(rest) - 1;
+                rcs += __shfl_sync(0xffffffffu, r, q);
+                ocs += __shfl_sync(0xffffffffu, o, q);
+            }
+        }
+    } else {
+        for (int k = 0; k < 2; ++k) {
+            const int j = a.sel[2 * lb + k];
+            if (j >= 0) {
+                if (lane == 0) a.candInd[cs + cnt] = cs + j;
+                rcs += a.redCost[cs + j];
+                ocs += a.obj[cs + j];
+                ++cnt;
+            }
+        }
+    }
+    if (lane == 0) {
+        a.blockRedCost[lb] = rcs - a.alpha[b];
+        a.blockOrigCost[lb] = ocs;
+        a.blockNnz[lb] = cnt;
+    }
+}
 
 // nItems = number of active items of the block.  Loads are L2-coherent (ld.global.cg): in the
 // fused path the decision bits were written earlier by this very kernel.
 __device__ __forceinline__ void backtrackOne(const BackArgs &a, int lb, int lane, int nItems)
 {
+    if (a.shortcut != nullptr) {
+        const int code = a.shortcut[lb];
+        if (code != 0) {
+            emitShortcut(a, lb, lane, code);
+            return;
+        }
+    }
     const int b = a.firstBlock + lb;
     const int cs = a.blockColStart[b];
     const int RC = a.rowCells;
@@ -203,6 +259,10 @@ struct KnapArgs {
     int firstBlock;
     int chunkCols;                 // columns staged per TMA chunk (multiple of 4)
     int guard;                     // -inf cells in front of each row buffer (even; 0 = predicated reads)
+    int profitMode;                // DIPGPU_PROFIT_*
+    const int32_t *scale;          // Pisinger mode: local block -> scale factor
+    const int32_t *shortcut;       // Pisinger mode: local block -> trivial-case code (0 = run the DP)
+    const double *zShort;          // Pisinger mode: local block -> optimum of a trivial case
     int fuseTail;                  // small shards: backtrack + filter run in this kernel's tail
     BackArgs back;
     FilterArgs filt;
@@ -264,7 +324,10 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const int lb = blockIdx.x;
     const int b = a.firstBlock + lb;
     const int colStart = a.blockColStart[b];
-    const int nCols = a.blockColStart[b + 1] - colStart;
+    const int shortCode = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? a.shortcut[lb] : 0;
+    // a trivial case of GAP_KnapPisinger::solve needs no DP: behave like an empty block here
+    const int nCols = shortCode != 0 ? 0 : a.blockColStart[b + 1] - colStart;
+    const double pScale = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? (double)a.scale[lb] : 0.0;
     const int cap = a.capacity[b];
     uint32_t *bitsBase = FUSE ? sBits : a.bits + a.bitsOff[lb];
     const int j0 = t * S;  // first owned cell
@@ -332,7 +395,9 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             }
             if (flag) {
                 const int pos = nIt + off + wpre;
-                itP[pos] = -rc;
+                // profit: -redCost (gap_func.py:104), or its scaled integer value
+                // floor(-rc*scale + 0.5) held exactly in fp64 (GAP_KnapPisinger.h:174-177)
+                itP[pos] = pScale != 0.0 ? (double)(long long)floor((-rc) * pScale + 0.5) : -rc;
                 itW[pos] = w;
                 if (FUSE) {
                     itC[pos] = cl;
@@ -436,14 +501,20 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         for (int s = 0; s < S; ++s) dst[s] = acc[s];
     }
     // z = c[n-1][capacity]  (gap_func.py:183)
+    if (shortCode != 0) {
+        if (t == 0) a.blockObj[lb] = a.zShort[lb];
+    } else {
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        if (j0 + s == cap) a.blockObj[lb] = mine[s];
+        for (int s = 0; s < S; ++s) {
+            if (j0 + s == cap) a.blockObj[lb] = mine[s];
+        }
     }
     if (t == 0) a.nItems[lb] = kGlobal;
     if (FUSE) {
         __syncthreads();
-        if (warp == 0) {
+        if (warp == 0 && shortCode != 0) {
+            emitShortcut(a.back, lb, lane, shortCode);
+        } else if (warp == 0) {
             // backtrack from (last item, capacity), gap_func.py:173-181, out of shared memory
             int j = cap;
             int i = kGlobal - 1;
@@ -665,6 +736,9 @@ static void fillBackArgs(Ctx *c, const double *dRedCost, const double *dAlpha, B
     a->nLocal = c->nLocal;
     a->rowCells = c->geom.rowCells;
     a->doneCounter = c->dDoneCounter;
+    const bool pis = c->profitMode == DIPGPU_PROFIT_PISINGER_INT;
+    a->shortcut = pis ? c->dShortcut : nullptr;
+    a->sel = pis ? c->dSel : nullptr;
 }
 
 int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st)
@@ -689,6 +763,10 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, doubl
     a.chunkCols = g.chunkCols;
     a.guard = g.guard;
     a.fuseTail = g.fuse;
+    a.profitMode = c->profitMode;
+    a.scale = c->dScale;
+    a.shortcut = c->dShortcut;
+    a.zShort = c->dZShort;
     fillBackArgs(c, dRedCost, dAlpha, &a.back);
     a.filt = makeFilterArgs(c, redCostEps);
     a.filt.fuseCopy = c->nLocal <= kFuseFilterMaxBlocks ? 2 : 1;

@@ -192,8 +192,12 @@ int dip_oracle_solve_block(int n, const double *redCost, const double *origCost,
     if (profitMode == 1) {
         /* GAP_KnapPisinger.h:203-238: trivial cases before combo */
         if (nItems == 1) {
-            x[0] = 1;
-            z = p[0];
+            /* the reference asserts w <= capacity here (:204); an item that does not fit
+             * is left out, as the DP would */
+            if (w[0] <= capacity) {
+                x[0] = 1;
+                z = p[0];
+            }
             solved = 1;
         } else if (nItems >= 1 && weightSum <= capacity) {
             for (int i = 0; i < nItems; ++i) {

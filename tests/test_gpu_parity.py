@@ -20,12 +20,12 @@ def _batch_from_cases(cases):
     return bcs, w, cap, rc
 
 
-def _check_against_oracle(oracle, pricer, bcs, w, cap, rc, oc, alpha, eps=1e-4):
+def _check_against_oracle(oracle, pricer, bcs, w, cap, rc, oc, alpha, eps=1e-4, profit_mode=0):
     m = len(cap)
     pricer.setObjective(oc)
-    pricer.setKnapsackBlocks(bcs, w, cap)
+    pricer.setKnapsackBlocks(bcs, w, cap, profit_mode)
     res = pricer.solveBlocks(rc, alpha, eps)
-    ref = oracle.solve_blocks(bcs, w, cap, rc, oc, alpha, red_cost_eps=eps)
+    ref = oracle.solve_blocks(bcs, w, cap, rc, oc, alpha, red_cost_eps=eps, profit_mode=profit_mode)
     np.testing.assert_array_equal(res.blockObj, ref.z)                 # bit-exact optimum
     np.testing.assert_array_equal(res.blockNnz, ref.col_nnz)
     np.testing.assert_allclose(res.blockRedCost, ref.col_red_cost, rtol=RC_RTOL, atol=1e-12)
@@ -326,3 +326,83 @@ def test_csp_full_size_properties(oracle, pricer):
         z, sol = oracle.knapsack01(-b.red_cost[s:e], b.weight[s:e], int(b.capacity[k]))
         assert z == res.blockObj[k]
         assert sorted(int(s + i) for i in sol) == list(res.column(k))
+
+
+# ------------------------------------------------------------------ Pisinger (scaled-integer) mode
+
+
+def _decimal_batch(m, nhi, caphi, seed, digits):
+    """Reduced costs with a bounded number of decimals, so calcScaleFactor lands on 1..10^4."""
+    rng = np.random.default_rng(seed)
+    b = I.random_batch(m, 0, nhi, 1, caphi, seed)
+    n = np.diff(b.block_col_start)
+    dig = np.repeat(rng.integers(0, digits + 1, size=m), n)   # per block: 0..digits decimals
+    q = 10.0 ** dig
+    b.red_cost = np.where(b.red_cost < 0, -np.maximum(np.round(-b.red_cost * q), 0) / q, b.red_cost)
+    return b
+
+
+@pytest.mark.parametrize("seed,m,nhi,caphi,digits", [(31, 200, 40, 120, 5), (32, 64, 300, 900, 3),
+                                                     (33, 500, 6, 40, 4), (34, 20, 1500, 3000, 2)])
+def test_pisinger_mode_batches(oracle, pricer, seed, m, nhi, caphi, digits):
+    """GAP_KnapPisinger::solve semantics: scale factor, integer profits, trivial cases; optimum and
+    column against the oracle's restatement (the DP stands in for combo.c on both sides)."""
+    from dip_b200.pricer import PROFIT_PISINGER_INT
+    b = _decimal_batch(m, nhi, caphi, seed, digits)
+    res, ref = _check_against_oracle(oracle, pricer, b.block_col_start, b.weight, b.capacity, b.red_cost,
+                                     b.orig_cost, b.alpha, profit_mode=PROFIT_PISINGER_INT)
+    # integer profits: the optimum is an integer
+    assert np.all(res.blockObj == np.round(res.blockObj))
+
+
+def test_pisinger_scale_factor_and_shortcuts(oracle, pricer):
+    from dip_b200.pricer import PROFIT_PISINGER_INT
+    # block 0: one item that fits; 1: one item that does not fit; 2: all fit (incl. a profit that
+    # rounds to 0); 3: two items, tie on profit (reference prefers item 1); 4: two items, both fit
+    # is impossible, unequal profits; 5: scale 10 (0.5 steps); 6: scale 10^4 (too many decimals);
+    # 7: no active item; 8: three items -> DP
+    bcs = np.array([0, 2, 4, 8, 10, 12, 15, 18, 20, 23], np.int32)
+    w = np.array([3, 1, 9, 1, 1, 2, 1, 1, 4, 4, 4, 5, 2, 2, 2, 3, 3, 3, 1, 1, 3, 3, 3], np.int32)
+    cap = np.array([5, 5, 10, 5, 6, 3, 4, 5, 5], np.int32)
+    rc = np.array([-2.5, 1.0, -7.0, 0.0, -1.0, -2.0, -0.00001, 3.0, -3.0, -3.0, -2.0, -4.5,
+                   -1.5, -2.5, -3.5, -0.12345, -0.5, -0.25, 1.0, 2.0, -1.0, -2.0, -3.0])
+    oc = np.arange(len(w), dtype=np.float64) + 1
+    alpha = np.zeros(9)
+    res, ref = _check_against_oracle(oracle, pricer, bcs, w, cap, rc, oc, alpha, eps=-np.inf,
+                                     profit_mode=PROFIT_PISINGER_INT)
+    assert list(res.column(0)) == [0] and list(res.column(1)) == []
+    assert list(res.column(2)) == [4, 5, 6]
+    assert list(res.column(3)) == [9]                # tie: {1} wins over {0}
+    for blk in range(9):
+        s, e = bcs[blk], bcs[blk + 1]
+        assert oracle.calc_scale_factor(rc[s:e]) in (1, 10, 100, 1000, 10000)
+
+
+def test_pisinger_matches_reference_hs_values(oracle, pricer, golden_knapsack):
+    """Integer profits make the optimum unique: the GPU's Pisinger-mode value must equal what the
+    reference's own Horowitz-Sahni B&B (compiled from Dip/src/UtilKnapsack.cpp) returned."""
+    from dip_b200.pricer import PROFIT_PISINGER_INT
+    cases = [c for c in golden_knapsack if c["hs_z"] is not None and c["hs_status"] == 0]
+    assert len(cases) >= 20
+    bcs, w, cap, rc = _batch_from_cases(cases)
+    pricer.setObjective(np.zeros(len(w)))
+    pricer.setKnapsackBlocks(bcs, w, cap, PROFIT_PISINGER_INT)
+    res = pricer.solveBlocks(rc, np.zeros(len(cases)), redCostEps=-np.inf)
+    for k, c in enumerate(cases):
+        assert res.blockObj[k] == c["hs_z"], c["tag"]
+
+
+def test_gap_d_round_pisinger(oracle, pricer):
+    from dip_b200.pricer import PROFIT_PISINGER_INT
+    model = I.gap_pricing_model(I.gap_class_d())
+    pricer.setModel(model, PROFIT_PISINGER_INT)
+    u = I.gap_duals(model, np.random.default_rng(8))
+    res, rcx = pricer.priceRound(u, want_redcost=True)
+    ref = oracle.price_round(model.R, model.N, model.row_start, model.col_ind, model.val, model.objective, u,
+                             model.n_base_rows, model.m, model.block_col_start, model.weight, model.capacity,
+                             profit_mode=1)
+    np.testing.assert_array_equal(rcx, ref.red_cost_x)
+    np.testing.assert_array_equal(res.blockObj, ref.z)
+    np.testing.assert_array_equal(res.blockRedCost, ref.col_red_cost)
+    for k in range(res.nCols):
+        assert list(res.column(k)) == list(ref.col_ind[int(res.colBlock[k])])
