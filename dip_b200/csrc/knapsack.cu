@@ -413,9 +413,80 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
 
         // ---- the DP proper: items sequential, cells parallel.  (w0,p0),(w1,p1) hold
         // items i and i+1, fetched one step ahead (itP/itW are padded by four entries).
-        int w0 = itW[0], w1 = itW[1];
-        double p0 = itP[0], p1 = itP[1];
         int i = 0;
+        if (S <= 3 && GUARD) {
+            // Latency-bound shapes (few cells per thread): whole 32-item words are processed by a
+            // fully unrolled body -- constant bit masks, compile-time buffer roles, item data
+            // fetched eight steps ahead -- so that a step is little more than its dependent chain
+            // barrier -> shifted load -> DADD -> DSETP -> select -> store -> barrier.
+            while (((kGlobal + i) & 31) == 0 && i + 32 <= nIt) {
+                double *bufA = rowBase + cur * bufStride + G + j0;        // holds c[i-1][.]
+                double *bufB = rowBase + (cur ^ 1) * bufStride + G + j0;
+                int wq[8];
+                double pq[8];
+#pragma unroll
+                for (int q = 0; q < 32; q += ITEMS) {
+                    if ((q & 7) == 0) {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            wq[r] = itW[i + q + r];
+                            pq[r] = itP[i + q + r];
+                        }
+                    }
+                    // ITEMS == 1: buffers alternate every step; ITEMS == 2: every pair
+                    const bool even = ((q / ITEMS) & 1) == 0;
+                    const double *rdBuf = even ? bufA : bufB;
+                    double *wrBuf = even ? bufB : bufA;
+                    if (ITEMS == 1) {
+                        const int w = wq[q & 7];
+                        const double p = pq[q & 7];
+                        const double *rd = rdBuf - w;
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            const double cand = p + rd[s];        // gap_func.py:164
+                            const bool take = cand > mine[s];     // :166 strict
+                            mine[s] = take ? cand : mine[s];
+                            if (take) acc[s] |= 1u << q;          // added[i][j]  (:168)
+                            wrBuf[s] = mine[s];
+                        }
+                    } else {
+                        const int wA = wq[q & 7], wB = wq[(q & 7) + 1];
+                        const double pA = pq[q & 7], pB = pq[(q & 7) + 1];
+                        const double *rdA = rdBuf - wA;
+                        const double *rdB = rdBuf - wB;
+                        const double *rdAB = rdA - wB;
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            const double shA = rdA[s], shB = rdB[s], shAB = rdAB[s];
+                            const double candA = pA + shA;
+                            const bool takeA = candA > mine[s];
+                            const double r1 = takeA ? candA : mine[s];
+                            const double candAB = pA + shAB;
+                            const double r1B = candAB > shB ? candAB : shB;
+                            const double candB = pB + r1B;
+                            const bool takeB = candB > r1;
+                            mine[s] = takeB ? candB : r1;
+                            if (takeA) acc[s] |= 1u << q;
+                            if (takeB) acc[s] |= 2u << q;
+                            wrBuf[s] = mine[s];
+                        }
+                    }
+                    __syncthreads();
+                }
+                // 32 / ITEMS steps: an even number of buffer swaps, `cur` is unchanged
+                {
+                    uint32_t *dst = bitsBase + (size_t)((kGlobal + i) >> 5) * RC + j0;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        dst[s] = acc[s];
+                        acc[s] = 0u;
+                    }
+                }
+                i += 32;
+            }
+        }
+        int w0 = itW[i], w1 = itW[i + 1];
+        double p0 = itP[i], p1 = itP[i + 1];
         while (i < nIt) {
             const int bitpos = (kGlobal + i) & 31;
             const double *base = rowBase + cur * bufStride + G + j0;

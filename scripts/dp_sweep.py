@@ -41,6 +41,9 @@ def time_dp(p, b, reps=4):
     return best, res
 
 
+SWEEP_S = tuple(int(x) for x in os.environ.get('SWEEP_S', '').split(',') if x)
+
+
 def main():
     names = sys.argv[1:] or ["gape", "csp_small"]
     for name in names:
@@ -56,7 +59,7 @@ def main():
             print(f"auto: dp={ms['knapsack_dp']*1e3:9.1f} us  backtrack={ms['backtrack_emit']*1e3:8.1f} us  "
                   f"gcups={cells/ms['knapsack_dp']/1e6:8.1f}")
             print("   S     T items guard   dp_us     gcups")
-            for S in (1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 25):
+            for S in (SWEEP_S or (1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 25)):
                 for items in (1, 2):
                     for noguard in (0, 1):
                         try:
