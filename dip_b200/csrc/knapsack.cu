@@ -732,7 +732,9 @@ static double geomCost(const Ctx *c, const DpGeom &g)
     // per item: dependent chain of one warp (GAP-E sweep: ~120 + 22 S cycles; the two-item
     // step issues 1.5x the instructions and loses in this regime)
     double chain = 120.0 + 22.0 * g.S + 2.0 * warps;
-    if (g.items == 2) chain *= 1.3;
+    // the unrolled two-item step (S <= 3 with guard cells) halves the barriers: 68 vs 76 us on
+    // GAP-E; the generic two-item step costs 1.3x (profiles/r01_dp_geometry_sweep.txt)
+    if (g.items == 2) chain *= (g.S <= 3 && g.guard > 0) ? 0.9 : 1.3;
     // throughput regime (CSP sweep): shared-memory floor times the measured inefficiency
     const double ineff = g.S <= 11 ? (g.items == 2 ? 1.52 : 1.61) : g.S <= 21 ? (g.items == 2 ? 1.40 : 1.53)
                                                                               : (g.items == 2 ? 1.69 : 1.81);

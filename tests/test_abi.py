@@ -78,12 +78,12 @@ def test_dp_geometry_planner_host_only():
         assert g["threads"] * g["cells_per_thread"] >= cap + 1
         assert g["smem_bytes"] <= 227 * 1024
         assert g["guard"] == 0 or g["guard"] >= mw * g["items_per_step"]
-    # latency regime (few small knapsacks): one cell per thread, one item per barrier
+    # latency regime (few small knapsacks): one cell per thread, fused backtrack + filter
     g = capi.plan_dp_geometry(80, 176, 1600, 60)
-    assert (g["cells_per_thread"], g["items_per_step"]) == (1, 1)
+    assert g["cells_per_thread"] == 1 and g["fused_tail"] == 1
     # throughput regime (many large knapsacks): many cells per thread
     g = capi.plan_dp_geometry(10_000, 10_000, 500, 1000)
-    assert g["cells_per_thread"] >= 11
+    assert g["cells_per_thread"] >= 11 and g["fused_tail"] == 0
     import pytest
     with pytest.raises(capi.DipGpuError) as e:
         capi.plan_dp_geometry(10, 1_000_000, 10, 10)
