@@ -245,15 +245,6 @@ __global__ void __launch_bounds__(kBackThreads) knap_backtrack_kernel(const __gr
 
 #define kNegInf (__longlong_as_double((long long)0xfff0000000000000ULL))
 
-// The strict '>' of gap_func.py:166 on DP values.  Every value that reaches it is a non-negative
-// finite double or the -inf of a guard cell (profits are > 0, rows start at +0.0), and on that set
-// the IEEE order equals the order of the bit patterns read as signed 64-bit integers -- same
-// decisions, but two short integer compares instead of a DSETP at the end of the DADD on the
-// per-item critical path (measured FP64 dependent-issue latency on B200: ~40 cycles per op).
-__device__ __forceinline__ bool dpGreater(double a, double b)
-{
-    return __double_as_longlong(a) > __double_as_longlong(b);
-}
 
 struct KnapArgs {
     const double *redCost;         // x-space reduced costs (16 B aligned, padded)
@@ -454,7 +445,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
 #pragma unroll
                         for (int s = 0; s < S; ++s) {
                             const double cand = p + rd[s];        // gap_func.py:164
-                            const bool take = dpGreater(cand, mine[s]);     // :166 strict
+                            const bool take = cand > mine[s];     // :166 strict
                             mine[s] = take ? cand : mine[s];
                             if (take) acc[s] |= 1u << q;          // added[i][j]  (:168)
                             wrBuf[s] = mine[s];
@@ -469,12 +460,12 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                         for (int s = 0; s < S; ++s) {
                             const double shA = rdA[s], shB = rdB[s], shAB = rdAB[s];
                             const double candA = pA + shA;
-                            const bool takeA = dpGreater(candA, mine[s]);
+                            const bool takeA = candA > mine[s];
                             const double r1 = takeA ? candA : mine[s];
                             const double candAB = pA + shAB;
-                            const double r1B = dpGreater(candAB, shB) ? candAB : shB;
+                            const double r1B = candAB > shB ? candAB : shB;
                             const double candB = pB + r1B;
-                            const bool takeB = dpGreater(candB, r1);
+                            const bool takeB = candB > r1;
                             mine[s] = takeB ? candB : r1;
                             if (takeA) acc[s] |= 1u << q;
                             if (takeB) acc[s] |= 2u << q;
@@ -524,14 +515,14 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                 for (int s = 0; s < S; ++s) {
                     // item A at cell j  (gap_func.py:164-168)
                     const double candA = pA + shA[s];
-                    const bool takeA = dpGreater(candA, mine[s]);
+                    const bool takeA = candA > mine[s];
                     const double r1 = takeA ? candA : mine[s];
                     // item A at cell j - wB, i.e. c[i][j-wB], which item B reads
                     const double candAB = pA + shAB[s];
-                    const double r1B = dpGreater(candAB, shB[s]) ? candAB : shB[s];
+                    const double r1B = candAB > shB[s] ? candAB : shB[s];
                     // item B at cell j
                     const double candB = pB + r1B;
-                    const bool takeB = dpGreater(candB, r1);
+                    const bool takeB = candB > r1;
                     mine[s] = takeB ? candB : r1;
                     acc[s] |= (takeA ? bmA : 0u) | (takeB ? bmB : 0u);
                     wr[s] = mine[s];
@@ -555,7 +546,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                     const double cand = p + sh[s];        // :164
-                    const bool take = dpGreater(cand, mine[s]);     // :166 strict
+                    const bool take = cand > mine[s];     // :166 strict
                     mine[s] = take ? cand : mine[s];
                     acc[s] |= take ? bm : 0u;             // added[i][j]  (:168)
                     wr[s] = mine[s];
