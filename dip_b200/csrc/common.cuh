@@ -147,6 +147,9 @@ struct Ctx {
 
     // shard
     int firstBlock = 0, nLocal = 0;
+    unsigned long long *dDbgTimes = nullptr;  // diagnostics (option dp_debug_times): 8 stamps per CTA
+    unsigned long long *dPubWord = nullptr, *dPubCells = nullptr;  // fused DP kernel: per-block publication
+    unsigned int epoch = 0;                                          // launch counter of the fused DP kernel
     unsigned int *dDoneCounter = nullptr;  // ticket of the fused backtrack+filter kernel
     // -1 auto (2 when nLocal <= kFuseFilterMaxBlocks, else 0); 0 three kernels; 1 filter in the
     // backtrack kernel's tail; 2 backtrack + filter in the DP kernel's tail

@@ -178,6 +178,10 @@ static int setBlockRange(Ctx *c, int first, int count)
     DIPGPU_CUDA(c, cudaMemcpy(c->dBitsOff, off.data(), sizeof(int64_t) * ((size_t)count + 1), cudaMemcpyHostToDevice));
     if ((rc = devAlloc(c, &c->dBits, c->bitsWords))) return rc;
     if ((rc = devAlloc(c, &c->dNItems, (size_t)count))) return rc;
+    if ((rc = devAlloc(c, &c->dPubWord, (size_t)count))) return rc;
+    if ((rc = devAlloc(c, &c->dPubCells, (size_t)count))) return rc;
+    DIPGPU_CUDA(c, cudaMemset(c->dPubWord, 0, sizeof(unsigned long long) * std::max<size_t>((size_t)count, 1)));
+    c->epoch = 0;
     if ((rc = devAlloc(c, &c->dScale, (size_t)count))) return rc;
     if ((rc = devAlloc(c, &c->dShortcut, (size_t)count))) return rc;
     if ((rc = devAlloc(c, &c->dSel, 2 * (size_t)count))) return rc;
@@ -349,7 +353,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (!c) return DIPGPU_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    devFree(&c->dDoneCounter); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
+    devFree(&c->dDoneCounter); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
     devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems); devFree(&c->dScale); devFree(&c->dShortcut); devFree(&c->dSel); devFree(&c->dZShort);
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
@@ -718,6 +722,23 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!c || !name) return DIPGPU_ERR_INVALID;
     if (!strcmp(name, "stage_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "spmv_lanes")) { c->spmvLanes = (int)value; return DIPGPU_OK; }
+    if (!strcmp(name, "dp_debug_times")) {
+        // diagnostics: value = host pointer (as integer) receiving 8 x nLocal uint64 globaltimer stamps of
+        // the LAST DP launch, or 1 to switch stamping on, 0 off
+        int rc = bind(c);
+        if (rc) return rc;
+        if (value == 0) { devFree(&c->dDbgTimes); return DIPGPU_OK; }
+        if (value == 1) {
+            if ((rc = devAlloc(c, &c->dDbgTimes, 8 * (size_t)std::max(c->m, 1)))) return rc;
+            DIPGPU_CUDA(c, cudaMemset(c->dDbgTimes, 0, 64 * (size_t)std::max(c->m, 1)));
+            return DIPGPU_OK;
+        }
+        if (!c->dDbgTimes) return fail(c, DIPGPU_ERR_STATE, "dp_debug_times is off");
+        DIPGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+        DIPGPU_CUDA(c, cudaMemcpy(reinterpret_cast<void *>(static_cast<uintptr_t>(value)), c->dDbgTimes,
+                                  64 * (size_t)std::max(c->nLocal, 1), cudaMemcpyDeviceToHost));
+        return DIPGPU_OK;
+    }
     if (!strcmp(name, "spmv_warps")) { c->optSpmvWarps = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "spmv_u_smem")) { c->optSpmvUSmem = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "dp_threads") || !strcmp(name, "dp_cells_per_thread") || !strcmp(name, "dp_items_per_step") ||

@@ -130,13 +130,28 @@ __device__ __forceinline__ void filterScanBody(const FilterArgs &a, const int NT
         __syncthreads();
         const int nKept = sCarryCnt;
         const long long total = sCarryNnz;
-        for (long long idx = t; idx < total; idx += NT) {
-            int lo = 0, hi = nKept - 1;
-            while (lo < hi) {  // last kept column whose first output index is <= idx
-                const int mid = (lo + hi + 1) >> 1;
-                if (sDst[mid] <= idx) lo = mid; else hi = mid - 1;
+        // batches of 8 independent loads per thread: the L2 round trips overlap instead of
+        // serialising (a warp issues in order and would stall at each load's first use)
+        for (long long base = t; base < total; base += 8LL * NT) {
+            int v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const long long idx = base + (long long)q * NT;
+                v[q] = 0;
+                if (idx < total) {
+                    int lo = 0, hi = nKept - 1;
+                    while (lo < hi) {  // last kept column whose first output index is <= idx
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (sDst[mid] <= idx) lo = mid; else hi = mid - 1;
+                    }
+                    v[q] = __ldcg(a.candInd + sSrc[lo] + (int)(idx - sDst[lo]));
+                }
             }
-            a.keptInd[idx] = __ldcg(a.candInd + sSrc[lo] + (int)(idx - sDst[lo]));
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const long long idx = base + (long long)q * NT;
+                if (idx < total) a.keptInd[idx] = v[q];
+            }
         }
     } else if (a.fuseCopy) {
         __threadfence_block();

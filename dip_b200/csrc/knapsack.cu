@@ -243,6 +243,15 @@ __global__ void __launch_bounds__(kBackThreads) knap_backtrack_kernel(const __gr
 
 // ------------------------------------------------------------------- DP kernel
 
+__device__ __forceinline__ void dbgStamp(unsigned long long *buf, int slot)
+{
+    if (buf != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        buf[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+}
+
 #define kNegInf (__longlong_as_double((long long)0xfff0000000000000ULL))
 
 
@@ -265,6 +274,10 @@ struct KnapArgs {
     const int32_t *shortcut;       // Pisinger mode: local block -> trivial-case code (0 = run the DP)
     const double *zShort;          // Pisinger mode: local block -> optimum of a trivial case
     int fuseTail;                  // small shards: backtrack + filter run in this kernel's tail
+    unsigned long long *dbgTimes;  // diagnostics: 8 globaltimer stamps per CTA (NULL = off)
+    unsigned long long *pubWord;   // FUSE: per local block (epoch << 32) | kept << 31 | nnz
+    unsigned long long *pubCells;  // FUSE: per local block DP cells
+    unsigned int epoch;            // FUSE: launch counter carried by pubWord
     BackArgs back;
     FilterArgs filt;
 };
@@ -330,9 +343,12 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const int nCols = shortCode != 0 ? 0 : a.blockColStart[b + 1] - colStart;
     const double pScale = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? (double)a.scale[lb] : 0.0;
     const int cap = a.capacity[b];
+    // fetched now so that the (possibly cold) load is long done when the tail needs it
+    const double alphaB = FUSE ? a.back.alpha[b] : 0.0;
     uint32_t *bitsBase = FUSE ? sBits : a.bits + a.bitsOff[lb];
     const int j0 = t * S;  // first owned cell
 
+    dbgStamp(a.dbgTimes, 0);
     if (t == 0) mbarInit(mbar, 1);
     // c[-1][.] = 0 (gap_func.py:156); guards = -inf
     for (int j = t; j < 2 * bufStride; j += T) {
@@ -367,50 +383,85 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         }
         mbarWait(mbar, parity);
         parity ^= 1u;
+        dbgStamp(a.dbgTimes, 1);
 
-        // ---- order-preserving compaction of the active items (gap_func.py:102-105)
+        // ---- order-preserving compaction of the active items (gap_func.py:102-105): thread t owns
+        // the contiguous run [t*per, (t+1)*per) of the chunk's columns (thread order == item order),
+        // counts its active items, one block-wide exclusive scan places them.
         int nIt = 0;
-        for (int base = 0; base < len; base += T) {
-            const int cl = base + t;
-            bool flag = false;
-            double rc = 0.0;
-            int w = 0;
-            if (cl < len) {
-                rc = rawRc[shiftRc + cl];
-                w = rawW[shiftW + cl];
-                flag = (rc < 0.0) && (w <= cap);  // w > cap can never be taken (:161)
+        if (FUSE) {
+            const int per = (len + T - 1) / T;
+            const int c0 = min(len, t * per), c1 = min(len, c0 + per);
+            int mineCnt = 0;
+            for (int cl = c0; cl < c1; ++cl)
+                mineCnt += (rawRc[shiftRc + cl] < 0.0 && rawW[shiftW + cl] <= cap) ? 1 : 0;
+            // warp-inclusive scan, then the warps' totals
+            int incl = mineCnt;
+#pragma unroll
+            for (int off2 = 1; off2 < 32; off2 <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, off2);
+                if (lane >= off2) incl += up;
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, flag);
-            const int wpre = __popc(bal & ((1u << lane) - 1u));
-            int off = 0, tot = __popc(bal);
-            if (nWarps > 1) {
-                if (lane == 0) warpCnt[warp] = tot;
-                __syncthreads();
-                tot = 0;
-                for (int v = 0; v < nWarps; ++v) {
-                    const int cv = warpCnt[v];
-                    off += v < warp ? cv : 0;
-                    tot += cv;
-                }
-                __syncthreads();
+            if (lane == 31) warpCnt[warp] = incl;
+            __syncthreads();
+            int off = 0;
+            for (int v = 0; v < nWarps; ++v) {
+                const int cv = warpCnt[v];
+                off += v < warp ? cv : 0;
+                nIt += cv;
             }
-            if (flag) {
-                const int pos = nIt + off + wpre;
-                // profit: -redCost (gap_func.py:104), or its scaled integer value
-                // floor(-rc*scale + 0.5) held exactly in fp64 (GAP_KnapPisinger.h:174-177)
-                itP[pos] = pScale != 0.0 ? (double)(long long)floor((-rc) * pScale + 0.5) : -rc;
-                itW[pos] = w;
-                if (FUSE) {
+            int pos = off + incl - mineCnt;
+            for (int cl = c0; cl < c1; ++cl) {
+                const double rc = rawRc[shiftRc + cl];
+                const int w = rawW[shiftW + cl];
+                if (rc < 0.0 && w <= cap) {  // w > cap can never be taken (:161)
+                    // profit: -redCost (gap_func.py:104), or its scaled integer value
+                    // floor(-rc*scale + 0.5) held exactly in fp64 (GAP_KnapPisinger.h:174-177)
+                    itP[pos] = pScale != 0.0 ? (double)(long long)floor((-rc) * pScale + 0.5) : -rc;
+                    itW[pos] = w;
                     itC[pos] = cl;
-                } else {
+                    ++pos;
+                }
+            }
+        } else {
+            // throughput shapes: strided ballot compaction (one column per thread and round)
+            for (int base = 0; base < len; base += T) {
+                const int cl = base + t;
+                bool flag = false;
+                double rc = 0.0;
+                int w = 0;
+                if (cl < len) {
+                    rc = rawRc[shiftRc + cl];
+                    w = rawW[shiftW + cl];
+                    flag = (rc < 0.0) && (w <= cap);  // w > cap can never be taken (:161)
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, flag);
+                const int wpre = __popc(bal & ((1u << lane) - 1u));
+                int off = 0, tot = __popc(bal);
+                if (nWarps > 1) {
+                    if (lane == 0) warpCnt[warp] = tot;
+                    __syncthreads();
+                    tot = 0;
+                    for (int v = 0; v < nWarps; ++v) {
+                        const int cv = warpCnt[v];
+                        off += v < warp ? cv : 0;
+                        tot += cv;
+                    }
+                    __syncthreads();
+                }
+                if (flag) {
+                    const int pos = nIt + off + wpre;
+                    itP[pos] = pScale != 0.0 ? (double)(long long)floor((-rc) * pScale + 0.5) : -rc;
+                    itW[pos] = w;
                     const int slot = colStart + kGlobal + pos;
                     a.itemW[slot] = w;
                     a.itemCol[slot] = chunkBase + cl;
                 }
+                nIt += tot;
             }
-            nIt += tot;
         }
         __syncthreads();
+        dbgStamp(a.dbgTimes, 2);
 
         // ---- the DP proper: items sequential, cells parallel.  (w0,p0),(w1,p1) hold
         // items i and i+1, fetched one step ahead (itP/itW are padded by four entries).
@@ -582,59 +633,169 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         }
     }
     if (t == 0) a.nItems[lb] = kGlobal;
+    dbgStamp(a.dbgTimes, 3);
     if (FUSE) {
+        // ---- stage (b) continued: the column of this block, out of shared memory
+        __shared__ int sCnt;
+        __shared__ double sRcSum, sOcSum;
+        int32_t *sFinal = itC;  // ascending x-space indices of the column (itC is free after the walk)
         __syncthreads();
-        if (warp == 0 && shortCode != 0) {
-            emitShortcut(a.back, lb, lane, shortCode);
-        } else if (warp == 0) {
-            // backtrack from (last item, capacity), gap_func.py:173-181, out of shared memory
-            int j = cap;
-            int i = kGlobal - 1;
+        if (warp == 0) {
             int cnt = 0;
-            while (i >= 0) {
-                const int kw = i >> 5;
-                const int wv = kw - lane;
-                uint32_t v = wv >= 0 ? sBits[(size_t)wv * RC + j] : 0u;
-                if (lane == 0) v &= 0xffffffffu >> (31 - (i & 31));
-                const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
-                if (nz == 0u) {
-                    i = ((kw - 32) << 5) | 31;
-                    continue;
+            if (shortCode == 1) {
+                // GAP_KnapPisinger.h:206-212: every item with negative reduced cost
+                const int nAll = a.blockColStart[b + 1] - colStart;
+                for (int base = 0; base < nAll; base += 32) {
+                    const int j = base + lane;
+                    const bool act = j < nAll && a.redCost[colStart + j] < 0.0;
+                    const unsigned bal = __ballot_sync(0xffffffffu, act);
+                    if (act) sFinal[cnt + __popc(bal & ((1u << lane) - 1u))] = colStart + j;
+                    cnt += __popc(bal);
                 }
-                const int L = __ffs(nz) - 1;
-                const uint32_t vL = __shfl_sync(0xffffffffu, v, L);
-                const int item = ((kw - L) << 5) + (31 - __clz(vL));
-                if (lane == 0) sTaken[cnt] = itC[item];
-                ++cnt;
-                j -= itW[item];
-                i = item - 1;
+            } else if (shortCode == 2) {
+                for (int k = 0; k < 2; ++k) {
+                    const int j = a.back.sel[2 * lb + k];
+                    if (j >= 0) {
+                        if (lane == 0) sFinal[cnt] = colStart + j;
+                        ++cnt;
+                    }
+                }
+            } else {
+                // backtrack from (last item, capacity), gap_func.py:173-181
+                int j = cap;
+                int i = kGlobal - 1;
+                while (i >= 0) {
+                    const int kw = i >> 5;
+                    const int wv = kw - lane;
+                    uint32_t v = wv >= 0 ? sBits[(size_t)wv * RC + j] : 0u;
+                    if (lane == 0) v &= 0xffffffffu >> (31 - (i & 31));
+                    const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
+                    if (nz == 0u) {
+                        i = ((kw - 32) << 5) | 31;
+                        continue;
+                    }
+                    const int L = __ffs(nz) - 1;
+                    const uint32_t vL = __shfl_sync(0xffffffffu, v, L);
+                    const int item = ((kw - L) << 5) + (31 - __clz(vL));
+                    if (lane == 0) sTaken[cnt] = itC[item];
+                    ++cnt;
+                    j -= itW[item];
+                    i = item - 1;
+                }
+                __syncwarp();
+                // the walk found the items last-to-first: reverse into ascending x-space indices
+                for (int k = lane; k < cnt; k += 32) sFinal[k] = colStart + sTaken[cnt - 1 - k];
             }
             __syncwarp();
-            // emit ascending x-space indices; sums in that order (GAP_KnapPisinger.h:263-272)
-            const int shiftRc = colStart & 1;
-            double rcs = 0.0, ocs = 0.0;
-            for (int base = 0; base < cnt; base += 32) {
-                const int k = base + lane;
-                double r = 0.0, o = 0.0;
-                if (k < cnt) {
-                    const int lc = sTaken[cnt - 1 - k];
-                    a.back.candInd[colStart + k] = colStart + lc;
-                    r = rawRc[shiftRc + lc];
-                    o = a.back.obj[colStart + lc];
+            // varRedCost / varOrigCost: added in ascending index order (GAP_KnapPisinger.h:263-272).
+            // All lanes fetch, one lane adds sequentially out of shared memory.
+            double *sVals = itP;  // free after the DP
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int k = lane; k < cnt; k += 32)
+                    sVals[k] = pass == 0 ? a.redCost[sFinal[k]] : a.back.obj[sFinal[k]];
+                __syncwarp();
+                if (lane == 0) {
+                    double acc2 = 0.0;
+                    for (int k = 0; k < cnt; ++k) acc2 += sVals[k];
+                    if (pass == 0) sRcSum = acc2; else sOcSum = acc2;
                 }
-                const int nn = min(32, cnt - base);
-                for (int q = 0; q < nn; ++q) {
-                    rcs += __shfl_sync(0xffffffffu, r, q);
-                    ocs += __shfl_sync(0xffffffffu, o, q);
+                __syncwarp();
+            }
+            if (lane == 0) sCnt = cnt;
+        }
+        __syncthreads();
+        dbgStamp(a.dbgTimes, 4);
+
+        // ---- stage (c), DecompAlgo.cpp:5151-5232, without a second launch and without a serial
+        // tail: every CTA publishes (kept?, nnz, cells) and waits only for the LOWER-numbered
+        // blocks to learn where its column goes (CTAs are dispatched in index order, block 0 never
+        // waits).  Words carry the launch epoch, so nothing has to be reset between rounds.
+        const int cnt = sCnt;
+        const double rcB = sRcSum - alphaB;  // DecompAlgo.cpp:6350-6356
+        const bool keep = rcB < -a.filt.eps;          // strict, :5216
+        const unsigned long long myCells = (unsigned long long)kGlobal * (unsigned long long)(cap + 1);
+        if (t == 0) {
+            // one 64-bit word per block: epoch (8) | kept (1) | cells (24) | nnz (31).  In the fused
+            // shapes cells = items (<= 2048) x row cells (<= 7168) < 2^24; every block publishes in
+            // every round, so a stale word always carries the previous epoch.  Published FIRST: the
+            // word is all the other blocks need, the result stores below are read by the host only.
+            const unsigned long long word = ((unsigned long long)(a.epoch & 0xffu) << 56) | (keep ? 1ull << 55 : 0ull) |
+                                            ((myCells & 0xffffffull) << 31) | (unsigned long long)cnt;
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.pubWord + lb), "l"(word) : "memory");
+            a.back.blockRedCost[lb] = rcB;
+            a.back.blockOrigCost[lb] = sOcSum;
+            a.back.blockNnz[lb] = cnt;
+            a.filt.blockMostNeg[lb] = rcB < 0.0 ? rcB : 0.0;  // min(0, rc): for EVERY block (:5212)
+        }
+        // prefix over the lower blocks: each thread polls its share, warp-shuffle reduction, then
+        // the per-warp partials (shared-memory 64-bit atomics would serialise through CAS loops)
+        __shared__ int sKeptW[32];
+        __shared__ unsigned long long sNnzW[32], sCellsW[32];
+        __shared__ int sKept;
+        __shared__ unsigned long long sNnz, sCells;
+        {
+            int kc = 0;
+            unsigned long long nz = 0ull, cl = 0ull;
+            for (int pB = t; pB < lb; pB += T) {
+                unsigned long long wv;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(wv) : "l"(a.pubWord + pB) : "memory");
+                } while ((unsigned int)(wv >> 56) != (a.epoch & 0xffu));
+                if (wv & (1ull << 55)) {
+                    ++kc;
+                    nz += wv & 0x7fffffffull;
                 }
+                cl += (wv >> 31) & 0xffffffull;
+            }
+#pragma unroll
+            for (int off2 = 16; off2 > 0; off2 >>= 1) {
+                kc += __shfl_xor_sync(0xffffffffu, kc, off2);
+                nz += __shfl_xor_sync(0xffffffffu, nz, off2);
+                cl += __shfl_xor_sync(0xffffffffu, cl, off2);
             }
             if (lane == 0) {
-                a.back.blockRedCost[lb] = rcs - a.back.alpha[b];  // DecompAlgo.cpp:6350-6356
-                a.back.blockOrigCost[lb] = ocs;
-                a.back.blockNnz[lb] = cnt;
+                sKeptW[warp] = kc;
+                sNnzW[warp] = nz;
+                sCellsW[warp] = cl;
             }
         }
-        ticketThenFilter(a.back.doneCounter, a.filt, T);
+        __syncthreads();
+        if (t == 0) {
+            int kc = 0;
+            unsigned long long nz = 0ull, cl = 0ull;
+            for (int v = 0; v < nWarps; ++v) {
+                kc += sKeptW[v];
+                nz += sNnzW[v];
+                cl += sCellsW[v];
+            }
+            sKept = kc;
+            sNnz = nz;
+            sCells = cl;
+        }
+        __syncthreads();
+        const int pos = sKept;
+        const long long off = (long long)sNnz;
+        if (keep) {
+            if (t == 0) {
+                a.filt.keptBlock[pos] = lb;
+                a.filt.keptStart[pos] = off;
+            }
+            for (int k = t; k < cnt; k += T) a.filt.keptInd[off + k] = sFinal[k];
+        }
+        if (lb == a.back.nLocal - 1 && t == 0) {
+            // the highest block has seen every other block: it closes the packed result
+            const int nKept = pos + (keep ? 1 : 0);
+            const long long nInd = off + (keep ? cnt : 0);
+            a.filt.keptStart[nKept] = nInd;
+            a.filt.hdr->magic = kResultMagic;
+            a.filt.hdr->m = a.back.nLocal;
+            a.filt.hdr->firstBlock = a.firstBlock;
+            a.filt.hdr->nKept = nKept;
+            a.filt.hdr->nInd = nInd;
+            a.filt.hdr->cells = (long long)(sCells + myCells);
+            a.filt.hdr->indCap = a.filt.indCap;
+        }
+        dbgStamp(a.dbgTimes, 5);
     }
 }
 
@@ -837,6 +998,10 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, doubl
     a.chunkCols = g.chunkCols;
     a.guard = g.guard;
     a.fuseTail = g.fuse;
+    a.dbgTimes = c->dDbgTimes;
+    a.pubWord = c->dPubWord;
+    a.pubCells = c->dPubCells;
+    a.epoch = ++c->epoch;
     a.profitMode = c->profitMode;
     a.scale = c->dScale;
     a.shortcut = c->dShortcut;

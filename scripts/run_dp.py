@@ -26,3 +26,17 @@ with GpuPricer(0) as p:
     for _ in range(reps):
         res = p.solveBlocks(b.red_cost, b.alpha, redCostEps=-np.inf)
         print(p.last_stage_ms(), res.cells)
+    if os.environ.get("DP_TIMES"):
+        p.set_option("dp_debug_times", 1)
+        res = p.solveBlocks(b.red_cost, b.alpha, redCostEps=-np.inf)
+        res = p.solveBlocks(b.red_cost, b.alpha, redCostEps=-np.inf)
+        tt = np.zeros((b.m, 8), np.uint64)
+        p.set_option("dp_debug_times", tt.ctypes.data)
+        t0 = tt[:, 0].min()
+        rel = (tt.astype(np.int64) - np.int64(t0)) / 1e3
+        names = ["start", "staged", "compacted", "dp_done", "backtracked", "filtered"]
+        print(p.dpGeometry())
+        for k, nm in enumerate(names):
+            col = rel[:, k]
+            print(f"{nm:12s} min {col.min():8.2f}  mean {col.mean():8.2f}  max {col.max():8.2f} us")
+        print("last CTA (max filtered) block", int(rel[:, 5].argmax()), "stamps", rel[int(rel[:, 5].argmax()), :6])
