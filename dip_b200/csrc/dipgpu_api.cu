@@ -91,7 +91,11 @@ static int uploadCore(Ctx *c)
         for (int j = 0; j <= N; ++j) cs32[j] = (int32_t)colStart[j];
         const bool row16 = (int64_t)R + c->numConvex <= 65536;
         const int64_t alignMask = row16 ? 7 : 3;  // 16 bytes of the row stream
-        const int maxCols = 32 * kSpmvColsPerLane;
+        // columns per warp tile: up to 32*kSpmvColsPerLane, fewer on small matrices so that every SM
+        // still gets ~16 warp tiles (a GAP-E sweep is latency-bound: more, shorter tiles in flight)
+        const int sms = c->smCount > 0 ? c->smCount : 148;
+        int maxCols = (int)std::min<int64_t>(32 * kSpmvColsPerLane, (int64_t)N / (16 * sms)) & ~31;
+        maxCols = std::max(32, maxCols);
         bool ok = true;
         int j = 0;
         tileCol.push_back(0);

@@ -215,9 +215,21 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sVal[k + 32 * j] = __dmul_rn(g[j], v[j]);
             }
-            for (; k < len; k += 32) {
-                const int r = sRow[k];
-                sVal[k] = __dmul_rn(U_SMEM ? sU[r] : __ldg(a.u + r), sVal[k]);
+            {
+                // remainder (< 4 rounds): still one batch, so the gathers overlap
+                int r[4];
+                double v[4], g[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int kk = k + 32 * j;
+                    r[j] = kk < len ? (int)sRow[kk] : 0;
+                    v[j] = kk < len ? sVal[kk] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g[j] = (k + 32 * j < len) ? (U_SMEM ? sU[r[j]] : __ldg(a.u + r[j])) : 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (k + 32 * j < len) sVal[k + 32 * j] = __dmul_rn(g[j], v[j]);
             }
         }
         __syncwarp();
