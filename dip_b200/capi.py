@@ -33,7 +33,7 @@ SYMBOLS = [
     "dipgpu_result_max_bytes", "dipgpu_unpack_result", "dipgpu_redcost_dev",
     "dipgpu_get_counters", "dipgpu_last_stage_ms", "dipgpu_set_option",
     "dipgpu_calc_redcost_dev", "dipgpu_measure_smem_gbs", "dipgpu_plan_dp_geometry",
-    "dipgpu_get_dp_geometry",
+    "dipgpu_get_dp_geometry", "dipgpu_expand_columns",
 ]
 
 
@@ -52,6 +52,14 @@ class Cols(C.Structure):
         ("nCols", C.c_int32), ("colBlock", C.c_void_p), ("colRedCost", C.c_void_p),
         ("colOrigCost", C.c_void_p), ("colStart", C.c_void_p), ("colInd", C.c_void_p),
         ("nInd", C.c_int64), ("mostNegReducedCost", C.c_double), ("cells", C.c_int64),
+    ]
+
+
+class MCols(C.Structure):
+    """struct dipgpu_mcols (include/dipgpu.h)."""
+    _fields_ = [
+        ("capCols", C.c_int32), ("capNnz", C.c_int64), ("nCols", C.c_int32), ("nNnz", C.c_int64),
+        ("colStart", C.c_void_p), ("rowInd", C.c_void_p), ("val", C.c_void_p), ("hash", C.c_void_p),
     ]
 
 
@@ -88,6 +96,7 @@ def lib() -> C.CDLL:
         "dipgpu_measure_smem_gbs": ([vp, C.POINTER(dbl)], C.c_int),
         "dipgpu_plan_dp_geometry": ([i32, i32, i32, i32, i32, C.POINTER(i32)], C.c_int),
         "dipgpu_get_dp_geometry": ([vp, C.POINTER(i32)], C.c_int),
+        "dipgpu_expand_columns": ([vp, dbl, C.POINTER(MCols)], C.c_int),
         "dipgpu_solve_blocks_dev": ([vp, vp, vp, dbl, vp], C.c_int),
         "dipgpu_result_dev": ([vp, C.POINTER(vp), C.POINTER(C.c_size_t)], C.c_int),
         "dipgpu_result_max_bytes": ([vp, C.POINTER(C.c_size_t)], C.c_int),

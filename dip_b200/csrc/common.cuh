@@ -73,6 +73,28 @@ constexpr int kSpmvChunk = 384;        // stored entries per warp tile (4.5 KiB 
 constexpr int kSpmvColsPerLane = 4;    // a warp tile spans at most 32*4 consecutive columns (fewer when the
                                        // kSpmvChunk entry budget is reached first)
 
+// ------------------------------------------------- packed master columns (expand.cu)
+//   MColsHeader                64 B
+//   int64  colStart[m + 1]     offsets into entries
+//   uint64 hash[m]             fingerprint of (block, x-space indices) for duplicate detection
+//   MColEntry entries[cap]     (master row ascending per column, value)
+struct MColsHeader {
+    uint32_t magic;  // 'DIPM'
+    uint32_t flags;  // bit 0: a column touched more rows than fit the staging area; bit 1: capacity
+    int32_t nCols;
+    int32_t pad;
+    int64_t nNnz;
+    int64_t reserved[5];
+};
+static_assert(sizeof(MColsHeader) == 64, "header is 64 bytes");
+constexpr uint32_t kMColsMagic = 0x4d504944u;
+struct MColEntry {
+    int32_t row;
+    int32_t pad;
+    double val;
+};
+static_assert(sizeof(MColEntry) == 16, "entry is 16 bytes");
+
 // ------------------------------------------------------------------ DP geometry
 //
 // A knapsack's DP row of (capacity+1) cells is owned by T threads, S consecutive
@@ -113,6 +135,21 @@ struct Ctx {
     void *spmvFn = nullptr;                   // kernel whose shared-memory limit is already set
     size_t spmvFnSmem = 0;
     uint16_t *dRowMaster16 = nullptr;         // rowMaster as uint16 when R + numConvex <= 65536
+
+    // row-major copy of A'' (expand.cu re-walks touched rows in the reference's storage order)
+    int32_t *dCsrRowStart = nullptr;  // R+1 (only when nnz < 2^31)
+    int32_t *dCsrColInd = nullptr;
+    double *dCsrVal = nullptr;
+    // packed master columns of the last expansion
+    void *dMCols = nullptr, *hMCols = nullptr;
+    size_t mcolsBytes = 0, mcolsOffColStart = 0, mcolsOffHash = 0, mcolsOffEntries = 0;
+    int64_t mcolsCapEntries = 0;
+    unsigned long long *dExpPub = nullptr;
+    unsigned int expEpoch = 0;
+    size_t expSmem = 0;
+    std::vector<int64_t> hColStart;  // host copy of the CSC column starts
+    int expMaxTouched = 0;           // bound on the rows one column can touch
+    bool lastRoundOnHost = false;  // hResult holds the header of the last round
 
     double *dObj = nullptr;  // c[N]
     bool haveObj = false;
@@ -214,6 +251,8 @@ int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, do
                         cudaStream_t st);
 // filter.cu -- stage (c)
 int launchFilter(Ctx *c, double redCostEps, cudaStream_t st);
+// expand.cu -- master columns of the kept variables (the step after the round)
+int launchExpandColumns(Ctx *c, double tolZero, int nKept, cudaStream_t st);
 // microbench.cu -- roofline denominators measured on the device
 int measureSmemGbs(Ctx *c, double *gbs);
 

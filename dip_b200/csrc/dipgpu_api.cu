@@ -81,6 +81,7 @@ static int uploadCore(Ctx *c)
         }
     }
     c->nnz = nnz;
+    c->hColStart = colStart;
     int rc;
     // warp tiles of the stream kernel: consecutive columns, <= kSpmvChunk stored entries (counted
     // from the 4-aligned start), <= 32*colsPerLane columns with colsPerLane fitted to the density
@@ -129,6 +130,20 @@ static int uploadCore(Ctx *c)
                 DIPGPU_CUDA(c, cudaMemcpy(c->dRowMaster16, r16.data(), sizeof(uint16_t) * r16.size(), cudaMemcpyHostToDevice));
             }
             c->nSpmvTiles = (int)tileCol.size() - 1;
+        }
+    }
+    // row-major copy for expand.cu
+    devFree(&c->dCsrRowStart); devFree(&c->dCsrColInd); devFree(&c->dCsrVal);
+    if (nnz < (int64_t)1 << 31) {
+        std::vector<int32_t> rs32((size_t)R + 1);
+        for (int i = 0; i <= R; ++i) rs32[i] = (int32_t)c->hRowStart[i];
+        if ((rc = devAlloc(c, &c->dCsrRowStart, (size_t)R + 1))) return rc;
+        if ((rc = devAlloc(c, &c->dCsrColInd, (size_t)nnz + 1))) return rc;
+        if ((rc = devAlloc(c, &c->dCsrVal, (size_t)nnz + 1))) return rc;
+        DIPGPU_CUDA(c, cudaMemcpy(c->dCsrRowStart, rs32.data(), sizeof(int32_t) * rs32.size(), cudaMemcpyHostToDevice));
+        if (nnz > 0) {
+            DIPGPU_CUDA(c, cudaMemcpy(c->dCsrColInd, c->hColInd.data(), sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+            DIPGPU_CUDA(c, cudaMemcpy(c->dCsrVal, c->hVal.data(), sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
         }
     }
     if ((rc = devAlloc(c, &c->dColStart, (size_t)N + 1))) return rc;
@@ -357,7 +372,9 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (!c) return DIPGPU_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    devFree(&c->dDoneCounter); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
+    devFree(&c->dDoneCounter); devFree(&c->dCsrRowStart); devFree(&c->dCsrColInd); devFree(&c->dCsrVal); devFree(&c->dExpPub);
+    if (c->dMCols) cudaFree(c->dMCols);
+    if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
     devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems); devFree(&c->dScale); devFree(&c->dShortcut); devFree(&c->dSel); devFree(&c->dZShort);
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
@@ -508,6 +525,7 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
         DIPGPU_CUDA(c, cudaMemset(c->dRedCost, 0, sizeof(double) * ((size_t)c->N + 16)));
     }
     c->haveBlocks = true;
+    c->lastRoundOnHost = false;
     return setBlockRange(c, 0, m);
 }
 
@@ -555,6 +573,7 @@ int dipgpu_solve_blocks(dipgpu_ctx *ctx, const double *redCostX, const double *a
     if (timed) { cudaEventRecord(c->ev[1], st); cudaEventRecord(c->ev[2], st); }
     if ((rc = enqueueSolve(c, c->dRedCost, c->dAlpha, redCostEps, st, timed))) return rc;
     if ((rc = fetchResult(c, st))) return rc;
+    c->lastRoundOnHost = true;
     collectStageMs(c);
     return unpack(c, c->hResult, c->resultBytes, out);
 }
@@ -589,8 +608,88 @@ int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t p
         c->d2h += (int64_t)sizeof(double) * c->N;
     }
     if ((rc = fetchResult(c, st))) return rc;
+    c->lastRoundOnHost = true;
     collectStageMs(c);
     return unpack(c, c->hResult, c->resultBytes, out);
+}
+
+int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
+{
+    CTX_OR_FAIL(ctx);
+    if (!out) return fail(c, DIPGPU_ERR_INVALID, "expand_columns: NULL output");
+    if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "expand_columns needs set_core_csr and set_knapsack_blocks");
+    if (!c->lastRoundOnHost) return fail(c, DIPGPU_ERR_STATE, "expand_columns: no host-buffer pricing round since the model was set");
+    if (!c->dCsrRowStart || !c->dColStart32) return fail(c, DIPGPU_ERR_UNSUPPORTED, "expand_columns: more than 2^31 stored entries");
+    const ResultHeader *rh = static_cast<const ResultHeader *>(c->hResult);
+    const int nKept = rh->nKept;
+    out->nCols = nKept;
+    out->nNnz = 0;
+    if (nKept == 0) {
+        if (out->colStart && out->capCols >= 0) out->colStart[0] = 0;
+        return DIPGPU_OK;
+    }
+    int rc;
+    // packed output buffer: worst case one entry per stored entry of A'' plus one per column
+    const int64_t capEntries = c->nnz + c->m + 16;
+    const size_t offColStart = sizeof(MColsHeader);
+    const size_t offHash = offColStart + sizeof(int64_t) * ((size_t)c->m + 1);
+    const size_t offEntries = ResultLayout::alignUp(offHash + sizeof(uint64_t) * (size_t)c->m, 16);
+    const size_t bytes = offEntries + sizeof(MColEntry) * (size_t)capEntries;
+    if (bytes != c->mcolsBytes) {
+        if (c->dMCols) cudaFree(c->dMCols);
+        if (c->hMCols) cudaFreeHost(c->hMCols);
+        c->dMCols = c->hMCols = nullptr;
+        c->mcolsBytes = 0;
+        DIPGPU_CUDA(c, cudaMalloc(&c->dMCols, bytes));
+        DIPGPU_CUDA(c, cudaMallocHost(&c->hMCols, bytes));
+        if ((rc = devAlloc(c, &c->dExpPub, (size_t)c->m))) return rc;
+        DIPGPU_CUDA(c, cudaMemset(c->dExpPub, 0, sizeof(unsigned long long) * (size_t)std::max(c->m, 1)));
+        c->expEpoch = 0;
+        c->mcolsBytes = bytes;
+        c->mcolsOffColStart = offColStart;
+        c->mcolsOffHash = offHash;
+        c->mcolsOffEntries = offEntries;
+        c->mcolsCapEntries = capEntries;
+    }
+    // a column of block b touches at most as many rows as block b's x-columns have stored entries
+    int64_t maxBlockNnz = 1;
+    for (int b = c->firstBlock; b < c->firstBlock + c->nLocal; ++b) {
+        const int s0 = c->hBlockColStart[b], s1 = c->hBlockColStart[b + 1];
+        if (s1 <= c->N) maxBlockNnz = std::max<int64_t>(maxBlockNnz, c->hColStart[s1] - c->hColStart[s0]);
+    }
+    c->expMaxTouched = (int)std::min<int64_t>(maxBlockNnz, c->R);
+    cudaStream_t st = c->stream;
+    if ((rc = launchExpandColumns(c, tolZero, nKept, st))) return rc;
+    // D2H: header + starts + fingerprints + a first slab of entries, the rest only if needed
+    const size_t spec = std::min(bytes, offEntries + (size_t)131072);
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->hMCols, c->dMCols, spec, cudaMemcpyDeviceToHost, st));
+    DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+    c->d2h += (int64_t)spec;
+    const char *hp = static_cast<const char *>(c->hMCols);
+    const MColsHeader *mh = reinterpret_cast<const MColsHeader *>(hp);
+    if (mh->magic != kMColsMagic || mh->nCols != nKept) return fail(c, DIPGPU_ERR_CUDA, "expand_columns: bad result header");
+    if (mh->flags & 1u) return fail(c, DIPGPU_ERR_UNSUPPORTED, "expand_columns: a column touches more rows than the shared-memory staging area holds");
+    if (mh->flags & 2u) return fail(c, DIPGPU_ERR_NOMEM, "expand_columns: device output capacity exceeded");
+    const size_t need = offEntries + sizeof(MColEntry) * (size_t)mh->nNnz;
+    if (need > spec) {
+        DIPGPU_CUDA(c, cudaMemcpyAsync(static_cast<char *>(c->hMCols) + spec, static_cast<char *>(c->dMCols) + spec,
+                                       need - spec, cudaMemcpyDeviceToHost, st));
+        DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+        c->d2h += (int64_t)(need - spec);
+    }
+    out->nNnz = mh->nNnz;
+    if (nKept > out->capCols || mh->nNnz > out->capNnz)
+        return fail(c, DIPGPU_ERR_OVERFLOW, "expand_columns needs capCols >= %d, capNnz >= %lld", nKept, (long long)mh->nNnz);
+    const int64_t *cs = reinterpret_cast<const int64_t *>(hp + offColStart);
+    const uint64_t *hs = reinterpret_cast<const uint64_t *>(hp + offHash);
+    const MColEntry *en = reinterpret_cast<const MColEntry *>(hp + offEntries);
+    if (out->colStart) memcpy(out->colStart, cs, sizeof(int64_t) * ((size_t)nKept + 1));
+    if (out->hash) memcpy(out->hash, hs, sizeof(uint64_t) * (size_t)nKept);
+    for (int64_t q = 0; q < mh->nNnz; ++q) {
+        if (out->rowInd) out->rowInd[q] = en[q].row;
+        if (out->val) out->val[q] = en[q].val;
+    }
+    return DIPGPU_OK;
 }
 
 int dipgpu_price_round_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, int32_t phase, double redCostEps, void *stream)

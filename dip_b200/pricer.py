@@ -234,6 +234,30 @@ class GpuPricer:
         if rc != capi.OK:
             self._check(rc)
 
+    def expandColumns(self, tolZero=1e-6):
+        """Master columns of the columns kept by the last round = the per-variable work of
+        DecompAlgo::addVarsToPool (DecompAlgo.cpp:5452-5558).  Returns (colStart, rowInd, val, hash):
+        column k = kept column k; rowInd ascending master rows; hash = 64-bit fingerprint of
+        (block, x-space indices) for duplicate detection."""
+        cap_cols = max(self.m, 1)
+        cap_nnz = 1 << 16
+        while True:
+            col_start = np.zeros(cap_cols + 1, np.int64)
+            row_ind = np.zeros(cap_nnz, np.int32)
+            val = np.zeros(cap_nnz, np.float64)
+            hsh = np.zeros(cap_cols, np.uint64)
+            mc = capi.MCols()
+            mc.capCols, mc.capNnz = cap_cols, cap_nnz
+            mc.colStart, mc.rowInd, mc.val, mc.hash = (capi.ptr(col_start), capi.ptr(row_ind), capi.ptr(val),
+                                                       capi.ptr(hsh))
+            rc = self._lib.dipgpu_expand_columns(self._ctx, float(tolZero), C.byref(mc))
+            if rc == capi.ERR_OVERFLOW and mc.nNnz > cap_nnz:
+                cap_nnz = int(mc.nNnz)
+                continue
+            self._check(rc)
+            n = mc.nCols
+            return col_start[:n + 1], row_ind[:mc.nNnz], val[:mc.nNnz], hsh[:n]
+
     # ---- the reference's two plugin surfaces ---------------------------------
     def generateVars(self, u, phase=PHASE_PRICE2, redCostEps=1e-4):
         """DecompAlgo::generateVars(newVars, mostNegReducedCost): returns (newVars, mostNegRC)."""

@@ -176,6 +176,32 @@ int dipgpu_solve_blocks(dipgpu_ctx *ctx, const double *redCostX, const double *a
 int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase,
                        double redCostEps, dipgpu_cols *out, double *redCostXOpt);
 
+/* ------------------------------------------------- after the round: master columns
+ *
+ * Master-LP columns of the columns kept by the LAST host-buffer round of this context
+ * (dipgpu_price_round / dipgpu_solve_blocks): what DecompAlgo::addVarsToPool computes per new
+ * variable (Dip/src/DecompAlgo.cpp:5452-5558) -- A''s through the row-ordered matrix, the cut rows
+ * moved behind the convexity rows, 1.0 in the block's convexity row, entries with |v| > tolZero
+ * (DecompParam::TolZero, 1e-6) in ascending master-row order -- plus a 64-bit fingerprint of
+ * (block, x-space indices) per column, to be compared where DecompVarPool::isDuplicate compares
+ * the string hash of Dip/src/UtilHash.cpp:52-68 (Dip/src/DecompVarPool.cpp:150-181).  Column k of
+ * the output is kept column k of the round.  Needs dipgpu_set_core_csr.
+ */
+typedef struct dipgpu_mcols {
+    /* in: capacities */
+    int32_t capCols; /* colStart has capCols+1, hash capCols entries */
+    int64_t capNnz;  /* rowInd / val */
+    /* out */
+    int32_t nCols;
+    int64_t nNnz; /* required capNnz on DIPGPU_ERR_OVERFLOW */
+    int64_t *colStart;
+    int32_t *rowInd; /* master row indices, ascending per column */
+    double *val;
+    uint64_t *hash;
+} dipgpu_mcols;
+
+int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out);
+
 /* ---------------------------------------- device-resident variants (multi-GPU)
  *
  * For the block-sharded multi-GPU driver: the dual vector is already in device

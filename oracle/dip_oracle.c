@@ -321,6 +321,41 @@ int dip_oracle_price_round(int R, int N, const int64_t *rowStart, const int32_t 
     return kept;
 }
 
+int dip_oracle_expand_column(int R, int N, const int64_t *rowStart, const int32_t *colInd,
+                             const double *val, int nBase, int numConvex, int nInd,
+                             const int32_t *ind, const double *els, int blockId, double tolZero,
+                             int32_t *outRow, double *outVal)
+{
+    /* DecompVar::fillDenseArr, DecompVar.cpp:58-70 */
+    double *x = (double *)calloc((size_t)(N > 0 ? N : 1), sizeof(double));
+    for (int k = 0; k < nInd; ++k) x[ind[k]] = els ? els[k] : 1.0;
+    /* modelCore->M->times(x, denseCol), DecompAlgo.cpp:5484 (row-major: one dot product per row) */
+    const int nRows = R + numConvex;
+    double *dense = (double *)calloc((size_t)(nRows > 0 ? nRows : 1), sizeof(double));
+    for (int i = 0; i < R; ++i) {
+        double y = 0.0;
+        for (int64_t k = rowStart[i]; k < rowStart[i + 1]; ++k) y += val[k] * x[colInd[k]];
+        dense[i] = y;
+    }
+    /* DecompAlgo.cpp:5532-5540: cuts slide behind the convexity rows, which are zeroed but for the block */
+    const int nCuts = R - nBase;
+    for (int r = nRows - 1; r >= nRows - nCuts; --r) dense[r] = dense[r - numConvex];
+    for (int b = 0; b < numConvex; ++b) dense[nBase + b] = 0.0;
+    dense[nBase + blockId] = 1.0;
+    /* UtilPackedVectorFromDense, UtilMacrosDecomp.cpp:46-60 */
+    int nnz = 0;
+    for (int i = 0; i < nRows; ++i) {
+        if (fabs(dense[i]) > tolZero) {
+            outRow[nnz] = i;
+            outVal[nnz] = dense[i];
+            ++nnz;
+        }
+    }
+    free(x);
+    free(dense);
+    return nnz;
+}
+
 int dip_oracle_string_hash(int len, const int32_t *ind, const double *els, char *buf,
                            int bufLen)
 {

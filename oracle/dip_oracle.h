@@ -104,6 +104,18 @@ int dip_oracle_solve_blocks(int m, const int32_t *blockColStart, const int32_t *
                             double *mostNegRC, double *z, int32_t *colIndOut,
                             double *mostNegReducedCost, int64_t *cellsOut);
 
+/* Master column of a variable = DecompAlgo::addVarsToPool, Dip/src/DecompAlgo.cpp:5452-5558:
+ *   fillDenseArr (Dip/src/DecompVar.cpp:58-70) -> modelCore->M->times(s, denseCol) on the row-ordered
+ *   A'' (y[i] = sum over row i's stored entries, in storage order, of val * s[col]) -> the cut rows
+ *   (core rows >= nBase) move behind the numConvex convexity rows (:5532-5534), 1.0 in the block's
+ *   convexity row (:5540) -> UtilPackedVectorFromDense keeps |v| > tolZero, ascending row
+ *   (Dip/src/UtilMacrosDecomp.cpp:46-60).  els == NULL means all elements are 1.0.
+ * outRow/outVal need R + numConvex entries.  Returns the number of nonzeros. */
+int dip_oracle_expand_column(int R, int N, const int64_t *rowStart, const int32_t *colInd,
+                             const double *val, int nBase, int numConvex, int nInd,
+                             const int32_t *ind, const double *els, int blockId, double tolZero,
+                             int32_t *outRow, double *outVal);
+
 /* UtilCreateStringHash, Dip/src/UtilHash.cpp:52-68 (ind_el_ at 6 significant
  * digits) for a 0/1 column: writes a NUL-terminated string, returns its length
  * (excluding NUL), or -1 if bufLen is too small. */

@@ -69,6 +69,9 @@ def _lib():
         _i32p, _i32p, C.c_int, C.c_double, C.c_int, C.c_int, _f64p, _i32p, _f64p, _f64p, _i32p,
         _f64p, _f64p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.dip_oracle_price_round.restype = C.c_int
+    lib.dip_oracle_expand_column.argtypes = [C.c_int, C.c_int, _i64p, _i32p, _f64p, C.c_int, C.c_int, C.c_int,
+                                             _i32p, C.c_void_p, C.c_int, C.c_double, _i32p, _f64p]
+    lib.dip_oracle_expand_column.restype = C.c_int
     lib.dip_oracle_string_hash.argtypes = [C.c_int, _i32p, _f64p, C.c_char_p, C.c_int]
     lib.dip_oracle_string_hash.restype = C.c_int
     _LIB = lib
@@ -190,6 +193,18 @@ def price_round(R, N, row_start, col_ind, val, c, u, n_base, m, block_col_start,
         mn, z, ind.ctypes.data if want_ind else None, C.byref(tot), C.byref(cells))
     cols = [ind[b, : nnz[b]].copy() for b in range(m)] if want_ind else []
     return RoundResult(rcx, nnz, rc, oc, keep, mn, z, cols, tot.value, kept, cells.value)
+
+
+def expand_column(R, N, row_start, col_ind, val, n_base, num_convex, ind, block_id, tol_zero=1e-6):
+    """Master column (rows ascending, values) of the 0/1 variable with x-space indices `ind`."""
+    ind = np.ascontiguousarray(ind, np.int32)
+    out_row = np.zeros(R + num_convex, np.int32)
+    out_val = np.zeros(R + num_convex, np.float64)
+    n = _lib().dip_oracle_expand_column(
+        R, N, np.ascontiguousarray(row_start, np.int64), np.ascontiguousarray(col_ind, np.int32),
+        np.ascontiguousarray(val, np.float64), int(n_base), int(num_convex), len(ind),
+        ind if len(ind) else np.zeros(1, np.int32), None, int(block_id), float(tol_zero), out_row, out_val)
+    return out_row[:n].copy(), out_val[:n].copy()
 
 
 def string_hash(ind, els) -> str:

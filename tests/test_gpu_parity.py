@@ -406,3 +406,94 @@ def test_gap_d_round_pisinger(oracle, pricer):
     np.testing.assert_array_equal(res.blockRedCost, ref.col_red_cost)
     for k in range(res.nCols):
         assert list(res.column(k)) == list(ref.col_ind[int(res.colBlock[k])])
+
+
+# ------------------------------------------------- after the round: master columns
+
+
+def _check_expand(oracle, pricer, model, res, tol=1e-6):
+    col_start, row_ind, val, hsh = pricer.expandColumns(tol)
+    assert len(col_start) == res.nCols + 1 and len(hsh) == res.nCols
+    for k in range(res.nCols):
+        b = int(res.colBlock[k])
+        rr, vv = oracle.expand_column(pricer.R, model.N, model._rs, model._ci, model._v, model.n_base_rows, model.m,
+                                      res.column(k), b, tol)
+        got_r = row_ind[col_start[k]:col_start[k + 1]]
+        got_v = val[col_start[k]:col_start[k + 1]]
+        np.testing.assert_array_equal(got_r, rr)
+        np.testing.assert_array_equal(got_v, vv)   # same additions in the same order: bit-equal
+    return col_start, row_ind, val, hsh
+
+
+def test_expand_columns_gap_d(oracle, pricer):
+    model = I.gap_pricing_model(I.gap_class_d())
+    model._rs, model._ci, model._v = model.row_start, model.col_ind, model.val
+    pricer.setModel(model)
+    u = I.gap_duals(model, np.random.default_rng(2))
+    res = pricer.priceRound(u)
+    assert res.nCols > 0
+    cs, ri, va, hs = _check_expand(oracle, pricer, model, res)
+    # every master column carries its block's convexity row with 1.0
+    for k in range(res.nCols):
+        rows = ri[cs[k]:cs[k + 1]]
+        assert model.n_base_rows + int(res.colBlock[k]) in rows
+    # fingerprints: same partition as the reference's string hash (UtilHash.cpp:52-68)
+    strs = [oracle.string_hash(res.column(k), np.ones(len(res.column(k)))) + f"|{int(res.colBlock[k])}"
+            for k in range(res.nCols)]
+    assert len(set(strs)) == len(set(int(h) for h in hs))
+    # the same round again: identical fingerprints (dedup would reject every column)
+    res2 = pricer.priceRound(u)
+    _, _, _, hs2 = pricer.expandColumns()
+    np.testing.assert_array_equal(hs, hs2)
+
+
+def test_expand_columns_general_matrix_with_cuts_and_cancellation(oracle, pricer):
+    """Non-GAP A'' with several entries per (row, block), negative coefficients that cancel
+    (dropped by TolZero) and cut rows appended behind the convexity rows."""
+    rng = np.random.default_rng(17)
+    m, n = 6, 40
+    N = m * n
+    R0, ncut = 50, 12
+    rows, cols, vals = [], [], []
+    for i in range(R0 + ncut):
+        k = int(rng.integers(3, 30))
+        cc = rng.choice(N, size=k, replace=False)
+        cc.sort()
+        for c in cc:
+            rows.append(i)
+            cols.append(int(c))
+            vals.append(float(rng.integers(-2, 3)))   # small integers: plenty of exact cancellation
+    rows = np.array(rows)
+    rs = np.zeros(R0 + ncut + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=R0 + ncut), out=rs[1:])
+    ci = np.array(cols, np.int32)
+    v = np.array(vals)
+    b = I.random_batch(m, n, n, 30, 200, seed=5)
+    pricer.setModelCore(R0, N, rs[:R0 + 1], ci[:rs[R0]], v[:rs[R0]], R0, m)
+    pricer.appendCoreRows(rs[R0:] - rs[R0], ci[rs[R0]:], v[rs[R0]:])   # the cut rows
+    pricer.setObjective(b.orig_cost)
+    pricer.setKnapsackBlocks(b.block_col_start, b.weight, b.capacity)
+    res = pricer.solveBlocks(b.red_cost, b.alpha, redCostEps=-np.inf)
+
+    class M:  # what _check_expand needs
+        pass
+    model = M()
+    model.N, model.n_base_rows, model.m = N, R0, m
+    model._rs, model._ci, model._v = rs, ci, v
+    cs, ri, va, hs = _check_expand(oracle, pricer, model, res)
+    assert (ri >= R0 + m).any()          # cut rows sit behind the convexity rows
+    assert np.all(np.abs(va) > 1e-6)
+
+
+def test_expand_columns_gap_e(oracle, pricer):
+    model = I.gap_pricing_model(I.gap_class_e())
+    model._rs, model._ci, model._v = model.row_start, model.col_ind, model.val
+    pricer.setModel(model)
+    res = pricer.priceRound(I.gap_duals(model, np.random.default_rng(4)))
+    cs, ri, va, hs = pricer.expandColumns()
+    assert len(cs) == res.nCols + 1 and cs[-1] == len(ri)
+    for k in list(range(0, res.nCols, 7)):
+        rr, vv = oracle.expand_column(model.R, model.N, model.row_start, model.col_ind, model.val, model.n_base_rows,
+                                      model.m, res.column(k), int(res.colBlock[k]))
+        np.testing.assert_array_equal(ri[cs[k]:cs[k + 1]], rr)
+        np.testing.assert_array_equal(va[cs[k]:cs[k + 1]], vv)
