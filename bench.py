@@ -326,6 +326,11 @@ def main():
     pr.set_option("stage_timing", 0)
     stage_ms = {nm: float(np.mean(v)) for nm, v in stage.items()}
 
+    # ---- the step after the round: master columns + fingerprints of the kept columns
+    expand = None
+    if not args.skip_extras:
+        expand = bench_expand(pr, model, duals, ptrs, res, flush_l2, torch, rank)
+
     extras = {}
     smem_peak = None
     if not args.skip_extras:
@@ -382,6 +387,8 @@ def main():
             line["roofline_dp_csp"] = extras["dp_csp"]
         if "spmv_milpblock" in extras:
             line["roofline_spmv"] = extras["spmv_milpblock"]
+        if expand is not None:
+            line["expand_columns"] = expand
         if sharded is not None:
             line["sharded"] = sharded
         if cpu is not None:
@@ -391,6 +398,47 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_expand(pr, model, duals, ptrs, res, flush_l2, torch, rank):
+    """dipgpu_expand_columns after each of 50 rounds (wall clock around the C-ABI call, D2H inside),
+    beside the CPU restatement of DecompAlgo::addVarsToPool's per-column work (single thread, as DIP)."""
+    from dip_b200 import capi
+    import ctypes as C
+    cap_nnz = 1 << 20
+    col_start = np.zeros(model.m + 1, np.int64)
+    row_ind = np.zeros(cap_nnz, np.int32)
+    val = np.zeros(cap_nnz, np.float64)
+    hsh = np.zeros(model.m, np.uint64)
+    mc = capi.MCols()
+    mc.capCols, mc.capNnz = model.m, cap_nnz
+    mc.colStart, mc.rowInd, mc.val, mc.hash = capi.ptr(col_start), capi.ptr(row_ind), capi.ptr(val), capi.ptr(hsh)
+    lib = capi.lib()
+    t_gpu = 0.0
+    reps = 50
+    for k in range(reps + 3):
+        pr.priceRoundRaw(ptrs[k % N_DUALS], model.u_len, capi.PHASE_PRICE2, RC_EPS, res)
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rc = lib.dipgpu_expand_columns(pr._ctx, 1e-6, C.byref(mc))
+        dt = time.perf_counter() - t0
+        assert rc == 0, rc
+        if k >= 3:
+            t_gpu += dt
+    out = {"gpu_ms_per_round": 1e3 * t_gpu / reps, "columns": int(mc.nCols), "master_nnz": int(mc.nNnz),
+           "timing": "host wall clock around dipgpu_expand_columns (kernel + D2H), L2 flushed"}
+    if rank == 0:
+        from oracle import dip_oracle as orc
+        cols = [res.column(k).copy() for k in range(res.nCols)]
+        blocks = [int(res.colBlock[k]) for k in range(res.nCols)]
+        t0 = time.perf_counter()
+        for ind, b in zip(cols, blocks):
+            orc.expand_column(model.R, model.N, model.row_start, model.col_ind, model.val, model.n_base_rows, model.m,
+                              ind, b)
+        out["cpu_ms_per_round"] = 1e3 * (time.perf_counter() - t0)
+        out["cpu"] = "oracle restatement of addVarsToPool per column (fillDenseArr + M->times + dense scan), 1 thread as DIP"
+    return out
 
 
 def sharded_rounds(dist, torch, dev, pr, model, u_dev, K, W, world, rank, flush_l2, barrier, max_over_ranks,

@@ -171,6 +171,42 @@ public:
     }
     void beginRound() { m_roundValid = false; }
 
+    // ---- after the round: DecompAlgo::addVarsToPool's per-variable work (DecompAlgo.cpp:5452-5558)
+    // Master columns [A''s ; e_block] of the columns the last generateVars / solveRelaxed round
+    // kept, in that order: column k spans [colStart[k], colStart[k+1]) of (rowInd ascending, val);
+    // hash[k] fingerprints (block, x-space indices) -- compare it where DecompVarPool::isDuplicate
+    // compares DecompVar::getStrHash() (DecompVarPool.cpp:150-181).
+    void expandColumns(double tolZero, std::vector<int64_t> &colStart, std::vector<int32_t> &rowInd,
+                       std::vector<double> &val, std::vector<uint64_t> &hash)
+    {
+        dipgpu_mcols mc;
+        std::memset(&mc, 0, sizeof(mc));
+        colStart.assign((size_t)m_m + 1, 0);
+        hash.assign((size_t)m_m, 0);
+        if (rowInd.size() < 1024) rowInd.resize(1024);
+        if (val.size() < rowInd.size()) val.resize(rowInd.size());
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            mc.capCols = m_m;
+            mc.capNnz = (int64_t)rowInd.size();
+            mc.colStart = colStart.data();
+            mc.rowInd = rowInd.data();
+            mc.val = val.data();
+            mc.hash = hash.data();
+            const int rc = dipgpu_expand_columns(m_ctx, tolZero, &mc);
+            if (rc == DIPGPU_ERR_OVERFLOW && attempt == 0 && mc.nNnz > (int64_t)rowInd.size()) {
+                rowInd.resize((size_t)mc.nNnz);
+                val.resize((size_t)mc.nNnz);
+                continue;
+            }
+            check(rc);
+            break;
+        }
+        colStart.resize((size_t)mc.nCols + 1);
+        hash.resize((size_t)mc.nCols);
+        rowInd.resize((size_t)mc.nNnz);
+        val.resize((size_t)mc.nNnz);
+    }
+
     // ---- stage (a) alone: generateVarsCalcRedCost (DecompAlgo.cpp:4506-4547) -------------------
     void calcRedCost(const double *u, int uLen, int phase, double *redCostX)
     {

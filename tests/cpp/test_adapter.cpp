@@ -88,6 +88,26 @@ int main()
     CHECK(mostNegRC == mostNegRef);
     CHECK(pricer->cells() == cells);
     for (int b = 0; b < m; ++b) CHECK(pricer->blockObj()[b] == z[b]);  // bit-exact knapsack optima
+    // ---- the step after the round: master columns of the kept variables (addVarsToPool)
+    {
+        std::vector<int64_t> cs;
+        std::vector<int32_t> ri;
+        std::vector<double> va;
+        std::vector<uint64_t> hs;
+        pricer->expandColumns(1e-6, cs, ri, va, hs);
+        CHECK((int)hs.size() == kept && (int)cs.size() == kept + 1);
+        std::vector<int32_t> oRow(R + m);
+        std::vector<double> oVal(R + m);
+        int k = 0;
+        for (dipgpu::DecompVar *v : newVars) {
+            const int nn = dip_oracle_expand_column(R, N, rowStart.data(), colInd.data(), val.data(), R, m,
+                                                    (int)v->ind.size(), v->ind.data(), nullptr, v->getBlockId(), 1e-6,
+                                                    oRow.data(), oVal.data());
+            CHECK(cs[k + 1] - cs[k] == nn);
+            for (int q = 0; q < nn; ++q) CHECK(ri[cs[k] + q] == oRow[q] && va[cs[k] + q] == oVal[q]);
+            ++k;
+        }
+    }
     for (dipgpu::DecompVar *v : newVars) {
         const int b = v->getBlockId();
         CHECK(colKeep[b] == 1 && v->getReducedCost() < -1e-4);
@@ -113,7 +133,7 @@ int main()
     }
     int64_t launches = 0;
     dipgpu_get_counters(pricer->ctx(), &launches, nullptr, nullptr);
-    CHECK(launches <= 6);  // 2 (round) + 1 (SpMV) + <=3 (ONE submission served all 12 solveRelaxed calls)
+    CHECK(launches <= 7);  // 2 (round) + 1 (expand) + 1 (SpMV) + <=3 (ONE submission served all 12 solveRelaxed calls)
     // phase 1 prices with c = 0
     pricer->calcRedCost(u.data(), (int)u.size(), dipgpu::PHASE_PRICE1, rcx.data());
     std::vector<double> uAdj(R);
