@@ -466,7 +466,99 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         // ---- the DP proper: items sequential, cells parallel.  (w0,p0),(w1,p1) hold
         // items i and i+1, fetched one step ahead (itP/itW are padded by four entries).
         int i = 0;
-        if (S <= 3 && GUARD) {
+        if (ITEMS == 3 && S <= 3 && GUARD) {
+            // THREE items per barrier (the fused GAP shapes): 7 shifted reads of c[i-1][.] rebuild, in
+            // registers, c[i][.] at j, j-wB, j-wC, j-wC-wB and c[i+1][.] at j, j-wC -- every one with
+            // the same single DADD and strict compare the one-item step would have applied to the
+            // same operands, so values and decisions are unchanged while the barrier + shared-memory
+            // round trip (52 of the 76 cycles of a one-item step, scripts/micro/lat.cu) is paid once
+            // per three items.  A 32-item word = 10 triples + 1 pair = 11 steps (odd: `cur` flips).
+            while (((kGlobal + i) & 31) == 0 && i + 32 <= nIt) {
+                double *bufA = rowBase + cur * bufStride + G + j0;        // holds c[i-1][.]
+                double *bufB = rowBase + (cur ^ 1) * bufStride + G + j0;
+                int wA = itW[i], wB = itW[i + 1], wC = itW[i + 2];
+                double pA = itP[i], pB = itP[i + 1], pC = itP[i + 2];
+#pragma unroll
+                for (int st = 0; st < 11; ++st) {
+                    const int q = 3 * st;  // bit of the step's first item
+                    const double *rdBuf = (st & 1) ? bufB : bufA;
+                    double *wrBuf = (st & 1) ? bufA : bufB;
+                    if (st < 10) {
+                        const double *rA = rdBuf - wA, *rB = rdBuf - wB, *rC = rdBuf - wC;
+                        const double *rAB = rA - wB, *rAC = rA - wC, *rBC = rB - wC, *rABC = rAB - wC;
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            const double c0A = rA[s], c0B = rB[s], c0C = rC[s];
+                            const double c0AB = rAB[s], c0AC = rAC[s], c0BC = rBC[s], c0ABC = rABC[s];
+                            // item A (row i) at j, j-wB, j-wC, j-wC-wB
+                            const double a0 = pA + c0A;
+                            const bool takeA = a0 > mine[s];
+                            const double c1 = takeA ? a0 : mine[s];
+                            const double a1 = pA + c0AB;
+                            const double c1B = a1 > c0B ? a1 : c0B;
+                            const double a2 = pA + c0AC;
+                            const double c1C = a2 > c0C ? a2 : c0C;
+                            const double a3 = pA + c0ABC;
+                            const double c1BC = a3 > c0BC ? a3 : c0BC;
+                            // item B (row i+1) at j, j-wC
+                            const double b0 = pB + c1B;
+                            const bool takeB = b0 > c1;
+                            const double c2 = takeB ? b0 : c1;
+                            const double b1 = pB + c1BC;
+                            const double c2C = b1 > c1C ? b1 : c1C;
+                            // item C (row i+2) at j
+                            const double d0 = pC + c2C;
+                            const bool takeC = d0 > c2;
+                            mine[s] = takeC ? d0 : c2;
+                            if (takeA) acc[s] |= 1u << q;
+                            if (takeB) acc[s] |= 2u << q;
+                            if (takeC) acc[s] |= 4u << q;
+                            wrBuf[s] = mine[s];
+                        }
+                    } else {  // the word's last two items
+                        const double *rA = rdBuf - wA, *rB = rdBuf - wB;
+                        const double *rAB = rA - wB;
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            const double c0A = rA[s], c0B = rB[s], c0AB = rAB[s];
+                            const double a0 = pA + c0A;
+                            const bool takeA = a0 > mine[s];
+                            const double c1 = takeA ? a0 : mine[s];
+                            const double a1 = pA + c0AB;
+                            const double c1B = a1 > c0B ? a1 : c0B;
+                            const double b0 = pB + c1B;
+                            const bool takeB = b0 > c1;
+                            mine[s] = takeB ? b0 : c1;
+                            if (takeA) acc[s] |= 1u << q;
+                            if (takeB) acc[s] |= 2u << q;
+                            wrBuf[s] = mine[s];
+                        }
+                    }
+                    // the next step's items, fetched before the barrier
+                    if (st < 10) {
+                        wA = itW[i + q + 3];
+                        pA = itP[i + q + 3];
+                        wB = itW[i + q + 4];
+                        pB = itP[i + q + 4];
+                        if (st < 9) {
+                            wC = itW[i + q + 5];
+                            pC = itP[i + q + 5];
+                        }
+                    }
+                    __syncthreads();
+                }
+                {
+                    uint32_t *dst = bitsBase + (size_t)((kGlobal + i) >> 5) * RC + j0;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        dst[s] = acc[s];
+                        acc[s] = 0u;
+                    }
+                }
+                i += 32;
+                cur ^= 1;  // 11 steps
+            }
+        } else if (S <= 3 && GUARD) {
             // Latency-bound shapes (few cells per thread): whole 32-item words are processed by a
             // fully unrolled body -- constant bit masks, compile-time buffer roles, item data
             // fetched eight steps ahead -- so that a step is little more than its dependent chain
@@ -543,7 +635,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             const int bitpos = (kGlobal + i) & 31;
             const double *base = rowBase + cur * bufStride + G + j0;
             double *wr = rowBase + (cur ^ 1) * bufStride + G + j0;
-            if (ITEMS == 2 && i + 1 < nIt && (bitpos & 1) == 0) {
+            if (ITEMS >= 2 && i + 1 < nIt && (bitpos & 1) == 0) {
                 const int wA = w0, wB = w1;
                 const double pA = p0, pB = p1;
                 const double *rdA = base - wA;
@@ -804,25 +896,34 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
 typedef void (*KnapFn)(const KnapArgs);
 struct GeomEntry {
     int S, maxT;
-    KnapFn fn[2][2];      // [guard][items-1]
-    KnapFn fnFuse[2][2];  // same, fused tail (NULL where not built)
+    KnapFn fn[2][3];      // [guard][items-1]; three items per barrier only with guard cells, S <= 3
+    KnapFn fnFuse[2][3];  // same, fused tail (NULL where not built)
 };
 
 #define GE_FNS(S, MT, F)                                                                         \
     {                                                                                            \
-        {knap_dp_kernel<S, false, 1, MT, F>, knap_dp_kernel<S, false, 2, MT, F>},                \
-        {knap_dp_kernel<S, true, 1, MT, F>, knap_dp_kernel<S, true, 2, MT, F>}                   \
+        {knap_dp_kernel<S, false, 1, MT, F>, knap_dp_kernel<S, false, 2, MT, F>, nullptr},       \
+        {knap_dp_kernel<S, true, 1, MT, F>, knap_dp_kernel<S, true, 2, MT, F>, nullptr}          \
     }
-#define GE_NULL {{nullptr, nullptr}, {nullptr, nullptr}}
+#define GE_FNS3(S, MT, F)                                                                        \
+    {                                                                                            \
+        {knap_dp_kernel<S, false, 1, MT, F>, knap_dp_kernel<S, false, 2, MT, F>, nullptr},       \
+        {knap_dp_kernel<S, true, 1, MT, F>, knap_dp_kernel<S, true, 2, MT, F>,                   \
+         knap_dp_kernel<S, true, 3, MT, F>}                                                      \
+    }
+#define GE_NULL {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}
 #define GE(S, MT) {S, MT, GE_FNS(S, MT, false), GE_NULL}
 #define GEF(S, MT) {S, MT, GE_FNS(S, MT, false), GE_FNS(S, MT, true)}
+#define GEF3(S, MT) {S, MT, GE_FNS3(S, MT, false), GE_FNS3(S, MT, true)}
 static const GeomEntry kGeoms[] = {
-    GEF(1, 1024), GEF(3, 1024), GEF(5, 1024), GEF(7, 1024), GE(9, 1024), GE(11, 1024),
-    GE(13, 512),  GE(15, 512),  GE(17, 512),  GE(19, 512),  GE(21, 512), GE(25, 512),
+    GEF3(1, 1024), GEF3(3, 1024), GEF(5, 1024), GEF(7, 1024), GE(9, 1024), GE(11, 1024),
+    GE(13, 512),   GE(15, 512),   GE(17, 512),  GE(19, 512),  GE(21, 512), GE(25, 512),
 };
 #undef GE
 #undef GEF
+#undef GEF3
 #undef GE_FNS
+#undef GE_FNS3
 #undef GE_NULL
 static const int kNumGeoms = (int)(sizeof(kGeoms) / sizeof(kGeoms[0]));
 static const size_t kMaxSmem = 227 * 1024 - 6 * 1024;  // the fused tail's static shared memory comes off the 227 KiB
@@ -840,6 +941,7 @@ static bool fitGeom(const Ctx *c, int T, int S, int items, bool fuse, DpGeom *g)
     const GeomEntry *e = findGeom(S);
     if (!e || T < 32 || T > e->maxT || (T & 31)) return false;
     if (fuse && (e->fnFuse[0][0] == nullptr || c->maxBlockCols > 2048)) return false;
+    if (items == 3 && (fuse ? e->fnFuse : e->fn)[1][2] == nullptr) return false;
     g->fuse = fuse ? 1 : 0;
     if ((int64_t)T * S < (int64_t)c->maxCapacity + 1) return false;
     g->T = T;
@@ -861,6 +963,7 @@ static bool fitGeom(const Ctx *c, int T, int S, int items, bool fuse, DpGeom *g)
         g->chunkCols = (g->chunkCols / 2 + 3) & ~3;
         g->smemBytes = dpSmemBytes(g->rowCells, g->guard, g->chunkCols, false);
     }
+    if (items == 3 && g->guard == 0) return false;  // the three-item step is built with guard cells only
     return g->smemBytes <= kMaxSmem;
 }
 
@@ -887,6 +990,7 @@ static double geomCost(const Ctx *c, const DpGeom &g)
     // the unrolled two-item step (S <= 3 with guard cells) halves the barriers: 68 vs 76 us on
     // GAP-E; the generic two-item step costs 1.3x (profiles/r01_dp_geometry_sweep.txt)
     if (g.items == 2) chain *= (g.S <= 3 && g.guard > 0) ? 0.9 : 1.3;
+    if (g.items == 3) chain *= 0.7;  // unrolled three-item step: barrier paid once per three items
     // throughput regime (CSP sweep): shared-memory floor times the measured inefficiency
     const double ineff = g.S <= 11 ? (g.items == 2 ? 1.52 : 1.61) : g.S <= 21 ? (g.items == 2 ? 1.40 : 1.53)
                                                                               : (g.items == 2 ? 1.69 : 1.81);
@@ -912,7 +1016,7 @@ int chooseDpGeom(Ctx *c, DpGeom *g, bool wantFuse)
             if (c->optThreads < T) continue;
             T = c->optThreads;
         }
-        for (int items = 1; items <= 2; ++items) {
+        for (int items = 1; items <= 3; ++items) {
             if (c->optItemsPerStep > 0 && items != c->optItemsPerStep) continue;
             DpGeom cand{};
             if (!fitGeom(c, T, S, items, fuse, &cand)) continue;
@@ -940,7 +1044,7 @@ int prepareKnapsackDp(Ctx *c)
     const DpGeom &g = c->geom;
     const GeomEntry *e = findGeom(g.S);
     if (!e) return fail(c, DIPGPU_ERR_STATE, "DP geometry not initialised");
-    KnapFn fn = (g.fuse ? e->fnFuse : e->fn)[g.guard > 0 ? 1 : 0][g.items == 2 ? 1 : 0];
+    KnapFn fn = (g.fuse ? e->fnFuse : e->fn)[g.guard > 0 ? 1 : 0][g.items - 1];
     if (c->dpFnConfigured != (void *)fn || c->dpFnSmem != g.smemBytes) {
         DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
         c->dpFnConfigured = (void *)fn;
@@ -982,7 +1086,7 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, doubl
     const DpGeom &g = c->geom;
     const GeomEntry *e = findGeom(g.S);
     if (!e) return fail(c, DIPGPU_ERR_STATE, "DP geometry not initialised");
-    KnapFn fn = (g.fuse ? e->fnFuse : e->fn)[g.guard > 0 ? 1 : 0][g.items == 2 ? 1 : 0];
+    KnapFn fn = (g.fuse ? e->fnFuse : e->fn)[g.guard > 0 ? 1 : 0][g.items - 1];
     KnapArgs a;
     a.redCost = dRedCost;
     a.weight = c->dWeight;

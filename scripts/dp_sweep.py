@@ -60,7 +60,7 @@ def main():
                   f"gcups={cells/ms['knapsack_dp']/1e6:8.1f}")
             print("   S     T items guard   dp_us     gcups")
             for S in (SWEEP_S or (1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 25)):
-                for items in (1, 2):
+                for items in (1, 2, 3):
                     for noguard in (0, 1):
                         try:
                             p.set_option("dp_cells_per_thread", S)

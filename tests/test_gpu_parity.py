@@ -117,7 +117,8 @@ def test_edge_blocks(oracle, pricer):
 
 
 @pytest.mark.parametrize("T,S,items,noguard", [(32, 7, 1, 0), (64, 9, 2, 0), (256, 5, 2, 1), (1024, 3, 1, 1),
-                                               (512, 13, 1, 0), (96, 1, 2, 0), (160, 25, 2, 0)])
+                                               (512, 13, 1, 0), (96, 1, 2, 0), (160, 25, 2, 0),
+                                               (192, 1, 3, 0), (64, 3, 3, 0), (1024, 1, 3, 0)])
 def test_forced_dp_geometries(oracle, pricer, T, S, items, noguard):
     """Same results whatever the shape of the DP row: threads x cells/thread, one or two items per
     barrier, guard cells or predicated shifted reads."""
