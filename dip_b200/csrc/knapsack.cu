@@ -990,7 +990,9 @@ static double geomCost(const Ctx *c, const DpGeom &g)
     // the unrolled two-item step (S <= 3 with guard cells) halves the barriers: 68 vs 76 us on
     // GAP-E; the generic two-item step costs 1.3x (profiles/r01_dp_geometry_sweep.txt)
     if (g.items == 2) chain *= (g.S <= 3 && g.guard > 0) ? 0.9 : 1.3;
-    if (g.items == 3) chain *= 0.7;  // unrolled three-item step: barrier paid once per three items
+    // three items per barrier: measured SLOWER than two on GAP-E (70 vs 60 us) -- 7 DADD + 7 DSETP per
+    // cell and step make the FP64 pipe, not the barrier, the limiter; kept as a tested option only
+    if (g.items == 3) chain *= 1.15;
     // throughput regime (CSP sweep): shared-memory floor times the measured inefficiency
     const double ineff = g.S <= 11 ? (g.items == 2 ? 1.52 : 1.61) : g.S <= 21 ? (g.items == 2 ? 1.40 : 1.53)
                                                                               : (g.items == 2 ? 1.69 : 1.81);
