@@ -51,6 +51,16 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(key, scale=1.0):
+    """dram__bytes_read + dram__bytes_write per launch from the committed ncu capture of this kernel
+    (profiles/ncu_traffic.json, written by scripts/summarize_ncu.py), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]
+        return (d["dram_bytes_read"] + d["dram_bytes_write"]) * scale
+    except Exception:
+        return None
+
+
 def workload():
     model = I.gap_pricing_model(I.gap_class_e())
     rng = np.random.default_rng(801600)
@@ -343,7 +353,9 @@ def main():
         "achieved": cells_mean * 24.0 / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None,
         "peak": smem_peak, "unit": "GB/s",
         "frac": (cells_mean * 24.0 / (dp_ms * 1e-3) / 1e9 / smem_peak) if (smem_peak and dp_ms > 0) else None,
-        "traffic": None,
+        "traffic": ncu_traffic("prof_dp_gape"),
+        "traffic_note": "DRAM bytes per launch, ncu --set full capture of this kernel on this shape "
+                        "(profiles/ncu_traffic.json); the bound is shared memory, HBM only sees inputs",
         "peak_source": "in-library shared-memory copy microbenchmark (dipgpu_measure_smem_gbs), this run",
         "note": "80 one-warp..few-warp CTAs on 148 SMs: the GAP-E round is latency-bound, see roofline_dp_csp "
                 "for the bandwidth-bound shape of the same kernel",
@@ -542,7 +554,9 @@ def bench_csp(torch, dev, pr_unused, args, world, rank, barrier, max_over_ranks,
             "bound": "smem", "gcups": cells / (dp_ms * 1e-3) / 1e9, "dp_ms": dp_ms, "backtrack_ms": bt_ms,
             "achieved": ach, "peak": (smem_peak * world) if smem_peak else None, "unit": "GB/s",
             "frac": ach / (smem_peak * world) if smem_peak else None,
-            "algorithmic_bytes_per_cell": 24, "cells": cells, "cells_this_rank": cells_local, "traffic": None,
+            "algorithmic_bytes_per_cell": 24, "cells": cells, "cells_this_rank": cells_local,
+            # ncu capture is of 1184 knapsacks (8 waves): scaled to this launch's block count
+            "traffic": ncu_traffic("prof_dp_csp", scale=(m_total / world) / 1184.0),
             "peak_source": "in-library shared-memory copy microbenchmark x n_gpus"}
 
 
@@ -573,7 +587,8 @@ def bench_spmv(torch, dev, local_rank, hbm_peak, peak_src, flush_l2, world, rank
     by = model.spmv_bytes()
     ach = by / (ms * 1e-3) / 1e9
     return {"kernel": "redcost_csc_kernel", "workload": model.name, "bound": "hbm", "achieved": ach,
-            "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "avg_launch_ms": ms,
+            "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic("prof_spmv_milp"),
+            "avg_launch_ms": ms,
             "min_launch_ms": float(np.min(times)), "algorithmic_bytes": by, "peak_source": peak_src,
             "l2": "flushed before every sweep (inputs 141 MB vs 126 MB L2)"}
 

@@ -69,7 +69,7 @@ struct ResultLayout {
 constexpr int kFuseFilterMaxBlocks = 256;
 
 // ---------------------------------------------------------------- SpMV tiling
-constexpr int kSpmvChunk = 384;        // stored entries per warp tile (4.5 KiB of shared memory per stage)
+constexpr int kSpmvChunk = 256;        // stored entries per warp tile (4.5 KiB of shared memory per stage)
 constexpr int kSpmvColsPerLane = 4;    // a warp tile spans at most 32*4 consecutive columns (fewer when the
                                        // kSpmvChunk entry budget is reached first)
 
@@ -134,6 +134,7 @@ struct Ctx {
     int optSpmvWarps = 0, optSpmvUSmem = -1;  // diagnostics knobs
     void *spmvFn = nullptr;                   // kernel whose shared-memory limit is already set
     size_t spmvFnSmem = 0;
+    int spmvClusters = 0;                     // resident CTA pairs of the cluster variant
     uint16_t *dRowMaster16 = nullptr;         // rowMaster as uint16 when R + numConvex <= 65536
 
     // row-major copy of A'' (expand.cu re-walks touched rows in the reference's storage order)

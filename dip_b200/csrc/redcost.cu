@@ -56,6 +56,7 @@ struct StreamArgs {
     int phase1;
     double *out;
     int uSmemBytes;             // 0: gather the duals from global memory
+    int uHalf;                  // UMODE 2: duals per CTA of the cluster pair (even)
 };
 
 // A stage holds up to kSpmvChunk entries counted from the aligned start (alignment: 16 bytes
@@ -96,10 +97,14 @@ __device__ __forceinline__ void loadColMeta(const StreamArgs &a, const int4 rec,
 // lane per column, sequentially in storage order.  The per-tile record and the per-column
 // extents / objective entries of tile k+1 are fetched into registers while tile k is being
 // reduced, so no cold global load sits on the warp's critical path; there is no CTA-wide
-// barrier in the loop.  U_SMEM keeps the whole dual vector in shared memory (it is gathered
-// once per stored entry; from L1 a random 8-byte gather costs a wavefront per lane).
-template <bool U_SMEM, bool ROW16>
-__global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_constant__ StreamArgs a)
+// barrier in the loop.  Where the duals are gathered from (UMODE): 0 = global memory (from L1 a
+// random 8-byte gather costs a wavefront per lane: fine for structured matrices, 71 us for 10^7
+// random gathers); 1 = the whole dual vector in shared memory; 2 = the dual vector SPLIT over the
+// two CTAs of a thread-block cluster, the other half read through distributed shared memory
+// (mapa + ld.shared::cluster) -- half the footprint, which doubles the bytes the TMA stages can
+// keep in flight per SM (the stream is in-flight-limited).
+template <int UMODE, bool ROW16>
+__global__ void __launch_bounds__(768) redcost_stream_kernel(const __grid_constant__ StreamArgs a)
 {
     typedef SpmvStage<ROW16> St;
     typedef typename std::conditional<ROW16, uint16_t, int32_t>::type RowT;
@@ -108,6 +113,21 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
     extern __shared__ __align__(16) unsigned char sm[];
     const double *sU = reinterpret_cast<const double *>(sm);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    unsigned int crank = 0;
+    if (UMODE == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int uHalf = a.uHalf;  // UMODE 2: duals [rank*uHalf, (rank+1)*uHalf) live in CTA `rank`
+    const uint32_t sUaddr = rcSmemAddr(sm);
+    auto gatherU = [&](int r) -> double {
+        if (UMODE == 0) return __ldg(a.u + r);
+        if (UMODE == 1) return sU[r];
+        const unsigned int owner = r >= uHalf ? 1u : 0u;
+        const uint32_t la = sUaddr + (uint32_t)(r - (owner ? uHalf : 0)) * 8u;
+        uint32_t ra;
+        double v;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(owner));
+        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra));
+        return v;
+    };
     unsigned char *wbase = sm + a.uSmemBytes + (size_t)warp * kSpmvWarpBytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
     unsigned char *stageBase = wbase + 16;
@@ -155,11 +175,15 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
     }
     ColMeta mc;
     loadColMeta(a, cur, lane, mc);
-    if (U_SMEM) {
-        // the dual vector: one bulk copy (16-byte granules) + a plain tail, on its own mbarrier
+    if (UMODE != 0) {
+        // the dual vector (UMODE 2: this CTA's half): one bulk copy (16-byte granules) + a plain
+        // tail, on its own mbarrier
         uint64_t *ubar = reinterpret_cast<uint64_t *>(sm + a.uSmemBytes - 16);
         double *w = const_cast<double *>(sU);
-        const int bulk = (reinterpret_cast<uintptr_t>(a.u) & 15u) == 0 ? (a.uLen & ~1) : 0;
+        const int lo = UMODE == 2 ? (int)crank * uHalf : 0;
+        const int cnt = UMODE == 2 ? max(0, min(a.uLen - lo, uHalf)) : a.uLen;
+        const double *src = a.u + lo;
+        const int bulk = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 ? (cnt & ~1) : 0;
         if (t == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(ubar)), "r"(1));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,15 +194,20 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
                 asm volatile(
                     "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                         rcSmemAddr(w)),
-                    "l"(a.u), "r"((uint32_t)bulk * 8u), "r"(rcSmemAddr(ubar))
+                    "l"(src), "r"((uint32_t)bulk * 8u), "r"(rcSmemAddr(ubar))
                     : "memory");
             } else {
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rcSmemAddr(ubar)) : "memory");
             }
         }
-        for (int k = bulk + t; k < a.uLen; k += blockDim.x) w[k] = __ldg(a.u + k);
+        for (int k = bulk + t; k < cnt; k += blockDim.x) w[k] = __ldg(src + k);
         __syncthreads();
         rcMbarWait(ubar, 0);
+        if (UMODE == 2) {
+            // both halves must be in place before anyone gathers across the cluster
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
     } else {
         __syncwarp();
     }
@@ -211,7 +240,7 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] = sVal[k + 32 * j];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) g[j] = U_SMEM ? sU[r[j]] : __ldg(a.u + r[j]);
+                for (int j = 0; j < 4; ++j) g[j] = gatherU(r[j]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sVal[k + 32 * j] = __dmul_rn(g[j], v[j]);
             }
@@ -226,7 +255,7 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
                     v[j] = kk < len ? sVal[kk] : 0.0;
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) g[j] = (k + 32 * j < len) ? (U_SMEM ? sU[r[j]] : __ldg(a.u + r[j])) : 0.0;
+                for (int j = 0; j < 4; ++j) g[j] = (k + 32 * j < len) ? gatherU(r[j]) : 0.0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (k + 32 * j < len) sVal[k + 32 * j] = __dmul_rn(g[j], v[j]);
@@ -260,6 +289,11 @@ __global__ void __launch_bounds__(512) redcost_stream_kernel(const __grid_consta
         cur = nxt;
         nxt = tnn < a.nTiles ? nn : none;
         mc = mn;
+    }
+    if (UMODE == 2) {
+        // a CTA's half of the duals must outlive its partner's last gather
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
 }
 
@@ -325,28 +359,38 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
         a.rowMaster = row16 ? static_cast<const void *>(c->dRowMaster16) : static_cast<const void *>(c->dRowMaster);
         const size_t warpBytes = row16 ? SpmvStage<true>::kWarpBytes : SpmvStage<false>::kWarpBytes;
         const size_t uBytes = (((size_t)a.uLen + 1) & ~(size_t)1) * 8 + 16;  // + the u mbarrier
+        const int uHalf = (((a.uLen + 1) / 2) + 1) & ~1;
+        const size_t uHalfBytes = (size_t)uHalf * 8 + 16;
         // u in shared memory pays when it is gathered irregularly and re-used: many more stored
-        // entries than duals, and at least 6 warp pipelines fit beside the copy
-        int warpsU = uBytes < maxSmem ? (int)((maxSmem - uBytes) / warpBytes) : 0;
-        warpsU = std::min(warpsU, 16);
-        if (c->optSpmvWarps > 0) warpsU = std::min(warpsU, c->optSpmvWarps);
-        bool uSmem = warpsU >= 6 && c->nnz >= 8 * (int64_t)a.uLen && c->nSpmvTiles >= 4 * sms * warpsU;
-        if (c->optSpmvUSmem >= 0) uSmem = c->optSpmvUSmem != 0 && warpsU >= 1;
+        // entries than duals.  mode 2 (split over a 2-CTA cluster) leaves twice the room for stages.
+        const bool reuse = c->nnz >= 8 * (int64_t)a.uLen;
+        int mode = 0;
+        // (mode 2 is never chosen automatically: on B200 the remote 8-byte gathers sustain only ~0.25
+        // per cycle and SM, 78 us on the MILPBlock shape against 44 us for mode 1)
+        if (reuse && uBytes + 6 * warpBytes <= maxSmem && c->nSpmvTiles >= 24 * sms) mode = 1;
+        if (c->optSpmvUSmem >= 0) mode = c->optSpmvUSmem;
+        if (mode == 1 && uBytes + warpBytes > maxSmem) mode = 0;
+        if (mode == 2 && uHalfBytes + warpBytes > maxSmem) mode = 0;
         typedef void (*Fn)(const StreamArgs);
         Fn fn;
         size_t bytes;
         int grid, threads;
-        if (uSmem) {
-            a.uSmemBytes = (int)uBytes;
-            bytes = uBytes + (size_t)warpsU * warpBytes;
-            fn = row16 ? redcost_stream_kernel<true, true> : redcost_stream_kernel<true, false>;
-            grid = sms;
-            threads = warpsU * 32;
+        a.uHalf = uHalf;
+        if (mode != 0) {
+            const size_t ub = mode == 2 ? uHalfBytes : uBytes;
+            int warps = (int)std::min<size_t>(24, (maxSmem - ub) / warpBytes);
+            if (c->optSpmvWarps > 0) warps = std::min(warps, c->optSpmvWarps);
+            a.uSmemBytes = (int)ub;
+            bytes = ub + (size_t)warps * warpBytes;
+            fn = mode == 2 ? (row16 ? redcost_stream_kernel<2, true> : redcost_stream_kernel<2, false>)
+                           : (row16 ? redcost_stream_kernel<1, true> : redcost_stream_kernel<1, false>);
+            grid = sms & ~1;
+            threads = warps * 32;
         } else {
             a.uSmemBytes = 0;
             const int warps = c->optSpmvWarps > 0 ? std::min(c->optSpmvWarps, 16) : 8;
             bytes = (size_t)warps * warpBytes;
-            fn = row16 ? redcost_stream_kernel<false, true> : redcost_stream_kernel<false, false>;
+            fn = row16 ? redcost_stream_kernel<0, true> : redcost_stream_kernel<0, false>;
             const int ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(4, maxSmem / bytes));
             grid = std::max(1, std::min((c->nSpmvTiles + warps - 1) / warps, ctasPerSm * sms));
             threads = warps * 32;
@@ -355,8 +399,32 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
             DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
             c->spmvFn = (void *)fn;
             c->spmvFnSmem = bytes;
+            c->spmvClusters = 0;
         }
-        fn<<<grid, threads, bytes, st>>>(a);
+        if (mode == 2) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.blockDim = dim3(threads, 1, 1);
+            cfg.dynamicSmemBytes = bytes;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (c->spmvClusters == 0) {
+                // persistent kernel: no more CTA pairs than can be resident at once
+                cfg.gridDim = dim3(grid, 1, 1);
+                int nc = 0;
+                DIPGPU_CUDA(c, cudaOccupancyMaxActiveClusters(&nc, fn, &cfg));
+                c->spmvClusters = std::max(1, std::min(nc, grid / 2));
+            }
+            cfg.gridDim = dim3(2 * c->spmvClusters, 1, 1);
+            DIPGPU_CUDA(c, cudaLaunchKernelEx(&cfg, fn, a));
+        } else {
+            fn<<<grid, threads, bytes, st>>>(a);
+        }
         c->launches++;
         DIPGPU_CUDA(c, cudaGetLastError());
         return DIPGPU_OK;

@@ -49,6 +49,6 @@ def run(name, model, u, lanes_opts, extra=()):
 
 
 model, u = I.milpblock_model()
-run("milpblock", model, u, [0, 8], extra=[(3, 1), (5, 1), (8, 1), (10, 1), (4, 0), (8, 0), (16, 0)])
+run("milpblock", model, u, [0, 8], extra=[(12, 1), (24, 1), (8, 2), (12, 2), (16, 2), (20, 2), (24, 2), (16, 0)])
 g = I.gap_pricing_model(I.gap_class_e())
 run("gap-e", g, I.gap_duals(g, np.random.default_rng(1)), [0, 1, 4])

@@ -53,6 +53,25 @@ def main():
                 f"{k.replace('smsp__pcsamp_warps_issue_stalled_', '')} {int(s)}" for s, k in stalls))
             lines.append("")
     open(os.path.join(PROF, f"{tag}_ncu_summary.md"), "w").write("\n".join(lines) + "\n")
+    # DRAM traffic per launch of the captured kernels (bench.py reports it as roofline.traffic)
+    import json
+    traffic = {}
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for name in sorted(os.listdir(OUT)):
+        if not name.endswith(".ncu-rep"):
+            continue
+        recs, units = raw(os.path.join(OUT, name))
+        for r in recs:
+            try:
+                rd = float(r["dram__bytes_read.sum"]) * unit[units["dram__bytes_read.sum"]]
+                wr = float(r["dram__bytes_write.sum"]) * unit[units["dram__bytes_write.sum"]]
+            except Exception:
+                continue
+            traffic[name.replace(".ncu-rep", "")] = {
+                "kernel": r.get("Kernel Name", "?"), "dram_bytes_read": rd, "dram_bytes_write": wr,
+                "grid": r.get("launch__grid_size"), "duration": r.get("gpu__time_duration.sum"),
+                "duration_unit": units.get("gpu__time_duration.sum")}
+    json.dump(traffic, open(os.path.join(PROF, "ncu_traffic.json"), "w"), indent=1)
     # launch list
     lc = os.path.join(OUT, "launches.csv")
     if os.path.exists(lc):
