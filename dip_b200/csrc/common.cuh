@@ -129,7 +129,9 @@ struct Ctx {
     double *dVal = nullptr;         // nnz
     int spmvLanes = 0;              // 0 = auto (stream kernel when every column fits a tile)
     int32_t *dColStart32 = nullptr; // N+1 (only when nnz < 2^31)
-    int32_t *dTileRec = nullptr;    // nSpmvTiles x {first col, end col, aligned first entry, entries} (int4)
+    int32_t *dTileRec = nullptr;    // nSpmvTiles x {first col, end col, first stored entry, entries} (int4)
+    unsigned char *dSpmvBlob = nullptr;  // tile-blocked [values | rows] copy of the streams
+    int64_t *dSpmvBlobOff = nullptr;     // nSpmvTiles byte offsets into dSpmvBlob
     int nSpmvTiles = 0;             // 0 = stream kernel not applicable
     int optSpmvWarps = 0, optSpmvUSmem = -1;  // diagnostics knobs
     void *spmvFn = nullptr;                   // kernel whose shared-memory limit is already set

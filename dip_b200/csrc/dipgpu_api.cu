@@ -91,7 +91,6 @@ static int uploadCore(Ctx *c)
         std::vector<int32_t> cs32((size_t)N + 1);
         for (int j = 0; j <= N; ++j) cs32[j] = (int32_t)colStart[j];
         const bool row16 = (int64_t)R + c->numConvex <= 65536;
-        const int64_t alignMask = row16 ? 7 : 3;  // 16 bytes of the row stream
         // columns per warp tile: up to 32*kSpmvColsPerLane, fewer on small matrices so that every SM
         // still gets ~16 warp tiles (a GAP-E sweep is latency-bound: more, shorter tiles in flight)
         const int sms = c->smCount > 0 ? c->smCount : 148;
@@ -101,25 +100,49 @@ static int uploadCore(Ctx *c)
         int j = 0;
         tileCol.push_back(0);
         while (j < N) {
-            const int64_t a0 = colStart[j] & ~alignMask;
             int e = j;
-            while (e < N && e - j < maxCols && colStart[e + 1] - a0 <= kSpmvChunk) ++e;
+            while (e < N && e - j < maxCols && colStart[e + 1] - colStart[j] <= kSpmvChunk) ++e;
             if (e == j) { ok = false; break; }  // a single column longer than a tile
             tileCol.push_back(e);
             j = e;
         }
         if (ok) {
-            if ((rc = devAlloc(c, &c->dColStart32, (size_t)N + 1))) return rc;
             const size_t nt = tileCol.size() - 1;
             std::vector<int32_t> rec(4 * std::max<size_t>(nt, 1));
+            std::vector<int64_t> blobOff(std::max<size_t>(nt, 1), 0);
+            // tile-blocked blob: per tile its values then its rows, each padded to 16 bytes, so that ONE
+            // bulk copy brings a tile into a shared-memory stage
+            size_t blobBytes = 0;
             for (size_t k = 0; k < nt; ++k) {
-                const int32_t a0 = cs32[tileCol[k]] & ~(int32_t)alignMask;
+                const int32_t first = cs32[tileCol[k]];
+                const int32_t len = cs32[tileCol[k + 1]] - first;
                 rec[4 * k + 0] = tileCol[k];
                 rec[4 * k + 1] = tileCol[k + 1];
-                rec[4 * k + 2] = a0;
-                rec[4 * k + 3] = cs32[tileCol[k + 1]] - a0;
+                rec[4 * k + 2] = first;
+                rec[4 * k + 3] = len;
+                blobOff[k] = (int64_t)blobBytes;
+                blobBytes += (size_t)(((len + 1) & ~1) * 8);
+                blobBytes += row16 ? (size_t)(((len + 7) & ~7) * 2) : (size_t)(((len + 3) & ~3) * 4);
+            }
+            std::vector<unsigned char> blob(blobBytes + 64, 0);
+            for (size_t k = 0; k < nt; ++k) {
+                const int32_t first = rec[4 * k + 2], len = rec[4 * k + 3];
+                unsigned char *p = blob.data() + blobOff[k];
+                memcpy(p, val.data() + first, sizeof(double) * (size_t)len);
+                p += (size_t)(((len + 1) & ~1) * 8);
+                if (row16) {
+                    uint16_t *r16 = reinterpret_cast<uint16_t *>(p);
+                    for (int q = 0; q < len; ++q) r16[q] = (uint16_t)rowMaster[(size_t)first + q];
+                } else {
+                    memcpy(p, rowMaster.data() + first, sizeof(int32_t) * (size_t)len);
+                }
             }
             if ((rc = devAlloc(c, &c->dTileRec, rec.size()))) return rc;
+            if ((rc = devAlloc(c, &c->dSpmvBlob, blob.size()))) return rc;
+            if ((rc = devAlloc(c, &c->dSpmvBlobOff, blobOff.size()))) return rc;
+            DIPGPU_CUDA(c, cudaMemcpy(c->dSpmvBlob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+            DIPGPU_CUDA(c, cudaMemcpy(c->dSpmvBlobOff, blobOff.data(), sizeof(int64_t) * blobOff.size(), cudaMemcpyHostToDevice));
+            if ((rc = devAlloc(c, &c->dColStart32, (size_t)N + 1))) return rc;
             DIPGPU_CUDA(c, cudaMemcpy(c->dColStart32, cs32.data(), sizeof(int32_t) * cs32.size(), cudaMemcpyHostToDevice));
             DIPGPU_CUDA(c, cudaMemcpy(c->dTileRec, rec.data(), sizeof(int32_t) * rec.size(), cudaMemcpyHostToDevice));
             devFree(&c->dRowMaster16);
@@ -374,7 +397,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (c->stream) cudaStreamSynchronize(c->stream);
     devFree(&c->dDoneCounter); devFree(&c->dCsrRowStart); devFree(&c->dCsrColInd); devFree(&c->dCsrVal); devFree(&c->dExpPub);
     if (c->dMCols) cudaFree(c->dMCols);
-    if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
+    if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dSpmvBlob); devFree(&c->dSpmvBlobOff); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
     devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems); devFree(&c->dScale); devFree(&c->dShortcut); devFree(&c->dSel); devFree(&c->dZShort);
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);

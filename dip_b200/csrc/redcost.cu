@@ -44,12 +44,19 @@ __device__ __forceinline__ void rcMbarWait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
+// byte sizes of a tile's two parts inside the blob / a stage (16-byte multiples)
+__host__ __device__ inline uint32_t tileValBytes(int len) { return (uint32_t)(((len + 1) & ~1) * 8); }
+template <bool ROW16> __host__ __device__ inline uint32_t tileRowBytes(int len)
+{
+    return ROW16 ? (uint32_t)(((len + 7) & ~7) * 2) : (uint32_t)(((len + 3) & ~3) * 4);
+}
+
 struct StreamArgs {
     int nTiles;
-    const int4 *tileRec;        // per tile {first column, end column, 4-aligned first entry, entries from there}
+    const int4 *tileRec;        // per tile {first column, end column, first stored entry, entries}
     const int32_t *colStart32;  // N+1
-    const void *rowMaster;      // per stored entry: MASTER dual index of its row (int32, or uint16 if ROW16)
-    const double *val;
+    const unsigned char *blob;  // tile-blocked copy of the streams: per tile [values | rows], 16-byte padded
+    const int64_t *blobOff;     // per tile: byte offset of its block in `blob`
     const double *u;
     int uLen;
     const double *c;
@@ -108,8 +115,7 @@ __global__ void __launch_bounds__(768) redcost_stream_kernel(const __grid_consta
 {
     typedef SpmvStage<ROW16> St;
     typedef typename std::conditional<ROW16, uint16_t, int32_t>::type RowT;
-    constexpr int kSpmvStageBytes = St::kBytes, kSpmvStageValBytes = St::kValBytes, kSpmvWarpBytes = St::kWarpBytes;
-    const RowT *gRow = static_cast<const RowT *>(a.rowMaster);
+    constexpr int kSpmvStageBytes = St::kBytes, kSpmvWarpBytes = St::kWarpBytes;
     extern __shared__ __align__(16) unsigned char sm[];
     const double *sU = reinterpret_cast<const double *>(sm);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -136,26 +142,19 @@ __global__ void __launch_bounds__(768) redcost_stream_kernel(const __grid_consta
     const int totalWarps = gridDim.x * warpsPerCta;
     const int4 none = make_int4(0, 0, 0, 0);
 
-    auto issue = [&](const int4 rec, int s) {
+    // one bulk copy per tile: its values and rows sit back to back in the tile-blocked blob
+    auto issue = [&](const int4 rec, int64_t off, int s) {
         uint64_t *bar = full + s;
         const int len = rec.w;
         if (len > 0) {
-            double *dv = reinterpret_cast<double *>(stageBase + (size_t)s * kSpmvStageBytes);
-            RowT *dr = reinterpret_cast<RowT *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
-            const uint32_t bytesVal = (uint32_t)(((len + 1) & ~1) * 8);
-            const uint32_t bytesRow = (uint32_t)(((len + St::kAlign - 1) & ~(St::kAlign - 1)) * sizeof(RowT));
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rcSmemAddr(bar)),
-                         "r"(bytesVal + bytesRow)
+            unsigned char *dst = stageBase + (size_t)s * kSpmvStageBytes;
+            const uint32_t bytes = tileValBytes(len) + tileRowBytes<ROW16>(len);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rcSmemAddr(bar)), "r"(bytes)
                          : "memory");
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    rcSmemAddr(dv)),
-                "l"(a.val + rec.z), "r"(bytesVal), "r"(rcSmemAddr(bar))
-                : "memory");
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    rcSmemAddr(dr)),
-                "l"(gRow + rec.z), "r"(bytesRow), "r"(rcSmemAddr(bar))
+                    rcSmemAddr(dst)),
+                "l"(a.blob + off), "r"(bytes), "r"(rcSmemAddr(bar))
                 : "memory");
         } else {
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rcSmemAddr(bar)) : "memory");
@@ -166,12 +165,14 @@ __global__ void __launch_bounds__(768) redcost_stream_kernel(const __grid_consta
     // nn = two ahead (issued when cur's stage is free)
     int4 cur = gw < a.nTiles ? __ldg(a.tileRec + gw) : none;
     int4 nxt = gw + totalWarps < a.nTiles ? __ldg(a.tileRec + gw + totalWarps) : none;
+    const int64_t offCur = gw < a.nTiles ? __ldg(a.blobOff + gw) : 0;
+    const int64_t offNxt = gw + totalWarps < a.nTiles ? __ldg(a.blobOff + gw + totalWarps) : 0;
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full)), "r"(1));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full + 1)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (gw < a.nTiles) issue(cur, 0);
-        if (gw + totalWarps < a.nTiles) issue(nxt, 1);
+        if (gw < a.nTiles) issue(cur, offCur, 0);
+        if (gw + totalWarps < a.nTiles) issue(nxt, offNxt, 1);
     }
     ColMeta mc;
     loadColMeta(a, cur, lane, mc);
@@ -218,11 +219,12 @@ __global__ void __launch_bounds__(768) redcost_stream_kernel(const __grid_consta
         const uint32_t parity = (uint32_t)((it >> 1) & 1);
         double *sVal = reinterpret_cast<double *>(stageBase + (size_t)s * kSpmvStageBytes);
         const RowT *sRow =
-            reinterpret_cast<const RowT *>(stageBase + (size_t)s * kSpmvStageBytes + kSpmvStageValBytes);
+            reinterpret_cast<const RowT *>(stageBase + (size_t)s * kSpmvStageBytes + tileValBytes(cur.w));
         // prefetch (registers) what the next two tiles need; consumed after this tile is done
         const int tn = tile + totalWarps, tnn = tile + 2 * totalWarps;
         // unconditional (clamped) load: a select on the result would stall the warp right here
         const int4 nn = __ldg(a.tileRec + min(tnn, a.nTiles - 1));
+        const int64_t offNn = __ldg(a.blobOff + min(tnn, a.nTiles - 1));
         ColMeta mn;
         loadColMeta(a, nxt, lane, mn);  // nxt is {0,0,0,0} past the end: no loads
         rcMbarWait(full + s, parity);
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(768) redcost_stream_kernel(const __grid_consta
         // (async proxy) that refills it
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0 && tnn < a.nTiles) issue(nn, s);
+        if (lane == 0 && tnn < a.nTiles) issue(nn, offNn, s);
         (void)tn;
         cur = nxt;
         nxt = tnn < a.nTiles ? nn : none;
@@ -347,7 +349,8 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
         a.nTiles = c->nSpmvTiles;
         a.tileRec = reinterpret_cast<const int4 *>(c->dTileRec);
         a.colStart32 = c->dColStart32;
-        a.val = c->dVal;
+        a.blob = c->dSpmvBlob;
+        a.blobOff = c->dSpmvBlobOff;
         a.u = dU;
         a.uLen = c->R + c->numConvex;
         a.c = c->dObj;
@@ -356,7 +359,6 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
         const int sms = c->smCount > 0 ? c->smCount : 148;
         const size_t maxSmem = 227 * 1024;
         const bool row16 = c->dRowMaster16 != nullptr;
-        a.rowMaster = row16 ? static_cast<const void *>(c->dRowMaster16) : static_cast<const void *>(c->dRowMaster);
         const size_t warpBytes = row16 ? SpmvStage<true>::kWarpBytes : SpmvStage<false>::kWarpBytes;
         const size_t uBytes = (((size_t)a.uLen + 1) & ~(size_t)1) * 8 + 16;  // + the u mbarrier
         const int uHalf = (((a.uLen + 1) / 2) + 1) & ~1;
