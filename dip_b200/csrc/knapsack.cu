@@ -273,7 +273,6 @@ struct KnapArgs {
     const int32_t *scale;          // Pisinger mode: local block -> scale factor
     const int32_t *shortcut;       // Pisinger mode: local block -> trivial-case code (0 = run the DP)
     const double *zShort;          // Pisinger mode: local block -> optimum of a trivial case
-    int fuseTail;                  // small shards: backtrack + filter run in this kernel's tail
     unsigned long long *dbgTimes;  // diagnostics: 8 globaltimer stamps per CTA (NULL = off)
     unsigned long long *pubWord;   // FUSE: per local block (epoch << 32) | kept << 31 | nnz
     unsigned long long *pubCells;  // FUSE: per local block DP cells
@@ -1103,7 +1102,6 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, doubl
     a.firstBlock = c->firstBlock;
     a.chunkCols = g.chunkCols;
     a.guard = g.guard;
-    a.fuseTail = g.fuse;
     a.dbgTimes = c->dDbgTimes;
     a.pubWord = c->dPubWord;
     a.pubCells = c->dPubCells;
