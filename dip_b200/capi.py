@@ -34,6 +34,10 @@ SYMBOLS = [
     "dipgpu_get_counters", "dipgpu_last_stage_ms", "dipgpu_set_option",
     "dipgpu_calc_redcost_dev", "dipgpu_measure_smem_gbs", "dipgpu_plan_dp_geometry",
     "dipgpu_get_dp_geometry", "dipgpu_expand_columns",
+    "dipgpu_price_rounds_batch", "dipgpu_select_batch_result", "dipgpu_stab_set_center", "dipgpu_stab_accept",
+    "dipgpu_price_round_stab", "dipgpu_price_round_stab_ladder", "dipgpu_get_smoothed_duals",
+    "dipgpu_pool_clear", "dipgpu_pool_size", "dipgpu_pool_append", "dipgpu_pool_append_expanded",
+    "dipgpu_pool_keep", "dipgpu_pool_set_reduced_costs",
 ]
 
 
@@ -105,6 +109,19 @@ def lib() -> C.CDLL:
         "dipgpu_get_counters": ([vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)], C.c_int),
         "dipgpu_last_stage_ms": ([vp, C.POINTER(C.c_float)], C.c_int),
         "dipgpu_set_option": ([vp, C.c_char_p, i64], C.c_int),
+        "dipgpu_price_rounds_batch": ([vp, i32, vp, i32, i32, dbl, C.POINTER(Cols)], C.c_int),
+        "dipgpu_select_batch_result": ([vp, i32], C.c_int),
+        "dipgpu_stab_set_center": ([vp, vp, i32], C.c_int),
+        "dipgpu_stab_accept": ([vp, i32], C.c_int),
+        "dipgpu_price_round_stab": ([vp, vp, i32, dbl, i32, dbl, C.POINTER(Cols), vp], C.c_int),
+        "dipgpu_price_round_stab_ladder": ([vp, vp, i32, dbl, dbl, i32, i32, dbl, C.POINTER(Cols), vp], C.c_int),
+        "dipgpu_get_smoothed_duals": ([vp, i32, vp, i32], C.c_int),
+        "dipgpu_pool_clear": ([vp], C.c_int),
+        "dipgpu_pool_size": ([vp, C.POINTER(i64), C.POINTER(i64)], C.c_int),
+        "dipgpu_pool_append": ([vp, i32, vp, vp, vp, vp], C.c_int),
+        "dipgpu_pool_append_expanded": ([vp, i32, vp], C.c_int),
+        "dipgpu_pool_keep": ([vp, i32, vp], C.c_int),
+        "dipgpu_pool_set_reduced_costs": ([vp, vp, i32, i32, vp, C.POINTER(i32)], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

@@ -69,10 +69,24 @@ struct ResultLayout {
 constexpr int kFuseFilterMaxBlocks = 256;
 
 // ---------------------------------------------------------------- SpMV tiling
-constexpr int kSpmvChunk = 256;        // stored entries per warp tile (4.5 KiB of shared memory per stage)
+constexpr int kSpmvChunk = 256;        // default entry budget of a warp tile (runtime knob "spmv_chunk")
+constexpr int kSpmvChunkMax = 4096;    // a single column longer than the budget -> lane-cooperative kernel
 constexpr int kSpmvColsPerLane = 4;    // a warp tile spans at most 32*4 consecutive columns (fewer when the
-                                       // kSpmvChunk entry budget is reached first)
-
+                                       // entry budget is reached first)
+constexpr int kSpmvMaxStages = 8;
+// A tile of the stream kernel is self-contained in the blob (one bulk copy).  Per slice of 32
+// columns, lane l owns the slice's l-th LONGEST column (host-side stable sort), so the columns that
+// still have an entry at step i are a prefix of the lanes:
+//   SpmvTileHeader                     16 B
+//   uint16 len[nSlices*32]             column length of lane l (0 past the tile's last column)
+//   uint16 col[nSlices*32]             column of lane l, relative to firstCol
+//   double c[nSlices*32]               objective entry of lane l's column
+//   uint16 stepOff[nSlices*stepStride] per slice: position of step i's first entry (padded to 16 B)
+//   double val[nEnt (+1 to even)]      JAGGED: per slice, step 0 of every lane, then step 1 of the
+//   RowT   row[nEnt (padded to 16 B)]  lanes whose column is longer than 1, ...
+struct SpmvTileHeader {
+    int32_t firstCol, nCols, nEnt, stepStride;
+};
 // ------------------------------------------------- packed master columns (expand.cu)
 //   MColsHeader                64 B
 //   int64  colStart[m + 1]     offsets into entries
@@ -129,11 +143,12 @@ struct Ctx {
     double *dVal = nullptr;         // nnz
     int spmvLanes = 0;              // 0 = auto (stream kernel when every column fits a tile)
     int32_t *dColStart32 = nullptr; // N+1 (only when nnz < 2^31)
-    int32_t *dTileRec = nullptr;    // nSpmvTiles x {first col, end col, first stored entry, entries} (int4)
-    unsigned char *dSpmvBlob = nullptr;  // tile-blocked [values | rows] copy of the streams
-    int64_t *dSpmvBlobOff = nullptr;     // nSpmvTiles byte offsets into dSpmvBlob
+    uint32_t *dTileRec = nullptr;   // nSpmvTiles x {byte offset / 16 into dSpmvBlob, bytes} (uint2)
+    unsigned char *dSpmvBlob = nullptr;  // self-contained jagged tiles (SpmvTileHeader)
     int nSpmvTiles = 0;             // 0 = stream kernel not applicable
-    int optSpmvWarps = 0, optSpmvUSmem = -1;  // diagnostics knobs
+    int spmvStageBytes = 0;         // largest tile, bytes
+    int optSpmvWarps = 0, optSpmvUSmem = -1, optSpmvChunk = 0, optSpmvStages = 0, optSpmvMaxCols = 0;  // diagnostics knobs
+    std::vector<double> hObj;       // host copy of the objective (tiles carry their columns' entries)
     void *spmvFn = nullptr;                   // kernel whose shared-memory limit is already set
     size_t spmvFnSmem = 0;
     int spmvClusters = 0;                     // resident CTA pairs of the cluster variant
@@ -208,6 +223,31 @@ struct Ctx {
     int64_t indCap = 0;
     ResultLayout layout{};
 
+    // batched dual vectors (dipgpu_price_rounds_batch / dipgpu_price_round_stab*): per-vector copies of
+    // the dual vector, the reduced costs, the packed result and the per-block publication / Pisinger arrays
+    int batchCap = 0;            // vectors the buffers below hold
+    size_t uStride = 0;          // doubles between dual vectors (even, >= uLen)
+    size_t rcStride = 0;         // doubles between reduced-cost vectors (even, >= N + 16)
+    size_t resStride = 0;        // bytes between packed results (multiple of 16, >= resultBytes)
+    double *dUBatch = nullptr, *dRedCostBatch = nullptr;
+    void *dResultBatch = nullptr, *hResultBatch = nullptr;
+    unsigned long long *dPubWordBatch = nullptr;
+    unsigned int epochBatch = 0;
+    int32_t *dScaleB = nullptr, *dShortcutB = nullptr, *dSelB = nullptr;
+    double *dZShortB = nullptr;
+    double *dAlphaLadder = nullptr;  // smoothing parameters of a ladder (device)
+    // dual stabilisation (DecompAlgoPC::adjustMasterDualSolution): m_dual, the stability centre
+    double *dCenter = nullptr;
+    size_t centerLen = 0;
+    bool haveCenter = false, haveST = false;  // haveST: dUBatch[0] holds the last smoothed vector
+    bool dualsResident = false;               // dU holds the dual vector of the last host-buffer call
+    // waiting-column pool (DecompVarPool): master columns in device memory
+    int64_t poolCols = 0, poolNnz = 0, poolColCap = 0, poolNnzCap = 0;
+    int64_t *dPoolStart = nullptr;   // poolCols + 1
+    int32_t *dPoolRow = nullptr;
+    double *dPoolVal = nullptr, *dPoolOrigCost = nullptr, *dPoolRedCost = nullptr;
+    int32_t *dPoolFlag = nullptr;    // [0]: some redCost <= -1e-10
+
     // pinned staging for pageable inputs
     double *hStage = nullptr;
     size_t hStageBytes = 0;
@@ -235,6 +275,7 @@ struct PrepArgs {
     const int32_t *blockColStart;
     const int32_t *capacity;
     int firstBlock;
+    long long rcStride; // batched dual vectors: vector v = blockIdx.y reads redCost + v*rcStride, writes slot v*gridDim.x + lb
     int32_t *scale;     // local block -> calcScaleFactor result
     int32_t *shortcut;  // local block -> 0 solve by DP, 1 take every active item, 2 explicit set (sel)
     int32_t *sel;       // 2 per local block: chosen local columns ascending, -1 = none
@@ -244,18 +285,30 @@ struct PrepArgs {
 // ------------------------------------------------------------------- launchers
 // redcost.cu -- stage (a)
 int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st);
+// nVec dual vectors at once: vector v reads dU + v*uStride and writes dOut + v*outStride
+int launchRedCostBatch(Ctx *c, const double *dU, int64_t uStride, double *dOut, int64_t outStride, int nVec, int phase,
+                       cudaStream_t st);
+int buildSpmvTiles(Ctx *c, const std::vector<int64_t> &colStart, const std::vector<int32_t> &rowMaster,
+                   const std::vector<double> &val);
 // pisinger.cu -- scale factor + trivial cases of GAP_KnapPisinger::solve (profit mode 1 only)
 int launchKnapsackPrep(Ctx *c, const double *dRedCost, cudaStream_t st);
+int launchKnapsackPrepBatch(Ctx *c, const double *dRedCost, int64_t rcStride, int nVec, cudaStream_t st);
 // knapsack.cu -- stage (b)
 int chooseDpGeom(Ctx *c, DpGeom *g, bool wantFuse);
 int prepareKnapsackDp(Ctx *c);  // loads the chosen kernel, sets its shared-memory limit
 int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st);
+int launchKnapsackDpBatch(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
+                          double redCostEps, int nVec, cudaStream_t st);
 int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseFilter,
                         cudaStream_t st);
 // filter.cu -- stage (c)
 int launchFilter(Ctx *c, double redCostEps, cudaStream_t st);
 // expand.cu -- master columns of the kept variables (the step after the round)
 int launchExpandColumns(Ctx *c, double tolZero, int nKept, cudaStream_t st);
+// pool.cu -- waiting-column pool re-pricing (DecompVarPool::setReducedCosts) and Wentges smoothing
+int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st);
+int launchSmoothDuals(Ctx *c, const double *dURM, const double *dCenter, const double *dAlphas, int nVec, int uLen,
+                      double *dOut, int64_t outStride, cudaStream_t st);
 // microbench.cu -- roofline denominators measured on the device
 int measureSmemGbs(Ctx *c, double *gbs);
 

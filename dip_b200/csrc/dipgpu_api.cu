@@ -52,6 +52,8 @@ static void devFree(T **p)
     *p = nullptr;
 }
 
+static void freeBatch(Ctx *c);
+
 static int bind(Ctx *c)
 {
     DIPGPU_CUDA(c, cudaSetDevice(c->device));
@@ -83,76 +85,20 @@ static int uploadCore(Ctx *c)
     c->nnz = nnz;
     c->hColStart = colStart;
     int rc;
-    // warp tiles of the stream kernel: consecutive columns, <= kSpmvChunk stored entries (counted
-    // from the 4-aligned start), <= 32*colsPerLane columns with colsPerLane fitted to the density
-    c->nSpmvTiles = 0;
+    // warp tiles of the stream kernel (redcost.cu)
+    if ((rc = buildSpmvTiles(c, colStart, rowMaster, val))) return rc;
+    devFree(&c->dColStart32);
+    devFree(&c->dRowMaster16);
     if (nnz < (int64_t)1 << 31 && N > 0) {
-        std::vector<int32_t> tileCol;
         std::vector<int32_t> cs32((size_t)N + 1);
         for (int j = 0; j <= N; ++j) cs32[j] = (int32_t)colStart[j];
-        const bool row16 = (int64_t)R + c->numConvex <= 65536;
-        // columns per warp tile: up to 32*kSpmvColsPerLane, fewer on small matrices so that every SM
-        // still gets ~16 warp tiles (a GAP-E sweep is latency-bound: more, shorter tiles in flight)
-        const int sms = c->smCount > 0 ? c->smCount : 148;
-        int maxCols = (int)std::min<int64_t>(32 * kSpmvColsPerLane, (int64_t)N / (16 * sms)) & ~31;
-        maxCols = std::max(32, maxCols);
-        bool ok = true;
-        int j = 0;
-        tileCol.push_back(0);
-        while (j < N) {
-            int e = j;
-            while (e < N && e - j < maxCols && colStart[e + 1] - colStart[j] <= kSpmvChunk) ++e;
-            if (e == j) { ok = false; break; }  // a single column longer than a tile
-            tileCol.push_back(e);
-            j = e;
-        }
-        if (ok) {
-            const size_t nt = tileCol.size() - 1;
-            std::vector<int32_t> rec(4 * std::max<size_t>(nt, 1));
-            std::vector<int64_t> blobOff(std::max<size_t>(nt, 1), 0);
-            // tile-blocked blob: per tile its values then its rows, each padded to 16 bytes, so that ONE
-            // bulk copy brings a tile into a shared-memory stage
-            size_t blobBytes = 0;
-            for (size_t k = 0; k < nt; ++k) {
-                const int32_t first = cs32[tileCol[k]];
-                const int32_t len = cs32[tileCol[k + 1]] - first;
-                rec[4 * k + 0] = tileCol[k];
-                rec[4 * k + 1] = tileCol[k + 1];
-                rec[4 * k + 2] = first;
-                rec[4 * k + 3] = len;
-                blobOff[k] = (int64_t)blobBytes;
-                blobBytes += (size_t)(((len + 1) & ~1) * 8);
-                blobBytes += row16 ? (size_t)(((len + 7) & ~7) * 2) : (size_t)(((len + 3) & ~3) * 4);
-            }
-            std::vector<unsigned char> blob(blobBytes + 64, 0);
-            for (size_t k = 0; k < nt; ++k) {
-                const int32_t first = rec[4 * k + 2], len = rec[4 * k + 3];
-                unsigned char *p = blob.data() + blobOff[k];
-                memcpy(p, val.data() + first, sizeof(double) * (size_t)len);
-                p += (size_t)(((len + 1) & ~1) * 8);
-                if (row16) {
-                    uint16_t *r16 = reinterpret_cast<uint16_t *>(p);
-                    for (int q = 0; q < len; ++q) r16[q] = (uint16_t)rowMaster[(size_t)first + q];
-                } else {
-                    memcpy(p, rowMaster.data() + first, sizeof(int32_t) * (size_t)len);
-                }
-            }
-            if ((rc = devAlloc(c, &c->dTileRec, rec.size()))) return rc;
-            if ((rc = devAlloc(c, &c->dSpmvBlob, blob.size()))) return rc;
-            if ((rc = devAlloc(c, &c->dSpmvBlobOff, blobOff.size()))) return rc;
-            DIPGPU_CUDA(c, cudaMemcpy(c->dSpmvBlob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-            DIPGPU_CUDA(c, cudaMemcpy(c->dSpmvBlobOff, blobOff.data(), sizeof(int64_t) * blobOff.size(), cudaMemcpyHostToDevice));
-            if ((rc = devAlloc(c, &c->dColStart32, (size_t)N + 1))) return rc;
-            DIPGPU_CUDA(c, cudaMemcpy(c->dColStart32, cs32.data(), sizeof(int32_t) * cs32.size(), cudaMemcpyHostToDevice));
-            DIPGPU_CUDA(c, cudaMemcpy(c->dTileRec, rec.data(), sizeof(int32_t) * rec.size(), cudaMemcpyHostToDevice));
-            devFree(&c->dRowMaster16);
-            if (row16) {
-                std::vector<uint16_t> r16((size_t)nnz + 16, 0);
-                for (int64_t k = 0; k < nnz; ++k) r16[k] = (uint16_t)rowMaster[k];
-                if ((rc = devAlloc(c, &c->dRowMaster16, r16.size()))) return rc;
-                DIPGPU_CUDA(c, cudaMemcpy(c->dRowMaster16, r16.data(), sizeof(uint16_t) * r16.size(), cudaMemcpyHostToDevice));
-            }
-            c->nSpmvTiles = (int)tileCol.size() - 1;
+        if ((rc = devAlloc(c, &c->dColStart32, (size_t)N + 1))) return rc;
+        DIPGPU_CUDA(c, cudaMemcpy(c->dColStart32, cs32.data(), sizeof(int32_t) * cs32.size(), cudaMemcpyHostToDevice));
+        if ((int64_t)R + c->numConvex <= 65536) {
+            std::vector<uint16_t> r16((size_t)nnz + 16, 0);
+            for (int64_t k = 0; k < nnz; ++k) r16[k] = (uint16_t)rowMaster[k];
+            if ((rc = devAlloc(c, &c->dRowMaster16, r16.size()))) return rc;
+            DIPGPU_CUDA(c, cudaMemcpy(c->dRowMaster16, r16.data(), sizeof(uint16_t) * r16.size(), cudaMemcpyHostToDevice));
         }
     }
     // row-major copy for expand.cu
@@ -196,6 +142,7 @@ static int setBlockRange(Ctx *c, int first, int count)
         return fail(c, DIPGPU_ERR_INVALID, "block range [%d,%d) outside [0,%d)", first, first + count, c->m);
     c->firstBlock = first;
     c->nLocal = count;
+    freeBatch(c);  // per-vector buffers are sized by the shard
     int maxCap = 0, maxCols = 0, maxW = 0;
     for (int b = first; b < first + count; ++b) {
         maxCap = std::max(maxCap, c->hCapacity[b]);
@@ -343,6 +290,159 @@ static void collectStageMs(Ctx *c)
     (void)cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------ batched dual vectors
+
+int launchPoolCopy(Ctx *c, int n, const void *dDesc, const void *srcEntries, const int32_t *srcRow, const double *srcVal,
+                   int32_t *dstRow, double *dstVal, cudaStream_t st);  // pool.cu
+
+static void freeBatch(Ctx *c)
+{
+    devFree(&c->dUBatch); devFree(&c->dRedCostBatch); devFree(&c->dPubWordBatch);
+    devFree(&c->dScaleB); devFree(&c->dShortcutB); devFree(&c->dSelB); devFree(&c->dZShortB); devFree(&c->dAlphaLadder);
+    if (c->dResultBatch) cudaFree(c->dResultBatch);
+    if (c->hResultBatch) cudaFreeHost(c->hResultBatch);
+    c->dResultBatch = c->hResultBatch = nullptr;
+    c->batchCap = 0;
+    c->haveST = false;
+}
+
+// Buffers for nVec dual vectors priced in one submission.
+static int ensureBatch(Ctx *c, int nVec)
+{
+    const size_t uLen = (size_t)c->R + c->numConvex;
+    const size_t uStride = (uLen + 17) & ~(size_t)1;
+    const size_t rcStride = ((size_t)c->N + 17) & ~(size_t)1;
+    const size_t resStride = ResultLayout::alignUp(c->resultBytes, 16);
+    if (c->batchCap >= nVec && c->uStride == uStride && c->rcStride == rcStride && c->resStride == resStride) return DIPGPU_OK;
+    freeBatch(c);
+    int rc;
+    const size_t V = (size_t)nVec, nl = (size_t)std::max(c->nLocal, 1);
+    if ((rc = devAlloc(c, &c->dUBatch, V * uStride))) return rc;
+    if ((rc = devAlloc(c, &c->dRedCostBatch, V * rcStride))) return rc;
+    DIPGPU_CUDA(c, cudaMemset(c->dUBatch, 0, sizeof(double) * V * uStride));
+    DIPGPU_CUDA(c, cudaMemset(c->dRedCostBatch, 0, sizeof(double) * V * rcStride));
+    if ((rc = devAlloc(c, &c->dPubWordBatch, V * nl))) return rc;
+    DIPGPU_CUDA(c, cudaMemset(c->dPubWordBatch, 0, sizeof(unsigned long long) * V * nl));
+    c->epochBatch = 0;
+    if ((rc = devAlloc(c, &c->dScaleB, V * nl))) return rc;
+    if ((rc = devAlloc(c, &c->dShortcutB, V * nl))) return rc;
+    if ((rc = devAlloc(c, &c->dSelB, 2 * V * nl))) return rc;
+    if ((rc = devAlloc(c, &c->dZShortB, V * nl))) return rc;
+    DIPGPU_CUDA(c, cudaMemset(c->dShortcutB, 0, sizeof(int32_t) * V * nl));
+    if ((rc = devAlloc(c, &c->dAlphaLadder, V))) return rc;
+    DIPGPU_CUDA(c, cudaMalloc(&c->dResultBatch, V * resStride));
+    DIPGPU_CUDA(c, cudaMemset(c->dResultBatch, 0, V * resStride));
+    DIPGPU_CUDA(c, cudaMallocHost(&c->hResultBatch, V * resStride));
+    c->batchCap = nVec;
+    c->uStride = uStride;
+    c->rcStride = rcStride;
+    c->resStride = resStride;
+    return DIPGPU_OK;
+}
+
+// Stages (a)-(c) for the nVec dual vectors held in dUBatch: three launches in all when the shard
+// runs the fused DP kernel (gridDim.y = vectors), else vector after vector through the large-shard path.
+static int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st)
+{
+    int rc;
+    if (c->geom.fuse || c->nLocal == 0) {
+        if ((rc = launchRedCostBatch(c, c->dUBatch, (int64_t)c->uStride, c->dRedCostBatch, (int64_t)c->rcStride, nVec, phase, st))) return rc;
+        if ((rc = launchKnapsackPrepBatch(c, c->dRedCostBatch, (int64_t)c->rcStride, nVec, st))) return rc;
+        return launchKnapsackDpBatch(c, c->dRedCostBatch, (int64_t)c->rcStride, c->dUBatch + c->nBaseRows, (int64_t)c->uStride, eps, nVec, st);
+    }
+    for (int v = 0; v < nVec; ++v) {
+        const double *u = c->dUBatch + (size_t)v * c->uStride;
+        if ((rc = launchRedCost(c, u, phase, st))) return rc;
+        if ((rc = enqueueSolve(c, c->dRedCost, u + c->nBaseRows, eps, st, false))) return rc;
+        DIPGPU_CUDA(c, cudaMemcpyAsync(static_cast<char *>(c->dResultBatch) + (size_t)v * c->resStride, c->dResult, c->resultBytes, cudaMemcpyDeviceToDevice, st));
+    }
+    return DIPGPU_OK;
+}
+
+// D2H of nVec packed results (one strided copy of the speculative prefix) and decoding.
+static int fetchBatch(Ctx *c, int nVec, dipgpu_cols *outs, cudaStream_t st)
+{
+    const size_t spec = std::min(c->resultBytes, c->layout.offInd + (size_t)65536);
+    DIPGPU_CUDA(c, cudaMemcpy2DAsync(c->hResultBatch, c->resStride, c->dResultBatch, c->resStride, spec, (size_t)nVec, cudaMemcpyDeviceToHost, st));
+    DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+    c->d2h += (int64_t)spec * nVec;
+    bool more = false;
+    for (int v = 0; v < nVec; ++v) {
+        char *hp = static_cast<char *>(c->hResultBatch) + (size_t)v * c->resStride;
+        const ResultHeader *h = reinterpret_cast<const ResultHeader *>(hp);
+        if (h->magic != kResultMagic) return fail(c, DIPGPU_ERR_CUDA, "batched round: result %d has no header", v);
+        const size_t need = c->layout.offInd + sizeof(int32_t) * (size_t)h->nInd;
+        if (need > spec) {
+            DIPGPU_CUDA(c, cudaMemcpyAsync(hp + spec, static_cast<char *>(c->dResultBatch) + (size_t)v * c->resStride + spec, need - spec, cudaMemcpyDeviceToHost, st));
+            c->d2h += (int64_t)(need - spec);
+            more = true;
+        }
+    }
+    if (more) DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+    int first = DIPGPU_OK;
+    for (int v = 0; v < nVec; ++v) {
+        const int rc = unpack(c, static_cast<char *>(c->hResultBatch) + (size_t)v * c->resStride, c->resultBytes, &outs[v]);
+        if (rc && !first) first = rc;
+    }
+    return first;
+}
+
+static int checkRoundReady(Ctx *c, const char *who, int32_t uLen, int32_t phase)
+{
+    if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "%s needs set_core_csr and set_knapsack_blocks", who);
+    if (phase != DIPGPU_PHASE_PRICE1 && !c->haveObj) return fail(c, DIPGPU_ERR_STATE, "%s (phase 2) before set_objective", who);
+    if (uLen != c->R + c->numConvex) return fail(c, DIPGPU_ERR_INVALID, "%s: uLen=%d, expected R+numConvex=%d", who, uLen, c->R + c->numConvex);
+    if (c->numConvex != c->m) return fail(c, DIPGPU_ERR_INVALID, "%s: numConvex=%d but %d blocks", who, c->numConvex, c->m);
+    return ensureObjective(c, c->N);
+}
+
+static int ensureDualBuffer(Ctx *c, int32_t uLen)
+{
+    if ((size_t)uLen > c->uCap) {
+        int rc;
+        if ((rc = devAlloc(c, &c->dU, (size_t)uLen + 16))) return rc;
+        c->uCap = (size_t)uLen;
+        c->dualsResident = false;
+    }
+    return DIPGPU_OK;
+}
+
+// ------------------------------------------------------------------ waiting-column pool
+
+static int poolReserve(Ctx *c, int64_t cols, int64_t nnz)
+{
+    int rc;
+    if (!c->dPoolFlag && (rc = devAlloc(c, &c->dPoolFlag, 4))) return rc;
+    if (cols > c->poolColCap) {
+        const int64_t cap = std::max<int64_t>(cols, std::max<int64_t>(1024, 2 * c->poolColCap));
+        int64_t *ns = nullptr; double *no = nullptr, *nr = nullptr;
+        if ((rc = devAlloc(c, &ns, (size_t)cap + 1))) return rc;
+        if ((rc = devAlloc(c, &no, (size_t)cap))) return rc;
+        if ((rc = devAlloc(c, &nr, (size_t)cap))) return rc;
+        if (c->dPoolStart) DIPGPU_CUDA(c, cudaMemcpy(ns, c->dPoolStart, sizeof(int64_t) * ((size_t)c->poolCols + 1), cudaMemcpyDeviceToDevice));
+        else DIPGPU_CUDA(c, cudaMemset(ns, 0, sizeof(int64_t)));
+        if (c->poolCols > 0) DIPGPU_CUDA(c, cudaMemcpy(no, c->dPoolOrigCost, sizeof(double) * (size_t)c->poolCols, cudaMemcpyDeviceToDevice));
+        devFree(&c->dPoolStart); devFree(&c->dPoolOrigCost); devFree(&c->dPoolRedCost);
+        c->dPoolStart = ns; c->dPoolOrigCost = no; c->dPoolRedCost = nr;
+        c->poolColCap = cap;
+    }
+    if (nnz > c->poolNnzCap) {
+        const int64_t cap = std::max<int64_t>(nnz, std::max<int64_t>(65536, 2 * c->poolNnzCap));
+        int32_t *nr = nullptr; double *nv = nullptr;
+        if ((rc = devAlloc(c, &nr, (size_t)cap))) return rc;
+        if ((rc = devAlloc(c, &nv, (size_t)cap))) return rc;
+        if (c->poolNnz > 0) {
+            DIPGPU_CUDA(c, cudaMemcpy(nr, c->dPoolRow, sizeof(int32_t) * (size_t)c->poolNnz, cudaMemcpyDeviceToDevice));
+            DIPGPU_CUDA(c, cudaMemcpy(nv, c->dPoolVal, sizeof(double) * (size_t)c->poolNnz, cudaMemcpyDeviceToDevice));
+        }
+        devFree(&c->dPoolRow); devFree(&c->dPoolVal);
+        c->dPoolRow = nr; c->dPoolVal = nv;
+        c->poolNnzCap = cap;
+    }
+    return DIPGPU_OK;
+}
+
 }  // namespace dipgpu
 
 using namespace dipgpu;
@@ -397,10 +497,13 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (c->stream) cudaStreamSynchronize(c->stream);
     devFree(&c->dDoneCounter); devFree(&c->dCsrRowStart); devFree(&c->dCsrColInd); devFree(&c->dCsrVal); devFree(&c->dExpPub);
     if (c->dMCols) cudaFree(c->dMCols);
-    if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dSpmvBlob); devFree(&c->dSpmvBlobOff); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
+    if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dSpmvBlob); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
     devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems); devFree(&c->dScale); devFree(&c->dShortcut); devFree(&c->dSel); devFree(&c->dZShort);
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
+    freeBatch(c);
+    devFree(&c->dCenter); devFree(&c->dPoolStart); devFree(&c->dPoolRow); devFree(&c->dPoolVal);
+    devFree(&c->dPoolOrigCost); devFree(&c->dPoolRedCost); devFree(&c->dPoolFlag);
     if (c->dResult) cudaFree(c->dResult);
     if (c->hResult) cudaFreeHost(c->hResult);
     if (c->hStage) cudaFreeHost(c->hStage);
@@ -450,9 +553,10 @@ int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *ro
     for (int64_t k = 0; k < nnz; ++k)
         if (colInd[k] < 0 || colInd[k] >= N) return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: column index %d out of range at %lld", colInd[k], (long long)k);
     if (c->haveBlocks && c->nBlockCols > N) return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: N=%d < block columns %d", N, c->nBlockCols);
-    if (c->haveObj && c->N != N) { devFree(&c->dObj); c->haveObj = false; }
+    if (c->haveObj && c->N != N) { devFree(&c->dObj); c->haveObj = false; c->hObj.clear(); }
     if (c->N != N) devFree(&c->dRedCost);
     c->R = R; c->N = N; c->nBaseRows = nBaseRows; c->numConvex = numConvex;
+    c->dualsResident = false; c->haveCenter = false; c->haveST = false;
     c->hRowStart.assign(rowStart, rowStart + R + 1);
     c->hColInd.assign(colInd, colInd + nnz);
     c->hVal.assign(val, val + nnz);
@@ -481,6 +585,7 @@ int dipgpu_append_core_rows(dipgpu_ctx *ctx, int32_t nNew, const int64_t *rowSta
     c->hColInd.insert(c->hColInd.end(), colInd, colInd + add);
     c->hVal.insert(c->hVal.end(), val, val + add);
     c->R += nNew;
+    c->dualsResident = false; c->haveCenter = false; c->haveST = false;  // the master dual vector grew
     return uploadCore(c);
 }
 
@@ -497,6 +602,8 @@ int dipgpu_set_objective(dipgpu_ctx *ctx, const double *obj, int32_t N)
     DIPGPU_CUDA(c, cudaMemcpy(c->dObj, obj, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice));
     if (!c->haveCore) c->N = std::max(c->N, (int)N);
     c->haveObj = true;
+    c->hObj.assign(obj, obj + N);
+    if (c->haveCore) return uploadCore(c);  // the SpMV tiles carry their columns' objective entries
     return DIPGPU_OK;
 }
 
@@ -573,6 +680,7 @@ int dipgpu_calc_redcost(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t 
     }
     DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, u, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, c->stream));
     c->h2d += (int64_t)sizeof(double) * uLen;
+    c->dualsResident = true;
     if ((rc = launchRedCost(c, c->dU, phase, c->stream))) return rc;
     DIPGPU_CUDA(c, cudaMemcpyAsync(redCostX, c->dRedCost, sizeof(double) * (size_t)c->N, cudaMemcpyDeviceToHost, c->stream));
     c->d2h += (int64_t)sizeof(double) * c->N;
@@ -605,22 +713,19 @@ int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t p
                        dipgpu_cols *out, double *redCostXOpt)
 {
     CTX_OR_FAIL(ctx);
-    if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "price_round needs set_core_csr and set_knapsack_blocks");
-    if (phase != DIPGPU_PHASE_PRICE1 && !c->haveObj) return fail(c, DIPGPU_ERR_STATE, "price_round (phase 2) before set_objective");
-    if (!u || !out || uLen != c->R + c->numConvex)
-        return fail(c, DIPGPU_ERR_INVALID, "price_round: uLen=%d, expected R+numConvex=%d", uLen, c->R + c->numConvex);
-    if (c->numConvex != c->m) return fail(c, DIPGPU_ERR_INVALID, "price_round: numConvex=%d but %d blocks", c->numConvex, c->m);
+    if (!out) return fail(c, DIPGPU_ERR_INVALID, "price_round: NULL output");
     int rc;
-    if ((rc = ensureObjective(c, c->N))) return rc;
-    if ((size_t)uLen > c->uCap) {
-        if ((rc = devAlloc(c, &c->dU, (size_t)uLen + 16))) return rc;
-        c->uCap = (size_t)uLen;
-    }
+    if ((rc = checkRoundReady(c, "price_round", uLen, phase))) return rc;
+    if (!u && !c->dualsResident) return fail(c, DIPGPU_ERR_STATE, "price_round: u == NULL but no dual vector is resident");
+    if ((rc = ensureDualBuffer(c, uLen))) return rc;
     const bool timed = c->stageTiming;
     cudaStream_t st = c->stream;
     if (timed) cudaEventRecord(c->ev[0], st);
-    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, u, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, st));
-    c->h2d += (int64_t)sizeof(double) * uLen;
+    if (u) {
+        DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, u, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, st));
+        c->h2d += (int64_t)sizeof(double) * uLen;
+        c->dualsResident = true;
+    }
     if (timed) cudaEventRecord(c->ev[1], st);
     if ((rc = launchRedCost(c, c->dU, phase, st))) return rc;
     if (timed) cudaEventRecord(c->ev[2], st);
@@ -634,6 +739,306 @@ int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t p
     c->lastRoundOnHost = true;
     collectStageMs(c);
     return unpack(c, c->hResult, c->resultBytes, out);
+}
+
+// ------------------------------------------------- batched / stabilised rounds
+
+int dipgpu_price_rounds_batch(dipgpu_ctx *ctx, int32_t nVec, const double *U, int32_t uLen, int32_t phase,
+                              double redCostEps, dipgpu_cols *outs)
+{
+    CTX_OR_FAIL(ctx);
+    if (nVec < 0 || (nVec > 0 && (!U || !outs))) return fail(c, DIPGPU_ERR_INVALID, "price_rounds_batch: bad arguments");
+    int rc;
+    if ((rc = checkRoundReady(c, "price_rounds_batch", uLen, phase))) return rc;
+    if (nVec == 0) return DIPGPU_OK;
+    if ((rc = ensureBatch(c, nVec))) return rc;
+    cudaStream_t st = c->stream;
+    DIPGPU_CUDA(c, cudaMemcpy2DAsync(c->dUBatch, sizeof(double) * c->uStride, U, sizeof(double) * (size_t)uLen,
+                                     sizeof(double) * (size_t)uLen, (size_t)nVec, cudaMemcpyHostToDevice, st));
+    c->h2d += (int64_t)sizeof(double) * uLen * nVec;
+    c->haveST = false;
+    if ((rc = enqueueBatch(c, nVec, phase, redCostEps, st))) return rc;
+    c->lastRoundOnHost = false;
+    return fetchBatch(c, nVec, outs, st);
+}
+
+int dipgpu_stab_set_center(dipgpu_ctx *ctx, const double *dual, int32_t uLen)
+{
+    CTX_OR_FAIL(ctx);
+    if (!dual || uLen <= 0) return fail(c, DIPGPU_ERR_INVALID, "stab_set_center: bad arguments");
+    int rc;
+    if ((size_t)uLen != c->centerLen) {
+        if ((rc = devAlloc(c, &c->dCenter, (size_t)uLen + 16))) return rc;
+        c->centerLen = (size_t)uLen;
+    }
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dCenter, dual, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, c->stream));
+    DIPGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h2d += (int64_t)sizeof(double) * uLen;
+    c->haveCenter = true;
+    return DIPGPU_OK;
+}
+
+int dipgpu_stab_accept(dipgpu_ctx *ctx, int32_t step)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->haveST || step < 0 || step >= c->batchCap) return fail(c, DIPGPU_ERR_STATE, "stab_accept: no smoothed dual vector %d", step);
+    if (!c->haveCenter) return fail(c, DIPGPU_ERR_STATE, "stab_accept: no stability centre");
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dCenter, c->dUBatch + (size_t)step * c->uStride, sizeof(double) * c->centerLen,
+                                   cudaMemcpyDeviceToDevice, c->stream));
+    DIPGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    return DIPGPU_OK;
+}
+
+int dipgpu_get_smoothed_duals(dipgpu_ctx *ctx, int32_t step, double *dualST, int32_t uLen)
+{
+    CTX_OR_FAIL(ctx);
+    if (!dualST) return fail(c, DIPGPU_ERR_INVALID, "get_smoothed_duals: NULL output");
+    if (!c->haveST || step < 0 || step >= c->batchCap || uLen != c->R + c->numConvex)
+        return fail(c, DIPGPU_ERR_STATE, "get_smoothed_duals: no smoothed dual vector %d of length %d", step, uLen);
+    DIPGPU_CUDA(c, cudaMemcpyAsync(dualST, c->dUBatch + (size_t)step * c->uStride, sizeof(double) * (size_t)uLen,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    DIPGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->d2h += (int64_t)sizeof(double) * uLen;
+    return DIPGPU_OK;
+}
+
+int dipgpu_price_round_stab_ladder(dipgpu_ctx *ctx, const double *uRM, int32_t uLen, double alpha, double shrink,
+                                   int32_t nSteps, int32_t phase, double redCostEps, dipgpu_cols *outs, double *alphasOut)
+{
+    CTX_OR_FAIL(ctx);
+    if (!uRM || !outs || nSteps <= 0 || nSteps > 64) return fail(c, DIPGPU_ERR_INVALID, "price_round_stab_ladder: bad arguments");
+    int rc;
+    if ((rc = checkRoundReady(c, "price_round_stab_ladder", uLen, phase))) return rc;
+    if ((rc = ensureBatch(c, nSteps))) return rc;
+    if ((rc = ensureDualBuffer(c, uLen))) return rc;
+    cudaStream_t st = c->stream;
+    // the ladder DualStabAlpha *= 0.90 (DecompAlgo.cpp:5646), by repeated multiplication as the reference
+    double al[64];
+    al[0] = alpha;
+    for (int k = 1; k < nSteps; ++k) al[k] = al[k - 1] * shrink;
+    if (alphasOut) memcpy(alphasOut, al, sizeof(double) * (size_t)nSteps);
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, uRM, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, st));
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dAlphaLadder, al, sizeof(double) * (size_t)nSteps, cudaMemcpyHostToDevice, st));
+    c->h2d += (int64_t)sizeof(double) * (uLen + nSteps);
+    c->dualsResident = true;
+    if (!c->haveCenter || c->centerLen != (size_t)uLen) {
+        // first price call: m_dual := m_dualRM (DecompAlgoPC.cpp:163-173)
+        if (c->centerLen != (size_t)uLen) {
+            if ((rc = devAlloc(c, &c->dCenter, (size_t)uLen + 16))) return rc;
+            c->centerLen = (size_t)uLen;
+        }
+        DIPGPU_CUDA(c, cudaMemcpyAsync(c->dCenter, c->dU, sizeof(double) * (size_t)uLen, cudaMemcpyDeviceToDevice, st));
+        c->haveCenter = true;
+    }
+    if ((rc = launchSmoothDuals(c, c->dU, c->dCenter, c->dAlphaLadder, nSteps, uLen, c->dUBatch, (int64_t)c->uStride, st))) return rc;
+    c->haveST = true;
+    if ((rc = enqueueBatch(c, nSteps, phase, redCostEps, st))) return rc;
+    c->lastRoundOnHost = false;
+    return fetchBatch(c, nSteps, outs, st);
+}
+
+int dipgpu_price_round_stab(dipgpu_ctx *ctx, const double *uRM, int32_t uLen, double alpha, int32_t phase,
+                            double redCostEps, dipgpu_cols *out, double *dualSTOpt)
+{
+    int rc = dipgpu_price_round_stab_ladder(ctx, uRM, uLen, alpha, 1.0, 1, phase, redCostEps, out, nullptr);
+    if (rc) return rc;
+    if ((rc = dipgpu_select_batch_result(ctx, 0))) return rc;
+    if (dualSTOpt) return dipgpu_get_smoothed_duals(ctx, 0, dualSTOpt, uLen);
+    return DIPGPU_OK;
+}
+
+int dipgpu_select_batch_result(dipgpu_ctx *ctx, int32_t which)
+{
+    CTX_OR_FAIL(ctx);
+    if (which < 0 || which >= c->batchCap || !c->dResultBatch) return fail(c, DIPGPU_ERR_STATE, "select_batch_result: no batched result %d", which);
+    const char *hp = static_cast<const char *>(c->hResultBatch) + (size_t)which * c->resStride;
+    const ResultHeader *h = reinterpret_cast<const ResultHeader *>(hp);
+    if (h->magic != kResultMagic) return fail(c, DIPGPU_ERR_STATE, "select_batch_result: result %d was never fetched", which);
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dResult, static_cast<char *>(c->dResultBatch) + (size_t)which * c->resStride, c->resultBytes,
+                                   cudaMemcpyDeviceToDevice, c->stream));
+    memcpy(c->hResult, hp, c->layout.offInd + sizeof(int32_t) * (size_t)h->nInd);
+    DIPGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->lastRoundOnHost = true;
+    return DIPGPU_OK;
+}
+
+// ------------------------------------------------------- waiting-column pool
+
+int dipgpu_pool_clear(dipgpu_ctx *ctx)
+{
+    CTX_OR_FAIL(ctx);
+    c->poolCols = c->poolNnz = 0;
+    if (c->dPoolStart) DIPGPU_CUDA(c, cudaMemset(c->dPoolStart, 0, sizeof(int64_t)));
+    return DIPGPU_OK;
+}
+
+int dipgpu_pool_size(const dipgpu_ctx *ctx, int64_t *nCols, int64_t *nNnz)
+{
+    const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
+    if (!c) return DIPGPU_ERR_INVALID;
+    if (nCols) *nCols = c->poolCols;
+    if (nNnz) *nNnz = c->poolNnz;
+    return DIPGPU_OK;
+}
+
+int dipgpu_pool_append(dipgpu_ctx *ctx, int32_t nCols, const int64_t *colStart, const int32_t *rowInd, const double *val,
+                       const double *origCost)
+{
+    CTX_OR_FAIL(ctx);
+    if (nCols < 0 || (nCols > 0 && (!colStart || !origCost)) || (nCols > 0 && colStart[0] != 0))
+        return fail(c, DIPGPU_ERR_INVALID, "pool_append: bad arguments");
+    if (nCols == 0) return DIPGPU_OK;
+    for (int k = 0; k < nCols; ++k)
+        if (colStart[k + 1] < colStart[k]) return fail(c, DIPGPU_ERR_INVALID, "pool_append: colStart not monotone at %d", k);
+    const int64_t add = colStart[nCols];
+    if (add > 0 && (!rowInd || !val)) return fail(c, DIPGPU_ERR_INVALID, "pool_append: NULL rowInd/val");
+    const int uLen = c->R + c->numConvex;
+    if (c->haveCore)
+        for (int64_t k = 0; k < add; ++k)
+            if (rowInd[k] < 0 || rowInd[k] >= uLen) return fail(c, DIPGPU_ERR_INVALID, "pool_append: master row %d out of range", rowInd[k]);
+    int rc;
+    if ((rc = poolReserve(c, c->poolCols + nCols, c->poolNnz + add))) return rc;
+    std::vector<int64_t> starts((size_t)nCols);
+    for (int k = 0; k < nCols; ++k) starts[k] = c->poolNnz + colStart[k + 1];
+    DIPGPU_CUDA(c, cudaMemcpy(c->dPoolStart + c->poolCols + 1, starts.data(), sizeof(int64_t) * (size_t)nCols, cudaMemcpyHostToDevice));
+    DIPGPU_CUDA(c, cudaMemcpy(c->dPoolOrigCost + c->poolCols, origCost, sizeof(double) * (size_t)nCols, cudaMemcpyHostToDevice));
+    if (add > 0) {
+        DIPGPU_CUDA(c, cudaMemcpy(c->dPoolRow + c->poolNnz, rowInd, sizeof(int32_t) * (size_t)add, cudaMemcpyHostToDevice));
+        DIPGPU_CUDA(c, cudaMemcpy(c->dPoolVal + c->poolNnz, val, sizeof(double) * (size_t)add, cudaMemcpyHostToDevice));
+    }
+    c->h2d += (int64_t)nCols * 16 + add * 12;
+    c->poolCols += nCols;
+    c->poolNnz += add;
+    return DIPGPU_OK;
+}
+
+// descriptors of a device-side column copy (PoolCopyDesc in pool.cu: src, dst, len)
+static int poolCopyColumns(Ctx *c, const std::vector<int64_t> &desc, const void *srcEntries, const int32_t *srcRow,
+                           const double *srcVal, int32_t *dstRow, double *dstVal)
+{
+    const int n = (int)(desc.size() / 3);
+    if (n == 0) return DIPGPU_OK;
+    int64_t *dDesc = nullptr;
+    int rc;
+    if ((rc = devAlloc(c, &dDesc, desc.size()))) return rc;
+    cudaError_t e = cudaMemcpyAsync(dDesc, desc.data(), sizeof(int64_t) * desc.size(), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        rc = launchPoolCopy(c, n, dDesc, srcEntries, srcRow, srcVal, dstRow, dstVal, c->stream);
+        e = cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(dDesc);
+    if (e != cudaSuccess) return cudaFail(c, e, "pool column copy");
+    return rc;
+}
+
+int dipgpu_pool_append_expanded(dipgpu_ctx *ctx, int32_t nWhich, const int32_t *which)
+{
+    CTX_OR_FAIL(ctx);
+    if (nWhich < 0 || (nWhich > 0 && !which)) return fail(c, DIPGPU_ERR_INVALID, "pool_append_expanded: bad arguments");
+    if (nWhich == 0) return DIPGPU_OK;
+    if (!c->hMCols || !c->lastRoundOnHost) return fail(c, DIPGPU_ERR_STATE, "pool_append_expanded: no expanded columns");
+    const char *hp = static_cast<const char *>(c->hMCols);
+    const MColsHeader *mh = reinterpret_cast<const MColsHeader *>(hp);
+    if (mh->magic != kMColsMagic) return fail(c, DIPGPU_ERR_STATE, "pool_append_expanded: no expanded columns");
+    const int64_t *cs = reinterpret_cast<const int64_t *>(hp + c->mcolsOffColStart);
+    // original cost of kept column k of the last round (packed result on the host)
+    const char *rp = static_cast<const char *>(c->hResult);
+    const ResultHeader *rh = reinterpret_cast<const ResultHeader *>(rp);
+    const double *oc = reinterpret_cast<const double *>(rp + c->layout.offOrigCost);
+    const int32_t *kb = reinterpret_cast<const int32_t *>(rp + c->layout.offKeptBlock);
+    if (rh->nKept != mh->nCols) return fail(c, DIPGPU_ERR_STATE, "pool_append_expanded: expansion does not belong to the last round");
+    int64_t add = 0;
+    for (int k = 0; k < nWhich; ++k) {
+        if (which[k] < 0 || which[k] >= mh->nCols) return fail(c, DIPGPU_ERR_INVALID, "pool_append_expanded: column %d out of range", which[k]);
+        add += cs[which[k] + 1] - cs[which[k]];
+    }
+    int rc;
+    if ((rc = poolReserve(c, c->poolCols + nWhich, c->poolNnz + add))) return rc;
+    std::vector<int64_t> desc(3 * (size_t)nWhich), starts((size_t)nWhich);
+    std::vector<double> cost((size_t)nWhich);
+    int64_t dst = c->poolNnz;
+    for (int k = 0; k < nWhich; ++k) {
+        const int64_t len = cs[which[k] + 1] - cs[which[k]];
+        desc[3 * k + 0] = cs[which[k]];
+        desc[3 * k + 1] = dst;
+        desc[3 * k + 2] = len;  // {int32 len, int32 pad}: little-endian, len < 2^31
+        dst += len;
+        starts[k] = dst;
+        cost[k] = oc[kb[which[k]]];
+    }
+    DIPGPU_CUDA(c, cudaMemcpy(c->dPoolStart + c->poolCols + 1, starts.data(), sizeof(int64_t) * (size_t)nWhich, cudaMemcpyHostToDevice));
+    DIPGPU_CUDA(c, cudaMemcpy(c->dPoolOrigCost + c->poolCols, cost.data(), sizeof(double) * (size_t)nWhich, cudaMemcpyHostToDevice));
+    if ((rc = poolCopyColumns(c, desc, static_cast<char *>(c->dMCols) + c->mcolsOffEntries, nullptr, nullptr, c->dPoolRow, c->dPoolVal))) return rc;
+    c->poolCols += nWhich;
+    c->poolNnz += add;
+    return DIPGPU_OK;
+}
+
+int dipgpu_pool_keep(dipgpu_ctx *ctx, int32_t nKeep, const int32_t *keepIdx)
+{
+    CTX_OR_FAIL(ctx);
+    if (nKeep < 0 || (nKeep > 0 && !keepIdx)) return fail(c, DIPGPU_ERR_INVALID, "pool_keep: bad arguments");
+    if (nKeep == 0) return dipgpu_pool_clear(ctx);
+    std::vector<int64_t> hs((size_t)c->poolCols + 1);
+    std::vector<double> hc((size_t)c->poolCols);
+    DIPGPU_CUDA(c, cudaMemcpy(hs.data(), c->dPoolStart, sizeof(int64_t) * hs.size(), cudaMemcpyDeviceToHost));
+    DIPGPU_CUDA(c, cudaMemcpy(hc.data(), c->dPoolOrigCost, sizeof(double) * hc.size(), cudaMemcpyDeviceToHost));
+    std::vector<int64_t> desc(3 * (size_t)nKeep), starts((size_t)nKeep + 1, 0);
+    std::vector<double> cost((size_t)nKeep);
+    int64_t dst = 0;
+    for (int k = 0; k < nKeep; ++k) {
+        const int j = keepIdx[k];
+        if (j < 0 || j >= c->poolCols || (k > 0 && j <= keepIdx[k - 1]))
+            return fail(c, DIPGPU_ERR_INVALID, "pool_keep: indices must be ascending and inside the pool");
+        const int64_t len = hs[j + 1] - hs[j];
+        desc[3 * k + 0] = hs[j];
+        desc[3 * k + 1] = dst;
+        desc[3 * k + 2] = len;
+        dst += len;
+        starts[k + 1] = dst;
+        cost[k] = hc[j];
+    }
+    int rc;
+    int32_t *nr = nullptr; double *nv = nullptr;
+    if ((rc = devAlloc(c, &nr, (size_t)std::max<int64_t>(c->poolNnzCap, 1)))) return rc;
+    if ((rc = devAlloc(c, &nv, (size_t)std::max<int64_t>(c->poolNnzCap, 1)))) { cudaFree(nr); return rc; }
+    if ((rc = poolCopyColumns(c, desc, nullptr, c->dPoolRow, c->dPoolVal, nr, nv))) { cudaFree(nr); cudaFree(nv); return rc; }
+    devFree(&c->dPoolRow); devFree(&c->dPoolVal);
+    c->dPoolRow = nr; c->dPoolVal = nv;
+    DIPGPU_CUDA(c, cudaMemcpy(c->dPoolStart, starts.data(), sizeof(int64_t) * starts.size(), cudaMemcpyHostToDevice));
+    DIPGPU_CUDA(c, cudaMemcpy(c->dPoolOrigCost, cost.data(), sizeof(double) * cost.size(), cudaMemcpyHostToDevice));
+    c->poolCols = nKeep;
+    c->poolNnz = dst;
+    return DIPGPU_OK;
+}
+
+int dipgpu_pool_set_reduced_costs(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t feasible, double *redCost,
+                                  int32_t *foundNegRC)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->haveCore) return fail(c, DIPGPU_ERR_STATE, "pool_set_reduced_costs before set_core_csr");
+    if (uLen != c->R + c->numConvex) return fail(c, DIPGPU_ERR_INVALID, "pool_set_reduced_costs: uLen=%d, expected R+numConvex=%d", uLen, c->R + c->numConvex);
+    if (!u && !c->dualsResident) return fail(c, DIPGPU_ERR_STATE, "pool_set_reduced_costs: u == NULL but no dual vector is resident");
+    int rc;
+    if ((rc = ensureDualBuffer(c, uLen))) return rc;
+    if ((rc = poolReserve(c, std::max<int64_t>(c->poolCols, 1), std::max<int64_t>(c->poolNnz, 1)))) return rc;
+    cudaStream_t st = c->stream;
+    if (u) {
+        DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, u, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, st));
+        c->h2d += (int64_t)sizeof(double) * uLen;
+        c->dualsResident = true;
+    }
+    if ((rc = launchPoolRedCost(c, c->dU, feasible ? 1 : 0, st))) return rc;
+    int32_t flag = 0;
+    if (redCost && c->poolCols > 0) {
+        DIPGPU_CUDA(c, cudaMemcpyAsync(redCost, c->dPoolRedCost, sizeof(double) * (size_t)c->poolCols, cudaMemcpyDeviceToHost, st));
+        c->d2h += (int64_t)sizeof(double) * c->poolCols;
+    }
+    DIPGPU_CUDA(c, cudaMemcpyAsync(&flag, c->dPoolFlag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+    c->d2h += 4;
+    if (foundNegRC) *foundNegRC = flag;
+    return DIPGPU_OK;
 }
 
 int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
@@ -866,6 +1271,17 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
         return DIPGPU_OK;
     }
     if (!strcmp(name, "spmv_warps")) { c->optSpmvWarps = (int)value; return DIPGPU_OK; }
+    if (!strcmp(name, "spmv_stages")) { c->optSpmvStages = (int)value; return DIPGPU_OK; }
+    if (!strcmp(name, "spmv_chunk") || !strcmp(name, "spmv_max_cols")) {
+        // re-tiles the matrix: entry budget / column budget of a warp tile
+        (!strcmp(name, "spmv_chunk") ? c->optSpmvChunk : c->optSpmvMaxCols) = (int)value;
+        if (c->haveCore) {
+            int rc = bind(c);
+            if (rc) return rc;
+            return uploadCore(c);
+        }
+        return DIPGPU_OK;
+    }
     if (!strcmp(name, "spmv_u_smem")) { c->optSpmvUSmem = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "dp_threads") || !strcmp(name, "dp_cells_per_thread") || !strcmp(name, "dp_items_per_step") ||
         !strcmp(name, "dp_no_guard") || !strcmp(name, "fuse_filter")) {

@@ -26,6 +26,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <type_traits>
 
 #include "filter.cuh"
 
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(kBackThreads) knap_backtrack_kernel(const __gr
 
 __device__ __forceinline__ void dbgStamp(unsigned long long *buf, int slot)
 {
-    if (buf != nullptr && threadIdx.x == 0) {
+    if (buf != nullptr && threadIdx.x == 0 && blockIdx.y == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
         buf[(size_t)blockIdx.x * 8 + slot] = t;
@@ -277,6 +278,10 @@ struct KnapArgs {
     unsigned long long *pubWord;   // FUSE: per local block (epoch << 32) | kept << 31 | nnz
     unsigned long long *pubCells;  // FUSE: per local block DP cells
     unsigned int epoch;            // FUSE: launch counter carried by pubWord
+    // FUSE, batched dual vectors (gridDim.y = vectors): vector v = blockIdx.y reads redCost + v*rcStride
+    // and alpha + v*alphaStride and writes the packed result at byte offset v*resStride; the per-block
+    // arrays pubWord / scale / shortcut / sel / zShort hold nLocal entries per vector
+    long long rcStride, alphaStride, resStride;
     BackArgs back;
     FilterArgs filt;
 };
@@ -336,14 +341,20 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const int nWarps = T >> 5;
     const int lb = blockIdx.x;
     const int b = a.firstBlock + lb;
+    // batched dual vectors (fused shapes only; gridDim.y == 1 otherwise): this CTA's vector
+    const long long vec = FUSE ? (long long)blockIdx.y : 0;
+    const int vlb = (int)vec * (int)gridDim.x + lb;  // slot of (vector, block) in the per-vector block arrays
+    const double *redCostV = a.redCost + vec * a.rcStride;
+    const long long resOff = vec * a.resStride;
+#define RESV(ptr) (reinterpret_cast<decltype(ptr)>(reinterpret_cast<char *>(const_cast<void *>(static_cast<const void *>(ptr))) + resOff))
     const int colStart = a.blockColStart[b];
-    const int shortCode = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? a.shortcut[lb] : 0;
+    const int shortCode = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? a.shortcut[vlb] : 0;
     // a trivial case of GAP_KnapPisinger::solve needs no DP: behave like an empty block here
     const int nCols = shortCode != 0 ? 0 : a.blockColStart[b + 1] - colStart;
-    const double pScale = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? (double)a.scale[lb] : 0.0;
+    const double pScale = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? (double)a.scale[vlb] : 0.0;
     const int cap = a.capacity[b];
     // fetched now so that the (possibly cold) load is long done when the tail needs it
-    const double alphaB = FUSE ? a.back.alpha[b] : 0.0;
+    const double alphaB = FUSE ? a.back.alpha[vec * a.alphaStride + b] : 0.0;
     uint32_t *bitsBase = FUSE ? sBits : a.bits + a.bitsOff[lb];
     const int j0 = t * S;  // first owned cell
 
@@ -377,7 +388,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             const uint32_t bytesRc = (uint32_t)(((shiftRc + len + 1) & ~1) * 8);
             const uint32_t bytesW = (uint32_t)(((shiftW + len + 3) & ~3) * 4);
             mbarExpectTx(mbar, bytesRc + bytesW);
-            tmaLoad1d(rawRc, a.redCost + (g0 - shiftRc), bytesRc, mbar);
+            tmaLoad1d(rawRc, redCostV + (g0 - shiftRc), bytesRc, mbar);
             tmaLoad1d(rawW, a.weight + (g0 - shiftW), bytesW, mbar);
         }
         mbarWait(mbar, parity);
@@ -716,14 +727,14 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     }
     // z = c[n-1][capacity]  (gap_func.py:183)
     if (shortCode != 0) {
-        if (t == 0) a.blockObj[lb] = a.zShort[lb];
+        if (t == 0) RESV(a.blockObj)[lb] = a.zShort[vlb];
     } else {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            if (j0 + s == cap) a.blockObj[lb] = mine[s];
+            if (j0 + s == cap) RESV(a.blockObj)[lb] = mine[s];
         }
     }
-    if (t == 0) a.nItems[lb] = kGlobal;
+    if (t == 0 && vec == 0) a.nItems[lb] = kGlobal;
     dbgStamp(a.dbgTimes, 3);
     if (FUSE) {
         // ---- stage (b) continued: the column of this block, out of shared memory
@@ -738,14 +749,14 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                 const int nAll = a.blockColStart[b + 1] - colStart;
                 for (int base = 0; base < nAll; base += 32) {
                     const int j = base + lane;
-                    const bool act = j < nAll && a.redCost[colStart + j] < 0.0;
+                    const bool act = j < nAll && redCostV[colStart + j] < 0.0;
                     const unsigned bal = __ballot_sync(0xffffffffu, act);
                     if (act) sFinal[cnt + __popc(bal & ((1u << lane) - 1u))] = colStart + j;
                     cnt += __popc(bal);
                 }
             } else if (shortCode == 2) {
                 for (int k = 0; k < 2; ++k) {
-                    const int j = a.back.sel[2 * lb + k];
+                    const int j = a.back.sel[2 * vlb + k];
                     if (j >= 0) {
                         if (lane == 0) sFinal[cnt] = colStart + j;
                         ++cnt;
@@ -783,7 +794,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             double *sVals = itP;  // free after the DP
             for (int pass = 0; pass < 2; ++pass) {
                 for (int k = lane; k < cnt; k += 32)
-                    sVals[k] = pass == 0 ? a.redCost[sFinal[k]] : a.back.obj[sFinal[k]];
+                    sVals[k] = pass == 0 ? redCostV[sFinal[k]] : a.back.obj[sFinal[k]];
                 __syncwarp();
                 if (lane == 0) {
                     double acc2 = 0.0;
@@ -812,11 +823,11 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             // word is all the other blocks need, the result stores below are read by the host only.
             const unsigned long long word = ((unsigned long long)(a.epoch & 0xffu) << 56) | (keep ? 1ull << 55 : 0ull) |
                                             ((myCells & 0xffffffull) << 31) | (unsigned long long)cnt;
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.pubWord + lb), "l"(word) : "memory");
-            a.back.blockRedCost[lb] = rcB;
-            a.back.blockOrigCost[lb] = sOcSum;
-            a.back.blockNnz[lb] = cnt;
-            a.filt.blockMostNeg[lb] = rcB < 0.0 ? rcB : 0.0;  // min(0, rc): for EVERY block (:5212)
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.pubWord + vlb), "l"(word) : "memory");
+            RESV(a.back.blockRedCost)[lb] = rcB;
+            RESV(a.back.blockOrigCost)[lb] = sOcSum;
+            RESV(a.back.blockNnz)[lb] = cnt;
+            RESV(a.filt.blockMostNeg)[lb] = rcB < 0.0 ? rcB : 0.0;  // min(0, rc): for EVERY block (:5212)
         }
         // prefix over the lower blocks: each thread polls its share, warp-shuffle reduction, then
         // the per-warp partials (shared-memory 64-bit atomics would serialise through CAS loops)
@@ -830,7 +841,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             for (int pB = t; pB < lb; pB += T) {
                 unsigned long long wv;
                 do {
-                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(wv) : "l"(a.pubWord + pB) : "memory");
+                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(wv) : "l"(a.pubWord + (vlb - lb) + pB) : "memory");
                 } while ((unsigned int)(wv >> 56) != (a.epoch & 0xffu));
                 if (wv & (1ull << 55)) {
                     ++kc;
@@ -868,26 +879,28 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         const long long off = (long long)sNnz;
         if (keep) {
             if (t == 0) {
-                a.filt.keptBlock[pos] = lb;
-                a.filt.keptStart[pos] = off;
+                RESV(a.filt.keptBlock)[pos] = lb;
+                RESV(a.filt.keptStart)[pos] = off;
             }
-            for (int k = t; k < cnt; k += T) a.filt.keptInd[off + k] = sFinal[k];
+            for (int k = t; k < cnt; k += T) RESV(a.filt.keptInd)[off + k] = sFinal[k];
         }
         if (lb == a.back.nLocal - 1 && t == 0) {
             // the highest block has seen every other block: it closes the packed result
             const int nKept = pos + (keep ? 1 : 0);
             const long long nInd = off + (keep ? cnt : 0);
-            a.filt.keptStart[nKept] = nInd;
-            a.filt.hdr->magic = kResultMagic;
-            a.filt.hdr->m = a.back.nLocal;
-            a.filt.hdr->firstBlock = a.firstBlock;
-            a.filt.hdr->nKept = nKept;
-            a.filt.hdr->nInd = nInd;
-            a.filt.hdr->cells = (long long)(sCells + myCells);
-            a.filt.hdr->indCap = a.filt.indCap;
+            RESV(a.filt.keptStart)[nKept] = nInd;
+            ResultHeader *hdr = RESV(a.filt.hdr);
+            hdr->magic = kResultMagic;
+            hdr->m = a.back.nLocal;
+            hdr->firstBlock = a.firstBlock;
+            hdr->nKept = nKept;
+            hdr->nInd = nInd;
+            hdr->cells = (long long)(sCells + myCells);
+            hdr->indCap = a.filt.indCap;
         }
         dbgStamp(a.dbgTimes, 5);
     }
+#undef RESV
 }
 
 // --------------------------------------------------------------- geometry table
@@ -1081,9 +1094,27 @@ static void fillBackArgs(Ctx *c, const double *dRedCost, const double *dAlpha, B
     a->sel = pis ? c->dSel : nullptr;
 }
 
+static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
+                    double redCostEps, int nVec, bool batch, cudaStream_t st);
+
 int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st)
 {
-    if (c->nLocal == 0) return DIPGPU_OK;
+    return launchDp(c, dRedCost, 0, dAlpha, 0, redCostEps, 1, false, st);
+}
+
+// Batched dual vectors: the fused kernel only (gridDim.y = vectors); the per-vector packed results,
+// publication words and Pisinger-mode block arrays live in the context's batch buffers.
+int launchKnapsackDpBatch(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
+                          double redCostEps, int nVec, cudaStream_t st)
+{
+    return launchDp(c, dRedCost, rcStride, dAlpha, alphaStride, redCostEps, nVec, true, st);
+}
+
+static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
+                    double redCostEps, int nVec, bool batch, cudaStream_t st)
+{
+    if (c->nLocal == 0 || nVec <= 0) return DIPGPU_OK;
+    if (batch && !c->geom.fuse) return fail(c, DIPGPU_ERR_STATE, "batched DP launch needs the fused kernel shape");
     const DpGeom &g = c->geom;
     const GeomEntry *e = findGeom(g.S);
     if (!e) return fail(c, DIPGPU_ERR_STATE, "DP geometry not initialised");
@@ -1098,26 +1129,40 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, doubl
     a.itemW = c->dItemW;
     a.itemCol = c->dItemCol;
     a.nItems = c->dNItems;
-    a.blockObj = reinterpret_cast<double *>(static_cast<char *>(c->dResult) + c->layout.offObj);
+    char *resBase = static_cast<char *>(batch ? c->dResultBatch : c->dResult);
+    a.blockObj = reinterpret_cast<double *>(resBase + c->layout.offObj);
+    a.rcStride = rcStride;
+    a.alphaStride = alphaStride;
+    a.resStride = batch ? (long long)c->resStride : 0;
     a.firstBlock = c->firstBlock;
     a.chunkCols = g.chunkCols;
     a.guard = g.guard;
     a.dbgTimes = c->dDbgTimes;
-    a.pubWord = c->dPubWord;
+    a.pubWord = batch ? c->dPubWordBatch : c->dPubWord;
     a.pubCells = c->dPubCells;
-    a.epoch = ++c->epoch;
+    a.epoch = batch ? ++c->epochBatch : ++c->epoch;
     a.profitMode = c->profitMode;
-    a.scale = c->dScale;
-    a.shortcut = c->dShortcut;
-    a.zShort = c->dZShort;
+    a.scale = batch ? c->dScaleB : c->dScale;
+    a.shortcut = batch ? c->dShortcutB : c->dShortcut;
+    a.zShort = batch ? c->dZShortB : c->dZShort;
     fillBackArgs(c, dRedCost, dAlpha, &a.back);
     a.filt = makeFilterArgs(c, redCostEps);
+    if (batch) {
+        // same layout, based at the batch buffer (vector 0); the kernel adds v*resStride
+        const ptrdiff_t d = resBase - static_cast<char *>(c->dResult);
+        auto mv = [d](auto *&ptr) { ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(reinterpret_cast<char *>(const_cast<void *>(static_cast<const void *>(ptr))) + d); };
+        mv(a.back.blockRedCost); mv(a.back.blockOrigCost); mv(a.back.blockNnz);
+        mv(a.filt.hdr); mv(a.filt.blockRedCost); mv(a.filt.blockMostNeg); mv(a.filt.blockNnz);
+        mv(a.filt.keptStart); mv(a.filt.keptBlock); mv(a.filt.keptInd);
+        a.back.sel = c->profitMode == DIPGPU_PROFIT_PISINGER_INT ? c->dSelB : nullptr;
+        a.back.shortcut = c->profitMode == DIPGPU_PROFIT_PISINGER_INT ? c->dShortcutB : nullptr;
+    }
     a.filt.fuseCopy = c->nLocal <= kFuseFilterMaxBlocks ? 2 : 1;
     {
         int rc = prepareKnapsackDp(c);
         if (rc) return rc;
     }
-    fn<<<c->nLocal, g.T, g.smemBytes, st>>>(a);
+    fn<<<dim3(c->nLocal, nVec, 1), g.T, g.smemBytes, st>>>(a);
     c->launches++;
     DIPGPU_CUDA(c, cudaGetLastError());
     return DIPGPU_OK;

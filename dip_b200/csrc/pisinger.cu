@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(kPrepThreads) knap_prep_kernel(const __grid_co
     const int cs = a.blockColStart[b];
     const int n = a.blockColStart[b + 1] - cs;
     const int cap = a.capacity[b];
+    const double *redCostV = a.redCost + (long long)blockIdx.y * a.rcStride;
+    const int vlb = (int)blockIdx.y * (int)gridDim.x + lb;
     // each thread owns a CONTIGUOUS run of columns so that thread order == item order
     const int per = (n + kPrepThreads - 1) / kPrepThreads;
     const int j0 = min(n, t * per), j1 = min(n, j0 + per);
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(kPrepThreads) knap_prep_kernel(const __grid_co
     long long wsum = 0;
     First2 f2{-1, -1};
     for (int j = j0; j < j1; ++j) {
-        const double rc = a.redCost[cs + j];
+        const double rc = redCostV[cs + j];
         if (rc >= 0) continue;  // :109, :173
         ++cnt;
         wsum += a.weight[cs + j];
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(kPrepThreads) knap_prep_kernel(const __grid_co
     const double scale = (double)sScale;
     const int nAll = sCntAll;
     // scaled integer profit of a column, :174-177
-    auto profit = [&](int j) { return (double)(long long)floor((-a.redCost[cs + j]) * scale + 0.5); };
+    auto profit = [&](int j) { return (double)(long long)floor((-redCostV[cs + j]) * scale + 0.5); };
     int code = 0, sel0 = -1, sel1 = -1;
     double z = 0.0;
     if (nAll == 0) {
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(kPrepThreads) knap_prep_kernel(const __grid_co
         code = 1;
         double part = 0.0;
         for (int j = j0; j < j1; ++j)
-            if (a.redCost[cs + j] < 0) part += profit(j);  // integers < 2^53: exact in any order
+            if (redCostV[cs + j] < 0) part += profit(j);  // integers < 2^53: exact in any order
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
         if (lane == 0) sZ[warp] = part;
@@ -186,31 +188,42 @@ __global__ void __launch_bounds__(kPrepThreads) knap_prep_kernel(const __grid_co
         else if (x1) sel0 = c1;
     }
     if (t == 0) {
-        a.scale[lb] = sScale;
-        a.shortcut[lb] = code;
-        a.sel[2 * lb] = sel0;
-        a.sel[2 * lb + 1] = sel1;
-        a.zShort[lb] = z;
+        a.scale[vlb] = sScale;
+        a.shortcut[vlb] = code;
+        a.sel[2 * vlb] = sel0;
+        a.sel[2 * vlb + 1] = sel1;
+        a.zShort[vlb] = z;
     }
 }
 
-int launchKnapsackPrep(Ctx *c, const double *dRedCost, cudaStream_t st)
+static int launchPrep(Ctx *c, const double *dRedCost, int64_t rcStride, int nVec, bool batch, cudaStream_t st)
 {
-    if (c->nLocal == 0 || c->profitMode != DIPGPU_PROFIT_PISINGER_INT) return DIPGPU_OK;
+    if (c->nLocal == 0 || nVec <= 0 || c->profitMode != DIPGPU_PROFIT_PISINGER_INT) return DIPGPU_OK;
     PrepArgs a;
     a.redCost = dRedCost;
     a.weight = c->dWeight;
     a.blockColStart = c->dBlockColStart;
     a.capacity = c->dCapacity;
     a.firstBlock = c->firstBlock;
-    a.scale = c->dScale;
-    a.shortcut = c->dShortcut;
-    a.sel = c->dSel;
-    a.zShort = c->dZShort;
-    knap_prep_kernel<<<c->nLocal, kPrepThreads, 0, st>>>(a);
+    a.rcStride = rcStride;
+    a.scale = batch ? c->dScaleB : c->dScale;
+    a.shortcut = batch ? c->dShortcutB : c->dShortcut;
+    a.sel = batch ? c->dSelB : c->dSel;
+    a.zShort = batch ? c->dZShortB : c->dZShort;
+    knap_prep_kernel<<<dim3(c->nLocal, nVec, 1), kPrepThreads, 0, st>>>(a);
     c->launches++;
     DIPGPU_CUDA(c, cudaGetLastError());
     return DIPGPU_OK;
+}
+
+int launchKnapsackPrep(Ctx *c, const double *dRedCost, cudaStream_t st)
+{
+    return launchPrep(c, dRedCost, 0, 1, false, st);
+}
+
+int launchKnapsackPrepBatch(Ctx *c, const double *dRedCost, int64_t rcStride, int nVec, cudaStream_t st)
+{
+    return launchPrep(c, dRedCost, rcStride, nVec, true, st);
 }
 
 }  // namespace dipgpu

@@ -1,0 +1,150 @@
+// pool.cu -- the two dual-vector passes that surround a pricing round in DecompAlgoPC:
+//
+//  * re-pricing of the waiting columns, DecompVarPool::setReducedCosts ->
+//    DecompWaitingCol::setReducedCost (Dip/src/DecompVarPool.cpp:185-203, :22-40; called once per
+//    price call, Dip/src/DecompAlgo.cpp:1890-1908):  redCost_s = origCost_s - col_s . u  (feasible
+//    master) or -col_s . u (dual ray), col_s = the waiting column in MASTER row space;
+//  * Wentges smoothing of the master duals, DecompAlgoPC::adjustMasterDualSolution
+//    (Dip/src/DecompAlgoPC.cpp:126-212):  dualST = alpha*dual + (1-alpha)*dualRM, for one alpha or
+//    for the whole ladder alpha, 0.9 alpha, ... that addVarsToPool walks when every new column is
+//    a duplicate (Dip/src/DecompAlgo.cpp:5642-5655).
+//
+// Both are HBM streams: the pool pass reads 12 B per stored entry + 24 B per column, the
+// smoothing reads 16 B and writes 8 B per row and vector.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace dipgpu {
+
+constexpr int kPoolWarps = 8;
+constexpr int kPoolChunk = 512;  // products staged per warp and pass (4 KiB)
+
+// One warp per 32 consecutive waiting columns.  Their stored entries are one contiguous span of
+// the pool; the warp walks it from the END in chunks: all lanes form the products val*u[row]
+// (coalesced loads, unfused multiply) into shared memory, then lane l adds the products of ITS
+// column, last entry first -- the order of CoinPackedVectorBase::dotProduct as the oracle restates
+// it (dp = 0; for i = n-1..0: dp += els[i]*u[ind[i]]), so the values are bit-equal to the oracle.
+__global__ void __launch_bounds__(kPoolWarps * 32)
+pool_redcost_kernel(long long nCols, const int64_t *__restrict__ colStart, const int32_t *__restrict__ row,
+                    const double *__restrict__ val, const double *__restrict__ origCost,
+                    const double *__restrict__ u, int feasible, double *__restrict__ out, int32_t *flag)
+{
+    __shared__ double sP[kPoolWarps][kPoolChunk];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long c0 = ((long long)blockIdx.x * kPoolWarps + warp) * 32;
+    if (c0 >= nCols) return;
+    const long long col = c0 + lane;
+    const long long cEnd = min(nCols, c0 + 32);
+    const int64_t B = colStart[c0], E = colStart[cEnd];
+    int64_t b = 0, e = 0;
+    double oc = 0.0;
+    if (col < nCols) {
+        b = colStart[col];
+        e = colStart[col + 1];
+        oc = origCost[col];
+    }
+    double sum = 0.0;
+    double *p = sP[warp];
+    for (int64_t hi = E; hi > B;) {
+        const int64_t lo = max(B, hi - kPoolChunk);
+        for (int64_t k = lo + lane; k < hi; k += 32) p[k - lo] = __dmul_rn(val[k], __ldg(u + row[k]));
+        __syncwarp();
+        const int64_t kHi = min(hi, e), kLo = max(lo, b);
+        for (int64_t k = kHi - 1; k >= kLo; --k) sum = __dadd_rn(sum, p[k - lo]);
+        __syncwarp();
+        hi = lo;
+    }
+    if (col < nCols) {
+        const double rc = feasible ? oc - sum : -sum;  // DecompVarPool.cpp:29 / :36
+        out[col] = rc;
+        if (rc <= -0.0000000001) *flag = 1;            // :30, :37 -> found_negrc_var (:199)
+    }
+}
+
+int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st)
+{
+    DIPGPU_CUDA(c, cudaMemsetAsync(c->dPoolFlag, 0, sizeof(int32_t), st));
+    if (c->poolCols == 0) return DIPGPU_OK;
+    const long long warps = (c->poolCols + 31) / 32;
+    const unsigned grid = (unsigned)((warps + kPoolWarps - 1) / kPoolWarps);
+    pool_redcost_kernel<<<grid, kPoolWarps * 32, 0, st>>>(c->poolCols, c->dPoolStart, c->dPoolRow, c->dPoolVal,
+                                                         c->dPoolOrigCost, dU, feasible, c->dPoolRedCost, c->dPoolFlag);
+    c->launches++;
+    DIPGPU_CUDA(c, cudaGetLastError());
+    return DIPGPU_OK;
+}
+
+// dualST_v[r] = (alpha_v * dual[r]) + ((1 - alpha_v) * dualRM[r])   (DecompAlgoPC.cpp:153-154, :179-181)
+// for nVec smoothing parameters at once; two unfused multiplies and one add, as the reference.
+__global__ void __launch_bounds__(256)
+smooth_duals_kernel(const double *__restrict__ uRM, const double *__restrict__ center,
+                    const double *__restrict__ alphas, int nVec, int uLen, double *__restrict__ out, long long outStride)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= uLen) return;
+    const double d = center[r], rm = uRM[r];
+    for (int v = 0; v < nVec; ++v) {
+        const double alpha = alphas[v];
+        const double alpha1 = __dsub_rn(1.0, alpha);
+        out[(long long)v * outStride + r] = __dadd_rn(__dmul_rn(alpha, d), __dmul_rn(alpha1, rm));
+    }
+}
+
+int launchSmoothDuals(Ctx *c, const double *dURM, const double *dCenter, const double *dAlphas, int nVec, int uLen,
+                      double *dOut, int64_t outStride, cudaStream_t st)
+{
+    if (uLen <= 0 || nVec <= 0) return DIPGPU_OK;
+    smooth_duals_kernel<<<(uLen + 255) / 256, 256, 0, st>>>(dURM, dCenter, dAlphas, nVec, uLen, dOut, outStride);
+    c->launches++;
+    DIPGPU_CUDA(c, cudaGetLastError());
+    return DIPGPU_OK;
+}
+
+// ------------------------------------------------------------------ pool upkeep
+//
+// Columns enter the pool either from host arrays (DecompVarPool::push_back of a waiting column
+// the host built) or straight from the packed master columns of the last expansion, and leave it
+// when addVarsFromPool moves them into the master (Dip/src/DecompAlgo.cpp:5678-5900).
+
+struct PoolCopyDesc {
+    int64_t src;  // first entry in the source
+    int64_t dst;  // first entry in the pool
+    int32_t len;
+    int32_t pad;
+};
+
+// srcEntries != NULL: packed master columns (MColEntry); else (srcRow, srcVal).
+__global__ void __launch_bounds__(256)
+pool_copy_kernel(int n, const PoolCopyDesc *__restrict__ d, const MColEntry *__restrict__ srcEntries,
+                 const int32_t *__restrict__ srcRow, const double *__restrict__ srcVal, int32_t *__restrict__ dstRow,
+                 double *__restrict__ dstVal)
+{
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const PoolCopyDesc dk = d[k];
+    for (int q = lane; q < dk.len; q += 32) {
+        if (srcEntries != nullptr) {
+            const MColEntry en = srcEntries[dk.src + q];
+            dstRow[dk.dst + q] = en.row;
+            dstVal[dk.dst + q] = en.val;
+        } else {
+            dstRow[dk.dst + q] = srcRow[dk.src + q];
+            dstVal[dk.dst + q] = srcVal[dk.src + q];
+        }
+    }
+}
+
+int launchPoolCopy(Ctx *c, int n, const void *dDesc, const void *srcEntries, const int32_t *srcRow, const double *srcVal,
+                   int32_t *dstRow, double *dstVal, cudaStream_t st)
+{
+    if (n <= 0) return DIPGPU_OK;
+    pool_copy_kernel<<<(n + 7) / 8, 256, 0, st>>>(n, static_cast<const PoolCopyDesc *>(dDesc),
+                                                  static_cast<const MColEntry *>(srcEntries), srcRow, srcVal, dstRow, dstVal);
+    c->launches++;
+    DIPGPU_CUDA(c, cudaGetLastError());
+    return DIPGPU_OK;
+}
+
+}  // namespace dipgpu

@@ -11,15 +11,16 @@
 // HBM-bound: algorithmic bytes = 12*nnz + 20*N + 8*R.
 //
 // Main kernel (redcost_stream_kernel): the columns are cut on the host into
-// tiles of at most kSpmvChunk stored entries; a warp pulls its tile's (value,
-// row) stream into shared memory with two TMA bulk copies (double-buffered),
-// all lanes multiply by the gathered duals in place, and then one lane per
-// column adds that column's products SEQUENTIALLY in storage order.  Entries are stored per column in
-// DESCENDING row order and the arithmetic is an unfused multiply followed by an
-// add, i.e. exactly the order and rounding of the reference's row-major scatter
-// (rows R-1..0, y[col] += u[i]*a), so the reduced costs are bit-identical to the
-// CPU restatement, not merely within 1e-12.  Matrices with a column longer than
-// one tile fall back to the lane-cooperative kernel below (tolerance parity).
+// self-contained tiles (<= 128 consecutive columns, <= "spmv_chunk" stored
+// entries) whose entries are stored JAGGED per 32-column slice; a warp pulls a
+// tile into shared memory with ONE TMA bulk copy (multi-stage ring per warp) and
+// each lane walks its own column: conflict-free contiguous reads of the value
+// and row streams, one gather of the dual, an unfused multiply and an add.
+// Entries of a column come in DESCENDING row order, i.e. exactly the order and
+// rounding of the reference's row-major scatter (rows R-1..0, y[col] += u[i]*a),
+// so the reduced costs are bit-identical to the CPU restatement, not merely
+// within 1e-12.  Matrices with a column longer than the largest tile fall back
+// to the lane-cooperative kernel below (tolerance parity).
 #include <algorithm>
 #include <type_traits>
 
@@ -44,7 +45,32 @@ __device__ __forceinline__ void rcMbarWait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
-// byte sizes of a tile's two parts inside the blob / a stage (16-byte multiples)
+__device__ __forceinline__ uint32_t ldsU32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ldsU16(uint32_t addr)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 ldsU64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ldsF64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// byte sizes of a tile's parts inside the blob / a stage (16-byte multiples)
 __host__ __device__ inline uint32_t tileValBytes(int len) { return (uint32_t)(((len + 1) & ~1) * 8); }
 template <bool ROW16> __host__ __device__ inline uint32_t tileRowBytes(int len)
 {
@@ -53,138 +79,74 @@ template <bool ROW16> __host__ __device__ inline uint32_t tileRowBytes(int len)
 
 struct StreamArgs {
     int nTiles;
-    const int4 *tileRec;        // per tile {first column, end column, first stored entry, entries}
-    const int32_t *colStart32;  // N+1
-    const unsigned char *blob;  // tile-blocked copy of the streams: per tile [values | rows], 16-byte padded
-    const int64_t *blobOff;     // per tile: byte offset of its block in `blob`
+    const uint2 *tileRec;       // per tile {byte offset / 16 into blob, bytes}
+    const unsigned char *blob;  // self-contained tiles (layout: SpmvTileHeader in common.cuh)
     const double *u;
     int uLen;
-    const double *c;
     int phase1;
     double *out;
     int uSmemBytes;             // 0: gather the duals from global memory
-    int uHalf;                  // UMODE 2: duals per CTA of the cluster pair (even)
+    int stageBytes;             // bytes of one stage (>= the largest tile, multiple of 16)
+    int nStages;                // stages per warp (2..kSpmvMaxStages)
+    int64_t uStride, outStride; // batched dual vectors: vector v = blockIdx.y reads u + v*uStride
 };
 
-// A stage holds up to kSpmvChunk entries counted from the aligned start (alignment: 16 bytes
-// of the row stream = 4 int32 or 8 uint16 entries) plus that much slack.
-template <bool ROW16> struct SpmvStage {
-    static constexpr int kAlign = ROW16 ? 8 : 4;
-    static constexpr int kValBytes = (kSpmvChunk + kAlign) * 8;
-    static constexpr int kRowBytes = (kSpmvChunk + kAlign) * (ROW16 ? 2 : 4);
-    static constexpr int kBytes = kValBytes + kRowBytes;  // multiple of 16
-    static constexpr int kWarpBytes = 16 + 2 * kBytes;    // 2 mbarriers + 2 stages
-};
-
-struct ColMeta {  // one lane's columns of a tile: RAW loaded values, consumed one tile later
-    int b[kSpmvColsPerLane], e[kSpmvColsPerLane];  // colStart32[col], colStart32[col+1]
-    double cj[kSpmvColsPerLane];
-};
-
-// Only issues the loads: nothing here may depend on their results (a warp issues in order,
-// so the first dependent instruction would stall everything behind it).
-__device__ __forceinline__ void loadColMeta(const StreamArgs &a, const int4 rec, int lane, ColMeta &m)
-{
-#pragma unroll
-    for (int q = 0; q < kSpmvColsPerLane; ++q) {
-        const int col = rec.x + lane + 32 * q;
-        m.b[q] = m.e[q] = 0;
-        m.cj[q] = 0.0;
-        if (col < rec.y) {
-            m.b[q] = __ldg(a.colStart32 + col);
-            m.e[q] = __ldg(a.colStart32 + col + 1);
-            if (!a.phase1) m.cj[q] = __ldg(a.c + col);
-        }
-    }
-}
-
-// Every WARP owns a two-stage TMA pipeline over its own tiles (<= 32*kSpmvColsPerLane
-// consecutive columns, <= kSpmvChunk stored entries): lane 0 issues the bulk copies of the
-// (value, row) streams of tile k+2 while the warp reduces tile k out of shared memory, one
-// lane per column, sequentially in storage order.  The per-tile record and the per-column
-// extents / objective entries of tile k+1 are fetched into registers while tile k is being
-// reduced, so no cold global load sits on the warp's critical path; there is no CTA-wide
-// barrier in the loop.  Where the duals are gathered from (UMODE): 0 = global memory (from L1 a
-// random 8-byte gather costs a wavefront per lane: fine for structured matrices, 71 us for 10^7
-// random gathers); 1 = the whole dual vector in shared memory; 2 = the dual vector SPLIT over the
-// two CTAs of a thread-block cluster, the other half read through distributed shared memory
-// (mapa + ld.shared::cluster) -- half the footprint, which doubles the bytes the TMA stages can
-// keep in flight per SM (the stream is in-flight-limited).
+// Every WARP owns an nStages-deep TMA pipeline over its own tiles.  A tile is SELF-CONTAINED in
+// the blob (header, column lengths / ids / objective entries, step offsets, values, rows: ONE bulk
+// copy, no other global read on the warp's critical path).  Within a slice of 32 columns the host
+// sorts the columns by DESCENDING length (lane l owns the l-th longest) and stores the entries
+// JAGGED: first every column's entry 0 (lane order), then every column's entry 1 (only the columns
+// that have one: a prefix of the lanes), ...  At step i lane l reads position stepOff[i] + l of the
+// value / row streams: contiguous, conflict-free shared-memory reads, no ballot / popc, no second
+// pass over stored products, and each lane adds its column's products SEQUENTIALLY in storage order
+// (descending rows), unfused -- the reference's scatter order.  The only irregular access is the
+// 8-byte gather of the dual (shared memory when the dual vector fits, else global/L2).
 template <int UMODE, bool ROW16>
-__global__ void __launch_bounds__(768) redcost_stream_kernel(const __grid_constant__ StreamArgs a)
+__global__ void __launch_bounds__(1024, 1) redcost_stream_kernel(const __grid_constant__ StreamArgs a)
 {
-    typedef SpmvStage<ROW16> St;
     typedef typename std::conditional<ROW16, uint16_t, int32_t>::type RowT;
-    constexpr int kSpmvStageBytes = St::kBytes, kSpmvWarpBytes = St::kWarpBytes;
     extern __shared__ __align__(16) unsigned char sm[];
     const double *sU = reinterpret_cast<const double *>(sm);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    unsigned int crank = 0;
-    if (UMODE == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-    const int uHalf = a.uHalf;  // UMODE 2: duals [rank*uHalf, (rank+1)*uHalf) live in CTA `rank`
-    const uint32_t sUaddr = rcSmemAddr(sm);
-    auto gatherU = [&](int r) -> double {
-        if (UMODE == 0) return __ldg(a.u + r);
-        if (UMODE == 1) return sU[r];
-        const unsigned int owner = r >= uHalf ? 1u : 0u;
-        const uint32_t la = sUaddr + (uint32_t)(r - (owner ? uHalf : 0)) * 8u;
-        uint32_t ra;
-        double v;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(owner));
-        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra));
-        return v;
-    };
-    unsigned char *wbase = sm + a.uSmemBytes + (size_t)warp * kSpmvWarpBytes;
+    const double *uVec = a.u + (int64_t)blockIdx.y * a.uStride;
+    double *outVec = a.out + (int64_t)blockIdx.y * a.outStride;
+    const int NST = a.nStages;
+    const int barBytes = (NST * 8 + 15) & ~15;
+    const size_t warpBytes = (size_t)barBytes + (size_t)NST * a.stageBytes;
+    unsigned char *wbase = sm + a.uSmemBytes + (size_t)warp * warpBytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
-    unsigned char *stageBase = wbase + 16;
+    unsigned char *stageBase = wbase + barBytes;
     const int warpsPerCta = blockDim.x >> 5;
     const int gw = blockIdx.x * warpsPerCta + warp;
     const int totalWarps = gridDim.x * warpsPerCta;
-    const int4 none = make_int4(0, 0, 0, 0);
 
-    // one bulk copy per tile: its values and rows sit back to back in the tile-blocked blob
-    auto issue = [&](const int4 rec, int64_t off, int s) {
+    auto issue = [&](const uint2 rec, int s) {
         uint64_t *bar = full + s;
-        const int len = rec.w;
-        if (len > 0) {
-            unsigned char *dst = stageBase + (size_t)s * kSpmvStageBytes;
-            const uint32_t bytes = tileValBytes(len) + tileRowBytes<ROW16>(len);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rcSmemAddr(bar)), "r"(bytes)
-                         : "memory");
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    rcSmemAddr(dst)),
-                "l"(a.blob + off), "r"(bytes), "r"(rcSmemAddr(bar))
-                : "memory");
-        } else {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rcSmemAddr(bar)) : "memory");
-        }
+        unsigned char *dst = stageBase + (size_t)s * a.stageBytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rcSmemAddr(bar)), "r"(rec.y)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                rcSmemAddr(dst)),
+            "l"(a.blob + (size_t)rec.x * 16u), "r"(rec.y), "r"(rcSmemAddr(bar))
+            : "memory");
     };
 
-    // tile records: cur = tile being reduced, nxt = the one after (already in flight),
-    // nn = two ahead (issued when cur's stage is free)
-    int4 cur = gw < a.nTiles ? __ldg(a.tileRec + gw) : none;
-    int4 nxt = gw + totalWarps < a.nTiles ? __ldg(a.tileRec + gw + totalWarps) : none;
-    const int64_t offCur = gw < a.nTiles ? __ldg(a.blobOff + gw) : 0;
-    const int64_t offNxt = gw + totalWarps < a.nTiles ? __ldg(a.blobOff + gw + totalWarps) : 0;
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full)), "r"(1));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full + 1)), "r"(1));
+        for (int s = 0; s < NST; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full + s)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (gw < a.nTiles) issue(cur, offCur, 0);
-        if (gw + totalWarps < a.nTiles) issue(nxt, offNxt, 1);
+        for (int s = 0; s < NST; ++s) {
+            const int tile = gw + s * totalWarps;
+            if (tile < a.nTiles) issue(__ldg(a.tileRec + tile), s);
+        }
     }
-    ColMeta mc;
-    loadColMeta(a, cur, lane, mc);
     if (UMODE != 0) {
-        // the dual vector (UMODE 2: this CTA's half): one bulk copy (16-byte granules) + a plain
-        // tail, on its own mbarrier
+        // the dual vector: one bulk copy (16-byte granules) + a plain tail, on its own mbarrier
         uint64_t *ubar = reinterpret_cast<uint64_t *>(sm + a.uSmemBytes - 16);
         double *w = const_cast<double *>(sU);
-        const int lo = UMODE == 2 ? (int)crank * uHalf : 0;
-        const int cnt = UMODE == 2 ? max(0, min(a.uLen - lo, uHalf)) : a.uLen;
-        const double *src = a.u + lo;
-        const int bulk = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 ? (cnt & ~1) : 0;
+        const int cnt = a.uLen;
+        const int bulk = (reinterpret_cast<uintptr_t>(uVec) & 15u) == 0 ? (cnt & ~1) : 0;
         if (t == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(ubar)), "r"(1));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -195,107 +157,88 @@ __global__ void __launch_bounds__(768) redcost_stream_kernel(const __grid_consta
                 asm volatile(
                     "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                         rcSmemAddr(w)),
-                    "l"(src), "r"((uint32_t)bulk * 8u), "r"(rcSmemAddr(ubar))
+                    "l"(uVec), "r"((uint32_t)bulk * 8u), "r"(rcSmemAddr(ubar))
                     : "memory");
             } else {
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rcSmemAddr(ubar)) : "memory");
             }
         }
-        for (int k = bulk + t; k < cnt; k += blockDim.x) w[k] = __ldg(src + k);
+        for (int k = bulk + t; k < cnt; k += blockDim.x) w[k] = __ldg(uVec + k);
         __syncthreads();
         rcMbarWait(ubar, 0);
-        if (UMODE == 2) {
-            // both halves must be in place before anyone gathers across the cluster
-            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-        }
     } else {
         __syncwarp();
     }
+    uint32_t sUaddr;  // computed ONCE (volatile: ptxas would otherwise rematerialise the conversion in the loop)
+    asm volatile("{ .reg .u64 t64; cvta.to.shared.u64 t64, %1; cvt.u32.u64 %0, t64; }" : "=r"(sUaddr) : "l"(sm));
 
-    int it = 0;
-    for (int tile = gw; tile < a.nTiles; tile += totalWarps, ++it) {
-        const int s = it & 1;
-        const uint32_t parity = (uint32_t)((it >> 1) & 1);
-        double *sVal = reinterpret_cast<double *>(stageBase + (size_t)s * kSpmvStageBytes);
-        const RowT *sRow =
-            reinterpret_cast<const RowT *>(stageBase + (size_t)s * kSpmvStageBytes + tileValBytes(cur.w));
-        // prefetch (registers) what the next two tiles need; consumed after this tile is done
-        const int tn = tile + totalWarps, tnn = tile + 2 * totalWarps;
-        // unconditional (clamped) load: a select on the result would stall the warp right here
-        const int4 nn = __ldg(a.tileRec + min(tnn, a.nTiles - 1));
-        const int64_t offNn = __ldg(a.blobOff + min(tnn, a.nTiles - 1));
-        ColMeta mn;
-        loadColMeta(a, nxt, lane, mn);  // nxt is {0,0,0,0} past the end: no loads
+    int s = 0;
+    uint32_t parity = 0;
+    for (int tile = gw; tile < a.nTiles; tile += totalWarps) {
+        // the record of the tile that will refill this stage: loaded now, used after the reduction
+        const int tRefill = tile + NST * totalWarps;
+        const uint2 recRefill = __ldg(a.tileRec + min(tRefill, a.nTiles - 1));
+        const unsigned char *stage = stageBase + (size_t)s * a.stageBytes;
         rcMbarWait(full + s, parity);
-        // phase 1, all lanes, coalesced: products u[i]*a in place (unfused multiply, as the
-        // reference's  y += u*a).  Entries in front of the tile's first column (alignment pad)
-        // are real entries of the previous column, so their rows are valid.
-        {
-            const int len = cur.w;
-            int k = lane;
-            for (; k + 96 < len; k += 128) {
-                int r[4];
-                double v[4], g[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) r[j] = sRow[k + 32 * j];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = sVal[k + 32 * j];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) g[j] = gatherU(r[j]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sVal[k + 32 * j] = __dmul_rn(g[j], v[j]);
-            }
-            {
-                // remainder (< 4 rounds): still one batch, so the gathers overlap
-                int r[4];
+        // shared-window addresses + ld.shared: the loads of a batch are issued back to back, in
+        // the order written (rows, values, then the dependent gathers of the duals)
+        const uint32_t stA = sUaddr + (uint32_t)(stage - sm);
+        const int firstCol = (int)ldsU32(stA), nCols = (int)ldsU32(stA + 4), nEnt = (int)ldsU32(stA + 8);
+        const uint32_t stepStride = ldsU32(stA + 12);
+        const int nSlices = (nCols + 31) >> 5;
+        const uint32_t lenA = stA + (uint32_t)sizeof(SpmvTileHeader);
+        const uint32_t colA = lenA + (uint32_t)nSlices * 64u;
+        const uint32_t cA = colA + (uint32_t)nSlices * 64u;
+        const uint32_t offA = cA + (uint32_t)nSlices * 256u;
+        const uint32_t valA = offA + (((uint32_t)nSlices * stepStride * 2u + 15u) & ~15u);
+        const uint32_t rowA = valA + tileValBytes(nEnt);
+        for (int q = 0; q < nSlices; ++q) {
+            const int len = (int)ldsU16(lenA + (uint32_t)(q * 32 + lane) * 2u);
+            const int colL = (int)ldsU16(colA + (uint32_t)(q * 32 + lane) * 2u);
+            const double cj = ldsF64(cA + (uint32_t)(q * 32 + lane) * 8u);
+            const int maxLen = (int)ldsU16(lenA + (uint32_t)q * 64u);  // lane 0 holds the slice's longest column
+            const uint32_t offQ = offA + (uint32_t)q * stepStride * 2u;
+            double sum = 0.0;
+            for (int i0 = 0; i0 < maxLen; i0 += 4) {
+                // first entry of steps i0..i0+3 (4 x uint16, warp-uniform); the lanes whose column is
+                // longer than the step are a PREFIX of the warp (columns sorted by length on the host)
+                const uint2 o = ldsU64(offQ + (uint32_t)i0 * 2u);
+                uint32_t pos[4];
+                pos[0] = (o.x & 0xffffu) + lane;
+                pos[1] = (o.x >> 16) + lane;
+                pos[2] = (o.y & 0xffffu) + lane;
+                pos[3] = (o.y >> 16) + lane;
+                uint32_t r[4];
                 double v[4], g[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int kk = k + 32 * j;
-                    r[j] = kk < len ? (int)sRow[kk] : 0;
-                    v[j] = kk < len ? sVal[kk] : 0.0;
+                    r[j] = 0u;
+                    if (len > i0 + j) r[j] = ROW16 ? ldsU16(rowA + pos[j] * 2u) : ldsU32(rowA + pos[j] * 4u);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) g[j] = (k + 32 * j < len) ? gatherU(r[j]) : 0.0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (k + 32 * j < len) sVal[k + 32 * j] = __dmul_rn(g[j], v[j]);
-            }
-        }
-        __syncwarp();
-        // phase 2, one lane per column: add the products sequentially in storage order
-#pragma unroll
-        for (int q = 0; q < kSpmvColsPerLane; ++q) {
-            const int col = cur.x + lane + 32 * q;
-            if (col < cur.y) {
-                int k = mc.b[q] - cur.z;
-                const int e = mc.e[q] - cur.z;
-                double sum = 0.0;
-                double p = sVal[k];  // the stage has 4 entries of slack: reading one past is safe
-                while (k < e) {
-                    const double pn = sVal[k + 1];
-                    sum = __dadd_rn(sum, p);
-                    p = pn;
-                    ++k;
+                for (int j = 0; j < 4; ++j) {
+                    v[j] = 0.0;
+                    if (len > i0 + j) v[j] = ldsF64(valA + pos[j] * 8u);
                 }
-                a.out[col] = a.phase1 ? -sum : mc.cj[q] - sum;  // DecompAlgo.cpp:4538-4545
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    g[j] = 0.0;
+                    if (len > i0 + j) g[j] = UMODE == 0 ? __ldg(uVec + r[j]) : ldsF64(sUaddr + r[j] * 8u);
+                }
+                // y += u*a, unfused.  A lane past its column's end adds 0*0 = +0, which leaves the sum
+                // unchanged bit for bit (the sum starts at +0 and x + (-x) rounds to +0, so it is never -0).
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sum = __dadd_rn(sum, __dmul_rn(g[j], v[j]));
             }
+            if (q * 32 + lane < nCols) outVec[firstCol + colL] = a.phase1 ? -sum : cj - sum;  // DecompAlgo.cpp:4538-4545
         }
-        // the stage was written through the generic proxy; order that before the bulk copy
-        // (async proxy) that refills it
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // every lane is done reading the stage before the bulk copy (async proxy) refills it
         __syncwarp();
-        if (lane == 0 && tnn < a.nTiles) issue(nn, offNn, s);
-        (void)tn;
-        cur = nxt;
-        nxt = tnn < a.nTiles ? nn : none;
-        mc = mn;
-    }
-    if (UMODE == 2) {
-        // a CTA's half of the duals must outlive its partner's last gather
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (lane == 0 && tRefill < a.nTiles) issue(recRefill, s);
+        if (++s == NST) {
+            s = 0;
+            parity ^= 1u;
+        }
     }
 }
 
@@ -341,92 +284,187 @@ redcost_csc_kernel(int N, const int64_t *__restrict__ colStart,
     }
 }
 
+
+// Host side of the stream kernel: cut the columns into tiles and lay each tile out as the kernel
+// reads it (SpmvTileHeader in common.cuh).  colStart/rowMaster/val: CSC of A'' with the entries
+// of a column in the reference's scatter order (descending rows).
+int buildSpmvTiles(Ctx *c, const std::vector<int64_t> &colStart, const std::vector<int32_t> &rowMaster,
+                   const std::vector<double> &val)
+{
+    const int N = c->N;
+    c->nSpmvTiles = 0;
+    c->spmvStageBytes = 0;
+    if (N <= 0 || colStart[N] >= (int64_t)1 << 31) return DIPGPU_OK;
+    const bool row16 = (int64_t)c->R + c->numConvex <= 65536;
+    const int sms = c->smCount > 0 ? c->smCount : 148;
+    // columns per warp tile: up to 32*kSpmvColsPerLane, fewer on small matrices so that every SM
+    // still gets ~16 warp tiles (a GAP-E sweep is latency-bound: more, shorter tiles in flight)
+    int maxCols = (int)std::min<int64_t>(32 * kSpmvColsPerLane, (int64_t)N / (16 * sms)) & ~31;
+    maxCols = std::max(32, maxCols);
+    if (c->optSpmvMaxCols > 0) maxCols = std::max(32, std::min(c->optSpmvMaxCols & ~31, 32 * kSpmvColsPerLane));
+    const int chunk = std::max(32, std::min(c->optSpmvChunk > 0 ? c->optSpmvChunk : kSpmvChunk, kSpmvChunkMax));
+    std::vector<int32_t> tileCol(1, 0);
+    for (int j = 0; j < N;) {
+        int e = j;
+        while (e < N && e - j < maxCols && colStart[e + 1] - colStart[j] <= chunk &&
+               colStart[e + 1] - colStart[e] <= 65535)
+            ++e;
+        if (e == j) return DIPGPU_OK;  // a single column longer than a tile: lane-cooperative kernel
+        tileCol.push_back(e);
+        j = e;
+    }
+    const size_t nt = tileCol.size() - 1;
+    std::vector<uint32_t> rec(2 * nt);
+    std::vector<size_t> off(nt + 1, 0);
+    std::vector<int32_t> stepStride(nt, 0);
+    size_t maxBytes = 0;
+    auto colLen = [&](int col) { return (int)(colStart[col + 1] - colStart[col]); };
+    for (size_t k = 0; k < nt; ++k) {
+        const int first = tileCol[k], nCols = tileCol[k + 1] - first;
+        const int nEnt = (int)(colStart[tileCol[k + 1]] - colStart[first]);
+        const int nSlices = (nCols + 31) / 32;
+        int maxLen = 0;
+        for (int col = first; col < first + nCols; ++col) maxLen = std::max(maxLen, colLen(col));
+        stepStride[k] = (maxLen + 1 + 3) & ~3;  // step offsets of a slice: maxLen + 1 entries, read 4 at a time
+        const size_t bytes = sizeof(SpmvTileHeader) + (size_t)nSlices * (64 + 64 + 256) +
+                             (((size_t)nSlices * stepStride[k] * 2 + 15) & ~(size_t)15) + tileValBytes(nEnt) +
+                             (row16 ? tileRowBytes<true>(nEnt) : tileRowBytes<false>(nEnt));
+        off[k + 1] = off[k] + bytes;
+        maxBytes = std::max(maxBytes, bytes);
+        rec[2 * k + 1] = (uint32_t)bytes;
+    }
+    if (off[nt] / 16 >= ((size_t)1 << 32)) return DIPGPU_OK;
+    std::vector<unsigned char> blob(off[nt] + 64, 0);
+    const bool haveObj = (int)c->hObj.size() >= N;
+    std::vector<int> order(32);
+    for (size_t k = 0; k < nt; ++k) {
+        rec[2 * k + 0] = (uint32_t)(off[k] / 16);
+        const int first = tileCol[k], nCols = tileCol[k + 1] - first;
+        const int nEnt = (int)(colStart[tileCol[k + 1]] - colStart[first]);
+        const int nSlices = (nCols + 31) / 32;
+        unsigned char *p = blob.data() + off[k];
+        SpmvTileHeader *h = reinterpret_cast<SpmvTileHeader *>(p);
+        h->firstCol = first;
+        h->nCols = nCols;
+        h->nEnt = nEnt;
+        h->stepStride = stepStride[k];
+        uint16_t *len = reinterpret_cast<uint16_t *>(p + sizeof(SpmvTileHeader));
+        uint16_t *colL = len + (size_t)nSlices * 32;
+        double *cc = reinterpret_cast<double *>(colL + (size_t)nSlices * 32);
+        uint16_t *stepOff = reinterpret_cast<uint16_t *>(cc + (size_t)nSlices * 32);
+        double *tv = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(stepOff) +
+                                                (((size_t)nSlices * stepStride[k] * 2 + 15) & ~(size_t)15));
+        unsigned char *tr = reinterpret_cast<unsigned char *>(tv) + tileValBytes(nEnt);
+        int w = 0;
+        for (int q = 0; q < nSlices; ++q) {
+            const int c0 = first + 32 * q, n = std::min(first + nCols, c0 + 32) - c0;
+            // lane l owns the l-th longest column of the slice (stable: equal lengths keep column order)
+            for (int l = 0; l < n; ++l) order[l] = c0 + l;
+            std::stable_sort(order.begin(), order.begin() + n, [&](int x, int y) { return colLen(x) > colLen(y); });
+            for (int l = 0; l < n; ++l) {
+                len[q * 32 + l] = (uint16_t)colLen(order[l]);
+                colL[q * 32 + l] = (uint16_t)(order[l] - first);
+                cc[q * 32 + l] = haveObj ? c->hObj[order[l]] : 0.0;
+            }
+            const int maxLen = n > 0 ? colLen(order[0]) : 0;
+            uint16_t *so = stepOff + (size_t)q * stepStride[k];
+            for (int i = 0; i < stepStride[k]; ++i) {
+                so[i] = (uint16_t)w;
+                if (i < maxLen)
+                    for (int l = 0; l < n && colLen(order[l]) > i; ++l) {
+                        const int64_t src = colStart[order[l]] + i;
+                        tv[w] = val[src];
+                        if (row16) reinterpret_cast<uint16_t *>(tr)[w] = (uint16_t)rowMaster[src];
+                        else reinterpret_cast<int32_t *>(tr)[w] = rowMaster[src];
+                        ++w;
+                    }
+            }
+        }
+    }
+    int rc;
+    if (c->dTileRec) { cudaFree(c->dTileRec); c->dTileRec = nullptr; }
+    if (c->dSpmvBlob) { cudaFree(c->dSpmvBlob); c->dSpmvBlob = nullptr; }
+    DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&c->dTileRec), sizeof(uint32_t) * rec.size()));
+    DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&c->dSpmvBlob), blob.size()));
+    DIPGPU_CUDA(c, cudaMemcpy(c->dSpmvBlob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    DIPGPU_CUDA(c, cudaMemcpy(c->dTileRec, rec.data(), sizeof(uint32_t) * rec.size(), cudaMemcpyHostToDevice));
+    (void)rc;
+    c->nSpmvTiles = (int)nt;
+    c->spmvStageBytes = (int)((maxBytes + 15) & ~(size_t)15);
+    return DIPGPU_OK;
+}
+
 int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
 {
-    if (c->N == 0) return DIPGPU_OK;
+    return launchRedCostBatch(c, dU, 0, c->dRedCost, 0, 1, phase, st);
+}
+
+int launchRedCostBatch(Ctx *c, const double *dU, int64_t uStride, double *dOut, int64_t outStride, int nVec, int phase,
+                       cudaStream_t st)
+{
+    if (c->N == 0 || nVec <= 0) return DIPGPU_OK;
     if (c->nSpmvTiles > 0 && c->spmvLanes == 0) {
         StreamArgs a;
         a.nTiles = c->nSpmvTiles;
-        a.tileRec = reinterpret_cast<const int4 *>(c->dTileRec);
-        a.colStart32 = c->dColStart32;
+        a.tileRec = reinterpret_cast<const uint2 *>(c->dTileRec);
         a.blob = c->dSpmvBlob;
-        a.blobOff = c->dSpmvBlobOff;
         a.u = dU;
         a.uLen = c->R + c->numConvex;
-        a.c = c->dObj;
         a.phase1 = phase == DIPGPU_PHASE_PRICE1 ? 1 : 0;
-        a.out = c->dRedCost;
+        a.out = dOut;
+        a.uStride = uStride;
+        a.outStride = outStride;
+        a.stageBytes = c->spmvStageBytes;
         const int sms = c->smCount > 0 ? c->smCount : 148;
         const size_t maxSmem = 227 * 1024;
-        const bool row16 = c->dRowMaster16 != nullptr;
-        const size_t warpBytes = row16 ? SpmvStage<true>::kWarpBytes : SpmvStage<false>::kWarpBytes;
+        const bool row16 = (int64_t)c->R + c->numConvex <= 65536;
         const size_t uBytes = (((size_t)a.uLen + 1) & ~(size_t)1) * 8 + 16;  // + the u mbarrier
-        const int uHalf = (((a.uLen + 1) / 2) + 1) & ~1;
-        const size_t uHalfBytes = (size_t)uHalf * 8 + 16;
+        auto warpBytesFor = [&](int nst) { return (size_t)((nst * 8 + 15) & ~15) + (size_t)nst * a.stageBytes; };
         // u in shared memory pays when it is gathered irregularly and re-used: many more stored
-        // entries than duals.  mode 2 (split over a 2-CTA cluster) leaves twice the room for stages.
+        // entries than duals, and enough room left for the stages
         const bool reuse = c->nnz >= 8 * (int64_t)a.uLen;
         int mode = 0;
-        // (mode 2 is never chosen automatically: on B200 the remote 8-byte gathers sustain only ~0.25
-        // per cycle and SM, 78 us on the MILPBlock shape against 44 us for mode 1)
-        if (reuse && uBytes + 6 * warpBytes <= maxSmem && c->nSpmvTiles >= 24 * sms) mode = 1;
-        if (c->optSpmvUSmem >= 0) mode = c->optSpmvUSmem;
-        if (mode == 1 && uBytes + warpBytes > maxSmem) mode = 0;
-        if (mode == 2 && uHalfBytes + warpBytes > maxSmem) mode = 0;
+        if (reuse && uBytes + 8 * warpBytesFor(2) <= maxSmem && c->nSpmvTiles >= 24 * sms) mode = 1;
+        if (c->optSpmvUSmem >= 0) mode = c->optSpmvUSmem != 0 ? 1 : 0;
+        if (mode == 1 && uBytes + warpBytesFor(2) > maxSmem) mode = 0;
         typedef void (*Fn)(const StreamArgs);
         Fn fn;
         size_t bytes;
         int grid, threads;
-        a.uHalf = uHalf;
         if (mode != 0) {
-            const size_t ub = mode == 2 ? uHalfBytes : uBytes;
-            int warps = (int)std::min<size_t>(24, (maxSmem - ub) / warpBytes);
+            // persistent, one CTA per SM: as many warps as fit beside the duals, each with a deep ring
+            int nst = c->optSpmvStages > 0 ? std::min(c->optSpmvStages, kSpmvMaxStages) : 2;  // measured: 2 x 16+ warps beats 3 x 11
+            nst = std::max(nst, 2);
+            while (nst > 2 && uBytes + 8 * warpBytesFor(nst) > maxSmem) --nst;
+            int warps = (int)std::min<size_t>(32, (maxSmem - uBytes) / warpBytesFor(nst));
             if (c->optSpmvWarps > 0) warps = std::min(warps, c->optSpmvWarps);
-            a.uSmemBytes = (int)ub;
-            bytes = ub + (size_t)warps * warpBytes;
-            fn = mode == 2 ? (row16 ? redcost_stream_kernel<2, true> : redcost_stream_kernel<2, false>)
-                           : (row16 ? redcost_stream_kernel<1, true> : redcost_stream_kernel<1, false>);
-            grid = sms & ~1;
+            warps = std::max(warps, 1);
+            a.nStages = nst;
+            a.uSmemBytes = (int)uBytes;
+            bytes = uBytes + (size_t)warps * warpBytesFor(nst);
+            fn = row16 ? redcost_stream_kernel<1, true> : redcost_stream_kernel<1, false>;
+            grid = sms;
             threads = warps * 32;
         } else {
+            int nst = c->optSpmvStages > 0 ? std::min(c->optSpmvStages, kSpmvMaxStages) : 2;
+            nst = std::max(nst, 2);
+            a.nStages = nst;
             a.uSmemBytes = 0;
-            const int warps = c->optSpmvWarps > 0 ? std::min(c->optSpmvWarps, 16) : 8;
-            bytes = (size_t)warps * warpBytes;
+            int warps = c->optSpmvWarps > 0 ? std::min(c->optSpmvWarps, 32) : 8;
+            while (warps > 1 && (size_t)warps * warpBytesFor(nst) > maxSmem) --warps;
+            bytes = (size_t)warps * warpBytesFor(nst);
             fn = row16 ? redcost_stream_kernel<0, true> : redcost_stream_kernel<0, false>;
-            const int ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(4, maxSmem / bytes));
+            const int ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(4, maxSmem / std::max<size_t>(bytes, 1)));
             grid = std::max(1, std::min((c->nSpmvTiles + warps - 1) / warps, ctasPerSm * sms));
             threads = warps * 32;
         }
+        if (bytes > maxSmem) return fail(c, DIPGPU_ERR_UNSUPPORTED, "reduced-cost tiles of %d bytes do not fit shared memory", a.stageBytes);
         if (c->spmvFn != (void *)fn || c->spmvFnSmem != bytes) {
             DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
             c->spmvFn = (void *)fn;
             c->spmvFnSmem = bytes;
-            c->spmvClusters = 0;
         }
-        if (mode == 2) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.blockDim = dim3(threads, 1, 1);
-            cfg.dynamicSmemBytes = bytes;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 2;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            if (c->spmvClusters == 0) {
-                // persistent kernel: no more CTA pairs than can be resident at once
-                cfg.gridDim = dim3(grid, 1, 1);
-                int nc = 0;
-                DIPGPU_CUDA(c, cudaOccupancyMaxActiveClusters(&nc, fn, &cfg));
-                c->spmvClusters = std::max(1, std::min(nc, grid / 2));
-            }
-            cfg.gridDim = dim3(2 * c->spmvClusters, 1, 1);
-            DIPGPU_CUDA(c, cudaLaunchKernelEx(&cfg, fn, a));
-        } else {
-            fn<<<grid, threads, bytes, st>>>(a);
-        }
+        fn<<<dim3(grid, nVec, 1), threads, bytes, st>>>(a);
         c->launches++;
         DIPGPU_CUDA(c, cudaGetLastError());
         return DIPGPU_OK;
@@ -442,17 +480,19 @@ int launchRedCost(Ctx *c, const double *dU, int phase, cudaStream_t st)
     const unsigned grid = (unsigned)((total + threads - 1) / threads);
 #define LAUNCH(LL)                                                                              \
     redcost_csc_kernel<LL><<<grid, threads, 0, st>>>(c->N, c->dColStart, c->dRowMaster, c->dVal, \
-                                                      dU, c->dObj, phase1, c->dRedCost)
-    switch (L) {
-        case 1: LAUNCH(1); break;
-        case 2: LAUNCH(2); break;
-        case 4: LAUNCH(4); break;
-        case 8: LAUNCH(8); break;
-        case 16: LAUNCH(16); break;
-        default: LAUNCH(32); break;
+                                                      dU + v * uStride, c->dObj, phase1, dOut + v * outStride)
+    for (int64_t v = 0; v < nVec; ++v) {
+        switch (L) {
+            case 1: LAUNCH(1); break;
+            case 2: LAUNCH(2); break;
+            case 4: LAUNCH(4); break;
+            case 8: LAUNCH(8); break;
+            case 16: LAUNCH(16); break;
+            default: LAUNCH(32); break;
+        }
+        c->launches++;
     }
 #undef LAUNCH
-    c->launches++;
     DIPGPU_CUDA(c, cudaGetLastError());
     return DIPGPU_OK;
 }

@@ -228,6 +228,121 @@ class GpuPricer:
                                                  C.byref(res.c), capi.ptr(rcx)))
         return (res, rcx) if want_redcost else res
 
+    # ---- several dual vectors in one submission ------------------------------
+    def _batch_results(self, n: int):
+        res = [RoundResult(self.m, self.m, max(self.nBlockCols, 1)) for _ in range(n)]
+        arr = (capi.Cols * n)()
+        for k in range(n):
+            arr[k] = res[k].c
+        return res, arr
+
+    @staticmethod
+    def _batch_finish(res, arr):
+        for k, r in enumerate(res):
+            r.c = arr[k]      # counts / sums written by the library; the array pointers are unchanged
+        return res
+
+    def priceRoundsBatch(self, U, phase=PHASE_PRICE2, redCostEps=1e-4) -> list[RoundResult]:
+        """nVec dual vectors (rows of U), each priced as priceRound would (dipgpu_price_rounds_batch)."""
+        U = np.ascontiguousarray(U, np.float64)
+        n, u_len = U.shape
+        res, arr = self._batch_results(n)
+        self._check(self._lib.dipgpu_price_rounds_batch(self._ctx, n, capi.ptr(U), u_len, phase, float(redCostEps), arr))
+        return self._batch_finish(res, arr)
+
+    def priceRoundsBatchRaw(self, n: int, u_ptr: int, u_len: int, phase: int, eps: float, arr):
+        rc = self._lib.dipgpu_price_rounds_batch(self._ctx, n, u_ptr, u_len, phase, eps, arr)
+        if rc != capi.OK:
+            self._check(rc)
+
+    def selectBatchResult(self, which: int):
+        self._check(self._lib.dipgpu_select_batch_result(self._ctx, int(which)))
+
+    # ---- dual stabilisation (DecompAlgoPC::adjustMasterDualSolution) ------------
+    def stabSetCenter(self, dual):
+        """m_dual := dual (first price call / first phase-2 call, DecompAlgoPC.cpp:163-177)."""
+        d = np.ascontiguousarray(dual, np.float64)
+        self._check(self._lib.dipgpu_stab_set_center(self._ctx, capi.ptr(d), len(d)))
+
+    def stabAccept(self, step: int = 0):
+        """m_dual := m_dualST (DecompAlgoPC::setObjBound, DecompAlgoPC.h:124-133)."""
+        self._check(self._lib.dipgpu_stab_accept(self._ctx, int(step)))
+
+    def priceRoundStab(self, uRM, alpha, phase=PHASE_PRICE2, redCostEps=1e-4, want_duals=True):
+        """adjustMasterDualSolution + generateVars with the smoothed duals; returns (RoundResult, dualST)."""
+        u = np.ascontiguousarray(uRM, np.float64)
+        res = RoundResult(self.m, self.m, max(self.nBlockCols, 1))
+        st = np.empty(len(u), np.float64) if want_duals else None
+        self._check(self._lib.dipgpu_price_round_stab(self._ctx, capi.ptr(u), len(u), float(alpha), phase,
+                                                      float(redCostEps), C.byref(res.c), capi.ptr(st)))
+        return res, st
+
+    def priceRoundStabLadder(self, uRM, alpha, n_steps, shrink=0.90, phase=PHASE_PRICE2, redCostEps=1e-4):
+        """The smoothing ladder alpha, shrink*alpha, ... (DecompAlgo.cpp:5642-5655) priced speculatively in
+        one submission; returns ([RoundResult per step], alphas)."""
+        u = np.ascontiguousarray(uRM, np.float64)
+        res, arr = self._batch_results(n_steps)
+        alphas = np.zeros(n_steps, np.float64)
+        self._check(self._lib.dipgpu_price_round_stab_ladder(self._ctx, capi.ptr(u), len(u), float(alpha), float(shrink),
+                                                             n_steps, phase, float(redCostEps), arr, capi.ptr(alphas)))
+        return self._batch_finish(res, arr), alphas
+
+    def priceRoundStabLadderRaw(self, u_ptr: int, u_len: int, alpha: float, shrink: float, n_steps: int, phase: int,
+                                eps: float, arr):
+        rc = self._lib.dipgpu_price_round_stab_ladder(self._ctx, u_ptr, u_len, alpha, shrink, n_steps, phase, eps, arr, None)
+        if rc != capi.OK:
+            self._check(rc)
+
+    def smoothedDuals(self, step: int = 0) -> np.ndarray:
+        out = np.empty(self.R + self.numConvex, np.float64)
+        self._check(self._lib.dipgpu_get_smoothed_duals(self._ctx, int(step), capi.ptr(out), len(out)))
+        return out
+
+    # ---- waiting-column pool (DecompVarPool) -----------------------------------
+    def poolClear(self):
+        self._check(self._lib.dipgpu_pool_clear(self._ctx))
+
+    def poolSize(self) -> tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._lib.dipgpu_pool_size(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def poolAppend(self, col_start, row_ind, val, orig_cost):
+        cs = np.ascontiguousarray(col_start, np.int64)
+        ri = np.ascontiguousarray(row_ind, np.int32)
+        v = np.ascontiguousarray(val, np.float64)
+        oc = np.ascontiguousarray(orig_cost, np.float64)
+        self._check(self._lib.dipgpu_pool_append(self._ctx, len(cs) - 1, capi.ptr(cs), capi.ptr(ri), capi.ptr(v), capi.ptr(oc)))
+
+    def poolAppendExpanded(self, which):
+        """Columns `which` of the last expandColumns() enter the pool device-to-device."""
+        w = np.ascontiguousarray(which, np.int32)
+        self._check(self._lib.dipgpu_pool_append_expanded(self._ctx, len(w), capi.ptr(w)))
+
+    def poolKeep(self, keep_idx):
+        k = np.ascontiguousarray(keep_idx, np.int32)
+        self._check(self._lib.dipgpu_pool_keep(self._ctx, len(k), capi.ptr(k)))
+
+    def poolSetReducedCosts(self, u=None, feasible=True):
+        """DecompVarPool::setReducedCosts(u, stat): returns (redCost per waiting column, found_negrc_var).
+        u=None re-uses the dual vector already on the device."""
+        n, _ = self.poolSize()
+        out = np.zeros(max(n, 1), np.float64)
+        found = C.c_int32(0)
+        if u is not None:
+            u = np.ascontiguousarray(u, np.float64)
+        u_len = len(u) if u is not None else self.R + self.numConvex
+        self._check(self._lib.dipgpu_pool_set_reduced_costs(self._ctx, capi.ptr(u), u_len, int(bool(feasible)),
+                                                            capi.ptr(out), C.byref(found)))
+        return out[:n], bool(found.value)
+
+    def priceRoundResident(self, phase=PHASE_PRICE2, redCostEps=1e-4, result: RoundResult | None = None):
+        """priceRound with the dual vector already on the device (u == NULL)."""
+        res = result or self._res()
+        self._check(self._lib.dipgpu_price_round(self._ctx, None, self.R + self.numConvex, phase, float(redCostEps),
+                                                 C.byref(res.c), None))
+        return res
+
     def priceRoundRaw(self, u_ptr: int, u_len: int, phase: int, eps: float, res: RoundResult):
         """Same call with a raw host pointer (pinned buffers in bench.py): no numpy marshalling."""
         rc = self._lib.dipgpu_price_round(self._ctx, u_ptr, u_len, phase, eps, C.byref(res.c), None)

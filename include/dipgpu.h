@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define DIPGPU_ABI_VERSION 1
+#define DIPGPU_ABI_VERSION 2
 
 typedef struct dipgpu_ctx dipgpu_ctx;
 
@@ -175,6 +175,81 @@ int dipgpu_solve_blocks(dipgpu_ctx *ctx, const double *redCostX, const double *a
  */
 int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase,
                        double redCostEps, dipgpu_cols *out, double *redCostXOpt);
+/* u == NULL prices with the dual vector already resident on the device: the one uploaded by the
+ * last host-buffer call (dipgpu_pool_set_reduced_costs, dipgpu_calc_redcost, dipgpu_price_round) --
+ * DIP re-prices the waiting columns and generates new ones with the same duals
+ * (Dip/src/DecompAlgo.cpp:1901 then :1914), so the vector crosses PCIe once. */
+
+/* ------------------------------------------- several dual vectors in one submission
+ *
+ * nVec master dual vectors (row v at U + v*uLen), each priced exactly as dipgpu_price_round would:
+ * outs[v] receives the round of vector v.  One reduced-cost launch, one DP launch (the fused kernel
+ * with gridDim.y = nVec) and one strided D2H copy for the whole batch, so the latency-bound GAP
+ * rounds fill the GPU.  Sources of such batches in DIP: the smoothing ladder below, and the dual
+ * vectors of several open nodes.  dipgpu_select_batch_result(which) makes result `which` the
+ * context's "last round" (for dipgpu_expand_columns).
+ */
+int dipgpu_price_rounds_batch(dipgpu_ctx *ctx, int32_t nVec, const double *U, int32_t uLen,
+                              int32_t phase, double redCostEps, dipgpu_cols *outs);
+int dipgpu_select_batch_result(dipgpu_ctx *ctx, int32_t which);
+
+/* ------------------------------------------------------- dual stabilisation (Wentges)
+ *
+ * DecompAlgoPC::adjustMasterDualSolution (Dip/src/DecompAlgoPC.cpp:126-212) followed by
+ * generateVars with the smoothed duals (DecompAlgoPC.h:99-108):
+ *     dualST = alpha * dual + (1 - alpha) * dualRM                       (:179-181)
+ * `dual` (m_dual, the stability centre) lives on the device: dipgpu_stab_set_center uploads it
+ * (first price call / first phase-2 call, :163-177, where the reference copies dualRM or calls
+ * DecompApp::initDualVector); dipgpu_stab_accept(step) copies smoothed vector `step` of the last
+ * stabilised call into it (DecompAlgoPC::setObjBound, DecompAlgoPC.h:124-133, when the bound
+ * improved).  Without a centre the first stabilised call uses dualRM itself (:172).
+ *
+ * dipgpu_price_round_stab: one smoothing parameter; dualSTOpt (length uLen, may be NULL) receives
+ * the smoothed duals the round was priced with (the host needs them for updateObjBound,
+ * Dip/src/DecompAlgo.cpp:3728).
+ *
+ * dipgpu_price_round_stab_ladder: when every new column is a duplicate the reference multiplies
+ * DualStabAlpha by 0.90 and prices again (Dip/src/DecompAlgo.cpp:5642-5655).  The ladder
+ * alpha_k = alpha * shrink^k, k < nSteps (repeated multiplication, as the reference) is priced
+ * speculatively in ONE submission from ONE upload of dualRM; outs[k] is the round of step k, and
+ * the host takes the first step with a column that is not a duplicate.  alphasOut (nSteps, may be
+ * NULL) receives the alpha_k.  nSteps <= 64.
+ */
+int dipgpu_stab_set_center(dipgpu_ctx *ctx, const double *dual, int32_t uLen);
+int dipgpu_stab_accept(dipgpu_ctx *ctx, int32_t step);
+int dipgpu_price_round_stab(dipgpu_ctx *ctx, const double *uRM, int32_t uLen, double alpha,
+                            int32_t phase, double redCostEps, dipgpu_cols *out, double *dualSTOpt);
+int dipgpu_price_round_stab_ladder(dipgpu_ctx *ctx, const double *uRM, int32_t uLen, double alpha,
+                                   double shrink, int32_t nSteps, int32_t phase, double redCostEps,
+                                   dipgpu_cols *outs, double *alphasOut);
+int dipgpu_get_smoothed_duals(dipgpu_ctx *ctx, int32_t step, double *dualST, int32_t uLen);
+
+/* ------------------------------------------------------- waiting-column pool
+ *
+ * DecompVarPool (Dip/src/DecompVarPool.h) as far as the dual vector touches it: the master
+ * columns of the waiting variables live in device memory, and once per price call
+ * DecompVarPool::setReducedCosts (Dip/src/DecompVarPool.cpp:185-203 -> :22-40; call site
+ * Dip/src/DecompAlgo.cpp:1890-1908) re-prices all of them:
+ *     feasible != 0:  redCost_s = origCost_s - col_s . u        (:29)
+ *     feasible == 0:  redCost_s =            - col_s . u        (:36, u = a dual ray)
+ * *foundNegRC = 1 iff some redCost <= -1e-10 (:30, :37, :199).  Columns are in MASTER row space
+ * (row indices into u, convexity entry included), each added last entry first (the order of
+ * CoinPackedVectorBase::dotProduct).  u == NULL uses the resident dual vector (see above).
+ *
+ * Columns enter from host arrays (dipgpu_pool_append: colStart has nCols+1 entries starting at 0)
+ * or device-to-device from the last dipgpu_expand_columns (dipgpu_pool_append_expanded: `which`
+ * indexes that expansion's columns, e.g. those that survived the duplicate test), and leave when
+ * DecompAlgo::addVarsFromPool moves them into the master (dipgpu_pool_keep: ascending indices of
+ * the columns that stay).
+ */
+int dipgpu_pool_clear(dipgpu_ctx *ctx);
+int dipgpu_pool_size(const dipgpu_ctx *ctx, int64_t *nCols, int64_t *nNnz);
+int dipgpu_pool_append(dipgpu_ctx *ctx, int32_t nCols, const int64_t *colStart, const int32_t *rowInd,
+                       const double *val, const double *origCost);
+int dipgpu_pool_append_expanded(dipgpu_ctx *ctx, int32_t nWhich, const int32_t *which);
+int dipgpu_pool_keep(dipgpu_ctx *ctx, int32_t nKeep, const int32_t *keepIdx);
+int dipgpu_pool_set_reduced_costs(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t feasible,
+                                  double *redCost, int32_t *foundNegRC);
 
 /* ------------------------------------------------- after the round: master columns
  *
@@ -263,7 +338,8 @@ int dipgpu_get_dp_geometry(const dipgpu_ctx *ctx, int32_t out[7]);
 
 /* Tuning / diagnostics knobs: "stage_timing", "dp_threads" (multiple of 32),
  * "dp_cells_per_thread" (odd, 1..25), "dp_items_per_step" (1, 2, or 3 with guard cells and <= 3 cells per thread), "dp_no_guard",
- * "spmv_lanes" (0 = TMA stream kernel), "fuse_filter" (-1 auto, 0 = three kernels,
+ * "spmv_lanes" (0 = TMA stream kernel), "spmv_chunk" / "spmv_max_cols" (entry / column budget of
+ * a warp tile; re-tiles the matrix), "spmv_stages", "spmv_warps", "spmv_u_smem", "fuse_filter" (-1 auto, 0 = three kernels,
  * 1 = filter in the backtrack tail, 2 = backtrack + filter in the DP tail); 0 restores the automatic
  * choice of the dp_* knobs.  Unknown names return
  * DIPGPU_ERR_INVALID. */

@@ -128,7 +128,8 @@ public:
     }
 
     // ---- surface 2: the whole round ------------------------------------------------------------
-    // DecompAlgo::generateVars: u = master duals (length R + numConvex), returns newVars.size().
+    // DecompAlgo::generateVars: u = master duals (length R + numConvex; NULL = the vector the last
+    // setReducedCosts / calcRedCost call left on the device), returns newVars.size().
     // mostNegReducedCost = sum_b min(0, rc_b) in block order (DecompAlgo.cpp:5229-5232).
     template <class VarT = DecompVar, class ListT = std::list<VarT *>>
     int generateVars(const double *u, int uLen, int phase, double redCostEps, ListT &newVars,
@@ -207,6 +208,91 @@ public:
         val.resize((size_t)mc.nNnz);
     }
 
+    // ---- dual stabilisation: DecompAlgoPC::adjustMasterDualSolution + generateVars -------------
+    // (Dip/src/DecompAlgoPC.cpp:126-212; DecompAlgoPC.h:99-133).  The stability centre m_dual lives on
+    // the device: setDualCentre <-> "Init dual to dualRM" / DecompApp::initDualVector (:163-177),
+    // acceptSmoothedDuals <-> the copy of m_dualST into m_dual in DecompAlgoPC::setObjBound.
+    void setDualCentre(const double *dual, int uLen) { check(dipgpu_stab_set_center(m_ctx, dual, uLen)); }
+    void acceptSmoothedDuals(int step = 0) { check(dipgpu_stab_accept(m_ctx, step)); }
+    // generateVars with dualST = alpha*dual + (1-alpha)*dualRM; dualST (length uLen, may be NULL)
+    // receives the vector the round was priced with (what getMasterDualSolution() returns under
+    // DualStab, DecompAlgoPC.h:99-108).
+    template <class VarT = DecompVar, class ListT = std::list<VarT *>>
+    int generateVarsStabilised(const double *dualRM, int uLen, double alpha, int phase, double redCostEps,
+                               ListT &newVars, double &mostNegReducedCost, double *dualST)
+    {
+        check(dipgpu_price_round_stab(m_ctx, dualRM, uLen, alpha, phase, redCostEps, &m_cols, dualST));
+        mostNegReducedCost = m_cols.mostNegReducedCost;
+        for (int k = 0; k < m_cols.nCols; ++k) newVars.push_back(makeVar<VarT>(k, m_colRedCost[k]));
+        return m_cols.nCols;
+    }
+    // One round per smoothing parameter of the ladder alpha, shrink*alpha, ... that addVarsToPool
+    // walks when every new column is a duplicate (DecompAlgo.cpp:5642-5655), priced speculatively in
+    // one GPU submission.  Round k's columns are materialised on demand with takeLadderVars(k, ...).
+    struct Round {
+        std::vector<double> blockRedCost, blockMostNeg, blockOrigCost, blockObj, colRedCost, colOrigCost;
+        std::vector<int32_t> blockNnz, colBlock, colInd;
+        std::vector<int64_t> colStart;
+        dipgpu_cols cols;
+    };
+    void generateVarsLadder(const double *dualRM, int uLen, double alpha, double shrink, int nSteps, int phase,
+                            double redCostEps, std::vector<double> &alphas)
+    {
+        m_ladder.resize((size_t)nSteps);
+        std::vector<dipgpu_cols> arr((size_t)nSteps);
+        for (int k = 0; k < nSteps; ++k) {
+            bindRound(m_ladder[(size_t)k]);
+            arr[(size_t)k] = m_ladder[(size_t)k].cols;
+        }
+        alphas.assign((size_t)nSteps, 0.0);
+        check(dipgpu_price_round_stab_ladder(m_ctx, dualRM, uLen, alpha, shrink, nSteps, phase, redCostEps, arr.data(),
+                                             alphas.data()));
+        for (int k = 0; k < nSteps; ++k) m_ladder[(size_t)k].cols = arr[(size_t)k];
+    }
+    const Round &ladderRound(int step) const { return m_ladder.at((size_t)step); }
+    template <class VarT = DecompVar, class ListT = std::list<VarT *>>
+    int takeLadderVars(int step, ListT &newVars, double &mostNegReducedCost)
+    {
+        const Round &r = m_ladder.at((size_t)step);
+        mostNegReducedCost = r.cols.mostNegReducedCost;
+        for (int k = 0; k < r.cols.nCols; ++k) {
+            const int64_t b = r.colStart[(size_t)k], e = r.colStart[(size_t)k + 1];
+            std::vector<int> ind(r.colInd.begin() + b, r.colInd.begin() + e);
+            std::vector<double> els(ind.size(), 1.0);
+            VarT *v = new VarT(ind, els, r.colRedCost[(size_t)k], r.colOrigCost[(size_t)k]);
+            v->setBlockId(r.colBlock[(size_t)k]);
+            newVars.push_back(v);
+        }
+        check(dipgpu_select_batch_result(m_ctx, step));  // expandColumns() now refers to this step
+        return r.cols.nCols;
+    }
+
+    // ---- the waiting-column pool: DecompVarPool::setReducedCosts (DecompVarPool.cpp:185-203) -----
+    // Call site DecompAlgo.cpp:1890-1908, right before generateVars with the same duals: pass the
+    // duals here and u == NULL to generateVars (they stay on the device).
+    void poolClear() { check(dipgpu_pool_clear(m_ctx)); }
+    void poolAppend(int nCols, const int64_t *colStart, const int32_t *rowInd, const double *val, const double *origCost)
+    {
+        check(dipgpu_pool_append(m_ctx, nCols, colStart, rowInd, val, origCost));
+    }
+    // columns `which` of the last expandColumns() (e.g. those that passed isDuplicate / isParallel)
+    void poolAppendExpanded(const std::vector<int32_t> &which)
+    {
+        check(dipgpu_pool_append_expanded(m_ctx, (int32_t)which.size(), which.data()));
+    }
+    // addVarsFromPool moved the others into the master (DecompAlgo.cpp:5678-5900)
+    void poolKeep(const std::vector<int32_t> &keepIdx) { check(dipgpu_pool_keep(m_ctx, (int32_t)keepIdx.size(), keepIdx.data())); }
+    // returns found_negrc_var; redCost[k] = reduced cost of waiting column k
+    bool setReducedCosts(const double *u, int uLen, bool feasible, std::vector<double> &redCost)
+    {
+        int64_t n = 0;
+        check(dipgpu_pool_size(m_ctx, &n, nullptr));
+        redCost.assign((size_t)n, 0.0);
+        int32_t found = 0;
+        check(dipgpu_pool_set_reduced_costs(m_ctx, u, uLen, feasible ? 1 : 0, redCost.data(), &found));
+        return found != 0;
+    }
+
     // ---- stage (a) alone: generateVarsCalcRedCost (DecompAlgo.cpp:4506-4547) -------------------
     void calcRedCost(const double *u, int uLen, int phase, double *redCostX)
     {
@@ -257,6 +343,21 @@ private:
         m_cols.colStart = m_colStart.data();
         m_cols.colInd = m_colInd.data();
     }
+    void bindRound(Round &r) const
+    {
+        const size_t m = (size_t)m_m, n = (size_t)(m_nBlockCols > 0 ? m_nBlockCols : 1);
+        r.blockRedCost.assign(m, 0.0); r.blockMostNeg.assign(m, 0.0); r.blockOrigCost.assign(m, 0.0);
+        r.blockObj.assign(m, 0.0); r.blockNnz.assign(m, 0); r.colBlock.assign(m + 1, 0);
+        r.colRedCost.assign(m + 1, 0.0); r.colOrigCost.assign(m + 1, 0.0); r.colStart.assign(m + 2, 0);
+        r.colInd.assign(n, 0);
+        std::memset(&r.cols, 0, sizeof(r.cols));
+        r.cols.capBlocks = m_m; r.cols.capCols = m_m; r.cols.capInd = (int64_t)n;
+        r.cols.blockRedCost = r.blockRedCost.data(); r.cols.blockMostNegRC = r.blockMostNeg.data();
+        r.cols.blockOrigCost = r.blockOrigCost.data(); r.cols.blockObj = r.blockObj.data();
+        r.cols.blockNnz = r.blockNnz.data(); r.cols.colBlock = r.colBlock.data();
+        r.cols.colRedCost = r.colRedCost.data(); r.cols.colOrigCost = r.colOrigCost.data();
+        r.cols.colStart = r.colStart.data(); r.cols.colInd = r.colInd.data();
+    }
     template <class VarT>
     VarT *makeVar(int k, double redCost) const
     {
@@ -295,6 +396,7 @@ private:
     const double *m_roundPtr = nullptr;
     uint64_t m_roundFp = 0;
     std::vector<char> m_served;
+    std::vector<Round> m_ladder;
 };
 
 }  // namespace dipgpu

@@ -371,3 +371,31 @@ int dip_oracle_string_hash(int len, const int32_t *ind, const double *els, char 
     }
     return pos;
 }
+
+/* ------------------------------------------------- var pool / smoothing -- */
+
+int dip_oracle_pool_reduced_costs(int nCols, const int64_t *colStart, const int32_t *rowInd,
+                                  const double *val, const double *origCost, const double *u,
+                                  int feasible, double *redCost)
+{
+    /* DecompVarPool.cpp:185-203: every waiting column; found |= (rc <= -1e-10) */
+    int found = 0;
+    for (int s = 0; s < nCols; ++s) {
+        /* CoinPackedVectorBase::dotProduct (CoinUtils, un-vendored): last entry first */
+        double dp = 0.0;
+        for (int64_t k = colStart[s + 1] - 1; k >= colStart[s]; --k) dp += val[k] * u[rowInd[k]];
+        /* DecompVarPool.cpp:29 (feasible) / :36 (dual ray) */
+        const double rc = feasible ? origCost[s] - dp : -dp;
+        redCost[s] = rc;
+        if (rc <= -0.0000000001) found = 1; /* :30, :37 */
+    }
+    return found;
+}
+
+void dip_oracle_smooth_duals(int nRows, double alpha, const double *dual, const double *dualRM,
+                             double *dualST)
+{
+    const double alpha1 = 1.0 - alpha; /* DecompAlgoPC.cpp:154 */
+    for (int r = 0; r < nRows; ++r)    /* :179-181 */
+        dualST[r] = (alpha * dual[r]) + (alpha1 * dualRM[r]);
+}

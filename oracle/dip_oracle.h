@@ -122,6 +122,23 @@ int dip_oracle_expand_column(int R, int N, const int64_t *rowStart, const int32_
 int dip_oracle_string_hash(int len, const int32_t *ind, const double *els, char *buf,
                            int bufLen);
 
+/* DecompVarPool::setReducedCosts -> DecompWaitingCol::setReducedCost,
+ * Dip/src/DecompVarPool.cpp:185-203, :22-40 (called once per price call, DecompAlgo.cpp:1890-1908):
+ *   feasible:  redCost_s = origCost_s - m_col.dotProduct(u)        (:29)
+ *   dual ray:  redCost_s =            - m_col.dotProduct(u)        (:36)
+ * m_col = the waiting column in MASTER row space (incl. the convexity 1.0), u = the whole master
+ * dual vector.  CoinPackedVectorBase::dotProduct is CoinUtils 2.11 (not vendored): restated as
+ * dp = 0; for i = n-1..0: dp += els[i]*u[ind[i]]  (order "parity unpinned"; any order meets 1e-12).
+ * redCost[nCols] receives the values; returns 1 iff some redCost <= -1e-10 (:30, :37, :199). */
+int dip_oracle_pool_reduced_costs(int nCols, const int64_t *colStart, const int32_t *rowInd,
+                                  const double *val, const double *origCost, const double *u,
+                                  int feasible, double *redCost);
+
+/* DecompAlgoPC::adjustMasterDualSolution, Dip/src/DecompAlgoPC.cpp:126-212 (Wentges smoothing):
+ *   dualST[r] = (alpha * dual[r]) + ((1.0 - alpha) * dualRM[r])    (:153-154, :179-181) */
+void dip_oracle_smooth_duals(int nRows, double alpha, const double *dual, const double *dualRM,
+                             double *dualST);
+
 #ifdef __cplusplus
 }
 #endif

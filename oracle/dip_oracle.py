@@ -74,6 +74,10 @@ def _lib():
     lib.dip_oracle_expand_column.restype = C.c_int
     lib.dip_oracle_string_hash.argtypes = [C.c_int, _i32p, _f64p, C.c_char_p, C.c_int]
     lib.dip_oracle_string_hash.restype = C.c_int
+    lib.dip_oracle_pool_reduced_costs.argtypes = [C.c_int, _i64p, _i32p, _f64p, _f64p, _f64p, C.c_int, _f64p]
+    lib.dip_oracle_pool_reduced_costs.restype = C.c_int
+    lib.dip_oracle_smooth_duals.argtypes = [C.c_int, C.c_double, _f64p, _f64p, _f64p]
+    lib.dip_oracle_smooth_duals.restype = None
     _LIB = lib
     return lib
 
@@ -205,6 +209,32 @@ def expand_column(R, N, row_start, col_ind, val, n_base, num_convex, ind, block_
         np.ascontiguousarray(val, np.float64), int(n_base), int(num_convex), len(ind),
         ind if len(ind) else np.zeros(1, np.int32), None, int(block_id), float(tol_zero), out_row, out_val)
     return out_row[:n].copy(), out_val[:n].copy()
+
+
+def pool_reduced_costs(col_start, row_ind, val, orig_cost, u, feasible=True):
+    """DecompVarPool::setReducedCosts: (redCost per waiting column, found_negrc_var)."""
+    cs = np.ascontiguousarray(col_start, np.int64)
+    n = len(cs) - 1
+    out = np.zeros(max(n, 1), np.float64)
+    ri = np.ascontiguousarray(row_ind, np.int32)
+    vv = np.ascontiguousarray(val, np.float64)
+    if len(ri) == 0:
+        ri, vv = np.zeros(1, np.int32), np.zeros(1, np.float64)
+    oc = np.ascontiguousarray(orig_cost, np.float64)
+    if len(oc) == 0:
+        oc = np.zeros(1, np.float64)
+    found = _lib().dip_oracle_pool_reduced_costs(n, cs, ri, vv, oc, np.ascontiguousarray(u, np.float64),
+                                                 int(bool(feasible)), out)
+    return out[:n].copy(), bool(found)
+
+
+def smooth_duals(alpha, dual, dual_rm) -> np.ndarray:
+    """DecompAlgoPC::adjustMasterDualSolution: alpha*dual + (1-alpha)*dualRM."""
+    dual = np.ascontiguousarray(dual, np.float64)
+    dual_rm = np.ascontiguousarray(dual_rm, np.float64)
+    out = np.empty_like(dual)
+    _lib().dip_oracle_smooth_duals(len(dual), float(alpha), dual, dual_rm, out)
+    return out
 
 
 def string_hash(ind, els) -> str:

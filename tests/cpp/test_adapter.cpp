@@ -141,6 +141,90 @@ int main()
     dip_oracle_calc_redcost(R, N, rowStart.data(), colInd.data(), val.data(), uAdj.data(), cost.data(), 1,
                             redCostX.data());
     for (int j = 0; j < N; ++j) CHECK(rcx[j] == redCostX[j]);
+    // ---- the price call as DecompAlgo::processNode runs it (DecompAlgo.cpp:1890-1914): pool
+    // re-pricing, then generateVars with the SAME duals (left on the device), under Wentges smoothing
+    {
+        dipgpu::DecompVarList vars0;
+        double mn0 = 0;
+        pricer->generateVars(u.data(), (int)u.size(), dipgpu::PHASE_PRICE2, 1e-4, vars0, mn0);
+        std::vector<int64_t> cs;
+        std::vector<int32_t> ri;
+        std::vector<double> va;
+        std::vector<uint64_t> hs;
+        pricer->expandColumns(1e-6, cs, ri, va, hs);
+        std::vector<int32_t> which;
+        std::vector<double> oc;
+        for (int k = 0; k < (int)hs.size(); k += 2) which.push_back(k);
+        {
+            int k = 0;
+            for (dipgpu::DecompVar *v : vars0) {
+                if (k % 2 == 0) oc.push_back(v->getOriginalCost());
+                ++k;
+                delete v;
+            }
+        }
+        pricer->poolClear();
+        pricer->poolAppendExpanded(which);
+        // host copy of the same waiting columns for the oracle
+        std::vector<int64_t> pcs(1, 0);
+        std::vector<int32_t> pri;
+        std::vector<double> pva;
+        for (int k : which) {
+            pri.insert(pri.end(), ri.begin() + cs[k], ri.begin() + cs[k + 1]);
+            pva.insert(pva.end(), va.begin() + cs[k], va.begin() + cs[k + 1]);
+            pcs.push_back((int64_t)pri.size());
+        }
+        std::vector<double> u2(u);
+        for (int j = 0; j < n; ++j) u2[j] = unif(seed) * 120.0;
+        // smoothed duals: centre = u, dualRM = u2
+        std::vector<double> st(u.size()), stRef(u.size());
+        pricer->setDualCentre(u.data(), (int)u.size());
+        dipgpu::DecompVarList varsS;
+        double mnS = 0;
+        const int nS = pricer->generateVarsStabilised(u2.data(), (int)u2.size(), 0.1, dipgpu::PHASE_PRICE2, 1e-4, varsS, mnS,
+                                                      st.data());
+        dip_oracle_smooth_duals((int)u.size(), 0.1, u.data(), u2.data(), stRef.data());
+        for (size_t r = 0; r < st.size(); ++r) CHECK(st[r] == stRef[r]);
+        const int keptS = dip_oracle_price_round(R, N, rowStart.data(), colInd.data(), val.data(), cost.data(), stRef.data(),
+                                                 R, 0, m, blockColStart.data(), weight.data(), capacity.data(), 0, 1e-4, 1, n,
+                                                 redCostX.data(), colNnz.data(), colRedCost.data(), colOrigCost.data(),
+                                                 colKeep.data(), mostNeg.data(), z.data(), ind.data(), &mostNegRef, &cells);
+        CHECK(nS == keptS && mnS == mostNegRef);
+        for (dipgpu::DecompVar *v : varsS) {
+            CHECK(v->getReducedCost() == colRedCost[v->getBlockId()]);
+            delete v;
+        }
+        // pool re-pricing with the smoothed duals, then generateVars(u == NULL) on the resident vector
+        std::vector<double> prc, prcRef(which.size());
+        const bool found = pricer->setReducedCosts(stRef.data(), (int)stRef.size(), true, prc);
+        const int foundRef = dip_oracle_pool_reduced_costs((int)which.size(), pcs.data(), pri.data(), pva.data(), oc.data(),
+                                                           stRef.data(), 1, prcRef.data());
+        CHECK(prc.size() == which.size() && found == (foundRef != 0));
+        for (size_t k = 0; k < prc.size(); ++k) CHECK(prc[k] == prcRef[k]);
+        dipgpu::DecompVarList varsR;
+        double mnR = 0;
+        const int nR = pricer->generateVars(nullptr, (int)stRef.size(), dipgpu::PHASE_PRICE2, 1e-4, varsR, mnR);
+        CHECK(nR == keptS && mnR == mostNegRef);
+        for (dipgpu::DecompVar *v : varsR) delete v;
+        // the alpha ladder in one submission: step k == the stabilised round with alpha * 0.9^k
+        std::vector<double> alphas;
+        pricer->generateVarsLadder(u2.data(), (int)u2.size(), 0.1, 0.90, 4, dipgpu::PHASE_PRICE2, 1e-4, alphas);
+        double a = 0.1;
+        for (int k = 0; k < 4; ++k) {
+            CHECK(alphas[(size_t)k] == a);
+            dip_oracle_smooth_duals((int)u.size(), a, u.data(), u2.data(), stRef.data());
+            const int kk = dip_oracle_price_round(R, N, rowStart.data(), colInd.data(), val.data(), cost.data(), stRef.data(),
+                                                  R, 0, m, blockColStart.data(), weight.data(), capacity.data(), 0, 1e-4, 1, n,
+                                                  redCostX.data(), colNnz.data(), colRedCost.data(), colOrigCost.data(),
+                                                  colKeep.data(), mostNeg.data(), z.data(), ind.data(), &mostNegRef, &cells);
+            dipgpu::DecompVarList varsL;
+            double mnL = 0;
+            CHECK(pricer->takeLadderVars(k, varsL, mnL) == kk && mnL == mostNegRef);
+            for (int b = 0; b < m; ++b) CHECK(pricer->ladderRound(k).blockObj[(size_t)b] == z[b]);
+            for (dipgpu::DecompVar *v : varsL) delete v;
+            a = a * 0.90;
+        }
+    }
     delete pricer;
     std::printf("PARITY_OK kept=%d mostNegRC=%.9f cells=%lld launches=%lld\n", kept, mostNegRC, (long long)cells,
                 (long long)launches);

@@ -1,0 +1,257 @@
+"""Parity of the rows SURVEY.md section 8(f) ranks after the round itself, through the C ABI:
+  f-2  waiting-column re-pricing   DecompVarPool::setReducedCosts   (Dip/src/DecompVarPool.cpp:185-203, :22-40)
+  f-3  Wentges smoothing + ladder  DecompAlgoPC::adjustMasterDualSolution (Dip/src/DecompAlgoPC.cpp:126-212),
+       the alpha *= 0.9 retry of DecompAlgo::addVarsToPool (Dip/src/DecompAlgo.cpp:5642-5655),
+       and batches of dual vectors priced in one submission.
+Every batched / stabilised round must equal, field by field, the single-vector round of the same
+dual vector (which the other GPU tests pin against the oracle), and the oracle itself."""
+import numpy as np
+import pytest
+
+from dip_b200 import instances as I
+from dip_b200.pricer import PROFIT_FP64, PROFIT_PISINGER_INT
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_round(a, b):
+    np.testing.assert_array_equal(a.blockObj, b.blockObj)
+    np.testing.assert_array_equal(a.blockNnz, b.blockNnz)
+    np.testing.assert_array_equal(a.blockRedCost, b.blockRedCost)
+    np.testing.assert_array_equal(a.blockOrigCost, b.blockOrigCost)
+    np.testing.assert_array_equal(a.blockMostNegRC, b.blockMostNegRC)
+    assert a.nCols == b.nCols and a.cells == b.cells
+    assert a.mostNegReducedCost == b.mostNegReducedCost
+    np.testing.assert_array_equal(a.colBlock[:a.nCols], b.colBlock[:b.nCols])
+    np.testing.assert_array_equal(a.colStart[:a.nCols + 1], b.colStart[:b.nCols + 1])
+    n = int(a.colStart[a.nCols])
+    np.testing.assert_array_equal(a.colInd[:n], b.colInd[:n])
+
+
+def _oracle_round(oracle, model, u, profit_mode=0, eps=1e-4):
+    return oracle.price_round(model.R, model.N, model.row_start, model.col_ind, model.val, model.objective, u,
+                              model.n_base_rows, model.m, model.block_col_start, model.weight, model.capacity,
+                              profit_mode=profit_mode, red_cost_eps=eps)
+
+
+def _check_vs_oracle(res, ref):
+    np.testing.assert_array_equal(res.blockObj, ref.z)
+    np.testing.assert_array_equal(res.blockNnz, ref.col_nnz)
+    kept = [b for b in range(len(ref.z)) if ref.col_keep[b]]
+    assert list(res.colBlock[:res.nCols]) == kept
+    for k, b in enumerate(kept):
+        assert list(res.column(k)) == list(ref.col_ind[b])
+    assert res.cells == ref.cells
+
+
+@pytest.mark.parametrize("profit_mode", [PROFIT_FP64, PROFIT_PISINGER_INT])
+@pytest.mark.parametrize("which", ["gap_d", "gap_c"])
+def test_batch_equals_single_rounds(oracle, pricer, which, profit_mode):
+    model = I.gap_pricing_model(I.gap_class_d() if which == "gap_d" else I.gap_class_c())
+    pricer.setModel(model, profit_mode)
+    rng = np.random.default_rng(31)
+    U = np.stack([I.gap_duals(model, rng) for _ in range(7)])
+    if profit_mode == PROFIT_PISINGER_INT:
+        U = np.round(U, 3)   # a few decimals, as calcScaleFactor expects
+    batch = pricer.priceRoundsBatch(U)
+    assert len(batch) == 7
+    for v in range(7):
+        single = pricer.priceRound(U[v])
+        _same_round(batch[v], single)
+        _check_vs_oracle(batch[v], _oracle_round(oracle, model, U[v], profit_mode))
+    # a second batch on the same context (publication epochs must carry over), other phase
+    batch1 = pricer.priceRoundsBatch(U[:3], phase=1)
+    for v in range(3):
+        _same_round(batch1[v], pricer.priceRound(U[v], phase=1))
+
+
+def test_batch_gap_e_and_select_for_expansion(oracle, pricer):
+    model = I.gap_pricing_model(I.gap_class_e())
+    pricer.setModel(model)
+    rng = np.random.default_rng(8)
+    U = np.stack([I.gap_duals(model, rng) for _ in range(5)])
+    batch = pricer.priceRoundsBatch(U)
+    _same_round(batch[0], pricer.priceRound(U[0]))
+    _same_round(batch[4], pricer.priceRound(U[4]))
+    _check_vs_oracle(batch[2], _oracle_round(oracle, model, U[2]))
+    # master columns of batch result 3 == those of the single round of vector 3
+    batch = pricer.priceRoundsBatch(U)
+    pricer.selectBatchResult(3)
+    cs, ri, va, hs = pricer.expandColumns()
+    pricer.priceRound(U[3])
+    cs2, ri2, va2, hs2 = pricer.expandColumns()
+    np.testing.assert_array_equal(cs, cs2)
+    np.testing.assert_array_equal(ri, ri2)
+    np.testing.assert_array_equal(va, va2)
+    np.testing.assert_array_equal(hs, hs2)
+
+
+def test_batch_on_a_large_shard_uses_the_unfused_path(oracle, pricer):
+    """More than 256 blocks: no fused kernel, the batch is priced vector after vector."""
+    b = I.random_batch(300, 0, 40, 0, 120, seed=3)
+    N = int(b.block_col_start[-1])
+    m = 300
+    # identity-like core: one assignment-style row per column group so that redCost = c - u[row]
+    R = 40
+    rows = np.arange(N) % R
+    order = np.argsort(rows, kind="stable")
+    rs = np.zeros(R + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=R), out=rs[1:])
+    ci = order.astype(np.int32)
+    v = np.ones(N)
+    pricer.setModelCore(R, N, rs, ci, v, R, m)
+    pricer.setObjective(b.orig_cost)
+    pricer.setKnapsackBlocks(b.block_col_start, b.weight, b.capacity)
+    rng = np.random.default_rng(5)
+    U = rng.uniform(0, 2 * b.orig_cost.mean(), size=(3, R + m))
+    U[:, R:] = rng.uniform(-10, 0, size=(3, m))
+    batch = pricer.priceRoundsBatch(U)
+    for k in range(3):
+        _same_round(batch[k], pricer.priceRound(U[k]))
+
+
+def test_smoothing_ladder_matches_oracle_and_single_rounds(oracle, pricer):
+    model = I.gap_pricing_model(I.gap_class_d())
+    pricer.setModel(model)
+    rng = np.random.default_rng(12)
+    center = I.gap_duals(model, rng)
+    uRM = I.gap_duals(model, rng)
+    pricer.stabSetCenter(center)
+    results, alphas = pricer.priceRoundStabLadder(uRM, 0.1, 6)
+    a = 0.1
+    for k in range(6):
+        assert alphas[k] == a                         # DualStabAlpha *= 0.90, repeated (DecompAlgo.cpp:5646)
+        st = oracle.smooth_duals(a, center, uRM)      # DecompAlgoPC.cpp:179-181
+        np.testing.assert_array_equal(pricer.smoothedDuals(k), st)
+        _same_round(results[k], pricer.priceRound(st))
+        _check_vs_oracle(results[k], _oracle_round(oracle, model, st))
+        a = a * 0.90
+    # accepting step 2 moves the centre there (DecompAlgoPC.h:124-133); the next smoothing starts from it
+    results, alphas = pricer.priceRoundStabLadder(uRM, 0.1, 3)
+    st2 = oracle.smooth_duals(alphas[2], center, uRM)
+    pricer.stabAccept(2)
+    uRM2 = I.gap_duals(model, rng)
+    res, st = pricer.priceRoundStab(uRM2, 0.25)
+    np.testing.assert_array_equal(st, oracle.smooth_duals(0.25, st2, uRM2))
+    _same_round(res, pricer.priceRound(st))
+    # the single stabilised round is also the context's "last round" for the expansion
+    cs, ri, va, hs = pricer.expandColumns()
+    assert len(cs) == res.nCols + 1
+
+
+def test_first_stabilised_call_uses_dual_rm_as_centre(oracle, pricer):
+    model = I.gap_pricing_model(I.gap_class_c())
+    pricer.setModel(model)
+    uRM = I.gap_duals(model, np.random.default_rng(2))
+    res, st = pricer.priceRoundStab(uRM, 0.1)
+    np.testing.assert_array_equal(st, oracle.smooth_duals(0.1, uRM, uRM))   # DecompAlgoPC.cpp:163-173
+    _same_round(res, pricer.priceRound(st))
+
+
+def _expanded_pool(oracle, pricer, model, n_rounds, rng):
+    """Prices n_rounds dual vectors, expands the kept columns and appends them to the pool; returns
+    the host copy (colStart, rowInd, val, origCost) assembled from the oracle's own expansion."""
+    cs_all, ri_all, va_all, oc_all = [0], [], [], []
+    for _ in range(n_rounds):
+        res = pricer.priceRound(I.gap_duals(model, rng))
+        cs, ri, va, hs = pricer.expandColumns()
+        which = np.arange(res.nCols, dtype=np.int32)[::2]   # every other column "survives the duplicate test"
+        pricer.poolAppendExpanded(which)
+        for k in which:
+            rr, vv = oracle.expand_column(model.R, model.N, model.row_start, model.col_ind, model.val, model.n_base_rows,
+                                          model.m, res.column(k), int(res.colBlock[k]))
+            ri_all.extend(rr.tolist())
+            va_all.extend(vv.tolist())
+            cs_all.append(len(ri_all))
+            oc_all.append(float(res.colOrigCost[k]))
+    return np.array(cs_all, np.int64), np.array(ri_all, np.int32), np.array(va_all), np.array(oc_all)
+
+
+def test_pool_reduced_costs_from_expanded_columns(oracle, pricer):
+    model = I.gap_pricing_model(I.gap_class_d())
+    pricer.setModel(model)
+    rng = np.random.default_rng(21)
+    cs, ri, va, oc = _expanded_pool(oracle, pricer, model, 4, rng)
+    assert pricer.poolSize() == (len(oc), len(ri))
+    u = I.gap_duals(model, rng)
+    for feasible in (True, False):
+        got, found = pricer.poolSetReducedCosts(u, feasible)
+        ref, ref_found = oracle.pool_reduced_costs(cs, ri, va, oc, u, feasible)
+        np.testing.assert_array_equal(got, ref)          # same products, same order: bit-equal
+        assert found == ref_found
+    # the duals are resident now: generateVars with u == NULL equals the round of u
+    res_resident = pricer.priceRoundResident()
+    res = pricer.priceRound(u)
+    _same_round(res_resident, res)
+    # addVarsFromPool took columns 1, 4, 5 out: the rest keep their values
+    keep = np.array([k for k in range(len(oc)) if k not in (1, 4, 5)], np.int32)
+    pricer.poolKeep(keep)
+    got, _ = pricer.poolSetReducedCosts(u)
+    np.testing.assert_array_equal(got, ref_after := oracle.pool_reduced_costs(cs, ri, va, oc, u)[0][keep])
+    assert pricer.poolSize()[0] == len(keep) and len(ref_after) == len(keep)
+    pricer.poolClear()
+    got, found = pricer.poolSetReducedCosts(u)
+    assert len(got) == 0 and not found
+
+
+def test_pool_from_host_columns_ragged_and_large(oracle, pricer):
+    """Host-built waiting columns: empty columns, a column longer than one staging chunk (512), many
+    columns; threshold semantics of found_negrc_var (<= -1e-10)."""
+    rng = np.random.default_rng(6)
+    R, N, m = 3000, 64, 4
+    rs = np.zeros(R + 1, np.int64)
+    pricer.setModelCore(R, N, rs, np.zeros(0, np.int32), np.zeros(0), R, m)
+    lens = np.concatenate([[0, 1, 2, 700, 0, 513, 512, 31, 33], rng.integers(0, 90, size=5000)])
+    cs = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=cs[1:])
+    ri = np.concatenate([np.sort(rng.choice(R + m, size=l, replace=False)) for l in lens]).astype(np.int32)
+    va = rng.uniform(-3, 3, size=len(ri))
+    oc = rng.uniform(-5, 50, size=len(lens))
+    pricer.poolAppend(cs[:101], ri[:cs[100]], va[:cs[100]], oc[:100])                    # two appends: growth path
+    pricer.poolAppend(cs[100:] - cs[100], ri[cs[100]:], va[cs[100]:], oc[100:])
+    u = rng.standard_normal(R + m)
+    u[rng.random(R + m) < 0.3] = 0.0
+    got, found = pricer.poolSetReducedCosts(u)
+    ref, ref_found = oracle.pool_reduced_costs(cs, ri, va, oc, u)
+    np.testing.assert_array_equal(got, ref)
+    assert found == ref_found is True
+    # no column prices out
+    pricer.poolClear()
+    pricer.poolAppend(np.array([0, 1, 1], np.int64), np.array([5], np.int32), np.array([1.0]), np.array([2.0, 0.0]))
+    uu = np.zeros(R + m)
+    uu[5] = 2.0
+    got, found = pricer.poolSetReducedCosts(uu)
+    np.testing.assert_array_equal(got, [0.0, 0.0])
+    assert not found
+    uu[5] = 2.0 + 1e-9
+    got, found = pricer.poolSetReducedCosts(uu)
+    assert found and got[0] < -1e-10
+
+
+def test_spmv_tile_shapes_are_bit_equal(oracle, pricer):
+    """Every tiling of the stream kernel (entry budget, column budget, ring depth, warps, duals in
+    shared / global memory) gives the same bits as the oracle's scatter."""
+    rng = np.random.default_rng(14)
+    R, N, m, nBase = 900, 20000, 8, 800
+    nnz = 150_000
+    r = np.sort(rng.integers(0, R, size=nnz))
+    rs = np.zeros(R + 1, np.int64)
+    np.cumsum(np.bincount(r, minlength=R), out=rs[1:])
+    ci = rng.integers(0, N, size=nnz).astype(np.int32)
+    v = rng.uniform(-10, 10, size=nnz)
+    c = rng.uniform(0, 100, size=N)
+    pricer.setModelCore(R, N, rs, ci, v, nBase, m)
+    pricer.setObjective(c)
+    u = rng.standard_normal(R + m)
+    u[rng.random(R + m) < 0.3] = 0.0
+    ref = oracle.calc_redcost(R, N, rs, ci, v, oracle.adjust_duals(u, nBase, m), c)
+    ref1 = oracle.calc_redcost(R, N, rs, ci, v, oracle.adjust_duals(u, nBase, m), c, True)
+    for chunk, max_cols, stages, warps, usmem in [(0, 0, 0, 0, -1), (64, 32, 2, 1, 1), (96, 64, 3, 5, 0), (512, 128, 4, 32, 1),
+                                                   (2048, 128, 2, 7, 1), (200, 96, 8, 3, 0)]:
+        pricer.set_option("spmv_chunk", chunk)
+        pricer.set_option("spmv_max_cols", max_cols)
+        pricer.set_option("spmv_stages", stages)
+        pricer.set_option("spmv_warps", warps)
+        pricer.set_option("spmv_u_smem", usmem)
+        np.testing.assert_array_equal(pricer.calcRedCost(u), ref)
+        np.testing.assert_array_equal(pricer.calcRedCost(u, 1), ref1)
