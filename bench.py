@@ -345,6 +345,9 @@ def main():
     smem_peak = None
     if not args.skip_extras:
         smem_peak = pr.measureSmemGBs()
+        extras["batched"] = bench_batched(pr, model, duals, u_pin, cells_per_round, flush_l2, torch, smem_peak, world,
+                                          max_over_ranks)
+        extras["pool"] = bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank)
     cells_mean = float(np.mean(cells_per_round))
     dp_ms = stage_ms["knapsack_dp"]
     # dominant kernel of the step = knap_dp_kernel; algorithmic shared-memory bytes = 24 B / cell
@@ -399,6 +402,10 @@ def main():
             line["roofline_dp_csp"] = extras["dp_csp"]
         if "spmv_milpblock" in extras:
             line["roofline_spmv"] = extras["spmv_milpblock"]
+        if "batched" in extras:
+            line["batched_rounds"] = extras["batched"]
+        if "pool" in extras:
+            line["roofline_pool"] = extras["pool"]
         if expand is not None:
             line["expand_columns"] = expand
         if sharded is not None:
@@ -410,6 +417,92 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_batched(pr, model, duals, u_pin, cells_per_round, flush_l2, torch, smem_peak, world, max_over_ranks):
+    """Several dual vectors per submission: (i) dipgpu_price_rounds_batch on the 16 pinned
+    dual vectors, (ii) the Wentges ladder of 8 smoothing parameters from ONE uploaded dualRM
+    (dipgpu_price_round_stab_ladder).  Host wall clock around the synchronous C-ABI calls, H2D and D2H
+    inside, L2 flushed before every call; stage times from the library's CUDA events."""
+    from dip_b200 import capi
+    import ctypes as C
+    out = {}
+    n = N_DUALS
+    res, arr = pr._batch_results(n)
+    reps = 30
+    for name, steps in (("batch16", n), ("ladder8", 8)):
+        def call():
+            if name == "batch16":
+                pr.priceRoundsBatchRaw(n, u_pin.array.ctypes.data, model.u_len, capi.PHASE_PRICE2, RC_EPS, arr)
+            else:
+                pr.priceRoundStabLadderRaw(u_pin.array[1].ctypes.data, model.u_len, 0.1, 0.90, 8, capi.PHASE_PRICE2,
+                                           RC_EPS, arr)
+        if name == "ladder8":
+            pr.stabSetCenter(duals[0])
+        for _ in range(3):
+            call()
+        pr.set_option("stage_timing", 1)
+        t, stage = 0.0, {}
+        for _ in range(reps):
+            flush_l2()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            call()
+            t += time.perf_counter() - t0
+            for nm, ms in pr.last_stage_ms().items():
+                stage.setdefault(nm, []).append(ms)
+        pr.set_option("stage_timing", 0)
+        t = max_over_ranks(t)
+        st = {nm: float(np.mean(v)) for nm, v in stage.items()}
+        cells = float(sum(arr[k].cells for k in range(steps)))
+        dp_ms = st["knapsack_dp"]
+        ach = cells * 24.0 / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None
+        out[name] = {
+            "rounds_per_call": steps, "e2e_rounds_per_s": world * steps * reps / t, "ms_per_call": 1e3 * t / reps,
+            "stage_ms": st, "dp_cells_per_call": cells,
+            "dp_roofline": {"kernel": "knap_dp_kernel (fused, gridDim.y = vectors)", "bound": "smem", "achieved": ach,
+                            "peak": smem_peak, "unit": "GB/s", "frac": ach / smem_peak if (ach and smem_peak) else None,
+                            "gcups": cells / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None},
+        }
+    out["note"] = ("value / e2e above stay ONE dual vector per step (what DecompAlgo::generateVars prices per call); "
+                   "these are the same rounds submitted several at a time")
+    return out
+
+
+def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank):
+    """Waiting-column re-pricing (SURVEY 8f-2, DecompVarPool::setReducedCosts) on a synthetic pool:
+    2*10^5 master columns of 20..80 entries over the GAP-E master rows.  Kernel time from the library's
+    CUDA events (L2 flushed), algorithmic bytes 12*nnz + 24*cols + 8*uLen."""
+    from dip_b200.pricer import GpuPricer
+    rng = np.random.default_rng(77)
+    u_len = 257_680
+    n_cols = 200_000
+    lens = rng.integers(20, 81, size=n_cols)
+    cs = np.zeros(n_cols + 1, np.int64)
+    np.cumsum(lens, out=cs[1:])
+    nnz = int(cs[-1])
+    ri = rng.integers(0, u_len, size=nnz).astype(np.int32)
+    va = np.ones(nnz)
+    oc = rng.uniform(0, 1000, size=n_cols)
+    u = rng.uniform(0, 50, size=u_len)
+    pr = GpuPricer(local_rank)
+    pr.setModelCore(u_len - 1, 1, np.zeros(u_len, np.int64), np.zeros(0, np.int32), np.zeros(0), u_len - 1, 1)
+    pr.poolAppend(cs, ri, va, oc)
+    pr.poolSetReducedCosts(u)
+    pr.set_option("stage_timing", 1)
+    ts = []
+    for _ in range(12):
+        flush_l2()
+        torch.cuda.synchronize()
+        pr.poolSetReducedCosts(None)
+        ts.append(pr.last_stage_ms()["redcost"])
+    pr.close()
+    ms = float(np.mean(ts[2:]))
+    by = 12 * nnz + 24 * n_cols + 8 * u_len
+    ach = by / (ms * 1e-3) / 1e9
+    return {"kernel": "pool_redcost_kernel", "workload": f"{n_cols} waiting columns, {nnz} entries, {u_len} master rows",
+            "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "avg_launch_ms": ms, "algorithmic_bytes": by, "peak_source": peak_src}
 
 
 def bench_expand(pr, model, duals, ptrs, res, flush_l2, torch, rank):
@@ -586,7 +679,7 @@ def bench_spmv(torch, dev, local_rank, hbm_peak, peak_src, flush_l2, world, rank
     pr.close()
     by = model.spmv_bytes()
     ach = by / (ms * 1e-3) / 1e9
-    return {"kernel": "redcost_csc_kernel", "workload": model.name, "bound": "hbm", "achieved": ach,
+    return {"kernel": "redcost_stream_kernel", "workload": model.name, "bound": "hbm", "achieved": ach,
             "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic("prof_spmv_milp"),
             "avg_launch_ms": ms,
             "min_launch_ms": float(np.min(times)), "algorithmic_bytes": by, "peak_source": peak_src,

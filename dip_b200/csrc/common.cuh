@@ -191,6 +191,11 @@ struct Ctx {
     double *dZShort = nullptr;
     int32_t *dCandInd = nullptr;        // per column slot: candidate column indices (ascending)
     int32_t *dScratch = nullptr;        // per column slot: descending taken list
+    // node bounds of the columns (DecompAlgo::setSubProbBounds): dipgpu_set_col_bounds
+    bool haveFix = false;
+    uint8_t *dFix = nullptr;            // per column: bit 0 = fixed to 1, bit 1 = fixed to 0
+    int32_t *dCapEff = nullptr;         // per block: capacity minus the fixed-to-1 weights (< 0: they do not fit)
+    std::vector<int32_t> hWeight;
     int maxCapacity = 0;       // of the shard
     int maxBlockCols = 0;      // of the shard
     int maxUsableWeight = 0;   // of the shard: max weight <= its block's capacity

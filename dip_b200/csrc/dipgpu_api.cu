@@ -346,17 +346,24 @@ static int ensureBatch(Ctx *c, int nVec)
 static int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st)
 {
     int rc;
+    const bool timed = c->stageTiming;
+    if (timed) cudaEventRecord(c->ev[1], st);
     if (c->geom.fuse || c->nLocal == 0) {
         if ((rc = launchRedCostBatch(c, c->dUBatch, (int64_t)c->uStride, c->dRedCostBatch, (int64_t)c->rcStride, nVec, phase, st))) return rc;
+        if (timed) cudaEventRecord(c->ev[2], st);
         if ((rc = launchKnapsackPrepBatch(c, c->dRedCostBatch, (int64_t)c->rcStride, nVec, st))) return rc;
-        return launchKnapsackDpBatch(c, c->dRedCostBatch, (int64_t)c->rcStride, c->dUBatch + c->nBaseRows, (int64_t)c->uStride, eps, nVec, st);
+        rc = launchKnapsackDpBatch(c, c->dRedCostBatch, (int64_t)c->rcStride, c->dUBatch + c->nBaseRows, (int64_t)c->uStride, eps, nVec, st);
+        if (timed) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
+        return rc;
     }
+    if (timed) { cudaEventRecord(c->ev[2], st); }
     for (int v = 0; v < nVec; ++v) {
         const double *u = c->dUBatch + (size_t)v * c->uStride;
         if ((rc = launchRedCost(c, u, phase, st))) return rc;
         if ((rc = enqueueSolve(c, c->dRedCost, u + c->nBaseRows, eps, st, false))) return rc;
         DIPGPU_CUDA(c, cudaMemcpyAsync(static_cast<char *>(c->dResultBatch) + (size_t)v * c->resStride, c->dResult, c->resultBytes, cudaMemcpyDeviceToDevice, st));
     }
+    if (timed) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
     return DIPGPU_OK;
 }
 
@@ -365,7 +372,9 @@ static int fetchBatch(Ctx *c, int nVec, dipgpu_cols *outs, cudaStream_t st)
 {
     const size_t spec = std::min(c->resultBytes, c->layout.offInd + (size_t)65536);
     DIPGPU_CUDA(c, cudaMemcpy2DAsync(c->hResultBatch, c->resStride, c->dResultBatch, c->resStride, spec, (size_t)nVec, cudaMemcpyDeviceToHost, st));
+    if (c->stageTiming) cudaEventRecord(c->ev[6], st);
     DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+    collectStageMs(c);
     c->d2h += (int64_t)spec * nVec;
     bool more = false;
     for (int v = 0; v < nVec; ++v) {
@@ -502,6 +511,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems); devFree(&c->dScale); devFree(&c->dShortcut); devFree(&c->dSel); devFree(&c->dZShort);
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
     freeBatch(c);
+    devFree(&c->dFix); devFree(&c->dCapEff);
     devFree(&c->dCenter); devFree(&c->dPoolStart); devFree(&c->dPoolRow); devFree(&c->dPoolVal);
     devFree(&c->dPoolOrigCost); devFree(&c->dPoolRedCost); devFree(&c->dPoolFlag);
     if (c->dResult) cudaFree(c->dResult);
@@ -629,6 +639,8 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
     c->profitMode = profitMode;
     c->hBlockColStart.assign(blockColStart, blockColStart + m + 1);
     c->hCapacity.assign(capacity, capacity + m);
+    c->hWeight.assign(weight, weight + nCols);
+    c->haveFix = false;  // node bounds refer to the previous block structure
     c->hMaxUsableW.assign((size_t)m, 0);
     for (int b = 0; b < m; ++b) {
         int mw = 0;
@@ -637,6 +649,7 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
         c->hMaxUsableW[b] = mw;
     }
     int rc;
+    devFree(&c->dFix); devFree(&c->dCapEff);
     if ((rc = devAlloc(c, &c->dBlockColStart, (size_t)m + 1))) return rc;
     if ((rc = devAlloc(c, &c->dCapacity, (size_t)m))) return rc;
     if ((rc = devAlloc(c, &c->dWeight, (size_t)nCols + 16))) return rc;
@@ -657,6 +670,42 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
     c->haveBlocks = true;
     c->lastRoundOnHost = false;
     return setBlockRange(c, 0, m);
+}
+
+int dipgpu_set_col_bounds(dipgpu_ctx *ctx, const double *colLB, const double *colUB, int32_t N)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "set_col_bounds before set_knapsack_blocks");
+    c->lastRoundOnHost = false;
+    if (!colLB && !colUB) {
+        c->haveFix = false;
+        return DIPGPU_OK;
+    }
+    if (!colLB || !colUB || N < c->nBlockCols) return fail(c, DIPGPU_ERR_INVALID, "set_col_bounds: need both bound arrays of length >= %d", c->nBlockCols);
+    if (c->profitMode == DIPGPU_PROFIT_PISINGER_INT)
+        return fail(c, DIPGPU_ERR_UNSUPPORTED, "set_col_bounds: node bounds are enforced in the fp64 DP mode only");
+    const int n = c->nBlockCols;
+    std::vector<uint8_t> fix((size_t)n + 16, 0);
+    std::vector<int32_t> capEff((size_t)std::max(c->m, 1), 0);
+    for (int b = 0; b < c->m; ++b) {
+        int64_t left = c->hCapacity[b];
+        bool clash = false;
+        for (int j = c->hBlockColStart[b]; j < c->hBlockColStart[b + 1]; ++j) {
+            const bool one = colLB[j] > 0.5, zero = colUB[j] < 0.5;  // binary columns: bounds are 0 or 1
+            fix[j] = (uint8_t)((one ? 1 : 0) | (zero ? 2 : 0));
+            if (one) left -= c->hWeight[j];
+            if (one && zero) clash = true;
+        }
+        capEff[b] = (clash || left < 0) ? -1 : (int32_t)left;
+    }
+    int rc;
+    if (!c->dFix && (rc = devAlloc(c, &c->dFix, (size_t)n + 16))) return rc;
+    if (!c->dCapEff && (rc = devAlloc(c, &c->dCapEff, (size_t)std::max(c->m, 1)))) return rc;
+    DIPGPU_CUDA(c, cudaMemcpy(c->dFix, fix.data(), fix.size(), cudaMemcpyHostToDevice));
+    DIPGPU_CUDA(c, cudaMemcpy(c->dCapEff, capEff.data(), sizeof(int32_t) * capEff.size(), cudaMemcpyHostToDevice));
+    c->h2d += (int64_t)fix.size() + 4 * c->m;
+    c->haveFix = true;
+    return DIPGPU_OK;
 }
 
 int dipgpu_set_block_range(dipgpu_ctx *ctx, int32_t first, int32_t count)
@@ -753,6 +802,7 @@ int dipgpu_price_rounds_batch(dipgpu_ctx *ctx, int32_t nVec, const double *U, in
     if (nVec == 0) return DIPGPU_OK;
     if ((rc = ensureBatch(c, nVec))) return rc;
     cudaStream_t st = c->stream;
+    if (c->stageTiming) cudaEventRecord(c->ev[0], st);
     DIPGPU_CUDA(c, cudaMemcpy2DAsync(c->dUBatch, sizeof(double) * c->uStride, U, sizeof(double) * (size_t)uLen,
                                      sizeof(double) * (size_t)uLen, (size_t)nVec, cudaMemcpyHostToDevice, st));
     c->h2d += (int64_t)sizeof(double) * uLen * nVec;
@@ -817,6 +867,7 @@ int dipgpu_price_round_stab_ladder(dipgpu_ctx *ctx, const double *uRM, int32_t u
     al[0] = alpha;
     for (int k = 1; k < nSteps; ++k) al[k] = al[k - 1] * shrink;
     if (alphasOut) memcpy(alphasOut, al, sizeof(double) * (size_t)nSteps);
+    if (c->stageTiming) cudaEventRecord(c->ev[0], st);
     DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, uRM, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, st));
     DIPGPU_CUDA(c, cudaMemcpyAsync(c->dAlphaLadder, al, sizeof(double) * (size_t)nSteps, cudaMemcpyHostToDevice, st));
     c->h2d += (int64_t)sizeof(double) * (uLen + nSteps);
@@ -1028,7 +1079,9 @@ int dipgpu_pool_set_reduced_costs(dipgpu_ctx *ctx, const double *u, int32_t uLen
         c->h2d += (int64_t)sizeof(double) * uLen;
         c->dualsResident = true;
     }
+    if (c->stageTiming) cudaEventRecord(c->ev[1], st);
     if ((rc = launchPoolRedCost(c, c->dU, feasible ? 1 : 0, st))) return rc;
+    if (c->stageTiming) cudaEventRecord(c->ev[2], st);
     int32_t flag = 0;
     if (redCost && c->poolCols > 0) {
         DIPGPU_CUDA(c, cudaMemcpyAsync(redCost, c->dPoolRedCost, sizeof(double) * (size_t)c->poolCols, cudaMemcpyDeviceToHost, st));
@@ -1036,6 +1089,12 @@ int dipgpu_pool_set_reduced_costs(dipgpu_ctx *ctx, const double *u, int32_t uLen
     }
     DIPGPU_CUDA(c, cudaMemcpyAsync(&flag, c->dPoolFlag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+    if (c->stageTiming) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) != cudaSuccess) ms = 0.f;
+        for (float &x : c->stageMs) x = 0.f;
+        c->stageMs[1] = ms;  // slot [1]: the dual-vector pass (here the pool kernel incl. its flag memset)
+    }
     c->d2h += 4;
     if (foundNegRC) *foundNegRC = flag;
     return DIPGPU_OK;

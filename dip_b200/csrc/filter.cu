@@ -43,7 +43,7 @@ FilterArgs makeFilterArgs(Ctx *c, double redCostEps)
     a.keptInd = reinterpret_cast<int32_t *>(res + c->layout.offInd);
     a.candInd = c->dCandInd;
     a.blockColStart = c->dBlockColStart;
-    a.capacity = c->dCapacity;
+    a.capacity = c->haveFix ? c->dCapEff : c->dCapacity;
     a.nItems = c->dNItems;
     a.firstBlock = c->firstBlock;
     a.nLocal = c->nLocal;

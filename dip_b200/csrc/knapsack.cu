@@ -104,6 +104,7 @@ struct BackArgs {
     unsigned int *doneCounter;  // non-NULL: the last CTA to finish runs the filter (stage c)
     const int32_t *shortcut;    // Pisinger mode (else NULL): per local block 0 = DP, 1 = all, 2 = sel
     const int32_t *sel;         // 2 per local block
+    const uint8_t *fix;         // node bounds (else NULL): per column bit 0 = fixed to 1, bit 1 = fixed to 0
 };
 
 constexpr int kBackThreads = 128;
@@ -171,6 +172,15 @@ __device__ __forceinline__ void backtrackOne(const BackArgs &a, int lb, int lane
     const int RC = a.rowCells;
     const uint32_t *bitsBase = a.bits + a.bitsOff[lb];
     int j = a.capacity[b];
+    if (j < 0) {
+        // the columns fixed to 1 by the node bounds do not fit: no column for this block
+        if (lane == 0) {
+            a.blockRedCost[lb] = __longlong_as_double(0x7ff0000000000000LL);
+            a.blockOrigCost[lb] = 0.0;
+            a.blockNnz[lb] = 0;
+        }
+        return;
+    }
     int i = nItems - 1;
     int cnt = 0;
     while (i >= 0) {
@@ -192,13 +202,46 @@ __device__ __forceinline__ void backtrackOne(const BackArgs &a, int lb, int lane
         i = item - 1;
     }
     __syncwarp();
+    if (a.fix != nullptr) {
+        // node bounds: the columns fixed to 1 join the column (they were kept out of the DP and their
+        // weight out of the capacity).  Chosen items ascending, then a backward merge with the fixed
+        // ones (ascending by construction) -- large shards only, the fused kernel merges in parallel.
+        for (int k = lane; k < cnt; k += 32) a.candInd[cs + k] = cs + __ldcg(a.scratch + cs + cnt - 1 - k);
+        __syncwarp();
+        const int n = a.blockColStart[b + 1] - cs;
+        int nf = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int q = base + lane;
+            const bool f = q < n && (a.fix[cs + q] & 1u);
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (f) a.scratch[cs + nf + __popc(bal & ((1u << lane) - 1u))] = cs + q;
+            nf += __popc(bal);
+        }
+        __syncwarp();
+        if (lane == 0 && nf > 0) {
+            __threadfence_block();
+            int x = cnt - 1, y = nf - 1, o = cnt + nf - 1;
+            while (y >= 0) {
+                const int fy = __ldcg(a.scratch + cs + y);
+                if (x >= 0 && __ldcg(a.candInd + cs + x) > fy) a.candInd[cs + o--] = __ldcg(a.candInd + cs + x--);
+                else { a.candInd[cs + o--] = fy; --y; }
+            }
+        }
+        cnt += nf;
+        __syncwarp();
+    }
     double rcs = 0.0, ocs = 0.0;
     for (int base = 0; base < cnt; base += 32) {
         const int k = base + lane;
         double r = 0.0, o = 0.0;
         if (k < cnt) {
-            const int col = cs + __ldcg(a.scratch + cs + cnt - 1 - k);
-            a.candInd[cs + k] = col;
+            int col;
+            if (a.fix != nullptr) {
+                col = __ldcg(a.candInd + cs + k);
+            } else {
+                col = cs + __ldcg(a.scratch + cs + cnt - 1 - k);
+                a.candInd[cs + k] = col;
+            }
             r = a.redCost[col];
             o = a.obj[col];
         }
@@ -286,19 +329,25 @@ struct KnapArgs {
     FilterArgs filt;
 };
 
+// Fused shapes: the TMA destinations of the raw reduced costs / weights are dead once the items are
+// compacted, so they share their bytes with the decision bits (written by the DP afterwards), and the
+// taken list of the backtrack lives in the compacted-profit array (dead after the DP): ~26 KB less
+// per CTA on GAP-E, i.e. three resident CTAs per SM instead of two when dual vectors are batched.
 __host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunkCols, bool fuse)
 {
     size_t b = 0;
     b += sizeof(double) * 2 * ((size_t)rowCells + (size_t)guard);  // two row buffers, each behind its guard
-    b += sizeof(double) * ((size_t)chunkCols + 2);      // raw reduced costs (TMA dst)
     b += sizeof(double) * ((size_t)chunkCols + 4);      // compacted profits (+ prefetch pad)
-    b += sizeof(int32_t) * ((size_t)chunkCols + 4);     // raw weights (TMA dst)
     b += sizeof(int32_t) * ((size_t)chunkCols + 4);     // compacted weights (+ prefetch pad)
     b += sizeof(int32_t) * 32;                          // per-warp counts
     b += 16;                                            // mbarrier
+    const size_t raw = sizeof(double) * ((size_t)chunkCols + 2) + sizeof(int32_t) * ((size_t)chunkCols + 4);
     if (fuse) {
-        b += sizeof(int32_t) * 2 * ((size_t)chunkCols + 4);                     // item columns, taken list
-        b += sizeof(uint32_t) * (size_t)((chunkCols + 31) / 32) * (size_t)rowCells;  // decision bits
+        b += sizeof(int32_t) * ((size_t)chunkCols + 4);                                          // item columns
+        const size_t bits = sizeof(uint32_t) * (size_t)((chunkCols + 31) / 32) * (size_t)rowCells;  // decision bits
+        b += bits > raw ? bits : raw;
+    } else {
+        b += raw;
     }
     return b;
 }
@@ -325,15 +374,16 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const int CH = a.chunkCols;
     double *rowBase = reinterpret_cast<double *>(smemRaw);
     const int bufStride = RC + G;
-    double *rawRc = rowBase + 2 * bufStride;
-    double *itP = rawRc + (CH + 2);
-    int32_t *rawW = reinterpret_cast<int32_t *>(itP + (CH + 4));
-    int32_t *itW = rawW + (CH + 4);
+    double *itP = rowBase + 2 * bufStride;
+    int32_t *itW = reinterpret_cast<int32_t *>(itP + (CH + 4));
     int32_t *warpCnt = itW + (CH + 4);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(warpCnt + 32);
-    int32_t *itC = reinterpret_cast<int32_t *>(mbar + 2);             // FUSE only
-    int32_t *sTaken = itC + (CH + 4);                                 // FUSE only
-    uint32_t *sBits = reinterpret_cast<uint32_t *>(sTaken + (CH + 4));  // FUSE only
+    int32_t *itC = reinterpret_cast<int32_t *>(mbar + 2);                       // FUSE only
+    // raw TMA destinations; FUSE: the same bytes hold the decision bits once the items are compacted
+    double *rawRc = reinterpret_cast<double *>(FUSE ? itC + (CH + 4) : reinterpret_cast<int32_t *>(mbar + 2));
+    int32_t *rawW = reinterpret_cast<int32_t *>(rawRc + (CH + 2));
+    uint32_t *sBits = reinterpret_cast<uint32_t *>(rawRc);                      // FUSE only
+    int32_t *sTaken = reinterpret_cast<int32_t *>(itP);                         // FUSE only: itP is dead after the DP
 
     const int t = threadIdx.x;
     const int lane = t & 31;
@@ -350,9 +400,10 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const int colStart = a.blockColStart[b];
     const int shortCode = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? a.shortcut[vlb] : 0;
     // a trivial case of GAP_KnapPisinger::solve needs no DP: behave like an empty block here
-    const int nCols = shortCode != 0 ? 0 : a.blockColStart[b + 1] - colStart;
+    const int capRaw = a.capacity[b];  // < 0: the columns fixed to 1 do not fit (no column for this block)
+    const int nCols = (shortCode != 0 || capRaw < 0) ? 0 : a.blockColStart[b + 1] - colStart;
     const double pScale = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? (double)a.scale[vlb] : 0.0;
-    const int cap = a.capacity[b];
+    const int cap = capRaw;
     // fetched now so that the (possibly cold) load is long done when the tail needs it
     const double alphaB = FUSE ? a.back.alpha[vec * a.alphaStride + b] : 0.0;
     uint32_t *bitsBase = FUSE ? sBits : a.bits + a.bitsOff[lb];
@@ -383,6 +434,8 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         const int len = min(CH, nCols - chunkBase);
         const int g0 = colStart + chunkBase;
         const int shiftRc = g0 & 1, shiftW = g0 & 3;
+        // node bounds (DecompAlgo::setSubProbBounds): a column fixed to 0 or to 1 stays out of the DP
+        const uint8_t *fixB = a.back.fix != nullptr ? a.back.fix + g0 : nullptr;
         // ---- stage the chunk's reduced costs and weights with TMA bulk copies
         if (t == 0) {
             const uint32_t bytesRc = (uint32_t)(((shiftRc + len + 1) & ~1) * 8);
@@ -404,7 +457,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             const int c0 = min(len, t * per), c1 = min(len, c0 + per);
             int mineCnt = 0;
             for (int cl = c0; cl < c1; ++cl)
-                mineCnt += (rawRc[shiftRc + cl] < 0.0 && rawW[shiftW + cl] <= cap) ? 1 : 0;
+                mineCnt += (rawRc[shiftRc + cl] < 0.0 && rawW[shiftW + cl] <= cap && (fixB == nullptr || fixB[cl] == 0)) ? 1 : 0;
             // warp-inclusive scan, then the warps' totals
             int incl = mineCnt;
 #pragma unroll
@@ -424,7 +477,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             for (int cl = c0; cl < c1; ++cl) {
                 const double rc = rawRc[shiftRc + cl];
                 const int w = rawW[shiftW + cl];
-                if (rc < 0.0 && w <= cap) {  // w > cap can never be taken (:161)
+                if (rc < 0.0 && w <= cap && (fixB == nullptr || fixB[cl] == 0)) {  // w > cap can never be taken (:161)
                     // profit: -redCost (gap_func.py:104), or its scaled integer value
                     // floor(-rc*scale + 0.5) held exactly in fp64 (GAP_KnapPisinger.h:174-177)
                     itP[pos] = pScale != 0.0 ? (double)(long long)floor((-rc) * pScale + 0.5) : -rc;
@@ -443,7 +496,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                 if (cl < len) {
                     rc = rawRc[shiftRc + cl];
                     w = rawW[shiftW + cl];
-                    flag = (rc < 0.0) && (w <= cap);  // w > cap can never be taken (:161)
+                    flag = (rc < 0.0) && (w <= cap) && (fixB == nullptr || fixB[cl] == 0);  // w > cap can never be taken (:161)
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, flag);
                 const int wpre = __popc(bal & ((1u << lane) - 1u));
@@ -728,6 +781,8 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     // z = c[n-1][capacity]  (gap_func.py:183)
     if (shortCode != 0) {
         if (t == 0) RESV(a.blockObj)[lb] = a.zShort[vlb];
+    } else if (cap < 0) {
+        if (t == 0) RESV(a.blockObj)[lb] = kNegInf;
     } else {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -789,6 +844,39 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                 for (int k = lane; k < cnt; k += 32) sFinal[k] = colStart + sTaken[cnt - 1 - k];
             }
             __syncwarp();
+            if (a.back.fix != nullptr && cap >= 0) {
+                // node bounds: the columns fixed to 1 join the column.  Both lists ascend; every element
+                // finds its place by a binary search in the other list (no column is in both).
+                const int nAll = a.blockColStart[b + 1] - colStart;
+                int32_t *sForced = sTaken;  // the taken list is consumed
+                int nf = 0;
+                for (int base = 0; base < nAll; base += 32) {
+                    const int q = base + lane;
+                    const bool f = q < nAll && (a.back.fix[colStart + q] & 1u);
+                    const unsigned bal = __ballot_sync(0xffffffffu, f);
+                    if (f) sForced[nf + __popc(bal & ((1u << lane) - 1u))] = colStart + q;
+                    nf += __popc(bal);
+                }
+                __syncwarp();
+                if (nf > 0) {
+                    int32_t *sMerged = itW;  // the compacted weights are consumed
+                    for (int k = lane; k < cnt + nf; k += 32) {
+                        const bool fromChosen = k < cnt;
+                        const int me = fromChosen ? sFinal[k] : sForced[k - cnt];
+                        const int32_t *other = fromChosen ? sForced : sFinal;
+                        int lo = 0, hi = fromChosen ? nf : cnt;  // elements of `other` below `me`
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (other[mid] < me) lo = mid + 1; else hi = mid;
+                        }
+                        sMerged[(fromChosen ? k : k - cnt) + lo] = me;
+                    }
+                    __syncwarp();
+                    for (int k = lane; k < cnt + nf; k += 32) sFinal[k] = sMerged[k];
+                    cnt += nf;
+                    __syncwarp();
+                }
+            }
             // varRedCost / varOrigCost: added in ascending index order (GAP_KnapPisinger.h:263-272).
             // All lanes fetch, one lane adds sequentially out of shared memory.
             double *sVals = itP;  // free after the DP
@@ -813,9 +901,10 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         // blocks to learn where its column goes (CTAs are dispatched in index order, block 0 never
         // waits).  Words carry the launch epoch, so nothing has to be reset between rounds.
         const int cnt = sCnt;
-        const double rcB = sRcSum - alphaB;  // DecompAlgo.cpp:6350-6356
+        // DecompAlgo.cpp:6350-6356; a block whose fixed columns do not fit has no column: rc = +inf
+        const double rcB = cap < 0 ? -kNegInf : sRcSum - alphaB;
         const bool keep = rcB < -a.filt.eps;          // strict, :5216
-        const unsigned long long myCells = (unsigned long long)kGlobal * (unsigned long long)(cap + 1);
+        const unsigned long long myCells = (unsigned long long)kGlobal * (unsigned long long)(cap + 1);  // kGlobal == 0 when cap < 0
         if (t == 0) {
             // one 64-bit word per block: epoch (8) | kept (1) | cells (24) | nnz (31).  In the fused
             // shapes cells = items (<= 2048) x row cells (<= 7168) < 2^24; every block publishes in
@@ -1092,6 +1181,8 @@ static void fillBackArgs(Ctx *c, const double *dRedCost, const double *dAlpha, B
     const bool pis = c->profitMode == DIPGPU_PROFIT_PISINGER_INT;
     a->shortcut = pis ? c->dShortcut : nullptr;
     a->sel = pis ? c->dSel : nullptr;
+    a->fix = c->haveFix ? c->dFix : nullptr;
+    if (c->haveFix) a->capacity = c->dCapEff;  // capacity left once the columns fixed to 1 are in
 }
 
 static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
@@ -1123,7 +1214,7 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     a.redCost = dRedCost;
     a.weight = c->dWeight;
     a.blockColStart = c->dBlockColStart;
-    a.capacity = c->dCapacity;
+    a.capacity = c->haveFix ? c->dCapEff : c->dCapacity;
     a.bitsOff = c->dBitsOff;
     a.bits = c->dBits;
     a.itemW = c->dItemW;

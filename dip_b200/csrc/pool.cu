@@ -48,10 +48,38 @@ pool_redcost_kernel(long long nCols, const int64_t *__restrict__ colStart, const
     double *p = sP[warp];
     for (int64_t hi = E; hi > B;) {
         const int64_t lo = max(B, hi - kPoolChunk);
-        for (int64_t k = lo + lane; k < hi; k += 32) p[k - lo] = __dmul_rn(val[k], __ldg(u + row[k]));
+        // batches of 8 independent (row, value) loads, then their 8 dependent gathers of the dual: the
+        // round trips overlap instead of serialising (a warp issues in order)
+        for (int64_t base = lo + lane; base < hi; base += 256) {
+            int r[8];
+            double v[8], g[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t k = base + 32 * j;
+                r[j] = k < hi ? __ldg(row + k) : 0;
+                v[j] = k < hi ? __ldg(val + k) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = (base + 32 * j < hi) ? __ldg(u + r[j]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (base + 32 * j < hi) p[base + 32 * j - lo] = __dmul_rn(v[j], g[j]);
+        }
         __syncwarp();
         const int64_t kHi = min(hi, e), kLo = max(lo, b);
-        for (int64_t k = kHi - 1; k >= kLo; --k) sum = __dadd_rn(sum, p[k - lo]);
+        if (kHi > kLo) {
+            // the next product is fetched while the current one is added (one load ahead of the DADD chain)
+            int q = (int)(kHi - 1 - lo);
+            const int qLo = (int)(kLo - lo);
+            double cur = p[q];
+            while (q > qLo) {
+                const double nxt = p[q - 1];
+                sum = __dadd_rn(sum, cur);
+                cur = nxt;
+                --q;
+            }
+            sum = __dadd_rn(sum, cur);
+        }
         __syncwarp();
         hi = lo;
     }

@@ -190,6 +190,17 @@ class GpuPricer:
         self.setObjective(model.objective)
         self.setKnapsackBlocks(model.block_col_start, model.weight, model.capacity, profit_mode)
 
+    def setColBounds(self, col_lb=None, col_ub=None):
+        """DecompAlgo::setSubProbBounds (DecompAlgo.cpp:2352-2371) under BranchEnforceInSubProb: node
+        bounds of the x-space columns, enforced inside the block knapsacks.  None, None removes them."""
+        if col_lb is None and col_ub is None:
+            self._check(self._lib.dipgpu_set_col_bounds(self._ctx, None, None, 0))
+            return
+        lb = np.ascontiguousarray(col_lb, np.float64)
+        ub = np.ascontiguousarray(col_ub, np.float64)
+        self._check(self._lib.dipgpu_set_col_bounds(self._ctx, capi.ptr(lb), capi.ptr(ub), len(lb)))
+        self._relax_cache = None
+
     def setBlockRange(self, first: int, count: int):
         self._check(self._lib.dipgpu_set_block_range(self._ctx, first, count))
 

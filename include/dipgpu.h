@@ -145,6 +145,23 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
                                const int32_t *weight, const int32_t *capacity,
                                int32_t profitMode);
 
+/*
+ * Node bounds of the x-space columns, enforced inside the block subproblems: what
+ * DecompAlgo::setSubProbBounds stores in m_colLBNode / m_colUBNode (Dip/src/DecompAlgo.cpp:2352-2371)
+ * and DecompAlgo::solveRelaxed hands to the subproblem with BranchEnforceInSubProb
+ * (setActiveColBounds, Dip/src/DecompAlgo.cpp:6403-6405; Dip/src/DecompModel.h:149-187) -- DIP's
+ * default branching mode (Dip/src/DecompParam.h:656).  For the 0-1 knapsack blocks a column with
+ * colUB < 0.5 never enters a column, a column with colLB > 0.5 is in every column of its block
+ * (whatever its reduced cost) and its weight comes off the capacity; the block's optimum
+ * min sum redCost*x over the remaining columns is the same DP.  A block whose fixed columns do not
+ * fit returns no column: blockRedCost = +inf, blockMostNegRC = 0, blockObj = -inf, blockNnz = 0
+ * (the reference's subproblem MILP is infeasible and pushes no variable).  blockObj excludes the
+ * fixed columns' profit.  Length N >= the block columns; both NULL removes the bounds.  Call after
+ * dipgpu_set_knapsack_blocks (which clears them); fp64 profit mode only
+ * (DIPGPU_ERR_UNSUPPORTED in Pisinger mode, whose example application branches in the master).
+ */
+int dipgpu_set_col_bounds(dipgpu_ctx *ctx, const double *colLB, const double *colUB, int32_t N);
+
 /* ----------------------------------------------------------------- pricing */
 
 /*

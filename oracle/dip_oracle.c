@@ -399,3 +399,92 @@ void dip_oracle_smooth_duals(int nRows, double alpha, const double *dual, const 
     for (int r = 0; r < nRows; ++r)    /* :179-181 */
         dualST[r] = (alpha * dual[r]) + (alpha1 * dualRM[r]);
 }
+
+/* ---------------------------------------------- node bounds in the blocks -- */
+
+int dip_oracle_solve_blocks_bounded(int m, const int32_t *blockColStart, const int32_t *weight,
+                                    const int32_t *capacity, const double *redCostX,
+                                    const double *origCost, const double *alpha, const double *colLB,
+                                    const double *colUB, double redCostEps, int maxBlockCols,
+                                    int32_t *colNnz, double *colRedCost, double *colOrigCost,
+                                    int32_t *colKeep, double *mostNegRC, double *z, int32_t *colIndOut,
+                                    double *mostNegReducedCost, int64_t *cellsOut)
+{
+    int64_t cellsTotal = 0;
+    for (int b = 0; b < m; ++b) {
+        const int s = blockColStart[b];
+        const int n = blockColStart[b + 1] - s;
+        int32_t *ind = colIndOut ? colIndOut + (size_t)b * (size_t)maxBlockCols : NULL;
+        /* DecompAlgo.cpp:6403-6405: the node's bounds on the block's columns */
+        long left = capacity[b];
+        int clash = 0;
+        for (int j = 0; j < n; ++j) {
+            if (colLB[s + j] > 0.5) left -= weight[s + j];
+            if (colLB[s + j] > 0.5 && colUB[s + j] < 0.5) clash = 1;
+        }
+        if (clash || left < 0) { /* infeasible subproblem: no variable comes back */
+            colNnz[b] = 0;
+            colRedCost[b] = INFINITY;
+            colOrigCost[b] = 0.0;
+            if (z) z[b] = -INFINITY;
+            continue;
+        }
+        /* free columns with negative reduced cost: gap_func.py:102-105 */
+        int32_t *toOrig = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+        int32_t *w = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+        double *p = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+        uint8_t *x = (uint8_t *)calloc((size_t)(n > 0 ? n : 1), 1);
+        int nItems = 0;
+        for (int j = 0; j < n; ++j) {
+            if (colLB[s + j] > 0.5) { x[j] = 1; continue; }
+            if (colUB[s + j] < 0.5) continue;
+            if (redCostX[s + j] < 0) {
+                toOrig[nItems] = j;
+                w[nItems] = weight[s + j];
+                p[nItems] = -redCostX[s + j];
+                ++nItems;
+            }
+        }
+        double zb = 0.0;
+        if (nItems > 0) {
+            int32_t *sol = (int32_t *)malloc(sizeof(int32_t) * (size_t)nItems);
+            int nSol = 0;
+            zb = dip_oracle_knapsack01(nItems, p, w, (int)left, sol, &nSol, NULL);
+            for (int k = 0; k < nSol; ++k) x[toOrig[sol[k]]] = 1;
+            free(sol);
+            for (int i = 0; i < nItems; ++i)
+                if (w[i] <= left) cellsTotal += (int64_t)left + 1;
+        }
+        int nnz = 0;
+        double rc = 0.0, oc = 0.0;
+        for (int j = 0; j < n; ++j)
+            if (x[j]) {
+                rc += redCostX[s + j];
+                oc += origCost[s + j];
+                if (ind) ind[nnz] = s + j;
+                ++nnz;
+            }
+        colNnz[b] = nnz;
+        colRedCost[b] = rc - alpha[b]; /* DecompAlgo.cpp:6350-6356 */
+        colOrigCost[b] = oc;
+        if (z) z[b] = zb;
+        free(toOrig);
+        free(w);
+        free(p);
+        free(x);
+    }
+    /* DecompAlgo.cpp:4761, 5151-5232 */
+    int kept = 0;
+    double sum = 0.0;
+    for (int b = 0; b < m; ++b) {
+        double mn = 0.0;
+        if (colRedCost[b] < mn) mn = colRedCost[b];
+        mostNegRC[b] = mn;
+        colKeep[b] = colRedCost[b] < -redCostEps ? 1 : 0;
+        kept += colKeep[b];
+    }
+    for (int b = 0; b < m; ++b) sum += mostNegRC[b];
+    if (mostNegReducedCost) *mostNegReducedCost = sum;
+    if (cellsOut) *cellsOut = cellsTotal;
+    return kept;
+}

@@ -122,6 +122,26 @@ int dip_oracle_expand_column(int R, int N, const int64_t *rowStart, const int32_
 int dip_oracle_string_hash(int len, const int32_t *ind, const double *els, char *buf,
                            int bufLen);
 
+/* Stage (b)+(c) under node bounds enforced in the subproblem (BranchEnforceInSubProb,
+ * Dip/src/DecompParam.h:656): DecompAlgo::setSubProbBounds stores the node's column bounds
+ * (Dip/src/DecompAlgo.cpp:2352-2371) and DecompAlgo::solveRelaxed imposes them on the block's
+ * subproblem (setActiveColBounds, :6403-6405), which then is
+ *     min sum redCost_j x_j  s.t.  sum w_j x_j <= cap,  colLB_j <= x_j <= colUB_j,  x binary.
+ * Restated exactly: columns with colLB > 0.5 are in (whatever their reduced cost), their weight comes
+ * off the capacity; columns with colUB < 0.5 are out; the rest is knapsack01 over the columns with
+ * redCost < 0 (fp64 profit mode).  Column = fixed-to-1 + chosen, ascending; z excludes the fixed
+ * columns.  A block whose fixed columns do not fit (or with colLB > colUB) is infeasible: colNnz 0,
+ * colRedCost +inf, mostNegRC 0, not kept, z -inf (the reference's MILP pushes no variable).  Which
+ * optimal solution a MILP solver returns on ties is "parity unpinned"; ours is the DP's.
+ * colLB / colUB are indexed by x-space column.  Other arguments as dip_oracle_solve_blocks. */
+int dip_oracle_solve_blocks_bounded(int m, const int32_t *blockColStart, const int32_t *weight,
+                                    const int32_t *capacity, const double *redCostX,
+                                    const double *origCost, const double *alpha, const double *colLB,
+                                    const double *colUB, double redCostEps, int maxBlockCols,
+                                    int32_t *colNnz, double *colRedCost, double *colOrigCost,
+                                    int32_t *colKeep, double *mostNegRC, double *z, int32_t *colIndOut,
+                                    double *mostNegReducedCost, int64_t *cellsOut);
+
 /* DecompVarPool::setReducedCosts -> DecompWaitingCol::setReducedCost,
  * Dip/src/DecompVarPool.cpp:185-203, :22-40 (called once per price call, DecompAlgo.cpp:1890-1908):
  *   feasible:  redCost_s = origCost_s - m_col.dotProduct(u)        (:29)

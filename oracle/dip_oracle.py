@@ -74,6 +74,10 @@ def _lib():
     lib.dip_oracle_expand_column.restype = C.c_int
     lib.dip_oracle_string_hash.argtypes = [C.c_int, _i32p, _f64p, C.c_char_p, C.c_int]
     lib.dip_oracle_string_hash.restype = C.c_int
+    lib.dip_oracle_solve_blocks_bounded.argtypes = [
+        C.c_int, _i32p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, _f64p, C.c_double, C.c_int,
+        _i32p, _f64p, _f64p, _i32p, _f64p, _f64p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.dip_oracle_solve_blocks_bounded.restype = C.c_int
     lib.dip_oracle_pool_reduced_costs.argtypes = [C.c_int, _i64p, _i32p, _f64p, _f64p, _f64p, C.c_int, _f64p]
     lib.dip_oracle_pool_reduced_costs.restype = C.c_int
     lib.dip_oracle_smooth_duals.argtypes = [C.c_int, C.c_double, _f64p, _f64p, _f64p]
@@ -174,6 +178,25 @@ def solve_blocks(block_col_start, weight, capacity, red_cost_x, orig_cost, alpha
         int(profit_mode), np.ascontiguousarray(red_cost_x, np.float64),
         np.ascontiguousarray(orig_cost, np.float64), np.ascontiguousarray(alpha, np.float64),
         float(red_cost_eps), int(n_threads), max_cols, nnz, rc, oc, keep, mn, z,
+        ind.ctypes.data if want_ind else None, C.byref(tot), C.byref(cells))
+    cols = [ind[b, : nnz[b]].copy() for b in range(m)] if want_ind else []
+    return RoundResult(None, nnz, rc, oc, keep, mn, z, cols, tot.value, kept, cells.value)
+
+
+def solve_blocks_bounded(block_col_start, weight, capacity, red_cost_x, orig_cost, alpha, col_lb, col_ub,
+                         red_cost_eps=1e-4, want_ind=True) -> RoundResult:
+    """Stage (b)+(c) with the node's column bounds enforced in the block subproblems."""
+    bcs = np.ascontiguousarray(block_col_start, np.int32)
+    m = len(bcs) - 1
+    max_cols = max(int(np.max(np.diff(bcs))) if m > 0 else 1, 1)
+    nnz, rc, oc, keep, mn, z, ind = _alloc(m, max_cols, want_ind)
+    tot = C.c_double(0.0)
+    cells = C.c_int64(0)
+    kept = _lib().dip_oracle_solve_blocks_bounded(
+        m, bcs, np.ascontiguousarray(weight, np.int32), np.ascontiguousarray(capacity, np.int32),
+        np.ascontiguousarray(red_cost_x, np.float64), np.ascontiguousarray(orig_cost, np.float64),
+        np.ascontiguousarray(alpha, np.float64), np.ascontiguousarray(col_lb, np.float64),
+        np.ascontiguousarray(col_ub, np.float64), float(red_cost_eps), max_cols, nnz, rc, oc, keep, mn, z,
         ind.ctypes.data if want_ind else None, C.byref(tot), C.byref(cells))
     cols = [ind[b, : nnz[b]].copy() for b in range(m)] if want_ind else []
     return RoundResult(None, nnz, rc, oc, keep, mn, z, cols, tot.value, kept, cells.value)

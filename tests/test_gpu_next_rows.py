@@ -255,3 +255,89 @@ def test_spmv_tile_shapes_are_bit_equal(oracle, pricer):
         pricer.set_option("spmv_u_smem", usmem)
         np.testing.assert_array_equal(pricer.calcRedCost(u), ref)
         np.testing.assert_array_equal(pricer.calcRedCost(u, 1), ref1)
+
+
+# ------------------------------------------------------------------ f-4: node bounds inside the blocks
+
+
+def _check_bounded(oracle, pricer, b, lb, ub, eps=1e-4):
+    res = pricer.solveBlocks(b.red_cost, b.alpha, eps)
+    ref = oracle.solve_blocks_bounded(b.block_col_start, b.weight, b.capacity, b.red_cost, b.orig_cost, b.alpha, lb, ub,
+                                      red_cost_eps=eps)
+    np.testing.assert_array_equal(res.blockObj, ref.z)                  # bit-exact optimum of the free part
+    np.testing.assert_array_equal(res.blockNnz, ref.col_nnz)
+    np.testing.assert_array_equal(res.blockRedCost, ref.col_red_cost)   # same additions, ascending index order
+    np.testing.assert_array_equal(res.blockOrigCost, ref.col_orig_cost)
+    np.testing.assert_array_equal(res.blockMostNegRC, ref.most_neg_rc)
+    kept = [k for k in range(len(ref.z)) if ref.col_keep[k]]
+    assert list(res.colBlock[:res.nCols]) == kept
+    for k, blk in enumerate(kept):
+        assert list(res.column(k)) == list(ref.col_ind[blk])
+    assert res.cells == ref.cells
+    assert res.mostNegReducedCost == ref.most_neg_reduced_cost
+    return res, ref
+
+
+@pytest.mark.parametrize("m,nhi,caphi,seed", [(40, 60, 150, 1), (200, 120, 400, 2), (400, 50, 120, 3), (6, 2300, 6000, 4)])
+def test_node_bounds_in_the_blocks(oracle, pricer, m, nhi, caphi, seed):
+    """Small shards run the fused kernel (parallel merge of the fixed columns), > 256 blocks and
+    multi-chunk blocks the three-kernel path (backward merge in the backtrack kernel)."""
+    b = I.random_batch(m, 1, nhi, 10, caphi, seed)
+    N = int(b.block_col_start[-1])
+    rng = np.random.default_rng(100 + seed)
+    pricer.setObjective(b.orig_cost)
+    pricer.setKnapsackBlocks(b.block_col_start, b.weight, b.capacity)
+    lb = (rng.random(N) < 0.03).astype(np.float64)
+    ub = 1.0 - (rng.random(N) < 0.10).astype(np.float64)
+    ub = np.maximum(ub, lb)
+    lb[b.block_col_start[0]:b.block_col_start[1]] = 1.0        # block 0: everything fixed in -> cannot fit
+    ub[b.block_col_start[0]:b.block_col_start[1]] = 1.0
+    if m > 2:
+        j = int(b.block_col_start[2])
+        lb[j], ub[j] = 1.0, 0.0                                   # block 2: lb > ub
+    pricer.setColBounds(lb, ub)
+    res, ref = _check_bounded(oracle, pricer, b, lb, ub)
+    assert np.isinf(res.blockRedCost[0]) and res.blockNnz[0] == 0
+    # fixed-to-1 columns with non-negative reduced cost are in the returned columns
+    forced_pos = [j for j in np.nonzero(lb > 0.5)[0] if b.red_cost[j] >= 0]
+    in_cols = set(int(x) for k in range(res.nCols) for x in res.column(k))
+    kept_blocks = set(int(x) for x in res.colBlock[:res.nCols])
+    for j in forced_pos:
+        blk = int(np.searchsorted(b.block_col_start, j, side="right") - 1)
+        if blk in kept_blocks:
+            assert int(j) in in_cols
+    # bounds off again: the plain round
+    pricer.setColBounds(None, None)
+    ref0 = oracle.solve_blocks(b.block_col_start, b.weight, b.capacity, b.red_cost, b.orig_cost, b.alpha)
+    res0 = pricer.solveBlocks(b.red_cost, b.alpha)
+    np.testing.assert_array_equal(res0.blockObj, ref0.z)
+    np.testing.assert_array_equal(res0.blockNnz, ref0.col_nnz)
+
+
+def test_node_bounds_through_the_round_and_batches(oracle, pricer):
+    model = I.gap_pricing_model(I.gap_class_d())
+    pricer.setModel(model)
+    rng = np.random.default_rng(9)
+    lb = (rng.random(model.N) < 0.01).astype(np.float64)
+    ub = np.maximum(1.0 - (rng.random(model.N) < 0.05).astype(np.float64), lb)
+    pricer.setColBounds(lb, ub)
+    U = np.stack([I.gap_duals(model, rng) for _ in range(4)])
+    batch = pricer.priceRoundsBatch(U)
+    for v in range(4):
+        res, rcx = pricer.priceRound(U[v], want_redcost=True)
+        _same_round(batch[v], res)
+        ref = oracle.solve_blocks_bounded(model.block_col_start, model.weight, model.capacity, rcx, model.objective,
+                                          U[v][model.n_base_rows:model.n_base_rows + model.m], lb, ub)
+        np.testing.assert_array_equal(res.blockObj, ref.z)
+        np.testing.assert_array_equal(res.blockRedCost, ref.col_red_cost)
+        assert [list(res.column(k)) for k in range(res.nCols)] == [list(ref.col_ind[b]) for b in range(model.m) if ref.col_keep[b]]
+
+
+def test_node_bounds_unsupported_in_pisinger_mode(pricer):
+    from dip_b200.capi import DipGpuError, ERR_UNSUPPORTED
+    b = I.random_batch(4, 5, 9, 10, 40, 1)
+    pricer.setObjective(b.orig_cost)
+    pricer.setKnapsackBlocks(b.block_col_start, b.weight, b.capacity, PROFIT_PISINGER_INT)
+    with pytest.raises(DipGpuError) as e:
+        pricer.setColBounds(np.zeros(len(b.weight)), np.ones(len(b.weight)))
+    assert e.value.code == ERR_UNSUPPORTED

@@ -100,3 +100,73 @@ def test_adjust_duals_and_phase1(oracle):
 def test_string_hash(oracle):
     assert oracle.string_hash([3, 17, 42], [1.0, 1.0, 1.0]) == "3_1_17_1_42_1_"
     assert oracle.string_hash([5], [0.123456789]) == "5_0.123457_"
+
+
+# ---------------------------------------------------------------- rows 8(f): pool, smoothing, node bounds
+
+
+def test_pool_reduced_costs_and_smoothing_restatements(oracle):
+    """DecompVarPool::setReducedCosts / DecompAlgoPC::adjustMasterDualSolution restated in C against
+    their formulas in numpy (Dip/src/DecompVarPool.cpp:22-40, Dip/src/DecompAlgoPC.cpp:179-181)."""
+    rng = np.random.default_rng(3)
+    nrows = 500
+    lens = rng.integers(0, 40, size=200)
+    cs = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=cs[1:])
+    ri = rng.integers(0, nrows, size=cs[-1]).astype(np.int32)
+    va = rng.uniform(-2, 2, size=cs[-1])
+    oc = rng.uniform(-1, 5, size=len(lens))
+    u = rng.standard_normal(nrows)
+    for feasible in (True, False):
+        got, found = oracle.pool_reduced_costs(cs, ri, va, oc, u, feasible)
+        for s in range(len(lens)):
+            dp = 0.0
+            for k in range(cs[s + 1] - 1, cs[s] - 1, -1):   # CoinPackedVectorBase::dotProduct, last entry first
+                dp += va[k] * u[ri[k]]
+            assert got[s] == (oc[s] - dp if feasible else -dp)
+        assert found == bool(np.any(got <= -1e-10))
+    a = 0.1 * 0.9 * 0.9
+    d, rm = rng.standard_normal(1000), rng.standard_normal(1000)
+    np.testing.assert_array_equal(oracle.smooth_duals(a, d, rm), (a * d) + ((1.0 - a) * rm))
+
+
+def test_bounded_blocks_against_enumeration(oracle):
+    """Node bounds enforced in the block (DecompAlgo.cpp:6403-6405): the restatement (fixed columns +
+    knapsack01 on the rest) reaches the optimum of min sum rc*x s.t. knapsack, lb <= x <= ub by
+    enumeration, returns fixed-to-1 columns whatever their reduced cost, and flags infeasible blocks."""
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        m = 4
+        n = int(rng.integers(1, 11))
+        bcs = (np.arange(m + 1) * n).astype(np.int32)
+        w = rng.integers(1, 12, size=m * n).astype(np.int32)
+        cap = rng.integers(0, 30, size=m).astype(np.int32)
+        rc = np.round(rng.uniform(-10, 6, size=m * n), 2)
+        oc = rng.uniform(0, 10, size=m * n)
+        alpha = rng.uniform(-3, 0, size=m)
+        lb = (rng.random(m * n) < 0.15).astype(np.float64)
+        ub = 1.0 - (rng.random(m * n) < 0.2).astype(np.float64)
+        if trial % 3:
+            ub = np.maximum(ub, lb)          # no clashes in most trials
+        res = oracle.solve_blocks_bounded(bcs, w, cap, rc, oc, alpha, lb, ub)
+        for b in range(m):
+            s = slice(b * n, (b + 1) * n)
+            best = None
+            for mask in range(1 << n):
+                x = np.array([(mask >> j) & 1 for j in range(n)], np.float64)
+                if np.any(x < lb[s]) or np.any(x > ub[s]) or np.dot(x, w[s]) > cap[b]:
+                    continue
+                val = float(np.dot(x, rc[s]))
+                if best is None or val < best - 1e-9:
+                    best = val
+            if best is None:
+                assert res.col_nnz[b] == 0 and np.isinf(res.col_red_cost[b]) and res.most_neg_rc[b] == 0.0
+                assert not res.col_keep[b] and res.z[b] == -np.inf
+                continue
+            ind = res.col_ind[b] - b * n
+            x = np.zeros(n)
+            x[ind] = 1
+            assert np.all(x >= lb[s]) and np.all(x <= ub[s]) and np.dot(x, w[s]) <= cap[b]
+            assert abs((res.col_red_cost[b] + alpha[b]) - best) <= 1e-9
+            assert list(ind) == sorted(ind)
+        assert res.most_neg_reduced_cost == float(np.sum(res.most_neg_rc))
