@@ -264,9 +264,14 @@ def main():
     sptr = stream.cuda_stream
     assert sptr != 0
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush_rd = torch.ones(64 << 20, dtype=torch.float32, device=dev)   # 256 MiB, read after the write
 
     def flush_l2():
+        # 256 MiB written, then 256 MiB read: every line of the timed kernels' inputs is evicted, and the
+        # L2 is left full of CLEAN lines -- after a write-only flush the timed kernel also pays the
+        # write-back of ~126 MB of the flush's dirty lines (scripts/spmv_timing.py: 37.0 vs 30.8 us)
         flush_buf.fill_(1)
+        flush_rd.sum()
 
     u_dev = [torch.from_numpy(u).to(dev) for u in duals]
     u_pin = capi.PinnedArray((N_DUALS, model.u_len), np.float64)
@@ -391,7 +396,7 @@ def main():
                             "one master dual vector per step, 16 dual vectors cycled",
                 "blocks": model.m, "cols": model.N, "rows": model.R, "nnz": model.nnz,
                 "cells_per_round": cells_mean, "kept_columns_round0": kept0, "red_cost_eps": RC_EPS,
-                "l2": "flushed between steps (256 MiB fill, outside the per-step CUDA-event pairs)",
+                "l2": "flushed between steps (256 MiB written then 256 MiB read, outside the per-step CUDA-event pairs)",
                 "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, independent rounds per rank (weak); "
                                                           "see `sharded` for one round partitioned over NCCL",
             },
@@ -475,13 +480,23 @@ def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank):
     CUDA events (L2 flushed), algorithmic bytes 12*nnz + 24*cols + 8*uLen."""
     from dip_b200.pricer import GpuPricer
     rng = np.random.default_rng(77)
-    u_len = 257_680
+    # master columns shaped like GAP-E's: for the ~16 jobs a machine takes, the assignment row j, the two
+    # branch rows of x[b,j] (x <= u, x >= l) and the block's convexity row -- ascending master rows
+    m, n = 80, 1600
+    N = m * n
+    n_base = n + 2 * N
+    u_len = n_base + m
     n_cols = 200_000
-    lens = rng.integers(20, 81, size=n_cols)
+    per = 16
+    blk = rng.integers(0, m, size=n_cols)
+    jobs = np.sort(rng.integers(0, n, size=(n_cols, per)), axis=1)
+    x = blk[:, None] * n + jobs
+    rows = np.concatenate([jobs, n + x, n + N + x, (n_base + blk)[:, None]], axis=1)
+    ri = rows.astype(np.int32).ravel()
+    lens = np.full(n_cols, 3 * per + 1)
     cs = np.zeros(n_cols + 1, np.int64)
     np.cumsum(lens, out=cs[1:])
     nnz = int(cs[-1])
-    ri = rng.integers(0, u_len, size=nnz).astype(np.int32)
     va = np.ones(nnz)
     oc = rng.uniform(0, 1000, size=n_cols)
     u = rng.uniform(0, 50, size=u_len)
@@ -500,7 +515,10 @@ def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank):
     ms = float(np.mean(ts[2:]))
     by = 12 * nnz + 24 * n_cols + 8 * u_len
     ach = by / (ms * 1e-3) / 1e9
-    return {"kernel": "pool_redcost_kernel", "workload": f"{n_cols} waiting columns, {nnz} entries, {u_len} master rows",
+    return {"kernel": "pool_redcost_kernel",
+            "workload": f"{n_cols} waiting columns shaped like GAP-E master columns, {nnz} entries, {u_len} master rows",
+            "note": "every stored entry gathers one dual (8 B of a 32 B sector, L2-resident): the sector traffic, "
+                    "not the 12 B/entry stream, bounds this pass",
             "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
             "avg_launch_ms": ms, "algorithmic_bytes": by, "peak_source": peak_src}
 
@@ -683,7 +701,7 @@ def bench_spmv(torch, dev, local_rank, hbm_peak, peak_src, flush_l2, world, rank
             "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic("prof_spmv_milp"),
             "avg_launch_ms": ms,
             "min_launch_ms": float(np.min(times)), "algorithmic_bytes": by, "peak_source": peak_src,
-            "l2": "flushed before every sweep (inputs 141 MB vs 126 MB L2)"}
+            "l2": "flushed before every sweep (256 MiB written then 256 MiB read; inputs 141 MB vs 126 MB L2)"}
 
 
 if __name__ == "__main__":

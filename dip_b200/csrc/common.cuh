@@ -69,24 +69,27 @@ struct ResultLayout {
 constexpr int kFuseFilterMaxBlocks = 256;
 
 // ---------------------------------------------------------------- SpMV tiling
-constexpr int kSpmvChunk = 256;        // default entry budget of a warp tile (runtime knob "spmv_chunk")
+constexpr int kSpmvChunk = 384;        // default entry budget of a warp tile (runtime knob "spmv_chunk")
 constexpr int kSpmvChunkMax = 4096;    // a single column longer than the budget -> lane-cooperative kernel
 constexpr int kSpmvColsPerLane = 4;    // a warp tile spans at most 32*4 consecutive columns (fewer when the
                                        // entry budget is reached first)
 constexpr int kSpmvMaxStages = 8;
 // A tile of the stream kernel is self-contained in the blob (one bulk copy).  Per slice of 32
-// columns, lane l owns the slice's l-th LONGEST column (host-side stable sort), so the columns that
-// still have an entry at step i are a prefix of the lanes:
+// columns, lane l owns the slice's l-th LONGEST column (host-side stable sort inside a window of
+// consecutive columns), so the columns that still have an entry at step i are a prefix of the lanes:
 //   SpmvTileHeader                     16 B
-//   uint16 len[nSlices*32]             column length of lane l (0 past the tile's last column)
-//   uint16 col[nSlices*32]             column of lane l, relative to firstCol
+//   uint16 len[nSlices*32]             entries of lane l's column inside this tile's step range
+//   uint16 col[nSlices*32]             column of lane l, relative to firstCol (0xffff = no column)
 //   double c[nSlices*32]               objective entry of lane l's column
 //   uint16 stepOff[nSlices*stepStride] per slice: position of step i's first entry (padded to 16 B)
 //   double val[nEnt (+1 to even)]      JAGGED: per slice, step 0 of every lane, then step 1 of the
 //   RowT   row[nEnt (padded to 16 B)]  lanes whose column is longer than 1, ...
+// strideFlags = stepStride | first << 16 | last << 17: a slice with more entries than the tile budget is
+// cut by step range into consecutive single-slice tiles; `first` zeroes the lanes' sums, `last` stores.
 struct SpmvTileHeader {
-    int32_t firstCol, nCols, nEnt, stepStride;
+    int32_t firstCol, nSlices, nEnt, strideFlags;
 };
+constexpr int kSpmvWindow = 1024;      // columns sorted by length together (runtime knob "spmv_window")
 // ------------------------------------------------- packed master columns (expand.cu)
 //   MColsHeader                64 B
 //   int64  colStart[m + 1]     offsets into entries
@@ -147,6 +150,9 @@ struct Ctx {
     unsigned char *dSpmvBlob = nullptr;  // self-contained jagged tiles (SpmvTileHeader)
     int nSpmvTiles = 0;             // 0 = stream kernel not applicable
     int spmvStageBytes = 0;         // largest tile, bytes
+    int32_t *dSpmvWarpStart = nullptr;  // launch warp -> first tile of its contiguous run (W + 1)
+    int spmvMode = 0, spmvNst = 2, spmvWarps = 8, spmvGrid = 1, spmvUBytes = 0, optSpmvWindow = 0;  // launch shape (planSpmvLaunch)
+    size_t spmvSmem = 0;
     int optSpmvWarps = 0, optSpmvUSmem = -1, optSpmvChunk = 0, optSpmvStages = 0, optSpmvMaxCols = 0;  // diagnostics knobs
     std::vector<double> hObj;       // host copy of the objective (tiles carry their columns' entries)
     void *spmvFn = nullptr;                   // kernel whose shared-memory limit is already set
@@ -195,6 +201,7 @@ struct Ctx {
     bool haveFix = false;
     uint8_t *dFix = nullptr;            // per column: bit 0 = fixed to 1, bit 1 = fixed to 0
     int32_t *dCapEff = nullptr;         // per block: capacity minus the fixed-to-1 weights (< 0: they do not fit)
+    double *dRcEff = nullptr;           // large-shard path: reduced costs with the fixed columns masked to +0
     std::vector<int32_t> hWeight;
     int maxCapacity = 0;       // of the shard
     int maxBlockCols = 0;      // of the shard

@@ -506,12 +506,12 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (c->stream) cudaStreamSynchronize(c->stream);
     devFree(&c->dDoneCounter); devFree(&c->dCsrRowStart); devFree(&c->dCsrColInd); devFree(&c->dCsrVal); devFree(&c->dExpPub);
     if (c->dMCols) cudaFree(c->dMCols);
-    if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dSpmvBlob); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
+    if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dSpmvBlob); devFree(&c->dSpmvWarpStart); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
     devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems); devFree(&c->dScale); devFree(&c->dShortcut); devFree(&c->dSel); devFree(&c->dZShort);
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
     freeBatch(c);
-    devFree(&c->dFix); devFree(&c->dCapEff);
+    devFree(&c->dFix); devFree(&c->dCapEff); devFree(&c->dRcEff);
     devFree(&c->dCenter); devFree(&c->dPoolStart); devFree(&c->dPoolRow); devFree(&c->dPoolVal);
     devFree(&c->dPoolOrigCost); devFree(&c->dPoolRedCost); devFree(&c->dPoolFlag);
     if (c->dResult) cudaFree(c->dResult);
@@ -564,7 +564,7 @@ int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *ro
         if (colInd[k] < 0 || colInd[k] >= N) return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: column index %d out of range at %lld", colInd[k], (long long)k);
     if (c->haveBlocks && c->nBlockCols > N) return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: N=%d < block columns %d", N, c->nBlockCols);
     if (c->haveObj && c->N != N) { devFree(&c->dObj); c->haveObj = false; c->hObj.clear(); }
-    if (c->N != N) devFree(&c->dRedCost);
+    if (c->N != N) { devFree(&c->dRedCost); devFree(&c->dRcEff); }
     c->R = R; c->N = N; c->nBaseRows = nBaseRows; c->numConvex = numConvex;
     c->dualsResident = false; c->haveCenter = false; c->haveST = false;
     c->hRowStart.assign(rowStart, rowStart + R + 1);
@@ -1329,11 +1329,14 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
                                   64 * (size_t)std::max(c->nLocal, 1), cudaMemcpyDeviceToHost));
         return DIPGPU_OK;
     }
-    if (!strcmp(name, "spmv_warps")) { c->optSpmvWarps = (int)value; return DIPGPU_OK; }
-    if (!strcmp(name, "spmv_stages")) { c->optSpmvStages = (int)value; return DIPGPU_OK; }
-    if (!strcmp(name, "spmv_chunk") || !strcmp(name, "spmv_max_cols")) {
-        // re-tiles the matrix: entry budget / column budget of a warp tile
-        (!strcmp(name, "spmv_chunk") ? c->optSpmvChunk : c->optSpmvMaxCols) = (int)value;
+    if (!strcmp(name, "spmv_warps") || !strcmp(name, "spmv_stages") || !strcmp(name, "spmv_u_smem") ||
+        !strcmp(name, "spmv_chunk") || !strcmp(name, "spmv_max_cols") || !strcmp(name, "spmv_window")) {
+        // re-tiles the matrix: the tiles are dealt to the warps of the launch shape on the host
+        int *opt = !strcmp(name, "spmv_warps") ? &c->optSpmvWarps : !strcmp(name, "spmv_stages") ? &c->optSpmvStages
+                 : !strcmp(name, "spmv_u_smem") ? &c->optSpmvUSmem : !strcmp(name, "spmv_chunk") ? &c->optSpmvChunk
+                 : !strcmp(name, "spmv_max_cols") ? &c->optSpmvMaxCols : &c->optSpmvWindow;
+        if (*opt == (int)value) return DIPGPU_OK;
+        *opt = (int)value;
         if (c->haveCore) {
             int rc = bind(c);
             if (rc) return rc;
@@ -1341,7 +1344,6 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
         }
         return DIPGPU_OK;
     }
-    if (!strcmp(name, "spmv_u_smem")) { c->optSpmvUSmem = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "dp_threads") || !strcmp(name, "dp_cells_per_thread") || !strcmp(name, "dp_items_per_step") ||
         !strcmp(name, "dp_no_guard") || !strcmp(name, "fuse_filter")) {
         if (!strcmp(name, "dp_threads")) c->optThreads = (int)value;

@@ -374,14 +374,20 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const int CH = a.chunkCols;
     double *rowBase = reinterpret_cast<double *>(smemRaw);
     const int bufStride = RC + G;
-    double *itP = rowBase + 2 * bufStride;
-    int32_t *itW = reinterpret_cast<int32_t *>(itP + (CH + 4));
+    // non-fused: rows | rawRc | itP | rawW | itW | counts | mbarrier
+    // fused:     rows | itP | itW | counts | mbarrier | itC | { rawRc, rawW } = decision bits
+    // (the TMA destinations are dead once the items are compacted, the bits are written afterwards)
+    double *rawRc = FUSE ? nullptr : rowBase + 2 * bufStride;
+    double *itP = FUSE ? rowBase + 2 * bufStride : rawRc + (CH + 2);
+    int32_t *rawW = FUSE ? nullptr : reinterpret_cast<int32_t *>(itP + (CH + 4));
+    int32_t *itW = FUSE ? reinterpret_cast<int32_t *>(itP + (CH + 4)) : rawW + (CH + 4);
     int32_t *warpCnt = itW + (CH + 4);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(warpCnt + 32);
     int32_t *itC = reinterpret_cast<int32_t *>(mbar + 2);                       // FUSE only
-    // raw TMA destinations; FUSE: the same bytes hold the decision bits once the items are compacted
-    double *rawRc = reinterpret_cast<double *>(FUSE ? itC + (CH + 4) : reinterpret_cast<int32_t *>(mbar + 2));
-    int32_t *rawW = reinterpret_cast<int32_t *>(rawRc + (CH + 2));
+    if (FUSE) {
+        rawRc = reinterpret_cast<double *>(itC + (CH + 4));
+        rawW = reinterpret_cast<int32_t *>(rawRc + (CH + 2));
+    }
     uint32_t *sBits = reinterpret_cast<uint32_t *>(rawRc);                      // FUSE only
     int32_t *sTaken = reinterpret_cast<int32_t *>(itP);                         // FUSE only: itP is dead after the DP
 
@@ -435,7 +441,9 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         const int g0 = colStart + chunkBase;
         const int shiftRc = g0 & 1, shiftW = g0 & 3;
         // node bounds (DecompAlgo::setSubProbBounds): a column fixed to 0 or to 1 stays out of the DP
-        const uint8_t *fixB = a.back.fix != nullptr ? a.back.fix + g0 : nullptr;
+        // (fused shapes test the flags here; the large-shard path is fed reduced costs in which the fixed
+        // columns are already +0, so that its hot kernels stay exactly as they are without bounds)
+        const uint8_t *fixB = (FUSE && a.back.fix != nullptr) ? a.back.fix + g0 : nullptr;
         // ---- stage the chunk's reduced costs and weights with TMA bulk copies
         if (t == 0) {
             const uint32_t bytesRc = (uint32_t)(((shiftRc + len + 1) & ~1) * 8);
@@ -1188,6 +1196,15 @@ static void fillBackArgs(Ctx *c, const double *dRedCost, const double *dAlpha, B
 static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
                     double redCostEps, int nVec, bool batch, cudaStream_t st);
 
+// Large-shard path under node bounds: the DP kernels read a copy of the reduced costs in which every
+// fixed column is +0 (so it is not an item); the backtrack kernel still sums the true reduced costs.
+__global__ void __launch_bounds__(256) mask_fixed_kernel(int n, const double *__restrict__ rc, const uint8_t *__restrict__ fix,
+                                                         double *__restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = fix[j] ? 0.0 : rc[j];
+}
+
 int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st)
 {
     return launchDp(c, dRedCost, 0, dAlpha, 0, redCostEps, 1, false, st);
@@ -1212,6 +1229,16 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     KnapFn fn = (g.fuse ? e->fnFuse : e->fn)[g.guard > 0 ? 1 : 0][g.items - 1];
     KnapArgs a;
     a.redCost = dRedCost;
+    if (c->haveFix && !g.fuse) {
+        const int n = c->nBlockCols;
+        if (!c->dRcEff) {
+            DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&c->dRcEff), sizeof(double) * ((size_t)c->N + 16)));
+            DIPGPU_CUDA(c, cudaMemset(c->dRcEff, 0, sizeof(double) * ((size_t)c->N + 16)));
+        }
+        mask_fixed_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, dRedCost, c->dFix, c->dRcEff);
+        c->launches++;
+        a.redCost = c->dRcEff;
+    }
     a.weight = c->dWeight;
     a.blockColStart = c->dBlockColStart;
     a.capacity = c->haveFix ? c->dCapEff : c->dCapacity;

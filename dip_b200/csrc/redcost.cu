@@ -79,7 +79,8 @@ template <bool ROW16> __host__ __device__ inline uint32_t tileRowBytes(int len)
 
 struct StreamArgs {
     int nTiles;
-    const uint2 *tileRec;       // per tile {byte offset / 16 into blob, bytes}
+    const uint2 *tileRec;       // per tile {byte offset / 16 into blob, bytes}, grouped by owning warp
+    const int32_t *warpStart;   // warp w of the launch owns tiles [warpStart[w], warpStart[w+1])
     const unsigned char *blob;  // self-contained tiles (layout: SpmvTileHeader in common.cuh)
     const double *u;
     int uLen;
@@ -118,7 +119,9 @@ __global__ void __launch_bounds__(1024, 1) redcost_stream_kernel(const __grid_co
     unsigned char *stageBase = wbase + barBytes;
     const int warpsPerCta = blockDim.x >> 5;
     const int gw = blockIdx.x * warpsPerCta + warp;
-    const int totalWarps = gridDim.x * warpsPerCta;
+    // this warp's tiles: one contiguous run of the (host-ordered) tile list, so that the pieces of a
+    // slice that was cut by step range follow each other on the same warp
+    const int t0 = __ldg(a.warpStart + gw), t1 = __ldg(a.warpStart + gw + 1);
 
     auto issue = [&](const uint2 rec, int s) {
         uint64_t *bar = full + s;
@@ -136,10 +139,8 @@ __global__ void __launch_bounds__(1024, 1) redcost_stream_kernel(const __grid_co
         for (int s = 0; s < NST; ++s)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rcSmemAddr(full + s)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int s = 0; s < NST; ++s) {
-            const int tile = gw + s * totalWarps;
-            if (tile < a.nTiles) issue(__ldg(a.tileRec + tile), s);
-        }
+        for (int s = 0; s < NST; ++s)
+            if (t0 + s < t1) issue(__ldg(a.tileRec + t0 + s), s);
     }
     if (UMODE != 0) {
         // the dual vector: one bulk copy (16-byte granules) + a plain tail, on its own mbarrier
@@ -174,18 +175,20 @@ __global__ void __launch_bounds__(1024, 1) redcost_stream_kernel(const __grid_co
 
     int s = 0;
     uint32_t parity = 0;
-    for (int tile = gw; tile < a.nTiles; tile += totalWarps) {
+    double sum = 0.0;  // lane's running column sum: carried across the pieces of a slice cut by step range
+    for (int tile = t0; tile < t1; ++tile) {
         // the record of the tile that will refill this stage: loaded now, used after the reduction
-        const int tRefill = tile + NST * totalWarps;
+        const int tRefill = tile + NST;
         const uint2 recRefill = __ldg(a.tileRec + min(tRefill, a.nTiles - 1));
         const unsigned char *stage = stageBase + (size_t)s * a.stageBytes;
         rcMbarWait(full + s, parity);
         // shared-window addresses + ld.shared: the loads of a batch are issued back to back, in
         // the order written (rows, values, then the dependent gathers of the duals)
         const uint32_t stA = sUaddr + (uint32_t)(stage - sm);
-        const int firstCol = (int)ldsU32(stA), nCols = (int)ldsU32(stA + 4), nEnt = (int)ldsU32(stA + 8);
-        const uint32_t stepStride = ldsU32(stA + 12);
-        const int nSlices = (nCols + 31) >> 5;
+        const int firstCol = (int)ldsU32(stA), nSlices = (int)ldsU32(stA + 4), nEnt = (int)ldsU32(stA + 8);
+        const uint32_t w3 = ldsU32(stA + 12);
+        const uint32_t stepStride = w3 & 0xffffu;
+        const bool pieceFirst = (w3 >> 16) & 1u, pieceLast = (w3 >> 17) & 1u;
         const uint32_t lenA = stA + (uint32_t)sizeof(SpmvTileHeader);
         const uint32_t colA = lenA + (uint32_t)nSlices * 64u;
         const uint32_t cA = colA + (uint32_t)nSlices * 64u;
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(1024, 1) redcost_stream_kernel(const __grid_co
             const double cj = ldsF64(cA + (uint32_t)(q * 32 + lane) * 8u);
             const int maxLen = (int)ldsU16(lenA + (uint32_t)q * 64u);  // lane 0 holds the slice's longest column
             const uint32_t offQ = offA + (uint32_t)q * stepStride * 2u;
-            double sum = 0.0;
+            if (pieceFirst) sum = 0.0;
             for (int i0 = 0; i0 < maxLen; i0 += 4) {
                 // first entry of steps i0..i0+3 (4 x uint16, warp-uniform); the lanes whose column is
                 // longer than the step are a PREFIX of the warp (columns sorted by length on the host)
@@ -230,11 +233,11 @@ __global__ void __launch_bounds__(1024, 1) redcost_stream_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 4; ++j) sum = __dadd_rn(sum, __dmul_rn(g[j], v[j]));
             }
-            if (q * 32 + lane < nCols) outVec[firstCol + colL] = a.phase1 ? -sum : cj - sum;  // DecompAlgo.cpp:4538-4545
+            if (pieceLast && colL != 0xffff) outVec[firstCol + colL] = a.phase1 ? -sum : cj - sum;  // DecompAlgo.cpp:4538-4545
         }
         // every lane is done reading the stage before the bulk copy (async proxy) refills it
         __syncwarp();
-        if (lane == 0 && tRefill < a.nTiles) issue(recRefill, s);
+        if (lane == 0 && tRefill < t1) issue(recRefill, s);
         if (++s == NST) {
             s = 0;
             parity ^= 1u;
@@ -285,9 +288,59 @@ redcost_csc_kernel(int N, const int64_t *__restrict__ colStart,
 }
 
 
+// Launch shape of the stream kernel for this matrix (decided when the tiles are built, because the
+// tiles are dealt to the launch's warps on the host).
+static void planSpmvLaunch(Ctx *c, int nTiles)
+{
+    const int sms = c->smCount > 0 ? c->smCount : 148;
+    const size_t maxSmem = 227 * 1024;
+    const int uLen = c->R + c->numConvex;
+    const size_t stageBytes = (size_t)c->spmvStageBytes;
+    const size_t uBytes = (((size_t)uLen + 1) & ~(size_t)1) * 8 + 16;  // + the u mbarrier
+    auto warpBytesFor = [&](int nst) { return (size_t)((nst * 8 + 15) & ~15) + (size_t)nst * stageBytes; };
+    // u in shared memory pays when it is gathered irregularly and re-used: many more stored
+    // entries than duals, and enough room left for the stages
+    const bool reuse = c->nnz >= 8 * (int64_t)uLen;
+    int mode = 0;
+    if (reuse && uBytes + 8 * warpBytesFor(2) <= maxSmem && nTiles >= 24 * sms) mode = 1;
+    if (c->optSpmvUSmem >= 0) mode = c->optSpmvUSmem != 0 ? 1 : 0;
+    if (mode == 1 && uBytes + warpBytesFor(2) > maxSmem) mode = 0;
+    int nst = c->optSpmvStages > 0 ? std::min(c->optSpmvStages, kSpmvMaxStages) : 2;  // measured: 2 x 16+ warps beats 3 x 11
+    nst = std::max(nst, 2);
+    int warps, grid;
+    size_t bytes;
+    if (mode != 0) {
+        // persistent, one CTA per SM: as many warps as fit beside the duals
+        while (nst > 2 && uBytes + 8 * warpBytesFor(nst) > maxSmem) --nst;
+        warps = (int)std::min<size_t>(32, (maxSmem - uBytes) / warpBytesFor(nst));
+        if (c->optSpmvWarps > 0) warps = std::min(warps, c->optSpmvWarps);
+        warps = std::max(warps, 1);
+        bytes = uBytes + (size_t)warps * warpBytesFor(nst);
+        grid = sms;
+    } else {
+        warps = c->optSpmvWarps > 0 ? std::min(c->optSpmvWarps, 32) : 8;
+        while (warps > 1 && (size_t)warps * warpBytesFor(nst) > maxSmem) --warps;
+        bytes = (size_t)warps * warpBytesFor(nst);
+        const int ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(4, maxSmem / std::max<size_t>(bytes, 1)));
+        grid = std::max(1, std::min((nTiles + warps - 1) / warps, ctasPerSm * sms));
+    }
+    c->spmvMode = mode;
+    c->spmvNst = nst;
+    c->spmvWarps = warps;
+    c->spmvGrid = grid;
+    c->spmvSmem = bytes;
+    c->spmvUBytes = mode != 0 ? (int)uBytes : 0;
+}
+
 // Host side of the stream kernel: cut the columns into tiles and lay each tile out as the kernel
 // reads it (SpmvTileHeader in common.cuh).  colStart/rowMaster/val: CSC of A'' with the entries
 // of a column in the reference's scatter order (descending rows).
+//
+// Columns are taken window by window ("spmv_window" consecutive columns); inside a window they are
+// sorted by length and cut into slices of 32, so the lanes of a slice carry nearly equal work.  Short
+// slices are packed several to a tile; a slice with more entries than the tile budget is cut by STEP
+// RANGE into pieces that follow each other on one warp, the lanes' running sums carried from piece
+// to piece -- any column length runs through the stream kernel, in the reference's order.
 int buildSpmvTiles(Ctx *c, const std::vector<int64_t> &colStart, const std::vector<int32_t> &rowMaster,
                    const std::vector<double> &val)
 {
@@ -297,82 +350,148 @@ int buildSpmvTiles(Ctx *c, const std::vector<int64_t> &colStart, const std::vect
     if (N <= 0 || colStart[N] >= (int64_t)1 << 31) return DIPGPU_OK;
     const bool row16 = (int64_t)c->R + c->numConvex <= 65536;
     const int sms = c->smCount > 0 ? c->smCount : 148;
-    // columns per warp tile: up to 32*kSpmvColsPerLane, fewer on small matrices so that every SM
-    // still gets ~16 warp tiles (a GAP-E sweep is latency-bound: more, shorter tiles in flight)
+    // slices per tile: up to kSpmvColsPerLane, fewer on small matrices so that every SM still gets
+    // ~16 warp tiles (a GAP-E sweep is latency-bound: more, shorter tiles in flight)
     int maxCols = (int)std::min<int64_t>(32 * kSpmvColsPerLane, (int64_t)N / (16 * sms)) & ~31;
     maxCols = std::max(32, maxCols);
     if (c->optSpmvMaxCols > 0) maxCols = std::max(32, std::min(c->optSpmvMaxCols & ~31, 32 * kSpmvColsPerLane));
+    const int maxSlices = maxCols / 32;
     const int chunk = std::max(32, std::min(c->optSpmvChunk > 0 ? c->optSpmvChunk : kSpmvChunk, kSpmvChunkMax));
-    std::vector<int32_t> tileCol(1, 0);
-    for (int j = 0; j < N;) {
-        int e = j;
-        while (e < N && e - j < maxCols && colStart[e + 1] - colStart[j] <= chunk &&
-               colStart[e + 1] - colStart[e] <= 65535)
-            ++e;
-        if (e == j) return DIPGPU_OK;  // a single column longer than a tile: lane-cooperative kernel
-        tileCol.push_back(e);
-        j = e;
-    }
-    const size_t nt = tileCol.size() - 1;
-    std::vector<uint32_t> rec(2 * nt);
-    std::vector<size_t> off(nt + 1, 0);
-    std::vector<int32_t> stepStride(nt, 0);
-    size_t maxBytes = 0;
+    int window = c->optSpmvWindow > 0 ? c->optSpmvWindow : kSpmvWindow;
+    window = std::max(32, std::min(window, 32768)) & ~31;
     auto colLen = [&](int col) { return (int)(colStart[col + 1] - colStart[col]); };
-    for (size_t k = 0; k < nt; ++k) {
-        const int first = tileCol[k], nCols = tileCol[k + 1] - first;
-        const int nEnt = (int)(colStart[tileCol[k + 1]] - colStart[first]);
-        const int nSlices = (nCols + 31) / 32;
-        int maxLen = 0;
-        for (int col = first; col < first + nCols; ++col) maxLen = std::max(maxLen, colLen(col));
-        stepStride[k] = (maxLen + 1 + 3) & ~3;  // step offsets of a slice: maxLen + 1 entries, read 4 at a time
-        const size_t bytes = sizeof(SpmvTileHeader) + (size_t)nSlices * (64 + 64 + 256) +
-                             (((size_t)nSlices * stepStride[k] * 2 + 15) & ~(size_t)15) + tileValBytes(nEnt) +
-                             (row16 ? tileRowBytes<true>(nEnt) : tileRowBytes<false>(nEnt));
-        off[k + 1] = off[k] + bytes;
-        maxBytes = std::max(maxBytes, bytes);
-        rec[2 * k + 1] = (uint32_t)bytes;
+
+    struct Slice { int lanes; int col[32]; int s0, s1; };       // columns (lane order) and step range
+    struct Tile { int winFirst; int nSl; int firstSlice; int nEnt; int stepStride; bool first, last; size_t bytes; };
+    std::vector<Slice> slices;
+    std::vector<Tile> tiles;
+    std::vector<std::pair<int, int>> units;  // {first tile, tiles}: pieces of one slice stay together
+    std::vector<int> order((size_t)window);
+    auto tileBytes = [&](int nSl, int stepStride, int nEnt) {
+        return sizeof(SpmvTileHeader) + (size_t)nSl * (64 + 64 + 256) + (((size_t)nSl * stepStride * 2 + 15) & ~(size_t)15) +
+               tileValBytes(nEnt) + (row16 ? tileRowBytes<true>(nEnt) : tileRowBytes<false>(nEnt));
+    };
+    auto entriesInSteps = [&](const Slice &sl, int s0, int s1) {
+        int e = 0;
+        for (int l = 0; l < sl.lanes; ++l) e += std::max(0, std::min(colLen(sl.col[l]), s1) - s0);
+        return e;
+    };
+    for (int wf = 0; wf < N; wf += window) {
+        const int wn = std::min(window, N - wf);
+        for (int l = 0; l < wn; ++l) order[l] = wf + l;
+        // lane l of a slice owns the slice's l-th longest column (stable: equal lengths keep column order)
+        std::stable_sort(order.begin(), order.begin() + wn, [&](int x, int y) { return colLen(x) > colLen(y); });
+        Tile pend{wf, 0, 0, 0, 0, true, true, 0};
+        auto flush = [&]() {
+            if (pend.nSl == 0) return;
+            pend.bytes = tileBytes(pend.nSl, pend.stepStride, pend.nEnt);
+            units.push_back({(int)tiles.size(), 1});
+            tiles.push_back(pend);
+            pend = Tile{wf, 0, 0, 0, 0, true, true, 0};
+        };
+        for (int q0 = 0; q0 < wn; q0 += 32) {
+            Slice sl;
+            sl.lanes = std::min(32, wn - q0);
+            for (int l = 0; l < sl.lanes; ++l) sl.col[l] = order[q0 + l];
+            const int maxLen = colLen(sl.col[0]);
+            sl.s0 = 0;
+            sl.s1 = maxLen;
+            const int ent = entriesInSteps(sl, 0, maxLen);
+            const int stride = (maxLen + 1 + 3) & ~3;  // step offsets: maxLen + 1 entries, read 4 at a time
+            if (ent <= chunk) {
+                if (pend.nSl > 0 && (pend.nEnt + ent > chunk || pend.nSl >= maxSlices)) flush();
+                if (pend.nSl == 0) pend.firstSlice = (int)slices.size();
+                slices.push_back(sl);
+                pend.nSl++;
+                pend.nEnt += ent;
+                pend.stepStride = std::max(pend.stepStride, stride);
+            } else {
+                flush();
+                // cut by step range: pieces of <= chunk entries (a step holds <= 32)
+                const int firstTile = (int)tiles.size();
+                for (int s0 = 0; s0 < maxLen;) {
+                    int s1 = s0, e = 0;
+                    while (s1 < maxLen) {
+                        const int add = entriesInSteps(sl, s1, s1 + 1);
+                        if (e + add > chunk && s1 > s0) break;
+                        e += add;
+                        ++s1;
+                    }
+                    Slice pc = sl;
+                    pc.s0 = s0;
+                    pc.s1 = s1;
+                    Tile t{wf, 1, (int)slices.size(), e, (s1 - s0 + 1 + 3) & ~3, s0 == 0, s1 == maxLen, 0};
+                    t.bytes = tileBytes(1, t.stepStride, e);
+                    slices.push_back(pc);
+                    tiles.push_back(t);
+                    s0 = s1;
+                }
+                units.push_back({firstTile, (int)tiles.size() - firstTile});
+            }
+        }
+        flush();
     }
-    if (off[nt] / 16 >= ((size_t)1 << 32)) return DIPGPU_OK;
+    const size_t nt = tiles.size();
+    size_t maxBytes = 0;
+    for (const Tile &t : tiles) maxBytes = std::max(maxBytes, t.bytes);
+    c->spmvStageBytes = (int)((maxBytes + 15) & ~(size_t)15);
+    planSpmvLaunch(c, (int)nt);
+    if (c->spmvSmem > 227 * 1024) { c->spmvStageBytes = 0; return DIPGPU_OK; }  // lane-cooperative kernel instead
+
+    // deal the units to the launch's warps (unit k -> warp k mod W): each warp's tiles become one
+    // contiguous run of the tile list
+    const int W = c->spmvGrid * c->spmvWarps;
+    std::vector<std::vector<int>> perWarp((size_t)W);
+    for (size_t k = 0; k < units.size(); ++k)
+        for (int q = 0; q < units[k].second; ++q) perWarp[k % (size_t)W].push_back(units[k].first + q);
+    std::vector<int32_t> warpStart((size_t)W + 1, 0);
+    std::vector<int> tileOrder;
+    tileOrder.reserve(nt);
+    for (int w = 0; w < W; ++w) {
+        warpStart[(size_t)w] = (int32_t)tileOrder.size();
+        tileOrder.insert(tileOrder.end(), perWarp[(size_t)w].begin(), perWarp[(size_t)w].end());
+    }
+    warpStart[(size_t)W] = (int32_t)tileOrder.size();
+
+    std::vector<size_t> off(nt + 1, 0);
+    for (size_t k = 0; k < nt; ++k) off[k + 1] = off[k] + tiles[(size_t)tileOrder[k]].bytes;
+    if (off[nt] / 16 >= ((size_t)1 << 32)) { c->spmvStageBytes = 0; return DIPGPU_OK; }
+    std::vector<uint32_t> rec(2 * std::max<size_t>(nt, 1), 0);
     std::vector<unsigned char> blob(off[nt] + 64, 0);
     const bool haveObj = (int)c->hObj.size() >= N;
-    std::vector<int> order(32);
     for (size_t k = 0; k < nt; ++k) {
+        const Tile &t = tiles[(size_t)tileOrder[k]];
         rec[2 * k + 0] = (uint32_t)(off[k] / 16);
-        const int first = tileCol[k], nCols = tileCol[k + 1] - first;
-        const int nEnt = (int)(colStart[tileCol[k + 1]] - colStart[first]);
-        const int nSlices = (nCols + 31) / 32;
+        rec[2 * k + 1] = (uint32_t)t.bytes;
         unsigned char *p = blob.data() + off[k];
         SpmvTileHeader *h = reinterpret_cast<SpmvTileHeader *>(p);
-        h->firstCol = first;
-        h->nCols = nCols;
-        h->nEnt = nEnt;
-        h->stepStride = stepStride[k];
+        h->firstCol = t.winFirst;
+        h->nSlices = t.nSl;
+        h->nEnt = t.nEnt;
+        h->strideFlags = (int32_t)((uint32_t)t.stepStride | (t.first ? 1u << 16 : 0u) | (t.last ? 1u << 17 : 0u));
         uint16_t *len = reinterpret_cast<uint16_t *>(p + sizeof(SpmvTileHeader));
-        uint16_t *colL = len + (size_t)nSlices * 32;
-        double *cc = reinterpret_cast<double *>(colL + (size_t)nSlices * 32);
-        uint16_t *stepOff = reinterpret_cast<uint16_t *>(cc + (size_t)nSlices * 32);
+        uint16_t *colL = len + (size_t)t.nSl * 32;
+        double *cc = reinterpret_cast<double *>(colL + (size_t)t.nSl * 32);
+        uint16_t *stepOff = reinterpret_cast<uint16_t *>(cc + (size_t)t.nSl * 32);
         double *tv = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(stepOff) +
-                                                (((size_t)nSlices * stepStride[k] * 2 + 15) & ~(size_t)15));
-        unsigned char *tr = reinterpret_cast<unsigned char *>(tv) + tileValBytes(nEnt);
+                                                (((size_t)t.nSl * t.stepStride * 2 + 15) & ~(size_t)15));
+        unsigned char *tr = reinterpret_cast<unsigned char *>(tv) + tileValBytes(t.nEnt);
         int w = 0;
-        for (int q = 0; q < nSlices; ++q) {
-            const int c0 = first + 32 * q, n = std::min(first + nCols, c0 + 32) - c0;
-            // lane l owns the l-th longest column of the slice (stable: equal lengths keep column order)
-            for (int l = 0; l < n; ++l) order[l] = c0 + l;
-            std::stable_sort(order.begin(), order.begin() + n, [&](int x, int y) { return colLen(x) > colLen(y); });
-            for (int l = 0; l < n; ++l) {
-                len[q * 32 + l] = (uint16_t)colLen(order[l]);
-                colL[q * 32 + l] = (uint16_t)(order[l] - first);
-                cc[q * 32 + l] = haveObj ? c->hObj[order[l]] : 0.0;
+        for (int q = 0; q < t.nSl; ++q) {
+            const Slice &sl = slices[(size_t)t.firstSlice + q];
+            for (int l = 0; l < 32; ++l) {
+                const bool on = l < sl.lanes;
+                len[q * 32 + l] = (uint16_t)(on ? std::max(0, std::min(colLen(sl.col[l]), sl.s1) - sl.s0) : 0);
+                colL[q * 32 + l] = (uint16_t)(on ? sl.col[l] - t.winFirst : 0xffff);
+                cc[q * 32 + l] = (on && haveObj) ? c->hObj[sl.col[l]] : 0.0;
             }
-            const int maxLen = n > 0 ? colLen(order[0]) : 0;
-            uint16_t *so = stepOff + (size_t)q * stepStride[k];
-            for (int i = 0; i < stepStride[k]; ++i) {
+            uint16_t *so = stepOff + (size_t)q * t.stepStride;
+            for (int i = 0; i < t.stepStride; ++i) {
                 so[i] = (uint16_t)w;
-                if (i < maxLen)
-                    for (int l = 0; l < n && colLen(order[l]) > i; ++l) {
-                        const int64_t src = colStart[order[l]] + i;
+                const int step = sl.s0 + i;
+                if (step < sl.s1)
+                    for (int l = 0; l < sl.lanes && colLen(sl.col[l]) > step; ++l) {
+                        const int64_t src = colStart[sl.col[l]] + step;
                         tv[w] = val[src];
                         if (row16) reinterpret_cast<uint16_t *>(tr)[w] = (uint16_t)rowMaster[src];
                         else reinterpret_cast<int32_t *>(tr)[w] = rowMaster[src];
@@ -381,16 +500,16 @@ int buildSpmvTiles(Ctx *c, const std::vector<int64_t> &colStart, const std::vect
             }
         }
     }
-    int rc;
     if (c->dTileRec) { cudaFree(c->dTileRec); c->dTileRec = nullptr; }
     if (c->dSpmvBlob) { cudaFree(c->dSpmvBlob); c->dSpmvBlob = nullptr; }
+    if (c->dSpmvWarpStart) { cudaFree(c->dSpmvWarpStart); c->dSpmvWarpStart = nullptr; }
     DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&c->dTileRec), sizeof(uint32_t) * rec.size()));
     DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&c->dSpmvBlob), blob.size()));
+    DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&c->dSpmvWarpStart), sizeof(int32_t) * warpStart.size()));
     DIPGPU_CUDA(c, cudaMemcpy(c->dSpmvBlob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     DIPGPU_CUDA(c, cudaMemcpy(c->dTileRec, rec.data(), sizeof(uint32_t) * rec.size(), cudaMemcpyHostToDevice));
-    (void)rc;
+    DIPGPU_CUDA(c, cudaMemcpy(c->dSpmvWarpStart, warpStart.data(), sizeof(int32_t) * warpStart.size(), cudaMemcpyHostToDevice));
     c->nSpmvTiles = (int)nt;
-    c->spmvStageBytes = (int)((maxBytes + 15) & ~(size_t)15);
     return DIPGPU_OK;
 }
 
@@ -407,6 +526,7 @@ int launchRedCostBatch(Ctx *c, const double *dU, int64_t uStride, double *dOut, 
         StreamArgs a;
         a.nTiles = c->nSpmvTiles;
         a.tileRec = reinterpret_cast<const uint2 *>(c->dTileRec);
+        a.warpStart = c->dSpmvWarpStart;
         a.blob = c->dSpmvBlob;
         a.u = dU;
         a.uLen = c->R + c->numConvex;
@@ -415,56 +535,19 @@ int launchRedCostBatch(Ctx *c, const double *dU, int64_t uStride, double *dOut, 
         a.uStride = uStride;
         a.outStride = outStride;
         a.stageBytes = c->spmvStageBytes;
-        const int sms = c->smCount > 0 ? c->smCount : 148;
-        const size_t maxSmem = 227 * 1024;
+        a.nStages = c->spmvNst;
+        a.uSmemBytes = c->spmvUBytes;
         const bool row16 = (int64_t)c->R + c->numConvex <= 65536;
-        const size_t uBytes = (((size_t)a.uLen + 1) & ~(size_t)1) * 8 + 16;  // + the u mbarrier
-        auto warpBytesFor = [&](int nst) { return (size_t)((nst * 8 + 15) & ~15) + (size_t)nst * a.stageBytes; };
-        // u in shared memory pays when it is gathered irregularly and re-used: many more stored
-        // entries than duals, and enough room left for the stages
-        const bool reuse = c->nnz >= 8 * (int64_t)a.uLen;
-        int mode = 0;
-        if (reuse && uBytes + 8 * warpBytesFor(2) <= maxSmem && c->nSpmvTiles >= 24 * sms) mode = 1;
-        if (c->optSpmvUSmem >= 0) mode = c->optSpmvUSmem != 0 ? 1 : 0;
-        if (mode == 1 && uBytes + warpBytesFor(2) > maxSmem) mode = 0;
         typedef void (*Fn)(const StreamArgs);
-        Fn fn;
-        size_t bytes;
-        int grid, threads;
-        if (mode != 0) {
-            // persistent, one CTA per SM: as many warps as fit beside the duals, each with a deep ring
-            int nst = c->optSpmvStages > 0 ? std::min(c->optSpmvStages, kSpmvMaxStages) : 2;  // measured: 2 x 16+ warps beats 3 x 11
-            nst = std::max(nst, 2);
-            while (nst > 2 && uBytes + 8 * warpBytesFor(nst) > maxSmem) --nst;
-            int warps = (int)std::min<size_t>(32, (maxSmem - uBytes) / warpBytesFor(nst));
-            if (c->optSpmvWarps > 0) warps = std::min(warps, c->optSpmvWarps);
-            warps = std::max(warps, 1);
-            a.nStages = nst;
-            a.uSmemBytes = (int)uBytes;
-            bytes = uBytes + (size_t)warps * warpBytesFor(nst);
-            fn = row16 ? redcost_stream_kernel<1, true> : redcost_stream_kernel<1, false>;
-            grid = sms;
-            threads = warps * 32;
-        } else {
-            int nst = c->optSpmvStages > 0 ? std::min(c->optSpmvStages, kSpmvMaxStages) : 2;
-            nst = std::max(nst, 2);
-            a.nStages = nst;
-            a.uSmemBytes = 0;
-            int warps = c->optSpmvWarps > 0 ? std::min(c->optSpmvWarps, 32) : 8;
-            while (warps > 1 && (size_t)warps * warpBytesFor(nst) > maxSmem) --warps;
-            bytes = (size_t)warps * warpBytesFor(nst);
-            fn = row16 ? redcost_stream_kernel<0, true> : redcost_stream_kernel<0, false>;
-            const int ctasPerSm = (int)std::max<size_t>(1, std::min<size_t>(4, maxSmem / std::max<size_t>(bytes, 1)));
-            grid = std::max(1, std::min((c->nSpmvTiles + warps - 1) / warps, ctasPerSm * sms));
-            threads = warps * 32;
-        }
-        if (bytes > maxSmem) return fail(c, DIPGPU_ERR_UNSUPPORTED, "reduced-cost tiles of %d bytes do not fit shared memory", a.stageBytes);
+        const Fn fn = c->spmvMode != 0 ? (row16 ? redcost_stream_kernel<1, true> : redcost_stream_kernel<1, false>)
+                                       : (row16 ? redcost_stream_kernel<0, true> : redcost_stream_kernel<0, false>);
+        const size_t bytes = c->spmvSmem;
         if (c->spmvFn != (void *)fn || c->spmvFnSmem != bytes) {
             DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
             c->spmvFn = (void *)fn;
             c->spmvFnSmem = bytes;
         }
-        fn<<<dim3(grid, nVec, 1), threads, bytes, st>>>(a);
+        fn<<<dim3(c->spmvGrid, nVec, 1), c->spmvWarps * 32, bytes, st>>>(a);
         c->launches++;
         DIPGPU_CUDA(c, cudaGetLastError());
         return DIPGPU_OK;

@@ -16,12 +16,14 @@ dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+rflush = torch.ones(64 << 20, dtype=torch.float32, device=dev)
 
 
 def timeit(p, ud, model, reps=13):
     ts = []
     for it in range(reps):
-        flush.fill_(1)
+        flush.fill_(1)   # 256 MiB written ...
+        rflush.sum()     # ... then 256 MiB read: the L2 holds clean lines, no write-back under the timed sweep
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         p.calcRedCostDev(ud.data_ptr(), model.u_len, stream=stream.cuda_stream)
@@ -38,17 +40,12 @@ def run(name, model, u, configs):
         p.setObjective(model.objective)
         ud = torch.from_numpy(u).to(dev)
         by = model.spmv_bytes()
-        last_chunk = None
         for cfg in configs:
             lanes = cfg.get("lanes", 0)
             p.set_option("spmv_lanes", lanes)
             if lanes == 0:
-                if cfg.get("chunk", 0) != last_chunk:
-                    p.set_option("spmv_chunk", cfg.get("chunk", 0))
-                    last_chunk = cfg.get("chunk", 0)
-                p.set_option("spmv_stages", cfg.get("stages", 0))
-                p.set_option("spmv_warps", cfg.get("warps", 0))
-                p.set_option("spmv_u_smem", cfg.get("usmem", -1))
+                for opt, dflt in (("chunk", 0), ("window", 0), ("stages", 0), ("warps", 0), ("u_smem", -1), ("max_cols", 0)):
+                    p.set_option("spmv_" + opt, cfg.get(opt, dflt))
             ms, mn = timeit(p, ud, model)
             print(f"{name:10s} {str(cfg):60s} {ms*1e3:8.1f} us  min {mn*1e3:8.1f} us  "
                   f"{by/ms/1e6:8.1f} GB/s ({by/1e6:.1f} MB)", flush=True)
@@ -58,14 +55,14 @@ which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "milp"):
     model, u = I.milpblock_model()
     cfgs = [{}]
-    for chunk in (256, 320, 384, 512):
-        for stages in (2, 3):
-            for warps in (12, 16, 32):
-                cfgs.append({"chunk": chunk, "stages": stages, "warps": warps})
+    for window in (32, 1024, 4096, 16384):
+        for chunk in (256, 384):
+            for warps in (16, 32):
+                cfgs.append({"window": window, "chunk": chunk, "warps": warps})
+    cfgs += [{"window": 4096, "chunk": 192}, {"window": 4096, "chunk": 256, "stages": 3}, {"window": 4096, "chunk": 512}]
     cfgs.append({"lanes": 8})
     run("milpblock", model, u, cfgs)
 if which in ("all", "gape"):
     g = I.gap_pricing_model(I.gap_class_e())
-    cfgs = [{}, {"stages": 2, "warps": 4}, {"stages": 2, "warps": 8}, {"stages": 3, "warps": 8}, {"chunk": 192},
-            {"chunk": 96}, {"lanes": 1}, {"lanes": 4}]
+    cfgs = [{}, {"warps": 4}, {"stages": 3}, {"chunk": 192}, {"max_cols": 64}, {"lanes": 1}]
     run("gap-e", g, I.gap_duals(g, np.random.default_rng(1)), cfgs)
