@@ -56,6 +56,7 @@ class Cols(C.Structure):
         ("nCols", C.c_int32), ("colBlock", C.c_void_p), ("colRedCost", C.c_void_p),
         ("colOrigCost", C.c_void_p), ("colStart", C.c_void_p), ("colInd", C.c_void_p),
         ("nInd", C.c_int64), ("mostNegReducedCost", C.c_double), ("cells", C.c_int64),
+        ("cellsEvaluated", C.c_int64),
     ]
 
 

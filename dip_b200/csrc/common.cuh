@@ -39,7 +39,7 @@ struct ResultHeader {
     int64_t nInd;
     int64_t cells;
     int64_t indCap;
-    int64_t reserved[3];
+    int64_t reserved[3];  // [0]: DP cells actually evaluated (<= cells: the fused kernel's reduction drops items)
 };
 static_assert(sizeof(ResultHeader) == 64, "header is 64 bytes");
 constexpr uint32_t kResultMagic = 0x52504944u;
@@ -207,7 +207,7 @@ struct Ctx {
     int maxBlockCols = 0;      // of the shard
     int maxUsableWeight = 0;   // of the shard: max weight <= its block's capacity
     std::vector<int32_t> hMaxUsableW;  // per block
-    int optThreads = 0, optCellsPerThread = 0, optItemsPerStep = 0, optNoGuard = 0;
+    int optThreads = 0, optCellsPerThread = 0, optItemsPerStep = 0, optNoGuard = 0, optNoPrune = 0;
     void *dpFnConfigured = nullptr;
     size_t dpFnSmem = 0;
     DpGeom geom{};

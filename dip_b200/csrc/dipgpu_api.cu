@@ -230,6 +230,7 @@ static int unpack(Ctx *c, const void *packed, size_t bytes, dipgpu_cols *out)
     out->nCols = h->nKept;
     out->nInd = h->nInd;
     out->cells = h->cells;
+    out->cellsEvaluated = h->reserved[0];
     const bool wantBlocks = out->blockRedCost || out->blockMostNegRC || out->blockOrigCost || out->blockObj || out->blockNnz;
     if (wantBlocks && out->capBlocks < h->firstBlock + m)
         return fail(c, DIPGPU_ERR_OVERFLOW, "capBlocks %d < %d", out->capBlocks, h->firstBlock + m);
@@ -1345,8 +1346,9 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
         return DIPGPU_OK;
     }
     if (!strcmp(name, "dp_threads") || !strcmp(name, "dp_cells_per_thread") || !strcmp(name, "dp_items_per_step") ||
-        !strcmp(name, "dp_no_guard") || !strcmp(name, "fuse_filter")) {
+        !strcmp(name, "dp_no_guard") || !strcmp(name, "fuse_filter") || !strcmp(name, "dp_no_prune")) {
         if (!strcmp(name, "dp_threads")) c->optThreads = (int)value;
+        else if (!strcmp(name, "dp_no_prune")) c->optNoPrune = value != 0;
         else if (!strcmp(name, "dp_cells_per_thread")) c->optCellsPerThread = (int)value;
         else if (!strcmp(name, "dp_items_per_step")) c->optItemsPerStep = (int)value;
         else if (!strcmp(name, "fuse_filter")) c->optFuseFilter = (int)value;

@@ -123,6 +123,7 @@ __device__ __forceinline__ void filterScanBody(const FilterArgs &a, const int NT
         a.hdr->nKept = sCarryCnt;
         a.hdr->nInd = sCarryNnz;
         a.hdr->cells = tot;
+        a.hdr->reserved[0] = tot;  // the large-shard path evaluates every cell
         a.hdr->indCap = a.indCap;
     }
     if (a.fuseCopy == 2) {

@@ -297,6 +297,11 @@ __device__ __forceinline__ void dbgStamp(unsigned long long *buf, int slot)
 }
 
 #define kNegInf (__longlong_as_double((long long)0xfff0000000000000ULL))
+constexpr int kPruneBuckets = 1024;   // efficiency histogram of the reduction pre-pass
+constexpr int kPruneMinItems = 256;   // (columns of the block) below this the DP is about as short as the pre-pass
+constexpr int kPruneTopFill = 2;      // pass 0 runs over the most efficient items worth this many capacities of weight
+constexpr int kPass0Words = 7;        // ... and over at most 32 * kPass0Words (its decision words sit in front of the raw arrays)
+constexpr size_t kPruneScratchBytes = sizeof(int) * 3 * kPruneBuckets + sizeof(double) * 6 + 16;
 
 
 struct KnapArgs {
@@ -325,6 +330,7 @@ struct KnapArgs {
     // and alpha + v*alphaStride and writes the packed result at byte offset v*resStride; the per-block
     // arrays pubWord / scale / shortcut / sel / zShort hold nLocal entries per vector
     long long rcStride, alphaStride, resStride;
+    int prune;                     // FUSE: drop items that cannot be in an optimal solution before the DP
     BackArgs back;
     FilterArgs filt;
 };
@@ -333,7 +339,13 @@ struct KnapArgs {
 // compacted, so they share their bytes with the decision bits (written by the DP afterwards), and the
 // taken list of the backtrack lives in the compacted-profit array (dead after the DP): ~26 KB less
 // per CTA on GAP-E, i.e. three resident CTAs per SM instead of two when dual vectors are batched.
-__host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunkCols, bool fuse)
+__host__ __device__ inline bool dpPruneLayout(int chunkCols, bool fuse, bool prune)
+{
+    // the reduction pre-pass needs its histograms to fit the (not yet written) compacted-item arrays
+    return fuse && prune && (size_t)(chunkCols + 4) * 12 >= kPruneScratchBytes;
+}
+
+__host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunkCols, bool fuse, bool prune)
 {
     size_t b = 0;
     b += sizeof(double) * 2 * ((size_t)rowCells + (size_t)guard);  // two row buffers, each behind its guard
@@ -341,10 +353,13 @@ __host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunk
     b += sizeof(int32_t) * ((size_t)chunkCols + 4);     // compacted weights (+ prefetch pad)
     b += sizeof(int32_t) * 32;                          // per-warp counts
     b += 16;                                            // mbarrier
-    const size_t raw = sizeof(double) * ((size_t)chunkCols + 2) + sizeof(int32_t) * ((size_t)chunkCols + 4);
+    size_t raw = sizeof(double) * ((size_t)chunkCols + 2) + sizeof(int32_t) * ((size_t)chunkCols + 4);
     if (fuse) {
         b += sizeof(int32_t) * ((size_t)chunkCols + 4);                                          // item columns
         const size_t bits = sizeof(uint32_t) * (size_t)((chunkCols + 31) / 32) * (size_t)rowCells;  // decision bits
+        // with the reduction, the raw arrays must outlive pass 0's decision words (its survivor test and
+        // pass 1 read them): they sit behind the first kPass0Words words instead of at the region's start
+        if (dpPruneLayout(chunkCols, fuse, prune)) raw += sizeof(uint32_t) * (size_t)kPass0Words * (size_t)rowCells;
         b += bits > raw ? bits : raw;
     } else {
         b += raw;
@@ -384,11 +399,12 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     int32_t *warpCnt = itW + (CH + 4);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(warpCnt + 32);
     int32_t *itC = reinterpret_cast<int32_t *>(mbar + 2);                       // FUSE only
+    uint32_t *sBits = reinterpret_cast<uint32_t *>(itC + (CH + 4));             // FUSE only
+    const bool pruneLayout = FUSE && dpPruneLayout(CH, true, a.prune != 0);
     if (FUSE) {
-        rawRc = reinterpret_cast<double *>(itC + (CH + 4));
+        rawRc = reinterpret_cast<double *>(sBits + (pruneLayout ? (size_t)kPass0Words * RC : 0));
         rawW = reinterpret_cast<int32_t *>(rawRc + (CH + 2));
     }
-    uint32_t *sBits = reinterpret_cast<uint32_t *>(rawRc);                      // FUSE only
     int32_t *sTaken = reinterpret_cast<int32_t *>(itP);                         // FUSE only: itP is dead after the DP
 
     const int t = threadIdx.x;
@@ -434,6 +450,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
 
     int cur = 0;        // buffer holding c[i-1][.]
     int kGlobal = 0;    // active items processed so far
+    int nItRef = 0;     // FUSE: items the reference's DP runs over (before the reduction)
     uint32_t parity = 0;
 
     for (int chunkBase = 0; chunkBase < nCols; chunkBase += CH) {
@@ -456,18 +473,179 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         parity ^= 1u;
         dbgStamp(a.dbgTimes, 1);
 
+        // ---- reduction, fused shapes (what Pisinger's combo does before its DP): an item is left out
+        // when NO optimal solution can contain it, so the DP over the remaining items -- same order, same
+        // additions, same strict compares -- returns the same optimum bit for bit and the same column,
+        // ties included (a dropped item could only ever have raised the losing side of a compare).
+        //   upper bound, any multiplier L >= 0 (Lagrangian relaxation of the capacity row):
+        //       z(x_j = 1) <= L*cap + sum_k max(0, p_k - L w_k) + min(0, p_j - L w_j)
+        //     with L at both edges of the efficiency bucket where the greedy fill crosses the capacity;
+        //   lower bound: the optimum of the DP over the ~64 most efficient items IN ITEM ORDER -- the
+        //     value the full DP assigns to that very column, so it needs no rounding allowance.
+        // Pass 0 runs the DP over those items; if no other item survives the bound (the usual case) its
+        // decision table is the final one, else pass 1 runs the DP over the survivors.  An item is
+        // dropped only if a bound is below the lower bound by a relative 1e-9, far more than the
+        // rounding of the bound's own sums.
+        auto isItem = [&](int cl) -> bool {
+            return rawRc[shiftRc + cl] < 0.0 && rawW[shiftW + cl] <= cap && (fixB == nullptr || fixB[cl] == 0);
+        };
+        // profit: -redCost (gap_func.py:104), or its scaled integer value
+        // floor(-rc*scale + 0.5) held exactly in fp64 (GAP_KnapPisinger.h:174-177)
+        auto profitOf = [&](int cl) -> double {
+            const double rc = rawRc[shiftRc + cl];
+            return pScale != 0.0 ? (double)(long long)floor((-rc) * pScale + 0.5) : -rc;
+        };
+        bool prune = false;
+        int thrBucket = 0;
+        double lamLo = 0.0, lamHi = 0.0, uLo = 0.0, uHi = 0.0, cut = 0.0, slack = 0.0;
+        // bucket of an item: monotone in its efficiency p/w -- the float's exponent and top five mantissa
+        // bits = 32 buckets per octave over 32 octaves from 2^-12 (times the Pisinger scale); weight 0 =
+        // infinite efficiency = top bucket.  No integer division, no min/max pass: with 1.5 warps per
+        // scheduler every instruction of this pre-pass is paid at its full latency.
+        const int bucket0 = ((127 - 12) << 5) + (pScale >= 1000.0 ? (10 << 5) : pScale >= 10.0 ? (3 << 5) : 0);
+        auto bucketOf = [&](int cl) -> int {
+            const int w = rawW[shiftW + cl];
+            if (w <= 0) return kPruneBuckets - 1;
+            const int q = (int)(__float_as_uint(__fdividef((float)profitOf(cl), (float)w)) >> 18) - bucket0;
+            return min(max(q, 0), kPruneBuckets - 1);
+        };
+        // per column, filled by the histogram pass: its bucket, or 0xffff when it is no item.  Lives in the
+        // UPPER half of the item-column array, which pass 0 (<= 32*kPass0Words items) never reaches.
+        uint16_t *meta = reinterpret_cast<uint16_t *>(itC) + (CH + 4);
+        if (pruneLayout && len >= kPruneMinItems) {
+            int *histW = reinterpret_cast<int *>(itP);          // itP | itW are contiguous and not written yet
+            int *histLo = histW + kPruneBuckets;                // profit sums, fixed point, low 20 bits ...
+            int *histHi = histLo + kPruneBuckets;               // ... and the bits above
+            double *sBound = reinterpret_cast<double *>(histHi + kPruneBuckets);  // lamLo, lamHi, uLo, uHi, sum of all profits
+            int *sCross = reinterpret_cast<int *>(sBound + 6);                    // crossing bucket, threshold bucket
+            for (int k = t; k < 3 * kPruneBuckets; k += T) histW[k] = 0;
+            __syncthreads();
+            // profits in units of 2^-12 (integers in Pisinger mode), rounded UP: the bound stays an upper
+            // bound, and the integer sums do not depend on the order of the atomics
+            const double fix = pScale != 0.0 ? 1.0 : 4096.0;
+            bool tooBig = false;
+            for (int cl = t; cl < len; cl += T) {
+                unsigned int m = 0xffffu;
+                if (isItem(cl)) {
+                    const double pk = profitOf(cl);
+                    tooBig |= !(pk < 268435456.0);
+                    const int bkt = bucketOf(cl);
+                    const unsigned long long v = (unsigned long long)ceil(pk * fix);
+                    atomicAdd(&histW[bkt], rawW[shiftW + cl]);
+                    atomicAdd(&histLo[bkt], (int)(v & 0xfffffull));
+                    atomicAdd(&histHi[bkt], (int)(v >> 20));
+                    m = (unsigned int)bkt;
+                }
+                meta[cl] = (uint16_t)m;
+            }
+            const int anyBig = __syncthreads_or(tooBig ? 1 : 0);
+            const double unfix = pScale != 0.0 ? 1.0 : 1.0 / 4096.0;
+            if (warp == 0) {
+                // From the most efficient bucket down (greedy fill).  With L = the lower edge of bucket c,
+                //     U(L) = L*cap + sum_{buckets >= c} (p - L w)      (every item there has p/w >= L,
+                // every item below has p/w < L), i.e. the bound needs only the buckets' sums.
+                constexpr int perLane = kPruneBuckets / 32;
+                auto histP = [&](int bkt) -> unsigned long long {
+                    return ((unsigned long long)(unsigned int)histHi[bkt] << 20) + (unsigned long long)(unsigned int)histLo[bkt];
+                };
+                long long wSum = 0;
+                unsigned long long pSum = 0ull;
+                for (int q = 0; q < perLane; ++q) {
+                    wSum += histW[lane * perLane + q];
+                    pSum += histP(lane * perLane + q);
+                }
+                long long aboveW = 0;
+                unsigned long long aboveP = 0ull;
+                for (int l2 = 0; l2 < 32; ++l2) {
+                    const long long ow = __shfl_sync(0xffffffffu, wSum, l2);
+                    const unsigned long long op = __shfl_sync(0xffffffffu, pSum, l2);
+                    if (l2 > lane) {
+                        aboveW += ow;
+                        aboveP += op;
+                    }
+                }
+                auto edgeOf = [&](int bkt) -> double {  // the smallest efficiency that falls in bucket bkt
+                    return bkt <= 0 ? 0.0 : (double)__uint_as_float((unsigned int)(bkt + bucket0) << 18);
+                };
+                int cross = -1, topB = -1;
+                long long cumW = aboveW;
+                unsigned long long cumP = aboveP;
+                for (int q = perLane - 1; q >= 0; --q) {
+                    const int bkt = lane * perLane + q;
+                    const long long beforeW = cumW;
+                    const unsigned long long beforeP = cumP;
+                    cumW += histW[bkt];
+                    cumP += histP(bkt);
+                    if (cross < 0 && cumW > (long long)cap && beforeW <= (long long)cap) {
+                        cross = bkt;
+                        const double lLo = edgeOf(bkt), lHi = edgeOf(bkt + 1);
+                        sBound[0] = lLo;
+                        sBound[1] = lHi;
+                        sBound[2] = lLo * (double)cap + ((double)cumP * unfix - lLo * (double)cumW);
+                        sBound[3] = lHi * (double)cap + ((double)beforeP * unfix - lHi * (double)beforeW);
+                    }
+                    // pass 0 takes the buckets down to kPruneTopFill capacities' worth of weight
+                    if (topB < 0 && cumW >= kPruneTopFill * (long long)cap && beforeW < kPruneTopFill * (long long)cap) topB = bkt;
+                }
+                if (lane == 0) sBound[4] = (double)cumP * unfix;  // lane 0 ends at bucket 0: every item
+                const unsigned balC = __ballot_sync(0xffffffffu, cross >= 0);
+                const unsigned balT = __ballot_sync(0xffffffffu, topB >= 0);
+                if (balC == 0u) {
+                    if (lane == 0) sCross[0] = -1;  // everything fits: nothing to drop
+                } else if (lane == 31 - __clz(balC)) {
+                    sCross[0] = cross;
+                }
+                if (balT == 0u) {
+                    if (lane == 0) sCross[1] = 0;   // not that much weight in all: every item
+                } else if (lane == 31 - __clz(balT)) {
+                    sCross[1] = topB;
+                }
+            }
+            __syncthreads();
+            const int cross = sCross[0];
+            if (cross >= 0 && !anyBig) {
+                thrBucket = min(cross, sCross[1]);
+                lamLo = sBound[0];
+                lamHi = sBound[1];
+                uLo = sBound[2];
+                uHi = sBound[3];
+                // an item whose efficiency is within float rounding (2^-21 relative) of a bucket edge may sit on
+                // the wrong side of it; each such item moves a bound by at most 2^-21 of its profit
+                slack = 2e-6 * sBound[4];
+                prune = true;
+            }
+            __syncthreads();  // the scratch is consumed: itP / itW may be written now
+        }
+        auto survives = [&](int cl) -> bool {  // valid once `cut` is set from a lower bound
+            const double pk = profitOf(cl), wk = (double)rawW[shiftW + cl];
+            const double dLo = pk - lamLo * wk, dHi = pk - lamHi * wk;
+            return !((dLo < 0.0 && uLo + dLo < cut) || (dHi < 0.0 && uHi + dHi < cut));
+        };
+        constexpr int kPasses = FUSE ? 2 : 1;
+        int nIt = 0;
+        for (int pass = 0; pass < kPasses; ++pass) {
         // ---- order-preserving compaction of the active items (gap_func.py:102-105): thread t owns
         // the contiguous run [t*per, (t+1)*per) of the chunk's columns (thread order == item order),
         // counts its active items, one block-wide exclusive scan places them.
-        int nIt = 0;
+        nIt = 0;
         if (FUSE) {
+            auto takes = [&](int cl) -> bool {
+                if (prune && pass == 0) {
+                    const int m = meta[cl];  // bucket, 0xffff = no item
+                    return m != 0xffff && m >= thrBucket;
+                }
+                if (!isItem(cl)) return false;
+                return prune ? survives(cl) : true;
+            };
             const int per = (len + T - 1) / T;
             const int c0 = min(len, t * per), c1 = min(len, c0 + per);
-            int mineCnt = 0;
-            for (int cl = c0; cl < c1; ++cl)
-                mineCnt += (rawRc[shiftRc + cl] < 0.0 && rawW[shiftW + cl] <= cap && (fixB == nullptr || fixB[cl] == 0)) ? 1 : 0;
-            // warp-inclusive scan, then the warps' totals
-            int incl = mineCnt;
+            int mineCnt = 0, mineRef = 0;
+            for (int cl = c0; cl < c1; ++cl) {
+                mineRef += ((prune && pass == 0) ? meta[cl] != 0xffff : isItem(cl)) ? 1 : 0;
+                mineCnt += takes(cl) ? 1 : 0;
+            }
+            // warp-inclusive scan, then the warps' totals (low half: taken items, high half: all items)
+            int incl = mineCnt | (mineRef << 16);
 #pragma unroll
             for (int off2 = 1; off2 < 32; off2 <<= 1) {
                 const int up = __shfl_up_sync(0xffffffffu, incl, off2);
@@ -476,20 +654,24 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             if (lane == 31) warpCnt[warp] = incl;
             __syncthreads();
             int off = 0;
+            nItRef = 0;
             for (int v = 0; v < nWarps; ++v) {
                 const int cv = warpCnt[v];
-                off += v < warp ? cv : 0;
-                nIt += cv;
+                off += v < warp ? (cv & 0xffff) : 0;
+                nIt += cv & 0xffff;
+                nItRef += cv >> 16;
             }
-            int pos = off + incl - mineCnt;
+            if (prune && pass == 0 && nIt > 32 * kPass0Words) {
+                // more items tie around the threshold than pass 0 has decision words for: plain DP over all
+                prune = false;
+                __syncthreads();
+                continue;
+            }
+            int pos = off + (incl & 0xffff) - mineCnt;
             for (int cl = c0; cl < c1; ++cl) {
-                const double rc = rawRc[shiftRc + cl];
-                const int w = rawW[shiftW + cl];
-                if (rc < 0.0 && w <= cap && (fixB == nullptr || fixB[cl] == 0)) {  // w > cap can never be taken (:161)
-                    // profit: -redCost (gap_func.py:104), or its scaled integer value
-                    // floor(-rc*scale + 0.5) held exactly in fp64 (GAP_KnapPisinger.h:174-177)
-                    itP[pos] = pScale != 0.0 ? (double)(long long)floor((-rc) * pScale + 0.5) : -rc;
-                    itW[pos] = w;
+                if (takes(cl)) {  // w > cap can never be taken (:161)
+                    itP[pos] = profitOf(cl);
+                    itW[pos] = rawW[shiftW + cl];
                     itC[pos] = cl;
                     ++pos;
                 }
@@ -778,6 +960,42 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             cur ^= 1;
             __syncthreads();
         }
+        if (!FUSE || !prune || pass == 1) break;
+        {
+            // pass 0 is done: its optimum is the lower bound; does any item outside pass 0 survive it?
+            double *sLB = reinterpret_cast<double *>(warpCnt);  // 32 ints: one double + the survivor counts
+            int *sExtra = warpCnt;
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2)
+                if (j0 + s2 == cap) *sLB = mine[s2];
+            __syncthreads();
+            const double lb = *sLB;
+            cut = lb - 1e-9 * (fabs(lb) + fmax(uLo, uHi) + 1.0) - slack;  // (the bound's own sums are rounded UP)
+            int extra = 0;
+            for (int cl = t; cl < len; cl += T)
+                if (meta[cl] < thrBucket && survives(cl)) ++extra;  // an item (0xffff is no bucket) outside pass 0
+            extra = __reduce_add_sync(0xffffffffu, extra);
+            __syncthreads();  // sLB is read by everyone before the counts overwrite it
+            if (lane == 0) sExtra[warp] = extra;
+            __syncthreads();
+            extra = 0;
+            for (int v = 0; v < nWarps; ++v) extra += sExtra[v];
+            __syncthreads();
+            if (extra == 0) break;  // no item outside pass 0 can be in an optimal solution
+            // pass 1 over the survivors: the DP starts again from c[-1][.] = 0
+            for (int j = t; j < 2 * bufStride; j += T) {
+                const int r = j >= bufStride ? j - bufStride : j;
+                rowBase[j] = r < G ? kNegInf : 0.0;
+            }
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2) {
+                mine[s2] = 0.0;
+                acc[s2] = 0u;
+            }
+            cur = 0;
+            __syncthreads();
+        }
+        }  // pass
         kGlobal += nIt;
     }
 
@@ -887,18 +1105,23 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             }
             // varRedCost / varOrigCost: added in ascending index order (GAP_KnapPisinger.h:263-272).
             // All lanes fetch, one lane adds sequentially out of shared memory.
-            double *sVals = itP;  // free after the DP
-            for (int pass = 0; pass < 2; ++pass) {
-                for (int k = lane; k < cnt; k += 32)
-                    sVals[k] = pass == 0 ? redCostV[sFinal[k]] : a.back.obj[sFinal[k]];
-                __syncwarp();
-                if (lane == 0) {
-                    double acc2 = 0.0;
-                    for (int k = 0; k < cnt; ++k) acc2 += sVals[k];
-                    if (pass == 0) sRcSum = acc2; else sOcSum = acc2;
-                }
-                __syncwarp();
+            // Both gathers are issued before either sum (one round trip), lanes 0 and 1 add side by side.
+            double *sValsRc = itP;                                  // free after the DP
+            double *sValsOc = reinterpret_cast<double *>(sBits);    // the decision bits are consumed
+            for (int k = lane; k < cnt; k += 32) {
+                const int col = sFinal[k];
+                const double r = redCostV[col], o = a.back.obj[col];
+                sValsRc[k] = r;
+                sValsOc[k] = o;
             }
+            __syncwarp();
+            if (lane < 2) {
+                const double *v = lane == 0 ? sValsRc : sValsOc;
+                double acc2 = 0.0;
+                for (int k = 0; k < cnt; ++k) acc2 += v[k];
+                if (lane == 0) sRcSum = acc2; else sOcSum = acc2;
+            }
+            __syncwarp();
             if (lane == 0) sCnt = cnt;
         }
         __syncthreads();
@@ -912,14 +1135,17 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         // DecompAlgo.cpp:6350-6356; a block whose fixed columns do not fit has no column: rc = +inf
         const double rcB = cap < 0 ? -kNegInf : sRcSum - alphaB;
         const bool keep = rcB < -a.filt.eps;          // strict, :5216
-        const unsigned long long myCells = (unsigned long long)kGlobal * (unsigned long long)(cap + 1);  // kGlobal == 0 when cap < 0
+        // cells of the reference's DP (items before the reduction) and cells actually evaluated
+        const unsigned long long myCells = (unsigned long long)nItRef * (unsigned long long)(cap + 1);  // 0 when cap < 0
+        const unsigned long long myEval = (unsigned long long)kGlobal * (unsigned long long)(cap + 1);
         if (t == 0) {
-            // one 64-bit word per block: epoch (8) | kept (1) | cells (24) | nnz (31).  In the fused
-            // shapes cells = items (<= 2048) x row cells (<= 7168) < 2^24; every block publishes in
-            // every round, so a stale word always carries the previous epoch.  Published FIRST: the
-            // word is all the other blocks need, the result stores below are read by the host only.
+            // one 64-bit word per block: epoch (8) | kept (1) | items (12) | evaluated items (12) | nnz (31).
+            // In the fused shapes a block has <= 2048 columns; every block publishes in every round, so a
+            // stale word always carries the previous epoch.  Published FIRST: the word is all the other
+            // blocks need, the result stores below are read by the host only.
             const unsigned long long word = ((unsigned long long)(a.epoch & 0xffu) << 56) | (keep ? 1ull << 55 : 0ull) |
-                                            ((myCells & 0xffffffull) << 31) | (unsigned long long)cnt;
+                                            ((unsigned long long)(cap < 0 ? 0 : nItRef) << 43) |
+                                            ((unsigned long long)kGlobal << 31) | (unsigned long long)cnt;
             asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.pubWord + vlb), "l"(word) : "memory");
             RESV(a.back.blockRedCost)[lb] = rcB;
             RESV(a.back.blockOrigCost)[lb] = sOcSum;
@@ -929,12 +1155,12 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         // prefix over the lower blocks: each thread polls its share, warp-shuffle reduction, then
         // the per-warp partials (shared-memory 64-bit atomics would serialise through CAS loops)
         __shared__ int sKeptW[32];
-        __shared__ unsigned long long sNnzW[32], sCellsW[32];
+        __shared__ unsigned long long sNnzW[32], sCellsW[32], sEvalW[32];
         __shared__ int sKept;
-        __shared__ unsigned long long sNnz, sCells;
+        __shared__ unsigned long long sNnz, sCells, sEval;
         {
             int kc = 0;
-            unsigned long long nz = 0ull, cl = 0ull;
+            unsigned long long nz = 0ull, cl = 0ull, ev = 0ull;
             for (int pB = t; pB < lb; pB += T) {
                 unsigned long long wv;
                 do {
@@ -942,34 +1168,40 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                 } while ((unsigned int)(wv >> 56) != (a.epoch & 0xffu));
                 if (wv & (1ull << 55)) {
                     ++kc;
-                    nz += wv & 0x7fffffffull;
+                    nz += wv & 0x7fffffffull;  // nnz <= 2048
                 }
-                cl += (wv >> 31) & 0xffffffull;
+                const unsigned long long rowB = (unsigned long long)max(a.capacity[a.firstBlock + pB], -1) + 1ull;
+                cl += ((wv >> 43) & 0xfffull) * rowB;
+                ev += ((wv >> 31) & 0xfffull) * rowB;
             }
 #pragma unroll
             for (int off2 = 16; off2 > 0; off2 >>= 1) {
                 kc += __shfl_xor_sync(0xffffffffu, kc, off2);
                 nz += __shfl_xor_sync(0xffffffffu, nz, off2);
                 cl += __shfl_xor_sync(0xffffffffu, cl, off2);
+                ev += __shfl_xor_sync(0xffffffffu, ev, off2);
             }
             if (lane == 0) {
                 sKeptW[warp] = kc;
                 sNnzW[warp] = nz;
                 sCellsW[warp] = cl;
+                sEvalW[warp] = ev;
             }
         }
         __syncthreads();
         if (t == 0) {
             int kc = 0;
-            unsigned long long nz = 0ull, cl = 0ull;
+            unsigned long long nz = 0ull, cl = 0ull, ev = 0ull;
             for (int v = 0; v < nWarps; ++v) {
                 kc += sKeptW[v];
                 nz += sNnzW[v];
                 cl += sCellsW[v];
+                ev += sEvalW[v];
             }
             sKept = kc;
             sNnz = nz;
             sCells = cl;
+            sEval = ev;
         }
         __syncthreads();
         const int pos = sKept;
@@ -993,6 +1225,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             hdr->nKept = nKept;
             hdr->nInd = nInd;
             hdr->cells = (long long)(sCells + myCells);
+            hdr->reserved[0] = (long long)(sEval + myEval);  // cells evaluated after the reduction
             hdr->indCap = a.filt.indCap;
         }
         dbgStamp(a.dbgTimes, 5);
@@ -1034,6 +1267,7 @@ static const GeomEntry kGeoms[] = {
 #undef GE_FNS
 #undef GE_FNS3
 #undef GE_NULL
+static_assert(kPruneBuckets % 32 == 0, "one lane scans kPruneBuckets / 32 buckets");
 static const int kNumGeoms = (int)(sizeof(kGeoms) / sizeof(kGeoms[0]));
 static const size_t kMaxSmem = 227 * 1024 - 6 * 1024;  // the fused tail's static shared memory comes off the 227 KiB
 
@@ -1063,14 +1297,14 @@ static bool fitGeom(const Ctx *c, int T, int S, int items, bool fuse, DpGeom *g)
     // guard: the largest usable weight (x2 when two items advance per barrier)
     int guard = ((c->maxUsableWeight * items) + 1) & ~1;
     g->guard = guard;
-    g->smemBytes = dpSmemBytes(g->rowCells, guard, ch, fuse);
+    g->smemBytes = dpSmemBytes(g->rowCells, guard, ch, fuse, c->optNoPrune == 0);
     if (g->smemBytes > kMaxSmem || c->optNoGuard) {
         g->guard = 0;  // predicated shifted reads instead
-        g->smemBytes = dpSmemBytes(g->rowCells, 0, ch, fuse);
+        g->smemBytes = dpSmemBytes(g->rowCells, 0, ch, fuse, c->optNoPrune == 0);
     }
     while (!fuse && g->smemBytes > kMaxSmem && g->chunkCols > 256) {
         g->chunkCols = (g->chunkCols / 2 + 3) & ~3;
-        g->smemBytes = dpSmemBytes(g->rowCells, g->guard, g->chunkCols, false);
+        g->smemBytes = dpSmemBytes(g->rowCells, g->guard, g->chunkCols, false, false);
     }
     if (items == 3 && g->guard == 0) return false;  // the three-item step is built with guard cells only
     return g->smemBytes <= kMaxSmem;
@@ -1249,6 +1483,7 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     a.nItems = c->dNItems;
     char *resBase = static_cast<char *>(batch ? c->dResultBatch : c->dResult);
     a.blockObj = reinterpret_cast<double *>(resBase + c->layout.offObj);
+    a.prune = c->optNoPrune ? 0 : 1;
     a.rcStride = rcStride;
     a.alphaStride = alphaStride;
     a.resStride = batch ? (long long)c->resStride : 0;

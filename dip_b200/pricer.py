@@ -74,6 +74,10 @@ class RoundResult:
     def cells(self) -> int:
         return self.c.cells
 
+    @property
+    def cellsEvaluated(self) -> int:
+        return self.c.cellsEvaluated
+
     def column(self, k: int) -> np.ndarray:
         return self.colInd[self.colStart[k]:self.colStart[k + 1]]
 
