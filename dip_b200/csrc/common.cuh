@@ -67,6 +67,7 @@ struct ResultLayout {
 };
 
 constexpr int kFuseFilterMaxBlocks = 256;
+constexpr int kPubWordStride = 16;     // fused DP kernel: one publication word per 128-byte line
 
 // ---------------------------------------------------------------- SpMV tiling
 constexpr int kSpmvChunk = 384;        // default entry budget of a warp tile (runtime knob "spmv_chunk")

@@ -167,9 +167,9 @@ static int setBlockRange(Ctx *c, int first, int count)
     DIPGPU_CUDA(c, cudaMemcpy(c->dBitsOff, off.data(), sizeof(int64_t) * ((size_t)count + 1), cudaMemcpyHostToDevice));
     if ((rc = devAlloc(c, &c->dBits, c->bitsWords))) return rc;
     if ((rc = devAlloc(c, &c->dNItems, (size_t)count))) return rc;
-    if ((rc = devAlloc(c, &c->dPubWord, (size_t)count))) return rc;
+    if ((rc = devAlloc(c, &c->dPubWord, (size_t)std::max(count, 1) * kPubWordStride))) return rc;
     if ((rc = devAlloc(c, &c->dPubCells, (size_t)count))) return rc;
-    DIPGPU_CUDA(c, cudaMemset(c->dPubWord, 0, sizeof(unsigned long long) * std::max<size_t>((size_t)count, 1)));
+    DIPGPU_CUDA(c, cudaMemset(c->dPubWord, 0, sizeof(unsigned long long) * std::max<size_t>((size_t)count, 1) * kPubWordStride));
     c->epoch = 0;
     if ((rc = devAlloc(c, &c->dScale, (size_t)count))) return rc;
     if ((rc = devAlloc(c, &c->dShortcut, (size_t)count))) return rc;
@@ -323,8 +323,8 @@ static int ensureBatch(Ctx *c, int nVec)
     if ((rc = devAlloc(c, &c->dRedCostBatch, V * rcStride))) return rc;
     DIPGPU_CUDA(c, cudaMemset(c->dUBatch, 0, sizeof(double) * V * uStride));
     DIPGPU_CUDA(c, cudaMemset(c->dRedCostBatch, 0, sizeof(double) * V * rcStride));
-    if ((rc = devAlloc(c, &c->dPubWordBatch, V * nl))) return rc;
-    DIPGPU_CUDA(c, cudaMemset(c->dPubWordBatch, 0, sizeof(unsigned long long) * V * nl));
+    if ((rc = devAlloc(c, &c->dPubWordBatch, V * nl * kPubWordStride))) return rc;
+    DIPGPU_CUDA(c, cudaMemset(c->dPubWordBatch, 0, sizeof(unsigned long long) * V * nl * kPubWordStride));
     c->epochBatch = 0;
     if ((rc = devAlloc(c, &c->dScaleB, V * nl))) return rc;
     if ((rc = devAlloc(c, &c->dShortcutB, V * nl))) return rc;

@@ -300,8 +300,10 @@ __device__ __forceinline__ void dbgStamp(unsigned long long *buf, int slot)
 constexpr int kPruneBuckets = 1024;   // efficiency histogram of the reduction pre-pass
 constexpr int kPruneMinItems = 256;   // (columns of the block) below this the DP is about as short as the pre-pass
 constexpr int kPruneTopFill = 2;      // pass 0 runs over the most efficient items worth this many capacities of weight
+constexpr int kSumsRcOff = 256, kSumsObjOff = 512;  // doubles into itP: prefetched reduced costs / objective entries
+constexpr int kPubStride = 16;        // publication words sit 128 bytes apart (one per L2 line)
 constexpr int kPass0Words = 7;        // ... and over at most 32 * kPass0Words (its decision words sit in front of the raw arrays)
-constexpr size_t kPruneScratchBytes = sizeof(int) * 3 * kPruneBuckets + sizeof(double) * 6 + 16;
+constexpr size_t kPruneScratchBytes = sizeof(int) * 3 * kPruneBuckets + sizeof(double) * 6 + 16 + 64;
 
 
 struct KnapArgs {
@@ -432,6 +434,17 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const int j0 = t * S;  // first owned cell
 
     dbgStamp(a.dbgTimes, 0);
+    unsigned long long touch = 0ull;
+    if (FUSE && t == 32 % T) {
+        // touch, now, the pages the tail will write and poll (publication words, packed result): a first
+        // access from this SM otherwise pays its translation miss (~4 us, seen on a random third of the
+        // blocks) on the critical path of the tail instead of under the DP
+        unsigned long long x0, x1, x2;
+        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x0) : "l"(a.pubWord + (size_t)vlb * kPubStride) : "memory");
+        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x1) : "l"(RESV(a.filt.hdr)) : "memory");
+        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x2) : "l"(RESV(a.filt.keptInd) + (size_t)(colStart - a.blockColStart[a.firstBlock]) / 2 * 2) : "memory");
+        touch = x0 ^ x1 ^ x2;  // consumed in the tail, so that nothing waits for these loads here
+    }
     if (t == 0) mbarInit(mbar, 1);
     // c[-1][.] = 0 (gap_func.py:156); guards = -inf
     for (int j = t; j < 2 * bufStride; j += T) {
@@ -451,6 +464,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     int cur = 0;        // buffer holding c[i-1][.]
     int kGlobal = 0;    // active items processed so far
     int nItRef = 0;     // FUSE: items the reference's DP runs over (before the reduction)
+    bool smemSums = false;  // FUSE: the items' reduced costs / objective entries were prefetched into shared memory
     uint32_t parity = 0;
 
     for (int chunkBase = 0; chunkBase < nCols; chunkBase += CH) {
@@ -540,65 +554,77 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             }
             const int anyBig = __syncthreads_or(tooBig ? 1 : 0);
             const double unfix = pScale != 0.0 ? 1.0 : 1.0 / 4096.0;
-            if (warp == 0) {
+            {
                 // From the most efficient bucket down (greedy fill).  With L = the lower edge of bucket c,
                 //     U(L) = L*cap + sum_{buckets >= c} (p - L w)      (every item there has p/w >= L,
                 // every item below has p/w < L), i.e. the bound needs only the buckets' sums.
-                constexpr int perLane = kPruneBuckets / 32;
+                // Up to four warps scan: a thread sums its run of buckets, a shuffle suffix-scan and the
+                // warps' totals give the sums above it, then it walks its run looking for the crossing.
                 auto histP = [&](int bkt) -> unsigned long long {
                     return ((unsigned long long)(unsigned int)histHi[bkt] << 20) + (unsigned long long)(unsigned int)histLo[bkt];
                 };
-                long long wSum = 0;
-                unsigned long long pSum = 0ull;
-                for (int q = 0; q < perLane; ++q) {
-                    wSum += histW[lane * perLane + q];
-                    pSum += histP(lane * perLane + q);
+                const int nScanW = nWarps >= 4 ? 4 : nWarps >= 2 ? 2 : 1;
+                const int perThr = kPruneBuckets / (32 * nScanW);
+                long long *sScanW = reinterpret_cast<long long *>(sCross + 4);
+                unsigned long long *sScanP = reinterpret_cast<unsigned long long *>(sScanW + 4);
+                long long wSum = 0, aboveW = 0;
+                unsigned long long pSum = 0ull, aboveP = 0ull;
+                if (t == 0) {
+                    sCross[0] = -1;  // everything fits: nothing to drop
+                    sCross[1] = 0;   // less weight in all than pass 0 may take: every item
                 }
-                long long aboveW = 0;
-                unsigned long long aboveP = 0ull;
-                for (int l2 = 0; l2 < 32; ++l2) {
-                    const long long ow = __shfl_sync(0xffffffffu, wSum, l2);
-                    const unsigned long long op = __shfl_sync(0xffffffffu, pSum, l2);
-                    if (l2 > lane) {
-                        aboveW += ow;
-                        aboveP += op;
+                if (warp < nScanW) {
+                    for (int q = 0; q < perThr; ++q) {
+                        wSum += histW[t * perThr + q];
+                        pSum += histP(t * perThr + q);
                     }
-                }
-                auto edgeOf = [&](int bkt) -> double {  // the smallest efficiency that falls in bucket bkt
-                    return bkt <= 0 ? 0.0 : (double)__uint_as_float((unsigned int)(bkt + bucket0) << 18);
-                };
-                int cross = -1, topB = -1;
-                long long cumW = aboveW;
-                unsigned long long cumP = aboveP;
-                for (int q = perLane - 1; q >= 0; --q) {
-                    const int bkt = lane * perLane + q;
-                    const long long beforeW = cumW;
-                    const unsigned long long beforeP = cumP;
-                    cumW += histW[bkt];
-                    cumP += histP(bkt);
-                    if (cross < 0 && cumW > (long long)cap && beforeW <= (long long)cap) {
-                        cross = bkt;
-                        const double lLo = edgeOf(bkt), lHi = edgeOf(bkt + 1);
-                        sBound[0] = lLo;
-                        sBound[1] = lHi;
-                        sBound[2] = lLo * (double)cap + ((double)cumP * unfix - lLo * (double)cumW);
-                        sBound[3] = lHi * (double)cap + ((double)beforeP * unfix - lHi * (double)beforeW);
+                    long long sw = wSum;
+                    unsigned long long sp = pSum;
+#pragma unroll
+                    for (int off2 = 1; off2 < 32; off2 <<= 1) {
+                        const long long ow = __shfl_down_sync(0xffffffffu, sw, off2);
+                        const unsigned long long op = __shfl_down_sync(0xffffffffu, sp, off2);
+                        if (lane + off2 < 32) {
+                            sw += ow;
+                            sp += op;
+                        }
                     }
-                    // pass 0 takes the buckets down to kPruneTopFill capacities' worth of weight
-                    if (topB < 0 && cumW >= kPruneTopFill * (long long)cap && beforeW < kPruneTopFill * (long long)cap) topB = bkt;
+                    if (lane == 0) {
+                        sScanW[warp] = sw;
+                        sScanP[warp] = sp;
+                    }
+                    aboveW = sw - wSum;
+                    aboveP = sp - pSum;
                 }
-                if (lane == 0) sBound[4] = (double)cumP * unfix;  // lane 0 ends at bucket 0: every item
-                const unsigned balC = __ballot_sync(0xffffffffu, cross >= 0);
-                const unsigned balT = __ballot_sync(0xffffffffu, topB >= 0);
-                if (balC == 0u) {
-                    if (lane == 0) sCross[0] = -1;  // everything fits: nothing to drop
-                } else if (lane == 31 - __clz(balC)) {
-                    sCross[0] = cross;
-                }
-                if (balT == 0u) {
-                    if (lane == 0) sCross[1] = 0;   // not that much weight in all: every item
-                } else if (lane == 31 - __clz(balT)) {
-                    sCross[1] = topB;
+                __syncthreads();
+                if (warp < nScanW) {
+                    for (int v = warp + 1; v < nScanW; ++v) {
+                        aboveW += sScanW[v];
+                        aboveP += sScanP[v];
+                    }
+                    auto edgeOf = [&](int bkt) -> double {  // the smallest efficiency that falls in bucket bkt
+                        return bkt <= 0 ? 0.0 : (double)__uint_as_float((unsigned int)(bkt + bucket0) << 18);
+                    };
+                    long long cumW = aboveW;
+                    unsigned long long cumP = aboveP;
+                    for (int q = perThr - 1; q >= 0; --q) {
+                        const int bkt = t * perThr + q;
+                        const long long beforeW = cumW;
+                        const unsigned long long beforeP = cumP;
+                        cumW += histW[bkt];
+                        cumP += histP(bkt);
+                        if (cumW > (long long)cap && beforeW <= (long long)cap) {
+                            const double lLo = edgeOf(bkt), lHi = edgeOf(bkt + 1);
+                            sBound[0] = lLo;
+                            sBound[1] = lHi;
+                            sBound[2] = lLo * (double)cap + ((double)cumP * unfix - lLo * (double)cumW);
+                            sBound[3] = lHi * (double)cap + ((double)beforeP * unfix - lHi * (double)beforeW);
+                            sCross[0] = bkt;
+                        }
+                        // pass 0 takes the buckets down to kPruneTopFill capacities' worth of weight
+                        if (cumW >= kPruneTopFill * (long long)cap && beforeW < kPruneTopFill * (long long)cap) sCross[1] = bkt;
+                    }
+                    if (t == 0) sBound[4] = (double)cumP * unfix;  // thread 0 ends at bucket 0: every item
                 }
             }
             __syncthreads();
@@ -667,15 +693,28 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                 __syncthreads();
                 continue;
             }
+            // pass 0 (<= 32*kPass0Words items): the items' true reduced costs and objective entries are
+            // fetched NOW into the unused upper part of itP (cp.async, consumed by the tail's sums), so the
+            // tail does not wait for two dependent global gathers
+            smemSums = prune && pass == 0 && a.back.fix == nullptr;
             int pos = off + (incl & 0xffff) - mineCnt;
             for (int cl = c0; cl < c1; ++cl) {
                 if (takes(cl)) {  // w > cap can never be taken (:161)
                     itP[pos] = profitOf(cl);
                     itW[pos] = rawW[shiftW + cl];
                     itC[pos] = cl;
+                    if (smemSums) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(itP + kSumsRcOff + pos)),
+                                     "l"(redCostV + colStart + cl)
+                                     : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(itP + kSumsObjOff + pos)),
+                                     "l"(a.back.obj + colStart + cl)
+                                     : "memory");
+                    }
                     ++pos;
                 }
             }
+            if (smemSums) asm volatile("cp.async.commit_group;" ::: "memory");
         } else {
             // throughput shapes: strided ballot compaction (one column per thread and round)
             for (int base = 0; base < len; base += T) {
@@ -982,6 +1021,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             for (int v = 0; v < nWarps; ++v) extra += sExtra[v];
             __syncthreads();
             if (extra == 0) break;  // no item outside pass 0 can be in an optimal solution
+            smemSums = false;
             // pass 1 over the survivors: the DP starts again from c[-1][.] = 0
             for (int j = t; j < 2 * bufStride; j += T) {
                 const int r = j >= bufStride ? j - bufStride : j;
@@ -1022,6 +1062,9 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         __shared__ int sCnt;
         __shared__ double sRcSum, sOcSum;
         int32_t *sFinal = itC;  // ascending x-space indices of the column (itC is free after the walk)
+        int32_t *sTakenIdx = sTaken + 256;  // item of each taken entry (pass-0 shapes: <= 32*kPass0Words)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        if (touch == 0x9e3779b97f4a7c15ull) sCnt = -1;  // never true in practice: keeps the page-touching loads alive
         __syncthreads();
         if (warp == 0) {
             int cnt = 0;
@@ -1047,6 +1090,34 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                 // backtrack from (last item, capacity), gap_func.py:173-181
                 int j = cap;
                 int i = kGlobal - 1;
+                if (kGlobal <= 96) {
+                    // few items (the usual case after the reduction): ONE lane walks, without the ballot /
+                    // shuffle round trip per taken item.  A single warp pays every dependent instruction at
+                    // full latency, so the step is kept short: the cell's three decision words are fetched
+                    // together, the items at or below i are isolated with two shifts, one select picks the
+                    // highest set bit.
+                    if (lane == 0) {
+                        const uint32_t *b0 = sBits, *b1 = sBits + RC, *b2 = sBits + 2 * RC;
+                        const bool has1 = kGlobal > 32, has2 = kGlobal > 64;
+                        while (i >= 0) {
+                            uint32_t v0 = b0[j], v1 = has1 ? b1[j] : 0u, v2 = has2 ? b2[j] : 0u;
+                            // keep the bits of items <= i: a 96-bit mask built from the shift count 95 - i
+                            const int sh = 95 - i;  // 0..95
+                            if (sh >= 64) { v2 = 0u; v1 = 0u; v0 &= 0xffffffffu >> (sh - 64); }
+                            else if (sh >= 32) { v2 = 0u; v1 &= 0xffffffffu >> (sh - 32); }
+                            else { v2 &= 0xffffffffu >> sh; }
+                            const int item = v2 ? 95 - __clz(v2) : v1 ? 63 - __clz(v1) : v0 ? 31 - __clz(v0) : -1;
+                            if (item < 0) break;
+                            sTaken[cnt] = itC[item];
+                            if (smemSums) sTakenIdx[cnt] = item;
+                            ++cnt;
+                            j -= itW[item];
+                            i = item - 1;
+                        }
+                    }
+                    cnt = __shfl_sync(0xffffffffu, cnt, 0);
+                    i = -1;
+                }
                 while (i >= 0) {
                     const int kw = i >> 5;
                     const int wv = kw - lane;
@@ -1060,7 +1131,10 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                     const int L = __ffs(nz) - 1;
                     const uint32_t vL = __shfl_sync(0xffffffffu, v, L);
                     const int item = ((kw - L) << 5) + (31 - __clz(vL));
-                    if (lane == 0) sTaken[cnt] = itC[item];
+                    if (lane == 0) {
+                        sTaken[cnt] = itC[item];
+                        if (smemSums) sTakenIdx[cnt] = item;
+                    }
                     ++cnt;
                     j -= itW[item];
                     i = item - 1;
@@ -1105,21 +1179,32 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             }
             // varRedCost / varOrigCost: added in ascending index order (GAP_KnapPisinger.h:263-272).
             // All lanes fetch, one lane adds sequentially out of shared memory.
-            // Both gathers are issued before either sum (one round trip), lanes 0 and 1 add side by side.
-            double *sValsRc = itP;                                  // free after the DP
-            double *sValsOc = reinterpret_cast<double *>(sBits);    // the decision bits are consumed
-            for (int k = lane; k < cnt; k += 32) {
-                const int col = sFinal[k];
-                const double r = redCostV[col], o = a.back.obj[col];
-                sValsRc[k] = r;
-                sValsOc[k] = o;
-            }
-            __syncwarp();
-            if (lane < 2) {
-                const double *v = lane == 0 ? sValsRc : sValsOc;
-                double acc2 = 0.0;
-                for (int k = 0; k < cnt; ++k) acc2 += v[k];
-                if (lane == 0) sRcSum = acc2; else sOcSum = acc2;
+            if (smemSums && shortCode == 0) {
+                // the values are already in shared memory (prefetched during the compaction); the walk found
+                // the items last to first, the sums run first to last
+                if (lane < 2) {
+                    const double *v = itP + (lane == 0 ? kSumsRcOff : kSumsObjOff);
+                    double acc2 = 0.0;
+                    for (int k = cnt - 1; k >= 0; --k) acc2 += v[sTakenIdx[k]];
+                    if (lane == 0) sRcSum = acc2; else sOcSum = acc2;
+                }
+            } else {
+                // Both gathers are issued before either sum (one round trip), lanes 0 and 1 add side by side.
+                double *sValsRc = itP;                                  // free after the DP
+                double *sValsOc = reinterpret_cast<double *>(sBits);    // the decision bits are consumed
+                for (int k = lane; k < cnt; k += 32) {
+                    const int col = sFinal[k];
+                    const double r = redCostV[col], o = a.back.obj[col];
+                    sValsRc[k] = r;
+                    sValsOc[k] = o;
+                }
+                __syncwarp();
+                if (lane < 2) {
+                    const double *v = lane == 0 ? sValsRc : sValsOc;
+                    double acc2 = 0.0;
+                    for (int k = 0; k < cnt; ++k) acc2 += v[k];
+                    if (lane == 0) sRcSum = acc2; else sOcSum = acc2;
+                }
             }
             __syncwarp();
             if (lane == 0) sCnt = cnt;
@@ -1146,7 +1231,9 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             const unsigned long long word = ((unsigned long long)(a.epoch & 0xffu) << 56) | (keep ? 1ull << 55 : 0ull) |
                                             ((unsigned long long)(cap < 0 ? 0 : nItRef) << 43) |
                                             ((unsigned long long)kGlobal << 31) | (unsigned long long)cnt;
-            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.pubWord + vlb), "l"(word) : "memory");
+            // relaxed: the word itself is everything the other blocks read (no other store has to be ordered before it)
+            // an atomic goes straight to the L2 slice (a plain store may wait in the SM's write path)
+            atomicExch(a.pubWord + (size_t)vlb * kPubStride, word);
             RESV(a.back.blockRedCost)[lb] = rcB;
             RESV(a.back.blockOrigCost)[lb] = sOcSum;
             RESV(a.back.blockNnz)[lb] = cnt;
@@ -1163,14 +1250,24 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             unsigned long long nz = 0ull, cl = 0ull, ev = 0ull;
             for (int pB = t; pB < lb; pB += T) {
                 unsigned long long wv;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(wv) : "l"(a.pubWord + (vlb - lb) + pB) : "memory");
-                } while ((unsigned int)(wv >> 56) != (a.epoch & 0xffu));
+                // (fetched before the spin, so that its latency hides behind the wait)
+                const unsigned long long rowB = (unsigned long long)max(a.capacity[a.firstBlock + pB], -1) + 1ull;
+                const unsigned long long *src = a.pubWord + (size_t)(vlb - lb + pB) * kPubStride;
+                for (;;) {
+                    // an atomic is performed at the line's home L2 slice: a plain (even .relaxed.gpu) load
+                    // was seen to return the old word for ~4.5 us on part of the SMs (the other die's L2)
+                    wv = atomicAdd(const_cast<unsigned long long *>(src), 0ull);
+                    if ((unsigned int)(wv >> 56) == (a.epoch & 0xffu)) break;
+                    // a short pause between polls (__nanosleep's granularity here is microseconds): 80 blocks
+                    // x up to 79 threads polling back to back congest the words' L2 slices, and the stores that
+                    // follow the wait queue up behind the polls
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < 400) {}
+                }
                 if (wv & (1ull << 55)) {
                     ++kc;
                     nz += wv & 0x7fffffffull;  // nnz <= 2048
                 }
-                const unsigned long long rowB = (unsigned long long)max(a.capacity[a.firstBlock + pB], -1) + 1ull;
                 cl += ((wv >> 43) & 0xfffull) * rowB;
                 ev += ((wv >> 31) & 0xfffull) * rowB;
             }
@@ -1189,6 +1286,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             }
         }
         __syncthreads();
+        dbgStamp(a.dbgTimes, 6);
         if (t == 0) {
             int kc = 0;
             unsigned long long nz = 0ull, cl = 0ull, ev = 0ull;
@@ -1204,6 +1302,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             sEval = ev;
         }
         __syncthreads();
+        dbgStamp(a.dbgTimes, 7);
         const int pos = sKept;
         const long long off = (long long)sNnz;
         if (keep) {

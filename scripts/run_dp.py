@@ -34,9 +34,12 @@ with GpuPricer(0) as p:
         p.set_option("dp_debug_times", tt.ctypes.data)
         t0 = tt[:, 0].min()
         rel = (tt.astype(np.int64) - np.int64(t0)) / 1e3
-        names = ["start", "staged", "compacted", "dp_done", "backtracked", "filtered"]
+        names = ["start", "staged", "compacted", "dp_done", "backtracked", "filtered", "polled", "prefixed"]
         print(p.dpGeometry())
         for k, nm in enumerate(names):
             col = rel[:, k]
             print(f"{nm:12s} min {col.min():8.2f}  mean {col.mean():8.2f}  max {col.max():8.2f} us")
+        if os.environ.get("DP_TIMES") == "2":
+            for blk in range(b.m):
+                print(blk, " ".join(f"{rel[blk, k]:7.2f}" for k in (3, 7, 4, 6, 5)))
         print("last CTA (max filtered) block", int(rel[:, 5].argmax()), "stamps", rel[int(rel[:, 5].argmax()), :6])
