@@ -498,3 +498,67 @@ def test_expand_columns_gap_e(oracle, pricer):
                                       model.m, res.column(k), int(res.colBlock[k]))
         np.testing.assert_array_equal(ri[cs[k]:cs[k + 1]], rr)
         np.testing.assert_array_equal(va[cs[k]:cs[k + 1]], vv)
+
+
+# ------------------------------------------------------------------ the fused kernel's reduction pre-pass
+
+
+def _reduction_batch(seed, m, n, cap_lo, cap_hi, kind):
+    """Blocks big enough (>= 1024 columns) for the fused kernel's reduction to engage."""
+    rng = np.random.default_rng(seed)
+    bcs = (np.arange(m + 1) * n).astype(np.int32)
+    N = m * n
+    cap = rng.integers(cap_lo, cap_hi + 1, size=m).astype(np.int32)
+    if kind == "gap":          # small weights, spread-out profits: a handful of items matter
+        w = np.floor(1 - 10 * np.log(rng.uniform(1e-9, 1, size=N))).astype(np.int32)
+        rc = -(rng.uniform(0, 1000, size=N) / w)
+    elif kind == "ties":       # small integer profits and weights: many optimal solutions
+        w = rng.integers(1, 12, size=N).astype(np.int32)
+        rc = -rng.integers(1, 7, size=N).astype(np.float64)
+    elif kind == "equal_eff":  # every item has the same efficiency: nothing can be dropped, one fat bucket
+        w = rng.integers(1, 40, size=N).astype(np.int32)
+        rc = -3.0 * w
+    elif kind == "subset_sum":
+        w = rng.integers(1, 200, size=N).astype(np.int32)
+        rc = -w.astype(np.float64) - rng.uniform(0, 1e-9, size=N)
+    else:                      # "wide": efficiencies over 30 octaves, zero weights, items that do not fit
+        w = rng.integers(0, 60, size=N).astype(np.int32)
+        rc = -np.exp(rng.uniform(-12, 12, size=N))
+        w[rng.random(N) < 0.02] = cap.max() + 7
+    rc = np.where(rng.random(N) < 0.25, rng.uniform(0, 5, size=N), rc)   # inactive columns
+    oc = rng.integers(1, 100, size=N).astype(np.float64)
+    alpha = rng.uniform(-10, 10, size=m)
+    return bcs, w, cap, rc, oc, alpha
+
+
+@pytest.mark.parametrize("kind,n,cap_lo,cap_hi", [("gap", 1600, 100, 250), ("gap", 2048, 20, 60), ("ties", 1200, 30, 90),
+                                                  ("equal_eff", 1100, 50, 400), ("subset_sum", 1024, 200, 600),
+                                                  ("wide", 1500, 10, 120), ("gap", 1030, 1, 5)])
+def test_reduction_keeps_optimum_column_and_ties(oracle, pricer, kind, n, cap_lo, cap_hi):
+    """Dropping the items no optimal solution can contain must not change anything the reference's DP
+    returns -- optimum bit for bit, the column (also among tied optima), sums, cells -- and switching the
+    pre-pass off gives the same round."""
+    seed = {"gap": 1, "ties": 2, "equal_eff": 3, "subset_sum": 4, "wide": 5}[kind] * 10000 + n
+    bcs, w, cap, rc, oc, alpha = _reduction_batch(seed, 40, n, cap_lo, cap_hi, kind)
+    res, ref = _check_against_oracle(oracle, pricer, bcs, w, cap, rc, oc, alpha)
+    assert pricer.dpGeometry()["fused_tail"] == 1
+    ev_on = res.cellsEvaluated
+    assert ev_on <= res.cells
+    if kind == "gap":
+        assert ev_on < res.cells               # the pre-pass engaged
+    cols_on = [list(res.column(k)) for k in range(res.nCols)]
+    obj_on = res.blockObj.copy()
+    pricer.set_option("dp_no_prune", 1)
+    res2, _ = _check_against_oracle(oracle, pricer, bcs, w, cap, rc, oc, alpha)
+    assert res2.cellsEvaluated == res2.cells
+    assert [list(res2.column(k)) for k in range(res2.nCols)] == cols_on
+    np.testing.assert_array_equal(res2.blockObj, obj_on)
+
+
+def test_reduction_in_pisinger_mode(oracle, pricer):
+    from dip_b200.pricer import PROFIT_PISINGER_INT
+    bcs, w, cap, rc, oc, alpha = _reduction_batch(77, 24, 1400, 60, 200, "gap")
+    rc = np.round(rc, 2)
+    _check_against_oracle(oracle, pricer, bcs, w, cap, rc, oc, alpha, profit_mode=PROFIT_PISINGER_INT)
+    res = pricer.solveBlocks(rc, alpha)
+    assert res.cellsEvaluated < res.cells
