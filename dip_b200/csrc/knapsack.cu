@@ -483,6 +483,14 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             tmaLoad1d(rawRc, redCostV + (g0 - shiftRc), bytesRc, mbar);
             tmaLoad1d(rawW, a.weight + (g0 - shiftW), bytesW, mbar);
         }
+        const bool pruneLayoutHere = FUSE && dpPruneLayout(CH, true, a.prune != 0) && len >= kPruneMinItems;
+        if (pruneLayoutHere) {
+            // the histograms of the reduction pre-pass (in the not yet written itP | itW): zeroed while the
+            // bulk copies are in flight
+            int *h0 = reinterpret_cast<int *>(itP);
+            for (int k = t; k < 3 * kPruneBuckets; k += T) h0[k] = 0;
+            __syncthreads();
+        }
         mbarWait(mbar, parity);
         parity ^= 1u;
         dbgStamp(a.dbgTimes, 1);
@@ -526,31 +534,51 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         // per column, filled by the histogram pass: its bucket, or 0xffff when it is no item.  Lives in the
         // UPPER half of the item-column array, which pass 0 (<= 32*kPass0Words items) never reaches.
         uint16_t *meta = reinterpret_cast<uint16_t *>(itC) + (CH + 4);
-        if (pruneLayout && len >= kPruneMinItems) {
+        if (pruneLayoutHere) {
             int *histW = reinterpret_cast<int *>(itP);          // itP | itW are contiguous and not written yet
             int *histLo = histW + kPruneBuckets;                // profit sums, fixed point, low 20 bits ...
             int *histHi = histLo + kPruneBuckets;               // ... and the bits above
             double *sBound = reinterpret_cast<double *>(histHi + kPruneBuckets);  // lamLo, lamHi, uLo, uHi, sum of all profits
             int *sCross = reinterpret_cast<int *>(sBound + 6);                    // crossing bucket, threshold bucket
-            for (int k = t; k < 3 * kPruneBuckets; k += T) histW[k] = 0;
-            __syncthreads();
             // profits in units of 2^-12 (integers in Pisinger mode), rounded UP: the bound stays an upper
             // bound, and the integer sums do not depend on the order of the atomics
             const double fix = pScale != 0.0 ? 1.0 : 4096.0;
             bool tooBig = false;
-            for (int cl = t; cl < len; cl += T) {
-                unsigned int m = 0xffffu;
-                if (isItem(cl)) {
-                    const double pk = profitOf(cl);
-                    tooBig |= !(pk < 268435456.0);
-                    const int bkt = bucketOf(cl);
-                    const unsigned long long v = (unsigned long long)ceil(pk * fix);
-                    atomicAdd(&histW[bkt], rawW[shiftW + cl]);
-                    atomicAdd(&histLo[bkt], (int)(v & 0xfffffull));
-                    atomicAdd(&histHi[bkt], (int)(v >> 20));
-                    m = (unsigned int)bkt;
+            // four columns per thread and step, their loads issued together: with 1.5 warps per scheduler a
+            // column's chain (load, compare, convert, divide, convert, three atomics) is paid at full latency,
+            // so independent chains are interleaved by hand
+            for (int base = t; base < len; base += 4 * T) {
+                double rcv[4];
+                int wv[4];
+                bool it[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cl = base + q * T;
+                    const bool in = cl < len;
+                    rcv[q] = in ? rawRc[shiftRc + cl] : 0.0;
+                    wv[q] = in ? rawW[shiftW + cl] : 0;
+                    it[q] = in && rcv[q] < 0.0 && wv[q] <= cap && (fixB == nullptr || fixB[cl] == 0);
                 }
-                meta[cl] = (uint16_t)m;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cl = base + q * T;
+                    unsigned int m = 0xffffu;
+                    if (it[q]) {
+                        const double pk = pScale != 0.0 ? (double)(long long)floor((-rcv[q]) * pScale + 0.5) : -rcv[q];
+                        tooBig |= !(pk < 268435456.0);
+                        int bkt = kPruneBuckets - 1;
+                        if (wv[q] > 0) {
+                            const int qb = (int)(__float_as_uint(__fdividef((float)pk, (float)wv[q])) >> 18) - bucket0;
+                            bkt = min(max(qb, 0), kPruneBuckets - 1);
+                        }
+                        const unsigned long long v = (unsigned long long)ceil(pk * fix);
+                        atomicAdd(&histW[bkt], wv[q]);
+                        atomicAdd(&histLo[bkt], (int)(v & 0xfffffull));
+                        atomicAdd(&histHi[bkt], (int)(v >> 20));
+                        m = (unsigned int)bkt;
+                    }
+                    if (cl < len) meta[cl] = (uint16_t)m;
+                }
             }
             const int anyBig = __syncthreads_or(tooBig ? 1 : 0);
             const double unfix = pScale != 0.0 ? 1.0 : 1.0 / 4096.0;
