@@ -371,6 +371,7 @@ def main():
         "cells_evaluated_per_launch": cells_eval_mean,
         "peak": smem_peak, "unit": "GB/s",
         "frac": (cells_mean * 24.0 / (dp_ms * 1e-3) / 1e9 / smem_peak) if (smem_peak and dp_ms > 0) else None,
+        "frac_evaluated": (cells_eval_mean * 24.0 / (dp_ms * 1e-3) / 1e9 / smem_peak) if (smem_peak and dp_ms > 0) else None,
         "traffic": ncu_traffic("prof_dp_gape"),
         "traffic_note": "DRAM bytes per launch, ncu --set full capture of this kernel on this shape "
                         "(profiles/ncu_traffic.json); the bound is shared memory, HBM only sees inputs",
@@ -480,6 +481,9 @@ def bench_batched(pr, model, duals, u_pin, cells_per_round, flush_l2, torch, sme
             "stage_ms": st, "dp_cells_per_call": cells, "dp_cells_evaluated_per_call": cells_ev,
             "dp_roofline": {"kernel": "knap_dp_kernel (fused, gridDim.y = vectors)", "bound": "smem", "achieved": ach,
                             "peak": smem_peak, "unit": "GB/s", "frac": ach / smem_peak if (ach and smem_peak) else None,
+                            "frac_evaluated": (cells_ev * 24.0 / (dp_ms * 1e-3) / 1e9 / smem_peak) if (smem_peak and dp_ms > 0) else None,
+                            "note": "achieved / frac count the reference DP's cells (24 B each); the kernel evaluates "
+                                    "dp_cells_evaluated_per_call of them after its reduction pre-pass",
                             "gcups": cells / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None},
         }
     out["note"] = ("value / e2e above stay ONE dual vector per step (what DecompAlgo::generateVars prices per call); "
