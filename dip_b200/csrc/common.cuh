@@ -233,6 +233,7 @@ struct Ctx {
     void *dResult = nullptr;
     void *hResult = nullptr;  // pinned mirror
     size_t resultBytes = 0;
+    size_t lastResultBytes = 0;  // bytes of the last packed result (sizes the next speculative D2H copy)
     int64_t indCap = 0;
     ResultLayout layout{};
 
@@ -254,6 +255,12 @@ struct Ctx {
     size_t centerLen = 0;
     bool haveCenter = false, haveST = false;  // haveST: dUBatch[0] holds the last smoothed vector
     bool dualsResident = false;               // dU holds the dual vector of the last host-buffer call
+    // rows of the master dual vector that can be nonzero (dipgpu_set_dual_support): only those cross PCIe
+    std::vector<int32_t> hSupport;
+    int32_t *dSupport = nullptr;
+    double *hSupVals = nullptr, *dSupVals = nullptr;  // pinned / device staging, supVecCap vectors of hSupport.size()
+    int supVecCap = 0;
+    bool dUClean = false, dUBatchClean = false;       // the device vectors are zero outside the support
     // waiting-column pool (DecompVarPool): master columns in device memory
     int64_t poolCols = 0, poolNnz = 0, poolColCap = 0, poolNnzCap = 0;
     int64_t *dPoolStart = nullptr;   // poolCols + 1
@@ -320,6 +327,8 @@ int launchFilter(Ctx *c, double redCostEps, cudaStream_t st);
 int launchExpandColumns(Ctx *c, double tolZero, int nKept, cudaStream_t st);
 // pool.cu -- waiting-column pool re-pricing (DecompVarPool::setReducedCosts) and Wentges smoothing
 int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st);
+int launchScatterDuals(Ctx *c, int n, const int32_t *dIdx, const double *dVals, int64_t valStride, double *dDst,
+                       int64_t dstStride, int nVec, cudaStream_t st);
 int launchSmoothDuals(Ctx *c, const double *dURM, const double *dCenter, const double *dAlphas, int nVec, int uLen,
                       double *dOut, int64_t outStride, cudaStream_t st);
 // microbench.cu -- roofline denominators measured on the device

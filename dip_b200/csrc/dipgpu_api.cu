@@ -180,6 +180,7 @@ static int setBlockRange(Ctx *c, int first, int count)
     c->indCap = count > 0 ? (int64_t)(c->hBlockColStart[first + count] - c->hBlockColStart[first]) : 0;
     c->layout = ResultLayout::make(count, c->indCap);
     c->resultBytes = c->layout.bytes;
+    c->lastResultBytes = 0;
     if (c->dResult) cudaFree(c->dResult);
     c->dResult = nullptr;
     DIPGPU_CUDA(c, cudaMalloc(&c->dResult, c->resultBytes));
@@ -264,13 +265,17 @@ static int unpack(Ctx *c, const void *packed, size_t bytes, dipgpu_cols *out)
 // the first 64 KiB of indices), a second one only if more indices were kept.
 static int fetchResult(Ctx *c, cudaStream_t st)
 {
-    const size_t spec = std::min(c->resultBytes, c->layout.offInd + (size_t)65536);
+    // speculative size: what the previous round needed plus a quarter (rounds of one node keep similar
+    // columns), at least 8 KiB of indices
+    const size_t guess = std::max<size_t>(c->lastResultBytes + c->lastResultBytes / 4, c->layout.offInd + (size_t)8192);
+    const size_t spec = std::min(c->resultBytes, ResultLayout::alignUp(guess, 256));
     DIPGPU_CUDA(c, cudaMemcpyAsync(c->hResult, c->dResult, spec, cudaMemcpyDeviceToHost, st));
     if (c->stageTiming) cudaEventRecord(c->ev[6], st);
     DIPGPU_CUDA(c, cudaStreamSynchronize(st));
     c->d2h += (int64_t)spec;
     const ResultHeader *h = static_cast<const ResultHeader *>(c->hResult);
     const size_t need = c->layout.offInd + sizeof(int32_t) * (size_t)h->nInd;
+    c->lastResultBytes = need;
     if (need > spec) {
         DIPGPU_CUDA(c, cudaMemcpyAsync(static_cast<char *>(c->hResult) + spec, static_cast<char *>(c->dResult) + spec,
                                        need - spec, cudaMemcpyDeviceToHost, st));
@@ -336,6 +341,7 @@ static int ensureBatch(Ctx *c, int nVec)
     DIPGPU_CUDA(c, cudaMemset(c->dResultBatch, 0, V * resStride));
     DIPGPU_CUDA(c, cudaMallocHost(&c->hResultBatch, V * resStride));
     c->batchCap = nVec;
+    c->dUBatchClean = true;  // freshly zeroed
     c->uStride = uStride;
     c->rcStride = rcStride;
     c->resStride = resStride;
@@ -414,8 +420,55 @@ static int ensureDualBuffer(Ctx *c, int32_t uLen)
         if ((rc = devAlloc(c, &c->dU, (size_t)uLen + 16))) return rc;
         c->uCap = (size_t)uLen;
         c->dualsResident = false;
+        c->dUClean = false;
     }
     return DIPGPU_OK;
+}
+
+static int ensureSupportStaging(Ctx *c, int nVec)
+{
+    if (nVec <= c->supVecCap) return DIPGPU_OK;
+    if (c->hSupVals) cudaFreeHost(c->hSupVals);
+    c->hSupVals = nullptr;
+    devFree(&c->dSupVals);
+    c->supVecCap = 0;
+    const size_t n = std::max<size_t>(c->hSupport.size(), 1) * (size_t)nVec;
+    DIPGPU_CUDA(c, cudaHostAlloc(reinterpret_cast<void **>(&c->hSupVals), sizeof(double) * n, cudaHostAllocMapped | cudaHostAllocPortable));
+    c->supVecCap = nVec;
+    return DIPGPU_OK;
+}
+
+// H2D of nVec master dual vectors (row v at u + v*uLen) into dDst (vector v at dDst + v*dstStride): the
+// whole vectors, or -- with a dual support -- only the entries that can be nonzero, gathered into pinned
+// staging on the host and scattered on the device (the rest of dDst is kept at zero).
+static int uploadDuals(Ctx *c, const double *u, int32_t uLen, int nVec, double *dDst, size_t dstStride, bool *clean,
+                       cudaStream_t st)
+{
+    const size_t ns = c->hSupport.size();
+    if (ns == 0) {
+        if (nVec == 1) DIPGPU_CUDA(c, cudaMemcpyAsync(dDst, u, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, st));
+        else DIPGPU_CUDA(c, cudaMemcpy2DAsync(dDst, sizeof(double) * dstStride, u, sizeof(double) * (size_t)uLen,
+                                              sizeof(double) * (size_t)uLen, (size_t)nVec, cudaMemcpyHostToDevice, st));
+        c->h2d += (int64_t)sizeof(double) * uLen * nVec;
+        *clean = false;
+        return DIPGPU_OK;
+    }
+    int rc;
+    if ((rc = ensureSupportStaging(c, nVec))) return rc;
+    if (!*clean) {
+        DIPGPU_CUDA(c, cudaMemsetAsync(dDst, 0, sizeof(double) * (nVec == 1 ? (size_t)uLen : dstStride * (size_t)nVec), st));
+        *clean = true;
+    }
+    const int32_t *idx = c->hSupport.data();
+    for (int v = 0; v < nVec; ++v) {
+        const double *uv = u + (size_t)v * (size_t)uLen;
+        double *dst = c->hSupVals + (size_t)v * ns;
+        for (size_t k = 0; k < ns; ++k) dst[k] = uv[idx[k]];
+    }
+    // the scatter kernel reads the pinned staging directly (mapped host memory): the few KB cross PCIe inside
+    // the kernel, without a separate copy and its latency
+    c->h2d += (int64_t)sizeof(double) * (int64_t)ns * nVec;
+    return launchScatterDuals(c, (int)ns, c->dSupport, c->hSupVals, (int64_t)ns, dDst, (int64_t)dstStride, nVec, st);
 }
 
 // ------------------------------------------------------------------ waiting-column pool
@@ -513,6 +566,8 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
     freeBatch(c);
     devFree(&c->dFix); devFree(&c->dCapEff); devFree(&c->dRcEff);
+    devFree(&c->dSupport); devFree(&c->dSupVals);
+    if (c->hSupVals) cudaFreeHost(c->hSupVals);
     devFree(&c->dCenter); devFree(&c->dPoolStart); devFree(&c->dPoolRow); devFree(&c->dPoolVal);
     devFree(&c->dPoolOrigCost); devFree(&c->dPoolRedCost); devFree(&c->dPoolFlag);
     if (c->dResult) cudaFree(c->dResult);
@@ -568,6 +623,7 @@ int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *ro
     if (c->N != N) { devFree(&c->dRedCost); devFree(&c->dRcEff); }
     c->R = R; c->N = N; c->nBaseRows = nBaseRows; c->numConvex = numConvex;
     c->dualsResident = false; c->haveCenter = false; c->haveST = false;
+    c->hSupport.clear();
     c->hRowStart.assign(rowStart, rowStart + R + 1);
     c->hColInd.assign(colInd, colInd + nnz);
     c->hVal.assign(val, val + nnz);
@@ -597,6 +653,7 @@ int dipgpu_append_core_rows(dipgpu_ctx *ctx, int32_t nNew, const int64_t *rowSta
     c->hVal.insert(c->hVal.end(), val, val + add);
     c->R += nNew;
     c->dualsResident = false; c->haveCenter = false; c->haveST = false;  // the master dual vector grew
+    c->hSupport.clear();
     return uploadCore(c);
 }
 
@@ -728,8 +785,7 @@ int dipgpu_calc_redcost(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t 
         if ((rc = devAlloc(c, &c->dU, (size_t)uLen + 16))) return rc;
         c->uCap = (size_t)uLen;
     }
-    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, u, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, c->stream));
-    c->h2d += (int64_t)sizeof(double) * uLen;
+    if ((rc = uploadDuals(c, u, uLen, 1, c->dU, 0, &c->dUClean, c->stream))) return rc;
     c->dualsResident = true;
     if ((rc = launchRedCost(c, c->dU, phase, c->stream))) return rc;
     DIPGPU_CUDA(c, cudaMemcpyAsync(redCostX, c->dRedCost, sizeof(double) * (size_t)c->N, cudaMemcpyDeviceToHost, c->stream));
@@ -772,8 +828,7 @@ int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t p
     cudaStream_t st = c->stream;
     if (timed) cudaEventRecord(c->ev[0], st);
     if (u) {
-        DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, u, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, st));
-        c->h2d += (int64_t)sizeof(double) * uLen;
+        if ((rc = uploadDuals(c, u, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
         c->dualsResident = true;
     }
     if (timed) cudaEventRecord(c->ev[1], st);
@@ -804,13 +859,31 @@ int dipgpu_price_rounds_batch(dipgpu_ctx *ctx, int32_t nVec, const double *U, in
     if ((rc = ensureBatch(c, nVec))) return rc;
     cudaStream_t st = c->stream;
     if (c->stageTiming) cudaEventRecord(c->ev[0], st);
-    DIPGPU_CUDA(c, cudaMemcpy2DAsync(c->dUBatch, sizeof(double) * c->uStride, U, sizeof(double) * (size_t)uLen,
-                                     sizeof(double) * (size_t)uLen, (size_t)nVec, cudaMemcpyHostToDevice, st));
-    c->h2d += (int64_t)sizeof(double) * uLen * nVec;
+    if ((rc = uploadDuals(c, U, uLen, nVec, c->dUBatch, c->uStride, &c->dUBatchClean, st))) return rc;
     c->haveST = false;
     if ((rc = enqueueBatch(c, nVec, phase, redCostEps, st))) return rc;
     c->lastRoundOnHost = false;
     return fetchBatch(c, nVec, outs, st);
+}
+
+int dipgpu_set_dual_support(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx)
+{
+    CTX_OR_FAIL(ctx);
+    if (!c->haveCore) return fail(c, DIPGPU_ERR_STATE, "set_dual_support before set_core_csr");
+    if (nIdx < 0 || (nIdx > 0 && !idx)) return fail(c, DIPGPU_ERR_INVALID, "set_dual_support: bad arguments");
+    const int uLen = c->R + c->numConvex;
+    for (int k = 0; k < nIdx; ++k)
+        if (idx[k] < 0 || idx[k] >= uLen || (k > 0 && idx[k] <= idx[k - 1]))
+            return fail(c, DIPGPU_ERR_INVALID, "set_dual_support: indices must be ascending, unique and below %d", uLen);
+    c->hSupport.assign(idx, idx + nIdx);
+    c->supVecCap = 0;          // staging is sized by the support
+    c->dUClean = false;        // whatever the device vectors hold now may be nonzero outside the new support
+    c->dUBatchClean = false;
+    c->dualsResident = false;
+    int rc;
+    if ((rc = devAlloc(c, &c->dSupport, (size_t)std::max(nIdx, 1)))) return rc;
+    if (nIdx > 0) DIPGPU_CUDA(c, cudaMemcpy(c->dSupport, idx, sizeof(int32_t) * (size_t)nIdx, cudaMemcpyHostToDevice));
+    return DIPGPU_OK;
 }
 
 int dipgpu_stab_set_center(dipgpu_ctx *ctx, const double *dual, int32_t uLen)
@@ -869,10 +942,11 @@ int dipgpu_price_round_stab_ladder(dipgpu_ctx *ctx, const double *uRM, int32_t u
     for (int k = 1; k < nSteps; ++k) al[k] = al[k - 1] * shrink;
     if (alphasOut) memcpy(alphasOut, al, sizeof(double) * (size_t)nSteps);
     if (c->stageTiming) cudaEventRecord(c->ev[0], st);
-    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, uRM, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, st));
+    if ((rc = uploadDuals(c, uRM, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
     DIPGPU_CUDA(c, cudaMemcpyAsync(c->dAlphaLadder, al, sizeof(double) * (size_t)nSteps, cudaMemcpyHostToDevice, st));
-    c->h2d += (int64_t)sizeof(double) * (uLen + nSteps);
+    c->h2d += (int64_t)sizeof(double) * nSteps;
     c->dualsResident = true;
+    c->dUBatchClean = false;  // the smoothing writes every entry of the batch vectors
     if (!c->haveCenter || c->centerLen != (size_t)uLen) {
         // first price call: m_dual := m_dualRM (DecompAlgoPC.cpp:163-173)
         if (c->centerLen != (size_t)uLen) {
@@ -1076,8 +1150,7 @@ int dipgpu_pool_set_reduced_costs(dipgpu_ctx *ctx, const double *u, int32_t uLen
     if ((rc = poolReserve(c, std::max<int64_t>(c->poolCols, 1), std::max<int64_t>(c->poolNnz, 1)))) return rc;
     cudaStream_t st = c->stream;
     if (u) {
-        DIPGPU_CUDA(c, cudaMemcpyAsync(c->dU, u, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, st));
-        c->h2d += (int64_t)sizeof(double) * uLen;
+        if ((rc = uploadDuals(c, u, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
         c->dualsResident = true;
     }
     if (c->stageTiming) cudaEventRecord(c->ev[1], st);

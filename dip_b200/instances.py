@@ -125,18 +125,32 @@ def gap_pricing_model(g: GapInstance, branch_rows=True) -> PricingModel:
         name=g.name, meta=dict(n=n, branch_rows=branch_rows))
 
 
-def gap_duals(model: PricingModel, rng: np.random.Generator, branch_density=0.01) -> np.ndarray:
+def gap_branch_rows(model: PricingModel, rng: np.random.Generator, branch_density=0.01) -> np.ndarray:
+    """The branch rows (positions relative to the first branch row) that carry a bound at one node of the
+    tree: `branch_density` of them, ascending.  Every other branch row is a free row (zero dual)."""
+    nb = model.n_base_rows - model.meta["n"]
+    return np.sort(rng.choice(nb, size=int(nb * branch_density), replace=False))
+
+
+def gap_dual_support(model: PricingModel, branch_rows: np.ndarray) -> np.ndarray:
+    """Master rows that can carry a dual at that node: assignment rows, the bounded branch rows, convexity rows."""
+    n = model.meta["n"]
+    return np.concatenate([np.arange(n), n + np.asarray(branch_rows), np.arange(model.n_base_rows, model.u_len)]).astype(np.int32)
+
+
+def gap_duals(model: PricingModel, rng: np.random.Generator, branch_density=0.01, branch_rows=None) -> np.ndarray:
     """A master dual vector in DIP's row layout for a GAP model: assignment duals
     U[0, 2 mean(c)] (about half of the items get a negative reduced cost), branch-row duals 0
-    except `branch_density` random entries, alpha_b ~ U[-10, 0]."""
+    except `branch_density` random entries (or exactly the rows `branch_rows`, see gap_branch_rows),
+    alpha_b ~ U[-10, 0]."""
     n = model.meta["n"]
     N = model.N
     u = np.zeros(model.u_len, np.float64)
     u[:n] = rng.uniform(0.0, 2.0 * model.objective.mean(), size=n)
     nb = model.n_base_rows - n
-    if nb > 0 and branch_density > 0:
-        k = int(nb * branch_density)
-        idx = rng.choice(nb, size=k, replace=False)
+    if nb > 0 and (branch_density > 0 or branch_rows is not None):
+        k = int(nb * branch_density) if branch_rows is None else len(branch_rows)
+        idx = rng.choice(nb, size=k, replace=False) if branch_rows is None else np.asarray(branch_rows)
         # x <= ub rows carry duals <= 0, x >= lb rows duals >= 0 (min-form)
         vals = rng.uniform(0.0, 3.0, size=k)
         u[n + idx] = np.where(idx < N, -vals, vals)

@@ -205,6 +205,15 @@ class GpuPricer:
         self._check(self._lib.dipgpu_set_col_bounds(self._ctx, capi.ptr(lb), capi.ptr(ub), len(lb)))
         self._relax_cache = None
 
+    def setDualSupport(self, idx=None):
+        """Rows of the master dual vector that can be nonzero (free branch rows have zero duals,
+        AlpsDecompTreeNode.cpp:215-238): only those are uploaded per round.  None removes the support."""
+        if idx is None:
+            self._check(self._lib.dipgpu_set_dual_support(self._ctx, 0, None))
+            return
+        ix = np.ascontiguousarray(idx, np.int32)
+        self._check(self._lib.dipgpu_set_dual_support(self._ctx, len(ix), capi.ptr(ix)))
+
     def setBlockRange(self, first: int, count: int):
         self._check(self._lib.dipgpu_set_block_range(self._ctx, first, count))
 

@@ -201,6 +201,19 @@ int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t p
  * DIP re-prices the waiting columns and generates new ones with the same duals
  * (Dip/src/DecompAlgo.cpp:1901 then :1914), so the vector crosses PCIe once. */
 
+/*
+ * Rows of the master dual vector that can be nonzero (ascending, unique; nIdx = 0 removes the support).
+ * DIP keeps one pair of branch rows per integer column in the master and relaxes all of them to free rows at
+ * the root, at the other nodes all but the rows of the bounds branched on (Dip/src/AlpsDecompTreeNode.cpp:215-238,
+ * DecompAlgo::setMasterBounds Dip/src/DecompAlgo.cpp:2373-2520); a free row's dual is 0.  Between two
+ * setMasterBounds calls the duals therefore live on the original rows, the few bounded branch rows, the
+ * convexity rows and the cuts -- on GAP-E about 4 000 of 257 680 entries.  With a support set, every entry
+ * point that takes host duals gathers u[idx] into pinned staging, uploads only that and scatters it on the
+ * device (the device vector stays zero elsewhere): 34 KB instead of 2 MB per round.  The caller guarantees
+ * u == 0 outside the support.  Cleared by dipgpu_set_core_csr / dipgpu_append_core_rows (the vector changes).
+ */
+int dipgpu_set_dual_support(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx);
+
 /* ------------------------------------------- several dual vectors in one submission
  *
  * nVec master dual vectors (row v at U + v*uLen), each priced exactly as dipgpu_price_round would:

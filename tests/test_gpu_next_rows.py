@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from dip_b200 import instances as I
-from dip_b200.pricer import PROFIT_FP64, PROFIT_PISINGER_INT
+from dip_b200.pricer import PROFIT_FP64, PROFIT_PISINGER_INT, RoundResult
 
 pytestmark = pytest.mark.gpu
 
@@ -341,3 +341,59 @@ def test_node_bounds_unsupported_in_pisinger_mode(pricer):
     with pytest.raises(DipGpuError) as e:
         pricer.setColBounds(np.zeros(len(b.weight)), np.ones(len(b.weight)))
     assert e.value.code == ERR_UNSUPPORTED
+
+
+# ------------------------------------------------------------------ sparse upload of the duals
+
+
+def test_dual_support_upload_equals_dense(oracle, pricer):
+    """With the rows that can carry a dual declared (free branch rows have none), only those cross PCIe:
+    rounds, batches, the smoothing ladder and the pool pass must equal their dense-upload results."""
+    from dip_b200.capi import DipGpuError, ERR_INVALID
+    model = I.gap_pricing_model(I.gap_class_d())
+    pricer.setModel(model)
+    n = model.meta["n"]
+    rng = np.random.default_rng(40)
+    nb = model.n_base_rows - n
+    branch = np.sort(rng.choice(nb, size=nb // 50, replace=False)) + n
+    support = np.concatenate([np.arange(n), branch, np.arange(model.n_base_rows, model.u_len)]).astype(np.int32)
+
+    def duals():
+        u = np.zeros(model.u_len)
+        u[:n] = rng.uniform(0, 2 * model.objective.mean(), size=n)
+        u[branch] = rng.uniform(-3, 3, size=len(branch))
+        u[model.n_base_rows:] = rng.uniform(-10, 0, size=model.m)
+        return u
+    U = np.stack([duals() for _ in range(5)])
+    dense = []
+    for v in range(5):
+        r, rcx = pricer.priceRound(U[v], want_redcost=True, result=RoundResult(model.m, model.m, model.N))
+        dense.append((r, rcx))
+    h0 = pricer.counters()["h2d_bytes"]
+    pricer.setDualSupport(support)
+    for v in (3, 0, 4):     # any order: entries of the previous vector must not linger
+        r, rcx = pricer.priceRound(U[v], want_redcost=True)
+        np.testing.assert_array_equal(rcx, dense[v][1])
+        _same_round(r, dense[v][0])
+    assert pricer.counters()["h2d_bytes"] - h0 == 3 * 8 * len(support)
+    batch = pricer.priceRoundsBatch(U)
+    for v in range(5):
+        _same_round(batch[v], dense[v][0])
+    pricer.stabSetCenter(U[0])
+    results, alphas = pricer.priceRoundStabLadder(U[1], 0.2, 3)
+    for k in range(3):
+        st = oracle.smooth_duals(alphas[k], U[0], U[1])
+        np.testing.assert_array_equal(pricer.smoothedDuals(k), st)
+    batch = pricer.priceRoundsBatch(U[:2])      # after the ladder wrote dense vectors into the batch buffer
+    _same_round(batch[1], dense[1][0])
+    # dense again
+    pricer.setDualSupport(None)
+    u_dense = duals()
+    u_dense[n + 7] = 1.25                        # outside the old support
+    r, rcx = pricer.priceRound(u_dense, want_redcost=True)
+    ref = oracle.calc_redcost(model.R, model.N, model.row_start, model.col_ind, model.val,
+                              oracle.adjust_duals(u_dense, model.n_base_rows, model.m), model.objective)
+    np.testing.assert_array_equal(rcx, ref)
+    with pytest.raises(DipGpuError) as e:
+        pricer.setDualSupport(np.array([3, 2], np.int32))
+    assert e.value.code == ERR_INVALID
