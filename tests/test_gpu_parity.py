@@ -562,3 +562,37 @@ def test_reduction_in_pisinger_mode(oracle, pricer):
     _check_against_oracle(oracle, pricer, bcs, w, cap, rc, oc, alpha, profit_mode=PROFIT_PISINGER_INT)
     res = pricer.solveBlocks(rc, alpha)
     assert res.cellsEvaluated < res.cells
+
+
+def test_gap_e_many_rounds_match_oracle(oracle, pricer):
+    """48 GAP-E 80x1600 rounds (3 840 blocks through the reduction pre-pass), singly and in batches of 16:
+    optimum bit for bit, columns, per-block reduced costs and the reference's cell count, every round."""
+    model = I.gap_pricing_model(I.gap_class_e())
+    pricer.setModel(model)
+    rng = np.random.default_rng(2024)
+    U = np.stack([I.gap_duals(model, rng, branch_density=0.002 * (1 + v % 7)) for v in range(48)])
+    U[5, :model.meta["n"]] *= 0.05          # almost no item prices out
+    U[6, :model.meta["n"]] *= 3.0           # nearly every item does
+    U[7, :model.meta["n"]] = np.round(U[7, :model.meta["n"]])   # integer duals: ties
+    refs = [oracle.price_round(model.R, model.N, model.row_start, model.col_ind, model.val, model.objective, U[v],
+                               model.n_base_rows, model.m, model.block_col_start, model.weight, model.capacity,
+                               n_threads=8) for v in range(48)]
+    evaluated = 0
+    for lo in range(0, 48, 16):
+        batch = pricer.priceRoundsBatch(U[lo:lo + 16])
+        for k, res in enumerate(batch):
+            ref = refs[lo + k]
+            np.testing.assert_array_equal(res.blockObj, ref.z)
+            np.testing.assert_array_equal(res.blockNnz, ref.col_nnz)
+            np.testing.assert_array_equal(res.blockRedCost, ref.col_red_cost)
+            kept = [b for b in range(model.m) if ref.col_keep[b]]
+            assert list(res.colBlock[:res.nCols]) == kept
+            for j, b in enumerate(kept):
+                assert list(res.column(j)) == list(ref.col_ind[b])
+            assert res.cells == ref.cells
+            evaluated += res.cellsEvaluated
+    for v in (0, 5, 6, 7, 47):
+        res = pricer.priceRound(U[v])
+        np.testing.assert_array_equal(res.blockObj, refs[v].z)
+        assert res.mostNegReducedCost == refs[v].most_neg_reduced_cost
+    assert evaluated < 0.5 * sum(r.cells for r in refs)
