@@ -258,7 +258,9 @@ struct Ctx {
     // rows of the master dual vector that can be nonzero (dipgpu_set_dual_support): only those cross PCIe
     std::vector<int32_t> hSupport;
     int32_t *dSupport = nullptr;
-    double *hSupVals = nullptr, *dSupVals = nullptr;  // pinned / device staging, supVecCap vectors of hSupport.size()
+    uint32_t *dSupportBits = nullptr;  // one bit per master row (pool.cu)
+    size_t poolFnSmem[2] = {0, 0};
+    double *hSupVals = nullptr;  // mapped pinned staging the scatter kernel reads: supVecCap vectors of hSupport.size()
     int supVecCap = 0;
     bool dUClean = false, dUBatchClean = false;       // the device vectors are zero outside the support
     // waiting-column pool (DecompVarPool): master columns in device memory

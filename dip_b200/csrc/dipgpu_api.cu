@@ -430,7 +430,6 @@ static int ensureSupportStaging(Ctx *c, int nVec)
     if (nVec <= c->supVecCap) return DIPGPU_OK;
     if (c->hSupVals) cudaFreeHost(c->hSupVals);
     c->hSupVals = nullptr;
-    devFree(&c->dSupVals);
     c->supVecCap = 0;
     const size_t n = std::max<size_t>(c->hSupport.size(), 1) * (size_t)nVec;
     DIPGPU_CUDA(c, cudaHostAlloc(reinterpret_cast<void **>(&c->hSupVals), sizeof(double) * n, cudaHostAllocMapped | cudaHostAllocPortable));
@@ -566,7 +565,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
     freeBatch(c);
     devFree(&c->dFix); devFree(&c->dCapEff); devFree(&c->dRcEff);
-    devFree(&c->dSupport); devFree(&c->dSupVals);
+    devFree(&c->dSupport); devFree(&c->dSupportBits);
     if (c->hSupVals) cudaFreeHost(c->hSupVals);
     devFree(&c->dCenter); devFree(&c->dPoolStart); devFree(&c->dPoolRow); devFree(&c->dPoolVal);
     devFree(&c->dPoolOrigCost); devFree(&c->dPoolRedCost); devFree(&c->dPoolFlag);
@@ -883,6 +882,10 @@ int dipgpu_set_dual_support(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx)
     int rc;
     if ((rc = devAlloc(c, &c->dSupport, (size_t)std::max(nIdx, 1)))) return rc;
     if (nIdx > 0) DIPGPU_CUDA(c, cudaMemcpy(c->dSupport, idx, sizeof(int32_t) * (size_t)nIdx, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> bits((size_t)(uLen + 31) / 32 + 1, 0u);
+    for (int k = 0; k < nIdx; ++k) bits[(size_t)idx[k] >> 5] |= 1u << (idx[k] & 31);
+    if ((rc = devAlloc(c, &c->dSupportBits, bits.size()))) return rc;
+    DIPGPU_CUDA(c, cudaMemcpy(c->dSupportBits, bits.data(), sizeof(uint32_t) * bits.size(), cudaMemcpyHostToDevice));
     return DIPGPU_OK;
 }
 

@@ -301,7 +301,6 @@ constexpr int kPruneBuckets = 1024;   // efficiency histogram of the reduction p
 constexpr int kPruneMinItems = 256;   // (columns of the block) below this the DP is about as short as the pre-pass
 constexpr int kPruneTopFill = 2;      // pass 0 runs over the most efficient items worth this many capacities of weight
 constexpr int kSumsRcOff = 256, kSumsObjOff = 512;  // doubles into itP: prefetched reduced costs / objective entries
-constexpr int kPubStride = 16;        // publication words sit 128 bytes apart (one per L2 line)
 constexpr int kPass0Words = 7;        // ... and over at most 32 * kPass0Words (its decision words sit in front of the raw arrays)
 constexpr size_t kPruneScratchBytes = sizeof(int) * 3 * kPruneBuckets + sizeof(double) * 6 + 16 + 64;
 
@@ -440,7 +439,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         // access from this SM otherwise pays its translation miss (~4 us, seen on a random third of the
         // blocks) on the critical path of the tail instead of under the DP
         unsigned long long x0, x1, x2;
-        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x0) : "l"(a.pubWord + (size_t)vlb * kPubStride) : "memory");
+        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x0) : "l"(a.pubWord + (size_t)vlb * kPubWordStride) : "memory");
         asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x1) : "l"(RESV(a.filt.hdr)) : "memory");
         asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x2) : "l"(RESV(a.filt.keptInd) + (size_t)(colStart - a.blockColStart[a.firstBlock]) / 2 * 2) : "memory");
         touch = x0 ^ x1 ^ x2;  // consumed in the tail, so that nothing waits for these loads here
@@ -1261,7 +1260,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                                             ((unsigned long long)kGlobal << 31) | (unsigned long long)cnt;
             // relaxed: the word itself is everything the other blocks read (no other store has to be ordered before it)
             // an atomic goes straight to the L2 slice (a plain store may wait in the SM's write path)
-            atomicExch(a.pubWord + (size_t)vlb * kPubStride, word);
+            atomicExch(a.pubWord + (size_t)vlb * kPubWordStride, word);
             RESV(a.back.blockRedCost)[lb] = rcB;
             RESV(a.back.blockOrigCost)[lb] = sOcSum;
             RESV(a.back.blockNnz)[lb] = cnt;
@@ -1280,7 +1279,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                 unsigned long long wv;
                 // (fetched before the spin, so that its latency hides behind the wait)
                 const unsigned long long rowB = (unsigned long long)max(a.capacity[a.firstBlock + pB], -1) + 1ull;
-                const unsigned long long *src = a.pubWord + (size_t)(vlb - lb + pB) * kPubStride;
+                const unsigned long long *src = a.pubWord + (size_t)(vlb - lb + pB) * kPubWordStride;
                 for (;;) {
                     // an atomic is performed at the line's home L2 slice: a plain (even .relaxed.gpu) load
                     // was seen to return the old word for ~4.5 us on part of the SMs (the other die's L2)

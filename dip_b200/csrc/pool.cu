@@ -18,21 +18,38 @@
 namespace dipgpu {
 
 constexpr int kPoolWarps = 8;
-constexpr int kPoolChunk = 512;  // products staged per warp and pass (4 KiB)
+constexpr int kPoolWarpsBitmap = 16;  // CTA width of the variant that keeps the dual-support bitmap in shared memory
+constexpr int kPoolChunk = 512;       // products staged per warp and pass (4 KiB)
 
 // One warp per 32 consecutive waiting columns.  Their stored entries are one contiguous span of
 // the pool; the warp walks it from the END in chunks: all lanes form the products val*u[row]
 // (coalesced loads, unfused multiply) into shared memory, then lane l adds the products of ITS
 // column, last entry first -- the order of CoinPackedVectorBase::dotProduct as the oracle restates
 // it (dp = 0; for i = n-1..0: dp += els[i]*u[ind[i]]), so the values are bit-equal to the oracle.
-__global__ void __launch_bounds__(kPoolWarps * 32)
+//
+// BITMAP: a dual support is declared (dipgpu_set_dual_support) and its bitmap (one bit per master row)
+// fits shared memory.  Most entries of a master column sit in rows that cannot carry a dual (GAP: the
+// free branch rows, 2/3 of every column): the gather of the dual -- one 32-byte sector per 8 useful
+// bytes, what bounds this pass -- is skipped for them, a shared-memory bit test decides.  The product
+// is still formed (val * 0), so the result is the same bit for bit.
+template <bool BITMAP>
+__global__ void __launch_bounds__(kPoolWarpsBitmap * 32)
 pool_redcost_kernel(long long nCols, const int64_t *__restrict__ colStart, const int32_t *__restrict__ row,
                     const double *__restrict__ val, const double *__restrict__ origCost,
-                    const double *__restrict__ u, int feasible, double *__restrict__ out, int32_t *flag)
+                    const double *__restrict__ u, int feasible, double *__restrict__ out, int32_t *flag,
+                    const uint32_t *__restrict__ supportBits, int bitWords)
 {
-    __shared__ double sP[kPoolWarps][kPoolChunk];
+    extern __shared__ __align__(16) unsigned char poolSm[];
+    const int warpsPerCta = blockDim.x >> 5;
+    double *sPall = reinterpret_cast<double *>(poolSm);
+    const uint32_t *sBits = reinterpret_cast<const uint32_t *>(sPall + (size_t)warpsPerCta * kPoolChunk);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long c0 = ((long long)blockIdx.x * kPoolWarps + warp) * 32;
+    if (BITMAP) {
+        uint32_t *w = const_cast<uint32_t *>(sBits);
+        for (int k = threadIdx.x; k < bitWords; k += blockDim.x) w[k] = __ldg(supportBits + k);
+        __syncthreads();
+    }
+    const long long c0 = ((long long)blockIdx.x * warpsPerCta + warp) * 32;
     if (c0 >= nCols) return;
     const long long col = c0 + lane;
     const long long cEnd = min(nCols, c0 + 32);
@@ -45,7 +62,7 @@ pool_redcost_kernel(long long nCols, const int64_t *__restrict__ colStart, const
         oc = origCost[col];
     }
     double sum = 0.0;
-    double *p = sP[warp];
+    double *p = sPall + (size_t)warp * kPoolChunk;
     for (int64_t hi = E; hi > B;) {
         const int64_t lo = max(B, hi - kPoolChunk);
         // batches of 8 independent (row, value) loads, then their 8 dependent gathers of the dual: the
@@ -60,7 +77,11 @@ pool_redcost_kernel(long long nCols, const int64_t *__restrict__ colStart, const
                 v[j] = k < hi ? __ldg(val + k) : 0.0;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = (base + 32 * j < hi) ? __ldg(u + r[j]) : 0.0;
+            for (int j = 0; j < 8; ++j) {
+                bool on = base + 32 * j < hi;
+                if (BITMAP) on = on && ((sBits[r[j] >> 5] >> (r[j] & 31)) & 1u);
+                g[j] = on ? __ldg(u + r[j]) : 0.0;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (base + 32 * j < hi) p[base + 32 * j - lo] = __dmul_rn(v[j], g[j]);
@@ -95,9 +116,20 @@ int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st)
     DIPGPU_CUDA(c, cudaMemsetAsync(c->dPoolFlag, 0, sizeof(int32_t), st));
     if (c->poolCols == 0) return DIPGPU_OK;
     const long long warps = (c->poolCols + 31) / 32;
-    const unsigned grid = (unsigned)((warps + kPoolWarps - 1) / kPoolWarps);
-    pool_redcost_kernel<<<grid, kPoolWarps * 32, 0, st>>>(c->poolCols, c->dPoolStart, c->dPoolRow, c->dPoolVal,
-                                                         c->dPoolOrigCost, dU, feasible, c->dPoolRedCost, c->dPoolFlag);
+    // the bitmap variant pays when the pool is large (the bitmap is loaded once per CTA) and the support small
+    const int bitWords = (c->R + c->numConvex + 31) / 32;
+    const bool bitmap = c->dSupportBits != nullptr && !c->hSupport.empty() && bitWords * 4 <= 64 * 1024 &&
+                        c->poolCols >= 32 * 1024 && (int64_t)c->hSupport.size() * 4 <= (int64_t)c->R + c->numConvex;
+    const int wpc = bitmap ? kPoolWarpsBitmap : kPoolWarps;
+    const size_t smem = sizeof(double) * (size_t)wpc * kPoolChunk + (bitmap ? sizeof(uint32_t) * (size_t)bitWords : 0);
+    const unsigned grid = (unsigned)((warps + wpc - 1) / wpc);
+    auto fn = bitmap ? pool_redcost_kernel<true> : pool_redcost_kernel<false>;
+    if (c->poolFnSmem[bitmap ? 1 : 0] < smem) {
+        DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->poolFnSmem[bitmap ? 1 : 0] = smem;
+    }
+    fn<<<grid, wpc * 32, smem, st>>>(c->poolCols, c->dPoolStart, c->dPoolRow, c->dPoolVal, c->dPoolOrigCost, dU, feasible,
+                                    c->dPoolRedCost, c->dPoolFlag, c->dSupportBits, bitWords);
     c->launches++;
     DIPGPU_CUDA(c, cudaGetLastError());
     return DIPGPU_OK;

@@ -35,7 +35,7 @@ enum {
     DIPGPU_ERR_CUDA = 2,        /* CUDA runtime / driver error, or no usable sm_100 device */
     DIPGPU_ERR_NOMEM = 3,       /* device or pinned-host allocation failed */
     DIPGPU_ERR_STATE = 4,       /* call order: model / blocks / objective not set yet */
-    DIPGPU_ERR_UNSUPPORTED = 5, /* e.g. capacity beyond what one thread-block cluster can stage */
+    DIPGPU_ERR_UNSUPPORTED = 5, /* e.g. a capacity beyond what one CTA can stage, node bounds in Pisinger mode */
     DIPGPU_ERR_OVERFLOW = 6     /* caller's output buffers too small; required sizes are reported */
 };
 

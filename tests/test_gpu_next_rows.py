@@ -397,3 +397,31 @@ def test_dual_support_upload_equals_dense(oracle, pricer):
     with pytest.raises(DipGpuError) as e:
         pricer.setDualSupport(np.array([3, 2], np.int32))
     assert e.value.code == ERR_INVALID
+
+
+def test_pool_with_dual_support_bitmap(oracle, pricer):
+    """A large pool (>= 32 Ki columns) with a declared dual support runs the kernel variant that skips the
+    gathers of rows without a dual (shared-memory bitmap); bit-equal to the oracle and to the plain variant."""
+    rng = np.random.default_rng(61)
+    R, m = 40_000, 16
+    pricer.setModelCore(R, 8, np.zeros(R + 1, np.int64), np.zeros(0, np.int32), np.zeros(0), R, m)
+    n_cols = 40_000
+    lens = rng.integers(0, 60, size=n_cols)
+    cs = np.zeros(n_cols + 1, np.int64)
+    np.cumsum(lens, out=cs[1:])
+    ri = rng.integers(0, R + m, size=cs[-1]).astype(np.int32)
+    va = rng.uniform(-2, 2, size=cs[-1])
+    oc = rng.uniform(-1, 30, size=n_cols)
+    pricer.poolAppend(cs, ri, va, oc)
+    support = np.sort(rng.choice(R + m, size=(R + m) // 10, replace=False)).astype(np.int32)
+    u = np.zeros(R + m)
+    u[support] = rng.standard_normal(len(support))
+    plain, found0 = pricer.poolSetReducedCosts(u)
+    ref, ref_found = oracle.pool_reduced_costs(cs, ri, va, oc, u)
+    np.testing.assert_array_equal(plain, ref)
+    pricer.setDualSupport(support)
+    got, found = pricer.poolSetReducedCosts(u)
+    np.testing.assert_array_equal(got, ref)
+    assert found == ref_found == found0
+    got_ray, _ = pricer.poolSetReducedCosts(None, feasible=False)     # resident duals, dual-ray form
+    np.testing.assert_array_equal(got_ray, oracle.pool_reduced_costs(cs, ri, va, oc, u, False)[0])

@@ -54,3 +54,21 @@ def test_random_batch_is_ragged():
     n = np.diff(b.block_col_start)
     assert n.min() == 0 or n.min() < 5
     assert (b.red_cost == 0).any() and (b.red_cost > 0).any()
+
+
+def test_gap_duals_of_one_node_share_their_support():
+    """bench.py prices 16 dual vectors of ONE node: the same branch rows carry a bound in all of them, and every
+    vector is zero outside the declared support (what dipgpu_set_dual_support relies on)."""
+    import numpy as np
+    from dip_b200 import instances as I
+    model = I.gap_pricing_model(I.gap_class_d())
+    rng = np.random.default_rng(3)
+    rows = I.gap_branch_rows(model, rng, branch_density=0.02)
+    assert len(rows) == int(0.02 * (model.n_base_rows - model.meta["n"])) and np.all(np.diff(rows) > 0)
+    support = I.gap_dual_support(model, rows)
+    assert np.all(np.diff(support) > 0) and support[-1] == model.u_len - 1
+    outside = np.ones(model.u_len, bool)
+    outside[support] = False
+    for _ in range(4):
+        u = I.gap_duals(model, rng, branch_rows=rows)
+        assert not np.any(u[outside]) and np.count_nonzero(u[support]) > 0.9 * len(support)
