@@ -208,7 +208,7 @@ struct Ctx {
     int maxBlockCols = 0;      // of the shard
     int maxUsableWeight = 0;   // of the shard: max weight <= its block's capacity
     std::vector<int32_t> hMaxUsableW;  // per block
-    int optThreads = 0, optCellsPerThread = 0, optItemsPerStep = 0, optNoGuard = 0, optNoPrune = 0;
+    int optThreads = 0, optCellsPerThread = 0, optItemsPerStep = 0, optNoGuard = 0, optNoPrune = 0, optPdl = 0;
     void *dpFnConfigured = nullptr;
     size_t dpFnSmem = 0;
     DpGeom geom{};

@@ -1388,6 +1388,7 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !name) return DIPGPU_ERR_INVALID;
     if (!strcmp(name, "stage_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "dp_pdl")) { c->optPdl = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "spmv_lanes")) { c->spmvLanes = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "dp_debug_times")) {
         // diagnostics: value = host pointer (as integer) receiving 8 x nLocal uint64 globaltimer stamps of

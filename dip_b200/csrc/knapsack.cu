@@ -332,6 +332,7 @@ struct KnapArgs {
     // arrays pubWord / scale / shortcut / sel / zShort hold nLocal entries per vector
     long long rcStride, alphaStride, resStride;
     int prune;                     // FUSE: drop items that cannot be in an optimal solution before the DP
+    int pdl;                       // FUSE: launched with programmatic stream serialization (griddepcontrol.wait before the reduced costs are read)
     BackArgs back;
     FilterArgs filt;
 };
@@ -474,6 +475,17 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         // (fused shapes test the flags here; the large-shard path is fed reduced costs in which the fixed
         // columns are already +0, so that its hot kernels stay exactly as they are without bounds)
         const uint8_t *fixB = (FUSE && a.back.fix != nullptr) ? a.back.fix + g0 : nullptr;
+        const bool pruneLayoutHere = FUSE && dpPruneLayout(CH, true, a.prune != 0) && len >= kPruneMinItems;
+        if (pruneLayoutHere) {
+            // the histograms of the reduction pre-pass (in the not yet written itP | itW), zeroed before the
+            // reduced costs are there
+            int *h0 = reinterpret_cast<int *>(itP);
+            for (int k = t; k < 3 * kPruneBuckets; k += T) h0[k] = 0;
+        }
+        // Programmatic dependent launch: this kernel may have started while the kernel that writes the
+        // reduced costs (the SpMV) is still running; everything above -- row buffers, histograms, page
+        // touches, the convexity dual -- overlapped with it.  From here on its output is read.
+        if (FUSE && a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
         // ---- stage the chunk's reduced costs and weights with TMA bulk copies
         if (t == 0) {
             const uint32_t bytesRc = (uint32_t)(((shiftRc + len + 1) & ~1) * 8);
@@ -482,14 +494,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             tmaLoad1d(rawRc, redCostV + (g0 - shiftRc), bytesRc, mbar);
             tmaLoad1d(rawW, a.weight + (g0 - shiftW), bytesW, mbar);
         }
-        const bool pruneLayoutHere = FUSE && dpPruneLayout(CH, true, a.prune != 0) && len >= kPruneMinItems;
-        if (pruneLayoutHere) {
-            // the histograms of the reduction pre-pass (in the not yet written itP | itW): zeroed while the
-            // bulk copies are in flight
-            int *h0 = reinterpret_cast<int *>(itP);
-            for (int k = t; k < 3 * kPruneBuckets; k += T) h0[k] = 0;
-            __syncthreads();
-        }
+        if (pruneLayoutHere) __syncthreads();  // the zeroed histograms are visible to every warp
         mbarWait(mbar, parity);
         parity ^= 1u;
         dbgStamp(a.dbgTimes, 1);
@@ -1641,7 +1646,27 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
         int rc = prepareKnapsackDp(c);
         if (rc) return rc;
     }
-    fn<<<dim3(c->nLocal, nVec, 1), g.T, g.smemBytes, st>>>(a);
+    // Option "dp_pdl" (fused fp64 shapes): programmatic dependent launch -- the CTAs may become resident while
+    // the preceding kernel of the stream (the SpMV) still runs; the kernel waits (griddepcontrol.wait) before it
+    // reads the reduced costs.  Measured SLOWER on GAP-E (39.5 vs 35.9 us per round: the early CTAs take SM
+    // resources from the 6 us SpMV they wait for), so it is off unless asked for.  (Pisinger mode reads the
+    // prep kernel's output at its very top: always a plain launch.)
+    a.pdl = (g.fuse && c->profitMode == DIPGPU_PROFIT_FP64 && c->optPdl) ? 1 : 0;
+    if (a.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(c->nLocal, nVec, 1);
+        cfg.blockDim = dim3(g.T, 1, 1);
+        cfg.dynamicSmemBytes = g.smemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DIPGPU_CUDA(c, cudaLaunchKernelEx(&cfg, fn, a));
+    } else {
+        fn<<<dim3(c->nLocal, nVec, 1), g.T, g.smemBytes, st>>>(a);
+    }
     c->launches++;
     DIPGPU_CUDA(c, cudaGetLastError());
     return DIPGPU_OK;

@@ -107,6 +107,9 @@ __global__ void __launch_bounds__(1024, 1) redcost_stream_kernel(const __grid_co
 {
     typedef typename std::conditional<ROW16, uint16_t, int32_t>::type RowT;
     extern __shared__ __align__(16) unsigned char sm[];
+    // programmatic dependent launch: the kernel that consumes the reduced costs may be scheduled now (it
+    // waits, griddepcontrol.wait, before it reads them)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const double *sU = reinterpret_cast<const double *>(sm);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const double *uVec = a.u + (int64_t)blockIdx.y * a.uStride;

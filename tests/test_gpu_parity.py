@@ -169,6 +169,17 @@ def test_gap_e_round(oracle, pricer):
         assert res.nCols > 0
 
 
+def test_gap_e_round_with_programmatic_dependent_launch(oracle, pricer):
+    """Option dp_pdl: the fused kernel is launched behind the SpMV with programmatic stream serialization
+    and waits (griddepcontrol.wait) before it reads the reduced costs; same round."""
+    model = I.gap_pricing_model(I.gap_class_e())
+    pricer.setModel(model)
+    pricer.set_option("dp_pdl", 1)
+    rng = np.random.default_rng(6)
+    for _ in range(3):
+        _check_round(oracle, pricer, model, I.gap_duals(model, rng))
+
+
 def test_gap12_class_c_round(oracle, pricer):
     model = I.gap_pricing_model(I.gap_class_c())
     pricer.setModel(model)
