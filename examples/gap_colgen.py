@@ -101,6 +101,92 @@ def run(model, price, max_rounds=200, eps=1e-4, log=None):
     return tr, cols
 
 
+def run_stabilised(model, price_ladder, price_plain, accept, alpha0=0.1, n_steps=6, max_rounds=300, eps=1e-4, log=None):
+    """The same loop under Wentges smoothing, following DecompAlgoPC's contract (Dip/src/DecompAlgoPC.cpp:126-212,
+    DecompAlgoPC.h:99-133, Dip/src/DecompAlgo.cpp:5642-5655):
+      * the round is priced with dualST = alpha*dual + (1-alpha)*dualRM, dual = the stability centre (first
+        call: dualRM itself);
+      * the bound of the round is the Lagrangian bound AT dualST: b.dualST + mostNegReducedCost
+        (updateObjBound reads getMasterDualSolution(), DecompAlgo.cpp:3728-3758); when it improves the best bound the
+        centre moves to dualST (setObjBound);
+      * if every new column is a duplicate, alpha *= 0.9 and the round is priced again -- here the whole ladder
+        alpha0 * 0.9^k, k < n_steps, is priced in ONE submission and the first step that yields a new column is
+        taken; if none does, the round is priced at dualRM itself (alpha = 0), and no new column there ends it.
+    price_ladder(uRM, alpha0, n_steps) -> [(cols, mostNeg, dualST)] per step; price_plain(uRM) -> (cols, mostNeg);
+    accept(step) moves the centre to that step's dualST (step None: to dualRM)."""
+    m = model.m
+    cols = [Column(b, (), 0.0, np.array([model.n_base_rows + b], np.int32), np.array([1.0])) for b in range(m)]
+    seen = {(b, ()) for b in range(m)}
+    rhs = np.ones(model.n_base_rows + m)
+    tr = Trace()
+    best_lb = -np.inf
+    for it in range(max_rounds):
+        z, u_rm, lam = solve_master(model, cols)
+        steps = price_ladder(u_rm, alpha0, n_steps)
+        added, used, most_neg, u_used = [], None, 0.0, u_rm
+        for k, (new, mn, u_st) in enumerate(steps):
+            fresh = [c for c in new if (c[0], tuple(int(i) for i in c[1])) not in seen]
+            lb = float(np.dot(rhs, u_st)) + mn
+            if lb > best_lb + 1e-9:          # the bound improved: this smoothed vector becomes the centre
+                best_lb = lb
+                accept(k)
+            if fresh:
+                added, used, most_neg, u_used = fresh, k, mn, u_st
+                break
+        if not added:                        # the ladder produced only duplicates: price at the master duals
+            new, mn = price_plain(u_rm)
+            best_lb = max(best_lb, z + mn)
+            added = [c for c in new if (c[0], tuple(int(i) for i in c[1])) not in seen]
+            most_neg, u_used = mn, u_rm
+        keys = []
+        for (b, ind, rc, oc, rows, vals) in added:
+            key = (b, tuple(int(i) for i in ind))
+            seen.add(key)
+            cols.append(Column(b, key[1], oc, np.asarray(rows, np.int32), np.asarray(vals, np.float64)))
+            keys.append(key)
+        tr.z_rmp.append(z)
+        tr.lower_bound.append(best_lb)
+        tr.n_new.append(len(keys))
+        tr.duals.append(u_used)
+        tr.columns.append(keys)
+        if log:
+            log(f"round {it:3d}  z_RMP {z:14.6f}  best LB {best_lb:14.6f}  step {used}  new cols {len(keys):3d}")
+        if not keys or z - best_lb <= eps:
+            break
+    return tr, cols
+
+
+def gpu_stab_pricer(model):
+    """The stabilised backend on the GPU: dipgpu_price_round_stab_ladder + dipgpu_select_batch_result +
+    dipgpu_expand_columns per step, dipgpu_stab_accept / dipgpu_stab_set_center for the centre."""
+    from dip_b200.pricer import GpuPricer
+    p = GpuPricer(0)
+    p.setModel(model)
+    state = {"u_rm": None}
+
+    def cols_of(res):
+        cs, ri, va, hs = p.expandColumns()
+        return [(int(res.colBlock[k]), res.column(k).copy(), float(res.colRedCost[k]), float(res.colOrigCost[k]),
+                 ri[cs[k]:cs[k + 1]].copy(), va[cs[k]:cs[k + 1]].copy()) for k in range(res.nCols)]
+
+    def price_ladder(u_rm, alpha0, n_steps):
+        state["u_rm"] = u_rm
+        results, alphas = p.priceRoundStabLadder(u_rm, alpha0, n_steps)
+        out = []
+        for k, res in enumerate(results):
+            p.selectBatchResult(k)
+            out.append((cols_of(res), res.mostNegReducedCost, p.smoothedDuals(k)))
+        return out
+
+    def price_plain(u_rm):
+        res = p.priceRound(u_rm)
+        return cols_of(res), res.mostNegReducedCost
+
+    def accept(step):
+        p.stabAccept(step)
+    return price_ladder, price_plain, accept, p
+
+
 def gpu_pricer(model):
     from dip_b200.pricer import GpuPricer
     p = GpuPricer(0)

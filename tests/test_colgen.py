@@ -73,3 +73,52 @@ def test_colgen_gap_d_gpu(oracle):
     p.close()
     tr_cpu, _ = cg.run(model, _oracle_pricer(model, oracle))
     assert tr.z_rmp == tr_cpu.z_rmp and tr.columns == tr_cpu.columns
+
+
+def _oracle_stab_pricer(model, oracle):
+    """The stabilised backend restated with the oracle: the centre is a host vector."""
+    plain = _oracle_pricer(model, oracle)
+    state = {"centre": None, "st": []}
+
+    def price_ladder(u_rm, alpha0, n_steps):
+        if state["centre"] is None:
+            state["centre"] = u_rm.copy()          # first call: dual := dualRM (DecompAlgoPC.cpp:163-173)
+        out, a, state["st"] = [], alpha0, []
+        for _ in range(n_steps):
+            u_st = oracle.smooth_duals(a, state["centre"], u_rm)
+            cols, mn = plain(u_st)
+            out.append((cols, mn, u_st))
+            state["st"].append(u_st)
+            a = a * 0.90
+        return out
+
+    def accept(step):
+        state["centre"] = state["st"][step].copy()
+    return price_ladder, plain, accept
+
+
+def test_stabilised_colgen_cpu_driver_reaches_the_known_optimum(oracle, golden_gap0515):
+    model = _gap0515(golden_gap0515)
+    ladder, plain, accept = _oracle_stab_pricer(model, oracle)
+    tr, cols = cg.run_stabilised(model, ladder, plain, accept)
+    assert abs(tr.z_rmp[-1] - golden_gap0515["known_optimum_min"]) <= 1e-6
+    assert tr.lower_bound[-1] <= tr.z_rmp[-1] + 1e-6 and tr.z_rmp[-1] - tr.lower_bound[-1] <= 1e-4
+    assert np.all(np.diff(tr.lower_bound) >= -1e-12)      # the best bound only moves up
+
+
+@pytest.mark.gpu
+def test_stabilised_colgen_gpu_matches_oracle_round_by_round(oracle, golden_gap0515):
+    """Wentges smoothing with the centre on the device, the alpha ladder priced in one submission, the chosen
+    step expanded on the GPU: same smoothed duals, same columns, same bounds as the oracle-driven loop."""
+    model = _gap0515(golden_gap0515)
+    ladder, plain, accept = _oracle_stab_pricer(model, oracle)
+    tr_cpu, cols_cpu = cg.run_stabilised(model, ladder, plain, accept)
+    gl, gp, ga, p = cg.gpu_stab_pricer(model)
+    tr_gpu, cols_gpu = cg.run_stabilised(model, gl, gp, ga)
+    p.close()
+    assert len(tr_gpu.z_rmp) == len(tr_cpu.z_rmp)
+    for k in range(len(tr_cpu.z_rmp)):
+        np.testing.assert_array_equal(tr_gpu.duals[k], tr_cpu.duals[k])
+        assert tr_gpu.columns[k] == tr_cpu.columns[k], f"round {k}"
+        assert tr_gpu.z_rmp[k] == tr_cpu.z_rmp[k] and tr_gpu.lower_bound[k] == tr_cpu.lower_bound[k]
+    assert abs(tr_gpu.z_rmp[-1] - golden_gap0515["known_optimum_min"]) <= 1e-6
