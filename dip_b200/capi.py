@@ -37,7 +37,7 @@ SYMBOLS = [
     "dipgpu_price_rounds_batch", "dipgpu_select_batch_result", "dipgpu_stab_set_center", "dipgpu_stab_accept",
     "dipgpu_price_round_stab", "dipgpu_price_round_stab_ladder", "dipgpu_get_smoothed_duals",
     "dipgpu_pool_clear", "dipgpu_pool_size", "dipgpu_pool_append", "dipgpu_pool_append_expanded",
-    "dipgpu_pool_keep", "dipgpu_pool_set_reduced_costs", "dipgpu_set_col_bounds", "dipgpu_set_dual_support",
+    "dipgpu_pool_keep", "dipgpu_pool_set_reduced_costs", "dipgpu_set_col_bounds", "dipgpu_set_dual_support", "dipgpu_set_mckp_blocks",
 ]
 
 
@@ -125,6 +125,7 @@ def lib() -> C.CDLL:
         "dipgpu_pool_set_reduced_costs": ([vp, vp, i32, i32, vp, C.POINTER(i32)], C.c_int),
         "dipgpu_set_col_bounds": ([vp, vp, vp, i32], C.c_int),
         "dipgpu_set_dual_support": ([vp, i32, vp], C.c_int),
+        "dipgpu_set_mckp_blocks": ([vp, i32, vp, vp, vp, vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

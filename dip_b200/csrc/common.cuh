@@ -184,6 +184,11 @@ struct Ctx {
     int nBlockCols = 0;     // blockColStart[m]
     bool haveBlocks = false;
     int profitMode = 0;
+    // block kind: 0 = 0-1 knapsack (GAP, CSP), 1 = multiple-choice knapsack (MMKP: groups of columns)
+    int blockKind = 0;
+    std::vector<int32_t> hBlockGroupStart, hGroupColStart;
+    int32_t *dBlockGroupStart = nullptr, *dGroupColStart = nullptr;
+    size_t mckpSmem = 0;
     std::vector<int32_t> hBlockColStart, hCapacity;
     int32_t *dBlockColStart = nullptr;  // m+1
     int32_t *dWeight = nullptr;         // nBlockCols (+pad)
@@ -323,6 +328,8 @@ int launchKnapsackDpBatch(Ctx *c, const double *dRedCost, int64_t rcStride, cons
                           double redCostEps, int nVec, cudaStream_t st);
 int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseFilter,
                         cudaStream_t st);
+// mckp.cu -- stage (b) for multiple-choice knapsack blocks (DP + backtrack; the filter kernels follow)
+int launchMckp(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_t st);
 // filter.cu -- stage (c)
 int launchFilter(Ctx *c, double redCostEps, cudaStream_t st);
 // expand.cu -- master columns of the kept variables (the step after the round)

@@ -153,16 +153,27 @@ static int setBlockRange(Ctx *c, int first, int count)
     c->maxBlockCols = maxCols;
     c->maxUsableWeight = maxW;
     int rc;
+    std::vector<int64_t> off((size_t)count + 1, 0);
+    if (c->blockKind == 1) {
+        // multiple-choice blocks: no DP geometry; dBits holds the uint16 argmin of every (group, cell),
+        // dBitsOff the first entry of each block's table
+        c->geom = DpGeom{};
+        for (int lb = 0; lb < count; ++lb) {
+            const int G = c->hBlockGroupStart[first + lb + 1] - c->hBlockGroupStart[first + lb];
+            off[lb + 1] = off[lb] + (int64_t)G * ((int64_t)c->hCapacity[first + lb] + 1);
+        }
+        c->bitsWords = (size_t)((off[count] + 1) / 2 + 1);  // uint16 entries in uint32 words
+    } else {
     const bool wantFuse = count > 0 && (c->optFuseFilter < 0 ? count <= kFuseFilterMaxBlocks : c->optFuseFilter == 2);
     if ((rc = chooseDpGeom(c, &c->geom, wantFuse))) return rc;
     if (count > 0 && (rc = prepareKnapsackDp(c))) return rc;
     // decision bits: ceil(n_b/32) words per cell, rowCells cells per block
-    std::vector<int64_t> off((size_t)count + 1, 0);
     for (int lb = 0; lb < count; ++lb) {
         const int n = c->hBlockColStart[first + lb + 1] - c->hBlockColStart[first + lb];
         off[lb + 1] = off[lb] + (int64_t)((n + 31) / 32) * c->geom.rowCells;
     }
     c->bitsWords = (size_t)off[count];
+    }
     if ((rc = devAlloc(c, &c->dBitsOff, (size_t)count + 1))) return rc;
     DIPGPU_CUDA(c, cudaMemcpy(c->dBitsOff, off.data(), sizeof(int64_t) * ((size_t)count + 1), cudaMemcpyHostToDevice));
     if ((rc = devAlloc(c, &c->dBits, c->bitsWords))) return rc;
@@ -197,6 +208,14 @@ static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, do
                         bool timed)
 {
     int rc;
+    if (c->blockKind == 1) {
+        // multiple-choice knapsack blocks: DP + backtrack (mckp.cu), then the stand-alone filter
+        if ((rc = launchMckp(c, dRedCost, dAlpha, st))) return rc;
+        if (timed) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); }
+        if ((rc = launchFilter(c, eps, st))) return rc;
+        if (timed) cudaEventRecord(c->ev[5], st);
+        return DIPGPU_OK;
+    }
     int mode = c->geom.fuse ? 2 : c->optFuseFilter < 0 ? (c->nLocal <= kFuseFilterMaxBlocks ? 1 : 0)
                                                        : (c->optFuseFilter == 1 ? 1 : 0);
     if (c->nLocal == 0) mode = 0;
@@ -565,6 +584,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
     freeBatch(c);
     devFree(&c->dFix); devFree(&c->dCapEff); devFree(&c->dRcEff);
+    devFree(&c->dBlockGroupStart); devFree(&c->dGroupColStart);
     devFree(&c->dSupport); devFree(&c->dSupportBits);
     if (c->hSupVals) cudaFreeHost(c->hSupVals);
     devFree(&c->dCenter); devFree(&c->dPoolStart); devFree(&c->dPoolRow); devFree(&c->dPoolVal);
@@ -694,6 +714,7 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
     c->m = m;
     c->nBlockCols = nCols;
     c->profitMode = profitMode;
+    c->blockKind = 0;
     c->hBlockColStart.assign(blockColStart, blockColStart + m + 1);
     c->hCapacity.assign(capacity, capacity + m);
     c->hWeight.assign(weight, weight + nCols);
@@ -729,6 +750,66 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
     return setBlockRange(c, 0, m);
 }
 
+int dipgpu_set_mckp_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockGroupStart, const int32_t *groupColStart,
+                           const int32_t *weight, const int32_t *capacity)
+{
+    CTX_OR_FAIL(ctx);
+    if (m < 0 || !blockGroupStart || !groupColStart || (m > 0 && !capacity) || blockGroupStart[0] != 0 || groupColStart[0] < 0)
+        return fail(c, DIPGPU_ERR_INVALID, "set_mckp_blocks: bad arguments");
+    for (int b = 0; b < m; ++b) {
+        if (blockGroupStart[b + 1] < blockGroupStart[b]) return fail(c, DIPGPU_ERR_INVALID, "set_mckp_blocks: blockGroupStart not monotone at block %d", b);
+        if (capacity[b] < 0) return fail(c, DIPGPU_ERR_INVALID, "set_mckp_blocks: negative capacity at block %d", b);
+    }
+    const int nGroups = blockGroupStart[m];
+    for (int g = 0; g < nGroups; ++g) {
+        const int n = groupColStart[g + 1] - groupColStart[g];
+        if (n < 1 || n >= 0xffff) return fail(c, DIPGPU_ERR_INVALID, "set_mckp_blocks: group %d has %d columns (1..65534)", g, n);
+    }
+    const int nCols = groupColStart[nGroups];
+    if (nCols > 0 && !weight) return fail(c, DIPGPU_ERR_INVALID, "set_mckp_blocks: NULL weight");
+    for (int j = groupColStart[0]; j < nCols; ++j)
+        if (weight[j] < 0) return fail(c, DIPGPU_ERR_INVALID, "set_mckp_blocks: negative weight at column %d", j);
+    if (c->haveCore && nCols > c->N) return fail(c, DIPGPU_ERR_INVALID, "set_mckp_blocks: %d block columns > N=%d", nCols, c->N);
+    c->m = m;
+    c->nBlockCols = nCols;
+    c->profitMode = DIPGPU_PROFIT_FP64;
+    c->blockKind = 1;
+    c->haveFix = false;
+    c->hBlockGroupStart.assign(blockGroupStart, blockGroupStart + m + 1);
+    c->hGroupColStart.assign(groupColStart, groupColStart + nGroups + 1);
+    c->hCapacity.assign(capacity, capacity + m);
+    c->hWeight.assign(weight, weight + nCols);
+    c->hBlockColStart.assign((size_t)m + 1, 0);
+    for (int b = 0; b <= m; ++b) c->hBlockColStart[b] = groupColStart[blockGroupStart[b]];
+    c->hMaxUsableW.assign((size_t)m, 0);
+    int rc;
+    devFree(&c->dFix); devFree(&c->dCapEff);
+    if ((rc = devAlloc(c, &c->dBlockColStart, (size_t)m + 1))) return rc;
+    if ((rc = devAlloc(c, &c->dBlockGroupStart, (size_t)m + 1))) return rc;
+    if ((rc = devAlloc(c, &c->dGroupColStart, (size_t)nGroups + 1))) return rc;
+    if ((rc = devAlloc(c, &c->dCapacity, (size_t)m))) return rc;
+    if ((rc = devAlloc(c, &c->dWeight, (size_t)nCols + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dItemW, (size_t)nCols + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dItemCol, (size_t)nCols + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dCandInd, (size_t)nCols + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dScratch, (size_t)nCols + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dAlpha, (size_t)m))) return rc;
+    DIPGPU_CUDA(c, cudaMemcpy(c->dBlockColStart, c->hBlockColStart.data(), sizeof(int32_t) * ((size_t)m + 1), cudaMemcpyHostToDevice));
+    DIPGPU_CUDA(c, cudaMemcpy(c->dBlockGroupStart, blockGroupStart, sizeof(int32_t) * ((size_t)m + 1), cudaMemcpyHostToDevice));
+    DIPGPU_CUDA(c, cudaMemcpy(c->dGroupColStart, groupColStart, sizeof(int32_t) * ((size_t)nGroups + 1), cudaMemcpyHostToDevice));
+    if (m > 0) DIPGPU_CUDA(c, cudaMemcpy(c->dCapacity, capacity, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice));
+    DIPGPU_CUDA(c, cudaMemset(c->dWeight, 0, sizeof(int32_t) * ((size_t)nCols + 16)));
+    if (nCols > 0) DIPGPU_CUDA(c, cudaMemcpy(c->dWeight, weight, sizeof(int32_t) * (size_t)nCols, cudaMemcpyHostToDevice));
+    if (!c->haveCore) {
+        c->N = std::max(c->N, nCols);
+        if ((rc = devAlloc(c, &c->dRedCost, (size_t)c->N + 16))) return rc;
+        DIPGPU_CUDA(c, cudaMemset(c->dRedCost, 0, sizeof(double) * ((size_t)c->N + 16)));
+    }
+    c->haveBlocks = true;
+    c->lastRoundOnHost = false;
+    return setBlockRange(c, 0, m);
+}
+
 int dipgpu_set_col_bounds(dipgpu_ctx *ctx, const double *colLB, const double *colUB, int32_t N)
 {
     CTX_OR_FAIL(ctx);
@@ -739,8 +820,8 @@ int dipgpu_set_col_bounds(dipgpu_ctx *ctx, const double *colLB, const double *co
         return DIPGPU_OK;
     }
     if (!colLB || !colUB || N < c->nBlockCols) return fail(c, DIPGPU_ERR_INVALID, "set_col_bounds: need both bound arrays of length >= %d", c->nBlockCols);
-    if (c->profitMode == DIPGPU_PROFIT_PISINGER_INT)
-        return fail(c, DIPGPU_ERR_UNSUPPORTED, "set_col_bounds: node bounds are enforced in the fp64 DP mode only");
+    if (c->profitMode == DIPGPU_PROFIT_PISINGER_INT || c->blockKind != 0)
+        return fail(c, DIPGPU_ERR_UNSUPPORTED, "set_col_bounds: node bounds are enforced in 0-1 knapsack blocks in the fp64 DP mode only");
     const int n = c->nBlockCols;
     std::vector<uint8_t> fix((size_t)n + 16, 0);
     std::vector<int32_t> capEff((size_t)std::max(c->m, 1), 0);

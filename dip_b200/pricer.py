@@ -187,6 +187,21 @@ class GpuPricer:
         self._result = None
         self._relax_cache = None
 
+    def setMckpBlocks(self, block_group_start, group_col_start, weight, capacity):
+        """Multiple-choice knapsack blocks (MMKP MCKP0 relaxation, MMKP_MCKnap.cpp:172-383): exactly one
+        column per group, weights <= capacity."""
+        bgs = np.ascontiguousarray(block_group_start, np.int32)
+        gcs = np.ascontiguousarray(group_col_start, np.int32)
+        w = np.ascontiguousarray(weight, np.int32)
+        cap = np.ascontiguousarray(capacity, np.int32)
+        m = len(bgs) - 1
+        self._check(self._lib.dipgpu_set_mckp_blocks(self._ctx, m, capi.ptr(bgs), capi.ptr(gcs), capi.ptr(w), capi.ptr(cap)))
+        self.m = m
+        self.nBlockCols = int(gcs[-1])
+        self.N = max(self.N, self.nBlockCols)
+        self._result = None
+        self._relax_cache = None
+
     def setModel(self, model, profit_mode=PROFIT_FP64):
         """Upload a dip_b200.instances.PricingModel."""
         self.setModelCore(model.R, model.N, model.row_start, model.col_ind, model.val, model.n_base_rows,

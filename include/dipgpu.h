@@ -150,6 +150,21 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
                                int32_t profitMode);
 
 /*
+ * The relaxation as m independent MULTIPLE-CHOICE knapsacks -- the MCKP0 relaxation of DIP's MMKP example
+ * (Dip/examples/MMKP/MMKP_DecompApp.cpp:493-557 -> MMKP_MCKnap::solveMCKnap,
+ * Dip/examples/MMKP/MMKP_MCKnap.cpp:172-383): block b = the groups [blockGroupStart[b], blockGroupStart[b+1]),
+ * group g = the contiguous x-space columns [groupColStart[g], groupColStart[g+1]) (1..65534 of them);
+ * exactly one column per group, sum of weights <= capacity[b], minimise the sum of reduced costs.  One
+ * column (one index per group) comes back per block; a block without a feasible choice returns none
+ * (blockRedCost = +inf, blockMostNegRC = 0, blockObj = +inf, blockNnz = 0).  blockObj = the minimum (alpha
+ * excluded).  Replaces dipgpu_set_knapsack_blocks (one kind of block per context); every pricing entry point
+ * then solves these blocks.  The reference's solver (Pisinger's mcknap behind an integer scaling of the
+ * costs) is not vendored: the exact fp64 DP over the groups takes its place, first minimal column on ties.
+ */
+int dipgpu_set_mckp_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockGroupStart,
+                           const int32_t *groupColStart, const int32_t *weight, const int32_t *capacity);
+
+/*
  * Node bounds of the x-space columns, enforced inside the block subproblems: what
  * DecompAlgo::setSubProbBounds stores in m_colLBNode / m_colUBNode (Dip/src/DecompAlgo.cpp:2352-2371)
  * and DecompAlgo::solveRelaxed hands to the subproblem with BranchEnforceInSubProb

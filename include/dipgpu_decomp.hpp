@@ -127,6 +127,19 @@ public:
         m_roundValid = false;
     }
 
+    // One multiple-choice knapsack per block (MMKP_DecompApp.cpp:52-90: one MMKP_MCKnap per block; group g owns
+    // the contiguous columns [groupColStart[g], groupColStart[g+1]), block b the groups
+    // [blockGroupStart[b], blockGroupStart[b+1])).
+    void setMckpBlocks(int m, const int *blockGroupStart, const int *groupColStart, const int *weight, const int *capacity)
+    {
+        check(dipgpu_set_mckp_blocks(m_ctx, m, blockGroupStart, groupColStart, weight, capacity));
+        m_m = m;
+        m_nBlockCols = groupColStart[blockGroupStart[m]];
+        if (m_nBlockCols > m_N) m_N = m_nBlockCols;
+        allocResult();
+        m_roundValid = false;
+    }
+
     // ---- surface 2: the whole round ------------------------------------------------------------
     // DecompAlgo::generateVars: u = master duals (length R + numConvex; NULL = the vector the last
     // setReducedCosts / calcRedCost call left on the device), returns newVars.size().

@@ -488,3 +488,82 @@ int dip_oracle_solve_blocks_bounded(int m, const int32_t *blockColStart, const i
     if (cellsOut) *cellsOut = cellsTotal;
     return kept;
 }
+
+/* ------------------------------------------- multiple-choice knapsack blocks -- */
+
+int dip_oracle_solve_mckp_blocks(int m, const int32_t *blockGroupStart, const int32_t *groupColStart,
+                                 const int32_t *weight, const int32_t *capacity, const double *redCostX,
+                                 const double *origCost, const double *alpha, double redCostEps,
+                                 int maxBlockCols, int32_t *colNnz, double *colRedCost,
+                                 double *colOrigCost, int32_t *colKeep, double *mostNegRC, double *z,
+                                 int32_t *colIndOut, double *mostNegReducedCost, int64_t *cellsOut)
+{
+    int64_t cellsTotal = 0;
+    for (int b = 0; b < m; ++b) {
+        const int g0 = blockGroupStart[b], g1 = blockGroupStart[b + 1];
+        const int G = g1 - g0;
+        const int cap = capacity[b];
+        const size_t W = (size_t)cap + 1;
+        int32_t *ind = colIndOut ? colIndOut + (size_t)b * (size_t)maxBlockCols : NULL;
+        double *prev = (double *)calloc(W, sizeof(double)); /* c[-1][.] = 0 */
+        double *cur = (double *)malloc(W * sizeof(double));
+        int32_t *choice = (int32_t *)malloc(sizeof(int32_t) * W * (size_t)(G > 0 ? G : 1));
+        for (int g = 0; g < G; ++g) {
+            const int cs = groupColStart[g0 + g], ce = groupColStart[g0 + g + 1];
+            cellsTotal += (int64_t)(ce - cs) * (int64_t)W;
+            for (int j = 0; j <= cap; ++j) {
+                double best = INFINITY;
+                int arg = -1;
+                for (int k = cs; k < ce; ++k) {
+                    if (weight[k] <= j) {
+                        const double cand = redCostX[k] + prev[j - weight[k]];
+                        if (cand < best) { best = cand; arg = k; } /* first minimal column */
+                    }
+                }
+                cur[j] = best;
+                choice[(size_t)g * W + (size_t)j] = arg;
+            }
+            double *t = prev; prev = cur; cur = t;
+        }
+        const double zb = prev[cap];
+        if (G == 0 || !(zb < INFINITY)) { /* no group, or no feasible choice */
+            colNnz[b] = 0;
+            colRedCost[b] = G == 0 ? 0.0 - alpha[b] : INFINITY;
+            colOrigCost[b] = 0.0;
+            if (z) z[b] = G == 0 ? 0.0 : INFINITY;
+        } else {
+            int j = cap;
+            for (int g = G - 1; g >= 0; --g) {
+                const int k = choice[(size_t)g * W + (size_t)j];
+                if (ind) ind[g] = k; /* groups ascend, so do the columns */
+                j -= weight[k];
+            }
+            double rc = 0.0, oc = 0.0;
+            for (int g = 0; g < G; ++g) {
+                const int k = ind ? ind[g] : 0;
+                rc += redCostX[k];
+                oc += origCost[k];
+            }
+            colNnz[b] = G;
+            colRedCost[b] = rc - alpha[b]; /* DecompAlgo.cpp:6350-6356 */
+            colOrigCost[b] = oc;
+            if (z) z[b] = zb;
+        }
+        free(prev);
+        free(cur);
+        free(choice);
+    }
+    int kept = 0;
+    double sum = 0.0;
+    for (int b = 0; b < m; ++b) {
+        double mn = 0.0;
+        if (colRedCost[b] < mn) mn = colRedCost[b];
+        mostNegRC[b] = mn;
+        colKeep[b] = colRedCost[b] < -redCostEps ? 1 : 0;
+        kept += colKeep[b];
+    }
+    for (int b = 0; b < m; ++b) sum += mostNegRC[b];
+    if (mostNegReducedCost) *mostNegReducedCost = sum;
+    if (cellsOut) *cellsOut = cellsTotal;
+    return kept;
+}

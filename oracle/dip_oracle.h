@@ -142,6 +142,26 @@ int dip_oracle_solve_blocks_bounded(int m, const int32_t *blockColStart, const i
                                     int32_t *colKeep, double *mostNegRC, double *z, int32_t *colIndOut,
                                     double *mostNegReducedCost, int64_t *cellsOut);
 
+/* Multiple-choice knapsack blocks = MMKP_DecompApp::solveRelaxed with the MCKP0 relaxation
+ * (Dip/examples/MMKP/MMKP_DecompApp.cpp:493-557 -> MMKP_MCKnap::solveMCKnap, MMKP_MCKnap.cpp:172-383):
+ * block b = groups [blockGroupStart[b], blockGroupStart[b+1]); group g = the contiguous x-space columns
+ * [groupColStart[g], groupColStart[g+1]); EXACTLY one column per group, sum of weights <= capacity,
+ * minimise sum redCost (:186-196 negates and offsets to feed a max solver).  The reference's solver is
+ * Pisinger's mcknap (fetched by get_pisinger.sh, NOT vendored) behind a lossy double -> int scaling of
+ * the costs (UtilScaleDblToIntArr with MCKP_EPSILON 1e-3, :213) -- "parity unpinned".  Restated as the
+ * exact fp64 DP over the groups in order:
+ *     c[g][j] = min over the group's columns k with w_k <= j of redCost_k + c[g-1][j - w_k],  c[-1][.] = 0
+ * first minimal column wins ('<'); backtrack from (last group, capacity).  A block with no feasible
+ * choice returns no column (colNnz 0, colRedCost +inf, mostNegRC 0, z +inf; the reference asserts).
+ * z = c[G-1][cap] = the column's sum of reduced costs (alpha excluded).  cells = columns * (cap + 1).
+ * Outputs as dip_oracle_solve_blocks; colIndOut holds the chosen columns ascending. */
+int dip_oracle_solve_mckp_blocks(int m, const int32_t *blockGroupStart, const int32_t *groupColStart,
+                                 const int32_t *weight, const int32_t *capacity, const double *redCostX,
+                                 const double *origCost, const double *alpha, double redCostEps,
+                                 int maxBlockCols, int32_t *colNnz, double *colRedCost,
+                                 double *colOrigCost, int32_t *colKeep, double *mostNegRC, double *z,
+                                 int32_t *colIndOut, double *mostNegReducedCost, int64_t *cellsOut);
+
 /* DecompVarPool::setReducedCosts -> DecompWaitingCol::setReducedCost,
  * Dip/src/DecompVarPool.cpp:185-203, :22-40 (called once per price call, DecompAlgo.cpp:1890-1908):
  *   feasible:  redCost_s = origCost_s - m_col.dotProduct(u)        (:29)

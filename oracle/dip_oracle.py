@@ -78,6 +78,10 @@ def _lib():
         C.c_int, _i32p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, _f64p, C.c_double, C.c_int,
         _i32p, _f64p, _f64p, _i32p, _f64p, _f64p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.dip_oracle_solve_blocks_bounded.restype = C.c_int
+    lib.dip_oracle_solve_mckp_blocks.argtypes = [
+        C.c_int, _i32p, _i32p, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_double, C.c_int,
+        _i32p, _f64p, _f64p, _i32p, _f64p, _f64p, _i32p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.dip_oracle_solve_mckp_blocks.restype = C.c_int
     lib.dip_oracle_pool_reduced_costs.argtypes = [C.c_int, _i64p, _i32p, _f64p, _f64p, _f64p, C.c_int, _f64p]
     lib.dip_oracle_pool_reduced_costs.restype = C.c_int
     lib.dip_oracle_smooth_duals.argtypes = [C.c_int, C.c_double, _f64p, _f64p, _f64p]
@@ -199,6 +203,25 @@ def solve_blocks_bounded(block_col_start, weight, capacity, red_cost_x, orig_cos
         np.ascontiguousarray(col_ub, np.float64), float(red_cost_eps), max_cols, nnz, rc, oc, keep, mn, z,
         ind.ctypes.data if want_ind else None, C.byref(tot), C.byref(cells))
     cols = [ind[b, : nnz[b]].copy() for b in range(m)] if want_ind else []
+    return RoundResult(None, nnz, rc, oc, keep, mn, z, cols, tot.value, kept, cells.value)
+
+
+def solve_mckp_blocks(block_group_start, group_col_start, weight, capacity, red_cost_x, orig_cost, alpha,
+                      red_cost_eps=1e-4) -> RoundResult:
+    """Multiple-choice knapsack blocks (MMKP MCKP0 relaxation): exactly one column per group."""
+    bgs = np.ascontiguousarray(block_group_start, np.int32)
+    gcs = np.ascontiguousarray(group_col_start, np.int32)
+    m = len(bgs) - 1
+    max_cols = max(int(np.max(np.diff(bgs))) if m > 0 else 1, 1)   # one column per group
+    nnz, rc, oc, keep, mn, z, ind = _alloc(m, max_cols, True)
+    tot = C.c_double(0.0)
+    cells = C.c_int64(0)
+    kept = _lib().dip_oracle_solve_mckp_blocks(
+        m, bgs, gcs, np.ascontiguousarray(weight, np.int32), np.ascontiguousarray(capacity, np.int32),
+        np.ascontiguousarray(red_cost_x, np.float64), np.ascontiguousarray(orig_cost, np.float64),
+        np.ascontiguousarray(alpha, np.float64), float(red_cost_eps), max_cols, nnz, rc, oc, keep, mn, z, ind,
+        C.byref(tot), C.byref(cells))
+    cols = [ind[b, : nnz[b]].copy() for b in range(m)]
     return RoundResult(None, nnz, rc, oc, keep, mn, z, cols, tot.value, kept, cells.value)
 
 

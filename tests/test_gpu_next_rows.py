@@ -425,3 +425,80 @@ def test_pool_with_dual_support_bitmap(oracle, pricer):
     assert found == ref_found == found0
     got_ray, _ = pricer.poolSetReducedCosts(None, feasible=False)     # resident duals, dual-ray form
     np.testing.assert_array_equal(got_ray, oracle.pool_reduced_costs(cs, ri, va, oc, u, False)[0])
+
+
+# ------------------------------------------------------------------ f-4: multiple-choice knapsack blocks (MMKP)
+
+
+def _mckp_instance(seed, m, g_lo, g_hi, k_lo, k_hi, cap_lo, cap_hi, w_hi):
+    rng = np.random.default_rng(seed)
+    groups_per_block = rng.integers(g_lo, g_hi + 1, size=m)
+    sizes = rng.integers(k_lo, k_hi + 1, size=int(groups_per_block.sum()))
+    gcs = np.zeros(len(sizes) + 1, np.int32)
+    np.cumsum(sizes, out=gcs[1:])
+    bgs = np.zeros(m + 1, np.int32)
+    np.cumsum(groups_per_block, out=bgs[1:])
+    N = int(gcs[-1])
+    w = rng.integers(0, w_hi + 1, size=N).astype(np.int32)
+    cap = rng.integers(cap_lo, cap_hi + 1, size=m).astype(np.int32)
+    rc = rng.uniform(-20, 20, size=N)
+    tie = rng.random(N) < 0.1
+    rc[tie] = np.round(rc[tie])                                      # some ties
+    oc = rng.integers(1, 100, size=N).astype(np.float64)
+    alpha = rng.uniform(-10, 10, size=m)
+    return bgs, gcs, w, cap, rc, oc, alpha
+
+
+def _check_mckp(oracle, pricer, bgs, gcs, w, cap, rc, oc, alpha, eps=1e-4):
+    pricer.setObjective(oc)
+    pricer.setMckpBlocks(bgs, gcs, w, cap)
+    res = pricer.solveBlocks(rc, alpha, eps)
+    ref = oracle.solve_mckp_blocks(bgs, gcs, w, cap, rc, oc, alpha, red_cost_eps=eps)
+    np.testing.assert_array_equal(res.blockObj, ref.z)                  # the same additions in the same order
+    np.testing.assert_array_equal(res.blockNnz, ref.col_nnz)
+    np.testing.assert_array_equal(res.blockRedCost, ref.col_red_cost)
+    np.testing.assert_array_equal(res.blockOrigCost, ref.col_orig_cost)
+    np.testing.assert_array_equal(res.blockMostNegRC, ref.most_neg_rc)
+    kept = [b for b in range(len(cap)) if ref.col_keep[b]]
+    assert list(res.colBlock[:res.nCols]) == kept
+    for k, b in enumerate(kept):
+        assert list(res.column(k)) == list(ref.col_ind[b])
+    assert res.cells == ref.cells and res.mostNegReducedCost == ref.most_neg_reduced_cost
+    return res, ref
+
+
+@pytest.mark.parametrize("seed,m,g_hi,k_hi,cap_hi,w_hi", [(1, 50, 12, 10, 120, 30), (2, 400, 6, 5, 60, 20),
+                                                         (3, 8, 60, 30, 3000, 150), (4, 30, 10, 8, 25, 15)])
+def test_mckp_blocks(oracle, pricer, seed, m, g_hi, k_hi, cap_hi, w_hi):
+    """Exactly one column per group (MMKP_MCKnap::solveMCKnap): optimum, column, sums, infeasible blocks."""
+    inst = _mckp_instance(seed, m, 0 if seed == 4 else 1, g_hi, 1, k_hi, cap_hi // 3, cap_hi, w_hi)
+    res, ref = _check_mckp(oracle, pricer, *inst)
+    if seed == 4:
+        assert np.isinf(res.blockRedCost).any()       # tight capacities: some block has no feasible choice
+
+
+def test_mckp_through_the_round_and_in_batches(oracle, pricer):
+    """The MMKP structure end to end: reduced costs from the SpMV, then the multiple-choice blocks."""
+    bgs, gcs, w, cap, _, oc, _ = _mckp_instance(9, 12, 4, 10, 3, 9, 40, 120, 25)
+    m, N = 12, int(gcs[-1])
+    rng = np.random.default_rng(10)
+    R = 30                                              # dense-ish side constraints over all columns
+    rows = np.repeat(np.arange(R), 40)
+    ci = np.concatenate([np.sort(rng.choice(N, size=40, replace=False)) for _ in range(R)]).astype(np.int32)
+    rs = np.arange(R + 1, dtype=np.int64) * 40
+    v = rng.uniform(1, 9, size=len(ci))
+    pricer.setModelCore(R, N, rs, ci, v, R, m)
+    pricer.setObjective(oc)
+    pricer.setMckpBlocks(bgs, gcs, w, cap)
+    U = rng.uniform(-2, 2, size=(3, R + m))
+    batch = pricer.priceRoundsBatch(U)
+    for k in range(3):
+        res, rcx = pricer.priceRound(U[k], want_redcost=True)
+        ref_rc = oracle.calc_redcost(R, N, rs, ci, v, oracle.adjust_duals(U[k], R, m), oc)
+        np.testing.assert_array_equal(rcx, ref_rc)
+        ref = oracle.solve_mckp_blocks(bgs, gcs, w, cap, rcx, oc, U[k][R:R + m])
+        np.testing.assert_array_equal(res.blockObj, ref.z)
+        assert [list(res.column(j)) for j in range(res.nCols)] == [list(ref.col_ind[b]) for b in range(m) if ref.col_keep[b]]
+        _same_round(batch[k], res)
+        cs, ri, va, hs = pricer.expandColumns()          # master columns of the multiple-choice columns
+        assert len(cs) == res.nCols + 1

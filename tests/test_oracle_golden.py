@@ -170,3 +170,41 @@ def test_bounded_blocks_against_enumeration(oracle):
             assert abs((res.col_red_cost[b] + alpha[b]) - best) <= 1e-9
             assert list(ind) == sorted(ind)
         assert res.most_neg_reduced_cost == float(np.sum(res.most_neg_rc))
+
+
+def test_mckp_blocks_against_enumeration(oracle):
+    """Multiple-choice knapsack blocks (MMKP_MCKnap::solveMCKnap, MMKP_MCKnap.cpp:172-383): the exact DP over
+    the groups reaches the optimum of min sum rc s.t. exactly one column per group, weights <= capacity, found
+    by enumeration; infeasible blocks return no column."""
+    import itertools
+    rng = np.random.default_rng(23)
+    for trial in range(40):
+        m = 3
+        groups_per_block = rng.integers(1, 5, size=m)
+        sizes = rng.integers(1, 5, size=int(groups_per_block.sum()))
+        gcs = np.zeros(len(sizes) + 1, np.int32)
+        np.cumsum(sizes, out=gcs[1:])
+        bgs = np.zeros(m + 1, np.int32)
+        np.cumsum(groups_per_block, out=bgs[1:])
+        N = int(gcs[-1])
+        w = rng.integers(0, 9, size=N).astype(np.int32)
+        cap = rng.integers(0, 18, size=m).astype(np.int32)
+        rc = np.round(rng.uniform(-8, 8, size=N), 3)
+        oc = rng.uniform(0, 10, size=N)
+        alpha = rng.uniform(-3, 0, size=m)
+        res = oracle.solve_mckp_blocks(bgs, gcs, w, cap, rc, oc, alpha)
+        for b in range(m):
+            gl = [range(gcs[g], gcs[g + 1]) for g in range(bgs[b], bgs[b + 1])]
+            best = None
+            for pick in itertools.product(*gl):
+                if sum(w[k] for k in pick) <= cap[b]:
+                    v = sum(rc[k] for k in pick)
+                    if best is None or v < best - 1e-12:
+                        best = v
+            if best is None:
+                assert res.col_nnz[b] == 0 and np.isinf(res.col_red_cost[b]) and not res.col_keep[b]
+                continue
+            assert abs(res.z[b] - best) <= 1e-9
+            assert len(res.col_ind[b]) == len(gl) and all(k in gl[i] for i, k in enumerate(res.col_ind[b]))
+            assert sum(w[k] for k in res.col_ind[b]) <= cap[b]
+            assert abs(res.col_red_cost[b] + alpha[b] - best) <= 1e-9
