@@ -372,6 +372,7 @@ def main():
         extras["batched"] = bench_batched(pr, model, duals, u_pin, cells_per_round, flush_l2, torch, smem_peak, world,
                                           max_over_ranks)
         extras["pool"] = bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank)
+        extras["mckp"] = bench_mckp(torch, local_rank, smem_peak, flush_l2)
     cells_mean = float(np.mean(cells_per_round))
     cells_eval_mean = float(np.mean(cells_eval_per_round))
     dp_ms = stage_ms["knapsack_dp"]
@@ -439,6 +440,8 @@ def main():
             line["batched_rounds"] = extras["batched"]
         if "pool" in extras:
             line["roofline_pool"] = extras["pool"]
+        if "mckp" in extras:
+            line["roofline_mckp"] = extras["mckp"]
         if expand is not None:
             line["expand_columns"] = expand
         if sharded is not None:
@@ -568,6 +571,40 @@ def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank):
             "avg_launch_ms": ms, "without_dual_support": {"avg_launch_ms": ms_plain, "achieved": by / (ms_plain * 1e-3) / 1e9,
                                                           "frac": by / (ms_plain * 1e-3) / 1e9 / hbm_peak},
             "algorithmic_bytes": by, "peak_source": peak_src}
+
+
+def bench_mckp(torch, local_rank, smem_peak, flush_l2):
+    """Multiple-choice knapsack blocks (the MMKP example's MCKP0 relaxation): 2 000 blocks of
+    25 groups x 10 columns, capacity 1 000 -- cells = columns x (capacity + 1), 8 B of shared memory read per
+    cell (the previous group's row) + the row write per group."""
+    from dip_b200.pricer import GpuPricer
+    rng = np.random.default_rng(88)
+    m, G, K, cap = 2000, 25, 10, 1000
+    gcs = (np.arange(m * G + 1) * K).astype(np.int32)
+    bgs = (np.arange(m + 1) * G).astype(np.int32)
+    N = m * G * K
+    w = rng.integers(1, 81, size=N).astype(np.int32)
+    rc = rng.uniform(-50, 50, size=N)
+    pr = GpuPricer(local_rank)
+    pr.setObjective(rng.uniform(1, 100, size=N))
+    pr.setMckpBlocks(bgs, gcs, w, np.full(m, cap, np.int32))
+    alpha = np.zeros(m)
+    res = pr.solveBlocks(rc, alpha, redCostEps=-np.inf)
+    pr.set_option("stage_timing", 1)
+    ts = []
+    for _ in range(6):
+        flush_l2()
+        torch.cuda.synchronize()
+        pr.solveBlocks(rc, alpha, redCostEps=-np.inf, result=res)
+        ts.append(pr.last_stage_ms()["knapsack_dp"])
+    pr.close()
+    ms = float(np.mean(ts[1:]))
+    cells = float(res.cells)
+    ach = cells * 24.0 / (ms * 1e-3) / 1e9
+    return {"kernel": "mckp_dp_kernel (+ mckp_backtrack_kernel)", "workload": f"{m} blocks x {G} groups x {K} columns, capacity {cap}",
+            "bound": "smem", "cells": cells, "ms": ms, "gcups": cells / (ms * 1e-3) / 1e9, "achieved": ach,
+            "peak": smem_peak, "unit": "GB/s", "frac": ach / smem_peak if smem_peak else None,
+            "algorithmic_bytes_per_cell": 24, "kept_columns": int(res.nCols)}
 
 
 def bench_expand(pr, model, duals, ptrs, res, flush_l2, torch, rank):
