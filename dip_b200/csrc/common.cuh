@@ -189,6 +189,7 @@ struct Ctx {
     std::vector<int32_t> hBlockGroupStart, hGroupColStart;
     int32_t *dBlockGroupStart = nullptr, *dGroupColStart = nullptr;
     size_t mckpSmem = 0;
+    int mckpMaxWeight = 0;              // largest column weight of the multiple-choice blocks (guard cells of the DP rows)
     std::vector<int32_t> hBlockColStart, hCapacity;
     int32_t *dBlockColStart = nullptr;  // m+1
     int32_t *dWeight = nullptr;         // nBlockCols (+pad)

@@ -779,6 +779,8 @@ int dipgpu_set_mckp_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockGroup
     c->hGroupColStart.assign(groupColStart, groupColStart + nGroups + 1);
     c->hCapacity.assign(capacity, capacity + m);
     c->hWeight.assign(weight, weight + nCols);
+    c->mckpMaxWeight = 0;
+    for (int j = groupColStart[0]; j < nCols; ++j) c->mckpMaxWeight = std::max(c->mckpMaxWeight, weight[j]);
     c->hBlockColStart.assign((size_t)m + 1, 0);
     for (int b = 0; b <= m; ++b) c->hBlockColStart[b] = groupColStart[blockGroupStart[b]];
     c->hMaxUsableW.assign((size_t)m, 0);

@@ -8,10 +8,11 @@
 // first minimal column wins, backtrack from (last group, capacity).
 //
 // Shape: one CTA per block, groups sequential (one barrier per group: every column of a group reads
-// the PREVIOUS group's row, so there is no dependency inside a group), cells strided over the
-// threads, the two rows in shared memory, the argmin of every (group, cell) streamed to HBM as
-// uint16 for the backtrack.  Shared-memory traffic per cell and column: one 8-byte read; the
-// columns' reduced costs and weights are warp-uniform L1 reads.
+// the PREVIOUS group's row, so there is no dependency inside a group), up to four cells per thread,
+// the two rows in shared memory behind a guard of +inf cells, the argmin of every (group, cell)
+// streamed to HBM as uint16 for the backtrack.  Shared-memory traffic per cell and column: one
+// 8-byte read; the columns' reduced costs and weights are warp-uniform L1 reads, once per thread
+// and four cells.
 #include <algorithm>
 
 #include "filter.cuh"
@@ -19,6 +20,7 @@
 namespace dipgpu {
 
 constexpr int kMckpThreads = 256;
+constexpr int kMckpStage = 256;  // columns staged in shared memory at a time (whole groups)
 
 struct MckpArgs {
     const double *redCost;
@@ -36,7 +38,124 @@ struct MckpArgs {
     double *blockObj, *blockRedCost, *blockOrigCost;
     int32_t *blockNnz;
     int firstBlock, nLocal;
+    int guard;                      // +inf cells in front of each DP row: min(max weight, max capacity + 1)
 };
+
+// The groups of one block, C cells per thread: the column's weight and reduced cost are read once
+// per thread and used for C cells (j = base + t + i*256), and "does the column fit" is not a
+// branch -- each row is preceded by `guard` cells of +inf, so a column that does not fit reads
+// +inf and never wins (guard >= every usable weight; heavier columns are clamped onto it).
+template <int OFF>
+__device__ __forceinline__ double ldsF64At(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+// One group of one block, C cells per thread: the column's weight and reduced cost are read once per
+// thread and used for C cells (j = base + t + i*256), and "does the column fit" is not a branch --
+// each row is preceded by `guard` cells of +inf, so a column that does not fit reads +inf and never
+// wins (guard >= every usable weight; heavier columns are clamped onto it).  STAGED: the group's
+// columns sit in shared memory as (redCost, 8 * min(weight, guard)) pairs, one 16-byte broadcast
+// read per column; otherwise (a group larger than the staging buffer) they are read through L1.
+template <int C, bool STAGED>
+__device__ __forceinline__ void mckpGroup(const MckpArgs &a, uint32_t prevA, uint32_t curA, uint16_t *ch, int cs, int ce, int W,
+                                          int guard, uint32_t itemA)
+{
+    const int t = threadIdx.x;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int base = 0; base < W; base += C * kMckpThreads) {
+        // cells past the row read whatever follows it (the other row, or the pad behind both) and are not stored
+        const uint32_t src = prevA + 8u * base;
+        double best[C];
+        int arg[C];
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            best[i] = inf;
+            arg[i] = 0xffff;
+        }
+#pragma unroll 2
+        for (int k = cs; k < ce; ++k) {
+            double r;
+            uint32_t at;
+            if (STAGED) {
+                unsigned long long lo, hi;
+                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(itemA + 16u * (uint32_t)(k - cs)));
+                r = __longlong_as_double((long long)lo);
+                at = src - (uint32_t)hi;
+            } else {
+                at = src - 8u * (uint32_t)min(__ldg(a.weight + k), guard);
+                r = __ldg(a.redCost + k);
+            }
+            double v[C];
+            v[0] = ldsF64At<0>(at);
+            if (C > 1) v[1] = ldsF64At<8 * kMckpThreads>(at);
+            if (C > 2) v[2] = ldsF64At<16 * kMckpThreads>(at);
+            if (C > 3) v[3] = ldsF64At<24 * kMckpThreads>(at);
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+                const double cand = __dadd_rn(r, v[i]);
+                if (cand < best[i]) {  // first minimal column
+                    best[i] = cand;
+                    arg[i] = k - cs;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const int j = base + t + i * kMckpThreads;
+            if (j < W) {
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(curA + 8u * (base + i * kMckpThreads)), "d"(best[i]) : "memory");
+                ch[j] = (uint16_t)arg[i];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// The groups of one block: runs of whole groups are staged into `items` (kMckpStage columns) and
+// solved from there; one barrier per group.  Returns the shared address of the final row.
+template <int C>
+__device__ __forceinline__ uint32_t mckpGroups(const MckpArgs &a, uint32_t rowA, uint32_t rowB, ulonglong2 *items, uint16_t *choice,
+                                               int g0, int g1, int W, int guard)
+{
+    const int t = threadIdx.x;
+    uint32_t prevA = rowA + 8u * t, curA = rowB + 8u * t;
+    const uint32_t itemA = (uint32_t)__cvta_generic_to_shared(items);
+    int g = g0;
+    while (g < g1) {
+        const int c0 = a.groupColStart[g];
+        int gEnd = g, cEnd = c0;
+        while (gEnd < g1) {
+            const int e = a.groupColStart[gEnd + 1];
+            if (e - c0 > kMckpStage) break;
+            cEnd = e;
+            ++gEnd;
+        }
+        if (gEnd == g) {  // one group larger than the staging buffer
+            mckpGroup<C, false>(a, prevA, curA, choice + (size_t)(g - g0) * W, c0, a.groupColStart[g + 1], W, guard, 0u);
+            const uint32_t x = prevA;
+            prevA = curA;
+            curA = x;
+            ++g;
+            continue;
+        }
+        // (the barrier that ended the previous group also released the staging buffer)
+        for (int k = c0 + t; k < cEnd; k += kMckpThreads)
+            items[k - c0] = make_ulonglong2((unsigned long long)__double_as_longlong(__ldg(a.redCost + k)),
+                                            (unsigned long long)(8u * (uint32_t)min(__ldg(a.weight + k), guard)));
+        __syncthreads();
+        for (; g < gEnd; ++g) {
+            const int cs = a.groupColStart[g], ce = a.groupColStart[g + 1];
+            mckpGroup<C, true>(a, prevA, curA, choice + (size_t)(g - g0) * W, cs, ce, W, guard, itemA + 16u * (uint32_t)(cs - c0));
+            const uint32_t x = prevA;
+            prevA = curA;
+            curA = x;
+        }
+    }
+    return prevA - 8u * t;
+}
 
 __global__ void __launch_bounds__(kMckpThreads) mckp_dp_kernel(const __grid_constant__ MckpArgs a)
 {
@@ -44,39 +163,24 @@ __global__ void __launch_bounds__(kMckpThreads) mckp_dp_kernel(const __grid_cons
     const int lb = blockIdx.x, b = a.firstBlock + lb, t = threadIdx.x;
     const int cap = a.capacity[b];
     const int g0 = a.blockGroupStart[b], g1 = a.blockGroupStart[b + 1];
-    const int W = cap + 1;
-    double *rowA = reinterpret_cast<double *>(mckpSm), *rowB = rowA + W;
+    const int W = cap + 1, guard = a.guard;
+    ulonglong2 *items = reinterpret_cast<ulonglong2 *>(mckpSm);
+    double *rowA = reinterpret_cast<double *>(mckpSm + sizeof(ulonglong2) * kMckpStage) + guard, *rowB = rowA + W + guard;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int j = t; j < guard; j += kMckpThreads) {
+        rowA[j - guard] = inf;
+        rowB[j - guard] = inf;
+    }
     for (int j = t; j < W; j += kMckpThreads) rowA[j] = 0.0;  // c[-1][.] = 0
     __syncthreads();
-    double *prev = rowA, *cur = rowB;
     uint16_t *choice = a.choice + a.choiceOff[lb];
-    for (int g = g0; g < g1; ++g) {
-        const int cs = a.groupColStart[g], ce = a.groupColStart[g + 1];
-        uint16_t *ch = choice + (size_t)(g - g0) * W;
-        for (int j = t; j < W; j += kMckpThreads) {
-            double best = inf;
-            int arg = 0xffff;
-            for (int k = cs; k < ce; ++k) {
-                const int w = __ldg(a.weight + k);
-                if (w <= j) {
-                    const double cand = __dadd_rn(__ldg(a.redCost + k), prev[j - w]);
-                    if (cand < best) {  // first minimal column
-                        best = cand;
-                        arg = k - cs;
-                    }
-                }
-            }
-            cur[j] = best;
-            ch[j] = (uint16_t)arg;
-        }
-        __syncthreads();
-        double *x = prev;
-        prev = cur;
-        cur = x;
-    }
+    const uint32_t ra = (uint32_t)__cvta_generic_to_shared(rowA), rb = (uint32_t)__cvta_generic_to_shared(rowB);
+    uint32_t last;
+    if (W <= kMckpThreads) last = mckpGroups<1>(a, ra, rb, items, choice, g0, g1, W, guard);
+    else if (W <= 2 * kMckpThreads) last = mckpGroups<2>(a, ra, rb, items, choice, g0, g1, W, guard);
+    else last = mckpGroups<4>(a, ra, rb, items, choice, g0, g1, W, guard);
     if (t == 0) {
-        a.blockObj[lb] = g1 > g0 ? prev[cap] : 0.0;
+        a.blockObj[lb] = g1 > g0 ? (last == ra ? rowA[cap] : rowB[cap]) : 0.0;
         a.nItems[lb] = a.blockColStart[b + 1] - a.blockColStart[b];  // cells = columns x (cap + 1)
     }
 }
@@ -145,7 +249,11 @@ int launchMckp(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_
     a.blockNnz = reinterpret_cast<int32_t *>(res + c->layout.offNnz);
     a.firstBlock = c->firstBlock;
     a.nLocal = c->nLocal;
-    const size_t smem = sizeof(double) * 2 * ((size_t)c->maxCapacity + 1);
+    a.guard = std::min(c->mckpMaxWeight, c->maxCapacity + 1);
+    // the staging buffer, two rows, each behind its guard, and a pad so that the last (partial) chunk of four cells per thread reads
+    // allocated memory
+    const size_t wMax = (size_t)c->maxCapacity + 1, chunk = 4 * kMckpThreads;
+    const size_t smem = sizeof(ulonglong2) * kMckpStage + sizeof(double) * (2 * (wMax + a.guard) + ((wMax + chunk - 1) / chunk * chunk - wMax));
     if (smem > 227 * 1024) return fail(c, DIPGPU_ERR_UNSUPPORTED, "capacity %d needs %zu bytes of DP rows", c->maxCapacity, smem);
     if (c->mckpSmem < smem) {
         DIPGPU_CUDA(c, cudaFuncSetAttribute(mckp_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -468,7 +468,8 @@ def _check_mckp(oracle, pricer, bgs, gcs, w, cap, rc, oc, alpha, eps=1e-4):
 
 
 @pytest.mark.parametrize("seed,m,g_hi,k_hi,cap_hi,w_hi", [(1, 50, 12, 10, 120, 30), (2, 400, 6, 5, 60, 20),
-                                                         (3, 8, 60, 30, 3000, 150), (4, 30, 10, 8, 25, 15)])
+                                                         (3, 8, 60, 30, 3000, 150), (4, 30, 10, 8, 25, 15),
+                                                         (5, 6, 5, 700, 900, 60)])   # groups beyond the staging buffer
 def test_mckp_blocks(oracle, pricer, seed, m, g_hi, k_hi, cap_hi, w_hi):
     """Exactly one column per group (MMKP_MCKnap::solveMCKnap): optimum, column, sums, infeasible blocks."""
     inst = _mckp_instance(seed, m, 0 if seed == 4 else 1, g_hi, 1, k_hi, cap_hi // 3, cap_hi, w_hi)
