@@ -237,7 +237,12 @@ struct Ctx {
 
     // results
     void *dResult = nullptr;
-    void *hResult = nullptr;  // pinned mirror
+    void *hResult = nullptr;  // pinned mirror (mapped: dResultHost is its device address)
+    void *dResultHost = nullptr;
+    bool wantMirror = false;      // the caller of enqueueSolve will read the result on the host right after
+    bool resultMirrored = false;  // the last fused launch wrote hResult itself
+    bool optZeroCopy = true;
+    bool optGatherPinned = true;  // sparse dual upload: read u[support] out of the caller's buffer when it is device-mapped
     size_t resultBytes = 0;
     size_t lastResultBytes = 0;  // bytes of the last packed result (sizes the next speculative D2H copy)
     int64_t indCap = 0;
@@ -337,7 +342,7 @@ int launchFilter(Ctx *c, double redCostEps, cudaStream_t st);
 int launchExpandColumns(Ctx *c, double tolZero, int nKept, cudaStream_t st);
 // pool.cu -- waiting-column pool re-pricing (DecompVarPool::setReducedCosts) and Wentges smoothing
 int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st);
-int launchScatterDuals(Ctx *c, int n, const int32_t *dIdx, const double *dVals, int64_t valStride, double *dDst,
+int launchScatterDuals(Ctx *c, int n, const int32_t *dIdx, const double *dVals, int64_t valStride, bool gather, double *dDst,
                        int64_t dstStride, int nVec, cudaStream_t st);
 int launchSmoothDuals(Ctx *c, const double *dURM, const double *dCenter, const double *dAlphas, int nVec, int uLen,
                       double *dOut, int64_t outStride, cudaStream_t st);

@@ -197,8 +197,10 @@ static int setBlockRange(Ctx *c, int first, int count)
     DIPGPU_CUDA(c, cudaMalloc(&c->dResult, c->resultBytes));
     DIPGPU_CUDA(c, cudaMemset(c->dResult, 0, c->resultBytes));
     if (c->hResult) cudaFreeHost(c->hResult);
-    c->hResult = nullptr;
-    DIPGPU_CUDA(c, cudaMallocHost(&c->hResult, c->resultBytes));
+    c->hResult = c->dResultHost = nullptr;
+    DIPGPU_CUDA(c, cudaHostAlloc(&c->hResult, c->resultBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(c->hResult, 0, c->resultBytes);
+    DIPGPU_CUDA(c, cudaHostGetDevicePointer(&c->dResultHost, c->hResult, 0));
     return DIPGPU_OK;
 }
 
@@ -208,6 +210,7 @@ static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, do
                         bool timed)
 {
     int rc;
+    c->resultMirrored = false;
     if (c->blockKind == 1) {
         // multiple-choice knapsack blocks: DP + backtrack (mckp.cu), then the stand-alone filter
         if ((rc = launchMckp(c, dRedCost, dAlpha, st))) return rc;
@@ -284,6 +287,15 @@ static int unpack(Ctx *c, const void *packed, size_t bytes, dipgpu_cols *out)
 // the first 64 KiB of indices), a second one only if more indices were kept.
 static int fetchResult(Ctx *c, cudaStream_t st)
 {
+    if (c->resultMirrored) {
+        // the fused kernel stored the result into hResult itself (mapped pinned memory): nothing to copy
+        if (c->stageTiming) cudaEventRecord(c->ev[6], st);
+        DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+        const ResultHeader *h = static_cast<const ResultHeader *>(c->hResult);
+        c->lastResultBytes = c->layout.offInd + sizeof(int32_t) * (size_t)h->nInd;
+        c->d2h += (int64_t)c->lastResultBytes;
+        return DIPGPU_OK;
+    }
     // speculative size: what the previous round needed plus a quarter (rounds of one node keep similar
     // columns), at least 8 KiB of indices
     const size_t guess = std::max<size_t>(c->lastResultBytes + c->lastResultBytes / 4, c->layout.offInd + (size_t)8192);
@@ -472,21 +484,35 @@ static int uploadDuals(Ctx *c, const double *u, int32_t uLen, int nVec, double *
         return DIPGPU_OK;
     }
     int rc;
-    if ((rc = ensureSupportStaging(c, nVec))) return rc;
     if (!*clean) {
         DIPGPU_CUDA(c, cudaMemsetAsync(dDst, 0, sizeof(double) * (nVec == 1 ? (size_t)uLen : dstStride * (size_t)nVec), st));
         *clean = true;
     }
+    c->h2d += (int64_t)sizeof(double) * (int64_t)ns * nVec;
+    if (c->optGatherPinned) {
+        // u in pinned (device-mapped) or managed host memory: the kernel picks u[support] out of the caller's
+        // buffer itself -- no pass over the vector on the host (a gather of cold cache lines: ~9 us for 4 240
+        // entries of a 2 MB vector)
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, u) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) &&
+            at.devicePointer)
+            return launchScatterDuals(c, (int)ns, c->dSupport, static_cast<const double *>(at.devicePointer), (int64_t)uLen, true,
+                                      dDst, (int64_t)dstStride, nVec, st);
+        (void)cudaGetLastError();
+    }
+    if ((rc = ensureSupportStaging(c, nVec))) return rc;
     const int32_t *idx = c->hSupport.data();
     for (int v = 0; v < nVec; ++v) {
         const double *uv = u + (size_t)v * (size_t)uLen;
         double *dst = c->hSupVals + (size_t)v * ns;
-        for (size_t k = 0; k < ns; ++k) dst[k] = uv[idx[k]];
+        for (size_t k = 0; k < ns; ++k) {
+            if (k + 32 < ns) __builtin_prefetch(uv + idx[k + 32]);
+            dst[k] = uv[idx[k]];
+        }
     }
     // the scatter kernel reads the pinned staging directly (mapped host memory): the few KB cross PCIe inside
     // the kernel, without a separate copy and its latency
-    c->h2d += (int64_t)sizeof(double) * (int64_t)ns * nVec;
-    return launchScatterDuals(c, (int)ns, c->dSupport, c->hSupVals, (int64_t)ns, dDst, (int64_t)dstStride, nVec, st);
+    return launchScatterDuals(c, (int)ns, c->dSupport, c->hSupVals, (int64_t)ns, false, dDst, (int64_t)dstStride, nVec, st);
 }
 
 // ------------------------------------------------------------------ waiting-column pool
@@ -890,7 +916,10 @@ int dipgpu_solve_blocks(dipgpu_ctx *ctx, const double *redCostX, const double *a
     DIPGPU_CUDA(c, cudaMemcpyAsync(c->dAlpha, alpha, sizeof(double) * (size_t)c->m, cudaMemcpyHostToDevice, st));
     c->h2d += (int64_t)sizeof(double) * ((int64_t)c->nBlockCols + c->m);
     if (timed) { cudaEventRecord(c->ev[1], st); cudaEventRecord(c->ev[2], st); }
-    if ((rc = enqueueSolve(c, c->dRedCost, c->dAlpha, redCostEps, st, timed))) return rc;
+    c->wantMirror = true;
+    rc = enqueueSolve(c, c->dRedCost, c->dAlpha, redCostEps, st, timed);
+    c->wantMirror = false;
+    if (rc) return rc;
     if ((rc = fetchResult(c, st))) return rc;
     c->lastRoundOnHost = true;
     collectStageMs(c);
@@ -917,7 +946,10 @@ int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t p
     if ((rc = launchRedCost(c, c->dU, phase, st))) return rc;
     if (timed) cudaEventRecord(c->ev[2], st);
     // alpha_b = u[nBaseRows + b]  (DecompAlgo.cpp:4820)
-    if ((rc = enqueueSolve(c, c->dRedCost, c->dU + c->nBaseRows, redCostEps, st, timed))) return rc;
+    c->wantMirror = true;
+    rc = enqueueSolve(c, c->dRedCost, c->dU + c->nBaseRows, redCostEps, st, timed);
+    c->wantMirror = false;
+    if (rc) return rc;
     if (redCostXOpt) {
         DIPGPU_CUDA(c, cudaMemcpyAsync(redCostXOpt, c->dRedCost, sizeof(double) * (size_t)c->N, cudaMemcpyDeviceToHost, st));
         c->d2h += (int64_t)sizeof(double) * c->N;
@@ -1472,6 +1504,8 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!c || !name) return DIPGPU_ERR_INVALID;
     if (!strcmp(name, "stage_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "dp_pdl")) { c->optPdl = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "result_zero_copy")) { c->optZeroCopy = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "gather_pinned_duals")) { c->optGatherPinned = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "spmv_lanes")) { c->spmvLanes = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "dp_debug_times")) {
         // diagnostics: value = host pointer (as integer) receiving 8 x nLocal uint64 globaltimer stamps of

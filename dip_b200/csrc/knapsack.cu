@@ -335,6 +335,10 @@ struct KnapArgs {
     int pdl;                       // FUSE: launched with programmatic stream serialization (griddepcontrol.wait before the reduced costs are read)
     BackArgs back;
     FilterArgs filt;
+    // FUSE, single vector: byte distance from the packed result in HBM to its mirror in mapped pinned host
+    // memory (0: none).  Every result store is repeated there, so the host needs no device-to-host copy after
+    // the kernel -- the stores cross PCIe while the other blocks still run.
+    long long hostOff;
 };
 
 // Fused shapes: the TMA destinations of the raw reduced costs / weights are dead once the items are
@@ -421,6 +425,14 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const double *redCostV = a.redCost + vec * a.rcStride;
     const long long resOff = vec * a.resStride;
 #define RESV(ptr) (reinterpret_cast<decltype(ptr)>(reinterpret_cast<char *>(const_cast<void *>(static_cast<const void *>(ptr))) + resOff))
+    // a result store: the packed result in HBM and, when asked for, its host mirror
+#define RES_PUT(ptr, idx, val)                                                                                  \
+    do {                                                                                                        \
+        auto *p__ = RESV(ptr) + (idx);                                                                          \
+        const auto v__ = (val);                                                                                 \
+        *p__ = v__;                                                                                             \
+        if (FUSE && a.hostOff != 0) *reinterpret_cast<decltype(p__)>(reinterpret_cast<char *>(p__) + a.hostOff) = v__; \
+    } while (0)
     const int colStart = a.blockColStart[b];
     const int shortCode = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? a.shortcut[vlb] : 0;
     // a trivial case of GAP_KnapPisinger::solve needs no DP: behave like an empty block here
@@ -1078,13 +1090,13 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     }
     // z = c[n-1][capacity]  (gap_func.py:183)
     if (shortCode != 0) {
-        if (t == 0) RESV(a.blockObj)[lb] = a.zShort[vlb];
+        if (t == 0) RES_PUT(a.blockObj, lb, a.zShort[vlb]);
     } else if (cap < 0) {
-        if (t == 0) RESV(a.blockObj)[lb] = kNegInf;
+        if (t == 0) RES_PUT(a.blockObj, lb, kNegInf);
     } else {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            if (j0 + s == cap) RESV(a.blockObj)[lb] = mine[s];
+            if (j0 + s == cap) RES_PUT(a.blockObj, lb, mine[s]);
         }
     }
     if (t == 0 && vec == 0) a.nItems[lb] = kGlobal;
@@ -1266,10 +1278,10 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             // relaxed: the word itself is everything the other blocks read (no other store has to be ordered before it)
             // an atomic goes straight to the L2 slice (a plain store may wait in the SM's write path)
             atomicExch(a.pubWord + (size_t)vlb * kPubWordStride, word);
-            RESV(a.back.blockRedCost)[lb] = rcB;
-            RESV(a.back.blockOrigCost)[lb] = sOcSum;
-            RESV(a.back.blockNnz)[lb] = cnt;
-            RESV(a.filt.blockMostNeg)[lb] = rcB < 0.0 ? rcB : 0.0;  // min(0, rc): for EVERY block (:5212)
+            RES_PUT(a.back.blockRedCost, lb, rcB);
+            RES_PUT(a.back.blockOrigCost, lb, sOcSum);
+            RES_PUT(a.back.blockNnz, lb, cnt);
+            RES_PUT(a.filt.blockMostNeg, lb, rcB < 0.0 ? rcB : 0.0);  // min(0, rc): for EVERY block (:5212)
         }
         // prefix over the lower blocks: each thread polls its share, warp-shuffle reduction, then
         // the per-warp partials (shared-memory 64-bit atomics would serialise through CAS loops)
@@ -1339,28 +1351,31 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         const long long off = (long long)sNnz;
         if (keep) {
             if (t == 0) {
-                RESV(a.filt.keptBlock)[pos] = lb;
-                RESV(a.filt.keptStart)[pos] = off;
+                RES_PUT(a.filt.keptBlock, pos, lb);
+                RES_PUT(a.filt.keptStart, pos, off);
             }
-            for (int k = t; k < cnt; k += T) RESV(a.filt.keptInd)[off + k] = sFinal[k];
+            for (int k = t; k < cnt; k += T) RES_PUT(a.filt.keptInd, off + k, sFinal[k]);
         }
         if (lb == a.back.nLocal - 1 && t == 0) {
             // the highest block has seen every other block: it closes the packed result
             const int nKept = pos + (keep ? 1 : 0);
             const long long nInd = off + (keep ? cnt : 0);
-            RESV(a.filt.keptStart)[nKept] = nInd;
-            ResultHeader *hdr = RESV(a.filt.hdr);
-            hdr->magic = kResultMagic;
-            hdr->m = a.back.nLocal;
-            hdr->firstBlock = a.firstBlock;
-            hdr->nKept = nKept;
-            hdr->nInd = nInd;
-            hdr->cells = (long long)(sCells + myCells);
-            hdr->reserved[0] = (long long)(sEval + myEval);  // cells evaluated after the reduction
-            hdr->indCap = a.filt.indCap;
+            RES_PUT(a.filt.keptStart, nKept, nInd);
+            ResultHeader h;
+            h.magic = kResultMagic;
+            h.m = a.back.nLocal;
+            h.firstBlock = a.firstBlock;
+            h.nKept = nKept;
+            h.nInd = nInd;
+            h.cells = (long long)(sCells + myCells);
+            h.indCap = a.filt.indCap;
+            h.reserved[0] = (long long)(sEval + myEval);  // cells evaluated after the reduction
+            h.reserved[1] = h.reserved[2] = 0;
+            RES_PUT(a.filt.hdr, 0, h);
         }
         dbgStamp(a.dbgTimes, 5);
     }
+#undef RES_PUT
 #undef RESV
 }
 
@@ -1642,6 +1657,10 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
         a.back.shortcut = c->profitMode == DIPGPU_PROFIT_PISINGER_INT ? c->dShortcutB : nullptr;
     }
     a.filt.fuseCopy = c->nLocal <= kFuseFilterMaxBlocks ? 2 : 1;
+    // host mirror of the packed result (the synchronous host entry points ask for it; option "result_zero_copy")
+    a.hostOff = (!batch && g.fuse && c->wantMirror && c->optZeroCopy && c->dResultHost)
+                    ? (long long)(static_cast<char *>(c->dResultHost) - static_cast<char *>(c->dResult)) : 0;
+    c->resultMirrored = a.hostOff != 0;
     {
         int rc = prepareKnapsackDp(c);
         if (rc) return rc;

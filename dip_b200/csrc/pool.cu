@@ -161,20 +161,27 @@ int launchSmoothDuals(Ctx *c, const double *dURM, const double *dCenter, const d
     return DIPGPU_OK;
 }
 
-// dst_v[idx[k]] = vals_v[k]: the support of a sparse dual upload (dipgpu_set_dual_support)
+// dst_v[idx[k]] = vals_v[k] (GATHER: vals_v[idx[k]] -- vals is the caller's whole dual vector in mapped host
+// memory): the support of a sparse dual upload (dipgpu_set_dual_support)
+template <bool GATHER>
 __global__ void __launch_bounds__(256)
 scatter_duals_kernel(int n, const int32_t *__restrict__ idx, const double *__restrict__ vals, long long valStride,
                      double *__restrict__ dst, long long dstStride)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) dst[(long long)blockIdx.y * dstStride + idx[k]] = vals[(long long)blockIdx.y * valStride + k];
+    if (k < n) {
+        const int i = idx[k];
+        dst[(long long)blockIdx.y * dstStride + i] = vals[(long long)blockIdx.y * valStride + (GATHER ? i : k)];
+    }
 }
 
-int launchScatterDuals(Ctx *c, int n, const int32_t *dIdx, const double *dVals, int64_t valStride, double *dDst,
+int launchScatterDuals(Ctx *c, int n, const int32_t *dIdx, const double *dVals, int64_t valStride, bool gather, double *dDst,
                        int64_t dstStride, int nVec, cudaStream_t st)
 {
     if (n <= 0 || nVec <= 0) return DIPGPU_OK;
-    scatter_duals_kernel<<<dim3((n + 255) / 256, nVec, 1), 256, 0, st>>>(n, dIdx, dVals, valStride, dDst, dstStride);
+    const dim3 grid((n + 255) / 256, nVec, 1);
+    if (gather) scatter_duals_kernel<true><<<grid, 256, 0, st>>>(n, dIdx, dVals, valStride, dDst, dstStride);
+    else scatter_duals_kernel<false><<<grid, 256, 0, st>>>(n, dIdx, dVals, valStride, dDst, dstStride);
     c->launches++;
     DIPGPU_CUDA(c, cudaGetLastError());
     return DIPGPU_OK;

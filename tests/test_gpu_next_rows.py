@@ -399,6 +399,45 @@ def test_dual_support_upload_equals_dense(oracle, pricer):
     assert e.value.code == ERR_INVALID
 
 
+def test_pinned_duals_and_host_mirror_paths(pricer):
+    """Two transfer shortcuts of the host entry points must not change a bit: with a dual support and u in
+    page-locked memory the kernel picks u[support] out of the caller's buffer (no host gather), and the fused
+    kernel stores the packed result into mapped host memory itself (no D2H copy).  All four combinations of
+    the options against the plain path (pageable u, both off)."""
+    from dip_b200 import capi
+    model = I.gap_pricing_model(I.gap_class_d())
+    pricer.setModel(model)
+    n = model.meta["n"]
+    rng = np.random.default_rng(41)
+    nb = model.n_base_rows - n
+    branch = np.sort(rng.choice(nb, size=nb // 40, replace=False)) + n
+    support = np.concatenate([np.arange(n), branch, np.arange(model.n_base_rows, model.u_len)]).astype(np.int32)
+    U = np.zeros((4, model.u_len))
+    for v in range(4):
+        U[v, :n] = rng.uniform(0, 2 * model.objective.mean(), size=n)
+        U[v, branch] = rng.uniform(-3, 3, size=len(branch))
+        U[v, model.n_base_rows:] = rng.uniform(-10, 0, size=model.m)
+    pricer.set_option("gather_pinned_duals", 0)
+    pricer.set_option("result_zero_copy", 0)
+    plain = [pricer.priceRound(U[v], result=RoundResult(model.m, model.m, model.N)) for v in range(4)]
+    pin = capi.PinnedArray(U.shape, np.float64)
+    pin.array[:] = U
+    pricer.setDualSupport(support)
+    for gather, mirror in ((1, 1), (1, 0), (0, 1), (0, 0)):
+        pricer.set_option("gather_pinned_duals", gather)
+        pricer.set_option("result_zero_copy", mirror)
+        for v in (2, 0, 3, 1):
+            _same_round(pricer.priceRound(pin.array[v]), plain[v])
+            _same_round(pricer.priceRound(U[v]), plain[v])            # pageable u: always the host gather
+        r = pricer.priceRound(pin.array[1])
+        cs, ri, va, hs = pricer.expandColumns()                        # reads the device copy of the result
+        assert len(cs) == r.nCols + 1
+        batch = pricer.priceRoundsBatch(pin.array)
+        for v in range(4):
+            _same_round(batch[v], plain[v])
+    pin.free()
+
+
 def test_pool_with_dual_support_bitmap(oracle, pricer):
     """A large pool (>= 32 Ki columns) with a declared dual support runs the kernel variant that skips the
     gathers of rows without a dual (shared-memory bitmap); bit-equal to the oracle and to the plain variant."""
