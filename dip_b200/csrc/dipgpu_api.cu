@@ -1504,7 +1504,11 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!c || !name) return DIPGPU_ERR_INVALID;
     if (!strcmp(name, "stage_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "dp_pdl")) { c->optPdl = value != 0; return DIPGPU_OK; }
-    if (!strcmp(name, "result_zero_copy")) { c->optZeroCopy = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "result_zero_copy")) {  // 2 (diagnostics): also from the device-resident entry points
+        c->optZeroCopy = value != 0;
+        c->optMirrorAlways = value == 2;
+        return DIPGPU_OK;
+    }
     if (!strcmp(name, "gather_pinned_duals")) { c->optGatherPinned = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "spmv_lanes")) { c->spmvLanes = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "dp_debug_times")) {

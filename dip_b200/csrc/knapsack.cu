@@ -1658,7 +1658,7 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     }
     a.filt.fuseCopy = c->nLocal <= kFuseFilterMaxBlocks ? 2 : 1;
     // host mirror of the packed result (the synchronous host entry points ask for it; option "result_zero_copy")
-    a.hostOff = (!batch && g.fuse && c->wantMirror && c->optZeroCopy && c->dResultHost)
+    a.hostOff = (!batch && g.fuse && (c->wantMirror || c->optMirrorAlways) && c->optZeroCopy && c->dResultHost)
                     ? (long long)(static_cast<char *>(c->dResultHost) - static_cast<char *>(c->dResult)) : 0;
     c->resultMirrored = a.hostOff != 0;
     {
