@@ -405,8 +405,9 @@ static int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st
     return DIPGPU_OK;
 }
 
-// D2H of nVec packed results (one strided copy of the speculative prefix) and decoding.
-static int fetchBatch(Ctx *c, int nVec, dipgpu_cols *outs, cudaStream_t st)
+// D2H of nVec packed results into hResultBatch (one strided copy of the speculative prefix, a second copy per
+// result that kept more indices).
+static int fetchBatchPacked(Ctx *c, int nVec, cudaStream_t st)
 {
     const size_t spec = std::min(c->resultBytes, c->layout.offInd + (size_t)65536);
     DIPGPU_CUDA(c, cudaMemcpy2DAsync(c->hResultBatch, c->resStride, c->dResultBatch, c->resStride, spec, (size_t)nVec, cudaMemcpyDeviceToHost, st));
@@ -427,7 +428,14 @@ static int fetchBatch(Ctx *c, int nVec, dipgpu_cols *outs, cudaStream_t st)
         }
     }
     if (more) DIPGPU_CUDA(c, cudaStreamSynchronize(st));
-    int first = DIPGPU_OK;
+    return DIPGPU_OK;
+}
+
+// ... and decoding.
+static int fetchBatch(Ctx *c, int nVec, dipgpu_cols *outs, cudaStream_t st)
+{
+    int first = fetchBatchPacked(c, nVec, st);
+    if (first) return first;
     for (int v = 0; v < nVec; ++v) {
         const int rc = unpack(c, static_cast<char *>(c->hResultBatch) + (size_t)v * c->resStride, c->resultBytes, &outs[v]);
         if (rc && !first) first = rc;
@@ -978,6 +986,123 @@ int dipgpu_price_rounds_batch(dipgpu_ctx *ctx, int32_t nVec, const double *U, in
     if ((rc = enqueueBatch(c, nVec, phase, redCostEps, st))) return rc;
     c->lastRoundOnHost = false;
     return fetchBatch(c, nVec, outs, st);
+}
+
+// Block subset with per-block user duals: every distinct dual vector is priced as one vector of
+// a batch (all blocks of the shard -- they run side by side, a subset costs the same), then the listed blocks
+// are picked out of the packed results of "their" vector on the host.
+int dipgpu_price_round_which(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase, double redCostEps,
+                             int32_t nWhich, const int32_t *whichBlocks, const double *const *userDuals,
+                             dipgpu_cols *out, int32_t *solvedAll)
+{
+    CTX_OR_FAIL(ctx);
+    if (!u || !out || nWhich < 0 || (nWhich > 0 && !whichBlocks)) return fail(c, DIPGPU_ERR_INVALID, "price_round_which: bad arguments");
+    int rc;
+    if ((rc = checkRoundReady(c, "price_round_which", uLen, phase))) return rc;
+    const int m = c->nLocal, first = c->firstBlock;
+    std::vector<int> vecOf((size_t)std::max(m, 1), -1);  // local block -> vector that prices it (-1: not listed)
+    std::vector<const double *> vecs(1, u);
+    for (int i = 0; i < nWhich; ++i) {
+        const int lb = whichBlocks[i] - first;
+        if (lb < 0 || lb >= m) return fail(c, DIPGPU_ERR_INVALID, "price_round_which: block %d outside this context's range [%d, %d)", whichBlocks[i], first, first + m);
+        if (vecOf[lb] >= 0) return fail(c, DIPGPU_ERR_INVALID, "price_round_which: block %d listed twice", whichBlocks[i]);
+        const double *ub = userDuals ? userDuals[i] : nullptr;
+        int v = 0;
+        if (ub && ub != u) {
+            v = (int)(std::find(vecs.begin(), vecs.end(), ub) - vecs.begin());
+            if (v == (int)vecs.size()) vecs.push_back(ub);
+        }
+        vecOf[lb] = v;
+    }
+    const int nVec = (int)vecs.size();
+    std::vector<double> U;
+    const double *Uptr = u;
+    if (nVec > 1) {
+        U.resize((size_t)nVec * (size_t)uLen);
+        for (int v = 0; v < nVec; ++v) memcpy(U.data() + (size_t)v * uLen, vecs[v], sizeof(double) * (size_t)uLen);
+        Uptr = U.data();
+    }
+    if ((rc = ensureBatch(c, nVec))) return rc;
+    cudaStream_t st = c->stream;
+    if (c->stageTiming) cudaEventRecord(c->ev[0], st);
+    if ((rc = uploadDuals(c, Uptr, uLen, nVec, c->dUBatch, c->uStride, &c->dUBatchClean, st))) return rc;
+    c->haveST = false;
+    if ((rc = enqueueBatch(c, nVec, phase, redCostEps, st))) return rc;
+    c->lastRoundOnHost = false;
+    if ((rc = fetchBatchPacked(c, nVec, st))) return rc;
+
+    const ResultLayout &L = c->layout;
+    auto packed = [&](int v) { return static_cast<const char *>(c->hResultBatch) + (size_t)v * c->resStride; };
+    auto dbl = [](const char *p, size_t off) { return reinterpret_cast<const double *>(p + off); };
+    bool found = false;
+    for (int lb = 0; lb < m && !found; ++lb)
+        if (vecOf[lb] >= 0 && dbl(packed(vecOf[lb]), L.offRedCost)[lb] < -redCostEps) found = true;  // strict (:5216)
+    char *dst = static_cast<char *>(c->hResult);
+    const ResultHeader *h0 = reinterpret_cast<const ResultHeader *>(packed(0));
+    long long cells = 0, evals = 0;
+    for (int v = 0; v < nVec; ++v) {
+        const ResultHeader *hv = reinterpret_cast<const ResultHeader *>(packed(v));
+        cells += hv->cells;
+        evals += hv->reserved[0];
+    }
+    double *dRc = reinterpret_cast<double *>(dst + L.offRedCost), *dMn = reinterpret_cast<double *>(dst + L.offMostNeg);
+    double *dOc = reinterpret_cast<double *>(dst + L.offOrigCost), *dOb = reinterpret_cast<double *>(dst + L.offObj);
+    int64_t *dKs = reinterpret_cast<int64_t *>(dst + L.offKeptStart);
+    int32_t *dNz = reinterpret_cast<int32_t *>(dst + L.offNnz), *dKb = reinterpret_cast<int32_t *>(dst + L.offKeptBlock);
+    int32_t *dKi = reinterpret_cast<int32_t *>(dst + L.offInd);
+    ResultHeader hd = *h0;
+    if (!found) {
+        // no listed block prices out: all blocks at the standard duals (DecompAlgo.cpp:5076-5148) -- that round is
+        // vector 0 of the batch.  The listed blocks' own candidates stay in the list the filter walks, so a
+        // block priced with user duals contributes min(both reduced costs, 0) to mostNegReducedCost (:5212-5214).
+        memcpy(dst, packed(0), L.offInd + sizeof(int32_t) * (size_t)h0->nInd);
+        for (int lb = 0; lb < m; ++lb)
+            if (vecOf[lb] > 0) dMn[lb] = std::min(dMn[lb], std::min(0.0, dbl(packed(vecOf[lb]), L.offRedCost)[lb]));
+    } else {
+        int nKept = 0;
+        int64_t nInd = 0;
+        for (int lb = 0; lb < m; ++lb) {
+            const int v = vecOf[lb];
+            if (v < 0) {  // not solved this round
+                dRc[lb] = dMn[lb] = dOc[lb] = dOb[lb] = 0.0;
+                dNz[lb] = 0;
+                continue;
+            }
+            const char *src = packed(v);
+            dRc[lb] = dbl(src, L.offRedCost)[lb];
+            dMn[lb] = dbl(src, L.offMostNeg)[lb];
+            dOc[lb] = dbl(src, L.offOrigCost)[lb];
+            dOb[lb] = dbl(src, L.offObj)[lb];
+            dNz[lb] = reinterpret_cast<const int32_t *>(src + L.offNnz)[lb];
+            if (!(dRc[lb] < -redCostEps)) continue;
+            const ResultHeader *hv = reinterpret_cast<const ResultHeader *>(src);
+            const int32_t *kb = reinterpret_cast<const int32_t *>(src + L.offKeptBlock);
+            const int64_t *ks = reinterpret_cast<const int64_t *>(src + L.offKeptStart);
+            const int32_t *pos = std::lower_bound(kb, kb + hv->nKept, lb);
+            if (pos == kb + hv->nKept || *pos != lb) return fail(c, DIPGPU_ERR_CUDA, "price_round_which: block %d priced out but is not among the kept columns", first + lb);
+            const int k = (int)(pos - kb);
+            const int64_t len = ks[k + 1] - ks[k];
+            dKb[nKept] = lb;
+            dKs[nKept] = nInd;
+            memcpy(dKi + nInd, reinterpret_cast<const int32_t *>(src + L.offInd) + ks[k], sizeof(int32_t) * (size_t)len);
+            nInd += len;
+            ++nKept;
+        }
+        dKs[nKept] = nInd;
+        hd.nKept = nKept;
+        hd.nInd = nInd;
+    }
+    hd.cells = cells;
+    hd.reserved[0] = evals;
+    memcpy(dst, &hd, sizeof(hd));
+    if (solvedAll) *solvedAll = found ? 0 : 1;
+    // the composed round becomes the context's "last round" (dipgpu_expand_columns reads the device copy)
+    const size_t need = L.offInd + sizeof(int32_t) * (size_t)hd.nInd;
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dResult, c->hResult, need, cudaMemcpyHostToDevice, st));
+    DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+    c->lastResultBytes = need;
+    c->lastRoundOnHost = true;
+    return unpack(c, c->hResult, c->resultBytes, out);
 }
 
 int dipgpu_set_dual_support(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx)

@@ -294,6 +294,31 @@ class GpuPricer:
         if rc != capi.OK:
             self._check(rc)
 
+    def priceRoundWhich(self, u, which, userDuals=None, phase=PHASE_PRICE2, redCostEps=1e-4, result=None):
+        """generateVars' round-robin branch (Dip/src/DecompAlgo.cpp:4929-5149): only the blocks DecompApp::
+        solveRelaxedWhich names are solved, `userDuals` = {block: dual vector} for the blocks priced with their
+        own master duals (userDualsByBlock).  Returns (RoundResult, solvedAll): solvedAll is True when no listed
+        block priced out and the full round at `u` was returned instead (DecompAlgo.cpp:5076-5148)."""
+        u = np.ascontiguousarray(u, np.float64)
+        which = np.ascontiguousarray(which, np.int32)
+        keep = []                                   # the vectors must outlive the call
+        ptrs = None
+        if userDuals:
+            ptrs = (C.c_void_p * max(len(which), 1))()
+            for i, b in enumerate(which):
+                ub = userDuals.get(int(b))
+                if ub is not None:
+                    ub = np.ascontiguousarray(ub, np.float64)
+                    if len(ub) != len(u):
+                        raise ValueError("The size of the user dual vector is not the same as the number of master rows")
+                    keep.append(ub)
+                    ptrs[i] = ub.ctypes.data
+        res = result if result is not None else RoundResult(self.m, self.m, max(self.nBlockCols, 1))
+        all_ = C.c_int32(0)
+        self._check(self._lib.dipgpu_price_round_which(self._ctx, capi.ptr(u), len(u), phase, float(redCostEps), len(which),
+                                                       capi.ptr(which), ptrs, C.byref(res.c), C.byref(all_)))
+        return res, bool(all_.value)
+
     def selectBatchResult(self, which: int):
         self._check(self._lib.dipgpu_select_batch_result(self._ctx, int(which)))
 

@@ -229,6 +229,32 @@ int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t p
  */
 int dipgpu_set_dual_support(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx);
 
+/* ------------------------------------------- a subset of the blocks, per-block user duals
+ *
+ * DecompAlgo::generateVars' round-robin branch (Dip/src/DecompAlgo.cpp:4929-5149; taken in phase 2 while
+ * m_rrIterSinceAll < RoundRobinInterval, :4755): DecompApp::solveRelaxedWhich (Dip/src/DecompApp.h:339-342)
+ * names the blocks to solve this round and may hand a different master dual vector to some of them
+ * (userDualsByBlock; the user-replaced vector of getDualForGenerateVars, DecompApp.h:330-332, is simply `u`).
+ *   whichBlocks[i]  global block ids (this context's block range; no duplicates), any order
+ *   userDuals       NULL, or nWhich pointers: userDuals[i] == NULL -> block i is priced with u, else with that
+ *                   vector (length uLen, DIP's layout [core rows | convexity rows]): reduced costs c - A''^T uhat
+ *                   for the block's columns and alpha = uhat[nBaseRows + block]
+ * The result has the layout of a normal round: only the listed blocks carry values (the others: no column,
+ * zeros), mostNegReducedCost sums min(0, rc) over the listed blocks (mostNegRCvec starts at 0, :4761).
+ * If no listed block prices out (rc < -redCostEps), DIP solves ALL blocks with u (:5076-5148): the call then
+ * returns that full round, *solvedAll = 1, and a block priced with user duals contributes the smaller of its
+ * two reduced costs to mostNegReducedCost, as the reference's filter loop does (:5212-5214).
+ * Differences, stated: kept columns come in ascending block order (the reference: list order); the reference
+ * reads alpha from the ADJUSTED user vector at [nBaseRows + block], an index past that array's convexity-free
+ * length (:5032) -- here alpha is the user vector's convexity dual, which is what the block's subproblem needs.
+ * Cost: one batch submission with one vector per distinct dual pointer; the blocks of a shard run side by
+ * side, so pricing a subset takes as long as pricing them all.  The composed round becomes the context's
+ * "last round" (dipgpu_expand_columns).
+ */
+int dipgpu_price_round_which(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase, double redCostEps,
+                             int32_t nWhich, const int32_t *whichBlocks, const double *const *userDuals,
+                             dipgpu_cols *out, int32_t *solvedAll);
+
 /* ------------------------------------------- several dual vectors in one submission
  *
  * nVec master dual vectors (row v at U + v*uLen), each priced exactly as dipgpu_price_round would:

@@ -28,6 +28,7 @@
 #include <cstring>
 #include <limits>
 #include <list>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -151,6 +152,33 @@ public:
         check(dipgpu_price_round(m_ctx, u, uLen, phase, redCostEps, &m_cols, nullptr));
         mostNegReducedCost = m_cols.mostNegReducedCost;
         for (int k = 0; k < m_cols.nCols; ++k) newVars.push_back(makeVar<VarT>(k, m_colRedCost[k]));
+        return m_cols.nCols;
+    }
+
+    // generateVars' round-robin branch (DecompAlgo.cpp:4929-5149): blocksToSolve / userDualsByBlock are what
+    // DecompApp::solveRelaxedWhich (DecompApp.h:339-342) filled in.  solvedAll: no listed block priced out and
+    // all blocks were solved with u instead (:5076-5148) -- the caller resets m_rrIterSinceAll then.
+    template <class VarT = DecompVar, class ListT = std::list<VarT *>>
+    int generateVarsWhich(const double *u, int uLen, int phase, double redCostEps, const std::vector<int> &blocksToSolve,
+                          const std::map<int, std::vector<double>> &userDualsByBlock, ListT &newVars,
+                          double &mostNegReducedCost, bool *solvedAll = nullptr)
+    {
+        std::vector<int32_t> which(blocksToSolve.begin(), blocksToSolve.end());
+        std::vector<const double *> ud(which.size(), nullptr);
+        for (size_t i = 0; i < which.size(); ++i) {
+            auto it = userDualsByBlock.find(which[i]);
+            if (it == userDualsByBlock.end()) continue;
+            if ((int)it->second.size() != uLen)
+                throw Error(DIPGPU_ERR_INVALID, "The size of the user dual vector is not the same as the number of master rows");
+            ud[i] = it->second.data();
+        }
+        int32_t all = 0;
+        check(dipgpu_price_round_which(m_ctx, u, uLen, phase, redCostEps, (int32_t)which.size(), which.data(),
+                                       userDualsByBlock.empty() ? nullptr : ud.data(), &m_cols, &all));
+        if (solvedAll) *solvedAll = all != 0;
+        mostNegReducedCost = m_cols.mostNegReducedCost;
+        for (int k = 0; k < m_cols.nCols; ++k) newVars.push_back(makeVar<VarT>(k, m_colRedCost[k]));
+        m_roundValid = false;
         return m_cols.nCols;
     }
 

@@ -245,6 +245,47 @@ def price_round(R, N, row_start, col_ind, val, c, u, n_base, m, block_col_start,
     return RoundResult(rcx, nnz, rc, oc, keep, mn, z, cols, tot.value, kept, cells.value)
 
 
+def price_round_which(R, N, row_start, col_ind, val, c, u, n_base, m, block_col_start, weight, capacity,
+                      which, user_duals=None, profit_mode=0, red_cost_eps=1e-4):
+    """DecompAlgo::generateVars' round-robin branch (Dip/src/DecompAlgo.cpp:4929-5149) followed by its
+    filter loop (:5151-5232), restated on top of price_round (blocks are independent given a dual vector,
+    so "solve block b with vector uhat" = block b of the round priced with uhat).
+      which       blocksToSolve, in the order solveRelaxedWhich returned them
+      user_duals  {block: master dual vector} = userDualsByBlock
+    Returns dict(new_vars=[(block, ind, redCost, origCost)] in the reference's push order, most_neg_vec,
+    most_neg_reduced_cost, solved_all).  alpha of a user-dual block is that vector's convexity dual (the
+    reference indexes the convexity-free adjusted copy at nBaseCoreRows + b, :5032, past its end)."""
+    user_duals = user_duals or {}
+    rounds = {}
+
+    def round_of(vec_id, vec):
+        if vec_id not in rounds:
+            rounds[vec_id] = price_round(R, N, row_start, col_ind, val, c, vec, n_base, m, block_col_start, weight,
+                                         capacity, profit_mode=profit_mode, red_cost_eps=red_cost_eps)
+        return rounds[vec_id]
+    potential = []                       # potentialVars: (block, ind, redCost, origCost)
+    for b in which:                      # :4952-5070
+        b = int(b)
+        r = round_of(id(user_duals[b]), user_duals[b]) if b in user_duals else round_of("u", u)
+        potential.append((b, r.col_ind[b], float(r.col_red_cost[b]), float(r.col_orig_cost[b])))
+    found = any(v[2] < -red_cost_eps for v in potential)     # :5063-5069
+    if not found:                        # :5076-5148: all blocks, standard duals
+        r = round_of("u", u)
+        for b in range(m):
+            potential.append((b, r.col_ind[b], float(r.col_red_cost[b]), float(r.col_orig_cost[b])))
+    most_neg_vec = np.zeros(m)           # :4761
+    new_vars = []
+    for (b, ind, rc, oc) in potential:   # :5151-5232
+        if rc < most_neg_vec[b]:
+            most_neg_vec[b] = rc
+        if rc < -red_cost_eps:
+            new_vars.append((b, ind, rc, oc))
+    tot = 0.0
+    for b in range(m):
+        tot += most_neg_vec[b]
+    return dict(new_vars=new_vars, most_neg_vec=most_neg_vec, most_neg_reduced_cost=tot, solved_all=not found)
+
+
 def expand_column(R, N, row_start, col_ind, val, n_base, num_convex, ind, block_id, tol_zero=1e-6):
     """Master column (rows ascending, values) of the 0/1 variable with x-space indices `ind`."""
     ind = np.ascontiguousarray(ind, np.int32)

@@ -5,6 +5,7 @@
 // the program then prints NO_GPU and exits 0.
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <vector>
 
 #include "../../include/dipgpu_decomp.hpp"
@@ -223,6 +224,44 @@ int main()
             for (int b = 0; b < m; ++b) CHECK(pricer->ladderRound(k).blockObj[(size_t)b] == z[b]);
             for (dipgpu::DecompVar *v : varsL) delete v;
             a = a * 0.90;
+        }
+        // round-robin branch: two listed blocks, one with its own dual vector; against two oracle rounds
+        {
+            std::vector<double> uh(u2);
+            for (int r = 0; r < R; ++r) uh[(size_t)r] *= 0.9;
+            std::vector<int> colNnzU(m), colKeepU(m);
+            std::vector<double> rcU(m), ocU(m), mnU(m), zU(m), rcxU(N);
+            std::vector<int> indU((size_t)m * n);
+            double tot = 0;
+            int64_t cl = 0;
+            dip_oracle_price_round(R, N, rowStart.data(), colInd.data(), val.data(), cost.data(), u2.data(), R, 0, m,
+                                   blockColStart.data(), weight.data(), capacity.data(), 0, 1e-4, 1, n, redCostX.data(),
+                                   colNnz.data(), colRedCost.data(), colOrigCost.data(), colKeep.data(), mostNeg.data(),
+                                   z.data(), ind.data(), &tot, &cl);
+            dip_oracle_price_round(R, N, rowStart.data(), colInd.data(), val.data(), cost.data(), uh.data(), R, 0, m,
+                                   blockColStart.data(), weight.data(), capacity.data(), 0, 1e-4, 1, n, rcxU.data(),
+                                   colNnzU.data(), rcU.data(), ocU.data(), colKeepU.data(), mnU.data(), zU.data(),
+                                   indU.data(), &tot, &cl);
+            const int bStd = 7, bUsr = 2;
+            std::map<int, std::vector<double>> userDuals;
+            userDuals[bUsr] = uh;
+            dipgpu::DecompVarList varsW;
+            double mnW = 0;
+            bool all = false;
+            const int nW = pricer->generateVarsWhich(u2.data(), (int)u2.size(), dipgpu::PHASE_PRICE2, 1e-4, {bStd, bUsr},
+                                                     userDuals, varsW, mnW, &all);
+            const bool anyNeg = colRedCost[bStd] < -1e-4 || rcU[bUsr] < -1e-4;
+            CHECK(all == !anyNeg);
+            if (anyNeg) {
+                CHECK(nW == (colRedCost[bStd] < -1e-4 ? 1 : 0) + (rcU[bUsr] < -1e-4 ? 1 : 0));
+                CHECK(mnW == std::min(0.0, rcU[bUsr]) + std::min(0.0, colRedCost[bStd]));   // block order: 2 then 7
+                for (dipgpu::DecompVar *v : varsW) {
+                    const int b = v->getBlockId();
+                    CHECK(b == bStd || b == bUsr);
+                    CHECK(v->getReducedCost() == (b == bStd ? colRedCost[bStd] : rcU[bUsr]));
+                }
+            }
+            for (dipgpu::DecompVar *v : varsW) delete v;
         }
     }
     delete pricer;

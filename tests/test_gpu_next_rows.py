@@ -343,6 +343,89 @@ def test_node_bounds_unsupported_in_pisinger_mode(pricer):
     assert e.value.code == ERR_UNSUPPORTED
 
 
+# ------------------------------------------------------------------ a10: block subsets, per-block user duals
+
+
+def _check_which(oracle, pricer, model, u, which, user=None, eps=1e-4):
+    res, solved_all = pricer.priceRoundWhich(u, which, user, redCostEps=eps)
+    ref = oracle.price_round_which(model.R, model.N, model.row_start, model.col_ind, model.val, model.objective, u,
+                                   model.n_base_rows, model.m, model.block_col_start, model.weight, model.capacity,
+                                   which, user, red_cost_eps=eps)
+    assert solved_all == ref["solved_all"]
+    want = sorted(ref["new_vars"], key=lambda v: v[0])       # the reference pushes in list order, we in block order
+    assert res.nCols == len(want)
+    for k, (b, ind, rc, oc) in enumerate(want):
+        assert int(res.colBlock[k]) == b and list(res.column(k)) == list(ind)
+        assert res.colRedCost[k] == rc and res.colOrigCost[k] == oc
+    np.testing.assert_array_equal(res.blockMostNegRC, ref["most_neg_vec"])
+    assert res.mostNegReducedCost == ref["most_neg_reduced_cost"]
+    return res, solved_all
+
+
+def test_block_subset_and_user_duals(oracle, pricer):
+    """generateVars' round-robin branch (DecompAlgo.cpp:4929-5149): the listed blocks only, some with their own
+    master dual vector; the all-blocks fallback when none of them prices out."""
+    from dip_b200.capi import DipGpuError, ERR_INVALID
+    model = I.gap_pricing_model(I.gap_class_d(6, 40, seed=3), branch_rows=False)
+    pricer.setModel(model)
+    rng = np.random.default_rng(70)
+    u = I.gap_duals(model, np.random.default_rng(12))
+    full = pricer.priceRound(u, result=RoundResult(model.m, model.m, model.N))
+    assert full.nCols >= 3
+    # one block, standard duals
+    res, all_ = _check_which(oracle, pricer, model, u, [3])
+    assert not all_ and res.nCols == 1 and res.colRedCost[0] == full.blockRedCost[3]
+    # several blocks in any order, two of them with the same user vector, one with another
+    ua = u * rng.uniform(0.8, 1.2, size=len(u))
+    ub = u * rng.uniform(0.5, 1.5, size=len(u))
+    res, all_ = _check_which(oracle, pricer, model, u, [5, 1, 2, 0], {1: ua, 2: ua, 0: ub})
+    assert not all_
+    cs, ri, va, hs = pricer.expandColumns()                   # the composed round is the "last round"
+    assert len(cs) == res.nCols + 1
+    for k in range(res.nCols):
+        rows, vals = oracle.expand_column(model.R, model.N, model.row_start, model.col_ind, model.val, model.n_base_rows,
+                                          model.m, res.column(k), int(res.colBlock[k]))
+        np.testing.assert_array_equal(ri[cs[k]:cs[k + 1]], rows)
+        np.testing.assert_array_equal(va[cs[k]:cs[k + 1]], vals)
+    # no listed block prices out -> all blocks at the standard duals; block 4's user vector has a hopeless alpha,
+    # block 2 does not price out under u either
+    u2 = u.copy()
+    u2[model.n_base_rows + 2] = -1e6
+    uc = u2.copy()
+    uc[model.n_base_rows + 4] = -1e6
+    res, all_ = _check_which(oracle, pricer, model, u2, [4, 2], {4: uc})
+    assert all_ and 4 in list(res.colBlock[:res.nCols]) and 2 not in list(res.colBlock[:res.nCols])
+    # ... and a user vector that prices worse than u does: mostNegRC of that block is the smaller of the two
+    ud = u2.copy()
+    ud[model.n_base_rows + 4] = u2[model.n_base_rows + 4] - 1e-3    # alpha lower -> rc higher, may still be < 0
+    _check_which(oracle, pricer, model, u2, [4], {4: ud})
+    # empty list: nothing prices out -> the full round
+    res, all_ = _check_which(oracle, pricer, model, u, [])
+    assert all_
+    _same_round(res, full)
+    for bad in ([1, 1], [model.m], [-1]):
+        with pytest.raises(DipGpuError) as e:
+            pricer.priceRoundWhich(u, bad)
+        assert e.value.code == ERR_INVALID
+
+
+def test_block_subset_in_pisinger_mode_and_large_shards(oracle, pricer):
+    """The same branch where the batch runs vector after vector (non-fused shapes) and in the scaled-integer mode."""
+    model = I.gap_pricing_model(I.gap_class_d(4, 30, seed=8), branch_rows=False)
+    pricer.setModel(model, profit_mode=PROFIT_PISINGER_INT)
+    u = I.gap_duals(model, np.random.default_rng(5))
+    ua = u * np.random.default_rng(3).uniform(0.9, 1.1, size=len(u))
+    res, solved_all = pricer.priceRoundWhich(u, [2, 0], {0: ua})
+    ref = oracle.price_round_which(model.R, model.N, model.row_start, model.col_ind, model.val, model.objective, u,
+                                   model.n_base_rows, model.m, model.block_col_start, model.weight, model.capacity,
+                                   [2, 0], {0: ua}, profit_mode=PROFIT_PISINGER_INT)
+    assert solved_all == ref["solved_all"]
+    want = sorted(ref["new_vars"], key=lambda v: v[0])
+    assert [int(b) for b in res.colBlock[:res.nCols]] == [v[0] for v in want]
+    for k, (b, ind, rc, oc) in enumerate(want):
+        assert list(res.column(k)) == list(ind) and res.colRedCost[k] == rc
+
+
 # ------------------------------------------------------------------ sparse upload of the duals
 
 

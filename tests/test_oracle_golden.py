@@ -208,3 +208,32 @@ def test_mckp_blocks_against_enumeration(oracle):
             assert len(res.col_ind[b]) == len(gl) and all(k in gl[i] for i, k in enumerate(res.col_ind[b]))
             assert sum(w[k] for k in res.col_ind[b]) <= cap[b]
             assert abs(res.col_red_cost[b] + alpha[b] - best) <= 1e-9
+
+
+def test_round_robin_branch_restatement(oracle):
+    """price_round_which (DecompAlgo.cpp:4929-5149 + the filter loop): listing every block with the standard
+    duals is the plain round; an empty list falls back to it; a user vector only changes its own block."""
+    from dip_b200 import instances as I
+    model = I.gap_pricing_model(I.gap_class_d(5, 30, seed=2), branch_rows=False)
+    u = I.gap_duals(model, np.random.default_rng(4))
+    args = (model.R, model.N, model.row_start, model.col_ind, model.val, model.objective)
+    blk = (model.n_base_rows, model.m, model.block_col_start, model.weight, model.capacity)
+    plain = oracle.price_round(*args, u, *blk)
+    kept = [b for b in range(model.m) if plain.col_keep[b]]
+    assert kept
+    everything = oracle.price_round_which(*args, u, *blk, list(range(model.m)))
+    assert not everything["solved_all"] and [v[0] for v in everything["new_vars"]] == kept
+    assert everything["most_neg_reduced_cost"] == plain.most_neg_reduced_cost
+    nothing = oracle.price_round_which(*args, u, *blk, [])
+    assert nothing["solved_all"] and [v[0] for v in nothing["new_vars"]] == kept
+    assert nothing["most_neg_reduced_cost"] == plain.most_neg_reduced_cost
+    b = kept[0]
+    uh = u.copy()
+    uh[model.n_base_rows + b] -= 0.5                       # alpha lower by 0.5 -> that block's rc higher by 0.5
+    one = oracle.price_round_which(*args, u, *blk, [b], {b: uh})
+    if not one["solved_all"]:
+        assert len(one["new_vars"]) == 1 and one["new_vars"][0][0] == b
+        assert abs(one["new_vars"][0][2] - (plain.col_red_cost[b] + 0.5)) <= 1e-9
+        assert one["most_neg_reduced_cost"] == one["new_vars"][0][2]
+    reorder = oracle.price_round_which(*args, u, *blk, kept[::-1])
+    assert [v[0] for v in reorder["new_vars"]] == kept[::-1]   # the reference's push order = list order
