@@ -1138,25 +1138,28 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                     // few items (the usual case after the reduction): ONE lane walks, without the ballot /
                     // shuffle round trip per taken item.  A single warp pays every dependent instruction at
                     // full latency, so the step is kept short: the cell's three decision words are fetched
-                    // together, the items at or below i are isolated with two shifts, one select picks the
-                    // highest set bit.
+                    // together and masked to the items at or below i, selects pick the highest set bit
+                    // (~155 cycles per taken item, two dependent shared-memory loads of ~33 among them;
+                    // GAP-E: 47 taken items per block, 3.8 us).
                     if (lane == 0) {
                         const uint32_t *b0 = sBits, *b1 = sBits + RC, *b2 = sBits + 2 * RC;
                         const bool has1 = kGlobal > 32, has2 = kGlobal > 64;
-                        while (i >= 0) {
-                            uint32_t v0 = b0[j], v1 = has1 ? b1[j] : 0u, v2 = has2 ? b2[j] : 0u;
-                            // keep the bits of items <= i: a 96-bit mask built from the shift count 95 - i
-                            const int sh = 95 - i;  // 0..95
-                            if (sh >= 64) { v2 = 0u; v1 = 0u; v0 &= 0xffffffffu >> (sh - 64); }
-                            else if (sh >= 32) { v2 = 0u; v1 &= 0xffffffffu >> (sh - 32); }
-                            else { v2 &= 0xffffffffu >> sh; }
-                            const int item = v2 ? 95 - __clz(v2) : v1 ? 63 - __clz(v1) : v0 ? 31 - __clz(v0) : -1;
+                        // the three masks depend on i only, which is known one shared-memory load before j is:
+                        // they are formed in the shadow of the weight fetch, without a branch
+                        auto low = [](int n) { return (uint32_t)((1ull << max(0, min(32, n))) - 1ull); };  // n low bits
+                        uint32_t m0 = low(i + 1), m1 = low(i - 31), m2 = low(i - 63);
+                        while (i >= 0) {  // (left by the break below)
+                            const uint32_t v0 = b0[j] & m0, v1 = (has1 ? b1[j] : 0u) & m1, v2 = (has2 ? b2[j] : 0u) & m2;
+                            const int i0 = 31 - __clz(v0), i1 = 63 - __clz(v1), i2 = 95 - __clz(v2);
+                            const int item = v2 ? i2 : v1 ? i1 : v0 ? i0 : -1;
                             if (item < 0) break;
+                            j -= itW[item];
+                            m0 = low(item);
+                            m1 = low(item - 32);
+                            m2 = low(item - 64);
                             sTaken[cnt] = itC[item];
                             if (smemSums) sTakenIdx[cnt] = item;
                             ++cnt;
-                            j -= itW[item];
-                            i = item - 1;
                         }
                     }
                     cnt = __shfl_sync(0xffffffffu, cnt, 0);
