@@ -23,7 +23,8 @@ for k, u in enumerate(duals):
 ptrs = [u_pin.array[k].ctypes.data for k in range(len(duals))]
 res = RoundResult(model.m, model.m, model.N)
 ref = None
-for val in (0, 1, 0, 1):
+vals = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 1, 0, 1]
+for val in vals:
     with GpuPricer(0) as pr:
         pr.setModel(model)
         pr.setDualSupport(model.dual_support)
