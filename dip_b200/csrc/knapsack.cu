@@ -1142,14 +1142,15 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                     // (~155 cycles per taken item, two dependent shared-memory loads of ~33 among them;
                     // GAP-E: 47 taken items per block, 3.8 us).
                     if (lane == 0) {
-                        const uint32_t *b0 = sBits, *b1 = sBits + RC, *b2 = sBits + 2 * RC;
-                        const bool has1 = kGlobal > 32, has2 = kGlobal > 64;
+                        // words 1 and 2 are read unconditionally (three independent loads, no branch in the step);
+                        // where they do not exist the pointer falls back to word 0 and the mask is zero anyway
+                        const uint32_t *b0 = sBits, *b1 = kGlobal > 32 ? sBits + RC : sBits, *b2 = kGlobal > 64 ? sBits + 2 * RC : sBits;
                         // the three masks depend on i only, which is known one shared-memory load before j is:
                         // they are formed in the shadow of the weight fetch, without a branch
                         auto low = [](int n) { return (uint32_t)((1ull << max(0, min(32, n))) - 1ull); };  // n low bits
                         uint32_t m0 = low(i + 1), m1 = low(i - 31), m2 = low(i - 63);
                         while (i >= 0) {  // (left by the break below)
-                            const uint32_t v0 = b0[j] & m0, v1 = (has1 ? b1[j] : 0u) & m1, v2 = (has2 ? b2[j] : 0u) & m2;
+                            const uint32_t v0 = b0[j] & m0, v1 = b1[j] & m1, v2 = b2[j] & m2;
                             const int i0 = 31 - __clz(v0), i1 = 63 - __clz(v1), i2 = 95 - __clz(v2);
                             const int item = v2 ? i2 : v1 ? i1 : v0 ? i0 : -1;
                             if (item < 0) break;
