@@ -416,7 +416,11 @@ int dipgpu_get_dp_geometry(const dipgpu_ctx *ctx, int32_t out[7]);
  * "spmv_lanes" (0 = TMA stream kernel), "spmv_chunk" / "spmv_max_cols" (entry / column budget of
  * a warp tile; re-tiles the matrix), "spmv_stages", "spmv_warps", "spmv_u_smem", "fuse_filter" (-1 auto, 0 = three kernels,
  * 1 = filter in the backtrack tail, 2 = backtrack + filter in the DP tail); 0 restores the automatic
- * choice of the dp_* knobs.  Unknown names return
+ * choice of the dp_* knobs.  Transfers of the synchronous host entry points, both on by default:
+ * "result_zero_copy" (the fused kernel stores the packed result into mapped pinned host memory itself instead
+ * of a device-to-host copy after it; 2 = also from the *_dev entry points, diagnostics), "gather_pinned_duals"
+ * (with a dual support and `u` in page-locked or managed memory -- e.g. from dipgpu_host_alloc -- the device
+ * picks u[support] out of the caller's buffer; a pageable `u` is gathered on the host).  Unknown names return
  * DIPGPU_ERR_INVALID. */
 int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value);
 
