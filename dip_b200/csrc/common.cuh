@@ -341,6 +341,7 @@ int launchMckp(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_
 int launchFilter(Ctx *c, double redCostEps, cudaStream_t st);
 // expand.cu -- master columns of the kept variables (the step after the round)
 int launchExpandColumns(Ctx *c, double tolZero, int nKept, cudaStream_t st);
+constexpr int kPoolPad = 512;  // entries allocated past the pool's capacity (aligned 512-entry windows are streamed whole)
 // pool.cu -- waiting-column pool re-pricing (DecompVarPool::setReducedCosts) and Wentges smoothing
 int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st);
 int launchScatterDuals(Ctx *c, int n, const int32_t *dIdx, const double *dVals, int64_t valStride, bool gather, double *dDst,

@@ -545,8 +545,9 @@ static int poolReserve(Ctx *c, int64_t cols, int64_t nnz)
     if (nnz > c->poolNnzCap) {
         const int64_t cap = std::max<int64_t>(nnz, std::max<int64_t>(65536, 2 * c->poolNnzCap));
         int32_t *nr = nullptr; double *nv = nullptr;
-        if ((rc = devAlloc(c, &nr, (size_t)cap))) return rc;
-        if ((rc = devAlloc(c, &nv, (size_t)cap))) return rc;
+        // (+ kPoolPad: the re-pricing kernel streams whole aligned 512-entry windows of the two arrays)
+        if ((rc = devAlloc(c, &nr, (size_t)cap + kPoolPad))) return rc;
+        if ((rc = devAlloc(c, &nv, (size_t)cap + kPoolPad))) return rc;
         if (c->poolNnz > 0) {
             DIPGPU_CUDA(c, cudaMemcpy(nr, c->dPoolRow, sizeof(int32_t) * (size_t)c->poolNnz, cudaMemcpyDeviceToDevice));
             DIPGPU_CUDA(c, cudaMemcpy(nv, c->dPoolVal, sizeof(double) * (size_t)c->poolNnz, cudaMemcpyDeviceToDevice));
@@ -1122,7 +1123,7 @@ int dipgpu_set_dual_support(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx)
     int rc;
     if ((rc = devAlloc(c, &c->dSupport, (size_t)std::max(nIdx, 1)))) return rc;
     if (nIdx > 0) DIPGPU_CUDA(c, cudaMemcpy(c->dSupport, idx, sizeof(int32_t) * (size_t)nIdx, cudaMemcpyHostToDevice));
-    std::vector<uint32_t> bits((size_t)(uLen + 31) / 32 + 1, 0u);
+    std::vector<uint32_t> bits(((size_t)(uLen + 31) / 32 + 4) & ~(size_t)3, 0u);  // whole 16-byte pieces (pool kernel)
     for (int k = 0; k < nIdx; ++k) bits[(size_t)idx[k] >> 5] |= 1u << (idx[k] & 31);
     if ((rc = devAlloc(c, &c->dSupportBits, bits.size()))) return rc;
     DIPGPU_CUDA(c, cudaMemcpy(c->dSupportBits, bits.data(), sizeof(uint32_t) * bits.size(), cudaMemcpyHostToDevice));
@@ -1369,8 +1370,8 @@ int dipgpu_pool_keep(dipgpu_ctx *ctx, int32_t nKeep, const int32_t *keepIdx)
     }
     int rc;
     int32_t *nr = nullptr; double *nv = nullptr;
-    if ((rc = devAlloc(c, &nr, (size_t)std::max<int64_t>(c->poolNnzCap, 1)))) return rc;
-    if ((rc = devAlloc(c, &nv, (size_t)std::max<int64_t>(c->poolNnzCap, 1)))) { cudaFree(nr); return rc; }
+    if ((rc = devAlloc(c, &nr, (size_t)std::max<int64_t>(c->poolNnzCap, 1) + kPoolPad))) return rc;
+    if ((rc = devAlloc(c, &nv, (size_t)std::max<int64_t>(c->poolNnzCap, 1) + kPoolPad))) { cudaFree(nr); return rc; }
     if ((rc = poolCopyColumns(c, desc, nullptr, c->dPoolRow, c->dPoolVal, nr, nv))) { cudaFree(nr); cudaFree(nv); return rc; }
     devFree(&c->dPoolRow); devFree(&c->dPoolVal);
     c->dPoolRow = nr; c->dPoolVal = nv;

@@ -17,23 +17,28 @@
 
 namespace dipgpu {
 
-constexpr int kPoolWarps = 8;
-constexpr int kPoolWarpsBitmap = 16;  // CTA width of the variant that keeps the dual-support bitmap in shared memory
-constexpr int kPoolChunk = 512;       // products staged per warp and pass (4 KiB)
+constexpr int kPoolWarpsMax = 16;
+constexpr int kPoolChunk = 512;   // entries per window: 4 KiB of values + 2 KiB of rows (256 / 32 warps: 66 us, 1024 / 8 warps: 88 us, this: 55 us)
+constexpr int kPoolStages = 2;    // windows in flight per warp
+static_assert(kPoolChunk <= kPoolPad, "the pool arrays are padded by one window");
+constexpr int kPoolPerLane = kPoolChunk / 32;
 
-// One warp per 32 consecutive waiting columns.  Their stored entries are one contiguous span of
-// the pool; the warp walks it from the END in chunks: all lanes form the products val*u[row]
-// (coalesced loads, unfused multiply) into shared memory, then lane l adds the products of ITS
-// column, last entry first -- the order of CoinPackedVectorBase::dotProduct as the oracle restates
-// it (dp = 0; for i = n-1..0: dp += els[i]*u[ind[i]]), so the values are bit-equal to the oracle.
+// One warp per 32 consecutive waiting columns.  Their stored entries are one contiguous span
+// [B, E) of the pool.  The warp walks the aligned 512-entry windows that intersect the span from
+// the END, two windows in flight: cp.async streams a window's rows and values into the warp's
+// shared-memory ring (16-byte pieces, nothing held in registers while the bytes travel), all lanes
+// then turn the values into products val*u[row] in place (unfused multiply), and lane l adds the
+// products of ITS column, last entry first -- the order of CoinPackedVectorBase::dotProduct as the
+// oracle restates it (dp = 0; for i = n-1..0: dp += els[i]*u[ind[i]]), so the values are bit-equal
+// to the oracle.
 //
 // BITMAP: a dual support is declared (dipgpu_set_dual_support) and its bitmap (one bit per master row)
 // fits shared memory.  Most entries of a master column sit in rows that cannot carry a dual (GAP: the
 // free branch rows, 2/3 of every column): the gather of the dual -- one 32-byte sector per 8 useful
-// bytes, what bounds this pass -- is skipped for them, a shared-memory bit test decides.  The product
-// is still formed (val * 0), so the result is the same bit for bit.
+// bytes -- is skipped for them, a shared-memory bit test decides.  The product is still formed
+// (val * 0), so the result is the same bit for bit.
 template <bool BITMAP>
-__global__ void __launch_bounds__(kPoolWarpsBitmap * 32)
+__global__ void __launch_bounds__(kPoolWarpsMax * 32, 1)
 pool_redcost_kernel(long long nCols, const int64_t *__restrict__ colStart, const int32_t *__restrict__ row,
                     const double *__restrict__ val, const double *__restrict__ origCost,
                     const double *__restrict__ u, int feasible, double *__restrict__ out, int32_t *flag,
@@ -41,19 +46,26 @@ pool_redcost_kernel(long long nCols, const int64_t *__restrict__ colStart, const
 {
     extern __shared__ __align__(16) unsigned char poolSm[];
     const int warpsPerCta = blockDim.x >> 5;
-    double *sPall = reinterpret_cast<double *>(poolSm);
-    const uint32_t *sBits = reinterpret_cast<const uint32_t *>(sPall + (size_t)warpsPerCta * kPoolChunk);
+    constexpr int kStageBytes = kPoolChunk * 12;  // values, then rows
+    const uint32_t *sBits = reinterpret_cast<const uint32_t *>(poolSm + (size_t)warpsPerCta * kPoolStages * kStageBytes);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (BITMAP) {
-        uint32_t *w = const_cast<uint32_t *>(sBits);
-        for (int k = threadIdx.x; k < bitWords; k += blockDim.x) w[k] = __ldg(supportBits + k);
-        __syncthreads();
+        // the bitmap travels as its own cp.async group (16-byte pieces; the array is padded to a multiple of 16
+        // bytes), behind it the warp's first windows: nobody waits for the 32 KiB before the stream has started
+        const uint32_t dstB = (uint32_t)__cvta_generic_to_shared(const_cast<uint32_t *>(sBits));
+        for (int k = threadIdx.x * 4; k < bitWords; k += blockDim.x * 4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstB + 4u * k), "l"(supportBits + k) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     const long long c0 = ((long long)blockIdx.x * warpsPerCta + warp) * 32;
-    if (c0 >= nCols) return;
+    const bool active = c0 < nCols;
     const long long col = c0 + lane;
     const long long cEnd = min(nCols, c0 + 32);
-    const int64_t B = colStart[c0], E = colStart[cEnd];
+    int64_t B = 0, E = 0;
+    if (active) {
+        B = colStart[c0];
+        E = colStart[cEnd];
+    }
     int64_t b = 0, e = 0;
     double oc = 0.0;
     if (col < nCols) {
@@ -62,47 +74,94 @@ pool_redcost_kernel(long long nCols, const int64_t *__restrict__ colStart, const
         oc = origCost[col];
     }
     double sum = 0.0;
-    double *p = sPall + (size_t)warp * kPoolChunk;
-    for (int64_t hi = E; hi > B;) {
-        const int64_t lo = max(B, hi - kPoolChunk);
-        // batches of 8 independent (row, value) loads, then their 8 dependent gathers of the dual: the
-        // round trips overlap instead of serialising (a warp issues in order)
-        for (int64_t base = lo + lane; base < hi; base += 256) {
-            int r[8];
-            double v[8], g[8];
+    unsigned char *ring = poolSm + (size_t)warp * kPoolStages * kStageBytes;
+    const uint32_t ringA = (uint32_t)__cvta_generic_to_shared(ring);
+    const int64_t kLast = E > B ? (E - 1) / kPoolChunk : -1, kFirst = E > B ? B / kPoolChunk : 0;  // no entries: no window
+    // window k -> ring slot, 16-byte pieces
+    auto issue = [&](int64_t k, int slot) {
+        const uint32_t dst = ringA + (uint32_t)slot * kStageBytes;
+        const char *sv = reinterpret_cast<const char *>(val + k * kPoolChunk);
+        const char *sr = reinterpret_cast<const char *>(row + k * kPoolChunk);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int64_t k = base + 32 * j;
-                r[j] = k < hi ? __ldg(row + k) : 0;
-                v[j] = k < hi ? __ldg(val + k) : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                bool on = base + 32 * j < hi;
-                if (BITMAP) on = on && ((sBits[r[j] >> 5] >> (r[j] & 31)) & 1u);
-                g[j] = on ? __ldg(u + r[j]) : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (base + 32 * j < hi) p[base + 32 * j - lo] = __dmul_rn(v[j], g[j]);
+        for (int j = 0; j < kPoolChunk / 64; ++j) {
+            const int off = (lane + 32 * j) * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(sv + off) : "memory");
         }
-        __syncwarp();
-        const int64_t kHi = min(hi, e), kLo = max(lo, b);
-        if (kHi > kLo) {
-            // the next product is fetched while the current one is added (one load ahead of the DADD chain)
-            int q = (int)(kHi - 1 - lo);
-            const int qLo = (int)(kLo - lo);
-            double cur = p[q];
-            while (q > qLo) {
-                const double nxt = p[q - 1];
-                sum = __dadd_rn(sum, cur);
-                cur = nxt;
-                --q;
-            }
-            sum = __dadd_rn(sum, cur);
+#pragma unroll
+        for (int j = 0; j < kPoolChunk / 128; ++j) {
+            const int off = (lane + 32 * j) * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + kPoolChunk * 8 + off), "l"(sr + off) : "memory");
         }
-        __syncwarp();
-        hi = lo;
+    };
+    int64_t kIssue = kLast;
+#pragma unroll
+    for (int s = 0; s < kPoolStages; ++s) {
+        if (kIssue >= kFirst) issue(kIssue--, s);
+        asm volatile("cp.async.commit_group;" ::: "memory");  // (possibly empty: the group count stays uniform)
+    }
+    if (BITMAP) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kPoolStages) : "memory");  // this thread's pieces of the bitmap
+        __syncthreads();                                                       // ... and everybody else's
+    }
+    if (!active) return;
+    {
+        int slot = 0;
+        for (int64_t k = kLast; k >= kFirst; --k) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(kPoolStages - 1) : "memory");
+            __syncwarp();
+            double *p = reinterpret_cast<double *>(ring + (size_t)slot * kStageBytes);
+            const int32_t *rw = reinterpret_cast<const int32_t *>(p + kPoolChunk);
+            const int64_t w0 = k * kPoolChunk;
+            const int lo = (int)(max(B, w0) - w0), hi = (int)(min(E, w0 + kPoolChunk) - w0);  // this warp's part of the window
+            // the lane's entries of the window at once: the rows, then their (few) dependent gathers of the dual
+            // -- all in flight together, one round trip per window --, then the products in place
+            {
+                double g[kPoolPerLane];
+#pragma unroll
+                for (int j = 0; j < kPoolPerLane; ++j) {
+                    const int i = lane + 32 * j;
+                    bool on = i >= lo && i < hi;
+                    int r = 0;
+                    if (on) {
+                        r = rw[i];
+                        if (BITMAP) on = (sBits[r >> 5] >> (r & 31)) & 1u;
+                    }
+                    g[j] = on ? __ldg(u + r) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < kPoolPerLane; ++j) {
+                    const int i = lane + 32 * j;
+                    if (i >= lo && i < hi) p[i] = __dmul_rn(p[i], g[j]);
+                }
+            }
+            __syncwarp();
+            const int64_t kHi = min(w0 + hi, e), kLo = max(w0 + lo, b);
+            if (kHi > kLo) {
+                // four products are fetched while the previous four are added: the chain of dependent additions
+                // (one lane, last entry first) never waits for shared memory
+                int q = (int)(kHi - 1 - w0);
+                const int qLo = (int)(kLo - w0);
+                if (q - 3 >= qLo) {
+                    double a0 = p[q], a1 = p[q - 1], a2 = p[q - 2], a3 = p[q - 3];
+                    q -= 4;
+                    while (q - 3 >= qLo) {
+                        const double n0 = p[q], n1 = p[q - 1], n2 = p[q - 2], n3 = p[q - 3];
+                        sum = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(sum, a0), a1), a2), a3);
+                        a0 = n0;
+                        a1 = n1;
+                        a2 = n2;
+                        a3 = n3;
+                        q -= 4;
+                    }
+                    sum = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(sum, a0), a1), a2), a3);
+                }
+                for (; q >= qLo; --q) sum = __dadd_rn(sum, p[q]);
+            }
+            __syncwarp();
+            if (kIssue >= kFirst) issue(kIssue--, slot);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            slot = slot + 1 == kPoolStages ? 0 : slot + 1;
+        }
     }
     if (col < nCols) {
         const double rc = feasible ? oc - sum : -sum;  // DecompVarPool.cpp:29 / :36
@@ -120,8 +179,12 @@ int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st)
     const int bitWords = (c->R + c->numConvex + 31) / 32;
     const bool bitmap = c->dSupportBits != nullptr && !c->hSupport.empty() && bitWords * 4 <= 64 * 1024 &&
                         c->poolCols >= 32 * 1024 && (int64_t)c->hSupport.size() * 4 <= (int64_t)c->R + c->numConvex;
-    const int wpc = bitmap ? kPoolWarpsBitmap : kPoolWarps;
-    const size_t smem = sizeof(double) * (size_t)wpc * kPoolChunk + (bitmap ? sizeof(uint32_t) * (size_t)bitWords : 0);
+    const size_t perWarp = (size_t)kPoolStages * kPoolChunk * 12, bits = bitmap ? sizeof(uint32_t) * (((size_t)bitWords + 3) & ~(size_t)3) : 0;
+    // one CTA per SM, as many warps as the ring buffers leave room for (12 KiB each); small pools: fewer warps per
+    // CTA so that the columns spread over the SMs
+    int wpc = (int)std::min<size_t>(kPoolWarpsMax, (227 * 1024 - bits) / perWarp);
+    while (wpc > 2 && (warps + wpc - 1) / wpc < c->smCount) wpc /= 2;
+    const size_t smem = perWarp * (size_t)wpc + bits;
     const unsigned grid = (unsigned)((warps + wpc - 1) / wpc);
     auto fn = bitmap ? pool_redcost_kernel<true> : pool_redcost_kernel<false>;
     if (c->poolFnSmem[bitmap ? 1 : 0] < smem) {
