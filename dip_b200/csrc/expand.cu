@@ -24,7 +24,7 @@
 
 namespace dipgpu {
 
-constexpr int kExpThreads = 256;
+constexpr int kExpThreads = 512;   // (256: 22.5 us, 512: 18.1 us, 1024: 19 us per GAP-E round, cold L2)
 
 struct ExpandArgs {
     // last round's packed result (device)
@@ -53,6 +53,7 @@ struct ExpandArgs {
     unsigned long long *pubWord;  // per column: epoch (8) | length (56)
     unsigned int epoch;
     int rowWords;   // ceil(R/32)
+    int rowWordsPhys;  // with the skew: rowWords + rowWords/32 + 1
     int colWords;   // ceil(maxBlockCols/32)
     int capStage;   // staged rows per column
 };
@@ -91,9 +92,12 @@ __device__ __forceinline__ int blockExclusiveScan(int v, int *sWarp, int *total)
 __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __grid_constant__ ExpandArgs a)
 {
     extern __shared__ __align__(16) unsigned char smRaw[];
-    uint32_t *rowBits = reinterpret_cast<uint32_t *>(smRaw);            // rowWords
-    uint32_t *colBits = rowBits + a.rowWords;                            // colWords
-    int32_t *sRows = reinterpret_cast<int32_t *>(colBits + a.colWords);  // capStage: touched core rows
+    // the row bitmap is stored skewed, word w at w + w/32: a thread scans a contiguous run of words (step 2), and
+    // 32 such runs side by side would otherwise sit in one shared-memory bank
+    uint32_t *rowBits = reinterpret_cast<uint32_t *>(smRaw);            // rowWordsPhys
+    uint32_t *colBits = rowBits + a.rowWordsPhys;                        // colWords
+#define RB(w) rowBits[(w) + ((w) >> 5)]
+    int32_t *sRows = reinterpret_cast<int32_t *>(rowBits + ((a.rowWordsPhys + a.colWords + 3) & ~3));  // capStage: touched core rows
     double *sVals = reinterpret_cast<double *>(sRows + ((a.capStage + 1) & ~1));  // capStage
     __shared__ int sWarp[kExpThreads / 32];
     __shared__ unsigned long long sHashW[kExpThreads / 32];
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __gri
     const uint16_t *row16 = static_cast<const uint16_t *>(a.rowMaster);
     const int32_t *row32 = static_cast<const int32_t *>(a.rowMaster);
 
-    for (int w = t; w < a.rowWords + a.colWords; w += kExpThreads) rowBits[w] = 0u;  // both bitmaps
+    for (int w = t; w < a.rowWordsPhys + a.colWords; w += kExpThreads) rowBits[w] = 0u;  // both bitmaps
     if (t == 0) sOverflow = 0;
     __syncthreads();
 
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __gri
         for (int e = a.colStart32[j]; e < a.colStart32[j + 1]; ++e) {
             const int rm = a.row16 ? (int)row16[e] : row32[e];
             const int i = rm < a.nBaseRows ? rm : rm - a.numConvex;  // master index -> core row
-            atomicOr(&rowBits[i >> 5], 1u << (i & 31));
+            atomicOr(&RB(i >> 5), 1u << (i & 31));
         }
     }
 #pragma unroll
@@ -135,29 +139,69 @@ __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __gri
     const int wpt = (a.rowWords + kExpThreads - 1) / kExpThreads;
     const int w0 = min(a.rowWords, t * wpt), w1 = min(a.rowWords, w0 + wpt);
     int cnt = 0;
-    for (int w = w0; w < w1; ++w) cnt += __popc(rowBits[w]);
+    for (int w = w0; w < w1; ++w) cnt += __popc(RB(w));
     int nTouched;
     int pos = blockExclusiveScan(cnt, sWarp, &nTouched);
     if (nTouched > a.capStage) {
         if (t == 0) sOverflow = 1;
     } else {
         for (int w = w0; w < w1; ++w)
-            for (uint32_t bits = rowBits[w]; bits; bits &= bits - 1) sRows[pos++] = (w << 5) + (__ffs(bits) - 1);
+            for (uint32_t bits = RB(w); bits; bits &= bits - 1) sRows[pos++] = (w << 5) + (__ffs(bits) - 1);
     }
     __syncthreads();
     const bool overflow = sOverflow != 0;
 
-    // ---- 3. one thread per touched row: the row's dot product with s, in storage order
+    // ---- 3. the touched rows' dot products with s, in storage order.  Short rows (GAP: the branch rows, one or
+    // two entries) take one thread each; a long row (an assignment row: one entry per block) takes a warp --
+    // 32 membership tests at a time, the member values added in entry order -- instead of one thread walking
+    // it alone while the others wait.
+    constexpr int kShortRow = 8;
     if (!overflow) {
+        auto member = [&](int e) -> bool {
+            const int jl = a.csrColInd[e] - cs;
+            return jl >= 0 && (jl >> 5) < a.colWords && ((colBits[jl >> 5] >> (jl & 31)) & 1u);
+        };
         for (int p = t; p < nTouched; p += kExpThreads) {
             const int i = sRows[p];
+            const int e0 = a.csrRowStart[i], e1 = a.csrRowStart[i + 1];
+            if (e1 - e0 > kShortRow) continue;
             double y = 0.0;
-            for (int e = a.csrRowStart[i]; e < a.csrRowStart[i + 1]; ++e) {
-                const int jl = a.csrColInd[e] - cs;
-                if (jl >= 0 && (jl >> 5) < a.colWords && ((colBits[jl >> 5] >> (jl & 31)) & 1u))
-                    y = __dadd_rn(y, a.csrVal[e]);  // val * 1.0
-            }
+            for (int e = e0; e < e1; ++e)
+                if (member(e)) y = __dadd_rn(y, a.csrVal[e]);  // val * 1.0
             sVals[p] = y;
+        }
+        for (int p = warp; p < nTouched; p += kExpThreads / 32) {
+            const int i = sRows[p];
+            const int e0 = a.csrRowStart[i], e1 = a.csrRowStart[i + 1];
+            if (e1 - e0 <= kShortRow) continue;
+            double y = 0.0;
+            // 128 entries per pass: the four column-index loads of a lane are independent (one round trip), the
+            // member values follow (a second one), then the ballots in entry order
+            for (int eb = e0; eb < e1; eb += 128) {
+                int jl[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = eb + 32 * q + lane;
+                    jl[q] = e < e1 ? a.csrColInd[e] - cs : -1;
+                }
+                bool mem[4];
+                double v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    mem[q] = jl[q] >= 0 && (jl[q] >> 5) < a.colWords && ((colBits[jl[q] >> 5] >> (jl[q] & 31)) & 1u);
+                    v[q] = mem[q] ? a.csrVal[eb + 32 * q + lane] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    unsigned m = __ballot_sync(0xffffffffu, mem[q]);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        y = __dadd_rn(y, __shfl_sync(0xffffffffu, v[q], src));
+                    }
+                }
+            }
+            if (lane == 0) sVals[p] = y;
         }
     }
     __syncthreads();
@@ -267,10 +311,11 @@ int launchExpandColumns(Ctx *c, double tolZero, int nKept, cudaStream_t st)
     a.pubWord = c->dExpPub;
     a.epoch = ++c->expEpoch;
     a.rowWords = (c->R + 31) / 32;
+    a.rowWordsPhys = a.rowWords + a.rowWords / 32 + 1;
     a.colWords = (c->maxBlockCols + 31) / 32;
     // shared memory: two bitmaps + staged (row, value) pairs
     const size_t maxSmem = 227 * 1024 - 1024;
-    const size_t bitmapBytes = sizeof(uint32_t) * ((size_t)a.rowWords + (size_t)a.colWords);
+    const size_t bitmapBytes = sizeof(uint32_t) * (((size_t)a.rowWordsPhys + (size_t)a.colWords + 3) & ~(size_t)3);
     if (bitmapBytes + 4096 > maxSmem)
         return fail(c, DIPGPU_ERR_UNSUPPORTED, "expand_columns: %d core rows do not fit the row bitmap", c->R);
     int cap = (int)((maxSmem - bitmapBytes) / 12) & ~1;
