@@ -242,6 +242,7 @@ struct Ctx {
     bool wantMirror = false;      // the caller of enqueueSolve will read the result on the host right after
     bool resultMirrored = false;  // the last fused launch wrote hResult itself
     bool optZeroCopy = true;
+    size_t lastMColsBytes = 0;    // bytes of packed master columns the last expansion produced (sizes the next speculative D2H copy)
     bool optMirrorAlways = false;
     bool optGatherPinned = true;  // sparse dual upload: read u[support] out of the caller's buffer when it is device-mapped
     size_t resultBytes = 0;

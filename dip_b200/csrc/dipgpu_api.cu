@@ -1466,7 +1466,8 @@ int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
     cudaStream_t st = c->stream;
     if ((rc = launchExpandColumns(c, tolZero, nKept, st))) return rc;
     // D2H: header + starts + fingerprints + a first slab of entries, the rest only if needed
-    const size_t spec = std::min(bytes, offEntries + (size_t)131072);
+    // (sized by what the previous expansion needed plus a quarter: rounds of one node keep similar columns)
+    const size_t spec = std::min(bytes, std::max(offEntries + (size_t)65536, ResultLayout::alignUp(c->lastMColsBytes + c->lastMColsBytes / 4, 256)));
     DIPGPU_CUDA(c, cudaMemcpyAsync(c->hMCols, c->dMCols, spec, cudaMemcpyDeviceToHost, st));
     DIPGPU_CUDA(c, cudaStreamSynchronize(st));
     c->d2h += (int64_t)spec;
@@ -1476,6 +1477,7 @@ int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
     if (mh->flags & 1u) return fail(c, DIPGPU_ERR_UNSUPPORTED, "expand_columns: a column touches more rows than the shared-memory staging area holds");
     if (mh->flags & 2u) return fail(c, DIPGPU_ERR_NOMEM, "expand_columns: device output capacity exceeded");
     const size_t need = offEntries + sizeof(MColEntry) * (size_t)mh->nNnz;
+    c->lastMColsBytes = need;
     if (need > spec) {
         DIPGPU_CUDA(c, cudaMemcpyAsync(static_cast<char *>(c->hMCols) + spec, static_cast<char *>(c->dMCols) + spec,
                                        need - spec, cudaMemcpyDeviceToHost, st));
