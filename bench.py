@@ -634,8 +634,23 @@ def bench_expand(pr, model, duals, ptrs, res, flush_l2, torch, rank):
         assert rc == 0, rc
         if k >= 3:
             t_gpu += dt
+    # the round and its expansion in one submission (dipgpu_price_round_expand), same clock
+    t_fused = 0.0
+    for k in range(reps + 3):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rc = lib.dipgpu_price_round_expand(pr._ctx, ptrs[k % N_DUALS], model.u_len, capi.PHASE_PRICE2, RC_EPS, 1e-6,
+                                           C.byref(res.c), C.byref(mc))
+        dt = time.perf_counter() - t0
+        assert rc == 0, rc
+        if k >= 3:
+            t_fused += dt
     out = {"gpu_ms_per_round": 1e3 * t_gpu / reps, "columns": int(mc.nCols), "master_nnz": int(mc.nNnz),
-           "timing": "host wall clock around dipgpu_expand_columns (kernel + D2H), L2 flushed"}
+           "timing": "host wall clock around dipgpu_expand_columns (kernel + D2H), L2 flushed",
+           "round_plus_expand_fused_ms": 1e3 * t_fused / reps,
+           "round_plus_expand_note": "dipgpu_price_round_expand: round and expansion in one submission, one wait; compare "
+                                     "with e2e.ms_per_step + gpu_ms_per_round for the two separate calls"}
     if rank == 0:
         from oracle import dip_oracle as orc
         cols = [res.column(k).copy() for k in range(res.nCols)]

@@ -38,7 +38,7 @@ SYMBOLS = [
     "dipgpu_price_round_stab", "dipgpu_price_round_stab_ladder", "dipgpu_get_smoothed_duals",
     "dipgpu_pool_clear", "dipgpu_pool_size", "dipgpu_pool_append", "dipgpu_pool_append_expanded",
     "dipgpu_pool_keep", "dipgpu_pool_set_reduced_costs", "dipgpu_set_col_bounds", "dipgpu_set_dual_support", "dipgpu_set_mckp_blocks",
-    "dipgpu_price_round_which",
+    "dipgpu_price_round_which", "dipgpu_price_round_expand",
 ]
 
 
@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         "dipgpu_set_option": ([vp, C.c_char_p, i64], C.c_int),
         "dipgpu_price_rounds_batch": ([vp, i32, vp, i32, i32, dbl, C.POINTER(Cols)], C.c_int),
         "dipgpu_select_batch_result": ([vp, i32], C.c_int),
+        "dipgpu_price_round_expand": ([vp, vp, i32, i32, dbl, dbl, C.POINTER(Cols), C.POINTER(MCols)], C.c_int),
         "dipgpu_price_round_which": ([vp, vp, i32, i32, dbl, i32, vp, vp, C.POINTER(Cols), C.POINTER(C.c_int32)], C.c_int),
         "dipgpu_stab_set_center": ([vp, vp, i32], C.c_int),
         "dipgpu_stab_accept": ([vp, i32], C.c_int),

@@ -1418,21 +1418,11 @@ int dipgpu_pool_set_reduced_costs(dipgpu_ctx *ctx, const double *u, int32_t uLen
     return DIPGPU_OK;
 }
 
-int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
+// Buffers and per-model constants of the expansion (allocated on first use, kept while the layout stays).
+static int prepareExpand(Ctx *c)
 {
-    CTX_OR_FAIL(ctx);
-    if (!out) return fail(c, DIPGPU_ERR_INVALID, "expand_columns: NULL output");
     if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "expand_columns needs set_core_csr and set_knapsack_blocks");
-    if (!c->lastRoundOnHost) return fail(c, DIPGPU_ERR_STATE, "expand_columns: no host-buffer pricing round since the model was set");
     if (!c->dCsrRowStart || !c->dColStart32) return fail(c, DIPGPU_ERR_UNSUPPORTED, "expand_columns: more than 2^31 stored entries");
-    const ResultHeader *rh = static_cast<const ResultHeader *>(c->hResult);
-    const int nKept = rh->nKept;
-    out->nCols = nKept;
-    out->nNnz = 0;
-    if (nKept == 0) {
-        if (out->colStart && out->capCols >= 0) out->colStart[0] = 0;
-        return DIPGPU_OK;
-    }
     int rc;
     // packed output buffer: worst case one entry per stored entry of A'' plus one per column
     const int64_t capEntries = c->nnz + c->m + 16;
@@ -1455,6 +1445,7 @@ int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
         c->mcolsOffHash = offHash;
         c->mcolsOffEntries = offEntries;
         c->mcolsCapEntries = capEntries;
+        c->lastMColsBytes = 0;
     }
     // a column of block b touches at most as many rows as block b's x-columns have stored entries
     int64_t maxBlockNnz = 1;
@@ -1463,20 +1454,27 @@ int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
         if (s1 <= c->N) maxBlockNnz = std::max<int64_t>(maxBlockNnz, c->hColStart[s1] - c->hColStart[s0]);
     }
     c->expMaxTouched = (int)std::min<int64_t>(maxBlockNnz, c->R);
-    cudaStream_t st = c->stream;
-    if ((rc = launchExpandColumns(c, tolZero, nKept, st))) return rc;
-    // D2H: header + starts + fingerprints + a first slab of entries, the rest only if needed
-    // (sized by what the previous expansion needed plus a quarter: rounds of one node keep similar columns)
-    const size_t spec = std::min(bytes, std::max(offEntries + (size_t)65536, ResultLayout::alignUp(c->lastMColsBytes + c->lastMColsBytes / 4, 256)));
-    DIPGPU_CUDA(c, cudaMemcpyAsync(c->hMCols, c->dMCols, spec, cudaMemcpyDeviceToHost, st));
-    DIPGPU_CUDA(c, cudaStreamSynchronize(st));
-    c->d2h += (int64_t)spec;
+    return DIPGPU_OK;
+}
+
+// speculative size of the D2H copy of the packed master columns: header + starts + fingerprints + a first slab
+// of entries sized by what the previous expansion needed plus a quarter (rounds of one node keep similar columns)
+static size_t expandSpecBytes(const Ctx *c)
+{
+    return std::min(c->mcolsBytes, std::max(c->mcolsOffEntries + (size_t)65536,
+                                            ResultLayout::alignUp(c->lastMColsBytes + c->lastMColsBytes / 4, 256)));
+}
+
+// The first `spec` bytes of the packed master columns are on the host (stream synchronised): checks, the rest of
+// the entries if the speculative copy was short, decoding into the caller's arrays.
+static int finishExpand(Ctx *c, int nKept, size_t spec, dipgpu_mcols *out, cudaStream_t st)
+{
     const char *hp = static_cast<const char *>(c->hMCols);
     const MColsHeader *mh = reinterpret_cast<const MColsHeader *>(hp);
     if (mh->magic != kMColsMagic || mh->nCols != nKept) return fail(c, DIPGPU_ERR_CUDA, "expand_columns: bad result header");
     if (mh->flags & 1u) return fail(c, DIPGPU_ERR_UNSUPPORTED, "expand_columns: a column touches more rows than the shared-memory staging area holds");
     if (mh->flags & 2u) return fail(c, DIPGPU_ERR_NOMEM, "expand_columns: device output capacity exceeded");
-    const size_t need = offEntries + sizeof(MColEntry) * (size_t)mh->nNnz;
+    const size_t need = c->mcolsOffEntries + sizeof(MColEntry) * (size_t)mh->nNnz;
     c->lastMColsBytes = need;
     if (need > spec) {
         DIPGPU_CUDA(c, cudaMemcpyAsync(static_cast<char *>(c->hMCols) + spec, static_cast<char *>(c->dMCols) + spec,
@@ -1484,12 +1482,13 @@ int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
         DIPGPU_CUDA(c, cudaStreamSynchronize(st));
         c->d2h += (int64_t)(need - spec);
     }
+    out->nCols = nKept;
     out->nNnz = mh->nNnz;
     if (nKept > out->capCols || mh->nNnz > out->capNnz)
         return fail(c, DIPGPU_ERR_OVERFLOW, "expand_columns needs capCols >= %d, capNnz >= %lld", nKept, (long long)mh->nNnz);
-    const int64_t *cs = reinterpret_cast<const int64_t *>(hp + offColStart);
-    const uint64_t *hs = reinterpret_cast<const uint64_t *>(hp + offHash);
-    const MColEntry *en = reinterpret_cast<const MColEntry *>(hp + offEntries);
+    const int64_t *cs = reinterpret_cast<const int64_t *>(hp + c->mcolsOffColStart);
+    const uint64_t *hs = reinterpret_cast<const uint64_t *>(hp + c->mcolsOffHash);
+    const MColEntry *en = reinterpret_cast<const MColEntry *>(hp + c->mcolsOffEntries);
     if (out->colStart) memcpy(out->colStart, cs, sizeof(int64_t) * ((size_t)nKept + 1));
     if (out->hash) memcpy(out->hash, hs, sizeof(uint64_t) * (size_t)nKept);
     for (int64_t q = 0; q < mh->nNnz; ++q) {
@@ -1497,6 +1496,73 @@ int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
         if (out->val) out->val[q] = en[q].val;
     }
     return DIPGPU_OK;
+}
+
+int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
+{
+    CTX_OR_FAIL(ctx);
+    if (!out) return fail(c, DIPGPU_ERR_INVALID, "expand_columns: NULL output");
+    if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "expand_columns needs set_core_csr and set_knapsack_blocks");
+    if (!c->lastRoundOnHost) return fail(c, DIPGPU_ERR_STATE, "expand_columns: no host-buffer pricing round since the model was set");
+    const ResultHeader *rh = static_cast<const ResultHeader *>(c->hResult);
+    const int nKept = rh->nKept;
+    out->nCols = nKept;
+    out->nNnz = 0;
+    if (nKept == 0) {
+        if (out->colStart && out->capCols >= 0) out->colStart[0] = 0;
+        return DIPGPU_OK;
+    }
+    int rc;
+    if ((rc = prepareExpand(c))) return rc;
+    cudaStream_t st = c->stream;
+    if ((rc = launchExpandColumns(c, tolZero, nKept, st))) return rc;
+    const size_t spec = expandSpecBytes(c);
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->hMCols, c->dMCols, spec, cudaMemcpyDeviceToHost, st));
+    DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+    c->d2h += (int64_t)spec;
+    return finishExpand(c, nKept, spec, out, st);
+}
+
+// generateVars + the per-variable work of addVarsToPool in ONE submission: the expansion kernel is enqueued
+// right behind the round (one CTA per block; the CTAs beyond the number of kept columns leave at once), the
+// packed master columns follow in the same stream, and the host waits once.
+int dipgpu_price_round_expand(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase, double redCostEps,
+                              double tolZero, dipgpu_cols *out, dipgpu_mcols *mout)
+{
+    CTX_OR_FAIL(ctx);
+    if (!out || !mout) return fail(c, DIPGPU_ERR_INVALID, "price_round_expand: NULL output");
+    int rc;
+    if ((rc = checkRoundReady(c, "price_round_expand", uLen, phase))) return rc;
+    if (!u && !c->dualsResident) return fail(c, DIPGPU_ERR_STATE, "price_round_expand: u == NULL but no dual vector is resident");
+    if ((rc = ensureDualBuffer(c, uLen))) return rc;
+    if ((rc = prepareExpand(c))) return rc;
+    cudaStream_t st = c->stream;
+    if (u) {
+        if ((rc = uploadDuals(c, u, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
+        c->dualsResident = true;
+    }
+    if ((rc = launchRedCost(c, c->dU, phase, st))) return rc;
+    c->wantMirror = true;
+    rc = enqueueSolve(c, c->dRedCost, c->dU + c->nBaseRows, redCostEps, st, false);
+    c->wantMirror = false;
+    if (rc) return rc;
+    size_t spec = 0;
+    if (c->nLocal > 0) {
+        if ((rc = launchExpandColumns(c, tolZero, c->nLocal, st))) return rc;
+        spec = expandSpecBytes(c);
+        DIPGPU_CUDA(c, cudaMemcpyAsync(c->hMCols, c->dMCols, spec, cudaMemcpyDeviceToHost, st));
+        c->d2h += (int64_t)spec;
+    }
+    if ((rc = fetchResult(c, st))) return rc;  // (synchronises the stream: the master columns are on the host too)
+    c->lastRoundOnHost = true;
+    if ((rc = unpack(c, c->hResult, c->resultBytes, out))) return rc;
+    mout->nCols = out->nCols;
+    mout->nNnz = 0;
+    if (c->nLocal == 0) {
+        if (mout->colStart && mout->capCols >= 0) mout->colStart[0] = 0;
+        return DIPGPU_OK;
+    }
+    return finishExpand(c, out->nCols, spec, mout, st);
 }
 
 int dipgpu_price_round_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, int32_t phase, double redCostEps, void *stream)

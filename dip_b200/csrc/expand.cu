@@ -106,7 +106,16 @@ __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __gri
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int k = blockIdx.x;
     const int nKept = a.hdr->nKept;
-    if (k >= nKept) return;
+    if (k >= nKept) {
+        // (launched with one CTA per block behind a round whose outcome the host does not know yet)
+        if (nKept == 0 && k == 0 && t == 0) {
+            a.outColStart[0] = 0;
+            a.outHdr->magic = kMColsMagic;
+            a.outHdr->nCols = 0;
+            a.outHdr->nNnz = 0;
+        }
+        return;
+    }
     const int lb = a.keptBlock[k];
     const int b = a.firstBlock + lb;
     const int cs = a.blockColStart[b];

@@ -437,6 +437,34 @@ class GpuPricer:
             n = mc.nCols
             return col_start[:n + 1], row_ind[:mc.nNnz], val[:mc.nNnz], hsh[:n]
 
+    def priceRoundExpand(self, u, phase=PHASE_PRICE2, redCostEps=1e-4, tolZero=1e-6, result=None, cap_nnz=1 << 16):
+        """priceRound + expandColumns in one submission (dipgpu_price_round_expand): returns
+        (RoundResult, (colStart, rowInd, val, hash))."""
+        u = np.ascontiguousarray(u, np.float64)
+        res = result if result is not None else RoundResult(self.m, self.m, max(self.nBlockCols, 1))
+        cap_cols = max(self.m, 1)
+        first = True
+        while True:
+            col_start = np.zeros(cap_cols + 1, np.int64)
+            row_ind = np.zeros(cap_nnz, np.int32)
+            val = np.zeros(cap_nnz, np.float64)
+            hsh = np.zeros(cap_cols, np.uint64)
+            mc = capi.MCols()
+            mc.capCols, mc.capNnz = cap_cols, cap_nnz
+            mc.colStart, mc.rowInd, mc.val, mc.hash = (capi.ptr(col_start), capi.ptr(row_ind), capi.ptr(val),
+                                                       capi.ptr(hsh))
+            if first:
+                rc = self._lib.dipgpu_price_round_expand(self._ctx, capi.ptr(u), len(u), phase, float(redCostEps),
+                                                         float(tolZero), C.byref(res.c), C.byref(mc))
+            else:        # only the output arrays were too small: the round itself is done
+                rc = self._lib.dipgpu_expand_columns(self._ctx, float(tolZero), C.byref(mc))
+            if rc == capi.ERR_OVERFLOW and mc.nNnz > cap_nnz:
+                cap_nnz, first = int(mc.nNnz), False
+                continue
+            self._check(rc)
+            n = mc.nCols
+            return res, (col_start[:n + 1], row_ind[:mc.nNnz], val[:mc.nNnz], hsh[:n])
+
     # ---- the reference's two plugin surfaces ---------------------------------
     def generateVars(self, u, phase=PHASE_PRICE2, redCostEps=1e-4):
         """DecompAlgo::generateVars(newVars, mostNegReducedCost): returns (newVars, mostNegRC)."""

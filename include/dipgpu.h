@@ -352,6 +352,16 @@ typedef struct dipgpu_mcols {
 
 int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out);
 
+/*
+ * dipgpu_price_round followed by dipgpu_expand_columns in ONE submission: what DecompAlgo::processNode does
+ * back to back in a price call -- generateVars (Dip/src/DecompAlgo.cpp:1914 -> :4622-5260), then
+ * addVarsToPool on its result (:1936 -> :5408-5675).  The expansion kernel is enqueued right behind the
+ * round, the packed master columns behind it, and the host waits once; `out` and `mout` are filled exactly
+ * as the two separate calls fill them.  u == NULL: the resident dual vector (see dipgpu_price_round).
+ */
+int dipgpu_price_round_expand(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase, double redCostEps,
+                              double tolZero, dipgpu_cols *out, dipgpu_mcols *mout);
+
 /* ---------------------------------------- device-resident variants (multi-GPU)
  *
  * For the block-sharded multi-GPU driver: the dual vector is already in device

@@ -249,6 +249,44 @@ public:
         val.resize((size_t)mc.nNnz);
     }
 
+    // generateVars and the expansion of its columns in one GPU submission (dipgpu_price_round_expand): what a
+    // price call of DecompAlgo::processNode does back to back (DecompAlgo.cpp:1914, :1936).
+    template <class VarT = DecompVar, class ListT = std::list<VarT *>>
+    int generateVarsExpanded(const double *u, int uLen, int phase, double redCostEps, double tolZero, ListT &newVars,
+                             double &mostNegReducedCost, std::vector<int64_t> &colStart, std::vector<int32_t> &rowInd,
+                             std::vector<double> &val, std::vector<uint64_t> &hash)
+    {
+        dipgpu_mcols mc;
+        std::memset(&mc, 0, sizeof(mc));
+        colStart.assign((size_t)m_m + 1, 0);
+        hash.assign((size_t)m_m, 0);
+        if (rowInd.size() < 1024) rowInd.resize(1024);
+        if (val.size() < rowInd.size()) val.resize(rowInd.size());
+        mc.capCols = m_m;
+        mc.capNnz = (int64_t)rowInd.size();
+        mc.colStart = colStart.data();
+        mc.rowInd = rowInd.data();
+        mc.val = val.data();
+        mc.hash = hash.data();
+        const int rc = dipgpu_price_round_expand(m_ctx, u, uLen, phase, redCostEps, tolZero, &m_cols, &mc);
+        if (rc == DIPGPU_ERR_OVERFLOW && mc.nNnz > (int64_t)rowInd.size()) {
+            // the round is done, only the caller's arrays were short: fetch the columns again
+            rowInd.resize((size_t)mc.nNnz);
+            val.resize((size_t)mc.nNnz);
+            expandColumns(tolZero, colStart, rowInd, val, hash);
+        } else {
+            check(rc);
+            colStart.resize((size_t)mc.nCols + 1);
+            hash.resize((size_t)mc.nCols);
+            rowInd.resize((size_t)mc.nNnz);
+            val.resize((size_t)mc.nNnz);
+        }
+        mostNegReducedCost = m_cols.mostNegReducedCost;
+        for (int k = 0; k < m_cols.nCols; ++k) newVars.push_back(makeVar<VarT>(k, m_colRedCost[k]));
+        m_roundValid = false;
+        return m_cols.nCols;
+    }
+
     // ---- dual stabilisation: DecompAlgoPC::adjustMasterDualSolution + generateVars -------------
     // (Dip/src/DecompAlgoPC.cpp:126-212; DecompAlgoPC.h:99-133).  The stability centre m_dual lives on
     // the device: setDualCentre <-> "Init dual to dualRM" / DecompApp::initDualVector (:163-177),

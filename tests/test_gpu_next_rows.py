@@ -343,6 +343,36 @@ def test_node_bounds_unsupported_in_pisinger_mode(pricer):
     assert e.value.code == ERR_UNSUPPORTED
 
 
+# ------------------------------------------------------------------ round + expansion in one submission
+
+
+def test_price_round_expand_equals_the_two_calls(oracle, pricer):
+    """dipgpu_price_round_expand == dipgpu_price_round followed by dipgpu_expand_columns, field by field --
+    rounds that keep every block, some blocks, and none (the expansion kernel is launched before the host
+    knows how many columns the round kept)."""
+    model = I.gap_pricing_model(I.gap_class_d(6, 40, seed=5), branch_rows=True)
+    pricer.setModel(model)
+    u = I.gap_duals(model, np.random.default_rng(21))
+    for eps, tiny_cap in ((1e-4, False), (-np.inf, False), (np.inf, False), (1e-4, True)):
+        two = pricer.priceRound(u, redCostEps=eps, result=RoundResult(model.m, model.m, model.N))
+        cs2, ri2, va2, hs2 = pricer.expandColumns()
+        one, (cs1, ri1, va1, hs1) = pricer.priceRoundExpand(u, redCostEps=eps, cap_nnz=4 if tiny_cap else 1 << 16)
+        _same_round(one, two)
+        np.testing.assert_array_equal(cs1, cs2)
+        np.testing.assert_array_equal(ri1, ri2)
+        np.testing.assert_array_equal(va1, va2)
+        np.testing.assert_array_equal(hs1, hs2)
+        if eps == np.inf:
+            assert one.nCols == 0 and len(ri1) == 0 and list(cs1) == [0]
+    # against the oracle's restatement of addVarsToPool, column by column
+    one, (cs1, ri1, va1, hs1) = pricer.priceRoundExpand(u)
+    for k in range(one.nCols):
+        rows, vals = oracle.expand_column(model.R, model.N, model.row_start, model.col_ind, model.val, model.n_base_rows,
+                                          model.m, one.column(k), int(one.colBlock[k]))
+        np.testing.assert_array_equal(ri1[cs1[k]:cs1[k + 1]], rows)
+        np.testing.assert_array_equal(va1[cs1[k]:cs1[k + 1]], vals)
+
+
 # ------------------------------------------------------------------ a10: block subsets, per-block user duals
 
 
