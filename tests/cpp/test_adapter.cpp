@@ -108,6 +108,23 @@ int main()
             for (int q = 0; q < nn; ++q) CHECK(ri[cs[k] + q] == oRow[q] && va[cs[k] + q] == oVal[q]);
             ++k;
         }
+        // ... and both steps in one submission: the same variables, the same master columns
+        std::vector<int64_t> cs1;
+        std::vector<int32_t> ri1(8);     // too short on purpose: the adapter fetches the columns again
+        std::vector<double> va1;
+        std::vector<uint64_t> hs1;
+        dipgpu::DecompVarList vars1;
+        double mn1 = 1.0;
+        const int n1 = pricer->generateVarsExpanded(u.data(), (int)u.size(), dipgpu::PHASE_PRICE2, 1e-4, 1e-6, vars1, mn1,
+                                                    cs1, ri1, va1, hs1);
+        CHECK(n1 == kept && mn1 == mostNegRef);
+        CHECK(cs1 == cs && ri1 == ri && va1 == va && hs1 == hs);
+        auto it = newVars.begin();
+        for (dipgpu::DecompVar *v : vars1) {
+            CHECK(v->getBlockId() == (*it)->getBlockId() && v->ind == (*it)->ind && v->getReducedCost() == (*it)->getReducedCost());
+            ++it;
+            delete v;
+        }
     }
     for (dipgpu::DecompVar *v : newVars) {
         const int b = v->getBlockId();
