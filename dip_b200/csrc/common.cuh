@@ -257,7 +257,7 @@ struct Ctx {
     size_t rcStride = 0;         // doubles between reduced-cost vectors (even, >= N + 16)
     size_t resStride = 0;        // bytes between packed results (multiple of 16, >= resultBytes)
     double *dUBatch = nullptr, *dRedCostBatch = nullptr;
-    void *dResultBatch = nullptr, *hResultBatch = nullptr;
+    void *dResultBatch = nullptr, *hResultBatch = nullptr, *dResultBatchHost = nullptr;  // (device address of the mapped host mirror)
     unsigned long long *dPubWordBatch = nullptr;
     unsigned int epochBatch = 0;
     int32_t *dScaleB = nullptr, *dShortcutB = nullptr, *dSelB = nullptr;

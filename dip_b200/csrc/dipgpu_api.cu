@@ -339,7 +339,7 @@ static void freeBatch(Ctx *c)
     devFree(&c->dScaleB); devFree(&c->dShortcutB); devFree(&c->dSelB); devFree(&c->dZShortB); devFree(&c->dAlphaLadder);
     if (c->dResultBatch) cudaFree(c->dResultBatch);
     if (c->hResultBatch) cudaFreeHost(c->hResultBatch);
-    c->dResultBatch = c->hResultBatch = nullptr;
+    c->dResultBatch = c->hResultBatch = c->dResultBatchHost = nullptr;
     c->batchCap = 0;
     c->haveST = false;
 }
@@ -370,7 +370,9 @@ static int ensureBatch(Ctx *c, int nVec)
     if ((rc = devAlloc(c, &c->dAlphaLadder, V))) return rc;
     DIPGPU_CUDA(c, cudaMalloc(&c->dResultBatch, V * resStride));
     DIPGPU_CUDA(c, cudaMemset(c->dResultBatch, 0, V * resStride));
-    DIPGPU_CUDA(c, cudaMallocHost(&c->hResultBatch, V * resStride));
+    DIPGPU_CUDA(c, cudaHostAlloc(&c->hResultBatch, V * resStride, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(c->hResultBatch, 0, V * resStride);
+    DIPGPU_CUDA(c, cudaHostGetDevicePointer(&c->dResultBatchHost, c->hResultBatch, 0));
     c->batchCap = nVec;
     c->dUBatchClean = true;  // freshly zeroed
     c->uStride = uStride;
@@ -385,12 +387,15 @@ static int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st
 {
     int rc;
     const bool timed = c->stageTiming;
+    c->resultMirrored = false;
     if (timed) cudaEventRecord(c->ev[1], st);
     if (c->geom.fuse || c->nLocal == 0) {
         if ((rc = launchRedCostBatch(c, c->dUBatch, (int64_t)c->uStride, c->dRedCostBatch, (int64_t)c->rcStride, nVec, phase, st))) return rc;
         if (timed) cudaEventRecord(c->ev[2], st);
         if ((rc = launchKnapsackPrepBatch(c, c->dRedCostBatch, (int64_t)c->rcStride, nVec, st))) return rc;
+        c->wantMirror = true;  // every caller reads the results on the host right after
         rc = launchKnapsackDpBatch(c, c->dRedCostBatch, (int64_t)c->rcStride, c->dUBatch + c->nBaseRows, (int64_t)c->uStride, eps, nVec, st);
+        c->wantMirror = false;
         if (timed) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
         return rc;
     }
@@ -409,6 +414,18 @@ static int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st
 // result that kept more indices).
 static int fetchBatchPacked(Ctx *c, int nVec, cudaStream_t st)
 {
+    if (c->resultMirrored) {
+        // the fused kernel stored every vector's result into hResultBatch itself (mapped pinned memory)
+        if (c->stageTiming) cudaEventRecord(c->ev[6], st);
+        DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+        collectStageMs(c);
+        for (int v = 0; v < nVec; ++v) {
+            const ResultHeader *h = reinterpret_cast<const ResultHeader *>(static_cast<char *>(c->hResultBatch) + (size_t)v * c->resStride);
+            if (h->magic != kResultMagic) return fail(c, DIPGPU_ERR_CUDA, "batched round: result %d has no header", v);
+            c->d2h += (int64_t)(c->layout.offInd + sizeof(int32_t) * (size_t)h->nInd);
+        }
+        return DIPGPU_OK;
+    }
     const size_t spec = std::min(c->resultBytes, c->layout.offInd + (size_t)65536);
     DIPGPU_CUDA(c, cudaMemcpy2DAsync(c->hResultBatch, c->resStride, c->dResultBatch, c->resStride, spec, (size_t)nVec, cudaMemcpyDeviceToHost, st));
     if (c->stageTiming) cudaEventRecord(c->ev[6], st);

@@ -1662,8 +1662,12 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     }
     a.filt.fuseCopy = c->nLocal <= kFuseFilterMaxBlocks ? 2 : 1;
     // host mirror of the packed result (the synchronous host entry points ask for it; option "result_zero_copy")
-    a.hostOff = (!batch && g.fuse && (c->wantMirror || c->optMirrorAlways) && c->optZeroCopy && c->dResultHost)
-                    ? (long long)(static_cast<char *>(c->dResultHost) - static_cast<char *>(c->dResult)) : 0;
+    a.hostOff = 0;
+    if (g.fuse && (c->wantMirror || c->optMirrorAlways) && c->optZeroCopy) {
+        if (!batch && c->dResultHost) a.hostOff = (long long)(static_cast<char *>(c->dResultHost) - static_cast<char *>(c->dResult));
+        if (batch && c->dResultBatchHost)  // same per-vector stride on both sides
+            a.hostOff = (long long)(static_cast<char *>(c->dResultBatchHost) - static_cast<char *>(c->dResultBatch));
+    }
     c->resultMirrored = a.hostOff != 0;
     {
         int rc = prepareKnapsackDp(c);
