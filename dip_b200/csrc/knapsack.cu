@@ -710,9 +710,16 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             const int per = (len + T - 1) / T;
             const int c0 = min(len, t * per), c1 = min(len, c0 + per);
             int mineCnt = 0, mineRef = 0;
+            // (runs of up to 32 columns: the taken columns are remembered as a bit mask, so that the write pass
+            // below visits only them instead of testing the whole run again)
+            unsigned tkMask = 0u;
+            const bool useMask = per <= 32;
+#pragma unroll 4
             for (int cl = c0; cl < c1; ++cl) {
                 mineRef += ((prune && pass == 0) ? meta[cl] != 0xffff : isItem(cl)) ? 1 : 0;
-                mineCnt += takes(cl) ? 1 : 0;
+                const bool tk = takes(cl);
+                mineCnt += tk ? 1 : 0;
+                tkMask |= (tk && useMask ? 1u : 0u) << ((cl - c0) & 31);
             }
             // warp-inclusive scan, then the warps' totals (low half: taken items, high half: all items)
             int incl = mineCnt | (mineRef << 16);
@@ -742,21 +749,25 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             // tail does not wait for two dependent global gathers
             smemSums = prune && pass == 0 && a.back.fix == nullptr;
             int pos = off + (incl & 0xffff) - mineCnt;
-            for (int cl = c0; cl < c1; ++cl) {
-                if (takes(cl)) {  // w > cap can never be taken (:161)
-                    itP[pos] = profitOf(cl);
-                    itW[pos] = rawW[shiftW + cl];
-                    itC[pos] = cl;
-                    if (smemSums) {
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(itP + kSumsRcOff + pos)),
-                                     "l"(redCostV + colStart + cl)
-                                     : "memory");
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(itP + kSumsObjOff + pos)),
-                                     "l"(a.back.obj + colStart + cl)
-                                     : "memory");
-                    }
-                    ++pos;
+            auto place = [&](int cl) {  // w > cap can never be taken (:161)
+                itP[pos] = profitOf(cl);
+                itW[pos] = rawW[shiftW + cl];
+                itC[pos] = cl;
+                if (smemSums) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(itP + kSumsRcOff + pos)),
+                                 "l"(redCostV + colStart + cl)
+                                 : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(itP + kSumsObjOff + pos)),
+                                 "l"(a.back.obj + colStart + cl)
+                                 : "memory");
                 }
+                ++pos;
+            };
+            if (useMask) {
+                for (unsigned mk = tkMask; mk; mk &= mk - 1) place(c0 + __ffs(mk) - 1);  // ascending
+            } else {
+                for (int cl = c0; cl < c1; ++cl)
+                    if (takes(cl)) place(cl);
             }
             if (smemSums) asm volatile("cp.async.commit_group;" ::: "memory");
         } else {
