@@ -373,6 +373,36 @@ def test_price_round_expand_equals_the_two_calls(oracle, pricer):
         np.testing.assert_array_equal(va1[cs1[k]:cs1[k + 1]], vals)
 
 
+def test_price_round_expand_in_pisinger_mode_and_on_a_shard(oracle, pricer):
+    """The one-submission call where the DP is not the fused fp64 kernel's default path: scaled-integer profits,
+    and a context restricted to a block range (a multi-GPU shard)."""
+    model = I.gap_pricing_model(I.gap_class_d(6, 40, seed=9), branch_rows=True)
+    pricer.setModel(model, profit_mode=PROFIT_PISINGER_INT)
+    u = I.gap_duals(model, np.random.default_rng(33))
+    two = pricer.priceRound(u, result=RoundResult(model.m, model.m, model.N))
+    cs2, ri2, va2, hs2 = pricer.expandColumns()
+    one, (cs1, ri1, va1, hs1) = pricer.priceRoundExpand(u)
+    _same_round(one, two)
+    for x, y in ((cs1, cs2), (ri1, ri2), (va1, va2), (hs1, hs2)):
+        np.testing.assert_array_equal(x, y)
+    pricer.setModel(model)
+    pricer.setBlockRange(2, 3)
+    two = pricer.priceRound(u, result=RoundResult(model.m, model.m, model.N))
+    cs2, ri2, va2, hs2 = pricer.expandColumns()
+    one, (cs1, ri1, va1, hs1) = pricer.priceRoundExpand(u)
+    _same_round(one, two)
+    assert all(2 <= int(b) < 5 for b in one.colBlock[:one.nCols])
+    for x, y in ((cs1, cs2), (ri1, ri2), (va1, va2), (hs1, hs2)):
+        np.testing.assert_array_equal(x, y)
+    # a block list on the shard: only blocks of the range are accepted
+    from dip_b200.capi import DipGpuError, ERR_INVALID
+    res, _ = pricer.priceRoundWhich(u, [4, 2])
+    assert all(int(b) in (2, 4) for b in res.colBlock[:res.nCols])
+    with pytest.raises(DipGpuError) as e:
+        pricer.priceRoundWhich(u, [1])
+    assert e.value.code == ERR_INVALID
+
+
 # ------------------------------------------------------------------ a10: block subsets, per-block user duals
 
 
