@@ -18,10 +18,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libdipgpu.so")
-SOURCES = ["dipgpu_api.cu", "redcost.cu", "knapsack.cu", "filter.cu", "microbench.cu", "pisinger.cu", "expand.cu", "pool.cu", "mckp.cu"]
+SOURCES = ["dipgpu_api.cu", "redcost.cu", "knapsack.cu", "filter.cu", "microbench.cu", "pisinger.cu", "expand.cu", "pool.cu", "mckp.cu", "multi.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "filter.cuh"), os.path.join(os.path.dirname(HERE), "include", "dipgpu.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+# -fmad=false: no fp contraction anywhere -- every product and sum is rounded on its own, as the reference's
+# C++ / Python arithmetic does it (e.g. floor(-rc*scale + 0.5) rounds the product first, GAP_KnapPisinger.h:174-175)
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
          "--expt-relaxed-constexpr"]
 
 

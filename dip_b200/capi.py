@@ -39,6 +39,8 @@ SYMBOLS = [
     "dipgpu_pool_clear", "dipgpu_pool_size", "dipgpu_pool_append", "dipgpu_pool_append_expanded",
     "dipgpu_pool_keep", "dipgpu_pool_set_reduced_costs", "dipgpu_set_col_bounds", "dipgpu_set_dual_support", "dipgpu_set_mckp_blocks",
     "dipgpu_price_round_which", "dipgpu_price_round_expand",
+    "dipgpu_create_multi", "dipgpu_device_count", "dipgpu_shard_ranges", "dipgpu_sync", "dipgpu_result_shards",
+    "dipgpu_unpack_results", "dipgpu_last_device_ms",
 ]
 
 
@@ -129,6 +131,13 @@ def lib() -> C.CDLL:
         "dipgpu_set_col_bounds": ([vp, vp, vp, i32], C.c_int),
         "dipgpu_set_dual_support": ([vp, i32, vp], C.c_int),
         "dipgpu_set_mckp_blocks": ([vp, i32, vp, vp, vp, vp], C.c_int),
+        "dipgpu_create_multi": ([C.POINTER(vp), vp, i32], C.c_int),
+        "dipgpu_device_count": ([vp, C.POINTER(i32), C.POINTER(i32)], C.c_int),
+        "dipgpu_shard_ranges": ([vp, i32, vp, vp], C.c_int),
+        "dipgpu_sync": ([vp], C.c_int),
+        "dipgpu_result_shards": ([vp, i32, C.POINTER(i32), vp, vp], C.c_int),
+        "dipgpu_unpack_results": ([vp, i32, vp, vp, C.POINTER(Cols)], C.c_int),
+        "dipgpu_last_device_ms": ([vp, i32, vp, C.POINTER(C.c_float)], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

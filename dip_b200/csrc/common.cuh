@@ -129,7 +129,12 @@ struct DpGeom {
 };
 
 // ---------------------------------------------------------------------- context
+struct Multi;  // multi.cu
+
 struct Ctx {
+    // non-NULL: this object is only the FRONT of a multi-device context (dipgpu_create_multi): it owns no device
+    // memory, every entry point is routed to the per-device contexts behind it (multi.cu)
+    Multi *multi = nullptr;
     int device = -1;
     int smCount = 0;
     cudaStream_t stream = nullptr;
@@ -150,6 +155,10 @@ struct Ctx {
     uint32_t *dTileRec = nullptr;   // nSpmvTiles x {byte offset / 16 into dSpmvBlob, bytes} (uint2)
     unsigned char *dSpmvBlob = nullptr;  // self-contained jagged tiles (SpmvTileHeader)
     int nSpmvTiles = 0;             // 0 = stream kernel not applicable
+    bool tilesDirty = false;        // the tiles are rebuilt by the next sweep (ensureSpmvTiles)
+    // columns the sweep covers: all of them, or (a block shard of a multi-device context) the shard's columns
+    bool shardCols = false;
+    int tileColFirst = 0, tileColEnd = -1;  // -1 = N
     int spmvStageBytes = 0;         // largest tile, bytes
     int32_t *dSpmvWarpStart = nullptr;  // launch warp -> first tile of its contiguous run (W + 1)
     int spmvMode = 0, spmvNst = 2, spmvWarps = 8, spmvGrid = 1, spmvUBytes = 0, optSpmvWindow = 0;  // launch shape (planSpmvLaunch)
@@ -170,13 +179,16 @@ struct Ctx {
     size_t mcolsBytes = 0, mcolsOffColStart = 0, mcolsOffHash = 0, mcolsOffEntries = 0;
     int64_t mcolsCapEntries = 0;
     unsigned long long *dExpPub = nullptr;
-    unsigned int expEpoch = 0;
     size_t expSmem = 0;
     std::vector<int64_t> hColStart;  // host copy of the CSC column starts
     int expMaxTouched = 0;           // bound on the rows one column can touch
     bool lastRoundOnHost = false;  // hResult holds the header of the last round
+    // every enqueued round (and every change of the "last round": dipgpu_select_batch_result) gets a serial;
+    // an expansion remembers the round it belongs to, so that stale master columns are never appended to the pool
+    uint64_t roundSerial = 0, expandSerial = ~0ull;
 
     double *dObj = nullptr;  // c[N]
+    size_t objLen = 0;       // entries of dObj
     bool haveObj = false;
 
     // blocks
@@ -223,7 +235,9 @@ struct Ctx {
     int firstBlock = 0, nLocal = 0;
     unsigned long long *dDbgTimes = nullptr;  // diagnostics (option dp_debug_times): 8 stamps per CTA
     unsigned long long *dPubWord = nullptr, *dPubCells = nullptr;  // fused DP kernel: per-block publication
-    unsigned int epoch = 0;                                          // launch counter of the fused DP kernel
+    unsigned long long *dTicket = nullptr;  // fused DP kernel: (launch epoch << 32) | CTAs started (KnapArgs::ticket)
+    unsigned long long *dExpTicket = nullptr;  // same for the expansion kernel
+    uint64_t fusedLaunches = 0;             // the publication words are cleared every 2^24 fused launches
     unsigned int *dDoneCounter = nullptr;  // ticket of the fused backtrack+filter kernel
     // -1 auto (2 when nLocal <= kFuseFilterMaxBlocks, else 0); 0 three kernels; 1 filter in the
     // backtrack kernel's tail; 2 backtrack + filter in the DP kernel's tail
@@ -244,6 +258,9 @@ struct Ctx {
     bool optZeroCopy = true;
     size_t lastMColsBytes = 0;    // bytes of packed master columns the last expansion produced (sizes the next speculative D2H copy)
     bool optMirrorAlways = false;
+    // non-NULL: the fused kernel mirrors the packed result THERE (device-visible: a peer device's gather buffer)
+    // instead of into hResult
+    void *mirrorBase = nullptr;
     bool optGatherPinned = true;  // sparse dual upload: read u[support] out of the caller's buffer when it is device-mapped
     size_t resultBytes = 0;
     size_t lastResultBytes = 0;  // bytes of the last packed result (sizes the next speculative D2H copy)
@@ -259,7 +276,6 @@ struct Ctx {
     double *dUBatch = nullptr, *dRedCostBatch = nullptr;
     void *dResultBatch = nullptr, *hResultBatch = nullptr, *dResultBatchHost = nullptr;  // (device address of the mapped host mirror)
     unsigned long long *dPubWordBatch = nullptr;
-    unsigned int epochBatch = 0;
     int32_t *dScaleB = nullptr, *dShortcutB = nullptr, *dSelB = nullptr;
     double *dZShortB = nullptr;
     double *dAlphaLadder = nullptr;  // smoothing parameters of a ladder (device)
@@ -294,6 +310,18 @@ struct Ctx {
     float stageMs[6] = {0, 0, 0, 0, 0, 0};
 };
 
+// Where a context takes the master dual vectors of a call from (feedDuals, dipgpu_api.cu).
+struct DualFeed {
+    const double *host = nullptr;    // the caller's host vectors, vector v at host + v*uLen (pageable or pinned)
+    const double *staged = nullptr;  // device-visible u[support], vector v at staged + v*stagedStride (needs a dual support)
+    int64_t stagedStride = 0;
+    const double *full = nullptr;    // device-visible whole vectors (mapped host memory, a peer device), v at full + v*fullStride
+    int64_t fullStride = 0;
+};
+int feedDuals(Ctx *c, const DualFeed &f, int32_t uLen, int nVec, double *dDst, size_t dstStride, bool *clean, cudaStream_t st);
+const double *deviceVisible(const double *u);
+void gatherSupport(const std::vector<int32_t> &support, const double *u, int32_t uLen, int nVec, double *dst);
+
 int fail(Ctx *c, int code, const char *fmt, ...);
 int cudaFail(Ctx *c, cudaError_t e, const char *what);
 
@@ -302,6 +330,47 @@ int cudaFail(Ctx *c, cudaError_t e, const char *what);
         cudaError_t e__ = (call);                                       \
         if (e__ != cudaSuccess) return ::dipgpu::cudaFail((c), e__, #call); \
     } while (0)
+
+// ------------------------------------------------ shared host-side pieces (dipgpu_api.cu)
+int bind(Ctx *c);
+int setBlockRange(Ctx *c, int first, int count);
+int checkRoundReady(Ctx *c, const char *who, int32_t uLen, int32_t phase);
+int ensureDualBuffer(Ctx *c, int32_t uLen);
+int ensureBatch(Ctx *c, int nVec);
+int enqueueRound(Ctx *c, const DualFeed *feed, int32_t uLen, int32_t phase, double eps, bool mirror, cudaStream_t st);
+int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st);
+int fetchResult(Ctx *c, cudaStream_t st);
+int fetchBatchPacked(Ctx *c, int nVec, cudaStream_t st);
+int fetchBatch(Ctx *c, int nVec, dipgpu_cols *outs, cudaStream_t st);
+void collectStageMs(Ctx *c);
+int unpack(Ctx *c, const void *packed, size_t bytes, dipgpu_cols *out);
+int batchCore(Ctx *c, int nVec, const DualFeed &f, int32_t uLen, int32_t phase, double eps, dipgpu_cols *outs);
+int ladderCore(Ctx *c, const DualFeed &f, int32_t uLen, const double *al, int nSteps, int32_t phase, double eps, dipgpu_cols *outs);
+
+// ------------------------------------------------ multi-device context (multi.cu)
+inline bool isMulti(const dipgpu_ctx *ctx) { return ctx && reinterpret_cast<const Ctx *>(ctx)->multi != nullptr; }
+dipgpu_ctx *multiPrimary(dipgpu_ctx *ctx);  // the primary device's whole-model context (serves what is not sharded)
+dipgpu_ctx *multiForward(dipgpu_ctx *ctx);  // same, and "the last round" now lives there
+int multiDestroy(dipgpu_ctx *ctx);
+// fn on the whole-model context of every device (and, alsoShards, on its block-shard context): the model calls
+int multiForAll(dipgpu_ctx *ctx, int (*fn)(dipgpu_ctx *sub, void *arg), void *arg, bool alsoShards, bool modelChanged);
+void multiClearSupport(dipgpu_ctx *ctx);
+int multiSolveBlocks(dipgpu_ctx *ctx, const double *redCostX, const double *alpha, double eps, dipgpu_cols *out);
+int multiEnqueueSolve(Ctx *c, double eps, cudaStream_t st, bool timed);  // dipgpu_api.cu: stages (b)+(c) on dRedCost / dAlpha, mirrored
+int multiSetBlocks(dipgpu_ctx *ctx);  // after the blocks are known everywhere: cut the block shards
+int multiSetDualSupport(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx);
+int multiPriceRound(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase, double eps, dipgpu_cols *out, double *redCostXOpt);
+int multiPriceRoundsBatch(dipgpu_ctx *ctx, int32_t nVec, const double *U, int32_t uLen, int32_t phase, double eps, dipgpu_cols *outs);
+int multiStabLadder(dipgpu_ctx *ctx, const double *uRM, int32_t uLen, const double *al, int nSteps, int32_t phase, double eps, dipgpu_cols *outs);
+int multiStabAccept(dipgpu_ctx *ctx, int32_t step);
+int multiGetSmoothedDuals(dipgpu_ctx *ctx, int32_t step, double *dualST, int32_t uLen);
+int multiSelectBatchResult(dipgpu_ctx *ctx, int32_t which);
+int multiCalcRedCost(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase, double *redCostX);
+int multiPriceRoundDev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, int32_t phase, double eps);
+int multiResultDev(dipgpu_ctx *ctx, void **devPtr, size_t *bytes);
+int multiGetCounters(const dipgpu_ctx *ctx, int64_t *launches, int64_t *h2d, int64_t *d2h);
+int multiLastStageMs(const dipgpu_ctx *ctx, float *ms6);
+int multiExpandColumns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out);
 
 // ------------------------------------------------ Pisinger-mode pre-processing
 struct PrepArgs {
@@ -325,6 +394,7 @@ int launchRedCostBatch(Ctx *c, const double *dU, int64_t uStride, double *dOut, 
                        cudaStream_t st);
 int buildSpmvTiles(Ctx *c, const std::vector<int64_t> &colStart, const std::vector<int32_t> &rowMaster,
                    const std::vector<double> &val);
+int ensureSpmvTiles(Ctx *c);  // dipgpu_api.cu
 // pisinger.cu -- scale factor + trivial cases of GAP_KnapPisinger::solve (profit mode 1 only)
 int launchKnapsackPrep(Ctx *c, const double *dRedCost, cudaStream_t st);
 int launchKnapsackPrepBatch(Ctx *c, const double *dRedCost, int64_t rcStride, int nVec, cudaStream_t st);

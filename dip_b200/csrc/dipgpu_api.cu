@@ -54,24 +54,24 @@ static void devFree(T **p)
 
 static void freeBatch(Ctx *c);
 
-static int bind(Ctx *c)
+int bind(Ctx *c)
 {
     DIPGPU_CUDA(c, cudaSetDevice(c->device));
     return DIPGPU_OK;
 }
 
-// Transpose the host CSR of A'' into the device CSC, folding the master-dual row
-// mapping (rows >= nBaseRows sit numConvex further down, DecompAlgo.cpp:4595-4597).
-static int uploadCore(Ctx *c)
+// Transpose the host CSR of A'' into CSC, folding the master-dual row mapping (rows >= nBaseRows sit
+// numConvex further down, DecompAlgo.cpp:4595-4597).
+void transposeCore(const Ctx *c, std::vector<int64_t> &colStart, std::vector<int32_t> &rowMaster, std::vector<double> &val)
 {
     const int R = c->R, N = c->N;
     const int64_t nnz = c->hRowStart[R];
-    std::vector<int64_t> colStart((size_t)N + 1, 0);
+    colStart.assign((size_t)N + 1, 0);
     for (int64_t k = 0; k < nnz; ++k) colStart[(size_t)c->hColInd[k] + 1]++;
     for (int j = 0; j < N; ++j) colStart[j + 1] += colStart[j];
     std::vector<int64_t> fill(colStart.begin(), colStart.end() - 1);
-    std::vector<int32_t> rowMaster((size_t)std::max<int64_t>(nnz, 1));
-    std::vector<double> val((size_t)std::max<int64_t>(nnz, 1));
+    rowMaster.resize((size_t)std::max<int64_t>(nnz, 1));
+    val.resize((size_t)std::max<int64_t>(nnz, 1));
     // rows descending: each column's entries are stored in the order the reference's scatter
     // adds them (CoinPackedMatrix::transposeTimes on a row-ordered matrix, rows R-1..0)
     for (int i = R - 1; i >= 0; --i) {
@@ -82,11 +82,35 @@ static int uploadCore(Ctx *c)
             val[dst] = c->hVal[k];
         }
     }
+}
+
+// The warp tiles of the stream kernel (redcost.cu) are built when a sweep first needs them: the model calls
+// (set_core_csr, set_objective, append_core_rows, a column range) each only mark them stale.
+int ensureSpmvTiles(Ctx *c)
+{
+    if (!c->tilesDirty) return DIPGPU_OK;
+    std::vector<int64_t> colStart;
+    std::vector<int32_t> rowMaster;
+    std::vector<double> val;
+    transposeCore(c, colStart, rowMaster, val);
+    const int rc = buildSpmvTiles(c, colStart, rowMaster, val);
+    if (rc == DIPGPU_OK) c->tilesDirty = false;
+    return rc;
+}
+
+static int uploadCore(Ctx *c)
+{
+    const int R = c->R, N = c->N;
+    const int64_t nnz = c->hRowStart[R];
+    std::vector<int64_t> colStart;
+    std::vector<int32_t> rowMaster;
+    std::vector<double> val;
+    transposeCore(c, colStart, rowMaster, val);
     c->nnz = nnz;
     c->hColStart = colStart;
     int rc;
-    // warp tiles of the stream kernel (redcost.cu)
-    if ((rc = buildSpmvTiles(c, colStart, rowMaster, val))) return rc;
+    c->tilesDirty = true;
+    c->nSpmvTiles = 0;
     devFree(&c->dColStart32);
     devFree(&c->dRowMaster16);
     if (nnz < (int64_t)1 << 31 && N > 0) {
@@ -126,16 +150,24 @@ static int uploadCore(Ctx *c)
     return DIPGPU_OK;
 }
 
+// The objective buffer covers at least n columns: zero-filled when no objective was set (phase 1 / solve_blocks
+// on reduced costs only), grown -- old entries kept, zeros behind them -- when the model gained columns without
+// a new set_objective.
 static int ensureObjective(Ctx *c, int n)
 {
-    if (c->dObj) return DIPGPU_OK;
+    if (c->dObj && c->objLen >= (size_t)n) return DIPGPU_OK;
+    double *nw = nullptr;
     int rc;
-    if ((rc = devAlloc(c, &c->dObj, (size_t)n + 16))) return rc;
-    DIPGPU_CUDA(c, cudaMemset(c->dObj, 0, sizeof(double) * ((size_t)n + 16)));
+    if ((rc = devAlloc(c, &nw, (size_t)n + 16))) return rc;
+    DIPGPU_CUDA(c, cudaMemset(nw, 0, sizeof(double) * ((size_t)n + 16)));
+    if (c->dObj && c->objLen > 0) DIPGPU_CUDA(c, cudaMemcpy(nw, c->dObj, sizeof(double) * c->objLen, cudaMemcpyDeviceToDevice));
+    devFree(&c->dObj);
+    c->dObj = nw;
+    c->objLen = (size_t)n;
     return DIPGPU_OK;
 }
 
-static int setBlockRange(Ctx *c, int first, int count)
+int setBlockRange(Ctx *c, int first, int count)
 {
     if (!c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "set_knapsack_blocks has not been called");
     if (first < 0 || count < 0 || first + count > c->m)
@@ -181,7 +213,6 @@ static int setBlockRange(Ctx *c, int first, int count)
     if ((rc = devAlloc(c, &c->dPubWord, (size_t)std::max(count, 1) * kPubWordStride))) return rc;
     if ((rc = devAlloc(c, &c->dPubCells, (size_t)count))) return rc;
     DIPGPU_CUDA(c, cudaMemset(c->dPubWord, 0, sizeof(unsigned long long) * std::max<size_t>((size_t)count, 1) * kPubWordStride));
-    c->epoch = 0;
     if ((rc = devAlloc(c, &c->dScale, (size_t)count))) return rc;
     if ((rc = devAlloc(c, &c->dShortcut, (size_t)count))) return rc;
     if ((rc = devAlloc(c, &c->dSel, 2 * (size_t)count))) return rc;
@@ -211,6 +242,8 @@ static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, do
 {
     int rc;
     c->resultMirrored = false;
+    ++c->roundSerial;
+    c->lastRoundOnHost = false;  // (the host entry points set it once the result has arrived)
     if (c->blockKind == 1) {
         // multiple-choice knapsack blocks: DP + backtrack (mckp.cu), then the stand-alone filter
         if ((rc = launchMckp(c, dRedCost, dAlpha, st))) return rc;
@@ -232,7 +265,7 @@ static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, do
     return DIPGPU_OK;
 }
 
-static int unpack(Ctx *c, const void *packed, size_t bytes, dipgpu_cols *out)
+int unpack(Ctx *c, const void *packed, size_t bytes, dipgpu_cols *out)
 {
     if (!packed || !out || bytes < sizeof(ResultHeader)) return fail(c, DIPGPU_ERR_INVALID, "bad packed result");
     const char *p = static_cast<const char *>(packed);
@@ -285,7 +318,7 @@ static int unpack(Ctx *c, const void *packed, size_t bytes, dipgpu_cols *out)
 
 // D2H of the packed result: one speculative copy (header + per-block arrays +
 // the first 64 KiB of indices), a second one only if more indices were kept.
-static int fetchResult(Ctx *c, cudaStream_t st)
+int fetchResult(Ctx *c, cudaStream_t st)
 {
     if (c->resultMirrored) {
         // the fused kernel stored the result into hResult itself (mapped pinned memory): nothing to copy
@@ -316,7 +349,7 @@ static int fetchResult(Ctx *c, cudaStream_t st)
     return DIPGPU_OK;
 }
 
-static void collectStageMs(Ctx *c)
+void collectStageMs(Ctx *c)
 {
     if (!c->stageTiming) return;
     for (int i = 0; i < 6; ++i) {
@@ -345,7 +378,7 @@ static void freeBatch(Ctx *c)
 }
 
 // Buffers for nVec dual vectors priced in one submission.
-static int ensureBatch(Ctx *c, int nVec)
+int ensureBatch(Ctx *c, int nVec)
 {
     const size_t uLen = (size_t)c->R + c->numConvex;
     const size_t uStride = (uLen + 17) & ~(size_t)1;
@@ -361,7 +394,6 @@ static int ensureBatch(Ctx *c, int nVec)
     DIPGPU_CUDA(c, cudaMemset(c->dRedCostBatch, 0, sizeof(double) * V * rcStride));
     if ((rc = devAlloc(c, &c->dPubWordBatch, V * nl * kPubWordStride))) return rc;
     DIPGPU_CUDA(c, cudaMemset(c->dPubWordBatch, 0, sizeof(unsigned long long) * V * nl * kPubWordStride));
-    c->epochBatch = 0;
     if ((rc = devAlloc(c, &c->dScaleB, V * nl))) return rc;
     if ((rc = devAlloc(c, &c->dShortcutB, V * nl))) return rc;
     if ((rc = devAlloc(c, &c->dSelB, 2 * V * nl))) return rc;
@@ -383,11 +415,13 @@ static int ensureBatch(Ctx *c, int nVec)
 
 // Stages (a)-(c) for the nVec dual vectors held in dUBatch: three launches in all when the shard
 // runs the fused DP kernel (gridDim.y = vectors), else vector after vector through the large-shard path.
-static int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st)
+int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st)
 {
     int rc;
     const bool timed = c->stageTiming;
     c->resultMirrored = false;
+    ++c->roundSerial;
+    c->lastRoundOnHost = false;
     if (timed) cudaEventRecord(c->ev[1], st);
     if (c->geom.fuse || c->nLocal == 0) {
         if ((rc = launchRedCostBatch(c, c->dUBatch, (int64_t)c->uStride, c->dRedCostBatch, (int64_t)c->rcStride, nVec, phase, st))) return rc;
@@ -412,7 +446,7 @@ static int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st
 
 // D2H of nVec packed results into hResultBatch (one strided copy of the speculative prefix, a second copy per
 // result that kept more indices).
-static int fetchBatchPacked(Ctx *c, int nVec, cudaStream_t st)
+int fetchBatchPacked(Ctx *c, int nVec, cudaStream_t st)
 {
     if (c->resultMirrored) {
         // the fused kernel stored every vector's result into hResultBatch itself (mapped pinned memory)
@@ -449,7 +483,7 @@ static int fetchBatchPacked(Ctx *c, int nVec, cudaStream_t st)
 }
 
 // ... and decoding.
-static int fetchBatch(Ctx *c, int nVec, dipgpu_cols *outs, cudaStream_t st)
+int fetchBatch(Ctx *c, int nVec, dipgpu_cols *outs, cudaStream_t st)
 {
     int first = fetchBatchPacked(c, nVec, st);
     if (first) return first;
@@ -460,7 +494,7 @@ static int fetchBatch(Ctx *c, int nVec, dipgpu_cols *outs, cudaStream_t st)
     return first;
 }
 
-static int checkRoundReady(Ctx *c, const char *who, int32_t uLen, int32_t phase)
+int checkRoundReady(Ctx *c, const char *who, int32_t uLen, int32_t phase)
 {
     if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "%s needs set_core_csr and set_knapsack_blocks", who);
     if (phase != DIPGPU_PHASE_PRICE1 && !c->haveObj) return fail(c, DIPGPU_ERR_STATE, "%s (phase 2) before set_objective", who);
@@ -469,7 +503,7 @@ static int checkRoundReady(Ctx *c, const char *who, int32_t uLen, int32_t phase)
     return ensureObjective(c, c->N);
 }
 
-static int ensureDualBuffer(Ctx *c, int32_t uLen)
+int ensureDualBuffer(Ctx *c, int32_t uLen)
 {
     if ((size_t)uLen > c->uCap) {
         int rc;
@@ -493,17 +527,22 @@ static int ensureSupportStaging(Ctx *c, int nVec)
     return DIPGPU_OK;
 }
 
-// H2D of nVec master dual vectors (row v at u + v*uLen) into dDst (vector v at dDst + v*dstStride): the
-// whole vectors, or -- with a dual support -- only the entries that can be nonzero, gathered into pinned
-// staging on the host and scattered on the device (the rest of dDst is kept at zero).
-static int uploadDuals(Ctx *c, const double *u, int32_t uLen, int nVec, double *dDst, size_t dstStride, bool *clean,
-                       cudaStream_t st)
+// The nVec master dual vectors of a call (vector v at dDst + v*dstStride afterwards), from wherever the
+// DualFeed says they are: the caller's host vectors (row v at host + v*uLen) -- the whole vectors, or, with a
+// dual support, only the entries that can be nonzero, gathered into pinned staging on the host and scattered
+// on the device (the rest of dDst is kept at zero) --, or a device-visible copy somebody else prepared
+// (a multi-device context gathers once for all its devices; a peer device holds the vector).
+int feedDuals(Ctx *c, const DualFeed &f, int32_t uLen, int nVec, double *dDst, size_t dstStride, bool *clean, cudaStream_t st)
 {
     const size_t ns = c->hSupport.size();
     if (ns == 0) {
-        if (nVec == 1) DIPGPU_CUDA(c, cudaMemcpyAsync(dDst, u, sizeof(double) * (size_t)uLen, cudaMemcpyHostToDevice, st));
-        else DIPGPU_CUDA(c, cudaMemcpy2DAsync(dDst, sizeof(double) * dstStride, u, sizeof(double) * (size_t)uLen,
-                                              sizeof(double) * (size_t)uLen, (size_t)nVec, cudaMemcpyHostToDevice, st));
+        const double *src = f.host ? f.host : f.full;
+        const cudaMemcpyKind kind = f.host ? cudaMemcpyHostToDevice : cudaMemcpyDefault;
+        if (!src) return fail(c, DIPGPU_ERR_INVALID, "no dual vector");
+        const size_t srcStride = f.host ? (size_t)uLen : (size_t)f.fullStride;
+        if (nVec == 1) DIPGPU_CUDA(c, cudaMemcpyAsync(dDst, src, sizeof(double) * (size_t)uLen, kind, st));
+        else DIPGPU_CUDA(c, cudaMemcpy2DAsync(dDst, sizeof(double) * dstStride, src, sizeof(double) * srcStride,
+                                              sizeof(double) * (size_t)uLen, (size_t)nVec, kind, st));
         c->h2d += (int64_t)sizeof(double) * uLen * nVec;
         *clean = false;
         return DIPGPU_OK;
@@ -514,30 +553,58 @@ static int uploadDuals(Ctx *c, const double *u, int32_t uLen, int nVec, double *
         *clean = true;
     }
     c->h2d += (int64_t)sizeof(double) * (int64_t)ns * nVec;
+    if (f.staged)  // u[support] of every vector, already gathered into device-visible memory
+        return launchScatterDuals(c, (int)ns, c->dSupport, f.staged, f.stagedStride, false, dDst, (int64_t)dstStride, nVec, st);
+    if (f.full)    // the whole vectors in device-visible memory: the kernel picks u[support] itself
+        return launchScatterDuals(c, (int)ns, c->dSupport, f.full, f.fullStride, true, dDst, (int64_t)dstStride, nVec, st);
+    const double *u = f.host;
+    if (!u) return fail(c, DIPGPU_ERR_INVALID, "no dual vector");
     if (c->optGatherPinned) {
         // u in pinned (device-mapped) or managed host memory: the kernel picks u[support] out of the caller's
         // buffer itself -- no pass over the vector on the host (a gather of cold cache lines: ~9 us for 4 240
         // entries of a 2 MB vector)
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, u) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) &&
-            at.devicePointer)
-            return launchScatterDuals(c, (int)ns, c->dSupport, static_cast<const double *>(at.devicePointer), (int64_t)uLen, true,
-                                      dDst, (int64_t)dstStride, nVec, st);
-        (void)cudaGetLastError();
+        const double *dv = deviceVisible(u);
+        if (dv) return launchScatterDuals(c, (int)ns, c->dSupport, dv, (int64_t)uLen, true, dDst, (int64_t)dstStride, nVec, st);
     }
     if ((rc = ensureSupportStaging(c, nVec))) return rc;
-    const int32_t *idx = c->hSupport.data();
-    for (int v = 0; v < nVec; ++v) {
-        const double *uv = u + (size_t)v * (size_t)uLen;
-        double *dst = c->hSupVals + (size_t)v * ns;
-        for (size_t k = 0; k < ns; ++k) {
-            if (k + 32 < ns) __builtin_prefetch(uv + idx[k + 32]);
-            dst[k] = uv[idx[k]];
-        }
-    }
+    gatherSupport(c->hSupport, u, uLen, nVec, c->hSupVals);
     // the scatter kernel reads the pinned staging directly (mapped host memory): the few KB cross PCIe inside
     // the kernel, without a separate copy and its latency
     return launchScatterDuals(c, (int)ns, c->dSupport, c->hSupVals, (int64_t)ns, false, dDst, (int64_t)dstStride, nVec, st);
+}
+
+// device address of a host pointer in page-locked (mapped) or managed memory, else NULL
+const double *deviceVisible(const double *u)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, u) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) &&
+        at.devicePointer)
+        return static_cast<const double *>(at.devicePointer);
+    (void)cudaGetLastError();
+    return nullptr;
+}
+
+// dst[v*ns + k] = u[v*uLen + idx[k]]
+void gatherSupport(const std::vector<int32_t> &support, const double *u, int32_t uLen, int nVec, double *dst)
+{
+    const size_t ns = support.size();
+    const int32_t *idx = support.data();
+    for (int v = 0; v < nVec; ++v) {
+        const double *uv = u + (size_t)v * (size_t)uLen;
+        double *d = dst + (size_t)v * ns;
+        for (size_t k = 0; k < ns; ++k) {
+            if (k + 32 < ns) __builtin_prefetch(uv + idx[k + 32]);
+            d[k] = uv[idx[k]];
+        }
+    }
+}
+
+static int uploadDuals(Ctx *c, const double *u, int32_t uLen, int nVec, double *dDst, size_t dstStride, bool *clean,
+                       cudaStream_t st)
+{
+    DualFeed f;
+    f.host = u;
+    return feedDuals(c, f, uLen, nVec, dDst, dstStride, clean, st);
 }
 
 // ------------------------------------------------------------------ waiting-column pool
@@ -574,6 +641,89 @@ static int poolReserve(Ctx *c, int64_t cols, int64_t nnz)
         c->poolNnzCap = cap;
     }
     return DIPGPU_OK;
+}
+
+int multiEnqueueSolve(Ctx *c, double eps, cudaStream_t st, bool timed)
+{
+    c->wantMirror = true;
+    const int rc = enqueueSolve(c, c->dRedCost, c->dAlpha, eps, st, timed);
+    c->wantMirror = false;
+    return rc;
+}
+
+// One pricing round, enqueued on `st`: the duals (feed == NULL: the vector already in dU), the reduced costs of
+// this context's columns, the block subproblems of its block range and the filter.  mirror: the fused kernel
+// also stores the packed result into the context's mirror (mapped host memory, or what mirrorBase names).
+int enqueueRound(Ctx *c, const DualFeed *feed, int32_t uLen, int32_t phase, double eps, bool mirror, cudaStream_t st)
+{
+    int rc;
+    if ((rc = ensureDualBuffer(c, uLen))) return rc;
+    const bool timed = c->stageTiming;
+    if (timed) cudaEventRecord(c->ev[0], st);
+    if (feed) {
+        if ((rc = feedDuals(c, *feed, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
+        c->dualsResident = true;
+    }
+    if (timed) cudaEventRecord(c->ev[1], st);
+    if ((rc = launchRedCost(c, c->dU, phase, st))) return rc;
+    if (timed) cudaEventRecord(c->ev[2], st);
+    // alpha_b = u[nBaseRows + b]  (DecompAlgo.cpp:4820)
+    c->wantMirror = mirror;
+    rc = enqueueSolve(c, c->dRedCost, c->dU + c->nBaseRows, eps, st, timed);
+    c->wantMirror = false;
+    return rc;
+}
+
+// nVec dual vectors priced in one submission and decoded into outs[0..nVec).
+int batchCore(Ctx *c, int nVec, const DualFeed &f, int32_t uLen, int32_t phase, double eps, dipgpu_cols *outs)
+{
+    int rc;
+    if ((rc = checkRoundReady(c, "price_rounds_batch", uLen, phase))) return rc;
+    if (nVec == 0) return DIPGPU_OK;
+    if ((rc = ensureBatch(c, nVec))) return rc;
+    cudaStream_t st = c->stream;
+    if (c->stageTiming) cudaEventRecord(c->ev[0], st);
+    if ((rc = feedDuals(c, f, uLen, nVec, c->dUBatch, c->uStride, &c->dUBatchClean, st))) return rc;
+    c->haveST = false;
+    if ((rc = enqueueBatch(c, nVec, phase, eps, st))) return rc;
+    c->lastRoundOnHost = false;
+    return fetchBatch(c, nVec, outs, st);
+}
+
+// The rounds of the smoothing parameters al[0..nSteps) from ONE upload of dualRM (dipgpu_price_round_stab_ladder).
+// nSteps == 0 (a device of a multi-device context without a step of its own): the upload and the first-call
+// initialisation of the stability centre only, so that every device holds the same centre and dualRM.
+int ladderCore(Ctx *c, const DualFeed &f, int32_t uLen, const double *al, int nSteps, int32_t phase, double eps, dipgpu_cols *outs)
+{
+    int rc;
+    if ((rc = checkRoundReady(c, "price_round_stab_ladder", uLen, phase))) return rc;
+    if (nSteps > 0 && (rc = ensureBatch(c, nSteps))) return rc;
+    if ((rc = ensureDualBuffer(c, uLen))) return rc;
+    cudaStream_t st = c->stream;
+    if (c->stageTiming) cudaEventRecord(c->ev[0], st);
+    if ((rc = feedDuals(c, f, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
+    c->dualsResident = true;
+    if (!c->haveCenter || c->centerLen != (size_t)uLen) {
+        // first price call: m_dual := m_dualRM (DecompAlgoPC.cpp:163-173)
+        if (c->centerLen != (size_t)uLen) {
+            if ((rc = devAlloc(c, &c->dCenter, (size_t)uLen + 16))) return rc;
+            c->centerLen = (size_t)uLen;
+        }
+        DIPGPU_CUDA(c, cudaMemcpyAsync(c->dCenter, c->dU, sizeof(double) * (size_t)uLen, cudaMemcpyDeviceToDevice, st));
+        c->haveCenter = true;
+    }
+    if (nSteps == 0) {
+        DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+        return DIPGPU_OK;
+    }
+    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dAlphaLadder, al, sizeof(double) * (size_t)nSteps, cudaMemcpyHostToDevice, st));
+    c->h2d += (int64_t)sizeof(double) * nSteps;
+    c->dUBatchClean = false;  // the smoothing writes every entry of the batch vectors
+    if ((rc = launchSmoothDuals(c, c->dU, c->dCenter, c->dAlphaLadder, nSteps, uLen, c->dUBatch, (int64_t)c->uStride, st))) return rc;
+    c->haveST = true;
+    if ((rc = enqueueBatch(c, nSteps, phase, eps, st))) return rc;
+    c->lastRoundOnHost = false;
+    return fetchBatch(c, nSteps, outs, st);
 }
 
 }  // namespace dipgpu
@@ -613,11 +763,17 @@ int dipgpu_create(dipgpu_ctx **ctx, int device)
         return DIPGPU_ERR_CUDA;
     }
     for (auto &e : c->ev) cudaEventCreate(&e);
+    const unsigned long long ticket0[2] = {1ull << 32, 1ull << 32};  // epoch 1, no CTA started
     if (cudaMalloc(reinterpret_cast<void **>(&c->dDoneCounter), sizeof(unsigned int)) != cudaSuccess ||
-        cudaMemset(c->dDoneCounter, 0, sizeof(unsigned int)) != cudaSuccess) {
+        cudaMemset(c->dDoneCounter, 0, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void **>(&c->dTicket), 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemcpy(c->dTicket, ticket0, sizeof(ticket0), cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (c->dDoneCounter) cudaFree(c->dDoneCounter);
+        if (c->dTicket) cudaFree(c->dTicket);
         delete c;
         return DIPGPU_ERR_NOMEM;
     }
+    c->dExpTicket = c->dTicket + 1;
     *ctx = reinterpret_cast<dipgpu_ctx *>(c);
     return DIPGPU_OK;
 }
@@ -626,9 +782,10 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
 {
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c) return DIPGPU_OK;
+    if (c->multi) return multiDestroy(ctx);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    devFree(&c->dDoneCounter); devFree(&c->dCsrRowStart); devFree(&c->dCsrColInd); devFree(&c->dCsrVal); devFree(&c->dExpPub);
+    devFree(&c->dDoneCounter); devFree(&c->dTicket); devFree(&c->dCsrRowStart); devFree(&c->dCsrColInd); devFree(&c->dCsrVal); devFree(&c->dExpPub);
     if (c->dMCols) cudaFree(c->dMCols);
     if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dSpmvBlob); devFree(&c->dSpmvWarpStart); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
@@ -654,6 +811,8 @@ int dipgpu_last_error(const dipgpu_ctx *ctx, char *buf, size_t bufLen)
 {
     const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
     if (!buf || bufLen == 0) return DIPGPU_ERR_INVALID;
+    // (a call a multi-device context handed to its primary device left its message there)
+    if (c && c->multi && c->err.empty()) c = reinterpret_cast<const Ctx *>(multiPrimary(const_cast<dipgpu_ctx *>(ctx)));
     const char *s = c ? c->err.c_str() : "null context";
     snprintf(buf, bufLen, "%s", s);
     return DIPGPU_OK;
@@ -662,7 +821,8 @@ int dipgpu_last_error(const dipgpu_ctx *ctx, char *buf, size_t bufLen)
 int dipgpu_host_alloc(void **ptr, size_t bytes)
 {
     if (!ptr) return DIPGPU_ERR_INVALID;
-    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    // portable + mapped: every device of a multi-device context can read the dual vectors out of it
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         return e == cudaErrorMemoryAllocation ? DIPGPU_ERR_NOMEM : DIPGPU_ERR_CUDA;
@@ -679,6 +839,14 @@ int dipgpu_host_free(void *ptr)
 int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *rowStart, const int32_t *colInd,
                         const double *val, int32_t nBaseRows, int32_t numConvex)
 {
+    if (isMulti(ctx)) {
+        struct A { int32_t R, N; const int64_t *rs; const int32_t *ci; const double *v; int32_t nb, nc; } a{R, N, rowStart, colInd, val, nBaseRows, numConvex};
+        multiClearSupport(ctx);
+        return multiForAll(ctx, [](dipgpu_ctx *sub, void *p) {
+            const A *q = static_cast<const A *>(p);
+            return dipgpu_set_core_csr(sub, q->R, q->N, q->rs, q->ci, q->v, q->nb, q->nc);
+        }, &a, true, true);
+    }
     CTX_OR_FAIL(ctx);
     if (R < 0 || N < 0 || !rowStart || nBaseRows < 0 || nBaseRows > R || numConvex < 0)
         return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: bad dimensions R=%d N=%d nBaseRows=%d numConvex=%d", R, N, nBaseRows, numConvex);
@@ -690,7 +858,7 @@ int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *ro
     for (int64_t k = 0; k < nnz; ++k)
         if (colInd[k] < 0 || colInd[k] >= N) return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: column index %d out of range at %lld", colInd[k], (long long)k);
     if (c->haveBlocks && c->nBlockCols > N) return fail(c, DIPGPU_ERR_INVALID, "set_core_csr: N=%d < block columns %d", N, c->nBlockCols);
-    if (c->haveObj && c->N != N) { devFree(&c->dObj); c->haveObj = false; c->hObj.clear(); }
+    if (c->N != N) { devFree(&c->dObj); c->haveObj = false; c->hObj.clear(); c->objLen = 0; }
     if (c->N != N) { devFree(&c->dRedCost); devFree(&c->dRcEff); }
     c->R = R; c->N = N; c->nBaseRows = nBaseRows; c->numConvex = numConvex;
     c->dualsResident = false; c->haveCenter = false; c->haveST = false;
@@ -710,6 +878,14 @@ int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *ro
 
 int dipgpu_append_core_rows(dipgpu_ctx *ctx, int32_t nNew, const int64_t *rowStart, const int32_t *colInd, const double *val)
 {
+    if (isMulti(ctx)) {
+        struct A { int32_t n; const int64_t *rs; const int32_t *ci; const double *v; } a{nNew, rowStart, colInd, val};
+        multiClearSupport(ctx);
+        return multiForAll(ctx, [](dipgpu_ctx *sub, void *p) {
+            const A *q = static_cast<const A *>(p);
+            return dipgpu_append_core_rows(sub, q->n, q->rs, q->ci, q->v);
+        }, &a, true, true);
+    }
     CTX_OR_FAIL(ctx);
     if (!c->haveCore) return fail(c, DIPGPU_ERR_STATE, "append_core_rows before set_core_csr");
     if (nNew < 0 || !rowStart || rowStart[0] != 0) return fail(c, DIPGPU_ERR_INVALID, "append_core_rows: bad arguments");
@@ -723,13 +899,35 @@ int dipgpu_append_core_rows(dipgpu_ctx *ctx, int32_t nNew, const int64_t *rowSta
     c->hColInd.insert(c->hColInd.end(), colInd, colInd + add);
     c->hVal.insert(c->hVal.end(), val, val + add);
     c->R += nNew;
-    c->dualsResident = false; c->haveCenter = false; c->haveST = false;  // the master dual vector grew
+    c->dualsResident = false; c->haveST = false;  // the master dual vector grew
     c->hSupport.clear();
+    if (c->haveCenter) {
+        // DecompAlgoPC::adjustMasterDualSolution resizes m_dual to the new row count (Dip/src/DecompAlgoPC.cpp:135-140):
+        // the stability centre is kept and zero-extended -- the cut rows sit at the end of the master dual vector
+        const size_t newLen = (size_t)c->R + (size_t)c->numConvex;
+        if (newLen > c->centerLen) {
+            double *nw = nullptr;
+            int rc;
+            if ((rc = devAlloc(c, &nw, newLen + 16))) return rc;
+            DIPGPU_CUDA(c, cudaMemset(nw, 0, sizeof(double) * (newLen + 16)));
+            DIPGPU_CUDA(c, cudaMemcpy(nw, c->dCenter, sizeof(double) * c->centerLen, cudaMemcpyDeviceToDevice));
+            devFree(&c->dCenter);
+            c->dCenter = nw;
+            c->centerLen = newLen;
+        }
+    }
     return uploadCore(c);
 }
 
 int dipgpu_set_objective(dipgpu_ctx *ctx, const double *obj, int32_t N)
 {
+    if (isMulti(ctx)) {
+        struct A { const double *c; int32_t N; } a{obj, N};
+        return multiForAll(ctx, [](dipgpu_ctx *sub, void *p) {
+            const A *q = static_cast<const A *>(p);
+            return dipgpu_set_objective(sub, q->c, q->N);
+        }, &a, true, true);
+    }
     CTX_OR_FAIL(ctx);
     if (!obj || N < 0) return fail(c, DIPGPU_ERR_INVALID, "set_objective: bad arguments");
     if (c->haveCore && N != c->N) return fail(c, DIPGPU_ERR_INVALID, "set_objective: N=%d but core has %d columns", N, c->N);
@@ -739,16 +937,25 @@ int dipgpu_set_objective(dipgpu_ctx *ctx, const double *obj, int32_t N)
     if ((rc = devAlloc(c, &c->dObj, (size_t)N + 16))) return rc;
     DIPGPU_CUDA(c, cudaMemset(c->dObj, 0, sizeof(double) * ((size_t)N + 16)));
     DIPGPU_CUDA(c, cudaMemcpy(c->dObj, obj, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice));
+    c->objLen = (size_t)N;
     if (!c->haveCore) c->N = std::max(c->N, (int)N);
     c->haveObj = true;
     c->hObj.assign(obj, obj + N);
-    if (c->haveCore) return uploadCore(c);  // the SpMV tiles carry their columns' objective entries
+    c->tilesDirty = true;  // the SpMV tiles carry their columns' objective entries
     return DIPGPU_OK;
 }
 
 int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockColStart, const int32_t *weight,
                                const int32_t *capacity, int32_t profitMode)
 {
+    if (isMulti(ctx)) {
+        struct A { int32_t m; const int32_t *bcs, *w, *cap; int32_t pm; } a{m, blockColStart, weight, capacity, profitMode};
+        const int rc = multiForAll(ctx, [](dipgpu_ctx *sub, void *p) {
+            const A *q = static_cast<const A *>(p);
+            return dipgpu_set_knapsack_blocks(sub, q->m, q->bcs, q->w, q->cap, q->pm);
+        }, &a, true, true);
+        return rc ? rc : multiSetBlocks(ctx);
+    }
     CTX_OR_FAIL(ctx);
     if (m < 0 || !blockColStart || (m > 0 && !capacity)) return fail(c, DIPGPU_ERR_INVALID, "set_knapsack_blocks: bad arguments");
     if (profitMode != DIPGPU_PROFIT_FP64 && profitMode != DIPGPU_PROFIT_PISINGER_INT)
@@ -805,6 +1012,14 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
 int dipgpu_set_mckp_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockGroupStart, const int32_t *groupColStart,
                            const int32_t *weight, const int32_t *capacity)
 {
+    if (isMulti(ctx)) {
+        struct A { int32_t m; const int32_t *bgs, *gcs, *w, *cap; } a{m, blockGroupStart, groupColStart, weight, capacity};
+        const int rc = multiForAll(ctx, [](dipgpu_ctx *sub, void *p) {
+            const A *q = static_cast<const A *>(p);
+            return dipgpu_set_mckp_blocks(sub, q->m, q->bgs, q->gcs, q->w, q->cap);
+        }, &a, true, true);
+        return rc ? rc : multiSetBlocks(ctx);
+    }
     CTX_OR_FAIL(ctx);
     if (m < 0 || !blockGroupStart || !groupColStart || (m > 0 && !capacity) || blockGroupStart[0] != 0 || groupColStart[0] < 0)
         return fail(c, DIPGPU_ERR_INVALID, "set_mckp_blocks: bad arguments");
@@ -866,6 +1081,13 @@ int dipgpu_set_mckp_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockGroup
 
 int dipgpu_set_col_bounds(dipgpu_ctx *ctx, const double *colLB, const double *colUB, int32_t N)
 {
+    if (isMulti(ctx)) {
+        struct A { const double *lb, *ub; int32_t N; } a{colLB, colUB, N};
+        return multiForAll(ctx, [](dipgpu_ctx *sub, void *p) {
+            const A *q = static_cast<const A *>(p);
+            return dipgpu_set_col_bounds(sub, q->lb, q->ub, q->N);
+        }, &a, true, true);
+    }
     CTX_OR_FAIL(ctx);
     if (!c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "set_col_bounds before set_knapsack_blocks");
     c->lastRoundOnHost = false;
@@ -902,12 +1124,14 @@ int dipgpu_set_col_bounds(dipgpu_ctx *ctx, const double *colLB, const double *co
 
 int dipgpu_set_block_range(dipgpu_ctx *ctx, int32_t first, int32_t count)
 {
+    if (isMulti(ctx)) return fail(reinterpret_cast<Ctx *>(ctx), DIPGPU_ERR_UNSUPPORTED, "set_block_range: a multi-device context cuts its own block shards");
     CTX_OR_FAIL(ctx);
     return setBlockRange(c, first, count);
 }
 
 int dipgpu_calc_redcost(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase, double *redCostX)
 {
+    if (isMulti(ctx)) return multiCalcRedCost(ctx, u, uLen, phase, redCostX);
     CTX_OR_FAIL(ctx);
     if (!c->haveCore) return fail(c, DIPGPU_ERR_STATE, "calc_redcost before set_core_csr");
     if (phase != DIPGPU_PHASE_PRICE1 && !c->haveObj) return fail(c, DIPGPU_ERR_STATE, "calc_redcost (phase 2) before set_objective");
@@ -930,6 +1154,7 @@ int dipgpu_calc_redcost(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t 
 
 int dipgpu_solve_blocks(dipgpu_ctx *ctx, const double *redCostX, const double *alpha, double redCostEps, dipgpu_cols *out)
 {
+    if (isMulti(ctx)) return multiSolveBlocks(ctx, redCostX, alpha, redCostEps, out);
     CTX_OR_FAIL(ctx);
     if (!c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "solve_blocks before set_knapsack_blocks");
     if (!redCostX || !alpha || !out) return fail(c, DIPGPU_ERR_INVALID, "solve_blocks: NULL argument");
@@ -955,27 +1180,16 @@ int dipgpu_solve_blocks(dipgpu_ctx *ctx, const double *redCostX, const double *a
 int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase, double redCostEps,
                        dipgpu_cols *out, double *redCostXOpt)
 {
+    if (isMulti(ctx)) return multiPriceRound(ctx, u, uLen, phase, redCostEps, out, redCostXOpt);
     CTX_OR_FAIL(ctx);
     if (!out) return fail(c, DIPGPU_ERR_INVALID, "price_round: NULL output");
     int rc;
     if ((rc = checkRoundReady(c, "price_round", uLen, phase))) return rc;
     if (!u && !c->dualsResident) return fail(c, DIPGPU_ERR_STATE, "price_round: u == NULL but no dual vector is resident");
-    if ((rc = ensureDualBuffer(c, uLen))) return rc;
-    const bool timed = c->stageTiming;
     cudaStream_t st = c->stream;
-    if (timed) cudaEventRecord(c->ev[0], st);
-    if (u) {
-        if ((rc = uploadDuals(c, u, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
-        c->dualsResident = true;
-    }
-    if (timed) cudaEventRecord(c->ev[1], st);
-    if ((rc = launchRedCost(c, c->dU, phase, st))) return rc;
-    if (timed) cudaEventRecord(c->ev[2], st);
-    // alpha_b = u[nBaseRows + b]  (DecompAlgo.cpp:4820)
-    c->wantMirror = true;
-    rc = enqueueSolve(c, c->dRedCost, c->dU + c->nBaseRows, redCostEps, st, timed);
-    c->wantMirror = false;
-    if (rc) return rc;
+    DualFeed f;
+    f.host = u;
+    if ((rc = enqueueRound(c, u ? &f : nullptr, uLen, phase, redCostEps, true, st))) return rc;
     if (redCostXOpt) {
         DIPGPU_CUDA(c, cudaMemcpyAsync(redCostXOpt, c->dRedCost, sizeof(double) * (size_t)c->N, cudaMemcpyDeviceToHost, st));
         c->d2h += (int64_t)sizeof(double) * c->N;
@@ -991,19 +1205,12 @@ int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t p
 int dipgpu_price_rounds_batch(dipgpu_ctx *ctx, int32_t nVec, const double *U, int32_t uLen, int32_t phase,
                               double redCostEps, dipgpu_cols *outs)
 {
+    if (isMulti(ctx)) return multiPriceRoundsBatch(ctx, nVec, U, uLen, phase, redCostEps, outs);
     CTX_OR_FAIL(ctx);
     if (nVec < 0 || (nVec > 0 && (!U || !outs))) return fail(c, DIPGPU_ERR_INVALID, "price_rounds_batch: bad arguments");
-    int rc;
-    if ((rc = checkRoundReady(c, "price_rounds_batch", uLen, phase))) return rc;
-    if (nVec == 0) return DIPGPU_OK;
-    if ((rc = ensureBatch(c, nVec))) return rc;
-    cudaStream_t st = c->stream;
-    if (c->stageTiming) cudaEventRecord(c->ev[0], st);
-    if ((rc = uploadDuals(c, U, uLen, nVec, c->dUBatch, c->uStride, &c->dUBatchClean, st))) return rc;
-    c->haveST = false;
-    if ((rc = enqueueBatch(c, nVec, phase, redCostEps, st))) return rc;
-    c->lastRoundOnHost = false;
-    return fetchBatch(c, nVec, outs, st);
+    DualFeed f;
+    f.host = U;
+    return batchCore(c, nVec, f, uLen, phase, redCostEps, outs);
 }
 
 // Block subset with per-block user duals: every distinct dual vector is priced as one vector of
@@ -1013,6 +1220,7 @@ int dipgpu_price_round_which(dipgpu_ctx *ctx, const double *u, int32_t uLen, int
                              int32_t nWhich, const int32_t *whichBlocks, const double *const *userDuals,
                              dipgpu_cols *out, int32_t *solvedAll)
 {
+    if (isMulti(ctx)) ctx = multiForward(ctx);  // not partitioned: the primary device's whole-model context
     CTX_OR_FAIL(ctx);
     if (!u || !out || nWhich < 0 || (nWhich > 0 && !whichBlocks)) return fail(c, DIPGPU_ERR_INVALID, "price_round_which: bad arguments");
     int rc;
@@ -1125,6 +1333,10 @@ int dipgpu_price_round_which(dipgpu_ctx *ctx, const double *u, int32_t uLen, int
 
 int dipgpu_set_dual_support(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx)
 {
+    if (isMulti(ctx)) {
+        if (nIdx < 0 || (nIdx > 0 && !idx)) return fail(reinterpret_cast<Ctx *>(ctx), DIPGPU_ERR_INVALID, "set_dual_support: bad arguments");
+        return multiSetDualSupport(ctx, nIdx, idx);
+    }
     CTX_OR_FAIL(ctx);
     if (!c->haveCore) return fail(c, DIPGPU_ERR_STATE, "set_dual_support before set_core_csr");
     if (nIdx < 0 || (nIdx > 0 && !idx)) return fail(c, DIPGPU_ERR_INVALID, "set_dual_support: bad arguments");
@@ -1149,6 +1361,13 @@ int dipgpu_set_dual_support(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx)
 
 int dipgpu_stab_set_center(dipgpu_ctx *ctx, const double *dual, int32_t uLen)
 {
+    if (isMulti(ctx)) {
+        struct A { const double *d; int32_t n; } a{dual, uLen};
+        return multiForAll(ctx, [](dipgpu_ctx *sub, void *p) {
+            const A *q = static_cast<const A *>(p);
+            return dipgpu_stab_set_center(sub, q->d, q->n);
+        }, &a, false, false);
+    }
     CTX_OR_FAIL(ctx);
     if (!dual || uLen <= 0) return fail(c, DIPGPU_ERR_INVALID, "stab_set_center: bad arguments");
     int rc;
@@ -1165,6 +1384,7 @@ int dipgpu_stab_set_center(dipgpu_ctx *ctx, const double *dual, int32_t uLen)
 
 int dipgpu_stab_accept(dipgpu_ctx *ctx, int32_t step)
 {
+    if (isMulti(ctx)) return multiStabAccept(ctx, step);
     CTX_OR_FAIL(ctx);
     if (!c->haveST || step < 0 || step >= c->batchCap) return fail(c, DIPGPU_ERR_STATE, "stab_accept: no smoothed dual vector %d", step);
     if (!c->haveCenter) return fail(c, DIPGPU_ERR_STATE, "stab_accept: no stability centre");
@@ -1176,6 +1396,7 @@ int dipgpu_stab_accept(dipgpu_ctx *ctx, int32_t step)
 
 int dipgpu_get_smoothed_duals(dipgpu_ctx *ctx, int32_t step, double *dualST, int32_t uLen)
 {
+    if (isMulti(ctx)) return multiGetSmoothedDuals(ctx, step, dualST, uLen);
     CTX_OR_FAIL(ctx);
     if (!dualST) return fail(c, DIPGPU_ERR_INVALID, "get_smoothed_duals: NULL output");
     if (!c->haveST || step < 0 || step >= c->batchCap || uLen != c->R + c->numConvex)
@@ -1190,38 +1411,19 @@ int dipgpu_get_smoothed_duals(dipgpu_ctx *ctx, int32_t step, double *dualST, int
 int dipgpu_price_round_stab_ladder(dipgpu_ctx *ctx, const double *uRM, int32_t uLen, double alpha, double shrink,
                                    int32_t nSteps, int32_t phase, double redCostEps, dipgpu_cols *outs, double *alphasOut)
 {
-    CTX_OR_FAIL(ctx);
-    if (!uRM || !outs || nSteps <= 0 || nSteps > 64) return fail(c, DIPGPU_ERR_INVALID, "price_round_stab_ladder: bad arguments");
-    int rc;
-    if ((rc = checkRoundReady(c, "price_round_stab_ladder", uLen, phase))) return rc;
-    if ((rc = ensureBatch(c, nSteps))) return rc;
-    if ((rc = ensureDualBuffer(c, uLen))) return rc;
-    cudaStream_t st = c->stream;
+    Ctx *c0 = reinterpret_cast<Ctx *>(ctx);
+    if (!c0) return DIPGPU_ERR_INVALID;
+    if (!uRM || !outs || nSteps <= 0 || nSteps > 64) return fail(c0, DIPGPU_ERR_INVALID, "price_round_stab_ladder: bad arguments");
     // the ladder DualStabAlpha *= 0.90 (DecompAlgo.cpp:5646), by repeated multiplication as the reference
     double al[64];
     al[0] = alpha;
     for (int k = 1; k < nSteps; ++k) al[k] = al[k - 1] * shrink;
     if (alphasOut) memcpy(alphasOut, al, sizeof(double) * (size_t)nSteps);
-    if (c->stageTiming) cudaEventRecord(c->ev[0], st);
-    if ((rc = uploadDuals(c, uRM, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
-    DIPGPU_CUDA(c, cudaMemcpyAsync(c->dAlphaLadder, al, sizeof(double) * (size_t)nSteps, cudaMemcpyHostToDevice, st));
-    c->h2d += (int64_t)sizeof(double) * nSteps;
-    c->dualsResident = true;
-    c->dUBatchClean = false;  // the smoothing writes every entry of the batch vectors
-    if (!c->haveCenter || c->centerLen != (size_t)uLen) {
-        // first price call: m_dual := m_dualRM (DecompAlgoPC.cpp:163-173)
-        if (c->centerLen != (size_t)uLen) {
-            if ((rc = devAlloc(c, &c->dCenter, (size_t)uLen + 16))) return rc;
-            c->centerLen = (size_t)uLen;
-        }
-        DIPGPU_CUDA(c, cudaMemcpyAsync(c->dCenter, c->dU, sizeof(double) * (size_t)uLen, cudaMemcpyDeviceToDevice, st));
-        c->haveCenter = true;
-    }
-    if ((rc = launchSmoothDuals(c, c->dU, c->dCenter, c->dAlphaLadder, nSteps, uLen, c->dUBatch, (int64_t)c->uStride, st))) return rc;
-    c->haveST = true;
-    if ((rc = enqueueBatch(c, nSteps, phase, redCostEps, st))) return rc;
-    c->lastRoundOnHost = false;
-    return fetchBatch(c, nSteps, outs, st);
+    if (isMulti(ctx)) return multiStabLadder(ctx, uRM, uLen, al, nSteps, phase, redCostEps, outs);
+    CTX_OR_FAIL(ctx);
+    DualFeed f;
+    f.host = uRM;
+    return ladderCore(c, f, uLen, al, nSteps, phase, redCostEps, outs);
 }
 
 int dipgpu_price_round_stab(dipgpu_ctx *ctx, const double *uRM, int32_t uLen, double alpha, int32_t phase,
@@ -1236,6 +1438,7 @@ int dipgpu_price_round_stab(dipgpu_ctx *ctx, const double *uRM, int32_t uLen, do
 
 int dipgpu_select_batch_result(dipgpu_ctx *ctx, int32_t which)
 {
+    if (isMulti(ctx)) return multiSelectBatchResult(ctx, which);
     CTX_OR_FAIL(ctx);
     if (which < 0 || which >= c->batchCap || !c->dResultBatch) return fail(c, DIPGPU_ERR_STATE, "select_batch_result: no batched result %d", which);
     const char *hp = static_cast<const char *>(c->hResultBatch) + (size_t)which * c->resStride;
@@ -1245,6 +1448,7 @@ int dipgpu_select_batch_result(dipgpu_ctx *ctx, int32_t which)
                                    cudaMemcpyDeviceToDevice, c->stream));
     memcpy(c->hResult, hp, c->layout.offInd + sizeof(int32_t) * (size_t)h->nInd);
     DIPGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    ++c->roundSerial;  // a different round is "the last round" now
     c->lastRoundOnHost = true;
     return DIPGPU_OK;
 }
@@ -1253,6 +1457,7 @@ int dipgpu_select_batch_result(dipgpu_ctx *ctx, int32_t which)
 
 int dipgpu_pool_clear(dipgpu_ctx *ctx)
 {
+    if (isMulti(ctx)) ctx = multiForward(ctx);  // not partitioned: the primary device's whole-model context
     CTX_OR_FAIL(ctx);
     c->poolCols = c->poolNnz = 0;
     if (c->dPoolStart) DIPGPU_CUDA(c, cudaMemset(c->dPoolStart, 0, sizeof(int64_t)));
@@ -1261,6 +1466,7 @@ int dipgpu_pool_clear(dipgpu_ctx *ctx)
 
 int dipgpu_pool_size(const dipgpu_ctx *ctx, int64_t *nCols, int64_t *nNnz)
 {
+    if (isMulti(ctx)) ctx = multiPrimary(const_cast<dipgpu_ctx *>(ctx));
     const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
     if (!c) return DIPGPU_ERR_INVALID;
     if (nCols) *nCols = c->poolCols;
@@ -1271,6 +1477,7 @@ int dipgpu_pool_size(const dipgpu_ctx *ctx, int64_t *nCols, int64_t *nNnz)
 int dipgpu_pool_append(dipgpu_ctx *ctx, int32_t nCols, const int64_t *colStart, const int32_t *rowInd, const double *val,
                        const double *origCost)
 {
+    if (isMulti(ctx)) ctx = multiForward(ctx);  // not partitioned: the primary device's whole-model context
     CTX_OR_FAIL(ctx);
     if (nCols < 0 || (nCols > 0 && (!colStart || !origCost)) || (nCols > 0 && colStart[0] != 0))
         return fail(c, DIPGPU_ERR_INVALID, "pool_append: bad arguments");
@@ -1320,6 +1527,7 @@ static int poolCopyColumns(Ctx *c, const std::vector<int64_t> &desc, const void 
 
 int dipgpu_pool_append_expanded(dipgpu_ctx *ctx, int32_t nWhich, const int32_t *which)
 {
+    if (isMulti(ctx)) ctx = multiForward(ctx);  // not partitioned: the primary device's whole-model context
     CTX_OR_FAIL(ctx);
     if (nWhich < 0 || (nWhich > 0 && !which)) return fail(c, DIPGPU_ERR_INVALID, "pool_append_expanded: bad arguments");
     if (nWhich == 0) return DIPGPU_OK;
@@ -1333,7 +1541,8 @@ int dipgpu_pool_append_expanded(dipgpu_ctx *ctx, int32_t nWhich, const int32_t *
     const ResultHeader *rh = reinterpret_cast<const ResultHeader *>(rp);
     const double *oc = reinterpret_cast<const double *>(rp + c->layout.offOrigCost);
     const int32_t *kb = reinterpret_cast<const int32_t *>(rp + c->layout.offKeptBlock);
-    if (rh->nKept != mh->nCols) return fail(c, DIPGPU_ERR_STATE, "pool_append_expanded: expansion does not belong to the last round");
+    if (c->expandSerial != c->roundSerial || rh->nKept != mh->nCols)
+        return fail(c, DIPGPU_ERR_STATE, "pool_append_expanded: expansion does not belong to the last round");
     int64_t add = 0;
     for (int k = 0; k < nWhich; ++k) {
         if (which[k] < 0 || which[k] >= mh->nCols) return fail(c, DIPGPU_ERR_INVALID, "pool_append_expanded: column %d out of range", which[k]);
@@ -1363,6 +1572,7 @@ int dipgpu_pool_append_expanded(dipgpu_ctx *ctx, int32_t nWhich, const int32_t *
 
 int dipgpu_pool_keep(dipgpu_ctx *ctx, int32_t nKeep, const int32_t *keepIdx)
 {
+    if (isMulti(ctx)) ctx = multiForward(ctx);  // not partitioned: the primary device's whole-model context
     CTX_OR_FAIL(ctx);
     if (nKeep < 0 || (nKeep > 0 && !keepIdx)) return fail(c, DIPGPU_ERR_INVALID, "pool_keep: bad arguments");
     if (nKeep == 0) return dipgpu_pool_clear(ctx);
@@ -1402,6 +1612,7 @@ int dipgpu_pool_keep(dipgpu_ctx *ctx, int32_t nKeep, const int32_t *keepIdx)
 int dipgpu_pool_set_reduced_costs(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t feasible, double *redCost,
                                   int32_t *foundNegRC)
 {
+    if (isMulti(ctx)) ctx = multiForward(ctx);  // not partitioned: the primary device's whole-model context
     CTX_OR_FAIL(ctx);
     if (!c->haveCore) return fail(c, DIPGPU_ERR_STATE, "pool_set_reduced_costs before set_core_csr");
     if (uLen != c->R + c->numConvex) return fail(c, DIPGPU_ERR_INVALID, "pool_set_reduced_costs: uLen=%d, expected R+numConvex=%d", uLen, c->R + c->numConvex);
@@ -1456,7 +1667,6 @@ static int prepareExpand(Ctx *c)
         DIPGPU_CUDA(c, cudaMallocHost(&c->hMCols, bytes));
         if ((rc = devAlloc(c, &c->dExpPub, (size_t)c->m))) return rc;
         DIPGPU_CUDA(c, cudaMemset(c->dExpPub, 0, sizeof(unsigned long long) * (size_t)std::max(c->m, 1)));
-        c->expEpoch = 0;
         c->mcolsBytes = bytes;
         c->mcolsOffColStart = offColStart;
         c->mcolsOffHash = offHash;
@@ -1493,6 +1703,7 @@ static int finishExpand(Ctx *c, int nKept, size_t spec, dipgpu_mcols *out, cudaS
     if (mh->flags & 2u) return fail(c, DIPGPU_ERR_NOMEM, "expand_columns: device output capacity exceeded");
     const size_t need = c->mcolsOffEntries + sizeof(MColEntry) * (size_t)mh->nNnz;
     c->lastMColsBytes = need;
+    c->expandSerial = c->roundSerial;
     if (need > spec) {
         DIPGPU_CUDA(c, cudaMemcpyAsync(static_cast<char *>(c->hMCols) + spec, static_cast<char *>(c->dMCols) + spec,
                                        need - spec, cudaMemcpyDeviceToHost, st));
@@ -1517,6 +1728,7 @@ static int finishExpand(Ctx *c, int nKept, size_t spec, dipgpu_mcols *out, cudaS
 
 int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
 {
+    if (isMulti(ctx)) return multiExpandColumns(ctx, tolZero, out);
     CTX_OR_FAIL(ctx);
     if (!out) return fail(c, DIPGPU_ERR_INVALID, "expand_columns: NULL output");
     if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "expand_columns needs set_core_csr and set_knapsack_blocks");
@@ -1527,6 +1739,7 @@ int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
     out->nNnz = 0;
     if (nKept == 0) {
         if (out->colStart && out->capCols >= 0) out->colStart[0] = 0;
+        c->expandSerial = ~0ull;  // nothing to append
         return DIPGPU_OK;
     }
     int rc;
@@ -1546,6 +1759,12 @@ int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
 int dipgpu_price_round_expand(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phase, double redCostEps,
                               double tolZero, dipgpu_cols *out, dipgpu_mcols *mout)
 {
+    if (isMulti(ctx)) {
+        // blocks partitioned over the devices: the round, then every shard expands the columns it kept
+        if (!out || !mout) return fail(reinterpret_cast<Ctx *>(ctx), DIPGPU_ERR_INVALID, "price_round_expand: NULL output");
+        const int rc = multiPriceRound(ctx, u, uLen, phase, redCostEps, out, nullptr);
+        return rc ? rc : multiExpandColumns(ctx, tolZero, mout);
+    }
     CTX_OR_FAIL(ctx);
     if (!out || !mout) return fail(c, DIPGPU_ERR_INVALID, "price_round_expand: NULL output");
     int rc;
@@ -1584,6 +1803,10 @@ int dipgpu_price_round_expand(dipgpu_ctx *ctx, const double *u, int32_t uLen, in
 
 int dipgpu_price_round_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, int32_t phase, double redCostEps, void *stream)
 {
+    if (isMulti(ctx)) {
+        if (stream) return fail(reinterpret_cast<Ctx *>(ctx), DIPGPU_ERR_INVALID, "price_round_dev: a multi-device context runs on its own streams (pass NULL, then dipgpu_sync)");
+        return multiPriceRoundDev(ctx, uDev, uLen, phase, redCostEps);
+    }
     CTX_OR_FAIL(ctx);
     if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "price_round_dev needs set_core_csr and set_knapsack_blocks");
     if (!uDev || uLen != c->R + c->numConvex) return fail(c, DIPGPU_ERR_INVALID, "price_round_dev: bad dual vector");
@@ -1597,6 +1820,7 @@ int dipgpu_price_round_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, in
 
 int dipgpu_calc_redcost_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, int32_t phase, void *stream)
 {
+    if (isMulti(ctx)) ctx = multiForward(ctx);  // not partitioned: the primary device's whole-model context
     CTX_OR_FAIL(ctx);
     if (!c->haveCore) return fail(c, DIPGPU_ERR_STATE, "calc_redcost_dev before set_core_csr");
     if (phase != DIPGPU_PHASE_PRICE1 && !c->haveObj) return fail(c, DIPGPU_ERR_STATE, "calc_redcost_dev (phase 2) before set_objective");
@@ -1609,6 +1833,7 @@ int dipgpu_calc_redcost_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, i
 
 int dipgpu_measure_smem_gbs(dipgpu_ctx *ctx, double *gbs)
 {
+    if (isMulti(ctx)) ctx = multiForward(ctx);  // not partitioned: the primary device's whole-model context
     CTX_OR_FAIL(ctx);
     if (!gbs) return fail(c, DIPGPU_ERR_INVALID, "measure_smem_gbs: NULL output");
     return measureSmemGbs(c, gbs);
@@ -1616,6 +1841,7 @@ int dipgpu_measure_smem_gbs(dipgpu_ctx *ctx, double *gbs)
 
 int dipgpu_solve_blocks_dev(dipgpu_ctx *ctx, const double *redCostXDev, const double *alphaDev, double redCostEps, void *stream)
 {
+    if (isMulti(ctx)) ctx = multiForward(ctx);  // not partitioned: the primary device's whole-model context
     CTX_OR_FAIL(ctx);
     if (!c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "solve_blocks_dev before set_knapsack_blocks");
     if (!redCostXDev || !alphaDev) return fail(c, DIPGPU_ERR_INVALID, "solve_blocks_dev: NULL argument");
@@ -1630,6 +1856,7 @@ int dipgpu_result_dev(dipgpu_ctx *ctx, void **devPtr, size_t *bytes)
 {
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !devPtr || !bytes) return DIPGPU_ERR_INVALID;
+    if (c->multi) return multiResultDev(ctx, devPtr, bytes);
     if (!c->dResult) return fail(c, DIPGPU_ERR_STATE, "no result buffer yet");
     *devPtr = c->dResult;
     *bytes = c->resultBytes;
@@ -1638,6 +1865,7 @@ int dipgpu_result_dev(dipgpu_ctx *ctx, void **devPtr, size_t *bytes)
 
 int dipgpu_result_max_bytes(const dipgpu_ctx *ctx, size_t *bytes)
 {
+    if (isMulti(ctx)) ctx = multiPrimary(const_cast<dipgpu_ctx *>(ctx));
     const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
     if (!c || !bytes) return DIPGPU_ERR_INVALID;
     *bytes = c->resultBytes;
@@ -1651,6 +1879,7 @@ int dipgpu_unpack_result(const void *packedHost, size_t bytes, dipgpu_cols *out)
 
 int dipgpu_redcost_dev(dipgpu_ctx *ctx, double **devPtr)
 {
+    if (isMulti(ctx)) ctx = multiPrimary(ctx);
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !devPtr) return DIPGPU_ERR_INVALID;
     if (!c->dRedCost) return fail(c, DIPGPU_ERR_STATE, "no reduced-cost buffer yet");
@@ -1662,6 +1891,7 @@ int dipgpu_get_counters(const dipgpu_ctx *ctx, int64_t *kernelLaunches, int64_t 
 {
     const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
     if (!c) return DIPGPU_ERR_INVALID;
+    if (c->multi) return multiGetCounters(ctx, kernelLaunches, h2dBytes, d2hBytes);
     if (kernelLaunches) *kernelLaunches = c->launches;
     if (h2dBytes) *h2dBytes = c->h2d;
     if (d2hBytes) *d2hBytes = c->d2h;
@@ -1672,7 +1902,7 @@ int dipgpu_last_stage_ms(const dipgpu_ctx *ctx, float *ms6)
 {
     const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
     if (!c || !ms6) return DIPGPU_ERR_INVALID;
-    for (int i = 0; i < 6; ++i) ms6[i] = c->stageMs[i];
+    for (int i = 0; i < 6; ++i) ms6[i] = c->stageMs[i];  // (the front of a multi-device context: per stage, the slowest device)
     return DIPGPU_OK;
 }
 
@@ -1702,6 +1932,7 @@ int dipgpu_plan_dp_geometry(int32_t smCount, int32_t nBlocks, int32_t maxCapacit
 
 int dipgpu_get_dp_geometry(const dipgpu_ctx *ctx, int32_t out[7])
 {
+    if (isMulti(ctx)) ctx = multiPrimary(const_cast<dipgpu_ctx *>(ctx));
     const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
     if (!c || !out) return DIPGPU_ERR_INVALID;
     if (!c->haveBlocks) return DIPGPU_ERR_STATE;
@@ -1713,6 +1944,17 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
 {
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !name) return DIPGPU_ERR_INVALID;
+    if (c->multi) {
+        if (!strcmp(name, "dp_debug_times")) return dipgpu_set_option(multiPrimary(ctx), name, value);
+        if (!strcmp(name, "stage_timing")) c->stageTiming = value != 0;
+        if (!strcmp(name, "gather_pinned_duals")) c->optGatherPinned = value != 0;
+        struct A { const char *n; int64_t v; } a{name, value};
+        const int rc = multiForAll(ctx, [](dipgpu_ctx *sub, void *p) {
+            const A *q = static_cast<const A *>(p);
+            return dipgpu_set_option(sub, q->n, q->v);
+        }, &a, true, false);
+        return rc;
+    }
     if (!strcmp(name, "stage_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "dp_pdl")) { c->optPdl = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "result_zero_copy")) {  // 2 (diagnostics): also from the device-resident entry points
@@ -1747,11 +1989,7 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
                  : !strcmp(name, "spmv_max_cols") ? &c->optSpmvMaxCols : &c->optSpmvWindow;
         if (*opt == (int)value) return DIPGPU_OK;
         *opt = (int)value;
-        if (c->haveCore) {
-            int rc = bind(c);
-            if (rc) return rc;
-            return uploadCore(c);
-        }
+        c->tilesDirty = true;
         return DIPGPU_OK;
     }
     if (!strcmp(name, "dp_threads") || !strcmp(name, "dp_cells_per_thread") || !strcmp(name, "dp_items_per_step") ||

@@ -50,8 +50,10 @@ struct ExpandArgs {
     MColEntry *outEntries;
     int64_t capEntries;
     // synchronisation
-    unsigned long long *pubWord;  // per column: epoch (8) | length (56)
-    unsigned int epoch;
+    unsigned long long *pubWord;  // per column: valid (1) | epoch (23) | length (40)
+    // (launch epoch << 32) | CTAs started: a CTA's column is the TICKET it draws on entry, so the columns it
+    // waits for below belong to CTAs that started before it, whatever the dispatch order (see knapsack.cu)
+    unsigned long long *ticket;
     int rowWords;   // ceil(R/32)
     int rowWordsPhys;  // with the skew: rowWords + rowWords/32 + 1
     int colWords;   // ceil(maxBlockCols/32)
@@ -104,7 +106,15 @@ __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __gri
     __shared__ unsigned long long sOffW[kExpThreads / 32];
     __shared__ int sOverflow;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int k = blockIdx.x;
+    __shared__ unsigned long long sTicket;
+    if (t == 0) {
+        const unsigned long long tk = atomicAdd(a.ticket, 1ull);
+        if ((unsigned int)tk == gridDim.x - 1u) atomicAdd(a.ticket, (1ull << 32) - (unsigned long long)gridDim.x);
+        sTicket = tk;
+    }
+    __syncthreads();
+    const int k = (int)(unsigned int)sTicket;
+    const unsigned long long epochTag = (1ull << 23) | ((sTicket >> 32) & 0x7fffffull);  // valid bit + epoch
     const int nKept = a.hdr->nKept;
     if (k >= nKept) {
         // (launched with one CTA per block behind a round whose outcome the host does not know yet)
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __gri
 
     // ---- 5. offset in the packed output: publish the length, poll the lower columns
     if (t == 0) {
-        const unsigned long long word = ((unsigned long long)(a.epoch & 0xffu) << 56) | len;
+        const unsigned long long word = (epochTag << 40) | len;
         asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.pubWord + k), "l"(word) : "memory");
     }
     unsigned long long off = 0ull;
@@ -240,8 +250,8 @@ __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __gri
         unsigned long long wv;
         do {
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(wv) : "l"(a.pubWord + c) : "memory");
-        } while ((unsigned int)(wv >> 56) != (a.epoch & 0xffu));
-        off += wv & 0x00ffffffffffffffull;
+        } while ((wv >> 40) != epochTag);
+        off += wv & 0xffffffffffull;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o);
@@ -318,7 +328,7 @@ int launchExpandColumns(Ctx *c, double tolZero, int nKept, cudaStream_t st)
     a.outEntries = reinterpret_cast<MColEntry *>(mc + c->mcolsOffEntries);
     a.capEntries = c->mcolsCapEntries;
     a.pubWord = c->dExpPub;
-    a.epoch = ++c->expEpoch;
+    a.ticket = c->dExpTicket;
     a.rowWords = (c->R + 31) / 32;
     a.rowWordsPhys = a.rowWords + a.rowWords / 32 + 1;
     a.colWords = (c->maxBlockCols + 31) / 32;

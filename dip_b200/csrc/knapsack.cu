@@ -287,14 +287,21 @@ __global__ void __launch_bounds__(kBackThreads) knap_backtrack_kernel(const __gr
 
 // ------------------------------------------------------------------- DP kernel
 
-__device__ __forceinline__ void dbgStamp(unsigned long long *buf, int slot)
+__device__ __forceinline__ void dbgStamp(unsigned long long *buf, int slot, int lb, int vec)
 {
-    if (buf != nullptr && threadIdx.x == 0 && blockIdx.y == 0) {
+    if (buf != nullptr && threadIdx.x == 0 && vec == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        buf[(size_t)blockIdx.x * 8 + slot] = t;
+        buf[(size_t)lb * 8 + slot] = t;
     }
 }
+
+// Publication word of a fused block: valid (1) | epoch (26) | kept (1) | items (12) | evaluated items (12) | nnz (12).
+// In the fused shapes a block has <= 2048 columns.  `valid` keeps a never-written (zero) word from matching
+// any epoch; the host clears the words every 2^24 launches (dipgpu_api.cu: pubEpochGuard), so a word a
+// launch did not rewrite (a vector beyond the launch's nVec) can never carry the current epoch again.
+constexpr unsigned int kPubEpochMask = (1u << 26) - 1u;
+constexpr int kPubEpochShift = 37, kPubKeptBit = 36, kPubItemsShift = 24, kPubEvalShift = 12;
 
 #define kNegInf (__longlong_as_double((long long)0xfff0000000000000ULL))
 constexpr int kPruneBuckets = 1024;   // efficiency histogram of the reduction pre-pass
@@ -324,9 +331,14 @@ struct KnapArgs {
     const int32_t *shortcut;       // Pisinger mode: local block -> trivial-case code (0 = run the DP)
     const double *zShort;          // Pisinger mode: local block -> optimum of a trivial case
     unsigned long long *dbgTimes;  // diagnostics: 8 globaltimer stamps per CTA (NULL = off)
-    unsigned long long *pubWord;   // FUSE: per local block (epoch << 32) | kept << 31 | nnz
+    unsigned long long *pubWord;   // FUSE: per (vector, local block) publication word (layout: kPub* below)
     unsigned long long *pubCells;  // FUSE: per local block DP cells
-    unsigned int epoch;            // FUSE: launch counter carried by pubWord
+    // FUSE: (launch epoch << 32) | CTAs started so far in this launch.  Every CTA draws ONE ticket on entry:
+    // the low half is its LOGICAL (vector, block) id -- so a CTA only ever waits for CTAs that started before
+    // it (no assumption on the order in which the hardware dispatches blockIdx) --, the high half the epoch
+    // its publication word carries.  The CTA that draws the last ticket of a launch moves the counter to
+    // (epoch + 1, 0): nothing is reset or counted by the host, a captured graph can replay the launch.
+    unsigned long long *ticket;
     // FUSE, batched dual vectors (gridDim.y = vectors): vector v = blockIdx.y reads redCost + v*rcStride
     // and alpha + v*alphaStride and writes the packed result at byte offset v*resStride; the per-block
     // arrays pubWord / scale / shortcut / sel / zShort hold nLocal entries per vector
@@ -417,10 +429,24 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const int lane = t & 31;
     const int warp = t >> 5;
     const int nWarps = T >> 5;
-    const int lb = blockIdx.x;
+    // FUSE: the ticket (see KnapArgs::ticket) is drawn first, the row buffers are initialised while it travels
+    __shared__ unsigned long long sTicket;
+    if (FUSE && t == 0) sTicket = atomicAdd(a.ticket, 1ull);
+    if (t == 0) mbarInit(mbar, 1);
+    // c[-1][.] = 0 (gap_func.py:156); guards = -inf
+    for (int j = t; j < 2 * bufStride; j += T) {
+        const int r = j >= bufStride ? j - bufStride : j;
+        rowBase[j] = r < G ? kNegInf : 0.0;
+    }
+    __syncthreads();
+    const unsigned int tkIdx = FUSE ? (unsigned int)sTicket : 0u;
+    const unsigned int epoch = FUSE ? (unsigned int)(sTicket >> 32) & kPubEpochMask : 0u;
+    if (FUSE && t == 0 && tkIdx == gridDim.x * gridDim.y - 1u)
+        atomicAdd(a.ticket, (1ull << 32) - (unsigned long long)(gridDim.x * gridDim.y));  // every ticket is drawn: next launch
+    const int lb = FUSE ? (int)(tkIdx % gridDim.x) : (int)blockIdx.x;
     const int b = a.firstBlock + lb;
     // batched dual vectors (fused shapes only; gridDim.y == 1 otherwise): this CTA's vector
-    const long long vec = FUSE ? (long long)blockIdx.y : 0;
+    const long long vec = FUSE ? (long long)(tkIdx / gridDim.x) : 0;
     const int vlb = (int)vec * (int)gridDim.x + lb;  // slot of (vector, block) in the per-vector block arrays
     const double *redCostV = a.redCost + vec * a.rcStride;
     const long long resOff = vec * a.resStride;
@@ -445,7 +471,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     uint32_t *bitsBase = FUSE ? sBits : a.bits + a.bitsOff[lb];
     const int j0 = t * S;  // first owned cell
 
-    dbgStamp(a.dbgTimes, 0);
+    dbgStamp(a.dbgTimes, 0, lb, (int)vec);
     unsigned long long touch = 0ull;
     if (FUSE && t == 32 % T) {
         // touch, now, the pages the tail will write and poll (publication words, packed result): a first
@@ -457,13 +483,6 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x2) : "l"(RESV(a.filt.keptInd) + (size_t)(colStart - a.blockColStart[a.firstBlock]) / 2 * 2) : "memory");
         touch = x0 ^ x1 ^ x2;  // consumed in the tail, so that nothing waits for these loads here
     }
-    if (t == 0) mbarInit(mbar, 1);
-    // c[-1][.] = 0 (gap_func.py:156); guards = -inf
-    for (int j = t; j < 2 * bufStride; j += T) {
-        const int r = j >= bufStride ? j - bufStride : j;
-        rowBase[j] = r < G ? kNegInf : 0.0;
-    }
-    __syncthreads();
 
     double mine[S];
     uint32_t acc[S];
@@ -509,7 +528,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         if (pruneLayoutHere) __syncthreads();  // the zeroed histograms are visible to every warp
         mbarWait(mbar, parity);
         parity ^= 1u;
-        dbgStamp(a.dbgTimes, 1);
+        dbgStamp(a.dbgTimes, 1, lb, (int)vec);
 
         // ---- reduction, fused shapes (what Pisinger's combo does before its DP): an item is left out
         // when NO optimal solution can contain it, so the DP over the remaining items -- same order, same
@@ -808,7 +827,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             }
         }
         __syncthreads();
-        dbgStamp(a.dbgTimes, 2);
+        dbgStamp(a.dbgTimes, 2, lb, (int)vec);
 
         // ---- the DP proper: items sequential, cells parallel.  (w0,p0),(w1,p1) hold
         // items i and i+1, fetched one step ahead (itP/itW are padded by four entries).
@@ -1111,7 +1130,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         }
     }
     if (t == 0 && vec == 0) a.nItems[lb] = kGlobal;
-    dbgStamp(a.dbgTimes, 3);
+    dbgStamp(a.dbgTimes, 3, lb, (int)vec);
     if (FUSE) {
         // ---- stage (b) continued: the column of this block, out of shared memory
         __shared__ int sCnt;
@@ -1269,12 +1288,14 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             if (lane == 0) sCnt = cnt;
         }
         __syncthreads();
-        dbgStamp(a.dbgTimes, 4);
+        dbgStamp(a.dbgTimes, 4, lb, (int)vec);
 
         // ---- stage (c), DecompAlgo.cpp:5151-5232, without a second launch and without a serial
         // tail: every CTA publishes (kept?, nnz, cells) and waits only for the LOWER-numbered
-        // blocks to learn where its column goes (CTAs are dispatched in index order, block 0 never
-        // waits).  Words carry the launch epoch, so nothing has to be reset between rounds.
+        // blocks to learn where its column goes.  Block ids are TICKETS drawn at CTA entry, so a lower
+        // block has always started before this one (whatever order the hardware dispatches CTAs in,
+        // however many fit on the GPU at once) and block 0 never waits.  Words carry the launch epoch,
+        // so nothing has to be reset between rounds.
         const int cnt = sCnt;
         // DecompAlgo.cpp:6350-6356; a block whose fixed columns do not fit has no column: rc = +inf
         const double rcB = cap < 0 ? -kNegInf : sRcSum - alphaB;
@@ -1283,13 +1304,13 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         const unsigned long long myCells = (unsigned long long)nItRef * (unsigned long long)(cap + 1);  // 0 when cap < 0
         const unsigned long long myEval = (unsigned long long)kGlobal * (unsigned long long)(cap + 1);
         if (t == 0) {
-            // one 64-bit word per block: epoch (8) | kept (1) | items (12) | evaluated items (12) | nnz (31).
-            // In the fused shapes a block has <= 2048 columns; every block publishes in every round, so a
-            // stale word always carries the previous epoch.  Published FIRST: the word is all the other
-            // blocks need, the result stores below are read by the host only.
-            const unsigned long long word = ((unsigned long long)(a.epoch & 0xffu) << 56) | (keep ? 1ull << 55 : 0ull) |
-                                            ((unsigned long long)(cap < 0 ? 0 : nItRef) << 43) |
-                                            ((unsigned long long)kGlobal << 31) | (unsigned long long)cnt;
+            // one 64-bit word per block (layout: kPub* above).  Every block publishes in every launch that
+            // prices its vector.  Published FIRST: the word is all the other blocks need, the result stores
+            // below are read by the host only.
+            const unsigned long long word = (1ull << 63) | ((unsigned long long)epoch << kPubEpochShift) |
+                                            (keep ? 1ull << kPubKeptBit : 0ull) |
+                                            ((unsigned long long)(cap < 0 ? 0 : nItRef) << kPubItemsShift) |
+                                            ((unsigned long long)kGlobal << kPubEvalShift) | (unsigned long long)cnt;
             // relaxed: the word itself is everything the other blocks read (no other store has to be ordered before it)
             // an atomic goes straight to the L2 slice (a plain store may wait in the SM's write path)
             atomicExch(a.pubWord + (size_t)vlb * kPubWordStride, word);
@@ -1316,19 +1337,19 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                     // an atomic is performed at the line's home L2 slice: a plain (even .relaxed.gpu) load
                     // was seen to return the old word for ~4.5 us on part of the SMs (the other die's L2)
                     wv = atomicAdd(const_cast<unsigned long long *>(src), 0ull);
-                    if ((unsigned int)(wv >> 56) == (a.epoch & 0xffu)) break;
+                    if ((wv >> kPubEpochShift) == ((1ull << 26) | (unsigned long long)epoch)) break;  // valid bit + epoch
                     // a short pause between polls (__nanosleep's granularity here is microseconds): 80 blocks
                     // x up to 79 threads polling back to back congest the words' L2 slices, and the stores that
                     // follow the wait queue up behind the polls
                     const long long t0 = clock64();
                     while (clock64() - t0 < 400) {}
                 }
-                if (wv & (1ull << 55)) {
+                if (wv & (1ull << kPubKeptBit)) {
                     ++kc;
-                    nz += wv & 0x7fffffffull;  // nnz <= 2048
+                    nz += wv & 0xfffull;  // nnz <= 2048
                 }
-                cl += ((wv >> 43) & 0xfffull) * rowB;
-                ev += ((wv >> 31) & 0xfffull) * rowB;
+                cl += ((wv >> kPubItemsShift) & 0xfffull) * rowB;
+                ev += ((wv >> kPubEvalShift) & 0xfffull) * rowB;
             }
 #pragma unroll
             for (int off2 = 16; off2 > 0; off2 >>= 1) {
@@ -1345,7 +1366,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             }
         }
         __syncthreads();
-        dbgStamp(a.dbgTimes, 6);
+        dbgStamp(a.dbgTimes, 6, lb, (int)vec);
         if (t == 0) {
             int kc = 0;
             unsigned long long nz = 0ull, cl = 0ull, ev = 0ull;
@@ -1361,7 +1382,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             sEval = ev;
         }
         __syncthreads();
-        dbgStamp(a.dbgTimes, 7);
+        dbgStamp(a.dbgTimes, 7, lb, (int)vec);
         const int pos = sKept;
         const long long off = (long long)sNnz;
         if (keep) {
@@ -1388,7 +1409,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             h.reserved[1] = h.reserved[2] = 0;
             RES_PUT(a.filt.hdr, 0, h);
         }
-        dbgStamp(a.dbgTimes, 5);
+        dbgStamp(a.dbgTimes, 5, lb, (int)vec);
     }
 #undef RES_PUT
 #undef RESV
@@ -1654,7 +1675,14 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     a.dbgTimes = c->dDbgTimes;
     a.pubWord = batch ? c->dPubWordBatch : c->dPubWord;
     a.pubCells = c->dPubCells;
-    a.epoch = batch ? ++c->epochBatch : ++c->epoch;
+    a.ticket = c->dTicket;
+    if (g.fuse && (++c->fusedLaunches & 0xffffffull) == 0) {
+        // a publication word that a launch does not rewrite (a vector beyond its nVec) must never meet its own
+        // 26-bit epoch again: all words are cleared long before the epoch wraps
+        DIPGPU_CUDA(c, cudaMemsetAsync(c->dPubWord, 0, sizeof(unsigned long long) * (size_t)std::max(c->nLocal, 1) * kPubWordStride, st));
+        if (c->dPubWordBatch)
+            DIPGPU_CUDA(c, cudaMemsetAsync(c->dPubWordBatch, 0, sizeof(unsigned long long) * (size_t)c->batchCap * (size_t)std::max(c->nLocal, 1) * kPubWordStride, st));
+    }
     a.profitMode = c->profitMode;
     a.scale = batch ? c->dScaleB : c->dScale;
     a.shortcut = batch ? c->dShortcutB : c->dShortcut;
@@ -1675,7 +1703,8 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     // host mirror of the packed result (the synchronous host entry points ask for it; option "result_zero_copy")
     a.hostOff = 0;
     if (g.fuse && (c->wantMirror || c->optMirrorAlways) && c->optZeroCopy) {
-        if (!batch && c->dResultHost) a.hostOff = (long long)(static_cast<char *>(c->dResultHost) - static_cast<char *>(c->dResult));
+        if (!batch && c->mirrorBase) a.hostOff = (long long)(static_cast<char *>(c->mirrorBase) - static_cast<char *>(c->dResult));
+        else if (!batch && c->dResultHost) a.hostOff = (long long)(static_cast<char *>(c->dResultHost) - static_cast<char *>(c->dResult));
         if (batch && c->dResultBatchHost)  // same per-vector stride on both sides
             a.hostOff = (long long)(static_cast<char *>(c->dResultBatchHost) - static_cast<char *>(c->dResultBatch));
     }

@@ -351,11 +351,15 @@ int buildSpmvTiles(Ctx *c, const std::vector<int64_t> &colStart, const std::vect
     c->nSpmvTiles = 0;
     c->spmvStageBytes = 0;
     if (N <= 0 || colStart[N] >= (int64_t)1 << 31) return DIPGPU_OK;
+    // a block shard of a multi-device context sweeps its own columns only (the SpMV is column-partitioned)
+    const int colFirst = std::max(0, std::min(c->tileColFirst, N));
+    const int colEnd = c->tileColEnd < 0 ? N : std::max(colFirst, std::min(c->tileColEnd, N));
+    const int nSweep = colEnd - colFirst;
     const bool row16 = (int64_t)c->R + c->numConvex <= 65536;
     const int sms = c->smCount > 0 ? c->smCount : 148;
     // slices per tile: up to kSpmvColsPerLane, fewer on small matrices so that every SM still gets
     // ~16 warp tiles (a GAP-E sweep is latency-bound: more, shorter tiles in flight)
-    int maxCols = (int)std::min<int64_t>(32 * kSpmvColsPerLane, (int64_t)N / (16 * sms)) & ~31;
+    int maxCols = (int)std::min<int64_t>(32 * kSpmvColsPerLane, (int64_t)nSweep / (16 * sms)) & ~31;
     maxCols = std::max(32, maxCols);
     if (c->optSpmvMaxCols > 0) maxCols = std::max(32, std::min(c->optSpmvMaxCols & ~31, 32 * kSpmvColsPerLane));
     const int maxSlices = maxCols / 32;
@@ -379,8 +383,8 @@ int buildSpmvTiles(Ctx *c, const std::vector<int64_t> &colStart, const std::vect
         for (int l = 0; l < sl.lanes; ++l) e += std::max(0, std::min(colLen(sl.col[l]), s1) - s0);
         return e;
     };
-    for (int wf = 0; wf < N; wf += window) {
-        const int wn = std::min(window, N - wf);
+    for (int wf = colFirst; wf < colEnd; wf += window) {
+        const int wn = std::min(window, colEnd - wf);
         for (int l = 0; l < wn; ++l) order[l] = wf + l;
         // lane l of a slice owns the slice's l-th longest column (stable: equal lengths keep column order)
         std::stable_sort(order.begin(), order.begin() + wn, [&](int x, int y) { return colLen(x) > colLen(y); });
@@ -525,6 +529,10 @@ int launchRedCostBatch(Ctx *c, const double *dU, int64_t uStride, double *dOut, 
                        cudaStream_t st)
 {
     if (c->N == 0 || nVec <= 0) return DIPGPU_OK;
+    {
+        const int rc = ensureSpmvTiles(c);
+        if (rc) return rc;
+    }
     if (c->nSpmvTiles > 0 && c->spmvLanes == 0) {
         StreamArgs a;
         a.nTiles = c->nSpmvTiles;

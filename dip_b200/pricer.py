@@ -89,10 +89,18 @@ class RoundResult:
 class GpuPricer:
     """One libdipgpu context = one GPU driven from one host thread."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: one CUDA ordinal (dipgpu_create), or a list of them -- one context over several GPUs of the box
+        (dipgpu_create_multi): single rounds are partitioned by blocks, batches / ladders by dual vectors."""
         self._lib = capi.lib()
         self._ctx = C.c_void_p()
-        rc = self._lib.dipgpu_create(C.byref(self._ctx), device)
+        if isinstance(device, (list, tuple, np.ndarray)):
+            devs = np.ascontiguousarray(device, np.int32)
+            rc = self._lib.dipgpu_create_multi(C.byref(self._ctx), capi.ptr(devs), len(devs))
+            self.devices = [int(d) for d in devs]
+        else:
+            rc = self._lib.dipgpu_create(C.byref(self._ctx), device)
+            self.devices = [int(device)]
         if rc != capi.OK:
             raise DipGpuError(rc, f"dipgpu_create(device={device}) failed: no usable sm_100 GPU "
                                   "(libdipgpu has no CPU fallback)")
@@ -148,6 +156,35 @@ class GpuPricer:
         ms = (C.c_float * 6)()
         self._check(self._lib.dipgpu_last_stage_ms(self._ctx, ms))
         return dict(zip(["h2d", "redcost", "knapsack_dp", "backtrack_emit", "filter", "d2h"], list(ms)))
+
+    # ------------------------------------------------------------ several devices
+    def deviceCount(self) -> tuple[int, bool]:
+        n, p = C.c_int32(), C.c_int32()
+        self._check(self._lib.dipgpu_device_count(self._ctx, C.byref(n), C.byref(p)))
+        return n.value, bool(p.value)
+
+    def shardRanges(self) -> list[tuple[int, int]]:
+        n = len(self.devices)
+        f, c = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._check(self._lib.dipgpu_shard_ranges(self._ctx, n, capi.ptr(f), capi.ptr(c)))
+        return [(int(a), int(b)) for a, b in zip(f, c)]
+
+    def sync(self):
+        self._check(self._lib.dipgpu_sync(self._ctx))
+
+    def lastDeviceMs(self) -> tuple[list[float], float]:
+        n = len(self.devices)
+        ms = np.zeros(n, np.float32)
+        mx = C.c_float()
+        self._check(self._lib.dipgpu_last_device_ms(self._ctx, n, capi.ptr(ms), C.byref(mx)))
+        return [float(x) for x in ms], float(mx.value)
+
+    def resultShards(self) -> tuple[np.ndarray, np.ndarray]:
+        n = C.c_int32()
+        cap = max(len(self.devices), 1)
+        off, siz = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+        self._check(self._lib.dipgpu_result_shards(self._ctx, cap, C.byref(n), capi.ptr(off), capi.ptr(siz)))
+        return off[:n.value], siz[:n.value]
 
     # --------------------------------------------------------------------- model
     def setModelCore(self, R, N, row_start, col_ind, val, n_base_rows, num_convex):
@@ -516,6 +553,19 @@ class GpuPricer:
         p = C.c_void_p()
         self._check(self._lib.dipgpu_redcost_dev(self._ctx, C.byref(p)))
         return p.value
+
+
+def unpack_results(packed: np.ndarray, offsets, sizes, m_total: int, cap_ind: int, result: RoundResult | None = None) -> RoundResult:
+    """dipgpu_unpack_results on a host copy of a multi-device context's gather buffer: the shards' packed results
+    decoded into ONE round, in block order."""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    off = np.ascontiguousarray(offsets, np.uint64)
+    siz = np.ascontiguousarray(sizes, np.uint64)
+    res = result or RoundResult(m_total, m_total, cap_ind)
+    rc = capi.lib().dipgpu_unpack_results(capi.ptr(packed), len(off), capi.ptr(off), capi.ptr(siz), C.byref(res.c))
+    if rc != capi.OK:
+        raise DipGpuError(rc, "dipgpu_unpack_results failed")
+    return res
 
 
 def unpack_result(packed: np.ndarray, m_total: int, cap_ind: int, result: RoundResult | None = None) -> RoundResult:

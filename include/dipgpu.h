@@ -3,8 +3,9 @@
  * DecompApp::solveRelaxed / DecompAlgo::generateVars plugin surface.
  *
  * Plain C: opaque context, caller-owned host buffers, plain pointers and sizes,
- * integer status codes (never throws).  One context drives one GPU from one
- * host thread.  There is NO CPU fallback: every entry point that computes
+ * integer status codes (never throws).  One context drives one GPU (dipgpu_create)
+ * or several GPUs of one box (dipgpu_create_multi) from one host thread.  There is
+ * NO CPU fallback: every entry point that computes
  * returns DIPGPU_ERR_CUDA when no sm_100 device / driver is usable.
  *
  * Each entry point names the reference interface it replaces (paths relative to
@@ -25,7 +26,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define DIPGPU_ABI_VERSION 2
+#define DIPGPU_ABI_VERSION 3
 
 typedef struct dipgpu_ctx dipgpu_ctx;
 
@@ -104,6 +105,34 @@ int dipgpu_abi_version(void);
 /* Opens CUDA device `device`, requires compute capability 10.x. */
 int dipgpu_create(dipgpu_ctx **ctx, int device);
 int dipgpu_destroy(dipgpu_ctx *ctx);
+
+/*
+ * One context over nDevices GPUs of one box ("int dipgpu_create(dipgpu_ctx**, const int* devices,
+ * int ndev)"), driven by the SAME caller thread through the SAME entry points -- DIP is one process whose
+ * generateVars loops over the independent blocks (under OpenMP with SubProbParallel,
+ * Dip/src/DecompAlgo.cpp:4815-4848) and whose DecompAlgoPC prices whole ladders of smoothed dual vectors
+ * (Dip/src/DecompAlgo.cpp:5642-5655).  devices[0] is the primary device (an ordinal may be listed more than once:
+ * its shards then share that GPU).  The model calls (set_core_csr,
+ * set_objective, set_knapsack_blocks, append_core_rows, set_col_bounds, set_dual_support, set_option) reach
+ * every device; the pricing calls are partitioned:
+ *   dipgpu_price_round, dipgpu_solve_blocks, dipgpu_calc_redcost, dipgpu_price_round_expand
+ *       the BLOCKS (contiguous ranges balanced by n_b*(cap_b+1), dipgpu_shard_ranges): device d computes the
+ *       reduced costs of its blocks' columns only, solves its blocks, filters; the result is merged in block
+ *       order on the host (mostNegReducedCost added in block order, Dip/src/DecompAlgo.cpp:5229-5232);
+ *   dipgpu_price_rounds_batch, dipgpu_price_round_stab, dipgpu_price_round_stab_ladder
+ *       the DUAL VECTORS: device d prices all blocks for its share of the vectors;
+ *   everything else (waiting-column pool, dipgpu_price_round_which, u == NULL rounds) runs on the primary.
+ * Exchange per call: every device reads the duals it needs out of the caller's buffer (u[support] when a dual
+ * support is declared: 34 KB on GAP-E instead of 2 MB) and writes its part of the packed result into mapped host
+ * memory itself; no collective.  Results are bit-identical to the one-GPU context.  Internally one worker
+ * thread per additional device issues that device's launches.
+ */
+int dipgpu_create_multi(dipgpu_ctx **ctx, const int32_t *devices, int32_t nDevices);
+/* Devices behind a context (1 for dipgpu_create); peerAccess = 1 when the primary and every other device can
+ * address each other's memory (NVLink / PCIe peer-to-peer). */
+int dipgpu_device_count(const dipgpu_ctx *ctx, int32_t *nDevices, int32_t *peerAccess);
+/* Block range [firstBlock[d], firstBlock[d] + blockCount[d]) of device d (arrays of length cap). */
+int dipgpu_shard_ranges(const dipgpu_ctx *ctx, int32_t cap, int32_t *firstBlock, int32_t *blockCount);
 
 /* Copies the last error text of this context (NUL-terminated) into buf. */
 int dipgpu_last_error(const dipgpu_ctx *ctx, char *buf, size_t bufLen);
@@ -385,6 +414,24 @@ int dipgpu_calc_redcost_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, i
 
 /* Device pointer + byte size of the packed result of the last *_dev call. */
 int dipgpu_result_dev(dipgpu_ctx *ctx, void **devPtr, size_t *bytes);
+
+/*
+ * Multi-device contexts, device-resident: dipgpu_price_round_dev(ctx, uDev, ..., stream = NULL) takes the
+ * master dual vector from the PRIMARY device's memory; every device pulls what it needs out of it over NVLink
+ * (peer loads of u[support]; a peer copy of the whole vector without a dual support) and its fused DP kernel
+ * repeats every result store into its slice of a gather buffer in the primary's memory (peer stores) -- the
+ * dual broadcast and the column gather of SURVEY 8e without a collective.  The call only enqueues, on every
+ * device's own stream; dipgpu_sync waits for all of them.  dipgpu_result_dev then returns the gather buffer
+ * (primary device), dipgpu_result_shards where each shard's packed result sits in it, and
+ * dipgpu_unpack_results decodes a host copy of it into ONE round (block order, as dipgpu_price_round).
+ * With option "stage_timing" every device brackets its part with CUDA events on its own stream;
+ * dipgpu_last_device_ms reports them (and their maximum) after dipgpu_sync / after a host-buffer call.
+ */
+int dipgpu_sync(dipgpu_ctx *ctx);
+int dipgpu_result_shards(const dipgpu_ctx *ctx, int32_t cap, int32_t *nShards, size_t *offsets, size_t *sizes);
+int dipgpu_unpack_results(const void *packedHost, int32_t nShards, const size_t *offsets, const size_t *sizes,
+                          dipgpu_cols *out);
+int dipgpu_last_device_ms(const dipgpu_ctx *ctx, int32_t cap, float *ms, float *maxMs);
 /* Fixed upper bound of the packed result size for this context's shard. */
 int dipgpu_result_max_bytes(const dipgpu_ctx *ctx, size_t *bytes);
 /* Decode a packed result (host copy) into `out`; block ids are global. */

@@ -83,6 +83,15 @@ public:
         if (rc != DIPGPU_OK)
             throw Error(rc, "dipgpu_create failed: no usable sm_100 GPU (libdipgpu has no CPU fallback)");
     }
+    // One pricer over several GPUs of the box (dipgpu_create_multi): the same calls, generateVars partitioned by
+    // blocks (DecompAlgo.cpp:4815-4848: the blocks are independent given the duals), the ladder by dual vectors.
+    explicit Pricer(const std::vector<int> &devices) : m_ctx(nullptr), m_m(0), m_N(0), m_nBlockCols(0), m_roundValid(false)
+    {
+        std::vector<int32_t> d(devices.begin(), devices.end());
+        const int rc = dipgpu_create_multi(&m_ctx, d.data(), (int32_t)d.size());
+        if (rc != DIPGPU_OK)
+            throw Error(rc, "dipgpu_create_multi failed: no usable sm_100 GPUs (libdipgpu has no CPU fallback)");
+    }
     ~Pricer() { dipgpu_destroy(m_ctx); }
     Pricer(const Pricer &) = delete;
     Pricer &operator=(const Pricer &) = delete;
@@ -140,6 +149,10 @@ public:
         allocResult();
         m_roundValid = false;
     }
+
+    // Rows of the master dual vector that can carry a dual at this node (the free branch rows of
+    // AlpsDecompTreeNode.cpp:215-238 cannot): only those cross PCIe per round.  Empty removes the support.
+    void setDualSupport(const std::vector<int32_t> &rows) { check(dipgpu_set_dual_support(m_ctx, (int32_t)rows.size(), rows.data())); }
 
     // ---- surface 2: the whole round ------------------------------------------------------------
     // DecompAlgo::generateVars: u = master duals (length R + numConvex; NULL = the vector the last

@@ -283,6 +283,69 @@ int main()
             for (dipgpu::DecompVar *v : varsW) delete v;
         }
     }
+    // ---- one pricer over two GPUs (the same GPU twice on a one-GPU box): generateVars partitioned by blocks,
+    // the ladder by dual vectors, the expansion by shards -- against the one-GPU pricer above
+    {
+        int nd = 0;
+        {
+            // (the C ABI has no device query of its own: a second context on ordinal 1 tells)
+            dipgpu_ctx *probe = nullptr;
+            nd = dipgpu_create(&probe, 1) == DIPGPU_OK ? 2 : 1;
+            dipgpu_destroy(probe);
+        }
+        dipgpu::Pricer multi(std::vector<int>{0, nd == 2 ? 1 : 0});
+        int32_t nDev = 0, peer = 0;
+        dipgpu_device_count(multi.ctx(), &nDev, &peer);
+        CHECK(nDev == 2);
+        multi.setModelCore(R, N, rowStart.data(), colInd.data(), val.data(), R, m);
+        multi.setObjective(cost.data(), N);
+        multi.setKnapsackBlocks(m, blockColStart.data(), weight.data(), capacity.data());
+        std::vector<int32_t> support;
+        for (int r = 0; r < R + m; ++r)
+            if (r < n || r >= R || u[(size_t)r] != 0.0) support.push_back(r);
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) {
+                pricer->setDualSupport(support);
+                multi.setDualSupport(support);
+            }
+            dipgpu::DecompVarList v1, v2;
+            double mn1 = 0, mn2 = 0;
+            const int n1 = pricer->generateVars(u.data(), (int)u.size(), dipgpu::PHASE_PRICE2, 1e-4, v1, mn1);
+            const int n2 = multi.generateVars(u.data(), (int)u.size(), dipgpu::PHASE_PRICE2, 1e-4, v2, mn2);
+            CHECK(n1 == n2 && mn1 == mn2 && multi.cells() == pricer->cells());
+            for (int b = 0; b < m; ++b) CHECK(multi.blockObj()[b] == pricer->blockObj()[b] && multi.blockRedCost()[b] == pricer->blockRedCost()[b]);
+            auto it = v1.begin();
+            for (dipgpu::DecompVar *v : v2) {
+                CHECK(v->getBlockId() == (*it)->getBlockId() && v->ind == (*it)->ind && v->getReducedCost() == (*it)->getReducedCost() &&
+                      v->getOriginalCost() == (*it)->getOriginalCost());
+                ++it;
+            }
+            for (dipgpu::DecompVar *v : v1) delete v;
+            for (dipgpu::DecompVar *v : v2) delete v;
+            std::vector<int64_t> csA, csB;
+            std::vector<int32_t> riA, riB;
+            std::vector<double> vaA, vaB;
+            std::vector<uint64_t> hsA, hsB;
+            pricer->expandColumns(1e-6, csA, riA, vaA, hsA);
+            multi.expandColumns(1e-6, csB, riB, vaB, hsB);
+            CHECK(csA == csB && riA == riB && vaA == vaB && hsA == hsB);
+        }
+        std::vector<double> u2(u), alA, alB;
+        for (int j = 0; j < n; ++j) u2[(size_t)j] = unif(seed) * 120.0;
+        pricer->setDualCentre(u.data(), (int)u.size());
+        multi.setDualCentre(u.data(), (int)u.size());
+        pricer->generateVarsLadder(u2.data(), (int)u2.size(), 0.2, 0.90, 5, dipgpu::PHASE_PRICE2, 1e-4, alA);
+        multi.generateVarsLadder(u2.data(), (int)u2.size(), 0.2, 0.90, 5, dipgpu::PHASE_PRICE2, 1e-4, alB);
+        CHECK(alA == alB);
+        for (int k = 0; k < 5; ++k) {
+            const dipgpu::Pricer::Round &a = pricer->ladderRound(k), &b = multi.ladderRound(k);
+            CHECK(a.cols.nCols == b.cols.nCols && a.cols.mostNegReducedCost == b.cols.mostNegReducedCost);
+            CHECK(a.blockObj == b.blockObj && a.blockRedCost == b.blockRedCost && a.colBlock == b.colBlock);
+            CHECK(std::vector<int32_t>(a.colInd.begin(), a.colInd.begin() + a.cols.nInd) ==
+                  std::vector<int32_t>(b.colInd.begin(), b.colInd.begin() + b.cols.nInd));
+        }
+        pricer->setDualSupport({});
+    }
     delete pricer;
     std::printf("PARITY_OK kept=%d mostNegRC=%.9f cells=%lld launches=%lld\n", kept, mostNegRC, (long long)cells,
                 (long long)launches);
