@@ -12,10 +12,13 @@ reduced costs c - A''^T u  ->  80 knapsack DPs  ->  backtrack  ->  negative-redu
           by CUDA events per step on the launching stream, L2 flushed between steps.
   e2e   : the same metric through the reference-facing C-ABI call dipgpu_price_round with HOST
           buffers (pinned u in, packed columns out), H2D + D2H inside the timed region.
-  N > 1 : one process per GPU (torchrun).  `value` is weak scaling -- every rank prices its own
-          GAP-E rounds (independent subproblem batches, no data-path collective); the `sharded`
-          object reports ONE round's 80 blocks partitioned across the N GPUs with the dual
-          broadcast and the column gather over NCCL (north_star's exchange step).
+  N > 1 : one process per GPU (torchrun) for the plumbing, ONE caller for the work: DIP is one host
+          process, so rank 0 prices its stream of dual vectors through ONE multi-device context
+          (dipgpu_create_multi over the N GPUs) while the other ranks wait.  `value` / `e2e` stay one
+          dual vector per step, its 80 blocks partitioned over the GPUs (strong scaling of a
+          latency-bound round: no faster than one GPU, and it says so); `batch16` / `batch64` /
+          `ladder8` are the calls that do scale (dual vectors partitioned), each beside the same call on
+          one GPU in the same run.  `replicas` (every rank pricing its own rounds) is an extra only.
 
 --impl reference runs the CPU pricing round (the oracle's restatement of the reference path,
 OpenMP over blocks like DecompAlgo.cpp:4815) on the host cores for the same workload.
@@ -40,6 +43,7 @@ from dip_b200 import instances as I  # noqa: E402
 METRIC = "pricing_rounds_per_s_gap_e_80x1600"
 UNIT = "rounds/s"
 N_DUALS = 16          # distinct master dual vectors cycled through the steps
+N_BATCH = 64          # ... and priced per call by the largest batch leg
 RC_EPS = 1e-4         # DecompParam::RedCostEpsilon (Dip/src/DecompParam.h:691)
 
 
@@ -67,9 +71,17 @@ def workload():
     model = I.gap_pricing_model(I.gap_class_e())
     rng = np.random.default_rng(801600)
     branch_rows = I.gap_branch_rows(model, rng)
-    duals = [I.gap_duals(model, rng, branch_rows=branch_rows) for _ in range(N_DUALS)]
+    duals = [I.gap_duals(model, rng, branch_rows=branch_rows) for _ in range(N_BATCH)]
     model.dual_support = I.gap_dual_support(model, branch_rows)
     return model, duals
+
+
+def workload_config(model):
+    """`config` of BOTH arms (the GPU path and --impl reference): the same dict, key for key."""
+    return {"workload": "GAP-E 80x1600 pricing round (SpMV c-A''^T u + 80 knapsack DPs + backtrack + filter), "
+                        "one master dual vector per step, 16 dual vectors of one node cycled",
+            "blocks": int(model.m), "cols": int(model.N), "rows": int(model.R), "nnz": int(model.nnz),
+            "red_cost_eps": RC_EPS}
 
 
 # ------------------------------------------------------------------------ clocks sampler
@@ -181,8 +193,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "GAP-E 80x1600 pricing round (SpMV + 80 knapsack DPs + filter), one dual vector per step",
-                   "blocks": model.m, "cols": model.N, "rows": model.R, "nnz": model.nnz},
+        "config": workload_config(model),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} whole rounds; the reference's GAP pricing needs Pisinger's combo.c "
                                    "(not vendored) so the oracle's restatement of knapsack01 + generateVars is timed"},
@@ -214,6 +225,29 @@ def _emit(line: dict):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
+class Flusher:
+    """L2 flush of every device a leg runs on: 256 MiB written, then 256 MiB read, so that the timed kernels
+    start with an L2 full of CLEAN foreign lines (after a write-only flush the timed kernel also pays the
+    write-back of ~126 MB of the flush's dirty lines -- scripts/spmv_timing.py: 37.0 vs 30.8 us)."""
+
+    def __init__(self, torch, devices):
+        self.torch, self.devices = torch, list(dict.fromkeys(devices))
+        self.bufs = []
+        for d in self.devices:
+            dev = torch.device("cuda", d)
+            self.bufs.append((torch.empty(256 << 20, dtype=torch.uint8, device=dev),
+                              torch.ones(64 << 20, dtype=torch.float32, device=dev)))
+
+    def __call__(self, sync=False):
+        for d, (w, r) in zip(self.devices, self.bufs):
+            with self.torch.cuda.device(d):
+                w.fill_(1)
+                r.sum()
+        if sync or len(self.devices) > 1:
+            for d in self.devices:
+                self.torch.cuda.synchronize(d)
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -223,6 +257,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-extras", action="store_true", help="skip the CSP GCUPS / SpMV / CPU legs")
     ap.add_argument("--csp-blocks", type=int, default=10_000)
+    ap.add_argument("--devices", default="", help="single process, several GPUs: comma-separated ordinals for the "
+                                                  "multi-device legs (what torchrun's rank 0 does with --gpus N)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -234,16 +270,16 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dip_b200.pricer import GpuPricer, RoundResult, unpack_result
-    from dip_b200 import capi
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the pricing path is CUDA-only (no CPU fallback); "
                          "use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")   # waiting ranks must not spin an NCCL kernel on a GPU rank 0 drives
 
     def barrier():
         if world > 1:
@@ -257,9 +293,70 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    devices = [int(d) for d in args.devices.split(",") if d != ""] if args.devices else list(range(world))
+    if world == 1 and len(devices) <= 1:
+        line = single_gpu_line(args, torch, dev, local_rank)
+        _emit(line)
+        return
+
+    # ---- N > 1.  Extra first: every rank prices its own rounds (independent replicas, no exchange).
+    model, duals = workload()
+    replicas = replica_rounds(args, torch, dev, local_rank, model, duals, world, barrier, max_over_ranks) if world > 1 else None
+    barrier()
+    if rank == 0:
+        line = multi_gpu_line(args, torch, devices, model, duals, replicas)
+    if world > 1:
+        dist.barrier(group=cpu_group)   # the other ranks wait on the host while rank 0 drives every GPU
+    if rank == 0:
+        _emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def replica_rounds(args, torch, dev, local_rank, model, duals, world, barrier, max_over_ranks):
+    """EXTRA at N > 1: every rank prices its own GAP-E rounds on its own GPU (device-resident, as `value` at
+    N = 1).  Independent replicas with no exchange: an upper bound on what N GPUs deliver, not a scaling result."""
+    from dip_b200.pricer import GpuPricer
+    K, W = min(args.steps, 100), args.warmup
+    pr = GpuPricer(local_rank)
+    pr.setModel(model)
+    stream = torch.cuda.Stream(device=dev)
+    flush = Flusher(torch, [local_rank])
+    u_dev = [torch.from_numpy(u).to(dev) for u in duals[:N_DUALS]]
+    with torch.cuda.stream(stream):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for k in range(W):
+            pr.priceRoundDev(u_dev[k % N_DUALS].data_ptr(), model.u_len, redCostEps=RC_EPS, stream=stream.cuda_stream)
+        barrier()
+        for k in range(K):
+            flush()
+            stream.wait_stream(torch.cuda.default_stream(dev))
+            ev[k][0].record(stream)
+            pr.priceRoundDev(u_dev[k % N_DUALS].data_ptr(), model.u_len, redCostEps=RC_EPS, stream=stream.cuda_stream)
+            ev[k][1].record(stream)
+        barrier()
+        stream.synchronize()
+    ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    pr.close()
+    return {"rounds_per_s": world * K / (ms * 1e-3), "ms_per_round_per_gpu": ms / K,
+            "note": "every rank prices its own rounds, no exchange: an upper bound, not a scaling result"}
+
+
+def single_gpu_line(args, torch, dev, local_rank):
+    from dip_b200.pricer import GpuPricer, RoundResult
+    from dip_b200 import capi
     hbm_peak, peak_src = load_peaks()
     model, duals = workload()
     K, W = args.steps, args.warmup
+    rank, world = 0, 1
+
+    def barrier():
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        return x
+
     pr = GpuPricer(local_rank)
     pr.setModel(model)
     # a non-default stream: the library treats a NULL stream as "use the context's own"
@@ -277,8 +374,8 @@ def main():
         flush_buf.fill_(1)
         flush_rd.sum()
 
-    u_dev = [torch.from_numpy(u).to(dev) for u in duals]
-    u_pin = capi.PinnedArray((N_DUALS, model.u_len), np.float64)
+    u_dev = [torch.from_numpy(u).to(dev) for u in duals[:N_DUALS]]
+    u_pin = capi.PinnedArray((N_BATCH, model.u_len), np.float64)
     for k, u in enumerate(duals):
         u_pin.array[k] = u
     res = RoundResult(model.m, model.m, model.N)
@@ -312,9 +409,8 @@ def main():
     wall_dev = time.perf_counter() - wall0
     c1 = pr.counters()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    dev_ms = max_over_ranks(dev_ms)
     launches = c1["kernel_launches"] - c0["kernel_launches"]
-    value = world * K / (dev_ms * 1e-3)
+    value = K / (dev_ms * 1e-3)
 
     # ---- end-to-end rounds through the host-buffer C-ABI call (e2e): pinned u in, packed columns out.
     # Twice: the whole 2 MB dual vector uploaded per round, and with the rows that can carry a dual at this
@@ -335,15 +431,15 @@ def main():
             pr.priceRoundRaw(ptrs[k % N_DUALS], model.u_len, capi.PHASE_PRICE2, RC_EPS, res)
             tot += time.perf_counter() - t0
         c1 = pr.counters()
-        return max_over_ranks(tot), (c1["h2d_bytes"] - c0["h2d_bytes"]) // K, (c1["d2h_bytes"] - c0["d2h_bytes"]) // K
+        return tot, (c1["h2d_bytes"] - c0["h2d_bytes"]) // K, (c1["d2h_bytes"] - c0["d2h_bytes"]) // K
 
     dense_s, dense_h2d, _ = e2e_loop()
     pr.setDualSupport(model.dual_support)
     e2e_s, h2d_b, d2h_b = e2e_loop()
-    e2e = {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+    e2e = {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
            "ms_per_step": 1e3 * e2e_s / K,
            "dual_support_rows": int(len(model.dual_support)),
-           "dense_upload": {"value": world * K / dense_s, "ms_per_step": 1e3 * dense_s / K, "h2d_bytes_per_step": dense_h2d},
+           "dense_upload": {"value": K / dense_s, "ms_per_step": 1e3 * dense_s / K, "h2d_bytes_per_step": dense_h2d},
            "timing": "host wall clock around the synchronous dipgpu_price_round call (pinned u in, columns out); "
                      "`value`: the rows that can carry a dual declared once, only they are uploaded; "
                      "`dense_upload`: the whole dual vector uploaded every round"}
@@ -369,110 +465,265 @@ def main():
     smem_peak = None
     if not args.skip_extras:
         smem_peak = pr.measureSmemGBs()
-        extras["batched"] = bench_batched(pr, model, duals, u_pin, cells_per_round, flush_l2, torch, smem_peak, world,
-                                          max_over_ranks)
+        extras["batched"] = bench_batched(pr, model, duals, u_pin, flush_l2, torch, smem_peak)
         extras["pool"] = bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank)
         extras["mckp"] = bench_mckp(torch, local_rank, smem_peak, flush_l2)
     cells_mean = float(np.mean(cells_per_round))
     cells_eval_mean = float(np.mean(cells_eval_per_round))
     dp_ms = stage_ms["knapsack_dp"]
-    # dominant kernel of the step = knap_dp_kernel; algorithmic shared-memory bytes = 24 B / cell of the
-    # reference's DP.  The fused kernel first drops the items no optimal solution can contain and
-    # evaluates only `cells_evaluated` of them: `achieved` is the ALGORITHMIC rate (reference cells / time),
-    # `achieved_evaluated` the cells it actually touched.
-    roofline = {
-        "kernel": "knap_dp_kernel", "bound": "smem",
-        "achieved": cells_mean * 24.0 / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None,
-        "achieved_evaluated": cells_eval_mean * 24.0 / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None,
-        "cells_evaluated_per_launch": cells_eval_mean,
-        "peak": smem_peak, "unit": "GB/s",
-        "frac": (cells_mean * 24.0 / (dp_ms * 1e-3) / 1e9 / smem_peak) if (smem_peak and dp_ms > 0) else None,
-        "frac_evaluated": (cells_eval_mean * 24.0 / (dp_ms * 1e-3) / 1e9 / smem_peak) if (smem_peak and dp_ms > 0) else None,
+    roofline = dp_roofline(cells_mean, cells_eval_mean, dp_ms, smem_peak)
+
+    if not args.skip_extras:
+        extras["dp_csp"] = bench_csp(torch, [local_rank], args, smem_peak, flush_l2)
+        extras["spmv_milpblock"] = bench_spmv(torch, dev, local_rank, hbm_peak, peak_src, flush_l2, world, rank,
+                                              max_over_ranks, barrier)
+    cpu = None
+    if not args.skip_extras:
+        cpu = cpu_baseline(model, duals)
+
+    cfg = workload_config(model)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "run": {"cells_per_round": cells_mean, "cells_evaluated_per_round": cells_eval_mean,
+                "kept_columns_round0": kept0, "parallelism": "1 GPU",
+                "l2": "flushed between steps (256 MiB written then 256 MiB read, outside the per-step CUDA-event pairs)"},
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+        "wall_s_device_loop": wall_dev, "stage_ms": stage_ms, "roofline": roofline,
+    }
+    if "dp_csp" in extras:
+        line["roofline_dp_csp"] = extras["dp_csp"]
+        line["dp_gcups_csp"] = extras["dp_csp"]["gcups"]
+        line["dp_csp_frac_smem_16B"] = extras["dp_csp"]["frac_16B"]
+    if "spmv_milpblock" in extras:
+        line["roofline_spmv"] = extras["spmv_milpblock"]
+        line["spmv_gbs"] = extras["spmv_milpblock"]["achieved"]
+        line["spmv_frac"] = extras["spmv_milpblock"]["frac"]
+    if "batched" in extras:
+        line["batched_rounds"] = extras["batched"]
+        for nm in ("batch16", "batch64", "ladder8"):
+            if nm in extras["batched"]:
+                line[nm + "_rounds_per_s"] = extras["batched"][nm]["e2e_rounds_per_s"]
+    if "pool" in extras:
+        line["roofline_pool"] = extras["pool"]
+    if "mckp" in extras:
+        line["roofline_mckp"] = extras["mckp"]
+    if expand is not None:
+        line["expand_columns"] = expand
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    pr.close()
+    return line
+
+
+def dp_roofline(cells_mean, cells_eval_mean, dp_ms, smem_peak):
+    """Dominant kernel of the step = knap_dp_kernel.  The fused kernel first drops the items no optimal solution
+    can contain and evaluates `cells_evaluated` of the reference DP's cells: `frac` is the fraction of the
+    shared-memory roofline the cells it TOUCHES account for (24 B each) -- the honest figure for a
+    kernel that is a chain of latencies; `algorithmic_*` count the reference's cells against the same time."""
+    ok = dp_ms > 0 and smem_peak
+    ach = cells_eval_mean * 24.0 / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None
+    alg = cells_mean * 24.0 / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None
+    return {
+        "kernel": "knap_dp_kernel", "bound": "smem", "achieved": ach, "peak": smem_peak, "unit": "GB/s",
+        "frac": ach / smem_peak if ok else None,
+        "cells_evaluated_per_launch": cells_eval_mean, "cells_per_launch": cells_mean,
+        "algorithmic_achieved": alg, "algorithmic_frac": alg / smem_peak if ok else None,
+        "algorithmic_gcups": cells_mean / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None,
         "traffic": ncu_traffic("prof_dp_gape"),
         "traffic_note": "DRAM bytes per launch, ncu --set full capture of this kernel on this shape "
                         "(profiles/ncu_traffic.json); the bound is shared memory, HBM only sees inputs",
         "peak_source": "in-library shared-memory copy microbenchmark (dipgpu_measure_smem_gbs), this run",
-        "note": "80 six-warp CTAs on 148 SMs: the GAP-E round is latency-bound (launch, staging, reduction pre-pass, "
-                "~70 DP steps, backtrack, in-kernel filter), see roofline_dp_csp for the bandwidth-bound shape "
-                "of the same kernel",
-        "avg_launch_ms": dp_ms, "cells_per_launch": cells_mean,
-        "gcups": cells_mean / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None,
+        "note": "80 six-warp CTAs on 148 SMs: the GAP-E round is LATENCY-bound (staging, reduction pre-pass, ~70 DP "
+                "steps, backtrack, in-kernel filter), not roofline-bound; roofline_dp_csp is the bandwidth-bound "
+                "shape of the same kernel",
+        "avg_launch_ms": dp_ms,
     }
 
-    # ---- N > 1: one round's blocks sharded across the ranks, NCCL broadcast + gather
-    sharded = None
-    if world > 1:
-        sharded = sharded_rounds(dist, torch, dev, pr, model, u_dev, K, W, world, rank, flush_l2, barrier,
-                                 max_over_ranks, unpack_result, RoundResult, kept0)
-        pr.setBlockRange(0, model.m)
 
-    if not args.skip_extras:
-        extras["dp_csp"] = bench_csp(torch, dev, pr, args, world, rank, barrier, max_over_ranks, smem_peak, flush_l2)
-        extras["spmv_milpblock"] = bench_spmv(torch, dev, local_rank, hbm_peak, peak_src, flush_l2, world, rank,
-                                              max_over_ranks, barrier)
-    cpu = None
-    if rank == 0 and world == 1 and not args.skip_extras:
-        cpu = cpu_baseline(model, duals)
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": "GAP-E 80x1600 pricing round (SpMV c-A''^T u + 80 knapsack DPs + backtrack + filter), "
-                            "one master dual vector per step, 16 dual vectors cycled",
-                "blocks": model.m, "cols": model.N, "rows": model.R, "nnz": model.nnz,
-                "cells_per_round": cells_mean, "cells_evaluated_per_round": cells_eval_mean,
-                "kept_columns_round0": kept0, "red_cost_eps": RC_EPS,
-                "l2": "flushed between steps (256 MiB written then 256 MiB read, outside the per-step CUDA-event pairs)",
-                "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, independent rounds per rank (weak); "
-                                                          "see `sharded` for one round partitioned over NCCL",
-            },
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
-            "wall_s_device_loop": wall_dev, "stage_ms": stage_ms, "roofline": roofline,
-        }
-        if "dp_csp" in extras:
-            line["roofline_dp_csp"] = extras["dp_csp"]
-        if "spmv_milpblock" in extras:
-            line["roofline_spmv"] = extras["spmv_milpblock"]
-        if "batched" in extras:
-            line["batched_rounds"] = extras["batched"]
-        if "pool" in extras:
-            line["roofline_pool"] = extras["pool"]
-        if "mckp" in extras:
-            line["roofline_mckp"] = extras["mckp"]
-        if expand is not None:
-            line["expand_columns"] = expand
-        if sharded is not None:
-            line["sharded"] = sharded
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
-        _emit(line)
-    pr.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-
-
-def bench_batched(pr, model, duals, u_pin, cells_per_round, flush_l2, torch, smem_peak, world, max_over_ranks):
-    """Several dual vectors per submission: (i) dipgpu_price_rounds_batch on the 16 pinned
-    dual vectors, (ii) the Wentges ladder of 8 smoothing parameters from ONE uploaded dualRM
-    (dipgpu_price_round_stab_ladder).  Host wall clock around the synchronous C-ABI calls, H2D and D2H
-    inside, L2 flushed before every call; stage times from the library's CUDA events."""
+def multi_gpu_line(args, torch, devices, model, duals, replicas):
+    """Rank 0 at N > 1 (or --devices): ONE caller, N GPUs, through one multi-device context."""
+    from dip_b200.pricer import GpuPricer, RoundResult, unpack_results
     from dip_b200 import capi
-    import ctypes as C
+    N = len(devices)
+    K, W = args.steps, args.warmup
+    dev0 = torch.device("cuda", devices[0])
+    flush = Flusher(torch, devices)
+    flush1 = Flusher(torch, devices[:1])
+    pm = GpuPricer(devices)
+    pm.setModel(model)
+    pm.setDualSupport(model.dual_support)
+    p1 = GpuPricer(devices[0])          # the same calls on ONE GPU, same run, same clock: the scaling baseline
+    p1.setModel(model)
+    p1.setDualSupport(model.dual_support)
+    pone = GpuPricer(devices[:1])       # the multi-device code path over one device: same timing method
+    pone.setModel(model)
+    pone.setDualSupport(model.dual_support)
+    n_dev, peer = pm.deviceCount()
+    ranges = pm.shardRanges()
+    u_dev = [torch.from_numpy(u).to(dev0) for u in duals[:N_DUALS]]
+    u_pin = capi.PinnedArray((N_BATCH, model.u_len), np.float64)
+    for k, u in enumerate(duals):
+        u_pin.array[k] = u
+    ptrs = [u_pin.array[k].ctypes.data for k in range(N_DUALS)]
+    res = RoundResult(model.m, model.m, model.N)
+    sup_bytes = 8 * len(model.dual_support)
+
+    class _DevBytes:
+        def __init__(self, p, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (p, False), "version": 2}
+
+    # ---- value: ONE dual vector per step, device-resident (duals in the primary's HBM, results gathered in the
+    # primary's HBM), the blocks partitioned; every device brackets its part with CUDA events on its own stream,
+    # the step costs the slowest device.
+    def dev_loop(p, fl, steps, warm):
+        p.set_option("round_timing", 1)
+        tot, per_dev = 0.0, None
+        for k in range(warm + steps):
+            fl(sync=True)
+            p.priceRoundDev(u_dev[k % N_DUALS].data_ptr(), model.u_len, redCostEps=RC_EPS)
+            p.sync()
+            ms, mx = p.lastDeviceMs()
+            if k >= warm:
+                tot += mx
+                per_dev = np.array(ms) if per_dev is None else per_dev + np.array(ms)
+        p.set_option("round_timing", 0)
+        return tot, (per_dev / steps).tolist()
+
+    c0 = pm.counters()
+    with ClockSampler(devices[0]) as clk:
+        dev_ms, per_dev_ms = dev_loop(pm, flush, K, W)
+    c1 = pm.counters()
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+    one_ms, _ = dev_loop(pone, flush1, min(K, 100), W)
+    one_ms = one_ms / min(K, 100)
+    # merged == unsharded, on the last dual vector priced
+    k_last = (W + K - 1) % N_DUALS
+    ptr, nbytes = pm.resultDev()
+    off, siz = pm.resultShards()
+    host = torch.as_tensor(_DevBytes(ptr, nbytes), device=dev0).cpu().numpy()
+    merged = unpack_results(host, off, siz, model.m, model.N)
+    full = p1.priceRound(duals[k_last], redCostEps=RC_EPS, result=RoundResult(model.m, model.m, model.N))
+    same = bool(merged.nCols == full.nCols and np.array_equal(merged.blockObj, full.blockObj)
+                and np.array_equal(merged.blockRedCost, full.blockRedCost)
+                and merged.mostNegReducedCost == full.mostNegReducedCost
+                and np.array_equal(merged.colInd[:merged.c.nInd], full.colInd[:full.c.nInd]))
+    result_bytes = int(sum(int(x) for x in siz[1:]))   # upper bound: the shards' whole packed buffers
+    kept_bytes = int(merged.c.nInd) * 4 + model.m * 44
+    value = K / (dev_ms * 1e-3)
+
+    # ---- e2e: the same round through the host-buffer call (pinned u in, merged columns out), wall clock
+    def e2e_loop(p, fl, steps, warm):
+        for k in range(warm):
+            p.priceRoundRaw(ptrs[k % N_DUALS], model.u_len, capi.PHASE_PRICE2, RC_EPS, res)
+        a = p.counters()
+        tot = 0.0
+        for k in range(steps):
+            fl(sync=True)
+            t0 = time.perf_counter()
+            p.priceRoundRaw(ptrs[k % N_DUALS], model.u_len, capi.PHASE_PRICE2, RC_EPS, res)
+            tot += time.perf_counter() - t0
+        b = p.counters()
+        return tot, (b["h2d_bytes"] - a["h2d_bytes"]) // steps, (b["d2h_bytes"] - a["d2h_bytes"]) // steps
+
+    e2e_s, h2d_b, d2h_b = e2e_loop(pm, flush, K, W)
+    e2e1_s, _, _ = e2e_loop(p1, flush1, min(K, 100), W)
+    e2e = {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
+           "ms_per_step": 1e3 * e2e_s / K, "one_gpu_ms_per_step": 1e3 * e2e1_s / min(K, 100),
+           "dual_support_rows": int(len(model.dual_support)),
+           "timing": "host wall clock around the synchronous dipgpu_price_round call on the multi-device context: "
+                     "every GPU reads u[support] out of the caller's pinned vector (PCIe) and mirrors its part of the "
+                     "packed result into mapped host memory; h2d / d2h bytes are summed over the GPUs"}
+
+    # ---- per-stage device times (slowest device per stage) and the DP roofline per device
+    pm.set_option("stage_timing", 1)
+    stage, cells, cells_ev = {}, [], []
+    for k in range(min(K, 60)):
+        flush(sync=True)
+        pm.priceRoundRaw(ptrs[k % N_DUALS], model.u_len, capi.PHASE_PRICE2, RC_EPS, res)
+        for nm, ms in pm.last_stage_ms().items():
+            stage.setdefault(nm, []).append(ms)
+        cells.append(res.cells)
+        cells_ev.append(res.cellsEvaluated)
+    pm.set_option("stage_timing", 0)
+    stage_ms = {nm: float(np.mean(v)) for nm, v in stage.items()}
+    smem_peak = p1.measureSmemGBs() if not args.skip_extras else None
+    roofline = dp_roofline(float(np.mean(cells)), float(np.mean(cells_ev)), stage_ms["knapsack_dp"], smem_peak * N if smem_peak else None)
+    roofline["note"] = f"{N} GPUs, each with 1/{N} of the 80 blocks: the slowest device's DP stage against {N} x the shared-memory peak; " + roofline["note"]
+
+    # ---- the calls that scale: several dual vectors per call, partitioned over the GPUs; same call on one GPU beside it
+    batched = None
+    if not args.skip_extras:
+        b_multi = bench_batched(pm, model, duals, u_pin, flush, torch, None)
+        b_one = bench_batched(p1, model, duals, u_pin, flush1, torch, None)
+        batched = {}
+        for nm in ("batch16", "batch64", "ladder8"):
+            batched[nm] = {"rounds_per_call": b_multi[nm]["rounds_per_call"],
+                           "rounds_per_s": b_multi[nm]["e2e_rounds_per_s"], "ms_per_call": b_multi[nm]["ms_per_call"],
+                           "one_gpu_rounds_per_s": b_one[nm]["e2e_rounds_per_s"], "one_gpu_ms_per_call": b_one[nm]["ms_per_call"],
+                           "speedup_vs_one_gpu": b_multi[nm]["e2e_rounds_per_s"] / b_one[nm]["e2e_rounds_per_s"],
+                           "efficiency": b_multi[nm]["e2e_rounds_per_s"] / b_one[nm]["e2e_rounds_per_s"] / N,
+                           "stage_ms_slowest_device": b_multi[nm]["stage_ms"]}
+        batched["timing"] = ("host wall clock around the synchronous C-ABI call (64 / 16 pinned dual vectors, or one dualRM and "
+                             "an 8-step smoothing ladder), duals in and columns out inside, L2 of every GPU flushed before each call")
+    csp = None
+    if not args.skip_extras:
+        csp = bench_csp(torch, devices, args, smem_peak, flush)
+    for p in (pm, p1, pone):
+        p.close()
+    cfg = workload_config(model)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg,
+        "run": {"parallelism": f"ONE caller (rank 0), one multi-device context over {N} GPUs: the 80 blocks of every round "
+                               "partitioned by DP work (dipgpu_shard_ranges), SpMV column-partitioned, no collective",
+                "blocks_per_gpu": [c for _, c in ranges],
+                "l2": "every GPU flushed between steps (256 MiB written then 256 MiB read, outside the per-device CUDA-event pairs)",
+                "timing": "per step: each GPU's CUDA-event pair on its own stream around its part, the step costs the slowest GPU"},
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "stage_ms": stage_ms, "roofline": roofline,
+        "sharded": {"ms_per_round": dev_ms / K, "ms_per_round_per_gpu": per_dev_ms,
+                    "one_gpu_same_method_ms": one_ms, "vs_one_gpu": one_ms / (dev_ms / K),
+                    "merged_equals_unsharded": same, "peer_access": bool(peer),
+                    "exchange": "duals: every GPU pulls u[support] out of the primary's HBM (peer loads over NVLink); results: "
+                                "every fused DP kernel mirrors its packed result into the primary's gather buffer (peer stores)",
+                    "nvlink_bytes_per_round": {"duals": (N - 1) * sup_bytes, "results_max": result_bytes, "results_kept_about": kept_bytes},
+                    "pcie_bytes_per_round_e2e": {"h2d": int(h2d_b), "d2h": int(d2h_b)}},
+        "sharded_ms_per_round": dev_ms / K, "sharded_vs_one_gpu": one_ms / (dev_ms / K),
+    }
+    if batched is not None:
+        line["batched_rounds"] = batched
+        for nm in ("batch16", "batch64", "ladder8"):
+            line[nm + "_rounds_per_s"] = batched[nm]["rounds_per_s"]
+            line[nm + "_speedup_vs_one_gpu"] = batched[nm]["speedup_vs_one_gpu"]
+    if csp is not None:
+        line["roofline_dp_csp"] = csp
+        line["dp_gcups_csp"] = csp["gcups"]
+        line["dp_csp_frac_smem_16B"] = csp["frac_16B"]
+    if replicas is not None:
+        line["replicas"] = replicas
+    return line
+
+
+def bench_batched(pr, model, duals, u_pin, flush_l2, torch, smem_peak):
+    """Several dual vectors per submission: dipgpu_price_rounds_batch on 16 and on 64 pinned dual
+    vectors, and the Wentges ladder of 8 smoothing parameters from ONE uploaded dualRM
+    (dipgpu_price_round_stab_ladder).  Host wall clock around the synchronous C-ABI calls, H2D and D2H
+    inside, L2 flushed before every call; stage times from the library's CUDA events (a multi-device context
+    reports the slowest device per stage)."""
+    from dip_b200 import capi
     out = {}
-    n = N_DUALS
-    res, arr = pr._batch_results(n)
+    res, arr = pr._batch_results(N_BATCH)
     reps = 30
-    for name, steps in (("batch16", n), ("ladder8", 8)):
+    for name, steps in (("batch16", 16), ("batch64", N_BATCH), ("ladder8", 8)):
         def call():
-            if name == "batch16":
-                pr.priceRoundsBatchRaw(n, u_pin.array.ctypes.data, model.u_len, capi.PHASE_PRICE2, RC_EPS, arr)
-            else:
+            if name == "ladder8":
                 pr.priceRoundStabLadderRaw(u_pin.array[1].ctypes.data, model.u_len, 0.1, 0.90, 8, capi.PHASE_PRICE2,
                                            RC_EPS, arr)
+            else:
+                pr.priceRoundsBatchRaw(steps, u_pin.array.ctypes.data, model.u_len, capi.PHASE_PRICE2, RC_EPS, arr)
         if name == "ladder8":
             pr.stabSetCenter(duals[0])
         for _ in range(3):
@@ -488,21 +739,19 @@ def bench_batched(pr, model, duals, u_pin, cells_per_round, flush_l2, torch, sme
             for nm, ms in pr.last_stage_ms().items():
                 stage.setdefault(nm, []).append(ms)
         pr.set_option("stage_timing", 0)
-        t = max_over_ranks(t)
         st = {nm: float(np.mean(v)) for nm, v in stage.items()}
         cells = float(sum(arr[k].cells for k in range(steps)))
         cells_ev = float(sum(arr[k].cellsEvaluated for k in range(steps)))
         dp_ms = st["knapsack_dp"]
-        ach = cells * 24.0 / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None
+        ach = cells_ev * 24.0 / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None
         out[name] = {
-            "rounds_per_call": steps, "e2e_rounds_per_s": world * steps * reps / t, "ms_per_call": 1e3 * t / reps,
+            "rounds_per_call": steps, "e2e_rounds_per_s": steps * reps / t, "ms_per_call": 1e3 * t / reps,
             "stage_ms": st, "dp_cells_per_call": cells, "dp_cells_evaluated_per_call": cells_ev,
             "dp_roofline": {"kernel": "knap_dp_kernel (fused, gridDim.y = vectors)", "bound": "smem", "achieved": ach,
                             "peak": smem_peak, "unit": "GB/s", "frac": ach / smem_peak if (ach and smem_peak) else None,
-                            "frac_evaluated": (cells_ev * 24.0 / (dp_ms * 1e-3) / 1e9 / smem_peak) if (smem_peak and dp_ms > 0) else None,
-                            "note": "achieved / frac count the reference DP's cells (24 B each); the kernel evaluates "
-                                    "dp_cells_evaluated_per_call of them after its reduction pre-pass",
-                            "gcups": cells / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None},
+                            "note": "achieved / frac count the cells the kernel evaluates after its reduction pre-pass (24 B "
+                                    "each); algorithmic_gcups counts the reference DP's cells against the same time",
+                            "algorithmic_gcups": cells / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None},
         }
     out["note"] = ("value / e2e above stay ONE dual vector per step (what DecompAlgo::generateVars prices per call); "
                    "these are the same rounds submitted several at a time")
@@ -567,7 +816,7 @@ def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank):
             "note": "every stored entry gathers one dual (8 B of a 32 B sector, L2-resident): the sector traffic, not the "
                     "12 B/entry stream, bounds this pass; with the dual support declared the gathers of rows without a "
                     "dual are skipped (shared-memory bitmap)",
-            "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic("prof_pool_bitmap"),
             "avg_launch_ms": ms, "without_dual_support": {"avg_launch_ms": ms_plain, "achieved": by / (ms_plain * 1e-3) / 1e9,
                                                           "frac": by / (ms_plain * 1e-3) / 1e9 / hbm_peak},
             "algorithmic_bytes": by, "peak_source": peak_src}
@@ -664,110 +913,45 @@ def bench_expand(pr, model, duals, ptrs, res, flush_l2, torch, rank):
     return out
 
 
-def sharded_rounds(dist, torch, dev, pr, model, u_dev, K, W, world, rank, flush_l2, barrier, max_over_ranks,
-                   unpack_result, RoundResult, kept_expected):
-    """One GAP-E round partitioned over the ranks: rank 0 owns the dual vector, ncclBroadcast(u),
-    every rank prices its contiguous block range, all_gather of the packed per-shard results
-    (fixed-size buffers), rank 0 decodes.  Strong scaling of a single round (latency-bound)."""
-    from dip_b200.sharding import block_range, merge_shards
-    m = model.m
-    work = np.diff(model.block_col_start).astype(np.int64) * (model.capacity.astype(np.int64) + 1)
-    first, count = block_range(m, world, rank, work)
-    per = count
-    pr.setBlockRange(first, count)
-    dptr, nbytes = pr.resultDev()
-    sizes = torch.tensor([nbytes], dtype=torch.int64, device=dev)
-    dist.all_reduce(sizes, op=dist.ReduceOp.MAX)
-    maxb = int(sizes.item())
-    maxb = (maxb + 15) // 16 * 16
-    send = torch.zeros(maxb, dtype=torch.uint8, device=dev)
-    recv = torch.zeros(maxb * world, dtype=torch.uint8, device=dev)
-    ubuf = torch.empty(model.u_len, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream()
-    sptr = stream.cuda_stream
-
-    class _DevBytes:  # torch view of the library's packed-result buffer (no copy)
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-    packed = torch.as_tensor(_DevBytes(dptr, nbytes), device=dev)
-
-    def one_round(k):
-        if rank == 0:
-            ubuf.copy_(u_dev[k % len(u_dev)])
-        dist.broadcast(ubuf, src=0)
-        pr.priceRoundDev(ubuf.data_ptr(), model.u_len, redCostEps=RC_EPS, stream=sptr)
-        # packed shard result -> fixed-size send buffer (device-to-device on the same stream)
-        send[:nbytes].copy_(packed, non_blocking=True)
-        dist.all_gather_into_tensor(recv, send)
-
-    for k in range(W):
-        one_round(k)
-    barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for k in range(K):
-        flush_l2()
-        evs[k][0].record(stream)
-        one_round(k)
-        evs[k][1].record(stream)
-    barrier()
-    ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
-    # decode on rank 0 (dipgpu_unpack_result per shard, merged in block order) and check the last
-    # round against the unsharded result of the same dual vector
-    ok = None
-    if rank == 0:
-        host = recv.cpu().numpy()
-        merged = merge_shards([host[r * maxb:(r + 1) * maxb] for r in range(world)], m, model.N)
-        k_last = (K - 1) % len(u_dev)
-        pr.setBlockRange(0, m)
-        full = pr.priceRound(u_dev[k_last].cpu().numpy(), redCostEps=RC_EPS, result=RoundResult(m, m, model.N))
-        ok = bool(merged.nCols == full.nCols and np.array_equal(merged.blockObj, full.blockObj)
-                  and np.array_equal(merged.blockRedCost, full.blockRedCost)
-                  and merged.mostNegReducedCost == full.mostNegReducedCost
-                  and np.array_equal(merged.colInd[:merged.c.nInd], full.colInd[:full.c.nInd]))
-    return {"rounds_per_s": K / (ms * 1e-3), "ms_per_round": ms / K, "scaling": "strong",
-            "blocks_per_gpu": per, "collectives": "ncclBroadcast(u, %d B) + ncclAllGather(%d B per rank)" % (
-                model.u_len * 8, maxb), "merged_equals_unsharded": ok}
-
-
-def bench_csp(torch, dev, pr_unused, args, world, rank, barrier, max_over_ranks, smem_peak, flush_l2):
-    """Knapsack DP GCUPS on the cutting-stock batch (BASELINE.json configs[3]): 10^4 knapsacks,
-    n = 500, capacity 10^4, split evenly over the ranks (strong scaling, no collective)."""
+def bench_csp(torch, devices, args, smem_peak, flush_l2):
+    """Knapsack DP GCUPS on the cutting-stock batch (BASELINE.json configs[3]): 10^4 knapsacks, n = 500,
+    capacity 10^4.  Several GPUs: ONE dipgpu_solve_blocks call on the multi-device context, the knapsacks
+    partitioned over the GPUs (no exchange but the result); DP time = the slowest device's DP stage."""
     from dip_b200.pricer import GpuPricer
     m_total = args.csp_blocks
-    per = (m_total + world - 1) // world
-    first = min(rank * per, m_total)
-    count = max(0, min(per, m_total - first))
     b = I.csp_batch(m=m_total)
     n = 500
-    lo, hi = first * n, (first + count) * n
-    pr = GpuPricer(torch.cuda.current_device())
-    pr.setObjective(b.orig_cost[lo:hi])
-    pr.setKnapsackBlocks((np.arange(count + 1) * n).astype(np.int32), b.weight[lo:hi], b.capacity[first:first + count])
+    ndev = len(devices)
+    pr = GpuPricer(devices if ndev > 1 else devices[0])
+    pr.setObjective(b.orig_cost)
+    pr.setKnapsackBlocks((np.arange(m_total + 1) * n).astype(np.int32), b.weight, b.capacity)
     pr.set_option("stage_timing", 1)
-    rc = b.red_cost[lo:hi].copy()
-    alpha = np.zeros(count)
+    rc = b.red_cost.copy()
+    alpha = np.zeros(m_total)
     res = pr.solveBlocks(rc, alpha, redCostEps=-np.inf)
-    cells_local = res.cells
     times = []
     for rep in range(4):
         flush_l2()
         torch.cuda.synchronize()
-        barrier()
         pr.solveBlocks(rc, alpha, redCostEps=-np.inf, result=res)
         times.append(pr.last_stage_ms())
     best = min(times[1:], key=lambda d: d["knapsack_dp"])
-    dp_ms = max_over_ranks(best["knapsack_dp"])
-    bt_ms = max_over_ranks(best["backtrack_emit"])
+    dp_ms, bt_ms = best["knapsack_dp"], best["backtrack_emit"]
     cells = m_total * n * (10_000 + 1)
+    assert res.cells == cells, (res.cells, cells)
     pr.close()
     ach = cells * 24.0 / (dp_ms * 1e-3) / 1e9
-    return {"kernel": "knap_dp_kernel", "workload": f"CSP batch {m_total} x n=500 x cap=10^4, {world} GPU(s)",
+    peak = (smem_peak * ndev) if smem_peak else None
+    return {"kernel": "knap_dp_kernel", "workload": f"CSP batch {m_total} x n=500 x cap=10^4, {ndev} GPU(s), one call",
             "bound": "smem", "gcups": cells / (dp_ms * 1e-3) / 1e9, "dp_ms": dp_ms, "backtrack_ms": bt_ms,
-            "achieved": ach, "peak": (smem_peak * world) if smem_peak else None, "unit": "GB/s",
-            "frac": ach / (smem_peak * world) if smem_peak else None,
-            "algorithmic_bytes_per_cell": 24, "cells": cells, "cells_this_rank": cells_local,
-            # ncu capture is of 1184 knapsacks (8 waves): scaled to this launch's block count
-            "traffic": ncu_traffic("prof_dp_csp", scale=(m_total / world) / 1184.0),
+            "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak if peak else None,
+            "frac_16B": (cells * 16.0 / (dp_ms * 1e-3) / 1e9 / peak) if peak else None,
+            "note": "achieved / frac at the 24 B/cell SURVEY 8d counts as algorithmic (row-in-smem formulation); the kernel keeps "
+                    "the cells in registers and moves 16 B/cell through shared memory: frac_16B is the share of the crossbar it uses",
+            "algorithmic_bytes_per_cell": 24, "cells": cells,
+            # ncu capture is of 1184 knapsacks (8 waves): scaled to one device's block count
+            "traffic": ncu_traffic("prof_dp_csp", scale=(m_total / ndev) / 1184.0),
             "peak_source": "in-library shared-memory copy microbenchmark x n_gpus"}
 
 

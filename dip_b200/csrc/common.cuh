@@ -323,6 +323,10 @@ const double *deviceVisible(const double *u);
 void gatherSupport(const std::vector<int32_t> &support, const double *u, int32_t uLen, int nVec, double *dst);
 
 int fail(Ctx *c, int code, const char *fmt, ...);
+// Opt-in dynamic shared memory of a kernel: the limit is a property of (function, device), shared by every
+// context of the process -- it is raised ONCE to what the device allows (227 KiB minus the kernel's static
+// shared memory) and never lowered, so contexts with different shapes cannot undercut each other.
+int ensureSmemLimit(Ctx *c, const void *fn, size_t bytes);
 int cudaFail(Ctx *c, cudaError_t e, const char *what);
 
 #define DIPGPU_CUDA(c, call)                                            \

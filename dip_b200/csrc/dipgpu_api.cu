@@ -8,7 +8,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
+#include <utility>
 
 #include "common.cuh"
 
@@ -31,6 +34,27 @@ int cudaFail(Ctx *c, cudaError_t e, const char *what)
 {
     return fail(c, e == cudaErrorMemoryAllocation ? DIPGPU_ERR_NOMEM : DIPGPU_ERR_CUDA, "CUDA error %d (%s) at %s",
                 (int)e, cudaGetErrorString(e), what);
+}
+
+int ensureSmemLimit(Ctx *c, const void *fn, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> limit;
+    std::lock_guard<std::mutex> lk(mu);
+    const std::pair<int, const void *> key(c->device, fn);
+    auto it = limit.find(key);
+    if (it == limit.end()) {
+        cudaFuncAttributes at;
+        DIPGPU_CUDA(c, cudaFuncGetAttributes(&at, fn));
+        int optin = 0;
+        DIPGPU_CUDA(c, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+        const size_t maxDyn = (size_t)optin > at.sharedSizeBytes ? (size_t)optin - at.sharedSizeBytes : 0;
+        if (maxDyn > 48 * 1024) DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxDyn));
+        it = limit.emplace(key, std::max<size_t>(maxDyn, 48 * 1024 - std::min<size_t>(at.sharedSizeBytes, 48 * 1024))).first;
+    }
+    if (bytes > it->second)
+        return fail(c, DIPGPU_ERR_UNSUPPORTED, "kernel needs %zu bytes of dynamic shared memory, the device allows %zu", bytes, it->second);
+    return DIPGPU_OK;
 }
 
 template <typename T>
@@ -1946,6 +1970,10 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!c || !name) return DIPGPU_ERR_INVALID;
     if (c->multi) {
         if (!strcmp(name, "dp_debug_times")) return dipgpu_set_option(multiPrimary(ctx), name, value);
+        if (!strcmp(name, "round_timing")) {  // device-resident rounds: ONE event pair per device (dipgpu_last_device_ms)
+            c->stageTiming = value != 0;
+            return DIPGPU_OK;
+        }
         if (!strcmp(name, "stage_timing")) c->stageTiming = value != 0;
         if (!strcmp(name, "gather_pinned_duals")) c->optGatherPinned = value != 0;
         struct A { const char *n; int64_t v; } a{name, value};
@@ -1955,7 +1983,7 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
         }, &a, true, false);
         return rc;
     }
-    if (!strcmp(name, "stage_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "stage_timing") || !strcmp(name, "round_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "dp_pdl")) { c->optPdl = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "result_zero_copy")) {  // 2 (diagnostics): also from the device-resident entry points
         c->optZeroCopy = value != 0;

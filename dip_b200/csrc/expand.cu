@@ -341,10 +341,9 @@ int launchExpandColumns(Ctx *c, double tolZero, int nKept, cudaStream_t st)
     cap = std::min(cap, std::max((c->expMaxTouched + 1) & ~1, 2));
     a.capStage = cap;
     const size_t bytes = bitmapBytes + sizeof(int32_t) * (size_t)((cap + 1) & ~1) + sizeof(double) * (size_t)cap;
-    if (c->expSmem != bytes) {
-        DIPGPU_CUDA(c, cudaFuncSetAttribute(expand_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)std::max<size_t>(bytes, 1024)));
-        c->expSmem = bytes;
+    {
+        const int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(expand_columns_kernel), bytes);
+        if (rc) return rc;
     }
     DIPGPU_CUDA(c, cudaMemsetAsync(&a.outHdr->flags, 0, sizeof(uint32_t), st));
     expand_columns_kernel<<<nKept, kExpThreads, bytes, st>>>(a);

@@ -1573,7 +1573,8 @@ int prepareKnapsackDp(Ctx *c)
     if (!e) return fail(c, DIPGPU_ERR_STATE, "DP geometry not initialised");
     KnapFn fn = (g.fuse ? e->fnFuse : e->fn)[g.guard > 0 ? 1 : 0][g.items - 1];
     if (c->dpFnConfigured != (void *)fn || c->dpFnSmem != g.smemBytes) {
-        DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
+        const int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(fn), g.smemBytes);
+        if (rc) return rc;
         c->dpFnConfigured = (void *)fn;
         c->dpFnSmem = g.smemBytes;
     }

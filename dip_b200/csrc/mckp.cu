@@ -256,7 +256,8 @@ int launchMckp(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_
     const size_t smem = sizeof(ulonglong2) * kMckpStage + sizeof(double) * (2 * (wMax + a.guard) + ((wMax + chunk - 1) / chunk * chunk - wMax));
     if (smem > 227 * 1024) return fail(c, DIPGPU_ERR_UNSUPPORTED, "capacity %d needs %zu bytes of DP rows", c->maxCapacity, smem);
     if (c->mckpSmem < smem) {
-        DIPGPU_CUDA(c, cudaFuncSetAttribute(mckp_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(mckp_dp_kernel), smem);
+        if (rc) return rc;
         c->mckpSmem = smem;
     }
     mckp_dp_kernel<<<c->nLocal, kMckpThreads, smem, st>>>(a);

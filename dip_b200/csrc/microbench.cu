@@ -42,7 +42,10 @@ int measureSmemGbs(Ctx *c, double *gbs)
     const int grid = (c->smCount > 0 ? c->smCount : 148);
     double *sink = nullptr;
     DIPGPU_CUDA(c, cudaMalloc(&sink, 64));
-    DIPGPU_CUDA(c, cudaFuncSetAttribute(smem_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        const int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(smem_copy_kernel), smem);
+        if (rc) { cudaFree(sink); return rc; }
+    }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);

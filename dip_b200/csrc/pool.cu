@@ -188,7 +188,8 @@ int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st)
     const unsigned grid = (unsigned)((warps + wpc - 1) / wpc);
     auto fn = bitmap ? pool_redcost_kernel<true> : pool_redcost_kernel<false>;
     if (c->poolFnSmem[bitmap ? 1 : 0] < smem) {
-        DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(fn), smem);
+        if (rc) return rc;
         c->poolFnSmem[bitmap ? 1 : 0] = smem;
     }
     fn<<<grid, wpc * 32, smem, st>>>(c->poolCols, c->dPoolStart, c->dPoolRow, c->dPoolVal, c->dPoolOrigCost, dU, feasible,

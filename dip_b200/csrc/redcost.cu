@@ -554,7 +554,8 @@ int launchRedCostBatch(Ctx *c, const double *dU, int64_t uStride, double *dOut, 
                                        : (row16 ? redcost_stream_kernel<0, true> : redcost_stream_kernel<0, false>);
         const size_t bytes = c->spmvSmem;
         if (c->spmvFn != (void *)fn || c->spmvFnSmem != bytes) {
-            DIPGPU_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            const int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(fn), bytes);
+            if (rc) return rc;
             c->spmvFn = (void *)fn;
             c->spmvFnSmem = bytes;
         }
