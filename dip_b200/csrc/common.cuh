@@ -235,8 +235,23 @@ struct Ctx {
     int firstBlock = 0, nLocal = 0;
     unsigned long long *dDbgTimes = nullptr;  // diagnostics (option dp_debug_times): 8 stamps per CTA
     unsigned long long *dPubWord = nullptr, *dPubCells = nullptr;  // fused DP kernel: per-block publication
-    unsigned long long *dTicket = nullptr;  // fused DP kernel: (launch epoch << 32) | CTAs started (KnapArgs::ticket)
-    unsigned long long *dExpTicket = nullptr;  // same for the expansion kernel
+    // fused DP kernel: [0] ticket counter, [1] launch epoch, [2] CTAs finished (KnapArgs::ticket / epochCtr / doneCtr);
+    // [4..5]: the expansion kernel's 64-bit (epoch << 32 | ticket)
+    unsigned int *dSyncWords = nullptr;
+    unsigned long long *dExpTicket = nullptr;
+    int dpCoResident = 0;                   // CTAs of the configured DP kernel that fit the GPU at once
+    // reduced costs formed inside the fused DP kernel (option "fuse_redcost", default on): the CSC with int32 row ids
+    // is dColStart32 / dRowMaster / dVal; with a dual support, a second CSC holding only the entries of rows that can
+    // carry a dual, indexed by SLOT in the compacted dual vector u[support] (dUCompact; slot ns = a zero)
+    bool optFuseRc = true;
+    int32_t *dCStart = nullptr, *dCIdx = nullptr;
+    double *dCVal = nullptr;
+    int32_t *dAlphaIdxDense = nullptr, *dAlphaIdxCompact = nullptr;  // per block: where its convexity dual sits
+    double *dUCompact = nullptr;      // (ns + 16) doubles, single rounds
+    double *dUBatchCompact = nullptr; // batchCap x cStride doubles
+    size_t cStride = 0;
+    bool compactValid = false;        // the compact CSC matches the current core / support / blocks
+    bool dualsCompact = false;        // dUCompact holds the duals of the last call (dU may not)
     uint64_t fusedLaunches = 0;             // the publication words are cleared every 2^24 fused launches
     unsigned int *dDoneCounter = nullptr;  // ticket of the fused backtrack+filter kernel
     // -1 auto (2 when nLocal <= kFuseFilterMaxBlocks, else 0); 0 three kernels; 1 filter in the
@@ -341,8 +356,10 @@ int setBlockRange(Ctx *c, int first, int count);
 int checkRoundReady(Ctx *c, const char *who, int32_t uLen, int32_t phase);
 int ensureDualBuffer(Ctx *c, int32_t uLen);
 int ensureBatch(Ctx *c, int nVec);
-int enqueueRound(Ctx *c, const DualFeed *feed, int32_t uLen, int32_t phase, double eps, bool mirror, cudaStream_t st);
-int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st);
+int enqueueRound(Ctx *c, const DualFeed *feed, int32_t uLen, int32_t phase, double eps, bool mirror, cudaStream_t st, bool needAllRedCosts = false);
+int enqueueRoundDev(Ctx *c, const double *uDev, int32_t uLen, int32_t phase, double eps, bool mirror, cudaStream_t st);
+bool rcFuseEligible(const Ctx *c);
+int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st, bool compact);
 int fetchResult(Ctx *c, cudaStream_t st);
 int fetchBatchPacked(Ctx *c, int nVec, cudaStream_t st);
 int fetchBatch(Ctx *c, int nVec, dipgpu_cols *outs, cudaStream_t st);
@@ -405,9 +422,19 @@ int launchKnapsackPrepBatch(Ctx *c, const double *dRedCost, int64_t rcStride, in
 // knapsack.cu -- stage (b)
 int chooseDpGeom(Ctx *c, DpGeom *g, bool wantFuse);
 int prepareKnapsackDp(Ctx *c);  // loads the chosen kernel, sets its shared-memory limit
-int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st);
+// rf != NULL (fused shapes): the kernel forms the reduced costs of its blocks' columns itself -- stage (a) without a
+// launch of its own -- from a CSC (start, idx, val) whose idx index uVec (vector v at uVec + v*uStride), writes
+// them to dRedCost and reads alpha_b = uVec[alphaIdx[b]]
+struct RcFuse {
+    const int32_t *start, *idx;
+    const double *val, *uVec;
+    const int32_t *alphaIdx;
+    int64_t uStride;
+    int phase1;
+};
+int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st, const RcFuse *rf = nullptr);
 int launchKnapsackDpBatch(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
-                          double redCostEps, int nVec, cudaStream_t st);
+                          double redCostEps, int nVec, cudaStream_t st, const RcFuse *rf = nullptr);
 int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseFilter,
                         cudaStream_t st);
 // mckp.cu -- stage (b) for multiple-choice knapsack blocks (DP + backtrack; the filter kernels follow)

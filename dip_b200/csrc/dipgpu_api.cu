@@ -259,10 +259,132 @@ int setBlockRange(Ctx *c, int first, int count)
     return DIPGPU_OK;
 }
 
+static int ensureSupportStaging(Ctx *c, int nVec);
+
+// ---------------------------------------------------------------- reduced costs inside the fused DP kernel
+//
+// Small shards (the GAP rounds) run stages (a)+(b)+(c) as ONE kernel: every block CTA forms the reduced costs of its
+// own columns from the CSC of A'' before it compacts its items (knapsack.cu, KnapArgs::rcIdx).  With a dual support
+// the kernel reads a second CSC that holds only the entries of rows that can carry a dual, indexed by slot in the
+// compacted dual vector u[support] -- on GAP-E 130 k of 384 k entries and a 34 KB vector instead of 2 MB.
+bool rcFuseEligible(const Ctx *c)
+{
+    return c->optFuseRc && c->geom.fuse && c->blockKind == 0 && c->profitMode == DIPGPU_PROFIT_FP64 && c->haveCore &&
+           c->dColStart32 != nullptr && c->nLocal > 0 && c->nBlockCols <= c->N && c->numConvex == c->m;
+}
+
+static int ensureRcFuse(Ctx *c)
+{
+    int rc;
+    const int m = c->m;
+    if (!c->dAlphaIdxDense || !c->compactValid) {
+        std::vector<int32_t> ai((size_t)std::max(m, 1));
+        for (int b = 0; b < m; ++b) ai[(size_t)b] = c->nBaseRows + b;  // alpha_b = u[nBaseRows + b]  (DecompAlgo.cpp:4820)
+        if ((rc = devAlloc(c, &c->dAlphaIdxDense, ai.size()))) return rc;
+        DIPGPU_CUDA(c, cudaMemcpy(c->dAlphaIdxDense, ai.data(), sizeof(int32_t) * ai.size(), cudaMemcpyHostToDevice));
+    }
+    if (c->compactValid) return DIPGPU_OK;
+    const size_t ns = c->hSupport.size();
+    if (ns > 0) {
+        const int uLen = c->R + c->numConvex;
+        std::vector<int32_t> slot((size_t)uLen, -1);
+        for (size_t k = 0; k < ns; ++k) slot[(size_t)c->hSupport[k]] = (int32_t)k;
+        std::vector<int64_t> colStart;
+        std::vector<int32_t> rowMaster;
+        std::vector<double> val;
+        transposeCore(c, colStart, rowMaster, val);
+        const int N = c->N;
+        std::vector<int32_t> cs((size_t)N + 1, 0), ci;
+        std::vector<double> cv;
+        ci.reserve((size_t)colStart[N] / 2 + 16);
+        cv.reserve((size_t)colStart[N] / 2 + 16);
+        for (int j = 0; j < N; ++j) {
+            for (int64_t e = colStart[j]; e < colStart[j + 1]; ++e) {
+                const int32_t sl = slot[(size_t)rowMaster[(size_t)e]];
+                if (sl >= 0) {  // (order kept: descending rows, the reference's scatter order)
+                    ci.push_back(sl);
+                    cv.push_back(val[(size_t)e]);
+                }
+            }
+            cs[(size_t)j + 1] = (int32_t)ci.size();
+        }
+        std::vector<int32_t> ai((size_t)std::max(m, 1));
+        for (int b = 0; b < m; ++b) {
+            const int32_t sl = slot[(size_t)(c->nBaseRows + b)];
+            ai[(size_t)b] = sl >= 0 ? sl : (int32_t)ns;  // slot ns holds 0.0
+        }
+        if ((rc = devAlloc(c, &c->dCStart, cs.size()))) return rc;
+        if ((rc = devAlloc(c, &c->dCIdx, ci.size() + 8))) return rc;
+        if ((rc = devAlloc(c, &c->dCVal, cv.size() + 8))) return rc;
+        if ((rc = devAlloc(c, &c->dAlphaIdxCompact, ai.size()))) return rc;
+        if ((rc = devAlloc(c, &c->dUCompact, ns + 16))) return rc;
+        DIPGPU_CUDA(c, cudaMemcpy(c->dCStart, cs.data(), sizeof(int32_t) * cs.size(), cudaMemcpyHostToDevice));
+        if (!ci.empty()) {
+            DIPGPU_CUDA(c, cudaMemcpy(c->dCIdx, ci.data(), sizeof(int32_t) * ci.size(), cudaMemcpyHostToDevice));
+            DIPGPU_CUDA(c, cudaMemcpy(c->dCVal, cv.data(), sizeof(double) * cv.size(), cudaMemcpyHostToDevice));
+        }
+        DIPGPU_CUDA(c, cudaMemcpy(c->dAlphaIdxCompact, ai.data(), sizeof(int32_t) * ai.size(), cudaMemcpyHostToDevice));
+        DIPGPU_CUDA(c, cudaMemset(c->dUCompact, 0, sizeof(double) * (ns + 16)));
+        devFree(&c->dUBatchCompact);  // sized by the support
+        c->cStride = 0;
+    }
+    c->dualsCompact = false;
+    c->compactValid = true;
+    return DIPGPU_OK;
+}
+
+static RcFuse rcFuseDense(const Ctx *c, const double *uVec, int64_t uStride, int phase)
+{
+    return RcFuse{c->dColStart32, c->dRowMaster, c->dVal, uVec, c->dAlphaIdxDense, uStride, phase == DIPGPU_PHASE_PRICE1 ? 1 : 0};
+}
+static RcFuse rcFuseCompact(const Ctx *c, const double *uVec, int64_t uStride, int phase)
+{
+    return RcFuse{c->dCStart, c->dCIdx, c->dCVal, uVec, c->dAlphaIdxCompact, uStride, phase == DIPGPU_PHASE_PRICE1 ? 1 : 0};
+}
+
+// u[support] of nVec dual vectors into the compact device vector(s) (vector v at dDst + v*dstStride): gathered on
+// the host into pinned staging -- or taken from staging somebody else filled -- and copied in one piece.
+static int feedCompact(Ctx *c, const DualFeed &f, int32_t uLen, int nVec, double *dDst, size_t dstStride, cudaStream_t st)
+{
+    const size_t ns = c->hSupport.size();
+    const double *src = f.staged;
+    size_t srcStride = (size_t)f.stagedStride;
+    if (!src) {
+        int rc;
+        if ((rc = ensureSupportStaging(c, nVec))) return rc;
+        gatherSupport(c->hSupport, f.host, uLen, nVec, c->hSupVals);
+        src = c->hSupVals;
+        srcStride = ns;
+    }
+    if (nVec == 1) DIPGPU_CUDA(c, cudaMemcpyAsync(dDst, src, sizeof(double) * ns, cudaMemcpyHostToDevice, st));
+    else DIPGPU_CUDA(c, cudaMemcpy2DAsync(dDst, sizeof(double) * dstStride, src, sizeof(double) * srcStride, sizeof(double) * ns,
+                                          (size_t)nVec, cudaMemcpyHostToDevice, st));
+    c->h2d += (int64_t)sizeof(double) * (int64_t)ns * nVec;
+    return DIPGPU_OK;
+}
+
+// The dense dual vector dU, for the passes that read it (pool re-pricing, smoothing): after a round that only filled
+// the compact vector it is formed on the device.
+static int ensureDenseDuals(Ctx *c, cudaStream_t st)
+{
+    if (c->dualsResident || !c->dualsCompact) return DIPGPU_OK;
+    const int uLen = c->R + c->numConvex;
+    int rc;
+    if ((rc = ensureDualBuffer(c, uLen))) return rc;
+    if (!c->dUClean) {
+        DIPGPU_CUDA(c, cudaMemsetAsync(c->dU, 0, sizeof(double) * (size_t)uLen, st));
+        c->dUClean = true;
+    }
+    const int ns = (int)c->hSupport.size();
+    if ((rc = launchScatterDuals(c, ns, c->dSupport, c->dUCompact, ns, false, c->dU, 0, 1, st))) return rc;
+    c->dualsResident = true;
+    return DIPGPU_OK;
+}
+
 // Enqueue stages (b) and (c) on `st`; dRedCost/dAlpha are device pointers
 // (alpha indexed by global block id).
 static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, double eps, cudaStream_t st,
-                        bool timed)
+                        bool timed, const RcFuse *rf = nullptr)
 {
     int rc;
     c->resultMirrored = false;
@@ -279,8 +401,8 @@ static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, do
     int mode = c->geom.fuse ? 2 : c->optFuseFilter < 0 ? (c->nLocal <= kFuseFilterMaxBlocks ? 1 : 0)
                                                        : (c->optFuseFilter == 1 ? 1 : 0);
     if (c->nLocal == 0) mode = 0;
-    if ((rc = launchKnapsackPrep(c, dRedCost, st))) return rc;
-    if ((rc = launchKnapsackDp(c, dRedCost, dAlpha, eps, st))) return rc;
+    if (!rf && (rc = launchKnapsackPrep(c, dRedCost, st))) return rc;
+    if ((rc = launchKnapsackDp(c, dRedCost, dAlpha, eps, st, rf))) return rc;
     if (timed) cudaEventRecord(c->ev[3], st);
     if (mode != 2 && (rc = launchBacktrackEmit(c, dRedCost, dAlpha, eps, mode == 1, st))) return rc;
     if (timed) cudaEventRecord(c->ev[4], st);
@@ -410,6 +532,8 @@ int ensureBatch(Ctx *c, int nVec)
     const size_t resStride = ResultLayout::alignUp(c->resultBytes, 16);
     if (c->batchCap >= nVec && c->uStride == uStride && c->rcStride == rcStride && c->resStride == resStride) return DIPGPU_OK;
     freeBatch(c);
+    devFree(&c->dUBatchCompact);
+    c->cStride = 0;
     int rc;
     const size_t V = (size_t)nVec, nl = (size_t)std::max(c->nLocal, 1);
     if ((rc = devAlloc(c, &c->dUBatch, V * uStride))) return rc;
@@ -439,7 +563,7 @@ int ensureBatch(Ctx *c, int nVec)
 
 // Stages (a)-(c) for the nVec dual vectors held in dUBatch: three launches in all when the shard
 // runs the fused DP kernel (gridDim.y = vectors), else vector after vector through the large-shard path.
-int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st)
+int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st, bool compact)
 {
     int rc;
     const bool timed = c->stageTiming;
@@ -448,6 +572,18 @@ int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st)
     c->lastRoundOnHost = false;
     if (timed) cudaEventRecord(c->ev[1], st);
     if (c->geom.fuse || c->nLocal == 0) {
+        if (rcFuseEligible(c)) {
+            // ONE kernel for the whole batch: CTA (block, vector) forms its columns' reduced costs for its vector
+            if ((rc = ensureRcFuse(c))) return rc;
+            const RcFuse rf = compact ? rcFuseCompact(c, c->dUBatchCompact, (int64_t)c->cStride, phase)
+                                      : rcFuseDense(c, c->dUBatch, (int64_t)c->uStride, phase);
+            if (timed) cudaEventRecord(c->ev[2], st);
+            c->wantMirror = true;
+            rc = launchKnapsackDpBatch(c, c->dRedCostBatch, (int64_t)c->rcStride, nullptr, 0, eps, nVec, st, &rf);
+            c->wantMirror = false;
+            if (timed) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
+            return rc;
+        }
         if ((rc = launchRedCostBatch(c, c->dUBatch, (int64_t)c->uStride, c->dRedCostBatch, (int64_t)c->rcStride, nVec, phase, st))) return rc;
         if (timed) cudaEventRecord(c->ev[2], st);
         if ((rc = launchKnapsackPrepBatch(c, c->dRedCostBatch, (int64_t)c->rcStride, nVec, st))) return rc;
@@ -466,6 +602,27 @@ int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st)
     }
     if (timed) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
     return DIPGPU_OK;
+}
+
+// The dual vectors of a batch: into dUBatch (dense), or -- fused shapes with a dual support, host vectors --
+// u[support] only into dUBatchCompact.  *compact tells enqueueBatch which.
+int feedBatchDuals(Ctx *c, const DualFeed &f, int32_t uLen, int nVec, cudaStream_t st, bool *compact)
+{
+    int rc;
+    *compact = false;
+    const size_t ns = c->hSupport.size();
+    if (rcFuseEligible(c) && ns > 0 && (f.host || f.staged)) {
+        if ((rc = ensureRcFuse(c))) return rc;
+        const size_t stride = (ns + 17) & ~(size_t)1;
+        if (!c->dUBatchCompact || c->cStride != stride) {
+            if ((rc = devAlloc(c, &c->dUBatchCompact, (size_t)std::max(c->batchCap, nVec) * stride))) return rc;
+            DIPGPU_CUDA(c, cudaMemset(c->dUBatchCompact, 0, sizeof(double) * (size_t)std::max(c->batchCap, nVec) * stride));
+            c->cStride = stride;
+        }
+        *compact = true;
+        return feedCompact(c, f, uLen, nVec, c->dUBatchCompact, stride, st);
+    }
+    return feedDuals(c, f, uLen, nVec, c->dUBatch, c->uStride, &c->dUBatchClean, st);
 }
 
 // D2H of nVec packed results into hResultBatch (one strided copy of the speculative prefix, a second copy per
@@ -678,24 +835,72 @@ int multiEnqueueSolve(Ctx *c, double eps, cudaStream_t st, bool timed)
 // One pricing round, enqueued on `st`: the duals (feed == NULL: the vector already in dU), the reduced costs of
 // this context's columns, the block subproblems of its block range and the filter.  mirror: the fused kernel
 // also stores the packed result into the context's mirror (mapped host memory, or what mirrorBase names).
-int enqueueRound(Ctx *c, const DualFeed *feed, int32_t uLen, int32_t phase, double eps, bool mirror, cudaStream_t st)
+int enqueueRound(Ctx *c, const DualFeed *feed, int32_t uLen, int32_t phase, double eps, bool mirror, cudaStream_t st, bool needAllRedCosts)
 {
     int rc;
     if ((rc = ensureDualBuffer(c, uLen))) return rc;
     const bool timed = c->stageTiming;
     if (timed) cudaEventRecord(c->ev[0], st);
+    if (rcFuseEligible(c) && !needAllRedCosts) {
+        // ONE kernel: the block CTAs form their columns' reduced costs themselves
+        if ((rc = ensureRcFuse(c))) return rc;
+        const size_t ns = c->hSupport.size();
+        RcFuse rf;
+        if (feed && ns > 0 && (feed->host || feed->staged)) {
+            if ((rc = feedCompact(c, *feed, uLen, 1, c->dUCompact, 0, st))) return rc;
+            c->dualsCompact = true;
+            c->dualsResident = false;
+            rf = rcFuseCompact(c, c->dUCompact, 0, phase);
+        } else if (feed && feed->full) {
+            rf = rcFuseDense(c, feed->full, 0, phase);  // a dense vector in device memory (this device or a peer): gathered from where it is
+        } else if (feed) {
+            if ((rc = feedDuals(c, *feed, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
+            c->dualsResident = true;
+            c->dualsCompact = false;
+            rf = rcFuseDense(c, c->dU, 0, phase);
+        } else {
+            rf = c->dualsCompact && !c->dualsResident ? rcFuseCompact(c, c->dUCompact, 0, phase) : rcFuseDense(c, c->dU, 0, phase);
+        }
+        if (timed) { cudaEventRecord(c->ev[1], st); cudaEventRecord(c->ev[2], st); }
+        c->wantMirror = mirror;
+        rc = enqueueSolve(c, c->dRedCost, nullptr, eps, st, timed, &rf);
+        c->wantMirror = false;
+        return rc;
+    }
+    const double *uUse = c->dU;
     if (feed) {
-        if ((rc = feedDuals(c, *feed, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
-        c->dualsResident = true;
+        cudaPointerAttributes at;
+        if (feed->full && cudaPointerGetAttributes(&at, feed->full) == cudaSuccess &&
+            at.type == cudaMemoryTypeDevice && at.device == c->device) {
+            uUse = feed->full;  // already a dense vector in this device's memory
+        } else {
+            (void)cudaGetLastError();
+            if ((rc = feedDuals(c, *feed, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
+            c->dualsResident = true;
+            c->dualsCompact = false;
+        }
+    } else if ((rc = ensureDenseDuals(c, st))) {
+        return rc;
     }
     if (timed) cudaEventRecord(c->ev[1], st);
-    if ((rc = launchRedCost(c, c->dU, phase, st))) return rc;
+    if ((rc = launchRedCost(c, uUse, phase, st))) return rc;
     if (timed) cudaEventRecord(c->ev[2], st);
     // alpha_b = u[nBaseRows + b]  (DecompAlgo.cpp:4820)
     c->wantMirror = mirror;
-    rc = enqueueSolve(c, c->dRedCost, c->dU + c->nBaseRows, eps, st, timed);
+    rc = enqueueSolve(c, c->dRedCost, uUse + c->nBaseRows, eps, st, timed);
     c->wantMirror = false;
     return rc;
+}
+
+// The round on a dense dual vector that already lies in device memory -- this device's or (multi-device contexts)
+// a peer's: fused shapes gather the duals straight from there, the others read a local vector directly and take a
+// peer's through a copy of what they need.
+int enqueueRoundDev(Ctx *c, const double *uDev, int32_t uLen, int32_t phase, double eps, bool mirror, cudaStream_t st)
+{
+    DualFeed f;
+    f.full = uDev;
+    f.fullStride = uLen;
+    return enqueueRound(c, &f, uLen, phase, eps, mirror, st, false);
 }
 
 // nVec dual vectors priced in one submission and decoded into outs[0..nVec).
@@ -707,9 +912,10 @@ int batchCore(Ctx *c, int nVec, const DualFeed &f, int32_t uLen, int32_t phase, 
     if ((rc = ensureBatch(c, nVec))) return rc;
     cudaStream_t st = c->stream;
     if (c->stageTiming) cudaEventRecord(c->ev[0], st);
-    if ((rc = feedDuals(c, f, uLen, nVec, c->dUBatch, c->uStride, &c->dUBatchClean, st))) return rc;
+    bool compact = false;
+    if ((rc = feedBatchDuals(c, f, uLen, nVec, st, &compact))) return rc;
     c->haveST = false;
-    if ((rc = enqueueBatch(c, nVec, phase, eps, st))) return rc;
+    if ((rc = enqueueBatch(c, nVec, phase, eps, st, compact))) return rc;
     c->lastRoundOnHost = false;
     return fetchBatch(c, nVec, outs, st);
 }
@@ -727,6 +933,7 @@ int ladderCore(Ctx *c, const DualFeed &f, int32_t uLen, const double *al, int nS
     if (c->stageTiming) cudaEventRecord(c->ev[0], st);
     if ((rc = feedDuals(c, f, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
     c->dualsResident = true;
+    c->dualsCompact = false;
     if (!c->haveCenter || c->centerLen != (size_t)uLen) {
         // first price call: m_dual := m_dualRM (DecompAlgoPC.cpp:163-173)
         if (c->centerLen != (size_t)uLen) {
@@ -745,7 +952,7 @@ int ladderCore(Ctx *c, const DualFeed &f, int32_t uLen, const double *al, int nS
     c->dUBatchClean = false;  // the smoothing writes every entry of the batch vectors
     if ((rc = launchSmoothDuals(c, c->dU, c->dCenter, c->dAlphaLadder, nSteps, uLen, c->dUBatch, (int64_t)c->uStride, st))) return rc;
     c->haveST = true;
-    if ((rc = enqueueBatch(c, nSteps, phase, eps, st))) return rc;
+    if ((rc = enqueueBatch(c, nSteps, phase, eps, st, false))) return rc;
     c->lastRoundOnHost = false;
     return fetchBatch(c, nSteps, outs, st);
 }
@@ -787,17 +994,17 @@ int dipgpu_create(dipgpu_ctx **ctx, int device)
         return DIPGPU_ERR_CUDA;
     }
     for (auto &e : c->ev) cudaEventCreate(&e);
-    const unsigned long long ticket0[2] = {1ull << 32, 1ull << 32};  // epoch 1, no CTA started
+    const unsigned int sync0[8] = {0u, 1u, 0u, 0u, 0u, 1u, 0u, 0u};  // epoch 1, no ticket drawn; expansion: (1 << 32) | 0
     if (cudaMalloc(reinterpret_cast<void **>(&c->dDoneCounter), sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(c->dDoneCounter, 0, sizeof(unsigned int)) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void **>(&c->dTicket), 2 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemcpy(c->dTicket, ticket0, sizeof(ticket0), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaMalloc(reinterpret_cast<void **>(&c->dSyncWords), sizeof(sync0)) != cudaSuccess ||
+        cudaMemcpy(c->dSyncWords, sync0, sizeof(sync0), cudaMemcpyHostToDevice) != cudaSuccess) {
         if (c->dDoneCounter) cudaFree(c->dDoneCounter);
-        if (c->dTicket) cudaFree(c->dTicket);
+        if (c->dSyncWords) cudaFree(c->dSyncWords);
         delete c;
         return DIPGPU_ERR_NOMEM;
     }
-    c->dExpTicket = c->dTicket + 1;
+    c->dExpTicket = reinterpret_cast<unsigned long long *>(c->dSyncWords + 4);
     *ctx = reinterpret_cast<dipgpu_ctx *>(c);
     return DIPGPU_OK;
 }
@@ -809,7 +1016,9 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (c->multi) return multiDestroy(ctx);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    devFree(&c->dDoneCounter); devFree(&c->dTicket); devFree(&c->dCsrRowStart); devFree(&c->dCsrColInd); devFree(&c->dCsrVal); devFree(&c->dExpPub);
+    devFree(&c->dDoneCounter); devFree(&c->dSyncWords); devFree(&c->dCsrRowStart);
+    devFree(&c->dCStart); devFree(&c->dCIdx); devFree(&c->dCVal); devFree(&c->dAlphaIdxDense); devFree(&c->dAlphaIdxCompact);
+    devFree(&c->dUCompact); devFree(&c->dUBatchCompact); devFree(&c->dCsrColInd); devFree(&c->dCsrVal); devFree(&c->dExpPub);
     if (c->dMCols) cudaFree(c->dMCols);
     if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dSpmvBlob); devFree(&c->dSpmvWarpStart); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
@@ -886,6 +1095,7 @@ int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *ro
     if (c->N != N) { devFree(&c->dRedCost); devFree(&c->dRcEff); }
     c->R = R; c->N = N; c->nBaseRows = nBaseRows; c->numConvex = numConvex;
     c->dualsResident = false; c->haveCenter = false; c->haveST = false;
+    c->dualsCompact = false; c->compactValid = false;
     c->hSupport.clear();
     c->hRowStart.assign(rowStart, rowStart + R + 1);
     c->hColInd.assign(colInd, colInd + nnz);
@@ -924,6 +1134,7 @@ int dipgpu_append_core_rows(dipgpu_ctx *ctx, int32_t nNew, const int64_t *rowSta
     c->hVal.insert(c->hVal.end(), val, val + add);
     c->R += nNew;
     c->dualsResident = false; c->haveST = false;  // the master dual vector grew
+    c->dualsCompact = false; c->compactValid = false;
     c->hSupport.clear();
     if (c->haveCenter) {
         // DecompAlgoPC::adjustMasterDualSolution resizes m_dual to the new row count (Dip/src/DecompAlgoPC.cpp:135-140):
@@ -1029,6 +1240,7 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
         DIPGPU_CUDA(c, cudaMemset(c->dRedCost, 0, sizeof(double) * ((size_t)c->N + 16)));
     }
     c->haveBlocks = true;
+    c->compactValid = false;  // (the convexity duals' positions are per block)
     c->lastRoundOnHost = false;
     return setBlockRange(c, 0, m);
 }
@@ -1099,6 +1311,7 @@ int dipgpu_set_mckp_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockGroup
         DIPGPU_CUDA(c, cudaMemset(c->dRedCost, 0, sizeof(double) * ((size_t)c->N + 16)));
     }
     c->haveBlocks = true;
+    c->compactValid = false;  // (the convexity duals' positions are per block)
     c->lastRoundOnHost = false;
     return setBlockRange(c, 0, m);
 }
@@ -1169,6 +1382,7 @@ int dipgpu_calc_redcost(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t 
     }
     if ((rc = uploadDuals(c, u, uLen, 1, c->dU, 0, &c->dUClean, c->stream))) return rc;
     c->dualsResident = true;
+    c->dualsCompact = false;
     if ((rc = launchRedCost(c, c->dU, phase, c->stream))) return rc;
     DIPGPU_CUDA(c, cudaMemcpyAsync(redCostX, c->dRedCost, sizeof(double) * (size_t)c->N, cudaMemcpyDeviceToHost, c->stream));
     c->d2h += (int64_t)sizeof(double) * c->N;
@@ -1209,11 +1423,11 @@ int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t p
     if (!out) return fail(c, DIPGPU_ERR_INVALID, "price_round: NULL output");
     int rc;
     if ((rc = checkRoundReady(c, "price_round", uLen, phase))) return rc;
-    if (!u && !c->dualsResident) return fail(c, DIPGPU_ERR_STATE, "price_round: u == NULL but no dual vector is resident");
+    if (!u && !c->dualsResident && !c->dualsCompact) return fail(c, DIPGPU_ERR_STATE, "price_round: u == NULL but no dual vector is resident");
     cudaStream_t st = c->stream;
     DualFeed f;
     f.host = u;
-    if ((rc = enqueueRound(c, u ? &f : nullptr, uLen, phase, redCostEps, true, st))) return rc;
+    if ((rc = enqueueRound(c, u ? &f : nullptr, uLen, phase, redCostEps, true, st, redCostXOpt != nullptr))) return rc;
     if (redCostXOpt) {
         DIPGPU_CUDA(c, cudaMemcpyAsync(redCostXOpt, c->dRedCost, sizeof(double) * (size_t)c->N, cudaMemcpyDeviceToHost, st));
         c->d2h += (int64_t)sizeof(double) * c->N;
@@ -1275,9 +1489,14 @@ int dipgpu_price_round_which(dipgpu_ctx *ctx, const double *u, int32_t uLen, int
     if ((rc = ensureBatch(c, nVec))) return rc;
     cudaStream_t st = c->stream;
     if (c->stageTiming) cudaEventRecord(c->ev[0], st);
-    if ((rc = uploadDuals(c, Uptr, uLen, nVec, c->dUBatch, c->uStride, &c->dUBatchClean, st))) return rc;
+    bool compact = false;
+    {
+        DualFeed f;
+        f.host = Uptr;
+        if ((rc = feedBatchDuals(c, f, uLen, nVec, st, &compact))) return rc;
+    }
     c->haveST = false;
-    if ((rc = enqueueBatch(c, nVec, phase, redCostEps, st))) return rc;
+    if ((rc = enqueueBatch(c, nVec, phase, redCostEps, st, compact))) return rc;
     c->lastRoundOnHost = false;
     if ((rc = fetchBatchPacked(c, nVec, st))) return rc;
 
@@ -1373,6 +1592,7 @@ int dipgpu_set_dual_support(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx)
     c->dUClean = false;        // whatever the device vectors hold now may be nonzero outside the new support
     c->dUBatchClean = false;
     c->dualsResident = false;
+    c->dualsCompact = false; c->compactValid = false;
     int rc;
     if ((rc = devAlloc(c, &c->dSupport, (size_t)std::max(nIdx, 1)))) return rc;
     if (nIdx > 0) DIPGPU_CUDA(c, cudaMemcpy(c->dSupport, idx, sizeof(int32_t) * (size_t)nIdx, cudaMemcpyHostToDevice));
@@ -1640,7 +1860,7 @@ int dipgpu_pool_set_reduced_costs(dipgpu_ctx *ctx, const double *u, int32_t uLen
     CTX_OR_FAIL(ctx);
     if (!c->haveCore) return fail(c, DIPGPU_ERR_STATE, "pool_set_reduced_costs before set_core_csr");
     if (uLen != c->R + c->numConvex) return fail(c, DIPGPU_ERR_INVALID, "pool_set_reduced_costs: uLen=%d, expected R+numConvex=%d", uLen, c->R + c->numConvex);
-    if (!u && !c->dualsResident) return fail(c, DIPGPU_ERR_STATE, "pool_set_reduced_costs: u == NULL but no dual vector is resident");
+    if (!u && !c->dualsResident && !c->dualsCompact) return fail(c, DIPGPU_ERR_STATE, "pool_set_reduced_costs: u == NULL but no dual vector is resident");
     int rc;
     if ((rc = ensureDualBuffer(c, uLen))) return rc;
     if ((rc = poolReserve(c, std::max<int64_t>(c->poolCols, 1), std::max<int64_t>(c->poolNnz, 1)))) return rc;
@@ -1648,6 +1868,9 @@ int dipgpu_pool_set_reduced_costs(dipgpu_ctx *ctx, const double *u, int32_t uLen
     if (u) {
         if ((rc = uploadDuals(c, u, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
         c->dualsResident = true;
+        c->dualsCompact = false;
+    } else if ((rc = ensureDenseDuals(c, st))) {
+        return rc;
     }
     if (c->stageTiming) cudaEventRecord(c->ev[1], st);
     if ((rc = launchPoolRedCost(c, c->dU, feasible ? 1 : 0, st))) return rc;
@@ -1793,19 +2016,14 @@ int dipgpu_price_round_expand(dipgpu_ctx *ctx, const double *u, int32_t uLen, in
     if (!out || !mout) return fail(c, DIPGPU_ERR_INVALID, "price_round_expand: NULL output");
     int rc;
     if ((rc = checkRoundReady(c, "price_round_expand", uLen, phase))) return rc;
-    if (!u && !c->dualsResident) return fail(c, DIPGPU_ERR_STATE, "price_round_expand: u == NULL but no dual vector is resident");
-    if ((rc = ensureDualBuffer(c, uLen))) return rc;
+    if (!u && !c->dualsResident && !c->dualsCompact) return fail(c, DIPGPU_ERR_STATE, "price_round_expand: u == NULL but no dual vector is resident");
     if ((rc = prepareExpand(c))) return rc;
     cudaStream_t st = c->stream;
-    if (u) {
-        if ((rc = uploadDuals(c, u, uLen, 1, c->dU, 0, &c->dUClean, st))) return rc;
-        c->dualsResident = true;
+    {
+        DualFeed f;
+        f.host = u;
+        if ((rc = enqueueRound(c, u ? &f : nullptr, uLen, phase, redCostEps, true, st, false))) return rc;
     }
-    if ((rc = launchRedCost(c, c->dU, phase, st))) return rc;
-    c->wantMirror = true;
-    rc = enqueueSolve(c, c->dRedCost, c->dU + c->nBaseRows, redCostEps, st, false);
-    c->wantMirror = false;
-    if (rc) return rc;
     size_t spec = 0;
     if (c->nLocal > 0) {
         if ((rc = launchExpandColumns(c, tolZero, c->nLocal, st))) return rc;
@@ -1838,8 +2056,7 @@ int dipgpu_price_round_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, in
     int rc;
     if ((rc = ensureObjective(c, c->N))) return rc;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
-    if ((rc = launchRedCost(c, uDev, phase, st))) return rc;
-    return enqueueSolve(c, c->dRedCost, uDev + c->nBaseRows, redCostEps, st, false);
+    return enqueueRoundDev(c, uDev, uLen, phase, redCostEps, c->optMirrorAlways, st);
 }
 
 int dipgpu_calc_redcost_dev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, int32_t phase, void *stream)
@@ -1985,6 +2202,7 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     }
     if (!strcmp(name, "stage_timing") || !strcmp(name, "round_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "dp_pdl")) { c->optPdl = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "fuse_redcost")) { c->optFuseRc = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "result_zero_copy")) {  // 2 (diagnostics): also from the device-resident entry points
         c->optZeroCopy = value != 0;
         c->optMirrorAlways = value == 2;

@@ -333,12 +333,30 @@ struct KnapArgs {
     unsigned long long *dbgTimes;  // diagnostics: 8 globaltimer stamps per CTA (NULL = off)
     unsigned long long *pubWord;   // FUSE: per (vector, local block) publication word (layout: kPub* below)
     unsigned long long *pubCells;  // FUSE: per local block DP cells
-    // FUSE: (launch epoch << 32) | CTAs started so far in this launch.  Every CTA draws ONE ticket on entry:
-    // the low half is its LOGICAL (vector, block) id -- so a CTA only ever waits for CTAs that started before
-    // it (no assumption on the order in which the hardware dispatches blockIdx) --, the high half the epoch
-    // its publication word carries.  The CTA that draws the last ticket of a launch moves the counter to
-    // (epoch + 1, 0): nothing is reset or counted by the host, a captured graph can replay the launch.
-    unsigned long long *ticket;
+    // FUSE: where a CTA waits for other CTAs (the publish/poll tail), the launch guarantees that those CTAs run:
+    //   * ticket == NULL: a COOPERATIVE launch -- the whole grid is co-resident (the runtime refuses the launch
+    //     otherwise), CTA (blockIdx.x, blockIdx.y) is (block, vector);
+    //   * ticket != NULL (grids too large to be co-resident): every CTA draws a ticket on entry and takes it as
+    //     its LOGICAL (vector, block) id, so it only ever waits for CTAs that started before it, whatever the
+    //     order the hardware dispatches blockIdx in.  The CTA that draws the last ticket resets the counter.
+    // epochCtr: the launch epoch the publication words carry, read at kernel start; the last CTA to EXIT
+    // (doneCtr) advances it.  Nothing is counted or reset by the host: a captured graph can replay the launch.
+    unsigned int *ticket;
+    unsigned int *epochCtr, *doneCtr;
+    // FUSE, reduced costs formed by THIS kernel (rcIdx != NULL; DecompAlgo::generateVarsCalcRedCost,
+    // Dip/src/DecompAlgo.cpp:4506-4547): column j = obj[j] - sum_e uVec[rcIdx[e]] * rcVal[e] over the entries
+    // e in [rcStart[j], rcStart[j+1]) -- stored in the reference's scatter order (descending rows), multiplied
+    // and added unfused, one after the other: the bits of redcost_stream_kernel and of the oracle.  (rcIdx, uVec)
+    // is either (master row, the dense dual vector) or (slot, u[support] compacted): rows that cannot carry a
+    // dual are not stored in the second form.  The reduced costs are also written to `redCost` (the tail's
+    // sums and the host read them there).  alpha_b = uVec[alphaIdx[b]].
+    const int32_t *rcStart;
+    const int32_t *rcIdx;
+    const double *rcVal;
+    const double *uVec;
+    const int32_t *alphaIdx;
+    long long uStride;
+    int phase1;
     // FUSE, batched dual vectors (gridDim.y = vectors): vector v = blockIdx.y reads redCost + v*rcStride
     // and alpha + v*alphaStride and writes the packed result at byte offset v*resStride; the per-block
     // arrays pubWord / scale / shortcut / sel / zShort hold nLocal entries per vector
@@ -429,25 +447,27 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const int lane = t & 31;
     const int warp = t >> 5;
     const int nWarps = T >> 5;
-    // FUSE: the ticket (see KnapArgs::ticket) is drawn first, the row buffers are initialised while it travels
-    __shared__ unsigned long long sTicket;
-    if (FUSE && t == 0) sTicket = atomicAdd(a.ticket, 1ull);
-    if (t == 0) mbarInit(mbar, 1);
-    // c[-1][.] = 0 (gap_func.py:156); guards = -inf
-    for (int j = t; j < 2 * bufStride; j += T) {
-        const int r = j >= bufStride ? j - bufStride : j;
-        rowBase[j] = r < G ? kNegInf : 0.0;
+    // FUSE: the CTA's (block, vector): its grid coordinates (cooperative launch), or the ticket it draws
+    __shared__ unsigned int sTicket;
+    unsigned int tkIdx = 0u;
+    if (FUSE && a.ticket != nullptr) {
+        if (t == 0) {
+            sTicket = atomicAdd(a.ticket, 1u);
+            if (sTicket == gridDim.x * gridDim.y - 1u) atomicExch(a.ticket, 0u);  // every ticket is drawn: next launch
+        }
+        __syncthreads();
+        tkIdx = sTicket;
     }
-    __syncthreads();
-    const unsigned int tkIdx = FUSE ? (unsigned int)sTicket : 0u;
-    const unsigned int epoch = FUSE ? (unsigned int)(sTicket >> 32) & kPubEpochMask : 0u;
-    if (FUSE && t == 0 && tkIdx == gridDim.x * gridDim.y - 1u)
-        atomicAdd(a.ticket, (1ull << 32) - (unsigned long long)(gridDim.x * gridDim.y));  // every ticket is drawn: next launch
-    const int lb = FUSE ? (int)(tkIdx % gridDim.x) : (int)blockIdx.x;
+    const bool ticketed = FUSE && a.ticket != nullptr;
+    const int lb = ticketed ? (int)(tkIdx % gridDim.x) : (int)blockIdx.x;
     const int b = a.firstBlock + lb;
     // batched dual vectors (fused shapes only; gridDim.y == 1 otherwise): this CTA's vector
-    const long long vec = FUSE ? (long long)(tkIdx / gridDim.x) : 0;
+    const long long vec = FUSE ? (ticketed ? (long long)(tkIdx / gridDim.x) : (long long)blockIdx.y) : 0;
     const int vlb = (int)vec * (int)gridDim.x + lb;  // slot of (vector, block) in the per-vector block arrays
+    // the launch epoch: needed at the publication only, the load travels under everything before it
+    unsigned int epochRaw = 0u;
+    if (FUSE) asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(epochRaw) : "l"(a.epochCtr) : "memory");
+    const bool rcFused = FUSE && a.rcIdx != nullptr;
     const double *redCostV = a.redCost + vec * a.rcStride;
     const long long resOff = vec * a.resStride;
 #define RESV(ptr) (reinterpret_cast<decltype(ptr)>(reinterpret_cast<char *>(const_cast<void *>(static_cast<const void *>(ptr))) + resOff))
@@ -467,7 +487,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
     const double pScale = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? (double)a.scale[vlb] : 0.0;
     const int cap = capRaw;
     // fetched now so that the (possibly cold) load is long done when the tail needs it
-    const double alphaB = FUSE ? a.back.alpha[vec * a.alphaStride + b] : 0.0;
+    const double alphaB = !FUSE ? 0.0 : rcFused ? a.uVec[vec * a.uStride + a.alphaIdx[b]] : a.back.alpha[vec * a.alphaStride + b];
     uint32_t *bitsBase = FUSE ? sBits : a.bits + a.bitsOff[lb];
     const int j0 = t * S;  // first owned cell
 
@@ -483,6 +503,13 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x2) : "l"(RESV(a.filt.keptInd) + (size_t)(colStart - a.blockColStart[a.firstBlock]) / 2 * 2) : "memory");
         touch = x0 ^ x1 ^ x2;  // consumed in the tail, so that nothing waits for these loads here
     }
+    if (t == 0) mbarInit(mbar, 1);
+    // c[-1][.] = 0 (gap_func.py:156); guards = -inf
+    for (int j = t; j < 2 * bufStride; j += T) {
+        const int r = j >= bufStride ? j - bufStride : j;
+        rowBase[j] = r < G ? kNegInf : 0.0;
+    }
+    __syncthreads();
 
     double mine[S];
     uint32_t acc[S];
@@ -519,13 +546,62 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         if (FUSE && a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
         // ---- stage the chunk's reduced costs and weights with TMA bulk copies
         if (t == 0) {
-            const uint32_t bytesRc = (uint32_t)(((shiftRc + len + 1) & ~1) * 8);
+            const uint32_t bytesRc = rcFused ? 0u : (uint32_t)(((shiftRc + len + 1) & ~1) * 8);
             const uint32_t bytesW = (uint32_t)(((shiftW + len + 3) & ~3) * 4);
             mbarExpectTx(mbar, bytesRc + bytesW);
-            tmaLoad1d(rawRc, redCostV + (g0 - shiftRc), bytesRc, mbar);
+            if (!rcFused) tmaLoad1d(rawRc, redCostV + (g0 - shiftRc), bytesRc, mbar);
             tmaLoad1d(rawW, a.weight + (g0 - shiftW), bytesW, mbar);
         }
-        if (pruneLayoutHere) __syncthreads();  // the zeroed histograms are visible to every warp
+        if (rcFused) {
+            // ---- stage (a) for this block's columns, by the block itself (no SpMV launch, no round trip of the
+            // reduced costs through HBM before they are used): thread t forms columns t, t + T, ... four at a
+            // time, the loads of the four issued together (entry offsets, then rows / values, then the gathers
+            // of the duals -- three dependent round trips for the batch, not per column)
+            const double *uV = a.uVec + vec * a.uStride;
+            double *rcOut = const_cast<double *>(redCostV);
+            for (int base = t; base < len; base += 4 * T) {
+                int e0[4], e1[4];
+                double cj[4], sum[4];
+                int maxLen = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cl = base + q * T;
+                    const bool in = cl < len;
+                    e0[q] = in ? a.rcStart[g0 + cl] : 0;
+                    e1[q] = in ? a.rcStart[g0 + cl + 1] : 0;
+                    cj[q] = (in && !a.phase1) ? a.back.obj[g0 + cl] : 0.0;
+                    sum[q] = 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) maxLen = max(maxLen, e1[q] - e0[q]);
+                for (int k = 0; k < maxLen; ++k) {
+                    int ix[4];
+                    double v[4], g[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const bool on = e0[q] + k < e1[q];
+                        ix[q] = on ? a.rcIdx[e0[q] + k] : -1;
+                        v[q] = on ? a.rcVal[e0[q] + k] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) g[q] = ix[q] >= 0 ? uV[ix[q]] : 0.0;
+                    // y += u*a, unfused, in storage order (CoinPackedMatrix::transposeTimes' scatter order).  A column
+                    // past its end adds 0*0 = +0, which leaves the sum unchanged bit for bit (it is never -0)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sum[q] = __dadd_rn(sum[q], __dmul_rn(g[q], v[q]));
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cl = base + q * T;
+                    if (cl < len) {
+                        const double rc = a.phase1 ? -sum[q] : cj[q] - sum[q];  // DecompAlgo.cpp:4538-4545
+                        rawRc[shiftRc + cl] = rc;
+                        rcOut[g0 + cl] = rc;
+                    }
+                }
+            }
+        }
+        if (pruneLayoutHere || rcFused) __syncthreads();  // the zeroed histograms / the reduced costs are visible to every warp
         mbarWait(mbar, parity);
         parity ^= 1u;
         dbgStamp(a.dbgTimes, 1, lb, (int)vec);
@@ -773,9 +849,11 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                 itW[pos] = rawW[shiftW + cl];
                 itC[pos] = cl;
                 if (smemSums) {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(itP + kSumsRcOff + pos)),
-                                 "l"(redCostV + colStart + cl)
-                                 : "memory");
+                    if (rcFused) itP[kSumsRcOff + pos] = rawRc[shiftRc + cl];
+                    else
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(itP + kSumsRcOff + pos)),
+                                     "l"(redCostV + colStart + cl)
+                                     : "memory");
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smemAddr(itP + kSumsObjOff + pos)),
                                  "l"(a.back.obj + colStart + cl)
                                  : "memory");
@@ -1307,7 +1385,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             // one 64-bit word per block (layout: kPub* above).  Every block publishes in every launch that
             // prices its vector.  Published FIRST: the word is all the other blocks need, the result stores
             // below are read by the host only.
-            const unsigned long long word = (1ull << 63) | ((unsigned long long)epoch << kPubEpochShift) |
+            const unsigned long long word = (1ull << 63) | ((unsigned long long)(epochRaw & kPubEpochMask) << kPubEpochShift) |
                                             (keep ? 1ull << kPubKeptBit : 0ull) |
                                             ((unsigned long long)(cap < 0 ? 0 : nItRef) << kPubItemsShift) |
                                             ((unsigned long long)kGlobal << kPubEvalShift) | (unsigned long long)cnt;
@@ -1337,7 +1415,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
                     // an atomic is performed at the line's home L2 slice: a plain (even .relaxed.gpu) load
                     // was seen to return the old word for ~4.5 us on part of the SMs (the other die's L2)
                     wv = atomicAdd(const_cast<unsigned long long *>(src), 0ull);
-                    if ((wv >> kPubEpochShift) == ((1ull << 26) | (unsigned long long)epoch)) break;  // valid bit + epoch
+                    if ((wv >> kPubEpochShift) == ((1ull << 26) | (unsigned long long)(epochRaw & kPubEpochMask))) break;  // valid bit + epoch
                     // a short pause between polls (__nanosleep's granularity here is microseconds): 80 blocks
                     // x up to 79 threads polling back to back congest the words' L2 slices, and the stores that
                     // follow the wait queue up behind the polls
@@ -1410,6 +1488,11 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             RES_PUT(a.filt.hdr, 0, h);
         }
         dbgStamp(a.dbgTimes, 5, lb, (int)vec);
+        // the last CTA to get here has seen every CTA of the launch read the epoch: the next launch gets a new one
+        if (t == 0 && atomicAdd(a.doneCtr, 1u) == gridDim.x * gridDim.y - 1u) {
+            *a.doneCtr = 0u;
+            *a.epochCtr = epochRaw + 1u;
+        }
     }
 #undef RES_PUT
 #undef RESV
@@ -1575,6 +1658,11 @@ int prepareKnapsackDp(Ctx *c)
     if (c->dpFnConfigured != (void *)fn || c->dpFnSmem != g.smemBytes) {
         const int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(fn), g.smemBytes);
         if (rc) return rc;
+        int perSm = 0;
+        c->dpCoResident = 0;
+        if (g.fuse && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, g.T, g.smemBytes) == cudaSuccess)
+            c->dpCoResident = perSm * std::max(c->smCount, 1);
+        (void)cudaGetLastError();
         c->dpFnConfigured = (void *)fn;
         c->dpFnSmem = g.smemBytes;
     }
@@ -1611,7 +1699,7 @@ static void fillBackArgs(Ctx *c, const double *dRedCost, const double *dAlpha, B
 }
 
 static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
-                    double redCostEps, int nVec, bool batch, cudaStream_t st);
+                    double redCostEps, int nVec, bool batch, cudaStream_t st, const RcFuse *rf);
 
 // Large-shard path under node bounds: the DP kernels read a copy of the reduced costs in which every
 // fixed column is +0 (so it is not an item); the backtrack kernel still sums the true reduced costs.
@@ -1622,21 +1710,21 @@ __global__ void __launch_bounds__(256) mask_fixed_kernel(int n, const double *__
     if (j < n) out[j] = fix[j] ? 0.0 : rc[j];
 }
 
-int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st)
+int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st, const RcFuse *rf)
 {
-    return launchDp(c, dRedCost, 0, dAlpha, 0, redCostEps, 1, false, st);
+    return launchDp(c, dRedCost, 0, dAlpha, 0, redCostEps, 1, false, st, rf);
 }
 
 // Batched dual vectors: the fused kernel only (gridDim.y = vectors); the per-vector packed results,
 // publication words and Pisinger-mode block arrays live in the context's batch buffers.
 int launchKnapsackDpBatch(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
-                          double redCostEps, int nVec, cudaStream_t st)
+                          double redCostEps, int nVec, cudaStream_t st, const RcFuse *rf)
 {
-    return launchDp(c, dRedCost, rcStride, dAlpha, alphaStride, redCostEps, nVec, true, st);
+    return launchDp(c, dRedCost, rcStride, dAlpha, alphaStride, redCostEps, nVec, true, st, rf);
 }
 
 static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
-                    double redCostEps, int nVec, bool batch, cudaStream_t st)
+                    double redCostEps, int nVec, bool batch, cudaStream_t st, const RcFuse *rf)
 {
     if (c->nLocal == 0 || nVec <= 0) return DIPGPU_OK;
     if (batch && !c->geom.fuse) return fail(c, DIPGPU_ERR_STATE, "batched DP launch needs the fused kernel shape");
@@ -1676,7 +1764,21 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     a.dbgTimes = c->dDbgTimes;
     a.pubWord = batch ? c->dPubWordBatch : c->dPubWord;
     a.pubCells = c->dPubCells;
-    a.ticket = c->dTicket;
+    // co-resident grids (a GAP round, a short ladder): cooperative launch, CTA ids = grid coordinates; larger ones
+    // (batches): tickets
+    const long long totalCtas = (long long)c->nLocal * nVec;
+    const bool coop = g.fuse && !c->optPdl && c->dpCoResident > 0 && totalCtas <= c->dpCoResident;
+    a.ticket = coop ? nullptr : c->dSyncWords;
+    a.epochCtr = c->dSyncWords + 1;
+    a.doneCtr = c->dSyncWords + 2;
+    a.rcStart = rf ? rf->start : nullptr;
+    a.rcIdx = rf ? rf->idx : nullptr;
+    a.rcVal = rf ? rf->val : nullptr;
+    a.uVec = rf ? rf->uVec : nullptr;
+    a.alphaIdx = rf ? rf->alphaIdx : nullptr;
+    a.uStride = rf ? (long long)rf->uStride : 0;
+    a.phase1 = rf ? rf->phase1 : 0;
+    if (rf && !g.fuse) return fail(c, DIPGPU_ERR_STATE, "reduced costs can only be formed inside the fused DP kernel");
     if (g.fuse && (++c->fusedLaunches & 0xffffffull) == 0) {
         // a publication word that a launch does not rewrite (a vector beyond its nVec) must never meet its own
         // 26-bit epoch again: all words are cleared long before the epoch wraps
@@ -1719,16 +1821,21 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     // reads the reduced costs.  Measured SLOWER on GAP-E (39.5 vs 35.9 us per round: the early CTAs take SM
     // resources from the 6 us SpMV they wait for), so it is off unless asked for.  (Pisinger mode reads the
     // prep kernel's output at its very top: always a plain launch.)
-    a.pdl = (g.fuse && c->profitMode == DIPGPU_PROFIT_FP64 && c->optPdl) ? 1 : 0;
-    if (a.pdl) {
+    a.pdl = (g.fuse && c->profitMode == DIPGPU_PROFIT_FP64 && c->optPdl && !rf) ? 1 : 0;
+    if (a.pdl || coop) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(c->nLocal, nVec, 1);
         cfg.blockDim = dim3(g.T, 1, 1);
         cfg.dynamicSmemBytes = g.smemBytes;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        if (coop) {
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+        } else {
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+        }
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         DIPGPU_CUDA(c, cudaLaunchKernelEx(&cfg, fn, a));

@@ -298,9 +298,9 @@ static int ensureStage(Multi *M, size_t doubles)
     return DIPGPU_OK;
 }
 
-// The master duals of a call, prepared ONCE for all devices: the caller's pinned vector(s) are handed to the
-// devices as they are (each picks u[support] out of them), pageable ones are gathered into shared pinned
-// staging (u[support], 34 KB per vector on GAP-E); without a dual support every device copies what it needs.
+// The master duals of a call, prepared ONCE for all devices: u[support] gathered into shared pinned staging
+// (34 KB per vector on GAP-E) that every device copies from; without a dual support every device copies the
+// whole vector from the caller's buffer.
 // gatherHere: false = the caller of this function gathers (per device, in parallel) -- only the feed is formed.
 static int stageDuals(Multi *M, const double *u, int32_t uLen, int nVec, bool gatherHere, DualFeed *f)
 {
@@ -309,14 +309,6 @@ static int stageDuals(Multi *M, const double *u, int32_t uLen, int nVec, bool ga
     if (ns == 0) {
         f->host = u;
         return DIPGPU_OK;
-    }
-    if (M->front->optGatherPinned) {
-        const double *dv = deviceVisible(u);
-        if (dv) {
-            f->full = dv;
-            f->fullStride = uLen;
-            return DIPGPU_OK;
-        }
     }
     const int rc = ensureStage(M, ns * (size_t)nVec);
     if (rc) return rc;

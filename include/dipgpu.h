@@ -469,7 +469,7 @@ int dipgpu_plan_dp_geometry(int32_t smCount, int32_t nBlocks, int32_t maxCapacit
 int dipgpu_get_dp_geometry(const dipgpu_ctx *ctx, int32_t out[7]);
 
 /* Tuning / diagnostics knobs: "stage_timing", "dp_threads" (multiple of 32),
- * "dp_cells_per_thread" (odd, 1..25), "dp_items_per_step" (1, 2, or 3 with guard cells and <= 3 cells per thread), "dp_no_guard", "dp_no_prune" (1 = the fused kernel runs the DP over every active item), "dp_pdl" (1 = programmatic dependent launch of the fused kernel behind the SpMV; measured slower, off by default),
+ * "dp_cells_per_thread" (odd, 1..25), "dp_items_per_step" (1, 2, or 3 with guard cells and <= 3 cells per thread), "dp_no_guard", "dp_no_prune" (1 = the fused kernel runs the DP over every active item), "fuse_redcost" (default 1: small shards form the reduced costs of their blocks' columns inside the fused DP kernel -- the whole round is ONE kernel; 0 = the stream SpMV kernel in front of it), "dp_pdl" (1 = programmatic dependent launch of the fused kernel behind the SpMV; measured slower, off by default),
  * "spmv_lanes" (0 = TMA stream kernel), "spmv_chunk" / "spmv_max_cols" (entry / column budget of
  * a warp tile; re-tiles the matrix), "spmv_stages", "spmv_warps", "spmv_u_smem", "fuse_filter" (-1 auto, 0 = three kernels,
  * 1 = filter in the backtrack tail, 2 = backtrack + filter in the DP tail); 0 restores the automatic

@@ -40,8 +40,8 @@ def _same_round(a, b, m):
     assert a.cells == b.cells and 0 <= b.cellsEvaluated <= b.cells
 
 
-def _gap(m=12, n=300, seed=5):
-    g = I.gap_class_d(m=m, n=n, seed=seed)
+def _gap(m=12, n=300, seed=5, cls="d"):
+    g = (I.gap_class_d if cls == "d" else I.gap_class_e)(m=m, n=n, seed=seed)
     model = I.gap_pricing_model(g)
     rng = np.random.default_rng(seed)
     br = I.gap_branch_rows(model, rng)
@@ -249,3 +249,73 @@ def _snap(r):
     n = r.nCols
     return (n, r.blockObj.tobytes(), r.blockRedCost.tobytes(), r.blockNnz.tobytes(), r.colBlock[:n].tobytes(),
             r.colStart[:n + 1].tobytes(), r.colInd[:r.c.nInd].tobytes(), r.mostNegReducedCost, r.cells)
+
+
+@pytest.mark.parametrize("support", [False, True])
+def test_one_kernel_round_equals_three_kernel_round(support):
+    """The fused shapes form the reduced costs inside the DP kernel (option fuse_redcost, default on): same bits as
+    the stream SpMV kernel in front of it -- single rounds, phase 1, resident duals, batches, the ladder, node bounds,
+    cut rows appended behind the convexity rows."""
+    from dip_b200.pricer import GpuPricer, RoundResult
+    model, duals = _gap(m=24, n=1100, seed=21, cls="e")   # blocks wide enough for the reduction pre-pass
+    with GpuPricer(0) as pa, GpuPricer(0) as pb:
+        pb.set_option("fuse_redcost", 0)
+        for p in (pa, pb):
+            p.setModel(model)
+            if support:
+                p.setDualSupport(model.dual_support)
+        la0 = pa.counters()["kernel_launches"]
+        for u in duals[:3]:
+            for phase in (capi.PHASE_PRICE2, capi.PHASE_PRICE1):
+                _same_round(pa.priceRound(u, phase=phase, result=RoundResult(model.m, model.m, model.N)),
+                            pb.priceRound(u, phase=phase, result=RoundResult(model.m, model.m, model.N)), model.m)
+        assert pa.counters()["kernel_launches"] - la0 == 6          # ONE kernel per round
+        _same_round(pa.priceRoundResident(result=RoundResult(model.m, model.m, model.N)),
+                    pb.priceRoundResident(result=RoundResult(model.m, model.m, model.N)), model.m)
+        ra, rca = pa.priceRound(duals[3], want_redcost=True, result=RoundResult(model.m, model.m, model.N))
+        rb, rcb = pb.priceRound(duals[3], want_redcost=True, result=RoundResult(model.m, model.m, model.N))
+        _same_round(ra, rb, model.m)
+        np.testing.assert_array_equal(rca, rcb)
+        for a, b in zip(pa.priceRoundsBatch(np.stack(duals[:5])), pb.priceRoundsBatch(np.stack(duals[:5]))):
+            _same_round(a, b, model.m)
+        for p in (pa, pb):
+            p.stabSetCenter(duals[0])
+        (la, _), (lb, _) = pa.priceRoundStabLadder(duals[1], 0.3, 4), pb.priceRoundStabLadder(duals[1], 0.3, 4)
+        for a, b in zip(la, lb):
+            _same_round(a, b, model.m)
+        # the pool re-pricing after a one-kernel round reads the dense vector (formed on the device from the compact one)
+        r = pa.priceRound(duals[2], result=RoundResult(model.m, model.m, model.N))
+        cs, ri, va, hs = pa.expandColumns()
+        for p in (pa, pb):
+            p.priceRound(duals[2], result=RoundResult(model.m, model.m, model.N))
+            p.poolClear()
+            p.poolAppend(cs, ri, va, r.colOrigCost[:r.nCols])
+        np.testing.assert_array_equal(pa.poolSetReducedCosts(None)[0], pb.poolSetReducedCosts(None)[0])
+        # node bounds
+        rng = np.random.default_rng(3)
+        lb_ = (rng.random(model.N) < 0.01).astype(np.float64)
+        ub_ = 1.0 - (rng.random(model.N) < 0.03) * (1 - lb_)
+        for p in (pa, pb):
+            p.setColBounds(lb_, ub_)
+        _same_round(pa.priceRound(duals[4], result=RoundResult(model.m, model.m, model.N)),
+                    pb.priceRound(duals[4], result=RoundResult(model.m, model.m, model.N)), model.m)
+        for p in (pa, pb):
+            p.setColBounds(None, None)
+        # cut rows behind the convexity rows
+        n_cut = 7
+        rs = np.zeros(n_cut + 1, np.int64)
+        ci, va2 = [], []
+        for k in range(n_cut):
+            cols = np.sort(rng.choice(model.N, size=25, replace=False))
+            ci.append(cols)
+            va2.append(rng.integers(1, 5, size=25).astype(np.float64))
+            rs[k + 1] = rs[k] + 25
+        for p in (pa, pb):
+            p.appendCoreRows(rs, np.concatenate(ci).astype(np.int32), np.concatenate(va2))
+        u2 = np.concatenate([duals[0], rng.uniform(-2, 2, size=n_cut)])
+        if support:
+            sup2 = np.concatenate([model.dual_support, np.arange(model.u_len, model.u_len + n_cut)]).astype(np.int32)
+            for p in (pa, pb):
+                p.setDualSupport(sup2)
+        _same_round(pa.priceRound(u2, result=RoundResult(model.m, model.m, model.N)),
+                    pb.priceRound(u2, result=RoundResult(model.m, model.m, model.N)), model.m)
