@@ -391,58 +391,62 @@ def single_gpu_line(args, torch, dev, local_rank):
         cells_eval_per_round.append(rk.cellsEvaluated)
     kept0 = r0.nCols
 
-    # ---- device-resident rounds (value)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for k in range(W):
-        flush_l2()
-        pr.priceRoundDev(u_dev[k % N_DUALS].data_ptr(), model.u_len, redCostEps=RC_EPS, stream=sptr)
-    barrier()
-    c0 = pr.counters()
-    wall0 = time.perf_counter()
-    with ClockSampler(local_rank) as clk:
-        for k in range(K):
+    # ---- device-resident rounds (value).  The rows that can carry a dual at this node are declared once
+    # (dipgpu_set_dual_support: free branch rows have zero duals), which is how the integration drives the library
+    # (INTEGRATION.md); `no_dual_support` repeats the measurement without the declaration.
+    def value_loop(steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(W):
+            flush_l2()
+            pr.priceRoundDev(u_dev[k % N_DUALS].data_ptr(), model.u_len, redCostEps=RC_EPS, stream=sptr)
+        barrier()
+        a = pr.counters()
+        t0 = time.perf_counter()
+        for k in range(steps):
             flush_l2()
             ev[k][0].record(stream)
             pr.priceRoundDev(u_dev[k % N_DUALS].data_ptr(), model.u_len, redCostEps=RC_EPS, stream=sptr)
             ev[k][1].record(stream)
         barrier()
-    wall_dev = time.perf_counter() - wall0
-    c1 = pr.counters()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    launches = c1["kernel_launches"] - c0["kernel_launches"]
-    value = K / (dev_ms * 1e-3)
+        wall = time.perf_counter() - t0
+        b = pr.counters()
+        return sum(x.elapsed_time(y) for x, y in ev), b["kernel_launches"] - a["kernel_launches"], wall
 
-    # ---- end-to-end rounds through the host-buffer C-ABI call (e2e): pinned u in, packed columns out.
-    # Twice: the whole 2 MB dual vector uploaded per round, and with the rows that can carry a dual at this
-    # node declared once (dipgpu_set_dual_support: free branch rows have zero duals), which is how the
-    # integration drives it and what `e2e.value` reports.
     ptrs = [u_pin.array[k].ctypes.data for k in range(N_DUALS)]
 
-    def e2e_loop():
+    # end-to-end rounds through the host-buffer C-ABI call (e2e): pinned u in, packed columns out
+    def e2e_loop(steps):
         for k in range(W):
             pr.priceRoundRaw(ptrs[k % N_DUALS], model.u_len, capi.PHASE_PRICE2, RC_EPS, res)
         barrier()
         c0 = pr.counters()
         tot = 0.0
-        for k in range(K):
+        for k in range(steps):
             flush_l2()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             pr.priceRoundRaw(ptrs[k % N_DUALS], model.u_len, capi.PHASE_PRICE2, RC_EPS, res)
             tot += time.perf_counter() - t0
         c1 = pr.counters()
-        return tot, (c1["h2d_bytes"] - c0["h2d_bytes"]) // K, (c1["d2h_bytes"] - c0["d2h_bytes"]) // K
+        return tot, (c1["h2d_bytes"] - c0["h2d_bytes"]) // steps, (c1["d2h_bytes"] - c0["d2h_bytes"]) // steps
 
-    dense_s, dense_h2d, _ = e2e_loop()
     pr.setDualSupport(model.dual_support)
-    e2e_s, h2d_b, d2h_b = e2e_loop()
+    with ClockSampler(local_rank) as clk:
+        dev_ms, launches, wall_dev = value_loop(K)
+    value = K / (dev_ms * 1e-3)
+    e2e_s, h2d_b, d2h_b = e2e_loop(K)
+    pr.setDualSupport(None)
+    Kd = min(K, 100)
+    dense_dev_ms, _, _ = value_loop(Kd)
+    dense_s, dense_h2d, _ = e2e_loop(Kd)
+    pr.setDualSupport(model.dual_support)
     e2e = {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
            "ms_per_step": 1e3 * e2e_s / K,
            "dual_support_rows": int(len(model.dual_support)),
-           "dense_upload": {"value": K / dense_s, "ms_per_step": 1e3 * dense_s / K, "h2d_bytes_per_step": dense_h2d},
+           "no_dual_support": {"value": Kd / dense_s, "ms_per_step": 1e3 * dense_s / Kd, "h2d_bytes_per_step": dense_h2d},
            "timing": "host wall clock around the synchronous dipgpu_price_round call (pinned u in, columns out); "
                      "`value`: the rows that can carry a dual declared once, only they are uploaded; "
-                     "`dense_upload`: the whole dual vector uploaded every round"}
+                     "`no_dual_support`: the whole dual vector uploaded every round"}
 
     # ---- per-stage device times of the timed workload (CUDA events on the library's stream)
     pr.set_option("stage_timing", 1)
@@ -492,6 +496,7 @@ def single_gpu_line(args, torch, dev, local_rank):
                 "l2": "flushed between steps (256 MiB written then 256 MiB read, outside the per-step CUDA-event pairs)"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
         "wall_s_device_loop": wall_dev, "stage_ms": stage_ms, "roofline": roofline,
+        "value_no_dual_support": {"value": Kd / (dense_dev_ms * 1e-3), "ms_per_step": dense_dev_ms / Kd},
     }
     if "dp_csp" in extras:
         line["roofline_dp_csp"] = extras["dp_csp"]

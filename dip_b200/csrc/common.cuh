@@ -222,6 +222,7 @@ struct Ctx {
     int32_t *dCapEff = nullptr;         // per block: capacity minus the fixed-to-1 weights (< 0: they do not fit)
     double *dRcEff = nullptr;           // large-shard path: reduced costs with the fixed columns masked to +0
     std::vector<int32_t> hWeight;
+    std::vector<int32_t> hCapEff;       // host copy of dCapEff
     int maxCapacity = 0;       // of the shard
     int maxBlockCols = 0;      // of the shard
     int maxUsableWeight = 0;   // of the shard: max weight <= its block's capacity
@@ -244,13 +245,16 @@ struct Ctx {
     // is dColStart32 / dRowMaster / dVal; with a dual support, a second CSC holding only the entries of rows that can
     // carry a dual, indexed by SLOT in the compacted dual vector u[support] (dUCompact; slot ns = a zero)
     bool optFuseRc = true;
-    int32_t *dCStart = nullptr, *dCIdx = nullptr;
+    bool optNoCoop = false;  // diagnostics (option "dp_coop" = 0): tickets even when the grid is co-resident
+    int32_t *dCStart = nullptr, *dCIdx = nullptr, *dCRow = nullptr;  // (dCRow: the same entries' master rows, for dense vectors)
     double *dCVal = nullptr;
     int32_t *dAlphaIdxDense = nullptr, *dAlphaIdxCompact = nullptr;  // per block: where its convexity dual sits
+    int32_t *dBlkEntFull = nullptr, *dBlkEntCompact = nullptr;       // per block (m + 1): its first stored entry in either CSC
     double *dUCompact = nullptr;      // (ns + 16) doubles, single rounds
     double *dUBatchCompact = nullptr; // batchCap x cStride doubles
     size_t cStride = 0;
     bool compactValid = false;        // the compact CSC matches the current core / support / blocks
+    std::vector<int32_t> hBlkEntFull, hBlkEntCompact;  // host copies (which blocks fit the kernel's staging areas)
     bool dualsCompact = false;        // dUCompact holds the duals of the last call (dU may not)
     uint64_t fusedLaunches = 0;             // the publication words are cleared every 2^24 fused launches
     unsigned int *dDoneCounter = nullptr;  // ticket of the fused backtrack+filter kernel
@@ -359,6 +363,7 @@ int ensureBatch(Ctx *c, int nVec);
 int enqueueRound(Ctx *c, const DualFeed *feed, int32_t uLen, int32_t phase, double eps, bool mirror, cudaStream_t st, bool needAllRedCosts = false);
 int enqueueRoundDev(Ctx *c, const double *uDev, int32_t uLen, int32_t phase, double eps, bool mirror, cudaStream_t st);
 bool rcFuseEligible(const Ctx *c);
+int rcFuseStageCap(const Ctx *c);  // knapsack.cu: stored entries of a block the fused kernel can stage
 int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st, bool compact);
 int fetchResult(Ctx *c, cudaStream_t st);
 int fetchBatchPacked(Ctx *c, int nVec, cudaStream_t st);
@@ -426,7 +431,7 @@ int prepareKnapsackDp(Ctx *c);  // loads the chosen kernel, sets its shared-memo
 // launch of its own -- from a CSC (start, idx, val) whose idx index uVec (vector v at uVec + v*uStride), writes
 // them to dRedCost and reads alpha_b = uVec[alphaIdx[b]]
 struct RcFuse {
-    const int32_t *start, *idx;
+    const int32_t *start, *hBlkEnt, *idx;  // hBlkEnt[b] (HOST array, m + 1): first stored entry of GLOBAL block b
     const double *val, *uVec;
     const int32_t *alphaIdx;
     int64_t uStride;

@@ -140,7 +140,8 @@ static int uploadCore(Ctx *c)
     if (nnz < (int64_t)1 << 31 && N > 0) {
         std::vector<int32_t> cs32((size_t)N + 1);
         for (int j = 0; j <= N; ++j) cs32[j] = (int32_t)colStart[j];
-        if ((rc = devAlloc(c, &c->dColStart32, (size_t)N + 1))) return rc;
+        if ((rc = devAlloc(c, &c->dColStart32, (size_t)N + 1 + 8))) return rc;  // (+8: bulk copies read whole 16-byte pieces)
+        DIPGPU_CUDA(c, cudaMemset(c->dColStart32, 0, sizeof(int32_t) * ((size_t)N + 1 + 8)));
         DIPGPU_CUDA(c, cudaMemcpy(c->dColStart32, cs32.data(), sizeof(int32_t) * cs32.size(), cudaMemcpyHostToDevice));
         if ((int64_t)R + c->numConvex <= 65536) {
             std::vector<uint16_t> r16((size_t)nnz + 16, 0);
@@ -282,6 +283,11 @@ static int ensureRcFuse(Ctx *c)
         for (int b = 0; b < m; ++b) ai[(size_t)b] = c->nBaseRows + b;  // alpha_b = u[nBaseRows + b]  (DecompAlgo.cpp:4820)
         if ((rc = devAlloc(c, &c->dAlphaIdxDense, ai.size()))) return rc;
         DIPGPU_CUDA(c, cudaMemcpy(c->dAlphaIdxDense, ai.data(), sizeof(int32_t) * ai.size(), cudaMemcpyHostToDevice));
+        std::vector<int32_t> be((size_t)m + 1);
+        for (int b = 0; b <= m; ++b) be[(size_t)b] = (int32_t)c->hColStart[(size_t)c->hBlockColStart[(size_t)b]];
+        if ((rc = devAlloc(c, &c->dBlkEntFull, be.size()))) return rc;
+        DIPGPU_CUDA(c, cudaMemcpy(c->dBlkEntFull, be.data(), sizeof(int32_t) * be.size(), cudaMemcpyHostToDevice));
+        c->hBlkEntFull = be;
     }
     if (c->compactValid) return DIPGPU_OK;
     const size_t ns = c->hSupport.size();
@@ -294,7 +300,7 @@ static int ensureRcFuse(Ctx *c)
         std::vector<double> val;
         transposeCore(c, colStart, rowMaster, val);
         const int N = c->N;
-        std::vector<int32_t> cs((size_t)N + 1, 0), ci;
+        std::vector<int32_t> cs((size_t)N + 1, 0), ci, cr;
         std::vector<double> cv;
         ci.reserve((size_t)colStart[N] / 2 + 16);
         cv.reserve((size_t)colStart[N] / 2 + 16);
@@ -303,6 +309,7 @@ static int ensureRcFuse(Ctx *c)
                 const int32_t sl = slot[(size_t)rowMaster[(size_t)e]];
                 if (sl >= 0) {  // (order kept: descending rows, the reference's scatter order)
                     ci.push_back(sl);
+                    cr.push_back(rowMaster[(size_t)e]);
                     cv.push_back(val[(size_t)e]);
                 }
             }
@@ -313,14 +320,24 @@ static int ensureRcFuse(Ctx *c)
             const int32_t sl = slot[(size_t)(c->nBaseRows + b)];
             ai[(size_t)b] = sl >= 0 ? sl : (int32_t)ns;  // slot ns holds 0.0
         }
-        if ((rc = devAlloc(c, &c->dCStart, cs.size()))) return rc;
+        if ((rc = devAlloc(c, &c->dCStart, cs.size() + 8))) return rc;
+        DIPGPU_CUDA(c, cudaMemset(c->dCStart, 0, sizeof(int32_t) * (cs.size() + 8)));
         if ((rc = devAlloc(c, &c->dCIdx, ci.size() + 8))) return rc;
+        if ((rc = devAlloc(c, &c->dCRow, cr.size() + 8))) return rc;
         if ((rc = devAlloc(c, &c->dCVal, cv.size() + 8))) return rc;
         if ((rc = devAlloc(c, &c->dAlphaIdxCompact, ai.size()))) return rc;
+        {
+            std::vector<int32_t> be((size_t)m + 1);
+            for (int b = 0; b <= m; ++b) be[(size_t)b] = cs[(size_t)c->hBlockColStart[(size_t)b]];
+            if ((rc = devAlloc(c, &c->dBlkEntCompact, be.size()))) return rc;
+            DIPGPU_CUDA(c, cudaMemcpy(c->dBlkEntCompact, be.data(), sizeof(int32_t) * be.size(), cudaMemcpyHostToDevice));
+            c->hBlkEntCompact = be;
+        }
         if ((rc = devAlloc(c, &c->dUCompact, ns + 16))) return rc;
         DIPGPU_CUDA(c, cudaMemcpy(c->dCStart, cs.data(), sizeof(int32_t) * cs.size(), cudaMemcpyHostToDevice));
         if (!ci.empty()) {
             DIPGPU_CUDA(c, cudaMemcpy(c->dCIdx, ci.data(), sizeof(int32_t) * ci.size(), cudaMemcpyHostToDevice));
+            DIPGPU_CUDA(c, cudaMemcpy(c->dCRow, cr.data(), sizeof(int32_t) * cr.size(), cudaMemcpyHostToDevice));
             DIPGPU_CUDA(c, cudaMemcpy(c->dCVal, cv.data(), sizeof(double) * cv.size(), cudaMemcpyHostToDevice));
         }
         DIPGPU_CUDA(c, cudaMemcpy(c->dAlphaIdxCompact, ai.data(), sizeof(int32_t) * ai.size(), cudaMemcpyHostToDevice));
@@ -333,13 +350,32 @@ static int ensureRcFuse(Ctx *c)
     return DIPGPU_OK;
 }
 
+// a dense dual vector: all stored entries, or -- with a dual support, outside of which the caller guarantees zeros --
+// only the entries of the rows that can carry a dual (the same sums: the others would add u*a = 0)
 static RcFuse rcFuseDense(const Ctx *c, const double *uVec, int64_t uStride, int phase)
 {
-    return RcFuse{c->dColStart32, c->dRowMaster, c->dVal, uVec, c->dAlphaIdxDense, uStride, phase == DIPGPU_PHASE_PRICE1 ? 1 : 0};
+    if (!c->hSupport.empty() && c->dCRow)
+        return RcFuse{c->dCStart, c->hBlkEntCompact.data(), c->dCRow, c->dCVal, uVec, c->dAlphaIdxDense, uStride, phase == DIPGPU_PHASE_PRICE1 ? 1 : 0};
+    return RcFuse{c->dColStart32, c->hBlkEntFull.data(), c->dRowMaster, c->dVal, uVec, c->dAlphaIdxDense, uStride, phase == DIPGPU_PHASE_PRICE1 ? 1 : 0};
 }
+// The whole round as one kernel?  Eligible shape, structures built, and every block of the shard fits the kernel's
+// staging areas in the CSC the call would read (support-restricted when a dual support is declared).
+static bool useRcFuse(Ctx *c, int *rcOut)
+{
+    *rcOut = DIPGPU_OK;
+    if (!rcFuseEligible(c) || c->nLocal > kFuseFilterMaxBlocks) return false;
+    if ((*rcOut = ensureRcFuse(c))) return false;
+    const std::vector<int32_t> &be = c->hSupport.empty() ? c->hBlkEntFull : c->hBlkEntCompact;
+    if ((int)be.size() != c->m + 1) return false;
+    const int cap = rcFuseStageCap(c);
+    for (int b = c->firstBlock; b < c->firstBlock + c->nLocal; ++b)
+        if (be[(size_t)b + 1] - be[(size_t)b] > cap) return false;
+    return true;
+}
+
 static RcFuse rcFuseCompact(const Ctx *c, const double *uVec, int64_t uStride, int phase)
 {
-    return RcFuse{c->dCStart, c->dCIdx, c->dCVal, uVec, c->dAlphaIdxCompact, uStride, phase == DIPGPU_PHASE_PRICE1 ? 1 : 0};
+    return RcFuse{c->dCStart, c->hBlkEntCompact.data(), c->dCIdx, c->dCVal, uVec, c->dAlphaIdxCompact, uStride, phase == DIPGPU_PHASE_PRICE1 ? 1 : 0};
 }
 
 // u[support] of nVec dual vectors into the compact device vector(s) (vector v at dDst + v*dstStride): gathered on
@@ -572,9 +608,10 @@ int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st, bool 
     c->lastRoundOnHost = false;
     if (timed) cudaEventRecord(c->ev[1], st);
     if (c->geom.fuse || c->nLocal == 0) {
-        if (rcFuseEligible(c)) {
+        const bool fused = useRcFuse(c, &rc);
+        if (rc) return rc;
+        if (fused) {
             // ONE kernel for the whole batch: CTA (block, vector) forms its columns' reduced costs for its vector
-            if ((rc = ensureRcFuse(c))) return rc;
             const RcFuse rf = compact ? rcFuseCompact(c, c->dUBatchCompact, (int64_t)c->cStride, phase)
                                       : rcFuseDense(c, c->dUBatch, (int64_t)c->uStride, phase);
             if (timed) cudaEventRecord(c->ev[2], st);
@@ -611,8 +648,9 @@ int feedBatchDuals(Ctx *c, const DualFeed &f, int32_t uLen, int nVec, cudaStream
     int rc;
     *compact = false;
     const size_t ns = c->hSupport.size();
-    if (rcFuseEligible(c) && ns > 0 && (f.host || f.staged)) {
-        if ((rc = ensureRcFuse(c))) return rc;
+    const bool fused = useRcFuse(c, &rc);
+    if (rc) return rc;
+    if (fused && ns > 0 && (f.host || f.staged)) {
         const size_t stride = (ns + 17) & ~(size_t)1;
         if (!c->dUBatchCompact || c->cStride != stride) {
             if ((rc = devAlloc(c, &c->dUBatchCompact, (size_t)std::max(c->batchCap, nVec) * stride))) return rc;
@@ -841,9 +879,10 @@ int enqueueRound(Ctx *c, const DualFeed *feed, int32_t uLen, int32_t phase, doub
     if ((rc = ensureDualBuffer(c, uLen))) return rc;
     const bool timed = c->stageTiming;
     if (timed) cudaEventRecord(c->ev[0], st);
-    if (rcFuseEligible(c) && !needAllRedCosts) {
+    const bool fused = !needAllRedCosts && useRcFuse(c, &rc);
+    if (rc) return rc;
+    if (fused) {
         // ONE kernel: the block CTAs form their columns' reduced costs themselves
-        if ((rc = ensureRcFuse(c))) return rc;
         const size_t ns = c->hSupport.size();
         RcFuse rf;
         if (feed && ns > 0 && (feed->host || feed->staged)) {
@@ -1017,7 +1056,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     devFree(&c->dDoneCounter); devFree(&c->dSyncWords); devFree(&c->dCsrRowStart);
-    devFree(&c->dCStart); devFree(&c->dCIdx); devFree(&c->dCVal); devFree(&c->dAlphaIdxDense); devFree(&c->dAlphaIdxCompact);
+    devFree(&c->dCStart); devFree(&c->dCIdx); devFree(&c->dCRow); devFree(&c->dCVal); devFree(&c->dAlphaIdxDense); devFree(&c->dAlphaIdxCompact); devFree(&c->dBlkEntFull); devFree(&c->dBlkEntCompact);
     devFree(&c->dUCompact); devFree(&c->dUBatchCompact); devFree(&c->dCsrColInd); devFree(&c->dCsrVal); devFree(&c->dExpPub);
     if (c->dMCols) cudaFree(c->dMCols);
     if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dSpmvBlob); devFree(&c->dSpmvWarpStart); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
@@ -1354,6 +1393,7 @@ int dipgpu_set_col_bounds(dipgpu_ctx *ctx, const double *colLB, const double *co
     if (!c->dCapEff && (rc = devAlloc(c, &c->dCapEff, (size_t)std::max(c->m, 1)))) return rc;
     DIPGPU_CUDA(c, cudaMemcpy(c->dFix, fix.data(), fix.size(), cudaMemcpyHostToDevice));
     DIPGPU_CUDA(c, cudaMemcpy(c->dCapEff, capEff.data(), sizeof(int32_t) * capEff.size(), cudaMemcpyHostToDevice));
+    c->hCapEff = capEff;
     c->h2d += (int64_t)fix.size() + 4 * c->m;
     c->haveFix = true;
     return DIPGPU_OK;
@@ -2203,6 +2243,7 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "stage_timing") || !strcmp(name, "round_timing")) { c->stageTiming = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "dp_pdl")) { c->optPdl = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "fuse_redcost")) { c->optFuseRc = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "dp_coop")) { c->optNoCoop = value == 0; return DIPGPU_OK; }
     if (!strcmp(name, "result_zero_copy")) {  // 2 (diagnostics): also from the device-resident entry points
         c->optZeroCopy = value != 0;
         c->optMirrorAlways = value == 2;

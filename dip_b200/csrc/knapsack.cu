@@ -369,6 +369,11 @@ struct KnapArgs {
     // memory (0: none).  Every result store is repeated there, so the host needs no device-to-host copy after
     // the kernel -- the stores cross PCIe while the other blocks still run.
     long long hostOff;
+    // FUSE (<= kFuseFilterMaxBlocks blocks): per LOCAL block {first column, capacity, first stored entry of its
+    // columns in the CSC of the in-block reduced costs}, entry nLocal closes the ranges.  In the kernel
+    // parameters: a CTA knows its block without a (cold) global load in front of everything else.
+    int32_t tab[kFuseFilterMaxBlocks + 1][3];
+    int useTab;  // 0: more blocks than the table holds (a forced fused launch): the global arrays are read instead
 };
 
 // Fused shapes: the TMA destinations of the raw reduced costs / weights are dead once the items are
@@ -403,6 +408,19 @@ __host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunk
     return b;
 }
 
+// In-block reduced costs (fused shapes): how many stored entries of a block fit the staging area of their values
+// and products, the not yet written itP | itW.  The host asks for in-block reduced costs only when every block of
+// the shard fits.
+__host__ __device__ inline int rcStageCap(int chunkCols)
+{
+    return (int)(((size_t)(chunkCols + 4) * 12) / 8) - 2;
+}
+
+int rcFuseStageCap(const Ctx *c)
+{
+    return rcStageCap(c->geom.chunkCols);
+}
+
 // One CTA per knapsack; T = blockDim.x threads (a multiple of 32), thread t owns
 // the S consecutive cells [t*S, t*S+S) of the DP row in registers.  S is odd, so
 // the 64-bit shared-memory accesses of a half-warp (stride S doubles) hit 16
@@ -416,7 +434,7 @@ __host__ __device__ inline size_t dpSmemBytes(int rowCells, int guard, int chunk
 // the taken list stay in shared memory, warp 0 walks the decisions as soon as the DP is done,
 // and the last CTA of the grid runs the filter -- stages (b) and (c) in one launch.
 template <int S, bool GUARD, int ITEMS, int MAXT, bool FUSE>
-__global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ KnapArgs a)
+__global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(const __grid_constant__ KnapArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int T = blockDim.x;
@@ -479,11 +497,14 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         *p__ = v__;                                                                                             \
         if (FUSE && a.hostOff != 0) *reinterpret_cast<decltype(p__)>(reinterpret_cast<char *>(p__) + a.hostOff) = v__; \
     } while (0)
-    const int colStart = a.blockColStart[b];
+    const bool tab = FUSE && a.useTab != 0;
+    const int colStart = tab ? a.tab[lb][0] : a.blockColStart[b];
+    const int colEnd = tab ? a.tab[lb + 1][0] : a.blockColStart[b + 1];
+    const int rcE0 = rcFused ? a.tab[lb][2] : 0, rcE1 = rcFused ? a.tab[lb + 1][2] : 0;  // the block's run of stored entries
     const int shortCode = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? a.shortcut[vlb] : 0;
     // a trivial case of GAP_KnapPisinger::solve needs no DP: behave like an empty block here
-    const int capRaw = a.capacity[b];  // < 0: the columns fixed to 1 do not fit (no column for this block)
-    const int nCols = (shortCode != 0 || capRaw < 0) ? 0 : a.blockColStart[b + 1] - colStart;
+    const int capRaw = tab ? a.tab[lb][1] : a.capacity[b];  // < 0: the columns fixed to 1 do not fit (no column for this block)
+    const int nCols = (shortCode != 0 || capRaw < 0) ? 0 : colEnd - colStart;
     const double pScale = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? (double)a.scale[vlb] : 0.0;
     const int cap = capRaw;
     // fetched now so that the (possibly cold) load is long done when the tail needs it
@@ -502,8 +523,48 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x1) : "l"(RESV(a.filt.hdr)) : "memory");
         asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x2) : "l"(RESV(a.filt.keptInd) + (size_t)(colStart - a.blockColStart[a.firstBlock]) / 2 * 2) : "memory");
         touch = x0 ^ x1 ^ x2;  // consumed in the tail, so that nothing waits for these loads here
+        if (rcFused) {  // ... and the first page of the dual vector, which the gathers of the reduced costs read
+            unsigned long long x3;
+            asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x3) : "l"(a.uVec + vec * a.uStride) : "memory");
+            touch ^= x3;
+        }
     }
     if (t == 0) mbarInit(mbar, 1);
+    // ---- in-block reduced costs (stage (a) by the block itself, see the chunk loop): everything is requested NOW --
+    // the bulk copies of the weights, the objective entries (into rawRc: c_j - sum is formed in place), the columns'
+    // entry offsets (into the not yet written item-column array) and the entries' values (into the not yet written
+    // item arrays), and, by every thread, the dual indices of ITS entries straight from memory followed by the
+    // gathers of those duals -- so the two dependent round trips of the gathers run under the bulk copies.
+    constexpr int kRcRegs = 9;  // entries per thread whose duals are gathered up front (GAP-E: 1 632 entries, 192 threads)
+    const int rcLen = FUSE ? nCols : 0;
+    const int rcNE = rcE1 - rcE0;
+    const bool rcStaged = rcFused && rcLen > 0 && rcNE <= rcStageCap(CH);
+    const double *uV = rcFused ? a.uVec + vec * a.uStride : nullptr;
+    double rcG[kRcRegs];
+    if (rcFused && rcLen > 0) {
+        if (t == 0) {
+            const int shRc = colStart & 1, shW = colStart & 3, shS = colStart & 3, shV = rcE0 & 1;
+            const uint32_t bytesObj = a.phase1 ? 0u : (uint32_t)(((shRc + rcLen + 1) & ~1) * 8);
+            const uint32_t bytesW = (uint32_t)(((shW + rcLen + 3) & ~3) * 4);
+            const uint32_t bytesS = (uint32_t)(((shS + rcLen + 1 + 3) & ~3) * 4);
+            const uint32_t bytesV = rcStaged ? (uint32_t)(((shV + rcNE + 1) & ~1) * 8) : 0u;
+            mbarExpectTx(mbar, bytesObj + bytesW + bytesS + bytesV);
+            tmaLoad1d(itC, a.rcStart + (colStart - shS), bytesS, mbar);
+            tmaLoad1d(rawW, a.weight + (colStart - shW), bytesW, mbar);
+            if (!a.phase1) tmaLoad1d(rawRc, a.back.obj + (colStart - shRc), bytesObj, mbar);
+            if (bytesV) tmaLoad1d(itP, a.rcVal + (rcE0 - shV), bytesV, mbar);
+        }
+        if (rcStaged) {
+            int ix[kRcRegs];
+#pragma unroll
+            for (int q = 0; q < kRcRegs; ++q) {
+                const int k = t + q * T;
+                ix[q] = k < rcNE ? a.rcIdx[rcE0 + k] : -1;
+            }
+#pragma unroll
+            for (int q = 0; q < kRcRegs; ++q) rcG[q] = ix[q] >= 0 ? uV[ix[q]] : 0.0;
+        }
+    }
     // c[-1][.] = 0 (gap_func.py:156); guards = -inf
     for (int j = t; j < 2 * bufStride; j += T) {
         const int r = j >= bufStride ? j - bufStride : j;
@@ -534,7 +595,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         // columns are already +0, so that its hot kernels stay exactly as they are without bounds)
         const uint8_t *fixB = (FUSE && a.back.fix != nullptr) ? a.back.fix + g0 : nullptr;
         const bool pruneLayoutHere = FUSE && dpPruneLayout(CH, true, a.prune != 0) && len >= kPruneMinItems;
-        if (pruneLayoutHere) {
+        if (pruneLayoutHere && !rcFused) {
             // the histograms of the reduction pre-pass (in the not yet written itP | itW), zeroed before the
             // reduced costs are there
             int *h0 = reinterpret_cast<int *>(itP);
@@ -544,66 +605,120 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
         // reduced costs (the SpMV) is still running; everything above -- row buffers, histograms, page
         // touches, the convexity dual -- overlapped with it.  From here on its output is read.
         if (FUSE && a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-        // ---- stage the chunk's reduced costs and weights with TMA bulk copies
-        if (t == 0) {
-            const uint32_t bytesRc = rcFused ? 0u : (uint32_t)(((shiftRc + len + 1) & ~1) * 8);
-            const uint32_t bytesW = (uint32_t)(((shiftW + len + 3) & ~3) * 4);
-            mbarExpectTx(mbar, bytesRc + bytesW);
-            if (!rcFused) tmaLoad1d(rawRc, redCostV + (g0 - shiftRc), bytesRc, mbar);
-            tmaLoad1d(rawW, a.weight + (g0 - shiftW), bytesW, mbar);
-        }
-        if (rcFused) {
+        if (!rcFused) {
+            // ---- stage the chunk's reduced costs and weights with TMA bulk copies
+            if (t == 0) {
+                const uint32_t bytesRc = (uint32_t)(((shiftRc + len + 1) & ~1) * 8);
+                const uint32_t bytesW = (uint32_t)(((shiftW + len + 3) & ~3) * 4);
+                mbarExpectTx(mbar, bytesRc + bytesW);
+                tmaLoad1d(rawRc, redCostV + (g0 - shiftRc), bytesRc, mbar);
+                tmaLoad1d(rawW, a.weight + (g0 - shiftW), bytesW, mbar);
+            }
+            if (pruneLayoutHere) __syncthreads();  // the zeroed histograms are visible to every warp
+            mbarWait(mbar, parity);
+            parity ^= 1u;
+        } else {
             // ---- stage (a) for this block's columns, by the block itself (no SpMV launch, no round trip of the
-            // reduced costs through HBM before they are used): thread t forms columns t, t + T, ... four at a
-            // time, the loads of the four issued together (entry offsets, then rows / values, then the gathers
-            // of the duals -- three dependent round trips for the batch, not per column)
-            const double *uV = a.uVec + vec * a.uStride;
+            // reduced costs through HBM before they are used).  The block's stored entries are ONE contiguous run
+            // [rcE0, rcE1) of the CSC; the bulk copies and the gathers of the duals were requested at the top of
+            // the kernel.  Out of shared memory and registers now:
+            //   1. flat over the entries: product u*a, unfused, written over the value;
+            //   2. one thread per column adds ITS products one after the other in storage order (descending
+            //      rows: CoinPackedMatrix::transposeTimes' scatter order) and subtracts from c_j.
+            const int32_t *st = itC + (g0 & 3);  // st[cl] = first entry of column cl
+            const int nE = rcNE;
+            const bool staged = rcStaged;
+            mbarWait(mbar, parity);
+            parity ^= 1u;
             double *rcOut = const_cast<double *>(redCostV);
-            for (int base = t; base < len; base += 4 * T) {
-                int e0[4], e1[4];
-                double cj[4], sum[4];
-                int maxLen = 0;
+            if (staged) {
+                double *vp = itP + (rcE0 & 1);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int cl = base + q * T;
-                    const bool in = cl < len;
-                    e0[q] = in ? a.rcStart[g0 + cl] : 0;
-                    e1[q] = in ? a.rcStart[g0 + cl + 1] : 0;
-                    cj[q] = (in && !a.phase1) ? a.back.obj[g0 + cl] : 0.0;
-                    sum[q] = 0.0;
+                for (int q = 0; q < kRcRegs; ++q) {
+                    const int k = t + q * T;
+                    if (k < nE) vp[k] = __dmul_rn(rcG[q], vp[k]);
                 }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) maxLen = max(maxLen, e1[q] - e0[q]);
-                for (int k = 0; k < maxLen; ++k) {
-                    int ix[4];
-                    double v[4], g[4];
+                for (int k = t + kRcRegs * T; k < nE; k += T) vp[k] = __dmul_rn(uV[a.rcIdx[rcE0 + k]], vp[k]);  // (longer blocks)
+                __syncthreads();
+                // four columns per thread and step: their (short) addition chains run side by side
+                for (int base = t; base < len; base += 4 * T) {
+                    int k0[4], k1[4];
+                    double sum[4], cj[4];
+                    int maxLen = 0;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const bool on = e0[q] + k < e1[q];
-                        ix[q] = on ? a.rcIdx[e0[q] + k] : -1;
-                        v[q] = on ? a.rcVal[e0[q] + k] : 0.0;
+                        const int cl = base + q * T;
+                        const bool in = cl < len;
+                        k0[q] = in ? st[cl] - rcE0 : 0;
+                        k1[q] = in ? st[cl + 1] - rcE0 : 0;
+                        cj[q] = (in && !a.phase1) ? rawRc[shiftRc + cl] : 0.0;
+                        sum[q] = 0.0;
+                        maxLen = max(maxLen, k1[q] - k0[q]);
+                    }
+                    for (int k = 0; k < maxLen; ++k) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (k0[q] + k < k1[q]) sum[q] = __dadd_rn(sum[q], vp[k0[q] + k]);
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) g[q] = ix[q] >= 0 ? uV[ix[q]] : 0.0;
-                    // y += u*a, unfused, in storage order (CoinPackedMatrix::transposeTimes' scatter order).  A column
-                    // past its end adds 0*0 = +0, which leaves the sum unchanged bit for bit (it is never -0)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) sum[q] = __dadd_rn(sum[q], __dmul_rn(g[q], v[q]));
+                    for (int q = 0; q < 4; ++q) {
+                        const int cl = base + q * T;
+                        if (cl < len) {
+                            const double rc = a.phase1 ? -sum[q] : cj[q] - sum[q];  // DecompAlgo.cpp:4538-4545
+                            rawRc[shiftRc + cl] = rc;
+                            rcOut[g0 + cl] = rc;
+                        }
+                    }
                 }
+            } else {
+                // (not taken when the host sized the call; kept correct: thread t forms columns t, t + T, ... four at a
+                // time straight from memory)
+                for (int base = t; base < len; base += 4 * T) {
+                    int e0[4], e1[4];
+                    double sum[4];
+                    int maxLen = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int cl = base + q * T;
-                    if (cl < len) {
-                        const double rc = a.phase1 ? -sum[q] : cj[q] - sum[q];  // DecompAlgo.cpp:4538-4545
-                        rawRc[shiftRc + cl] = rc;
-                        rcOut[g0 + cl] = rc;
+                    for (int q = 0; q < 4; ++q) {
+                        const int cl = base + q * T;
+                        const bool in = cl < len;
+                        e0[q] = in ? st[cl] : 0;
+                        e1[q] = in ? st[cl + 1] : 0;
+                        sum[q] = 0.0;
+                        maxLen = max(maxLen, e1[q] - e0[q]);
+                    }
+                    for (int k = 0; k < maxLen; ++k) {
+                        int ix[4];
+                        double v[4], g[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const bool on = e0[q] + k < e1[q];
+                            ix[q] = on ? a.rcIdx[e0[q] + k] : -1;
+                            v[q] = on ? a.rcVal[e0[q] + k] : 0.0;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) g[q] = ix[q] >= 0 ? uV[ix[q]] : 0.0;
+                        // (a column past its end adds 0*0 = +0, which leaves the sum unchanged bit for bit: it is never -0)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) sum[q] = __dadd_rn(sum[q], __dmul_rn(g[q], v[q]));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cl = base + q * T;
+                        if (cl < len) {
+                            const double rc = a.phase1 ? -sum[q] : rawRc[shiftRc + cl] - sum[q];
+                            rawRc[shiftRc + cl] = rc;
+                            rcOut[g0 + cl] = rc;
+                        }
                     }
                 }
             }
+            __syncthreads();  // the reduced costs are visible to every warp, the staging areas are free again
+            if (pruneLayoutHere) {
+                int *h0 = reinterpret_cast<int *>(itP);
+                for (int k = t; k < 3 * kPruneBuckets; k += T) h0[k] = 0;
+                __syncthreads();
+            }
         }
-        if (pruneLayoutHere || rcFused) __syncthreads();  // the zeroed histograms / the reduced costs are visible to every warp
-        mbarWait(mbar, parity);
-        parity ^= 1u;
         dbgStamp(a.dbgTimes, 1, lb, (int)vec);
 
         // ---- reduction, fused shapes (what Pisinger's combo does before its DP): an item is left out
@@ -1222,7 +1337,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             int cnt = 0;
             if (shortCode == 1) {
                 // GAP_KnapPisinger.h:206-212: every item with negative reduced cost
-                const int nAll = a.blockColStart[b + 1] - colStart;
+                const int nAll = colEnd - colStart;
                 for (int base = 0; base < nAll; base += 32) {
                     const int j = base + lane;
                     const bool act = j < nAll && redCostV[colStart + j] < 0.0;
@@ -1303,7 +1418,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             if (a.back.fix != nullptr && cap >= 0) {
                 // node bounds: the columns fixed to 1 join the column.  Both lists ascend; every element
                 // finds its place by a binary search in the other list (no column is in both).
-                const int nAll = a.blockColStart[b + 1] - colStart;
+                const int nAll = colEnd - colStart;
                 int32_t *sForced = sTaken;  // the taken list is consumed
                 int nf = 0;
                 for (int base = 0; base < nAll; base += 32) {
@@ -1409,7 +1524,7 @@ __global__ void __launch_bounds__(MAXT) knap_dp_kernel(const __grid_constant__ K
             for (int pB = t; pB < lb; pB += T) {
                 unsigned long long wv;
                 // (fetched before the spin, so that its latency hides behind the wait)
-                const unsigned long long rowB = (unsigned long long)max(a.capacity[a.firstBlock + pB], -1) + 1ull;
+                const unsigned long long rowB = (unsigned long long)max(tab ? a.tab[pB][1] : a.capacity[a.firstBlock + pB], -1) + 1ull;
                 const unsigned long long *src = a.pubWord + (size_t)(vlb - lb + pB) * kPubWordStride;
                 for (;;) {
                     // an atomic is performed at the line's home L2 slice: a plain (even .relaxed.gpu) load
@@ -1505,6 +1620,9 @@ struct GeomEntry {
     int S, maxT;
     KnapFn fn[2][3];      // [guard][items-1]; three items per barrier only with guard cells, S <= 3
     KnapFn fnFuse[2][3];  // same, fused tail (NULL where not built)
+    // the fused kernel built for <= 256 threads (the GAP shapes: a row of a few hundred cells): 85 registers per
+    // thread instead of the 64 a 1024-thread build is held to -- no spills, room to keep loads in flight
+    KnapFn fnFuseSmall[2][3];
 };
 
 #define GE_FNS(S, MT, F)                                                                         \
@@ -1519,9 +1637,9 @@ struct GeomEntry {
          knap_dp_kernel<S, true, 3, MT, F>}                                                      \
     }
 #define GE_NULL {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}
-#define GE(S, MT) {S, MT, GE_FNS(S, MT, false), GE_NULL}
-#define GEF(S, MT) {S, MT, GE_FNS(S, MT, false), GE_FNS(S, MT, true)}
-#define GEF3(S, MT) {S, MT, GE_FNS3(S, MT, false), GE_FNS3(S, MT, true)}
+#define GE(S, MT) {S, MT, GE_FNS(S, MT, false), GE_NULL, GE_NULL}
+#define GEF(S, MT) {S, MT, GE_FNS(S, MT, false), GE_FNS(S, MT, true), GE_FNS(S, 256, true)}
+#define GEF3(S, MT) {S, MT, GE_FNS3(S, MT, false), GE_FNS3(S, MT, true), GE_FNS3(S, 256, true)}
 static const GeomEntry kGeoms[] = {
     GEF3(1, 1024), GEF3(3, 1024), GEF(5, 1024), GEF(7, 1024), GE(9, 1024), GE(11, 1024),
     GE(13, 512),   GE(15, 512),   GE(17, 512),  GE(19, 512),  GE(21, 512), GE(25, 512),
@@ -1535,6 +1653,15 @@ static const GeomEntry kGeoms[] = {
 static_assert(kPruneBuckets % 32 == 0, "one lane scans kPruneBuckets / 32 buckets");
 static const int kNumGeoms = (int)(sizeof(kGeoms) / sizeof(kGeoms[0]));
 static const size_t kMaxSmem = 227 * 1024 - 6 * 1024;  // the fused tail's static shared memory comes off the 227 KiB
+
+static KnapFn pickKnapFn(const GeomEntry *e, const DpGeom &g)
+{
+    const int gi = g.guard > 0 ? 1 : 0, ii = g.items - 1;
+    if (g.fuse && g.T <= 256 && e->fnFuseSmall[gi][ii] != nullptr) return e->fnFuseSmall[gi][ii];
+    return (g.fuse ? e->fnFuse : e->fn)[gi][ii];
+}
+
+static const GeomEntry *findGeom(int S);
 
 static const GeomEntry *findGeom(int S)
 {
@@ -1654,7 +1781,7 @@ int prepareKnapsackDp(Ctx *c)
     const DpGeom &g = c->geom;
     const GeomEntry *e = findGeom(g.S);
     if (!e) return fail(c, DIPGPU_ERR_STATE, "DP geometry not initialised");
-    KnapFn fn = (g.fuse ? e->fnFuse : e->fn)[g.guard > 0 ? 1 : 0][g.items - 1];
+    KnapFn fn = pickKnapFn(e, g);
     if (c->dpFnConfigured != (void *)fn || c->dpFnSmem != g.smemBytes) {
         const int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(fn), g.smemBytes);
         if (rc) return rc;
@@ -1731,7 +1858,7 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     const DpGeom &g = c->geom;
     const GeomEntry *e = findGeom(g.S);
     if (!e) return fail(c, DIPGPU_ERR_STATE, "DP geometry not initialised");
-    KnapFn fn = (g.fuse ? e->fnFuse : e->fn)[g.guard > 0 ? 1 : 0][g.items - 1];
+    KnapFn fn = pickKnapFn(e, g);
     KnapArgs a;
     a.redCost = dRedCost;
     if (c->haveFix && !g.fuse) {
@@ -1767,7 +1894,7 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     // co-resident grids (a GAP round, a short ladder): cooperative launch, CTA ids = grid coordinates; larger ones
     // (batches): tickets
     const long long totalCtas = (long long)c->nLocal * nVec;
-    const bool coop = g.fuse && !c->optPdl && c->dpCoResident > 0 && totalCtas <= c->dpCoResident;
+    const bool coop = g.fuse && !c->optPdl && !c->optNoCoop && c->dpCoResident > 0 && totalCtas <= c->dpCoResident;
     a.ticket = coop ? nullptr : c->dSyncWords;
     a.epochCtr = c->dSyncWords + 1;
     a.doneCtr = c->dSyncWords + 2;
@@ -1779,6 +1906,17 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     a.uStride = rf ? (long long)rf->uStride : 0;
     a.phase1 = rf ? rf->phase1 : 0;
     if (rf && !g.fuse) return fail(c, DIPGPU_ERR_STATE, "reduced costs can only be formed inside the fused DP kernel");
+    a.useTab = (g.fuse && c->nLocal <= kFuseFilterMaxBlocks) ? 1 : 0;
+    if (rf && !a.useTab) return fail(c, DIPGPU_ERR_STATE, "in-block reduced costs: %d blocks", c->nLocal);
+    if (a.useTab) {
+        const std::vector<int32_t> &capH = c->haveFix ? c->hCapEff : c->hCapacity;
+        for (int lb = 0; lb <= c->nLocal; ++lb) {
+            const int b = c->firstBlock + lb;
+            a.tab[lb][0] = c->hBlockColStart[(size_t)b];
+            a.tab[lb][1] = lb < c->nLocal ? capH[(size_t)b] : 0;
+            a.tab[lb][2] = rf ? rf->hBlkEnt[b] : 0;
+        }
+    }
     if (g.fuse && (++c->fusedLaunches & 0xffffffull) == 0) {
         // a publication word that a launch does not rewrite (a vector beyond its nVec) must never meet its own
         // 26-bit epoch again: all words are cleared long before the epoch wraps

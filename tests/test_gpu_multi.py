@@ -269,7 +269,9 @@ def test_one_kernel_round_equals_three_kernel_round(support):
             for phase in (capi.PHASE_PRICE2, capi.PHASE_PRICE1):
                 _same_round(pa.priceRound(u, phase=phase, result=RoundResult(model.m, model.m, model.N)),
                             pb.priceRound(u, phase=phase, result=RoundResult(model.m, model.m, model.N)), model.m)
-        assert pa.counters()["kernel_launches"] - la0 == 6          # ONE kernel per round
+        if support:   # (without a declared support a block's 3 x 1100 stored entries exceed the kernel's staging areas:
+            #  the stream SpMV stays in front)
+            assert pa.counters()["kernel_launches"] - la0 == 6          # ONE kernel per round
         _same_round(pa.priceRoundResident(result=RoundResult(model.m, model.m, model.N)),
                     pb.priceRoundResident(result=RoundResult(model.m, model.m, model.N)), model.m)
         ra, rca = pa.priceRound(duals[3], want_redcost=True, result=RoundResult(model.m, model.m, model.N))
