@@ -131,6 +131,23 @@ struct DpGeom {
 // ---------------------------------------------------------------------- context
 struct Multi;  // multi.cu
 
+// rf != NULL (fused shapes): the kernel forms the reduced costs of its blocks' columns itself -- stage (a) without a
+// launch of its own -- from a CSC (start, idx, val) whose idx index uVec (vector v at uVec + v*uStride), writes
+// them to dRedCost and reads alpha_b = uVec[alphaIdx[b]]
+struct RcFuse {
+    const int32_t *start, *hBlkEnt, *idx;  // hBlkEnt[b] (HOST array, m + 1): first stored entry of GLOBAL block b
+    const double *val, *uVec;
+    const int32_t *alphaIdx;
+    int64_t uStride;
+    int phase1;
+    // co-resident grids: the kernel fetches u[support] from host memory itself (KnapArgs::pullSrc)
+    const double *pullSrc = nullptr;
+    const int32_t *pullIdx = nullptr;
+    int64_t pullStride = 0;
+    int pullN = 0;
+};
+
+
 struct Ctx {
     // non-NULL: this object is only the FRONT of a multi-device context (dipgpu_create_multi): it owns no device
     // memory, every entry point is routed to the per-device contexts behind it (multi.cu)
@@ -241,6 +258,9 @@ struct Ctx {
     unsigned int *dSyncWords = nullptr;
     unsigned long long *dExpTicket = nullptr;
     int dpCoResident = 0;                   // CTAs of the configured DP kernel that fit the GPU at once
+    unsigned int *dPullCtr = nullptr;       // 64 per-vector arrival counters of the in-kernel dual upload
+    RcFuse batchPull;                       // (feedBatchDuals -> enqueueBatch: where the batch's kernel pulls its duals from)
+    bool optPull = true;                    // option "pull_duals": co-resident fused launches fetch u[support] from host memory themselves
     // reduced costs formed inside the fused DP kernel (option "fuse_redcost", default on): the CSC with int32 row ids
     // is dColStart32 / dRowMaster / dVal; with a dual support, a second CSC holding only the entries of rows that can
     // carry a dual, indexed by SLOT in the compacted dual vector u[support] (dUCompact; slot ns = a zero)
@@ -427,16 +447,6 @@ int launchKnapsackPrepBatch(Ctx *c, const double *dRedCost, int64_t rcStride, in
 // knapsack.cu -- stage (b)
 int chooseDpGeom(Ctx *c, DpGeom *g, bool wantFuse);
 int prepareKnapsackDp(Ctx *c);  // loads the chosen kernel, sets its shared-memory limit
-// rf != NULL (fused shapes): the kernel forms the reduced costs of its blocks' columns itself -- stage (a) without a
-// launch of its own -- from a CSC (start, idx, val) whose idx index uVec (vector v at uVec + v*uStride), writes
-// them to dRedCost and reads alpha_b = uVec[alphaIdx[b]]
-struct RcFuse {
-    const int32_t *start, *hBlkEnt, *idx;  // hBlkEnt[b] (HOST array, m + 1): first stored entry of GLOBAL block b
-    const double *val, *uVec;
-    const int32_t *alphaIdx;
-    int64_t uStride;
-    int phase1;
-};
 int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st, const RcFuse *rf = nullptr);
 int launchKnapsackDpBatch(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
                           double redCostEps, int nVec, cudaStream_t st, const RcFuse *rf = nullptr);
@@ -453,6 +463,8 @@ constexpr int kPoolPad = 512;  // entries allocated past the pool's capacity (al
 int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st);
 int launchScatterDuals(Ctx *c, int n, const int32_t *dIdx, const double *dVals, int64_t valStride, bool gather, double *dDst,
                        int64_t dstStride, int nVec, cudaStream_t st);
+int launchGatherDuals(Ctx *c, int n, const int32_t *dIdx, const double *dVals, int64_t valStride, double *dDst, int64_t dstStride,
+                      int nVec, cudaStream_t st);
 int launchSmoothDuals(Ctx *c, const double *dURM, const double *dCenter, const double *dAlphas, int nVec, int uLen,
                       double *dOut, int64_t outStride, cudaStream_t st);
 // microbench.cu -- roofline denominators measured on the device

@@ -378,6 +378,41 @@ static RcFuse rcFuseCompact(const Ctx *c, const double *uVec, int64_t uStride, i
     return RcFuse{c->dCStart, c->hBlkEntCompact.data(), c->dCIdx, c->dCVal, uVec, c->dAlphaIdxCompact, uStride, phase == DIPGPU_PHASE_PRICE1 ? 1 : 0};
 }
 
+// Would the fused DP kernel for nVec vectors be launched cooperatively (knapsack.cu: launchDp)?
+static bool dpWouldCoop(const Ctx *c, int nVec)
+{
+    return c->geom.fuse && !c->optPdl && !c->optNoCoop && c->dpCoResident > 0 && (long long)c->nLocal * nVec <= c->dpCoResident;
+}
+
+// Co-resident launches fetch u[support] from host memory themselves: where from.  A page-locked `u` is read in
+// place (the kernel picks u[support[k]]), a pageable one is gathered into mapped pinned staging first, staging
+// somebody else filled (a multi-device context) is read as it is.
+static int pullSource(Ctx *c, const DualFeed &f, int32_t uLen, int nVec, RcFuse *rf)
+{
+    const size_t ns = c->hSupport.size();
+    rf->pullN = (int)ns;
+    if (f.staged) {
+        rf->pullSrc = f.staged;
+        rf->pullStride = f.stagedStride;
+        return DIPGPU_OK;
+    }
+    if (c->optGatherPinned) {
+        const double *dv = deviceVisible(f.host);
+        if (dv) {
+            rf->pullSrc = dv;
+            rf->pullIdx = c->dSupport;
+            rf->pullStride = uLen;
+            return DIPGPU_OK;
+        }
+    }
+    int rc;
+    if ((rc = ensureSupportStaging(c, nVec))) return rc;
+    gatherSupport(c->hSupport, f.host, uLen, nVec, c->hSupVals);
+    rf->pullSrc = c->hSupVals;  // (mapped + portable: one address on the host and on every device)
+    rf->pullStride = (int64_t)ns;
+    return DIPGPU_OK;
+}
+
 // u[support] of nVec dual vectors into the compact device vector(s) (vector v at dDst + v*dstStride): gathered on
 // the host into pinned staging -- or taken from staging somebody else filled -- and copied in one piece.
 static int feedCompact(Ctx *c, const DualFeed &f, int32_t uLen, int nVec, double *dDst, size_t dstStride, cudaStream_t st)
@@ -385,6 +420,15 @@ static int feedCompact(Ctx *c, const DualFeed &f, int32_t uLen, int nVec, double
     const size_t ns = c->hSupport.size();
     const double *src = f.staged;
     size_t srcStride = (size_t)f.stagedStride;
+    if (!src && c->optGatherPinned) {
+        // page-locked dual vectors: the device picks u[support] out of them itself -- no pass over the (cold) vectors
+        // on the host (12 us per 2 MB vector against 5 us of kernel)
+        const double *dv = deviceVisible(f.host);
+        if (dv) {
+            c->h2d += (int64_t)sizeof(double) * (int64_t)ns * nVec;
+            return launchGatherDuals(c, (int)ns, c->dSupport, dv, (int64_t)uLen, dDst, (int64_t)dstStride, nVec, st);
+        }
+    }
     if (!src) {
         int rc;
         if ((rc = ensureSupportStaging(c, nVec))) return rc;
@@ -612,8 +656,15 @@ int enqueueBatch(Ctx *c, int nVec, int phase, double eps, cudaStream_t st, bool 
         if (rc) return rc;
         if (fused) {
             // ONE kernel for the whole batch: CTA (block, vector) forms its columns' reduced costs for its vector
-            const RcFuse rf = compact ? rcFuseCompact(c, c->dUBatchCompact, (int64_t)c->cStride, phase)
-                                      : rcFuseDense(c, c->dUBatch, (int64_t)c->uStride, phase);
+            RcFuse rf = compact ? rcFuseCompact(c, c->dUBatchCompact, (int64_t)c->cStride, phase)
+                                : rcFuseDense(c, c->dUBatch, (int64_t)c->uStride, phase);
+            if (compact && c->batchPull.pullSrc) {
+                rf.pullSrc = c->batchPull.pullSrc;
+                rf.pullIdx = c->batchPull.pullIdx;
+                rf.pullStride = c->batchPull.pullStride;
+                rf.pullN = c->batchPull.pullN;
+            }
+            c->batchPull = RcFuse();
             if (timed) cudaEventRecord(c->ev[2], st);
             c->wantMirror = true;
             rc = launchKnapsackDpBatch(c, c->dRedCostBatch, (int64_t)c->rcStride, nullptr, 0, eps, nVec, st, &rf);
@@ -658,6 +709,11 @@ int feedBatchDuals(Ctx *c, const DualFeed &f, int32_t uLen, int nVec, cudaStream
             c->cStride = stride;
         }
         *compact = true;
+        c->batchPull = RcFuse();
+        if (c->optPull && nVec <= 64 && dpWouldCoop(c, nVec)) {  // (64 per-vector arrival counters)
+            c->h2d += (int64_t)sizeof(double) * (int64_t)ns * nVec;
+            return pullSource(c, f, uLen, nVec, &c->batchPull);
+        }
         return feedCompact(c, f, uLen, nVec, c->dUBatchCompact, stride, st);
     }
     return feedDuals(c, f, uLen, nVec, c->dUBatch, c->uStride, &c->dUBatchClean, st);
@@ -886,10 +942,15 @@ int enqueueRound(Ctx *c, const DualFeed *feed, int32_t uLen, int32_t phase, doub
         const size_t ns = c->hSupport.size();
         RcFuse rf;
         if (feed && ns > 0 && (feed->host || feed->staged)) {
-            if ((rc = feedCompact(c, *feed, uLen, 1, c->dUCompact, 0, st))) return rc;
+            rf = rcFuseCompact(c, c->dUCompact, 0, phase);
+            if (c->optPull && dpWouldCoop(c, 1)) {
+                if ((rc = pullSource(c, *feed, uLen, 1, &rf))) return rc;
+                c->h2d += (int64_t)sizeof(double) * (int64_t)ns;
+            } else if ((rc = feedCompact(c, *feed, uLen, 1, c->dUCompact, 0, st))) {
+                return rc;
+            }
             c->dualsCompact = true;
             c->dualsResident = false;
-            rf = rcFuseCompact(c, c->dUCompact, 0, phase);
         } else if (feed && feed->full) {
             rf = rcFuseDense(c, feed->full, 0, phase);  // a dense vector in device memory (this device or a peer): gathered from where it is
         } else if (feed) {
@@ -1033,7 +1094,7 @@ int dipgpu_create(dipgpu_ctx **ctx, int device)
         return DIPGPU_ERR_CUDA;
     }
     for (auto &e : c->ev) cudaEventCreate(&e);
-    const unsigned int sync0[8] = {0u, 1u, 0u, 0u, 0u, 1u, 0u, 0u};  // epoch 1, no ticket drawn; expansion: (1 << 32) | 0
+    unsigned int sync0[8 + 64] = {0u, 1u, 0u, 0u, 0u, 1u, 0u, 0u};  // epoch 1, no ticket drawn; expansion: (1 << 32) | 0; 64 pull counters
     if (cudaMalloc(reinterpret_cast<void **>(&c->dDoneCounter), sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(c->dDoneCounter, 0, sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void **>(&c->dSyncWords), sizeof(sync0)) != cudaSuccess ||
@@ -1044,6 +1105,7 @@ int dipgpu_create(dipgpu_ctx **ctx, int device)
         return DIPGPU_ERR_NOMEM;
     }
     c->dExpTicket = reinterpret_cast<unsigned long long *>(c->dSyncWords + 4);
+    c->dPullCtr = c->dSyncWords + 8;
     *ctx = reinterpret_cast<dipgpu_ctx *>(c);
     return DIPGPU_OK;
 }
@@ -2244,6 +2306,7 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "dp_pdl")) { c->optPdl = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "fuse_redcost")) { c->optFuseRc = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "dp_coop")) { c->optNoCoop = value == 0; return DIPGPU_OK; }
+    if (!strcmp(name, "pull_duals")) { c->optPull = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "result_zero_copy")) {  // 2 (diagnostics): also from the device-resident entry points
         c->optZeroCopy = value != 0;
         c->optMirrorAlways = value == 2;

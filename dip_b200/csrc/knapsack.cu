@@ -357,6 +357,16 @@ struct KnapArgs {
     const int32_t *alphaIdx;
     long long uStride;
     int phase1;
+    // FUSE, cooperative launches only (pullSrc != NULL): the grid itself brings u[support] in from HOST memory.  The
+    // CTAs of a vector each fetch a slice of the support -- pullIdx == NULL: pullSrc is staging that already holds
+    // u[support] contiguously; else pullSrc is the caller's whole (page-locked) dual vector and pullIdx the support's
+    // rows -- into uVec (vector v: source + v*pullStride), then meet at a per-vector counter (pullCtr[v], reset by the
+    // last CTA to exit) before anybody gathers duals.  No upload in front of the kernel, no host pass over the vector.
+    const double *pullSrc;
+    const int32_t *pullIdx;
+    long long pullStride;
+    int pullN;
+    unsigned int *pullCtr;
     // FUSE, batched dual vectors (gridDim.y = vectors): vector v = blockIdx.y reads redCost + v*rcStride
     // and alpha + v*alphaStride and writes the packed result at byte offset v*resStride; the per-block
     // arrays pubWord / scale / shortcut / sel / zShort hold nLocal entries per vector
@@ -508,7 +518,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
     const double pScale = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? (double)a.scale[vlb] : 0.0;
     const int cap = capRaw;
     // fetched now so that the (possibly cold) load is long done when the tail needs it
-    const double alphaB = !FUSE ? 0.0 : rcFused ? a.uVec[vec * a.uStride + a.alphaIdx[b]] : a.back.alpha[vec * a.alphaStride + b];
+    const bool pulls = rcFused && a.pullSrc != nullptr;
+    double alphaB = !FUSE ? 0.0 : rcFused ? (pulls ? 0.0 : a.uVec[vec * a.uStride + a.alphaIdx[b]]) : a.back.alpha[vec * a.alphaStride + b];
     uint32_t *bitsBase = FUSE ? sBits : a.bits + a.bitsOff[lb];
     const int j0 = t * S;  // first owned cell
 
@@ -523,7 +534,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
         asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x1) : "l"(RESV(a.filt.hdr)) : "memory");
         asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x2) : "l"(RESV(a.filt.keptInd) + (size_t)(colStart - a.blockColStart[a.firstBlock]) / 2 * 2) : "memory");
         touch = x0 ^ x1 ^ x2;  // consumed in the tail, so that nothing waits for these loads here
-        if (rcFused) {  // ... and the first page of the dual vector, which the gathers of the reduced costs read
+        if (rcFused && !pulls) {  // ... and the first page of the dual vector, which the gathers of the reduced costs read
             unsigned long long x3;
             asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x3) : "l"(a.uVec + vec * a.uStride) : "memory");
             touch ^= x3;
@@ -535,7 +546,10 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
     // entry offsets (into the not yet written item-column array) and the entries' values (into the not yet written
     // item arrays), and, by every thread, the dual indices of ITS entries straight from memory followed by the
     // gathers of those duals -- so the two dependent round trips of the gathers run under the bulk copies.
-    constexpr int kRcRegs = 9;  // entries per thread whose duals are gathered up front (GAP-E: 1 632 entries, 192 threads)
+    // entries per thread whose duals are gathered up front (GAP-E: 1 632 entries, 192 threads); the 1024-thread
+    // build (64 registers; picked for large batches, where occupancy counts) gathers them after the bulk copies
+    constexpr int kRcRegs = MAXT <= 256 ? 9 : 1;
+    constexpr int kRcPre = MAXT <= 256 ? 9 : 0;
     const int rcLen = FUSE ? nCols : 0;
     const int rcNE = rcE1 - rcE0;
     const bool rcStaged = rcFused && rcLen > 0 && rcNE <= rcStageCap(CH);
@@ -554,15 +568,45 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
             if (!a.phase1) tmaLoad1d(rawRc, a.back.obj + (colStart - shRc), bytesObj, mbar);
             if (bytesV) tmaLoad1d(itP, a.rcVal + (rcE0 - shV), bytesV, mbar);
         }
+        int ix[kRcRegs];
         if (rcStaged) {
-            int ix[kRcRegs];
 #pragma unroll
-            for (int q = 0; q < kRcRegs; ++q) {
+            for (int q = 0; q < kRcPre; ++q) {
                 const int k = t + q * T;
                 ix[q] = k < rcNE ? a.rcIdx[rcE0 + k] : -1;
             }
+        }
+        if (!pulls && rcStaged) {
 #pragma unroll
-            for (int q = 0; q < kRcRegs; ++q) rcG[q] = ix[q] >= 0 ? uV[ix[q]] : 0.0;
+            for (int q = 0; q < kRcPre; ++q) rcG[q] = ix[q] >= 0 ? uV[ix[q]] : 0.0;
+        }
+    }
+    if (pulls) {
+        // ---- this CTA's slice of u[support], straight out of host memory (every block of the vector takes part,
+        // also an empty one), then the vector's CTAs meet: the grid is co-resident (cooperative launch)
+        const int per = (a.pullN + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int k0 = min(a.pullN, lb * per), k1 = min(a.pullN, k0 + per);
+        const double *src = a.pullSrc + vec * a.pullStride;
+        double *dst = const_cast<double *>(a.uVec) + vec * a.uStride;
+        for (int k = k0 + t; k < k1; k += T) dst[k] = src[a.pullIdx != nullptr ? a.pullIdx[k] : k];
+        __threadfence();
+        __syncthreads();
+        if (t == 0) {
+            atomicAdd(a.pullCtr + vec, 1u);
+            while (atomicAdd(a.pullCtr + vec, 0u) < gridDim.x) {}
+            __threadfence();
+        }
+        __syncthreads();
+        alphaB = __ldcg(a.uVec + vec * a.uStride + a.alphaIdx[b]);
+        if (rcStaged) {
+            int ix2[kRcRegs];
+#pragma unroll
+            for (int q = 0; q < kRcPre; ++q) {
+                const int k = t + q * T;
+                ix2[q] = k < rcNE ? a.rcIdx[rcE0 + k] : -1;   // (L1-resident by now; keeps the indices out of the wait)
+            }
+#pragma unroll
+            for (int q = 0; q < kRcPre; ++q) rcG[q] = ix2[q] >= 0 ? __ldcg(uV + ix2[q]) : 0.0;
         }
     }
     // c[-1][.] = 0 (gap_func.py:156); guards = -inf
@@ -634,11 +678,11 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
             if (staged) {
                 double *vp = itP + (rcE0 & 1);
 #pragma unroll
-                for (int q = 0; q < kRcRegs; ++q) {
+                for (int q = 0; q < kRcPre; ++q) {
                     const int k = t + q * T;
                     if (k < nE) vp[k] = __dmul_rn(rcG[q], vp[k]);
                 }
-                for (int k = t + kRcRegs * T; k < nE; k += T) vp[k] = __dmul_rn(uV[a.rcIdx[rcE0 + k]], vp[k]);  // (longer blocks)
+                for (int k = t + kRcPre * T; k < nE; k += T) vp[k] = __dmul_rn(__ldcg(uV + a.rcIdx[rcE0 + k]), vp[k]);  // (longer blocks)
                 __syncthreads();
                 // four columns per thread and step: their (short) addition chains run side by side
                 for (int base = t; base < len; base += 4 * T) {
@@ -696,7 +740,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
                             v[q] = on ? a.rcVal[e0[q] + k] : 0.0;
                         }
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) g[q] = ix[q] >= 0 ? uV[ix[q]] : 0.0;
+                        for (int q = 0; q < 4; ++q) g[q] = ix[q] >= 0 ? __ldcg(uV + ix[q]) : 0.0;
                         // (a column past its end adds 0*0 = +0, which leaves the sum unchanged bit for bit: it is never -0)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) sum[q] = __dadd_rn(sum[q], __dmul_rn(g[q], v[q]));
@@ -1606,6 +1650,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
         // the last CTA to get here has seen every CTA of the launch read the epoch: the next launch gets a new one
         if (t == 0 && atomicAdd(a.doneCtr, 1u) == gridDim.x * gridDim.y - 1u) {
             *a.doneCtr = 0u;
+            if (pulls)
+                for (unsigned int v = 0; v < gridDim.y; ++v) a.pullCtr[v] = 0u;
             *a.epochCtr = epochRaw + 1u;
         }
     }
@@ -1654,10 +1700,12 @@ static_assert(kPruneBuckets % 32 == 0, "one lane scans kPruneBuckets / 32 bucket
 static const int kNumGeoms = (int)(sizeof(kGeoms) / sizeof(kGeoms[0]));
 static const size_t kMaxSmem = 227 * 1024 - 6 * 1024;  // the fused tail's static shared memory comes off the 227 KiB
 
-static KnapFn pickKnapFn(const GeomEntry *e, const DpGeom &g)
+static KnapFn pickKnapFn(const GeomEntry *e, const DpGeom &g, bool latency = true)
 {
     const int gi = g.guard > 0 ? 1 : 0, ii = g.items - 1;
-    if (g.fuse && g.T <= 256 && e->fnFuseSmall[gi][ii] != nullptr) return e->fnFuseSmall[gi][ii];
+    // latency-bound launches (a round, a short ladder: co-resident grids): the <= 256-thread build with registers to
+    // spare; large batches: the 64-register build, three CTAs per SM
+    if (latency && g.fuse && g.T <= 256 && e->fnFuseSmall[gi][ii] != nullptr) return e->fnFuseSmall[gi][ii];
     return (g.fuse ? e->fnFuse : e->fn)[gi][ii];
 }
 
@@ -1858,7 +1906,19 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     const DpGeom &g = c->geom;
     const GeomEntry *e = findGeom(g.S);
     if (!e) return fail(c, DIPGPU_ERR_STATE, "DP geometry not initialised");
-    KnapFn fn = pickKnapFn(e, g);
+    {
+        int rc = prepareKnapsackDp(c);  // (the latency build: shared-memory limit, co-resident CTA count)
+        if (rc) return rc;
+    }
+    // co-resident grids (a GAP round, a short ladder): cooperative launch, CTA ids = grid coordinates; larger ones
+    // (batches): tickets, and the build that fits three CTAs per SM
+    const long long totalCtas = (long long)c->nLocal * nVec;
+    const bool coop = g.fuse && !c->optPdl && !c->optNoCoop && c->dpCoResident > 0 && totalCtas <= c->dpCoResident;
+    KnapFn fn = pickKnapFn(e, g, coop || !g.fuse || totalCtas <= c->dpCoResident);
+    if (fn != (KnapFn)c->dpFnConfigured) {
+        const int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(fn), g.smemBytes);
+        if (rc) return rc;
+    }
     KnapArgs a;
     a.redCost = dRedCost;
     if (c->haveFix && !g.fuse) {
@@ -1891,10 +1951,6 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     a.dbgTimes = c->dDbgTimes;
     a.pubWord = batch ? c->dPubWordBatch : c->dPubWord;
     a.pubCells = c->dPubCells;
-    // co-resident grids (a GAP round, a short ladder): cooperative launch, CTA ids = grid coordinates; larger ones
-    // (batches): tickets
-    const long long totalCtas = (long long)c->nLocal * nVec;
-    const bool coop = g.fuse && !c->optPdl && !c->optNoCoop && c->dpCoResident > 0 && totalCtas <= c->dpCoResident;
     a.ticket = coop ? nullptr : c->dSyncWords;
     a.epochCtr = c->dSyncWords + 1;
     a.doneCtr = c->dSyncWords + 2;
@@ -1905,6 +1961,12 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     a.alphaIdx = rf ? rf->alphaIdx : nullptr;
     a.uStride = rf ? (long long)rf->uStride : 0;
     a.phase1 = rf ? rf->phase1 : 0;
+    a.pullSrc = (rf && coop) ? rf->pullSrc : nullptr;
+    a.pullIdx = rf ? rf->pullIdx : nullptr;
+    a.pullStride = rf ? (long long)rf->pullStride : 0;
+    a.pullN = rf ? rf->pullN : 0;
+    a.pullCtr = c->dPullCtr;
+    if (rf && rf->pullSrc && !coop) return fail(c, DIPGPU_ERR_STATE, "in-kernel dual upload needs a co-resident grid");
     if (rf && !g.fuse) return fail(c, DIPGPU_ERR_STATE, "reduced costs can only be formed inside the fused DP kernel");
     a.useTab = (g.fuse && c->nLocal <= kFuseFilterMaxBlocks) ? 1 : 0;
     if (rf && !a.useTab) return fail(c, DIPGPU_ERR_STATE, "in-block reduced costs: %d blocks", c->nLocal);
@@ -1950,10 +2012,6 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
             a.hostOff = (long long)(static_cast<char *>(c->dResultBatchHost) - static_cast<char *>(c->dResultBatch));
     }
     c->resultMirrored = a.hostOff != 0;
-    {
-        int rc = prepareKnapsackDp(c);
-        if (rc) return rc;
-    }
     // Option "dp_pdl" (fused fp64 shapes): programmatic dependent launch -- the CTAs may become resident while
     // the preceding kernel of the stream (the SpMV) still runs; the kernel waits (griddepcontrol.wait) before it
     // reads the reduced costs.  Measured SLOWER on GAP-E (39.5 vs 35.9 us per round: the early CTAs take SM

@@ -298,9 +298,9 @@ static int ensureStage(Multi *M, size_t doubles)
     return DIPGPU_OK;
 }
 
-// The master duals of a call, prepared ONCE for all devices: u[support] gathered into shared pinned staging
-// (34 KB per vector on GAP-E) that every device copies from; without a dual support every device copies the
-// whole vector from the caller's buffer.
+// The master duals of a call, prepared ONCE for all devices: a page-locked vector is left where it is (every
+// device reads u[support] out of it), a pageable one is gathered into shared pinned staging (u[support], 34 KB
+// per vector on GAP-E) that every device reads; without a dual support every device copies the whole vector.
 // gatherHere: false = the caller of this function gathers (per device, in parallel) -- only the feed is formed.
 static int stageDuals(Multi *M, const double *u, int32_t uLen, int nVec, bool gatherHere, DualFeed *f)
 {
@@ -308,6 +308,10 @@ static int stageDuals(Multi *M, const double *u, int32_t uLen, int nVec, bool ga
     const size_t ns = M->support.size();
     if (ns == 0) {
         f->host = u;
+        return DIPGPU_OK;
+    }
+    if (M->front->optGatherPinned && deviceVisible(u)) {
+        f->host = u;  // page-locked: every device picks u[support] out of the caller's buffer itself
         return DIPGPU_OK;
     }
     const int rc = ensureStage(M, ns * (size_t)nVec);

@@ -239,6 +239,26 @@ scatter_duals_kernel(int n, const int32_t *__restrict__ idx, const double *__res
     }
 }
 
+// dst_v[k] = vals_v[idx[k]]: u[support] picked out of whole dual vectors in device-visible (page-locked host) memory
+// into the compact vectors the fused kernel's in-block reduced costs read
+__global__ void __launch_bounds__(256)
+gather_duals_kernel(int n, const int32_t *__restrict__ idx, const double *__restrict__ vals, long long valStride,
+                    double *__restrict__ dst, long long dstStride)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) dst[(long long)blockIdx.y * dstStride + k] = vals[(long long)blockIdx.y * valStride + idx[k]];
+}
+
+int launchGatherDuals(Ctx *c, int n, const int32_t *dIdx, const double *dVals, int64_t valStride, double *dDst, int64_t dstStride,
+                      int nVec, cudaStream_t st)
+{
+    if (n <= 0 || nVec <= 0) return DIPGPU_OK;
+    gather_duals_kernel<<<dim3((n + 255) / 256, nVec, 1), 256, 0, st>>>(n, dIdx, dVals, valStride, dDst, dstStride);
+    c->launches++;
+    DIPGPU_CUDA(c, cudaGetLastError());
+    return DIPGPU_OK;
+}
+
 int launchScatterDuals(Ctx *c, int n, const int32_t *dIdx, const double *dVals, int64_t valStride, bool gather, double *dDst,
                        int64_t dstStride, int nVec, cudaStream_t st)
 {
