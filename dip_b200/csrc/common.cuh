@@ -125,6 +125,7 @@ struct DpGeom {
     int chunkCols; // columns staged per TMA chunk
     int guard;     // -inf cells in front of each row buffer (0 = predicated reads)
     int fuse;      // 1: backtrack + filter run in the DP kernel's tail, decision bits stay in shared memory
+    int big;       // 1: the row does not fit one CTA (> 12 800 cells): rows in global memory (bigdp.cu), bits [item][cell/32]
     size_t smemBytes;
 };
 
@@ -225,6 +226,8 @@ struct Ctx {
     int32_t *dCapacity = nullptr;       // m
     int64_t *dBitsOff = nullptr;        // m+1 word offsets into dBits (shard-local)
     uint32_t *dBits = nullptr;          // decision bits [word][cell]
+    int64_t *dBigRowOff = nullptr;      // big rows (geom.big): local block -> first cell of its two global-memory rows
+    double *dBigRows = nullptr, *dBigItemP = nullptr;
     size_t bitsWords = 0;
     int32_t *dItemW = nullptr;          // per column slot: weight of compacted item k of block b
     int32_t *dItemCol = nullptr;        // per column slot: local column of compacted item
@@ -424,6 +427,7 @@ struct PrepArgs {
     const int32_t *weight;
     const int32_t *blockColStart;
     const int32_t *capacity;
+    const uint8_t *fix; // node bounds (else NULL): per column bit 0 = fixed to 1, bit 1 = fixed to 0
     int firstBlock;
     long long rcStride; // batched dual vectors: vector v = blockIdx.y reads redCost + v*rcStride, writes slot v*gridDim.x + lb
     int32_t *scale;     // local block -> calcScaleFactor result
@@ -452,6 +456,8 @@ int launchKnapsackDpBatch(Ctx *c, const double *dRedCost, int64_t rcStride, cons
                           double redCostEps, int nVec, cudaStream_t st, const RcFuse *rf = nullptr);
 int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseFilter,
                         cudaStream_t st);
+// bigdp.cu -- stage (b) for rows that do not fit one CTA
+int launchBigDp(Ctx *c, const double *dRedCost, cudaStream_t st);
 // mckp.cu -- stage (b) for multiple-choice knapsack blocks (DP + backtrack; the filter kernels follow)
 int launchMckp(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_t st);
 // filter.cu -- stage (c)

@@ -223,6 +223,22 @@ int setBlockRange(Ctx *c, int first, int count)
     } else {
     const bool wantFuse = count > 0 && (c->optFuseFilter < 0 ? count <= kFuseFilterMaxBlocks : c->optFuseFilter == 2);
     if ((rc = chooseDpGeom(c, &c->geom, wantFuse))) return rc;
+    devFree(&c->dBigRowOff); devFree(&c->dBigRows); devFree(&c->dBigItemP);
+    if (c->geom.big) {
+        // rows in global memory (bigdp.cu): per block two rows of (capacity + 1) cells, decisions [item][cell / 32]
+        std::vector<int64_t> rowOff((size_t)count + 1, 0);
+        for (int lb = 0; lb < count; ++lb) {
+            const int n = c->hBlockColStart[first + lb + 1] - c->hBlockColStart[first + lb];
+            const int64_t cells = (int64_t)c->hCapacity[first + lb] + 1;
+            off[lb + 1] = off[lb] + (int64_t)n * ((cells + 31) >> 5);
+            rowOff[lb + 1] = rowOff[lb] + 2 * ((cells + 3) & ~(int64_t)3);
+        }
+        c->bitsWords = (size_t)off[count];
+        if ((rc = devAlloc(c, &c->dBigRowOff, (size_t)count + 1))) return rc;
+        DIPGPU_CUDA(c, cudaMemcpy(c->dBigRowOff, rowOff.data(), sizeof(int64_t) * ((size_t)count + 1), cudaMemcpyHostToDevice));
+        if ((rc = devAlloc(c, &c->dBigRows, (size_t)rowOff[count] + 8))) return rc;
+        if ((rc = devAlloc(c, &c->dBigItemP, (size_t)c->nBlockCols + 16))) return rc;
+    } else {
     if (count > 0 && (rc = prepareKnapsackDp(c))) return rc;
     // decision bits: ceil(n_b/32) words per cell, rowCells cells per block
     for (int lb = 0; lb < count; ++lb) {
@@ -230,6 +246,7 @@ int setBlockRange(Ctx *c, int first, int count)
         off[lb + 1] = off[lb] + (int64_t)((n + 31) / 32) * c->geom.rowCells;
     }
     c->bitsWords = (size_t)off[count];
+    }
     }
     if ((rc = devAlloc(c, &c->dBitsOff, (size_t)count + 1))) return rc;
     DIPGPU_CUDA(c, cudaMemcpy(c->dBitsOff, off.data(), sizeof(int64_t) * ((size_t)count + 1), cudaMemcpyHostToDevice));
@@ -482,7 +499,11 @@ static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, do
                                                        : (c->optFuseFilter == 1 ? 1 : 0);
     if (c->nLocal == 0) mode = 0;
     if (!rf && (rc = launchKnapsackPrep(c, dRedCost, st))) return rc;
-    if ((rc = launchKnapsackDp(c, dRedCost, dAlpha, eps, st, rf))) return rc;
+    if (c->geom.big) {
+        if ((rc = launchBigDp(c, dRedCost, st))) return rc;
+    } else if ((rc = launchKnapsackDp(c, dRedCost, dAlpha, eps, st, rf))) {
+        return rc;
+    }
     if (timed) cudaEventRecord(c->ev[3], st);
     if (mode != 2 && (rc = launchBacktrackEmit(c, dRedCost, dAlpha, eps, mode == 1, st))) return rc;
     if (timed) cudaEventRecord(c->ev[4], st);
@@ -1123,7 +1144,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (c->dMCols) cudaFree(c->dMCols);
     if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dSpmvBlob); devFree(&c->dSpmvWarpStart); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
-    devFree(&c->dBits); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems); devFree(&c->dScale); devFree(&c->dShortcut); devFree(&c->dSel); devFree(&c->dZShort);
+    devFree(&c->dBits); devFree(&c->dBigRowOff); devFree(&c->dBigRows); devFree(&c->dBigItemP); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems); devFree(&c->dScale); devFree(&c->dShortcut); devFree(&c->dSel); devFree(&c->dZShort);
     devFree(&c->dCandInd); devFree(&c->dScratch); devFree(&c->dU); devFree(&c->dRedCost); devFree(&c->dAlpha);
     freeBatch(c);
     devFree(&c->dFix); devFree(&c->dCapEff); devFree(&c->dRcEff);
@@ -1434,8 +1455,8 @@ int dipgpu_set_col_bounds(dipgpu_ctx *ctx, const double *colLB, const double *co
         return DIPGPU_OK;
     }
     if (!colLB || !colUB || N < c->nBlockCols) return fail(c, DIPGPU_ERR_INVALID, "set_col_bounds: need both bound arrays of length >= %d", c->nBlockCols);
-    if (c->profitMode == DIPGPU_PROFIT_PISINGER_INT || c->blockKind != 0)
-        return fail(c, DIPGPU_ERR_UNSUPPORTED, "set_col_bounds: node bounds are enforced in 0-1 knapsack blocks in the fp64 DP mode only");
+    if (c->blockKind != 0)
+        return fail(c, DIPGPU_ERR_UNSUPPORTED, "set_col_bounds: node bounds are enforced in 0-1 knapsack blocks only");
     const int n = c->nBlockCols;
     std::vector<uint8_t> fix((size_t)n + 16, 0);
     std::vector<int32_t> capEff((size_t)std::max(c->m, 1), 0);
@@ -2251,7 +2272,7 @@ int dipgpu_last_stage_ms(const dipgpu_ctx *ctx, float *ms6)
 
 static void geomOut(const DpGeom &g, int32_t out[7])
 {
-    out[0] = g.T; out[1] = g.S; out[2] = g.items; out[3] = g.guard; out[4] = g.chunkCols; out[5] = (int32_t)g.smemBytes;
+    out[0] = g.T; out[1] = g.big ? 0 : g.S; out[2] = g.items; out[3] = g.guard; out[4] = g.chunkCols; out[5] = (int32_t)g.smemBytes;
     out[6] = g.fuse;
 }
 

@@ -105,6 +105,7 @@ struct BackArgs {
     const int32_t *shortcut;    // Pisinger mode (else NULL): per local block 0 = DP, 1 = all, 2 = sel
     const int32_t *sel;         // 2 per local block
     const uint8_t *fix;         // node bounds (else NULL): per column bit 0 = fixed to 1, bit 1 = fixed to 0
+    int bigLayout;              // 1: bits are [item][cell / 32] (bigdp.cu), rowCells is unused
 };
 
 constexpr int kBackThreads = 128;
@@ -112,61 +113,39 @@ constexpr int kBackThreads = 128;
 // Pisinger-mode trivial cases (GAP_KnapPisinger.h:203-238), decided by knap_prep_kernel: the
 // column is either every item with negative reduced cost (code 1) or an explicit set of at most
 // two columns (code 2).  Emitted ascending with the sums of GAP_KnapPisinger.h:263-272.
-__device__ __forceinline__ void emitShortcut(const BackArgs &a, int lb, int lane, int code)
+__device__ __forceinline__ int emitShortcut(const BackArgs &a, int lb, int lane, int code)
 {
+    // fills candInd[cs ..) with the chosen columns, ascending; returns their number (the caller merges the columns
+    // the node bounds fix to 1 and forms the sums)
     const int b = a.firstBlock + lb;
     const int cs = a.blockColStart[b];
     const int n = a.blockColStart[b + 1] - cs;
     int cnt = 0;
-    double rcs = 0.0, ocs = 0.0;
     if (code == 1) {
         for (int base = 0; base < n; base += 32) {
             const int j = base + lane;
-            double r = 0.0, o = 0.0;
-            bool act = false;
-            if (j < n) {
-                r = a.redCost[cs + j];
-                act = r < 0.0;
-                if (act) o = a.obj[cs + j];
-            }
+            const bool act = j < n && a.redCost[cs + j] < 0.0 && (a.fix == nullptr || a.fix[cs + j] == 0);
             const unsigned bal = __ballot_sync(0xffffffffu, act);
             if (act) a.candInd[cs + cnt + __popc(bal & ((1u << lane) - 1u))] = cs + j;
             cnt += __popc(bal);
-            for (unsigned rest = bal; rest; rest &= rest - 1) {  // ascending column order
-                const int q = __ffs(rest) - 1;
-                rcs += __shfl_sync(0xffffffffu, r, q);
-                ocs += __shfl_sync(0xffffffffu, o, q);
-            }
         }
     } else {
         for (int k = 0; k < 2; ++k) {
             const int j = a.sel[2 * lb + k];
             if (j >= 0) {
                 if (lane == 0) a.candInd[cs + cnt] = cs + j;
-                rcs += a.redCost[cs + j];
-                ocs += a.obj[cs + j];
                 ++cnt;
             }
         }
     }
-    if (lane == 0) {
-        a.blockRedCost[lb] = rcs - a.alpha[b];
-        a.blockOrigCost[lb] = ocs;
-        a.blockNnz[lb] = cnt;
-    }
+    __syncwarp();
+    return cnt;
 }
 
 // nItems = number of active items of the block.  Loads are L2-coherent (ld.global.cg): in the
 // fused path the decision bits were written earlier by this very kernel.
 __device__ __forceinline__ void backtrackOne(const BackArgs &a, int lb, int lane, int nItems)
 {
-    if (a.shortcut != nullptr) {
-        const int code = a.shortcut[lb];
-        if (code != 0) {
-            emitShortcut(a, lb, lane, code);
-            return;
-        }
-    }
     const int b = a.firstBlock + lb;
     const int cs = a.blockColStart[b];
     const int RC = a.rowCells;
@@ -181,33 +160,64 @@ __device__ __forceinline__ void backtrackOne(const BackArgs &a, int lb, int lane
         }
         return;
     }
-    int i = nItems - 1;
+    const int code = a.shortcut != nullptr ? a.shortcut[lb] : 0;
     int cnt = 0;
-    while (i >= 0) {
-        const int kw = i >> 5;
-        const int wv = kw - lane;
-        uint32_t v = wv >= 0 ? __ldcg(bitsBase + (size_t)wv * RC + j) : 0u;
-        if (lane == 0) v &= 0xffffffffu >> (31 - (i & 31));
-        const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
-        if (nz == 0u) {
-            i = ((kw - 32) << 5) | 31;  // nothing taken in these 1024 items
-            continue;
+    if (code != 0) {
+        // Pisinger-mode trivial case: the chosen columns are already ascending in candInd
+        cnt = emitShortcut(a, lb, lane, code);
+    } else if (a.bigLayout) {
+        // rows in global memory (bigdp.cu): bit (item, cell) at word item * cellWords + cell / 32.  The lanes fetch the
+        // 32 items below the current one at the current cell together, the walk lands on the next TAKEN item.
+        const long long cellWords = ((long long)j + 1 + 31) >> 5;
+        int i = nItems - 1;
+        while (i >= 0) {
+            const int it = i - lane;
+            const bool taken = it >= 0 && ((__ldcg(bitsBase + (long long)it * cellWords + (j >> 5)) >> (j & 31)) & 1u);
+            const unsigned nz = __ballot_sync(0xffffffffu, taken);
+            if (nz == 0u) {
+                i -= 32;
+                continue;
+            }
+            const int item = i - (__ffs(nz) - 1);
+            if (lane == 0) a.scratch[cs + cnt] = __ldcg(a.itemCol + cs + item);
+            ++cnt;
+            j -= __ldcg(a.itemW + cs + item);
+            i = item - 1;
         }
-        const int L = __ffs(nz) - 1;
-        const uint32_t vL = __shfl_sync(0xffffffffu, v, L);
-        const int item = ((kw - L) << 5) + (31 - __clz(vL));
-        if (lane == 0) a.scratch[cs + cnt] = __ldcg(a.itemCol + cs + item);
-        ++cnt;
-        j -= __ldcg(a.itemW + cs + item);
-        i = item - 1;
+        __syncwarp();
+        if (a.fix != nullptr)
+            for (int k = lane; k < cnt; k += 32) a.candInd[cs + k] = cs + __ldcg(a.scratch + cs + cnt - 1 - k);
+        __syncwarp();
+    } else {
+        int i = nItems - 1;
+        while (i >= 0) {
+            const int kw = i >> 5;
+            const int wv = kw - lane;
+            uint32_t v = wv >= 0 ? __ldcg(bitsBase + (size_t)wv * RC + j) : 0u;
+            if (lane == 0) v &= 0xffffffffu >> (31 - (i & 31));
+            const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
+            if (nz == 0u) {
+                i = ((kw - 32) << 5) | 31;  // nothing taken in these 1024 items
+                continue;
+            }
+            const int L = __ffs(nz) - 1;
+            const uint32_t vL = __shfl_sync(0xffffffffu, v, L);
+            const int item = ((kw - L) << 5) + (31 - __clz(vL));
+            if (lane == 0) a.scratch[cs + cnt] = __ldcg(a.itemCol + cs + item);
+            ++cnt;
+            j -= __ldcg(a.itemW + cs + item);
+            i = item - 1;
+        }
+        __syncwarp();
+        // chosen items ascending
+        if (a.fix != nullptr)
+            for (int k = lane; k < cnt; k += 32) a.candInd[cs + k] = cs + __ldcg(a.scratch + cs + cnt - 1 - k);
+        __syncwarp();
     }
-    __syncwarp();
     if (a.fix != nullptr) {
         // node bounds: the columns fixed to 1 join the column (they were kept out of the DP and their
-        // weight out of the capacity).  Chosen items ascending, then a backward merge with the fixed
-        // ones (ascending by construction) -- large shards only, the fused kernel merges in parallel.
-        for (int k = lane; k < cnt; k += 32) a.candInd[cs + k] = cs + __ldcg(a.scratch + cs + cnt - 1 - k);
-        __syncwarp();
+        // weight out of the capacity): a backward merge of the chosen columns (ascending in candInd) with the
+        // fixed ones (ascending by construction) -- large shards only, the fused kernel merges in parallel.
         const int n = a.blockColStart[b + 1] - cs;
         int nf = 0;
         for (int base = 0; base < n; base += 32) {
@@ -230,13 +240,15 @@ __device__ __forceinline__ void backtrackOne(const BackArgs &a, int lb, int lane
         cnt += nf;
         __syncwarp();
     }
+    // varRedCost / varOrigCost in ascending index order (GAP_KnapPisinger.h:263-272), then alpha (DecompAlgo.cpp:6350-6356)
+    const bool inCand = a.fix != nullptr || code != 0;  // else the walk's descending list is still in scratch
     double rcs = 0.0, ocs = 0.0;
     for (int base = 0; base < cnt; base += 32) {
         const int k = base + lane;
         double r = 0.0, o = 0.0;
         if (k < cnt) {
             int col;
-            if (a.fix != nullptr) {
+            if (inCand) {
                 col = __ldcg(a.candInd + cs + k);
             } else {
                 col = cs + __ldcg(a.scratch + cs + cnt - 1 - k);
@@ -1356,10 +1368,10 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
         for (int s = 0; s < S; ++s) dst[s] = acc[s];
     }
     // z = c[n-1][capacity]  (gap_func.py:183)
-    if (shortCode != 0) {
-        if (t == 0) RES_PUT(a.blockObj, lb, a.zShort[vlb]);
-    } else if (cap < 0) {
+    if (cap < 0) {
         if (t == 0) RES_PUT(a.blockObj, lb, kNegInf);
+    } else if (shortCode != 0) {
+        if (t == 0) RES_PUT(a.blockObj, lb, a.zShort[vlb]);
     } else {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -1384,7 +1396,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
                 const int nAll = colEnd - colStart;
                 for (int base = 0; base < nAll; base += 32) {
                     const int j = base + lane;
-                    const bool act = j < nAll && redCostV[colStart + j] < 0.0;
+                    const bool act = j < nAll && redCostV[colStart + j] < 0.0 && (a.back.fix == nullptr || a.back.fix[colStart + j] == 0);
                     const unsigned bal = __ballot_sync(0xffffffffu, act);
                     if (act) sFinal[cnt + __popc(bal & ((1u << lane) - 1u))] = colStart + j;
                     cnt += __popc(bal);
@@ -1817,8 +1829,13 @@ int chooseDpGeom(Ctx *c, DpGeom *g, bool wantFuse)
         if (c->optThreads > 0 || c->optCellsPerThread > 0)
             return fail(c, DIPGPU_ERR_INVALID, "no DP geometry with threads=%d cellsPerThread=%d covers %d cells",
                         c->optThreads, c->optCellsPerThread, cells);
-        return fail(c, DIPGPU_ERR_UNSUPPORTED, "capacity %d needs %d DP cells; one CTA stages at most %d",
-                    c->maxCapacity, cells, 512 * 25);
+        // more cells than one CTA holds in registers / shared memory: rows in global memory (bigdp.cu)
+        DpGeom big{};
+        big.T = 1024;
+        big.items = 1;
+        big.big = 1;
+        *g = big;
+        return DIPGPU_OK;
     }
     *g = best;
     return DIPGPU_OK;
@@ -1870,6 +1887,7 @@ static void fillBackArgs(Ctx *c, const double *dRedCost, const double *dAlpha, B
     a->shortcut = pis ? c->dShortcut : nullptr;
     a->sel = pis ? c->dSel : nullptr;
     a->fix = c->haveFix ? c->dFix : nullptr;
+    a->bigLayout = c->geom.big;
     if (c->haveFix) a->capacity = c->dCapEff;  // capacity left once the columns fixed to 1 are in
 }
 

@@ -88,9 +88,12 @@ __global__ void __launch_bounds__(kPrepThreads) knap_prep_kernel(const __grid_co
     int cnt = 0;
     long long wsum = 0;
     First2 f2{-1, -1};
+    // node bounds (DecompAlgo::setSubProbBounds): a fixed column is no item -- the scale factor, the counts and the
+    // trivial cases are those of the FREE columns against the capacity left after the columns fixed to 1
+    auto isItem = [&](int j) { return redCostV[cs + j] < 0 && (a.fix == nullptr || a.fix[cs + j] == 0); };
     for (int j = j0; j < j1; ++j) {
         const double rc = redCostV[cs + j];
-        if (rc >= 0) continue;  // :109, :173
+        if (!isItem(j)) continue;  // :109, :173
         ++cnt;
         wsum += a.weight[cs + j];
         if (f2.c0 < 0) f2.c0 = j; else if (f2.c1 < 0) f2.c1 = j;
@@ -151,7 +154,9 @@ __global__ void __launch_bounds__(kPrepThreads) knap_prep_kernel(const __grid_co
     auto profit = [&](int j) { return (double)(long long)floor((-redCostV[cs + j]) * scale + 0.5); };
     int code = 0, sel0 = -1, sel1 = -1;
     double z = 0.0;
-    if (nAll == 0) {
+    if (cap < 0) {
+        code = 2;  // the columns fixed to 1 do not fit: the block returns no column (the DP kernel sees capacity < 0)
+    } else if (nAll == 0) {
         code = 2;
     } else if (nAll == 1) {
         // :203-205 (the reference asserts w <= capacity; an item that does not fit is left out)
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(kPrepThreads) knap_prep_kernel(const __grid_co
         code = 1;
         double part = 0.0;
         for (int j = j0; j < j1; ++j)
-            if (redCostV[cs + j] < 0) part += profit(j);  // integers < 2^53: exact in any order
+            if (isItem(j)) part += profit(j);  // integers < 2^53: exact in any order
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
         if (lane == 0) sZ[warp] = part;
@@ -203,7 +208,8 @@ static int launchPrep(Ctx *c, const double *dRedCost, int64_t rcStride, int nVec
     a.redCost = dRedCost;
     a.weight = c->dWeight;
     a.blockColStart = c->dBlockColStart;
-    a.capacity = c->dCapacity;
+    a.capacity = c->haveFix ? c->dCapEff : c->dCapacity;
+    a.fix = c->haveFix ? c->dFix : nullptr;
     a.firstBlock = c->firstBlock;
     a.rcStride = rcStride;
     a.scale = batch ? c->dScaleB : c->dScale;

@@ -36,7 +36,7 @@ enum {
     DIPGPU_ERR_CUDA = 2,        /* CUDA runtime / driver error, or no usable sm_100 device */
     DIPGPU_ERR_NOMEM = 3,       /* device or pinned-host allocation failed */
     DIPGPU_ERR_STATE = 4,       /* call order: model / blocks / objective not set yet */
-    DIPGPU_ERR_UNSUPPORTED = 5, /* e.g. a capacity beyond what one CTA can stage, node bounds in Pisinger mode */
+    DIPGPU_ERR_UNSUPPORTED = 5, /* e.g. node bounds on multiple-choice blocks, more than 2^31 stored entries */
     DIPGPU_ERR_OVERFLOW = 6     /* caller's output buffers too small; required sizes are reported */
 };
 
@@ -205,8 +205,9 @@ int dipgpu_set_mckp_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockGroup
  * fit returns no column: blockRedCost = +inf, blockMostNegRC = 0, blockObj = -inf, blockNnz = 0
  * (the reference's subproblem MILP is infeasible and pushes no variable).  blockObj excludes the
  * fixed columns' profit.  Length N >= the block columns; both NULL removes the bounds.  Call after
- * dipgpu_set_knapsack_blocks (which clears them); fp64 profit mode only
- * (DIPGPU_ERR_UNSUPPORTED in Pisinger mode, whose example application branches in the master).
+ * dipgpu_set_knapsack_blocks (which clears them).  In Pisinger mode the scale factor, the n <= 2 / all-fit cases
+ * and the integer profits of GAP_KnapPisinger::solve are those of the FREE columns against the capacity left.
+ * 0-1 knapsack blocks only (DIPGPU_ERR_UNSUPPORTED for multiple-choice blocks).
  */
 int dipgpu_set_col_bounds(dipgpu_ctx *ctx, const double *colLB, const double *colUB, int32_t N);
 

@@ -333,14 +333,68 @@ def test_node_bounds_through_the_round_and_batches(oracle, pricer):
         assert [list(res.column(k)) for k in range(res.nCols)] == [list(ref.col_ind[b]) for b in range(model.m) if ref.col_keep[b]]
 
 
-def test_node_bounds_unsupported_in_pisinger_mode(pricer):
-    from dip_b200.capi import DipGpuError, ERR_UNSUPPORTED
-    b = I.random_batch(4, 5, 9, 10, 40, 1)
+def _bounded_pisinger_reference(oracle, b, lb, ub, eps=1e-4):
+    """Node bounds in Pisinger mode, composed from pinned pieces: the fixed columns leave the problem (fixed to 1: in the
+    column, their weight off the capacity), GAP_KnapPisinger::solve's restatement prices the free columns, the sums run
+    over the merged column in ascending index order."""
+    m = len(b.capacity)
+    rc_free = b.red_cost.copy()
+    cap_left = b.capacity.astype(np.int64).copy()
+    forced = []
+    for k in range(m):
+        s, e = b.block_col_start[k], b.block_col_start[k + 1]
+        one = lb[s:e] > 0.5
+        zero = ub[s:e] < 0.5
+        rc_free[s:e][one | zero] = 1.0          # no item
+        cap_left[k] -= int(b.weight[s:e][one].sum())
+        forced.append((s + np.nonzero(one)[0]).tolist())
+    feas = cap_left >= 0
+    ref = oracle.solve_blocks(b.block_col_start, b.weight, np.maximum(cap_left, 0).astype(np.int32), rc_free, b.orig_cost,
+                              np.zeros(m), profit_mode=1, red_cost_eps=eps)
+    cols, rcs, ocs, zs = [], [], [], []
+    for k in range(m):
+        if not feas[k]:
+            cols.append([]); rcs.append(np.inf); ocs.append(0.0); zs.append(-np.inf)
+            continue
+        col = sorted(list(ref.col_ind[k]) + forced[k])
+        r = 0.0
+        o = 0.0
+        for j in col:
+            r += b.red_cost[j]
+            o += b.orig_cost[j]
+        cols.append(col); rcs.append(r - b.alpha[k]); ocs.append(o); zs.append(ref.z[k])
+    return cols, np.array(rcs), np.array(ocs), np.array(zs)
+
+
+@pytest.mark.parametrize("m,nhi,caphi,seed", [(40, 60, 200, 1), (700, 30, 90, 2), (6, 1400, 600, 3)])
+def test_node_bounds_in_pisinger_mode(oracle, pricer, m, nhi, caphi, seed):
+    """DecompAlgo::setSubProbBounds (DecompAlgo.cpp:2352-2371) with GAP_KnapPisinger pricing: fused and large shards,
+    trivial cases (n <= 2 free items, all fit) and DP blocks, blocks whose fixed columns do not fit."""
+    b = I.random_batch(m, 0, nhi, 0, caphi, seed)
+    # reduced costs with a few decimals, so that the scale factor varies
+    b.red_cost = np.round(b.red_cost, 2)
+    rng = np.random.default_rng(seed)
+    n = len(b.weight)
+    lb = (rng.random(n) < 0.03).astype(np.float64)
+    ub = 1.0 - (rng.random(n) < 0.06) * (1 - lb)
     pricer.setObjective(b.orig_cost)
     pricer.setKnapsackBlocks(b.block_col_start, b.weight, b.capacity, PROFIT_PISINGER_INT)
-    with pytest.raises(DipGpuError) as e:
-        pricer.setColBounds(np.zeros(len(b.weight)), np.ones(len(b.weight)))
-    assert e.value.code == ERR_UNSUPPORTED
+    pricer.setColBounds(lb, ub)
+    res = pricer.solveBlocks(b.red_cost, b.alpha, redCostEps=-np.inf)
+    cols, rcs, ocs, zs = _bounded_pisinger_reference(oracle, b, lb, ub)
+    np.testing.assert_array_equal(res.blockObj, zs)
+    np.testing.assert_array_equal(res.blockRedCost, rcs)
+    np.testing.assert_array_equal(res.blockOrigCost, ocs)
+    kept = [k for k in range(m) if rcs[k] < np.inf]
+    assert list(res.colBlock[:res.nCols]) == kept
+    for q, k in enumerate(kept):
+        assert list(res.column(q)) == cols[k], k
+    # bounds removed: the plain Pisinger-mode round again
+    pricer.setColBounds(None, None)
+    res2 = pricer.solveBlocks(b.red_cost, b.alpha, redCostEps=-np.inf)
+    ref2 = oracle.solve_blocks(b.block_col_start, b.weight, b.capacity, b.red_cost, b.orig_cost, b.alpha, profit_mode=1,
+                               red_cost_eps=-np.inf)
+    np.testing.assert_array_equal(res2.blockObj, ref2.z)
 
 
 # ------------------------------------------------------------------ round + expansion in one submission

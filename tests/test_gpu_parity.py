@@ -304,16 +304,47 @@ def test_generate_vars_surface(oracle, pricer):
 
 
 def test_error_codes(pricer):
-    from dip_b200.capi import DipGpuError, ERR_STATE, ERR_INVALID, ERR_UNSUPPORTED
+    from dip_b200.capi import DipGpuError, ERR_STATE, ERR_INVALID
     with pytest.raises(DipGpuError) as e:
         pricer.priceRound(np.zeros(4))
     assert e.value.code == ERR_STATE
     with pytest.raises(DipGpuError) as e:
         pricer.setKnapsackBlocks([0, 2], [1, -1], [3])
     assert e.value.code == ERR_INVALID
-    with pytest.raises(DipGpuError) as e:
-        pricer.setKnapsackBlocks([0, 2], [1, 1], [10_000_000])
-    assert e.value.code == ERR_UNSUPPORTED
+    # any capacity is priced (rows beyond one CTA live in global memory): no UNSUPPORTED below 10^6 and beyond
+    pricer.setObjective(np.array([3.0, 4.0]))
+    pricer.setKnapsackBlocks([0, 2], [700_000, 400_000], [1_000_000])
+    r = pricer.solveBlocks(np.array([-2.5, -1.25]), np.zeros(1), redCostEps=-np.inf)
+    assert r.blockObj[0] == 2.5 and list(r.column(0)) == [0]
+
+
+@pytest.mark.parametrize("profit_mode", [0, 1])
+@pytest.mark.parametrize("cap,nhi,m,seed", [(13_000, 300, 5, 1), (100_000, 500, 3, 2), (40_000, 90, 12, 3)])
+def test_capacity_beyond_one_cta(oracle, pricer, profit_mode, cap, nhi, m, seed):
+    """Rows of more than 12 800 cells (GAP_KnapPisinger.h:243-249 prices any capacity): DP rows in global memory,
+    bit-exact optimum, identical columns; with node bounds as well."""
+    rng = np.random.default_rng(seed)
+    n = rng.integers(nhi // 2, nhi + 1, size=m)
+    bcs = np.zeros(m + 1, np.int32)
+    np.cumsum(n, out=bcs[1:])
+    N = int(bcs[-1])
+    w = rng.integers(1, cap // 8, size=N).astype(np.int32)
+    rc = np.round(rng.uniform(-60, 20, size=N), 2 if profit_mode else 9)
+    oc = rng.uniform(1, 100, size=N)
+    capv = rng.integers(cap // 2, cap + 1, size=m).astype(np.int32)
+    capv[0] = cap
+    alpha = rng.uniform(-5, 0, size=m)
+    res, ref = _check_against_oracle(oracle, pricer, bcs, w, capv, rc, oc, alpha, profit_mode=profit_mode)
+    assert pricer.dpGeometry()["cells_per_thread"] == 0
+    if profit_mode == 0:
+        lb = (rng.random(N) < 0.01).astype(np.float64)
+        ub = 1.0 - (rng.random(N) < 0.05) * (1 - lb)
+        pricer.setColBounds(lb, ub)
+        r2 = pricer.solveBlocks(rc, alpha)
+        ref2 = oracle.solve_blocks_bounded(bcs, w, capv, rc, oc, alpha, lb, ub)
+        np.testing.assert_array_equal(r2.blockObj, ref2.z)
+        np.testing.assert_array_equal(r2.blockRedCost, ref2.col_red_cost)
+        assert [list(r2.column(k)) for k in range(r2.nCols)] == [list(ref2.col_ind[b]) for b in range(m) if ref2.col_keep[b]]
 
 
 def test_csp_full_size_properties(oracle, pricer):
