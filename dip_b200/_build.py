@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libdipgpu.so")
-SOURCES = ["dipgpu_api.cu", "redcost.cu", "knapsack.cu", "filter.cu", "microbench.cu", "pisinger.cu", "expand.cu", "pool.cu", "mckp.cu", "multi.cu", "bigdp.cu"]
+SOURCES = ["dipgpu_api.cu", "redcost.cu", "knapsack.cu", "filter.cu", "microbench.cu", "pisinger.cu", "expand.cu", "pool.cu", "mckp.cu", "multi.cu", "bigdp.cu", "intknap.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "filter.cuh"), os.path.join(os.path.dirname(HERE), "include", "dipgpu.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: no fp contraction anywhere -- every product and sum is rounded on its own, as the reference's

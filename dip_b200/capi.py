@@ -38,6 +38,7 @@ SYMBOLS = [
     "dipgpu_price_round_stab", "dipgpu_price_round_stab_ladder", "dipgpu_get_smoothed_duals",
     "dipgpu_pool_clear", "dipgpu_pool_size", "dipgpu_pool_append", "dipgpu_pool_append_expanded",
     "dipgpu_pool_keep", "dipgpu_pool_set_reduced_costs", "dipgpu_set_col_bounds", "dipgpu_set_dual_support", "dipgpu_set_mckp_blocks",
+    "dipgpu_set_intknap_blocks",
     "dipgpu_price_round_which", "dipgpu_price_round_expand",
     "dipgpu_create_multi", "dipgpu_device_count", "dipgpu_shard_ranges", "dipgpu_sync", "dipgpu_result_shards",
     "dipgpu_unpack_results", "dipgpu_last_device_ms",
@@ -59,7 +60,7 @@ class Cols(C.Structure):
         ("nCols", C.c_int32), ("colBlock", C.c_void_p), ("colRedCost", C.c_void_p),
         ("colOrigCost", C.c_void_p), ("colStart", C.c_void_p), ("colInd", C.c_void_p),
         ("nInd", C.c_int64), ("mostNegReducedCost", C.c_double), ("cells", C.c_int64),
-        ("cellsEvaluated", C.c_int64),
+        ("cellsEvaluated", C.c_int64), ("colEl", C.c_void_p),
     ]
 
 
@@ -131,6 +132,7 @@ def lib() -> C.CDLL:
         "dipgpu_set_col_bounds": ([vp, vp, vp, i32], C.c_int),
         "dipgpu_set_dual_support": ([vp, i32, vp], C.c_int),
         "dipgpu_set_mckp_blocks": ([vp, i32, vp, vp, vp, vp], C.c_int),
+        "dipgpu_set_intknap_blocks": ([vp, i32, vp, vp, vp, vp], C.c_int),
         "dipgpu_create_multi": ([C.POINTER(vp), vp, i32], C.c_int),
         "dipgpu_device_count": ([vp, C.POINTER(i32), C.POINTER(i32)], C.c_int),
         "dipgpu_shard_ranges": ([vp, i32, vp, vp], C.c_int),

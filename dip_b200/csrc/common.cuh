@@ -40,6 +40,8 @@ struct ResultHeader {
     int64_t cells;
     int64_t indCap;
     int64_t reserved[3];  // [0]: DP cells actually evaluated (<= cells: the fused kernel's reduction drops items)
+                          // [1]: 1 = the index region holds (index, multiplicity) PAIRS (integer knapsack blocks): nInd,
+                          //      keptStart and nnz count int32 words, two per entry
 };
 static_assert(sizeof(ResultHeader) == 64, "header is 64 bytes");
 constexpr uint32_t kResultMagic = 0x52504944u;
@@ -65,6 +67,22 @@ struct ResultLayout {
         return L;
     }
 };
+
+// Host side: the kept entries of a packed result into the caller's arrays.  wordsPerEntry == 2: (index, multiplicity)
+// pairs (integer knapsack blocks); els (may be NULL) receives the multiplicities, 1.0 for plain index lists.
+inline void unpackEntries(const int32_t *words, int64_t nWords, int wordsPerEntry, int32_t *ind, double *els)
+{
+    const int64_t n = nWords / wordsPerEntry;
+    if (wordsPerEntry == 1) {
+        if (ind && n > 0) memcpy(ind, words, sizeof(int32_t) * (size_t)n);
+        if (els) for (int64_t q = 0; q < n; ++q) els[q] = 1.0;
+        return;
+    }
+    for (int64_t q = 0; q < n; ++q) {
+        if (ind) ind[q] = words[2 * q];
+        if (els) els[q] = (double)words[2 * q + 1];
+    }
+}
 
 constexpr int kFuseFilterMaxBlocks = 256;
 constexpr int kPubWordStride = 16;     // fused DP kernel: one publication word per 128-byte line
@@ -214,8 +232,13 @@ struct Ctx {
     int nBlockCols = 0;     // blockColStart[m]
     bool haveBlocks = false;
     int profitMode = 0;
-    // block kind: 0 = 0-1 knapsack (GAP, CSP), 1 = multiple-choice knapsack (MMKP: groups of columns)
+    // block kind: 0 = 0-1 knapsack (GAP, CSP), 1 = multiple-choice knapsack (MMKP: groups of columns),
+    // 2 = integer (unbounded) knapsack with an optional use column (cutting-stock pricing, intknap.cu)
     int blockKind = 0;
+    std::vector<int32_t> hUseCol;
+    int32_t *dUseCol = nullptr;         // m (blockKind 2; NULL: no block has a use column)
+    int32_t *dCandStart = nullptr;      // m + 1 (blockKind 2): first word of block b's candidate pairs in dCandInd
+    size_t ikSmem = 0;
     std::vector<int32_t> hBlockGroupStart, hGroupColStart;
     int32_t *dBlockGroupStart = nullptr, *dGroupColStart = nullptr;
     size_t mckpSmem = 0;
@@ -460,6 +483,8 @@ int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, do
 int launchBigDp(Ctx *c, const double *dRedCost, cudaStream_t st);
 // mckp.cu -- stage (b) for multiple-choice knapsack blocks (DP + backtrack; the filter kernels follow)
 int launchMckp(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_t st);
+// intknap.cu -- stage (b) for integer knapsack blocks (table + counts + column; the filter kernels follow)
+int launchIntKnap(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_t st);
 // filter.cu -- stage (c)
 int launchFilter(Ctx *c, double redCostEps, cudaStream_t st);
 // expand.cu -- master columns of the kept variables (the step after the round)

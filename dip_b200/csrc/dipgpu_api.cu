@@ -220,6 +220,11 @@ int setBlockRange(Ctx *c, int first, int count)
             off[lb + 1] = off[lb] + (int64_t)G * ((int64_t)c->hCapacity[first + lb] + 1);
         }
         c->bitsWords = (size_t)((off[count] + 1) / 2 + 1);  // uint16 entries in uint32 words
+    } else if (c->blockKind == 2) {
+        // integer knapsack blocks: no DP geometry; dBits is the global scratch of the tables (F, item, src: 16 bytes per
+        // cell) for shards whose rows do not fit shared memory beside the items (intknap.cu: launchIntKnap)
+        c->geom = DpGeom{};
+        c->bitsWords = (size_t)std::max(count, 1) * ((size_t)maxCap + 1) * 4 + 16;
     } else {
     const bool wantFuse = count > 0 && (c->optFuseFilter < 0 ? count <= kFuseFilterMaxBlocks : c->optFuseFilter == 2);
     if ((rc = chooseDpGeom(c, &c->geom, wantFuse))) return rc;
@@ -262,6 +267,7 @@ int setBlockRange(Ctx *c, int first, int count)
     DIPGPU_CUDA(c, cudaMemset(c->dShortcut, 0, sizeof(int32_t) * std::max<size_t>((size_t)count, 1)));
     // packed result
     c->indCap = count > 0 ? (int64_t)(c->hBlockColStart[first + count] - c->hBlockColStart[first]) : 0;
+    if (c->blockKind == 2) c->indCap = 2 * (c->indCap + count);  // (index, multiplicity) pairs, one more per block for the use column
     c->layout = ResultLayout::make(count, c->indCap);
     c->resultBytes = c->layout.bytes;
     c->lastResultBytes = 0;
@@ -495,6 +501,14 @@ static int enqueueSolve(Ctx *c, const double *dRedCost, const double *dAlpha, do
         if (timed) cudaEventRecord(c->ev[5], st);
         return DIPGPU_OK;
     }
+    if (c->blockKind == 2) {
+        // integer knapsack blocks: table + counts + column (intknap.cu), then the stand-alone filter
+        if ((rc = launchIntKnap(c, dRedCost, dAlpha, st))) return rc;
+        if (timed) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); }
+        if ((rc = launchFilter(c, eps, st))) return rc;
+        if (timed) cudaEventRecord(c->ev[5], st);
+        return DIPGPU_OK;
+    }
     int mode = c->geom.fuse ? 2 : c->optFuseFilter < 0 ? (c->nLocal <= kFuseFilterMaxBlocks ? 1 : 0)
                                                        : (c->optFuseFilter == 1 ? 1 : 0);
     if (c->nLocal == 0) mode = 0;
@@ -530,8 +544,10 @@ int unpack(Ctx *c, const void *packed, size_t bytes, dipgpu_cols *out)
     const int32_t *nz = reinterpret_cast<const int32_t *>(p + L.offNnz);
     const int32_t *kb = reinterpret_cast<const int32_t *>(p + L.offKeptBlock);
     const int32_t *ki = reinterpret_cast<const int32_t *>(p + L.offInd);
+    // integer knapsack blocks: the index region holds (index, multiplicity) pairs and every count is in words
+    const int wpe = h->reserved[1] == 1 ? 2 : 1;
     out->nCols = h->nKept;
-    out->nInd = h->nInd;
+    out->nInd = h->nInd / wpe;
     out->cells = h->cells;
     out->cellsEvaluated = h->reserved[0];
     const bool wantBlocks = out->blockRedCost || out->blockMostNegRC || out->blockOrigCost || out->blockObj || out->blockNnz;
@@ -544,22 +560,22 @@ int unpack(Ctx *c, const void *packed, size_t bytes, dipgpu_cols *out)
         if (out->blockMostNegRC) out->blockMostNegRC[b] = mn[lb];
         if (out->blockOrigCost) out->blockOrigCost[b] = oc[lb];
         if (out->blockObj) out->blockObj[b] = ob[lb];
-        if (out->blockNnz) out->blockNnz[b] = nz[lb];
+        if (out->blockNnz) out->blockNnz[b] = nz[lb] / wpe;
         sum += mn[lb];  // block order, DecompAlgo.cpp:5229-5232
     }
     out->mostNegReducedCost = sum;
-    if (h->nKept > out->capCols || h->nInd > out->capInd)
+    if (h->nKept > out->capCols || h->nInd / wpe > out->capInd)
         return fail(c, DIPGPU_ERR_OVERFLOW, "kept columns need capCols >= %d, capInd >= %lld", h->nKept,
-                    (long long)h->nInd);
+                    (long long)(h->nInd / wpe));
     for (int k = 0; k < h->nKept; ++k) {
         const int lb = kb[k];
         if (out->colBlock) out->colBlock[k] = h->firstBlock + lb;
         if (out->colRedCost) out->colRedCost[k] = rc[lb];
         if (out->colOrigCost) out->colOrigCost[k] = oc[lb];
-        if (out->colStart) out->colStart[k] = ks[k];
+        if (out->colStart) out->colStart[k] = ks[k] / wpe;
     }
-    if (out->colStart) out->colStart[h->nKept] = h->nInd;
-    if (out->colInd && h->nInd > 0) memcpy(out->colInd, ki, sizeof(int32_t) * (size_t)h->nInd);
+    if (out->colStart) out->colStart[h->nKept] = h->nInd / wpe;
+    unpackEntries(ki, h->nInd, wpe, out->colInd, out->colEl);
     return DIPGPU_OK;
 }
 
@@ -1438,6 +1454,81 @@ int dipgpu_set_mckp_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockGroup
     return setBlockRange(c, 0, m);
 }
 
+int dipgpu_set_intknap_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockColStart, const int32_t *weight,
+                              const int32_t *capacity, const int32_t *useCol)
+{
+    if (isMulti(ctx)) {
+        struct A { int32_t m; const int32_t *bcs, *w, *cap, *use; } a{m, blockColStart, weight, capacity, useCol};
+        const int rc = multiForAll(ctx, [](dipgpu_ctx *sub, void *p) {
+            const A *q = static_cast<const A *>(p);
+            return dipgpu_set_intknap_blocks(sub, q->m, q->bcs, q->w, q->cap, q->use);
+        }, &a, true, true);
+        return rc ? rc : multiSetBlocks(ctx);
+    }
+    CTX_OR_FAIL(ctx);
+    if (m < 0 || !blockColStart || (m > 0 && !capacity) || blockColStart[0] < 0)
+        return fail(c, DIPGPU_ERR_INVALID, "set_intknap_blocks: bad arguments");
+    for (int b = 0; b < m; ++b) {
+        if (blockColStart[b + 1] < blockColStart[b]) return fail(c, DIPGPU_ERR_INVALID, "set_intknap_blocks: blockColStart not monotone at block %d", b);
+        if (capacity[b] < 0) return fail(c, DIPGPU_ERR_INVALID, "set_intknap_blocks: negative capacity at block %d", b);
+    }
+    const int nItemCols = blockColStart[m];
+    if (nItemCols > 0 && !weight) return fail(c, DIPGPU_ERR_INVALID, "set_intknap_blocks: NULL weight");
+    // kp recurses on capacity - weight (test_cutting_stock.py:171): a weight below 1 never terminates there
+    for (int j = blockColStart[0]; j < nItemCols; ++j)
+        if (weight[j] < 1) return fail(c, DIPGPU_ERR_INVALID, "set_intknap_blocks: weight %d at column %d (must be >= 1)", weight[j], j);
+    int nCols = nItemCols;
+    if (useCol) {
+        for (int b = 0; b < m; ++b) {
+            const int u = useCol[b];
+            if (u < -1) return fail(c, DIPGPU_ERR_INVALID, "set_intknap_blocks: useCol[%d] = %d", b, u);
+            if (u >= blockColStart[b] && u < blockColStart[b + 1])
+                return fail(c, DIPGPU_ERR_INVALID, "set_intknap_blocks: the use column of block %d is one of its item columns", b);
+            nCols = std::max(nCols, u + 1);
+        }
+    }
+    if (c->haveCore && nCols > c->N) return fail(c, DIPGPU_ERR_INVALID, "set_intknap_blocks: column %d beyond N=%d", nCols - 1, c->N);
+    c->m = m;
+    c->nBlockCols = nCols;  // every column the blocks read (the use columns may lie behind the item columns)
+    c->profitMode = DIPGPU_PROFIT_FP64;
+    c->blockKind = 2;
+    c->haveFix = false;
+    c->hBlockColStart.assign(blockColStart, blockColStart + m + 1);
+    c->hCapacity.assign(capacity, capacity + m);
+    c->hWeight.assign(weight, weight + nItemCols);
+    c->hUseCol.clear();
+    if (useCol) c->hUseCol.assign(useCol, useCol + m);
+    c->hMaxUsableW.assign((size_t)m, 0);
+    std::vector<int32_t> candStart((size_t)m + 1);
+    for (int b = 0; b <= m; ++b) candStart[(size_t)b] = 2 * (blockColStart[b] - blockColStart[0] + b);
+    int rc;
+    devFree(&c->dFix); devFree(&c->dCapEff); devFree(&c->dUseCol);
+    if ((rc = devAlloc(c, &c->dBlockColStart, (size_t)m + 1))) return rc;
+    if ((rc = devAlloc(c, &c->dCandStart, (size_t)m + 1))) return rc;
+    if ((rc = devAlloc(c, &c->dCapacity, (size_t)m))) return rc;
+    if ((rc = devAlloc(c, &c->dWeight, (size_t)nItemCols + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dCandInd, 2 * ((size_t)nItemCols + (size_t)m) + 16))) return rc;
+    if ((rc = devAlloc(c, &c->dAlpha, (size_t)m))) return rc;
+    DIPGPU_CUDA(c, cudaMemcpy(c->dBlockColStart, blockColStart, sizeof(int32_t) * ((size_t)m + 1), cudaMemcpyHostToDevice));
+    DIPGPU_CUDA(c, cudaMemcpy(c->dCandStart, candStart.data(), sizeof(int32_t) * ((size_t)m + 1), cudaMemcpyHostToDevice));
+    if (m > 0) DIPGPU_CUDA(c, cudaMemcpy(c->dCapacity, capacity, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice));
+    DIPGPU_CUDA(c, cudaMemset(c->dWeight, 0, sizeof(int32_t) * ((size_t)nItemCols + 16)));
+    if (nItemCols > 0) DIPGPU_CUDA(c, cudaMemcpy(c->dWeight, weight, sizeof(int32_t) * (size_t)nItemCols, cudaMemcpyHostToDevice));
+    if (useCol && m > 0) {
+        if ((rc = devAlloc(c, &c->dUseCol, (size_t)m))) return rc;
+        DIPGPU_CUDA(c, cudaMemcpy(c->dUseCol, useCol, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice));
+    }
+    if (!c->haveCore) {
+        c->N = std::max(c->N, nCols);
+        if ((rc = devAlloc(c, &c->dRedCost, (size_t)c->N + 16))) return rc;
+        DIPGPU_CUDA(c, cudaMemset(c->dRedCost, 0, sizeof(double) * ((size_t)c->N + 16)));
+    }
+    c->haveBlocks = true;
+    c->compactValid = false;
+    c->lastRoundOnHost = false;
+    return setBlockRange(c, 0, m);
+}
+
 int dipgpu_set_col_bounds(dipgpu_ctx *ctx, const double *colLB, const double *colUB, int32_t N)
 {
     if (isMulti(ctx)) {
@@ -2020,6 +2111,7 @@ int dipgpu_pool_set_reduced_costs(dipgpu_ctx *ctx, const double *u, int32_t uLen
 static int prepareExpand(Ctx *c)
 {
     if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "expand_columns needs set_core_csr and set_knapsack_blocks");
+    if (c->blockKind == 2) return fail(c, DIPGPU_ERR_UNSUPPORTED, "expand_columns: columns of integer knapsack blocks carry multiplicities (expand them on the host)");
     if (!c->dCsrRowStart || !c->dColStart32) return fail(c, DIPGPU_ERR_UNSUPPORTED, "expand_columns: more than 2^31 stored entries");
     int rc;
     // packed output buffer: worst case one entry per stored entry of A'' plus one per column
@@ -2102,6 +2194,7 @@ int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
     CTX_OR_FAIL(ctx);
     if (!out) return fail(c, DIPGPU_ERR_INVALID, "expand_columns: NULL output");
     if (!c->haveCore || !c->haveBlocks) return fail(c, DIPGPU_ERR_STATE, "expand_columns needs set_core_csr and set_knapsack_blocks");
+    if (c->blockKind == 2) return fail(c, DIPGPU_ERR_UNSUPPORTED, "expand_columns: columns of integer knapsack blocks carry multiplicities (expand them on the host)");
     if (!c->lastRoundOnHost) return fail(c, DIPGPU_ERR_STATE, "expand_columns: no host-buffer pricing round since the model was set");
     const ResultHeader *rh = static_cast<const ResultHeader *>(c->hResult);
     const int nKept = rh->nKept;

@@ -42,7 +42,8 @@ FilterArgs makeFilterArgs(Ctx *c, double redCostEps)
     a.keptBlock = reinterpret_cast<int32_t *>(res + c->layout.offKeptBlock);
     a.keptInd = reinterpret_cast<int32_t *>(res + c->layout.offInd);
     a.candInd = c->dCandInd;
-    a.blockColStart = c->dBlockColStart;
+    a.blockColStart = c->blockKind == 2 ? c->dCandStart : c->dBlockColStart;  // (where block b's candidates start)
+    a.pairs = c->blockKind == 2 ? 1 : 0;
     a.capacity = c->haveFix ? c->dCapEff : c->dCapacity;
     a.nItems = c->dNItems;
     a.firstBlock = c->firstBlock;

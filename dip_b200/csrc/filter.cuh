@@ -22,6 +22,7 @@ struct FilterArgs {
     int64_t indCap;
     double eps;
     int fuseCopy;
+    int pairs;  // 1: candidate / kept entries are (index, multiplicity) pairs, counted in words (ResultHeader::reserved[1])
 };
 
 
@@ -124,6 +125,7 @@ __device__ __forceinline__ void filterScanBody(const FilterArgs &a, const int NT
         a.hdr->nInd = sCarryNnz;
         a.hdr->cells = tot;
         a.hdr->reserved[0] = tot;  // the large-shard path evaluates every cell
+        a.hdr->reserved[1] = a.pairs;
         a.hdr->indCap = a.indCap;
     }
     if (a.fuseCopy == 2) {

@@ -331,6 +331,7 @@ static int unpackShards(Ctx *front, const void *const *packed, const size_t *byt
     int64_t nInd = 0, cells = 0, evals = 0;
     double sum = 0.0;
     int needBlocks = 0;
+    int wpe = 1;  // words per kept entry: 2 = (index, multiplicity) pairs (integer knapsack blocks)
     struct Part { const char *p; const ResultHeader *h; ResultLayout L; };
     std::vector<Part> parts((size_t)nShards);
     for (int s = 0; s < nShards; ++s) {
@@ -339,12 +340,14 @@ static int unpackShards(Ctx *front, const void *const *packed, const size_t *byt
         if (!p || bytes[s] < sizeof(ResultHeader) || h->magic != kResultMagic) return fail(front, DIPGPU_ERR_INVALID, "packed result of shard %d: bad header", s);
         parts[(size_t)s] = Part{p, h, ResultLayout::make(h->m, h->indCap)};
         if (bytes[s] < parts[(size_t)s].L.offInd + sizeof(int32_t) * (size_t)h->nInd) return fail(front, DIPGPU_ERR_INVALID, "packed result of shard %d truncated", s);
+        if (h->reserved[1] == 1) wpe = 2;
         nKept += h->nKept;
         nInd += h->nInd;
         cells += h->cells;
         evals += h->reserved[0];
         needBlocks = std::max(needBlocks, h->firstBlock + h->m);
     }
+    nInd /= wpe;
     out->nCols = nKept;
     out->nInd = nInd;
     out->cells = cells;
@@ -363,7 +366,7 @@ static int unpackShards(Ctx *front, const void *const *packed, const size_t *byt
             if (out->blockMostNegRC) out->blockMostNegRC[b] = mn[lb];
             if (out->blockOrigCost) out->blockOrigCost[b] = oc[lb];
             if (out->blockObj) out->blockObj[b] = ob[lb];
-            if (out->blockNnz) out->blockNnz[b] = nz[lb];
+            if (out->blockNnz) out->blockNnz[b] = nz[lb] / wpe;
             sum += mn[lb];
         }
     }
@@ -383,11 +386,11 @@ static int unpackShards(Ctx *front, const void *const *packed, const size_t *byt
             if (out->colBlock) out->colBlock[k0 + k] = q.h->firstBlock + lb;
             if (out->colRedCost) out->colRedCost[k0 + k] = rc[lb];
             if (out->colOrigCost) out->colOrigCost[k0 + k] = oc[lb];
-            if (out->colStart) out->colStart[k0 + k] = i0 + ks[k];
+            if (out->colStart) out->colStart[k0 + k] = i0 + ks[k] / wpe;
         }
-        if (out->colInd && q.h->nInd > 0) memcpy(out->colInd + i0, ki, sizeof(int32_t) * (size_t)q.h->nInd);
+        unpackEntries(ki, q.h->nInd, wpe, out->colInd ? out->colInd + i0 : nullptr, out->colEl ? out->colEl + i0 : nullptr);
         k0 += q.h->nKept;
-        i0 += q.h->nInd;
+        i0 += q.h->nInd / wpe;
     }
     if (out->colStart) out->colStart[nKept] = nInd;
     return DIPGPU_OK;

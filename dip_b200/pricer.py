@@ -31,10 +31,11 @@ class DecompVar:
     origCost: float          # m_origCost
     redCost: float           # m_redCost
     blockId: int             # m_blockId
+    elements: np.ndarray | None = None  # m_s elements when they are not all 1.0 (integer knapsack blocks)
 
     @property
     def els(self) -> np.ndarray:
-        return np.ones(len(self.ind), np.float64)
+        return np.ones(len(self.ind), np.float64) if self.elements is None else self.elements
 
 
 class RoundResult:
@@ -52,6 +53,7 @@ class RoundResult:
         self.colOrigCost = np.zeros(max(cap_cols, 1), np.float64)
         self.colStart = np.zeros(max(cap_cols, 1) + 1, np.int64)
         self.colInd = np.zeros(max(cap_ind, 1), np.int32)
+        self.colEl = np.zeros(max(cap_ind, 1), np.float64)
         s = capi.Cols()
         s.capBlocks, s.capCols, s.capInd = m, cap_cols, cap_ind
         s.blockRedCost, s.blockMostNegRC = capi.ptr(self.blockRedCost), capi.ptr(self.blockMostNegRC)
@@ -60,6 +62,7 @@ class RoundResult:
         s.colBlock, s.colRedCost, s.colOrigCost = (capi.ptr(self.colBlock), capi.ptr(self.colRedCost),
                                                    capi.ptr(self.colOrigCost))
         s.colStart, s.colInd = capi.ptr(self.colStart), capi.ptr(self.colInd)
+        s.colEl = capi.ptr(self.colEl)
         self.c = s
 
     @property
@@ -81,9 +84,13 @@ class RoundResult:
     def column(self, k: int) -> np.ndarray:
         return self.colInd[self.colStart[k]:self.colStart[k + 1]]
 
+    def elements(self, k: int) -> np.ndarray:
+        """Elements of kept column k (1.0 except for integer knapsack blocks: the multiplicities)."""
+        return self.colEl[self.colStart[k]:self.colStart[k + 1]]
+
     def vars(self) -> list[DecompVar]:
         return [DecompVar(self.column(k).copy(), float(self.colOrigCost[k]), float(self.colRedCost[k]),
-                          int(self.colBlock[k])) for k in range(self.nCols)]
+                          int(self.colBlock[k]), self.elements(k).copy()) for k in range(self.nCols)]
 
 
 class GpuPricer:
@@ -239,6 +246,22 @@ class GpuPricer:
         self._result = None
         self._relax_cache = None
 
+    def setIntKnapBlocks(self, block_col_start, weight, capacity, use_col=None):
+        """Integer (unbounded) knapsack blocks with an optional use column per block: the cutting-stock pricing
+        problem (kp / relaxed_solver of Dip/src/dippy/tests/test_cutting_stock.py:98-179)."""
+        bcs = np.ascontiguousarray(block_col_start, np.int32)
+        w = np.ascontiguousarray(weight, np.int32)
+        cap = np.ascontiguousarray(capacity, np.int32)
+        use = None if use_col is None else np.ascontiguousarray(use_col, np.int32)
+        m = len(bcs) - 1
+        self._check(self._lib.dipgpu_set_intknap_blocks(self._ctx, m, capi.ptr(bcs), capi.ptr(w), capi.ptr(cap),
+                                                        None if use is None else capi.ptr(use)))
+        self.m = m
+        self.nBlockCols = max(int(bcs[-1]), int(use.max()) + 1 if use is not None and len(use) else 0)
+        self.N = max(self.N, self.nBlockCols)
+        self._result = None
+        self._relax_cache = None
+
     def setModel(self, model, profit_mode=PROFIT_FP64):
         """Upload a dip_b200.instances.PricingModel."""
         self.setModelCore(model.R, model.N, model.row_start, model.col_ind, model.val, model.n_base_rows,
@@ -271,7 +294,7 @@ class GpuPricer:
 
     def _res(self) -> RoundResult:
         if self._result is None:
-            self._result = RoundResult(self.m, self.m, max(self.nBlockCols, 1))
+            self._result = RoundResult(self.m, self.m, max(self.nBlockCols + self.m, 1))
         return self._result
 
     # ------------------------------------------------------------------- pricing
@@ -306,7 +329,7 @@ class GpuPricer:
 
     # ---- several dual vectors in one submission ------------------------------
     def _batch_results(self, n: int):
-        res = [RoundResult(self.m, self.m, max(self.nBlockCols, 1)) for _ in range(n)]
+        res = [RoundResult(self.m, self.m, max(self.nBlockCols + self.m, 1)) for _ in range(n)]
         arr = (capi.Cols * n)()
         for k in range(n):
             arr[k] = res[k].c
@@ -350,7 +373,7 @@ class GpuPricer:
                         raise ValueError("The size of the user dual vector is not the same as the number of master rows")
                     keep.append(ub)
                     ptrs[i] = ub.ctypes.data
-        res = result if result is not None else RoundResult(self.m, self.m, max(self.nBlockCols, 1))
+        res = result if result is not None else RoundResult(self.m, self.m, max(self.nBlockCols + self.m, 1))
         all_ = C.c_int32(0)
         self._check(self._lib.dipgpu_price_round_which(self._ctx, capi.ptr(u), len(u), phase, float(redCostEps), len(which),
                                                        capi.ptr(which), ptrs, C.byref(res.c), C.byref(all_)))
@@ -372,7 +395,7 @@ class GpuPricer:
     def priceRoundStab(self, uRM, alpha, phase=PHASE_PRICE2, redCostEps=1e-4, want_duals=True):
         """adjustMasterDualSolution + generateVars with the smoothed duals; returns (RoundResult, dualST)."""
         u = np.ascontiguousarray(uRM, np.float64)
-        res = RoundResult(self.m, self.m, max(self.nBlockCols, 1))
+        res = RoundResult(self.m, self.m, max(self.nBlockCols + self.m, 1))
         st = np.empty(len(u), np.float64) if want_duals else None
         self._check(self._lib.dipgpu_price_round_stab(self._ctx, capi.ptr(u), len(u), float(alpha), phase,
                                                       float(redCostEps), C.byref(res.c), capi.ptr(st)))
@@ -478,7 +501,7 @@ class GpuPricer:
         """priceRound + expandColumns in one submission (dipgpu_price_round_expand): returns
         (RoundResult, (colStart, rowInd, val, hash))."""
         u = np.ascontiguousarray(u, np.float64)
-        res = result if result is not None else RoundResult(self.m, self.m, max(self.nBlockCols, 1))
+        res = result if result is not None else RoundResult(self.m, self.m, max(self.nBlockCols + self.m, 1))
         cap_cols = max(self.m, 1)
         first = True
         while True:
@@ -517,7 +540,7 @@ class GpuPricer:
         rc = np.ascontiguousarray(redCostX, np.float64)
         fp = (rc.ctypes.data, hash(rc.tobytes()))
         if self._relax_cache is None or self._relax_cache[0] != fp:
-            res = RoundResult(self.m, self.m, max(self.nBlockCols, 1))
+            res = RoundResult(self.m, self.m, max(self.nBlockCols + self.m, 1))
             self.solveBlocks(rc, np.zeros(self.m), redCostEps=-np.inf, result=res)
             self._relax_cache = (fp, res)
         res = self._relax_cache[1]

@@ -26,7 +26,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define DIPGPU_ABI_VERSION 3
+#define DIPGPU_ABI_VERSION 4
 
 typedef struct dipgpu_ctx dipgpu_ctx;
 
@@ -67,8 +67,9 @@ enum { DIPGPU_PHASE_PRICE1 = 1, DIPGPU_PHASE_PRICE2 = 2 };
  *   blockNnz[b]      = |column b|
  * Kept columns (rc < -redCostEps, :5216), in block order:
  *   colBlock[k] (DecompVar::setBlockId), colRedCost[k], colOrigCost[k],
- *   colStart[k]..colStart[k+1] into colInd: x-space indices ascending, every
- *   element is 1.0 (GAP_KnapPisinger.h:265-270).
+ *   colStart[k]..colStart[k+1] into colInd: x-space indices ascending; colEl (may
+ *   be NULL) receives the elements: 1.0 for the 0-1 and multiple-choice blocks
+ *   (GAP_KnapPisinger.h:265-270), the multiplicities for integer knapsack blocks.
  * mostNegReducedCost = sum_b blockMostNegRC[b], added in block order (:5229-5232).
  */
 typedef struct dipgpu_cols {
@@ -96,6 +97,8 @@ typedef struct dipgpu_cols {
      * can contain (a Lagrangian bound against a greedy lower bound, the reduction Pisinger's combo
      * performs before its DP); optimum, column and ties are those of the full DP. */
     int64_t cellsEvaluated;
+    /* out, optional (NULL to skip): element of every kept index, parallel to colInd (capInd entries) */
+    double *colEl;
 } dipgpu_cols;
 
 /* ---------------------------------------------------------------- lifetime */
@@ -192,6 +195,24 @@ int dipgpu_set_knapsack_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockC
  */
 int dipgpu_set_mckp_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockGroupStart,
                            const int32_t *groupColStart, const int32_t *weight, const int32_t *capacity);
+
+/*
+ * The relaxation as m independent INTEGER (unbounded) knapsacks -- the pricing problem of DIP's cutting-stock
+ * example: relaxed_solver and kp of Dip/src/dippy/tests/test_cutting_stock.py:98-151, :154-179 (the copy of kp in
+ * Dip/src/dippy/examples/csp/cutting_stock_func.py:92-118 compares the wrong way round and returns 0).  Block b owns
+ * the item columns [blockColStart[b], blockColStart[b+1]) with weights >= 1 (the piece lengths) and, optionally, a
+ * "use" column useCol[b] anywhere else in x-space (-1 or useCol == NULL: none): the roll of
+ * sum_i w_i x_i <= capacity_b * use_b.  Items are the columns with redCost < 0, profit -redCost;
+ *     F[c] = max(F[c-1], max_i F[c - w_i] + profit_i),  first maximum in the order (skip, item 0, item 1, ...),
+ * evaluated cell by cell in that order so that value AND multiplicities are the recursion's, bit for bit.  When
+ * something is cut the column is {item: multiplicity} plus {use: 1} and varRedCost = -z + redCost[use]; otherwise the
+ * column is empty with varRedCost 0 (then blockRedCost = -alpha_b).  blockObj = z; blockOrigCost = sum c_j x_j in
+ * ascending column order; colEl carries the multiplicities.  The reduced cost excludes the convexity dual as on the
+ * C++ plugin surface (the Python relaxed_solver subtracts convexDual itself).  Replaces the other block kinds of the
+ * context; dipgpu_expand_columns and dipgpu_set_col_bounds do not apply (DIPGPU_ERR_UNSUPPORTED).
+ */
+int dipgpu_set_intknap_blocks(dipgpu_ctx *ctx, int32_t m, const int32_t *blockColStart, const int32_t *weight,
+                              const int32_t *capacity, const int32_t *useCol);
 
 /*
  * Node bounds of the x-space columns, enforced inside the block subproblems: what

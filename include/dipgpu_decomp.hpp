@@ -23,6 +23,7 @@
 #ifndef DIPGPU_DECOMP_HPP
 #define DIPGPU_DECOMP_HPP
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -132,6 +133,20 @@ public:
         check(dipgpu_set_knapsack_blocks(m_ctx, m, blockColStart, weight, capacity, profitMode));
         m_m = m;
         m_nBlockCols = blockColStart[m];
+        if (m_nBlockCols > m_N) m_N = m_nBlockCols;
+        allocResult();
+        m_roundValid = false;
+    }
+
+    // One integer knapsack per block with an optional use column: the cutting-stock pricing problem (relaxed_solver /
+    // kp of Dip/src/dippy/tests/test_cutting_stock.py:98-179); the columns come back with multiplicities as elements.
+    void setIntKnapBlocks(int m, const int *blockColStart, const int *weight, const int *capacity, const int *useCol)
+    {
+        check(dipgpu_set_intknap_blocks(m_ctx, m, blockColStart, weight, capacity, useCol));
+        m_m = m;
+        m_nBlockCols = blockColStart[m];
+        if (useCol)
+            for (int b = 0; b < m; ++b) m_nBlockCols = std::max(m_nBlockCols, useCol[b] + 1);
         if (m_nBlockCols > m_N) m_N = m_nBlockCols;
         allocResult();
         m_roundValid = false;
@@ -418,12 +433,13 @@ private:
         m_colRedCost.assign(m + 1, 0.0);
         m_colOrigCost.assign(m + 1, 0.0);
         m_colStart.assign(m + 2, 0);
-        m_colInd.assign(n, 0);
+        m_colInd.assign(n + m, 0);
+        m_colEl.assign(n + m, 1.0);
         m_served.assign(m, 0);
         std::memset(&m_cols, 0, sizeof(m_cols));
         m_cols.capBlocks = m_m;
         m_cols.capCols = m_m;
-        m_cols.capInd = (int64_t)n;
+        m_cols.capInd = (int64_t)(n + m);
         m_cols.blockRedCost = m_blockRedCost.data();
         m_cols.blockMostNegRC = m_blockMostNeg.data();
         m_cols.blockOrigCost = m_blockOrigCost.data();
@@ -434,6 +450,7 @@ private:
         m_cols.colOrigCost = m_colOrigCost.data();
         m_cols.colStart = m_colStart.data();
         m_cols.colInd = m_colInd.data();
+        m_cols.colEl = m_colEl.data();
     }
     void bindRound(Round &r) const
     {
@@ -455,7 +472,8 @@ private:
     {
         const int64_t b = m_colStart[(size_t)k], e = m_colStart[(size_t)k + 1];
         std::vector<int> ind(m_colInd.begin() + b, m_colInd.begin() + e);
-        std::vector<double> els(ind.size(), 1.0);  // GAP_KnapPisinger.h:265-270
+        // 1.0 for 0-1 blocks (GAP_KnapPisinger.h:265-270), the multiplicities for integer knapsack blocks
+        std::vector<double> els(m_colEl.begin() + b, m_colEl.begin() + e);
         VarT *v = new VarT(ind, els, redCost, m_colOrigCost[(size_t)k]);
         v->setBlockId(m_colBlock[(size_t)k]);
         return v;
@@ -483,6 +501,7 @@ private:
     dipgpu_cols m_cols;
     std::vector<double> m_blockRedCost, m_blockMostNeg, m_blockOrigCost, m_blockObj, m_colRedCost, m_colOrigCost;
     std::vector<int32_t> m_blockNnz, m_colBlock, m_colInd;
+    std::vector<double> m_colEl;
     std::vector<int64_t> m_colStart;
     bool m_roundValid;
     const double *m_roundPtr = nullptr;

@@ -567,3 +567,124 @@ int dip_oracle_solve_mckp_blocks(int m, const int32_t *blockGroupStart, const in
     if (cellsOut) *cellsOut = cellsTotal;
     return kept;
 }
+
+/* ------------------------------------------- integer (unbounded) knapsack blocks -- */
+
+/*
+ * kp(obj, weights, capacity): the pricing knapsack of DIP's cutting-stock example,
+ * Dip/src/dippy/tests/test_cutting_stock.py:154-179 (the copy with `if zyes > zbest`; the copy in
+ * Dip/src/dippy/examples/csp/cutting_stock_func.py:92-118 compares the other way round and returns 0).
+ * The reference is a plain recursion on the capacity:
+ *     kp(0) = (0, zeros);   kp(c): best = kp(c-1);  for i = 0..n-1: if w_i <= c:
+ *         zyes = kp(c - w_i).z + obj_i;  if zyes > zbest: best = (zyes, kp(c - w_i).sol + e_i)
+ * i.e. F[c] = max(F[c-1], max_i F[c-w_i] + obj_i) with the FIRST candidate in the order
+ * (skip, item 0, item 1, ...) that reaches the maximum, and the value of a cell is the chain sum
+ * "value of the source cell + obj_i".  Memoised over the capacity that is this table; the counts
+ * follow the recorded choices back from `capacity`.  Weights must be >= 1 (the recursion does not
+ * terminate on a zero weight).  n == 0 returns 0 and no counts (:158-159).
+ */
+double dip_oracle_intknap_kp(int n, const double *obj, const int32_t *weights, int capacity, int32_t *counts)
+{
+    for (int i = 0; i < n; ++i) counts[i] = 0;
+    if (n == 0 || capacity <= 0) return 0.0;
+    double *F = (double *)malloc(sizeof(double) * ((size_t)capacity + 1));
+    int32_t *choice = (int32_t *)malloc(sizeof(int32_t) * ((size_t)capacity + 1));
+    F[0] = 0.0;
+    choice[0] = -1;
+    for (int c = 1; c <= capacity; ++c) {
+        double zbest = F[c - 1]; /* :167 "don't include item" */
+        int arg = -1;
+        for (int i = 0; i < n; ++i) {
+            if (weights[i] <= c) {                       /* :170 */
+                const double zyes = F[c - weights[i]] + obj[i]; /* :171-173 */
+                if (zyes > zbest) { zbest = zyes; arg = i; }    /* :175-177, strict */
+            }
+        }
+        F[c] = zbest;
+        choice[c] = arg;
+    }
+    int c = capacity;
+    while (c > 0) {
+        const int i = choice[c];
+        if (i < 0) { --c; continue; }
+        counts[i] += 1;
+        c -= weights[i];
+    }
+    const double z = F[capacity];
+    free(F);
+    free(choice);
+    return z;
+}
+
+/*
+ * Blocks priced by kp: relaxed_solver of Dip/src/dippy/tests/test_cutting_stock.py:98-151 in the
+ * convention of the C++ plugin surface (the variable's reduced cost comes back WITHOUT the convexity
+ * dual, DecompAlgo::solveRelaxed subtracts it, Dip/src/DecompAlgo.cpp:6350-6356).  Block b owns the
+ * item columns [blockColStart[b], blockColStart[b+1]) and optionally a "use" column useCol[b] (-1:
+ * none): items = columns with redCost < 0 in ascending order (:103-104), obj = -redCost (:106),
+ * (z, counts) = kp; when something is cut the column is {item: count} + {use: 1} with reduced cost
+ * -z + redCost[use] (:129); otherwise an empty column with reduced cost 0 (:131).  origCost = sum of
+ * c_j * x_j in ascending column order.  The filter is the one of generateVars.
+ * Output per block: colNnz (entries), colIndOut / colCntOut (ascending x-space index, multiplicity),
+ * rows of maxEntries.
+ */
+int dip_oracle_solve_intknap_blocks(int m, const int32_t *blockColStart, const int32_t *weight,
+                                    const int32_t *capacity, const int32_t *useCol, const double *redCostX,
+                                    const double *origCost, const double *alpha, double redCostEps,
+                                    int maxEntries, int32_t *colNnz, double *colRedCost, double *colOrigCost,
+                                    int32_t *colKeep, double *mostNegRC, double *z, int32_t *colIndOut,
+                                    int32_t *colCntOut, double *mostNegReducedCost, int64_t *cellsOut)
+{
+    int64_t cellsTotal = 0;
+    for (int b = 0; b < m; ++b) {
+        const int cs = blockColStart[b], ce = blockColStart[b + 1];
+        const int nAll = ce - cs;
+        double *obj = (double *)malloc(sizeof(double) * (size_t)(nAll > 0 ? nAll : 1));
+        int32_t *w = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nAll > 0 ? nAll : 1));
+        int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nAll > 0 ? nAll : 1));
+        int32_t *cnt = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nAll > 0 ? nAll : 1));
+        int n = 0;
+        for (int j = cs; j < ce; ++j) {
+            if (redCostX[j] < 0.0) { obj[n] = -redCostX[j]; w[n] = weight[j]; idx[n] = j; ++n; }
+        }
+        const double zb = dip_oracle_intknap_kp(n, obj, w, capacity[b], cnt);
+        cellsTotal += (int64_t)n * ((int64_t)capacity[b] + 1);
+        int total = 0;
+        for (int i = 0; i < n; ++i) total += cnt[i];
+        int32_t *ind = colIndOut + (size_t)b * (size_t)maxEntries;
+        int32_t *mul = colCntOut + (size_t)b * (size_t)maxEntries;
+        int e = 0;
+        double rc = 0.0, oc = 0.0;
+        if (total > 0) {
+            const int use = useCol ? useCol[b] : -1;
+            int usePlaced = use < 0;
+            for (int i = 0; i < n; ++i) {
+                if (cnt[i] == 0) continue;
+                if (!usePlaced && use < idx[i]) { ind[e] = use; mul[e] = 1; ++e; oc += origCost[use] * 1.0; usePlaced = 1; }
+                ind[e] = idx[i]; mul[e] = cnt[i]; ++e;
+                oc += origCost[idx[i]] * (double)cnt[i];
+            }
+            if (!usePlaced) { ind[e] = use; mul[e] = 1; ++e; oc += origCost[use] * 1.0; }
+            rc = -zb;
+            if (use >= 0) rc = rc + redCostX[use]; /* :129 */
+        }
+        colNnz[b] = e;
+        colRedCost[b] = rc - alpha[b];
+        colOrigCost[b] = oc;
+        if (z) z[b] = zb;
+        free(obj); free(w); free(idx); free(cnt);
+    }
+    int kept = 0;
+    double sum = 0.0;
+    for (int b = 0; b < m; ++b) {
+        double mn = 0.0;
+        if (colRedCost[b] < mn) mn = colRedCost[b];
+        mostNegRC[b] = mn;
+        colKeep[b] = colRedCost[b] < -redCostEps ? 1 : 0;
+        kept += colKeep[b];
+    }
+    for (int b = 0; b < m; ++b) sum += mostNegRC[b];
+    if (mostNegReducedCost) *mostNegReducedCost = sum;
+    if (cellsOut) *cellsOut = cellsTotal;
+    return kept;
+}

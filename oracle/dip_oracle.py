@@ -82,6 +82,12 @@ def _lib():
         C.c_int, _i32p, _i32p, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_double, C.c_int,
         _i32p, _f64p, _f64p, _i32p, _f64p, _f64p, _i32p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.dip_oracle_solve_mckp_blocks.restype = C.c_int
+    lib.dip_oracle_intknap_kp.argtypes = [C.c_int, _f64p, _i32p, C.c_int, _i32p]
+    lib.dip_oracle_intknap_kp.restype = C.c_double
+    lib.dip_oracle_solve_intknap_blocks.argtypes = [
+        C.c_int, _i32p, _i32p, _i32p, C.c_void_p, _f64p, _f64p, _f64p, C.c_double, C.c_int,
+        _i32p, _f64p, _f64p, _i32p, _f64p, _f64p, _i32p, _i32p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.dip_oracle_solve_intknap_blocks.restype = C.c_int
     lib.dip_oracle_pool_reduced_costs.argtypes = [C.c_int, _i64p, _i32p, _f64p, _f64p, _f64p, C.c_int, _f64p]
     lib.dip_oracle_pool_reduced_costs.restype = C.c_int
     lib.dip_oracle_smooth_duals.argtypes = [C.c_int, C.c_double, _f64p, _f64p, _f64p]
@@ -223,6 +229,39 @@ def solve_mckp_blocks(block_group_start, group_col_start, weight, capacity, red_
         C.byref(tot), C.byref(cells))
     cols = [ind[b, : nnz[b]].copy() for b in range(m)]
     return RoundResult(None, nnz, rc, oc, keep, mn, z, cols, tot.value, kept, cells.value)
+
+
+def intknap_kp(obj, weights, capacity):
+    """kp of Dip/src/dippy/tests/test_cutting_stock.py:154-179: (z, counts per item)."""
+    obj = np.ascontiguousarray(obj, np.float64)
+    w = np.ascontiguousarray(weights, np.int32)
+    cnt = np.zeros(max(len(obj), 1), np.int32)
+    z = _lib().dip_oracle_intknap_kp(len(obj), obj if len(obj) else np.zeros(1), w if len(w) else np.zeros(1, np.int32),
+                                     int(capacity), cnt)
+    return z, cnt[: len(obj)].copy()
+
+
+def solve_intknap_blocks(block_col_start, weight, capacity, use_col, red_cost_x, orig_cost, alpha,
+                         red_cost_eps=1e-4) -> RoundResult:
+    """Integer-knapsack blocks (cutting-stock pricing): col_ind[b] ascending x-space indices, col_cnt[b] their
+    multiplicities (attribute added to the RoundResult)."""
+    bcs = np.ascontiguousarray(block_col_start, np.int32)
+    m = len(bcs) - 1
+    max_e = max(int(np.max(np.diff(bcs))) if m > 0 else 1, 1) + 1
+    nnz, rc, oc, keep, mn, z, ind = _alloc(m, max_e, True)
+    cnt = np.zeros((m, max_e), np.int32)
+    tot = C.c_double(0.0)
+    cells = C.c_int64(0)
+    use = None if use_col is None else np.ascontiguousarray(use_col, np.int32)
+    kept = _lib().dip_oracle_solve_intknap_blocks(
+        m, bcs, np.ascontiguousarray(weight, np.int32), np.ascontiguousarray(capacity, np.int32),
+        None if use is None else use.ctypes.data, np.ascontiguousarray(red_cost_x, np.float64),
+        np.ascontiguousarray(orig_cost, np.float64), np.ascontiguousarray(alpha, np.float64), float(red_cost_eps),
+        max_e, nnz, rc, oc, keep, mn, z, ind, cnt, C.byref(tot), C.byref(cells))
+    res = RoundResult(None, nnz, rc, oc, keep, mn, z, [ind[b, : nnz[b]].copy() for b in range(m)], tot.value, kept,
+                      cells.value)
+    res.col_cnt = [cnt[b, : nnz[b]].copy() for b in range(m)]
+    return res
 
 
 def price_round(R, N, row_start, col_ind, val, c, u, n_base, m, block_col_start, weight,

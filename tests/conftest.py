@@ -38,6 +38,13 @@ def golden_knapsack():
 
 
 @pytest.fixture(scope="session")
+def golden_intknap():
+    d = json.load(open(os.path.join(GOLDEN, "intknap_kp_cases.json")))
+    return [dict(tag=c["tag"], obj=_unhex(c["obj"]), w=np.array(c["w"], np.int32), cap=int(c["cap"]),
+                 z=float.fromhex(c["z"]), counts=list(c["counts"]), plain=bool(c["plain"])) for c in d["cases"]]
+
+
+@pytest.fixture(scope="session")
 def golden_gap0515():
     d = json.load(open(os.path.join(GOLDEN, "gap0515_2_rounds.json")))
     for r in d["rounds"]:

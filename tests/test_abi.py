@@ -22,7 +22,7 @@ def test_header_symbols_are_exported(gpu_lib):
     assert set(names) == set(capi.SYMBOLS)
     for n in names:
         assert hasattr(gpu_lib, n), n
-    assert gpu_lib.dipgpu_abi_version() == 3
+    assert gpu_lib.dipgpu_abi_version() == 4
 
 
 def test_only_the_abi_is_exported():
