@@ -43,7 +43,8 @@ from dip_b200 import instances as I  # noqa: E402
 METRIC = "pricing_rounds_per_s_gap_e_80x1600"
 UNIT = "rounds/s"
 N_DUALS = 16          # distinct master dual vectors cycled through the steps
-N_BATCH = 64          # ... and priced per call by the largest batch leg
+N_BATCH = 64          # ... and priced per call by the batch legs
+N_BIG = 512           # multi-GPU runs: a batch that leaves every one of 8 GPUs 64 vectors
 RC_EPS = 1e-4         # DecompParam::RedCostEpsilon (Dip/src/DecompParam.h:691)
 
 
@@ -566,8 +567,13 @@ def multi_gpu_line(args, torch, devices, model, duals, replicas):
     pone = GpuPricer(devices[:1])       # the multi-device code path over one device: same timing method
     pone.setModel(model)
     pone.setDualSupport(model.dual_support)
+    pf = GpuPricer(devices)             # the blocks FORCED onto all devices (the default policy keeps a round whose
+    pf.set_option("shard_rounds", N)    # blocks are co-resident on one GPU on the primary device)
+    pf.setModel(model)
+    pf.setDualSupport(model.dual_support)
     n_dev, peer = pm.deviceCount()
     ranges = pm.shardRanges()
+    ranges_forced = pf.shardRanges()
     u_dev = [torch.from_numpy(u).to(dev0) for u in duals[:N_DUALS]]
     u_pin = capi.PinnedArray((N_BATCH, model.u_len), np.float64)
     for k, u in enumerate(duals):
@@ -604,18 +610,23 @@ def multi_gpu_line(args, torch, devices, model, duals, replicas):
     launches = c1["kernel_launches"] - c0["kernel_launches"]
     one_ms, _ = dev_loop(pone, flush1, min(K, 100), W)
     one_ms = one_ms / min(K, 100)
-    # merged == unsharded, on the last dual vector priced
-    k_last = (W + K - 1) % N_DUALS
-    ptr, nbytes = pm.resultDev()
-    off, siz = pm.resultShards()
-    host = torch.as_tensor(_DevBytes(ptr, nbytes), device=dev0).cpu().numpy()
-    merged = unpack_results(host, off, siz, model.m, model.N)
-    full = p1.priceRound(duals[k_last], redCostEps=RC_EPS, result=RoundResult(model.m, model.m, model.N))
-    same = bool(merged.nCols == full.nCols and np.array_equal(merged.blockObj, full.blockObj)
-                and np.array_equal(merged.blockRedCost, full.blockRedCost)
-                and merged.mostNegReducedCost == full.mostNegReducedCost
-                and np.array_equal(merged.colInd[:merged.c.nInd], full.colInd[:full.c.nInd]))
-    result_bytes = int(sum(int(x) for x in siz[1:]))   # upper bound: the shards' whole packed buffers
+    forced_ms, forced_per_dev = dev_loop(pf, flush, min(K, 100), W)
+    forced_ms = forced_ms / min(K, 100)
+    # merged == unsharded, on the last dual vector priced (default policy and forced partition)
+    full = None
+    same_all = []
+    for p, k_last in ((pm, (W + K - 1) % N_DUALS), (pf, (W + min(K, 100) - 1) % N_DUALS)):
+        ptr, nbytes = p.resultDev()
+        off, siz = p.resultShards()
+        host = torch.as_tensor(_DevBytes(ptr, nbytes), device=dev0).cpu().numpy()
+        merged = unpack_results(host, off, siz, model.m, model.N)
+        full = p1.priceRound(duals[k_last], redCostEps=RC_EPS, result=RoundResult(model.m, model.m, model.N))
+        same_all.append(bool(merged.nCols == full.nCols and np.array_equal(merged.blockObj, full.blockObj)
+                             and np.array_equal(merged.blockRedCost, full.blockRedCost)
+                             and merged.mostNegReducedCost == full.mostNegReducedCost
+                             and np.array_equal(merged.colInd[:merged.c.nInd], full.colInd[:full.c.nInd])))
+    same = all(same_all)
+    result_bytes = int(sum(int(x) for x in siz[1:]))   # (forced partition) upper bound: the shards' whole packed buffers
     kept_bytes = int(merged.c.nInd) * 4 + model.m * 44
     value = K / (dev_ms * 1e-3)
 
@@ -635,6 +646,7 @@ def multi_gpu_line(args, torch, devices, model, duals, replicas):
 
     e2e_s, h2d_b, d2h_b = e2e_loop(pm, flush, K, W)
     e2e1_s, _, _ = e2e_loop(p1, flush1, min(K, 100), W)
+    e2ef_s, h2df_b, d2hf_b = e2e_loop(pf, flush, min(K, 100), W)
     e2e = {"value": K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
            "ms_per_step": 1e3 * e2e_s / K, "one_gpu_ms_per_step": 1e3 * e2e1_s / min(K, 100),
            "dual_support_rows": int(len(model.dual_support)),
@@ -661,46 +673,59 @@ def multi_gpu_line(args, torch, devices, model, duals, replicas):
     # ---- the calls that scale: several dual vectors per call, partitioned over the GPUs; same call on one GPU beside it
     batched = None
     if not args.skip_extras:
-        b_multi = bench_batched(pm, model, duals, u_pin, flush, torch, None)
-        b_one = bench_batched(p1, model, duals, u_pin, flush1, torch, None)
+        b_multi = bench_batched(pm, model, duals, u_pin, flush, torch, None, big=N_BIG)
+        b_one = bench_batched(p1, model, duals, u_pin, flush1, torch, None, big=N_BIG)
         batched = {}
-        for nm in ("batch16", "batch64", "ladder8"):
+        for nm in ("batch16", "batch64", f"batch{N_BIG}", "ladder8"):
             batched[nm] = {"rounds_per_call": b_multi[nm]["rounds_per_call"],
                            "rounds_per_s": b_multi[nm]["e2e_rounds_per_s"], "ms_per_call": b_multi[nm]["ms_per_call"],
                            "one_gpu_rounds_per_s": b_one[nm]["e2e_rounds_per_s"], "one_gpu_ms_per_call": b_one[nm]["ms_per_call"],
                            "speedup_vs_one_gpu": b_multi[nm]["e2e_rounds_per_s"] / b_one[nm]["e2e_rounds_per_s"],
                            "efficiency": b_multi[nm]["e2e_rounds_per_s"] / b_one[nm]["e2e_rounds_per_s"] / N,
                            "stage_ms_slowest_device": b_multi[nm]["stage_ms"]}
-        batched["timing"] = ("host wall clock around the synchronous C-ABI call (64 / 16 pinned dual vectors, or one dualRM and "
-                             "an 8-step smoothing ladder), duals in and columns out inside, L2 of every GPU flushed before each call")
+        batched["timing"] = (f"host wall clock around the synchronous C-ABI call ({N_BIG} / 64 / 16 pinned dual vectors, or one dualRM "
+                             "and an 8-step smoothing ladder), duals in and columns out inside, L2 of every GPU flushed before "
+                             "each call; efficiency = speed-up over the same call on one GPU / number of GPUs")
     csp = None
     if not args.skip_extras:
         csp = bench_csp(torch, devices, args, smem_peak, flush)
-    for p in (pm, p1, pone):
+    for p in (pm, p1, pone, pf):
         p.close()
     cfg = workload_config(model)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": cfg,
-        "run": {"parallelism": f"ONE caller (rank 0), one multi-device context over {N} GPUs: the 80 blocks of every round "
-                               "partitioned by DP work (dipgpu_shard_ranges), SpMV column-partitioned, no collective",
+        "run": {"parallelism": f"ONE caller (rank 0), one multi-device context over {N} GPUs.  value / e2e: ONE dual vector per "
+                               "step under the library's default policy -- the 80 blocks of a GAP-E round are 80 one-CTA latency "
+                               "chains that run side by side on one GPU's 148 SMs, so the round stays on the primary device "
+                               "(`sharded`: the same round with the blocks forced onto all GPUs); the calls that do scale "
+                               "(several dual vectors per call, partitioned over the GPUs) are `batched_rounds`",
                 "blocks_per_gpu": [c for _, c in ranges],
                 "l2": "every GPU flushed between steps (256 MiB written then 256 MiB read, outside the per-device CUDA-event pairs)",
                 "timing": "per step: each GPU's CUDA-event pair on its own stream around its part, the step costs the slowest GPU"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches, "stage_ms": stage_ms, "roofline": roofline,
-        "sharded": {"ms_per_round": dev_ms / K, "ms_per_round_per_gpu": per_dev_ms,
-                    "one_gpu_same_method_ms": one_ms, "vs_one_gpu": one_ms / (dev_ms / K),
+        "sharded": {"default_policy_ms_per_round": dev_ms / K, "default_policy_blocks_per_gpu": [c for _, c in ranges],
+                    "ms_per_round": forced_ms, "ms_per_round_per_gpu": forced_per_dev,
+                    "blocks_per_gpu": [c for _, c in ranges_forced],
+                    "e2e_ms_per_round": 1e3 * e2ef_s / min(K, 100),
+                    "one_gpu_same_method_ms": one_ms, "vs_one_gpu": one_ms / forced_ms,
+                    "default_policy_vs_one_gpu": one_ms / (dev_ms / K),
                     "merged_equals_unsharded": same, "peer_access": bool(peer),
                     "exchange": "duals: every GPU pulls u[support] out of the primary's HBM (peer loads over NVLink); results: "
                                 "every fused DP kernel mirrors its packed result into the primary's gather buffer (peer stores)",
                     "nvlink_bytes_per_round": {"duals": (N - 1) * sup_bytes, "results_max": result_bytes, "results_kept_about": kept_bytes},
-                    "pcie_bytes_per_round_e2e": {"h2d": int(h2d_b), "d2h": int(d2h_b)}},
-        "sharded_ms_per_round": dev_ms / K, "sharded_vs_one_gpu": one_ms / (dev_ms / K),
+                    "pcie_bytes_per_round_e2e": {"h2d": int(h2df_b), "d2h": int(d2hf_b)},
+                    "note": "forced partition (option shard_rounds = N): duals pulled from the primary's HBM over NVLink, "
+                            "results mirrored into the primary's gather buffer by peer stores; a remote device pays the "
+                            "NVLink round trips on top of the same per-block latency chain, which is why the default "
+                            "policy does not partition co-resident rounds"},
+        "sharded_ms_per_round": forced_ms, "sharded_vs_one_gpu": one_ms / forced_ms,
+        "round_default_policy_ms": dev_ms / K, "round_default_policy_vs_one_gpu": one_ms / (dev_ms / K),
     }
     if batched is not None:
         line["batched_rounds"] = batched
-        for nm in ("batch16", "batch64", "ladder8"):
+        for nm in ("batch16", "batch64", f"batch{N_BIG}", "ladder8"):
             line[nm + "_rounds_per_s"] = batched[nm]["rounds_per_s"]
             line[nm + "_speedup_vs_one_gpu"] = batched[nm]["speedup_vs_one_gpu"]
     if csp is not None:
@@ -712,7 +737,7 @@ def multi_gpu_line(args, torch, devices, model, duals, replicas):
     return line
 
 
-def bench_batched(pr, model, duals, u_pin, flush_l2, torch, smem_peak):
+def bench_batched(pr, model, duals, u_pin, flush_l2, torch, smem_peak, big=0):
     """Several dual vectors per submission: dipgpu_price_rounds_batch on 16 and on 64 pinned dual
     vectors, and the Wentges ladder of 8 smoothing parameters from ONE uploaded dualRM
     (dipgpu_price_round_stab_ladder).  Host wall clock around the synchronous C-ABI calls, H2D and D2H
@@ -720,15 +745,25 @@ def bench_batched(pr, model, duals, u_pin, flush_l2, torch, smem_peak):
     reports the slowest device per stage)."""
     from dip_b200 import capi
     out = {}
-    res, arr = pr._batch_results(N_BATCH)
-    reps = 30
-    for name, steps in (("batch16", 16), ("batch64", N_BATCH), ("ladder8", 8)):
+    res, arr = pr._batch_results(max(N_BATCH, big))
+    legs = [("batch16", 16), ("batch64", N_BATCH), ("ladder8", 8)]
+    u_big = None
+    if big > N_BATCH:
+        # a batch large enough that every one of 8 GPUs still gets tens of vectors: the N_BATCH dual vectors repeated
+        u_big = capi.PinnedArray((big, model.u_len), np.float64)
+        for k in range(big):
+            u_big.array[k] = u_pin.array[k % N_BATCH]
+        legs.append((f"batch{big}", big))
+    for name, steps in legs:
+        reps = 30 if steps <= N_BATCH else 8
+        src = u_big if steps > N_BATCH else u_pin
+
         def call():
             if name == "ladder8":
                 pr.priceRoundStabLadderRaw(u_pin.array[1].ctypes.data, model.u_len, 0.1, 0.90, 8, capi.PHASE_PRICE2,
                                            RC_EPS, arr)
             else:
-                pr.priceRoundsBatchRaw(steps, u_pin.array.ctypes.data, model.u_len, capi.PHASE_PRICE2, RC_EPS, arr)
+                pr.priceRoundsBatchRaw(steps, src.array.ctypes.data, model.u_len, capi.PHASE_PRICE2, RC_EPS, arr)
         if name == "ladder8":
             pr.stabSetCenter(duals[0])
         for _ in range(3):

@@ -372,6 +372,12 @@ struct Ctx {
     int64_t launches = 0, h2d = 0, d2h = 0;
     bool stageTiming = false;
     cudaEvent_t ev[8] = {};
+    // batches priced in chunks: the gathers of the chunks' duals run on a second stream, chunk k's DP launch waits
+    // for event k (batchPipelined in dipgpu_api.cu); option "batch_pipeline" (default 0: measured, gains <= 5 % on
+    // batches of 64+ vectors and loses on smaller ones -- the gathers get no faster beside a DP launch)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t evChunk[9] = {};
+    bool optBatchPipeline = false;
     float stageMs[6] = {0, 0, 0, 0, 0, 0};
 };
 
@@ -421,6 +427,7 @@ int ladderCore(Ctx *c, const DualFeed &f, int32_t uLen, const double *al, int nS
 
 // ------------------------------------------------ multi-device context (multi.cu)
 inline bool isMulti(const dipgpu_ctx *ctx) { return ctx && reinterpret_cast<const Ctx *>(ctx)->multi != nullptr; }
+int multiSetShardRounds(dipgpu_ctx *ctx, int64_t value);
 dipgpu_ctx *multiPrimary(dipgpu_ctx *ctx);  // the primary device's whole-model context (serves what is not sharded)
 dipgpu_ctx *multiForward(dipgpu_ctx *ctx);  // same, and "the last round" now lives there
 int multiDestroy(dipgpu_ctx *ctx);
@@ -476,7 +483,7 @@ int chooseDpGeom(Ctx *c, DpGeom *g, bool wantFuse);
 int prepareKnapsackDp(Ctx *c);  // loads the chosen kernel, sets its shared-memory limit
 int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, cudaStream_t st, const RcFuse *rf = nullptr);
 int launchKnapsackDpBatch(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
-                          double redCostEps, int nVec, cudaStream_t st, const RcFuse *rf = nullptr);
+                          double redCostEps, int nVec, cudaStream_t st, const RcFuse *rf = nullptr, int vecBase = 0);
 int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, double redCostEps, bool fuseFilter,
                         cudaStream_t st);
 // bigdp.cu -- stage (b) for rows that do not fit one CTA

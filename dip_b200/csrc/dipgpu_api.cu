@@ -1040,6 +1040,71 @@ int enqueueRoundDev(Ctx *c, const double *uDev, int32_t uLen, int32_t phase, dou
     return enqueueRound(c, &f, uLen, phase, eps, mirror, st, false);
 }
 
+// A large batch of page-locked dual vectors on a fused shape with a dual support: what bounds it is not the DP but the
+// gather of u[support] out of host memory -- thousands of small PCIe reads per vector, a request-rate limit of the
+// link (5-9 us per GAP-E vector).  The batch is therefore priced in chunks: the gathers run one after the other on a
+// second stream, chunk k's fused launch (vectors [k0, k0 + n) of the same per-vector buffers, KnapArgs::vecBase) waits
+// only for ITS gather, so the DP of a chunk runs under the gathers of the next ones.  Returns 1 when it took the batch.
+static int batchPipelined(Ctx *c, int nVec, const DualFeed &f, int32_t uLen, int32_t phase, double eps, cudaStream_t st, int *took)
+{
+    *took = 0;
+    int rc;
+    const size_t ns = c->hSupport.size();
+    if (!c->optBatchPipeline || nVec < 8 || ns == 0 || !f.host || f.staged || !c->optGatherPinned) return DIPGPU_OK;
+    const bool fused = useRcFuse(c, &rc);
+    if (rc) return rc;
+    if (!fused) return DIPGPU_OK;
+    if (c->optPull && nVec <= 64 && dpWouldCoop(c, nVec)) return DIPGPU_OK;  // (the kernel fetches the duals itself)
+    const double *dv = deviceVisible(f.host);
+    if (!dv) return DIPGPU_OK;
+    if (!c->stream2) {
+        // highest priority: a gather's few CTAs must get the SM slots that free up while a fused launch still has
+        // CTAs waiting, or the gathers would only run in the tails of the DP launches
+        int prLo = 0, prHi = 0;
+        DIPGPU_CUDA(c, cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+        DIPGPU_CUDA(c, cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prHi));
+        for (auto &e : c->evChunk) DIPGPU_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const size_t stride = (ns + 17) & ~(size_t)1;
+    if (!c->dUBatchCompact || c->cStride != stride) {
+        if ((rc = devAlloc(c, &c->dUBatchCompact, (size_t)std::max(c->batchCap, nVec) * stride))) return rc;
+        DIPGPU_CUDA(c, cudaMemset(c->dUBatchCompact, 0, sizeof(double) * (size_t)std::max(c->batchCap, nVec) * stride));
+        c->cStride = stride;
+    }
+    // chunks: a quarter of the batch, at least 4 vectors (a fused launch below ~300 CTAs is all latency), at most 8 chunks
+    int chunk = std::max(4, (nVec + 3) / 4);
+    while ((nVec + chunk - 1) / chunk > 8) ++chunk;
+    const int nChunks = (nVec + chunk - 1) / chunk;
+    const bool timed = c->stageTiming;
+    c->resultMirrored = false;
+    ++c->roundSerial;
+    c->lastRoundOnHost = false;
+    c->batchPull = RcFuse();
+    DIPGPU_CUDA(c, cudaEventRecord(c->evChunk[8], st));            // (whatever the stream still holds comes first)
+    DIPGPU_CUDA(c, cudaStreamWaitEvent(c->stream2, c->evChunk[8], 0));
+    for (int k = 0; k < nChunks; ++k) {
+        const int k0 = k * chunk, n = std::min(chunk, nVec - k0);
+        if ((rc = launchGatherDuals(c, (int)ns, c->dSupport, dv + (size_t)k0 * (size_t)uLen, (int64_t)uLen,
+                                    c->dUBatchCompact + (size_t)k0 * stride, (int64_t)stride, n, c->stream2))) return rc;
+        DIPGPU_CUDA(c, cudaEventRecord(c->evChunk[k], c->stream2));
+    }
+    c->h2d += (int64_t)sizeof(double) * (int64_t)ns * nVec;
+    if (timed) cudaEventRecord(c->ev[1], st);
+    const RcFuse rf = rcFuseCompact(c, c->dUBatchCompact, (int64_t)stride, phase);
+    for (int k = 0; k < nChunks; ++k) {
+        const int k0 = k * chunk, n = std::min(chunk, nVec - k0);
+        DIPGPU_CUDA(c, cudaStreamWaitEvent(st, c->evChunk[k], 0));
+        if (timed && k == 0) cudaEventRecord(c->ev[2], st);       // "h2d" + "redcost" = the wait for the first gather
+        c->wantMirror = true;
+        rc = launchKnapsackDpBatch(c, c->dRedCostBatch, (int64_t)c->rcStride, nullptr, 0, eps, n, st, &rf, k0);
+        c->wantMirror = false;
+        if (rc) return rc;
+    }
+    if (timed) { cudaEventRecord(c->ev[3], st); cudaEventRecord(c->ev[4], st); cudaEventRecord(c->ev[5], st); }
+    *took = 1;
+    return DIPGPU_OK;
+}
+
 // nVec dual vectors priced in one submission and decoded into outs[0..nVec).
 int batchCore(Ctx *c, int nVec, const DualFeed &f, int32_t uLen, int32_t phase, double eps, dipgpu_cols *outs)
 {
@@ -1049,6 +1114,12 @@ int batchCore(Ctx *c, int nVec, const DualFeed &f, int32_t uLen, int32_t phase, 
     if ((rc = ensureBatch(c, nVec))) return rc;
     cudaStream_t st = c->stream;
     if (c->stageTiming) cudaEventRecord(c->ev[0], st);
+    int took = 0;
+    if ((rc = batchPipelined(c, nVec, f, uLen, phase, eps, st, &took))) return rc;
+    if (took) {
+        c->haveST = false;
+        return fetchBatch(c, nVec, outs, st);
+    }
     bool compact = false;
     if ((rc = feedBatchDuals(c, f, uLen, nVec, st, &compact))) return rc;
     c->haveST = false;
@@ -1174,6 +1245,10 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (c->hStage) cudaFreeHost(c->hStage);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream2) {
+        cudaStreamDestroy(c->stream2);
+        for (auto &e : c->evChunk) if (e) cudaEventDestroy(e);
+    }
     delete c;
     return DIPGPU_OK;
 }
@@ -2403,6 +2478,7 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!c || !name) return DIPGPU_ERR_INVALID;
     if (c->multi) {
         if (!strcmp(name, "dp_debug_times")) return dipgpu_set_option(multiPrimary(ctx), name, value);
+        if (!strcmp(name, "shard_rounds")) return multiSetShardRounds(ctx, value);
         if (!strcmp(name, "round_timing")) {  // device-resident rounds: ONE event pair per device (dipgpu_last_device_ms)
             c->stageTiming = value != 0;
             return DIPGPU_OK;
@@ -2421,6 +2497,8 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "fuse_redcost")) { c->optFuseRc = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "dp_coop")) { c->optNoCoop = value == 0; return DIPGPU_OK; }
     if (!strcmp(name, "pull_duals")) { c->optPull = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "batch_pipeline")) { c->optBatchPipeline = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "shard_rounds")) return DIPGPU_OK;  // (multi-device contexts only)
     if (!strcmp(name, "result_zero_copy")) {  // 2 (diagnostics): also from the device-resident entry points
         c->optZeroCopy = value != 0;
         c->optMirrorAlways = value == 2;

@@ -374,6 +374,7 @@ struct KnapArgs {
     // u[support] contiguously; else pullSrc is the caller's whole (page-locked) dual vector and pullIdx the support's
     // rows -- into uVec (vector v: source + v*pullStride), then meet at a per-vector counter (pullCtr[v], reset by the
     // last CTA to exit) before anybody gathers duals.  No upload in front of the kernel, no host pass over the vector.
+    int vecBase;  // first vector of this launch (a batch priced in chunks: vector = vecBase + the CTA's vector coordinate)
     const double *pullSrc;
     const int32_t *pullIdx;
     long long pullStride;
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
     const int lb = ticketed ? (int)(tkIdx % gridDim.x) : (int)blockIdx.x;
     const int b = a.firstBlock + lb;
     // batched dual vectors (fused shapes only; gridDim.y == 1 otherwise): this CTA's vector
-    const long long vec = FUSE ? (ticketed ? (long long)(tkIdx / gridDim.x) : (long long)blockIdx.y) : 0;
+    const long long vec = FUSE ? (long long)a.vecBase + (ticketed ? (long long)(tkIdx / gridDim.x) : (long long)blockIdx.y) : 0;
     const int vlb = (int)vec * (int)gridDim.x + lb;  // slot of (vector, block) in the per-vector block arrays
     // the launch epoch: needed at the publication only, the load travels under everything before it
     unsigned int epochRaw = 0u;
@@ -600,7 +601,22 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
         const int k0 = min(a.pullN, lb * per), k1 = min(a.pullN, k0 + per);
         const double *src = a.pullSrc + vec * a.pullStride;
         double *dst = const_cast<double *>(a.uVec) + vec * a.uStride;
-        for (int k = k0 + t; k < k1; k += T) dst[k] = src[a.pullIdx != nullptr ? a.pullIdx[k] : k];
+        // (four fetches in flight per thread: a slice of more than T entries -- few blocks per device -- must not pay
+        // one PCIe / NVLink round trip per pass)
+        for (int kb = k0 + t; kb < k1; kb += 4 * T) {
+            int ix4[4];
+            double v4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = kb + q * T;
+                ix4[q] = k < k1 ? (a.pullIdx != nullptr ? a.pullIdx[k] : k) : -1;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v4[q] = ix4[q] >= 0 ? src[ix4[q]] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (ix4[q] >= 0) dst[kb + q * T] = v4[q];
+        }
         __threadfence();
         __syncthreads();
         if (t == 0) {
@@ -1892,7 +1908,7 @@ static void fillBackArgs(Ctx *c, const double *dRedCost, const double *dAlpha, B
 }
 
 static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
-                    double redCostEps, int nVec, bool batch, cudaStream_t st, const RcFuse *rf);
+                    double redCostEps, int nVec, bool batch, cudaStream_t st, const RcFuse *rf, int vecBase = 0);
 
 // Large-shard path under node bounds: the DP kernels read a copy of the reduced costs in which every
 // fixed column is +0 (so it is not an item); the backtrack kernel still sums the true reduced costs.
@@ -1911,13 +1927,13 @@ int launchKnapsackDp(Ctx *c, const double *dRedCost, const double *dAlpha, doubl
 // Batched dual vectors: the fused kernel only (gridDim.y = vectors); the per-vector packed results,
 // publication words and Pisinger-mode block arrays live in the context's batch buffers.
 int launchKnapsackDpBatch(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
-                          double redCostEps, int nVec, cudaStream_t st, const RcFuse *rf)
+                          double redCostEps, int nVec, cudaStream_t st, const RcFuse *rf, int vecBase)
 {
-    return launchDp(c, dRedCost, rcStride, dAlpha, alphaStride, redCostEps, nVec, true, st, rf);
+    return launchDp(c, dRedCost, rcStride, dAlpha, alphaStride, redCostEps, nVec, true, st, rf, vecBase);
 }
 
 static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const double *dAlpha, int64_t alphaStride,
-                    double redCostEps, int nVec, bool batch, cudaStream_t st, const RcFuse *rf)
+                    double redCostEps, int nVec, bool batch, cudaStream_t st, const RcFuse *rf, int vecBase)
 {
     if (c->nLocal == 0 || nVec <= 0) return DIPGPU_OK;
     if (batch && !c->geom.fuse) return fail(c, DIPGPU_ERR_STATE, "batched DP launch needs the fused kernel shape");
@@ -1984,6 +2000,7 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     a.pullStride = rf ? (long long)rf->pullStride : 0;
     a.pullN = rf ? rf->pullN : 0;
     a.pullCtr = c->dPullCtr;
+    a.vecBase = vecBase;
     if (rf && rf->pullSrc && !coop) return fail(c, DIPGPU_ERR_STATE, "in-kernel dual upload needs a co-resident grid");
     if (rf && !g.fuse) return fail(c, DIPGPU_ERR_STATE, "reduced costs can only be formed inside the fused DP kernel");
     a.useTab = (g.fuse && c->nLocal <= kFuseFilterMaxBlocks) ? 1 : 0;

@@ -94,6 +94,12 @@ struct Multi {
     std::vector<Worker *> workers;  // [1, ndev)
     uint64_t posted = 0;
     std::vector<int> shardFirst, shardCount;
+    // devices that take part in a SINGLE round (block partition).  Option "shard_rounds": -1 (default) = all of them
+    // unless one GPU runs every block side by side anyway (a fused shape whose blocks are co-resident on the primary:
+    // each block is one CTA-long latency chain, a partition cannot shorten it and pays the exchange) -- then 1;
+    // k >= 1 forces min(k, ndev).  Batches of dual vectors always use every device.
+    int nRound = 1;
+    int optShardRounds = -1;
     bool peerOK = false;  // the primary device and every other device can address each other's memory
     // duals staged once for all devices (mapped, portable pinned memory): vector v at hStage + v * support.size()
     std::vector<int32_t> support;
@@ -228,6 +234,7 @@ int multiForAll(dipgpu_ctx *ctx, int (*fn)(dipgpu_ctx *sub, void *arg), void *ar
 }
 
 void multiClearSupport(dipgpu_ctx *ctx) { M_(ctx)->support.clear(); }
+int multiSetDualSupport(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx);
 
 // Contiguous block ranges balanced by the DP work n_b * (cap_b + 1), and the columns each shard's
 // reduced-cost sweep covers: its blocks' columns, the first shard also everything in front of block 0, the
@@ -236,9 +243,13 @@ int multiSetBlocks(dipgpu_ctx *ctx)
 {
     Multi *M = M_(ctx);
     Ctx *f0 = M->full[0];
-    const int m = f0->m, n = M->ndev;
-    M->shardFirst.assign((size_t)n, 0);
-    M->shardCount.assign((size_t)n, 0);
+    const int m = f0->m;
+    int n = M->ndev;
+    if (M->optShardRounds >= 1) n = std::min(M->optShardRounds, M->ndev);
+    else if (f0->blockKind == 0 && f0->geom.fuse && f0->dpCoResident > 0 && m <= f0->dpCoResident) n = 1;
+    M->nRound = n;
+    M->shardFirst.assign((size_t)M->ndev, m);
+    M->shardCount.assign((size_t)M->ndev, 0);
     std::vector<double> pre((size_t)m + 1, 0.0);
     for (int b = 0; b < m; ++b)
         pre[(size_t)b + 1] = pre[(size_t)b] + (double)std::max(f0->hBlockColStart[(size_t)b + 1] - f0->hBlockColStart[(size_t)b], 1) *
@@ -255,19 +266,37 @@ int multiSetBlocks(dipgpu_ctx *ctx)
         M->shardFirst[(size_t)d] = cut[(size_t)d];
         M->shardCount[(size_t)d] = cut[(size_t)d + 1] - cut[(size_t)d];
     }
-    if (n == 1) return DIPGPU_OK;
+    if (M->ndev == 1) return DIPGPU_OK;
     return runAll(M, [&](int d) {
         Ctx *s = M->shard[(size_t)d];
         int rc = bind(s);
         if (!rc) rc = setBlockRange(s, M->shardFirst[(size_t)d], M->shardCount[(size_t)d]);
         if (!rc) {
-            s->shardCols = true;
+            s->shardCols = n > 1;
             s->tileColFirst = d == 0 ? 0 : s->hBlockColStart[(size_t)M->shardFirst[(size_t)d]];
-            s->tileColEnd = d == n - 1 ? -1 : s->hBlockColStart[(size_t)(M->shardFirst[(size_t)d] + M->shardCount[(size_t)d])];
+            s->tileColEnd = d >= n - 1 ? -1 : s->hBlockColStart[(size_t)(M->shardFirst[(size_t)d] + M->shardCount[(size_t)d])];
             s->tilesDirty = true;
         }
         return subFail(M, s, rc);
     });
+}
+
+// option "shard_rounds" (see Multi::nRound): re-partitions the blocks when they are already set
+int multiSetShardRounds(dipgpu_ctx *ctx, int64_t value)
+{
+    Multi *M = M_(ctx);
+    M->optShardRounds = value < 1 ? -1 : (int)std::min<int64_t>(value, 64);
+    M->lastCtx = nullptr;
+    M->shardedRoundValid = false;
+    if (!M->full[0]->haveBlocks) return DIPGPU_OK;
+    const int rc = multiSetBlocks(ctx);
+    if (rc) return rc;
+    if (!M->support.empty()) {
+        // (the shards' compact structures follow the block ranges)
+        std::vector<int32_t> sup = M->support;
+        return multiSetDualSupport(ctx, (int32_t)sup.size(), sup.data());
+    }
+    return DIPGPU_OK;
 }
 
 int multiSetDualSupport(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx)
@@ -416,7 +445,7 @@ int multiPriceRound(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phas
     Multi *M = M_(ctx);
     Ctx *front = M->front;
     if (!out) return fail(front, DIPGPU_ERR_INVALID, "price_round: NULL output");
-    if (!u || M->ndev == 1) {
+    if (!u || M->nRound == 1) {
         // the dual vector already on the primary device (left there by the pool re-pricing, which is not partitioned)
         M->lastCtx = M->full[0];
         M->shardedRoundValid = false;
@@ -448,18 +477,18 @@ int multiPriceRound(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t phas
         s->lastRoundOnHost = true;
         collectStageMs(s);
         return 0;
-    });
+    }, M->nRound);
     if (rc) return rc;
-    collectDevMs(M, M->shard, M->ndev);
+    collectDevMs(M, M->shard, M->nRound);
     M->lastCtx = nullptr;
     M->shardedRoundValid = true;
     const void *packed[64];
     size_t bytes[64];
-    for (int d = 0; d < M->ndev; ++d) {
+    for (int d = 0; d < M->nRound; ++d) {
         packed[d] = M->shard[(size_t)d]->hResult;
         bytes[d] = M->shard[(size_t)d]->resultBytes;
     }
-    return unpackShards(front, packed, bytes, M->ndev, out);
+    return unpackShards(front, packed, bytes, M->nRound, out);
 }
 
 // vectors [v0[d], v0[d+1]) go to device d: as even as possible over the first min(nVec, ndev) devices
@@ -604,7 +633,7 @@ int multiSolveBlocks(dipgpu_ctx *ctx, const double *redCostX, const double *alph
     Multi *M = M_(ctx);
     Ctx *front = M->front;
     if (!redCostX || !alpha || !out) return fail(front, DIPGPU_ERR_INVALID, "solve_blocks: NULL argument");
-    if (M->ndev == 1 || M->shardCount.empty()) {
+    if (M->nRound == 1 || M->shardCount.empty()) {
         M->lastCtx = M->full[0];
         const int rc = dipgpu_solve_blocks(H_(M->full[0]), redCostX, alpha, eps, out);
         if (rc) front->err = M->full[0]->err;
@@ -630,18 +659,18 @@ int multiSolveBlocks(dipgpu_ctx *ctx, const double *redCostX, const double *alph
         s->lastRoundOnHost = true;
         collectStageMs(s);
         return 0;
-    });
+    }, M->nRound);
     if (rc) return rc;
-    collectDevMs(M, M->shard, M->ndev);
+    collectDevMs(M, M->shard, M->nRound);
     M->lastCtx = nullptr;
     M->shardedRoundValid = true;
     const void *packed[64];
     size_t bytes[64];
-    for (int d = 0; d < M->ndev; ++d) {
+    for (int d = 0; d < M->nRound; ++d) {
         packed[d] = M->shard[(size_t)d]->hResult;
         bytes[d] = M->shard[(size_t)d]->resultBytes;
     }
-    return unpackShards(front, packed, bytes, M->ndev, out);
+    return unpackShards(front, packed, bytes, M->nRound, out);
 }
 
 // Stage (a) alone, column-partitioned: every shard sweeps its own columns and copies them into the caller's vector.
@@ -649,7 +678,7 @@ int multiCalcRedCost(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t pha
 {
     Multi *M = M_(ctx);
     if (!u || !redCostX) return fail(M->front, DIPGPU_ERR_INVALID, "calc_redcost: NULL argument");
-    if (M->ndev == 1 || M->shardCount.empty()) {
+    if (M->nRound == 1 || M->shardCount.empty()) {
         const int rc = dipgpu_calc_redcost(H_(M->full[0]), u, uLen, phase, redCostX);
         if (rc) M->front->err = M->full[0]->err;
         return rc;
@@ -675,7 +704,7 @@ int multiCalcRedCost(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t pha
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         s->d2h += (int64_t)sizeof(double) * (c1 - c0);
         return e == cudaSuccess ? 0 : subFail(M, s, cudaFail(s, e, "calc_redcost"));
-    });
+    }, M->nRound);
 }
 
 // ---------------------------------------------------------------- device-resident round over NVLink
@@ -688,12 +717,12 @@ int multiCalcRedCost(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t pha
 static int ensureGather(Multi *M)
 {
     size_t tot = 0;
-    std::vector<size_t> off((size_t)M->ndev + 1, 0);
-    for (int d = 0; d < M->ndev; ++d) {
+    std::vector<size_t> off((size_t)M->nRound + 1, 0);
+    for (int d = 0; d < M->nRound; ++d) {
         off[(size_t)d] = tot;
         tot += ResultLayout::alignUp(M->shard[(size_t)d]->resultBytes, 256);
     }
-    off[(size_t)M->ndev] = tot;
+    off[(size_t)M->nRound] = tot;
     if (M->dGather && tot == M->gatherBytes && off == M->gatherOff) return DIPGPU_OK;
     cudaSetDevice(M->dev[0]);
     if (M->dGather) cudaFree(M->dGather);
@@ -740,7 +769,7 @@ int multiPriceRoundDev(dipgpu_ctx *ctx, const double *uDev, int32_t uLen, int32_
         }
         if (front->stageTiming) cudaEventRecord(s->ev[6], st);
         return 0;
-    });
+    }, M->nRound);
     return rc;
 }
 
@@ -786,7 +815,7 @@ int multiExpandColumns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
     Multi *M = M_(ctx);
     Ctx *front = M->front;
     if (!out) return fail(front, DIPGPU_ERR_INVALID, "expand_columns: NULL output");
-    if (M->lastCtx || M->ndev == 1) {
+    if (M->lastCtx || M->nRound == 1) {
         Ctx *c = M->lastCtx ? M->lastCtx : M->full[0];
         const int rc = dipgpu_expand_columns(H_(c), tolZero, out);
         if (rc) front->err = c->err;
@@ -800,7 +829,7 @@ int multiExpandColumns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
         std::vector<uint64_t> hs;
         dipgpu_mcols mc;
     };
-    std::vector<Piece> pc((size_t)M->ndev);
+    std::vector<Piece> pc((size_t)M->nRound);
     int rc = runAll(M, [&](int d) {
         Ctx *s = M->shard[(size_t)d];
         Piece &p = pc[(size_t)d];
@@ -826,7 +855,7 @@ int multiExpandColumns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
             return subFail(M, s, r);
         }
         return 0;
-    });
+    }, M->nRound);
     if (rc) return rc;
     int nCols = 0;
     int64_t nNnz = 0;
@@ -986,7 +1015,8 @@ int dipgpu_sync(dipgpu_ctx *ctx)
     if (!rc && c->stageTiming) {
         // device time of each device's part of the last device-resident round (events on its own stream)
         for (int k = 0; k < 6; ++k) c->stageMs[k] = 0.f;
-        for (int d = 0; d < M->ndev; ++d) {
+        for (int d = 0; d < M->ndev; ++d) M->devMs[(size_t)d] = 0.f;
+        for (int d = 0; d < M->nRound; ++d) {
             Ctx *s = M->shard[(size_t)d];
             float ms = 0.f;
             cudaSetDevice(s->device);
@@ -1033,8 +1063,8 @@ int dipgpu_result_shards(const dipgpu_ctx *ctx, int32_t cap, int32_t *nShards, s
         return DIPGPU_OK;
     }
     const Multi *M = c->multi;
-    *nShards = M->ndev;
-    for (int d = 0; d < std::min<int>(cap, M->ndev); ++d) {
+    *nShards = M->nRound;
+    for (int d = 0; d < std::min<int>(cap, M->nRound); ++d) {
         if (offsets) offsets[d] = d < (int)M->gatherOff.size() ? M->gatherOff[(size_t)d] : 0;
         if (sizes) sizes[d] = M->shard[(size_t)d]->resultBytes;
     }

@@ -121,7 +121,11 @@ int dipgpu_destroy(dipgpu_ctx *ctx);
  *   dipgpu_price_round, dipgpu_solve_blocks, dipgpu_calc_redcost, dipgpu_price_round_expand
  *       the BLOCKS (contiguous ranges balanced by n_b*(cap_b+1), dipgpu_shard_ranges): device d computes the
  *       reduced costs of its blocks' columns only, solves its blocks, filters; the result is merged in block
- *       order on the host (mostNegReducedCost added in block order, Dip/src/DecompAlgo.cpp:5229-5232);
+ *       order on the host (mostNegReducedCost added in block order, Dip/src/DecompAlgo.cpp:5229-5232).
+ *       By default (option "shard_rounds" = -1) the blocks are partitioned only when that can pay: a shape whose
+ *       blocks all run side by side on ONE GPU (one CTA per block, all co-resident: GAP-E's 80 blocks on 148 SMs)
+ *       is a set of equally long latency chains -- no partition shortens it, each one adds the NVLink exchange --
+ *       so such rounds stay on the primary device; "shard_rounds" = k >= 1 forces min(k, nDevices) devices;
  *   dipgpu_price_rounds_batch, dipgpu_price_round_stab, dipgpu_price_round_stab_ladder
  *       the DUAL VECTORS: device d prices all blocks for its share of the vectors;
  *   everything else (waiting-column pool, dipgpu_price_round_which, u == NULL rounds) runs on the primary.
@@ -491,7 +495,7 @@ int dipgpu_plan_dp_geometry(int32_t smCount, int32_t nBlocks, int32_t maxCapacit
 int dipgpu_get_dp_geometry(const dipgpu_ctx *ctx, int32_t out[7]);
 
 /* Tuning / diagnostics knobs: "stage_timing", "dp_threads" (multiple of 32),
- * "dp_cells_per_thread" (odd, 1..25), "dp_items_per_step" (1, 2, or 3 with guard cells and <= 3 cells per thread), "dp_no_guard", "dp_no_prune" (1 = the fused kernel runs the DP over every active item), "fuse_redcost" (default 1: small shards form the reduced costs of their blocks' columns inside the fused DP kernel -- the whole round is ONE kernel; 0 = the stream SpMV kernel in front of it), "dp_pdl" (1 = programmatic dependent launch of the fused kernel behind the SpMV; measured slower, off by default),
+ * "dp_cells_per_thread" (odd, 1..25), "dp_items_per_step" (1, 2, or 3 with guard cells and <= 3 cells per thread), "dp_no_guard", "dp_no_prune" (1 = the fused kernel runs the DP over every active item), "fuse_redcost" (default 1: small shards form the reduced costs of their blocks' columns inside the fused DP kernel -- the whole round is ONE kernel; 0 = the stream SpMV kernel in front of it), "dp_pdl" (1 = programmatic dependent launch of the fused kernel behind the SpMV; measured slower, off by default), "shard_rounds" (multi-device contexts: see dipgpu_create_multi), "batch_pipeline" (1 = batches of >= 8 page-locked dual vectors are priced in chunks, the gathers of u[support] on a second stream beside the previous chunk's DP launch; measured: +5 % at best, off by default),
  * "spmv_lanes" (0 = TMA stream kernel), "spmv_chunk" / "spmv_max_cols" (entry / column budget of
  * a warp tile; re-tiles the matrix), "spmv_stages", "spmv_warps", "spmv_u_smem", "fuse_filter" (-1 auto, 0 = three kernels,
  * 1 = filter in the backtrack tail, 2 = backtrack + filter in the DP tail); 0 restores the automatic

@@ -296,6 +296,7 @@ int main()
         dipgpu::Pricer multi(std::vector<int>{0, nd == 2 ? 1 : 0});
         int32_t nDev = 0, peer = 0;
         dipgpu_device_count(multi.ctx(), &nDev, &peer);
+        CHECK(dipgpu_set_option(multi.ctx(), "shard_rounds", 2) == DIPGPU_OK);  // partition the blocks (the default keeps co-resident rounds on one GPU)
         CHECK(nDev == 2);
         multi.setModelCore(R, N, rowStart.data(), colInd.data(), val.data(), R, m);
         multi.setObjective(cost.data(), N);

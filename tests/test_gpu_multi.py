@@ -63,16 +63,25 @@ def single():
 @pytest.mark.parametrize("devs", _device_lists())
 @pytest.mark.parametrize("support", [False, True])
 @pytest.mark.parametrize("pinned", [False, True])
-def test_sharded_round_equals_single(single, devs, support, pinned):
+@pytest.mark.parametrize("force", [True, False])
+def test_sharded_round_equals_single(single, devs, support, pinned, force):
+    """force: option shard_rounds = number of devices (the blocks ARE partitioned); else the default policy -- this
+    model's blocks are co-resident on one GPU, so the single round stays on the primary device."""
     from dip_b200.pricer import GpuPricer, RoundResult
     p1, model, duals = single
     p1.setDualSupport(model.dual_support if support else None)
     with GpuPricer(devs) as pm:
+        if force:
+            pm.set_option("shard_rounds", len(devs))
         pm.setModel(model)
         assert pm.deviceCount()[0] == len(devs)
         rng = pm.shardRanges()
         assert rng[0][0] == 0 and sum(c for _, c in rng) == model.m
-        assert all(rng[d][0] + rng[d][1] == rng[d + 1][0] for d in range(len(devs) - 1))
+        if force:
+            assert all(rng[d][0] + rng[d][1] == rng[d + 1][0] for d in range(len(devs) - 1))
+            assert len(devs) == 1 or rng[0][1] < model.m
+        else:
+            assert rng[0][1] == model.m
         if support:
             pm.setDualSupport(model.dual_support)
         pin = capi.PinnedArray((model.u_len,), np.float64) if pinned else None
@@ -140,6 +149,25 @@ def test_batches_and_ladder_equal_single(devs, profit_mode):
 
 
 @pytest.mark.parametrize("devs", _device_lists())
+def test_shard_policy_switches_after_the_model_is_set(single, devs):
+    """shard_rounds set AFTER the blocks: the partition follows, rounds stay equal to the one-GPU round."""
+    from dip_b200.pricer import GpuPricer, RoundResult
+    p1, model, duals = single
+    p1.setDualSupport(model.dual_support)
+    with GpuPricer(devs) as pm:
+        pm.setModel(model)
+        pm.setDualSupport(model.dual_support)
+        want = p1.priceRound(duals[1], result=RoundResult(model.m, model.m, model.N))
+        for k in (len(devs), -1, 1, len(devs)):
+            pm.set_option("shard_rounds", k)
+            rng = pm.shardRanges()
+            assert sum(c for _, c in rng) == model.m
+            assert (rng[0][1] < model.m) == (k == len(devs) and len(devs) > 1)
+            _same_round(want, pm.priceRound(duals[1], result=RoundResult(model.m, model.m, model.N)), model.m)
+    p1.setDualSupport(None)
+
+
+@pytest.mark.parametrize("devs", _device_lists())
 def test_solve_blocks_partitioned(devs):
     """Stages (b)+(c) on caller-supplied reduced costs: fused shards (few blocks) and large shards (the
     three-kernel path), ragged and empty blocks, node bounds."""
@@ -147,6 +175,7 @@ def test_solve_blocks_partitioned(devs):
     for m, nhi, caphi, seed in ((40, 90, 300, 3), (900, 40, 150, 4), (5, 1500, 900, 6)):
         b = I.random_batch(m, 0, nhi, 0, caphi, seed)
         with GpuPricer(0) as p1, GpuPricer(devs) as pm:
+            pm.set_option("shard_rounds", len(devs))
             for p in (p1, pm):
                 p.setObjective(b.orig_cost)
                 p.setKnapsackBlocks(b.block_col_start, b.weight, b.capacity)
@@ -169,6 +198,7 @@ def test_device_resident_round_over_peer_memory(single, devs, support):
     p1, model, duals = single
     p1.setDualSupport(None)
     with GpuPricer(devs) as pm:
+        pm.set_option("shard_rounds", len(devs))
         pm.setModel(model)
         if support:
             pm.setDualSupport(model.dual_support)
@@ -226,6 +256,37 @@ def test_errors_and_forwarded_calls():
         assert alla == allb
         k = pm.counters()
         assert k["kernel_launches"] > 0 and k["h2d_bytes"] > 0
+
+
+@pytest.mark.parametrize("n_vec", [8, 13, 37])
+def test_pipelined_batch_of_pinned_vectors(single, n_vec):
+    """A batch of page-locked dual vectors with a dual support is priced in chunks (the gathers of u[support] on a
+    second stream, chunk k's fused launch behind its own gather): equal, vector by vector, to the unpipelined batch
+    and to the single rounds; on one GPU and partitioned over a multi-device context."""
+    from dip_b200.pricer import GpuPricer
+    p1, model, duals = single
+    p1.setDualSupport(model.dual_support)
+    pin = capi.PinnedArray((n_vec, model.u_len), np.float64)
+    for k in range(n_vec):
+        pin.array[k] = duals[k % len(duals)]
+        pin.array[k][:model.meta["n"]] *= 1.0 + 0.01 * k   # distinct vectors (the assignment rows are in the support)
+    ref = [_snap(p1.priceRound(pin.array[k].copy())) for k in range(n_vec)]
+    for pipe in (1, 0, 1):
+        p1.set_option("batch_pipeline", pipe)
+        res, arr = p1._batch_results(n_vec)
+        p1.priceRoundsBatchRaw(n_vec, pin.array.ctypes.data, model.u_len, capi.PHASE_PRICE2, 1e-4, arr)
+        got = p1._batch_finish(res, arr)
+        assert [_snap(g) for g in got] == ref, pipe
+    p1.set_option("batch_pipeline", 0)
+    with GpuPricer([0, 0]) as pm:
+        pm.set_option("batch_pipeline", 1)
+        pm.setModel(model)
+        pm.setDualSupport(model.dual_support)
+        res, arr = pm._batch_results(n_vec)
+        pm.priceRoundsBatchRaw(n_vec, pin.array.ctypes.data, model.u_len, capi.PHASE_PRICE2, 1e-4, arr)
+        assert [_snap(g) for g in pm._batch_finish(res, arr)] == ref
+    p1.setDualSupport(None)
+    pin.free()
 
 
 def test_mixed_batch_sizes_over_many_launches(single):
