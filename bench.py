@@ -147,21 +147,26 @@ class ClockSampler:
 # ------------------------------------------------------------------------- CPU baseline
 
 
-def cpu_round_fn(model, threads):
+def cpu_round_fn(model, threads, solver="dp"):
+    """One whole pricing round on the host cores (oracle/dip_oracle.c): SpMV single-threaded as DIP does it, the blocks
+    under OpenMP schedule(dynamic,1) like Dip/src/DecompAlgo.cpp:4815.  solver "dp": the restatement of the reference's
+    knapsack01 DP; "hs": the reference's own KnapsackOptimizeHS compiled from Dip/src/UtilKnapsack.cpp (oracle/_ref)."""
     from oracle import dip_oracle as orc
     orc.build()
+    mode = 0
+    if solver == "hs":
+        if not orc.enable_ref_hs():
+            raise RuntimeError("oracle/_ref is not built")
+        mode = orc.PROFIT_REF_HS
 
     def run(u):
         return orc.price_round(model.R, model.N, model.row_start, model.col_ind, model.val, model.objective, u,
                                model.n_base_rows, model.m, model.block_col_start, model.weight, model.capacity,
-                               red_cost_eps=RC_EPS, n_threads=threads, want_ind=True)
+                               profit_mode=mode, red_cost_eps=RC_EPS, n_threads=threads, want_ind=True)
     return run
 
 
-def cpu_baseline(model, duals, budget_s=10.0):
-    """The oracle ("port") timed on the host cores: whole pricing rounds, OpenMP over blocks."""
-    cores = os.cpu_count() or 1
-    run = cpu_round_fn(model, cores)
+def _time_rounds(run, duals, budget_s, max_n=2000):
     run(duals[0])
     t0 = time.perf_counter()
     n = 0
@@ -169,11 +174,64 @@ def cpu_baseline(model, duals, budget_s=10.0):
         run(duals[n % len(duals)])
         n += 1
         el = time.perf_counter() - t0
-        if el > budget_s or n >= 2000:
-            break
-    return {"value": n / el, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} whole GAP-E 80x1600 pricing rounds in {el:.2f} s (oracle/dip_oracle.c, "
-                      f"SpMV single-thread as DIP, knapsacks OpenMP dynamic,1 over blocks on {cores} threads)"}
+        if el > budget_s or n >= max_n:
+            return n, el
+
+
+def reference_solver():
+    """The CPU arm's knapsack solver: the reference's compiled Horowitz-Sahni B&B when oracle/_ref exists, else the
+    DP port."""
+    from oracle import dip_oracle as orc
+    orc.build()
+    return ("hs", "reference") if orc.have_ref() else ("dp", "port")
+
+
+def cpu_baseline(model, duals, budget_s=2.0):
+    """CPU pricing timed on the host cores: whole GAP-E rounds with the blocks priced (i) by the
+    reference's own Horowitz-Sahni B&B (KnapsackOptimizeHS, Dip/src/UtilKnapsack.cpp:246-502, compiled from the
+    reference into oracle/_ref) and (ii) by the DP port (knapsack01), each at 1 thread, at 4 (DIP's default
+    NumConcurrentThreadsSubProb, Dip/src/DecompParam.h:636) and at all host cores; and the reduced-cost sweep alone,
+    single-threaded row-major as DIP does it and column-partitioned over 8 threads.  `value` is the reference arm's
+    configuration (HS at all cores when oracle/_ref exists)."""
+    from oracle import dip_oracle as orc
+    cores = os.cpu_count() or 1
+    solver, kind = reference_solver()
+    variants = {}
+    for sv in (["hs"] if orc.have_ref() else []) + ["dp"]:
+        variants[sv] = {}
+        for th in sorted({1, min(4, cores), cores}):
+            n, el = _time_rounds(cpu_round_fn(model, th, sv), duals, budget_s)
+            variants[sv][str(th)] = n / el
+    # how far the B&B's optimum is from the exact DP's on this workload (it prunes with tolerances)
+    hs_note = None
+    if orc.have_ref():
+        a = cpu_round_fn(model, cores, "hs")(duals[0])
+        b = cpu_round_fn(model, cores, "dp")(duals[0])
+        rel = np.abs(a.z - b.z) / np.maximum(np.abs(b.z), 1.0)
+        hs_note = {"blocks_whose_optimum_differs_by_more_than_1e-9_rel": int(np.sum(rel > 1e-9)), "max_rel_diff": float(rel.max()),
+                   "note": "the B&B adds the profits in ratio order (last-bit differences) and prunes with tolerances"}
+    ua = orc.adjust_duals(duals[0], model.n_base_rows, model.m)
+    cs, ri, va = orc.csc_descending(model.R, model.N, model.row_start, model.col_ind, model.val)
+    spmv = {}
+    t0 = time.perf_counter()
+    for k in range(40):
+        orc.calc_redcost(model.R, model.N, model.row_start, model.col_ind, model.val, ua, model.objective)
+    spmv["row_major_1_thread_ms"] = (time.perf_counter() - t0) / 40 * 1e3
+    for th in sorted({1, min(8, cores)}):
+        t0 = time.perf_counter()
+        for k in range(40):
+            orc.calc_redcost_csc(model.N, cs, ri, va, ua, model.objective, n_threads=th)
+        spmv[f"column_ordered_{th}_threads_ms"] = (time.perf_counter() - t0) / 40 * 1e3
+    val = variants[solver][str(cores)]
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"whole GAP-E 80x1600 pricing rounds for {budget_s:.0f} s per variant (16 dual vectors cycled); value = "
+                      + ("KnapsackOptimizeHS from oracle/_ref" if solver == "hs" else "the DP port")
+                      + f" under OpenMP dynamic,1 over blocks on {cores} threads, SpMV single-thread as DIP",
+            "rounds_per_s": {"reference_hs_bnb": variants.get("hs"), "dp_port_knapsack01": variants["dp"]},
+            "hs_vs_exact_dp": hs_note,
+            "spmv_gap_e": spmv,
+            "note": "DIP's GAP example prices with Pisinger's combo (un-vendored, cannot be built here) and MILP "
+                    "subproblems with Cbc (absent): neither can be timed; HS is the exact solver the reference ships"}
 
 
 def run_reference(args, rank, world):
@@ -181,7 +239,8 @@ def run_reference(args, rank, world):
         return
     model, duals = workload()
     cores = os.cpu_count() or 1
-    run = cpu_round_fn(model, cores)
+    solver, kind = reference_solver()
+    run = cpu_round_fn(model, cores, solver)
     for k in range(max(args.warmup, 1)):
         run(duals[k % N_DUALS])
     # a CPU round takes milliseconds: bound the run to a few minutes
@@ -190,14 +249,17 @@ def run_reference(args, rank, world):
         run(duals[k % N_DUALS])
     el = time.perf_counter() - t0
     val = args.steps / el
+    what = ("the reference's KnapsackOptimizeHS (Dip/src/UtilKnapsack.cpp, compiled into oracle/_ref) under the OpenMP block loop "
+            "of DecompAlgo.cpp:4815" if solver == "hs" else
+            "the oracle's restatement of knapsack01 + generateVars (oracle/_ref absent)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(model),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} whole rounds; the reference's GAP pricing needs Pisinger's combo.c "
-                                   "(not vendored) so the oracle's restatement of knapsack01 + generateVars is timed"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} whole rounds on {cores} host threads: {what}; DIP's GAP example itself prices "
+                                   "with Pisinger's combo.c (not vendored)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -473,6 +535,8 @@ def single_gpu_line(args, torch, dev, local_rank):
         extras["batched"] = bench_batched(pr, model, duals, u_pin, flush_l2, torch, smem_peak)
         extras["pool"] = bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank)
         extras["mckp"] = bench_mckp(torch, local_rank, smem_peak, flush_l2)
+        extras["other_shapes"] = bench_other_shapes(torch, dev, local_rank, flush_l2)
+        extras["real_duals"] = bench_real_duals(torch, dev, local_rank, flush_l2)
     cells_mean = float(np.mean(cells_per_round))
     cells_eval_mean = float(np.mean(cells_eval_per_round))
     dp_ms = stage_ms["knapsack_dp"]
@@ -516,6 +580,14 @@ def single_gpu_line(args, torch, dev, local_rank):
         line["roofline_pool"] = extras["pool"]
     if "mckp" in extras:
         line["roofline_mckp"] = extras["mckp"]
+    if "other_shapes" in extras:
+        line["other_shapes"] = extras["other_shapes"]
+        line["gap_d_e2e_rounds_per_s"] = extras["other_shapes"]["gap_d_20x200"]["e2e_rounds_per_s"]
+        line["gap12_e2e_rounds_per_s"] = extras["other_shapes"]["gap12_class_c_10x60"]["e2e_rounds_per_s"]
+    if extras.get("real_duals"):
+        line["real_duals"] = extras["real_duals"]
+        for nm, r in extras["real_duals"].items():
+            line["real_duals_" + nm + "_e2e_rounds_per_s"] = r["e2e_rounds_per_s"]
     if expand is not None:
         line["expand_columns"] = expand
     if cpu is not None:
@@ -795,6 +867,100 @@ def bench_batched(pr, model, duals, u_pin, flush_l2, torch, smem_peak, big=0):
         }
     out["note"] = ("value / e2e above stay ONE dual vector per step (what DecompAlgo::generateVars prices per call); "
                    "these are the same rounds submitted several at a time")
+    return out
+
+
+def _time_shape(torch, dev, local_rank, model, dual_list, support, flush_l2, steps, warm=5):
+    """Rounds of `model` under the dual vectors `dual_list` (cycled): device-resident (CUDA events on the launching
+    stream, like `value`) and through the host-buffer call with pinned duals (wall clock, like `e2e`)."""
+    from dip_b200.pricer import GpuPricer, RoundResult
+    from dip_b200 import capi
+    pr = GpuPricer(local_rank)
+    pr.setModel(model)
+    if support is not None:
+        pr.setDualSupport(support)
+    stream = torch.cuda.current_stream(dev)
+    nd = len(dual_list)
+    u_dev = [torch.from_numpy(np.ascontiguousarray(u)).to(dev) for u in dual_list]
+    u_pin = capi.PinnedArray((nd, model.u_len), np.float64)
+    for k, u in enumerate(dual_list):
+        u_pin.array[k] = u
+    ptrs = [u_pin.array[k].ctypes.data for k in range(nd)]
+    res = RoundResult(model.m, model.m, model.N)
+    kept, cells, cells_ev = [], [], []
+    for k in range(nd):
+        r = pr.priceRound(dual_list[k], redCostEps=RC_EPS, result=res)
+        kept.append(r.nCols)
+        cells.append(r.cells)
+        cells_ev.append(r.cellsEvaluated)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(warm + steps):
+        flush_l2()
+        if k >= warm:
+            ev[k - warm][0].record(stream)
+        pr.priceRoundDev(u_dev[k % nd].data_ptr(), model.u_len, redCostEps=RC_EPS, stream=stream.cuda_stream)
+        if k >= warm:
+            ev[k - warm][1].record(stream)
+    torch.cuda.synchronize()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    tot = 0.0
+    for k in range(warm + steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pr.priceRoundRaw(ptrs[k % nd], model.u_len, capi.PHASE_PRICE2, RC_EPS, res)
+        if k >= warm:
+            tot += time.perf_counter() - t0
+    geom = pr.dpGeometry() if hasattr(pr, "dpGeometry") else None
+    pr.close()
+    u_pin.free()
+    return {"blocks": int(model.m), "cols": int(model.N), "rows": int(model.R), "nnz": int(model.nnz), "dual_vectors": nd,
+            "device_ms_per_round": dev_ms, "device_rounds_per_s": 1e3 / dev_ms,
+            "e2e_ms_per_round": 1e3 * tot / steps, "e2e_rounds_per_s": steps / tot,
+            "kept_columns_mean": float(np.mean(kept)), "cells_per_round": float(np.mean(cells)),
+            "cells_evaluated_per_round": float(np.mean(cells_ev))}
+
+
+def bench_other_shapes(torch, dev, local_rank, flush_l2):
+    """The other GAP shapes BASELINE.json names, same method as value / e2e: GAP class D 20x200 (configs[1]) and the
+    gap12-sized class C 10x60 (configs[0]; the OR-Library file is not in the reference tree, so a class-C instance of
+    that size is generated), each under 16 synthetic dual vectors of one node (1 % of the branch rows bounded)."""
+    out = {}
+    for name, g in (("gap_d_20x200", I.gap_class_d()), ("gap12_class_c_10x60", I.gap_class_c())):
+        model = I.gap_pricing_model(g)
+        rng = np.random.default_rng(20200 if "d_" in name else 1060)
+        br = I.gap_branch_rows(model, rng)
+        duals = [I.gap_duals(model, rng, branch_rows=br) for _ in range(16)]
+        out[name] = _time_shape(torch, dev, local_rank, model, duals, I.gap_dual_support(model, br), flush_l2, 100)
+    return out
+
+
+def bench_real_duals(torch, dev, local_rank, flush_l2):
+    """Replay of RECORDED master duals beside the synthetic ones: the dual vectors of real column-generation
+    runs (scripts/record_dual_trace.py: examples/gap_colgen.py's loop, restricted master in HiGHS) -- the whole
+    root-node run of GAP-D 20x200 (every 4th round) and the first rounds of GAP-E 80x1600 -- scattered into DIP's
+    master layout (root node: every branch row free, zero duals) and priced one vector per call."""
+    out = {}
+    for name, g in (("gap_d_20x200", I.gap_class_d()), ("gap_e_80x1600", I.gap_class_e())):
+        path = os.path.join(ROOT, "tests", "golden", "dual_trace_" + ("gap_d" if "gap_d" in name else "gap_e") + ".npz")
+        if not os.path.exists(path):
+            continue
+        tr = np.load(path)
+        model = I.gap_pricing_model(g)
+        n, m = int(tr["n"]), int(tr["m"])
+        assert n == model.meta["n"] and m == model.m
+        U = []
+        for row in tr["duals"]:
+            u = np.zeros(model.u_len)
+            u[:n] = row[:n]
+            u[model.n_base_rows:model.n_base_rows + m] = row[n:n + m]
+            U.append(u)
+        support = np.concatenate([np.arange(n), model.n_base_rows + np.arange(m)]).astype(np.int32)
+        r = _time_shape(torch, dev, local_rank, model, U, support, flush_l2, min(100, 4 * len(U)))
+        r["trace"] = {"rounds_recorded": int(tr["rounds"][-1]) + 1, "vectors_replayed": len(U),
+                      "run_converged": bool(tr["converged"]), "z_rmp_last": float(tr["z_rmp"][-1]),
+                      "lower_bound_last": float(tr["lower_bound"][-1])}
+        out[name] = r
     return out
 
 

@@ -70,13 +70,20 @@ def solve_master(model, cols):
     return float(res.fun), u, res.x[:ncol]
 
 
-def run(model, price, max_rounds=200, eps=1e-4, log=None):
-    """price(u) -> (list of (block, ind tuple, redCost, origCost, rows, vals), mostNegReducedCost)."""
+def run(model, price, max_rounds=200, eps=1e-4, log=None, init_cols=()):
+    """price(u) -> (list of (block, ind tuple, redCost, origCost, rows, vals), mostNegReducedCost).
+    init_cols: columns (block, ind, origCost, rows, vals) the master starts with beside the empty ones -- what
+    DecompAlgo::generateInitVars provides (Dip/src/DecompAlgo.cpp:3400-3560)."""
     m = model.m
     # the empty column of every block (cost 0, only its convexity row), as GAP_DecompApp returns
     # when nothing prices out (GAP_DecompApp.cpp:278-284)
     cols = [Column(b, (), 0.0, np.array([model.n_base_rows + b], np.int32), np.array([1.0])) for b in range(m)]
     seen = {(b, ()) for b in range(m)}
+    for (b, ind, oc, rows, vals) in init_cols:
+        key = (int(b), tuple(int(i) for i in ind))
+        if key not in seen:
+            seen.add(key)
+            cols.append(Column(key[0], key[1], float(oc), np.asarray(rows, np.int32), np.asarray(vals, np.float64)))
     tr = Trace()
     for it in range(max_rounds):
         z, u, lam = solve_master(model, cols)

@@ -147,6 +147,51 @@ int dip_oracle_calc_scale_factor(int n, const double *redCost, double *work)
     return scale;
 }
 
+/* ---- CPU-baseline variant (bench.py only): the reference's own Horowitz-Sahni branch and bound,
+ * KnapsackOptimizeHS (Dip/src/UtilKnapsack.cpp:246-502), compiled from the reference sources into
+ * oracle/_ref/libdip_ref_knap.so and handed in as a function pointer.  profitMode 2 prices a block with it:
+ * items = columns with redCost < 0 that fit, sorted by non-increasing p/w as KnapsackSortRatioOut does
+ * (UtilKnapsack.cpp:204-243; its own sort prints from inside the loop and is restated here), the solution mapped
+ * back to ascending column order.  n == 1 is decided directly (the reference's n == 1 branch writes x[1], :314). */
+typedef int (*dip_hs_fn)(const int, const double, double *, double *, int *, double *, int *);
+static dip_hs_fn g_hs = 0;
+void dip_oracle_set_hs(void *fn) { g_hs = (dip_hs_fn)fn; }
+
+typedef struct { double r; int i; } ratio_t;
+static int ratio_cmp(const void *a, const void *b)
+{
+    const ratio_t *x = (const ratio_t *)a, *y = (const ratio_t *)b;
+    if (x->r > y->r) return -1;
+    if (x->r < y->r) return 1;
+    return x->i - y->i;
+}
+
+static double solve_hs(int nItems, const double *p, const int32_t *w, int capacity, uint8_t *x)
+{
+    ratio_t *ra = (ratio_t *)malloc(sizeof(ratio_t) * (size_t)nItems);
+    int n = 0;
+    for (int i = 0; i < nItems; ++i)
+        if (w[i] <= capacity && w[i] > 0) { ra[n].r = p[i] / (double)w[i]; ra[n].i = i; ++n; }
+    double z = 0.0;
+    if (n == 1) {
+        x[ra[0].i] = 1;
+        z = p[ra[0].i];
+    } else if (n >= 2) {
+        qsort(ra, (size_t)n, sizeof(ratio_t), ratio_cmp);
+        double *ps = (double *)malloc(sizeof(double) * (size_t)(n + 2));
+        double *ws = (double *)malloc(sizeof(double) * (size_t)(n + 2));
+        int *xs = (int *)calloc((size_t)(n + 2), sizeof(int));
+        for (int k = 0; k < n; ++k) { ps[k] = p[ra[k].i]; ws[k] = (double)w[ra[k].i]; }
+        ps[n] = 0.0; ws[n] = 1.0e20; ps[n + 1] = 0.0; ws[n + 1] = 1.0e20;
+        int status = 0;
+        g_hs(n, (double)capacity, ps, ws, xs, &z, &status);
+        for (int k = 0; k < n; ++k) if (xs[k]) x[ra[k].i] = 1;
+        free(ps); free(ws); free(xs);
+    }
+    free(ra);
+    return z;
+}
+
 int dip_oracle_solve_block(int n, const double *redCost, const double *origCost,
                            const int32_t *weight, int capacity, int colOffset, int profitMode,
                            int32_t *ind, double *varRedCost, double *varOrigCost, double *zOut,
@@ -160,7 +205,7 @@ int dip_oracle_solve_block(int n, const double *redCost, const double *origCost,
     long weightSum = 0;
     double z = 0.0;
 
-    if (profitMode == 0) {
+    if (profitMode == 0 || profitMode == 2) {
         /* gap_func.py:102-105: tasks with negative reduced cost, obj = -rc */
         for (int j = 0; j < n; ++j) {
             if (redCost[j] < 0) {
@@ -213,6 +258,10 @@ int dip_oracle_solve_block(int n, const double *redCost, const double *origCost,
             z = best;
             solved = 1;
         }
+    }
+    if (!solved && nItems > 0 && profitMode == 2 && g_hs) {
+        z = solve_hs(nItems, p, w, capacity, x);
+        solved = 1;
     }
     if (!solved && nItems > 0) {
         /* gap_func.py:107 / GAP_KnapPisinger.h:243-249 (combo stand-in) */
@@ -687,4 +736,25 @@ int dip_oracle_solve_intknap_blocks(int m, const int32_t *blockColStart, const i
     if (mostNegReducedCost) *mostNegReducedCost = sum;
     if (cellsOut) *cellsOut = cellsTotal;
     return kept;
+}
+
+/* ---- CPU-baseline variant (bench.py only): the reduced costs on several threads.  DIP's own sweep is the
+ * single-threaded row-major scatter above; this one walks a column-ordered copy (entries of a column in DESCENDING
+ * row order, so every column adds the same products in the same order and the result is bit-equal), the columns
+ * dealt to the threads in contiguous ranges. */
+void dip_oracle_calc_redcost_csc(int N, const int64_t *colStart, const int32_t *rowInd, const double *val,
+                                 const double *uAdj, const double *c, int phase1, int nThreads, double *redCost)
+{
+    (void)nThreads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nThreads > 0 ? nThreads : 1)
+#endif
+    for (int j = 0; j < N; ++j) {
+        double y = 0.0;
+        for (int64_t e = colStart[j]; e < colStart[j + 1]; ++e) {
+            const double ui = uAdj[rowInd[e]];
+            if (ui != 0.0) y += ui * val[e];
+        }
+        redCost[j] = phase1 ? -y : c[j] - y;
+    }
 }

@@ -82,6 +82,10 @@ def _lib():
         C.c_int, _i32p, _i32p, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_double, C.c_int,
         _i32p, _f64p, _f64p, _i32p, _f64p, _f64p, _i32p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.dip_oracle_solve_mckp_blocks.restype = C.c_int
+    lib.dip_oracle_set_hs.argtypes = [C.c_void_p]
+    lib.dip_oracle_set_hs.restype = None
+    lib.dip_oracle_calc_redcost_csc.argtypes = [C.c_int, _i64p, _i32p, _f64p, _f64p, _f64p, C.c_int, C.c_int, _f64p]
+    lib.dip_oracle_calc_redcost_csc.restype = None
     lib.dip_oracle_intknap_kp.argtypes = [C.c_int, _f64p, _i32p, C.c_int, _i32p]
     lib.dip_oracle_intknap_kp.restype = C.c_double
     lib.dip_oracle_solve_intknap_blocks.argtypes = [
@@ -370,6 +374,37 @@ def string_hash(ind, els) -> str:
     k = _lib().dip_oracle_string_hash(len(ind), ind, els, buf, len(buf))
     assert k >= 0
     return buf.value.decode()
+
+
+PROFIT_REF_HS = 2   # bench.py CPU baseline: blocks priced by the reference's compiled KnapsackOptimizeHS
+
+
+def enable_ref_hs() -> bool:
+    """Hands the reference's KnapsackOptimizeHS (oracle/_ref) to the C oracle for profit_mode=PROFIT_REF_HS."""
+    if not have_ref():
+        return False
+    fn = _ref()
+    _lib().dip_oracle_set_hs(C.cast(fn, C.c_void_p))
+    return True
+
+
+def csc_descending(R, N, row_start, col_ind, val):
+    """Column-ordered copy of a row-ordered matrix, the entries of a column in DESCENDING row order."""
+    rs = np.asarray(row_start, np.int64)
+    rows = np.repeat(np.arange(R, dtype=np.int32), np.diff(rs))
+    ci = np.asarray(col_ind, np.int64)
+    order = np.lexsort((-rows.astype(np.int64), ci))
+    cs = np.zeros(N + 1, np.int64)
+    np.cumsum(np.bincount(ci, minlength=N), out=cs[1:])
+    return cs, np.ascontiguousarray(rows[order]), np.ascontiguousarray(np.asarray(val, np.float64)[order])
+
+
+def calc_redcost_csc(N, col_start, row_ind, val, u_adj, c, phase1=False, n_threads=1) -> np.ndarray:
+    out = np.zeros(N, np.float64)
+    _lib().dip_oracle_calc_redcost_csc(N, np.ascontiguousarray(col_start, np.int64), np.ascontiguousarray(row_ind, np.int32),
+                                       np.ascontiguousarray(val, np.float64), np.ascontiguousarray(u_adj, np.float64),
+                                       np.ascontiguousarray(c, np.float64), int(bool(phase1)), int(n_threads), out)
+    return out
 
 
 def ref_knapsack_hs(p, w, capacity):
