@@ -135,7 +135,7 @@ public:
         m_nBlockCols = blockColStart[m];
         if (m_nBlockCols > m_N) m_N = m_nBlockCols;
         allocResult();
-        m_roundValid = false;
+        setBlockSlices(m, [&](int b) { return blockColStart[b]; }, nullptr);
     }
 
     // One integer knapsack per block with an optional use column: the cutting-stock pricing problem (relaxed_solver /
@@ -149,7 +149,7 @@ public:
             for (int b = 0; b < m; ++b) m_nBlockCols = std::max(m_nBlockCols, useCol[b] + 1);
         if (m_nBlockCols > m_N) m_N = m_nBlockCols;
         allocResult();
-        m_roundValid = false;
+        setBlockSlices(m, [&](int b) { return blockColStart[b]; }, useCol);
     }
 
     // One multiple-choice knapsack per block (MMKP_DecompApp.cpp:52-90: one MMKP_MCKnap per block; group g owns
@@ -162,7 +162,7 @@ public:
         m_nBlockCols = groupColStart[blockGroupStart[m]];
         if (m_nBlockCols > m_N) m_N = m_nBlockCols;
         allocResult();
-        m_roundValid = false;
+        setBlockSlices(m, [&](int b) { return groupColStart[blockGroupStart[b]]; }, nullptr);
     }
 
     // Rows of the master dual vector that can carry a dual at this node (the free branch rows of
@@ -215,24 +215,28 @@ public:
     // cost EXCLUDING the convexity dual `target` -- DecompAlgo::solveRelaxed subtracts it
     // (DecompAlgo.cpp:6350-6356) -- and DecompSolStatOptimal is returned
     // (GAP_DecompApp.cpp:278-284).  All blocks of a round are solved in ONE GPU submission the
-    // first time a new reduced-cost vector is seen; the other calls of the round are served from
-    // that result.  A new round is recognised by (pointer, fingerprint of 64 sampled entries,
-    // block already served); call beginRound() to force it.  Thread-safe across different blocks
-    // only after the round's first call has returned (serialise that one, or use surface 2).
+    // first time a block's reduced costs are seen; the other calls of the round are served from
+    // that result.  Block b's column depends on redCostX only through b's own entries, so a call is
+    // served from the stored round exactly when those entries are bit-for-bit the ones the round was
+    // solved with (one memcmp of the block's slice against the round's copy of redCostX) and b was not
+    // served yet -- nothing is sampled or guessed: DIP allocates redCostX afresh every round
+    // (DecompAlgo.cpp:4700) and allocators reuse addresses, so the pointer says nothing.  Any other
+    // call starts a new round with the vector it brings.  beginRound() forces one.  Thread-safe
+    // across different blocks only after the round's first call has returned (serialise that one, or
+    // use surface 2).
     template <class VarT = DecompVar, class ListT = std::list<VarT *>>
     DecompSolverStatus solveRelaxed(int whichBlock, const double *redCostX, double /*target*/,
                                     ListT &varList)
     {
         if (whichBlock < 0 || whichBlock >= m_m) throw Error(DIPGPU_ERR_INVALID, "solveRelaxed: bad block");
-        const uint64_t fp = fingerprint(redCostX);
-        if (!m_roundValid || redCostX != m_roundPtr || fp != m_roundFp || m_served[(size_t)whichBlock]) {
+        if (!m_roundValid || m_served[(size_t)whichBlock] || !sliceUnchanged(whichBlock, redCostX)) {
             std::vector<double> zero((size_t)m_m, 0.0);
             check(dipgpu_solve_blocks(m_ctx, redCostX, zero.data(),
                                       -std::numeric_limits<double>::infinity(), &m_cols));
             m_roundValid = true;
-            m_roundPtr = redCostX;
-            m_roundFp = fp;
+            m_roundX.assign(redCostX, redCostX + m_nBlockCols);
             m_served.assign((size_t)m_m, 0);
+            ++m_roundsSolved;
         }
         m_served[(size_t)whichBlock] = 1;
         // eps = -inf keeps every block, in block order: kept column k == block k
@@ -240,6 +244,8 @@ public:
         return DecompSolStatOptimal;
     }
     void beginRound() { m_roundValid = false; }
+    // GPU submissions surface 1 has made so far (one per recognised round)
+    long roundsSolved() const { return m_roundsSolved; }
 
     // ---- after the round: DecompAlgo::addVarsToPool's per-variable work (DecompAlgo.cpp:5452-5558)
     // Master columns [A''s ; e_block] of the columns the last generateVars / solveRelaxed round
@@ -478,22 +484,23 @@ private:
         v->setBlockId(m_colBlock[(size_t)k]);
         return v;
     }
-    uint64_t fingerprint(const double *x) const
+    // the entries of redCostX block b reads: its columns [lo, hi) and, for an integer knapsack block, its use column
+    template <class F>
+    void setBlockSlices(int m, F firstCol, const int *useCol)
     {
-        uint64_t h = 1469598103934665603ull;
-        const int n = m_nBlockCols;
-        const int step = n > 64 ? n / 64 : 1;
-        for (int i = 0; i < n; i += step) {
-            uint64_t b;
-            std::memcpy(&b, x + i, 8);
-            h = (h ^ b) * 1099511628211ull;
-        }
-        if (n > 0) {
-            uint64_t b;
-            std::memcpy(&b, x + n - 1, 8);
-            h = (h ^ b) * 1099511628211ull;
-        }
-        return h;
+        m_sliceLo.resize((size_t)m + 1);
+        for (int b = 0; b <= m; ++b) m_sliceLo[(size_t)b] = firstCol(b);
+        m_sliceExtra.assign((size_t)m, -1);
+        if (useCol)
+            for (int b = 0; b < m; ++b) m_sliceExtra[(size_t)b] = useCol[b];
+        m_roundValid = false;
+    }
+    bool sliceUnchanged(int b, const double *x) const
+    {
+        const int lo = m_sliceLo[(size_t)b], hi = m_sliceLo[(size_t)b + 1];
+        if (hi > lo && std::memcmp(x + lo, m_roundX.data() + lo, sizeof(double) * (size_t)(hi - lo)) != 0) return false;
+        const int e = m_sliceExtra[(size_t)b];
+        return e < 0 || std::memcmp(x + e, m_roundX.data() + e, sizeof(double)) == 0;
     }
 
     dipgpu_ctx *m_ctx;
@@ -504,8 +511,9 @@ private:
     std::vector<double> m_colEl;
     std::vector<int64_t> m_colStart;
     bool m_roundValid;
-    const double *m_roundPtr = nullptr;
-    uint64_t m_roundFp = 0;
+    std::vector<double> m_roundX;  // the reduced costs the stored round was solved with (block columns)
+    std::vector<int> m_sliceLo, m_sliceExtra;
+    long m_roundsSolved = 0;
     std::vector<char> m_served;
     std::vector<Round> m_ladder;
 };

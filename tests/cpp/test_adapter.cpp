@@ -154,6 +154,34 @@ int main()
     // 2 (round) + 1 (expand) + 2 + 1 (+1: the columns fetched again) (round + expansion in one submission) + 1 (SpMV)
     // + <=3 (ONE submission served all 12 solveRelaxed calls)
     CHECK(launches <= 11);
+    // ---- surface 1 recognises rounds by content, not by address: DIP allocates redCostX afresh every round
+    // (DecompAlgo.cpp:4700) and the allocator may hand back the same address.  ONE entry changes in place -- one the
+    // former 64-sample fingerprint did not look at -- and the first call of the new round names a block that the
+    // stored round has not served yet: the column must come from the new vector.
+    {
+        std::vector<double> x(redCostX);
+        const long r0 = pricer->roundsSolved();
+        dipgpu::DecompVarList v0;
+        pricer->solveRelaxed(0, x.data(), u[R + 0], v0);          // every block was served above: a new round
+        CHECK(pricer->roundsSolved() == r0 + 1);
+        const int j = 3 * n + 1;                                  // block 3, not a multiple of N/64, not the last entry
+        CHECK(weight[j] <= capacity[3]);
+        x[j] = -1.0e6;                                            // the optimal column of block 3 now contains j
+        dipgpu::DecompVarList v3, v4, v3f;
+        pricer->solveRelaxed(3, x.data(), u[R + 3], v3);
+        CHECK(pricer->roundsSolved() == r0 + 2);                  // block 3's entries changed: not served from the stored round
+        CHECK(std::find(v3.front()->ind.begin(), v3.front()->ind.end(), j) != v3.front()->ind.end());
+        CHECK(v3.front()->getReducedCost() <= -1.0e6);
+        pricer->solveRelaxed(4, x.data(), u[R + 4], v4);          // block 4's entries are the stored round's: served from it
+        CHECK(pricer->roundsSolved() == r0 + 2);
+        CHECK((int)v4.front()->ind.size() == colNnz[4] && v4.front()->getReducedCost() - u[R + 4] == colRedCost[4]);
+        pricer->beginRound();                                     // forced: the same answer
+        pricer->solveRelaxed(3, x.data(), u[R + 3], v3f);
+        CHECK(pricer->roundsSolved() == r0 + 3);
+        CHECK(v3f.front()->ind == v3.front()->ind && v3f.front()->getReducedCost() == v3.front()->getReducedCost());
+        for (auto *l : {&v0, &v3, &v4, &v3f})
+            for (dipgpu::DecompVar *v : *l) delete v;
+    }
     // phase 1 prices with c = 0
     pricer->calcRedCost(u.data(), (int)u.size(), dipgpu::PHASE_PRICE1, rcx.data());
     std::vector<double> uAdj(R);
