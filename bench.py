@@ -535,6 +535,8 @@ def single_gpu_line(args, torch, dev, local_rank):
         extras["batched"] = bench_batched(pr, model, duals, u_pin, flush_l2, torch, smem_peak)
         extras["pool"] = bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank)
         extras["mckp"] = bench_mckp(torch, local_rank, smem_peak, flush_l2)
+        extras["bigdp"] = bench_bigdp(torch, local_rank, smem_peak, flush_l2)
+        extras["intknap"] = bench_intknap(torch, local_rank, smem_peak, flush_l2)
         extras["other_shapes"] = bench_other_shapes(torch, dev, local_rank, flush_l2)
         extras["real_duals"] = bench_real_duals(torch, dev, local_rank, flush_l2)
     cells_mean = float(np.mean(cells_per_round))
@@ -580,6 +582,11 @@ def single_gpu_line(args, torch, dev, local_rank):
         line["roofline_pool"] = extras["pool"]
     if "mckp" in extras:
         line["roofline_mckp"] = extras["mckp"]
+    if "bigdp" in extras:
+        line["roofline_dp_big"] = extras["bigdp"]
+        line["dp_gcups_cap1e5"] = extras["bigdp"]["gcups"]
+    if "intknap" in extras:
+        line["roofline_intknap"] = extras["intknap"]
     if "other_shapes" in extras:
         line["other_shapes"] = extras["other_shapes"]
         line["gap_d_e2e_rounds_per_s"] = extras["other_shapes"]["gap_d_20x200"]["e2e_rounds_per_s"]
@@ -1061,6 +1068,68 @@ def bench_mckp(torch, local_rank, smem_peak, flush_l2):
             "bound": "smem", "cells": cells, "ms": ms, "gcups": cells / (ms * 1e-3) / 1e9, "achieved": ach,
             "peak": smem_peak, "unit": "GB/s", "frac": ach / smem_peak if smem_peak else None,
             "algorithmic_bytes_per_cell": by_cell, "kept_columns": int(res.nCols)}
+
+
+def bench_bigdp(torch, local_rank, smem_peak, flush_l2, m=64, n=500, cap=100_000):
+    """Knapsacks whose DP row exceeds one CTA (VERDICT r1 item 5 / GAP_KnapPisinger.h:243-249: any capacity):
+    m knapsacks, n = 500, capacity 10^5, weights U{1..cap/10}."""
+    from dip_b200.pricer import GpuPricer
+    b = I.csp_batch(m=m, n=n, cap=cap, seed=77, wmax=cap // 10)
+    pr = GpuPricer(local_rank)
+    pr.setObjective(b.orig_cost)
+    pr.setKnapsackBlocks(b.block_col_start, b.weight, b.capacity)
+    geo = pr.dpGeometry()
+    pr.set_option("stage_timing", 1)
+    alpha = np.zeros(m)
+    res = pr.solveBlocks(b.red_cost, alpha, redCostEps=-np.inf)
+    ts = []
+    for _ in range(3):
+        flush_l2()
+        torch.cuda.synchronize()
+        pr.solveBlocks(b.red_cost, alpha, redCostEps=-np.inf, result=res)
+        ts.append(pr.last_stage_ms())
+    pr.close()
+    best = min(ts, key=lambda d: d["knapsack_dp"])
+    cells = float(m) * n * (cap + 1)
+    assert res.cells == cells, (res.cells, cells)
+    dp_ms = best["knapsack_dp"]
+    ach = cells * 24.0 / (dp_ms * 1e-3) / 1e9
+    return {"kernel": "knap_dp_cluster_kernel" if geo.get("cluster") else "knap_dp_big_kernel",
+            "workload": f"{m} knapsacks x n={n} x cap={cap}", "bound": "smem", "gcups": cells / (dp_ms * 1e-3) / 1e9,
+            "dp_ms": dp_ms, "backtrack_ms": best["backtrack_emit"], "achieved": ach, "peak": smem_peak, "unit": "GB/s",
+            "frac": ach / smem_peak if smem_peak else None, "algorithmic_bytes_per_cell": 24, "cells": cells, "geometry": geo}
+
+
+def bench_intknap(torch, local_rank, smem_peak, flush_l2, m=2000, n=60, cap=2000):
+    """Integer (unbounded) knapsack blocks of cutting-stock pricing (kp of
+    Dip/src/dippy/tests/test_cutting_stock.py:154-179): m patterns' pricing problems, n item lengths each, roll
+    length `cap`; cells = n x (cap + 1) table entries per block, 16 B each (value + item/source)."""
+    from dip_b200.pricer import GpuPricer
+    rng = np.random.default_rng(99)
+    bcs = (np.arange(m + 1) * n).astype(np.int32)
+    w = rng.integers(cap // 40, cap // 3, size=m * n).astype(np.int32)
+    rc = -rng.uniform(0.01, 1.0, size=m * n) * w / cap
+    pr = GpuPricer(local_rank)
+    pr.setObjective(np.zeros(m * n))
+    pr.setIntKnapBlocks(bcs, w, np.full(m, cap, np.int32))
+    pr.set_option("stage_timing", 1)
+    alpha = np.zeros(m)
+    res = pr.solveBlocks(rc, alpha, redCostEps=-np.inf)
+    ts = []
+    for _ in range(5):
+        flush_l2()
+        torch.cuda.synchronize()
+        pr.solveBlocks(rc, alpha, redCostEps=-np.inf, result=res)
+        ts.append(pr.last_stage_ms()["knapsack_dp"])
+    pr.close()
+    ms = float(min(ts[1:]))
+    cells = float(m) * n * (cap + 1)
+    ach = cells * 16.0 / (ms * 1e-3) / 1e9
+    return {"kernel": "intknap_kernel", "workload": f"{m} integer knapsacks x n={n} x cap={cap}", "bound": "smem",
+            "cells": cells, "ms": ms, "gcups": cells / (ms * 1e-3) / 1e9, "achieved": ach, "peak": smem_peak, "unit": "GB/s",
+            "frac": ach / smem_peak if smem_peak else None, "algorithmic_bytes_per_cell": 16,
+            "note": "capacity-sequential, item-parallel table (the recurrence's cell F[j] needs every F[j - w_i]): a latency "
+                    "chain of cap + 1 steps per block, many blocks side by side", "kept_columns": int(res.nCols)}
 
 
 def bench_expand(pr, model, duals, ptrs, res, flush_l2, torch, rank):

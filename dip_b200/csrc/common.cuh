@@ -206,10 +206,34 @@ struct Ctx {
     int spmvClusters = 0;                     // resident CTA pairs of the cluster variant
     uint16_t *dRowMaster16 = nullptr;         // rowMaster as uint16 when R + numConvex <= 65536
 
-    // row-major copy of A'' (expand.cu re-walks touched rows in the reference's storage order)
+    // Rows appended since the transposed structures (CSC, tiles) were last built -- dipgpu_append_core_rows on a large
+    // model (DecompConstraintSet::appendRow, Dip/src/DecompConstraintSet.h:143-163): rows [0, baseR) are in the CSC and
+    // the tiles, rows [baseR, R) in a small CSC of their own.  They are the LAST rows, i.e. the FIRST terms of every
+    // column's sum in the reference's scatter order (rows R-1..0): redcost_delta_kernel forms those leading partial
+    // sums (dSpmvInit; +0 for the untouched columns) and the stream kernel starts from them -- the same additions in
+    // the same order as after a full rebuild.  mergeDelta() folds them in (any re-tiling, or the delta growing large).
+    int baseR = 0;
+    int64_t baseNnz = 0;
+    int nDeltaCols = 0;               // columns with an entry in an appended row
+    int64_t deltaNnz = 0;
+    int32_t *dDeltaCol = nullptr;     // nDeltaCols: the columns
+    int32_t *dDeltaStart = nullptr;   // nDeltaCols + 1
+    int32_t *dDeltaRow = nullptr;     // master dual index of the entries, descending rows within a column
+    double *dDeltaVal = nullptr;
+    size_t deltaCapCols = 0, deltaCapNnz = 0;
+    double *dSpmvInit = nullptr;      // initVecs x N leading partial sums (zero outside the delta's columns)
+    int spmvInitVecs = 0;
+    int spmvULen = 0;                 // dual entries the tiles' rows index (baseR + numConvex): what the u-in-smem mode stages
+    bool spmvRow16 = false;           // the tiles store uint16 row ids
+    int64_t optDeltaMinNnz = (int64_t)1 << 20;  // option "append_delta_min_nnz": smaller models are simply rebuilt
+
+    // row-major copy of A'' (expand.cu re-walks touched rows in the reference's storage order); allocated with slack so
+    // that appended rows are copied behind the old ones
     int32_t *dCsrRowStart = nullptr;  // R+1 (only when nnz < 2^31)
     int32_t *dCsrColInd = nullptr;
     double *dCsrVal = nullptr;
+    size_t csrCapRows = 0, csrCapNnz = 0;
+    int mcolsM = 0;                   // block count the packed master-column buffer was laid out for
     // packed master columns of the last expansion
     void *dMCols = nullptr, *hMCols = nullptr;
     size_t mcolsBytes = 0, mcolsOffColStart = 0, mcolsOffHash = 0, mcolsOffEntries = 0;
@@ -326,6 +350,16 @@ struct Ctx {
     // non-NULL: the fused kernel mirrors the packed result THERE (device-visible: a peer device's gather buffer)
     // instead of into hResult
     void *mirrorBase = nullptr;
+    // Completion of a mirrored single round without cudaStreamSynchronize: the last CTA of the fused kernel to finish
+    // stores the round's serial into this word of mapped host memory (behind a system-scope fence: every CTA's part
+    // of the mirrored result is visible first) and the host entry point spins on it -- the kernel's teardown and the
+    // driver's completion handshake are off the caller's critical path (option "flag_wait", default on)
+    unsigned int *hDoneFlag = nullptr, *dDoneFlagHost = nullptr;
+    unsigned int doneSerial = 0;
+    bool flagArmed = false, wantFlag = false, optFlagWait = true;
+    bool hostTiming = false;      // option "host_timing": wall-clock stamps of the last dipgpu_price_round (diagnostics)
+    double hostUs[4] = {0, 0, 0, 0};  // enqueue done, result seen, unpacked, DP launch call begins (us after entry)
+    long long hostT0 = 0;             // entry time (steady clock, ns)
     bool optGatherPinned = true;  // sparse dual upload: read u[support] out of the caller's buffer when it is device-mapped
     size_t resultBytes = 0;
     size_t lastResultBytes = 0;  // bytes of the last packed result (sizes the next speculative D2H copy)
@@ -475,6 +509,7 @@ int launchRedCostBatch(Ctx *c, const double *dU, int64_t uStride, double *dOut, 
 int buildSpmvTiles(Ctx *c, const std::vector<int64_t> &colStart, const std::vector<int32_t> &rowMaster,
                    const std::vector<double> &val);
 int ensureSpmvTiles(Ctx *c);  // dipgpu_api.cu
+int mergeDelta(Ctx *c);       // dipgpu_api.cu: folds the rows appended since the last full build into the CSC / tiles
 // pisinger.cu -- scale factor + trivial cases of GAP_KnapPisinger::solve (profit mode 1 only)
 int launchKnapsackPrep(Ctx *c, const double *dRedCost, cudaStream_t st);
 int launchKnapsackPrepBatch(Ctx *c, const double *dRedCost, int64_t rcStride, int nVec, cudaStream_t st);

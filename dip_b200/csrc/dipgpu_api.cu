@@ -4,6 +4,8 @@
 //   H2D(u) -> reduced costs -> knapsack DP -> backtrack+emit -> filter -> D2H.
 // No CPU fallback: every compute entry point needs a live sm_100 device.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -85,10 +87,11 @@ int bind(Ctx *c)
 }
 
 // Transpose the host CSR of A'' into CSC, folding the master-dual row mapping (rows >= nBaseRows sit
-// numConvex further down, DecompAlgo.cpp:4595-4597).
+// numConvex further down, DecompAlgo.cpp:4595-4597).  Rows [0, baseR): the rows appended since the last full
+// build live in the delta (Ctx::baseR).
 void transposeCore(const Ctx *c, std::vector<int64_t> &colStart, std::vector<int32_t> &rowMaster, std::vector<double> &val)
 {
-    const int R = c->R, N = c->N;
+    const int R = c->baseR, N = c->N;
     const int64_t nnz = c->hRowStart[R];
     colStart.assign((size_t)N + 1, 0);
     for (int64_t k = 0; k < nnz; ++k) colStart[(size_t)c->hColInd[k] + 1]++;
@@ -110,9 +113,15 @@ void transposeCore(const Ctx *c, std::vector<int64_t> &colStart, std::vector<int
 
 // The warp tiles of the stream kernel (redcost.cu) are built when a sweep first needs them: the model calls
 // (set_core_csr, set_objective, append_core_rows, a column range) each only mark them stale.
+static int uploadCore(Ctx *c);
+
 int ensureSpmvTiles(Ctx *c)
 {
     if (!c->tilesDirty) return DIPGPU_OK;
+    if (c->baseR != c->R) {  // re-tiling anyway: the appended rows go into the tiles
+        const int rc = uploadCore(c);
+        if (rc) return rc;
+    }
     std::vector<int64_t> colStart;
     std::vector<int32_t> rowMaster;
     std::vector<double> val;
@@ -122,10 +131,18 @@ int ensureSpmvTiles(Ctx *c)
     return rc;
 }
 
+// Full (re)build of the device copies of A'' from the host CSR: every row, also the ones appended since the last
+// build (the delta is folded in and dropped).
 static int uploadCore(Ctx *c)
 {
     const int R = c->R, N = c->N;
     const int64_t nnz = c->hRowStart[R];
+    c->baseR = R;
+    c->baseNnz = nnz;
+    c->nDeltaCols = 0;
+    c->deltaNnz = 0;
+    devFree(&c->dSpmvInit);  // (stale leading sums must not survive the merge)
+    c->spmvInitVecs = 0;
     std::vector<int64_t> colStart;
     std::vector<int32_t> rowMaster;
     std::vector<double> val;
@@ -152,12 +169,16 @@ static int uploadCore(Ctx *c)
     }
     // row-major copy for expand.cu
     devFree(&c->dCsrRowStart); devFree(&c->dCsrColInd); devFree(&c->dCsrVal);
+    c->csrCapRows = c->csrCapNnz = 0;
     if (nnz < (int64_t)1 << 31) {
         std::vector<int32_t> rs32((size_t)R + 1);
         for (int i = 0; i <= R; ++i) rs32[i] = (int32_t)c->hRowStart[i];
-        if ((rc = devAlloc(c, &c->dCsrRowStart, (size_t)R + 1))) return rc;
-        if ((rc = devAlloc(c, &c->dCsrColInd, (size_t)nnz + 1))) return rc;
-        if ((rc = devAlloc(c, &c->dCsrVal, (size_t)nnz + 1))) return rc;
+        // (slack: rows appended later are copied behind these, appendCsrRows)
+        c->csrCapRows = (size_t)R + (size_t)R / 16 + 64;
+        c->csrCapNnz = (size_t)nnz + (size_t)nnz / 16 + 1024;
+        if ((rc = devAlloc(c, &c->dCsrRowStart, c->csrCapRows + 1))) return rc;
+        if ((rc = devAlloc(c, &c->dCsrColInd, c->csrCapNnz + 1))) return rc;
+        if ((rc = devAlloc(c, &c->dCsrVal, c->csrCapNnz + 1))) return rc;
         DIPGPU_CUDA(c, cudaMemcpy(c->dCsrRowStart, rs32.data(), sizeof(int32_t) * rs32.size(), cudaMemcpyHostToDevice));
         if (nnz > 0) {
             DIPGPU_CUDA(c, cudaMemcpy(c->dCsrColInd, c->hColInd.data(), sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
@@ -173,6 +194,12 @@ static int uploadCore(Ctx *c)
         DIPGPU_CUDA(c, cudaMemcpy(c->dVal, val.data(), sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
     }
     return DIPGPU_OK;
+}
+
+int mergeDelta(Ctx *c)
+{
+    if (c->baseR == c->R) return DIPGPU_OK;
+    return uploadCore(c);
 }
 
 // The objective buffer covers at least n columns: zero-filled when no objective was set (phase 1 / solve_blocks
@@ -387,6 +414,7 @@ static bool useRcFuse(Ctx *c, int *rcOut)
 {
     *rcOut = DIPGPU_OK;
     if (!rcFuseEligible(c) || c->nLocal > kFuseFilterMaxBlocks) return false;
+    if (c->baseR != c->R) return false;  // appended rows not folded in yet: the CSC the kernel reads lacks them
     if ((*rcOut = ensureRcFuse(c))) return false;
     const std::vector<int32_t> &be = c->hSupport.empty() ? c->hBlkEntFull : c->hBlkEntCompact;
     if ((int)be.size() != c->m + 1) return false;
@@ -586,7 +614,22 @@ int fetchResult(Ctx *c, cudaStream_t st)
     if (c->resultMirrored) {
         // the fused kernel stored the result into hResult itself (mapped pinned memory): nothing to copy
         if (c->stageTiming) cudaEventRecord(c->ev[6], st);
-        DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+        bool seen = false;
+        if (c->flagArmed) {
+            // ... and it announces the complete result through the done word: no stream synchronisation on the
+            // caller's critical path (a kernel that never gets there -- a fault -- ends the wait after 20 ms and the
+            // synchronisation below reports it)
+            const volatile unsigned int *flag = c->hDoneFlag;
+            const unsigned int want = c->doneSerial;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned int spins = 1;; ++spins) {
+                if (*flag == want) { seen = true; break; }
+                if ((spins & 0xfffu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(20)) break;
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            c->flagArmed = false;
+        }
+        if (!seen) DIPGPU_CUDA(c, cudaStreamSynchronize(st));
         const ResultHeader *h = static_cast<const ResultHeader *>(c->hResult);
         c->lastResultBytes = c->layout.offInd + sizeof(int32_t) * (size_t)h->nInd;
         c->d2h += (int64_t)c->lastResultBytes;
@@ -1225,10 +1268,11 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     if (c->multi) return multiDestroy(ctx);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    devFree(&c->dDoneCounter); devFree(&c->dSyncWords); devFree(&c->dCsrRowStart);
+    devFree(&c->dDoneCounter); devFree(&c->dSyncWords); devFree(&c->dCsrRowStart); devFree(&c->dDeltaCol); devFree(&c->dDeltaStart); devFree(&c->dDeltaRow); devFree(&c->dDeltaVal); devFree(&c->dSpmvInit);
     devFree(&c->dCStart); devFree(&c->dCIdx); devFree(&c->dCRow); devFree(&c->dCVal); devFree(&c->dAlphaIdxDense); devFree(&c->dAlphaIdxCompact); devFree(&c->dBlkEntFull); devFree(&c->dBlkEntCompact);
     devFree(&c->dUCompact); devFree(&c->dUBatchCompact); devFree(&c->dCsrColInd); devFree(&c->dCsrVal); devFree(&c->dExpPub);
     if (c->dMCols) cudaFree(c->dMCols);
+    if (c->hDoneFlag) cudaFreeHost(c->hDoneFlag);
     if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dSpmvBlob); devFree(&c->dSpmvWarpStart); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
     devFree(&c->dBits); devFree(&c->dBigRowOff); devFree(&c->dBigRows); devFree(&c->dBigItemP); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems); devFree(&c->dScale); devFree(&c->dShortcut); devFree(&c->dSel); devFree(&c->dZShort);
@@ -1323,6 +1367,81 @@ int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *ro
     return DIPGPU_OK;
 }
 
+// Rows [oldR, R) were appended to the host CSR: copy them behind the device's row-major copy and rebuild the (small)
+// CSC of all rows appended since the last full build, [baseR, R).
+static int appendDelta(Ctx *c, int oldR)
+{
+    int rc;
+    const int R = c->R;
+    const int64_t nnzOld = c->hRowStart[oldR], nnzNew = c->hRowStart[R];
+    // ---- row-major copy (expand.cu): grow by half when the slack is used up (a device-to-device copy)
+    if ((size_t)R > c->csrCapRows || (size_t)nnzNew > c->csrCapNnz) {
+        const size_t capRows = std::max((size_t)R + (size_t)R / 2 + 64, c->csrCapRows);
+        const size_t capNnz = std::max((size_t)nnzNew + (size_t)nnzNew / 2 + 1024, c->csrCapNnz);
+        int32_t *rs = nullptr, *ci = nullptr;
+        double *v = nullptr;
+        if ((rc = devAlloc(c, &rs, capRows + 1))) return rc;
+        if ((rc = devAlloc(c, &ci, capNnz + 1))) return rc;
+        if ((rc = devAlloc(c, &v, capNnz + 1))) return rc;
+        DIPGPU_CUDA(c, cudaMemcpy(rs, c->dCsrRowStart, sizeof(int32_t) * ((size_t)oldR + 1), cudaMemcpyDeviceToDevice));
+        if (nnzOld > 0) {
+            DIPGPU_CUDA(c, cudaMemcpy(ci, c->dCsrColInd, sizeof(int32_t) * (size_t)nnzOld, cudaMemcpyDeviceToDevice));
+            DIPGPU_CUDA(c, cudaMemcpy(v, c->dCsrVal, sizeof(double) * (size_t)nnzOld, cudaMemcpyDeviceToDevice));
+        }
+        devFree(&c->dCsrRowStart); devFree(&c->dCsrColInd); devFree(&c->dCsrVal);
+        c->dCsrRowStart = rs; c->dCsrColInd = ci; c->dCsrVal = v;
+        c->csrCapRows = capRows; c->csrCapNnz = capNnz;
+    }
+    {
+        std::vector<int32_t> rs32((size_t)(R - oldR));
+        for (int i = oldR + 1; i <= R; ++i) rs32[(size_t)(i - oldR - 1)] = (int32_t)c->hRowStart[(size_t)i];
+        DIPGPU_CUDA(c, cudaMemcpy(c->dCsrRowStart + oldR + 1, rs32.data(), sizeof(int32_t) * rs32.size(), cudaMemcpyHostToDevice));
+        if (nnzNew > nnzOld) {
+            DIPGPU_CUDA(c, cudaMemcpy(c->dCsrColInd + nnzOld, c->hColInd.data() + nnzOld, sizeof(int32_t) * (size_t)(nnzNew - nnzOld), cudaMemcpyHostToDevice));
+            DIPGPU_CUDA(c, cudaMemcpy(c->dCsrVal + nnzOld, c->hVal.data() + nnzOld, sizeof(double) * (size_t)(nnzNew - nnzOld), cudaMemcpyHostToDevice));
+        }
+    }
+    // ---- the delta's CSC: entries of a column in descending row order, the order the reference's scatter adds them
+    struct E { int32_t col, row; double val; };
+    std::vector<E> ent;
+    ent.reserve((size_t)(nnzNew - c->baseNnz));
+    for (int i = R - 1; i >= c->baseR; --i) {
+        const int32_t rm = i < c->nBaseRows ? i : i + c->numConvex;
+        for (int64_t k = c->hRowStart[(size_t)i]; k < c->hRowStart[(size_t)i + 1]; ++k) ent.push_back(E{c->hColInd[(size_t)k], rm, c->hVal[(size_t)k]});
+    }
+    std::stable_sort(ent.begin(), ent.end(), [](const E &x, const E &y) { return x.col < y.col; });
+    std::vector<int32_t> cols, start, rows(ent.size());
+    std::vector<double> vals(ent.size());
+    for (size_t k = 0; k < ent.size(); ++k) {
+        if (k == 0 || ent[k].col != ent[k - 1].col) { cols.push_back(ent[k].col); start.push_back((int32_t)k); }
+        rows[k] = ent[k].row;
+        vals[k] = ent[k].val;
+    }
+    start.push_back((int32_t)ent.size());
+    if (cols.size() + 1 > c->deltaCapCols) {
+        c->deltaCapCols = 2 * cols.size() + 64;
+        if ((rc = devAlloc(c, &c->dDeltaCol, c->deltaCapCols))) return rc;
+        if ((rc = devAlloc(c, &c->dDeltaStart, c->deltaCapCols + 1))) return rc;
+    }
+    if (ent.size() > c->deltaCapNnz) {
+        c->deltaCapNnz = 2 * ent.size() + 64;
+        if ((rc = devAlloc(c, &c->dDeltaRow, c->deltaCapNnz))) return rc;
+        if ((rc = devAlloc(c, &c->dDeltaVal, c->deltaCapNnz))) return rc;
+    }
+    // (synchronous copies: a sweep enqueued earlier has finished with the old arrays)
+    DIPGPU_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!cols.empty()) {
+        DIPGPU_CUDA(c, cudaMemcpy(c->dDeltaCol, cols.data(), sizeof(int32_t) * cols.size(), cudaMemcpyHostToDevice));
+        DIPGPU_CUDA(c, cudaMemcpy(c->dDeltaRow, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice));
+        DIPGPU_CUDA(c, cudaMemcpy(c->dDeltaVal, vals.data(), sizeof(double) * vals.size(), cudaMemcpyHostToDevice));
+    }
+    DIPGPU_CUDA(c, cudaMemcpy(c->dDeltaStart, start.data(), sizeof(int32_t) * start.size(), cudaMemcpyHostToDevice));
+    c->nDeltaCols = (int)cols.size();
+    c->deltaNnz = (int64_t)ent.size();
+    c->nnz = nnzNew;
+    return DIPGPU_OK;
+}
+
 int dipgpu_append_core_rows(dipgpu_ctx *ctx, int32_t nNew, const int64_t *rowStart, const int32_t *colInd, const double *val)
 {
     if (isMulti(ctx)) {
@@ -1364,7 +1483,15 @@ int dipgpu_append_core_rows(dipgpu_ctx *ctx, int32_t nNew, const int64_t *rowSta
             c->centerLen = newLen;
         }
     }
-    return uploadCore(c);
+    // Large model whose tiles are in use: the new rows go into the delta (O(new entries)), nothing is re-transposed
+    // or re-tiled.  Otherwise (small model, tiles not built yet or about to be rebuilt, the lane-cooperative kernel,
+    // the delta grown past an eighth of the matrix) everything is rebuilt with the new rows in it.
+    const int64_t total = c->hRowStart[c->R];
+    const int64_t deltaAfter = total - c->baseNnz;
+    const bool useDelta = nNew > 0 && c->baseNnz >= c->optDeltaMinNnz && !c->tilesDirty && c->nSpmvTiles > 0 && c->spmvLanes == 0 &&
+                          c->dCsrRowStart != nullptr && total < ((int64_t)1 << 31) && deltaAfter * 8 <= c->baseNnz;
+    if (!useDelta) return uploadCore(c);
+    return appendDelta(c, c->R - nNew);
 }
 
 int dipgpu_set_objective(dipgpu_ctx *ctx, const double *obj, int32_t N)
@@ -1716,15 +1843,25 @@ int dipgpu_price_round(dipgpu_ctx *ctx, const double *u, int32_t uLen, int32_t p
     cudaStream_t st = c->stream;
     DualFeed f;
     f.host = u;
-    if ((rc = enqueueRound(c, u ? &f : nullptr, uLen, phase, redCostEps, true, st, redCostXOpt != nullptr))) return rc;
+    const auto tEntry = std::chrono::steady_clock::now();
+    c->hostT0 = std::chrono::duration_cast<std::chrono::nanoseconds>(tEntry.time_since_epoch()).count();
+    auto usSince = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tEntry).count(); };
+    c->wantFlag = redCostXOpt == nullptr;  // (the copy of the reduced costs needs the stream synchronised anyway)
+    rc = enqueueRound(c, u ? &f : nullptr, uLen, phase, redCostEps, true, st, redCostXOpt != nullptr);
+    c->wantFlag = false;
+    if (rc) return rc;
+    if (c->hostTiming) c->hostUs[0] = usSince();
     if (redCostXOpt) {
         DIPGPU_CUDA(c, cudaMemcpyAsync(redCostXOpt, c->dRedCost, sizeof(double) * (size_t)c->N, cudaMemcpyDeviceToHost, st));
         c->d2h += (int64_t)sizeof(double) * c->N;
     }
     if ((rc = fetchResult(c, st))) return rc;
+    if (c->hostTiming) c->hostUs[1] = usSince();
     c->lastRoundOnHost = true;
     collectStageMs(c);
-    return unpack(c, c->hResult, c->resultBytes, out);
+    rc = unpack(c, c->hResult, c->resultBytes, out);
+    if (c->hostTiming) c->hostUs[2] = usSince();
+    return rc;
 }
 
 // ------------------------------------------------- batched / stabilised rounds
@@ -2189,13 +2326,15 @@ static int prepareExpand(Ctx *c)
     if (c->blockKind == 2) return fail(c, DIPGPU_ERR_UNSUPPORTED, "expand_columns: columns of integer knapsack blocks carry multiplicities (expand them on the host)");
     if (!c->dCsrRowStart || !c->dColStart32) return fail(c, DIPGPU_ERR_UNSUPPORTED, "expand_columns: more than 2^31 stored entries");
     int rc;
-    // packed output buffer: worst case one entry per stored entry of A'' plus one per column
-    const int64_t capEntries = c->nnz + c->m + 16;
-    const size_t offColStart = sizeof(MColsHeader);
-    const size_t offHash = offColStart + sizeof(int64_t) * ((size_t)c->m + 1);
-    const size_t offEntries = ResultLayout::alignUp(offHash + sizeof(uint64_t) * (size_t)c->m, 16);
-    const size_t bytes = offEntries + sizeof(MColEntry) * (size_t)capEntries;
-    if (bytes != c->mcolsBytes) {
+    // packed output buffer: worst case one entry per stored entry of A'' plus one per column (kept, with its slack,
+    // while rows are appended: pinned host memory of this size is expensive to allocate)
+    const int64_t needEntries = c->nnz + c->m + 16;
+    if (!c->dMCols || c->mcolsM != c->m || needEntries > c->mcolsCapEntries) {
+        const int64_t capEntries = needEntries + (c->baseR != c->R ? needEntries / 8 : 0);
+        const size_t offColStart = sizeof(MColsHeader);
+        const size_t offHash = offColStart + sizeof(int64_t) * ((size_t)c->m + 1);
+        const size_t offEntries = ResultLayout::alignUp(offHash + sizeof(uint64_t) * (size_t)c->m, 16);
+        const size_t bytes = offEntries + sizeof(MColEntry) * (size_t)capEntries;
         if (c->dMCols) cudaFree(c->dMCols);
         if (c->hMCols) cudaFreeHost(c->hMCols);
         c->dMCols = c->hMCols = nullptr;
@@ -2209,6 +2348,7 @@ static int prepareExpand(Ctx *c)
         c->mcolsOffHash = offHash;
         c->mcolsOffEntries = offEntries;
         c->mcolsCapEntries = capEntries;
+        c->mcolsM = c->m;
         c->lastMColsBytes = 0;
     }
     // a column of block b touches at most as many rows as block b's x-columns have stored entries
@@ -2217,7 +2357,7 @@ static int prepareExpand(Ctx *c)
         const int s0 = c->hBlockColStart[b], s1 = c->hBlockColStart[b + 1];
         if (s1 <= c->N) maxBlockNnz = std::max<int64_t>(maxBlockNnz, c->hColStart[s1] - c->hColStart[s0]);
     }
-    c->expMaxTouched = (int)std::min<int64_t>(maxBlockNnz, c->R);
+    c->expMaxTouched = (int)std::min<int64_t>(maxBlockNnz + (c->R - c->baseR), c->R);  // (+ every appended row: expand.cu walks them all)
     return DIPGPU_OK;
 }
 
@@ -2505,6 +2645,14 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
         return DIPGPU_OK;
     }
     if (!strcmp(name, "gather_pinned_duals")) { c->optGatherPinned = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "flag_wait")) { c->optFlagWait = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "host_timing")) {  // diagnostics: 1 = on, 0 = off, else a host pointer receiving 4 doubles (us)
+        if (value == 0 || value == 1) { c->hostTiming = value != 0; return DIPGPU_OK; }
+        memcpy(reinterpret_cast<void *>(static_cast<uintptr_t>(value)), c->hostUs, sizeof(c->hostUs));
+        return DIPGPU_OK;
+    }
+    if (!strcmp(name, "append_delta_min_nnz")) { c->optDeltaMinNnz = value; return DIPGPU_OK; }
+    if (!strcmp(name, "merge_appended_rows")) { int rc = bind(c); return rc ? rc : mergeDelta(c); }
     if (!strcmp(name, "spmv_lanes")) { c->spmvLanes = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "dp_debug_times")) {
         // diagnostics: value = host pointer (as integer) receiving 8 x nLocal uint64 globaltimer stamps of

@@ -42,6 +42,7 @@ struct ExpandArgs {
     const int32_t *csrColInd;
     const double *csrVal;
     int R, nBaseRows, numConvex;
+    int deltaRow0;  // rows [deltaRow0, R) were appended after the column-major copy was built (Ctx::baseR): not in it
     double tolZero;
     // output
     MColsHeader *outHdr;
@@ -149,6 +150,9 @@ __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __gri
             atomicOr(&RB(i >> 5), 1u << (i & 31));
         }
     }
+    // rows appended since the column-major copy was built: every one of them is walked (step 3 finds the ones the
+    // column does not touch at exactly +0, which step 4 drops like any other zero)
+    for (int i = a.deltaRow0 + t; i < a.R; i += kExpThreads) atomicOr(&RB(i >> 5), 1u << (i & 31));
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(0xffffffffu, h, off);
     if (lane == 0) sHashW[warp] = h;
@@ -319,6 +323,7 @@ int launchExpandColumns(Ctx *c, double tolZero, int nKept, cudaStream_t st)
     a.csrColInd = c->dCsrColInd;
     a.csrVal = c->dCsrVal;
     a.R = c->R;
+    a.deltaRow0 = c->baseR;
     a.nBaseRows = c->nBaseRows;
     a.numConvex = c->numConvex;
     a.tolZero = tolZero;

@@ -23,6 +23,7 @@
 // owned cell) and streamed to HBM as coalesced 32-bit words, laid out
 // [itemWord][cell] so that the backtrack can skip 1024 items per warp load.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -392,6 +393,10 @@ struct KnapArgs {
     // memory (0: none).  Every result store is repeated there, so the host needs no device-to-host copy after
     // the kernel -- the stores cross PCIe while the other blocks still run.
     long long hostOff;
+    // non-NULL: a word of mapped host memory that receives doneVal once EVERY CTA's stores (device and host mirror)
+    // are visible system-wide -- the host waits on it instead of synchronising the stream
+    unsigned int *doneFlag;
+    unsigned int doneVal;
     // FUSE (<= kFuseFilterMaxBlocks blocks): per LOCAL block {first column, capacity, first stored entry of its
     // columns in the CSC of the in-block reduced costs}, entry nLocal closes the ranges.  In the kernel
     // parameters: a CTA knows its block without a (cold) global load in front of everything else.
@@ -1676,11 +1681,22 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
         }
         dbgStamp(a.dbgTimes, 5, lb, (int)vec);
         // the last CTA to get here has seen every CTA of the launch read the epoch: the next launch gets a new one
-        if (t == 0 && atomicAdd(a.doneCtr, 1u) == gridDim.x * gridDim.y - 1u) {
-            *a.doneCtr = 0u;
-            if (pulls)
-                for (unsigned int v = 0; v < gridDim.y; ++v) a.pullCtr[v] = 0u;
-            *a.epochCtr = epochRaw + 1u;
+        if (a.doneFlag != nullptr) __syncthreads();  // every thread's mirrored stores are ordered before thread 0's fence
+        if (t == 0) {
+            if (a.doneFlag != nullptr) __threadfence_system();
+            if (atomicAdd(a.doneCtr, 1u) == gridDim.x * gridDim.y - 1u) {
+                *a.doneCtr = 0u;
+                if (pulls)
+                    for (unsigned int v = 0; v < gridDim.y; ++v) a.pullCtr[v] = 0u;
+                *a.epochCtr = epochRaw + 1u;
+                if (a.doneFlag != nullptr) {
+                    // every CTA's stores were performed system-wide (its fence.sys above) before its arrival was
+                    // counted, and the count was read before this store is issued: a device-scope fence orders the
+                    // rest (a second fence.sys would only wait once more for the link)
+                    __threadfence();
+                    *reinterpret_cast<volatile unsigned int *>(a.doneFlag) = a.doneVal;
+                }
+            }
         }
     }
 #undef RES_PUT
@@ -2047,12 +2063,31 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
             a.hostOff = (long long)(static_cast<char *>(c->dResultBatchHost) - static_cast<char *>(c->dResultBatch));
     }
     c->resultMirrored = a.hostOff != 0;
+    a.doneFlag = nullptr;
+    a.doneVal = 0u;
+    c->flagArmed = false;
+    if (c->wantFlag && c->optFlagWait && a.hostOff != 0 && !batch && !c->mirrorBase && !c->stageTiming) {
+        if (!c->hDoneFlag) {
+            void *hp = nullptr, *dp = nullptr;
+            DIPGPU_CUDA(c, cudaHostAlloc(&hp, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+            memset(hp, 0, 64);
+            DIPGPU_CUDA(c, cudaHostGetDevicePointer(&dp, hp, 0));
+            c->hDoneFlag = static_cast<unsigned int *>(hp);
+            c->dDoneFlagHost = static_cast<unsigned int *>(dp);
+        }
+        if (++c->doneSerial == 0u) ++c->doneSerial;
+        a.doneFlag = c->dDoneFlagHost;
+        a.doneVal = c->doneSerial;
+        c->flagArmed = true;
+    }
     // Option "dp_pdl" (fused fp64 shapes): programmatic dependent launch -- the CTAs may become resident while
     // the preceding kernel of the stream (the SpMV) still runs; the kernel waits (griddepcontrol.wait) before it
     // reads the reduced costs.  Measured SLOWER on GAP-E (39.5 vs 35.9 us per round: the early CTAs take SM
     // resources from the 6 us SpMV they wait for), so it is off unless asked for.  (Pisinger mode reads the
     // prep kernel's output at its very top: always a plain launch.)
     a.pdl = (g.fuse && c->profitMode == DIPGPU_PROFIT_FP64 && c->optPdl && !rf) ? 1 : 0;
+    if (c->hostTiming)
+        c->hostUs[3] = 1e-3 * (double)(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() - c->hostT0);
     if (a.pdl || coop) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(c->nLocal, nVec, 1);

@@ -90,6 +90,10 @@ struct StreamArgs {
     int stageBytes;             // bytes of one stage (>= the largest tile, multiple of 16)
     int nStages;                // stages per warp (2..kSpmvMaxStages)
     int64_t uStride, outStride; // batched dual vectors: vector v = blockIdx.y reads u + v*uStride
+    // rows appended since the tiles were built (Ctx::baseR): init[col] = the column's sum over THOSE rows, the first
+    // terms of the reference's scatter order (redcost_delta_kernel); NULL = every sum starts at +0
+    const double *init;
+    int64_t initStride;
 };
 
 // Every WARP owns an nStages-deep TMA pipeline over its own tiles.  A tile is SELF-CONTAINED in
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(1024, 1) redcost_stream_kernel(const __grid_co
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const double *uVec = a.u + (int64_t)blockIdx.y * a.uStride;
     double *outVec = a.out + (int64_t)blockIdx.y * a.outStride;
+    const double *initVec = a.init != nullptr ? a.init + (int64_t)blockIdx.y * a.initStride : nullptr;
     const int NST = a.nStages;
     const int barBytes = (NST * 8 + 15) & ~15;
     const size_t warpBytes = (size_t)barBytes + (size_t)NST * a.stageBytes;
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(1024, 1) redcost_stream_kernel(const __grid_co
             const double cj = ldsF64(cA + (uint32_t)(q * 32 + lane) * 8u);
             const int maxLen = (int)ldsU16(lenA + (uint32_t)q * 64u);  // lane 0 holds the slice's longest column
             const uint32_t offQ = offA + (uint32_t)q * stepStride * 2u;
-            if (pieceFirst) sum = 0.0;
+            if (pieceFirst) sum = (initVec != nullptr && colL != 0xffff) ? __ldg(initVec + firstCol + colL) : 0.0;
             for (int i0 = 0; i0 < maxLen; i0 += 4) {
                 // first entry of steps i0..i0+3 (4 x uint16, warp-uniform); the lanes whose column is
                 // longer than the step are a PREFIX of the warp (columns sorted by length on the host)
@@ -290,6 +295,21 @@ redcost_csc_kernel(int N, const int64_t *__restrict__ colStart,
     }
 }
 
+// The leading partial sums of the columns that have entries in appended rows (Ctx::baseR .. R): one thread per such
+// column and dual vector adds its entries' products one after the other, from +0, in descending row order, unfused --
+// what the reference's scatter has added to y[col] by the time it reaches row baseR - 1.
+__global__ void __launch_bounds__(256)
+redcost_delta_kernel(int nCols, const int32_t *__restrict__ cols, const int32_t *__restrict__ start,
+                     const int32_t *__restrict__ rowMaster, const double *__restrict__ val, const double *__restrict__ u,
+                     int64_t uStride, double *__restrict__ init, int64_t initStride)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nCols) return;
+    const double *uVec = u + (int64_t)blockIdx.y * uStride;
+    double sum = 0.0;
+    for (int e = start[k]; e < start[k + 1]; ++e) sum = __dadd_rn(sum, __dmul_rn(__ldg(uVec + rowMaster[e]), val[e]));
+    init[(int64_t)blockIdx.y * initStride + cols[k]] = sum;
+}
 
 // Launch shape of the stream kernel for this matrix (decided when the tiles are built, because the
 // tiles are dealt to the launch's warps on the host).
@@ -297,7 +317,8 @@ static void planSpmvLaunch(Ctx *c, int nTiles)
 {
     const int sms = c->smCount > 0 ? c->smCount : 148;
     const size_t maxSmem = 227 * 1024;
-    const int uLen = c->R + c->numConvex;
+    const int uLen = c->baseR + c->numConvex;  // (rows appended later are not in the tiles)
+    c->spmvULen = uLen;
     const size_t stageBytes = (size_t)c->spmvStageBytes;
     const size_t uBytes = (((size_t)uLen + 1) & ~(size_t)1) * 8 + 16;  // + the u mbarrier
     auto warpBytesFor = [&](int nst) { return (size_t)((nst * 8 + 15) & ~15) + (size_t)nst * stageBytes; };
@@ -355,7 +376,8 @@ int buildSpmvTiles(Ctx *c, const std::vector<int64_t> &colStart, const std::vect
     const int colFirst = std::max(0, std::min(c->tileColFirst, N));
     const int colEnd = c->tileColEnd < 0 ? N : std::max(colFirst, std::min(c->tileColEnd, N));
     const int nSweep = colEnd - colFirst;
-    const bool row16 = (int64_t)c->R + c->numConvex <= 65536;
+    const bool row16 = (int64_t)c->baseR + c->numConvex <= 65536;
+    c->spmvRow16 = row16;
     const int sms = c->smCount > 0 ? c->smCount : 148;
     // slices per tile: up to kSpmvColsPerLane, fewer on small matrices so that every SM still gets
     // ~16 warp tiles (a GAP-E sweep is latency-bound: more, shorter tiles in flight)
@@ -533,14 +555,40 @@ int launchRedCostBatch(Ctx *c, const double *dU, int64_t uStride, double *dOut, 
         const int rc = ensureSpmvTiles(c);
         if (rc) return rc;
     }
+    const bool delta = c->baseR != c->R;
+    if (delta && !(c->nSpmvTiles > 0 && c->spmvLanes == 0)) {
+        // the lane-cooperative kernel reads the plain CSC: fold the appended rows in first
+        int rc = mergeDelta(c);
+        if (rc || (rc = ensureSpmvTiles(c))) return rc;
+    }
     if (c->nSpmvTiles > 0 && c->spmvLanes == 0) {
         StreamArgs a;
+        a.init = nullptr;
+        a.initStride = 0;
+        if (c->baseR != c->R) {
+            if (c->spmvInitVecs < nVec) {
+                if (c->dSpmvInit) { cudaFree(c->dSpmvInit); c->dSpmvInit = nullptr; }
+                c->spmvInitVecs = 0;
+                const size_t cnt = (size_t)nVec * (size_t)c->N + 16;
+                DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&c->dSpmvInit), sizeof(double) * cnt));
+                DIPGPU_CUDA(c, cudaMemsetAsync(c->dSpmvInit, 0, sizeof(double) * cnt, st));
+                c->spmvInitVecs = nVec;
+            }
+            if (c->nDeltaCols > 0) {
+                redcost_delta_kernel<<<dim3((unsigned)((c->nDeltaCols + 255) / 256), (unsigned)nVec, 1), 256, 0, st>>>(
+                    c->nDeltaCols, c->dDeltaCol, c->dDeltaStart, c->dDeltaRow, c->dDeltaVal, dU, uStride, c->dSpmvInit, (int64_t)c->N);
+                c->launches++;
+                DIPGPU_CUDA(c, cudaGetLastError());
+            }
+            a.init = c->dSpmvInit;
+            a.initStride = (int64_t)c->N;
+        }
         a.nTiles = c->nSpmvTiles;
         a.tileRec = reinterpret_cast<const uint2 *>(c->dTileRec);
         a.warpStart = c->dSpmvWarpStart;
         a.blob = c->dSpmvBlob;
         a.u = dU;
-        a.uLen = c->R + c->numConvex;
+        a.uLen = c->spmvULen;
         a.phase1 = phase == DIPGPU_PHASE_PRICE1 ? 1 : 0;
         a.out = dOut;
         a.uStride = uStride;
@@ -548,7 +596,7 @@ int launchRedCostBatch(Ctx *c, const double *dU, int64_t uStride, double *dOut, 
         a.stageBytes = c->spmvStageBytes;
         a.nStages = c->spmvNst;
         a.uSmemBytes = c->spmvUBytes;
-        const bool row16 = (int64_t)c->R + c->numConvex <= 65536;
+        const bool row16 = c->spmvRow16;
         typedef void (*Fn)(const StreamArgs);
         const Fn fn = c->spmvMode != 0 ? (row16 ? redcost_stream_kernel<1, true> : redcost_stream_kernel<1, false>)
                                        : (row16 ? redcost_stream_kernel<0, true> : redcost_stream_kernel<0, false>);

@@ -19,6 +19,10 @@ if which == "pool":
     print(bench.bench_pool(torch, 0, 6542.4, "n/a", flush, 0))
 elif which == "mckp":
     print(bench.bench_mckp(torch, 0, 37000.0, flush))
+elif which == "bigdp":
+    print(bench.bench_bigdp(torch, 0, 37000.0, flush, m=int(sys.argv[2]) if len(sys.argv) > 2 else 64))
+elif which == "intknap":
+    print(bench.bench_intknap(torch, 0, 37000.0, flush))
 else:
     model, duals = bench.workload()
     with GpuPricer(0) as p:

@@ -638,3 +638,82 @@ def test_gap_e_many_rounds_match_oracle(oracle, pricer):
         np.testing.assert_array_equal(res.blockObj, refs[v].z)
         assert res.mostNegReducedCost == refs[v].most_neg_reduced_cost
     assert evaluated < 0.5 * sum(r.cells for r in refs)
+
+
+# ------------------------------------------------- cut rows appended in place (DecompConstraintSet::appendRow)
+
+
+def _random_rows(rng, k, N, nn, lo=-5, hi=5):
+    r = np.sort(rng.integers(0, k, size=nn))
+    rs = np.zeros(k + 1, np.int64)
+    np.cumsum(np.bincount(r, minlength=k), out=rs[1:])
+    return rs, rng.integers(0, N, size=nn).astype(np.int32), rng.uniform(lo, hi, size=nn)
+
+
+@pytest.mark.parametrize("spmv_u_smem", [0, 1])
+def test_appended_rows_stay_a_delta_and_match_a_full_rebuild(oracle, pricer, spmv_u_smem):
+    """dipgpu_append_core_rows on a model above "append_delta_min_nnz": nothing is re-transposed or re-tiled, the new
+    rows are a small CSC whose sums START every column's addition chain (they are the first terms of the reference's
+    scatter order).  Reduced costs stay bit-equal to the oracle on the whole matrix through three appends (single
+    vector, both phases, a batch), the expansion walks the new rows, and the explicit merge changes nothing."""
+    rng = np.random.default_rng(90 + spmv_u_smem)
+    m, n = 8, 300
+    N = m * n
+    R, nBase = 400, 330
+    rs, ci, v = _random_rows(rng, R, N, 30_000, -10, 10)
+    c = rng.uniform(0, 100, size=N)
+    pricer.set_option("append_delta_min_nnz", 0)
+    pricer.set_option("spmv_u_smem", spmv_u_smem)
+    pricer.setModelCore(R, N, rs, ci, v, nBase, m)
+    pricer.setObjective(c)
+    b = I.random_batch(m, n, n, 30, 400, seed=6)
+    pricer.setKnapsackBlocks(b.block_col_start, b.weight, b.capacity)
+    u = rng.standard_normal(R + m)
+    np.testing.assert_array_equal(pricer.calcRedCost(u), oracle.calc_redcost(R, N, rs, ci, v, oracle.adjust_duals(u, nBase, m), c))
+    l0 = pricer.counters()["kernel_launches"]
+    for step, (k, nn) in enumerate(((25, 700), (1, 40), (10, 0))):   # (an append of empty rows too)
+        rs2, ci2, v2 = _random_rows(rng, k, N, nn)
+        if step == 1:
+            v2[:] = np.round(v2)      # integers: exact cancellations inside a column's leading sum
+        pricer.appendCoreRows(rs2, ci2, v2)
+        rs = np.concatenate([rs, rs[-1] + rs2[1:]])
+        ci = np.concatenate([ci, ci2])
+        v = np.concatenate([v, v2])
+        R += k
+        assert pricer.R == R
+        u = rng.standard_normal(R + m)
+        u[rng.random(R + m) < 0.2] = 0.0
+        for phase in (2, 1):
+            ref = oracle.calc_redcost(R, N, rs, ci, v, oracle.adjust_duals(u, nBase, m), c, phase == 1)
+            l1 = pricer.counters()["kernel_launches"]
+            np.testing.assert_array_equal(pricer.calcRedCost(u, phase), ref)
+            # the delta kernel in front of the stream kernel: the appended rows were NOT folded into the tiles
+            assert pricer.counters()["kernel_launches"] - l1 == (2 if len(ci) > 30_000 else 1)
+        # whole rounds and a batch of them on the grown matrix
+        U = np.stack([rng.standard_normal(R + m) for _ in range(3)])
+        batch = pricer.priceRoundsBatch(U)
+        for q in range(3):
+            refq = oracle.price_round(R, N, rs, ci, v, c, U[q], nBase, m, b.block_col_start, b.weight, b.capacity)
+            np.testing.assert_array_equal(batch[q].blockObj, refq.z)
+            np.testing.assert_array_equal(batch[q].blockRedCost, refq.col_red_cost)
+            single = pricer.priceRound(U[q])
+            np.testing.assert_array_equal(single.blockObj, refq.z)
+            assert single.nCols == batch[q].nCols == int(np.sum(refq.col_keep))
+    # the expansion of the last round's columns touches the appended rows
+    res = pricer.priceRound(U[2], redCostEps=-np.inf)   # keeps every block's column
+
+    class M:
+        pass
+    model = M()
+    model.N, model.n_base_rows, model.m = N, nBase, m
+    model._rs, model._ci, model._v = rs, ci, v
+    cs, ri, va, hs = _check_expand(oracle, pricer, model, res)
+    assert (ri >= R - 36 + m).any()
+    # folding the rows in gives the same bits with one launch
+    before = pricer.calcRedCost(u)
+    pricer.set_option("merge_appended_rows", 1)
+    l1 = pricer.counters()["kernel_launches"]
+    np.testing.assert_array_equal(pricer.calcRedCost(u), before)
+    assert pricer.counters()["kernel_launches"] - l1 == 1
+    _check_expand(oracle, pricer, model, pricer.priceRound(U[2], redCostEps=-np.inf))
+    assert l0 > 0
