@@ -971,7 +971,7 @@ def bench_real_duals(torch, dev, local_rank, flush_l2):
     return out
 
 
-def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank):
+def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank, pool_kernel=None):
     """Waiting-column re-pricing (SURVEY 8f-2, DecompVarPool::setReducedCosts) on a synthetic pool:
     2*10^5 master columns of 20..80 entries over the GAP-E master rows.  Kernel time from the library's
     CUDA events (L2 flushed), algorithmic bytes 12*nnz + 24*cols + 8*uLen."""
@@ -1002,6 +1002,8 @@ def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank):
     u = np.zeros(u_len)
     u[support] = rng.uniform(0, 50, size=len(support))
     pr = GpuPricer(local_rank)
+    if pool_kernel is not None:
+        pr.set_option("pool_kernel", pool_kernel)
     pr.setModelCore(u_len - 1, 1, np.zeros(u_len, np.int64), np.zeros(0, np.int32), np.zeros(0), u_len - 1, 1)
     pr.poolAppend(cs, ri, va, oc)
     by = 12 * nnz + 24 * n_cols + 8 * u_len
@@ -1023,12 +1025,12 @@ def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank):
     ms = timed()
     pr.close()
     ach = by / (ms * 1e-3) / 1e9
-    return {"kernel": "pool_redcost_kernel<BITMAP>",
+    return {"kernel": "pool_redcost_kernel<BITMAP>" if pool_kernel == 0 else "pool_redcost_persist_kernel<%d>" % (2 if pool_kernel == 2 else 1),
             "workload": f"{n_cols} waiting columns shaped like GAP-E master columns, {nnz} entries, {u_len} master rows, "
                         f"{len(support)} of them with a dual (one node: 1 % of the branch rows bounded)",
             "note": "every stored entry gathers one dual (8 B of a 32 B sector, L2-resident): the sector traffic, not the "
                     "12 B/entry stream, bounds this pass; with the dual support declared the gathers of rows without a "
-                    "dual are skipped (shared-memory bitmap)",
+                    "dual are skipped (shared-memory bitmap); persistent CTAs, the window ring streams across tile borders",
             "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic("prof_pool_bitmap"),
             "avg_launch_ms": ms, "without_dual_support": {"avg_launch_ms": ms_plain, "achieved": by / (ms_plain * 1e-3) / 1e9,
                                                           "frac": by / (ms_plain * 1e-3) / 1e9 / hbm_peak},
@@ -1070,9 +1072,11 @@ def bench_mckp(torch, local_rank, smem_peak, flush_l2):
             "algorithmic_bytes_per_cell": by_cell, "kept_columns": int(res.nCols)}
 
 
-def bench_bigdp(torch, local_rank, smem_peak, flush_l2, m=64, n=500, cap=100_000):
+def bench_bigdp(torch, local_rank, smem_peak, flush_l2, m=60, n=500, cap=100_000):
     """Knapsacks whose DP row exceeds one CTA (VERDICT r1 item 5 / GAP_KnapPisinger.h:243-249: any capacity):
-    m knapsacks, n = 500, capacity 10^5, weights U{1..cap/10}."""
+    m knapsacks, n = 500, capacity 10^5, weights U{1..cap/10}.  One 8-CTA cluster per knapsack holds the row in
+    distributed shared memory; 15 such clusters are resident on a B200 (ncu: launch__cluster_max_active), m = 60 is
+    four full waves."""
     from dip_b200.pricer import GpuPricer
     b = I.csp_batch(m=m, n=n, cap=cap, seed=77, wmax=cap // 10)
     pr = GpuPricer(local_rank)
@@ -1094,7 +1098,7 @@ def bench_bigdp(torch, local_rank, smem_peak, flush_l2, m=64, n=500, cap=100_000
     assert res.cells == cells, (res.cells, cells)
     dp_ms = best["knapsack_dp"]
     ach = cells * 24.0 / (dp_ms * 1e-3) / 1e9
-    return {"kernel": "knap_dp_cluster_kernel" if geo.get("cluster") else "knap_dp_big_kernel",
+    return {"kernel": "knap_dp_cluster_kernel<%d>" % geo["cells_per_thread"] if geo["cells_per_thread"] > 0 else "knap_dp_big_kernel",
             "workload": f"{m} knapsacks x n={n} x cap={cap}", "bound": "smem", "gcups": cells / (dp_ms * 1e-3) / 1e9,
             "dp_ms": dp_ms, "backtrack_ms": best["backtrack_emit"], "achieved": ach, "peak": smem_peak, "unit": "GB/s",
             "frac": ach / smem_peak if smem_peak else None, "algorithmic_bytes_per_cell": 24, "cells": cells, "geometry": geo}

@@ -128,6 +128,247 @@ __global__ void __launch_bounds__(kBigThreads, 1) knap_dp_big_kernel(const __gri
     (void)sTotal;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Rows up to 16 x 13 312 cells: ONE THREAD-BLOCK CLUSTER per knapsack, the row distributed over the shared memories of
+// its CTAs (distributed shared memory) -- the same recurrence at shared-memory speed instead of L2 speed.
+//
+// CTA r of a cluster of C owns the cells [r L, (r+1) L), L = S * 1024; inside it thread t owns the cells
+// r L + s 1024 + t (s = 0..S-1), their values in REGISTERS.  For a fixed s the 32 lanes of a warp hold 32 consecutive
+// cells: the shifted read c[i-1][j-w] is a conflict-free row of shared memory -- of this CTA or of a lower-ranked one,
+// read through the cluster window (mapa + ld.shared::cluster) --, and the warp's ballot is one decision word of the
+// [item][cell / 32] table the backtrack kernel walks.  Per item: S shifted reads, S adds, S strict compares, S stores
+// of the new cells into the CTA's other row buffer, ONE cluster barrier (release / acquire: the stores are visible to
+// the next item's remote reads, and nobody overwrites a buffer somebody still reads).  Items, order, operands and tie
+// rule are those of knapsack01 (gap_func.py:160-181): optimum and decisions are bit-identical to every other DP
+// kernel here.
+constexpr int kClusterThreads = 1024;
+constexpr int kClusterMaxS = 13;   // 2 x 13 x 1024 x 8 B = 213 KB of row buffers per CTA
+constexpr int kClusterStage = 8;   // items whose decision words are staged in shared memory between two flushes
+
+struct ClusterDpArgs {
+    BigDpArgs b;
+    int S;            // cells per thread
+    int clusterSize;  // CTAs per knapsack
+};
+
+__device__ __forceinline__ unsigned clusterCtaRank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void clusterSync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ldClusterF64(uint32_t localAddr, unsigned rank)
+{
+    uint32_t remote;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(localAddr), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+template <int S>
+__global__ void __launch_bounds__(kClusterThreads, 1) knap_dp_cluster_kernel(const __grid_constant__ ClusterDpArgs ca)
+{
+    extern __shared__ __align__(16) unsigned char clSm[];
+    __shared__ int sWarpCnt[kClusterThreads / 32];
+    const BigDpArgs &a = ca.b;
+    constexpr int T = kClusterThreads;
+    constexpr int L = S * T;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int C = ca.clusterSize;
+    const int r = (int)clusterCtaRank();
+    const int lb = blockIdx.x / C, b = a.firstBlock + lb;
+    const int cs = a.blockColStart[b];
+    const int shortCode = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? a.shortcut[lb] : 0;
+    const int cap = a.capacity[b];
+    const int n = (shortCode != 0 || cap < 0) ? 0 : a.blockColStart[b + 1] - cs;
+    const double pScale = a.profitMode == DIPGPU_PROFIT_PISINGER_INT ? (double)a.scale[lb] : 0.0;
+    const long long cells = (long long)cap + 1;
+    const long long cellWords = (cells + 31) >> 5;
+    uint32_t *bits = a.bits + a.bitsOff[lb];
+    double *buf0 = reinterpret_cast<double *>(clSm);
+    // decision words of the last kClusterStage items, [item][s * 32 + warp]: written to HBM eight items at a time, so
+    // that the GPU-scope fence inside every cluster barrier (MEMBAR.ALL.GPU) rarely finds a global store in flight
+    uint32_t *sWords = reinterpret_cast<uint32_t *>(clSm + (size_t)2 * L * sizeof(double));
+    constexpr int kWordsPerItem = S * 32;
+    auto flushWords = [&](int iFirst, int count) {
+        for (int idx = t; idx < count * kWordsPerItem; idx += T) {
+            const int k = idx / kWordsPerItem, wi = idx - k * kWordsPerItem;
+            const long long gw = (long long)r * kWordsPerItem + wi;
+            if (gw < cellWords) bits[(long long)(iFirst + k) * cellWords + gw] = sWords[idx];
+        }
+    };
+    // ---- order-preserving compaction of the active items (gap_func.py:102-105): every CTA of the cluster counts,
+    // rank 0 writes the global arrays (the backtrack kernel reads them too)
+    int nIt = 0;
+    for (int base = 0; base < n; base += T) {
+        const int cl = base + t;
+        bool flag = false;
+        double rc = 0.0;
+        int w = 0;
+        if (cl < n) {
+            rc = a.redCost[cs + cl];
+            w = a.weight[cs + cl];
+            flag = rc < 0.0 && w <= cap && (a.fix == nullptr || a.fix[cs + cl] == 0);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) sWarpCnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int v = 0; v < T / 32; ++v) {
+            off += v < warp ? sWarpCnt[v] : 0;
+            tot += sWarpCnt[v];
+        }
+        if (flag && r == 0) {
+            const int pos = cs + nIt + off + __popc(bal & ((1u << lane) - 1u));
+            a.itemP[pos] = pScale != 0.0 ? (double)(long long)floor((-rc) * pScale + 0.5) : -rc;
+            a.itemW[pos] = w;
+            a.itemCol[pos] = cl;
+        }
+        nIt += tot;
+        __syncthreads();
+    }
+    if (r == 0 && t == 0) a.nItems[lb] = nIt;
+    // c[-1][.] = 0 (gap_func.py:156)
+    double mine[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        mine[s] = 0.0;
+        buf0[s * T + t] = 0.0;
+    }
+    __threadfence();   // rank 0's item arrays, before the other CTAs of the cluster read them
+    clusterSync();
+    const uint32_t bufA = (uint32_t)__cvta_generic_to_shared(buf0);
+    int cur = 0;
+    int w = nIt > 0 ? __ldcg(a.itemW + cs) : 0;
+    double p = nIt > 0 ? __ldcg(a.itemP + cs) : 0.0;
+    for (int i = 0; i < nIt; ++i) {
+        // the next item's weight and profit travel under this item's work
+        const int wNext = i + 1 < nIt ? __ldcg(a.itemW + cs + i + 1) : 0;
+        const double pNext = i + 1 < nIt ? __ldcg(a.itemP + cs + i + 1) : 0.0;
+        // cell j - w of this thread's cell (s = 0): CTA rq0 of the cluster, offset off0 of its slice; the cells s > 0 lie
+        // s T further on, in the next CTA once the offset passes L
+        const int wq = w / L, wr = w - wq * L;
+        int off0 = t - wr, rq0 = r - wq;
+        if (off0 < 0) {
+            off0 += L;
+            rq0 -= 1;
+        }
+        const uint32_t rdBase = bufA + (uint32_t)cur * (uint32_t)(L * 8);
+        double *wr_ = buf0 + (cur ^ 1) * L;
+        uint32_t myWord = 0u;
+        // the shifted cell of (s, t): this CTA's own slice (plain ld.shared -- the cluster window or a generic load of
+        // the own slice runs at the remote rate: 343 instead of 443 GCUPS), a lower CTA's (mapa + ld.shared::cluster), or
+        // none (j < w: -inf never wins, gap_func.py:161)
+        auto loadShift = [&](int off, int rq) -> double {
+            double v = __longlong_as_double((long long)0xfff0000000000000ULL);
+            const uint32_t addr = rdBase + (uint32_t)off * 8u;
+            if (rq == r) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+            else if (rq >= 0) v = ldClusterF64(addr, (unsigned)rq);
+            return v;
+        };
+        constexpr int kBatch = S > 7 ? (S + 1) / 2 : S;   // shifted reads in flight per thread (registers: 1 024 threads)
+#pragma unroll
+        for (int s0 = 0; s0 < S; s0 += kBatch) {
+            double sh[kBatch];
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+                const int s = s0 + q;
+                if (s < S) {
+                    int off = off0 + s * T, rq = rq0;
+                    if (off >= L) {
+                        off -= L;
+                        rq += 1;
+                    }
+                    sh[q] = loadShift(off, rq);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+                const int s = s0 + q;
+                if (s < S) {
+                    const double keep = mine[s];
+                    const double cand = p + sh[q];                 // gap_func.py:164
+                    const bool take = cand > keep;                 // :166 strict
+                    if (take) mine[s] = cand;
+                    wr_[s * T + t] = mine[s];
+                    const unsigned word = __ballot_sync(0xffffffffu, take);
+                    if (lane == s) myWord = word;                  // added[i][j]  (:168): lane s keeps the word of the cells s T + warp 32 ..
+                }
+            }
+        }
+        if (lane < S) sWords[(i % kClusterStage) * kWordsPerItem + lane * 32 + warp] = myWord;
+        if ((i % kClusterStage) == kClusterStage - 1) {
+            // (before the arrival: a warp that leaves the barrier may overwrite the staging area at once)
+            __syncthreads();
+            flushWords(i - (kClusterStage - 1), kClusterStage);
+        }
+        // (DIPGPU_CLUSTER_RELAXED: a CTA-scope fence and a relaxed arrival instead of the cluster-scope release, which is a
+        // MEMBAR.ALL.GPU in SASS -- measured 553 instead of 520 GCUPS, not used: the PTX memory model asks for the release)
+#ifdef DIPGPU_CLUSTER_RELAXED
+        asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+#else
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+#endif
+        cur ^= 1;
+        w = wNext;
+        p = pNext;
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    if (nIt % kClusterStage != 0) {
+        __syncthreads();
+        flushWords(nIt - nIt % kClusterStage, nIt % kClusterStage);
+    }
+    // z = c[n-1][capacity]  (gap_func.py:183)
+    if (cap < 0 || shortCode != 0) {
+        if (r == 0 && t == 0)
+            a.blockObj[lb] = cap < 0 ? __longlong_as_double((long long)0xfff0000000000000ULL) : a.zShort[lb];
+    } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            if ((long long)r * L + s * T + t == (long long)cap) a.blockObj[lb] = mine[s];
+    }
+}
+
+typedef void (*ClusterFn)(const ClusterDpArgs);
+static ClusterFn clusterFnFor(int S)
+{
+    switch (S) {
+        case 1: return knap_dp_cluster_kernel<1>;
+        case 2: return knap_dp_cluster_kernel<2>;
+        case 3: return knap_dp_cluster_kernel<3>;
+        case 4: return knap_dp_cluster_kernel<4>;
+        case 5: return knap_dp_cluster_kernel<5>;
+        case 6: return knap_dp_cluster_kernel<6>;
+        case 7: return knap_dp_cluster_kernel<7>;
+        case 8: return knap_dp_cluster_kernel<8>;
+        case 9: return knap_dp_cluster_kernel<9>;
+        case 10: return knap_dp_cluster_kernel<10>;
+        case 11: return knap_dp_cluster_kernel<11>;
+        case 12: return knap_dp_cluster_kernel<12>;
+        default: return knap_dp_cluster_kernel<13>;
+    }
+}
+
+// Cluster shape for rows of `cells` cells: the smallest power-of-two cluster whose CTAs hold them with <= 13 cells per
+// thread, then the fewest cells per thread that still cover the row.  0 = no cluster covers it (rows in global memory).
+void planClusterDp(int64_t cells, int *clusterSize, int *S)
+{
+    *clusterSize = 0;
+    *S = 0;
+    for (int C = 2; C <= 16; C *= 2) {
+        if ((int64_t)C * kClusterMaxS * kClusterThreads >= cells) {
+            *clusterSize = C;
+            *S = (int)((cells + (int64_t)C * kClusterThreads - 1) / ((int64_t)C * kClusterThreads));
+            return;
+        }
+    }
+}
+
 int launchBigDp(Ctx *c, const double *dRedCost, cudaStream_t st)
 {
     if (c->nLocal == 0) return DIPGPU_OK;
@@ -151,6 +392,47 @@ int launchBigDp(Ctx *c, const double *dRedCost, cudaStream_t st)
     a.shortcut = c->dShortcut;
     a.zShort = c->dZShort;
     a.fix = c->haveFix ? c->dFix : nullptr;
+    if (c->geom.cluster > 0 && !c->clusterUnavailable) {
+        ClusterDpArgs ca;
+        ca.b = a;
+        ca.S = c->geom.S;
+        ca.clusterSize = c->geom.cluster;
+        const ClusterFn fn = clusterFnFor(c->geom.S);
+        const size_t smem = (size_t)2 * c->geom.S * kClusterThreads * sizeof(double) + (size_t)kClusterStage * c->geom.S * 32 * sizeof(uint32_t);
+        if (c->clusterFnConfigured != (void *)fn) {
+            int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(fn), smem);
+            if (rc) return rc;
+            if (c->geom.cluster > 8)
+                DIPGPU_CUDA(c, cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)c->nLocal * (unsigned)c->geom.cluster, 1, 1);
+        cfg.blockDim = dim3(kClusterThreads, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)c->geom.cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (c->clusterFnConfigured != (void *)fn) {
+            // can the device place one such cluster at all (a 16-CTA cluster of whole-SM CTAs needs 16 free SMs in one GPC)?
+            int nClusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nClusters, fn, &cfg) != cudaSuccess || nClusters < 1) {
+                (void)cudaGetLastError();
+                c->clusterUnavailable = true;
+            }
+            c->clusterFnConfigured = (void *)fn;
+        }
+        if (!c->clusterUnavailable) {
+            DIPGPU_CUDA(c, cudaLaunchKernelEx(&cfg, fn, ca));
+            c->launches++;
+            DIPGPU_CUDA(c, cudaGetLastError());
+            return DIPGPU_OK;
+        }
+    }
     knap_dp_big_kernel<<<c->nLocal, kBigThreads, 0, st>>>(a);
     c->launches++;
     DIPGPU_CUDA(c, cudaGetLastError());

@@ -143,7 +143,8 @@ struct DpGeom {
     int chunkCols; // columns staged per TMA chunk
     int guard;     // -inf cells in front of each row buffer (0 = predicated reads)
     int fuse;      // 1: backtrack + filter run in the DP kernel's tail, decision bits stay in shared memory
-    int big;       // 1: the row does not fit one CTA (> 12 800 cells): rows in global memory (bigdp.cu), bits [item][cell/32]
+    int big;       // 1: the row does not fit one CTA (> 12 800 cells): bits [item][cell/32] (bigdp.cu)
+    int cluster;   // big: CTAs of the thread-block cluster that holds the row in distributed shared memory (S cells per thread); 0 = rows in global memory
     size_t smemBytes;
 };
 
@@ -296,6 +297,9 @@ struct Ctx {
     std::vector<int32_t> hMaxUsableW;  // per block
     int optThreads = 0, optCellsPerThread = 0, optItemsPerStep = 0, optNoGuard = 0, optNoPrune = 0, optPdl = 0;
     void *dpFnConfigured = nullptr;
+    void *clusterFnConfigured = nullptr;
+    bool clusterUnavailable = false;  // the device cannot place the planned cluster: rows in global memory instead
+    int optNoCluster = 0;   // option "dp_no_cluster": rows beyond one CTA in global memory even when a cluster would hold them
     size_t dpFnSmem = 0;
     DpGeom geom{};
 
@@ -388,6 +392,9 @@ struct Ctx {
     int32_t *dSupport = nullptr;
     uint32_t *dSupportBits = nullptr;  // one bit per master row (pool.cu)
     size_t poolFnSmem[2] = {0, 0};
+    size_t poolFnSmem2[3] = {0, 0, 0};
+    int optPoolKernel = 1;             // option "pool_kernel": 1 persistent (default), 2 persistent without the in-SM gather, 0 one CTA per 16 tiles
+    uint16_t *dSupportRank = nullptr;  // per bitmap word: support rows below it (supports of < 65 536 rows)
     double *hSupVals = nullptr;  // mapped pinned staging the scatter kernel reads: supVecCap vectors of hSupport.size()
     int supVecCap = 0;
     bool dUClean = false, dUBatchClean = false;       // the device vectors are zero outside the support
@@ -523,6 +530,7 @@ int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, do
                         cudaStream_t st);
 // bigdp.cu -- stage (b) for rows that do not fit one CTA
 int launchBigDp(Ctx *c, const double *dRedCost, cudaStream_t st);
+void planClusterDp(int64_t cells, int *clusterSize, int *S);  // bigdp.cu
 // mckp.cu -- stage (b) for multiple-choice knapsack blocks (DP + backtrack; the filter kernels follow)
 int launchMckp(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_t st);
 // intknap.cu -- stage (b) for integer knapsack blocks (table + counts + column; the filter kernels follow)

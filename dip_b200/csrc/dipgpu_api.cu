@@ -1280,7 +1280,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     freeBatch(c);
     devFree(&c->dFix); devFree(&c->dCapEff); devFree(&c->dRcEff);
     devFree(&c->dBlockGroupStart); devFree(&c->dGroupColStart);
-    devFree(&c->dSupport); devFree(&c->dSupportBits);
+    devFree(&c->dSupport); devFree(&c->dSupportBits); devFree(&c->dSupportRank);
     if (c->hSupVals) cudaFreeHost(c->hSupVals);
     devFree(&c->dCenter); devFree(&c->dPoolStart); devFree(&c->dPoolRow); devFree(&c->dPoolVal);
     devFree(&c->dPoolOrigCost); devFree(&c->dPoolRedCost); devFree(&c->dPoolFlag);
@@ -2022,10 +2022,22 @@ int dipgpu_set_dual_support(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx)
     int rc;
     if ((rc = devAlloc(c, &c->dSupport, (size_t)std::max(nIdx, 1)))) return rc;
     if (nIdx > 0) DIPGPU_CUDA(c, cudaMemcpy(c->dSupport, idx, sizeof(int32_t) * (size_t)nIdx, cudaMemcpyHostToDevice));
-    std::vector<uint32_t> bits(((size_t)(uLen + 31) / 32 + 4) & ~(size_t)3, 0u);  // whole 16-byte pieces (pool kernel)
+    std::vector<uint32_t> bits(((size_t)(uLen + 31) / 32 + 8) & ~(size_t)7, 0u);  // whole 16-byte pieces (pool kernel)
     for (int k = 0; k < nIdx; ++k) bits[(size_t)idx[k] >> 5] |= 1u << (idx[k] & 31);
     if ((rc = devAlloc(c, &c->dSupportBits, bits.size()))) return rc;
     DIPGPU_CUDA(c, cudaMemcpy(c->dSupportBits, bits.data(), sizeof(uint32_t) * bits.size(), cudaMemcpyHostToDevice));
+    // rank table of the bitmap (pool.cu, MODE 2): support rows below each word
+    devFree(&c->dSupportRank);
+    if (nIdx > 0 && nIdx < 65536) {
+        std::vector<uint16_t> pre(bits.size(), 0);
+        unsigned acc = 0;
+        for (size_t w = 0; w < bits.size(); ++w) {
+            pre[w] = (uint16_t)acc;
+            acc += (unsigned)__builtin_popcount(bits[w]);
+        }
+        if ((rc = devAlloc(c, &c->dSupportRank, pre.size()))) return rc;
+        DIPGPU_CUDA(c, cudaMemcpy(c->dSupportRank, pre.data(), sizeof(uint16_t) * pre.size(), cudaMemcpyHostToDevice));
+    }
     return DIPGPU_OK;
 }
 
@@ -2580,7 +2592,7 @@ int dipgpu_last_stage_ms(const dipgpu_ctx *ctx, float *ms6)
 
 static void geomOut(const DpGeom &g, int32_t out[7])
 {
-    out[0] = g.T; out[1] = g.big ? 0 : g.S; out[2] = g.items; out[3] = g.guard; out[4] = g.chunkCols; out[5] = (int32_t)g.smemBytes;
+    out[0] = g.T; out[1] = (g.big && !g.cluster) ? 0 : g.S; out[2] = g.items; out[3] = g.guard; out[4] = g.chunkCols; out[5] = (int32_t)g.smemBytes;
     out[6] = g.fuse;
 }
 
@@ -2645,6 +2657,14 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
         return DIPGPU_OK;
     }
     if (!strcmp(name, "gather_pinned_duals")) { c->optGatherPinned = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "dp_no_cluster")) {
+        c->optNoCluster = value != 0;
+        c->clusterFnConfigured = nullptr;
+        c->clusterUnavailable = false;
+        if (c->haveBlocks && c->blockKind == 0) return setBlockRange(c, c->firstBlock, c->nLocal);
+        return DIPGPU_OK;
+    }
+    if (!strcmp(name, "pool_kernel")) { c->optPoolKernel = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "flag_wait")) { c->optFlagWait = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "host_timing")) {  // diagnostics: 1 = on, 0 = off, else a host pointer receiving 4 doubles (us)
         if (value == 0 || value == 1) { c->hostTiming = value != 0; return DIPGPU_OK; }

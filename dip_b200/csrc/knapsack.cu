@@ -1866,6 +1866,8 @@ int chooseDpGeom(Ctx *c, DpGeom *g, bool wantFuse)
         big.T = 1024;
         big.items = 1;
         big.big = 1;
+        // ... or, up to 16 x 13 312 cells, distributed over the shared memories of a thread-block cluster
+        if (!c->optNoCluster) planClusterDp((int64_t)cells, &big.cluster, &big.S);
         *g = big;
         return DIPGPU_OK;
     }

@@ -170,16 +170,267 @@ pool_redcost_kernel(long long nCols, const int64_t *__restrict__ colStart, const
     }
 }
 
+// ---- persistent variant: one CTA per SM, every warp walks the 32-column tiles  w, w + W, w + 2W, ...  (W = warps of
+// the launch) with ONE window ring that keeps streaming across tile borders: no wave quantisation (391 CTAs of 16
+// tiles on 148 SMs were 2.6 waves), the per-CTA set-up paid once per SM, and the next tile's first windows already in
+// flight while the last ones of the current tile are added.
+//   MODE 0: duals gathered from global memory (L2);
+//   MODE 1: dual support declared: shared-memory bitmap skips the rows that cannot carry a dual;
+//   MODE 2: as 1, and the gather itself stays on the SM: u[support] is compacted into shared memory once per CTA
+//           (GAP-E: 4 240 doubles) and a row finds its slot by rank = prefix[word] + popc(bits below it in the
+//           word); no L2 round trip between a window's arrival and its products.
+// The additions and their order are those of the kernel above (per column: last entry first, unfused products).
+struct PoolArgs {
+    long long nCols;
+    const int64_t *colStart;
+    const int32_t *row;
+    const double *val;
+    const double *origCost;
+    const double *u;
+    int feasible;
+    double *out;
+    int32_t *flag;
+    const uint32_t *supportBits;   // MODE >= 1
+    int bitWords;                  // padded to a multiple of 4
+    const uint16_t *rankPrefix;    // MODE 2: support rows below word w
+    const int32_t *support;        // MODE 2
+    int nSupport;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kPoolWarpsMax * 32, 1) pool_redcost_persist_kernel(const __grid_constant__ PoolArgs a)
+{
+    extern __shared__ __align__(16) unsigned char poolSm[];
+    const int warpsPerCta = blockDim.x >> 5;
+    constexpr int kStageBytes = kPoolChunk * 12;  // values, then rows
+    unsigned char *extra = poolSm + (size_t)warpsPerCta * kPoolStages * kStageBytes;
+    const uint32_t *sBits = reinterpret_cast<const uint32_t *>(extra);
+    const uint16_t *sPre = reinterpret_cast<const uint16_t *>(extra + (size_t)a.bitWords * 4);
+    double *sU = reinterpret_cast<double *>(extra + (size_t)a.bitWords * 4 + (((size_t)a.bitWords * 2 + 15) & ~(size_t)15));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (MODE >= 1) {
+        const uint32_t dstB = (uint32_t)__cvta_generic_to_shared(const_cast<uint32_t *>(sBits));
+        for (int k = threadIdx.x * 4; k < a.bitWords; k += blockDim.x * 4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstB + 4u * k), "l"(a.supportBits + k) : "memory");
+        if (MODE == 2) {
+            const uint32_t dstP = (uint32_t)__cvta_generic_to_shared(const_cast<uint16_t *>(sPre));
+            for (int k = threadIdx.x * 8; k < a.bitWords; k += blockDim.x * 8)  // (bitWords % 8 == 0 in this mode)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstP + 2u * k), "l"(a.rankPrefix + k) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    const long long nTiles = (a.nCols + 31) / 32;
+    const long long W = (long long)gridDim.x * warpsPerCta;
+    // a tile as the warp sees it: its span [B, E) of the pool (uniform) and the lane's own column [b, e), cost oc
+    struct Tile { long long id; int64_t B, E, kFirst, kLast, b, e; double oc; };
+    auto loadTile = [&](long long id) {
+        Tile t;
+        t.id = id;
+        t.B = t.E = t.b = t.e = 0;
+        t.kFirst = 0;
+        t.kLast = -1;
+        t.oc = 0.0;
+        if (id < nTiles) {
+            const long long c0 = id * 32, col = c0 + lane;
+            const int64_t cs = a.colStart[min(col, a.nCols)];
+            t.E = a.colStart[min(c0 + 32, a.nCols)];
+            t.B = __shfl_sync(0xffffffffu, cs, 0);
+            const int64_t nx = __shfl_down_sync(0xffffffffu, cs, 1);
+            t.b = cs;
+            t.e = lane == 31 ? t.E : nx;
+            t.oc = col < a.nCols ? a.origCost[col] : 0.0;
+            if (t.E > t.B) {
+                t.kLast = (t.E - 1) / kPoolChunk;
+                t.kFirst = t.B / kPoolChunk;
+            }
+        }
+        return t;
+    };
+    unsigned char *ring = poolSm + (size_t)warp * kPoolStages * kStageBytes;
+    const uint32_t ringA = (uint32_t)__cvta_generic_to_shared(ring);
+    auto issue = [&](int64_t k, int slot) {
+        const uint32_t dst = ringA + (uint32_t)slot * kStageBytes;
+        const char *sv = reinterpret_cast<const char *>(a.val + k * kPoolChunk);
+        const char *sr = reinterpret_cast<const char *>(a.row + k * kPoolChunk);
+#pragma unroll
+        for (int j = 0; j < kPoolChunk / 64; ++j) {
+            const int off = (lane + 32 * j) * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(sv + off) : "memory");
+        }
+#pragma unroll
+        for (int j = 0; j < kPoolChunk / 128; ++j) {
+            const int off = (lane + 32 * j) * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + kPoolChunk * 8 + off), "l"(sr + off) : "memory");
+        }
+    };
+
+    Tile A = loadTile((long long)blockIdx.x * warpsPerCta + warp);
+    Tile N = loadTile(A.id + W);
+    unsigned pc = 0, cc = 0;     // windows issued / consumed by this warp (ring slot = count % kPoolStages)
+    int prodInNext = 0;          // the producer has moved on to tile N
+    int64_t pk = A.kLast;        // next window the producer issues (descending), in A or in N
+    auto topUp = [&]() {
+        while (pc - cc < (unsigned)kPoolStages) {
+            if (!prodInNext && pk < A.kFirst) {
+                if (N.kLast < N.kFirst) break;   // (no next tile, or an empty one: the producer waits for the rotation)
+                prodInNext = 1;
+                pk = N.kLast;
+            }
+            if (prodInNext && pk < N.kFirst) break;
+            issue(pk--, (int)(pc % kPoolStages));
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            ++pc;
+        }
+    };
+    topUp();   // the stream starts before anybody waits for the bitmap / the compacted duals
+    if (MODE == 2) {
+        for (int k = threadIdx.x; k < a.nSupport; k += blockDim.x) sU[k] = __ldg(a.u + __ldg(a.support + k));
+        if (threadIdx.x == 0) sU[a.nSupport] = 0.0;   // where the rows without a dual point
+    }
+    if (MODE >= 1) {
+        // this thread's pieces of the bitmap: the group committed first, i.e. everything but the windows issued since
+        if (pc == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        else if (pc == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncthreads();
+    }
+    static_assert(kPoolStages == 2, "the group accounting below is written for two stages");
+
+    int64_t ck = A.kLast;
+    double sum = 0.0;
+    while (A.id < nTiles) {
+        if (ck >= A.kFirst) {
+            // the group of window cc: (pc - cc - 1) younger groups may stay in flight
+            if (pc - cc >= 2u) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            double *p = reinterpret_cast<double *>(ring + (size_t)(cc % kPoolStages) * kStageBytes);
+            const int32_t *rw = reinterpret_cast<const int32_t *>(p + kPoolChunk);
+            const int64_t w0 = ck * kPoolChunk;
+            const int lo = (int)(max(A.B, w0) - w0), hi = (int)(min(A.E, w0 + kPoolChunk) - w0);
+            {
+                double g[kPoolPerLane];
+#pragma unroll
+                for (int j = 0; j < kPoolPerLane; ++j) {
+                    const int i = lane + 32 * j;
+                    const bool in = i >= lo && i < hi;
+                    const int r = in ? rw[i] : 0;
+                    if (MODE == 2) {
+                        const uint32_t bw = sBits[r >> 5];
+                        const uint32_t bit = 1u << (r & 31);
+                        const int slot = (int)sPre[r >> 5] + __popc(bw & (bit - 1u));
+                        g[j] = sU[(in && (bw & bit)) ? slot : a.nSupport];
+                    } else {
+                        bool on = in;
+                        if (MODE == 1 && on) on = (sBits[r >> 5] >> (r & 31)) & 1u;
+                        g[j] = on ? __ldg(a.u + r) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kPoolPerLane; ++j) {
+                    const int i = lane + 32 * j;
+                    if (i >= lo && i < hi) p[i] = __dmul_rn(p[i], g[j]);
+                }
+            }
+            __syncwarp();
+            const int64_t kHi = min(w0 + hi, A.e), kLo = max(w0 + lo, A.b);
+            if (kHi > kLo) {
+                int q = (int)(kHi - 1 - w0);
+                const int qLo = (int)(kLo - w0);
+                if (q - 3 >= qLo) {
+                    double a0 = p[q], a1 = p[q - 1], a2 = p[q - 2], a3 = p[q - 3];
+                    q -= 4;
+                    while (q - 3 >= qLo) {
+                        const double n0 = p[q], n1 = p[q - 1], n2 = p[q - 2], n3 = p[q - 3];
+                        sum = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(sum, a0), a1), a2), a3);
+                        a0 = n0;
+                        a1 = n1;
+                        a2 = n2;
+                        a3 = n3;
+                        q -= 4;
+                    }
+                    sum = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(sum, a0), a1), a2), a3);
+                }
+                for (; q >= qLo; --q) sum = __dadd_rn(sum, p[q]);
+            }
+            __syncwarp();
+            --ck;
+            ++cc;
+            topUp();
+        }
+        if (ck < A.kFirst) {
+            // the tile is done: its 32 reduced costs, then the next tile becomes the current one
+            const long long col = A.id * 32 + lane;
+            if (col < a.nCols) {
+                const double rc = a.feasible ? A.oc - sum : -sum;  // DecompVarPool.cpp:29 / :36
+                a.out[col] = rc;
+                if (rc <= -0.0000000001) *a.flag = 1;              // :30, :37 -> found_negrc_var (:199)
+            }
+            A = N;
+            sum = 0.0;
+            if (prodInNext) prodInNext = 0;   // (pk keeps counting down inside what is now A)
+            else pk = A.kLast;
+            ck = A.kLast;
+            N = loadTile(A.id + W);
+            topUp();
+        }
+    }
+}
+
 int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st)
 {
     DIPGPU_CUDA(c, cudaMemsetAsync(c->dPoolFlag, 0, sizeof(int32_t), st));
     if (c->poolCols == 0) return DIPGPU_OK;
     const long long warps = (c->poolCols + 31) / 32;
-    // the bitmap variant pays when the pool is large (the bitmap is loaded once per CTA) and the support small
-    const int bitWords = (c->R + c->numConvex + 31) / 32;
-    const bool bitmap = c->dSupportBits != nullptr && !c->hSupport.empty() && bitWords * 4 <= 64 * 1024 &&
+    // the bitmap variants pay when the pool is large (the bitmap is loaded once per CTA) and the support small
+    const int bitWordsRaw = (c->R + c->numConvex + 31) / 32;
+    const bool bitmap = c->dSupportBits != nullptr && !c->hSupport.empty() && bitWordsRaw * 4 <= 64 * 1024 &&
                         c->poolCols >= 32 * 1024 && (int64_t)c->hSupport.size() * 4 <= (int64_t)c->R + c->numConvex;
-    const size_t perWarp = (size_t)kPoolStages * kPoolChunk * 12, bits = bitmap ? sizeof(uint32_t) * (((size_t)bitWords + 3) & ~(size_t)3) : 0;
+    const size_t perWarp = (size_t)kPoolStages * kPoolChunk * 12;
+    if (c->optPoolKernel != 0) {
+        // persistent kernel (default).  MODE 2 (option "pool_kernel" = 2) needs the rank table and room for at least
+        // 8 warps' rings beside bitmap + prefixes + compacted duals; measured SLOWER than the L2 gathers of MODE 1 on
+        // the GAP-E pool (66 vs 55 us: 82 KB of per-CTA set-up and 12 instead of 16 warps), so it is not the default
+        const int bitWords = (bitWordsRaw + 7) & ~7;   // (the arrays are allocated with this padding)
+        const size_t ns = c->hSupport.size();
+        const size_t bitsB = sizeof(uint32_t) * (size_t)bitWords, preB = ((size_t)bitWords * 2 + 15) & ~(size_t)15, uB = sizeof(double) * (ns + 2);
+        int mode = bitmap ? 1 : 0;
+        if (bitmap && c->dSupportRank != nullptr && 227 * 1024 >= bitsB + preB + uB + 8 * perWarp && c->optPoolKernel == 2) mode = 2;
+        const size_t extra = mode == 2 ? bitsB + preB + uB : mode == 1 ? bitsB : 0;
+        int wpc = (int)std::min<size_t>(kPoolWarpsMax, (227 * 1024 - extra) / perWarp);
+        const int sms = std::max(c->smCount, 1);
+        while (wpc > 2 && (warps + wpc - 1) / wpc < sms) wpc /= 2;
+        const unsigned grid = (unsigned)std::min<long long>(sms, (warps + wpc - 1) / wpc);
+        const size_t smem = perWarp * (size_t)wpc + extra;
+        auto fn = mode == 2 ? pool_redcost_persist_kernel<2> : mode == 1 ? pool_redcost_persist_kernel<1> : pool_redcost_persist_kernel<0>;
+        if (c->poolFnSmem2[mode] < smem) {
+            const int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(fn), smem);
+            if (rc) return rc;
+            c->poolFnSmem2[mode] = smem;
+        }
+        PoolArgs a;
+        a.nCols = c->poolCols;
+        a.colStart = c->dPoolStart;
+        a.row = c->dPoolRow;
+        a.val = c->dPoolVal;
+        a.origCost = c->dPoolOrigCost;
+        a.u = dU;
+        a.feasible = feasible;
+        a.out = c->dPoolRedCost;
+        a.flag = c->dPoolFlag;
+        a.supportBits = c->dSupportBits;
+        a.bitWords = bitWords;
+        a.rankPrefix = c->dSupportRank;
+        a.support = c->dSupport;
+        a.nSupport = (int)ns;
+        fn<<<grid, wpc * 32, smem, st>>>(a);
+        c->launches++;
+        DIPGPU_CUDA(c, cudaGetLastError());
+        return DIPGPU_OK;
+    }
+    const int bitWords = bitWordsRaw;
+    const size_t bits = bitmap ? sizeof(uint32_t) * (((size_t)bitWords + 3) & ~(size_t)3) : 0;
     // one CTA per SM, as many warps as the ring buffers leave room for (12 KiB each); small pools: fewer warps per
     // CTA so that the columns spread over the SMs
     int wpc = (int)std::min<size_t>(kPoolWarpsMax, (227 * 1024 - bits) / perWarp);

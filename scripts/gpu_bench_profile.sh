@@ -11,6 +11,11 @@ python bench.py --steps 5 --warmup 3 --skip-extras > gpurun_out/plain.log 2>&1 &
 cap() { # name, kernel regex, skip, command...
   name=$1; rx=$2; skip=$3; shift 3
   "$@" > gpurun_out/p_$name.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -f -o gpurun_out/prof_$name "$@" > gpurun_out/n_$name.log 2>&1; echo "ncu $name rc=$?"
+  # gpurun brings back at most 64 MiB: keep the raw page (all metrics) as CSV, and the per-line source page of
+  # the top kernel; the .ncu-rep itself stays on the box
+  ncu -i gpurun_out/prof_$name.ncu-rep --page raw --csv > gpurun_out/prof_$name.raw.csv 2>/dev/null
+  if [ "$name" = round_gape_dev ] || [ "$name" = pool_bitmap ]; then ncu -i gpurun_out/prof_$name.ncu-rep --page source --csv > gpurun_out/prof_$name.source.csv 2>/dev/null; fi
+  rm -f gpurun_out/prof_$name.ncu-rep
 }
 cap round_gape_dev knap_dp 2 python scripts/run_round.py dev
 cap round_gape_host knap_dp 2 python scripts/run_round.py host

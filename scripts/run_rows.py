@@ -20,7 +20,7 @@ if which == "pool":
 elif which == "mckp":
     print(bench.bench_mckp(torch, 0, 37000.0, flush))
 elif which == "bigdp":
-    print(bench.bench_bigdp(torch, 0, 37000.0, flush, m=int(sys.argv[2]) if len(sys.argv) > 2 else 64))
+    print(bench.bench_bigdp(torch, 0, 37000.0, flush, m=int(sys.argv[2]) if len(sys.argv) > 2 else 60))
 elif which == "intknap":
     print(bench.bench_intknap(torch, 0, 37000.0, flush))
 else:

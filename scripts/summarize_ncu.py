@@ -24,7 +24,10 @@ KEYS = [
 
 
 def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):   # exported on the GPU box (scripts/gpu_bench_profile.sh)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     return [dict(zip(hdr, r)) for r in rows[2:]], dict(zip(hdr, units))
@@ -35,7 +38,7 @@ def main():
     os.makedirs(PROF, exist_ok=True)
     lines = [f"# ncu summaries, round {tag[1:]} (from gpurun_out/*.ncu-rep; `--set full --clock-control none`)\n"]
     for name in sorted(os.listdir(OUT)):
-        if not name.endswith(".ncu-rep"):
+        if not (name.endswith(".ncu-rep") or name.endswith(".raw.csv")):
             continue
         recs, units = raw(os.path.join(OUT, name))
         for r in recs:
@@ -58,7 +61,7 @@ def main():
     traffic = {}
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for name in sorted(os.listdir(OUT)):
-        if not name.endswith(".ncu-rep"):
+        if not (name.endswith(".ncu-rep") or name.endswith(".raw.csv")):
             continue
         recs, units = raw(os.path.join(OUT, name))
         for r in recs:
@@ -67,7 +70,7 @@ def main():
                 wr = float(r["dram__bytes_write.sum"]) * unit[units["dram__bytes_write.sum"]]
             except Exception:
                 continue
-            traffic[name.replace(".ncu-rep", "")] = {
+            traffic[name.replace(".ncu-rep", "").replace(".raw.csv", "")] = {
                 "kernel": r.get("Kernel Name", "?"), "dram_bytes_read": rd, "dram_bytes_write": wr,
                 "grid": r.get("launch__grid_size"), "duration": r.get("gpu__time_duration.sum"),
                 "duration_unit": units.get("gpu__time_duration.sum")}

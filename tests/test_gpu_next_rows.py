@@ -194,9 +194,12 @@ def test_pool_reduced_costs_from_expanded_columns(oracle, pricer):
     assert len(got) == 0 and not found
 
 
-def test_pool_from_host_columns_ragged_and_large(oracle, pricer):
+@pytest.mark.parametrize("pool_kernel", [1, 0])
+def test_pool_from_host_columns_ragged_and_large(oracle, pricer, pool_kernel):
     """Host-built waiting columns: empty columns, a column longer than one staging chunk (512), many
-    columns; threshold semantics of found_negrc_var (<= -1e-10)."""
+    columns; threshold semantics of found_negrc_var (<= -1e-10).  pool_kernel: the persistent kernel (tiles
+    streamed across tile borders) and the one-CTA-per-16-tiles kernel."""
+    pricer.set_option("pool_kernel", pool_kernel)
     rng = np.random.default_rng(6)
     R, N, m = 3000, 64, 4
     rs = np.zeros(R + 1, np.int64)
@@ -635,9 +638,13 @@ def test_pinned_duals_and_host_mirror_paths(pricer):
     pin.free()
 
 
-def test_pool_with_dual_support_bitmap(oracle, pricer):
+@pytest.mark.parametrize("pool_kernel", [1, 2, 0])
+def test_pool_with_dual_support_bitmap(oracle, pricer, pool_kernel):
     """A large pool (>= 32 Ki columns) with a declared dual support runs the kernel variant that skips the
-    gathers of rows without a dual (shared-memory bitmap); bit-equal to the oracle and to the plain variant."""
+    gathers of rows without a dual (shared-memory bitmap); bit-equal to the oracle and to the plain variant.
+    pool_kernel 1: persistent kernel, gathers from L2; 2: u[support] compacted in shared memory and found by rank
+    in the bitmap; 0: the one-CTA-per-16-tiles kernel."""
+    pricer.set_option("pool_kernel", pool_kernel)
     rng = np.random.default_rng(61)
     R, m = 40_000, 16
     pricer.setModelCore(R, 8, np.zeros(R + 1, np.int64), np.zeros(0, np.int32), np.zeros(0), R, m)

@@ -318,11 +318,15 @@ def test_error_codes(pricer):
     assert r.blockObj[0] == 2.5 and list(r.column(0)) == [0]
 
 
+@pytest.mark.parametrize("no_cluster", [0, 1])
 @pytest.mark.parametrize("profit_mode", [0, 1])
-@pytest.mark.parametrize("cap,nhi,m,seed", [(13_000, 300, 5, 1), (100_000, 500, 3, 2), (40_000, 90, 12, 3)])
-def test_capacity_beyond_one_cta(oracle, pricer, profit_mode, cap, nhi, m, seed):
-    """Rows of more than 12 800 cells (GAP_KnapPisinger.h:243-249 prices any capacity): DP rows in global memory,
-    bit-exact optimum, identical columns; with node bounds as well."""
+@pytest.mark.parametrize("cap,nhi,m,seed", [(13_000, 300, 5, 1), (100_000, 500, 3, 2), (40_000, 90, 12, 3), (29_000, 120, 40, 4),
+                                            (200_000, 60, 2, 5), (230_000, 40, 2, 6)])
+def test_capacity_beyond_one_cta(oracle, pricer, profit_mode, cap, nhi, m, seed, no_cluster):
+    """Rows of more than 12 800 cells (GAP_KnapPisinger.h:243-249 prices any capacity): the row distributed over the
+    shared memories of a thread-block cluster (2, 4, 8 or 16 CTAs; up to 212 992 cells) or, beyond that and with
+    option dp_no_cluster, in global memory; bit-exact optimum, identical columns; with node bounds as well."""
+    pricer.set_option("dp_no_cluster", no_cluster)
     rng = np.random.default_rng(seed)
     n = rng.integers(nhi // 2, nhi + 1, size=m)
     bcs = np.zeros(m + 1, np.int32)
@@ -335,7 +339,8 @@ def test_capacity_beyond_one_cta(oracle, pricer, profit_mode, cap, nhi, m, seed)
     capv[0] = cap
     alpha = rng.uniform(-5, 0, size=m)
     res, ref = _check_against_oracle(oracle, pricer, bcs, w, capv, rc, oc, alpha, profit_mode=profit_mode)
-    assert pricer.dpGeometry()["cells_per_thread"] == 0
+    geo = pricer.dpGeometry()
+    assert (geo["cells_per_thread"] == 0) == (no_cluster == 1 or cap + 1 > 16 * 13 * 1024)
     if profit_mode == 0:
         lb = (rng.random(N) < 0.01).astype(np.float64)
         ub = 1.0 - (rng.random(N) < 0.05) * (1 - lb)
