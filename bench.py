@@ -1257,10 +1257,52 @@ def bench_spmv(torch, dev, local_rank, hbm_peak, peak_src, flush_l2, world, rank
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
     ms = float(np.mean(times))
+    # ---- 25 cut rows appended in place (DecompConstraintSet::appendRow, DecompAlgo.cpp:6074): the rows stay a
+    # delta (O(new entries)); beside it the same append with everything re-transposed and re-tiled
+    append = None
+    if not getattr(bench_spmv, "skip_append", False):
+        rng = np.random.default_rng(25)
+        k, nn = 25, 2000
+        r2 = np.sort(rng.integers(0, k, size=nn))
+        rs2 = np.zeros(k + 1, np.int64)
+        np.cumsum(np.bincount(r2, minlength=k), out=rs2[1:])
+        ci2 = rng.integers(0, model.N, size=nn).astype(np.int32)
+        v2 = rng.uniform(-5, 5, size=nn)
+        u2 = np.concatenate([u, rng.standard_normal(k)])   # master layout: [base rows | convexity | cut rows], new cuts last
+        out = {}
+        for label, min_nnz in (("delta", 0), ("full_rebuild", 1 << 40)):
+            q = GpuPricer(local_rank)
+            q.set_option("append_delta_min_nnz", min_nnz)
+            q.setModelCore(model.R, model.N, model.row_start, model.col_ind, model.val, model.n_base_rows, model.m)
+            q.setObjective(model.objective)
+            q.calcRedCost(u)                      # tiles built, as in a running column generation
+            t0 = time.perf_counter()
+            q.appendCoreRows(rs2, ci2, v2)
+            t_app = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            rc_first = q.calcRedCost(u2)          # the first sweep after the append (the rebuild re-tiles here)
+            t_first = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            q.calcRedCost(u2)                     # steady state of the same host call (8 MB of reduced costs back)
+            t_second = time.perf_counter() - t0
+            u2d = torch.from_numpy(u2).to(dev)
+            ts = []
+            for _ in range(8):
+                flush_l2()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                q.calcRedCostDev(u2d.data_ptr(), len(u2), stream=sptr)
+                b.record(stream)
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            out[label] = {"append_call_ms": 1e3 * t_app, "first_sweep_call_ms": 1e3 * t_first, "next_sweep_call_ms": 1e3 * t_second, "sweep_ms": float(np.mean(ts[1:])), "_rc": rc_first}
+            q.close()
+        same = bool(np.array_equal(out["delta"].pop("_rc"), out["full_rebuild"].pop("_rc")))
+        append = {"rows": k, "new_entries": nn, "bit_equal_to_full_rebuild": same, **out}
     pr.close()
     by = model.spmv_bytes()
     ach = by / (ms * 1e-3) / 1e9
-    return {"kernel": "redcost_stream_kernel", "workload": model.name, "bound": "hbm", "achieved": ach,
+    return {"kernel": "redcost_stream_kernel", "workload": model.name, "bound": "hbm", "achieved": ach, "append_cut_rows": append,
             "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic("prof_spmv_milp"),
             "avg_launch_ms": ms,
             "min_launch_ms": float(np.min(times)), "algorithmic_bytes": by, "peak_source": peak_src,

@@ -1354,6 +1354,11 @@ int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *ro
     c->dualsResident = false; c->haveCenter = false; c->haveST = false;
     c->dualsCompact = false; c->compactValid = false;
     c->hSupport.clear();
+    // (with room for cut rows: an append must not copy the whole host CSR because a vector ran out of capacity)
+    c->hRowStart.clear(); c->hColInd.clear(); c->hVal.clear();
+    c->hRowStart.reserve((size_t)R + (size_t)R / 16 + 1024);
+    c->hColInd.reserve((size_t)nnz + (size_t)nnz / 16 + 4096);
+    c->hVal.reserve((size_t)nnz + (size_t)nnz / 16 + 4096);
     c->hRowStart.assign(rowStart, rowStart + R + 1);
     c->hColInd.assign(colInd, colInd + nnz);
     c->hVal.assign(val, val + nnz);
