@@ -541,8 +541,12 @@ def single_gpu_line(args, torch, dev, local_rank):
         extras["real_duals"] = bench_real_duals(torch, dev, local_rank, flush_l2)
     cells_mean = float(np.mean(cells_per_round))
     cells_eval_mean = float(np.mean(cells_eval_per_round))
-    dp_ms = stage_ms["knapsack_dp"]
+    # the dominant kernel of the step IS the step: one fused kernel per device-resident round (gpu_launches == steps),
+    # its average launch duration = the CUDA-event time of the timed region / steps
+    dp_ms = dev_ms / K if launches == K else stage_ms["knapsack_dp"]
     roofline = dp_roofline(cells_mean, cells_eval_mean, dp_ms, smem_peak)
+    roofline["avg_launch_ms_source"] = ("CUDA events of the timed region (value loop), one kernel per step" if launches == K
+                                        else "library stage events of the host-buffer call")
 
     if not args.skip_extras:
         extras["dp_csp"] = bench_csp(torch, [local_rank], args, smem_peak, flush_l2)
@@ -617,7 +621,7 @@ def dp_roofline(cells_mean, cells_eval_mean, dp_ms, smem_peak):
         "cells_evaluated_per_launch": cells_eval_mean, "cells_per_launch": cells_mean,
         "algorithmic_achieved": alg, "algorithmic_frac": alg / smem_peak if ok else None,
         "algorithmic_gcups": cells_mean / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else None,
-        "traffic": ncu_traffic("prof_dp_gape"),
+        "traffic": ncu_traffic("prof_round_gape_dev"),
         "traffic_note": "DRAM bytes per launch, ncu --set full capture of this kernel on this shape "
                         "(profiles/ncu_traffic.json); the bound is shared memory, HBM only sees inputs",
         "peak_source": "in-library shared-memory copy microbenchmark (dipgpu_measure_smem_gbs), this run",

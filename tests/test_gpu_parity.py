@@ -180,6 +180,33 @@ def test_gap_e_round_with_programmatic_dependent_launch(oracle, pricer):
         _check_round(oracle, pricer, model, I.gap_duals(model, rng))
 
 
+@pytest.mark.parametrize("flag_wait", [1, 0])
+def test_round_completion_word_and_stream_synchronise_agree(oracle, pricer, flag_wait):
+    """The host entry point learns that a mirrored round is complete from a word the kernel's last CTA stores into
+    mapped host memory (option flag_wait, default on) or from cudaStreamSynchronize: the same rounds, many in a row
+    (the word carries a serial: a stale word must never end a wait), with and without the reduced costs handed back
+    (that call copies device memory and always synchronises)."""
+    pricer.set_option("flag_wait", flag_wait)
+    model = I.gap_pricing_model(I.gap_class_d())
+    rng = np.random.default_rng(77)
+    branch_rows = I.gap_branch_rows(model, rng)
+    pricer.setModel(model)
+    pricer.setDualSupport(I.gap_dual_support(model, branch_rows))
+    duals = [I.gap_duals(model, rng, branch_rows=branch_rows) for _ in range(6)]
+    refs = [oracle.price_round(model.R, model.N, model.row_start, model.col_ind, model.val, model.objective, u,
+                               model.n_base_rows, model.m, model.block_col_start, model.weight, model.capacity) for u in duals]
+    for it in range(120):
+        k = it % 6
+        if it % 17 == 5:
+            res, rcx = pricer.priceRound(duals[k], want_redcost=True)
+            np.testing.assert_array_equal(rcx, refs[k].red_cost_x)
+        else:
+            res = pricer.priceRound(duals[k])
+        np.testing.assert_array_equal(res.blockObj, refs[k].z)
+        np.testing.assert_array_equal(res.blockRedCost, refs[k].col_red_cost)
+        assert res.nCols == int(np.sum(refs[k].col_keep)) and res.mostNegReducedCost == refs[k].most_neg_reduced_cost
+
+
 def test_gap12_class_c_round(oracle, pricer):
     model = I.gap_pricing_model(I.gap_class_c())
     pricer.setModel(model)
