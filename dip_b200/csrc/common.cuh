@@ -313,6 +313,10 @@ struct Ctx {
     unsigned long long *dExpTicket = nullptr;
     int dpCoResident = 0;                   // CTAs of the configured DP kernel that fit the GPU at once
     unsigned int *dPullCtr = nullptr;       // 64 per-vector arrival counters of the in-kernel dual upload
+    unsigned int *dPullCtrBatch = nullptr;  // batchCap of them for batched launches (ensureBatch)
+    int dpResidentBatch = 0;                // CTAs of the batch build (tickets) resident at once
+    bool optBatchPull = true;               // option "batch_pull": ticketed batch launches fetch u[support] themselves
+    int optBatchPullMin = 24;               // ... from this many vectors per launch on (16: 245 vs 237 us, 64: 725 vs 890 us per call)
     RcFuse batchPull;                       // (feedBatchDuals -> enqueueBatch: where the batch's kernel pulls its duals from)
     bool optPull = true;                    // option "pull_duals": co-resident fused launches fetch u[support] from host memory themselves
     // reduced costs formed inside the fused DP kernel (option "fuse_redcost", default on): the CSC with int32 row ids

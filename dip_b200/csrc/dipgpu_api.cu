@@ -675,7 +675,7 @@ int launchPoolCopy(Ctx *c, int n, const void *dDesc, const void *srcEntries, con
 static void freeBatch(Ctx *c)
 {
     devFree(&c->dUBatch); devFree(&c->dRedCostBatch); devFree(&c->dPubWordBatch);
-    devFree(&c->dScaleB); devFree(&c->dShortcutB); devFree(&c->dSelB); devFree(&c->dZShortB); devFree(&c->dAlphaLadder);
+    devFree(&c->dScaleB); devFree(&c->dShortcutB); devFree(&c->dSelB); devFree(&c->dZShortB); devFree(&c->dAlphaLadder); devFree(&c->dPullCtrBatch);
     if (c->dResultBatch) cudaFree(c->dResultBatch);
     if (c->hResultBatch) cudaFreeHost(c->hResultBatch);
     c->dResultBatch = c->hResultBatch = c->dResultBatchHost = nullptr;
@@ -708,6 +708,8 @@ int ensureBatch(Ctx *c, int nVec)
     if ((rc = devAlloc(c, &c->dZShortB, V * nl))) return rc;
     DIPGPU_CUDA(c, cudaMemset(c->dShortcutB, 0, sizeof(int32_t) * V * nl));
     if ((rc = devAlloc(c, &c->dAlphaLadder, V))) return rc;
+    if ((rc = devAlloc(c, &c->dPullCtrBatch, V + 64))) return rc;
+    DIPGPU_CUDA(c, cudaMemset(c->dPullCtrBatch, 0, sizeof(unsigned int) * (V + 64)));
     DIPGPU_CUDA(c, cudaMalloc(&c->dResultBatch, V * resStride));
     DIPGPU_CUDA(c, cudaMemset(c->dResultBatch, 0, V * resStride));
     DIPGPU_CUDA(c, cudaHostAlloc(&c->hResultBatch, V * resStride, cudaHostAllocMapped | cudaHostAllocPortable));
@@ -790,7 +792,12 @@ int feedBatchDuals(Ctx *c, const DualFeed &f, int32_t uLen, int nVec, cudaStream
         }
         *compact = true;
         c->batchPull = RcFuse();
-        if (c->optPull && nVec <= 64 && dpWouldCoop(c, nVec)) {  // (64 per-vector arrival counters)
+        // the kernel fetches u[support] itself: co-resident grids, and ticketed ones when a whole vector's CTAs are
+        // resident at once (knapsack.cu: launchDp) -- the gathers of the later vectors then run under the DP of the
+        // earlier ones instead of in a kernel of their own in front of it
+        const bool ticketPull = c->optBatchPull && c->geom.fuse && c->dpResidentBatch >= c->nLocal && c->dPullCtrBatch != nullptr &&
+                                !dpWouldCoop(c, nVec) && !c->optPdl && nVec >= c->optBatchPullMin;
+        if (c->optPull && (dpWouldCoop(c, nVec) || ticketPull)) {
             c->h2d += (int64_t)sizeof(double) * (int64_t)ns * nVec;
             return pullSource(c, f, uLen, nVec, &c->batchPull);
         }
@@ -2669,6 +2676,8 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
         if (c->haveBlocks && c->blockKind == 0) return setBlockRange(c, c->firstBlock, c->nLocal);
         return DIPGPU_OK;
     }
+    if (!strcmp(name, "batch_pull")) { c->optBatchPull = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "batch_pull_min")) { c->optBatchPullMin = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "pool_kernel")) { c->optPoolKernel = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "flag_wait")) { c->optFlagWait = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "host_timing")) {  // diagnostics: 1 = on, 0 = off, else a host pointer receiving 4 doubles (us)

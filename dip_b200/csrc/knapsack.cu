@@ -1687,7 +1687,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) knap_dp_kernel(co
             if (atomicAdd(a.doneCtr, 1u) == gridDim.x * gridDim.y - 1u) {
                 *a.doneCtr = 0u;
                 if (pulls)
-                    for (unsigned int v = 0; v < gridDim.y; ++v) a.pullCtr[v] = 0u;
+                    for (unsigned int v = 0; v < gridDim.y; ++v) a.pullCtr[a.vecBase + v] = 0u;
                 *a.epochCtr = epochRaw + 1u;
                 if (a.doneFlag != nullptr) {
                     // every CTA's stores were performed system-wide (its fence.sys above) before its arrival was
@@ -1889,6 +1889,17 @@ int prepareKnapsackDp(Ctx *c)
         if (g.fuse && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, g.T, g.smemBytes) == cudaSuccess)
             c->dpCoResident = perSm * std::max(c->smCount, 1);
         (void)cudaGetLastError();
+        // the build large batches run (tickets): how many of its CTAs are resident at once
+        c->dpResidentBatch = 0;
+        if (g.fuse) {
+            KnapFn fb = pickKnapFn(e, g, false);
+            int rcB = ensureSmemLimit(c, reinterpret_cast<const void *>(fb), g.smemBytes);
+            if (rcB) return rcB;
+            perSm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fb, g.T, g.smemBytes) == cudaSuccess)
+                c->dpResidentBatch = perSm * std::max(c->smCount, 1);
+            (void)cudaGetLastError();
+        }
         c->dpFnConfigured = (void *)fn;
         c->dpFnSmem = g.smemBytes;
     }
@@ -2013,13 +2024,17 @@ static int launchDp(Ctx *c, const double *dRedCost, int64_t rcStride, const doub
     a.alphaIdx = rf ? rf->alphaIdx : nullptr;
     a.uStride = rf ? (long long)rf->uStride : 0;
     a.phase1 = rf ? rf->phase1 : 0;
-    a.pullSrc = (rf && coop) ? rf->pullSrc : nullptr;
+    // in-kernel dual upload: a co-resident grid, or a ticketed one in which at least one whole vector's CTAs are
+    // resident at once (tickets are drawn in start order and a CTA leaves only after its vector's CTAs have met: the
+    // lowest unfinished vector always has all its CTAs started)
+    const bool ticketPull = rf && rf->pullSrc && !coop && batch && g.fuse && c->dpResidentBatch >= c->nLocal && c->dPullCtrBatch != nullptr;
+    a.pullSrc = (rf && (coop || ticketPull)) ? rf->pullSrc : nullptr;
     a.pullIdx = rf ? rf->pullIdx : nullptr;
     a.pullStride = rf ? (long long)rf->pullStride : 0;
     a.pullN = rf ? rf->pullN : 0;
-    a.pullCtr = c->dPullCtr;
+    a.pullCtr = (batch && c->dPullCtrBatch) ? c->dPullCtrBatch : c->dPullCtr;
     a.vecBase = vecBase;
-    if (rf && rf->pullSrc && !coop) return fail(c, DIPGPU_ERR_STATE, "in-kernel dual upload needs a co-resident grid");
+    if (rf && rf->pullSrc && !coop && !ticketPull) return fail(c, DIPGPU_ERR_STATE, "in-kernel dual upload needs a co-resident grid");
     if (rf && !g.fuse) return fail(c, DIPGPU_ERR_STATE, "reduced costs can only be formed inside the fused DP kernel");
     a.useTab = (g.fuse && c->nLocal <= kFuseFilterMaxBlocks) ? 1 : 0;
     if (rf && !a.useTab) return fail(c, DIPGPU_ERR_STATE, "in-block reduced costs: %d blocks", c->nLocal);

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Batched GAP-E rounds through the host-buffer call: wall clock per call with the chunk pipeline on / off.
+"""Batched GAP-E rounds through the host-buffer call: wall clock per call with the in-kernel dual pull of ticketed batches on / off.
     python scripts/batch_probe.py [devices, e.g. 0,1,2,3] [batch sizes ...]"""
 import sys
 import time
@@ -19,6 +19,7 @@ def main():
     model, duals = B.workload()
     p = GpuPricer(devs if len(devs) > 1 else devs[0])
     p.setModel(model)
+    p.set_option("batch_pull_min", 0)
     p.setDualSupport(model.dual_support)
     big = max(sizes)
     pin = capi.PinnedArray((big, model.u_len), np.float64)
@@ -28,7 +29,7 @@ def main():
     res, arr = p._batch_results(big)
     for n in sizes:
         for pipe in (0, 1, 0, 1):
-            p.set_option("batch_pipeline", pipe)
+            p.set_option("batch_pull", pipe)
             for _ in range(3):
                 p.priceRoundsBatchRaw(n, pin.array.ctypes.data, model.u_len, capi.PHASE_PRICE2, 1e-4, arr)
             t = 0.0
@@ -38,7 +39,7 @@ def main():
                 t0 = time.perf_counter()
                 p.priceRoundsBatchRaw(n, pin.array.ctypes.data, model.u_len, capi.PHASE_PRICE2, 1e-4, arr)
                 t += time.perf_counter() - t0
-            print(f"devices {devs} batch {n:4d} pipeline={pipe}: {1e6 * t / reps:9.1f} us/call  {n * reps / t:10.0f} rounds/s", flush=True)
+            print(f"devices {devs} batch {n:4d} batch_pull={pipe}: {1e6 * t / reps:9.1f} us/call  {n * reps / t:10.0f} rounds/s", flush=True)
     p.close()
 
 

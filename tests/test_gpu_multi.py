@@ -289,6 +289,45 @@ def test_pipelined_batch_of_pinned_vectors(single, n_vec):
     pin.free()
 
 
+@pytest.mark.parametrize("n_vec,coop", [(7, 0), (40, 0), (150, 1), (333, 1)])
+def test_ticketed_batch_pulls_its_duals_itself(n_vec, coop):
+    """Batches too large to be co-resident (or any batch with dp_coop = 0) draw tickets; with a dual support their
+    CTAs fetch u[support] from host memory themselves (option batch_pull, from batch_pull_min vectors on) -- CTA
+    (vector, block) its slice, the CTAs of a vector meet at a counter -- instead of a gather kernel in front of
+    the launch: equal, vector by vector, to the gathered batch and to the single rounds; pinned and pageable
+    vectors; the counters are left clean for the next launch (three launches in a row)."""
+    from dip_b200.pricer import GpuPricer
+    model, duals = _gap(m=40, n=260, seed=33, cls="e")
+    with GpuPricer(0) as p:
+        p.set_option("dp_coop", coop)
+        p.set_option("batch_pull_min", 0)
+        p.setModel(model)
+        p.setDualSupport(model.dual_support)
+        pin = capi.PinnedArray((n_vec, model.u_len), np.float64)
+        for k in range(n_vec):
+            pin.array[k] = duals[k % len(duals)]
+            pin.array[k][:model.meta["n"]] *= 1.0 + 0.003 * k
+        ref = [_snap(p.priceRound(pin.array[k].copy())) for k in range(min(n_vec, 24))]
+        outs = {}
+        for pull in (1, 0, 1, 1):
+            p.set_option("batch_pull", pull)
+            l0 = p.counters()["kernel_launches"]
+            res, arr = p._batch_results(n_vec)
+            p.priceRoundsBatchRaw(n_vec, pin.array.ctypes.data, model.u_len, capi.PHASE_PRICE2, 1e-4, arr)
+            got = [_snap(g) for g in p._batch_finish(res, arr)]
+            assert got[:len(ref)] == ref, pull
+            outs.setdefault(pull, got)
+            assert got == outs[pull]
+            if pull:
+                assert p.counters()["kernel_launches"] - l0 == 1      # no gather kernel in front
+        assert outs[0] == outs[1]
+        # pageable vectors: gathered on the host into mapped staging, pulled from there
+        p.set_option("batch_pull", 1)
+        got = [_snap(g) for g in p.priceRoundsBatch(np.array(pin.array[:min(n_vec, 30)]))]
+        assert got == outs[1][:len(got)]
+        pin.free()
+
+
 def test_mixed_batch_sizes_over_many_launches(single):
     """a publication word that a launch does not rewrite (vector >= the launch's nVec) must never be
     taken for a current one, however many launches lie in between: batch(4), 260 x batch(1), batch(4)."""
