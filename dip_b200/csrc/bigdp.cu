@@ -10,6 +10,7 @@
 // decisions are bit-identical.  Decisions go to HBM as one bit per (item, cell), laid out [item][cell / 32]
 // (a warp's ballot is one word), and the backtrack kernel of knapsack.cu walks them one item at a time.
 #include <algorithm>
+#include <utility>
 
 #include "common.cuh"
 
@@ -170,13 +171,12 @@ __device__ __forceinline__ double ldClusterF64(uint32_t localAddr, unsigned rank
     return v;
 }
 
-template <int S>
-__global__ void __launch_bounds__(kClusterThreads, 1) knap_dp_cluster_kernel(const __grid_constant__ ClusterDpArgs ca)
+template <int S, int T>
+__global__ void __launch_bounds__(T, 1) knap_dp_cluster_kernel(const __grid_constant__ ClusterDpArgs ca)
 {
     extern __shared__ __align__(16) unsigned char clSm[];
-    __shared__ int sWarpCnt[kClusterThreads / 32];
+    __shared__ int sWarpCnt[T / 32];
     const BigDpArgs &a = ca.b;
-    constexpr int T = kClusterThreads;
     constexpr int L = S * T;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int C = ca.clusterSize;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) knap_dp_cluster_kernel(con
     // decision words of the last kClusterStage items, [item][s * 32 + warp]: written to HBM eight items at a time, so
     // that the GPU-scope fence inside every cluster barrier (MEMBAR.ALL.GPU) rarely finds a global store in flight
     uint32_t *sWords = reinterpret_cast<uint32_t *>(clSm + (size_t)2 * L * sizeof(double));
-    constexpr int kWordsPerItem = S * 32;
+    constexpr int kWordsPerItem = S * (T / 32);
     auto flushWords = [&](int iFirst, int count) {
         for (int idx = t; idx < count * kWordsPerItem; idx += T) {
             const int k = idx / kWordsPerItem, wi = idx - k * kWordsPerItem;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1) knap_dp_cluster_kernel(con
                 }
             }
         }
-        if (lane < S) sWords[(i % kClusterStage) * kWordsPerItem + lane * 32 + warp] = myWord;
+        if (lane < S) sWords[(i % kClusterStage) * kWordsPerItem + lane * (T / 32) + warp] = myWord;
         if ((i % kClusterStage) == kClusterStage - 1) {
             // (before the arrival: a warp that leaves the barrier may overwrite the staging area at once)
             __syncthreads();
@@ -335,35 +335,31 @@ __global__ void __launch_bounds__(kClusterThreads, 1) knap_dp_cluster_kernel(con
 }
 
 typedef void (*ClusterFn)(const ClusterDpArgs);
-static ClusterFn clusterFnFor(int S)
+template <int T, int... Ss>
+static ClusterFn clusterFnTable(int S, std::integer_sequence<int, Ss...>)
 {
-    switch (S) {
-        case 1: return knap_dp_cluster_kernel<1>;
-        case 2: return knap_dp_cluster_kernel<2>;
-        case 3: return knap_dp_cluster_kernel<3>;
-        case 4: return knap_dp_cluster_kernel<4>;
-        case 5: return knap_dp_cluster_kernel<5>;
-        case 6: return knap_dp_cluster_kernel<6>;
-        case 7: return knap_dp_cluster_kernel<7>;
-        case 8: return knap_dp_cluster_kernel<8>;
-        case 9: return knap_dp_cluster_kernel<9>;
-        case 10: return knap_dp_cluster_kernel<10>;
-        case 11: return knap_dp_cluster_kernel<11>;
-        case 12: return knap_dp_cluster_kernel<12>;
-        default: return knap_dp_cluster_kernel<13>;
-    }
+    ClusterFn fn = nullptr;
+    ((S == Ss + 1 ? (fn = knap_dp_cluster_kernel<Ss + 1, T>) : nullptr), ...);
+    return fn;
+}
+static ClusterFn clusterFnFor(int S, int T)
+{
+    if (T == 512) return clusterFnTable<512>(S, std::make_integer_sequence<int, 2 * kClusterMaxS>{});
+    return clusterFnTable<1024>(S, std::make_integer_sequence<int, kClusterMaxS>{});
 }
 
 // Cluster shape for rows of `cells` cells: the smallest power-of-two cluster whose CTAs hold them with <= 13 cells per
 // thread, then the fewest cells per thread that still cover the row.  0 = no cluster covers it (rows in global memory).
-void planClusterDp(int64_t cells, int *clusterSize, int *S)
+void planClusterDp(int64_t cells, int threads, int maxCells, int *clusterSize, int *S)
 {
     *clusterSize = 0;
     *S = 0;
+    int maxS = kClusterMaxS * (kClusterThreads / threads);   // the same 213 KB of row buffers per CTA
+    if (maxCells > 0) maxS = std::min(maxS, maxCells);
     for (int C = 2; C <= 16; C *= 2) {
-        if ((int64_t)C * kClusterMaxS * kClusterThreads >= cells) {
+        if ((int64_t)C * maxS * threads >= cells) {
             *clusterSize = C;
-            *S = (int)((cells + (int64_t)C * kClusterThreads - 1) / ((int64_t)C * kClusterThreads));
+            *S = (int)((cells + (int64_t)C * threads - 1) / ((int64_t)C * threads));
             return;
         }
     }
@@ -397,8 +393,9 @@ int launchBigDp(Ctx *c, const double *dRedCost, cudaStream_t st)
         ca.b = a;
         ca.S = c->geom.S;
         ca.clusterSize = c->geom.cluster;
-        const ClusterFn fn = clusterFnFor(c->geom.S);
-        const size_t smem = (size_t)2 * c->geom.S * kClusterThreads * sizeof(double) + (size_t)kClusterStage * c->geom.S * 32 * sizeof(uint32_t);
+        const int T = c->geom.T;
+        const ClusterFn fn = clusterFnFor(c->geom.S, T);
+        const size_t smem = (size_t)2 * c->geom.S * T * sizeof(double) + (size_t)kClusterStage * c->geom.S * (T / 32) * sizeof(uint32_t);
         if (c->clusterFnConfigured != (void *)fn) {
             int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(fn), smem);
             if (rc) return rc;
@@ -407,7 +404,7 @@ int launchBigDp(Ctx *c, const double *dRedCost, cudaStream_t st)
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)c->nLocal * (unsigned)c->geom.cluster, 1, 1);
-        cfg.blockDim = dim3(kClusterThreads, 1, 1);
+        cfg.blockDim = dim3((unsigned)T, 1, 1);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];

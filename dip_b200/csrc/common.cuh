@@ -299,6 +299,8 @@ struct Ctx {
     void *dpFnConfigured = nullptr;
     void *clusterFnConfigured = nullptr;
     bool clusterUnavailable = false;  // the device cannot place the planned cluster: rows in global memory instead
+    int optClusterMaxCells = 0;    // option "dp_cluster_max_cells": cap on the cells per thread (smaller CTAs, larger clusters, two CTAs per SM)
+    int optClusterThreads = 1024;  // option "dp_cluster_threads": 1024 (<= 13 cells per thread) or 512 (<= 26)
     int optNoCluster = 0;   // option "dp_no_cluster": rows beyond one CTA in global memory even when a cluster would hold them
     size_t dpFnSmem = 0;
     DpGeom geom{};
@@ -534,7 +536,7 @@ int launchBacktrackEmit(Ctx *c, const double *dRedCost, const double *dAlpha, do
                         cudaStream_t st);
 // bigdp.cu -- stage (b) for rows that do not fit one CTA
 int launchBigDp(Ctx *c, const double *dRedCost, cudaStream_t st);
-void planClusterDp(int64_t cells, int *clusterSize, int *S);  // bigdp.cu
+void planClusterDp(int64_t cells, int threads, int maxCells, int *clusterSize, int *S);  // bigdp.cu
 // mckp.cu -- stage (b) for multiple-choice knapsack blocks (DP + backtrack; the filter kernels follow)
 int launchMckp(Ctx *c, const double *dRedCost, const double *dAlpha, cudaStream_t st);
 // intknap.cu -- stage (b) for integer knapsack blocks (table + counts + column; the filter kernels follow)

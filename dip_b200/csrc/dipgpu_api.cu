@@ -2669,8 +2669,11 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
         return DIPGPU_OK;
     }
     if (!strcmp(name, "gather_pinned_duals")) { c->optGatherPinned = value != 0; return DIPGPU_OK; }
-    if (!strcmp(name, "dp_no_cluster")) {
-        c->optNoCluster = value != 0;
+    if (!strcmp(name, "dp_no_cluster") || !strcmp(name, "dp_cluster_threads") || !strcmp(name, "dp_cluster_max_cells")) {
+        if (!strcmp(name, "dp_no_cluster")) c->optNoCluster = value != 0;
+        else if (!strcmp(name, "dp_cluster_max_cells")) c->optClusterMaxCells = (int)value;
+        else if (value == 512 || value == 1024) c->optClusterThreads = (int)value;
+        else return fail(c, DIPGPU_ERR_INVALID, "dp_cluster_threads: 512 or 1024");
         c->clusterFnConfigured = nullptr;
         c->clusterUnavailable = false;
         if (c->haveBlocks && c->blockKind == 0) return setBlockRange(c, c->firstBlock, c->nLocal);

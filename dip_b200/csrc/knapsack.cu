@@ -1867,7 +1867,10 @@ int chooseDpGeom(Ctx *c, DpGeom *g, bool wantFuse)
         big.items = 1;
         big.big = 1;
         // ... or, up to 16 x 13 312 cells, distributed over the shared memories of a thread-block cluster
-        if (!c->optNoCluster) planClusterDp((int64_t)cells, &big.cluster, &big.S);
+        if (!c->optNoCluster) {
+            planClusterDp((int64_t)cells, c->optClusterThreads, c->optClusterMaxCells, &big.cluster, &big.S);
+            if (big.cluster > 0) big.T = c->optClusterThreads;
+        }
         *g = big;
         return DIPGPU_OK;
     }
