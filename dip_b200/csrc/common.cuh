@@ -367,6 +367,7 @@ struct Ctx {
     unsigned int *hDoneFlag = nullptr, *dDoneFlagHost = nullptr;
     unsigned int doneSerial = 0;
     bool flagArmed = false, wantFlag = false, optFlagWait = true;
+    long long flagWaits = 0, flagTimeouts = 0;   // rounds completed through the done word / waits that fell back to the synchronise
     bool hostTiming = false;      // option "host_timing": wall-clock stamps of the last dipgpu_price_round (diagnostics)
     double hostUs[4] = {0, 0, 0, 0};  // enqueue done, result seen, unpacked, DP launch call begins (us after entry)
     long long hostT0 = 0;             // entry time (steady clock, ns)

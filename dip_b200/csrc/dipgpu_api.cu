@@ -628,6 +628,7 @@ int fetchResult(Ctx *c, cudaStream_t st)
             }
             std::atomic_thread_fence(std::memory_order_acquire);
             c->flagArmed = false;
+            ++(seen ? c->flagWaits : c->flagTimeouts);
         }
         if (!seen) DIPGPU_CUDA(c, cudaStreamSynchronize(st));
         const ResultHeader *h = static_cast<const ResultHeader *>(c->hResult);
@@ -2683,6 +2684,11 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "batch_pull_min")) { c->optBatchPullMin = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "pool_kernel")) { c->optPoolKernel = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "flag_wait")) { c->optFlagWait = value != 0; return DIPGPU_OK; }
+    if (!strcmp(name, "flag_stats")) {  // diagnostics: value = host pointer receiving {rounds completed through the done word, timeouts}
+        long long v[2] = {c->flagWaits, c->flagTimeouts};
+        memcpy(reinterpret_cast<void *>(static_cast<uintptr_t>(value)), v, sizeof(v));
+        return DIPGPU_OK;
+    }
     if (!strcmp(name, "host_timing")) {  // diagnostics: 1 = on, 0 = off, else a host pointer receiving 4 doubles (us)
         if (value == 0 || value == 1) { c->hostTiming = value != 0; return DIPGPU_OK; }
         memcpy(reinterpret_cast<void *>(static_cast<uintptr_t>(value)), c->hostUs, sizeof(c->hostUs));
