@@ -150,6 +150,7 @@ struct ClusterDpArgs {
     BigDpArgs b;
     int S;            // cells per thread
     int clusterSize;  // CTAs per knapsack
+    int dbg;          // timing experiments only (WRONG results): 1 = no cluster barrier per item, 2 = every shifted read from the own slice
 };
 
 __device__ __forceinline__ unsigned clusterCtaRank()
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(T, 1) knap_dp_cluster_kernel(const __grid_cons
         auto loadShift = [&](int off, int rq) -> double {
             double v = __longlong_as_double((long long)0xfff0000000000000ULL);
             const uint32_t addr = rdBase + (uint32_t)off * 8u;
-            if (rq == r) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+            if (rq == r || ((ca.dbg & 2) && rq >= 0)) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
             else if (rq >= 0) v = ldClusterF64(addr, (unsigned)rq);
             return v;
         };
@@ -312,17 +313,19 @@ __global__ void __launch_bounds__(T, 1) knap_dp_cluster_kernel(const __grid_cons
 #ifdef DIPGPU_CLUSTER_RELAXED
         asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 #else
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        if (!(ca.dbg & 1)) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 #endif
         cur ^= 1;
         w = wNext;
         p = pNext;
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (!(ca.dbg & 1)) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        else __syncthreads();
     }
     if (nIt % kClusterStage != 0) {
         __syncthreads();
         flushWords(nIt - nIt % kClusterStage, nIt % kClusterStage);
     }
+    if (ca.dbg & 1) clusterSync();   // (timing experiment without the per-item barrier: nobody leaves while a peer may still read its slice)
     // z = c[n-1][capacity]  (gap_func.py:183)
     if (cap < 0 || shortCode != 0) {
         if (r == 0 && t == 0)
@@ -393,6 +396,7 @@ int launchBigDp(Ctx *c, const double *dRedCost, cudaStream_t st)
         ca.b = a;
         ca.S = c->geom.S;
         ca.clusterSize = c->geom.cluster;
+        ca.dbg = c->optClusterDebug;
         const int T = c->geom.T;
         const ClusterFn fn = clusterFnFor(c->geom.S, T);
         const size_t smem = (size_t)2 * c->geom.S * T * sizeof(double) + (size_t)kClusterStage * c->geom.S * (T / 32) * sizeof(uint32_t);

@@ -299,6 +299,7 @@ struct Ctx {
     void *dpFnConfigured = nullptr;
     void *clusterFnConfigured = nullptr;
     bool clusterUnavailable = false;  // the device cannot place the planned cluster: rows in global memory instead
+    int optClusterDebug = 0;       // option "dp_cluster_debug" (timing experiments, wrong results): see ClusterDpArgs::dbg
     int optClusterMaxCells = 0;    // option "dp_cluster_max_cells": cap on the cells per thread (smaller CTAs, larger clusters, two CTAs per SM)
     int optClusterThreads = 1024;  // option "dp_cluster_threads": 1024 (<= 13 cells per thread) or 512 (<= 26)
     int optNoCluster = 0;   // option "dp_no_cluster": rows beyond one CTA in global memory even when a cluster would hold them

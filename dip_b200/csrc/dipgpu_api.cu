@@ -2682,6 +2682,7 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     }
     if (!strcmp(name, "batch_pull")) { c->optBatchPull = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "batch_pull_min")) { c->optBatchPullMin = (int)value; return DIPGPU_OK; }
+    if (!strcmp(name, "dp_cluster_debug")) { c->optClusterDebug = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "pool_kernel")) { c->optPoolKernel = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "flag_wait")) { c->optFlagWait = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "flag_stats")) {  // diagnostics: value = host pointer receiving {rounds completed through the done word, timeouts}
