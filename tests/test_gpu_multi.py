@@ -421,3 +421,34 @@ def test_one_kernel_round_equals_three_kernel_round(support):
                 p.setDualSupport(sup2)
         _same_round(pa.priceRound(u2, result=RoundResult(model.m, model.m, model.N)),
                     pb.priceRound(u2, result=RoundResult(model.m, model.m, model.N)), model.m)
+
+
+def test_cut_rows_appended_as_a_delta_on_a_multi_device_context():
+    """dipgpu_append_core_rows reaches every device; each keeps the new rows as a delta (append_delta_min_nnz = 0
+    forces the path on this small model) and sweeps its own column range: forced block partition, whole rounds and a
+    batch equal to the one-GPU context that rebuilds everything."""
+    from dip_b200.pricer import GpuPricer
+    model, duals = _gap(m=16, n=280, seed=41, cls="e")
+    rng = np.random.default_rng(4)
+    with GpuPricer(0) as p1, GpuPricer([0, 0, 0]) as pm:
+        pm.set_option("append_delta_min_nnz", 0)
+        pm.set_option("shard_rounds", 3)
+        for p in (p1, pm):
+            p.setModel(model)
+            p.calcRedCost(duals[0])          # tiles built on every device
+        R = model.R
+        for k, nn in ((6, 300), (3, 40)):
+            r2 = np.sort(rng.integers(0, k, size=nn))
+            rs2 = np.zeros(k + 1, np.int64)
+            np.cumsum(np.bincount(r2, minlength=k), out=rs2[1:])
+            ci2 = rng.integers(0, model.N, size=nn).astype(np.int32)
+            v2 = np.round(rng.uniform(-3, 3, size=nn), 1)
+            for p in (p1, pm):
+                p.appendCoreRows(rs2, ci2, v2)
+            R += k
+            U = [np.concatenate([u, rng.standard_normal(R - model.R)]) for u in duals[:4]]
+            np.testing.assert_array_equal(pm.calcRedCost(U[0]), p1.calcRedCost(U[0]))
+            np.testing.assert_array_equal(pm.calcRedCost(U[1], capi.PHASE_PRICE1), p1.calcRedCost(U[1], capi.PHASE_PRICE1))
+            for u in U[:2]:
+                assert _snap(pm.priceRound(u)) == _snap(p1.priceRound(u))
+            assert [_snap(g) for g in pm.priceRoundsBatch(np.stack(U))] == [_snap(g) for g in p1.priceRoundsBatch(np.stack(U))]

@@ -379,6 +379,29 @@ def test_capacity_beyond_one_cta(oracle, pricer, profit_mode, cap, nhi, m, seed,
         assert [list(r2.column(k)) for k in range(r2.nCols)] == [list(ref2.col_ind[b]) for b in range(m) if ref2.col_keep[b]]
 
 
+@pytest.mark.parametrize("cap,m,n,seed", [(30_000, 6, 40, 11), (100_000, 3, 36, 12), (150_000, 2, 30, 13)])
+def test_cluster_rows_with_weights_spanning_several_ctas(oracle, pricer, cap, m, n, seed):
+    """The cluster kernel reads c[i-1][j-w] from the CTA that owns cell j-w: with weights up to the capacity that is
+    any lower-ranked CTA of the cluster (not just the neighbour), cells below w have no candidate, and weights that
+    are exact multiples of a CTA's slice land on slice borders.  Bit-exact optimum and identical columns."""
+    rng = np.random.default_rng(seed)
+    bcs = (np.arange(m + 1) * n).astype(np.int32)
+    N = m * n
+    w = rng.integers(1, cap + 1, size=N).astype(np.int32)          # any weight up to the capacity
+    small = rng.random(N) < 0.5
+    w[small] = rng.integers(1, cap // 20, size=int(small.sum()))    # ... mixed with small ones, so that columns have several items
+    for slice_cells in (13 * 1024, 7 * 1024, 2 * 13 * 1024):        # multiples of possible slice lengths
+        w[rng.integers(0, N, size=3)] = min(slice_cells, cap)
+    rc = -rng.uniform(0.5, 50.0, size=N)
+    oc = rng.uniform(1, 100, size=N)
+    capv = np.full(m, cap, np.int32)
+    capv[1:] = rng.integers(cap // 2, cap + 1, size=m - 1)
+    res, ref = _check_against_oracle(oracle, pricer, bcs, w, capv, rc, oc, np.zeros(m))
+    assert pricer.dpGeometry()["cells_per_thread"] > 0     # the cluster kernel ran
+    pricer.set_option("dp_no_cluster", 1)
+    _check_against_oracle(oracle, pricer, bcs, w, capv, rc, oc, np.zeros(m))
+
+
 def test_csp_full_size_properties(oracle, pricer):
     """BASELINE config 4 at full size (10^4 x 500 x 10^4): size-independent properties on every
     block + bit-exact oracle parity on a sample of blocks."""
