@@ -4,6 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/micro/launch_lat scripts/micro/launch_lat.cu
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
 
@@ -29,6 +30,10 @@ static double us(std::chrono::steady_clock::time_point a, std::chrono::steady_cl
     return std::chrono::duration<double, std::micro>(b - a).count();
 }
 
+static char *gThrash = nullptr;         // host-cache thrash between launches ("cold" launch call, as after an LP solve)
+static size_t gThrashBytes = 0;
+static volatile long gSink = 0;
+
 template <class P>
 static void run(const char *name, bool coop, bool flush, int spinNs, cudaStream_t st, unsigned *hFlags, unsigned *dFlags, void *flushBuf, size_t flushBytes)
 {
@@ -45,6 +50,11 @@ static void run(const char *name, bool coop, bool flush, int spinNs, cudaStream_
     for (int it = 0; it < reps + 10; ++it) {
         if (flush) cudaMemsetAsync(flushBuf, it & 0xff, flushBytes, st);
         cudaStreamSynchronize(st);
+        if (gThrash) {
+            long acc = 0;
+            for (size_t k = 0; k < gThrashBytes; k += 64) acc += gThrash[k]++;
+            gSink += acc;
+        }
         p.val = (unsigned)(it + 1) + 1000u * (unsigned)spinNs;
         const auto t0 = std::chrono::steady_clock::now();
         cudaLaunchConfig_t cfg = {};
@@ -83,6 +93,13 @@ int main()
     void *flushBuf;
     const size_t flushBytes = 256u << 20;
     cudaMalloc(&flushBuf, flushBytes);
+    for (int cold = 0; cold < 2; ++cold) {
+    if (cold) {
+        gThrashBytes = 96u << 20;
+        gThrash = (char *)malloc(gThrashBytes);
+        memset(gThrash, 1, gThrashBytes);
+        printf("---- host caches thrashed (96 MiB touched) before every launch call\n");
+    }
     for (int spin : {0, 30000}) {
         for (int flush = 0; flush < 2; ++flush) {
             run<Small>(flush ? "plain, 64 B params, L2 flushed" : "plain, 64 B params, warm", false, flush, spin, st, hFlags, dFlags, flushBuf, flushBytes);
@@ -90,6 +107,7 @@ int main()
             run<Small>(flush ? "cooperative, 64 B params, flushed" : "cooperative, 64 B params, warm", true, flush, spin, st, hFlags, dFlags, flushBuf, flushBytes);
             run<Big>(flush ? "cooperative, 4 KB params, flushed" : "cooperative, 4 KB params, warm", true, flush, spin, st, hFlags, dFlags, flushBuf, flushBytes);
         }
+    }
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
