@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(kIkThreads) intknap_kernel(const __grid_consta
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ int sWarpCnt[kIkThreads / 32];
     __shared__ int sBase, sN, sNRef, sWmin, sTotal, sEntries, sUsePos;
+    __shared__ double sPartV[kIkThreads];   // phase A: best candidate of (item run, cell)
+    __shared__ int sPartI[kIkThreads];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     constexpr int NW = kIkThreads / 32;
     const int lb = blockIdx.x;
@@ -128,24 +130,43 @@ __global__ void __launch_bounds__(kIkThreads) intknap_kernel(const __grid_consta
         __syncthreads();
         for (int c0 = 1; c0 <= cap; c0 += wmin) {
             const int c1 = min(cap, c0 + wmin - 1);
-            // phase A: candidates of the items, one warp per cell
-            for (int c = c0 + warp; c <= c1; c += NW) {
+            // phase A: candidates of the items.  The CTA's threads are laid over (cell of the window) x (group of
+            // items): thread (ci, g) scans a CONTIGUOUS run of items, ascending, under
+            // a strict >, so the first maximum of its run stays; the runs of a cell are then combined in run order,
+            // again under a strict >: the first maximum over (item 0, item 1, ...) wins, as in the reference's loop.
+            for (int cb = c0; cb <= c1; cb += kIkThreads) {
+                const int wc = min(c1 - cb + 1, kIkThreads);            // cells of this pass
+                const int G = max(1, min(kIkThreads / wc, (n + 3) / 4)); // item runs per cell (>= 4 items each)
+                const int per = (n + G - 1) / G;
+                const int ci = t % wc, g = t / wc;
+                const int c = cb + ci;
                 double best = negInf;
                 int arg = 0x7fffffff;
-                for (int i = lane; i < n; i += 32) {
-                    const int w = sW[i];
-                    if (w <= c) {                                  // :170
-                        const double zyes = F[c - w] + sP[i];      // :171-173
-                        if (zyes > best) { best = zyes; arg = i; } // :175 (ascending i per lane: the first maximum stays)
+                if (g < G) {
+                    const int i1 = min(n, (g + 1) * per);
+                    for (int i = g * per; i < i1; ++i) {
+                        const int w = sW[i];
+                        if (w <= c) {                                  // :170
+                            const double zyes = F[c - w] + sP[i];      // :171-173
+                            if (zyes > best) { best = zyes; arg = i; } // :175 (ascending i: the first maximum stays)
+                        }
                     }
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
-                    if (ov > best || (ov == best && oa < arg)) { best = ov; arg = oa; }
+                if (G == 1) {
+                    if (g == 0) { F[c] = best; item[c] = arg; }        // (cells of the window are not read in phase A)
+                } else {
+                    if (g < G) { sPartV[g * wc + ci] = best; sPartI[g * wc + ci] = arg; }
+                    __syncthreads();
+                    if (g == 0) {
+                        for (int q = 1; q < G; ++q) {
+                            const double ov = sPartV[q * wc + ci];
+                            if (ov > best) { best = ov; arg = sPartI[q * wc + ci]; }
+                        }
+                        F[c] = best;
+                        item[c] = arg;
+                    }
+                    __syncthreads();   // the partials are free for the next pass
                 }
-                if (lane == 0) { F[c] = best; item[c] = arg; }
             }
             __syncthreads();
             // phase B: F[c] = max(F[c-1], M[c]); taken iff M[c] > F[c-1]
