@@ -1000,7 +1000,7 @@ def bench_real_duals(torch, dev, local_rank, flush_l2):
     return out
 
 
-def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank, pool_kernel=None):
+def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank, pool_kernel=None, options=None):
     """Waiting-column re-pricing (SURVEY 8f-2, DecompVarPool::setReducedCosts) on a synthetic pool:
     2*10^5 master columns of 20..80 entries over the GAP-E master rows.  Kernel time from the library's
     CUDA events (L2 flushed), algorithmic bytes 12*nnz + 24*cols + 8*uLen."""
@@ -1033,6 +1033,8 @@ def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank, pool_kerne
     pr = GpuPricer(local_rank)
     if pool_kernel is not None:
         pr.set_option("pool_kernel", pool_kernel)
+    for k_, v_ in (options or {}).items():
+        pr.set_option(k_, v_)
     pr.setModelCore(u_len - 1, 1, np.zeros(u_len, np.int64), np.zeros(0, np.int32), np.zeros(0), u_len - 1, 1)
     pr.poolAppend(cs, ri, va, oc)
     by = 12 * nnz + 24 * n_cols + 8 * u_len
@@ -1054,12 +1056,21 @@ def bench_pool(torch, local_rank, hbm_peak, peak_src, flush_l2, rank, pool_kerne
     ms = timed()
     pr.close()
     ach = by / (ms * 1e-3) / 1e9
-    return {"kernel": "pool_redcost_kernel<BITMAP>" if pool_kernel == 0 else "pool_redcost_persist_kernel<%d>" % (2 if pool_kernel == 2 else 1),
+    # with the support declared the pass reads a compacted copy of the pool (entries of rows that can carry a dual):
+    # what it really streams
+    in_support = np.zeros(u_len, bool)
+    in_support[support] = True
+    nnz_eval = int(in_support[ri].sum())
+    by_eval = 12 * nnz_eval + 24 * n_cols + 8 * len(support)
+    return {"entries_evaluated": nnz_eval, "evaluated_bytes": by_eval, "frac_evaluated": by_eval / (ms * 1e-3) / 1e9 / hbm_peak,
+            "kernel": "pool_redcost_kernel<BITMAP>" if pool_kernel == 0 else "pool_redcost_persist_kernel<0, 256> over the compacted copy",
             "workload": f"{n_cols} waiting columns shaped like GAP-E master columns, {nnz} entries, {u_len} master rows, "
                         f"{len(support)} of them with a dual (one node: 1 % of the branch rows bounded)",
             "note": "every stored entry gathers one dual (8 B of a 32 B sector, L2-resident): the sector traffic, not the "
                     "12 B/entry stream, bounds this pass; with the dual support declared the gathers of rows without a "
-                    "dual are skipped (shared-memory bitmap); persistent CTAs, the window ring streams across tile borders",
+                    "dual are left out altogether: the pass streams a compacted copy of the pool (they add +-0 to a sum that is "
+                    "never -0: same bits); `achieved` / `frac` count the whole pool's 12 B/entry against the time, "
+                    "`frac_evaluated` only what the kernel streams; persistent CTAs, the window ring streams across tile borders",
             "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic("prof_pool_bitmap"),
             "avg_launch_ms": ms, "without_dual_support": {"avg_launch_ms": ms_plain, "achieved": by / (ms_plain * 1e-3) / 1e9,
                                                           "frac": by / (ms_plain * 1e-3) / 1e9 / hbm_peak},

@@ -400,7 +400,8 @@ struct Ctx {
     int32_t *dSupport = nullptr;
     uint32_t *dSupportBits = nullptr;  // one bit per master row (pool.cu)
     size_t poolFnSmem[2] = {0, 0};
-    size_t poolFnSmem2[3] = {0, 0, 0};
+    size_t poolFnSmem2[4] = {0, 0, 0, 0};
+    int optPoolChunk = 256, optPoolWarps = 24;   // options "pool_chunk" / "pool_warps": window size and warps per CTA of the pass over the compacted copy
     int optPoolKernel = 1;             // option "pool_kernel": 1 persistent (default), 2 persistent without the in-SM gather, 0 one CTA per 16 tiles
     uint16_t *dSupportRank = nullptr;  // per bitmap word: support rows below it (supports of < 65 536 rows)
     double *hSupVals = nullptr;  // mapped pinned staging the scatter kernel reads: supVecCap vectors of hSupport.size()
@@ -412,6 +413,19 @@ struct Ctx {
     int32_t *dPoolRow = nullptr;
     double *dPoolVal = nullptr, *dPoolOrigCost = nullptr, *dPoolRedCost = nullptr;
     int32_t *dPoolFlag = nullptr;    // [0]: some redCost <= -1e-10
+    // With a dual support declared the re-pricing pass reads a COMPACTED copy of the pool that holds only the entries
+    // of rows that can carry a dual (GAP master columns: one third of the entries).  The others contribute val * 0 =
+    // +-0 to their column's sum, and a running sum that starts at +0 is never -0 (x + (-x) rounds to +0), so adding
+    // +-0 is the identity bit for bit: leaving those entries out changes nothing.  Rebuilt (count, scan, fill) when the
+    // pool or the support has changed since the last pass (option "pool_compact", default on).
+    uint64_t poolSerial = 1, supportSerial = 1, poolCompactPool = 0, poolCompactSupport = 0;
+    int64_t *dPoolCStart = nullptr, *dPoolCCount = nullptr;
+    int32_t *dPoolCRow = nullptr;
+    double *dPoolCVal = nullptr;
+    int64_t poolCNnz = 0, poolCColCap = 0, poolCNnzCap = 0;
+    void *dPoolScanTmp = nullptr;
+    size_t poolScanTmpBytes = 0;
+    bool optPoolCompact = true;
 
     // pinned staging for pageable inputs
     double *hStage = nullptr;

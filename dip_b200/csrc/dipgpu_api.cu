@@ -1291,6 +1291,8 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     devFree(&c->dSupport); devFree(&c->dSupportBits); devFree(&c->dSupportRank);
     if (c->hSupVals) cudaFreeHost(c->hSupVals);
     devFree(&c->dCenter); devFree(&c->dPoolStart); devFree(&c->dPoolRow); devFree(&c->dPoolVal);
+    devFree(&c->dPoolCStart); devFree(&c->dPoolCCount); devFree(&c->dPoolCRow); devFree(&c->dPoolCVal);
+    if (c->dPoolScanTmp) cudaFree(c->dPoolScanTmp);
     devFree(&c->dPoolOrigCost); devFree(&c->dPoolRedCost); devFree(&c->dPoolFlag);
     if (c->dResult) cudaFree(c->dResult);
     if (c->hResult) cudaFreeHost(c->hResult);
@@ -1362,6 +1364,7 @@ int dipgpu_set_core_csr(dipgpu_ctx *ctx, int32_t R, int32_t N, const int64_t *ro
     c->dualsResident = false; c->haveCenter = false; c->haveST = false;
     c->dualsCompact = false; c->compactValid = false;
     c->hSupport.clear();
+    ++c->supportSerial;
     // (with room for cut rows: an append must not copy the whole host CSR because a vector ran out of capacity)
     c->hRowStart.clear(); c->hColInd.clear(); c->hVal.clear();
     c->hRowStart.reserve((size_t)R + (size_t)R / 16 + 1024);
@@ -1481,6 +1484,7 @@ int dipgpu_append_core_rows(dipgpu_ctx *ctx, int32_t nNew, const int64_t *rowSta
     c->dualsResident = false; c->haveST = false;  // the master dual vector grew
     c->dualsCompact = false; c->compactValid = false;
     c->hSupport.clear();
+    ++c->supportSerial;
     if (c->haveCenter) {
         // DecompAlgoPC::adjustMasterDualSolution resizes m_dual to the new row count (Dip/src/DecompAlgoPC.cpp:135-140):
         // the stability centre is kept and zero-extended -- the cut rows sit at the end of the master dual vector
@@ -2027,6 +2031,7 @@ int dipgpu_set_dual_support(dipgpu_ctx *ctx, int32_t nIdx, const int32_t *idx)
         if (idx[k] < 0 || idx[k] >= uLen || (k > 0 && idx[k] <= idx[k - 1]))
             return fail(c, DIPGPU_ERR_INVALID, "set_dual_support: indices must be ascending, unique and below %d", uLen);
     c->hSupport.assign(idx, idx + nIdx);
+    ++c->supportSerial;
     c->supVecCap = 0;          // staging is sized by the support
     c->dUClean = false;        // whatever the device vectors hold now may be nonzero outside the new support
     c->dUBatchClean = false;
@@ -2155,6 +2160,7 @@ int dipgpu_pool_clear(dipgpu_ctx *ctx)
     if (isMulti(ctx)) ctx = multiForward(ctx);  // not partitioned: the primary device's whole-model context
     CTX_OR_FAIL(ctx);
     c->poolCols = c->poolNnz = 0;
+    ++c->poolSerial;
     if (c->dPoolStart) DIPGPU_CUDA(c, cudaMemset(c->dPoolStart, 0, sizeof(int64_t)));
     return DIPGPU_OK;
 }
@@ -2198,6 +2204,7 @@ int dipgpu_pool_append(dipgpu_ctx *ctx, int32_t nCols, const int64_t *colStart, 
     c->h2d += (int64_t)nCols * 16 + add * 12;
     c->poolCols += nCols;
     c->poolNnz += add;
+    ++c->poolSerial;
     return DIPGPU_OK;
 }
 
@@ -2262,6 +2269,7 @@ int dipgpu_pool_append_expanded(dipgpu_ctx *ctx, int32_t nWhich, const int32_t *
     if ((rc = poolCopyColumns(c, desc, static_cast<char *>(c->dMCols) + c->mcolsOffEntries, nullptr, nullptr, c->dPoolRow, c->dPoolVal))) return rc;
     c->poolCols += nWhich;
     c->poolNnz += add;
+    ++c->poolSerial;
     return DIPGPU_OK;
 }
 
@@ -2301,6 +2309,7 @@ int dipgpu_pool_keep(dipgpu_ctx *ctx, int32_t nKeep, const int32_t *keepIdx)
     DIPGPU_CUDA(c, cudaMemcpy(c->dPoolOrigCost, cost.data(), sizeof(double) * cost.size(), cudaMemcpyHostToDevice));
     c->poolCols = nKeep;
     c->poolNnz = dst;
+    ++c->poolSerial;
     return DIPGPU_OK;
 }
 
@@ -2683,6 +2692,9 @@ int dipgpu_set_option(dipgpu_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "batch_pull")) { c->optBatchPull = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "batch_pull_min")) { c->optBatchPullMin = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "dp_cluster_debug")) { c->optClusterDebug = (int)value; return DIPGPU_OK; }
+    if (!strcmp(name, "pool_chunk")) { c->optPoolChunk = (int)value; return DIPGPU_OK; }
+    if (!strcmp(name, "pool_warps")) { c->optPoolWarps = std::max(1, std::min(24, (int)value)); return DIPGPU_OK; }
+    if (!strcmp(name, "pool_compact")) { c->optPoolCompact = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "pool_kernel")) { c->optPoolKernel = (int)value; return DIPGPU_OK; }
     if (!strcmp(name, "flag_wait")) { c->optFlagWait = value != 0; return DIPGPU_OK; }
     if (!strcmp(name, "flag_stats")) {  // diagnostics: value = host pointer receiving {rounds completed through the done word, timeouts}

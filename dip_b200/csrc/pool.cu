@@ -13,6 +13,8 @@
 // smoothing reads 16 B and writes 8 B per row and vector.
 #include <algorithm>
 
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
 namespace dipgpu {
@@ -197,12 +199,13 @@ struct PoolArgs {
     int nSupport;
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(kPoolWarpsMax * 32, 1) pool_redcost_persist_kernel(const __grid_constant__ PoolArgs a)
+template <int MODE, int CH>
+__global__ void __launch_bounds__(CH == 512 ? kPoolWarpsMax * 32 : 768, 1) pool_redcost_persist_kernel(const __grid_constant__ PoolArgs a)
 {
+    constexpr int kPerLane = CH / 32;
     extern __shared__ __align__(16) unsigned char poolSm[];
     const int warpsPerCta = blockDim.x >> 5;
-    constexpr int kStageBytes = kPoolChunk * 12;  // values, then rows
+    constexpr int kStageBytes = CH * 12;  // values, then rows
     unsigned char *extra = poolSm + (size_t)warpsPerCta * kPoolStages * kStageBytes;
     const uint32_t *sBits = reinterpret_cast<const uint32_t *>(extra);
     const uint16_t *sPre = reinterpret_cast<const uint16_t *>(extra + (size_t)a.bitWords * 4);
@@ -241,8 +244,8 @@ __global__ void __launch_bounds__(kPoolWarpsMax * 32, 1) pool_redcost_persist_ke
             t.e = lane == 31 ? t.E : nx;
             t.oc = col < a.nCols ? a.origCost[col] : 0.0;
             if (t.E > t.B) {
-                t.kLast = (t.E - 1) / kPoolChunk;
-                t.kFirst = t.B / kPoolChunk;
+                t.kLast = (t.E - 1) / CH;
+                t.kFirst = t.B / CH;
             }
         }
         return t;
@@ -251,17 +254,17 @@ __global__ void __launch_bounds__(kPoolWarpsMax * 32, 1) pool_redcost_persist_ke
     const uint32_t ringA = (uint32_t)__cvta_generic_to_shared(ring);
     auto issue = [&](int64_t k, int slot) {
         const uint32_t dst = ringA + (uint32_t)slot * kStageBytes;
-        const char *sv = reinterpret_cast<const char *>(a.val + k * kPoolChunk);
-        const char *sr = reinterpret_cast<const char *>(a.row + k * kPoolChunk);
+        const char *sv = reinterpret_cast<const char *>(a.val + k * CH);
+        const char *sr = reinterpret_cast<const char *>(a.row + k * CH);
 #pragma unroll
-        for (int j = 0; j < kPoolChunk / 64; ++j) {
+        for (int j = 0; j < CH / 64; ++j) {
             const int off = (lane + 32 * j) * 16;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(sv + off) : "memory");
         }
 #pragma unroll
-        for (int j = 0; j < kPoolChunk / 128; ++j) {
+        for (int j = 0; j < CH / 128; ++j) {
             const int off = (lane + 32 * j) * 16;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + kPoolChunk * 8 + off), "l"(sr + off) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + CH * 8 + off), "l"(sr + off) : "memory");
         }
     };
 
@@ -306,13 +309,13 @@ __global__ void __launch_bounds__(kPoolWarpsMax * 32, 1) pool_redcost_persist_ke
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
             double *p = reinterpret_cast<double *>(ring + (size_t)(cc % kPoolStages) * kStageBytes);
-            const int32_t *rw = reinterpret_cast<const int32_t *>(p + kPoolChunk);
-            const int64_t w0 = ck * kPoolChunk;
-            const int lo = (int)(max(A.B, w0) - w0), hi = (int)(min(A.E, w0 + kPoolChunk) - w0);
+            const int32_t *rw = reinterpret_cast<const int32_t *>(p + CH);
+            const int64_t w0 = ck * CH;
+            const int lo = (int)(max(A.B, w0) - w0), hi = (int)(min(A.E, w0 + CH) - w0);
             {
-                double g[kPoolPerLane];
+                double g[kPerLane];
 #pragma unroll
-                for (int j = 0; j < kPoolPerLane; ++j) {
+                for (int j = 0; j < kPerLane; ++j) {
                     const int i = lane + 32 * j;
                     const bool in = i >= lo && i < hi;
                     const int r = in ? rw[i] : 0;
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(kPoolWarpsMax * 32, 1) pool_redcost_persist_ke
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < kPoolPerLane; ++j) {
+                for (int j = 0; j < kPerLane; ++j) {
                     const int i = lane + 32 * j;
                     if (i >= lo && i < hi) p[i] = __dmul_rn(p[i], g[j]);
                 }
@@ -378,6 +381,92 @@ __global__ void __launch_bounds__(kPoolWarpsMax * 32, 1) pool_redcost_persist_ke
     }
 }
 
+// ---- the compacted copy of the pool (Ctx::dPoolC*): entries of rows that can carry a dual, in their column's order.
+// One warp per column; count pass, exclusive scan (cub), fill pass.
+__global__ void __launch_bounds__(256)
+pool_compact_kernel(long long nCols, const int64_t *__restrict__ colStart, const int32_t *__restrict__ row,
+                    const double *__restrict__ val, const uint32_t *__restrict__ supportBits,
+                    int64_t *__restrict__ count, const int64_t *__restrict__ cStart, int32_t *__restrict__ cRow,
+                    double *__restrict__ cVal)
+{
+    const long long col = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (col >= nCols) return;
+    const int64_t b = colStart[col], e = colStart[col + 1];
+    int64_t out = cStart != nullptr ? cStart[col] : 0;
+    int64_t n = 0;
+    for (int64_t k0 = b; k0 < e; k0 += 32) {
+        const int64_t k = k0 + lane;
+        int r = 0;
+        bool on = false;
+        if (k < e) {
+            r = row[k];
+            on = (supportBits[r >> 5] >> (r & 31)) & 1u;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (cStart != nullptr && on) {
+            const int64_t dst = out + __popc(bal & ((1u << lane) - 1u));
+            cRow[dst] = r;
+            cVal[dst] = val[k];
+        }
+        out += __popc(bal);
+        n += __popc(bal);
+    }
+    if (cStart == nullptr && lane == 0) count[col] = n;
+}
+
+// Builds the compacted copy when the pool or the support changed since it was last built.
+static int ensurePoolCompact(Ctx *c, cudaStream_t st)
+{
+    if (c->poolCompactPool == c->poolSerial && c->poolCompactSupport == c->supportSerial) return DIPGPU_OK;
+    const long long n = c->poolCols;
+    if (n + 1 > c->poolCColCap) {
+        if (c->dPoolCStart) cudaFree(c->dPoolCStart);
+        if (c->dPoolCCount) cudaFree(c->dPoolCCount);
+        c->dPoolCStart = c->dPoolCCount = nullptr;
+        c->poolCColCap = n + n / 4 + 64;
+        DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&c->dPoolCStart), sizeof(int64_t) * (size_t)c->poolCColCap));
+        DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&c->dPoolCCount), sizeof(int64_t) * (size_t)c->poolCColCap));
+    }
+    const unsigned grid = (unsigned)((n * 32 + 255) / 256);
+    DIPGPU_CUDA(c, cudaMemsetAsync(c->dPoolCCount + n, 0, sizeof(int64_t), st));   // the scan's last input: the total comes out at [n]
+    pool_compact_kernel<<<grid, 256, 0, st>>>(n, c->dPoolStart, c->dPoolRow, c->dPoolVal, c->dSupportBits, c->dPoolCCount, nullptr, nullptr, nullptr);
+    c->launches++;
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->dPoolCCount, c->dPoolCStart, (int)(n + 1), st);
+    if (tmp > c->poolScanTmpBytes) {
+        if (c->dPoolScanTmp) cudaFree(c->dPoolScanTmp);
+        c->dPoolScanTmp = nullptr;
+        DIPGPU_CUDA(c, cudaMalloc(&c->dPoolScanTmp, tmp + 256));
+        c->poolScanTmpBytes = tmp + 256;
+    }
+    tmp = c->poolScanTmpBytes;
+    if (cub::DeviceScan::ExclusiveSum(c->dPoolScanTmp, tmp, c->dPoolCCount, c->dPoolCStart, (int)(n + 1), st) != cudaSuccess)
+        return fail(c, DIPGPU_ERR_CUDA, "pool compaction: scan failed");
+    c->launches++;
+    int64_t total = 0;
+    DIPGPU_CUDA(c, cudaMemcpyAsync(&total, c->dPoolCStart + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+    if (total + kPoolPad > c->poolCNnzCap) {
+        if (c->dPoolCRow) cudaFree(c->dPoolCRow);
+        if (c->dPoolCVal) cudaFree(c->dPoolCVal);
+        c->dPoolCRow = nullptr;
+        c->dPoolCVal = nullptr;
+        c->poolCNnzCap = total + total / 4 + kPoolPad + 64;
+        DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&c->dPoolCRow), sizeof(int32_t) * (size_t)c->poolCNnzCap));
+        DIPGPU_CUDA(c, cudaMalloc(reinterpret_cast<void **>(&c->dPoolCVal), sizeof(double) * (size_t)c->poolCNnzCap));
+        DIPGPU_CUDA(c, cudaMemsetAsync(c->dPoolCRow, 0, sizeof(int32_t) * (size_t)c->poolCNnzCap, st));   // (whole windows are streamed: defined bytes behind the end)
+        DIPGPU_CUDA(c, cudaMemsetAsync(c->dPoolCVal, 0, sizeof(double) * (size_t)c->poolCNnzCap, st));
+    }
+    pool_compact_kernel<<<grid, 256, 0, st>>>(n, c->dPoolStart, c->dPoolRow, c->dPoolVal, c->dSupportBits, c->dPoolCCount, c->dPoolCStart, c->dPoolCRow, c->dPoolCVal);
+    c->launches++;
+    DIPGPU_CUDA(c, cudaGetLastError());
+    c->poolCNnz = total;
+    c->poolCompactPool = c->poolSerial;
+    c->poolCompactSupport = c->supportSerial;
+    return DIPGPU_OK;
+}
+
 int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st)
 {
     DIPGPU_CUDA(c, cudaMemsetAsync(c->dPoolFlag, 0, sizeof(int32_t), st));
@@ -397,23 +486,35 @@ int launchPoolRedCost(Ctx *c, const double *dU, int feasible, cudaStream_t st)
         const size_t bitsB = sizeof(uint32_t) * (size_t)bitWords, preB = ((size_t)bitWords * 2 + 15) & ~(size_t)15, uB = sizeof(double) * (ns + 2);
         int mode = bitmap ? 1 : 0;
         if (bitmap && c->dSupportRank != nullptr && 227 * 1024 >= bitsB + preB + uB + 8 * perWarp && c->optPoolKernel == 2) mode = 2;
+        // the compacted copy (only support-row entries): every entry left has a dual to gather, no bitmap in the kernel
+        const bool compact = bitmap && c->optPoolCompact && mode == 1;
+        if (compact) {
+            const int rc = ensurePoolCompact(c, st);
+            if (rc) return rc;
+            mode = 0;
+        }
         const size_t extra = mode == 2 ? bitsB + preB + uB : mode == 1 ? bitsB : 0;
-        int wpc = (int)std::min<size_t>(kPoolWarpsMax, (227 * 1024 - extra) / perWarp);
+        // the compacted copy has short columns (GAP: 17 entries): 256-entry windows and more warps per SM
+        const bool small = compact && c->optPoolChunk != 512;
+        const size_t perWarpK = small ? perWarp / 2 : perWarp;
+        int wpc = (int)std::min<size_t>(small ? (size_t)c->optPoolWarps : (size_t)kPoolWarpsMax, (227 * 1024 - extra) / perWarpK);
         const int sms = std::max(c->smCount, 1);
         while (wpc > 2 && (warps + wpc - 1) / wpc < sms) wpc /= 2;
         const unsigned grid = (unsigned)std::min<long long>(sms, (warps + wpc - 1) / wpc);
-        const size_t smem = perWarp * (size_t)wpc + extra;
-        auto fn = mode == 2 ? pool_redcost_persist_kernel<2> : mode == 1 ? pool_redcost_persist_kernel<1> : pool_redcost_persist_kernel<0>;
-        if (c->poolFnSmem2[mode] < smem) {
+        const size_t smem = perWarpK * (size_t)wpc + extra;
+        auto fn = small ? pool_redcost_persist_kernel<0, 256>
+                        : mode == 2 ? pool_redcost_persist_kernel<2, 512> : mode == 1 ? pool_redcost_persist_kernel<1, 512> : pool_redcost_persist_kernel<0, 512>;
+        const int slot = small ? 3 : mode;
+        if (c->poolFnSmem2[slot] < smem) {
             const int rc = ensureSmemLimit(c, reinterpret_cast<const void *>(fn), smem);
             if (rc) return rc;
-            c->poolFnSmem2[mode] = smem;
+            c->poolFnSmem2[slot] = smem;
         }
         PoolArgs a;
         a.nCols = c->poolCols;
-        a.colStart = c->dPoolStart;
-        a.row = c->dPoolRow;
-        a.val = c->dPoolVal;
+        a.colStart = compact ? c->dPoolCStart : c->dPoolStart;
+        a.row = compact ? c->dPoolCRow : c->dPoolRow;
+        a.val = compact ? c->dPoolCVal : c->dPoolVal;
         a.origCost = c->dPoolOrigCost;
         a.u = dU;
         a.feasible = feasible;

@@ -638,13 +638,14 @@ def test_pinned_duals_and_host_mirror_paths(pricer):
     pin.free()
 
 
-@pytest.mark.parametrize("pool_kernel", [1, 2, 0])
-def test_pool_with_dual_support_bitmap(oracle, pricer, pool_kernel):
+@pytest.mark.parametrize("pool_kernel,compact", [(1, 1), (1, 0), (2, 0), (0, 0)])
+def test_pool_with_dual_support_bitmap(oracle, pricer, pool_kernel, compact):
     """A large pool (>= 32 Ki columns) with a declared dual support runs the kernel variant that skips the
     gathers of rows without a dual (shared-memory bitmap); bit-equal to the oracle and to the plain variant.
     pool_kernel 1: persistent kernel, gathers from L2; 2: u[support] compacted in shared memory and found by rank
     in the bitmap; 0: the one-CTA-per-16-tiles kernel."""
     pricer.set_option("pool_kernel", pool_kernel)
+    pricer.set_option("pool_compact", compact)   # 1: the pass reads a copy of the pool without the rows that cannot carry a dual
     rng = np.random.default_rng(61)
     R, m = 40_000, 16
     pricer.setModelCore(R, 8, np.zeros(R + 1, np.int64), np.zeros(0, np.int32), np.zeros(0), R, m)
@@ -668,6 +669,32 @@ def test_pool_with_dual_support_bitmap(oracle, pricer, pool_kernel):
     assert found == ref_found == found0
     got_ray, _ = pricer.poolSetReducedCosts(None, feasible=False)     # resident duals, dual-ray form
     np.testing.assert_array_equal(got_ray, oracle.pool_reduced_costs(cs, ri, va, oc, u, False)[0])
+    # the pool and the support change: the compacted copy follows (columns removed, columns appended, another support)
+    keep = np.arange(0, n_cols, 3).astype(np.int32)
+    pricer.poolKeep(keep)
+    extra = 500
+    lens2 = rng.integers(0, 40, size=extra)
+    cs2 = np.zeros(extra + 1, np.int64)
+    np.cumsum(lens2, out=cs2[1:])
+    ri2 = rng.integers(0, R + m, size=cs2[-1]).astype(np.int32)
+    va2 = np.round(rng.uniform(-2, 2, size=cs2[-1]), 1)
+    oc2 = rng.uniform(-1, 30, size=extra)
+    pricer.poolAppend(cs2, ri2, va2, oc2)
+    lens_k = (cs[1:] - cs[:-1])[keep]
+    csk = np.zeros(len(keep) + 1, np.int64)
+    np.cumsum(lens_k, out=csk[1:])
+    rik = np.concatenate([ri[cs[j]:cs[j + 1]] for j in keep])
+    vak = np.concatenate([va[cs[j]:cs[j + 1]] for j in keep])
+    csA = np.concatenate([csk, csk[-1] + cs2[1:]])
+    riA, vaA, ocA = np.concatenate([rik, ri2]), np.concatenate([vak, va2]), np.concatenate([oc[keep], oc2])
+    got, _ = pricer.poolSetReducedCosts(u)
+    np.testing.assert_array_equal(got, oracle.pool_reduced_costs(csA, riA, vaA, ocA, u)[0])
+    support2 = np.sort(rng.choice(R + m, size=(R + m) // 7, replace=False)).astype(np.int32)
+    u2 = np.zeros(R + m)
+    u2[support2] = rng.standard_normal(len(support2))
+    pricer.setDualSupport(support2)
+    got, _ = pricer.poolSetReducedCosts(u2)
+    np.testing.assert_array_equal(got, oracle.pool_reduced_costs(csA, riA, vaA, ocA, u2)[0])
 
 
 # ------------------------------------------------------------------ f-4: multiple-choice knapsack blocks (MMKP)
