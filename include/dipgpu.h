@@ -496,6 +496,15 @@ int dipgpu_get_dp_geometry(const dipgpu_ctx *ctx, int32_t out[7]);
 
 /* Tuning / diagnostics knobs: "stage_timing", "dp_threads" (multiple of 32),
  * "dp_cells_per_thread" (odd, 1..25), "dp_items_per_step" (1, 2, or 3 with guard cells and <= 3 cells per thread), "dp_no_guard", "dp_no_prune" (1 = the fused kernel runs the DP over every active item), "fuse_redcost" (default 1: small shards form the reduced costs of their blocks' columns inside the fused DP kernel -- the whole round is ONE kernel; 0 = the stream SpMV kernel in front of it), "dp_pdl" (1 = programmatic dependent launch of the fused kernel behind the SpMV; measured slower, off by default), "shard_rounds" (multi-device contexts: see dipgpu_create_multi), "batch_pipeline" (1 = batches of >= 8 page-locked dual vectors are priced in chunks, the gathers of u[support] on a second stream beside the previous chunk's DP launch; measured: +5 % at best, off by default),
+ * "batch_pull" / "batch_pull_min" (default 1 / 24: batched launches of at least that many dual vectors fetch u[support] from host
+ * memory themselves, CTA (vector, block) its slice, instead of a gather kernel in front), "flag_wait" (default 1: a mirrored single
+ * round announces its result through a word in mapped host memory, the host entry point spins on it instead of synchronising the
+ * stream), "append_delta_min_nnz" (default 2^20: dipgpu_append_core_rows on models with at least that many stored entries keeps the
+ * new rows as a delta -- O(new entries) -- instead of rebuilding; "merge_appended_rows" folds the delta in), "pool_compact" (default
+ * 1: with a dual support the pool re-pricing pass reads a compacted copy of the pool without the rows that cannot carry a dual),
+ * "pool_kernel" (1 persistent, default; 2 persistent with u[support] and a rank table in shared memory; 0 one CTA per 16 tiles),
+ * "dp_no_cluster" (1 = DP rows beyond one CTA in global memory even when a thread-block cluster would hold them),
+ * "dp_cluster_threads" (1024 or 512), "dp_cluster_max_cells", diagnostics "host_timing", "flag_stats", "dp_cluster_debug",
  * "spmv_lanes" (0 = TMA stream kernel), "spmv_chunk" / "spmv_max_cols" (entry / column budget of
  * a warp tile; re-tiles the matrix), "spmv_stages", "spmv_warps", "spmv_u_smem", "fuse_filter" (-1 auto, 0 = three kernels,
  * 1 = filter in the backtrack tail, 2 = backtrack + filter in the DP tail); 0 restores the automatic
