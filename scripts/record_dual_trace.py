@@ -1,9 +1,11 @@
 #!/usr/bin/env python3
 """Record the master dual vectors of real column-generation runs (examples/gap_colgen.py: restricted master in
 HiGHS, DIP's row layout) for bench.py's replay legs: tests/golden/dual_trace_gap_d.npz (the whole root-node run of
-GAP-D 20x200, every 4th round kept) and dual_trace_gap_e.npz (150 rounds of GAP-E 80x1600, every 3rd kept, from a greedy primal start
--- the role of generateInitVars -- so that the duals are on the scale of the costs; a master solve of that size
-takes seconds in HiGHS, so the run is cut short).  The core is built without branch rows (root node: they
+GAP-D 20x200, every 4th round kept) and dual_trace_gap_e.npz (the first 16 rounds of GAP-E 80x1600 from a greedy primal
+start -- the role of generateInitVars.  That is where the committed trace ends: from round 17 on the restricted master
+takes HiGHS 15, 30, 60, 130 ... seconds per solve (measured with DIP_TRACE_LOG=1; z_RMP has not left the greedy
+start's value by then and the bound is still of big-M scale), so the GAP-E replay prices EARLY-round duals;
+DIP_TRACE_ROUNDS / DIP_TRACE_KEEP set the cut).  The core is built without branch rows (root node: they
 are free rows with zero duals), a vector is stored as [assignment duals | convexity duals]; bench.py scatters it
 into the full layout.  Pricing here runs on the CPU oracle (bit-equal to the GPU path, tests/test_colgen.py), so
 the script needs no GPU.
@@ -75,7 +77,8 @@ def record(name, g, max_rounds, keep_every, start=False):
     init, placed = greedy_start(g, model) if start else ((), 0)
     if start:
         print(f"{name}: greedy start places {placed} of {g.n} jobs")
-    tr, cols = G.run(model, oracle_price(model), max_rounds=max_rounds, init_cols=init)
+    log = (lambda msg: print(f"[{time.perf_counter() - t0:7.1f} s] {msg}", flush=True)) if os.environ.get("DIP_TRACE_LOG") else None
+    tr, cols = G.run(model, oracle_price(model), max_rounds=max_rounds, init_cols=init, log=log)
     U = np.stack(tr.duals)[::keep_every]
     path = os.path.join(ROOT, "tests", "golden", f"dual_trace_{name}.npz")
     np.savez_compressed(path, duals=U, rounds=np.arange(len(tr.duals))[::keep_every], z_rmp=np.array(tr.z_rmp),
@@ -90,7 +93,8 @@ def main():
     if "gap_d" in which:
         record("gap_d", I.gap_class_d(), 600, 4)
     if "gap_e" in which:
-        record("gap_e", I.gap_class_e(), 150, 3, start=True)
+        # (DIP_TRACE_ROUNDS: a master solve of this size takes tens of seconds in HiGHS once a few thousand columns are in)
+        record("gap_e", I.gap_class_e(), int(os.environ.get("DIP_TRACE_ROUNDS", "150")), int(os.environ.get("DIP_TRACE_KEEP", "3")), start=True)
 
 
 if __name__ == "__main__":
