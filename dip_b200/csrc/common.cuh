@@ -237,6 +237,10 @@ struct Ctx {
     int mcolsM = 0;                   // block count the packed master-column buffer was laid out for
     // packed master columns of the last expansion
     void *dMCols = nullptr, *hMCols = nullptr;
+    void *dMColsHost = nullptr;        // device address of hMCols (mapped): the expansion kernel mirrors its output there
+    unsigned int *hExpFlag = nullptr, *dExpFlagHost = nullptr;   // the expansion's done word (as Ctx::hDoneFlag for the round)
+    unsigned int expSerialFlag = 0;
+    bool expandFlagArmed = false, wantExpandMirror = false;
     size_t mcolsBytes = 0, mcolsOffColStart = 0, mcolsOffHash = 0, mcolsOffEntries = 0;
     int64_t mcolsCapEntries = 0;
     unsigned long long *dExpPub = nullptr;

@@ -1281,6 +1281,7 @@ int dipgpu_destroy(dipgpu_ctx *ctx)
     devFree(&c->dUCompact); devFree(&c->dUBatchCompact); devFree(&c->dCsrColInd); devFree(&c->dCsrVal); devFree(&c->dExpPub);
     if (c->dMCols) cudaFree(c->dMCols);
     if (c->hDoneFlag) cudaFreeHost(c->hDoneFlag);
+    if (c->hExpFlag) cudaFreeHost(c->hExpFlag);
     if (c->hMCols) cudaFreeHost(c->hMCols); devFree(&c->dPubWord); devFree(&c->dPubCells); devFree(&c->dDbgTimes); devFree(&c->dColStart); devFree(&c->dColStart32); devFree(&c->dTileRec); devFree(&c->dRowMaster16); devFree(&c->dSpmvBlob); devFree(&c->dSpmvWarpStart); devFree(&c->dRowMaster); devFree(&c->dVal); devFree(&c->dObj);
     devFree(&c->dBlockColStart); devFree(&c->dWeight); devFree(&c->dCapacity); devFree(&c->dBitsOff);
     devFree(&c->dBits); devFree(&c->dBigRowOff); devFree(&c->dBigRows); devFree(&c->dBigItemP); devFree(&c->dItemW); devFree(&c->dItemCol); devFree(&c->dNItems); devFree(&c->dScale); devFree(&c->dShortcut); devFree(&c->dSel); devFree(&c->dZShort);
@@ -2374,7 +2375,13 @@ static int prepareExpand(Ctx *c)
         c->dMCols = c->hMCols = nullptr;
         c->mcolsBytes = 0;
         DIPGPU_CUDA(c, cudaMalloc(&c->dMCols, bytes));
-        DIPGPU_CUDA(c, cudaMallocHost(&c->hMCols, bytes));
+        DIPGPU_CUDA(c, cudaHostAlloc(&c->hMCols, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        c->dMColsHost = nullptr;
+        if (cudaHostGetDevicePointer(&c->dMColsHost, c->hMCols, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            c->dMColsHost = nullptr;
+        }
+        memset(c->hMCols, 0, sizeof(MColsHeader));
         if ((rc = devAlloc(c, &c->dExpPub, (size_t)c->m))) return rc;
         DIPGPU_CUDA(c, cudaMemset(c->dExpPub, 0, sizeof(unsigned long long) * (size_t)std::max(c->m, 1)));
         c->mcolsBytes = bytes;
@@ -2405,6 +2412,23 @@ static size_t expandSpecBytes(const Ctx *c)
 
 // The first `spec` bytes of the packed master columns are on the host (stream synchronised): checks, the rest of
 // the entries if the speculative copy was short, decoding into the caller's arrays.
+// The expansion mirrored its output into hMCols and rings c->hExpFlag: wait for the word (20 ms, then the stream).
+static int waitExpandFlag(Ctx *c, cudaStream_t st)
+{
+    const volatile unsigned int *flag = c->hExpFlag;
+    const unsigned int want = c->expSerialFlag;
+    const auto t0 = std::chrono::steady_clock::now();
+    bool seen = false;
+    for (unsigned int spins = 1;; ++spins) {
+        if (*flag == want) { seen = true; break; }
+        if ((spins & 0xfffu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(20)) break;
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    c->expandFlagArmed = false;
+    if (!seen) DIPGPU_CUDA(c, cudaStreamSynchronize(st));
+    return DIPGPU_OK;
+}
+
 static int finishExpand(Ctx *c, int nKept, size_t spec, dipgpu_mcols *out, cudaStream_t st)
 {
     const char *hp = static_cast<const char *>(c->hMCols);
@@ -2457,7 +2481,18 @@ int dipgpu_expand_columns(dipgpu_ctx *ctx, double tolZero, dipgpu_mcols *out)
     int rc;
     if ((rc = prepareExpand(c))) return rc;
     cudaStream_t st = c->stream;
-    if ((rc = launchExpandColumns(c, tolZero, nKept, st))) return rc;
+    c->wantExpandMirror = true;
+    rc = launchExpandColumns(c, tolZero, nKept, st);
+    c->wantExpandMirror = false;
+    if (rc) return rc;
+    if (c->expandFlagArmed) {
+        // the kernel wrote the packed master columns into hMCols itself: no copy, no stream synchronisation
+        if ((rc = waitExpandFlag(c, st))) return rc;
+        const MColsHeader *mh = static_cast<const MColsHeader *>(c->hMCols);
+        const size_t got = c->mcolsOffEntries + sizeof(MColEntry) * (size_t)std::max<int64_t>(mh->nNnz, 0);
+        c->d2h += (int64_t)got;
+        return finishExpand(c, nKept, c->mcolsBytes, out, st);
+    }
     const size_t spec = expandSpecBytes(c);
     DIPGPU_CUDA(c, cudaMemcpyAsync(c->hMCols, c->dMCols, spec, cudaMemcpyDeviceToHost, st));
     DIPGPU_CUDA(c, cudaStreamSynchronize(st));
@@ -2490,13 +2525,36 @@ int dipgpu_price_round_expand(dipgpu_ctx *ctx, const double *u, int32_t uLen, in
         if ((rc = enqueueRound(c, u ? &f : nullptr, uLen, phase, redCostEps, true, st, false))) return rc;
     }
     size_t spec = 0;
+    bool expMirrored = false;
     if (c->nLocal > 0) {
-        if ((rc = launchExpandColumns(c, tolZero, c->nLocal, st))) return rc;
-        spec = expandSpecBytes(c);
-        DIPGPU_CUDA(c, cudaMemcpyAsync(c->hMCols, c->dMCols, spec, cudaMemcpyDeviceToHost, st));
-        c->d2h += (int64_t)spec;
+        c->wantExpandMirror = true;
+        rc = launchExpandColumns(c, tolZero, c->nLocal, st);
+        c->wantExpandMirror = false;
+        if (rc) return rc;
+        expMirrored = c->expandFlagArmed;
+        if (!expMirrored) {
+            spec = expandSpecBytes(c);
+            DIPGPU_CUDA(c, cudaMemcpyAsync(c->hMCols, c->dMCols, spec, cudaMemcpyDeviceToHost, st));
+            c->d2h += (int64_t)spec;
+        }
     }
-    if ((rc = fetchResult(c, st))) return rc;  // (synchronises the stream: the master columns are on the host too)
+    if (expMirrored && !c->resultMirrored) {
+        // (the round's result was not mirrored by its kernel: copy it, synchronise; the master columns are there by then)
+        if ((rc = fetchResult(c, st))) return rc;
+        c->expandFlagArmed = false;
+        spec = c->mcolsBytes;
+    } else if (expMirrored) {
+        // the expansion rings its own word once its CTAs (which start behind the round's kernel) are done: the round's
+        // result has landed by then too
+        if ((rc = waitExpandFlag(c, st))) return rc;
+        spec = c->mcolsBytes;
+        c->flagArmed = false;
+        const ResultHeader *h = static_cast<const ResultHeader *>(c->hResult);
+        c->lastResultBytes = c->layout.offInd + sizeof(int32_t) * (size_t)h->nInd;
+        c->d2h += (int64_t)c->lastResultBytes;
+        const MColsHeader *mh = static_cast<const MColsHeader *>(c->hMCols);
+        c->d2h += (int64_t)(c->mcolsOffEntries + sizeof(MColEntry) * (size_t)std::max<int64_t>(mh->nNnz, 0));
+    } else if ((rc = fetchResult(c, st))) return rc;  // (synchronises the stream: the master columns are on the host too)
     c->lastRoundOnHost = true;
     if ((rc = unpack(c, c->hResult, c->resultBytes, out))) return rc;
     mout->nCols = out->nCols;

@@ -19,6 +19,7 @@
 //      lower-numbered columns (same scheme as the fused DP kernel), so the output is tight and
 //      needs no second launch.
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -55,6 +56,13 @@ struct ExpandArgs {
     // (launch epoch << 32) | CTAs started: a CTA's column is the TICKET it draws on entry, so the columns it
     // waits for below belong to CTAs that started before it, whatever the dispatch order (see knapsack.cu)
     unsigned long long *ticket;
+    // host mirror (0 = none): every store into the packed master columns is repeated hostOff bytes further on, in mapped
+    // host memory; the last CTA to finish then stores doneVal into doneFlag (mapped host memory) behind a system-scope
+    // fence -- the host reads the columns without a device-to-host copy and without synchronising the stream
+    long long hostOff;
+    unsigned int *doneCtr;   // device: CTAs finished (reset by the last one)
+    unsigned int *doneFlag;
+    unsigned int doneVal;
     int rowWords;   // ceil(R/32)
     int rowWordsPhys;  // with the skew: rowWords + rowWords/32 + 1
     int colWords;   // ceil(maxBlockCols/32)
@@ -115,16 +123,43 @@ __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __gri
     }
     __syncthreads();
     const int k = (int)(unsigned int)sTicket;
+    // a store into the packed master columns and, when asked for, into their host mirror
+#define MC_PUT(lhs, val)                                                                                          \
+    do {                                                                                                          \
+        auto *p__ = &(lhs);                                                                                       \
+        const auto v__ = (val);                                                                                   \
+        *p__ = v__;                                                                                               \
+        if (a.hostOff != 0) *reinterpret_cast<decltype(p__)>(reinterpret_cast<char *>(p__) + a.hostOff) = v__;    \
+    } while (0)
+    // every CTA of the launch reports here when its stores are out; the last one rings the host
+    auto finish = [&]() {
+        if (a.doneFlag == nullptr) return;
+        __syncthreads();
+        if (t == 0) {
+            __threadfence_system();
+            if (atomicAdd(a.doneCtr, 1u) == gridDim.x - 1u) {
+                *a.doneCtr = 0u;
+                __threadfence();
+                // (the error flags are OR-ed into the device header by atomics; the host's copy gets their final value here)
+                if (a.hostOff != 0)
+                    *reinterpret_cast<volatile unsigned int *>(reinterpret_cast<char *>(&a.outHdr->flags) + a.hostOff) =
+                        *reinterpret_cast<volatile unsigned int *>(&a.outHdr->flags);
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned int *>(a.doneFlag) = a.doneVal;
+            }
+        }
+    };
     const unsigned long long epochTag = (1ull << 23) | ((sTicket >> 32) & 0x7fffffull);  // valid bit + epoch
     const int nKept = a.hdr->nKept;
     if (k >= nKept) {
         // (launched with one CTA per block behind a round whose outcome the host does not know yet)
         if (nKept == 0 && k == 0 && t == 0) {
-            a.outColStart[0] = 0;
-            a.outHdr->magic = kMColsMagic;
-            a.outHdr->nCols = 0;
-            a.outHdr->nNnz = 0;
+            MC_PUT(a.outColStart[0], (int64_t)0);
+            MC_PUT(a.outHdr->magic, kMColsMagic);
+            MC_PUT(a.outHdr->nCols, 0);
+            MC_PUT(a.outHdr->nNnz, (int64_t)0);
         }
+        finish();
         return;
     }
     const int lb = a.keptBlock[k];
@@ -277,7 +312,7 @@ __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __gri
                 e.row = cut ? i + a.numConvex : i;  // DecompAlgo.cpp:5532-5534
                 e.pad = 0;
                 e.val = v;
-                a.outEntries[off + q + (cut ? 1 : 0)] = e;
+                MC_PUT(a.outEntries[off + q + (cut ? 1 : 0)], e);
                 ++q;
             }
         }
@@ -286,22 +321,26 @@ __global__ void __launch_bounds__(kExpThreads) expand_columns_kernel(const __gri
             e.row = a.nBaseRows + b;  // the block's convexity row, DecompAlgo.cpp:5540
             e.pad = 0;
             e.val = 1.0;
-            a.outEntries[off + totBelow] = e;
+            MC_PUT(a.outEntries[off + totBelow], e);
         }
     }
     if (t == 0) {
         unsigned long long hh = 0ull;
         for (int w = 0; w < kExpThreads / 32; ++w) hh += sHashW[w];
-        a.outHash[k] = mix64(hh ^ ((uint64_t)(uint32_t)b << 40) ^ (uint64_t)(i1 - i0));
-        a.outColStart[k] = (int64_t)off;
-        if (overflow || !fits) atomicOr(&a.outHdr->flags, overflow ? 1u : 2u);
+        MC_PUT(a.outHash[k], mix64(hh ^ ((uint64_t)(uint32_t)b << 40) ^ (uint64_t)(i1 - i0)));
+        MC_PUT(a.outColStart[k], (int64_t)off);
+        if (overflow || !fits) {
+            atomicOr(&a.outHdr->flags, overflow ? 1u : 2u);
+        }
         if (k == nKept - 1) {
-            a.outColStart[nKept] = (int64_t)(off + len);
-            a.outHdr->magic = kMColsMagic;
-            a.outHdr->nCols = nKept;
-            a.outHdr->nNnz = (int64_t)(off + len);
+            MC_PUT(a.outColStart[nKept], (int64_t)(off + len));
+            MC_PUT(a.outHdr->magic, kMColsMagic);
+            MC_PUT(a.outHdr->nCols, nKept);
+            MC_PUT(a.outHdr->nNnz, (int64_t)(off + len));
         }
     }
+    finish();
+#undef MC_PUT
 }
 
 int launchExpandColumns(Ctx *c, double tolZero, int nKept, cudaStream_t st)
@@ -334,6 +373,26 @@ int launchExpandColumns(Ctx *c, double tolZero, int nKept, cudaStream_t st)
     a.capEntries = c->mcolsCapEntries;
     a.pubWord = c->dExpPub;
     a.ticket = c->dExpTicket;
+    a.hostOff = 0;
+    a.doneCtr = c->dSyncWords + 6;
+    a.doneFlag = nullptr;
+    a.doneVal = 0u;
+    c->expandFlagArmed = false;
+    if (c->optFlagWait && c->optZeroCopy && c->wantExpandMirror && !c->stageTiming && c->hMCols != nullptr && c->dMColsHost != nullptr) {
+        if (!c->hExpFlag) {
+            void *hp = nullptr, *dp = nullptr;
+            DIPGPU_CUDA(c, cudaHostAlloc(&hp, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+            memset(hp, 0, 64);
+            DIPGPU_CUDA(c, cudaHostGetDevicePointer(&dp, hp, 0));
+            c->hExpFlag = static_cast<unsigned int *>(hp);
+            c->dExpFlagHost = static_cast<unsigned int *>(dp);
+        }
+        if (++c->expSerialFlag == 0u) ++c->expSerialFlag;
+        a.hostOff = (long long)(static_cast<char *>(c->dMColsHost) - static_cast<char *>(c->dMCols));
+        a.doneFlag = c->dExpFlagHost;
+        a.doneVal = c->expSerialFlag;
+        c->expandFlagArmed = true;
+    }
     a.rowWords = (c->R + 31) / 32;
     a.rowWordsPhys = a.rowWords + a.rowWords / 32 + 1;
     a.colWords = (c->maxBlockCols + 31) / 32;
